@@ -1,0 +1,15 @@
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+REF = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")

@@ -1,0 +1,155 @@
+// fd_common.cuh -- context, error handling, device buffers, stage timers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/folddisco_b200.h"
+
+#define FD_NUM_SMS_FALLBACK 148
+
+struct FdStage {
+    double ms = 0.0;
+    uint64_t launches = 0;
+};
+
+// Device copy of the attached inverted index (layout documented in DESIGN.md "HBM layout").
+struct FdDeviceIndex {
+    bool attached = false;
+    uint64_t count = 0;       // number of distinct hashes
+    uint64_t value_bytes = 0; // posting bytes
+    uint64_t n_structs = 0;
+    uint32_t *hashes = nullptr;   // [count] ascending
+    uint64_t *offsets = nullptr;  // [count+1] byte offsets into values
+    uint8_t *values = nullptr;    // [value_bytes + 16] delta+LEB128 postings, padded for vector loads
+    uint32_t *counts = nullptr;   // [count] postings per list
+    uint32_t *dir = nullptr;      // [FD_DIR_SIZE+1] hashes[] position of the first hash with (hash >> FD_DIR_SHIFT) >= b
+    uint32_t *skip_id = nullptr;  // [n_skip] see fd_query.cu
+    uint32_t *skip_pos = nullptr; // [n_skip]
+    uint64_t n_skip = 0;
+    uint32_t *nres = nullptr; // [n_structs]
+    float *plddt = nullptr;   // [n_structs]
+};
+
+// Device copy of the compact-structure store used by candidate verification.
+struct FdDeviceStore {
+    bool attached = false;
+    uint64_t n_structs = 0, n_res = 0;
+    uint64_t *row_offsets = nullptr;
+    float *n_xyz = nullptr, *ca_xyz = nullptr, *cb_xyz = nullptr;
+    uint8_t *aa = nullptr, *cb_valid = nullptr;
+};
+
+struct fd_ctx {
+    int device = 0;
+    int num_sms = FD_NUM_SMS_FALLBACK;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    std::map<std::string, FdStage> stages;
+    FdDeviceIndex idx;
+    FdDeviceStore store;
+    uint64_t last_posting_bytes = 0;
+};
+
+extern thread_local std::string fd_g_create_error;
+
+inline int fd_fail(fd_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else fd_g_create_error = msg;
+    return code;
+}
+
+#define FD_CUDA(ctx, call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            char b__[512];                                                                             \
+            snprintf(b__, sizeof(b__), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return fd_fail((ctx), e__ == cudaErrorMemoryAllocation ? FD_ERR_NOMEM : FD_ERR_CUDA, b__); \
+        }                                                                                              \
+    } while (0)
+
+#define FD_TRY(expr)              \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ != FD_OK) return r__; \
+    } while (0)
+
+// Owning device buffer; freed on scope exit.  Plain cudaMalloc: sizes are large and calls are few.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    T *take() {
+        T *q = p;
+        p = nullptr;
+        n = 0;
+        return q;
+    }
+};
+
+// Brackets one stage with CUDA events on the library stream and accumulates its device time.
+struct StageTimer {
+    fd_ctx *ctx;
+    const char *name;
+    uint64_t launches0;
+    StageTimer(fd_ctx *c, const char *n) : ctx(c), name(n), launches0(c->launches) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+    }
+    // call after the stage's last launch; synchronises the stream
+    cudaError_t finish() {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(ctx->ev1);
+        if (e != cudaSuccess) return e;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        FdStage &s = ctx->stages[name];
+        s.ms += ms;
+        s.launches += ctx->launches - launches0;
+        return cudaGetLastError();
+    }
+};
+
+#define FD_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+        (ctx)->launches++;                                                      \
+    } while (0)
+
+inline uint32_t fd_div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// Shared between fd_hash.cu (index build) and fd_postings.cu
+int fd_postings_from_keys(fd_ctx *ctx, uint64_t *d_keys /* hash<<32|id, consumed */, uint64_t n_keys,
+                          uint64_t *d_tmp /* same size scratch */, fd_index_buffers *out);
+
+// device batch upload helper (fd_hash.cu)
+struct FdDeviceBatch {
+    DevBuf<uint64_t> row_offsets;
+    DevBuf<float> n_xyz, ca_xyz, cb_xyz;
+    DevBuf<uint8_t> aa, cb_valid;
+    uint64_t n_structs = 0, n_res = 0;
+};
+int fd_upload_batch(fd_ctx *ctx, const fd_struct_batch *b, FdDeviceBatch *d);

@@ -1,0 +1,136 @@
+// fd_ctx.cu -- lifecycle of the C ABI (include/folddisco_b200.h) and the math parity probes.
+#include "fd_common.cuh"
+#include "fd_geom.cuh"
+
+thread_local std::string fd_g_create_error;
+
+static void fd_release_index(FdDeviceIndex &ix) {
+    cudaFree(ix.hashes);
+    cudaFree(ix.offsets);
+    cudaFree(ix.values);
+    cudaFree(ix.counts);
+    cudaFree(ix.dir);
+    cudaFree(ix.skip_id);
+    cudaFree(ix.skip_pos);
+    cudaFree(ix.nres);
+    cudaFree(ix.plddt);
+    ix = FdDeviceIndex();
+}
+static void fd_release_store(FdDeviceStore &st) {
+    cudaFree(st.row_offsets);
+    cudaFree(st.n_xyz);
+    cudaFree(st.ca_xyz);
+    cudaFree(st.cb_xyz);
+    cudaFree(st.aa);
+    cudaFree(st.cb_valid);
+    st = FdDeviceStore();
+}
+void fd_ctx_release_index(fd_ctx *ctx) { fd_release_index(ctx->idx); }
+void fd_ctx_release_store(fd_ctx *ctx) { fd_release_store(ctx->store); }
+
+__global__ void fd_math_probe_kernel(int op, const float *a, const float *b, uint64_t n, float *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, c;
+    switch (op) {
+        case 0:
+            fdm::sincosf_exact(a[i], &s, &c);
+            out[i] = s;
+            break;
+        case 1:
+            fdm::sincosf_exact(a[i], &s, &c);
+            out[i] = c;
+            break;
+        case 2: out[i] = fdm::acosf_exact(a[i]); break;
+        default: out[i] = fdm::atan2f_exact(a[i], b[i]); break;
+    }
+}
+
+extern "C" {
+
+const char *fd_version(void) { return "folddisco_b200 0.1 (sm_100a)"; }
+
+int fd_create(fd_ctx **out, int device) {
+    if (!out) return fd_fail(nullptr, FD_ERR_ARG, "fd_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fd_fail(nullptr, FD_ERR_CUDA,
+                       std::string("fd_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                           "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fd_fail(nullptr, FD_ERR_ARG, "fd_create: device index out of range");
+    fd_ctx *ctx = new fd_ctx();
+    ctx->device = device;
+    FD_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FD_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    FD_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    FD_CUDA(nullptr, cudaEventCreate(&ctx->ev0));
+    FD_CUDA(nullptr, cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    return FD_OK;
+}
+
+void fd_destroy(fd_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    fd_release_index(ctx->idx);
+    fd_release_store(ctx->store);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fd_last_error(const fd_ctx *ctx) { return ctx ? ctx->err.c_str() : fd_g_create_error.c_str(); }
+void fd_free(void *p) { free(p); }
+uint64_t fd_kernel_launches(const fd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+double fd_stage_ms(const fd_ctx *ctx, const char *stage) {
+    if (!ctx || !stage) return -1.0;
+    auto it = ctx->stages.find(stage);
+    return it == ctx->stages.end() ? 0.0 : it->second.ms;
+}
+uint64_t fd_stage_launches(const fd_ctx *ctx, const char *stage) {
+    if (!ctx || !stage) return 0;
+    auto it = ctx->stages.find(stage);
+    return it == ctx->stages.end() ? 0 : it->second.launches;
+}
+uint64_t fd_last_posting_bytes(const fd_ctx *ctx) { return ctx ? ctx->last_posting_bytes : 0; }
+
+int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t n, float *out) {
+    if (!ctx || !a || !out || (op == 3 && !b)) return fd_fail(ctx, FD_ERR_ARG, "fd_math_probe: bad argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<float> da, db, dout;
+    FD_CUDA(ctx, da.alloc(n));
+    FD_CUDA(ctx, db.alloc(n));
+    FD_CUDA(ctx, dout.alloc(n));
+    FD_CUDA(ctx, cudaMemcpyAsync(da.p, a, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (b) FD_CUDA(ctx, cudaMemcpyAsync(db.p, b, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) FD_LAUNCH(ctx, fd_math_probe_kernel, fd_div_up(n, 256), 256, 0, op, da.p, db.p, n, dout.p);
+    FD_CUDA(ctx, cudaGetLastError());
+    FD_CUDA(ctx, cudaMemcpyAsync(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FD_OK;
+}
+
+void fd_math_host(int op, const float *a, const float *b, uint64_t n, float *out) {
+    for (uint64_t i = 0; i < n; i++) {
+        float s, c;
+        switch (op) {
+            case 0:
+                fdm::sincosf_exact(a[i], &s, &c);
+                out[i] = s;
+                break;
+            case 1:
+                fdm::sincosf_exact(a[i], &s, &c);
+                out[i] = c;
+                break;
+            case 2: out[i] = fdm::acosf_exact(a[i]); break;
+            default: out[i] = fdm::atan2f_exact(a[i], b[i]); break;
+        }
+    }
+}
+
+} // extern "C"

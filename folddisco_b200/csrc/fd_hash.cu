@@ -1,0 +1,317 @@
+// fd_hash.cu -- K1: all-residue-pair geometric hashing (index build path (i)).
+//
+// Replaces the rayon loop of Folddisco::collect_and_count / add_entries
+// (reference src/controller/mod.rs:274-441): get_geometric_hash_as_u32_from_structure
+// (src/controller/feature.rs:198-231) over every structure, followed by sort+dedup (:343-344).
+//
+// Work decomposition.  A tile = 32 consecutive rows i of one structure against all of its columns j.
+// One CTA (256 threads) per tile:
+//   phase A  the CTA's warps sweep the tile's pairs in rounds of 8 rows x 512 columns and run only the cheap
+//            C-alpha distance test; survivors (about 115 per row on real proteins) are compacted into a
+//            shared-memory queue with one ballot + one shared atomic per warp;
+//   phase B  the queue is drained densely, one survivor per thread: ~250 f32 flops plus three binary64
+//            sincos, one acos and two atan2 (fd_geom.cuh), so no lane idles on pairs beyond the cutoff.
+// The kernel is ALU bound (37 B of coordinates in, ~115 x ~1 kflop out per residue), so coordinates are read
+// straight from global memory through L1/L2; nothing is staged by TMA.
+// Output is a flat list of 64-bit keys in arbitrary order (one warp-aggregated global atomic per warp per
+// drain round); the keys are sorted afterwards, which also performs the per-structure dedup.
+#include <cub/cub.cuh>
+
+#include "fd_common.cuh"
+#include "fd_geom.cuh"
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_TILE_ROWS = 32;
+constexpr int K1_COL_CHUNK = 512;
+constexpr int K1_QUEUE_CAP = K1_WARPS * K1_COL_CHUNK; // a round can never overflow the queue
+
+struct Tile {
+    uint32_t s;  // structure (row in the batch)
+    uint32_t i0; // first row of the tile
+};
+
+struct BatchView {
+    const uint64_t *row_offsets;
+    const float *n_xyz, *ca_xyz, *cb_xyz;
+    const uint8_t *aa, *cb_valid;
+};
+
+__device__ __forceinline__ fdg::V3 ld3(const float *p, uint64_t r) {
+    return {p[3 * r], p[3 * r + 1], p[3 * r + 2]};
+}
+
+__device__ __forceinline__ bool residue_ok(const BatchView &b, uint64_t r) {
+    return b.aa[r] != 255 && (b.cb_valid == nullptr || b.cb_valid[r] != 0);
+}
+
+// MODE 0: count survivors per tile (sizes the key buffer exactly).
+// MODE 1: emit key = hash << 32 | (first_id + s)   (posting build)
+// MODE 2: emit key = s << 32 | hash                (per-structure sorted unique output)
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS)
+    k1_pair_hash(BatchView b, const Tile *tiles, uint32_t n_tiles, fdg::HashParams hp, uint64_t first_id,
+                 uint64_t hash_lo, uint64_t hash_hi, uint64_t *out_keys, unsigned long long *out_count) {
+    __shared__ uint32_t q_ij[MODE == 0 ? 1 : K1_QUEUE_CAP]; // i_local << 16 | j
+    __shared__ float q_d[MODE == 0 ? 1 : K1_QUEUE_CAP];     // ca_dist of the survivor
+    __shared__ uint32_t q_n;
+    __shared__ unsigned long long tile_count;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile tile = tiles[t];
+        const uint64_t base = b.row_offsets[tile.s];
+        const uint32_t n = (uint32_t)(b.row_offsets[tile.s + 1] - base);
+        const uint32_t rows = min((uint32_t)K1_TILE_ROWS, n - tile.i0);
+        if (threadIdx.x == 0) {
+            q_n = 0;
+            tile_count = 0;
+        }
+        __syncthreads();
+        unsigned long long my_count = 0;
+        for (uint32_t r0 = 0; r0 < rows; r0 += K1_WARPS) {
+            const uint32_t il = r0 + warp; // this warp's row within the tile
+            const bool row_live = il < rows;
+            const uint32_t i = tile.i0 + il;
+            fdg::V3 cai = {0.f, 0.f, 0.f};
+            bool iok = false;
+            if (row_live) {
+                iok = residue_ok(b, base + i);
+                cai = ld3(b.ca_xyz, base + i);
+            }
+            for (uint32_t c0 = 0; c0 < n; c0 += K1_COL_CHUNK) {
+                // ---- phase A: distance screen ----
+                const uint32_t cend = min(n, c0 + K1_COL_CHUNK);
+                for (uint32_t j = c0 + lane; j < c0 + K1_COL_CHUNK; j += 32) { // uniform trip count per warp
+                    bool pass = false;
+                    float d = 0.f;
+                    if (iok && j < cend && j != i && residue_ok(b, base + j)) {
+                        d = fdg::dist(cai, ld3(b.ca_xyz, base + j));
+                        pass = !(d > hp.dist_cutoff); // reference: `if ca_dist > dist_cutoff { return None }`
+                    }
+                    if (MODE == 0) {
+                        my_count += pass;
+                    } else {
+                        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                        if (m) {
+                            uint32_t pos = 0;
+                            if (lane == 0) pos = atomicAdd(&q_n, __popc(m));
+                            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                            if (pass) {
+                                q_ij[pos] = (il << 16) | j;
+                                q_d[pos] = d;
+                            }
+                        }
+                    }
+                }
+                if (MODE != 0) {
+                    __syncthreads();
+                    // ---- phase B: dense drain ----
+                    const uint32_t qn = q_n;
+                    for (uint32_t k0 = 0; k0 < qn; k0 += K1_THREADS) {
+                        const uint32_t k = k0 + threadIdx.x;
+                        bool emit = false;
+                        uint64_t key = 0;
+                        if (k < qn) {
+                            const uint32_t ij = q_ij[k];
+                            const uint64_t ri = base + tile.i0 + (ij >> 16), rj = base + (ij & 0xffffu);
+                            const uint32_t h = fdg::pair_hash(ld3(b.n_xyz, ri), ld3(b.ca_xyz, ri), ld3(b.cb_xyz, ri),
+                                                              ld3(b.n_xyz, rj), ld3(b.ca_xyz, rj), ld3(b.cb_xyz, rj),
+                                                              b.aa[ri] & 0x7Fu, b.aa[rj] & 0x7Fu, q_d[k], hp);
+                            emit = (uint64_t)h >= hash_lo && (uint64_t)h < hash_hi;
+                            key = MODE == 1 ? ((uint64_t)h << 32) | (first_id + tile.s)
+                                            : ((uint64_t)tile.s << 32) | h;
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                        if (m) {
+                            unsigned long long pos = 0;
+                            if (lane == 0) pos = atomicAdd(out_count, (unsigned long long)__popc(m));
+                            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                            if (emit) out_keys[pos] = key;
+                        }
+                    }
+                    __syncthreads();
+                    if (threadIdx.x == 0) q_n = 0;
+                    __syncthreads();
+                }
+            }
+        }
+        if (MODE == 0) {
+            // block reduce of my_count -> one global atomic per tile
+            for (int o = 16; o > 0; o >>= 1) my_count += __shfl_down_sync(0xffffffffu, my_count, o);
+            if (lane == 0 && my_count) atomicAdd(&tile_count, my_count);
+            __syncthreads();
+            if (threadIdx.x == 0 && tile_count) atomicAdd(out_count, tile_count);
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void k1_split_keys(const uint64_t *keys, uint64_t n, uint32_t *hashes, uint64_t *row_counts) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint64_t key = keys[k];
+    hashes[k] = (uint32_t)key;
+    atomicAdd((unsigned long long *)&row_counts[key >> 32], 1ull);
+}
+
+int build_tiles(const fd_struct_batch *b, std::vector<Tile> &tiles) {
+    for (uint64_t s = 0; s < b->n_structs; s++) {
+        uint64_t n = b->row_offsets[s + 1] - b->row_offsets[s];
+        if (n > 65535) return FD_ERR_LIMIT; // DEFAULT_MAX_RESIDUE of the reference (src/controller/mod.rs:40)
+        for (uint64_t i0 = 0; i0 < n; i0 += K1_TILE_ROWS) tiles.push_back({(uint32_t)s, (uint32_t)i0});
+    }
+    return FD_OK;
+}
+
+// Runs the count pass and the emit pass; returns the device key array.
+template <int MODE>
+int run_pair_hash(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_params *params, uint64_t first_id,
+                  uint64_t hash_lo, uint64_t hash_hi, DevBuf<uint64_t> &keys, uint64_t *n_keys) {
+    FdDeviceBatch d;
+    FD_TRY(fd_upload_batch(ctx, batch, &d));
+    std::vector<Tile> tiles;
+    if (build_tiles(batch, tiles) != FD_OK)
+        return fd_fail(ctx, FD_ERR_LIMIT, "structure with more than 65535 residues (reference max_residue)");
+    *n_keys = 0;
+    if (tiles.empty()) return FD_OK;
+    if (tiles.size() > 0xffffffffull) return fd_fail(ctx, FD_ERR_LIMIT, "too many tiles in one batch; split it");
+    DevBuf<Tile> d_tiles;
+    DevBuf<unsigned long long> d_count;
+    FD_CUDA(ctx, d_tiles.alloc(tiles.size()));
+    FD_CUDA(ctx, d_count.alloc(1));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), ctx->stream));
+    BatchView v{d.row_offsets.p, d.n_xyz.p, d.ca_xyz.p, d.cb_xyz.p, d.aa.p, batch->cb_valid ? d.cb_valid.p : nullptr};
+    fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
+    const uint32_t n_tiles = (uint32_t)tiles.size();
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms * 8);
+    StageTimer st(ctx, "hash");
+    FD_LAUNCH(ctx, k1_pair_hash<0>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo, hash_hi,
+              (uint64_t *)nullptr, d_count.p);
+    unsigned long long total = 0;
+    FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FD_CUDA(ctx, keys.alloc(total));
+    FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (total)
+        FD_LAUNCH(ctx, k1_pair_hash<MODE>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo,
+                  hash_hi, keys.p, d_count.p);
+    FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    FD_CUDA(ctx, st.finish());
+    *n_keys = total;
+    return FD_OK;
+}
+
+} // namespace
+
+int fd_upload_batch(fd_ctx *ctx, const fd_struct_batch *b, FdDeviceBatch *d) {
+    if (!b || !b->row_offsets || (b->n_structs && (!b->n_xyz || !b->ca_xyz || !b->cb_xyz || !b->aa)))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_struct_batch: NULL array");
+    const uint64_t S = b->n_structs, R = b->row_offsets[S];
+    if (b->row_offsets[0] != 0) return fd_fail(ctx, FD_ERR_ARG, "fd_struct_batch: row_offsets[0] must be 0");
+    for (uint64_t s = 0; s < S; s++)
+        if (b->row_offsets[s + 1] < b->row_offsets[s])
+            return fd_fail(ctx, FD_ERR_ARG, "fd_struct_batch: row_offsets not monotone");
+    d->n_structs = S;
+    d->n_res = R;
+    FD_CUDA(ctx, d->row_offsets.alloc(S + 1));
+    FD_CUDA(ctx, d->n_xyz.alloc(3 * R));
+    FD_CUDA(ctx, d->ca_xyz.alloc(3 * R));
+    FD_CUDA(ctx, d->cb_xyz.alloc(3 * R));
+    FD_CUDA(ctx, d->aa.alloc(R));
+    FD_CUDA(ctx, d->cb_valid.alloc(R));
+    cudaStream_t st = ctx->stream;
+    FD_CUDA(ctx, cudaMemcpyAsync(d->row_offsets.p, b->row_offsets, (S + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (R) {
+        FD_CUDA(ctx, cudaMemcpyAsync(d->n_xyz.p, b->n_xyz, 12 * R, cudaMemcpyHostToDevice, st));
+        FD_CUDA(ctx, cudaMemcpyAsync(d->ca_xyz.p, b->ca_xyz, 12 * R, cudaMemcpyHostToDevice, st));
+        FD_CUDA(ctx, cudaMemcpyAsync(d->cb_xyz.p, b->cb_xyz, 12 * R, cudaMemcpyHostToDevice, st));
+        FD_CUDA(ctx, cudaMemcpyAsync(d->aa.p, b->aa, R, cudaMemcpyHostToDevice, st));
+        if (b->cb_valid) FD_CUDA(ctx, cudaMemcpyAsync(d->cb_valid.p, b->cb_valid, R, cudaMemcpyHostToDevice, st));
+    }
+    return FD_OK;
+}
+
+extern "C" {
+
+int fd_hash_structures(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_params *params,
+                       uint32_t **out_hashes, uint64_t **out_row_offsets) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!batch || !params || !out_hashes || !out_row_offsets)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_hash_structures: NULL argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    *out_hashes = nullptr;
+    *out_row_offsets = nullptr;
+    const uint64_t S = batch->n_structs;
+    DevBuf<uint64_t> keys;
+    uint64_t n_keys = 0;
+    FD_TRY(run_pair_hash<2>(ctx, batch, params, 0, 0, 1ull << 32, keys, &n_keys));
+    uint64_t *h_rows = (uint64_t *)calloc(S + 1, sizeof(uint64_t));
+    if (!h_rows) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    uint64_t n_unique = 0;
+    uint32_t *h_hashes = nullptr;
+    if (n_keys) {
+        // sort by (structure, hash) then drop duplicates == per-structure sort_unstable + dedup
+        StageTimer st(ctx, "hash");
+        DevBuf<uint64_t> sorted, uniq, d_nsel, d_rows;
+        DevBuf<uint32_t> d_hashes;
+        DevBuf<uint8_t> tmp;
+        FD_CUDA(ctx, sorted.alloc(n_keys));
+        FD_CUDA(ctx, uniq.alloc(n_keys));
+        FD_CUDA(ctx, d_nsel.alloc(1));
+        FD_CUDA(ctx, d_rows.alloc(S + 1));
+        int end_bit = 32;
+        for (uint64_t v = S; v > 1; v >>= 1) end_bit++;
+        end_bit = std::min(64, end_bit + 1);
+        size_t tb1 = 0, tb2 = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tb1, keys.p, sorted.p, n_keys, 0, end_bit, ctx->stream);
+        cub::DeviceSelect::Unique(nullptr, tb2, sorted.p, uniq.p, d_nsel.p, n_keys, ctx->stream);
+        FD_CUDA(ctx, tmp.alloc(std::max(tb1, tb2)));
+        size_t tb = std::max(tb1, tb2);
+        FD_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, tb, keys.p, sorted.p, n_keys, 0, end_bit, ctx->stream));
+        ctx->launches += 4;
+        tb = std::max(tb1, tb2);
+        FD_CUDA(ctx, cub::DeviceSelect::Unique(tmp.p, tb, sorted.p, uniq.p, d_nsel.p, n_keys, ctx->stream));
+        ctx->launches += 2;
+        FD_CUDA(ctx, cudaMemcpyAsync(&n_unique, d_nsel.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FD_CUDA(ctx, d_hashes.alloc(n_unique));
+        FD_CUDA(ctx, cudaMemsetAsync(d_rows.p, 0, (S + 1) * 8, ctx->stream));
+        FD_LAUNCH(ctx, k1_split_keys, fd_div_up(n_unique, 256), 256, 0, uniq.p, n_unique, d_hashes.p, d_rows.p + 1);
+        h_hashes = (uint32_t *)malloc(std::max<uint64_t>(n_unique, 1) * sizeof(uint32_t));
+        if (!h_hashes) {
+            free(h_rows);
+            return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+        }
+        FD_CUDA(ctx, cudaMemcpyAsync(h_hashes, d_hashes.p, n_unique * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, cudaMemcpyAsync(h_rows, d_rows.p, (S + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, st.finish());
+        for (uint64_t s = 0; s < S; s++) h_rows[s + 1] += h_rows[s];
+    } else {
+        h_hashes = (uint32_t *)malloc(sizeof(uint32_t));
+    }
+    *out_hashes = h_hashes;
+    *out_row_offsets = h_rows;
+    return FD_OK;
+}
+
+int fd_build_index(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_params *params, uint64_t first_id,
+                   uint64_t hash_lo, uint64_t hash_hi, fd_index_buffers *out) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!batch || !params || !out) return fd_fail(ctx, FD_ERR_ARG, "fd_build_index: NULL argument");
+    if (first_id + batch->n_structs > 0xffffffffull)
+        return fd_fail(ctx, FD_ERR_LIMIT, "structure ids must fit in 32 bits");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    DevBuf<uint64_t> keys, tmp;
+    uint64_t n_keys = 0;
+    FD_TRY(run_pair_hash<1>(ctx, batch, params, first_id, hash_lo, hash_hi, keys, &n_keys));
+    FD_CUDA(ctx, tmp.alloc(n_keys));
+    return fd_postings_from_keys(ctx, keys.p, n_keys, tmp.p, out);
+}
+
+} // extern "C"

@@ -1,0 +1,261 @@
+// fd_kabsch.cu -- K5: batched Kabsch superposition + RMSD (query path (ii), verification tail).
+//
+// Replaces KabschSuperimposer::run -> kabsch(x = moving, y = reference, mode 2)
+// (reference src/structure/kabsch.rs:73-95, 157-554; called from rmsd_with_calpha_and_rottran,
+// src/controller/retrieve.rs:756-834) for a whole batch of alignments.  One thread per alignment: an alignment
+// is 2m points (CA, CB of m <= ~10 matched residues), i.e. a few hundred bytes and ~2 kflop of binary64, so the
+// batch dimension is the only parallelism worth having.  Same closed-form eigen decomposition of R^T R
+// (TM-align) and the same operation order as the reference, binary64 inside, binary32 out; RMSD is computed
+// from the explicitly transformed points like kabsch.rs:517-533.  Tolerance vs the reference: 1e-4 (f64 libm
+// sin/cos/atan2 differ in the last ulp between CUDA and glibc).
+#include "fd_common.cuh"
+
+namespace {
+
+__device__ void kabsch_one(const float *x, const float *y, uint32_t n, float *U, float *T, float *rmsd_out) {
+    const double EPSILON = 1.0e-8, TOLERANCE = 0.01, SQRT3 = 1.7320508075688772;
+    const int IP[9] = {0, 1, 3, 1, 2, 4, 3, 4, 5};
+    const int IP2312[4] = {1, 2, 0, 1};
+    double u[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    double t[3] = {0, 0, 0};
+    if (n == 0) {
+        for (int i = 0; i < 9; i++) U[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+        T[0] = T[1] = T[2] = 0.0f;
+        *rmsd_out = 3.40282347e+38f;
+        return;
+    }
+    double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0}, sx[3] = {0, 0, 0}, sy[3] = {0, 0, 0}, sz[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < n; i++) {
+        const double c1[3] = {(double)x[3 * i], (double)x[3 * i + 1], (double)x[3 * i + 2]};
+        const double c2[3] = {(double)y[3 * i], (double)y[3 * i + 1], (double)y[3 * i + 2]};
+        for (int j = 0; j < 3; j++) {
+            s1[j] += c1[j];
+            s2[j] += c2[j];
+        }
+        sx[0] += c1[0] * c2[0];
+        sx[1] += c1[0] * c2[1];
+        sx[2] += c1[0] * c2[2];
+        sy[0] += c1[1] * c2[0];
+        sy[1] += c1[1] * c2[1];
+        sy[2] += c1[1] * c2[2];
+        sz[0] += c1[2] * c2[0];
+        sz[1] += c1[2] * c2[1];
+        sz[2] += c1[2] * c2[2];
+    }
+    double xc[3], yc[3];
+    for (int j = 0; j < 3; j++) {
+        xc[j] = s1[j] / (double)n;
+        yc[j] = s2[j] / (double)n;
+    }
+    double r[3][3];
+    for (int j = 0; j < 3; j++) {
+        r[j][0] = sx[j] - s1[0] * s2[j] / (double)n;
+        r[j][1] = sy[j] - s1[1] * s2[j] / (double)n;
+        r[j][2] = sz[j] - s1[2] * s2[j] / (double)n;
+    }
+    const double det_r = r[0][0] * (r[1][1] * r[2][2] - r[1][2] * r[2][1]) -
+                         r[0][1] * (r[1][0] * r[2][2] - r[1][2] * r[2][0]) +
+                         r[0][2] * (r[1][0] * r[2][1] - r[1][1] * r[2][0]);
+    double rr[6];
+    {
+        int m = 0;
+        for (int j = 0; j < 3; j++)
+            for (int i = 0; i <= j; i++) rr[m++] = r[0][i] * r[0][j] + r[1][i] * r[1][j] + r[2][i] * r[2][j];
+    }
+    const double spur = (rr[0] + rr[2] + rr[5]) / 3.0;
+    const double cof =
+        (((rr[2] * rr[5] - rr[4] * rr[4]) + rr[0] * rr[5] - rr[3] * rr[3]) + rr[0] * rr[2] - rr[1] * rr[1]) / 3.0;
+    const double det = det_r * det_r;
+    if (spur > 0.0) {
+        const double d = spur * spur;
+        const double h = d - cof;
+        const double g = (spur * cof - det) / 2.0 - spur * h;
+        if (h > 0.0) {
+            const double sqrth = sqrt(h);
+            double disc = h * h * h - g * g;
+            if (disc < 0.0) disc = 0.0;
+            const double sqrt_disc = sqrt(disc);
+            double d_ang;
+            if (fabs(g) > 1e18) d_ang = g > 0.0 ? 3.14159265358979323846 / 3.0 : 0.0;
+            else d_ang = atan2(sqrt_disc, -g) / 3.0;
+            const double cth = sqrth * cos(d_ang);
+            const double sth = sqrth * SQRT3 * sin(d_ang);
+            double e[3];
+            e[0] = spur + 2.0 * cth;
+            e[1] = spur - cth + sth;
+            e[2] = spur - cth - sth;
+            double a[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, b[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            bool a_failed = false, b_failed = false;
+            for (int li = 0; li < 2; li++) {
+                const int l = li == 0 ? 0 : 2;
+                const double dl = e[l];
+                double ss[6];
+                ss[0] = (dl - rr[2]) * (dl - rr[5]) - rr[4] * rr[4];
+                ss[1] = (dl - rr[5]) * rr[1] + rr[3] * rr[4];
+                ss[2] = (dl - rr[0]) * (dl - rr[5]) - rr[3] * rr[3];
+                ss[3] = (dl - rr[2]) * rr[3] + rr[1] * rr[4];
+                ss[4] = (dl - rr[0]) * rr[4] + rr[1] * rr[3];
+                ss[5] = (dl - rr[0]) * (dl - rr[2]) - rr[1] * rr[1];
+                for (int k = 0; k < 6; k++)
+                    if (fabs(ss[k]) <= EPSILON) ss[k] = 0.0;
+                const double A = fabs(ss[0]), B = fabs(ss[2]), C = fabs(ss[5]);
+                const int j = (A >= B && A >= C) ? 0 : (B >= C ? 1 : 2);
+                double dn = 0.0;
+                for (int i = 0; i < 3; i++) {
+                    const int k = IP[3 * j + i];
+                    a[i][l] = ss[k];
+                    dn += ss[k] * ss[k];
+                }
+                dn = dn > EPSILON ? 1.0 / sqrt(dn) : 0.0;
+                for (int i = 0; i < 3; i++) a[i][l] *= dn;
+            }
+            const double dot = a[0][0] * a[0][2] + a[1][0] * a[1][2] + a[2][0] * a[2][2];
+            int m1, mm;
+            if (e[0] - e[1] > e[1] - e[2]) {
+                m1 = 2;
+                mm = 0;
+            } else {
+                m1 = 0;
+                mm = 2;
+            }
+            double p = 0.0;
+            for (int i = 0; i < 3; i++) {
+                a[i][m1] = a[i][m1] - dot * a[i][mm];
+                p += a[i][m1] * a[i][m1];
+            }
+            if (p <= TOLERANCE) {
+                int j = 0;
+                p = 1.0;
+                for (int i = 0; i < 3; i++)
+                    if (p < fabs(a[i][mm])) {
+                        p = fabs(a[i][mm]);
+                        j = i;
+                    }
+                const int k = IP2312[j], l = IP2312[j + 1];
+                p = sqrt(a[k][mm] * a[k][mm] + a[l][mm] * a[l][mm]);
+                if (p > TOLERANCE) {
+                    a[j][m1] = 0.0;
+                    a[k][m1] = -a[l][mm] / p;
+                    a[l][m1] = a[k][mm] / p;
+                } else {
+                    a_failed = true;
+                }
+            } else {
+                p = 1.0 / sqrt(p);
+                for (int i = 0; i < 3; i++) a[i][m1] *= p;
+            }
+            if (!a_failed) {
+                a[0][1] = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+                a[1][1] = a[2][2] * a[0][0] - a[2][0] * a[0][2];
+                a[2][1] = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+                for (int l = 0; l < 2; l++) {
+                    double db = 0.0;
+                    for (int i = 0; i < 3; i++) {
+                        b[i][l] = r[i][0] * a[0][l] + r[i][1] * a[1][l] + r[i][2] * a[2][l];
+                        db += b[i][l] * b[i][l];
+                    }
+                    db = db > EPSILON ? 1.0 / sqrt(db) : 0.0;
+                    for (int i = 0; i < 3; i++) b[i][l] *= db;
+                }
+                double dot_b = 0.0;
+                for (int i = 0; i < 3; i++) dot_b += b[i][0] * b[i][1];
+                double pb = 0.0;
+                for (int i = 0; i < 3; i++) {
+                    b[i][1] -= dot_b * b[i][0];
+                    pb += b[i][1] * b[i][1];
+                }
+                if (pb <= TOLERANCE) {
+                    pb = 1.0;
+                    int j = 0;
+                    for (int i = 0; i < 3; i++)
+                        if (pb < fabs(b[i][0])) {
+                            pb = fabs(b[i][0]);
+                            j = i;
+                        }
+                    const int k = IP2312[j], l = IP2312[j + 1];
+                    pb = sqrt(b[k][0] * b[k][0] + b[l][0] * b[l][0]);
+                    if (pb > TOLERANCE) {
+                        b[j][1] = 0.0;
+                        b[k][1] = -b[l][0] / pb;
+                        b[l][1] = b[k][0] / pb;
+                    } else {
+                        b_failed = true;
+                    }
+                } else {
+                    pb = 1.0 / sqrt(pb);
+                    for (int i = 0; i < 3; i++) b[i][1] *= pb;
+                }
+                if (!b_failed) {
+                    b[0][2] = b[1][0] * b[2][1] - b[1][1] * b[2][0];
+                    b[1][2] = b[2][0] * b[0][1] - b[2][1] * b[0][0];
+                    b[2][2] = b[0][0] * b[1][1] - b[0][1] * b[1][0];
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++)
+                            u[i][j] = b[i][0] * a[j][0] + b[i][1] * a[j][1] + b[i][2] * a[j][2];
+                    for (int i = 0; i < 3; i++)
+                        t[i] = yc[i] - (u[i][0] * xc[0] + u[i][1] * xc[1] + u[i][2] * xc[2]);
+                }
+            }
+        }
+    } else {
+        for (int i = 0; i < 3; i++) t[i] = yc[i] - (u[i][0] * xc[0] + u[i][1] * xc[1] + u[i][2] * xc[2]);
+    }
+    double sum_sq = 0.0;
+    for (uint32_t i = 0; i < n; i++) {
+        const double x0 = x[3 * i], x1 = x[3 * i + 1], x2 = x[3 * i + 2];
+        const double tr[3] = {u[0][0] * x0 + u[0][1] * x1 + u[0][2] * x2 + t[0],
+                              u[1][0] * x0 + u[1][1] * x1 + u[1][2] * x2 + t[1],
+                              u[2][0] * x0 + u[2][1] * x1 + u[2][2] * x2 + t[2]};
+        for (int j = 0; j < 3; j++) {
+            const double diff = tr[j] - (double)y[3 * i + j];
+            sum_sq += diff * diff;
+        }
+    }
+    const double rms = sqrt(sum_sq / (double)n);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) U[3 * i + j] = (float)u[i][j];
+    for (int i = 0; i < 3; i++) T[i] = (float)t[i];
+    float rf = (float)rms;
+    if (rf != rf) rf = 3.40282347e+38f;
+    *rmsd_out = rf;
+}
+
+__global__ void k5_kabsch(const float *mov, const float *ref, const uint32_t *pt_offsets, uint32_t n_align,
+                          float *rmsd, float *U9, float *t3) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_align) return;
+    const uint32_t p0 = pt_offsets[a], p1 = pt_offsets[a + 1];
+    kabsch_one(mov + 3 * (size_t)p0, ref + 3 * (size_t)p0, p1 - p0, U9 + 9 * (size_t)a, t3 + 3 * (size_t)a, rmsd + a);
+}
+
+} // namespace
+
+extern "C" int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *ref_xyz, const uint32_t *pt_offsets,
+                               uint32_t n_align, float *rmsd, float *U9, float *t3) {
+    if (!ctx) return FD_ERR_ARG;
+    if (n_align == 0) return FD_OK;
+    if (!mov_xyz || !ref_xyz || !pt_offsets || !rmsd || !U9 || !t3)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_kabsch_batch: NULL argument");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t npts = pt_offsets[n_align];
+    DevBuf<float> d_mov, d_ref, d_rmsd, d_U, d_t;
+    DevBuf<uint32_t> d_off;
+    FD_CUDA(ctx, d_mov.alloc(3 * npts));
+    FD_CUDA(ctx, d_ref.alloc(3 * npts));
+    FD_CUDA(ctx, d_off.alloc((size_t)n_align + 1));
+    FD_CUDA(ctx, d_rmsd.alloc(n_align));
+    FD_CUDA(ctx, d_U.alloc(9 * (size_t)n_align));
+    FD_CUDA(ctx, d_t.alloc(3 * (size_t)n_align));
+    cudaStream_t s = ctx->stream;
+    FD_CUDA(ctx, cudaMemcpyAsync(d_mov.p, mov_xyz, 12 * npts, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_ref.p, ref_xyz, 12 * npts, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_off.p, pt_offsets, ((size_t)n_align + 1) * 4, cudaMemcpyHostToDevice, s));
+    StageTimer st(ctx, "kabsch");
+    FD_LAUNCH(ctx, k5_kabsch, fd_div_up(n_align, 128), 128, 0, d_mov.p, d_ref.p, d_off.p, n_align, d_rmsd.p, d_U.p,
+              d_t.p);
+    FD_CUDA(ctx, cudaMemcpyAsync(rmsd, d_rmsd.p, 4 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(U9, d_U.p, 36 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(t3, d_t.p, 12 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, st.finish());
+    return FD_OK;
+}

@@ -1,0 +1,214 @@
+/* folddisco_b200.h -- C ABI of libfolddisco_b200.so
+ *
+ * B200 (sm_100a) drop-in for the data-parallel hot path of steineggerlab/folddisco @ 9375a2d:
+ *   (i)  index build : all-residue-pair geometric hashing  -> delta+LEB128 posting lists
+ *   (ii) query       : posting-list scan -> per-structure vote -> candidate re-hash -> Kabsch RMSD
+ * The reference has no plugin/operator registry; this seam is modelled on its one existing FFI
+ * (lib/foldcomp/foldcompffi.h:18-21 create/process/free/destroy, called from src/structure/io/fcz.rs:80-94).
+ * Each entry point names the reference call site it replaces.  INTEGRATION.md shows the Rust binding.
+ *
+ * Conventions: plain C structs and pointers only.  The caller owns every input buffer; the library owns
+ * device memory.  Outputs documented as "library-allocated" are released with fd_free().  Every call
+ * returns FD_OK (0) or a negative error code and records a message readable with fd_last_error(); no C++
+ * exception crosses the ABI.  An fd_ctx is bound to one CUDA device and is not thread-safe (one per host
+ * thread / one per rank).  Calls are synchronous on return.  There is no CPU fallback: without a usable
+ * CUDA device fd_create fails.
+ */
+#ifndef FOLDDISCO_B200_H
+#define FOLDDISCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_OK 0
+#define FD_ERR_CUDA (-1)     /* CUDA runtime error (message has the cudaError string) */
+#define FD_ERR_ARG (-2)      /* invalid argument */
+#define FD_ERR_STATE (-3)    /* call order: e.g. query before fd_index_attach */
+#define FD_ERR_NOMEM (-4)    /* host or device allocation failed */
+#define FD_ERR_LIMIT (-5)    /* an implementation limit was exceeded (message says which) */
+
+typedef struct fd_ctx fd_ctx;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+int fd_create(fd_ctx **out, int device);
+void fd_destroy(fd_ctx *ctx);
+const char *fd_last_error(const fd_ctx *ctx); /* ctx may be NULL: last error of a failed fd_create */
+void fd_free(void *p);                        /* for library-allocated host outputs */
+const char *fd_version(void);
+/* number of this library's kernels launched through ctx since creation (bench.py's gpu_launches) */
+uint64_t fd_kernel_launches(const fd_ctx *ctx);
+/* cumulative device time (ms, CUDA events on the library's stream) of the named stage since creation:
+ * "hash", "postings", "lookup", "scan", "select", "edges", "kabsch"; returns <0 if unknown */
+double fd_stage_ms(const fd_ctx *ctx, const char *stage);
+uint64_t fd_stage_launches(const fd_ctx *ctx, const char *stage);
+
+/* ---- structures ---------------------------------------------------------------------------------- */
+/* A batch of CompactStructures (reference src/structure/core.rs:55-67) as one SoA; structure s owns the
+ * residues [row_offsets[s], row_offsets[s+1]).  xyz arrays are interleaved x,y,z per residue.
+ * aa = map_aa_to_u8(residue name) (src/utils/convert.rs:53-81): 0..19, 255 = unknown.  A residue whose name is
+ * not the canonical three-letter code of its amino acid (MSE -> MET, SEP -> SER, ...) carries 128 + code: it
+ * hashes like the amino acid but is skipped by prefilter_amino_acid, which matches names exactly
+ * (src/controller/retrieve.rs:580-596).  cb_valid may be NULL (all valid): 0 marks a residue without CB and
+ * without a backbone C to place a virtual one (src/structure/core.rs:129-155); it yields no features. */
+typedef struct {
+    uint64_t n_structs;
+    const uint64_t *row_offsets; /* n_structs + 1 */
+    const float *n_xyz;
+    const float *ca_xyz;
+    const float *cb_xyz;
+    const uint8_t *aa;
+    const uint8_t *cb_valid;
+} fd_struct_batch;
+
+/* hash_type PDBTrRosetta; nbin 0 = default (16 / 4), larger values clamp (src/geometry/pdb_tr.rs:21-35) */
+typedef struct {
+    uint32_t nbin_dist;
+    uint32_t nbin_angle;
+    float dist_cutoff; /* IndexConfig.grid_width, default 20.0 (src/cli/main.rs:41) */
+} fd_hash_params;
+
+/* ---- (i) index build ----------------------------------------------------------------------------- */
+/* Replaces get_geometric_hash_as_u32_from_structure(...) + sort_unstable + dedup at
+ * src/controller/mod.rs:334-344 (and :414-421) for a whole batch: per structure the sorted unique hashes.
+ * Outputs are library-allocated: (*out_hashes)[(*out_row_offsets)[s] .. (*out_row_offsets)[s+1]). */
+int fd_hash_structures(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_params *params,
+                       uint32_t **out_hashes, uint64_t **out_row_offsets);
+
+/* The three arrays of the reference's on-disk index, byte-identical to what
+ * FolddiscoIndex::save_offset_to_file / wrapup_offset_and_save_entries write
+ * (src/index/indextable.rs:239-264, 297-326):
+ *   PREFIX.offset = u64 count | u32 hashes[count] | u64 offsets[count+1];   PREFIX = values[value_bytes] */
+typedef struct {
+    uint64_t count;
+    uint32_t *hashes;
+    uint64_t *offsets;
+    uint64_t value_bytes;
+    uint8_t *values;
+} fd_index_buffers;
+
+/* Replaces count_single_entry / allocate_entries / add_single_entry / prune_to_sparse
+ * (src/index/indextable.rs:88-105, 171-237, 267-295) given per-structure sorted unique hashes;
+ * structure ids are first_id + row number. */
+int fd_build_postings(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *row_offsets, uint64_t n_structs,
+                      uint64_t first_id, fd_index_buffers *out);
+/* Fused: Folddisco::collect_and_count + allocate_entries + add_entries (src/controller/mod.rs:274-441) for a
+ * batch resident in host memory; hashes never leave the device.  Only hashes in [hash_lo, hash_hi) are kept
+ * (hash-range shard of a multi-GPU build; pass 0, 0xFFFFFFFF+1 = 1<<32 for everything). */
+int fd_build_index(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_params *params, uint64_t first_id,
+                   uint64_t hash_lo, uint64_t hash_hi, fd_index_buffers *out);
+void fd_free_index_buffers(fd_index_buffers *b);
+
+/* ---- (ii) query ---------------------------------------------------------------------------------- */
+/* Replaces load_folddisco_index (src/index/indextable.rs:331-394) + load_lookup_from_file: copies the index
+ * (host buffers may be the mmaps of PREFIX.offset / PREFIX) to the device and builds the device-side
+ * directory, skip table and per-list posting counts.  nres / plddt are the .lookup columns
+ * (src/index/lookup.rs:77-91); ids in the postings are positions in these arrays. */
+int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets, uint64_t count,
+                    const uint8_t *values, uint64_t value_bytes, uint64_t n_structs, const uint32_t *nres,
+                    const float *plddt);
+/* FolddiscoIndex::get_entries(hash).len() (src/index/indextable.rs:83-86) for n hashes; 0 if absent. */
+int fd_posting_counts(fd_ctx *ctx, const uint32_t *hashes, uint64_t n, uint32_t *out_counts);
+/* Decode one posting list (debug / parity helper).  Library-allocated *out_ids. */
+int fd_get_entries(fd_ctx *ctx, uint32_t hash, uint64_t **out_ids, uint64_t *out_n);
+
+/* One query = the key set of make_query_map's hash map (src/controller/query.rs:208-329) with, per hash, the
+ * query edge it came from.  edge_of_hash[h] indexes the query's distinct (i, j) edges; edge_node[e] is a dense
+ * id of the edge's source residue i (the node group of src/controller/count_query.rs:256-273). */
+typedef struct {
+    uint32_t n_hashes;
+    const uint32_t *hashes;
+    const uint16_t *edge_of_hash;
+    uint32_t n_edges;
+    const uint16_t *edge_node;
+    uint32_t n_nodes;
+    uint32_t expected_node_count; /* residue_count of src/cli/workflows/query_pdb.rs:355-359 */
+} fd_query;
+
+/* count_query arguments (src/controller/count_query.rs:82-88) + StructureFilter::filter_before_matching
+ * (src/controller/filter.rs:76-100) + --top (query_pdb.rs:404-411).  Negative sampling/freq = None. */
+typedef struct {
+    float sampling_ratio;
+    int64_t sampling_count;
+    float freq_filter;
+    float length_penalty; /* default 0.5 */
+    uint64_t total_match_count;
+    uint64_t covered_node_count;
+    float covered_node_ratio;
+    float idf_score_cutoff;
+    uint64_t num_res_cutoff; /* default 50000 */
+    float plddt_cutoff;
+    uint64_t top_n; /* UINT64_MAX = all */
+} fd_prefilter_params;
+
+typedef struct {
+    uint32_t nid;
+    uint32_t match_count;
+    uint32_t node_count;
+    uint32_t edge_count;
+    float idf;
+} fd_struct_hit;
+
+/* Replaces count_query(...) (src/cli/workflows/query_pdb.rs:391-394) followed by filter_before_matching,
+ * the stable sort by idf descending and truncate(top_n) (:395-411) for a batch of queries.
+ * Library-allocated: hits of query q are (*out_hits)[(*out_offsets)[q] .. (*out_offsets)[q+1]), ordered by
+ * idf descending, ties by ascending nid. */
+int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries,
+                         const fd_prefilter_params *params, fd_struct_hit **out_hits, uint64_t **out_offsets);
+/* posting bytes the last fd_count_query_batch had to read (sum over found query hashes of their list
+ * length in bytes) -- the algorithmic bytes of SURVEY 8d */
+uint64_t fd_last_posting_bytes(const fd_ctx *ctx);
+
+/* HBM-resident compact-structure store replacing the per-candidate file re-read of retrieval_wrapper
+ * (src/controller/retrieve.rs:375-376); ids = positions in the batch = posting ids. */
+int fd_store_attach(fd_ctx *ctx, const fd_struct_batch *batch);
+
+/* Per-query inputs of retrieve_with_prefilter (src/controller/retrieve.rs:52-156). */
+typedef struct {
+    uint32_t n_hashes;
+    const uint32_t *hashes_sorted; /* the query hash set, ascending */
+    uint32_t n_aa_dist;            /* observed_distance_map flattened (query.rs:271-280), map-insertion order */
+    const uint8_t *aa1;
+    const uint8_t *aa2;
+    const float *ca_dist;
+    const uint32_t *q_index; /* query residue index i of the entry */
+} fd_retrieval_query;
+
+typedef struct {
+    uint32_t cand; /* index into the candidate arrays */
+    uint32_t i, j; /* target residue indices */
+    uint32_t hash;
+} fd_cand_edge;
+typedef struct {
+    uint32_t cand;
+    uint32_t q_index;
+    uint32_t i, j;
+    uint32_t k; /* position of the aa_dist entry inside its (aa1,aa2) list: candidate_pairs order */
+} fd_cand_pair;
+
+/* Replaces prefilter_amino_acid + retrieve_with_prefilter (src/controller/retrieve.rs:563-602, 52-156) for
+ * n_cand (query, target) candidates against the attached store.  Library-allocated outputs, sorted by
+ * (cand, i, j[, k]) which is the reference's emission order. */
+int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uint32_t n_queries,
+                             const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
+                             const fd_hash_params *params, float ca_dist_cutoff, fd_cand_edge **out_edges,
+                             uint64_t *out_n_edges, fd_cand_pair **out_pairs, uint64_t *out_n_pairs);
+
+/* Replaces KabschSuperimposer::run -> kabsch(x, y, mode 2) (src/structure/kabsch.rs:73-95, 157-554) for a
+ * batch: alignment a rotates mov[pt_offsets[a]..pt_offsets[a+1]) onto ref[...]; f64 inside, f32 out.
+ * rmsd[n], U9[9n] row-major, t3[3n] are caller-allocated. */
+int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *ref_xyz, const uint32_t *pt_offsets,
+                    uint32_t n_align, float *rmsd, float *U9, float *t3);
+
+/* ---- parity / debug probes ------------------------------------------------------------------------- */
+/* op: 0 sin, 1 cos, 2 acos, 3 atan2(a, b); evaluates the device math used by the hash kernels */
+int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t n, float *out);
+/* same functions evaluated by the host build of the same header (no device needed) */
+void fd_math_host(int op, const float *a, const float *b, uint64_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOLDDISCO_B200_H */

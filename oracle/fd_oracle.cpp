@@ -1373,8 +1373,11 @@ fdo_compact *fdo_compact_from_soa(int64_t n, const float *nx, const float *cax, 
         c->ca.push_back({cax[3 * i], cax[3 * i + 1], cax[3 * i + 2]});
         c->cb.push_back({cbx[3 * i], cbx[3 * i + 1], cbx[3 * i + 2]});
         c->cb_valid.push_back(cbv ? cbv[i] : 1);
-        c->aa.push_back(aa[i]);
-        const char *nm = map_u8_to_aa(aa[i]);
+        // 128 + code: a modified residue (non-canonical name) that maps to amino acid `code`
+        const bool modified = aa[i] != 255 && (aa[i] & 0x80);
+        const uint8_t code = modified ? (uint8_t)(aa[i] & 0x7F) : aa[i];
+        c->aa.push_back(code);
+        const char *nm = modified ? "mod" : map_u8_to_aa(code);
         c->res_name.push_back({(uint8_t)nm[0], (uint8_t)nm[1], (uint8_t)nm[2]});
         c->chain.push_back(chain ? chain[i] : (uint8_t)'A');
         c->serial.push_back(serial ? serial[i] : (uint64_t)(i + 1));

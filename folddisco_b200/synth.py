@@ -49,13 +49,16 @@ def _random_rotations(rng, n):
     return R
 
 
-def generate(n_structs, seed, mean_len=300.0, sigma=0.6, min_len=40, max_len=2000, jitter=0.35, mutate=0.15):
+def generate(n_structs, seed, mean_len=300.0, sigma=0.6, min_len=40, max_len=2000, jitter=0.35, mutate=0.15,
+             template_ids=None):
     """-> dict(row_offsets u64[S+1], n_xyz, ca_xyz, cb_xyz f32[R,3], aa u8[R]); vectorised, deterministic."""
     t = templates()
     rng = np.random.Generator(np.random.PCG64(seed))
     toff = t["offsets"]
     tlen = np.diff(toff)
     which = rng.integers(0, len(tlen), n_structs)
+    if template_ids is not None:  # restrict to a few templates: near-duplicate structures, long posting lists
+        which = np.asarray(template_ids, np.int64)[which % len(template_ids)]
     want = np.clip(np.exp(rng.normal(np.log(mean_len), sigma, n_structs)), min_len, max_len).astype(np.int64)
     length = np.minimum(want, tlen[which])
     start = (rng.random(n_structs) * (tlen[which] - length + 1)).astype(np.int64)

@@ -1,0 +1,177 @@
+/* folddisco_b200_host.h -- host side above the C ABI of folddisco_b200.h.
+ *
+ * The reference's host orchestration is Rust; no Rust toolchain exists in this environment, so the host side
+ * is C++ compiled into the same shared library and exported with C linkage.  It mirrors the reference's own
+ * interface for the hot path (same names, argument meaning and error behaviour) so a Rust host can either
+ * bind the kernels directly (folddisco_b200.h) or these orchestration entry points:
+ *
+ *   reference                                               here
+ *   read_structure_from_path + Structure::to_compact        fdh_compact_read_pdb / fdh_compact_from_atoms
+ *     (src/controller/io.rs:337-379, src/structure/core.rs:70-214)
+ *   parse_query_string (src/controller/query.rs:331-384)    fdh_parse_query_string
+ *   Folddisco::{collect_and_count, add_entries} + writers   fdh_store_* + fdh_index_build / fdh_index_save
+ *     (src/controller/mod.rs:274-441, src/index/indextable.rs, src/index/lookup.rs, src/cli/config.rs)
+ *   load_folddisco_index + load_lookup_from_file            fdh_index_load
+ *   make_query_map + count_query + retrieval_wrapper        fdh_query_batch_* (one call per batch of queries)
+ *     (src/cli/workflows/query_pdb.rs:348-452)
+ *
+ * Every compute step goes through the CUDA kernels of folddisco_b200.h; nothing here hashes structures,
+ * scans postings or superposes on the CPU except the per-query feature of the k(k-1) query residue pairs
+ * (make_query_map, microseconds) which uses the same fd_geom.cuh source as the kernels.
+ */
+#ifndef FOLDDISCO_B200_HOST_H
+#define FOLDDISCO_B200_HOST_H
+
+#include "folddisco_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdh_compact fdh_compact; /* CompactStructure */
+typedef struct fdh_store fdh_store;     /* an ordered set of CompactStructures = the database / lookup */
+typedef struct fdh_index fdh_index;     /* host copy (or mmap) of PREFIX / PREFIX.offset / .lookup / .type */
+typedef struct fdh_queries fdh_queries; /* a batch of parsed queries with their query maps */
+typedef struct fdh_results fdh_results; /* per-structure and per-match rows of a batch */
+
+const char *fdh_last_error(void);
+
+/* ---- structures ---- */
+fdh_compact *fdh_compact_read_pdb(const char *path); /* NULL + fdh_last_error() on failure */
+fdh_compact *fdh_compact_from_atoms(int64_t n_atoms, const float *x, const float *y, const float *z,
+                                    const uint8_t *atom_name4, const uint8_t *chain, const uint8_t *res_name3,
+                                    const uint64_t *res_serial, const float *b_factor);
+/* aa uses the fd_struct_batch convention (128 + code = modified residue) */
+fdh_compact *fdh_compact_from_soa(int64_t n, const float *n_xyz, const float *ca_xyz, const float *cb_xyz,
+                                  const uint8_t *cb_valid, const uint8_t *aa, const uint8_t *chain,
+                                  const uint64_t *serial, const float *b_factor);
+int64_t fdh_compact_nres(const fdh_compact *c);
+int64_t fdh_compact_num_residues_raw(const fdh_compact *c); /* Structure.num_residues (serial changes) */
+int fdh_compact_first_chain(const fdh_compact *c);
+float fdh_compact_avg_plddt(const fdh_compact *c);
+void fdh_compact_get(const fdh_compact *c, float *n_xyz, float *ca_xyz, float *cb_xyz, uint8_t *cb_valid,
+                     uint8_t *aa, uint8_t *chain, uint64_t *serial, float *b_factor);
+void fdh_compact_free(fdh_compact *c);
+
+/* ---- store ---- */
+fdh_store *fdh_store_new(void);
+/* takes a copy; returns the structure id (position) */
+int64_t fdh_store_add(fdh_store *s, const fdh_compact *c, const char *name);
+/* bulk add of n structures from one SoA (synthetic data); names are "prefix%llu" */
+int64_t fdh_store_add_soa(fdh_store *s, uint64_t n_structs, const uint64_t *row_offsets, const float *n_xyz,
+                          const float *ca_xyz, const float *cb_xyz, const uint8_t *aa, const char *name_prefix);
+uint64_t fdh_store_size(const fdh_store *s);
+uint64_t fdh_store_num_residues(const fdh_store *s);
+void fdh_store_get_lookup(const fdh_store *s, uint32_t *nres, float *plddt);
+const char *fdh_store_name(const fdh_store *s, uint64_t id);
+/* view usable with fd_build_index / fd_store_attach; valid until the store changes */
+int fdh_store_batch(const fdh_store *s, fd_struct_batch *out);
+void fdh_store_free(fdh_store *s);
+
+/* ---- index files ---- */
+/* Folddisco::collect_and_count .. save_offset_to_file on the GPU (fd_build_index) */
+fdh_index *fdh_index_build(fd_ctx *ctx, const fdh_store *s, const fd_hash_params *params);
+/* writes PREFIX, PREFIX.offset, PREFIX.lookup, PREFIX.type exactly like `folddisco index` */
+int fdh_index_save(const fdh_index *ix, const fdh_store *s, const char *prefix, uint64_t max_residue,
+                   const char *foldcomp_db /* NULL omits the key */);
+/* load_folddisco_index (mmap) + load_lookup_from_file + read_index_config_from_file */
+fdh_index *fdh_index_load(const char *prefix);
+int fdh_index_get(const fdh_index *ix, fd_index_buffers *view); /* pointers owned by ix */
+uint64_t fdh_index_num_structs(const fdh_index *ix);
+void fdh_index_get_lookup(const fdh_index *ix, uint32_t *nres, float *plddt);
+const char *fdh_index_name(const fdh_index *ix, uint64_t id);
+void fdh_index_get_params(const fdh_index *ix, fd_hash_params *params);
+/* fd_index_attach with this index and its lookup */
+int fdh_index_attach(fd_ctx *ctx, const fdh_index *ix);
+void fdh_index_free(fdh_index *ix);
+
+/* ---- queries ---- */
+/* Returns number of residues or <0; see query.rs:331-384.  subs_off[i] < 0 = no substitution for residue i,
+ * else subs[subs_off[i] .. subs_end[i]). */
+int64_t fdh_parse_query_string(const char *q, uint8_t default_chain, uint8_t *chains, uint64_t *serials,
+                               int64_t *subs_off, int64_t *subs_end, uint8_t *subs, int64_t cap_res,
+                               int64_t cap_subs);
+
+typedef struct {
+    fd_hash_params hash;    /* from the index .type */
+    const float *dist_thr;  /* -d, default {0.5} */
+    int n_dist_thr;
+    const float *angle_thr; /* -a, default {5.0} (degrees) */
+    int n_angle_thr;
+    int serial_query;       /* --serial-index */
+} fdh_query_params;
+
+fdh_queries *fdh_queries_new(const fdh_query_params *p);
+/* adds one query: structure + query string (empty string = whole structure is NOT supported in this version).
+ * The structure is copied.  Returns the query number or <0. */
+int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *structure, const char *query_string);
+int64_t fdh_queries_size(const fdh_queries *qs);
+/* finishes make_query_map for the whole batch: one fd_posting_counts call supplies the per-edge idf
+ * (calculate_idf_for_hash, query.rs:17-32).  Needs an attached index. */
+int fdh_queries_finalize(fdh_queries *qs, fd_ctx *ctx);
+int64_t fdh_queries_num_hashes(const fdh_queries *qs, int64_t q);
+/* query-map entries of query q in insertion order */
+void fdh_queries_get_map(const fdh_queries *qs, int64_t q, uint32_t *hash, int64_t *qi, int64_t *qj,
+                         uint8_t *primary, float *idf);
+int64_t fdh_queries_num_indices(const fdh_queries *qs, int64_t q);
+void fdh_queries_get_indices(const fdh_queries *qs, int64_t q, int64_t *indices);
+void fdh_queries_free(fdh_queries *qs);
+
+typedef struct {
+    fd_prefilter_params prefilter;
+    float ca_dist_cutoff;             /* --ca-distance, default 1.0 */
+    int skip_match;                   /* --skip-match */
+    uint64_t max_matching_node_count; /* --max-node */
+    float max_matching_node_ratio;    /* --max-node-ratio */
+    float rmsd_cutoff;                /* --rmsd, 0 = none */
+    uint64_t connected_node_count;    /* --connected-node */
+    float connected_node_ratio;       /* --connected-node-ratio */
+    int skip_ca_match;                /* --skip-ca-match */
+    int host_threads;                 /* threads for the graph / residue-mapping step, 0 = all cores */
+} fdh_search_params;
+
+/* query_pdb.rs:348-452 for the whole batch: count_query -> filter/sort/top -> retrieval -> Kabsch ->
+ * filter_after_matching -> MatchFilter -> default sorts.  Needs fd_index_attach and, unless skip_match,
+ * fd_store_attach on ctx. */
+fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p);
+
+/* per-structure rows: query q owns [struct_offsets[q], struct_offsets[q+1]) ordered idf desc, min_rmsd asc */
+typedef struct {
+    uint32_t nid, total_match_count, node_count, edge_count;
+    float idf;
+    uint32_t max_matching_node_count;
+    float min_rmsd_with_max_match;
+    uint64_t match_begin, match_end; /* this structure's matches in match-emission order (unsorted view) */
+} fdh_struct_row;
+/* per-match rows: query q owns [match_offsets[q], match_offsets[q+1]) ordered idf desc, rmsd asc */
+typedef struct {
+    uint32_t nid;
+    uint32_t node_count;
+    float idf;
+    float rmsd;
+    float U[9];
+    float t[3];
+    uint64_t res_begin; /* n_query_residues entries in the residue arrays */
+} fdh_match_row;
+typedef struct {
+    uint8_t some;
+    uint8_t chain;
+    uint64_t serial;
+} fdh_residue_match;
+
+uint64_t fdh_results_num_queries(const fdh_results *r);
+const uint64_t *fdh_results_struct_offsets(const fdh_results *r);
+const fdh_struct_row *fdh_results_struct_rows(const fdh_results *r);
+const uint64_t *fdh_results_match_offsets(const fdh_results *r);
+const fdh_match_row *fdh_results_match_rows(const fdh_results *r);
+const uint64_t *fdh_results_match_order(const fdh_results *r); /* sorted position -> emission index */
+const fdh_residue_match *fdh_results_residues(const fdh_results *r);
+uint64_t fdh_results_num_residues(const fdh_results *r);
+/* wall-clock milliseconds of the host-only part of the last search (graph + mapping + assembly) */
+double fdh_results_host_ms(const fdh_results *r);
+void fdh_results_free(fdh_results *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

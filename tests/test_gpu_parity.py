@@ -48,9 +48,11 @@ def make_batch(soas):
     return fd.StructBatch.from_list([soa_to_struct(d) for d in soas])
 
 
-def synth_compacts(n, seed):
+def synth_compacts(n, seed, **kw):
     from folddisco_b200 import synth
-    b = synth.generate(n, seed, mean_len=120.0, max_len=400)
+    kw.setdefault("mean_len", 120.0)
+    kw.setdefault("max_len", 400)
+    b = synth.generate(n, seed, **kw)
     parts = synth.split(b)
     comps = [O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"]) for p in parts]
     return b, parts, comps
@@ -166,8 +168,8 @@ def test_build_index_synthetic_and_shards(ctx):
     assert np.array_equal(np.concatenate([lo.offsets[:-1], hi.offsets + lo.offsets[-1]]), ix.offsets)
 
 
-def _attach_synth(ctx, n, seed):
-    b, parts, comps = synth_compacts(n, seed)
+def _attach_synth(ctx, n, seed, **kw):
+    b, parts, comps = synth_compacts(n, seed, **kw)
     import folddisco_b200 as fd
     batch = fd.StructBatch(b["row_offsets"], b["n_xyz"], b["ca_xyz"], b["cb_xyz"], b["aa"])
     ix = ctx.build_index(batch)
@@ -181,7 +183,8 @@ def _attach_synth(ctx, n, seed):
 
 def test_attach_counts_and_decode(ctx):
     """directory + skip table + counts: posting counts and decoded lists == oracle get_entries (bit-exact)."""
-    env = _attach_synth(ctx, 3000, 77)
+    # three templates, tiny jitter: near-duplicate structures give posting lists that span several 256 B segments
+    env = _attach_synth(ctx, 3000, 77, jitter=0.02, mutate=0.0, template_ids=[4, 5, 9])
     ix, oix = env["ix"], env["oix"]
     lens = np.diff(ix.offsets.astype(np.int64))
     longest = np.argsort(lens)[-40:]
@@ -266,11 +269,13 @@ def test_count_query_config1(ctx, config1):
     assert rows == {t: ("%.4f" % v[0], v[1], v[2], v[3]) for t, v in F.README_STRUCT_ROWS.items()}
 
 
-@pytest.mark.parametrize("n_structs,seed", [(700, 21), (9000, 22)])
-def test_count_query_synthetic(ctx, n_structs, seed):
-    """single-tile (700) and multi-tile (9000 > tile capacity) vote kernels vs the oracle, with filters / top-N."""
+@pytest.mark.parametrize("n_structs,seed,kw", [(700, 21, {}), (9000, 22, {}),
+                                               (12000, 23, dict(jitter=0.05, mutate=0.02, template_ids=[4, 5, 9, 10]))])
+def test_count_query_synthetic(ctx, n_structs, seed, kw):
+    """single-tile (700) and multi-tile (9000, 12000 > tile capacity) vote kernels vs the oracle, with filters /
+    top-N; the third case has long multi-segment posting lists that cross tile boundaries."""
     import folddisco_b200 as fd
-    env = _attach_synth(ctx, n_structs, seed)
+    env = _attach_synth(ctx, n_structs, seed, **kw)
     oix, nres, plddt = env["oix"], env["nres"], env["plddt"]
     qms = _motif_qmaps(oix, n_structs, extra=[("query/4CHA.pdb", "B57:X,B102,C195:ST", None)])
     queries = [_query_inputs(qm) for qm in qms]

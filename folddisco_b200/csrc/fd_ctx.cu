@@ -98,6 +98,7 @@ uint64_t fd_stage_launches(const fd_ctx *ctx, const char *stage) {
     return it == ctx->stages.end() ? 0 : it->second.launches;
 }
 uint64_t fd_last_posting_bytes(const fd_ctx *ctx) { return ctx ? ctx->last_posting_bytes : 0; }
+uint64_t fd_index_num_structs(const fd_ctx *ctx) { return ctx && ctx->idx.attached ? ctx->idx.n_structs : 0; }
 
 int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t n, float *out) {
     if (!ctx || !a || !out || (op == 3 && !b)) return fd_fail(ctx, FD_ERR_ARG, "fd_math_probe: bad argument");

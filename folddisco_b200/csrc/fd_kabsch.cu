@@ -12,7 +12,26 @@
 
 namespace {
 
-__device__ void kabsch_one(const float *x, const float *y, uint32_t n, float *U, float *T, float *rmsd_out) {
+struct P3 {
+    double x, y, z;
+};
+struct FlatPoints { // points stored contiguously as xyz triples
+    const float *p;
+    __device__ P3 operator()(uint32_t i) const { return {(double)p[3 * i], (double)p[3 * i + 1], (double)p[3 * i + 2]}; }
+};
+struct GatherPoints { // CA, CB interleaved, gathered by residue index: point 2k = CA(res[k]), 2k+1 = CB(res[k])
+    const float *ca, *cb;
+    const uint32_t *res;
+    uint64_t base;
+    __device__ P3 operator()(uint32_t i) const {
+        const uint64_t r = base + res[i >> 1];
+        const float *s = (i & 1) ? cb : ca;
+        return {(double)s[3 * r], (double)s[3 * r + 1], (double)s[3 * r + 2]};
+    }
+};
+
+template <class PX, class PY>
+__device__ void kabsch_one(PX px, PY py, uint32_t n, float *U, float *T, float *rmsd_out) {
     const double EPSILON = 1.0e-8, TOLERANCE = 0.01, SQRT3 = 1.7320508075688772;
     const int IP[9] = {0, 1, 3, 1, 2, 4, 3, 4, 5};
     const int IP2312[4] = {1, 2, 0, 1};
@@ -26,8 +45,9 @@ __device__ void kabsch_one(const float *x, const float *y, uint32_t n, float *U,
     }
     double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0}, sx[3] = {0, 0, 0}, sy[3] = {0, 0, 0}, sz[3] = {0, 0, 0};
     for (uint32_t i = 0; i < n; i++) {
-        const double c1[3] = {(double)x[3 * i], (double)x[3 * i + 1], (double)x[3 * i + 2]};
-        const double c2[3] = {(double)y[3 * i], (double)y[3 * i + 1], (double)y[3 * i + 2]};
+        const P3 a1 = px(i), a2 = py(i);
+        const double c1[3] = {a1.x, a1.y, a1.z};
+        const double c2[3] = {a2.x, a2.y, a2.z};
         for (int j = 0; j < 3; j++) {
             s1[j] += c1[j];
             s2[j] += c2[j];
@@ -202,12 +222,14 @@ __device__ void kabsch_one(const float *x, const float *y, uint32_t n, float *U,
     }
     double sum_sq = 0.0;
     for (uint32_t i = 0; i < n; i++) {
-        const double x0 = x[3 * i], x1 = x[3 * i + 1], x2 = x[3 * i + 2];
+        const P3 xp = px(i), yp = py(i);
+        const double x0 = xp.x, x1 = xp.y, x2 = xp.z;
+        const double yv[3] = {yp.x, yp.y, yp.z};
         const double tr[3] = {u[0][0] * x0 + u[0][1] * x1 + u[0][2] * x2 + t[0],
                               u[1][0] * x0 + u[1][1] * x1 + u[1][2] * x2 + t[1],
                               u[2][0] * x0 + u[2][1] * x1 + u[2][2] * x2 + t[2]};
         for (int j = 0; j < 3; j++) {
-            const double diff = tr[j] - (double)y[3 * i + j];
+            const double diff = tr[j] - yv[j];
             sum_sq += diff * diff;
         }
     }
@@ -225,7 +247,21 @@ __global__ void k5_kabsch(const float *mov, const float *ref, const uint32_t *pt
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n_align) return;
     const uint32_t p0 = pt_offsets[a], p1 = pt_offsets[a + 1];
-    kabsch_one(mov + 3 * (size_t)p0, ref + 3 * (size_t)p0, p1 - p0, U9 + 9 * (size_t)a, t3 + 3 * (size_t)a, rmsd + a);
+    kabsch_one(FlatPoints{mov + 3 * (size_t)p0}, FlatPoints{ref + 3 * (size_t)p0}, p1 - p0, U9 + 9 * (size_t)a,
+               t3 + 3 * (size_t)a, rmsd + a);
+}
+
+// alignment a: target residues pair_t[k] of stored structure nid[a] (moving) onto query residues pair_q[k]
+__global__ void k5_kabsch_store(const float *q_ca, const float *q_cb, const float *s_ca, const float *s_cb,
+                                const uint64_t *s_row_offsets, const uint32_t *nid, const uint32_t *pair_offsets,
+                                const uint32_t *pair_q, const uint32_t *pair_t, uint32_t n_align, float *rmsd,
+                                float *U9, float *t3) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_align) return;
+    const uint32_t p0 = pair_offsets[a], p1 = pair_offsets[a + 1];
+    GatherPoints mov{s_ca, s_cb, pair_t + p0, s_row_offsets[nid[a]]};
+    GatherPoints ref{q_ca, q_cb, pair_q + p0, 0};
+    kabsch_one(mov, ref, 2 * (p1 - p0), U9 + 9 * (size_t)a, t3 + 3 * (size_t)a, rmsd + a);
 }
 
 } // namespace
@@ -253,6 +289,52 @@ extern "C" int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *r
     StageTimer st(ctx, "kabsch");
     FD_LAUNCH(ctx, k5_kabsch, fd_div_up(n_align, 128), 128, 0, d_mov.p, d_ref.p, d_off.p, n_align, d_rmsd.p, d_U.p,
               d_t.p);
+    FD_CUDA(ctx, cudaMemcpyAsync(rmsd, d_rmsd.p, 4 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(U9, d_U.p, 36 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(t3, d_t.p, 12 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, st.finish());
+    return FD_OK;
+}
+
+// rmsd_with_calpha_and_rottran (src/controller/retrieve.rs:756-834) for a batch: coordinates of the matched
+// target residues are gathered on the device from the attached store, CA and CB interleaved (:761-767).
+extern "C" int fd_kabsch_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_xyz, uint64_t n_q_res,
+                                     const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
+                                     const uint32_t *pair_qres, const uint32_t *pair_tres, float *rmsd, float *U9,
+                                     float *t3) {
+    if (!ctx) return FD_ERR_ARG;
+    if (n_align == 0) return FD_OK;
+    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_kabsch_store_batch: no structure store attached");
+    if (!q_ca_xyz || !q_cb_xyz || !align_nid || !pair_offsets || !pair_qres || !pair_tres || !rmsd || !U9 || !t3)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_kabsch_store_batch: NULL argument");
+    const uint64_t np = pair_offsets[n_align];
+    for (uint32_t a = 0; a < n_align; a++)
+        if (align_nid[a] >= ctx->store.n_structs) return fd_fail(ctx, FD_ERR_ARG, "align_nid outside the store");
+    for (uint64_t k = 0; k < np; k++)
+        if (pair_qres[k] >= n_q_res) return fd_fail(ctx, FD_ERR_ARG, "pair_qres out of range");
+    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf<float> d_qca, d_qcb, d_rmsd, d_U, d_t;
+    DevBuf<uint32_t> d_nid, d_off, d_pq, d_pt;
+    FD_CUDA(ctx, d_qca.alloc(3 * n_q_res));
+    FD_CUDA(ctx, d_qcb.alloc(3 * n_q_res));
+    FD_CUDA(ctx, d_nid.alloc(n_align));
+    FD_CUDA(ctx, d_off.alloc((size_t)n_align + 1));
+    FD_CUDA(ctx, d_pq.alloc(np));
+    FD_CUDA(ctx, d_pt.alloc(np));
+    FD_CUDA(ctx, d_rmsd.alloc(n_align));
+    FD_CUDA(ctx, d_U.alloc(9 * (size_t)n_align));
+    FD_CUDA(ctx, d_t.alloc(3 * (size_t)n_align));
+    cudaStream_t s = ctx->stream;
+    FD_CUDA(ctx, cudaMemcpyAsync(d_qca.p, q_ca_xyz, 12 * n_q_res, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_qcb.p, q_cb_xyz, 12 * n_q_res, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_nid.p, align_nid, 4 * (size_t)n_align, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_off.p, pair_offsets, 4 * ((size_t)n_align + 1), cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_pq.p, pair_qres, 4 * np, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_pt.p, pair_tres, 4 * np, cudaMemcpyHostToDevice, s));
+    StageTimer st(ctx, "kabsch");
+    const FdDeviceStore &S = ctx->store;
+    FD_LAUNCH(ctx, k5_kabsch_store, fd_div_up(n_align, 128), 128, 0, d_qca.p, d_qcb.p, S.ca_xyz, S.cb_xyz,
+              S.row_offsets, d_nid.p, d_off.p, d_pq.p, d_pt.p, n_align, d_rmsd.p, d_U.p, d_t.p);
     FD_CUDA(ctx, cudaMemcpyAsync(rmsd, d_rmsd.p, 4 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
     FD_CUDA(ctx, cudaMemcpyAsync(U9, d_U.p, 36 * (size_t)n_align, cudaMemcpyDeviceToHost, s));
     FD_CUDA(ctx, cudaMemcpyAsync(t3, d_t.p, 12 * (size_t)n_align, cudaMemcpyDeviceToHost, s));

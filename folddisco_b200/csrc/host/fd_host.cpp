@@ -1,0 +1,1480 @@
+// fd_host.cpp -- host side above the C ABI (include/folddisco_b200_host.h).
+//
+// Mirrors the reference's host orchestration for the hot path.  All heavy lifting is delegated to the CUDA
+// kernels through the fd_* entry points; what runs here is parsing, query-map construction for the k(k-1)
+// query pairs, and the small irregular graph / residue-assignment step between K4 and K5.
+// Compiled by nvcc (-x cu) so that fd_geom.cuh is the same source the kernels use.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <charconv>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/folddisco_b200_host.h"
+#include "../fd_geom.cuh"
+
+namespace {
+thread_local std::string g_err;
+void set_err(const std::string &s) { g_err = s; }
+
+const char *CANON[20] = {"ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE",
+                         "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL"};
+
+// map_aa_to_u8 (src/utils/convert.rs:53-81) as a sorted table of three-letter codes.
+struct AaName {
+    char n[4];
+    uint8_t v;
+};
+const AaName AA_TABLE[] = {
+    {"0AF", 17}, {"0TD", 3},  {"ABA", 0},  {"AGM", 1},  {"AIB", 0},  {"ALA", 0},  {"ALC", 0},  {"ALY", 11},
+    {"ARG", 1},  {"ASN", 2},  {"ASP", 3},  {"ASX", 3},  {"B3E", 6},  {"BFD", 3},  {"BMT", 16}, {"CAF", 4},
+    {"CAS", 4},  {"CGU", 6},  {"CIR", 1},  {"CME", 4},  {"CR2", 7},  {"CR8", 8},  {"CRF", 16}, {"CRO", 16},
+    {"CRQ", 5},  {"CSD", 4},  {"CSH", 15}, {"CSO", 4},  {"CSS", 4},  {"CSX", 4},  {"CXM", 12}, {"CYS", 4},
+    {"DAB", 0},  {"DAL", 0},  {"DAR", 1},  {"DAS", 3},  {"DCY", 4},  {"DGL", 6},  {"DGN", 5},  {"DHA", 15},
+    {"DHI", 8},  {"DIL", 9},  {"DLE", 10}, {"DLY", 11}, {"DPN", 13}, {"DPR", 14}, {"DSG", 2},  {"DSN", 15},
+    {"DTH", 16}, {"DTR", 17}, {"DTY", 18}, {"DVA", 19}, {"FGA", 6},  {"FME", 12}, {"FVA", 19}, {"GHP", 7},
+    {"GL3", 7},  {"GLN", 5},  {"GLU", 6},  {"GLX", 6},  {"GLY", 7},  {"GYS", 15}, {"HIC", 8},  {"HIS", 8},
+    {"HYP", 14}, {"IAS", 3},  {"ILE", 9},  {"KCX", 11}, {"KPI", 11}, {"LEU", 10}, {"LLP", 11}, {"LYS", 11},
+    {"M3L", 11}, {"MAA", 0},  {"MDO", 0},  {"MEA", 13}, {"MED", 12}, {"MEN", 2},  {"MEQ", 5},  {"MET", 12},
+    {"MHO", 12}, {"MHS", 8},  {"MK8", 10}, {"MLE", 10}, {"MLY", 11}, {"MLZ", 11}, {"MSE", 12}, {"MVA", 19},
+    {"NEP", 8},  {"NLE", 10}, {"NRQ", 12}, {"OAS", 15}, {"OCS", 4},  {"OMY", 18}, {"ORN", 0},  {"PCA", 6},
+    {"PHD", 3},  {"PHE", 13}, {"PHI", 13}, {"PHL", 13}, {"PRO", 14}, {"PTR", 18}, {"PYL", 11}, {"SAC", 15},
+    {"SAR", 7},  {"SCH", 4},  {"SCY", 4},  {"SEC", 4},  {"SEP", 15}, {"SER", 15}, {"SMC", 4},  {"SME", 12},
+    {"SNC", 4},  {"SNN", 2},  {"THR", 16}, {"TOX", 17}, {"TPO", 16}, {"TPQ", 18}, {"TRP", 17}, {"TRQ", 17},
+    {"TYR", 18}, {"TYS", 18}, {"VAL", 19}, {"YCM", 4},
+};
+// -> fd_struct_batch convention: code, 128 + code for a non-canonical name, 255 unknown
+uint8_t aa_code(const uint8_t *name) {
+    int lo = 0, hi = (int)(sizeof(AA_TABLE) / sizeof(AA_TABLE[0])) - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) / 2;
+        int c = memcmp(AA_TABLE[mid].n, name, 3);
+        if (c == 0) {
+            uint8_t v = AA_TABLE[mid].v;
+            return memcmp(CANON[v], name, 3) == 0 ? v : (uint8_t)(128 + v);
+        }
+        if (c < 0) lo = mid + 1;
+        else hi = mid - 1;
+    }
+    return 255;
+}
+
+struct Atoms {
+    std::vector<float> x, y, z, b;
+    std::vector<uint8_t> name; // 4 per atom
+    std::vector<uint8_t> rname; // 3 per atom
+    std::vector<uint8_t> chain;
+    std::vector<uint64_t> serial;
+    size_t size() const { return x.size(); }
+};
+
+} // namespace
+
+struct fdh_compact {
+    std::vector<float> n, ca, cb; // 3 per residue
+    std::vector<uint8_t> cb_valid, aa, chain;
+    std::vector<uint64_t> serial;
+    std::vector<float> bfac;
+    std::vector<uint8_t> chains;
+    uint64_t raw_residues = 0;
+    size_t nres() const { return aa.size(); }
+    fdg::V3 N(size_t i) const { return {n[3 * i], n[3 * i + 1], n[3 * i + 2]}; }
+    fdg::V3 CA(size_t i) const { return {ca[3 * i], ca[3 * i + 1], ca[3 * i + 2]}; }
+    fdg::V3 CB(size_t i) const { return {cb[3 * i], cb[3 * i + 1], cb[3 * i + 2]}; }
+};
+
+namespace {
+
+// virtual C-beta (src/structure/coordinate.rs:167-186), f32, same operation order
+fdg::V3 approx_cb(fdg::V3 ca, fdg::V3 n, fdg::V3 c) {
+    using namespace fdg;
+    auto add = [](V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; };
+    auto scale = [](V3 a, float f) { return V3{a.x * f, a.y * f, a.z * f}; };
+    V3 v1 = normalize(sub(c, ca));
+    V3 v2 = normalize(sub(n, ca));
+    V3 b1 = add(v2, scale(v1, 1.0f / 3.0f));
+    V3 b2 = cross(v1, b1);
+    V3 u1 = normalize(b1), u2 = normalize(b2);
+    V3 v4 = sub(scale(u1, -1.0f / 2.0f), scale(u2, sqrtf(3.0f) / 2.0f));
+    v4 = scale(v4, sqrtf(8.0f) / 3.0f);
+    v4 = add(v4, scale(v1, -1.0f / 3.0f));
+    return add(ca, scale(v4, 1.5336f));
+}
+
+// CompactStructure::build (src/structure/core.rs:70-214).  A residue is flushed when res_serial changes or at
+// the last atom index; chain and B-factor come from the atom that triggered the flush; the backbone C used for
+// a virtual CB is the most recent one seen (never reset); residues without N or CA are dropped.
+fdh_compact *compact_from_atoms(const Atoms &a) {
+    fdh_compact *c = new fdh_compact();
+    { // Structure::update bookkeeping (core.rs:29-43)
+        uint8_t rc = ' ';
+        uint64_t rs = 0;
+        for (size_t i = 0; i < a.size(); i++) {
+            if (rc != a.chain[i]) {
+                c->chains.push_back(a.chain[i]);
+                rc = a.chain[i];
+            }
+            if (rs != a.serial[i]) {
+                c->raw_residues++;
+                rs = a.serial[i];
+            }
+        }
+    }
+    enum { HAS_N = 1, HAS_CA = 2, HAS_CB = 4 };
+    int have = 0;
+    bool have_c = false, started = false;
+    fdg::V3 n{}, ca{}, cb{}, cc{};
+    uint64_t cur_serial = 0;
+    size_t cur_first = 0;
+    const size_t na = a.size();
+    for (size_t idx = 0; idx < na; idx++) {
+        if (!started || cur_serial != a.serial[idx] || idx + 1 == na) {
+            if ((have & HAS_N) && (have & HAS_CA)) {
+                fdg::V3 cbv{0.f, 0.f, 0.f};
+                uint8_t ok = 1;
+                if (have & HAS_CB) cbv = cb;
+                else if (have_c) cbv = approx_cb(ca, n, cc);
+                else ok = 0;
+                c->n.insert(c->n.end(), {n.x, n.y, n.z});
+                c->ca.insert(c->ca.end(), {ca.x, ca.y, ca.z});
+                c->cb.insert(c->cb.end(), {cbv.x, cbv.y, cbv.z});
+                c->cb_valid.push_back(ok);
+                c->aa.push_back(aa_code(&a.rname[3 * cur_first]));
+                c->serial.push_back(cur_serial);
+                c->chain.push_back(a.chain[idx]);
+                c->bfac.push_back(a.b[idx]);
+            }
+            have = 0;
+            started = true;
+            cur_serial = a.serial[idx];
+            cur_first = idx;
+        }
+        const uint8_t *nm = &a.name[4 * idx];
+        const fdg::V3 p{a.x[idx], a.y[idx], a.z[idx]};
+        if (memcmp(nm, " CA ", 4) == 0) {
+            ca = p;
+            have |= HAS_CA;
+        } else if (memcmp(nm, " CB ", 4) == 0) {
+            cb = p;
+            have |= HAS_CB;
+        } else if (memcmp(nm, " C  ", 4) == 0) {
+            cc = p;
+            have_c = true;
+        } else if (memcmp(nm, " N  ", 4) == 0) {
+            n = p; // GLY and non-GLY both end up here (core.rs:176-183)
+            have |= HAS_N;
+        }
+    }
+    return c;
+}
+
+bool field_f32(const char *s, size_t len, float *out) {
+    while (len && isspace((unsigned char)*s)) s++, len--;
+    while (len && isspace((unsigned char)s[len - 1])) len--;
+    if (!len || len > 63) return false;
+    char buf[64];
+    memcpy(buf, s, len);
+    buf[len] = 0;
+    for (size_t i = 0; i < len; i++)
+        if (buf[i] == 'x' || buf[i] == 'X' || buf[i] == '(' || isspace((unsigned char)buf[i])) return false;
+    char *end = nullptr;
+    float v = strtof(buf, &end);
+    if (end != buf + len) return false;
+    *out = v;
+    return true;
+}
+bool field_u64(const char *s, size_t len, uint64_t *out) {
+    while (len && isspace((unsigned char)*s)) s++, len--;
+    while (len && isspace((unsigned char)s[len - 1])) len--;
+    if (len && *s == '+') s++, len--;
+    if (!len) return false;
+    uint64_t v = 0;
+    for (size_t i = 0; i < len; i++) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        uint64_t nv = v * 10 + (uint64_t)(s[i] - '0');
+        if (nv / 10 != v) return false;
+        v = nv;
+    }
+    *out = v;
+    return true;
+}
+
+// PDB reader: src/structure/io/pdb.rs:37-76 + parser.rs:3-55 (first model, ATOM records only; records whose
+// fixed columns do not parse are skipped, negative residue numbers included)
+bool read_pdb_atoms(const char *path, Atoms &a) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    std::string data;
+    char buf[1 << 16];
+    size_t r;
+    while ((r = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, r);
+    fclose(f);
+    int model = 0;
+    size_t pos = 0;
+    while (pos < data.size()) {
+        size_t nl = data.find('\n', pos);
+        if (nl == std::string::npos) nl = data.size();
+        size_t len = nl - pos;
+        const char *l = data.data() + pos;
+        pos = nl + 1;
+        if (len && l[len - 1] == '\r') len--;
+        if (model > 1) break;
+        if (len < 6) continue;
+        if (memcmp(l, "MODEL ", 6) == 0) {
+            model++;
+            continue;
+        }
+        if (memcmp(l, "ATOM  ", 6) != 0 || len < 54) continue;
+        float x, y, z, b = 1.0f;
+        uint64_t as, rs;
+        if (!field_f32(l + 30, 8, &x) || !field_f32(l + 38, 8, &y) || !field_f32(l + 46, 8, &z)) continue;
+        if (!field_u64(l + 6, 5, &as) || !field_u64(l + 22, 4, &rs)) continue;
+        if (len >= 66 && !field_f32(l + 60, 6, &b)) continue;
+        a.x.push_back(x);
+        a.y.push_back(y);
+        a.z.push_back(z);
+        a.b.push_back(b);
+        a.name.insert(a.name.end(), l + 12, l + 16);
+        a.rname.insert(a.rname.end(), l + 17, l + 20);
+        a.chain.push_back((uint8_t)l[21]);
+        a.serial.push_back(rs);
+    }
+    return true;
+}
+
+std::string rust_f32(float v) { // Rust `{}`: shortest round-trip, never scientific
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    char buf[512];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct fdh_store {
+    std::vector<uint64_t> row_offsets{0};
+    std::vector<float> n, ca, cb;
+    std::vector<uint8_t> aa, cb_valid;
+    std::vector<std::string> names;
+    std::vector<float> plddt;
+    // per residue labels for result formatting
+    std::vector<uint8_t> chain;
+    std::vector<uint64_t> serial;
+};
+
+struct fdh_index {
+    // owned buffers (build) or mmaps (load)
+    std::vector<uint32_t> own_hashes;
+    std::vector<uint64_t> own_offsets;
+    std::vector<uint8_t> own_values;
+    void *map_off = nullptr, *map_val = nullptr;
+    size_t map_off_len = 0, map_val_len = 0;
+    const uint32_t *hashes = nullptr;
+    const uint64_t *offsets = nullptr; // may be unaligned when mapped and count is odd -> copied instead
+    const uint8_t *values = nullptr;
+    uint64_t count = 0, value_bytes = 0;
+    std::vector<std::string> names;
+    std::vector<uint32_t> nres;
+    std::vector<float> plddt;
+    fd_hash_params params{0, 0, 20.0f};
+    ~fdh_index() {
+        if (map_off) munmap(map_off, map_off_len);
+        if (map_val) munmap(map_val, map_val_len);
+    }
+};
+
+namespace {
+
+struct QEntry {
+    uint32_t hash;
+    uint32_t qi, qj; // structure indices of the query residues
+    uint8_t primary;
+    uint32_t pair; // which ordered query pair produced it (its idf is the idf of that pair's observed hash)
+    float idf;
+};
+struct AAD {
+    uint8_t aa1, aa2;
+    float dist;
+    uint32_t qi;
+};
+struct Query {
+    fdh_compact st;
+    std::string qstring;
+    std::vector<uint32_t> indices;
+    std::vector<QEntry> entries;
+    std::unordered_map<uint32_t, uint32_t> pos;
+    std::vector<uint32_t> pair_hash; // observed hash per pair
+    std::vector<AAD> aad;
+    // derived
+    std::vector<uint16_t> edge_of_hash, edge_node;
+    uint32_t n_nodes = 0;
+    std::vector<uint32_t> hashes_sorted;
+    std::unordered_map<uint32_t, uint8_t> symmetric;
+    uint32_t max_q = 0;
+    std::vector<uint32_t> hashes_flat;
+    std::vector<uint8_t> aad_aa1, aad_aa2;
+    std::vector<float> aad_dist;
+    std::vector<uint32_t> aad_qi;
+};
+
+// pdb_tr.rs:95-162 with default bins
+bool hash_is_symmetric(uint32_t h) {
+    auto cont = [](uint32_t v, float mn, float mx, float nb) { return (float)v * ((mx - mn) / (nb - 1.0f)) + mn; };
+    const float deg = 180.0f / 3.14159274101257324f;
+    if (((h >> 25) & 31u) != ((h >> 20) & 31u)) return false;
+    float s1 = cont((h >> 6) & 3u, -1.f, 1.f, 4.f), c1 = cont((h >> 4) & 3u, -1.f, 1.f, 4.f);
+    float s2 = cont((h >> 2) & 3u, -1.f, 1.f, 4.f), c2 = cont(h & 3u, -1.f, 1.f, 4.f);
+    return fdm::atan2f_exact(s1, c1) * deg == fdm::atan2f_exact(s2, c2) * deg;
+}
+
+bool host_pair_feature(const fdh_compact &c, size_t i, size_t j, float cutoff, float *f) {
+    if (i == j) return false;
+    const uint8_t a1 = c.aa[i], a2 = c.aa[j];
+    if (a1 == 255 || a2 == 255 || !c.cb_valid[i] || !c.cb_valid[j]) return false;
+    const float d = fdg::dist(c.CA(i), c.CA(j));
+    if (d > cutoff) return false;
+    fdg::pair_feature(c.N(i), c.CA(i), c.CB(i), c.N(j), c.CA(j), c.CB(j), (float)(a1 & 0x7F), (float)(a2 & 0x7F), d, f);
+    return true;
+}
+
+void one_letter(char ch, std::vector<uint8_t> &o) { // convert.rs:223-262
+    static const char *std20 = "ARNDCQEGHILKMFPSTWYV";
+    const char *p = ch ? strchr(std20, ch) : nullptr;
+    if (p) {
+        o.push_back((uint8_t)(p - std20));
+        return;
+    }
+    auto put = [&](std::initializer_list<int> l) {
+        for (int v : l) o.push_back((uint8_t)v);
+    };
+    switch (ch) {
+        case 'B': put({2, 3}); break;
+        case 'Z': put({5, 6}); break;
+        case 'X':
+        case 'x':
+            for (int i = 0; i < 20; i++) o.push_back((uint8_t)i);
+            break;
+        case 'J': put({9, 10}); break;
+        case 'U': put({4}); break;
+        case 'O': put({11}); break;
+        case 'p': put({1, 8, 11}); break;
+        case 'n': put({3, 6}); break;
+        case 'h': put({2, 5, 15, 16, 18}); break;
+        case 'b': put({0, 4, 7, 9, 10, 12, 13, 14, 19}); break;
+        case 'a': put({8, 13, 17, 18}); break;
+        default: o.push_back(255);
+    }
+}
+
+struct ParsedQuery {
+    std::vector<uint8_t> chains;
+    std::vector<uint64_t> serials;
+    std::vector<int> has_sub;
+    std::vector<std::vector<uint8_t>> subs;
+};
+// parse_query_string (src/controller/query.rs:331-384)
+bool parse_query(const char *q, uint8_t default_chain, ParsedQuery &out) {
+    std::string s;
+    for (const char *p = q; *p; p++)
+        if (*p != ' ') s.push_back(*p);
+    if (s.empty()) return true;
+    if (!isalpha(default_chain)) default_chain = 'A';
+    size_t pos = 0;
+    while (pos <= s.size()) {
+        size_t comma = s.find(',', pos);
+        std::string seg = s.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+        pos = comma == std::string::npos ? s.size() + 1 : comma + 1;
+        uint8_t chain = default_chain;
+        std::string rest = seg;
+        if (!seg.empty() && isalpha((unsigned char)seg[0])) {
+            chain = (uint8_t)seg[0];
+            rest = seg.substr(1);
+        }
+        bool hs = false;
+        std::vector<uint8_t> sub;
+        std::string range = rest;
+        size_t colon = rest.find(':');
+        if (colon != std::string::npos) {
+            hs = true;
+            range = rest.substr(0, colon);
+            for (char ch : rest.substr(colon + 1))
+                if (isalpha((unsigned char)ch)) one_letter(ch, sub);
+        }
+        uint64_t a, b;
+        size_t dash = range.find('-');
+        if (dash != std::string::npos) {
+            if (!field_u64(range.data(), dash, &a) || !field_u64(range.data() + dash + 1, range.size() - dash - 1, &b))
+                return false;
+        } else {
+            if (!field_u64(range.data(), range.size(), &a)) return false;
+            b = a;
+        }
+        for (uint64_t r = a; r <= b; r++) {
+            out.chains.push_back(chain);
+            out.serials.push_back(r);
+            out.has_sub.push_back(hs);
+            out.subs.push_back(sub);
+        }
+    }
+    return true;
+}
+
+} // namespace
+
+struct fdh_queries {
+    fdh_query_params p;
+    std::vector<float> dist_thr, angle_thr;
+    std::vector<Query> q;
+    bool finalized = false;
+};
+
+namespace {
+
+void qinsert(Query &Q, const float *f, const fdg::HashParams &hp, uint32_t qi, uint32_t qj, bool primary,
+             uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
+    const uint32_t h = fdg::perfect_hash(f, hp);
+    if (Q.pos.count(h)) return;
+    Q.pos[h] = (uint32_t)Q.entries.size();
+    Q.entries.push_back(QEntry{h, qi, qj, (uint8_t)primary, pair, 0.f});
+}
+
+// make_query_map (src/controller/query.rs:208-329) minus the idf values, which need the index
+bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
+    const fdh_compact &c = Q.st;
+    const fdg::HashParams hp = fdg::make_params(qs.p.hash.nbin_dist, qs.p.hash.nbin_angle, qs.p.hash.dist_cutoff);
+    std::unordered_map<uint32_t, std::vector<uint8_t>> submap;
+    for (size_t i = 0; i < pq.chains.size(); i++) {
+        int64_t idx = -1;
+        if (qs.p.serial_query) {
+            idx = (int64_t)pq.serials[i];
+        } else {
+            for (size_t r = 0; r < c.nres(); r++) // CompactStructure::get_index (core.rs:215-223)
+                if (c.chain[r] == pq.chains[i] && c.serial[r] == pq.serials[i]) {
+                    idx = (int64_t)r;
+                    break;
+                }
+        }
+        if (idx < 0) continue;
+        Q.indices.push_back((uint32_t)idx);
+        if (pq.has_sub[i]) submap[(uint32_t)idx] = pq.subs[i];
+    }
+    const float rad = 3.14159274101257324f / 180.0f; // f32::to_radians
+    float f[7], fn[7], ff[7];
+    const size_t K = Q.indices.size();
+    for (size_t a = 0; a < K; a++)
+        for (size_t b = 0; b < K; b++) {
+            if (a == b) continue;
+            const uint32_t I = Q.indices[a], J = Q.indices[b];
+            if (I >= c.nres() || J >= c.nres()) continue;
+            if (!host_pair_feature(c, I, J, hp.dist_cutoff, f)) continue;
+            memcpy(fn, f, sizeof(f));
+            memcpy(ff, f, sizeof(f));
+            if (f[2] <= 20.0f) Q.aad.push_back(AAD{(uint8_t)(c.aa[I] & 0x7F), (uint8_t)(c.aa[J] & 0x7F), f[2], I});
+            const uint32_t pair = (uint32_t)Q.pair_hash.size();
+            Q.pair_hash.push_back(fdg::perfect_hash(f, hp));
+            qinsert(Q, f, hp, I, J, true, pair);
+            { // apply_substitutions (query.rs:86-156)
+                const float o1 = fn[0], o2 = fn[1];
+                auto si = submap.find(I), sj = submap.find(J);
+                if (si != submap.end()) {
+                    for (uint8_t s : si->second) {
+                        float t[7];
+                        memcpy(t, fn, sizeof(t));
+                        t[0] = (float)s;
+                        qinsert(Q, t, hp, I, J, false, pair);
+                    }
+                    if (sj != submap.end())
+                        for (uint8_t s : si->second)
+                            for (uint8_t s2 : sj->second) {
+                                fn[0] = (float)s;
+                                fn[1] = (float)s2;
+                                qinsert(Q, fn, hp, I, J, false, pair);
+                                fn[0] = o1;
+                                fn[1] = o2;
+                            }
+                } else if (sj != submap.end()) {
+                    for (uint8_t s : sj->second) {
+                        float t[7];
+                        memcpy(t, fn, sizeof(t));
+                        t[1] = (float)s;
+                        qinsert(Q, t, hp, I, J, false, pair);
+                    }
+                }
+            }
+            auto expand = [&](std::initializer_list<int> idxs, const std::vector<float> &thr, bool to_rad) {
+                for (float t : thr) { // expand_and_insert (query.rs:179-206): mutate, hash, restore
+                    const float delta = to_rad ? t * rad : t;
+                    for (int k : idxs) {
+                        fn[k] -= delta;
+                        ff[k] += delta;
+                        qinsert(Q, fn, hp, I, J, false, pair);
+                        qinsert(Q, ff, hp, I, J, false, pair);
+                        fn[k] += delta;
+                        ff[k] -= delta;
+                    }
+                }
+            };
+            expand({2, 3}, qs.dist_thr, false);
+            expand({4, 5, 6}, qs.angle_thr, true);
+        }
+    // derived kernel inputs
+    std::unordered_map<uint64_t, uint16_t> edges;
+    std::unordered_map<uint32_t, uint16_t> nodes;
+    for (auto &e : Q.entries) {
+        const uint64_t key = ((uint64_t)e.qi << 32) | e.qj;
+        auto it = edges.find(key);
+        if (it == edges.end()) {
+            if (edges.size() >= 65535) return false;
+            it = edges.emplace(key, (uint16_t)edges.size()).first;
+            auto nn = nodes.find(e.qi);
+            if (nn == nodes.end()) nn = nodes.emplace(e.qi, (uint16_t)nodes.size()).first;
+            Q.edge_node.push_back(nn->second);
+        }
+        Q.edge_of_hash.push_back(it->second);
+        Q.hashes_flat.push_back(e.hash);
+        Q.hashes_sorted.push_back(e.hash);
+        Q.symmetric[e.hash] = hash_is_symmetric(e.hash);
+        Q.max_q = std::max(Q.max_q, std::max(e.qi, e.qj));
+    }
+    Q.n_nodes = (uint32_t)nodes.size();
+    std::sort(Q.hashes_sorted.begin(), Q.hashes_sorted.end());
+    for (auto &d : Q.aad) {
+        Q.aad_aa1.push_back(d.aa1);
+        Q.aad_aa2.push_back(d.aa2);
+        Q.aad_dist.push_back(d.dist);
+        Q.aad_qi.push_back(d.qi);
+    }
+    return true;
+}
+
+// ---- graph components (src/controller/graph.rs:29-50): Tarjan SCCs U undirected components, size >= 2,
+// each sorted by node id, list sorted and deduped.  Graphs here have a handful of nodes.
+struct Graph {
+    std::vector<uint32_t> node_res;               // node id -> target residue
+    std::vector<std::pair<uint32_t, uint32_t>> e; // directed edges (node ids), insertion order
+};
+
+void graph_components(const Graph &g, std::vector<std::vector<uint32_t>> &out) {
+    const uint32_t n = (uint32_t)g.node_res.size();
+    out.clear();
+    std::vector<std::vector<uint32_t>> adj(n), und(n);
+    for (auto &e : g.e) {
+        adj[e.first].push_back(e.second);
+        und[e.first].push_back(e.second);
+        und[e.second].push_back(e.first);
+    }
+    std::vector<int> index(n, -1), low(n, 0);
+    std::vector<uint8_t> on(n, 0);
+    std::vector<uint32_t> stack;
+    int counter = 0;
+    struct Fr {
+        uint32_t v, k;
+    };
+    std::vector<Fr> cs;
+    for (uint32_t s = 0; s < n; s++) {
+        if (index[s] >= 0) continue;
+        cs.push_back({s, 0});
+        index[s] = low[s] = counter++;
+        stack.push_back(s);
+        on[s] = 1;
+        while (!cs.empty()) {
+            Fr &f = cs.back();
+            if (f.k < adj[f.v].size()) {
+                const uint32_t w = adj[f.v][f.k++];
+                if (index[w] < 0) {
+                    index[w] = low[w] = counter++;
+                    stack.push_back(w);
+                    on[w] = 1;
+                    cs.push_back({w, 0});
+                } else if (on[w]) {
+                    low[f.v] = std::min(low[f.v], index[w]);
+                }
+            } else {
+                const uint32_t v = f.v;
+                cs.pop_back();
+                if (!cs.empty()) low[cs.back().v] = std::min(low[cs.back().v], low[v]);
+                if (low[v] == index[v]) {
+                    std::vector<uint32_t> comp;
+                    uint32_t w;
+                    do {
+                        w = stack.back();
+                        stack.pop_back();
+                        on[w] = 0;
+                        comp.push_back(w);
+                    } while (w != v);
+                    if (comp.size() >= 2) out.push_back(std::move(comp));
+                }
+            }
+        }
+    }
+    std::vector<uint8_t> seen(n, 0);
+    std::vector<uint32_t> st;
+    for (uint32_t s = 0; s < n; s++) {
+        if (seen[s]) continue;
+        std::vector<uint32_t> comp;
+        st.assign(1, s);
+        seen[s] = 1;
+        while (!st.empty()) {
+            const uint32_t v = st.back();
+            st.pop_back();
+            comp.push_back(v);
+            for (uint32_t w : und[v])
+                if (!seen[w]) {
+                    seen[w] = 1;
+                    st.push_back(w);
+                }
+        }
+        if (comp.size() >= 2) out.push_back(std::move(comp));
+    }
+    for (auto &c : out) std::sort(c.begin(), c.end());
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+struct MatchTmp {             // one connected component of one candidate
+    uint32_t cand;
+    float idf;
+    std::vector<uint32_t> res_hash, res_final; // per query residue: target residue index + 1, 0 = none
+    std::vector<uint32_t> aq, at;              // alignment pairs (query structure idx, target residue idx)
+    uint32_t node_count_final = 0;
+};
+
+// map_query_and_retrieved_residues + the rescue loop (retrieve.rs:604-702, 453-516)
+void match_component(const Query &Q, const std::vector<fd_cand_edge> &edges, const std::vector<uint32_t> &sub,
+                     const fd_cand_pair *pairs, size_t n_pairs, uint32_t node_count, bool skip_ca_match,
+                     MatchTmp &m) {
+    uint32_t max_r = 0;
+    for (uint32_t k : sub) max_r = std::max(max_r, std::max(edges[k].i, edges[k].j));
+    const size_t q_size = (size_t)Q.max_q + 1, r_size = (size_t)max_r + 1;
+    std::vector<uint8_t> counts(q_size * r_size, 0);
+    std::vector<std::pair<uint8_t, uint32_t>> best(q_size, {0, 0});
+    float idf = 0.f;
+    for (uint32_t k : sub) {
+        const fd_cand_edge &e = edges[k];
+        const QEntry &qe = Q.entries[Q.pos.at(e.hash)];
+        idf += qe.idf; // calculate_subgraph_idf (retrieve.rs:705-719), edge order
+        std::pair<uint32_t, uint32_t> pr[2];
+        if (Q.symmetric.at(e.hash)) {
+            const uint32_t q1 = std::min(qe.qi, qe.qj), q2 = std::max(qe.qi, qe.qj);
+            const uint32_t r1 = std::min(e.i, e.j), r2 = std::max(e.i, e.j);
+            pr[0] = {q1, r1};
+            pr[1] = {q2, r2};
+        } else {
+            pr[0] = {qe.qi, e.i};
+            pr[1] = {qe.qj, e.j};
+        }
+        for (auto &qr : pr) {
+            uint8_t &c = counts[qr.first * r_size + qr.second];
+            if (c != 255) c++;
+            auto &b = best[qr.first];
+            if (c > b.first || (c == b.first && qr.second < b.second)) b = {c, qr.second};
+        }
+    }
+    m.idf = idf;
+    // bucket by count (descending), queries ascending inside a bucket; greedy one-to-one assignment
+    std::vector<uint32_t> order;
+    for (uint32_t q = 0; q < q_size; q++)
+        if (best[q].first > 0) order.push_back(q);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return best[a].first > best[b].first; });
+    std::vector<uint8_t> q_used(q_size, 0), r_used(r_size, 0);
+    std::vector<uint32_t> qidx, ridx;
+    for (uint32_t q : order) {
+        const uint32_t r = best[q].second;
+        if (!q_used[q] && !r_used[r]) {
+            qidx.push_back(q);
+            ridx.push_back(r);
+            q_used[q] = r_used[r] = 1;
+            if (qidx.size() == node_count) break;
+        }
+    }
+    // rescue loop over all query residues
+    const size_t NQ = Q.indices.size();
+    m.res_hash.assign(NQ, 0);
+    m.res_final.clear();
+    std::vector<uint32_t> q_scan, r_scan;
+    auto in_ridx = [&](uint32_t r) { return std::find(ridx.begin(), ridx.end(), r) != ridx.end(); };
+    for (size_t qi_pos = 0; qi_pos < NQ; qi_pos++) {
+        const uint32_t qi = Q.indices[qi_pos];
+        int64_t mapped = -1;
+        for (size_t k = 0; k < qidx.size(); k++)
+            if (qidx[k] == qi) mapped = ridx[k]; // last wins, like collecting into a HashMap
+        if (mapped >= 0) {
+            const uint32_t ri = (uint32_t)mapped;
+            m.res_hash[qi_pos] = ri + 1;
+            auto pos = std::find(r_scan.begin(), r_scan.end(), ri);
+            if (pos == r_scan.end()) {
+                m.res_final.push_back(ri + 1);
+                q_scan.push_back(qi);
+                r_scan.push_back(ri);
+            } else {
+                const size_t pp = pos - r_scan.begin();
+                m.res_final[pp] = 0; // sic (retrieve.rs:475): the scanned position indexes res_vec
+                m.res_final.push_back(ri + 1);
+                q_scan.erase(q_scan.begin() + pp);
+                r_scan.erase(r_scan.begin() + pp);
+                q_scan.push_back(qi);
+                r_scan.push_back(ri);
+            }
+        } else {
+            // candidate pairs (q_index == qi) whose second residue is already matched vote for their first
+            std::vector<std::pair<uint32_t, uint32_t>> cm; // (target residue, count)
+            for (size_t k = 0; k < n_pairs; k++) {
+                if (pairs[k].q_index != qi || !in_ridx(pairs[k].j)) continue;
+                bool found = false;
+                for (auto &kv : cm)
+                    if (kv.first == pairs[k].i) {
+                        kv.second++;
+                        found = true;
+                        break;
+                    }
+                if (!found) cm.push_back({pairs[k].i, 1});
+            }
+            uint32_t mx = 0, nmax = 0, arg = 0;
+            for (auto &kv : cm) mx = std::max(mx, kv.second);
+            for (auto &kv : cm)
+                if (kv.second == mx) {
+                    nmax++;
+                    arg = kv.first;
+                }
+            if (!cm.empty() && nmax == 1 && mx >= 2 &&
+                std::find(r_scan.begin(), r_scan.end(), arg) == r_scan.end()) {
+                m.res_final.push_back(arg + 1);
+                q_scan.push_back(qi);
+                r_scan.push_back(arg);
+            } else {
+                m.res_final.push_back(0);
+            }
+        }
+    }
+    const bool same = m.res_final == m.res_hash;
+    if (skip_ca_match || same) {
+        m.aq = qidx;
+        m.at = ridx;
+    } else {
+        m.aq = q_scan;
+        m.at = r_scan;
+    }
+    if (skip_ca_match) m.res_final = m.res_hash;
+    m.node_count_final = 0;
+    for (uint32_t v : m.res_final) m.node_count_final += v != 0;
+}
+
+} // namespace
+
+struct fdh_results {
+    std::vector<uint64_t> struct_off, match_off, match_order;
+    std::vector<fdh_struct_row> structs;
+    std::vector<fdh_match_row> matches;
+    std::vector<fdh_residue_match> residues;
+    double host_ms = 0.0;
+};
+
+// =============================================================================================
+extern "C" {
+
+const char *fdh_last_error(void) { return g_err.c_str(); }
+
+fdh_compact *fdh_compact_read_pdb(const char *path) {
+    Atoms a;
+    if (!read_pdb_atoms(path, a)) {
+        set_err(std::string("Failed to read PDB file: ") + path);
+        return nullptr;
+    }
+    return compact_from_atoms(a);
+}
+fdh_compact *fdh_compact_from_atoms(int64_t n, const float *x, const float *y, const float *z, const uint8_t *an,
+                                    const uint8_t *ch, const uint8_t *rn, const uint64_t *rs, const float *bf) {
+    Atoms a;
+    a.x.assign(x, x + n);
+    a.y.assign(y, y + n);
+    a.z.assign(z, z + n);
+    a.b.assign(bf, bf + n);
+    a.name.assign(an, an + 4 * n);
+    a.rname.assign(rn, rn + 3 * n);
+    a.chain.assign(ch, ch + n);
+    a.serial.assign(rs, rs + n);
+    return compact_from_atoms(a);
+}
+fdh_compact *fdh_compact_from_soa(int64_t n, const float *nx, const float *cax, const float *cbx, const uint8_t *cbv,
+                                  const uint8_t *aa, const uint8_t *chain, const uint64_t *serial, const float *bf) {
+    fdh_compact *c = new fdh_compact();
+    c->n.assign(nx, nx + 3 * n);
+    c->ca.assign(cax, cax + 3 * n);
+    c->cb.assign(cbx, cbx + 3 * n);
+    if (cbv) c->cb_valid.assign(cbv, cbv + n);
+    else c->cb_valid.assign((size_t)n, 1);
+    c->aa.assign(aa, aa + n);
+    if (chain) c->chain.assign(chain, chain + n);
+    else c->chain.assign((size_t)n, (uint8_t)'A');
+    c->serial.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) c->serial[i] = serial ? serial[i] : (uint64_t)(i + 1);
+    if (bf) c->bfac.assign(bf, bf + n);
+    else c->bfac.assign((size_t)n, 0.f);
+    if (n) c->chains.push_back(c->chain[0]);
+    c->raw_residues = (uint64_t)n;
+    return c;
+}
+int64_t fdh_compact_nres(const fdh_compact *c) { return (int64_t)c->nres(); }
+int64_t fdh_compact_num_residues_raw(const fdh_compact *c) { return (int64_t)c->raw_residues; }
+int fdh_compact_first_chain(const fdh_compact *c) { return c->chains.empty() ? -1 : c->chains[0]; }
+float fdh_compact_avg_plddt(const fdh_compact *c) { // core.rs:446-456
+    float s = 0.f;
+    for (float b : c->bfac) s += b;
+    return s / (float)c->nres();
+}
+void fdh_compact_get(const fdh_compact *c, float *nx, float *cax, float *cbx, uint8_t *cbv, uint8_t *aa,
+                     uint8_t *chain, uint64_t *serial, float *bf) {
+    const size_t n = c->nres();
+    if (nx) memcpy(nx, c->n.data(), 12 * n);
+    if (cax) memcpy(cax, c->ca.data(), 12 * n);
+    if (cbx) memcpy(cbx, c->cb.data(), 12 * n);
+    if (cbv) memcpy(cbv, c->cb_valid.data(), n);
+    if (aa) memcpy(aa, c->aa.data(), n);
+    if (chain) memcpy(chain, c->chain.data(), n);
+    if (serial) memcpy(serial, c->serial.data(), 8 * n);
+    if (bf) memcpy(bf, c->bfac.data(), 4 * n);
+}
+void fdh_compact_free(fdh_compact *c) { delete c; }
+
+// ---- store ----
+fdh_store *fdh_store_new(void) { return new fdh_store(); }
+int64_t fdh_store_add(fdh_store *s, const fdh_compact *c, const char *name) {
+    s->n.insert(s->n.end(), c->n.begin(), c->n.end());
+    s->ca.insert(s->ca.end(), c->ca.begin(), c->ca.end());
+    s->cb.insert(s->cb.end(), c->cb.begin(), c->cb.end());
+    s->aa.insert(s->aa.end(), c->aa.begin(), c->aa.end());
+    s->cb_valid.insert(s->cb_valid.end(), c->cb_valid.begin(), c->cb_valid.end());
+    s->chain.insert(s->chain.end(), c->chain.begin(), c->chain.end());
+    s->serial.insert(s->serial.end(), c->serial.begin(), c->serial.end());
+    s->row_offsets.push_back(s->row_offsets.back() + c->nres());
+    s->names.push_back(name ? name : "");
+    s->plddt.push_back(fdh_compact_avg_plddt(c));
+    return (int64_t)s->names.size() - 1;
+}
+int64_t fdh_store_add_soa(fdh_store *s, uint64_t S, const uint64_t *ro, const float *nx, const float *cax,
+                          const float *cbx, const uint8_t *aa, const char *prefix) {
+    const uint64_t R = ro[S];
+    const uint64_t base = s->row_offsets.back();
+    s->n.insert(s->n.end(), nx, nx + 3 * R);
+    s->ca.insert(s->ca.end(), cax, cax + 3 * R);
+    s->cb.insert(s->cb.end(), cbx, cbx + 3 * R);
+    s->aa.insert(s->aa.end(), aa, aa + R);
+    s->cb_valid.insert(s->cb_valid.end(), R, 1);
+    s->chain.insert(s->chain.end(), R, (uint8_t)'A');
+    const int64_t first = (int64_t)s->names.size();
+    for (uint64_t k = 0; k < S; k++) {
+        for (uint64_t r = ro[k]; r < ro[k + 1]; r++) s->serial.push_back(r - ro[k] + 1);
+        s->row_offsets.push_back(base + ro[k + 1]);
+        s->names.push_back(std::string(prefix ? prefix : "s") + std::to_string(first + (int64_t)k));
+        s->plddt.push_back(0.f);
+    }
+    return first;
+}
+uint64_t fdh_store_size(const fdh_store *s) { return s->names.size(); }
+uint64_t fdh_store_num_residues(const fdh_store *s) { return s->row_offsets.back(); }
+void fdh_store_get_lookup(const fdh_store *s, uint32_t *nres, float *plddt) {
+    for (size_t k = 0; k < s->names.size(); k++) {
+        if (nres) nres[k] = (uint32_t)(s->row_offsets[k + 1] - s->row_offsets[k]);
+        if (plddt) plddt[k] = s->plddt[k];
+    }
+}
+const char *fdh_store_name(const fdh_store *s, uint64_t id) { return id < s->names.size() ? s->names[id].c_str() : ""; }
+int fdh_store_batch(const fdh_store *s, fd_struct_batch *out) {
+    out->n_structs = s->names.size();
+    out->row_offsets = s->row_offsets.data();
+    out->n_xyz = s->n.data();
+    out->ca_xyz = s->ca.data();
+    out->cb_xyz = s->cb.data();
+    out->aa = s->aa.data();
+    out->cb_valid = s->cb_valid.data();
+    return FD_OK;
+}
+void fdh_store_free(fdh_store *s) { delete s; }
+
+// ---- index ----
+fdh_index *fdh_index_build(fd_ctx *ctx, const fdh_store *s, const fd_hash_params *params) {
+    fd_struct_batch b;
+    fdh_store_batch(s, &b);
+    fd_index_buffers out;
+    if (fd_build_index(ctx, &b, params, 0, 0, 1ull << 32, &out) != FD_OK) {
+        set_err(fd_last_error(ctx));
+        return nullptr;
+    }
+    fdh_index *ix = fdh_index_from_buffers(&out, s, params);
+    fd_free_index_buffers(&out);
+    return ix;
+}
+
+fdh_index *fdh_index_from_buffers(const fd_index_buffers *out, const fdh_store *s, const fd_hash_params *params) {
+    fdh_index *ix = new fdh_index();
+    ix->own_hashes.assign(out->hashes, out->hashes + out->count);
+    ix->own_offsets.assign(out->offsets, out->offsets + out->count + 1);
+    ix->own_values.assign(out->values, out->values + out->value_bytes);
+    ix->hashes = ix->own_hashes.data();
+    ix->offsets = ix->own_offsets.data();
+    ix->values = ix->own_values.data();
+    ix->count = ix->own_hashes.size();
+    ix->value_bytes = ix->own_values.size();
+    ix->names = s->names;
+    ix->nres.resize(s->names.size());
+    ix->plddt.resize(s->names.size());
+    fdh_store_get_lookup(s, ix->nres.data(), ix->plddt.data());
+    ix->params = *params;
+    return ix;
+}
+
+int fdh_index_save(const fdh_index *ix, const fdh_store *s, const char *prefix, uint64_t max_residue,
+                   const char *foldcomp_db) {
+    auto wr = [&](const std::string &path, const void *p, size_t n, FILE *f) {
+        return n == 0 || fwrite(p, 1, n, f) == n;
+    };
+    { // PREFIX: posting bytes (indextable.rs:239-264)
+        FILE *f = fopen(prefix, "wb");
+        if (!f || !wr(prefix, ix->values, ix->value_bytes, f)) {
+            set_err(std::string("cannot write ") + prefix);
+            if (f) fclose(f);
+            return FD_ERR_ARG;
+        }
+        fclose(f);
+    }
+    { // PREFIX.offset: u64 count | u32 hashes | u64 offsets (indextable.rs:297-326)
+        std::string p = std::string(prefix) + ".offset";
+        FILE *f = fopen(p.c_str(), "wb");
+        uint64_t count = ix->count;
+        if (!f || !wr(p, &count, 8, f) || !wr(p, ix->hashes, 4 * count, f) || !wr(p, ix->offsets, 8 * (count + 1), f)) {
+            set_err("cannot write " + p);
+            if (f) fclose(f);
+            return FD_ERR_ARG;
+        }
+        fclose(f);
+    }
+    { // PREFIX.lookup: id \t name \t nres \t plddt \t db_key (lookup.rs:17-58)
+        std::string p = std::string(prefix) + ".lookup";
+        FILE *f = fopen(p.c_str(), "wb");
+        if (!f) {
+            set_err("cannot write " + p);
+            return FD_ERR_ARG;
+        }
+        (void)s;
+        for (size_t i = 0; i < ix->names.size(); i++)
+            fprintf(f, "%zu\t%s\t%u\t%s\t%zu\n", i, ix->names[i].c_str(), ix->nres[i], rust_f32(ix->plddt[i]).c_str(), i);
+        fclose(f);
+    }
+    { // PREFIX.type: TOML with sorted keys (cli/config.rs:64-97)
+        std::string p = std::string(prefix) + ".type";
+        FILE *f = fopen(p.c_str(), "wb");
+        if (!f) {
+            set_err("cannot write " + p);
+            return FD_ERR_ARG;
+        }
+        char buf[64];
+        auto r = std::to_chars(buf, buf + sizeof(buf), (double)ix->params.dist_cutoff, std::chars_format::fixed);
+        std::string g(buf, r.ptr);
+        if (g.find('.') == std::string::npos) g += ".0";
+        fprintf(f, "chunk_size = %zu\n", ix->names.size());
+        if (foldcomp_db) fprintf(f, "foldcomp_db = \"%s\"\n", foldcomp_db);
+        fprintf(f, "grid_width = %s\nhash_type = \"PDBTrRosetta\"\ninput_format = \"PDB\"\nmax_residue = %llu\n"
+                   "num_bin_angle = %u\nnum_bin_dist = %u\n",
+                g.c_str(), (unsigned long long)max_residue, ix->params.nbin_angle, ix->params.nbin_dist);
+        fclose(f);
+    }
+    return FD_OK;
+}
+
+fdh_index *fdh_index_load(const char *prefix) {
+    auto map_file = [](const std::string &p, void **addr, size_t *len) {
+        int fd = open(p.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) {
+            close(fd);
+            return false;
+        }
+        *len = (size_t)st.st_size;
+        *addr = *len ? mmap(nullptr, *len, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+        close(fd);
+        return *len == 0 || *addr != MAP_FAILED;
+    };
+    fdh_index *ix = new fdh_index();
+    std::string vp = std::string(prefix) + ".value";
+    if (access(vp.c_str(), F_OK) != 0) vp = prefix; // indextable.rs:333-337
+    if (!map_file(vp, &ix->map_val, &ix->map_val_len) || !map_file(std::string(prefix) + ".offset", &ix->map_off, &ix->map_off_len)) {
+        set_err(std::string("cannot open index ") + prefix);
+        ix->map_off = ix->map_val = nullptr;
+        delete ix;
+        return nullptr;
+    }
+    const uint8_t *o = (const uint8_t *)ix->map_off;
+    if (ix->map_off_len < 8) {
+        set_err("offset file too short");
+        delete ix;
+        return nullptr;
+    }
+    memcpy(&ix->count, o, 8);
+    const size_t need = 8 + ix->count * 4 + (ix->count + 1) * 8;
+    if (ix->map_off_len < need) { // indextable.rs:347-355
+        set_err("Offset file appears to be in old format or corrupted");
+        delete ix;
+        return nullptr;
+    }
+    ix->hashes = (const uint32_t *)(o + 8);
+    ix->own_offsets.resize(ix->count + 1); // unaligned when count is odd: copy
+    memcpy(ix->own_offsets.data(), o + 8 + ix->count * 4, (ix->count + 1) * 8);
+    ix->offsets = ix->own_offsets.data();
+    ix->values = (const uint8_t *)ix->map_val;
+    ix->value_bytes = ix->map_val_len;
+    { // lookup
+        std::ifstream in(std::string(prefix) + ".lookup");
+        std::string line;
+        while (std::getline(in, line)) {
+            size_t a = line.find('\t'), b = line.find('\t', a + 1), c = line.find('\t', b + 1);
+            if (a == std::string::npos || b == std::string::npos || c == std::string::npos) continue;
+            size_t d = line.find('\t', c + 1);
+            ix->names.push_back(line.substr(a + 1, b - a - 1));
+            ix->nres.push_back((uint32_t)strtoul(line.substr(b + 1, c - b - 1).c_str(), nullptr, 10));
+            ix->plddt.push_back(strtof(line.substr(c + 1, d == std::string::npos ? std::string::npos : d - c - 1).c_str(), nullptr));
+        }
+    }
+    { // type (TOML subset written by the reference)
+        std::ifstream in(std::string(prefix) + ".type");
+        std::string line;
+        while (std::getline(in, line)) {
+            size_t eq = line.find('=');
+            if (eq == std::string::npos) continue;
+            std::string k = line.substr(0, eq), v = line.substr(eq + 1);
+            while (!k.empty() && k.back() == ' ') k.pop_back();
+            if (k == "num_bin_dist") ix->params.nbin_dist = (uint32_t)atoi(v.c_str());
+            else if (k == "num_bin_angle") ix->params.nbin_angle = (uint32_t)atoi(v.c_str());
+            else if (k == "grid_width") ix->params.dist_cutoff = strtof(v.c_str(), nullptr);
+        }
+    }
+    return ix;
+}
+int fdh_index_get(const fdh_index *ix, fd_index_buffers *v) {
+    v->count = ix->count;
+    v->hashes = const_cast<uint32_t *>(ix->hashes);
+    v->offsets = const_cast<uint64_t *>(ix->offsets);
+    v->value_bytes = ix->value_bytes;
+    v->values = const_cast<uint8_t *>(ix->values);
+    return FD_OK;
+}
+uint64_t fdh_index_num_structs(const fdh_index *ix) { return ix->nres.size(); }
+void fdh_index_get_lookup(const fdh_index *ix, uint32_t *nres, float *plddt) {
+    if (nres) memcpy(nres, ix->nres.data(), 4 * ix->nres.size());
+    if (plddt) memcpy(plddt, ix->plddt.data(), 4 * ix->plddt.size());
+}
+const char *fdh_index_name(const fdh_index *ix, uint64_t id) { return id < ix->names.size() ? ix->names[id].c_str() : ""; }
+void fdh_index_get_params(const fdh_index *ix, fd_hash_params *p) { *p = ix->params; }
+int fdh_index_attach(fd_ctx *ctx, const fdh_index *ix) {
+    return fd_index_attach(ctx, ix->hashes, ix->offsets, ix->count, ix->values, ix->value_bytes, ix->nres.size(),
+                           ix->nres.data(), ix->plddt.data());
+}
+void fdh_index_free(fdh_index *ix) { delete ix; }
+
+// ---- queries ----
+int64_t fdh_parse_query_string(const char *q, uint8_t default_chain, uint8_t *chains, uint64_t *serials,
+                               int64_t *subs_off, int64_t *subs_end, uint8_t *subs, int64_t cap_res, int64_t cap_subs) {
+    ParsedQuery pq;
+    if (!parse_query(q, default_chain, pq)) return -1;
+    int64_t ns = 0;
+    if ((int64_t)pq.chains.size() > cap_res) return -2;
+    for (size_t i = 0; i < pq.chains.size(); i++) {
+        chains[i] = pq.chains[i];
+        serials[i] = pq.serials[i];
+        if (pq.has_sub[i]) {
+            subs_off[i] = ns;
+            for (uint8_t v : pq.subs[i]) {
+                if (ns >= cap_subs) return -2;
+                subs[ns++] = v;
+            }
+            subs_end[i] = ns;
+        } else {
+            subs_off[i] = -1;
+            subs_end[i] = -1;
+        }
+    }
+    return (int64_t)pq.chains.size();
+}
+
+fdh_queries *fdh_queries_new(const fdh_query_params *p) {
+    fdh_queries *qs = new fdh_queries();
+    qs->p = *p;
+    qs->dist_thr.assign(p->dist_thr, p->dist_thr + p->n_dist_thr);
+    qs->angle_thr.assign(p->angle_thr, p->angle_thr + p->n_angle_thr);
+    qs->p.dist_thr = nullptr;
+    qs->p.angle_thr = nullptr;
+    return qs;
+}
+int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *st, const char *query_string) {
+    ParsedQuery pq;
+    const int fc = fdh_compact_first_chain(st);
+    if (!parse_query(query_string, fc < 0 ? (uint8_t)'A' : (uint8_t)fc, pq)) {
+        set_err(std::string("Invalid residue in query string: ") + query_string);
+        return -1;
+    }
+    if (pq.chains.empty()) {
+        set_err("whole-structure queries (empty query string) are not supported in this version");
+        return -1;
+    }
+    qs->q.emplace_back();
+    Query &Q = qs->q.back();
+    Q.st = *st;
+    Q.qstring = query_string;
+    if (!build_query_map(Q, pq, *qs)) {
+        qs->q.pop_back();
+        set_err("query has too many edges");
+        return -1;
+    }
+    qs->finalized = false;
+    return (int64_t)qs->q.size() - 1;
+}
+int64_t fdh_queries_size(const fdh_queries *qs) { return (int64_t)qs->q.size(); }
+
+int fdh_queries_finalize(fdh_queries *qs, fd_ctx *ctx) {
+    // calculate_idf_for_hash (query.rs:17-32) for the observed hash of every query pair, one device call
+    std::vector<uint32_t> all;
+    for (auto &Q : qs->q) all.insert(all.end(), Q.pair_hash.begin(), Q.pair_hash.end());
+    std::vector<uint32_t> counts(all.size());
+    if (!all.empty()) {
+        int rc = fd_posting_counts(ctx, all.data(), all.size(), counts.data());
+        if (rc != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return rc;
+        }
+    }
+    size_t base = 0;
+    const float total = (float)fd_index_num_structs(ctx); // total_structures = lookup.len() as f32
+    for (auto &Q : qs->q) {
+        for (auto &e : Q.entries) {
+            const uint32_t c = counts[base + e.pair];
+            e.idf = c > 0 ? log2f(total / (float)c) : 0.0f;
+        }
+        base += Q.pair_hash.size();
+    }
+    qs->finalized = true;
+    return FD_OK;
+}
+int64_t fdh_queries_num_hashes(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].entries.size(); }
+void fdh_queries_get_map(const fdh_queries *qs, int64_t q, uint32_t *hash, int64_t *qi, int64_t *qj,
+                         uint8_t *primary, float *idf) {
+    const Query &Q = qs->q[q];
+    for (size_t k = 0; k < Q.entries.size(); k++) {
+        if (hash) hash[k] = Q.entries[k].hash;
+        if (qi) qi[k] = Q.entries[k].qi;
+        if (qj) qj[k] = Q.entries[k].qj;
+        if (primary) primary[k] = Q.entries[k].primary;
+        if (idf) idf[k] = Q.entries[k].idf;
+    }
+}
+int64_t fdh_queries_num_indices(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].indices.size(); }
+void fdh_queries_get_indices(const fdh_queries *qs, int64_t q, int64_t *indices) {
+    for (size_t k = 0; k < qs->q[q].indices.size(); k++) indices[k] = qs->q[q].indices[k];
+}
+void fdh_queries_free(fdh_queries *qs) { delete qs; }
+
+// ---- search ----
+fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels) {
+    if (!qs->finalized) {
+        set_err("fdh_search: call fdh_queries_finalize first");
+        return nullptr;
+    }
+    const uint32_t nq = (uint32_t)qs->q.size();
+    fdh_results *R = new fdh_results();
+    R->struct_off.assign(nq + 1, 0);
+    R->match_off.assign(nq + 1, 0);
+    if (nq == 0) return R;
+    // --- K3: count_query + filter + sort + top ---
+    std::vector<fd_query> fq(nq);
+    for (uint32_t q = 0; q < nq; q++) {
+        const Query &Q = qs->q[q];
+        fq[q] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.edge_of_hash.data(),
+                         (uint32_t)Q.edge_node.size(), Q.edge_node.data(), Q.n_nodes, (uint32_t)Q.indices.size()};
+    }
+    fd_struct_hit *hits = nullptr;
+    uint64_t *hoff = nullptr;
+    if (fd_count_query_batch(ctx, fq.data(), nq, &p->prefilter, &hits, &hoff) != FD_OK) {
+        set_err(fd_last_error(ctx));
+        delete R;
+        return nullptr;
+    }
+    const uint64_t n_cand = hoff[nq];
+    struct CandOut {
+        uint32_t max_node = 0;
+        float min_rmsd = 0.f;
+        uint64_t m_begin = 0, m_end = 0;
+    };
+    std::vector<CandOut> cout_(n_cand);
+    std::vector<MatchTmp> mt; // all matches in candidate order
+    double host_ms = 0.0;
+    std::vector<float> rmsd, U, T;
+    if (!p->skip_match && n_cand) {
+        // --- K4: candidate edges ---
+        std::vector<fd_retrieval_query> rq(nq);
+        for (uint32_t q = 0; q < nq; q++) {
+            const Query &Q = qs->q[q];
+            rq[q] = fd_retrieval_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), (uint32_t)Q.aad.size(),
+                                       Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data()};
+        }
+        std::vector<uint32_t> cand_q(n_cand), cand_n(n_cand);
+        for (uint32_t q = 0; q < nq; q++)
+            for (uint64_t k = hoff[q]; k < hoff[q + 1]; k++) {
+                cand_q[k] = q;
+                cand_n[k] = hits[k].nid;
+            }
+        fd_cand_edge *edges = nullptr;
+        fd_cand_pair *pairs = nullptr;
+        uint64_t ne = 0, np = 0;
+        // the kernel takes at most 2^24-1 candidates per call
+        std::vector<fd_cand_edge> all_edges;
+        std::vector<fd_cand_pair> all_pairs;
+        const uint64_t CH = (1ull << 24) - 1;
+        for (uint64_t c0 = 0; c0 < n_cand; c0 += CH) {
+            const uint64_t cn = std::min(CH, n_cand - c0);
+            if (fd_candidate_edges_batch(ctx, rq.data(), nq, cand_q.data() + c0, cand_n.data() + c0, cn, &qs->p.hash,
+                                         p->ca_dist_cutoff, &edges, &ne, &pairs, &np) != FD_OK) {
+                set_err(fd_last_error(ctx));
+                fd_free(hits);
+                fd_free(hoff);
+                delete R;
+                return nullptr;
+            }
+            for (uint64_t k = 0; k < ne; k++) {
+                edges[k].cand += (uint32_t)c0;
+                all_edges.push_back(edges[k]);
+            }
+            for (uint64_t k = 0; k < np; k++) {
+                pairs[k].cand += (uint32_t)c0;
+                all_pairs.push_back(pairs[k]);
+            }
+            fd_free(edges);
+            fd_free(pairs);
+        }
+        // --- host: graph components + residue assignment per candidate, candidate-parallel ---
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<uint64_t> e_begin(n_cand + 1, 0), p_begin(n_cand + 1, 0);
+        for (auto &e : all_edges) e_begin[e.cand + 1]++;
+        for (auto &e : all_pairs) p_begin[e.cand + 1]++;
+        for (uint64_t c = 0; c < n_cand; c++) {
+            e_begin[c + 1] += e_begin[c];
+            p_begin[c + 1] += p_begin[c];
+        }
+        int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, 64));
+        std::vector<std::vector<MatchTmp>> per_thread(nt);
+        std::vector<std::vector<uint64_t>> per_thread_cand(nt);
+        std::atomic<uint64_t> next{0};
+        const uint64_t GRAIN = 256;
+        struct Chunk {
+            uint64_t c0;
+            int thread;
+            size_t begin, end;
+        };
+        std::vector<std::vector<Chunk>> chunks(nt);
+        auto worker = [&](int tid) {
+            std::vector<fd_cand_edge> ce;
+            std::vector<std::vector<uint32_t>> comps;
+            Graph g;
+            std::vector<MatchTmp> &out = per_thread[tid];
+            for (;;) {
+                const uint64_t c0 = next.fetch_add(GRAIN);
+                if (c0 >= n_cand) break;
+                const size_t begin = out.size();
+                for (uint64_t c = c0; c < std::min(n_cand, c0 + GRAIN); c++) {
+                    const uint64_t eb = e_begin[c], ee = e_begin[c + 1];
+                    if (ee == eb) continue;
+                    const Query &Q = qs->q[cand_q[c]];
+                    ce.assign(all_edges.begin() + eb, all_edges.begin() + ee);
+                    // create_index_graph (graph.rs:16-27): node ids by first appearance
+                    g.node_res.clear();
+                    g.e.clear();
+                    auto node_of = [&](uint32_t r) {
+                        for (uint32_t k = 0; k < g.node_res.size(); k++)
+                            if (g.node_res[k] == r) return k;
+                        g.node_res.push_back(r);
+                        return (uint32_t)g.node_res.size() - 1;
+                    };
+                    for (auto &e : ce) {
+                        const uint32_t a = node_of(e.i);
+                        const uint32_t b = node_of(e.j);
+                        g.e.push_back({a, b});
+                    }
+                    graph_components(g, comps);
+                    for (auto &comp : comps) {
+                        std::vector<uint32_t> sub;
+                        for (uint32_t k = 0; k < ce.size(); k++) {
+                            const bool ia = std::find(comp.begin(), comp.end(), g.e[k].first) != comp.end();
+                            const bool ib = std::find(comp.begin(), comp.end(), g.e[k].second) != comp.end();
+                            if (ia && ib) sub.push_back(k);
+                        }
+                        out.emplace_back();
+                        MatchTmp &m = out.back();
+                        m.cand = (uint32_t)c;
+                        match_component(Q, ce, sub, all_pairs.data() + p_begin[c], p_begin[c + 1] - p_begin[c],
+                                        (uint32_t)comp.size(), p->skip_ca_match != 0, m);
+                    }
+                }
+                chunks[tid].push_back(Chunk{c0, tid, begin, out.size()});
+            }
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+            worker(0);
+            for (auto &t : th) t.join();
+        }
+        // merge in candidate order
+        std::vector<Chunk> allc;
+        for (auto &v : chunks) allc.insert(allc.end(), v.begin(), v.end());
+        std::sort(allc.begin(), allc.end(), [](const Chunk &a, const Chunk &b) { return a.c0 < b.c0; });
+        for (auto &ch : allc)
+            for (size_t k = ch.begin; k < ch.end; k++) mt.push_back(std::move(per_thread[ch.thread][k]));
+        host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        // --- K5: batched Kabsch, coordinates gathered on the device from the store ---
+        const uint32_t n_align = (uint32_t)mt.size();
+        rmsd.assign(n_align, 0.f);
+        U.assign(9 * (size_t)n_align, 0.f);
+        T.assign(3 * (size_t)n_align, 0.f);
+        if (n_align) {
+            std::vector<uint64_t> q_res_off(nq + 1, 0);
+            for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q].st.nres();
+            std::vector<float> q_ca(3 * q_res_off[nq]), q_cb(3 * q_res_off[nq]);
+            for (uint32_t q = 0; q < nq; q++) {
+                memcpy(q_ca.data() + 3 * q_res_off[q], qs->q[q].st.ca.data(), 12 * qs->q[q].st.nres());
+                memcpy(q_cb.data() + 3 * q_res_off[q], qs->q[q].st.cb.data(), 12 * qs->q[q].st.nres());
+            }
+            std::vector<uint32_t> a_nid(n_align), a_off(n_align + 1, 0), pq_, pt_;
+            for (uint32_t a = 0; a < n_align; a++) {
+                const MatchTmp &m = mt[a];
+                a_nid[a] = cand_n[m.cand];
+                const uint64_t qb = q_res_off[cand_q[m.cand]];
+                for (size_t k = 0; k < m.aq.size(); k++) {
+                    pq_.push_back((uint32_t)(qb + m.aq[k]));
+                    pt_.push_back(m.at[k]);
+                }
+                a_off[a + 1] = (uint32_t)pq_.size();
+            }
+            if (fd_kabsch_store_batch(ctx, q_ca.data(), q_cb.data(), q_res_off[nq], a_nid.data(), a_off.data(), n_align,
+                                      pq_.data(), pt_.data(), rmsd.data(), U.data(), T.data()) != FD_OK) {
+                set_err(fd_last_error(ctx));
+                fd_free(hits);
+                fd_free(hoff);
+                delete R;
+                return nullptr;
+            }
+        }
+        // per-candidate summary (retrieve.rs:539-551)
+        for (uint32_t a = 0; a < n_align; a++) {
+            CandOut &co = cout_[mt[a].cand];
+            if (a == 0 || mt[a - 1].cand != mt[a].cand) co.m_begin = a;
+            co.m_end = a + 1;
+            const uint32_t cnt = mt[a].node_count_final;
+            if (cnt > co.max_node) {
+                co.max_node = cnt;
+                co.min_rmsd = rmsd[a];
+            } else if (cnt == co.max_node && rmsd[a] < co.min_rmsd) {
+                co.min_rmsd = rmsd[a];
+            }
+        }
+    }
+    // --- assemble rows: filter_after_matching (filter.rs:103-116), MatchFilter (:194-235), default sorts ---
+    auto t1 = std::chrono::steady_clock::now();
+    for (uint32_t q = 0; q < nq; q++) {
+        const Query &Q = qs->q[q];
+        const float expected = (float)Q.indices.size();
+        const size_t s_begin = R->structs.size();
+        const size_t m_begin = R->matches.size();
+        for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
+            const CandOut &co = cout_[c];
+            if (!p->skip_match) {
+                bool pass = true;
+                if (p->max_matching_node_count > 0) pass = pass && co.max_node >= p->max_matching_node_count;
+                if (p->max_matching_node_ratio > 0.f) pass = pass && (float)co.max_node / expected >= p->max_matching_node_ratio;
+                if (p->rmsd_cutoff > 0.f) pass = pass && co.min_rmsd <= p->rmsd_cutoff;
+                if (!pass) continue;
+            }
+            fdh_struct_row sr{hits[c].nid, hits[c].match_count, hits[c].node_count, hits[c].edge_count, hits[c].idf,
+                              co.max_node, co.min_rmsd, 0, 0};
+            sr.match_begin = R->matches.size();
+            for (uint64_t a = co.m_begin; a < co.m_end; a++) {
+                const MatchTmp &m = mt[a];
+                bool pass = true;
+                if (p->connected_node_count > 0) pass = pass && m.node_count_final >= p->connected_node_count;
+                if (p->connected_node_ratio > 0.f) pass = pass && (float)m.node_count_final / expected >= p->connected_node_ratio;
+                if (p->prefilter.idf_score_cutoff > 0.f) pass = pass && m.idf >= p->prefilter.idf_score_cutoff;
+                if (p->rmsd_cutoff > 0.f) pass = pass && rmsd[a] <= p->rmsd_cutoff;
+                if (!pass) continue;
+                fdh_match_row mr;
+                mr.nid = hits[c].nid;
+                mr.node_count = m.node_count_final;
+                mr.idf = m.idf;
+                mr.rmsd = rmsd[a];
+                memcpy(mr.U, &U[9 * a], sizeof(mr.U));
+                memcpy(mr.t, &T[3 * a], sizeof(mr.t));
+                mr.res_begin = R->residues.size();
+                for (uint32_t v : m.res_final) {
+                    fdh_residue_match rm{(uint8_t)(v != 0), 0, v ? (uint64_t)(v - 1) : 0};
+                    if (v && labels && hits[c].nid < labels->names.size()) { // (chain, residue number) of the target
+                        const uint64_t r = labels->row_offsets[hits[c].nid] + (v - 1);
+                        rm.chain = labels->chain[r];
+                        rm.serial = labels->serial[r];
+                    }
+                    R->residues.push_back(rm);
+                }
+                R->matches.push_back(mr);
+            }
+            sr.match_end = R->matches.size();
+            R->structs.push_back(sr);
+        }
+        // StructureSortStrategy::default: idf desc, min_rmsd asc (sort.rs:454-458), stable
+        std::stable_sort(R->structs.begin() + s_begin, R->structs.end(), [](const fdh_struct_row &a, const fdh_struct_row &b) {
+            if (a.idf != b.idf) return a.idf > b.idf;
+            return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
+        });
+        // MatchSortStrategy::default: idf desc, rmsd asc (sort.rs:218-222), stable over emission order
+        const size_t m_end = R->matches.size();
+        std::vector<uint64_t> ord(m_end - m_begin);
+        for (size_t k = 0; k < ord.size(); k++) ord[k] = m_begin + k;
+        std::stable_sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) {
+            const fdh_match_row &x = R->matches[a], &y = R->matches[b];
+            if (x.idf != y.idf) return x.idf > y.idf;
+            return x.rmsd < y.rmsd;
+        });
+        R->match_order.insert(R->match_order.end(), ord.begin(), ord.end());
+        R->struct_off[q + 1] = R->structs.size();
+        R->match_off[q + 1] = R->matches.size();
+    }
+    host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    R->host_ms = host_ms;
+    fd_free(hits);
+    fd_free(hoff);
+    return R;
+}
+
+uint64_t fdh_results_num_queries(const fdh_results *r) { return r->struct_off.size() - 1; }
+const uint64_t *fdh_results_struct_offsets(const fdh_results *r) { return r->struct_off.data(); }
+const fdh_struct_row *fdh_results_struct_rows(const fdh_results *r) { return r->structs.data(); }
+const uint64_t *fdh_results_match_offsets(const fdh_results *r) { return r->match_off.data(); }
+const fdh_match_row *fdh_results_match_rows(const fdh_results *r) { return r->matches.data(); }
+const uint64_t *fdh_results_match_order(const fdh_results *r) { return r->match_order.data(); }
+const fdh_residue_match *fdh_results_residues(const fdh_results *r) { return r->residues.data(); }
+uint64_t fdh_results_num_residues(const fdh_results *r) { return r->residues.size(); }
+double fdh_results_host_ms(const fdh_results *r) { return r->host_ms; }
+void fdh_results_free(fdh_results *r) { delete r; }
+
+} // extern "C"

@@ -1,0 +1,382 @@
+"""Python mirror of the reference's host interface for the hot path, over include/folddisco_b200_host.h.
+
+Names follow the reference (src/lib.rs prelude): read_structure_from_path, parse_query_string, Folddisco
+(index builder), load_folddisco_index, query (make_query_map + count_query + retrieval_wrapper for a batch).
+All compute runs in the CUDA kernels behind the C ABI.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from .capi import FdError, HashParams, PrefilterParams, VP, _StructBatch, _IndexBuffers, _ptr
+
+UINT64_MAX = capi.UINT64_MAX
+
+
+class _QueryParams(C.Structure):
+    _fields_ = [("hash", HashParams), ("dist_thr", VP), ("n_dist_thr", C.c_int), ("angle_thr", VP),
+                ("n_angle_thr", C.c_int), ("serial_query", C.c_int)]
+
+
+class SearchParams(C.Structure):
+    """Reference CLI defaults (src/cli/main.rs:49-97)."""
+    _fields_ = [("prefilter", PrefilterParams), ("ca_dist_cutoff", C.c_float), ("skip_match", C.c_int),
+                ("max_matching_node_count", C.c_uint64), ("max_matching_node_ratio", C.c_float),
+                ("rmsd_cutoff", C.c_float), ("connected_node_count", C.c_uint64), ("connected_node_ratio", C.c_float),
+                ("skip_ca_match", C.c_int), ("host_threads", C.c_int)]
+
+    def __init__(self, top_n=UINT64_MAX, ca_dist_cutoff=1.0, skip_match=False, host_threads=0, **prefilter):
+        super().__init__(PrefilterParams(top_n=top_n, **prefilter), ca_dist_cutoff, int(skip_match), 0, 0.0, 0.0, 0,
+                         0.0, 0, host_threads)
+
+
+STRUCT_ROW = np.dtype([("nid", np.uint32), ("total_match_count", np.uint32), ("node_count", np.uint32),
+                       ("edge_count", np.uint32), ("idf", np.float32), ("max_matching_node_count", np.uint32),
+                       ("min_rmsd_with_max_match", np.float32), ("_pad", np.uint32), ("match_begin", np.uint64),
+                       ("match_end", np.uint64)])
+MATCH_ROW = np.dtype([("nid", np.uint32), ("node_count", np.uint32), ("idf", np.float32), ("rmsd", np.float32),
+                      ("U", np.float32, 9), ("t", np.float32, 3), ("res_begin", np.uint64)])
+RES_MATCH = np.dtype([("some", np.uint8), ("chain", np.uint8), ("_pad", np.uint8, 6), ("serial", np.uint64)])
+
+_sigs_done = False
+
+
+def _lib():
+    global _sigs_done
+    L = capi.lib()
+    if _sigs_done:
+        return L
+
+    def sig(name, res, args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+
+    PP = C.POINTER
+    sig("fdh_last_error", C.c_char_p, [])
+    sig("fdh_compact_read_pdb", VP, [C.c_char_p])
+    sig("fdh_compact_from_atoms", VP, [C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP])
+    sig("fdh_compact_from_soa", VP, [C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP])
+    sig("fdh_compact_nres", C.c_int64, [VP])
+    sig("fdh_compact_num_residues_raw", C.c_int64, [VP])
+    sig("fdh_compact_first_chain", C.c_int, [VP])
+    sig("fdh_compact_avg_plddt", C.c_float, [VP])
+    sig("fdh_compact_get", None, [VP] + [VP] * 8)
+    sig("fdh_compact_free", None, [VP])
+    sig("fdh_store_new", VP, [])
+    sig("fdh_store_add", C.c_int64, [VP, VP, C.c_char_p])
+    sig("fdh_store_add_soa", C.c_int64, [VP, C.c_uint64, VP, VP, VP, VP, VP, C.c_char_p])
+    sig("fdh_store_size", C.c_uint64, [VP])
+    sig("fdh_store_num_residues", C.c_uint64, [VP])
+    sig("fdh_store_get_lookup", None, [VP, VP, VP])
+    sig("fdh_store_name", C.c_char_p, [VP, C.c_uint64])
+    sig("fdh_store_batch", C.c_int, [VP, PP(_StructBatch)])
+    sig("fdh_store_free", None, [VP])
+    sig("fdh_index_build", VP, [VP, VP, PP(HashParams)])
+    sig("fdh_index_from_buffers", VP, [PP(_IndexBuffers), VP, PP(HashParams)])
+    sig("fdh_index_save", C.c_int, [VP, VP, C.c_char_p, C.c_uint64, C.c_char_p])
+    sig("fdh_index_load", VP, [C.c_char_p])
+    sig("fdh_index_get", C.c_int, [VP, PP(_IndexBuffers)])
+    sig("fdh_index_num_structs", C.c_uint64, [VP])
+    sig("fdh_index_get_lookup", None, [VP, VP, VP])
+    sig("fdh_index_name", C.c_char_p, [VP, C.c_uint64])
+    sig("fdh_index_get_params", None, [VP, PP(HashParams)])
+    sig("fdh_index_attach", C.c_int, [VP, VP])
+    sig("fdh_index_free", None, [VP])
+    sig("fdh_parse_query_string", C.c_int64, [C.c_char_p, C.c_uint8, VP, VP, VP, VP, VP, C.c_int64, C.c_int64])
+    sig("fdh_queries_new", VP, [PP(_QueryParams)])
+    sig("fdh_queries_add", C.c_int64, [VP, VP, C.c_char_p])
+    sig("fdh_queries_size", C.c_int64, [VP])
+    sig("fdh_queries_finalize", C.c_int, [VP, VP])
+    sig("fdh_queries_num_hashes", C.c_int64, [VP, C.c_int64])
+    sig("fdh_queries_get_map", None, [VP, C.c_int64, VP, VP, VP, VP, VP])
+    sig("fdh_queries_num_indices", C.c_int64, [VP, C.c_int64])
+    sig("fdh_queries_get_indices", None, [VP, C.c_int64, VP])
+    sig("fdh_queries_free", None, [VP])
+    sig("fdh_search", VP, [VP, VP, PP(SearchParams), VP])
+    sig("fdh_results_num_queries", C.c_uint64, [VP])
+    for n in ("struct_offsets", "struct_rows", "match_offsets", "match_rows", "match_order", "residues"):
+        sig("fdh_results_" + n, VP, [VP])
+    sig("fdh_results_num_residues", C.c_uint64, [VP])
+    sig("fdh_results_host_ms", C.c_double, [VP])
+    sig("fdh_results_free", None, [VP])
+    _sigs_done = True
+    return L
+
+
+def _err():
+    return _lib().fdh_last_error().decode()
+
+
+class CompactStructure:
+    """src/structure/core.rs:55-67"""
+
+    def __init__(self, handle):
+        if not handle:
+            raise FdError(_err())
+        self.h = handle
+
+    @classmethod
+    def from_atoms(cls, a):
+        arrs = [np.ascontiguousarray(a["x"], np.float32), np.ascontiguousarray(a["y"], np.float32),
+                np.ascontiguousarray(a["z"], np.float32), np.ascontiguousarray(a["atom_name"], np.uint8).reshape(-1),
+                np.ascontiguousarray(a["chain"], np.uint8), np.ascontiguousarray(a["res_name"], np.uint8).reshape(-1),
+                np.ascontiguousarray(a["res_serial"], np.uint64), np.ascontiguousarray(a["b_factor"], np.float32)]
+        return cls(_lib().fdh_compact_from_atoms(len(arrs[0]), *[_ptr(x) for x in arrs]))
+
+    @classmethod
+    def from_soa(cls, n_xyz, ca_xyz, cb_xyz, aa, cb_valid=None, chain=None, serial=None, b_factor=None):
+        req = [np.ascontiguousarray(n_xyz, np.float32), np.ascontiguousarray(ca_xyz, np.float32),
+               np.ascontiguousarray(cb_xyz, np.float32)]
+        aa = np.ascontiguousarray(aa, np.uint8)
+        opt = [None if v is None else np.ascontiguousarray(v, dt) for v, dt in
+               ((cb_valid, np.uint8), (chain, np.uint8), (serial, np.uint64), (b_factor, np.float32))]
+        return cls(_lib().fdh_compact_from_soa(len(aa), _ptr(req[0]), _ptr(req[1]), _ptr(req[2]), _ptr(opt[0]),
+                                               _ptr(aa), _ptr(opt[1]), _ptr(opt[2]), _ptr(opt[3])))
+
+    @property
+    def num_residues(self):
+        return _lib().fdh_compact_nres(self.h)
+
+    @property
+    def first_chain(self):
+        return _lib().fdh_compact_first_chain(self.h)
+
+    @property
+    def avg_plddt(self):
+        return _lib().fdh_compact_avg_plddt(self.h)
+
+    def soa(self):
+        n = self.num_residues
+        d = dict(n_xyz=np.zeros((n, 3), np.float32), ca_xyz=np.zeros((n, 3), np.float32),
+                 cb_xyz=np.zeros((n, 3), np.float32), cb_valid=np.zeros(n, np.uint8), aa=np.zeros(n, np.uint8),
+                 chain=np.zeros(n, np.uint8), serial=np.zeros(n, np.uint64), b_factor=np.zeros(n, np.float32))
+        _lib().fdh_compact_get(self.h, *[_ptr(d[k]) for k in ("n_xyz", "ca_xyz", "cb_xyz", "cb_valid", "aa", "chain",
+                                                               "serial", "b_factor")])
+        return d
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().fdh_compact_free(self.h)
+            self.h = None
+
+
+def read_structure_from_path(path):
+    """read_structure_from_path(path).to_compact()  (src/controller/io.rs:337-379); PDB only."""
+    if not (path.endswith(".pdb") or path.endswith(".ent")):
+        raise FdError("only .pdb/.ent inputs are supported in this version: %s" % path)
+    return CompactStructure(_lib().fdh_compact_read_pdb(os.fsencode(path)))
+
+
+def parse_query_string(q, default_chain=ord("A")):
+    """src/controller/query.rs:331-384 -> ([(chain, residue)], [None | [aa,...]])"""
+    cap = 1 << 16
+    chains, serials = np.zeros(cap, np.uint8), np.zeros(cap, np.uint64)
+    off, end, subs = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap * 20, np.uint8)
+    n = _lib().fdh_parse_query_string(q.encode(), default_chain, _ptr(chains), _ptr(serials), _ptr(off), _ptr(end),
+                                      _ptr(subs), cap, cap * 20)
+    if n < 0:
+        raise ValueError("Invalid residue in query string %r" % q)
+    res = [(int(chains[i]), int(serials[i])) for i in range(n)]
+    sub = [None if off[i] < 0 else subs[off[i]:end[i]].tolist() for i in range(n)]
+    return res, sub
+
+
+class Store:
+    """The database: an ordered set of CompactStructures (ids = positions = `.lookup` ids)."""
+
+    def __init__(self):
+        self.h = _lib().fdh_store_new()
+
+    def add(self, compact, name):
+        return _lib().fdh_store_add(self.h, compact.h, name.encode())
+
+    def add_soa(self, batch, prefix="synth_"):
+        """batch: dict from folddisco_b200.synth.generate"""
+        ro = np.ascontiguousarray(batch["row_offsets"], np.uint64)
+        return _lib().fdh_store_add_soa(self.h, len(ro) - 1, _ptr(ro), _ptr(np.ascontiguousarray(batch["n_xyz"], np.float32)),
+                                        _ptr(np.ascontiguousarray(batch["ca_xyz"], np.float32)),
+                                        _ptr(np.ascontiguousarray(batch["cb_xyz"], np.float32)),
+                                        _ptr(np.ascontiguousarray(batch["aa"], np.uint8)), prefix.encode())
+
+    def __len__(self):
+        return _lib().fdh_store_size(self.h)
+
+    @property
+    def num_residues(self):
+        return _lib().fdh_store_num_residues(self.h)
+
+    def lookup(self):
+        n = len(self)
+        nres, plddt = np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        _lib().fdh_store_get_lookup(self.h, _ptr(nres), _ptr(plddt))
+        return nres, plddt
+
+    def name(self, i):
+        return _lib().fdh_store_name(self.h, i).decode()
+
+    def batch_view(self):
+        b = _StructBatch()
+        _lib().fdh_store_batch(self.h, C.byref(b))
+        return b
+
+    def attach(self, ctx):
+        """fd_store_attach: copy the compact structures to HBM for candidate verification"""
+        b = self.batch_view()
+        ctx._check(capi.lib().fd_store_attach(ctx.h, C.byref(b)), "fd_store_attach")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().fdh_store_free(self.h)
+            self.h = None
+
+
+class FolddiscoIndex:
+    """src/index/indextable.rs FolddiscoIndex + lookup + config."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise FdError(_err())
+        self.h = handle
+
+    @classmethod
+    def build(cls, ctx, store, params=None):
+        """Folddisco::collect_and_count / allocate_entries / add_entries on the GPU"""
+        params = params or HashParams()
+        return cls(_lib().fdh_index_build(ctx.h, store.h, C.byref(params)))
+
+    def save(self, store, prefix, max_residue=50000, foldcomp_db=None):
+        rc = _lib().fdh_index_save(self.h, store.h if store is not None else None, os.fsencode(prefix), max_residue,
+                                   None if foldcomp_db is None else foldcomp_db.encode())
+        if rc != 0:
+            raise FdError(_err())
+
+    def buffers(self):
+        v = _IndexBuffers()
+        _lib().fdh_index_get(self.h, C.byref(v))
+        return capi.IndexBuffers(
+            np.ctypeslib.as_array(v.hashes, (v.count,)).copy() if v.count else np.zeros(0, np.uint32),
+            np.ctypeslib.as_array(v.offsets, (v.count + 1,)).copy(),
+            np.ctypeslib.as_array(v.values, (v.value_bytes,)).copy() if v.value_bytes else np.zeros(0, np.uint8))
+
+    @property
+    def num_structs(self):
+        return _lib().fdh_index_num_structs(self.h)
+
+    def lookup(self):
+        n = self.num_structs
+        nres, plddt = np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        _lib().fdh_index_get_lookup(self.h, _ptr(nres), _ptr(plddt))
+        return nres, plddt
+
+    def name(self, i):
+        return _lib().fdh_index_name(self.h, i).decode()
+
+    @property
+    def params(self):
+        p = HashParams()
+        _lib().fdh_index_get_params(self.h, C.byref(p))
+        return p
+
+    def attach(self, ctx):
+        ctx._check(_lib().fdh_index_attach(ctx.h, self.h), "fd_index_attach")
+        ctx.n_structs = self.num_structs
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().fdh_index_free(self.h)
+            self.h = None
+
+
+def load_folddisco_index(prefix):
+    """load_folddisco_index + load_lookup_from_file + read_index_config_from_file"""
+    return FolddiscoIndex(_lib().fdh_index_load(os.fsencode(prefix)))
+
+
+class QueryBatch:
+    """A batch of (structure, query string) with their query maps (make_query_map, query.rs:208-329)."""
+
+    def __init__(self, hash_params=None, dist_thr=(0.5,), angle_thr=(5.0,), serial_query=False):
+        self._dt = np.asarray(dist_thr, np.float32)
+        self._at = np.asarray(angle_thr, np.float32)
+        p = _QueryParams(hash_params or HashParams(), _ptr(self._dt), len(self._dt), _ptr(self._at), len(self._at),
+                         int(serial_query))
+        self.h = _lib().fdh_queries_new(C.byref(p))
+        self.query_strings = []
+
+    def add(self, compact, query_string):
+        q = _lib().fdh_queries_add(self.h, compact.h, query_string.encode())
+        if q < 0:
+            raise FdError(_err())
+        self.query_strings.append(query_string)
+        return q
+
+    def __len__(self):
+        return _lib().fdh_queries_size(self.h)
+
+    def finalize(self, ctx):
+        rc = _lib().fdh_queries_finalize(self.h, ctx.h)
+        if rc != 0:
+            raise FdError(_err())
+
+    def query_map(self, q):
+        n = _lib().fdh_queries_num_hashes(self.h, q)
+        d = dict(hash=np.zeros(n, np.uint32), qi=np.zeros(n, np.int64), qj=np.zeros(n, np.int64),
+                 primary=np.zeros(n, np.uint8), idf=np.zeros(n, np.float32))
+        _lib().fdh_queries_get_map(self.h, q, _ptr(d["hash"]), _ptr(d["qi"]), _ptr(d["qj"]), _ptr(d["primary"]),
+                                   _ptr(d["idf"]))
+        return d
+
+    def indices(self, q):
+        n = _lib().fdh_queries_num_indices(self.h, q)
+        out = np.zeros(n, np.int64)
+        _lib().fdh_queries_get_indices(self.h, q, _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().fdh_queries_free(self.h)
+            self.h = None
+
+
+class Results:
+    def __init__(self, handle):
+        if not handle:
+            raise FdError(_err())
+        L = _lib()
+        nq = L.fdh_results_num_queries(handle)
+
+        def arr(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.zeros(0, dt)
+            return np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt, count=n).copy()
+
+        self.struct_offsets = arr(L.fdh_results_struct_offsets(handle), nq + 1, np.uint64)
+        self.match_offsets = arr(L.fdh_results_match_offsets(handle), nq + 1, np.uint64)
+        ns, nm = int(self.struct_offsets[-1]), int(self.match_offsets[-1])
+        self.structs = arr(L.fdh_results_struct_rows(handle), ns, STRUCT_ROW)
+        self.matches = arr(L.fdh_results_match_rows(handle), nm, MATCH_ROW)
+        self.match_order = arr(L.fdh_results_match_order(handle), nm, np.uint64)
+        self.residues = arr(L.fdh_results_residues(handle), L.fdh_results_num_residues(handle), RES_MATCH)
+        self.host_ms = L.fdh_results_host_ms(handle)
+        L.fdh_results_free(handle)
+
+    def structures(self, q):
+        return self.structs[int(self.struct_offsets[q]):int(self.struct_offsets[q + 1])]
+
+    def sorted_matches(self, q):
+        """per-match rows of query q in the default output order (idf desc, rmsd asc)"""
+        o = self.match_order[int(self.match_offsets[q]):int(self.match_offsets[q + 1])]
+        return self.matches[o.astype(np.int64)]
+
+    def residue_string(self, match_row, n_query_residues):
+        r = self.residues[int(match_row["res_begin"]):int(match_row["res_begin"]) + n_query_residues]
+        return ",".join("%s%d" % (chr(x["chain"]), x["serial"]) if x["some"] else "_" for x in r)
+
+
+def search(ctx, queries, params=None, labels=None):
+    """query_pdb.rs:348-452 for the batch: count_query -> filter/sort/top -> retrieval -> Kabsch -> filters -> sort"""
+    params = params or SearchParams()
+    return Results(_lib().fdh_search(ctx.h, queries.h, C.byref(params), labels.h if labels is not None else None))

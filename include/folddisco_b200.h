@@ -202,6 +202,16 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
 int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *ref_xyz, const uint32_t *pt_offsets,
                     uint32_t n_align, float *rmsd, float *U9, float *t3);
 
+/* rmsd_with_calpha_and_rottran (src/controller/retrieve.rs:756-834) for a batch, without moving target
+ * coordinates through the host: alignment a superposes, for k in [pair_offsets[a], pair_offsets[a+1]), CA and CB
+ * of residue pair_tres[k] of stored structure align_nid[a] onto CA and CB of query residue pair_qres[k]
+ * (an index into q_ca_xyz / q_cb_xyz, the concatenated query structures, n_q_res residues). */
+int fd_kabsch_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_xyz, uint64_t n_q_res,
+                          const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
+                          const uint32_t *pair_qres, const uint32_t *pair_tres, float *rmsd, float *U9, float *t3);
+/* number of structures of the attached index (lookup.len()); 0 if none */
+uint64_t fd_index_num_structs(const fd_ctx *ctx);
+
 /* ---- parity / debug probes ------------------------------------------------------------------------- */
 /* op: 0 sin, 1 cos, 2 acos, 3 atan2(a, b); evaluates the device math used by the hash kernels */
 int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t n, float *out);

@@ -71,6 +71,8 @@ void fdh_store_free(fdh_store *s);
 /* ---- index files ---- */
 /* Folddisco::collect_and_count .. save_offset_to_file on the GPU (fd_build_index) */
 fdh_index *fdh_index_build(fd_ctx *ctx, const fdh_store *s, const fd_hash_params *params);
+/* wraps existing arrays (copied) with the lookup of store s; for callers that built the index elsewhere */
+fdh_index *fdh_index_from_buffers(const fd_index_buffers *b, const fdh_store *s, const fd_hash_params *params);
 /* writes PREFIX, PREFIX.offset, PREFIX.lookup, PREFIX.type exactly like `folddisco index` */
 int fdh_index_save(const fdh_index *ix, const fdh_store *s, const char *prefix, uint64_t max_residue,
                    const char *foldcomp_db /* NULL omits the key */);
@@ -133,7 +135,9 @@ typedef struct {
 /* query_pdb.rs:348-452 for the whole batch: count_query -> filter/sort/top -> retrieval -> Kabsch ->
  * filter_after_matching -> MatchFilter -> default sorts.  Needs fd_index_attach and, unless skip_match,
  * fd_store_attach on ctx. */
-fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p);
+/* labels (may be NULL): store whose per-residue (chain, residue number) label the matched target residues;
+ * without it fdh_residue_match.serial is the residue index inside the target and chain is 0. */
+fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels);
 
 /* per-structure rows: query q owns [struct_offsets[q], struct_offsets[q+1]) ordered idf desc, min_rmsd asc */
 typedef struct {

@@ -1,0 +1,156 @@
+"""CPU tests of the host side (folddisco_b200/csrc/host): parsing, CompactStructure quirks, query-map construction
+and index files against the oracle.  No GPU needed: nothing here launches a kernel."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import fixtures as F
+import oracle_lib as O
+from conftest import REF, needs_reference
+
+
+@pytest.fixture(scope="module")
+def host():
+    from folddisco_b200 import build
+    build.build()
+    from folddisco_b200 import host
+    return host
+
+
+def _same_compact(h, o):
+    d, e = h.soa(), o.soa()
+    assert h.num_residues == o.nres
+    for k in ("n_xyz", "ca_xyz", "cb_xyz", "cb_valid", "chain", "serial", "b_factor"):
+        assert np.array_equal(d[k], e[k]), k
+    code = np.where(d["aa"] == 255, 255, d["aa"] & 0x7F)
+    assert np.array_equal(code, e["aa"])
+    canon = [b"ALA", b"ARG", b"ASN", b"ASP", b"CYS", b"GLN", b"GLU", b"GLY", b"HIS", b"ILE", b"LEU", b"LYS", b"MET",
+             b"PHE", b"PRO", b"SER", b"THR", b"TRP", b"TYR", b"VAL"]
+    for i in range(len(code)):
+        if code[i] != 255:
+            assert (d["aa"][i] >= 128) == (bytes(e["res_name"][i]) != canon[code[i]])
+
+
+def test_compact_builder_matches_oracle(host):
+    for name, a in F.config1_atoms().items():
+        _same_compact(host.CompactStructure.from_atoms(a), O.Structure.from_atoms(a).compact())
+
+
+def test_compact_builder_quirks(host):
+    """SURVEY 8a Q1-Q5 on a hand-made atom list: last atom never consumed, chain/B taken from the flush atom, stale
+    backbone C reused, residues without N/CA dropped, virtual CB for any residue lacking CB, modified residues."""
+    rows = [  # name, res, chain, serial, xyz, b
+        (" N  ", "ALA", "A", 1, (0.0, 0.0, 0.0), 10.0), (" CA ", "ALA", "A", 1, (1.4, 0.0, 0.0), 11.0),
+        (" C  ", "ALA", "A", 1, (2.0, 1.4, 0.0), 12.0), (" CB ", "ALA", "A", 1, (1.9, -0.8, 1.2), 13.0),
+        (" N  ", "GLY", "A", 2, (3.3, 1.5, 0.0), 20.0), (" CA ", "GLY", "A", 2, (4.0, 2.8, 0.0), 21.0),
+        (" C  ", "GLY", "A", 2, (5.5, 2.6, 0.0), 22.0),
+        (" CA ", "SER", "A", 3, (6.9, 3.9, 0.2), 30.0),                       # no N: dropped (Q4)
+        (" N  ", "MSE", "B", 4, (8.0, 4.0, 1.0), 40.0), (" CA ", "MSE", "B", 4, (9.2, 4.8, 1.2), 41.0),  # no C, no CB
+        (" N  ", "LYS", "B", 5, (10.0, 6.0, 2.0), 50.0), (" CA ", "LYS", "B", 5, (11.2, 6.5, 2.5), 51.0),
+        (" CB ", "LYS", "B", 5, (11.0, 7.5, 3.6), 52.0), (" O  ", "LYS", "B", 5, (12.0, 5.0, 3.0), 53.0),
+    ]
+    a = dict(x=np.array([r[4][0] for r in rows], np.float32), y=np.array([r[4][1] for r in rows], np.float32),
+             z=np.array([r[4][2] for r in rows], np.float32),
+             atom_name=np.array([list(r[0].encode()) for r in rows], np.uint8),
+             chain=np.array([ord(r[2]) for r in rows], np.uint8),
+             res_name=np.array([list(r[1].encode()) for r in rows], np.uint8),
+             res_serial=np.array([r[3] for r in rows], np.uint64), b_factor=np.array([r[5] for r in rows], np.float32))
+    h = host.CompactStructure.from_atoms(a)
+    _same_compact(h, O.Structure.from_atoms(a).compact())
+    d = h.soa()
+    assert d["serial"].tolist() == [1, 2, 4, 5]
+    assert d["aa"].tolist() == [0, 7, 128 + 12, 11]
+    assert d["cb_valid"].tolist() == [1, 1, 1, 1]          # MSE reuses the stale C of GLY 2 (Q3, Q5)
+    assert d["chain"].tolist() == [65, 65, 66, 66]         # Q2: chain of the atom that triggered the flush
+    assert d["b_factor"].tolist() == [20.0, 30.0, 50.0, 53.0]
+    assert h.first_chain == ord("A")
+
+
+def test_parse_query_string(host):
+    """src/controller/query.rs:425-465"""
+    for q, dc in (("A250,A232,A269", "A"), ("A250-252,B232:H,269:NDp", "C"), ("1-3:X", "1"), ("B57,B102,C195", "B"),
+                  ("164:H,195,221,247:ND,297:H", "A"), (" A1 , A2 ", "A")):
+        res, sub = host.parse_query_string(q, ord(dc))
+        ch, se, osub = O.parse_query_string(q, ord(dc))
+        assert res == list(zip(ch.tolist(), se.tolist())) and sub == osub, q
+    assert host.parse_query_string("", ord("A")) == ([], [])
+    with pytest.raises(ValueError):
+        host.parse_query_string("A12,", ord("A"))
+    with pytest.raises(ValueError):
+        host.parse_query_string("Axx", ord("A"))
+
+
+@pytest.mark.parametrize("dist_thr,angle_thr", [((0.5,), (5.0,)), ((0.5, 1.0), (5.0, 10.0)), ((), ())])
+def test_query_map_matches_oracle(host, dist_thr, angle_thr):
+    """make_query_map: same hashes, same edge per hash, same insertion order as the oracle (idf needs the GPU)."""
+    atoms = F.config1_atoms()
+    qb = host.QueryBatch(dist_thr=dist_thr, angle_thr=angle_thr)
+    cases = list(F.MOTIFS) + [("query/4CHA.pdb", "B57:X,B102,C195:ST", None), ("query/4CHA.pdb", "B57,B57,Z9,C195", None)]
+    for path, q, _ in cases:
+        qb.add(host.CompactStructure.from_atoms(atoms[path]), q)
+    for k, (path, q, want_n) in enumerate(cases):
+        s = O.Structure.from_atoms(atoms[path])
+        ch, se, subs = O.parse_query_string(q, s.first_chain)
+        om = O.QueryMap(s.compact(), ch, se, subs, dist_thr=dist_thr, angle_thr=angle_thr)
+        e, g = om.entries(), qb.query_map(k)
+        for f in ("hash", "qi", "qj", "primary"):
+            assert np.array_equal(e[f], g[f]), (path, f)
+        assert np.array_equal(om.indices(), qb.indices(k))
+        if want_n is not None and dist_thr == (0.5,):
+            assert len(g["hash"]) == want_n
+
+
+def test_index_files_byte_identical(host, tmp_path):
+    """fdh_index_save writes PREFIX / .offset / .lookup / .type byte-identical to the oracle's writers."""
+    import ctypes as C
+    from folddisco_b200 import capi
+    atoms = F.config1_atoms()
+    names = F.serine_names()
+    store = host.Store()
+    comps = []
+    for n in names:
+        store.add(host.CompactStructure.from_atoms(atoms[n]), n)
+        comps.append(O.Structure.from_atoms(atoms[n]).compact())
+    oix = O.Index.build(comps)
+    hashes, offsets, values = oix.hashes, oix.offsets, oix.values
+    b = capi._IndexBuffers(len(hashes), hashes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                           offsets.ctypes.data_as(C.POINTER(C.c_uint64)), len(values),
+                           values.ctypes.data_as(C.POINTER(C.c_uint8)))
+    p = capi.HashParams(0, 0, 20.0)
+    ix = host.FolddiscoIndex(host._lib().fdh_index_from_buffers(C.byref(b), store.h, C.byref(p)))
+    mine, ref = str(tmp_path / "mine"), str(tmp_path / "ref")
+    ix.save(store, mine, max_residue=50000, foldcomp_db="data/serine_peptidases")
+    oix.save(ref)
+    nres = np.array([c.nres for c in comps], np.uint64)
+    plddt = np.array([c.avg_plddt for c in comps], np.float32)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    O.lib().fdo_lookup_save((ref + ".lookup").encode(), len(names), arr, nres, plddt)
+    O.lib().fdo_type_save((ref + ".type").encode(), 0, 0, 20.0, len(names), 50000, b"data/serine_peptidases")
+    for ext in ("", ".offset", ".lookup", ".type"):
+        assert open(mine + ext, "rb").read() == open(ref + ext, "rb").read(), ext
+    assert os.path.getsize(mine) == F.CONFIG1_VALUE_BYTES
+    assert os.path.getsize(mine + ".offset") == F.CONFIG1_OFFSET_FILE_BYTES
+    first = open(mine + ".lookup").readline().rstrip("\n").split("\t")
+    assert first[:3] == ["0", names[0], "626"] and "%.4f" % float(first[3]) == "34.2399" and first[4] == "0"
+    # load back (mmap) and compare
+    back = host.load_folddisco_index(mine)
+    bb = back.buffers()
+    assert np.array_equal(bb.hashes, hashes) and np.array_equal(bb.offsets, offsets) and np.array_equal(bb.values, values)
+    nr, pl = back.lookup()
+    assert nr.tolist() == nres.tolist() and np.allclose(pl, plddt)
+    assert back.name(4) == names[4] and back.params.dist_cutoff == 20.0
+
+
+@needs_reference
+def test_pdb_reader_on_reference_files(host):
+    files = sorted(glob.glob(REF + "/data/serine_peptidases/*.pdb")) + sorted(glob.glob(REF + "/query/*.pdb")) + \
+        sorted(glob.glob(REF + "/data/homeobox/*.pdb")) + [REF + "/data/AF-P17538-F1-model_v4.pdb"] + \
+        sorted(glob.glob(REF + "/data/long/*.pdb"))[:2] + sorted(glob.glob(REF + "/data/io_test/*.pdb"))
+    assert len(files) > 15
+    for p in files:
+        _same_compact(host.read_structure_from_path(p), O.Structure.read_pdb(p).compact())
+    assert host.read_structure_from_path(REF + "/data/homeobox/1akha-.pdb").num_residues == 49  # pdb.rs:142
+    with pytest.raises(Exception):
+        host.read_structure_from_path("/nonexistent/x.pdb")

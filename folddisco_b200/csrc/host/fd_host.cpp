@@ -783,6 +783,7 @@ struct fdh_results {
     std::vector<fdh_match_row> matches;
     std::vector<fdh_residue_match> residues;
     double host_ms = 0.0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0; // bytes this search moved between host and device
 };
 
 // =============================================================================================
@@ -1188,7 +1189,183 @@ void fdh_queries_get_indices(const fdh_queries *qs, int64_t q, int64_t *indices)
 }
 void fdh_queries_free(fdh_queries *qs) { delete qs; }
 
+} // extern "C"
+
 // ---- search ----
+namespace {
+
+struct FinalMatch { // one verified component of one candidate
+    uint64_t cand;
+    uint32_t node_count;
+    float idf, rmsd;
+    float U[9], t[3];
+    std::vector<uint32_t> res; // per query residue: target residue index + 1, 0 = none
+};
+
+// General verification path for an arbitrary candidate list: K4 (fd_candidate_edges_batch) -> host graph /
+// mapping / rescue (candidate-parallel) -> K5 (fd_kabsch_store_batch).  Handles what the fused kernel cannot.
+int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const std::vector<uint32_t> &cand_q,
+                   const std::vector<uint32_t> &cand_n, const std::vector<uint64_t> &cand_global,
+                   std::vector<FinalMatch> &out, fdh_results *R, double *host_ms) {
+    const uint32_t nq = (uint32_t)qs->q.size();
+    const uint64_t n_cand = cand_q.size();
+    if (n_cand == 0) return FD_OK;
+    std::vector<fd_retrieval_query> rq(nq);
+    for (uint32_t q = 0; q < nq; q++) {
+        const Query &Q = qs->q[q];
+        rq[q] = fd_retrieval_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), (uint32_t)Q.aad.size(),
+                                   Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data()};
+        R->h2d_bytes += 4ull * Q.hashes_sorted.size() + 12ull * Q.aad.size() + 28;
+    }
+    std::vector<fd_cand_edge> all_edges;
+    std::vector<fd_cand_pair> all_pairs;
+    const uint64_t CH = (1ull << 24) - 1; // the kernel takes at most 2^24-1 candidates per call
+    for (uint64_t c0 = 0; c0 < n_cand; c0 += CH) {
+        const uint64_t cn = std::min(CH, n_cand - c0);
+        fd_cand_edge *edges = nullptr;
+        fd_cand_pair *pairs = nullptr;
+        uint64_t ne = 0, np = 0;
+        if (fd_candidate_edges_batch(ctx, rq.data(), nq, cand_q.data() + c0, cand_n.data() + c0, cn, &qs->p.hash,
+                                     p->ca_dist_cutoff, &edges, &ne, &pairs, &np) != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return FD_ERR_CUDA;
+        }
+        R->d2h_bytes += ne * sizeof(fd_cand_edge) + np * sizeof(fd_cand_pair) + 16;
+        R->h2d_bytes += 8ull * cn;
+        for (uint64_t k = 0; k < ne; k++) {
+            edges[k].cand += (uint32_t)c0;
+            all_edges.push_back(edges[k]);
+        }
+        for (uint64_t k = 0; k < np; k++) {
+            pairs[k].cand += (uint32_t)c0;
+            all_pairs.push_back(pairs[k]);
+        }
+        fd_free(edges);
+        fd_free(pairs);
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint64_t> e_begin(n_cand + 1, 0), p_begin(n_cand + 1, 0);
+    for (auto &e : all_edges) e_begin[e.cand + 1]++;
+    for (auto &e : all_pairs) p_begin[e.cand + 1]++;
+    for (uint64_t c = 0; c < n_cand; c++) {
+        e_begin[c + 1] += e_begin[c];
+        p_begin[c + 1] += p_begin[c];
+    }
+    int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 64));
+    std::vector<std::vector<MatchTmp>> per_thread(nt);
+    std::atomic<uint64_t> next{0};
+    const uint64_t GRAIN = 256;
+    struct Chunk {
+        uint64_t c0;
+        int thread;
+        size_t begin, end;
+    };
+    std::vector<std::vector<Chunk>> chunks(nt);
+    auto worker = [&](int tid) {
+        std::vector<fd_cand_edge> ce;
+        std::vector<std::vector<uint32_t>> comps;
+        Graph g;
+        std::vector<MatchTmp> &outv = per_thread[tid];
+        for (;;) {
+            const uint64_t c0 = next.fetch_add(GRAIN);
+            if (c0 >= n_cand) break;
+            const size_t begin = outv.size();
+            for (uint64_t c = c0; c < std::min(n_cand, c0 + GRAIN); c++) {
+                const uint64_t eb = e_begin[c], ee = e_begin[c + 1];
+                if (ee == eb) continue;
+                const Query &Q = qs->q[cand_q[c]];
+                ce.assign(all_edges.begin() + eb, all_edges.begin() + ee);
+                g.node_res.clear(); // create_index_graph (graph.rs:16-27): node ids by first appearance
+                g.e.clear();
+                auto node_of = [&](uint32_t r) {
+                    for (uint32_t k = 0; k < g.node_res.size(); k++)
+                        if (g.node_res[k] == r) return k;
+                    g.node_res.push_back(r);
+                    return (uint32_t)g.node_res.size() - 1;
+                };
+                for (auto &e : ce) {
+                    const uint32_t a = node_of(e.i);
+                    const uint32_t b = node_of(e.j);
+                    g.e.push_back({a, b});
+                }
+                graph_components(g, comps);
+                for (auto &comp : comps) {
+                    std::vector<uint32_t> sub;
+                    for (uint32_t k = 0; k < ce.size(); k++) {
+                        const bool ia = std::find(comp.begin(), comp.end(), g.e[k].first) != comp.end();
+                        const bool ib = std::find(comp.begin(), comp.end(), g.e[k].second) != comp.end();
+                        if (ia && ib) sub.push_back(k);
+                    }
+                    outv.emplace_back();
+                    MatchTmp &m = outv.back();
+                    m.cand = (uint32_t)c;
+                    match_component(Q, ce, sub, all_pairs.data() + p_begin[c], p_begin[c + 1] - p_begin[c],
+                                    (uint32_t)comp.size(), p->skip_ca_match != 0, m);
+                }
+            }
+            chunks[tid].push_back(Chunk{c0, tid, begin, outv.size()});
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto &t : th) t.join();
+    }
+    std::vector<MatchTmp> mt;
+    std::vector<Chunk> allc;
+    for (auto &v : chunks) allc.insert(allc.end(), v.begin(), v.end());
+    std::sort(allc.begin(), allc.end(), [](const Chunk &a, const Chunk &b) { return a.c0 < b.c0; });
+    for (auto &ch : allc)
+        for (size_t k = ch.begin; k < ch.end; k++) mt.push_back(std::move(per_thread[ch.thread][k]));
+    *host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const uint32_t n_align = (uint32_t)mt.size();
+    if (!n_align) return FD_OK;
+    std::vector<float> rmsd(n_align), U(9 * (size_t)n_align), T(3 * (size_t)n_align);
+    std::vector<uint64_t> q_res_off(nq + 1, 0);
+    for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q].st.nres();
+    std::vector<float> q_ca(3 * q_res_off[nq]), q_cb(3 * q_res_off[nq]);
+    for (uint32_t q = 0; q < nq; q++) {
+        memcpy(q_ca.data() + 3 * q_res_off[q], qs->q[q].st.ca.data(), 12 * qs->q[q].st.nres());
+        memcpy(q_cb.data() + 3 * q_res_off[q], qs->q[q].st.cb.data(), 12 * qs->q[q].st.nres());
+    }
+    std::vector<uint32_t> a_nid(n_align), a_off(n_align + 1, 0), pq_, pt_;
+    for (uint32_t a = 0; a < n_align; a++) {
+        const MatchTmp &m = mt[a];
+        a_nid[a] = cand_n[m.cand];
+        const uint64_t qb = q_res_off[cand_q[m.cand]];
+        for (size_t k = 0; k < m.aq.size(); k++) {
+            pq_.push_back((uint32_t)(qb + m.aq[k]));
+            pt_.push_back(m.at[k]);
+        }
+        a_off[a + 1] = (uint32_t)pq_.size();
+    }
+    R->h2d_bytes += 4ull * (q_ca.size() + q_cb.size()) + 4ull * (a_nid.size() + a_off.size() + pq_.size() + pt_.size());
+    R->d2h_bytes += 52ull * n_align;
+    if (fd_kabsch_store_batch(ctx, q_ca.data(), q_cb.data(), q_res_off[nq], a_nid.data(), a_off.data(), n_align,
+                              pq_.data(), pt_.data(), rmsd.data(), U.data(), T.data()) != FD_OK) {
+        set_err(fd_last_error(ctx));
+        return FD_ERR_CUDA;
+    }
+    for (uint32_t a = 0; a < n_align; a++) {
+        FinalMatch fm;
+        fm.cand = cand_global[mt[a].cand];
+        fm.node_count = mt[a].node_count_final;
+        fm.idf = mt[a].idf;
+        fm.rmsd = rmsd[a];
+        memcpy(fm.U, &U[9 * (size_t)a], sizeof(fm.U));
+        memcpy(fm.t, &T[3 * (size_t)a], sizeof(fm.t));
+        fm.res = mt[a].res_final;
+        out.push_back(std::move(fm));
+    }
+    return FD_OK;
+}
+
+} // namespace
+
+extern "C" {
+
 fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels) {
     if (!qs->finalized) {
         set_err("fdh_search: call fdh_queries_finalize first");
@@ -1205,6 +1382,7 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
         const Query &Q = qs->q[q];
         fq[q] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.edge_of_hash.data(),
                          (uint32_t)Q.edge_node.size(), Q.edge_node.data(), Q.n_nodes, (uint32_t)Q.indices.size()};
+        R->h2d_bytes += 6ull * Q.hashes_flat.size() + 2ull * Q.edge_node.size() + 24;
     }
     fd_struct_hit *hits = nullptr;
     uint64_t *hoff = nullptr;
@@ -1214,220 +1392,138 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
         return nullptr;
     }
     const uint64_t n_cand = hoff[nq];
-    struct CandOut {
-        uint32_t max_node = 0;
-        float min_rmsd = 0.f;
-        uint64_t m_begin = 0, m_end = 0;
-    };
-    std::vector<CandOut> cout_(n_cand);
-    std::vector<MatchTmp> mt; // all matches in candidate order
+    R->d2h_bytes += n_cand * sizeof(fd_struct_hit) + (nq + 1) * 8ull + nq * 16ull;
+    std::vector<FinalMatch> fm; // all matches, grouped by candidate after the sort below
     double host_ms = 0.0;
-    std::vector<float> rmsd, U, T;
+    auto fail = [&]() {
+        fd_free(hits);
+        fd_free(hoff);
+        delete R;
+        return (fdh_results *)nullptr;
+    };
     if (!p->skip_match && n_cand) {
-        // --- K4: candidate edges ---
-        std::vector<fd_retrieval_query> rq(nq);
-        for (uint32_t q = 0; q < nq; q++) {
-            const Query &Q = qs->q[q];
-            rq[q] = fd_retrieval_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), (uint32_t)Q.aad.size(),
-                                       Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data()};
-        }
         std::vector<uint32_t> cand_q(n_cand), cand_n(n_cand);
         for (uint32_t q = 0; q < nq; q++)
             for (uint64_t k = hoff[q]; k < hoff[q + 1]; k++) {
                 cand_q[k] = q;
                 cand_n[k] = hits[k].nid;
             }
-        fd_cand_edge *edges = nullptr;
-        fd_cand_pair *pairs = nullptr;
-        uint64_t ne = 0, np = 0;
-        // the kernel takes at most 2^24-1 candidates per call
-        std::vector<fd_cand_edge> all_edges;
-        std::vector<fd_cand_pair> all_pairs;
-        const uint64_t CH = (1ull << 24) - 1;
-        for (uint64_t c0 = 0; c0 < n_cand; c0 += CH) {
-            const uint64_t cn = std::min(CH, n_cand - c0);
-            if (fd_candidate_edges_batch(ctx, rq.data(), nq, cand_q.data() + c0, cand_n.data() + c0, cn, &qs->p.hash,
-                                         p->ca_dist_cutoff, &edges, &ne, &pairs, &np) != FD_OK) {
-                set_err(fd_last_error(ctx));
-                fd_free(hits);
-                fd_free(hoff);
-                delete R;
-                return nullptr;
+        // --- K6: fused verification; candidates beyond its limits come back flagged ---
+        std::vector<fd_verify_query> vq(nq);
+        std::vector<std::vector<uint32_t>> v_qi(nq), v_qj(nq);
+        std::vector<std::vector<float>> v_idf(nq);
+        std::vector<std::vector<uint8_t>> v_sym(nq);
+        for (uint32_t q = 0; q < nq; q++) {
+            const Query &Q = qs->q[q];
+            for (uint32_t h : Q.hashes_sorted) {
+                const QEntry &e = Q.entries[Q.pos.at(h)];
+                v_qi[q].push_back(e.qi);
+                v_qj[q].push_back(e.qj);
+                v_idf[q].push_back(e.idf);
+                v_sym[q].push_back(Q.symmetric.at(h));
             }
-            for (uint64_t k = 0; k < ne; k++) {
-                edges[k].cand += (uint32_t)c0;
-                all_edges.push_back(edges[k]);
-            }
-            for (uint64_t k = 0; k < np; k++) {
-                pairs[k].cand += (uint32_t)c0;
-                all_pairs.push_back(pairs[k]);
-            }
-            fd_free(edges);
-            fd_free(pairs);
+            vq[q] = fd_verify_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), v_qi[q].data(),
+                                    v_qj[q].data(), v_idf[q].data(), v_sym[q].data(), (uint32_t)Q.aad.size(),
+                                    Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data(),
+                                    (uint32_t)Q.indices.size(), Q.indices.data(), (uint32_t)Q.st.nres(), Q.st.ca.data(),
+                                    Q.st.cb.data()};
+            R->h2d_bytes += 14ull * Q.hashes_sorted.size() + 8ull * Q.aad.size() + Q.indices.size() + 24ull * 16 + 48;
         }
-        // --- host: graph components + residue assignment per candidate, candidate-parallel ---
+        fd_match_record *recs = nullptr;
+        uint64_t n_recs = 0;
+        uint8_t *flags = nullptr;
+        if (p->verify_mode == 1) { // general path for everything
+            flags = (uint8_t *)malloc(n_cand);
+            recs = (fd_match_record *)malloc(sizeof(fd_match_record));
+            if (!flags || !recs) return fail();
+            memset(flags, 1, n_cand);
+        } else if (fd_verify_candidates_batch(ctx, vq.data(), nq, cand_q.data(), cand_n.data(), n_cand, &qs->p.hash,
+                                              p->ca_dist_cutoff, p->skip_ca_match, &recs, &n_recs, &flags) != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return fail();
+        }
+        R->h2d_bytes += 8ull * n_cand;
+        R->d2h_bytes += n_recs * sizeof(fd_match_record) + n_cand;
         auto t0 = std::chrono::steady_clock::now();
-        std::vector<uint64_t> e_begin(n_cand + 1, 0), p_begin(n_cand + 1, 0);
-        for (auto &e : all_edges) e_begin[e.cand + 1]++;
-        for (auto &e : all_pairs) p_begin[e.cand + 1]++;
-        for (uint64_t c = 0; c < n_cand; c++) {
-            e_begin[c + 1] += e_begin[c];
-            p_begin[c + 1] += p_begin[c];
+        fm.reserve(n_recs);
+        for (uint64_t k = 0; k < n_recs; k++) {
+            FinalMatch m;
+            m.cand = recs[k].cand;
+            m.node_count = recs[k].node_count;
+            m.idf = recs[k].idf;
+            m.rmsd = recs[k].rmsd;
+            memcpy(m.U, recs[k].U, sizeof(m.U));
+            memcpy(m.t, recs[k].t, sizeof(m.t));
+            const size_t NQ = qs->q[cand_q[m.cand]].indices.size();
+            m.res.assign(recs[k].res, recs[k].res + std::min<size_t>(NQ, 16));
+            fm.push_back(std::move(m));
         }
-        int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
-        nt = std::max(1, std::min(nt, 64));
-        std::vector<std::vector<MatchTmp>> per_thread(nt);
-        std::vector<std::vector<uint64_t>> per_thread_cand(nt);
-        std::atomic<uint64_t> next{0};
-        const uint64_t GRAIN = 256;
-        struct Chunk {
-            uint64_t c0;
-            int thread;
-            size_t begin, end;
-        };
-        std::vector<std::vector<Chunk>> chunks(nt);
-        auto worker = [&](int tid) {
-            std::vector<fd_cand_edge> ce;
-            std::vector<std::vector<uint32_t>> comps;
-            Graph g;
-            std::vector<MatchTmp> &out = per_thread[tid];
-            for (;;) {
-                const uint64_t c0 = next.fetch_add(GRAIN);
-                if (c0 >= n_cand) break;
-                const size_t begin = out.size();
-                for (uint64_t c = c0; c < std::min(n_cand, c0 + GRAIN); c++) {
-                    const uint64_t eb = e_begin[c], ee = e_begin[c + 1];
-                    if (ee == eb) continue;
-                    const Query &Q = qs->q[cand_q[c]];
-                    ce.assign(all_edges.begin() + eb, all_edges.begin() + ee);
-                    // create_index_graph (graph.rs:16-27): node ids by first appearance
-                    g.node_res.clear();
-                    g.e.clear();
-                    auto node_of = [&](uint32_t r) {
-                        for (uint32_t k = 0; k < g.node_res.size(); k++)
-                            if (g.node_res[k] == r) return k;
-                        g.node_res.push_back(r);
-                        return (uint32_t)g.node_res.size() - 1;
-                    };
-                    for (auto &e : ce) {
-                        const uint32_t a = node_of(e.i);
-                        const uint32_t b = node_of(e.j);
-                        g.e.push_back({a, b});
-                    }
-                    graph_components(g, comps);
-                    for (auto &comp : comps) {
-                        std::vector<uint32_t> sub;
-                        for (uint32_t k = 0; k < ce.size(); k++) {
-                            const bool ia = std::find(comp.begin(), comp.end(), g.e[k].first) != comp.end();
-                            const bool ib = std::find(comp.begin(), comp.end(), g.e[k].second) != comp.end();
-                            if (ia && ib) sub.push_back(k);
-                        }
-                        out.emplace_back();
-                        MatchTmp &m = out.back();
-                        m.cand = (uint32_t)c;
-                        match_component(Q, ce, sub, all_pairs.data() + p_begin[c], p_begin[c + 1] - p_begin[c],
-                                        (uint32_t)comp.size(), p->skip_ca_match != 0, m);
-                    }
-                }
-                chunks[tid].push_back(Chunk{c0, tid, begin, out.size()});
+        std::vector<uint32_t> fq_, fn_;
+        std::vector<uint64_t> fglobal;
+        for (uint64_t c = 0; c < n_cand; c++)
+            if (flags[c]) {
+                fq_.push_back(cand_q[c]);
+                fn_.push_back(cand_n[c]);
+                fglobal.push_back(c);
             }
-        };
-        {
-            std::vector<std::thread> th;
-            for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
-            worker(0);
-            for (auto &t : th) t.join();
-        }
-        // merge in candidate order
-        std::vector<Chunk> allc;
-        for (auto &v : chunks) allc.insert(allc.end(), v.begin(), v.end());
-        std::sort(allc.begin(), allc.end(), [](const Chunk &a, const Chunk &b) { return a.c0 < b.c0; });
-        for (auto &ch : allc)
-            for (size_t k = ch.begin; k < ch.end; k++) mt.push_back(std::move(per_thread[ch.thread][k]));
         host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        // --- K5: batched Kabsch, coordinates gathered on the device from the store ---
-        const uint32_t n_align = (uint32_t)mt.size();
-        rmsd.assign(n_align, 0.f);
-        U.assign(9 * (size_t)n_align, 0.f);
-        T.assign(3 * (size_t)n_align, 0.f);
-        if (n_align) {
-            std::vector<uint64_t> q_res_off(nq + 1, 0);
-            for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q].st.nres();
-            std::vector<float> q_ca(3 * q_res_off[nq]), q_cb(3 * q_res_off[nq]);
-            for (uint32_t q = 0; q < nq; q++) {
-                memcpy(q_ca.data() + 3 * q_res_off[q], qs->q[q].st.ca.data(), 12 * qs->q[q].st.nres());
-                memcpy(q_cb.data() + 3 * q_res_off[q], qs->q[q].st.cb.data(), 12 * qs->q[q].st.nres());
-            }
-            std::vector<uint32_t> a_nid(n_align), a_off(n_align + 1, 0), pq_, pt_;
-            for (uint32_t a = 0; a < n_align; a++) {
-                const MatchTmp &m = mt[a];
-                a_nid[a] = cand_n[m.cand];
-                const uint64_t qb = q_res_off[cand_q[m.cand]];
-                for (size_t k = 0; k < m.aq.size(); k++) {
-                    pq_.push_back((uint32_t)(qb + m.aq[k]));
-                    pt_.push_back(m.at[k]);
-                }
-                a_off[a + 1] = (uint32_t)pq_.size();
-            }
-            if (fd_kabsch_store_batch(ctx, q_ca.data(), q_cb.data(), q_res_off[nq], a_nid.data(), a_off.data(), n_align,
-                                      pq_.data(), pt_.data(), rmsd.data(), U.data(), T.data()) != FD_OK) {
-                set_err(fd_last_error(ctx));
-                fd_free(hits);
-                fd_free(hoff);
-                delete R;
-                return nullptr;
-            }
-        }
-        // per-candidate summary (retrieve.rs:539-551)
-        for (uint32_t a = 0; a < n_align; a++) {
-            CandOut &co = cout_[mt[a].cand];
-            if (a == 0 || mt[a - 1].cand != mt[a].cand) co.m_begin = a;
-            co.m_end = a + 1;
-            const uint32_t cnt = mt[a].node_count_final;
-            if (cnt > co.max_node) {
-                co.max_node = cnt;
-                co.min_rmsd = rmsd[a];
-            } else if (cnt == co.max_node && rmsd[a] < co.min_rmsd) {
-                co.min_rmsd = rmsd[a];
-            }
+        fd_free(recs);
+        fd_free(flags);
+        if (!fglobal.empty()) {
+            if (verify_general(ctx, qs, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
+            std::stable_sort(fm.begin(), fm.end(), [](const FinalMatch &a, const FinalMatch &b) { return a.cand < b.cand; });
         }
     }
-    // --- assemble rows: filter_after_matching (filter.rs:103-116), MatchFilter (:194-235), default sorts ---
+    // --- assemble rows: per-candidate summary (retrieve.rs:539-551), filter_after_matching (filter.rs:103-116),
+    //     MatchFilter (:194-235), default sorts ---
     auto t1 = std::chrono::steady_clock::now();
+    size_t mpos = 0;
     for (uint32_t q = 0; q < nq; q++) {
         const Query &Q = qs->q[q];
         const float expected = (float)Q.indices.size();
         const size_t s_begin = R->structs.size();
         const size_t m_begin = R->matches.size();
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
-            const CandOut &co = cout_[c];
+            const size_t a0 = mpos;
+            while (mpos < fm.size() && fm[mpos].cand == c) mpos++;
+            const size_t a1 = mpos;
+            uint32_t max_node = 0;
+            float min_rmsd = 0.f;
+            for (size_t a = a0; a < a1; a++) {
+                if (fm[a].node_count > max_node) {
+                    max_node = fm[a].node_count;
+                    min_rmsd = fm[a].rmsd;
+                } else if (fm[a].node_count == max_node && fm[a].rmsd < min_rmsd) {
+                    min_rmsd = fm[a].rmsd;
+                }
+            }
             if (!p->skip_match) {
                 bool pass = true;
-                if (p->max_matching_node_count > 0) pass = pass && co.max_node >= p->max_matching_node_count;
-                if (p->max_matching_node_ratio > 0.f) pass = pass && (float)co.max_node / expected >= p->max_matching_node_ratio;
-                if (p->rmsd_cutoff > 0.f) pass = pass && co.min_rmsd <= p->rmsd_cutoff;
+                if (p->max_matching_node_count > 0) pass = pass && max_node >= p->max_matching_node_count;
+                if (p->max_matching_node_ratio > 0.f) pass = pass && (float)max_node / expected >= p->max_matching_node_ratio;
+                if (p->rmsd_cutoff > 0.f) pass = pass && min_rmsd <= p->rmsd_cutoff;
                 if (!pass) continue;
             }
             fdh_struct_row sr{hits[c].nid, hits[c].match_count, hits[c].node_count, hits[c].edge_count, hits[c].idf,
-                              co.max_node, co.min_rmsd, 0, 0};
+                              max_node, min_rmsd, 0, 0};
             sr.match_begin = R->matches.size();
-            for (uint64_t a = co.m_begin; a < co.m_end; a++) {
-                const MatchTmp &m = mt[a];
+            for (size_t a = a0; a < a1; a++) {
+                const FinalMatch &m = fm[a];
                 bool pass = true;
-                if (p->connected_node_count > 0) pass = pass && m.node_count_final >= p->connected_node_count;
-                if (p->connected_node_ratio > 0.f) pass = pass && (float)m.node_count_final / expected >= p->connected_node_ratio;
+                if (p->connected_node_count > 0) pass = pass && m.node_count >= p->connected_node_count;
+                if (p->connected_node_ratio > 0.f) pass = pass && (float)m.node_count / expected >= p->connected_node_ratio;
                 if (p->prefilter.idf_score_cutoff > 0.f) pass = pass && m.idf >= p->prefilter.idf_score_cutoff;
-                if (p->rmsd_cutoff > 0.f) pass = pass && rmsd[a] <= p->rmsd_cutoff;
+                if (p->rmsd_cutoff > 0.f) pass = pass && m.rmsd <= p->rmsd_cutoff;
                 if (!pass) continue;
                 fdh_match_row mr;
                 mr.nid = hits[c].nid;
-                mr.node_count = m.node_count_final;
+                mr.node_count = m.node_count;
                 mr.idf = m.idf;
-                mr.rmsd = rmsd[a];
-                memcpy(mr.U, &U[9 * a], sizeof(mr.U));
-                memcpy(mr.t, &T[3 * a], sizeof(mr.t));
+                mr.rmsd = m.rmsd;
+                memcpy(mr.U, m.U, sizeof(mr.U));
+                memcpy(mr.t, m.t, sizeof(mr.t));
                 mr.res_begin = R->residues.size();
-                for (uint32_t v : m.res_final) {
+                for (uint32_t v : m.res) {
                     fdh_residue_match rm{(uint8_t)(v != 0), 0, v ? (uint64_t)(v - 1) : 0};
                     if (v && labels && hits[c].nid < labels->names.size()) { // (chain, residue number) of the target
                         const uint64_t r = labels->row_offsets[hits[c].nid] + (v - 1);
@@ -1475,6 +1571,8 @@ const uint64_t *fdh_results_match_order(const fdh_results *r) { return r->match_
 const fdh_residue_match *fdh_results_residues(const fdh_results *r) { return r->residues.data(); }
 uint64_t fdh_results_num_residues(const fdh_results *r) { return r->residues.size(); }
 double fdh_results_host_ms(const fdh_results *r) { return r->host_ms; }
+uint64_t fdh_results_h2d_bytes(const fdh_results *r) { return r->h2d_bytes; }
+uint64_t fdh_results_d2h_bytes(const fdh_results *r) { return r->d2h_bytes; }
 void fdh_results_free(fdh_results *r) { delete r; }
 
 } // extern "C"

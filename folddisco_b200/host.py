@@ -25,11 +25,12 @@ class SearchParams(C.Structure):
     _fields_ = [("prefilter", PrefilterParams), ("ca_dist_cutoff", C.c_float), ("skip_match", C.c_int),
                 ("max_matching_node_count", C.c_uint64), ("max_matching_node_ratio", C.c_float),
                 ("rmsd_cutoff", C.c_float), ("connected_node_count", C.c_uint64), ("connected_node_ratio", C.c_float),
-                ("skip_ca_match", C.c_int), ("host_threads", C.c_int)]
+                ("skip_ca_match", C.c_int), ("host_threads", C.c_int), ("verify_mode", C.c_int)]
 
-    def __init__(self, top_n=UINT64_MAX, ca_dist_cutoff=1.0, skip_match=False, host_threads=0, **prefilter):
+    def __init__(self, top_n=UINT64_MAX, ca_dist_cutoff=1.0, skip_match=False, host_threads=0, verify_mode=0,
+                 **prefilter):
         super().__init__(PrefilterParams(top_n=top_n, **prefilter), ca_dist_cutoff, int(skip_match), 0, 0.0, 0.0, 0,
-                         0.0, 0, host_threads)
+                         0.0, 0, host_threads, verify_mode)
 
 
 STRUCT_ROW = np.dtype([("nid", np.uint32), ("total_match_count", np.uint32), ("node_count", np.uint32),
@@ -101,6 +102,8 @@ def _lib():
         sig("fdh_results_" + n, VP, [VP])
     sig("fdh_results_num_residues", C.c_uint64, [VP])
     sig("fdh_results_host_ms", C.c_double, [VP])
+    sig("fdh_results_h2d_bytes", C.c_uint64, [VP])
+    sig("fdh_results_d2h_bytes", C.c_uint64, [VP])
     sig("fdh_results_free", None, [VP])
     _sigs_done = True
     return L
@@ -361,6 +364,8 @@ class Results:
         self.match_order = arr(L.fdh_results_match_order(handle), nm, np.uint64)
         self.residues = arr(L.fdh_results_residues(handle), L.fdh_results_num_residues(handle), RES_MATCH)
         self.host_ms = L.fdh_results_host_ms(handle)
+        self.h2d_bytes = L.fdh_results_h2d_bytes(handle)
+        self.d2h_bytes = L.fdh_results_d2h_bytes(handle)
         L.fdh_results_free(handle)
 
     def structures(self, q):

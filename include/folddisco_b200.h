@@ -209,6 +209,54 @@ int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *ref_xyz, con
 int fd_kabsch_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_xyz, uint64_t n_q_res,
                           const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
                           const uint32_t *pair_qres, const uint32_t *pair_tres, float *rmsd, float *U9, float *t3);
+/* One verified match = one connected component of one candidate (a row of retrieval_wrapper's result vector,
+ * src/controller/retrieve.rs:364-552).  res[k] = 1 + index of the target residue matched to the k-th query
+ * residue, 0 = none ("_"). */
+typedef struct {
+    uint32_t cand;
+    uint32_t node_count;
+    float idf;  /* calculate_subgraph_idf (retrieve.rs:705-719) */
+    float rmsd; /* rmsd_with_calpha_and_rottran (retrieve.rs:756-834) */
+    float U[9];
+    float t[3];
+    uint32_t res[16];
+} fd_match_record;
+
+/* Per-query inputs of retrieval_wrapper: the query map (sorted by hash) with, per hash, its edge (i, j) as
+ * residue indices of the query structure, its idf and is_symmetric() (src/geometry/pdb_tr.rs:158-162); the
+ * observed distance map; the query residue list (query_indices, make_query_map's second output); and the query
+ * structure's CA / CB coordinates. */
+typedef struct {
+    uint32_t n_hashes;
+    const uint32_t *hashes_sorted;
+    const uint32_t *hash_qi;
+    const uint32_t *hash_qj;
+    const float *hash_idf;
+    const uint8_t *hash_symmetric;
+    uint32_t n_aa_dist;
+    const uint8_t *aa1;
+    const uint8_t *aa2;
+    const float *ca_dist;
+    const uint32_t *q_index;
+    uint32_t n_indices;
+    const uint32_t *indices;
+    uint32_t n_residues;
+    const float *ca_xyz;
+    const float *cb_xyz;
+} fd_verify_query;
+
+/* Fused replacement of retrieval_wrapper(...) (src/cli/workflows/query_pdb.rs:425-447, src/controller/
+ * retrieve.rs:364-552) for n_cand (query, candidate) pairs against the attached store: candidate re-hash,
+ * graph components, residue mapping + rescue and Kabsch RMSD in one kernel.  Library-allocated outputs:
+ * records grouped by candidate in component order; flags[c] != 0 marks a candidate that exceeds the kernel's
+ * shared-memory limits (more than 256 matching edges, 64 graph nodes, 16 components or 16 query residues) and
+ * must be verified with fd_candidate_edges_batch + fd_kabsch_store_batch instead (no records are emitted
+ * for it). */
+int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *queries, uint32_t n_queries,
+                               const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
+                               const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
+                               fd_match_record **out_records, uint64_t *out_n, uint8_t **out_flags);
+
 /* number of structures of the attached index (lookup.len()); 0 if none */
 uint64_t fd_index_num_structs(const fd_ctx *ctx);
 

@@ -130,6 +130,7 @@ typedef struct {
     float connected_node_ratio;       /* --connected-node-ratio */
     int skip_ca_match;                /* --skip-ca-match */
     int host_threads;                 /* threads for the graph / residue-mapping step, 0 = all cores */
+    int verify_mode;                  /* 0: fused kernel, general path only for flagged candidates; 1: general path only */
 } fdh_search_params;
 
 /* query_pdb.rs:348-452 for the whole batch: count_query -> filter/sort/top -> retrieval -> Kabsch ->
@@ -173,6 +174,10 @@ const fdh_residue_match *fdh_results_residues(const fdh_results *r);
 uint64_t fdh_results_num_residues(const fdh_results *r);
 /* wall-clock milliseconds of the host-only part of the last search (graph + mapping + assembly) */
 double fdh_results_host_ms(const fdh_results *r);
+/* bytes the search copied host->device (query descriptors, candidate lists, alignment indices) and
+ * device->host (hits, candidate edges/pairs, RMSD/U/t) */
+uint64_t fdh_results_h2d_bytes(const fdh_results *r);
+uint64_t fdh_results_d2h_bytes(const fdh_results *r);
 void fdh_results_free(fdh_results *r);
 
 #ifdef __cplusplus

@@ -467,8 +467,32 @@ namespace {
 // The reference counts varint bytes per hash (indextable.rs:88-105), prefix-sums the dense 2^30 table
 // (:204-237), fills (:171-202), prunes to sparse (:267-295).  The result only depends on the multiset
 // of (hash, id) pairs with ids ascending per hash; build that directly.
-fdo_index *index_from_pairs(std::vector<std::pair<uint32_t, uint64_t>> &pairs) {
-    std::sort(pairs.begin(), pairs.end());
+// sort (hash, id) pairs; large inputs are bucketed by the top hash bits and the buckets sorted in parallel
+void sort_pairs(std::vector<std::pair<uint32_t, uint64_t>> &pairs, int threads) {
+    if (pairs.size() < (1u << 20) || threads <= 1) {
+        std::sort(pairs.begin(), pairs.end());
+        return;
+    }
+    const int B = 4096; // hash >> 18 (hashes are 30-bit; overflowed bins land in the last buckets)
+    auto bucket = [](uint32_t h) { return (int)std::min<uint32_t>(h >> 18, 4095u); };
+    std::vector<size_t> cnt(B + 1, 0);
+    for (auto &p : pairs) cnt[bucket(p.first) + 1]++;
+    for (int b = 0; b < B; b++) cnt[b + 1] += cnt[b];
+    std::vector<std::pair<uint32_t, uint64_t>> out(pairs.size());
+    std::vector<size_t> cur(cnt.begin(), cnt.end() - 1);
+    for (auto &p : pairs) out[cur[bucket(p.first)]++] = p;
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&] {
+            for (int b; (b = next++) < B;) std::sort(out.begin() + cnt[b], out.begin() + cnt[b + 1]);
+        });
+    for (auto &t : th) t.join();
+    pairs.swap(out);
+}
+
+fdo_index *index_from_pairs(std::vector<std::pair<uint32_t, uint64_t>> &pairs, int threads = 1) {
+    sort_pairs(pairs, threads);
     fdo_index *ix = new fdo_index();
     size_t total = 0;
     {
@@ -1461,9 +1485,14 @@ fdo_index *fdo_index_build(const fdo_compact *const *structs, uint64_t S, uint32
         for (auto &t : th) t.join();
     }
     std::vector<std::pair<uint32_t, uint64_t>> pairs;
-    for (uint64_t s = 0; s < S; s++)
+    size_t total = 0;
+    for (uint64_t s = 0; s < S; s++) total += per[s].size();
+    pairs.reserve(total);
+    for (uint64_t s = 0; s < S; s++) {
         for (uint32_t h : per[s]) pairs.push_back({h, s});
-    return index_from_pairs(pairs);
+        std::vector<uint32_t>().swap(per[s]);
+    }
+    return index_from_pairs(pairs, threads);
 }
 fdo_index *fdo_index_from_buffers(const uint32_t *hashes, const uint64_t *offsets, uint64_t count,
                                   const uint8_t *values, uint64_t vb) {

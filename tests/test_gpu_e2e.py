@@ -26,8 +26,10 @@ def env():
     ctx.close()
 
 
-def test_config1_readme_rows(env, tmp_path):
-    """configs[0]: index data/serine_peptidases + query 4CHA.pdb B57,B102,C195 -> README.md:218-224, 237-241"""
+@pytest.mark.parametrize("verify_mode", [0, 1])
+def test_config1_readme_rows(env, tmp_path, verify_mode):
+    """verify_mode 0 = fused verification kernel, 1 = general path (K4 + host graph step + K5).
+    configs[0]: index data/serine_peptidases + query 4CHA.pdb B57,B102,C195 -> README.md:218-224, 237-241"""
     host, ctx, store, names = env["host"], env["ctx"], env["store"], env["names"]
     ix = host.FolddiscoIndex.build(ctx, store)
     prefix = str(tmp_path / "serine_folddisco")
@@ -41,7 +43,7 @@ def test_config1_readme_rows(env, tmp_path):
     qb.add(host.CompactStructure.from_atoms(env["atoms"]["query/4CHA.pdb"]), "B57,B102,C195")
     qb.finalize(ctx)
     assert len(qb.query_map(0)["hash"]) == F.CONFIG1_NUM_QUERY_HASHES
-    res = host.search(ctx, qb, host.SearchParams(), labels=store)
+    res = host.search(ctx, qb, host.SearchParams(verify_mode=verify_mode), labels=store)
     srows = {os.path.basename(names[int(r["nid"])]): ("%.4f" % r["idf"], int(r["total_match_count"]),
              int(r["node_count"]), int(r["edge_count"])) for r in res.structures(0)}
     assert srows == {t: ("%.4f" % v[0], v[1], v[2], v[3]) for t, v in F.README_STRUCT_ROWS.items() if t != "1azw.pdb"} | \
@@ -58,7 +60,7 @@ def test_config1_readme_rows(env, tmp_path):
            for r in res.structures(0)}
     assert per["4cha.pdb"] == (3, "0.0000") and per["1pq5.pdb"] == (3, "0.2609") and per["1l7a.pdb"] == (2, "0.7883")
     # the 1azw row of the README needs --ca-distance 1.5 (golden 3)
-    res15 = host.search(ctx, qb, host.SearchParams(ca_dist_cutoff=1.5), labels=store)
+    res15 = host.search(ctx, qb, host.SearchParams(ca_dist_cutoff=1.5, verify_mode=verify_mode), labels=store)
     t, n, i, r, s = F.README_MATCH_ROW_1AZW_CA15
     rows15 = [(os.path.basename(names[int(m["nid"])]), int(m["node_count"]), "%.4f" % m["idf"], "%.4f" % m["rmsd"],
                res15.residue_string(m, 3)) for m in res15.sorted_matches(0)]
@@ -75,8 +77,9 @@ def _oracle_rows(qm, comps, hits, ca_cutoff=1.0, which=0):
     return rows
 
 
-@pytest.mark.parametrize("n_structs,seed,top_n", [(600, 5, None), (5000, 6, 40)])
-def test_synthetic_pipeline_vs_oracle(env, n_structs, seed, top_n):
+@pytest.mark.parametrize("n_structs,seed,top_n,verify_mode", [(600, 5, None, 0), (600, 5, None, 1), (5000, 6, 40, 0),
+                                                            (5000, 6, 40, 1)])
+def test_synthetic_pipeline_vs_oracle(env, n_structs, seed, top_n, verify_mode):
     """all five shipped motifs against a synthetic database: matches (residues, node_count) bit-exact,
     idf / RMSD within 1e-4, vs the oracle's count_query + retrieval_wrapper."""
     from folddisco_b200 import synth
@@ -103,7 +106,7 @@ def test_synthetic_pipeline_vs_oracle(env, n_structs, seed, top_n):
     qb.finalize(ctx)
     for k, om in enumerate(oqms):  # per-edge idf of the query map (query.rs:288)
         assert np.allclose(qb.query_map(k)["idf"], om.entries()["idf"], rtol=1e-5, atol=1e-6)
-    sp = host.SearchParams() if top_n is None else host.SearchParams(top_n=top_n)
+    sp = host.SearchParams(verify_mode=verify_mode) if top_n is None else host.SearchParams(top_n=top_n, verify_mode=verify_mode)
     res = host.search(ctx, qb, sp, labels=store)
     total_matches = 0
     for k, om in enumerate(oqms):

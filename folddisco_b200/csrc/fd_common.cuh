@@ -83,7 +83,12 @@ inline int fd_fail(fd_ctx *ctx, int code, const std::string &msg) {
         if (r__ != FD_OK) return r__; \
     } while (0)
 
-// Owning device buffer; freed on scope exit.  Plain cudaMalloc: sizes are large and calls are few.
+// Stream of the API call currently executing on this host thread (set by FD_ENTER).  Temporaries are
+// allocated and freed stream-ordered from the device's default memory pool, whose release threshold is
+// raised at fd_create so that freed blocks stay cached: a call costs no cudaMalloc/cudaFree round trips.
+extern thread_local cudaStream_t fd_tls_stream;
+
+// Owning device buffer for per-call temporaries; freed (stream-ordered) on scope exit.
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -93,7 +98,7 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, fd_tls_stream);
         p = nullptr;
         n = 0;
     }
@@ -101,15 +106,21 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) count = 1;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        return cudaMallocAsync((void **)&p, count * sizeof(T), fd_tls_stream);
     }
-    T *take() {
+    T *take() { // ownership passes to the caller, who frees it with cudaFree (after a stream sync)
         T *q = p;
         p = nullptr;
         n = 0;
         return q;
     }
 };
+
+#define FD_ENTER(ctx)                                 \
+    do {                                              \
+        FD_CUDA((ctx), cudaSetDevice((ctx)->device)); \
+        fd_tls_stream = (ctx)->stream;                \
+    } while (0)
 
 // Brackets one stage with CUDA events on the library stream and accumulates its device time.
 struct StageTimer {

@@ -3,6 +3,7 @@
 #include "fd_geom.cuh"
 
 thread_local std::string fd_g_create_error;
+thread_local cudaStream_t fd_tls_stream = nullptr;
 
 static void fd_release_index(FdDeviceIndex &ix) {
     cudaFree(ix.hashes);
@@ -69,6 +70,12 @@ int fd_create(fd_ctx **out, int device) {
     FD_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     FD_CUDA(nullptr, cudaEventCreate(&ctx->ev0));
     FD_CUDA(nullptr, cudaEventCreate(&ctx->ev1));
+    { // keep freed temporaries cached in the default pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        FD_CUDA(nullptr, cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        FD_CUDA(nullptr, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
     *out = ctx;
     return FD_OK;
 }
@@ -102,7 +109,7 @@ uint64_t fd_index_num_structs(const fd_ctx *ctx) { return ctx && ctx->idx.attach
 
 int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t n, float *out) {
     if (!ctx || !a || !out || (op == 3 && !b)) return fd_fail(ctx, FD_ERR_ARG, "fd_math_probe: bad argument");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     DevBuf<float> da, db, dout;
     FD_CUDA(ctx, da.alloc(n));
     FD_CUDA(ctx, db.alloc(n));

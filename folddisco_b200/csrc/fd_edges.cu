@@ -249,7 +249,7 @@ extern "C" {
 
 int fd_store_attach(fd_ctx *ctx, const fd_struct_batch *batch) {
     if (!ctx) return FD_ERR_ARG;
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     FdDeviceBatch d;
     FD_TRY(fd_upload_batch(ctx, batch, &d));
     for (uint64_t s = 0; s < batch->n_structs; s++)
@@ -281,7 +281,7 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
         return fd_fail(ctx, FD_ERR_ARG, "fd_candidate_edges_batch: NULL argument");
     if (n_cand >= (1ull << 24))
         return fd_fail(ctx, FD_ERR_LIMIT, "at most 2^24 - 1 candidates per call; split the batch");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     *out_edges = nullptr;
     *out_pairs = nullptr;
     *out_n_edges = 0;

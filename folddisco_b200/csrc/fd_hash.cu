@@ -243,7 +243,7 @@ int fd_hash_structures(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_
     if (!ctx) return FD_ERR_ARG;
     if (!batch || !params || !out_hashes || !out_row_offsets)
         return fd_fail(ctx, FD_ERR_ARG, "fd_hash_structures: NULL argument");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     *out_hashes = nullptr;
     *out_row_offsets = nullptr;
     const uint64_t S = batch->n_structs;
@@ -305,7 +305,7 @@ int fd_build_index(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_para
     if (!batch || !params || !out) return fd_fail(ctx, FD_ERR_ARG, "fd_build_index: NULL argument");
     if (first_id + batch->n_structs > 0xffffffffull)
         return fd_fail(ctx, FD_ERR_LIMIT, "structure ids must fit in 32 bits");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     memset(out, 0, sizeof(*out));
     DevBuf<uint64_t> keys, tmp;
     uint64_t n_keys = 0;

@@ -45,7 +45,7 @@ extern "C" int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *r
     if (n_align == 0) return FD_OK;
     if (!mov_xyz || !ref_xyz || !pt_offsets || !rmsd || !U9 || !t3)
         return fd_fail(ctx, FD_ERR_ARG, "fd_kabsch_batch: NULL argument");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     const uint64_t npts = pt_offsets[n_align];
     DevBuf<float> d_mov, d_ref, d_rmsd, d_U, d_t;
     DevBuf<uint32_t> d_off;
@@ -85,7 +85,7 @@ extern "C" int fd_kabsch_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const f
         if (align_nid[a] >= ctx->store.n_structs) return fd_fail(ctx, FD_ERR_ARG, "align_nid outside the store");
     for (uint64_t k = 0; k < np; k++)
         if (pair_qres[k] >= n_q_res) return fd_fail(ctx, FD_ERR_ARG, "pair_qres out of range");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     DevBuf<float> d_qca, d_qcb, d_rmsd, d_U, d_t;
     DevBuf<uint32_t> d_nid, d_off, d_pq, d_pt;
     FD_CUDA(ctx, d_qca.alloc(3 * n_q_res));

@@ -168,7 +168,7 @@ int fd_build_postings(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *row_o
     if (!row_offsets || !out || (n_structs && row_offsets[n_structs] && !hashes))
         return fd_fail(ctx, FD_ERR_ARG, "fd_build_postings: NULL argument");
     if (first_id + n_structs > 0xffffffffull) return fd_fail(ctx, FD_ERR_LIMIT, "structure ids must fit in 32 bits");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     const uint64_t n = row_offsets[n_structs];
     DevBuf<uint32_t> d_h;
     DevBuf<uint64_t> d_ro, keys, tmp;

@@ -554,7 +554,7 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     if (n_structs > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "structure ids must fit in 32 bits");
     if (offsets[0] != 0 || offsets[count] != value_bytes)
         return fd_fail(ctx, FD_ERR_ARG, "fd_index_attach: offsets[0] must be 0 and offsets[count] == value_bytes");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     fd_ctx_release_index(ctx);
     FdDeviceIndex &d = ctx->idx;
     cudaStream_t s = ctx->stream;
@@ -620,7 +620,7 @@ int fd_posting_counts(fd_ctx *ctx, const uint32_t *hashes, uint64_t n, uint32_t 
     if (!ctx) return FD_ERR_ARG;
     if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_posting_counts: no index attached");
     if (n && (!hashes || !out_counts)) return fd_fail(ctx, FD_ERR_ARG, "fd_posting_counts: NULL argument");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     if (n == 0) return FD_OK;
     DevBuf<uint32_t> dh, dc;
     FD_CUDA(ctx, dh.alloc(n));
@@ -637,7 +637,7 @@ int fd_get_entries(fd_ctx *ctx, uint32_t hash, uint64_t **out_ids, uint64_t *out
     if (!ctx) return FD_ERR_ARG;
     if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_get_entries: no index attached");
     if (!out_ids || !out_n) return fd_fail(ctx, FD_ERR_ARG, "fd_get_entries: NULL argument");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     uint32_t cnt = 0;
     FD_TRY(fd_posting_counts(ctx, &hash, 1, &cnt));
     DevBuf<uint64_t> d_ids;
@@ -663,7 +663,7 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
     if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_count_query_batch: no index attached");
     if ((nq && !queries) || !params || !out_hits || !out_offsets)
         return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_batch: NULL argument");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     *out_hits = nullptr;
     *out_offsets = nullptr;
     cudaStream_t s = ctx->stream;

@@ -25,7 +25,7 @@ namespace {
 constexpr int V_THREADS = 128;
 constexpr int V_LIST_CAP = 4096;
 constexpr int V_CHUNK = V_THREADS * 8;
-constexpr int V_MAX_AAD = 256;
+constexpr int V_MAX_AAD = 255; // start and count of an amino-acid pair's run each fit 8 bits
 constexpr int V_MAX_E = 256;
 constexpr int V_MAX_NODES = 64;
 constexpr int V_MAX_C = 16;
@@ -78,12 +78,14 @@ __global__ void __launch_bounds__(V_THREADS)
     __shared__ uint32_t n1, n2, q_n, n_e;
     __shared__ uint32_t q_ij[V_CHUNK];
     __shared__ float q_d[V_CHUNK];
-    __shared__ VAad aad[V_MAX_AAD];
+    __shared__ VAad aad[V_MAX_AAD];        // sorted by (aa1, aa2) on the host
+    __shared__ uint16_t aa_range[400];      // aa1 * 20 + aa2 -> start << 8 | count of its entries (0 = pair not in query)
     __shared__ uint32_t e_key[V_MAX_E]; // i << 16 | j, sorted
     __shared__ uint16_t e_ent[V_MAX_E]; // index of the edge's hash inside the query's sorted hash set
     __shared__ uint8_t e_a[V_MAX_E], e_b[V_MAX_E];
     __shared__ uint16_t node_res[V_MAX_NODES];
     __shared__ uint64_t comp_mask[V_MAX_C];
+    __shared__ uint64_t reach[V_MAX_NODES], und[V_MAX_NODES]; // directed / undirected reachability closures
     __shared__ uint32_t n_nodes, n_comp, s_flag;
     __shared__ uint8_t counts[V_MAX_NQ * V_MAX_NODES];
     // per-component results
@@ -113,8 +115,18 @@ __global__ void __launch_bounds__(V_THREADS)
         n_comp = 0;
     }
     for (uint32_t k = tid; k < Q.n_aad; k += V_THREADS) aad[k] = vaad[Q.aad_begin + k];
+    for (uint32_t k = tid; k < 400; k += V_THREADS) aa_range[k] = 0;
     __syncthreads();
     if (Q.n_hashes == 0 || Q.n_aad == 0) return;
+    for (uint32_t k = tid; k < Q.n_aad; k += V_THREADS) { // heads of runs of equal (aa1, aa2)
+        const uint32_t key = aad[k].aa1 * 20u + aad[k].aa2;
+        if (k == 0 || aad[k - 1].aa1 * 20u + aad[k - 1].aa2 != key) {
+            uint32_t e = k + 1;
+            while (e < Q.n_aad && aad[e].aa1 * 20u + aad[e].aa2 == key) e++;
+            aa_range[key] = (uint16_t)((k << 8) | (e - k));
+        }
+    }
+    __syncthreads();
 
     // ---- prefilter sets (prefilter_amino_acid, retrieve.rs:563-602) ----
     bool all_pairs = !Q.use_prefilter;
@@ -162,12 +174,12 @@ __global__ void __launch_bounds__(V_THREADS)
                 i = all_pairs ? a : list1[a];
                 j = all_pairs ? b : list2[b];
                 const uint8_t ai = st.aa[base + i], aj = st.aa[base + j];
-                if (i != j && ai != 255 && aj != 255) {
+                if (i != j && ai != 255 && aj != 255 && aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)] != 0) {
                     d = fdg::dist(ld3(st.ca_xyz, base + i), ld3(st.ca_xyz, base + j));
                     if (d <= hp.dist_cutoff) {
-                        const uint8_t ci = ai & 0x7Fu, cj = aj & 0x7Fu;
-                        for (uint32_t k = 0; k < Q.n_aad; k++)
-                            if (aad[k].aa1 == ci && aad[k].aa2 == cj && fabsf(d - aad[k].dist) < ca_cutoff) {
+                        const uint32_t rg = aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)];
+                        for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
+                            if (fabsf(d - aad[k].dist) < ca_cutoff) {
                                 pass = true;
                                 break;
                             }
@@ -220,11 +232,13 @@ __global__ void __launch_bounds__(V_THREADS)
         return;
     }
     // ---- sort edges by (i, j): the reference's emission order (graph node numbering, f32 sum order) ----
-    for (uint32_t k = ne + tid; k < V_MAX_E; k += V_THREADS) e_key[k] = 0xffffffffu;
+    uint32_t sort_n = 2;
+    while (sort_n < ne) sort_n <<= 1;
+    for (uint32_t k = ne + tid; k < sort_n; k += V_THREADS) e_key[k] = 0xffffffffu;
     __syncthreads();
-    for (uint32_t size = 2; size <= V_MAX_E; size <<= 1)
+    for (uint32_t size = 2; size <= sort_n; size <<= 1)
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t k = tid; k < V_MAX_E / 2; k += V_THREADS) {
+            for (uint32_t k = tid; k < sort_n / 2; k += V_THREADS) {
                 const uint32_t lo_i = 2 * k - (k & (stride - 1));
                 const uint32_t hi_i = lo_i + stride;
                 const bool up = (lo_i & size) == 0;
@@ -266,7 +280,6 @@ __global__ void __launch_bounds__(V_THREADS)
             s_flag = 1;
         } else {
             n_nodes = nn;
-            uint64_t reach[V_MAX_NODES], und[V_MAX_NODES];
             for (uint32_t v = 0; v < nn; v++) reach[v] = und[v] = 1ull << v;
             bool changed = true;
             while (changed) {
@@ -328,9 +341,10 @@ __global__ void __launch_bounds__(V_THREADS)
     for (uint32_t ci = 0; ci < ncomp; ci++) {
         // ---- mapping (thread 0): votes, best per query residue, greedy assignment ----
         const uint64_t mask = comp_mask[ci];
+        for (uint32_t k = tid; k < Q.n_dq * V_MAX_NODES; k += V_THREADS) counts[k] = 0;
+        __syncthreads();
         if (tid == 0) {
             const uint32_t nq_d = Q.n_dq;
-            for (uint32_t k = 0; k < nq_d * V_MAX_NODES; k++) counts[k] = 0;
             uint8_t best_c[V_MAX_NQ], best_r[V_MAX_NQ];
             for (uint32_t q = 0; q < nq_d; q++) {
                 best_c[q] = 0;
@@ -456,11 +470,9 @@ __global__ void __launch_bounds__(V_THREADS)
                         if (!all_pairs && !(((aj & 0x80u) == 0) && ((Q.aa2_mask >> (aj & 31u)) & 1u))) continue;
                         const float d = fdg::dist(cai, ld3(st.ca_xyz, base + rj));
                         if (!(d <= hp.dist_cutoff)) continue;
-                        const uint8_t cja = aj & 0x7Fu;
-                        for (uint32_t e = 0; e < Q.n_aad; e++)
-                            if (aad[e].dq == dq && aad[e].aa1 == cia && aad[e].aa2 == cja &&
-                                fabsf(d - aad[e].dist) < ca_cutoff)
-                                cnt++;
+                        const uint32_t rg = aa_range[cia * 20u + (aj & 0x7Fu)];
+                        for (uint32_t e = rg >> 8, ee = (rg >> 8) + (rg & 0xffu); e < ee; e++)
+                            if (aad[e].dq == dq && fabsf(d - aad[e].dist) < ca_cutoff) cnt++;
                     }
                     return cnt;
                 };
@@ -556,7 +568,7 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
     if ((nq && !queries) || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags)
         return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates_batch: NULL argument");
     if (n_cand > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "too many candidates in one call");
-    FD_CUDA(ctx, cudaSetDevice(ctx->device));
+    FD_ENTER(ctx);
     *out_records = nullptr;
     *out_flags = nullptr;
     *out_n = 0;
@@ -603,8 +615,20 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
             d.aa1_mask |= 1u << ((Q.hashes_sorted[k] >> 25) & 31u);
             d.aa2_mask |= 1u << ((Q.hashes_sorted[k] >> 20) & 31u);
         }
-        for (uint32_t k = 0; k < Q.n_aa_dist && !q_unfit[q]; k++)
-            f_aad.push_back(VAad{Q.aa1[k], Q.aa2[k], dense(Q.q_index[k]), 0, Q.ca_dist[k]});
+        if (!q_unfit[q]) { // entries grouped by amino-acid pair (the kernel indexes them through a 20x20 table)
+            std::vector<uint32_t> ord(Q.n_aa_dist);
+            for (uint32_t k = 0; k < Q.n_aa_dist; k++) ord[k] = k;
+            std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
+                return Q.aa1[a] * 20u + Q.aa2[a] < Q.aa1[b] * 20u + Q.aa2[b];
+            });
+            for (uint32_t k : ord) {
+                if (Q.aa1[k] >= 20 || Q.aa2[k] >= 20) {
+                    free(h_flags);
+                    return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
+                }
+                f_aad.push_back(VAad{Q.aa1[k], Q.aa2[k], dense(Q.q_index[k]), 0, Q.ca_dist[k]});
+            }
+        }
         if (q_unfit[q]) d.n_aad = 0; // kernel returns immediately for this query's candidates
         for (uint32_t k = 0; k < Q.n_indices; k++) f_idx.push_back(dense(Q.indices[k]));
         for (uint32_t r : dq) { // only the residues the query touches travel to the device
@@ -687,9 +711,22 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
     FD_CUDA(ctx, st.finish());
     for (uint64_t c = 0; c < n_cand; c++)
         if (q_unfit[cand_query[c]]) h_flags[c] = 1;
-    // records arrive in arbitrary CTA order: group by candidate, keep component order within a candidate
-    std::stable_sort(h_out, h_out + produced,
-                     [](const fd_match_record &a, const fd_match_record &b) { return a.cand < b.cand; });
+    // records arrive in arbitrary CTA order (each candidate's block is contiguous and in component order):
+    // counting sort by candidate
+    if (produced) {
+        std::vector<uint32_t> start(n_cand + 1, 0);
+        for (unsigned int k = 0; k < produced; k++) start[h_out[k].cand + 1]++;
+        for (uint64_t c = 0; c < n_cand; c++) start[c + 1] += start[c];
+        fd_match_record *sorted = (fd_match_record *)malloc((size_t)produced * sizeof(fd_match_record));
+        if (!sorted) {
+            free(h_out);
+            free(h_flags);
+            return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+        }
+        for (unsigned int k = 0; k < produced; k++) sorted[start[h_out[k].cand]++] = h_out[k];
+        free(h_out);
+        h_out = sorted;
+    }
     *out_records = h_out;
     *out_n = produced;
     *out_flags = h_flags;

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -314,7 +315,7 @@ struct AAD {
     uint32_t qi;
 };
 struct Query {
-    fdh_compact st;
+    std::shared_ptr<const fdh_compact> st; // shared between the queries of a batch that use the same structure
     std::string qstring;
     std::vector<uint32_t> indices;
     std::vector<QEntry> entries;
@@ -456,7 +457,7 @@ void qinsert(Query &Q, const float *f, const fdg::HashParams &hp, uint32_t qi, u
 
 // make_query_map (src/controller/query.rs:208-329) minus the idf values, which need the index
 bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
-    const fdh_compact &c = Q.st;
+    const fdh_compact &c = *Q.st;
     const fdg::HashParams hp = fdg::make_params(qs.p.hash.nbin_dist, qs.p.hash.nbin_angle, qs.p.hash.dist_cutoff);
     std::unordered_map<uint32_t, std::vector<uint8_t>> submap;
     for (size_t i = 0; i < pq.chains.size(); i++) {
@@ -784,6 +785,7 @@ struct fdh_results {
     std::vector<fdh_residue_match> residues;
     double host_ms = 0.0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0; // bytes this search moved between host and device
+    double wall_ms[4] = {0, 0, 0, 0};      // count_query call, verification call(s), row assembly, total
 };
 
 // =============================================================================================
@@ -1122,28 +1124,73 @@ fdh_queries *fdh_queries_new(const fdh_query_params *p) {
     qs->p.angle_thr = nullptr;
     return qs;
 }
-int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *st, const char *query_string) {
+static bool prepare_query(const fdh_queries *qs, std::shared_ptr<const fdh_compact> st, const char *query_string,
+                          Query &Q, std::string &err) {
     ParsedQuery pq;
-    const int fc = fdh_compact_first_chain(st);
+    const int fc = fdh_compact_first_chain(st.get());
     if (!parse_query(query_string, fc < 0 ? (uint8_t)'A' : (uint8_t)fc, pq)) {
-        set_err(std::string("Invalid residue in query string: ") + query_string);
-        return -1;
+        err = std::string("Invalid residue in query string: ") + query_string;
+        return false;
     }
     if (pq.chains.empty()) {
-        set_err("whole-structure queries (empty query string) are not supported in this version");
-        return -1;
+        err = "whole-structure queries (empty query string) are not supported in this version";
+        return false;
     }
-    qs->q.emplace_back();
-    Query &Q = qs->q.back();
-    Q.st = *st;
+    Q.st = std::move(st);
     Q.qstring = query_string;
     if (!build_query_map(Q, pq, *qs)) {
-        qs->q.pop_back();
-        set_err("query has too many edges");
+        err = "query has too many edges";
+        return false;
+    }
+    return true;
+}
+
+
+int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *st, const char *query_string) {
+    Query Q;
+    std::string err;
+    if (!prepare_query(qs, std::make_shared<const fdh_compact>(*st), query_string, Q, err)) {
+        set_err(err);
         return -1;
     }
+    qs->q.push_back(std::move(Q));
     qs->finalized = false;
     return (int64_t)qs->q.size() - 1;
+}
+
+// make_query_map for n (structure, query string) pairs at once, query-parallel (query_pdb.rs:348 into_par_iter)
+int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,
+                             int64_t n, int threads) {
+    // one copy per distinct source structure (all sources are alive for the duration of this call)
+    std::vector<std::shared_ptr<const fdh_compact>> sp((size_t)n);
+    std::unordered_map<const fdh_compact *, std::shared_ptr<const fdh_compact>> seen;
+    for (int64_t k = 0; k < n; k++) {
+        auto it = seen.find(structures[k]);
+        if (it == seen.end()) it = seen.emplace(structures[k], std::make_shared<const fdh_compact>(*structures[k])).first;
+        sp[k] = it->second;
+    }
+    std::vector<Query> out((size_t)n);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<uint8_t> ok((size_t)n, 0);
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min<int>(nt, 64));
+    std::atomic<int64_t> next{0};
+    auto worker = [&] {
+        for (int64_t k; (k = next.fetch_add(1)) < n;) ok[k] = prepare_query(qs, sp[k], query_strings[k], out[k], errs[k]);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    for (int64_t k = 0; k < n; k++)
+        if (!ok[k]) {
+            set_err(errs[k]);
+            return -1;
+        }
+    const int64_t first = (int64_t)qs->q.size();
+    for (auto &Q : out) qs->q.push_back(std::move(Q));
+    qs->finalized = false;
+    return first;
 }
 int64_t fdh_queries_size(const fdh_queries *qs) { return (int64_t)qs->q.size(); }
 
@@ -1199,7 +1246,10 @@ struct FinalMatch { // one verified component of one candidate
     uint32_t node_count;
     float idf, rmsd;
     float U[9], t[3];
-    std::vector<uint32_t> res; // per query residue: target residue index + 1, 0 = none
+    uint32_t n_res;
+    uint32_t res16[16];            // per query residue: target residue index + 1, 0 = none
+    std::vector<uint32_t> res_big; // only when the query has more than 16 residues (general path)
+    const uint32_t *res() const { return n_res <= 16 ? res16 : res_big.data(); }
 };
 
 // General verification path for an arbitrary candidate list: K4 (fd_candidate_edges_batch) -> host graph /
@@ -1324,11 +1374,11 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *
     if (!n_align) return FD_OK;
     std::vector<float> rmsd(n_align), U(9 * (size_t)n_align), T(3 * (size_t)n_align);
     std::vector<uint64_t> q_res_off(nq + 1, 0);
-    for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q].st.nres();
+    for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q].st->nres();
     std::vector<float> q_ca(3 * q_res_off[nq]), q_cb(3 * q_res_off[nq]);
     for (uint32_t q = 0; q < nq; q++) {
-        memcpy(q_ca.data() + 3 * q_res_off[q], qs->q[q].st.ca.data(), 12 * qs->q[q].st.nres());
-        memcpy(q_cb.data() + 3 * q_res_off[q], qs->q[q].st.cb.data(), 12 * qs->q[q].st.nres());
+        memcpy(q_ca.data() + 3 * q_res_off[q], qs->q[q].st->ca.data(), 12 * qs->q[q].st->nres());
+        memcpy(q_cb.data() + 3 * q_res_off[q], qs->q[q].st->cb.data(), 12 * qs->q[q].st->nres());
     }
     std::vector<uint32_t> a_nid(n_align), a_off(n_align + 1, 0), pq_, pt_;
     for (uint32_t a = 0; a < n_align; a++) {
@@ -1356,7 +1406,9 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *
         fm.rmsd = rmsd[a];
         memcpy(fm.U, &U[9 * (size_t)a], sizeof(fm.U));
         memcpy(fm.t, &T[3 * (size_t)a], sizeof(fm.t));
-        fm.res = mt[a].res_final;
+        fm.n_res = (uint32_t)mt[a].res_final.size();
+        if (fm.n_res <= 16) memcpy(fm.res16, mt[a].res_final.data(), 4 * fm.n_res);
+        else fm.res_big = mt[a].res_final;
         out.push_back(std::move(fm));
     }
     return FD_OK;
@@ -1386,12 +1438,20 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
     }
     fd_struct_hit *hits = nullptr;
     uint64_t *hoff = nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    const auto t_all = now();
+    auto t_stage = now();
     if (fd_count_query_batch(ctx, fq.data(), nq, &p->prefilter, &hits, &hoff) != FD_OK) {
         set_err(fd_last_error(ctx));
         delete R;
         return nullptr;
     }
     const uint64_t n_cand = hoff[nq];
+    R->wall_ms[0] = ms_since(t_stage);
+    t_stage = now();
     R->d2h_bytes += n_cand * sizeof(fd_struct_hit) + (nq + 1) * 8ull + nq * 16ull;
     std::vector<FinalMatch> fm; // all matches, grouped by candidate after the sort below
     double host_ms = 0.0;
@@ -1425,8 +1485,8 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
             vq[q] = fd_verify_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), v_qi[q].data(),
                                     v_qj[q].data(), v_idf[q].data(), v_sym[q].data(), (uint32_t)Q.aad.size(),
                                     Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data(),
-                                    (uint32_t)Q.indices.size(), Q.indices.data(), (uint32_t)Q.st.nres(), Q.st.ca.data(),
-                                    Q.st.cb.data()};
+                                    (uint32_t)Q.indices.size(), Q.indices.data(), (uint32_t)Q.st->nres(), Q.st->ca.data(),
+                                    Q.st->cb.data()};
             R->h2d_bytes += 14ull * Q.hashes_sorted.size() + 8ull * Q.aad.size() + Q.indices.size() + 24ull * 16 + 48;
         }
         fd_match_record *recs = nullptr;
@@ -1445,18 +1505,17 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
         R->h2d_bytes += 8ull * n_cand;
         R->d2h_bytes += n_recs * sizeof(fd_match_record) + n_cand;
         auto t0 = std::chrono::steady_clock::now();
-        fm.reserve(n_recs);
+        fm.resize(n_recs);
         for (uint64_t k = 0; k < n_recs; k++) {
-            FinalMatch m;
+            FinalMatch &m = fm[k];
             m.cand = recs[k].cand;
             m.node_count = recs[k].node_count;
             m.idf = recs[k].idf;
             m.rmsd = recs[k].rmsd;
             memcpy(m.U, recs[k].U, sizeof(m.U));
             memcpy(m.t, recs[k].t, sizeof(m.t));
-            const size_t NQ = qs->q[cand_q[m.cand]].indices.size();
-            m.res.assign(recs[k].res, recs[k].res + std::min<size_t>(NQ, 16));
-            fm.push_back(std::move(m));
+            m.n_res = (uint32_t)std::min<size_t>(qs->q[cand_q[m.cand]].indices.size(), 16);
+            memcpy(m.res16, recs[k].res, sizeof(m.res16));
         }
         std::vector<uint32_t> fq_, fn_;
         std::vector<uint64_t> fglobal;
@@ -1475,18 +1534,25 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
         }
     }
     // --- assemble rows: per-candidate summary (retrieve.rs:539-551), filter_after_matching (filter.rs:103-116),
-    //     MatchFilter (:194-235), default sorts ---
+    //     MatchFilter (:194-235), default sorts; query-parallel, then concatenated in query order ---
+    R->wall_ms[1] = ms_since(t_stage);
     auto t1 = std::chrono::steady_clock::now();
-    size_t mpos = 0;
-    for (uint32_t q = 0; q < nq; q++) {
+    struct QOut {
+        std::vector<fdh_struct_row> structs;
+        std::vector<fdh_match_row> matches;
+        std::vector<fdh_residue_match> residues;
+        std::vector<uint64_t> order;
+    };
+    std::vector<QOut> qout(nq);
+    std::vector<size_t> fm_begin(n_cand + 1, 0); // matches of candidate c: fm[fm_begin[c] .. fm_begin[c+1])
+    for (auto &m : fm) fm_begin[m.cand + 1]++;
+    for (uint64_t c = 0; c < n_cand; c++) fm_begin[c + 1] += fm_begin[c];
+    auto build_query = [&](uint32_t q) {
         const Query &Q = qs->q[q];
+        QOut &O = qout[q];
         const float expected = (float)Q.indices.size();
-        const size_t s_begin = R->structs.size();
-        const size_t m_begin = R->matches.size();
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
-            const size_t a0 = mpos;
-            while (mpos < fm.size() && fm[mpos].cand == c) mpos++;
-            const size_t a1 = mpos;
+            const size_t a0 = fm_begin[c], a1 = fm_begin[c + 1];
             uint32_t max_node = 0;
             float min_rmsd = 0.f;
             for (size_t a = a0; a < a1; a++) {
@@ -1506,7 +1572,7 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
             }
             fdh_struct_row sr{hits[c].nid, hits[c].match_count, hits[c].node_count, hits[c].edge_count, hits[c].idf,
                               max_node, min_rmsd, 0, 0};
-            sr.match_begin = R->matches.size();
+            sr.match_begin = O.matches.size(); // relative to the query; rebased below
             for (size_t a = a0; a < a1; a++) {
                 const FinalMatch &m = fm[a];
                 bool pass = true;
@@ -1522,41 +1588,88 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
                 mr.rmsd = m.rmsd;
                 memcpy(mr.U, m.U, sizeof(mr.U));
                 memcpy(mr.t, m.t, sizeof(mr.t));
-                mr.res_begin = R->residues.size();
-                for (uint32_t v : m.res) {
+                mr.res_begin = O.residues.size();
+                const uint32_t *res = m.res();
+                for (uint32_t k = 0; k < m.n_res; k++) {
+                    const uint32_t v = res[k];
                     fdh_residue_match rm{(uint8_t)(v != 0), 0, v ? (uint64_t)(v - 1) : 0};
                     if (v && labels && hits[c].nid < labels->names.size()) { // (chain, residue number) of the target
                         const uint64_t r = labels->row_offsets[hits[c].nid] + (v - 1);
                         rm.chain = labels->chain[r];
                         rm.serial = labels->serial[r];
                     }
-                    R->residues.push_back(rm);
+                    O.residues.push_back(rm);
                 }
-                R->matches.push_back(mr);
+                O.matches.push_back(mr);
             }
-            sr.match_end = R->matches.size();
-            R->structs.push_back(sr);
+            sr.match_end = O.matches.size();
+            O.structs.push_back(sr);
         }
         // StructureSortStrategy::default: idf desc, min_rmsd asc (sort.rs:454-458), stable
-        std::stable_sort(R->structs.begin() + s_begin, R->structs.end(), [](const fdh_struct_row &a, const fdh_struct_row &b) {
+        std::stable_sort(O.structs.begin(), O.structs.end(), [](const fdh_struct_row &a, const fdh_struct_row &b) {
             if (a.idf != b.idf) return a.idf > b.idf;
             return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
         });
         // MatchSortStrategy::default: idf desc, rmsd asc (sort.rs:218-222), stable over emission order
-        const size_t m_end = R->matches.size();
-        std::vector<uint64_t> ord(m_end - m_begin);
-        for (size_t k = 0; k < ord.size(); k++) ord[k] = m_begin + k;
-        std::stable_sort(ord.begin(), ord.end(), [&](uint64_t a, uint64_t b) {
-            const fdh_match_row &x = R->matches[a], &y = R->matches[b];
+        O.order.resize(O.matches.size());
+        for (size_t k = 0; k < O.order.size(); k++) O.order[k] = k;
+        std::stable_sort(O.order.begin(), O.order.end(), [&](uint64_t a, uint64_t b) {
+            const fdh_match_row &x = O.matches[a], &y = O.matches[b];
             if (x.idf != y.idf) return x.idf > y.idf;
             return x.rmsd < y.rmsd;
         });
-        R->match_order.insert(R->match_order.end(), ord.begin(), ord.end());
-        R->struct_off[q + 1] = R->structs.size();
-        R->match_off[q + 1] = R->matches.size();
+    };
+    {
+        int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, 64));
+        std::atomic<uint32_t> next{0};
+        auto worker = [&] {
+            for (uint32_t q; (q = next.fetch_add(1)) < nq;) build_query(q);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &t : th) t.join();
+        std::vector<uint64_t> res_off(nq + 1, 0);
+        for (uint32_t q = 0; q < nq; q++) {
+            R->struct_off[q + 1] = R->struct_off[q] + qout[q].structs.size();
+            R->match_off[q + 1] = R->match_off[q] + qout[q].matches.size();
+            res_off[q + 1] = res_off[q] + qout[q].residues.size();
+        }
+        R->structs.resize(R->struct_off[nq]);
+        R->matches.resize(R->match_off[nq]);
+        R->match_order.resize(R->match_off[nq]);
+        R->residues.resize(res_off[nq]);
+        next = 0;
+        auto copier = [&] {
+            for (uint32_t q; (q = next.fetch_add(1)) < nq;) {
+                QOut &O = qout[q];
+                const uint64_t mb = R->match_off[q], rb = res_off[q];
+                for (size_t k = 0; k < O.structs.size(); k++) {
+                    fdh_struct_row sr = O.structs[k];
+                    sr.match_begin += mb;
+                    sr.match_end += mb;
+                    R->structs[R->struct_off[q] + k] = sr;
+                }
+                for (size_t k = 0; k < O.matches.size(); k++) {
+                    fdh_match_row mr = O.matches[k];
+                    mr.res_begin += rb;
+                    R->matches[mb + k] = mr;
+                    R->match_order[mb + k] = mb + O.order[k];
+                }
+                if (!O.residues.empty())
+                    memcpy(&R->residues[rb], O.residues.data(), O.residues.size() * sizeof(fdh_residue_match));
+            }
+        };
+        th.clear();
+        for (int t = 1; t < nt; t++) th.emplace_back(copier);
+        copier();
+        for (auto &t : th) t.join();
     }
     host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     R->host_ms = host_ms;
+    R->wall_ms[2] = ms_since(t1);
+    R->wall_ms[3] = ms_since(t_all);
     fd_free(hits);
     fd_free(hoff);
     return R;
@@ -1572,6 +1685,7 @@ const fdh_residue_match *fdh_results_residues(const fdh_results *r) { return r->
 uint64_t fdh_results_num_residues(const fdh_results *r) { return r->residues.size(); }
 double fdh_results_host_ms(const fdh_results *r) { return r->host_ms; }
 uint64_t fdh_results_h2d_bytes(const fdh_results *r) { return r->h2d_bytes; }
+double fdh_results_wall_ms(const fdh_results *r, int which) { return which >= 0 && which < 4 ? r->wall_ms[which] : -1.0; }
 uint64_t fdh_results_d2h_bytes(const fdh_results *r) { return r->d2h_bytes; }
 void fdh_results_free(fdh_results *r) { delete r; }
 

@@ -89,6 +89,7 @@ def _lib():
     sig("fdh_parse_query_string", C.c_int64, [C.c_char_p, C.c_uint8, VP, VP, VP, VP, VP, C.c_int64, C.c_int64])
     sig("fdh_queries_new", VP, [PP(_QueryParams)])
     sig("fdh_queries_add", C.c_int64, [VP, VP, C.c_char_p])
+    sig("fdh_queries_add_many", C.c_int64, [VP, PP(VP), PP(C.c_char_p), C.c_int64, C.c_int])
     sig("fdh_queries_size", C.c_int64, [VP])
     sig("fdh_queries_finalize", C.c_int, [VP, VP])
     sig("fdh_queries_num_hashes", C.c_int64, [VP, C.c_int64])
@@ -103,6 +104,7 @@ def _lib():
     sig("fdh_results_num_residues", C.c_uint64, [VP])
     sig("fdh_results_host_ms", C.c_double, [VP])
     sig("fdh_results_h2d_bytes", C.c_uint64, [VP])
+    sig("fdh_results_wall_ms", C.c_double, [VP, C.c_int])
     sig("fdh_results_d2h_bytes", C.c_uint64, [VP])
     sig("fdh_results_free", None, [VP])
     _sigs_done = True
@@ -316,6 +318,17 @@ class QueryBatch:
         self.query_strings.append(query_string)
         return q
 
+    def add_many(self, compacts, query_strings, threads=0):
+        """make_query_map for many (structure, query string) pairs, query-parallel on the host"""
+        n = len(compacts)
+        hs = (VP * n)(*[c.h for c in compacts])
+        qs = (C.c_char_p * n)(*[q.encode() for q in query_strings])
+        first = _lib().fdh_queries_add_many(self.h, hs, qs, n, threads)
+        if first < 0:
+            raise FdError(_err())
+        self.query_strings.extend(query_strings)
+        return first
+
     def __len__(self):
         return _lib().fdh_queries_size(self.h)
 
@@ -345,16 +358,19 @@ class QueryBatch:
 
 
 class Results:
+    """Rows of a batch search.  The arrays are zero-copy views of the library-owned result object."""
+
     def __init__(self, handle):
         if not handle:
             raise FdError(_err())
         L = _lib()
+        self.h = handle
         nq = L.fdh_results_num_queries(handle)
 
         def arr(ptr, n, dt):
             if n == 0 or not ptr:
                 return np.zeros(0, dt)
-            return np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt, count=n).copy()
+            return np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt, count=n)
 
         self.struct_offsets = arr(L.fdh_results_struct_offsets(handle), nq + 1, np.uint64)
         self.match_offsets = arr(L.fdh_results_match_offsets(handle), nq + 1, np.uint64)
@@ -366,7 +382,14 @@ class Results:
         self.host_ms = L.fdh_results_host_ms(handle)
         self.h2d_bytes = L.fdh_results_h2d_bytes(handle)
         self.d2h_bytes = L.fdh_results_d2h_bytes(handle)
-        L.fdh_results_free(handle)
+        self.wall_ms = {k: L.fdh_results_wall_ms(handle, i) for i, k in enumerate(("count_query", "verify", "assemble", "total"))}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            for k in ("struct_offsets", "match_offsets", "structs", "matches", "match_order", "residues"):
+                setattr(self, k, None)
+            _lib().fdh_results_free(self.h)
+            self.h = None
 
     def structures(self, q):
         return self.structs[int(self.struct_offsets[q]):int(self.struct_offsets[q + 1])]

@@ -107,6 +107,9 @@ fdh_queries *fdh_queries_new(const fdh_query_params *p);
 /* adds one query: structure + query string (empty string = whole structure is NOT supported in this version).
  * The structure is copied.  Returns the query number or <0. */
 int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *structure, const char *query_string);
+/* n queries at once, query maps built on `threads` host threads (0 = all cores); returns the first query number */
+int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,
+                             int64_t n, int threads);
 int64_t fdh_queries_size(const fdh_queries *qs);
 /* finishes make_query_map for the whole batch: one fd_posting_counts call supplies the per-edge idf
  * (calculate_idf_for_hash, query.rs:17-32).  Needs an attached index. */
@@ -177,6 +180,8 @@ double fdh_results_host_ms(const fdh_results *r);
 /* bytes the search copied host->device (query descriptors, candidate lists, alignment indices) and
  * device->host (hits, candidate edges/pairs, RMSD/U/t) */
 uint64_t fdh_results_h2d_bytes(const fdh_results *r);
+/* wall-clock ms of the last search: 0 = fd_count_query_batch call, 1 = verification, 2 = row assembly, 3 = total */
+double fdh_results_wall_ms(const fdh_results *r, int which);
 uint64_t fdh_results_d2h_bytes(const fdh_results *r);
 void fdh_results_free(fdh_results *r);
 

@@ -40,7 +40,7 @@ class _IndexBuffers(C.Structure):
 
 class _Query(C.Structure):
     _fields_ = [("n_hashes", C.c_uint32), ("hashes", VP), ("edge_of_hash", VP), ("n_edges", C.c_uint32),
-                ("edge_node", VP), ("n_nodes", C.c_uint32), ("expected_node_count", C.c_uint32)]
+                ("edge_node", VP), ("n_nodes", C.c_uint32), ("expected_node_count", C.c_uint32), ("edge_group", VP)]
 
 
 class PrefilterParams(C.Structure):
@@ -54,6 +54,21 @@ class PrefilterParams(C.Structure):
         super().__init__(-1.0, -1, -1.0, length_penalty, 0, 0, 0.0, 0.0, num_res_cutoff, 0.0, top_n)
         for k, v in kw.items():
             setattr(self, k, v)
+
+
+class VotesLayout(C.Structure):
+    """fd_votes_layout: u32 votes[planes][n_queries][n_structs] in device memory"""
+    _fields_ = [("n_queries", C.c_uint32), ("n_structs", C.c_uint32), ("narrow", C.c_uint32), ("edge_words", C.c_uint32),
+                ("planes", C.c_uint32), ("words", C.c_uint64)]
+
+
+class DeviceWords:
+    """A library-owned device buffer of u32 words exposed through __cuda_array_interface__ (as int32, so that any
+    collective library can sum it in place; two's-complement addition is bit-identical to unsigned)."""
+
+    def __init__(self, ptr, words):
+        self.__cuda_array_interface__ = {"shape": (int(words),), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
 
 
 class _StructHit(C.Structure):
@@ -108,6 +123,9 @@ def lib():
     sig("fd_count_query_batch", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(PP(_StructHit)),
                                           PP(PP(C.c_uint64))])
     sig("fd_last_posting_bytes", C.c_uint64, [VP])
+    sig("fd_votes_scan", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), PP(VP)])
+    sig("fd_votes_select", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), VP, C.c_uint32,
+                                     C.c_uint32, PP(PP(_StructHit)), PP(PP(C.c_uint64))])
     sig("fd_store_attach", C.c_int, [VP, PP(_StructBatch)])
     sig("fd_candidate_edges_batch", C.c_int, [VP, PP(_RetrievalQuery), C.c_uint32, VP, VP, C.c_uint64, PP(HashParams),
                                               C.c_float, PP(VP), PP(C.c_uint64), PP(VP), PP(C.c_uint64)])
@@ -286,10 +304,7 @@ class Context:
         self._check(lib().fd_get_entries(self.h, int(h), C.byref(p), C.byref(n)), "fd_get_entries")
         return _take(p, n.value, np.uint64)
 
-    def count_query_batch(self, queries, params=None):
-        """queries: list of dicts {hashes u32[], edge_of_hash u16[], edge_node u16[], n_nodes, expected_node_count}
-        -> list of structured arrays (HIT_DTYPE), one per query, idf descending / nid ascending"""
-        params = params or PrefilterParams()
+    def _query_array(self, queries):
         nq = len(queries)
         arr = (_Query * max(nq, 1))()
         keep = []
@@ -298,14 +313,47 @@ class Context:
             e = np.ascontiguousarray(q["edge_of_hash"], np.uint16)
             en = np.ascontiguousarray(q["edge_node"], np.uint16)
             keep += [h, e, en]
+            eg = None
+            if q.get("edge_group") is not None:
+                eg = np.ascontiguousarray(q["edge_group"], np.uint16)
+                keep.append(eg)
             arr[k] = _Query(len(h), _ptr(h), _ptr(e), len(en), _ptr(en), int(q["n_nodes"]),
-                            int(q.get("expected_node_count", q["n_nodes"])))
+                            int(q.get("expected_node_count", q["n_nodes"])), _ptr(eg))
+        return arr, keep
+
+    def count_query_batch(self, queries, params=None):
+        """queries: list of dicts {hashes u32[], edge_of_hash u16[], edge_node u16[], n_nodes, expected_node_count
+        [, edge_group u16[]]} -> list of structured arrays (HIT_DTYPE), one per query, idf descending / nid ascending"""
+        params = params or PrefilterParams()
+        nq = len(queries)
+        arr, keep = self._query_array(queries)
         ph, po = C.POINTER(_StructHit)(), C.POINTER(C.c_uint64)()
         self._check(lib().fd_count_query_batch(self.h, arr, nq, C.byref(params), C.byref(ph), C.byref(po)),
                     "fd_count_query_batch")
         off = _take(po, nq + 1, np.uint64)
         hits = _take(ph, int(off[-1]), HIT_DTYPE)
         return [hits[int(off[k]):int(off[k + 1])] for k in range(nq)]
+
+    # ---- multi-GPU: partial votes of a hash-range shard ----
+    def votes_scan(self, queries, params=None):
+        """-> (VotesLayout, device pointer) : partial votes of the attached shard for the whole batch"""
+        params = params or PrefilterParams()
+        arr, keep = self._query_array(queries)
+        lay, ptr = VotesLayout(), VP()
+        self._check(lib().fd_votes_scan(self.h, arr, len(queries), C.byref(params), C.byref(lay), C.byref(ptr)),
+                    "fd_votes_scan")
+        return lay, ptr.value
+
+    def votes_select(self, queries, layout, d_votes, q_begin, q_end, params=None):
+        params = params or PrefilterParams()
+        arr, keep = self._query_array(queries)
+        ph, po = C.POINTER(_StructHit)(), C.POINTER(C.c_uint64)()
+        self._check(lib().fd_votes_select(self.h, arr, len(queries), C.byref(params), C.byref(layout), VP(d_votes),
+                                          q_begin, q_end, C.byref(ph), C.byref(po)), "fd_votes_select")
+        n = q_end - q_begin
+        off = _take(po, n + 1, np.uint64)
+        hits = _take(ph, int(off[-1]), HIT_DTYPE)
+        return [hits[int(off[k]):int(off[k + 1])] for k in range(n)]
 
     def store_attach(self, batch):
         self._check(lib().fd_store_attach(self.h, C.byref(batch.c)), "fd_store_attach")

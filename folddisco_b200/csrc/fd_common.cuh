@@ -31,7 +31,7 @@ struct FdDeviceIndex {
     uint32_t *counts = nullptr;   // [count] postings per list
     uint32_t *dir = nullptr;      // [FD_DIR_SIZE+1] hashes[] position of the first hash with (hash >> FD_DIR_SHIFT) >= b
     uint32_t *skip_id = nullptr;  // [n_skip] see fd_query.cu
-    uint32_t *skip_pos = nullptr; // [n_skip]
+    uint8_t *skip_off = nullptr;  // [n_skip]
     uint64_t n_skip = 0;
     uint32_t *nres = nullptr; // [n_structs]
     float *plddt = nullptr;   // [n_structs]
@@ -57,6 +57,8 @@ struct fd_ctx {
     FdDeviceIndex idx;
     FdDeviceStore store;
     uint64_t last_posting_bytes = 0;
+    uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
+    uint64_t votes_cap = 0;    // capacity in u32 words
 };
 
 extern thread_local std::string fd_g_create_error;

@@ -12,7 +12,7 @@ static void fd_release_index(FdDeviceIndex &ix) {
     cudaFree(ix.counts);
     cudaFree(ix.dir);
     cudaFree(ix.skip_id);
-    cudaFree(ix.skip_pos);
+    cudaFree(ix.skip_off);
     cudaFree(ix.nres);
     cudaFree(ix.plddt);
     ix = FdDeviceIndex();
@@ -85,6 +85,7 @@ void fd_destroy(fd_ctx *ctx) {
     cudaSetDevice(ctx->device);
     fd_release_index(ctx->idx);
     fd_release_store(ctx->store);
+    cudaFree(ctx->votes);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -7,23 +7,30 @@
 // HBM layout of the attached index (fd_index_attach):
 //   hashes[count] u32 ascending | offsets[count+1] u64 | values[value_bytes] raw delta+LEB128 bytes (the file,
 //   unmodified) | counts[count] u32 postings per list | dir[2^20+1] u32 bucket directory over hash>>12 |
-//   skip_pos/skip_id[value_bytes/256+1]: for every 256-byte boundary of values[] the first varint start at or
-//   after it and the running structure id of its list at that point, so a list can be entered at any 256 B
-//   segment without decoding its prefix (the LEB128 stream is otherwise strictly sequential).
+//   skip_off u8 / skip_id u32 [value_bytes/64+2]: for every 64-byte granule of values[] the offset of the first
+//   varint that STARTS at or after the granule boundary and the running structure id of its list at that point,
+//   so a list can be entered at any granule without decoding its prefix (the LEB128 stream is otherwise strictly
+//   sequential) and every granule can be decoded independently of its neighbours.
 //
 // Kernels per batch:
 //   k3_lookup : one thread per query hash: directory + binary search -> byte range, posting count, idf weight
-//   k3_scan   : one CTA per (structure-id tile, query).  The tile's votes live in shared memory
-//               (packed match_count|idf fixed point, plus an edge bitmask per structure).  Work items are the
-//               256-byte segments of the query's lists that intersect the tile; each lane decodes one segment
-//               and votes with shared-memory atomics.  The epilogue derives node/edge counts, applies the
-//               length penalty and the structure filter, and appends survivors to the query's hit region.
+//   k3_scan   : one CTA per (structure-id tile, query).  The tile's votes live in shared memory (packed
+//               match_count|idf fixed point, plus edge-bitmask planes).  Work items are the 64-byte granules of
+//               the query's lists that intersect the tile; a granule is decoded by 8 lanes (one aligned 8-byte
+//               load each, 4 granules = 256 contiguous-per-granule bytes per warp step): every lane finds the
+//               varints that start in its 8 bytes from the terminator bits, decodes them from its own bytes plus
+//               the next lane's, an 8-lane scan turns deltas into ids, and votes are shared-memory atomics.
+//               The epilogue compacts the non-empty cells warp by warp, derives node/edge counts, applies the
+//               length penalty and the structure filter and appends survivors to the query's hit region --
+//               or (multi-GPU) dumps the tile's planes to the dense partial-vote buffer.
+//   k3_select_dense : the same epilogue over merged dense votes (multi-GPU, after the all-reduce).
 //   (cub segmented sort) + k3_gather: order hits by (idf desc, nid asc) and keep top_n.
 // Only posting bytes, skip entries and survivors touch HBM; the N-sized per-node-group arrays and O(N * edges)
 // bit sweeps of the reference never exist.
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cmath>
 
 #include "fd_common.cuh"
 
@@ -33,10 +40,12 @@ namespace {
 
 constexpr int DIR_SHIFT = 12;
 constexpr uint32_t DIR_SIZE = 1u << (32 - DIR_SHIFT);
-constexpr int SKIP_SHIFT = 8; // 256-byte segments
+constexpr int SKIP_SHIFT = 6; // 64-byte granules
 constexpr uint32_t SKIP_BYTES = 1u << SKIP_SHIFT;
+constexpr uint32_t VALUES_PAD = 256; // readable bytes after the last posting byte (vector loads of the last granule)
 
 constexpr int K3_THREADS = 256;
+constexpr int K3_WARPS = K3_THREADS / 32;
 constexpr int K3_MAX_HASHES_NARROW = 255; // match_count fits 8 bits
 constexpr int K3_MAX_HASHES = 4095;       // smem prefix array
 constexpr int K3_MAX_EDGE_WORDS = 8;      // 256 edges
@@ -55,7 +64,7 @@ __global__ void k3_build_dir(const uint32_t *hashes, uint64_t count, uint32_t *d
     for (uint32_t b = lo; b <= hi && b <= DIR_SIZE; b++) dir[b] = (uint32_t)k;
 }
 
-// number of varint terminators (bytes with the top bit clear) per 256-byte block
+// number of varint terminators (bytes with the top bit clear) per granule
 __global__ void k3_block_terms(const uint8_t *values, uint64_t nbytes, uint64_t nblocks, uint32_t *terms) {
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
@@ -91,33 +100,33 @@ __device__ __forceinline__ uint64_t list_containing(const uint64_t *offsets, uin
     return lo;
 }
 
-// first varint start >= p inside the list that begins at lstart (p > lstart)
+// first varint start >= p inside a list that begins before p
 __device__ __forceinline__ uint64_t varint_start_at_or_after(const uint8_t *values, uint64_t p) {
     while (values[p - 1] & 0x80u) p++;
     return p;
 }
 
-// For every 256-byte boundary b: skip_pos[b] and a (reset flag, partial id sum) pair whose segmented inclusive
-// scan is the running structure id at skip_pos[b].
+// For every granule boundary b: skip_off[b] and a (reset flag, partial id sum) pair whose segmented inclusive
+// scan is the running structure id at the first varint start at or after the boundary.
 __global__ void k3_skip_partials(const uint8_t *values, const uint64_t *offsets, uint64_t count, uint64_t nbytes,
-                                 uint64_t nblocks, uint32_t *skip_pos, uint64_t *partial) {
+                                 uint64_t nblocks, uint8_t *skip_off, uint64_t *partial) {
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const uint64_t p0 = b << SKIP_SHIFT;
     if (p0 >= nbytes) { // pad entry
-        skip_pos[b] = (uint32_t)min(nbytes, (uint64_t)0xffffffffu);
+        skip_off[b] = 0;
         partial[b] = 1ull << 32;
         return;
     }
     const uint64_t l = list_containing(offsets, count, p0);
     const uint64_t lstart = offsets[l];
     if (lstart == p0) {
-        skip_pos[b] = (uint32_t)p0;
+        skip_off[b] = 0;
         partial[b] = 1ull << 32; // reset, running id 0
         return;
     }
     const uint64_t pos = varint_start_at_or_after(values, p0);
-    skip_pos[b] = (uint32_t)pos;
+    skip_off[b] = (uint8_t)(pos - p0);
     uint64_t from;
     uint64_t flag;
     const uint64_t prev0 = p0 - SKIP_BYTES; // b >= 1 here because lstart < p0
@@ -173,7 +182,7 @@ struct IndexView {
     const uint8_t *values;
     const uint32_t *counts;
     const uint32_t *dir;
-    const uint32_t *skip_pos;
+    const uint8_t *skip_off;
     const uint32_t *skip_id;
     const uint32_t *nres;
     const float *plddt;
@@ -207,6 +216,7 @@ struct QueryDesc {       // one per query (device copy)
     uint32_t n_edges;
     uint32_t n_nodes;
     uint32_t expected_node_count;
+    uint32_t group_iters; // (largest number of vote bits that stand for one query edge) - 1; 0 = no groups
 };
 
 __global__ void k3_lookup(IndexView ix, const uint32_t *qhashes, uint32_t n_qhashes, float freq_filter, QHash *out) {
@@ -229,9 +239,11 @@ __global__ void k3_lookup(IndexView ix, const uint32_t *qhashes, uint32_t n_qhas
     out[k] = r;
 }
 
-// per-query totals in a fixed order (deterministic): postings, posting bytes, sum of idf weights
-__global__ void k3_query_sums(const QueryDesc *queries, const QHash *qh, uint32_t n_queries,
-                              unsigned long long *postings, unsigned long long *bytes, float *idf_sum) {
+// per-query totals in a fixed order (deterministic): postings, posting bytes, bound of the idf sum.
+// bound_mode: n_hashes * log2(N) -- the same on every rank of a sharded index, whatever the shard holds.
+__global__ void k3_query_sums(const QueryDesc *queries, const QHash *qh, uint32_t n_queries, uint32_t n_structs,
+                              int bound_mode, unsigned long long *postings, unsigned long long *bytes,
+                              float *idf_sum) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_queries) return;
     const QueryDesc d = queries[q];
@@ -245,7 +257,7 @@ __global__ void k3_query_sums(const QueryDesc *queries, const QHash *qh, uint32_
     }
     postings[q] = p;
     bytes[q] = b;
-    idf_sum[q] = s;
+    idf_sum[q] = bound_mode ? (float)d.n_hashes * log2f((float)max(n_structs, 2u)) : s;
 }
 
 __global__ void k3_counts_only(IndexView ix, const uint32_t *qhashes, uint64_t n, uint32_t *out) {
@@ -280,6 +292,12 @@ __global__ void k3_decode_list(IndexView ix, uint32_t hash, uint64_t *out, unsig
     *n_out = n;
 }
 
+// pen[nid] = (nres as f32).powf(-lp)  (count_query.rs:199), once per batch instead of once per (query, structure)
+__global__ void k3_length_penalty(const uint32_t *nres, uint32_t n, float lp, float *pen) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) pen[k] = powf((float)nres[k], -lp);
+}
+
 struct HitRec { // 16 bytes; key/value for the segmented sort are derived from it
     uint32_t nid;
     uint32_t match_count;
@@ -295,14 +313,141 @@ struct FilterParams {
     float plddt_cutoff;
 };
 
-// Shared-memory vote tile.  NARROW: one word = match_count (8 bits) | idf fixed point (24 bits);
-// wide: separate match and idf words.  EW edge-bitmask words per structure.
+// idf fixed-point scale: the sum over all of the query's hashes must fit the accumulator
+template <bool NARROW>
+__device__ __forceinline__ float idf_scale(float idf_total) {
+    return exp2f(floorf(log2f((NARROW ? 16777215.0f : 4294967040.0f) / (idf_total + 1.0f))));
+}
+
+// terminator bits (top bit clear) of the four bytes of w as a 4-bit mask, bit i = byte i
+__device__ __forceinline__ uint32_t term_mask4(uint32_t w) {
+    return ((((~w) >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+// LEB128 value starting at the low byte of x0 (4 bytes) with the fifth byte in the low bits of x1
+__device__ __forceinline__ uint32_t varint_at(uint32_t x0, uint32_t x1) {
+    uint32_t v = x0 & 0x7Fu;
+    if (x0 & 0x80u) {
+        v |= (x0 >> 1) & 0x3F80u;
+        if (x0 & 0x8000u) {
+            v |= (x0 >> 2) & 0x1FC000u;
+            if (x0 & 0x800000u) {
+                v |= (x0 >> 3) & 0xFE00000u;
+                if (x0 & 0x80000000u) v |= x1 << 28;
+            }
+        }
+    }
+    return v;
+}
+
+// Count/filter/append epilogue over a range of vote cells [0, T) (ids lo .. lo+T).  acc / match / edge are the
+// planes (shared or global memory); edge plane i is edge + i * edge_stride.  Non-empty cells are compacted warp
+// by warp through a small shared-memory queue so that the per-cell work runs with full lanes.
 template <bool NARROW, int EW>
+__device__ __forceinline__ void emit_cells(const uint32_t *acc, const uint32_t *match, const uint32_t *edge,
+                                           size_t edge_stride, uint32_t T, uint32_t lo, const QueryDesc &qd,
+                                           const uint32_t *node_mask, const uint32_t *cont_mask /* [EW] */,
+                                           uint32_t *wqueue /* [K3_WARPS * 64] */,
+                                           float inv_scale, const IndexView &ix, const float *pen,
+                                           const FilterParams &fp, unsigned int *hit_count, HitRec *hits_out) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wq = wqueue + warp * 64;
+    uint32_t pending = 0;
+    const uint32_t n_chunks = (T + 31) >> 5;
+    auto process = [&](uint32_t n_take) { // the first n_take queue entries, one per lane
+        bool pass = false;
+        HitRec rec{0, 0, 0, 0.f};
+        if (lane < n_take) {
+            const uint32_t x = wq[lane];
+            const uint32_t a = acc[x];
+            const uint32_t mc = NARROW ? (a >> 24) : match[x];
+            const uint32_t fixed = NARROW ? (a & 0xffffffu) : a;
+            uint32_t ew[EW];
+            uint32_t ec = 0;
+#pragma unroll
+            for (int i = 0; i < EW; i++) {
+                ew[i] = edge[(size_t)i * edge_stride + x];
+                // bits of one group (fd_query.edge_group) count once: smear every set bit down to the first
+                // bit of its group, then count first bits
+                uint32_t g = ew[i];
+                const uint32_t cm = cont_mask[i];
+                for (uint32_t it = 0; it < qd.group_iters; it++) g |= (g & cm) >> 1;
+                ec += __popc(g & ~cm);
+            }
+            uint32_t nc = 0;
+            for (uint32_t nd = 0; nd < qd.n_nodes; nd++) {
+                uint32_t any = 0;
+#pragma unroll
+                for (int i = 0; i < EW; i++) any |= ew[i] & node_mask[nd * EW + i];
+                nc += any != 0;
+            }
+            const uint32_t nid = lo + x;
+            const uint32_t nr = ix.nres[nid];
+            const float idf = ((float)fixed * inv_scale) * pen[nid];
+            pass = true; // filter.rs:76-100
+            if (fp.total_match_count > 0) pass = pass && mc >= fp.total_match_count;
+            if (fp.covered_node_count > 0) pass = pass && nc >= fp.covered_node_count;
+            if (fp.covered_node_ratio > 0.f)
+                pass = pass && (float)nc / (float)qd.expected_node_count >= fp.covered_node_ratio;
+            if (fp.idf_score_cutoff > 0.f) pass = pass && idf >= fp.idf_score_cutoff;
+            if (fp.num_res_cutoff > 0) pass = pass && nr <= fp.num_res_cutoff;
+            if (fp.plddt_cutoff > 0.f) pass = pass && ix.plddt[nid] >= fp.plddt_cutoff;
+            rec = HitRec{nid, mc, (nc << 16) | (ec & 0xffffu), idf};
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(hit_count, (unsigned int)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+            if (pass) hits_out[pos] = rec;
+        }
+    };
+    for (uint32_t c = warp; c < n_chunks; c += K3_WARPS) {
+        const uint32_t x = (c << 5) + lane;
+        bool nonempty = false;
+        if (x < T) nonempty = NARROW ? (acc[x] >> 24) != 0 : match[x] != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, nonempty);
+        if (nonempty) wq[pending + __popc(m & ((1u << lane) - 1))] = x;
+        pending += __popc(m);
+        __syncwarp();
+        if (pending >= 32) {
+            process(32);
+            __syncwarp();
+            const uint32_t rest = pending - 32;
+            uint32_t t = 0;
+            if (lane < rest) t = wq[32 + lane];
+            __syncwarp();
+            if (lane < rest) wq[lane] = t;
+            pending = rest;
+            __syncwarp();
+        }
+    }
+    if (pending) process(pending);
+}
+
+// node_mask[nd * EW + w]: vote bits whose source node is nd; cont_mask[w]: vote bits that continue the group of
+// the previous bit.  Caller zeroes both and synchronises before and after.
+template <int EW>
+__device__ __forceinline__ void build_edge_masks(const QueryDesc &qd, const uint16_t *edge_node,
+                                                 const uint16_t *edge_group, uint32_t *node_mask,
+                                                 uint32_t *cont_mask) {
+    for (uint32_t e = threadIdx.x; e < qd.n_edges; e += K3_THREADS) {
+        atomicOr(&node_mask[edge_node[qd.edge_begin + e] * EW + (e >> 5)], 1u << (e & 31));
+        if (qd.group_iters && (e & 31) && edge_group[qd.edge_begin + e] == edge_group[qd.edge_begin + e - 1])
+            atomicOr(&cont_mask[e >> 5], 1u << (e & 31));
+    }
+}
+
+// Shared-memory vote tile.  NARROW: plane 0 = match_count (8 bits) | idf fixed point (24 bits);
+// wide: separate idf and match planes.  EW edge-bitmask planes.  DUMP: write the planes to the dense
+// partial-vote buffer instead of running the epilogue (multi-GPU).
+template <bool NARROW, int EW, bool DUMP>
 __global__ void __launch_bounds__(K3_THREADS)
     k3_scan(IndexView ix, const QueryDesc *queries, const QHash *qh, const uint16_t *edge_of_hash,
-            const uint16_t *edge_node, const float *idf_sum_per_query, uint32_t tile_ids, FilterParams fp,
-            const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits) {
-    extern __shared__ uint32_t smem[];
+            const uint16_t *edge_node, const uint16_t *edge_group, const float *idf_sum_per_query, const float *pen, uint32_t tile_ids,
+            FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits,
+            uint32_t *dense /* DUMP: [planes][nq][N] */) {
+    extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t q = blockIdx.y;
     const QueryDesc qd = queries[q];
     const uint32_t lo = blockIdx.x * tile_ids;
@@ -310,33 +455,27 @@ __global__ void __launch_bounds__(K3_THREADS)
     const uint32_t T = hi - lo;
     const bool single_tile = gridDim.x == 1;
     const uint32_t Q = qd.n_hashes;
+    constexpr uint32_t PLANES = (NARROW ? 1 : 2) + EW;
 
-    // smem carve-up
+    // smem carve-up (tile_ids is a multiple of 32, so every plane is 16-byte aligned)
     uint32_t *w_acc = smem;                                  // [tile_ids] narrow: packed; wide: idf fixed
     uint32_t *w_match = NARROW ? nullptr : w_acc + tile_ids; // [tile_ids] wide only
-    uint32_t *w_edge = w_acc + (NARROW ? 1 : 2) * tile_ids;  // [tile_ids * EW]
-    uint32_t *item_prefix = w_edge + (size_t)tile_ids * EW;  // [Q + 1]
-    uint32_t *seg_lo = item_prefix + (Q + 1);                // [Q] first relevant segment of each list
+    uint32_t *w_edge = w_acc + (NARROW ? 1 : 2) * tile_ids;  // EW planes of [tile_ids]
+    uint32_t *item_prefix = w_acc + (size_t)PLANES * tile_ids; // [Q + 1]
+    uint32_t *seg_lo = item_prefix + (Q + 1);                // [Q] first relevant granule of each list
     uint32_t *node_mask = seg_lo + Q;                        // [n_nodes * EW]
+    uint32_t *cont_mask = node_mask + qd.n_nodes * EW;       // [EW]
+    uint32_t *wqueue = cont_mask + EW;                       // [K3_WARPS * 64]
     __shared__ uint32_t s_total_items;
 
-    for (uint32_t i = threadIdx.x; i < T * (NARROW ? 1u : 2u); i += K3_THREADS) w_acc[i] = 0;
-    if (NARROW) {
-        for (uint32_t i = threadIdx.x; i < T * EW; i += K3_THREADS) w_edge[i] = 0;
-    } else {
-        for (uint32_t i = threadIdx.x; i < T * EW; i += K3_THREADS) w_edge[i] = 0;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem);
+        const uint32_t n4 = (PLANES * tile_ids) >> 2;
+        for (uint32_t i = threadIdx.x; i < n4; i += K3_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
-    for (uint32_t i = threadIdx.x; i < qd.n_nodes * EW; i += K3_THREADS) node_mask[i] = 0;
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < qd.n_edges; e += K3_THREADS)
-        atomicOr(&node_mask[edge_node[qd.edge_begin + e] * EW + (e >> 5)], 1u << (e & 31));
+    for (uint32_t i = threadIdx.x; i < qd.n_nodes * EW + EW; i += K3_THREADS) node_mask[i] = 0; // + cont_mask
 
-    // fixed-point scale for idf: the sum over all of the query's hashes must fit the accumulator
-    const float idf_total = idf_sum_per_query[q] + 1.0f;
-    const float scale = exp2f(floorf(log2f((NARROW ? 16777215.0f : 4294967040.0f) / idf_total)));
-    const float inv_scale = 1.0f / scale;
-
-    // ---- which 256-byte segments of each list intersect this tile ----
+    // ---- which 64-byte granules of each list intersect this tile ----
     for (uint32_t k = threadIdx.x; k < Q; k += K3_THREADS) {
         const QHash h = qh[qd.hash_begin + k];
         uint32_t n_items = 0, first = 0;
@@ -347,9 +486,10 @@ __global__ void __launch_bounds__(K3_THREADS)
                 first = 0;
                 n_items = nseg;
             } else {
-                // r(k') = skip_id[b0 + k'] for k' in [1, nseg-1], non-decreasing
+                // r(k') = skip_id[b0 + k'] for k' in [1, nseg-1], non-decreasing: the id of the last posting
+                // that starts before granule k'
                 const uint32_t *r = ix.skip_id + b0;
-                uint32_t a = 1, b = nseg; // count of k' with r(k') < lo
+                uint32_t a = 1, b = nseg; // first k' with r(k') >= lo
                 while (a < b) {
                     uint32_t m = (a + b) >> 1;
                     if (r[m] < lo) a = m + 1;
@@ -364,8 +504,8 @@ __global__ void __launch_bounds__(K3_THREADS)
                     else b = m;
                 }
                 const uint32_t below_hi = a - 1;
-                first = below_lo;                 // segment below_lo may still hold ids >= lo
-                n_items = below_hi + 1 - below_lo; // segments [below_lo, below_hi]
+                first = below_lo;                  // granule below_lo may still hold ids >= lo
+                n_items = below_hi + 1 - below_lo; // granules [below_lo, below_hi]
             }
         }
         seg_lo[k] = first;
@@ -373,6 +513,7 @@ __global__ void __launch_bounds__(K3_THREADS)
     }
     if (threadIdx.x == 0) item_prefix[0] = 0;
     __syncthreads();
+    build_edge_masks<EW>(qd, edge_node, edge_group, node_mask, cont_mask);
     // inclusive scan of item_prefix[1..Q] (Q is small; one warp, chunked)
     if (threadIdx.x < 32) {
         uint32_t carry = 0;
@@ -392,99 +533,136 @@ __global__ void __launch_bounds__(K3_THREADS)
     __syncthreads();
     const uint32_t total_items = s_total_items;
 
-    // ---- decode + vote ----
-    for (uint32_t it = threadIdx.x; it < total_items; it += K3_THREADS) {
-        // list index: last k with item_prefix[k] <= it
-        uint32_t a = 0, b = Q;
-        while (b - a > 1) {
-            uint32_t m = (a + b) >> 1;
-            if (item_prefix[m] <= it) a = m;
-            else b = m;
-        }
-        const uint32_t k = a;
-        const QHash h = qh[qd.hash_begin + k];
-        const uint32_t seg = seg_lo[k] + (it - item_prefix[k]);
-        const uint64_t b0 = h.start >> SKIP_SHIFT;
-        const uint64_t last_block = (h.end - 1) >> SKIP_SHIFT;
-        uint64_t p = seg == 0 ? h.start : (uint64_t)ix.skip_pos[b0 + seg];
-        uint32_t id = seg == 0 ? 0u : ix.skip_id[b0 + seg];
-        const uint64_t pend = (b0 + seg) < last_block ? (uint64_t)ix.skip_pos[b0 + seg + 1] : h.end;
-        const uint32_t e = edge_of_hash[qd.hash_begin + k];
-        const uint32_t ebit = 1u << (e & 31), eword = e >> 5;
-        const uint32_t w = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
-        const uint32_t add = NARROW ? ((1u << 24) | w) : w;
-        uint32_t cur = 0;
-        int shift = 0;
-        for (; p < pend; p++) {
-            const uint32_t v = ix.values[p];
-            cur |= (v & 0x7Fu) << shift;
-            if (v & 0x80u) {
-                shift += 7;
-                continue;
+    const float scale = idf_scale<NARROW>(idf_sum_per_query[q]);
+    const float inv_scale = 1.0f / scale;
+
+    // ---- decode + vote: 8 lanes per granule, 32 granules per CTA step ----
+    const uint32_t sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    for (uint32_t it0 = 0; it0 < total_items; it0 += K3_THREADS / 8) {
+        const uint32_t it = it0 + grp;
+        const bool act = it < total_items;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, base = 0, add = 0, ebit = 0, eword = 0;
+        uint64_t A = 0, start_pos = 0, lim = 0;
+        if (act) {
+            uint32_t a = 0, b = Q; // list index: last k with item_prefix[k] <= it
+            while (b - a > 1) {
+                uint32_t m = (a + b) >> 1;
+                if (item_prefix[m] <= it) a = m;
+                else b = m;
             }
-            id += cur;
-            cur = 0;
-            shift = 0;
-            if (id >= hi) break;
-            if (id >= lo) {
-                const uint32_t x = id - lo;
-                atomicAdd(&w_acc[x], add);
-                if (!NARROW) atomicAdd(&w_match[x], 1u);
-                atomicOr(&w_edge[x * EW + eword], ebit);
+            const uint32_t k = a;
+            const QHash h = qh[qd.hash_begin + k];
+            const uint32_t seg = seg_lo[k] + (it - item_prefix[k]);
+            const uint64_t gi = (h.start >> SKIP_SHIFT) + seg;
+            const uint64_t G0 = gi << SKIP_SHIFT;
+            if (seg == 0) {
+                start_pos = h.start;
+            } else {
+                start_pos = G0 + ix.skip_off[gi];
+                base = ix.skip_id[gi];
+            }
+            lim = min(h.end, G0 + SKIP_BYTES);
+            A = G0 + 8u * sub;
+            const uint2 w = *reinterpret_cast<const uint2 *>(ix.values + A);
+            w0 = w.x;
+            w1 = w.y;
+            if (sub == 7) w2 = *reinterpret_cast<const uint32_t *>(ix.values + G0 + SKIP_BYTES);
+            const uint32_t e = edge_of_hash[qd.hash_begin + k];
+            ebit = 1u << (e & 31);
+            eword = e >> 5;
+            const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
+            add = NARROW ? ((1u << 24) | wgt) : wgt;
+        }
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, w0, 1, 8);
+        if (sub != 7) w2 = nxt;
+        const uint32_t tm8 = term_mask4(w0) | (term_mask4(w1) << 4);
+        uint32_t prevterm = (__shfl_up_sync(0xffffffffu, tm8, 1, 8) >> 7) & 1u;
+        if (sub == 0) prevterm = 0;
+        uint32_t sm = ((tm8 << 1) | prevterm) & 0xffu; // byte i starts a varint iff byte i-1 terminates one
+        {
+            const uint32_t v0 = start_pos > A ? (uint32_t)min(start_pos - A, (uint64_t)8) : 0u;
+            const uint32_t v1 = lim > A ? (uint32_t)min(lim - A, (uint64_t)8) : 0u;
+            const uint32_t valid = v1 > v0 ? (((1u << v1) - 1u) & ~((1u << v0) - 1u)) : 0u;
+            sm &= valid;
+            if (start_pos >= A && start_pos < A + 8 && start_pos < lim) sm |= 1u << (uint32_t)(start_pos - A);
+            if (!act) sm = 0;
+        }
+        // running sums of the deltas of the varints that start in this lane's bytes
+        uint32_t ds[8];
+        uint32_t run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if ((sm >> i) & 1u) {
+                const uint32_t x0 = i == 0 ? w0
+                                    : i < 4 ? __funnelshift_r(w0, w1, 8 * i)
+                                    : i == 4 ? w1
+                                             : __funnelshift_r(w1, w2, 8 * (i - 4));
+                const uint32_t x1 = i < 4 ? (w1 >> (8 * i)) : (w2 >> (8 * (i - 4)));
+                run += varint_at(x0, x1 & 0xffu);
+            }
+            ds[i] = run;
+        }
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o, 8);
+            if ((int)sub >= o) inc += t;
+        }
+        const uint32_t lane_base = base + inc - run;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if ((sm >> i) & 1u) {
+                const uint32_t id = lane_base + ds[i];
+                if (id >= lo && id < hi) {
+                    const uint32_t x = id - lo;
+                    atomicAdd(&w_acc[x], add);
+                    if (!NARROW) atomicAdd(&w_match[x], 1u);
+                    atomicOr(&w_edge[eword * tile_ids + x], ebit);
+                }
             }
         }
     }
     __syncthreads();
 
-    // ---- epilogue: counts, length penalty, filter, append ----
-    const uint64_t out_base = hit_offsets[q];
-    for (uint32_t x0 = 0; x0 < T; x0 += K3_THREADS) {
-        const uint32_t x = x0 + threadIdx.x;
-        bool pass = false;
-        HitRec rec{0, 0, 0, 0.f};
-        if (x < T) {
-            const uint32_t acc = w_acc[x];
-            const uint32_t mc = NARROW ? (acc >> 24) : w_match[x];
-            if (mc > 0) {
-                const uint32_t fixed = NARROW ? (acc & 0xffffffu) : acc;
-                uint32_t ew[EW];
-                uint32_t ec = 0;
-#pragma unroll
-                for (int i = 0; i < EW; i++) {
-                    ew[i] = w_edge[x * EW + i];
-                    ec += __popc(ew[i]);
-                }
-                uint32_t nc = 0;
-                for (uint32_t nd = 0; nd < qd.n_nodes; nd++) {
-                    uint32_t any = 0;
-#pragma unroll
-                    for (int i = 0; i < EW; i++) any |= ew[i] & node_mask[nd * EW + i];
-                    nc += any != 0;
-                }
-                const uint32_t nid = lo + x;
-                const uint32_t nr = ix.nres[nid];
-                // count_query.rs:199: idf_sum *= (nres as f32).powf(-lp)
-                const float idf = ((float)fixed * inv_scale) * powf((float)nr, -fp.length_penalty);
-                pass = true; // filter.rs:76-100
-                if (fp.total_match_count > 0) pass = pass && mc >= fp.total_match_count;
-                if (fp.covered_node_count > 0) pass = pass && nc >= fp.covered_node_count;
-                if (fp.covered_node_ratio > 0.f)
-                    pass = pass && (float)nc / (float)qd.expected_node_count >= fp.covered_node_ratio;
-                if (fp.idf_score_cutoff > 0.f) pass = pass && idf >= fp.idf_score_cutoff;
-                if (fp.num_res_cutoff > 0) pass = pass && nr <= fp.num_res_cutoff;
-                if (fp.plddt_cutoff > 0.f) pass = pass && ix.plddt[nid] >= fp.plddt_cutoff;
-                rec = HitRec{nid, mc, (nc << 16) | (ec & 0xffffu), idf};
-            }
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            const int lane = threadIdx.x & 31;
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(&hit_counts[q], (unsigned int)__popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
-            if (pass) hits[out_base + pos] = rec;
-        }
+    if (DUMP) {
+        // planes of this tile -> dense[plane][q][lo .. hi)
+        const size_t plane_stride = (size_t)gridDim.y * ix.n_structs;
+        uint32_t *dst = dense + (size_t)q * ix.n_structs + lo;
+        for (uint32_t p = 0; p < PLANES; p++)
+            for (uint32_t x = threadIdx.x; x < T; x += K3_THREADS)
+                dst[p * plane_stride + x] = w_acc[(size_t)p * tile_ids + x];
+    } else {
+        emit_cells<NARROW, EW>(w_acc, w_match, w_edge, tile_ids, T, lo, qd, node_mask, cont_mask, wqueue, inv_scale, ix,
+                               pen, fp, &hit_counts[q], hits + hit_offsets[q]);
     }
+}
+
+// The epilogue of k3_scan over merged dense votes: grid (id tiles, queries of the slice).
+template <bool NARROW, int EW>
+__global__ void __launch_bounds__(K3_THREADS)
+    k3_select_dense(IndexView ix, const QueryDesc *queries, const uint16_t *edge_node, const uint16_t *edge_group,
+                    const float *idf_sum_per_query, const float *pen, const uint32_t *dense, uint32_t n_queries,
+                    uint32_t q_begin, uint32_t tile_ids, FilterParams fp,
+                    const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits) {
+    __shared__ uint32_t node_mask[K3_MAX_NODES * EW];
+    __shared__ uint32_t cont_mask[EW];
+    __shared__ uint32_t wqueue[K3_WARPS * 64];
+    const uint32_t qs = blockIdx.y, q = q_begin + qs;
+    const QueryDesc qd = queries[q];
+    const uint32_t lo = blockIdx.x * tile_ids;
+    const uint32_t hi = min(ix.n_structs, lo + tile_ids);
+    for (uint32_t i = threadIdx.x; i < qd.n_nodes * EW; i += K3_THREADS) node_mask[i] = 0;
+    if (threadIdx.x < EW) cont_mask[threadIdx.x] = 0;
+    __syncthreads();
+    build_edge_masks<EW>(qd, edge_node, edge_group, node_mask, cont_mask);
+    __syncthreads();
+    const float inv_scale = 1.0f / idf_scale<NARROW>(idf_sum_per_query[q]);
+    const size_t plane_stride = (size_t)n_queries * ix.n_structs;
+    const uint32_t *acc = dense + (size_t)q * ix.n_structs + lo;
+    const uint32_t *match = NARROW ? nullptr : acc + plane_stride;
+    const uint32_t *edge = acc + (NARROW ? 1 : 2) * plane_stride;
+    emit_cells<NARROW, EW>(acc, match, edge, plane_stride, hi - lo, lo, qd, node_mask, cont_mask, wqueue, inv_scale, ix,
+                           pen, fp, &hit_counts[qs], hits + hit_offsets[qs]);
 }
 
 // sort key: idf descending, nid ascending  (query_pdb.rs:404 stable sort over ascending nid)
@@ -522,19 +700,261 @@ __global__ void k3_gather(const HitRec *hits, const uint32_t *sorted_vals, const
 
 IndexView make_view(const fd_ctx *ctx) {
     const FdDeviceIndex &d = ctx->idx;
-    return IndexView{d.hashes, d.offsets, d.values, d.counts, d.dir, d.skip_pos, d.skip_id, d.nres, d.plddt,
+    return IndexView{d.hashes, d.offsets, d.values, d.counts, d.dir, d.skip_off, d.skip_id, d.nres, d.plddt,
                      d.count, (uint32_t)d.n_structs};
 }
 
-template <bool NARROW, int EW>
-int launch_scan(fd_ctx *ctx, dim3 grid, size_t smem, IndexView ix, const QueryDesc *queries, const QHash *qh,
-                const uint16_t *edge_of_hash, const uint16_t *edge_node, const float *idf_sum, uint32_t tile_ids,
-                FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits) {
-    auto kern = k3_scan<NARROW, EW>;
-    FD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, K3_THREADS, smem, ctx->stream>>>(ix, queries, qh, edge_of_hash, edge_node, idf_sum, tile_ids, fp,
-                                                  hit_offsets, hit_counts, hits);
+// ------------------------------------------------------------------------------------------------
+// host side of a batch
+// ------------------------------------------------------------------------------------------------
+
+FilterParams make_filter(const fd_prefilter_params *params) {
+    return FilterParams{params->length_penalty,
+                        (uint32_t)std::min<uint64_t>(params->total_match_count, 0xffffffffu),
+                        (uint32_t)std::min<uint64_t>(params->covered_node_count, 0xffffffffu),
+                        params->covered_node_ratio,
+                        params->idf_score_cutoff,
+                        (uint32_t)std::min<uint64_t>(params->num_res_cutoff, 0xffffffffu),
+                        params->plddt_cutoff};
+}
+
+// The batch flattened on the host and uploaded: per-hash arrays, per-edge node ids, query descriptors.
+struct Batch {
+    std::vector<uint32_t> f_hash;
+    std::vector<uint16_t> f_edge, f_edge_node, f_edge_group;
+    std::vector<QueryDesc> descs;
+    uint32_t max_hashes = 0, max_edges = 0, max_nodes = 0;
+    bool narrow = true;
+    int ew = 1;
+    DevBuf<uint32_t> d_hash;
+    DevBuf<uint16_t> d_edge, d_edge_node, d_edge_group;
+    DevBuf<QueryDesc> d_desc;
+    DevBuf<QHash> d_qh;
+    DevBuf<unsigned long long> d_postings, d_bytes;
+    DevBuf<float> d_idfsum, d_pen;
+    std::vector<unsigned long long> h_postings;
+};
+
+// flatten + sample_query (count_query.rs:222-253) + upload + lookup + per-query sums + length-penalty table.
+// need_hashes = false: only descriptors and edge nodes are needed (fd_votes_select).
+int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                  bool need_hashes, int bound_mode, Batch &B) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t N = (uint32_t)ctx->idx.n_structs;
+    const bool has_r = params->sampling_ratio >= 0.f, has_c = params->sampling_count >= 0;
+    const bool sampling = has_r != has_c;
+    B.descs.resize(nq);
+    std::vector<uint32_t> sample_counts;
+    if (sampling) {
+        std::vector<uint32_t> all;
+        for (uint32_t q = 0; q < nq; q++) all.insert(all.end(), queries[q].hashes, queries[q].hashes + queries[q].n_hashes);
+        sample_counts.resize(all.size());
+        FD_TRY(fd_posting_counts(ctx, all.data(), all.size(), sample_counts.data()));
+    }
+    size_t sample_base = 0;
+    std::vector<uint32_t> order;
+    for (uint32_t q = 0; q < nq; q++) {
+        const fd_query &Q = queries[q];
+        if (Q.n_hashes && (!Q.hashes || !Q.edge_of_hash)) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL array");
+        if (Q.n_edges && !Q.edge_node) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL edge_node");
+        order.resize(Q.n_hashes);
+        for (uint32_t k = 0; k < Q.n_hashes; k++) order[k] = k;
+        if (sampling) {
+            const uint32_t *cnt = sample_counts.data() + sample_base;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cnt[a] < cnt[b]; });
+            size_t keep = has_r ? (size_t)std::ceil(params->sampling_ratio * (float)Q.n_hashes)
+                                : (size_t)params->sampling_count;
+            if (keep < order.size()) order.resize(keep);
+            sample_base += Q.n_hashes;
+        }
+        uint32_t group_iters = 0;
+        if (Q.edge_group) { // runs of equal values = one query edge; a run must stay inside one 32-bit mask word
+            uint32_t run = 1;
+            for (uint32_t e = 1; e < Q.n_edges; e++) {
+                if (Q.edge_group[e] == Q.edge_group[e - 1]) {
+                    if ((e & 31) == 0) return fd_fail(ctx, FD_ERR_ARG, "fd_query: an edge_group run crosses a multiple of 32");
+                    run++;
+                } else {
+                    run = 1;
+                }
+                group_iters = std::max(group_iters, run - 1);
+            }
+        }
+        B.descs[q] = QueryDesc{(uint32_t)B.f_hash.size(), (uint32_t)order.size(), (uint32_t)B.f_edge_node.size(),
+                               Q.n_edges, Q.n_nodes, Q.expected_node_count, group_iters};
+        for (uint32_t k : order) {
+            if (Q.edge_of_hash[k] >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
+            B.f_hash.push_back(Q.hashes[k]);
+            B.f_edge.push_back(Q.edge_of_hash[k]);
+        }
+        for (uint32_t e = 0; e < Q.n_edges; e++) {
+            if (Q.edge_node[e] >= Q.n_nodes) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_node out of range");
+            B.f_edge_node.push_back(Q.edge_node[e]);
+            B.f_edge_group.push_back(Q.edge_group ? Q.edge_group[e] : (uint16_t)e);
+        }
+        B.max_hashes = std::max<uint32_t>(B.max_hashes, (uint32_t)order.size());
+        B.max_edges = std::max(B.max_edges, Q.n_edges);
+        B.max_nodes = std::max(B.max_nodes, Q.n_nodes);
+    }
+    if (B.max_hashes > K3_MAX_HASHES || B.max_edges > 32 * K3_MAX_EDGE_WORDS || B.max_nodes > K3_MAX_NODES)
+        return fd_fail(ctx, FD_ERR_LIMIT,
+                       "query too large for the shared-memory vote kernel (limits: 4095 hashes, 256 edges, 256 "
+                       "nodes per query); whole-structure queries are not supported in this version");
+    B.narrow = B.max_hashes <= K3_MAX_HASHES_NARROW;
+    B.ew = B.max_edges <= 32 ? 1 : (B.max_edges <= 64 ? 2 : (B.max_edges <= 128 ? 4 : 8));
+    if (nq == 0 || N == 0) return FD_OK;
+    const uint32_t nqh = (uint32_t)B.f_hash.size();
+    FD_CUDA(ctx, B.d_edge_node.alloc(B.f_edge_node.size()));
+    FD_CUDA(ctx, B.d_edge_group.alloc(B.f_edge_group.size()));
+    FD_CUDA(ctx, B.d_desc.alloc(nq));
+    FD_CUDA(ctx, B.d_idfsum.alloc(nq));
+    FD_CUDA(ctx, B.d_pen.alloc(N));
+    FD_CUDA(ctx, B.d_postings.alloc(nq));
+    FD_CUDA(ctx, B.d_bytes.alloc(nq));
+    FD_CUDA(ctx, B.d_hash.alloc(nqh));
+    FD_CUDA(ctx, B.d_edge.alloc(nqh));
+    FD_CUDA(ctx, B.d_qh.alloc(nqh));
+    FD_CUDA(ctx, cudaMemcpyAsync(B.d_edge_node.p, B.f_edge_node.data(), B.f_edge_node.size() * 2, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(B.d_edge_group.p, B.f_edge_group.data(), B.f_edge_group.size() * 2, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(B.d_desc.p, B.descs.data(), nq * sizeof(QueryDesc), cudaMemcpyHostToDevice, s));
+    IndexView ix = make_view(ctx);
+    B.h_postings.assign(nq, 0);
+    StageTimer st(ctx, "lookup");
+    FD_LAUNCH(ctx, k3_length_penalty, fd_div_up(N, 256), 256, 0, ix.nres, N, params->length_penalty, B.d_pen.p);
+    if (need_hashes && nqh) {
+        FD_CUDA(ctx, cudaMemcpyAsync(B.d_hash.p, B.f_hash.data(), nqh * 4, cudaMemcpyHostToDevice, s));
+        FD_CUDA(ctx, cudaMemcpyAsync(B.d_edge.p, B.f_edge.data(), nqh * 2, cudaMemcpyHostToDevice, s));
+        FD_LAUNCH(ctx, k3_lookup, fd_div_up(nqh, 256), 256, 0, ix, B.d_hash.p, nqh, params->freq_filter, B.d_qh.p);
+    } else if (nqh) {
+        FD_CUDA(ctx, cudaMemsetAsync(B.d_qh.p, 0, nqh * sizeof(QHash), s));
+    }
+    FD_LAUNCH(ctx, k3_query_sums, fd_div_up(nq, 128), 128, 0, B.d_desc.p, B.d_qh.p, nq, N, bound_mode, B.d_postings.p,
+              B.d_bytes.p, B.d_idfsum.p);
+    if (need_hashes) {
+        std::vector<unsigned long long> h_bytes(nq);
+        FD_CUDA(ctx, cudaMemcpyAsync(B.h_postings.data(), B.d_postings.p, nq * 8, cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, cudaMemcpyAsync(h_bytes.data(), B.d_bytes.p, nq * 8, cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, st.finish());
+        ctx->last_posting_bytes = 0;
+        for (unsigned long long b : h_bytes) ctx->last_posting_bytes += b;
+    } else {
+        FD_CUDA(ctx, st.finish());
+    }
+    return FD_OK;
+}
+
+struct TilePlan {
+    uint32_t tile_ids, n_tiles;
+    size_t smem;
+};
+
+int plan_tiles(fd_ctx *ctx, const Batch &B, uint32_t N, TilePlan &tp) {
+    const uint32_t bytes_per_id = (B.narrow ? 4 : 8) + 4 * B.ew;
+    const size_t fixed_smem = (size_t)(2 * B.max_hashes + 2 + B.max_nodes * B.ew + B.ew + K3_WARPS * 64) * 4 + 64;
+    size_t budget = 72 * 1024; // 3 CTAs per SM
+    if (const char *e = getenv("FD_K3_TILE_KB")) budget = (size_t)std::max(8, atoi(e)) * 1024;
+    budget = std::min<size_t>(budget, 220 * 1024);
+    const size_t avail = budget > fixed_smem + 256 * bytes_per_id ? budget - fixed_smem : 256 * bytes_per_id;
+    uint32_t tile_ids = (uint32_t)(avail / bytes_per_id) & ~31u;
+    tile_ids = std::max<uint32_t>(256, tile_ids);
+    if (tile_ids > N) tile_ids = (N + 31) & ~31u;
+    tp.tile_ids = tile_ids;
+    tp.n_tiles = fd_div_up(N, tile_ids);
+    tp.smem = (size_t)tile_ids * bytes_per_id + fixed_smem;
+    if (tp.smem > 220 * 1024) return fd_fail(ctx, FD_ERR_LIMIT, "query needs more shared memory than one SM has");
+    return FD_OK;
+}
+
+template <bool NARROW, int EW, bool DUMP>
+int launch_scan_t(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
+                  const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense) {
+    auto kern = k3_scan<NARROW, EW, DUMP>;
+    FD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
+    kern<<<grid, K3_THREADS, tp.smem, ctx->stream>>>(ix, B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p,
+                                                     B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, tp.tile_ids, fp, hit_offsets, hit_counts,
+                                                     hits, dense);
     ctx->launches++;
+    return FD_OK;
+}
+
+template <bool DUMP>
+int launch_scan(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
+                const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense) {
+#define FD_SCAN_CASE(NARROW, EW) \
+    return launch_scan_t<NARROW, EW, DUMP>(ctx, grid, tp, ix, B, fp, hit_offsets, hit_counts, hits, dense)
+    if (B.narrow) {
+        if (B.ew == 1) FD_SCAN_CASE(true, 1);
+        else if (B.ew == 2) FD_SCAN_CASE(true, 2);
+        else if (B.ew == 4) FD_SCAN_CASE(true, 4);
+        else FD_SCAN_CASE(true, 8);
+    } else {
+        if (B.ew == 1) FD_SCAN_CASE(false, 1);
+        else if (B.ew == 2) FD_SCAN_CASE(false, 2);
+        else if (B.ew == 4) FD_SCAN_CASE(false, 4);
+        else FD_SCAN_CASE(false, 8);
+    }
+#undef FD_SCAN_CASE
+    return FD_ERR_ARG;
+}
+
+template <bool NARROW, int EW>
+int launch_select_t(fd_ctx *ctx, dim3 grid, IndexView ix, const Batch &B, const uint32_t *dense, uint32_t q_begin,
+                    uint32_t tile_ids, FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts,
+                    HitRec *hits) {
+    k3_select_dense<NARROW, EW><<<grid, K3_THREADS, 0, ctx->stream>>>(
+        ix, B.d_desc.p, B.d_edge_node.p, B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, dense, (uint32_t)B.descs.size(),
+        q_begin, tile_ids, fp, hit_offsets, hit_counts, hits);
+    ctx->launches++;
+    return FD_OK;
+}
+
+// Orders the hit regions by (idf desc, nid asc), keeps top_n per query and copies them to the host.
+// hit_off (host) / d_hit_off: region offsets of nsel queries; d_hit_cnt: survivors per query.
+int select_and_copy(fd_ctx *ctx, uint32_t nsel, const std::vector<uint64_t> &hit_off, const DevBuf<uint64_t> &d_hit_off,
+                    const DevBuf<unsigned int> &d_hit_cnt, const DevBuf<HitRec> &d_hits, uint64_t top_n, uint32_t N,
+                    fd_struct_hit **out_hits, uint64_t *h_off) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t pool = hit_off[nsel];
+    std::vector<unsigned int> h_cnt(nsel);
+    DevBuf<uint64_t> d_seg_end, d_keys, d_keys2, d_out_off;
+    DevBuf<uint32_t> d_vals, d_vals2;
+    StageTimer st(ctx, "select");
+    FD_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_hit_cnt.p, nsel * 4, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, d_keys.alloc(pool));
+    FD_CUDA(ctx, d_keys2.alloc(pool));
+    FD_CUDA(ctx, d_vals.alloc(pool));
+    FD_CUDA(ctx, d_vals2.alloc(pool));
+    FD_CUDA(ctx, d_seg_end.alloc(nsel));
+    dim3 g2(std::max<uint32_t>(1, std::min<uint32_t>(64, fd_div_up(N, 256))), nsel);
+    FD_LAUNCH(ctx, k3_make_sort_keys, g2, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, nsel, d_keys.p, d_vals.p);
+    FD_LAUNCH(ctx, k3_segment_ends, fd_div_up(nsel, 256), 256, 0, d_hit_off.p, d_hit_cnt.p, nsel, d_seg_end.p);
+    size_t tb = 0;
+    cub::DeviceSegmentedSort::SortPairs(nullptr, tb, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p, (int64_t)pool,
+                                        (int64_t)nsel, d_hit_off.p, d_seg_end.p, s);
+    DevBuf<uint8_t> tmp;
+    FD_CUDA(ctx, tmp.alloc(tb));
+    if (pool)
+        FD_CUDA(ctx, cub::DeviceSegmentedSort::SortPairs(tmp.p, tb, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p,
+                                                         (int64_t)pool, (int64_t)nsel, d_hit_off.p, d_seg_end.p, s));
+    ctx->launches += 3;
+    FD_CUDA(ctx, cudaStreamSynchronize(s));
+    h_off[0] = 0;
+    for (uint32_t q = 0; q < nsel; q++) h_off[q + 1] = h_off[q] + std::min<uint64_t>(h_cnt[q], top_n);
+    const uint64_t n_out = h_off[nsel];
+    DevBuf<fd_struct_hit> d_out;
+    FD_CUDA(ctx, d_out.alloc(n_out));
+    FD_CUDA(ctx, d_out_off.alloc(nsel + 1));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_out_off.p, h_off, (nsel + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (n_out) FD_LAUNCH(ctx, k3_gather, g2, 256, 0, d_hits.p, d_vals2.p, d_hit_off.p, d_out_off.p, d_out.p);
+    fd_struct_hit *h_hits = (fd_struct_hit *)malloc(std::max<uint64_t>(n_out, 1) * sizeof(fd_struct_hit));
+    if (!h_hits) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    cudaError_t e = cudaMemcpyAsync(h_hits, d_out.p, n_out * sizeof(fd_struct_hit), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = st.finish();
+    if (e != cudaSuccess) {
+        free(h_hits);
+        return fd_fail(ctx, FD_ERR_CUDA, std::string("select: ") + cudaGetErrorString(e));
+    }
+    *out_hits = h_hits;
     return FD_OK;
 }
 
@@ -549,8 +969,6 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     if (!offsets || (count && (!hashes || !values)) || (n_structs && !nres))
         return fd_fail(ctx, FD_ERR_ARG, "fd_index_attach: NULL argument");
     if (count > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "more than 2^32 distinct hashes");
-    if (value_bytes > 0xfffffff0ull)
-        return fd_fail(ctx, FD_ERR_LIMIT, "posting bytes per device must stay below 4 GiB in this version; shard the index");
     if (n_structs > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "structure ids must fit in 32 bits");
     if (offsets[0] != 0 || offsets[count] != value_bytes)
         return fd_fail(ctx, FD_ERR_ARG, "fd_index_attach: offsets[0] must be 0 and offsets[count] == value_bytes");
@@ -561,10 +979,10 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     const uint64_t nblocks = (value_bytes >> SKIP_SHIFT) + 2;
     FD_CUDA(ctx, cudaMalloc(&d.hashes, std::max<uint64_t>(count, 1) * 4));
     FD_CUDA(ctx, cudaMalloc(&d.offsets, (count + 1) * 8));
-    FD_CUDA(ctx, cudaMalloc(&d.values, value_bytes + 16));
+    FD_CUDA(ctx, cudaMalloc(&d.values, value_bytes + VALUES_PAD));
     FD_CUDA(ctx, cudaMalloc(&d.counts, std::max<uint64_t>(count, 1) * 4));
     FD_CUDA(ctx, cudaMalloc(&d.dir, ((uint64_t)DIR_SIZE + 2) * 4));
-    FD_CUDA(ctx, cudaMalloc(&d.skip_pos, nblocks * 4));
+    FD_CUDA(ctx, cudaMalloc(&d.skip_off, nblocks));
     FD_CUDA(ctx, cudaMalloc(&d.skip_id, nblocks * 4));
     FD_CUDA(ctx, cudaMalloc(&d.nres, std::max<uint64_t>(n_structs, 1) * 4));
     FD_CUDA(ctx, cudaMalloc(&d.plddt, std::max<uint64_t>(n_structs, 1) * 4));
@@ -575,7 +993,9 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     FD_CUDA(ctx, cudaMemcpyAsync(d.hashes, hashes, count * 4, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d.offsets, offsets, (count + 1) * 8, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d.values, values, value_bytes, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemsetAsync(d.values + value_bytes, 0, 16, s));
+    FD_CUDA(ctx, cudaMemsetAsync(d.values + value_bytes, 0, VALUES_PAD, s));
+    FD_CUDA(ctx, cudaMemsetAsync(d.skip_off, 0, nblocks, s));
+    FD_CUDA(ctx, cudaMemsetAsync(d.skip_id, 0, nblocks * 4, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d.nres, nres, n_structs * 4, cudaMemcpyHostToDevice, s));
     if (plddt) FD_CUDA(ctx, cudaMemcpyAsync(d.plddt, plddt, n_structs * 4, cudaMemcpyHostToDevice, s));
     else FD_CUDA(ctx, cudaMemsetAsync(d.plddt, 0, std::max<uint64_t>(n_structs, 1) * 4, s));
@@ -605,7 +1025,7 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     // skip table
     if (count) {
         FD_LAUNCH(ctx, k3_skip_partials, fd_div_up(nblocks, 256), 256, 0, d.values, d.offsets, count, value_bytes,
-                  nblocks, d.skip_pos, partial.p);
+                  nblocks, d.skip_off, partial.p);
         tb = tb2;
         FD_CUDA(ctx, cub::DeviceScan::InclusiveScan(tmp.p, tb, partial.p, scanned.p, SegScanOp(), nblocks, s));
         ctx->launches += 2;
@@ -668,195 +1088,145 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
     *out_offsets = nullptr;
     cudaStream_t s = ctx->stream;
     const uint32_t N = (uint32_t)ctx->idx.n_structs;
-
-    // ---- flatten the batch on the host, applying sample_query (count_query.rs:222-253) if requested ----
-    const bool has_r = params->sampling_ratio >= 0.f, has_c = params->sampling_count >= 0;
-    const bool sampling = has_r != has_c;
-    std::vector<uint32_t> f_hash, f_query;
-    std::vector<uint16_t> f_edge, f_edge_node;
-    std::vector<QueryDesc> descs(nq);
-    uint32_t max_hashes = 0, max_edges = 0, max_nodes = 0;
-    std::vector<uint32_t> sample_counts;
-    if (sampling) {
-        std::vector<uint32_t> all;
-        for (uint32_t q = 0; q < nq; q++) all.insert(all.end(), queries[q].hashes, queries[q].hashes + queries[q].n_hashes);
-        sample_counts.resize(all.size());
-        FD_TRY(fd_posting_counts(ctx, all.data(), all.size(), sample_counts.data()));
-    }
-    size_t sample_base = 0;
-    for (uint32_t q = 0; q < nq; q++) {
-        const fd_query &Q = queries[q];
-        if (Q.n_hashes && (!Q.hashes || !Q.edge_of_hash)) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL array");
-        if (Q.n_edges && !Q.edge_node) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL edge_node");
-        std::vector<uint32_t> order(Q.n_hashes);
-        for (uint32_t k = 0; k < Q.n_hashes; k++) order[k] = k;
-        if (sampling) {
-            const uint32_t *cnt = sample_counts.data() + sample_base;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cnt[a] < cnt[b]; });
-            size_t keep = has_r ? (size_t)std::ceil(params->sampling_ratio * (float)Q.n_hashes)
-                                : (size_t)params->sampling_count;
-            if (keep < order.size()) order.resize(keep);
-            sample_base += Q.n_hashes;
-        }
-        descs[q] = QueryDesc{(uint32_t)f_hash.size(), (uint32_t)order.size(), (uint32_t)f_edge_node.size(),
-                             Q.n_edges, Q.n_nodes, Q.expected_node_count};
-        for (uint32_t k : order) {
-            if (Q.edge_of_hash[k] >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
-            f_hash.push_back(Q.hashes[k]);
-            f_query.push_back(q);
-            f_edge.push_back(Q.edge_of_hash[k]);
-        }
-        for (uint32_t e = 0; e < Q.n_edges; e++) {
-            if (Q.edge_node[e] >= Q.n_nodes) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_node out of range");
-            f_edge_node.push_back(Q.edge_node[e]);
-        }
-        max_hashes = std::max<uint32_t>(max_hashes, (uint32_t)order.size());
-        max_edges = std::max(max_edges, Q.n_edges);
-        max_nodes = std::max(max_nodes, Q.n_nodes);
-    }
-    if (max_hashes > K3_MAX_HASHES || max_edges > 32 * K3_MAX_EDGE_WORDS || max_nodes > K3_MAX_NODES)
-        return fd_fail(ctx, FD_ERR_LIMIT,
-                       "query too large for the shared-memory vote kernel (limits: 4095 hashes, 256 edges, 256 "
-                       "nodes per query); whole-structure queries are not supported in this version");
+    ctx->last_posting_bytes = 0;
+    Batch B;
+    FD_TRY(prepare_batch(ctx, queries, nq, params, true, 0, B));
     uint64_t *h_off = (uint64_t *)calloc((size_t)nq + 1, 8);
     if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
-    ctx->last_posting_bytes = 0;
-    if (nq == 0 || N == 0 || f_hash.empty()) {
+    if (nq == 0 || N == 0 || B.f_hash.empty()) {
         *out_offsets = h_off;
         *out_hits = (fd_struct_hit *)malloc(sizeof(fd_struct_hit));
         return FD_OK;
     }
-    const uint32_t nqh = (uint32_t)f_hash.size();
-
-    DevBuf<uint32_t> d_hash;
-    DevBuf<uint16_t> d_edge, d_edge_node;
-    DevBuf<QueryDesc> d_desc;
-    DevBuf<QHash> d_qh;
-    DevBuf<unsigned long long> d_postings, d_bytes;
-    DevBuf<float> d_idfsum;
-    FD_CUDA(ctx, d_hash.alloc(nqh));
-    FD_CUDA(ctx, d_edge.alloc(nqh));
-    FD_CUDA(ctx, d_edge_node.alloc(f_edge_node.size()));
-    FD_CUDA(ctx, d_desc.alloc(nq));
-    FD_CUDA(ctx, d_qh.alloc(nqh));
-    FD_CUDA(ctx, d_postings.alloc(nq));
-    FD_CUDA(ctx, d_bytes.alloc(nq));
-    FD_CUDA(ctx, d_idfsum.alloc(nq));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_hash.p, f_hash.data(), nqh * 4, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_edge.p, f_edge.data(), nqh * 2, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_edge_node.p, f_edge_node.data(), f_edge_node.size() * 2, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_desc.p, descs.data(), nq * sizeof(QueryDesc), cudaMemcpyHostToDevice, s));
-
-    IndexView ix = make_view(ctx);
-    std::vector<unsigned long long> h_postings(nq);
-    {
-        StageTimer st(ctx, "lookup");
-        FD_LAUNCH(ctx, k3_lookup, fd_div_up(nqh, 256), 256, 0, ix, d_hash.p, nqh, params->freq_filter, d_qh.p);
-        FD_LAUNCH(ctx, k3_query_sums, fd_div_up(nq, 128), 128, 0, d_desc.p, d_qh.p, nq, d_postings.p, d_bytes.p,
-                  d_idfsum.p);
-        std::vector<unsigned long long> h_bytes(nq);
-        FD_CUDA(ctx, cudaMemcpyAsync(h_postings.data(), d_postings.p, nq * 8, cudaMemcpyDeviceToHost, s));
-        FD_CUDA(ctx, cudaMemcpyAsync(h_bytes.data(), d_bytes.p, nq * 8, cudaMemcpyDeviceToHost, s));
-        FD_CUDA(ctx, st.finish());
-        for (unsigned long long b : h_bytes) ctx->last_posting_bytes += b;
-    }
     // hit regions: a query can hit at most min(N, its postings) structures
     std::vector<uint64_t> hit_off(nq + 1, 0);
-    for (uint32_t q = 0; q < nq; q++) hit_off[q + 1] = hit_off[q] + std::min<uint64_t>(N, h_postings[q]);
-    const uint64_t pool = hit_off[nq];
-    DevBuf<uint64_t> d_hit_off, d_seg_end, d_keys, d_keys2, d_out_off;
+    for (uint32_t q = 0; q < nq; q++) hit_off[q + 1] = hit_off[q] + std::min<uint64_t>(N, B.h_postings[q]);
+    DevBuf<uint64_t> d_hit_off;
     DevBuf<unsigned int> d_hit_cnt;
-    DevBuf<uint32_t> d_vals, d_vals2;
     DevBuf<HitRec> d_hits;
-    FD_CUDA(ctx, d_hit_off.alloc(nq + 1));
-    FD_CUDA(ctx, d_hit_cnt.alloc(nq));
-    FD_CUDA(ctx, d_hits.alloc(pool));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_hit_off.p, hit_off.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemsetAsync(d_hit_cnt.p, 0, nq * 4, s));
-
-    // ---- scan + vote ----
-    const bool narrow = max_hashes <= K3_MAX_HASHES_NARROW;
-    const int ew = max_edges <= 32 ? 1 : (max_edges <= 64 ? 2 : (max_edges <= 128 ? 4 : 8));
-    const uint32_t bytes_per_id = (narrow ? 4 : 8) + 4 * ew;
-    const size_t fixed_smem = (size_t)(2 * max_hashes + 2 + max_nodes * ew) * 4;
-    const size_t budget = 64 * 1024; // ~3 CTAs per SM
-    uint32_t tile_ids = (uint32_t)((budget - std::min(budget / 2, fixed_smem)) / bytes_per_id);
-    tile_ids = std::max<uint32_t>(256, tile_ids & ~31u);
-    if (tile_ids > N) tile_ids = (N + 31) & ~31u;
-    const uint32_t n_tiles = fd_div_up(N, tile_ids);
-    const size_t smem = (size_t)tile_ids * bytes_per_id + fixed_smem + 64;
-    if (smem > 220 * 1024) return fd_fail(ctx, FD_ERR_LIMIT, "query needs more shared memory than one SM has");
-    FilterParams fp{params->length_penalty,
-                    (uint32_t)std::min<uint64_t>(params->total_match_count, 0xffffffffu),
-                    (uint32_t)std::min<uint64_t>(params->covered_node_count, 0xffffffffu),
-                    params->covered_node_ratio,
-                    params->idf_score_cutoff,
-                    (uint32_t)std::min<uint64_t>(params->num_res_cutoff, 0xffffffffu),
-                    params->plddt_cutoff};
-    {
-        StageTimer st(ctx, "scan");
-        dim3 grid(n_tiles, nq);
-        int rc;
-#define FD_SCAN_CASE(NARROW, EW)                                                                              \
-    rc = launch_scan<NARROW, EW>(ctx, grid, smem, ix, d_desc.p, d_qh.p, d_edge.p, d_edge_node.p, d_idfsum.p, \
-                                 tile_ids, fp, d_hit_off.p, d_hit_cnt.p, d_hits.p)
-        if (narrow) {
-            if (ew == 1) FD_SCAN_CASE(true, 1);
-            else if (ew == 2) FD_SCAN_CASE(true, 2);
-            else if (ew == 4) FD_SCAN_CASE(true, 4);
-            else FD_SCAN_CASE(true, 8);
-        } else {
-            if (ew == 1) FD_SCAN_CASE(false, 1);
-            else if (ew == 2) FD_SCAN_CASE(false, 2);
-            else if (ew == 4) FD_SCAN_CASE(false, 4);
-            else FD_SCAN_CASE(false, 8);
+    int rc = FD_OK;
+    auto body = [&]() -> int {
+        FD_CUDA(ctx, d_hit_off.alloc(nq + 1));
+        FD_CUDA(ctx, d_hit_cnt.alloc(nq));
+        FD_CUDA(ctx, d_hits.alloc(hit_off[nq]));
+        FD_CUDA(ctx, cudaMemcpyAsync(d_hit_off.p, hit_off.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s));
+        FD_CUDA(ctx, cudaMemsetAsync(d_hit_cnt.p, 0, nq * 4, s));
+        TilePlan tp;
+        FD_TRY(plan_tiles(ctx, B, N, tp));
+        {
+            StageTimer st(ctx, "scan");
+            FD_TRY(launch_scan<false>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
+                                      d_hit_cnt.p, d_hits.p, nullptr));
+            FD_CUDA(ctx, st.finish());
         }
-#undef FD_SCAN_CASE
-        FD_TRY(rc);
-        FD_CUDA(ctx, st.finish());
+        return select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, params->top_n, N, out_hits, h_off);
+    };
+    rc = body();
+    if (rc != FD_OK) {
+        free(h_off);
+        return rc;
     }
+    *out_offsets = h_off;
+    return FD_OK;
+}
 
-    // ---- order by (idf desc, nid asc), keep top_n ----
-    std::vector<unsigned int> h_cnt(nq);
-    fd_struct_hit *h_hits = nullptr;
-    {
-        StageTimer st(ctx, "select");
-        FD_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_hit_cnt.p, nq * 4, cudaMemcpyDeviceToHost, s));
-        FD_CUDA(ctx, d_keys.alloc(pool));
-        FD_CUDA(ctx, d_keys2.alloc(pool));
-        FD_CUDA(ctx, d_vals.alloc(pool));
-        FD_CUDA(ctx, d_vals2.alloc(pool));
-        FD_CUDA(ctx, d_seg_end.alloc(nq));
-        dim3 g2(std::max<uint32_t>(1, std::min<uint32_t>(64, fd_div_up(N, 256))), nq);
-        FD_LAUNCH(ctx, k3_make_sort_keys, g2, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, nq, d_keys.p, d_vals.p);
-        FD_LAUNCH(ctx, k3_segment_ends, fd_div_up(nq, 256), 256, 0, d_hit_off.p, d_hit_cnt.p, nq, d_seg_end.p);
-        size_t tb = 0;
-        cub::DeviceSegmentedSort::SortPairs(nullptr, tb, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p, (int64_t)pool,
-                                            (int64_t)nq, d_hit_off.p, d_seg_end.p, s);
-        DevBuf<uint8_t> tmp;
-        FD_CUDA(ctx, tmp.alloc(tb));
-        if (pool)
-            FD_CUDA(ctx, cub::DeviceSegmentedSort::SortPairs(tmp.p, tb, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p,
-                                                             (int64_t)pool, (int64_t)nq, d_hit_off.p, d_seg_end.p, s));
-        ctx->launches += 3;
-        FD_CUDA(ctx, cudaStreamSynchronize(s));
-        for (uint32_t q = 0; q < nq; q++)
-            h_off[q + 1] = h_off[q] + std::min<uint64_t>(h_cnt[q], params->top_n);
-        const uint64_t n_out = h_off[nq];
-        DevBuf<fd_struct_hit> d_out;
-        FD_CUDA(ctx, d_out.alloc(n_out));
-        FD_CUDA(ctx, d_out_off.alloc(nq + 1));
-        FD_CUDA(ctx, cudaMemcpyAsync(d_out_off.p, h_off, (nq + 1) * 8, cudaMemcpyHostToDevice, s));
-        if (n_out) FD_LAUNCH(ctx, k3_gather, g2, 256, 0, d_hits.p, d_vals2.p, d_hit_off.p, d_out_off.p, d_out.p);
-        h_hits = (fd_struct_hit *)malloc(std::max<uint64_t>(n_out, 1) * sizeof(fd_struct_hit));
-        if (!h_hits) {
-            free(h_off);
-            return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
-        }
-        FD_CUDA(ctx, cudaMemcpyAsync(h_hits, d_out.p, n_out * sizeof(fd_struct_hit), cudaMemcpyDeviceToHost, s));
-        FD_CUDA(ctx, st.finish());
+int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                  fd_votes_layout *layout, uint32_t **d_votes) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_votes_scan: no index attached");
+    if ((nq && !queries) || !params || !layout || !d_votes) return fd_fail(ctx, FD_ERR_ARG, "fd_votes_scan: NULL argument");
+    FD_ENTER(ctx);
+    const uint32_t N = (uint32_t)ctx->idx.n_structs;
+    Batch B;
+    FD_TRY(prepare_batch(ctx, queries, nq, params, true, 1, B));
+    const uint32_t planes = (B.narrow ? 1 : 2) + B.ew;
+    *layout = fd_votes_layout{nq, N, B.narrow ? 1u : 0u, (uint32_t)B.ew, planes, (uint64_t)planes * nq * N};
+    if (layout->words > ctx->votes_cap) {
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->votes);
+        ctx->votes = nullptr;
+        ctx->votes_cap = 0;
+        FD_CUDA(ctx, cudaMalloc(&ctx->votes, layout->words * 4));
+        ctx->votes_cap = layout->words;
     }
-    *out_hits = h_hits;
+    *d_votes = ctx->votes;
+    if (nq == 0 || N == 0) return FD_OK;
+    TilePlan tp;
+    FD_TRY(plan_tiles(ctx, B, N, tp));
+    StageTimer st(ctx, "scan");
+    // every (query, tile) CTA writes its planes, so the buffer needs no clearing
+    FD_TRY(launch_scan<true>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), nullptr, nullptr,
+                             nullptr, ctx->votes));
+    FD_CUDA(ctx, st.finish());
+    return FD_OK;
+}
+
+int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                    const fd_votes_layout *layout, const uint32_t *d_votes, uint32_t q_begin, uint32_t q_end,
+                    fd_struct_hit **out_hits, uint64_t **out_offsets) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_votes_select: no index attached");
+    if ((nq && !queries) || !params || !layout || !out_hits || !out_offsets || (layout->words && !d_votes))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_votes_select: NULL argument");
+    if (q_begin > q_end || q_end > nq || layout->n_queries != nq || layout->n_structs != ctx->idx.n_structs)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_votes_select: layout / query range mismatch");
+    FD_ENTER(ctx);
+    *out_hits = nullptr;
+    *out_offsets = nullptr;
+    cudaStream_t s = ctx->stream;
+    const uint32_t N = (uint32_t)ctx->idx.n_structs;
+    const uint32_t nsel = q_end - q_begin;
+    Batch B;
+    FD_TRY(prepare_batch(ctx, queries, nq, params, false, 1, B));
+    if ((B.narrow ? 1u : 0u) != layout->narrow || (uint32_t)B.ew != layout->edge_words)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_votes_select: layout does not match the batch");
+    uint64_t *h_off = (uint64_t *)calloc((size_t)nsel + 1, 8);
+    if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    if (nsel == 0 || N == 0) {
+        *out_offsets = h_off;
+        *out_hits = (fd_struct_hit *)malloc(sizeof(fd_struct_hit));
+        return FD_OK;
+    }
+    std::vector<uint64_t> hit_off(nsel + 1, 0);
+    for (uint32_t q = 0; q < nsel; q++) hit_off[q + 1] = hit_off[q] + N;
+    DevBuf<uint64_t> d_hit_off;
+    DevBuf<unsigned int> d_hit_cnt;
+    DevBuf<HitRec> d_hits;
+    auto body = [&]() -> int {
+        FD_CUDA(ctx, d_hit_off.alloc(nsel + 1));
+        FD_CUDA(ctx, d_hit_cnt.alloc(nsel));
+        FD_CUDA(ctx, d_hits.alloc(hit_off[nsel]));
+        FD_CUDA(ctx, cudaMemcpyAsync(d_hit_off.p, hit_off.data(), (nsel + 1) * 8, cudaMemcpyHostToDevice, s));
+        FD_CUDA(ctx, cudaMemsetAsync(d_hit_cnt.p, 0, nsel * 4, s));
+        const uint32_t tile_ids = 8192;
+        dim3 grid(fd_div_up(N, tile_ids), nsel);
+        IndexView ix = make_view(ctx);
+        FilterParams fp = make_filter(params);
+        {
+            StageTimer st(ctx, "select");
+#define FD_SEL_CASE(NARROW, EW) \
+    FD_TRY((launch_select_t<NARROW, EW>(ctx, grid, ix, B, d_votes, q_begin, tile_ids, fp, d_hit_off.p, d_hit_cnt.p, d_hits.p)))
+            if (B.narrow) {
+                if (B.ew == 1) FD_SEL_CASE(true, 1);
+                else if (B.ew == 2) FD_SEL_CASE(true, 2);
+                else if (B.ew == 4) FD_SEL_CASE(true, 4);
+                else FD_SEL_CASE(true, 8);
+            } else {
+                if (B.ew == 1) FD_SEL_CASE(false, 1);
+                else if (B.ew == 2) FD_SEL_CASE(false, 2);
+                else if (B.ew == 4) FD_SEL_CASE(false, 4);
+                else FD_SEL_CASE(false, 8);
+            }
+#undef FD_SEL_CASE
+            FD_CUDA(ctx, st.finish());
+        }
+        return select_and_copy(ctx, nsel, hit_off, d_hit_off, d_hit_cnt, d_hits, params->top_n, N, out_hits, h_off);
+    };
+    const int rc = body();
+    if (rc != FD_OK) {
+        free(h_off);
+        return rc;
+    }
     *out_offsets = h_off;
     return FD_OK;
 }

@@ -332,6 +332,8 @@ struct Query {
     std::vector<uint8_t> aad_aa1, aad_aa2;
     std::vector<float> aad_dist;
     std::vector<uint32_t> aad_qi;
+    // hash-range shards (fdh_queries_set_shards): one vote bit per (query edge, rank that owns some of its hashes)
+    std::vector<uint16_t> s_edge_of_hash, s_edge_node, s_edge_group;
 };
 
 // pdb_tr.rs:95-162 with default bins
@@ -443,6 +445,7 @@ struct fdh_queries {
     std::vector<float> dist_thr, angle_thr;
     std::vector<Query> q;
     bool finalized = false;
+    std::vector<uint64_t> shard_bounds; // world + 1 ascending hash boundaries; empty = unsharded
 };
 
 namespace {
@@ -1206,17 +1209,8 @@ int fdh_queries_finalize(fdh_queries *qs, fd_ctx *ctx) {
             return rc;
         }
     }
-    size_t base = 0;
-    const float total = (float)fd_index_num_structs(ctx); // total_structures = lookup.len() as f32
-    for (auto &Q : qs->q) {
-        for (auto &e : Q.entries) {
-            const uint32_t c = counts[base + e.pair];
-            e.idf = c > 0 ? log2f(total / (float)c) : 0.0f;
-        }
-        base += Q.pair_hash.size();
-    }
-    qs->finalized = true;
-    return FD_OK;
+    // total_structures = lookup.len() as f32
+    return fdh_queries_finalize_with_counts(qs, counts.data(), fd_index_num_structs(ctx));
 }
 int64_t fdh_queries_num_hashes(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].entries.size(); }
 void fdh_queries_get_map(const fdh_queries *qs, int64_t q, uint32_t *hash, int64_t *qi, int64_t *qj,
@@ -1254,15 +1248,15 @@ struct FinalMatch { // one verified component of one candidate
 
 // General verification path for an arbitrary candidate list: K4 (fd_candidate_edges_batch) -> host graph /
 // mapping / rescue (candidate-parallel) -> K5 (fd_kabsch_store_batch).  Handles what the fused kernel cannot.
-int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const std::vector<uint32_t> &cand_q,
-                   const std::vector<uint32_t> &cand_n, const std::vector<uint64_t> &cand_global,
-                   std::vector<FinalMatch> &out, fdh_results *R, double *host_ms) {
-    const uint32_t nq = (uint32_t)qs->q.size();
+int verify_general(fd_ctx *ctx, const fdh_queries *qs, uint32_t q_begin, uint32_t nq, const fdh_search_params *p,
+                   const std::vector<uint32_t> &cand_q, const std::vector<uint32_t> &cand_n,
+                   const std::vector<uint64_t> &cand_global, std::vector<FinalMatch> &out, fdh_results *R,
+                   double *host_ms) {
     const uint64_t n_cand = cand_q.size();
     if (n_cand == 0) return FD_OK;
     std::vector<fd_retrieval_query> rq(nq);
     for (uint32_t q = 0; q < nq; q++) {
-        const Query &Q = qs->q[q];
+        const Query &Q = qs->q[q_begin + q];
         rq[q] = fd_retrieval_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), (uint32_t)Q.aad.size(),
                                    Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data()};
         R->h2d_bytes += 4ull * Q.hashes_sorted.size() + 12ull * Q.aad.size() + 28;
@@ -1324,7 +1318,7 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *
             for (uint64_t c = c0; c < std::min(n_cand, c0 + GRAIN); c++) {
                 const uint64_t eb = e_begin[c], ee = e_begin[c + 1];
                 if (ee == eb) continue;
-                const Query &Q = qs->q[cand_q[c]];
+                const Query &Q = qs->q[q_begin + cand_q[c]];
                 ce.assign(all_edges.begin() + eb, all_edges.begin() + ee);
                 g.node_res.clear(); // create_index_graph (graph.rs:16-27): node ids by first appearance
                 g.e.clear();
@@ -1374,11 +1368,12 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *
     if (!n_align) return FD_OK;
     std::vector<float> rmsd(n_align), U(9 * (size_t)n_align), T(3 * (size_t)n_align);
     std::vector<uint64_t> q_res_off(nq + 1, 0);
-    for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q].st->nres();
+    for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q_begin + q].st->nres();
     std::vector<float> q_ca(3 * q_res_off[nq]), q_cb(3 * q_res_off[nq]);
     for (uint32_t q = 0; q < nq; q++) {
-        memcpy(q_ca.data() + 3 * q_res_off[q], qs->q[q].st->ca.data(), 12 * qs->q[q].st->nres());
-        memcpy(q_cb.data() + 3 * q_res_off[q], qs->q[q].st->cb.data(), 12 * qs->q[q].st->nres());
+        const Query &Q = qs->q[q_begin + q];
+        memcpy(q_ca.data() + 3 * q_res_off[q], Q.st->ca.data(), 12 * Q.st->nres());
+        memcpy(q_cb.data() + 3 * q_res_off[q], Q.st->cb.data(), 12 * Q.st->nres());
     }
     std::vector<uint32_t> a_nid(n_align), a_off(n_align + 1, 0), pq_, pt_;
     for (uint32_t a = 0; a < n_align; a++) {
@@ -1418,24 +1413,43 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *
 
 extern "C" {
 
-fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels) {
+// fd_query descriptors of queries [q_begin, q_end) (views into qs)
+static void make_fd_queries(const fdh_queries *qs, uint32_t q_begin, uint32_t q_end, std::vector<fd_query> &fq,
+                            uint64_t *h2d_bytes) {
+    fq.resize(q_end - q_begin);
+    for (uint32_t q = q_begin; q < q_end; q++) {
+        const Query &Q = qs->q[q];
+        if (!qs->shard_bounds.empty())
+            fq[q - q_begin] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.s_edge_of_hash.data(),
+                                       (uint32_t)Q.s_edge_node.size(), Q.s_edge_node.data(), Q.n_nodes,
+                                       (uint32_t)Q.indices.size(), Q.s_edge_group.data()};
+        else
+            fq[q - q_begin] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.edge_of_hash.data(),
+                                       (uint32_t)Q.edge_node.size(), Q.edge_node.data(), Q.n_nodes,
+                                       (uint32_t)Q.indices.size(), nullptr};
+        if (h2d_bytes) *h2d_bytes += 6ull * Q.hashes_flat.size() + 2ull * Q.edge_node.size() + 24;
+    }
+}
+
+// query_pdb.rs:348-452 for queries [q_begin, q_end) of the batch.  votes == nullptr: count_query on this
+// context's index (fd_count_query_batch); otherwise finish count_query from merged dense votes (fd_votes_select).
+static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels,
+                                uint32_t q_begin, uint32_t q_end, const fd_votes_layout *layout, const uint32_t *votes) {
     if (!qs->finalized) {
         set_err("fdh_search: call fdh_queries_finalize first");
         return nullptr;
     }
-    const uint32_t nq = (uint32_t)qs->q.size();
+    if (q_begin > q_end || q_end > qs->q.size()) {
+        set_err("fdh_search: query range out of bounds");
+        return nullptr;
+    }
+    const uint32_t nq = q_end - q_begin;
     fdh_results *R = new fdh_results();
     R->struct_off.assign(nq + 1, 0);
     R->match_off.assign(nq + 1, 0);
     if (nq == 0) return R;
     // --- K3: count_query + filter + sort + top ---
-    std::vector<fd_query> fq(nq);
-    for (uint32_t q = 0; q < nq; q++) {
-        const Query &Q = qs->q[q];
-        fq[q] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.edge_of_hash.data(),
-                         (uint32_t)Q.edge_node.size(), Q.edge_node.data(), Q.n_nodes, (uint32_t)Q.indices.size()};
-        R->h2d_bytes += 6ull * Q.hashes_flat.size() + 2ull * Q.edge_node.size() + 24;
-    }
+    std::vector<fd_query> fq;
     fd_struct_hit *hits = nullptr;
     uint64_t *hoff = nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -1444,7 +1458,15 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
     };
     const auto t_all = now();
     auto t_stage = now();
-    if (fd_count_query_batch(ctx, fq.data(), nq, &p->prefilter, &hits, &hoff) != FD_OK) {
+    int rc;
+    if (votes) {
+        make_fd_queries(qs, 0, (uint32_t)qs->q.size(), fq, nullptr);
+        rc = fd_votes_select(ctx, fq.data(), (uint32_t)fq.size(), &p->prefilter, layout, votes, q_begin, q_end, &hits, &hoff);
+    } else {
+        make_fd_queries(qs, q_begin, q_end, fq, &R->h2d_bytes);
+        rc = fd_count_query_batch(ctx, fq.data(), nq, &p->prefilter, &hits, &hoff);
+    }
+    if (rc != FD_OK) {
         set_err(fd_last_error(ctx));
         delete R;
         return nullptr;
@@ -1474,7 +1496,7 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
         std::vector<std::vector<float>> v_idf(nq);
         std::vector<std::vector<uint8_t>> v_sym(nq);
         for (uint32_t q = 0; q < nq; q++) {
-            const Query &Q = qs->q[q];
+            const Query &Q = qs->q[q_begin + q];
             for (uint32_t h : Q.hashes_sorted) {
                 const QEntry &e = Q.entries[Q.pos.at(h)];
                 v_qi[q].push_back(e.qi);
@@ -1514,7 +1536,7 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
             m.rmsd = recs[k].rmsd;
             memcpy(m.U, recs[k].U, sizeof(m.U));
             memcpy(m.t, recs[k].t, sizeof(m.t));
-            m.n_res = (uint32_t)std::min<size_t>(qs->q[cand_q[m.cand]].indices.size(), 16);
+            m.n_res = (uint32_t)std::min<size_t>(qs->q[q_begin + cand_q[m.cand]].indices.size(), 16);
             memcpy(m.res16, recs[k].res, sizeof(m.res16));
         }
         std::vector<uint32_t> fq_, fn_;
@@ -1529,7 +1551,7 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
         fd_free(recs);
         fd_free(flags);
         if (!fglobal.empty()) {
-            if (verify_general(ctx, qs, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
+            if (verify_general(ctx, qs, q_begin, nq, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
             std::stable_sort(fm.begin(), fm.end(), [](const FinalMatch &a, const FinalMatch &b) { return a.cand < b.cand; });
         }
     }
@@ -1548,7 +1570,7 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
     for (auto &m : fm) fm_begin[m.cand + 1]++;
     for (uint64_t c = 0; c < n_cand; c++) fm_begin[c + 1] += fm_begin[c];
     auto build_query = [&](uint32_t q) {
-        const Query &Q = qs->q[q];
+        const Query &Q = qs->q[q_begin + q];
         QOut &O = qout[q];
         const float expected = (float)Q.indices.size();
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
@@ -1673,6 +1695,110 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
     fd_free(hits);
     fd_free(hoff);
     return R;
+}
+
+fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels) {
+    return search_impl(ctx, qs, p, labels, 0, (uint32_t)qs->q.size(), nullptr, nullptr);
+}
+
+// ---- hash-range sharded index: the same search in three steps around the caller's collective ----
+// The index is split into `world` hash ranges [bounds[r], bounds[r+1]).  count_query's edge bit masks must merge
+// by addition, so every (query edge, rank owning at least one of the edge's hashes) pair gets its own vote bit;
+// bits of one edge are consecutive, never cross a 32-bit word and are counted once (fd_query.edge_group).
+int fdh_queries_set_shards(fdh_queries *qs, const uint64_t *bounds, int world) {
+    if (world < 1 || world > 64 || !bounds) {
+        set_err("fdh_queries_set_shards: world must be in 1..64");
+        return FD_ERR_ARG;
+    }
+    for (int r = 0; r < world; r++)
+        if (bounds[r] > bounds[r + 1]) {
+            set_err("fdh_queries_set_shards: bounds must be ascending");
+            return FD_ERR_ARG;
+        }
+    std::vector<uint64_t> b(bounds, bounds + world + 1);
+    for (auto &Q : qs->q) {
+        const size_t E = Q.edge_node.size();
+        std::vector<uint64_t> owners(E, 0);
+        std::vector<uint8_t> rank_of(Q.hashes_flat.size());
+        for (size_t k = 0; k < Q.hashes_flat.size(); k++) {
+            const uint64_t h = Q.hashes_flat[k];
+            int r = (int)(std::upper_bound(b.begin() + 1, b.end() - 1, h) - (b.begin() + 1)); // ranges cover everything
+            rank_of[k] = (uint8_t)r;
+            owners[Q.edge_of_hash[k]] |= 1ull << r;
+        }
+        Q.s_edge_node.clear();
+        Q.s_edge_group.clear();
+        std::vector<uint32_t> first_bit(E, 0);
+        uint16_t gid = 0;
+        for (size_t e = 0; e < E; e++) {
+            const uint32_t g = std::max(1, __builtin_popcountll(owners[e]));
+            while ((Q.s_edge_node.size() & 31) + g > 32) { // padding bit: never voted for, its own group
+                Q.s_edge_node.push_back(Q.edge_node[e]);
+                Q.s_edge_group.push_back(gid++);
+            }
+            first_bit[e] = (uint32_t)Q.s_edge_node.size();
+            for (uint32_t k = 0; k < g; k++) {
+                Q.s_edge_node.push_back(Q.edge_node[e]);
+                Q.s_edge_group.push_back(gid);
+            }
+            gid++;
+        }
+        if (Q.s_edge_node.size() > 256) {
+            set_err("fdh_queries_set_shards: query needs more than 256 vote bits");
+            return FD_ERR_LIMIT;
+        }
+        Q.s_edge_of_hash.resize(Q.hashes_flat.size());
+        for (size_t k = 0; k < Q.hashes_flat.size(); k++) {
+            const uint32_t e = Q.edge_of_hash[k];
+            const uint64_t below = owners[e] & ((1ull << rank_of[k]) - 1);
+            Q.s_edge_of_hash[k] = (uint16_t)(first_bit[e] + __builtin_popcountll(below));
+        }
+    }
+    qs->shard_bounds = std::move(b);
+    return FD_OK;
+}
+int64_t fdh_queries_num_pairs(const fdh_queries *qs) {
+    int64_t n = 0;
+    for (auto &Q : qs->q) n += (int64_t)Q.pair_hash.size();
+    return n;
+}
+int fdh_queries_pair_counts(const fdh_queries *qs, fd_ctx *ctx, uint32_t *out_counts) {
+    std::vector<uint32_t> all;
+    for (auto &Q : qs->q) all.insert(all.end(), Q.pair_hash.begin(), Q.pair_hash.end());
+    if (all.empty()) return FD_OK;
+    const int rc = fd_posting_counts(ctx, all.data(), all.size(), out_counts);
+    if (rc != FD_OK) set_err(fd_last_error(ctx));
+    return rc;
+}
+int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, uint64_t total_structures) {
+    size_t base = 0;
+    const float total = (float)total_structures;
+    for (auto &Q : qs->q) {
+        for (auto &e : Q.entries) {
+            const uint32_t c = counts[base + e.pair];
+            e.idf = c > 0 ? log2f(total / (float)c) : 0.0f;
+        }
+        base += Q.pair_hash.size();
+    }
+    qs->finalized = true;
+    return FD_OK;
+}
+int fdh_votes_scan(fd_ctx *ctx, const fdh_queries *qs, const fd_prefilter_params *prefilter, fd_votes_layout *layout,
+                   uint32_t **d_votes) {
+    std::vector<fd_query> fq;
+    make_fd_queries(qs, 0, (uint32_t)qs->q.size(), fq, nullptr);
+    const int rc = fd_votes_scan(ctx, fq.data(), (uint32_t)fq.size(), prefilter, layout, d_votes);
+    if (rc != FD_OK) set_err(fd_last_error(ctx));
+    return rc;
+}
+fdh_results *fdh_search_from_votes(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p,
+                                   const fdh_store *labels, const fd_votes_layout *layout, const uint32_t *d_votes,
+                                   uint32_t q_begin, uint32_t q_end) {
+    if (!layout || !d_votes) {
+        set_err("fdh_search_from_votes: NULL votes");
+        return nullptr;
+    }
+    return search_impl(ctx, qs, p, labels, q_begin, q_end, layout, d_votes);
 }
 
 uint64_t fdh_results_num_queries(const fdh_results *r) { return r->struct_off.size() - 1; }

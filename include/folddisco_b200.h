@@ -125,6 +125,11 @@ typedef struct {
     const uint16_t *edge_node;
     uint32_t n_nodes;
     uint32_t expected_node_count; /* residue_count of src/cli/workflows/query_pdb.rs:355-359 */
+    /* Optional (NULL = every entry of edge_node is its own query edge).  edge_group[e] names the query edge that
+     * vote bit e belongs to; equal values must be consecutive and must not cross a multiple of 32.  Bits of one
+     * group count as ONE edge in edge_count.  Used with hash-range shards: an edge whose hashes live on several
+     * ranks gets one bit per rank, so that the ranks' edge masks are disjoint and a sum merges them exactly. */
+    const uint16_t *edge_group;
 } fd_query;
 
 /* count_query arguments (src/controller/count_query.rs:82-88) + StructureFilter::filter_before_matching
@@ -160,6 +165,40 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t n_querie
 /* posting bytes the last fd_count_query_batch had to read (sum over found query hashes of their list
  * length in bytes) -- the algorithmic bytes of SURVEY 8d */
 uint64_t fd_last_posting_bytes(const fd_ctx *ctx);
+
+/* ---- multi-GPU: hash-range shards ------------------------------------------------------------------
+ * With the index split by hash range across ranks (fd_build_index(hash_lo, hash_hi) or a slice of the on-disk
+ * arrays), count_query's per-structure accumulators (src/controller/count_query.rs:60-67 CompactEntry, :133-159)
+ * are additive over shards: every rank produces PARTIAL votes for the whole batch in device memory, the caller
+ * merges them with ONE sum all-reduce over the whole buffer (the edge planes are bit masks: the caller gives every
+ * (query edge, owning rank) pair its own bit through fd_query.edge_group, so the ranks' masks are disjoint and the
+ * sum is their OR), and fd_votes_select finishes count_query (node/edge counts, length penalty,
+ * filter_before_matching, idf sort, --top) for a slice of the batch.
+ *
+ * Device layout: u32 votes[planes][n_queries][n_structs];
+ *   narrow = 1: plane 0 = match_count << 24 | idf fixed point (24 bit)         (queries of at most 255 hashes)
+ *   narrow = 0: plane 0 = idf fixed point (32 bit), plane 1 = match_count
+ *   then edge_words planes of edge bitmask (bit e of word e/32 = query edge e has a hit in the structure).
+ * The idf fixed-point scale of query q is 2^floor(log2(range / (n_hashes_q * log2(n_structs) + 1))): identical on
+ * every rank. */
+typedef struct {
+    uint32_t n_queries;
+    uint32_t n_structs;
+    uint32_t narrow;
+    uint32_t edge_words;
+    uint32_t planes;
+    uint64_t words; /* planes * n_queries * n_structs */
+} fd_votes_layout;
+
+/* Scan this rank's shard for the whole batch.  *d_votes is a DEVICE pointer owned by ctx (valid until the next
+ * fd_votes_scan / fd_destroy); the call returns after the scan has completed on the device. */
+int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,
+                  fd_votes_layout *layout, uint32_t **d_votes);
+/* Finish count_query from merged votes (any device pointer with the layout above) for queries
+ * [q_begin, q_end) of the batch; outputs as fd_count_query_batch, offsets has q_end - q_begin + 1 entries. */
+int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,
+                    const fd_votes_layout *layout, const uint32_t *d_votes, uint32_t q_begin, uint32_t q_end,
+                    fd_struct_hit **out_hits, uint64_t **out_offsets);
 
 /* HBM-resident compact-structure store replacing the per-candidate file re-read of retrieval_wrapper
  * (src/controller/retrieve.rs:375-376); ids = positions in the batch = posting ids. */

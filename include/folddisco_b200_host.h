@@ -143,6 +143,24 @@ typedef struct {
  * without it fdh_residue_match.serial is the residue index inside the target and chain is 0. */
 fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels);
 
+/* ---- hash-range sharded index (one rank per GPU): the same search in three steps around the caller's collective.
+ *   0. every rank: fdh_queries_set_shards (gives every (query edge, owning rank) pair its own vote bit)
+ *   1. every rank: fdh_queries_pair_counts -> all-reduce(sum) of the counts -> fdh_queries_finalize_with_counts
+ *      (a posting list lives on exactly one shard, so the sum is the global list length; total_structures = lookup.len())
+ *   2. every rank: fdh_votes_scan (partial votes of its shard for the whole batch, fd_votes_scan) -> all-reduce
+ *   3. rank r: fdh_search_from_votes for its slice [q_begin, q_end) of the batch (fd_votes_select + verification
+ *      against the replicated store); the results object has q_end - q_begin queries. */
+/* bounds[world + 1]: rank r owns the hashes in [bounds[r], bounds[r+1]); call once per batch before step 2 */
+int fdh_queries_set_shards(fdh_queries *qs, const uint64_t *bounds, int world);
+int64_t fdh_queries_num_pairs(const fdh_queries *qs);
+int fdh_queries_pair_counts(const fdh_queries *qs, fd_ctx *ctx, uint32_t *out_counts /* fdh_queries_num_pairs */);
+int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, uint64_t total_structures);
+int fdh_votes_scan(fd_ctx *ctx, const fdh_queries *qs, const fd_prefilter_params *prefilter, fd_votes_layout *layout,
+                   uint32_t **d_votes);
+fdh_results *fdh_search_from_votes(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p,
+                                   const fdh_store *labels, const fd_votes_layout *layout, const uint32_t *d_votes,
+                                   uint32_t q_begin, uint32_t q_end);
+
 /* per-structure rows: query q owns [struct_offsets[q], struct_offsets[q+1]) ordered idf desc, min_rmsd asc */
 typedef struct {
     uint32_t nid, total_match_count, node_count, edge_count;

@@ -204,7 +204,10 @@ def run_ours(args, rank, world, local_rank):
         qb = host.QueryBatch(index.params)
         qb.add_many([motif_structs[k % len(motif_structs)][0] for k in range(args.batch)],
                     [motif_structs[k % len(motif_structs)][1] for k in range(args.batch)])
-        qb.finalize(ctx)
+        if sharded is None:
+            qb.finalize(ctx)
+        else:
+            sharded.finalize(ctx, qb, dist)
         return qb
 
     def search(qb):

@@ -1757,6 +1757,24 @@ int fdh_queries_set_shards(fdh_queries *qs, const uint64_t *bounds, int world) {
     qs->shard_bounds = std::move(b);
     return FD_OK;
 }
+int64_t fdh_queries_num_vote_bits(const fdh_queries *qs, int64_t q) {
+    return (int64_t)(qs->shard_bounds.empty() ? qs->q[q].edge_node.size() : qs->q[q].s_edge_node.size());
+}
+void fdh_queries_get_vote_bits(const fdh_queries *qs, int64_t q, uint32_t *hashes, uint16_t *bit_of_hash,
+                               uint16_t *bit_node, uint16_t *bit_group) {
+    const Query &Q = qs->q[q];
+    const bool sh = !qs->shard_bounds.empty();
+    const std::vector<uint16_t> &eoh = sh ? Q.s_edge_of_hash : Q.edge_of_hash;
+    const std::vector<uint16_t> &en = sh ? Q.s_edge_node : Q.edge_node;
+    for (size_t k = 0; k < Q.hashes_flat.size(); k++) {
+        if (hashes) hashes[k] = Q.hashes_flat[k];
+        if (bit_of_hash) bit_of_hash[k] = eoh[k];
+    }
+    for (size_t e = 0; e < en.size(); e++) {
+        if (bit_node) bit_node[e] = en[e];
+        if (bit_group) bit_group[e] = sh ? Q.s_edge_group[e] : (uint16_t)e;
+    }
+}
 int64_t fdh_queries_num_pairs(const fdh_queries *qs) {
     int64_t n = 0;
     for (auto &Q : qs->q) n += (int64_t)Q.pair_hash.size();

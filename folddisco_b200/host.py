@@ -98,6 +98,14 @@ def _lib():
     sig("fdh_queries_get_indices", None, [VP, C.c_int64, VP])
     sig("fdh_queries_free", None, [VP])
     sig("fdh_search", VP, [VP, VP, PP(SearchParams), VP])
+    sig("fdh_queries_set_shards", C.c_int, [VP, VP, C.c_int])
+    sig("fdh_queries_num_vote_bits", C.c_int64, [VP, C.c_int64])
+    sig("fdh_queries_get_vote_bits", None, [VP, C.c_int64, VP, VP, VP, VP])
+    sig("fdh_queries_num_pairs", C.c_int64, [VP])
+    sig("fdh_queries_pair_counts", C.c_int, [VP, VP, VP])
+    sig("fdh_queries_finalize_with_counts", C.c_int, [VP, VP, C.c_uint64])
+    sig("fdh_votes_scan", C.c_int, [VP, VP, PP(PrefilterParams), PP(capi.VotesLayout), PP(VP)])
+    sig("fdh_search_from_votes", VP, [VP, VP, PP(SearchParams), VP, PP(capi.VotesLayout), VP, C.c_uint32, C.c_uint32])
     sig("fdh_results_num_queries", C.c_uint64, [VP])
     for n in ("struct_offsets", "struct_rows", "match_offsets", "match_rows", "match_order", "residues"):
         sig("fdh_results_" + n, VP, [VP])
@@ -337,6 +345,33 @@ class QueryBatch:
         if rc != 0:
             raise FdError(_err())
 
+    # ---- hash-range shards (see folddisco_b200/sharded.py) ----
+    def set_shards(self, bounds):
+        b = np.ascontiguousarray(bounds, np.uint64)
+        if _lib().fdh_queries_set_shards(self.h, _ptr(b), len(b) - 1) != 0:
+            raise FdError(_err())
+
+    def vote_bits(self, q):
+        """the fd_query arrays of query q: hashes, bit_of_hash (per hash), bit_node, bit_group (per vote bit)"""
+        nh, nb = _lib().fdh_queries_num_hashes(self.h, q), _lib().fdh_queries_num_vote_bits(self.h, q)
+        d = dict(hashes=np.zeros(nh, np.uint32), bit_of_hash=np.zeros(nh, np.uint16), bit_node=np.zeros(nb, np.uint16),
+                 bit_group=np.zeros(nb, np.uint16))
+        _lib().fdh_queries_get_vote_bits(self.h, q, *[_ptr(d[k]) for k in ("hashes", "bit_of_hash", "bit_node", "bit_group")])
+        return d
+
+    def pair_counts(self, ctx):
+        """posting counts of every query pair's observed hash in the index attached to ctx (0 if absent)"""
+        out = np.zeros(_lib().fdh_queries_num_pairs(self.h), np.uint32)
+        if _lib().fdh_queries_pair_counts(self.h, ctx.h, _ptr(out)) != 0:
+            raise FdError(_err())
+        return out
+
+    def finalize_with_counts(self, counts, total_structures):
+        c = np.ascontiguousarray(counts, np.uint32)
+        assert len(c) == _lib().fdh_queries_num_pairs(self.h)
+        if _lib().fdh_queries_finalize_with_counts(self.h, _ptr(c), int(total_structures)) != 0:
+            raise FdError(_err())
+
     def query_map(self, q):
         n = _lib().fdh_queries_num_hashes(self.h, q)
         d = dict(hash=np.zeros(n, np.uint32), qi=np.zeros(n, np.int64), qj=np.zeros(n, np.int64),
@@ -402,6 +437,20 @@ class Results:
     def residue_string(self, match_row, n_query_residues):
         r = self.residues[int(match_row["res_begin"]):int(match_row["res_begin"]) + n_query_residues]
         return ",".join("%s%d" % (chr(x["chain"]), x["serial"]) if x["some"] else "_" for x in r)
+
+
+def votes_scan(ctx, queries, prefilter):
+    """partial votes of ctx's index shard for the whole batch -> (VotesLayout, device pointer owned by ctx)"""
+    lay, ptr = capi.VotesLayout(), VP()
+    if _lib().fdh_votes_scan(ctx.h, queries.h, C.byref(prefilter), C.byref(lay), C.byref(ptr)) != 0:
+        raise FdError(_err())
+    return lay, ptr.value
+
+
+def search_from_votes(ctx, queries, params, layout, d_votes, q_begin, q_end, labels=None):
+    """the rest of the search for queries [q_begin, q_end) from merged votes"""
+    return Results(_lib().fdh_search_from_votes(ctx.h, queries.h, C.byref(params), labels.h if labels is not None else None,
+                                                C.byref(layout), VP(d_votes), q_begin, q_end))
 
 
 def search(ctx, queries, params=None, labels=None):

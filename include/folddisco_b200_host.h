@@ -152,6 +152,11 @@ fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_par
  *      against the replicated store); the results object has q_end - q_begin queries. */
 /* bounds[world + 1]: rank r owns the hashes in [bounds[r], bounds[r+1]); call once per batch before step 2 */
 int fdh_queries_set_shards(fdh_queries *qs, const uint64_t *bounds, int world);
+/* the fd_query arrays of query q as the scan will see them (hashes / bit_of_hash: fdh_queries_num_hashes entries in
+ * scan order; bit_node / bit_group: fdh_queries_num_vote_bits entries) */
+int64_t fdh_queries_num_vote_bits(const fdh_queries *qs, int64_t q);
+void fdh_queries_get_vote_bits(const fdh_queries *qs, int64_t q, uint32_t *hashes, uint16_t *bit_of_hash,
+                               uint16_t *bit_node, uint16_t *bit_group);
 int64_t fdh_queries_num_pairs(const fdh_queries *qs);
 int fdh_queries_pair_counts(const fdh_queries *qs, fd_ctx *ctx, uint32_t *out_counts /* fdh_queries_num_pairs */);
 int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, uint64_t total_structures);

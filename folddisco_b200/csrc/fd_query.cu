@@ -46,6 +46,7 @@ constexpr uint32_t VALUES_PAD = 256; // readable bytes after the last posting by
 
 constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
+constexpr int K3_WQ = 160;               // per-warp compaction queue of the epilogue (31 pending + 128 new)
 constexpr int K3_MAX_HASHES_NARROW = 255; // match_count fits 8 bits
 constexpr int K3_MAX_HASHES = 4095;       // smem prefix array
 constexpr int K3_MAX_EDGE_WORDS = 8;      // 256 edges
@@ -347,18 +348,18 @@ template <bool NARROW, int EW>
 __device__ __forceinline__ void emit_cells(const uint32_t *acc, const uint32_t *match, const uint32_t *edge,
                                            size_t edge_stride, uint32_t T, uint32_t lo, const QueryDesc &qd,
                                            const uint32_t *node_mask, const uint32_t *cont_mask /* [EW] */,
-                                           uint32_t *wqueue /* [K3_WARPS * 64] */,
+                                           uint32_t *wqueue /* [K3_WARPS * K3_WQ] */,
                                            float inv_scale, const IndexView &ix, const float *pen,
                                            const FilterParams &fp, unsigned int *hit_count, HitRec *hits_out) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *wq = wqueue + warp * 64;
+    uint32_t *wq = wqueue + warp * K3_WQ;
     uint32_t pending = 0;
-    const uint32_t n_chunks = (T + 31) >> 5;
-    auto process = [&](uint32_t n_take) { // the first n_take queue entries, one per lane
+    const uint32_t n_chunks = (T + 127) >> 7;
+    auto process = [&](uint32_t first, uint32_t n_take) { // queue entries [first, first + n_take), one per lane
         bool pass = false;
         HitRec rec{0, 0, 0, 0.f};
         if (lane < n_take) {
-            const uint32_t x = wq[lane];
+            const uint32_t x = wq[first + lane];
             const uint32_t a = acc[x];
             const uint32_t mc = NARROW ? (a >> 24) : match[x];
             const uint32_t fixed = NARROW ? (a & 0xffffffu) : a;
@@ -402,27 +403,37 @@ __device__ __forceinline__ void emit_cells(const uint32_t *acc, const uint32_t *
             if (pass) hits_out[pos] = rec;
         }
     };
+    // 128 cells per warp step (4 coalesced loads per lane); a warp prefix sum places the non-empty ones in the queue
     for (uint32_t c = warp; c < n_chunks; c += K3_WARPS) {
-        const uint32_t x = (c << 5) + lane;
-        bool nonempty = false;
-        if (x < T) nonempty = NARROW ? (acc[x] >> 24) != 0 : match[x] != 0;
-        const uint32_t m = __ballot_sync(0xffffffffu, nonempty);
-        if (nonempty) wq[pending + __popc(m & ((1u << lane) - 1))] = x;
-        pending += __popc(m);
-        __syncwarp();
-        if (pending >= 32) {
-            process(32);
-            __syncwarp();
-            const uint32_t rest = pending - 32;
-            uint32_t t = 0;
-            if (lane < rest) t = wq[32 + lane];
-            __syncwarp();
-            if (lane < rest) wq[lane] = t;
-            pending = rest;
-            __syncwarp();
+        const uint32_t x0 = (c << 7) + lane;
+        uint32_t nz = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t x = x0 + 32 * j;
+            uint32_t v = 0;
+            if (x < T) v = NARROW ? (acc[x] >> 24) : match[x];
+            nz |= (v != 0 ? 1u : 0u) << j;
         }
+        const uint32_t cnt = __popc(nz);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        uint32_t pos = pending + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((nz >> j) & 1u) wq[pos++] = x0 + 32 * j;
+        pending += __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        while (pending >= 32) { // take from the back: no queue shifting, hit order is irrelevant (sorted later)
+            process(pending - 32, 32);
+            pending -= 32;
+        }
+        __syncwarp();
     }
-    if (pending) process(pending);
+    if (pending) process(0, pending);
 }
 
 // node_mask[nd * EW + w]: vote bits whose source node is nd; cont_mask[w]: vote bits that continue the group of
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(K3_THREADS)
     uint32_t *seg_lo = item_prefix + (Q + 1);                // [Q] first relevant granule of each list
     uint32_t *node_mask = seg_lo + Q;                        // [n_nodes * EW]
     uint32_t *cont_mask = node_mask + qd.n_nodes * EW;       // [EW]
-    uint32_t *wqueue = cont_mask + EW;                       // [K3_WARPS * 64]
+    uint32_t *wqueue = cont_mask + EW;                       // [K3_WARPS * K3_WQ]
     __shared__ uint32_t s_total_items;
 
     {
@@ -646,7 +657,7 @@ __global__ void __launch_bounds__(K3_THREADS)
                     const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits) {
     __shared__ uint32_t node_mask[K3_MAX_NODES * EW];
     __shared__ uint32_t cont_mask[EW];
-    __shared__ uint32_t wqueue[K3_WARPS * 64];
+    __shared__ uint32_t wqueue[K3_WARPS * K3_WQ];
     const uint32_t qs = blockIdx.y, q = q_begin + qs;
     const QueryDesc qd = queries[q];
     const uint32_t lo = blockIdx.x * tile_ids;
@@ -850,7 +861,7 @@ struct TilePlan {
 
 int plan_tiles(fd_ctx *ctx, const Batch &B, uint32_t N, TilePlan &tp) {
     const uint32_t bytes_per_id = (B.narrow ? 4 : 8) + 4 * B.ew;
-    const size_t fixed_smem = (size_t)(2 * B.max_hashes + 2 + B.max_nodes * B.ew + B.ew + K3_WARPS * 64) * 4 + 64;
+    const size_t fixed_smem = (size_t)(2 * B.max_hashes + 2 + B.max_nodes * B.ew + B.ew + K3_WARPS * K3_WQ) * 4 + 64;
     size_t budget = 72 * 1024; // 3 CTAs per SM
     if (const char *e = getenv("FD_K3_TILE_KB")) budget = (size_t)std::max(8, atoi(e)) * 1024;
     budget = std::min<size_t>(budget, 220 * 1024);

@@ -46,6 +46,12 @@ struct FdDeviceStore {
     uint8_t *aa = nullptr, *cb_valid = nullptr;
 };
 
+// Pinned host staging buffer (grow-only) for results that the host side consumes right after the call.
+struct FdPinned {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
 struct fd_ctx {
     int device = 0;
     int num_sms = FD_NUM_SMS_FALLBACK;
@@ -57,11 +63,16 @@ struct fd_ctx {
     FdDeviceIndex idx;
     FdDeviceStore store;
     uint64_t last_posting_bytes = 0;
+    FdPinned pinned[8];
+    cudaEvent_t ev_extra[4] = {nullptr, nullptr, nullptr, nullptr}; // finer stage timing inside one call
     uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
     uint64_t votes_cap = 0;    // capacity in u32 words
 };
 
 extern thread_local std::string fd_g_create_error;
+// pinned staging buffer `slot` of at least `bytes` bytes (contents not preserved when it grows)
+int fd_pinned(fd_ctx *ctx, int slot, size_t bytes, void **out);
+cudaError_t fd_ensure_events(fd_ctx *ctx);
 
 inline int fd_fail(fd_ctx *ctx, int code, const std::string &msg) {
     if (ctx) ctx->err = msg;

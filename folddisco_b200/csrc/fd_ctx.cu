@@ -26,6 +26,28 @@ static void fd_release_store(FdDeviceStore &st) {
     cudaFree(st.cb_valid);
     st = FdDeviceStore();
 }
+int fd_pinned(fd_ctx *ctx, int slot, size_t bytes, void **out) {
+    FdPinned &b = ctx->pinned[slot];
+    if (bytes > b.cap) {
+        if (b.p) cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fd_fail(ctx, FD_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        b.cap = want;
+    }
+    *out = b.p;
+    return FD_OK;
+}
+cudaError_t fd_ensure_events(fd_ctx *ctx) {
+    for (auto &e : ctx->ev_extra)
+        if (!e) {
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+        }
+    return cudaSuccess;
+}
 void fd_ctx_release_index(fd_ctx *ctx) { fd_release_index(ctx->idx); }
 void fd_ctx_release_store(fd_ctx *ctx) { fd_release_store(ctx->store); }
 
@@ -86,6 +108,10 @@ void fd_destroy(fd_ctx *ctx) {
     fd_release_index(ctx->idx);
     fd_release_store(ctx->store);
     cudaFree(ctx->votes);
+    for (auto &b : ctx->pinned)
+        if (b.p) cudaFreeHost(b.p);
+    for (auto &e : ctx->ev_extra)
+        if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

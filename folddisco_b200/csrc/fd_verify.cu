@@ -1,17 +1,24 @@
-// fd_verify.cu -- K6: fused candidate verification (query path (ii), everything after the prefilter).
+// fd_verify.cu -- K6: candidate verification (query path (ii), everything after the prefilter).
 //
 // Replaces retrieval_wrapper (reference src/controller/retrieve.rs:364-552) for a batch of
-// (query, candidate structure) pairs in ONE kernel, so that nothing but the final match records leaves HBM:
+// (query, candidate structure) pairs, so that nothing but the final match records leaves HBM:
 //   retrieve_with_prefilter   (:52-156)    re-hash of the candidate's residue pairs from the HBM structure store
 //   create_index_graph + connected_components_with_given_node_count (graph.rs:16-50)
 //   map_query_and_retrieved_residues (:604-702), calculate_subgraph_idf (:705-719), the rescue loop (:453-516)
 //   rmsd_with_calpha_and_rottran -> kabsch (:756-834, kabsch.rs:157-554)
 // The un-fused pieces (fd_candidate_edges_batch + host graph step + fd_kabsch_store_batch) remain as the general
-// path; this kernel handles candidates that fit its shared-memory limits and flags the rest (V_OVERFLOW).
+// path; these kernels handle candidates that fit their shared-memory limits and flag the rest.
 //
-// One CTA (128 threads) per candidate.  Parallel phases (pair screen, hashing, rescue voting, Kabsch per
-// component) use the whole CTA; the small irregular graph phase runs on thread 0 over shared-memory state:
-// graphs have <= 64 nodes, so reachability closures, components and "used" sets are single 64-bit masks.
+// Three kernels, one per kind of work (a single fused kernel was 145 KB of SASS and spent 40 % of its issue time
+// waiting for instruction fetch, with 6 candidates per SM in flight -- profiles/r01a):
+//   k6a_edges      CTA per candidate: amino-acid prefilter lists, pair screen through a 20x20 amino-acid-pair
+//                  table, f32 feature + binary64 trig hash of the survivors (queued across chunks so the expensive
+//                  hash runs with full lanes), membership in the query's hash set, bitonic sort by (i, j);
+//                  the candidate's edges go to a compact pool in HBM.
+//   k6b_components warp per candidate (no CTA barriers): graph components via 64-bit reachability masks
+//                  (<= 64 nodes), residue mapping, rescue vote; one 128-byte spec per component.
+//   k6c_kabsch     thread per component: f64 Kabsch, match record written at its final position
+//                  (candidate order, component order) from an exclusive scan of the per-candidate counts.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -22,9 +29,11 @@
 
 namespace {
 
-constexpr int V_THREADS = 128;
-constexpr int V_LIST_CAP = 4096;
-constexpr int V_CHUNK = V_THREADS * 8;
+constexpr int VA_THREADS = 128;            // k6a CTA
+constexpr int VA_CHUNK = VA_THREADS * 8;   // pairs screened per round
+constexpr int VA_QUEUE = VA_CHUNK + VA_THREADS; // survivor queue: hashed when >= VA_THREADS are waiting
+constexpr int V_LIST_CAP = 2048;           // prefilter-list capacity (larger candidates take the general path)
+constexpr int VB_WARPS = 4;                // k6b: candidates per CTA
 constexpr int V_MAX_AAD = 255; // start and count of an amino-acid pair's run each fit 8 bits
 constexpr int V_MAX_E = 256;
 constexpr int V_MAX_NODES = 64;
@@ -69,37 +78,64 @@ __device__ __forceinline__ bool mask_less(uint64_t a, uint64_t b) {
     return (a & above) == 0;                      // b has d; a smaller only if a is a prefix of b
 }
 
-__global__ void __launch_bounds__(V_THREADS)
-    k6_verify(StoreView st, const VQDesc *vq, const VHash *vhash, const VAad *vaad, const uint8_t *idx_dense,
-              const float *q_ca, const float *q_cb, const uint32_t *cand_query,
-              const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp, float ca_cutoff, int skip_ca_match,
-              fd_match_record *out, unsigned int *out_count, uint32_t out_cap, uint8_t *cand_flags) {
+struct CompSpec { // one connected component of one candidate, k6b -> k6c (128 bytes)
+    uint32_t cand;
+    uint16_t ci, nal;        // component number inside the candidate; residue pairs to superpose
+    float idf;               // calculate_subgraph_idf
+    uint32_t pad;
+    uint32_t res[V_MAX_NQ];  // reported target residue index + 1 per query position, 0 = none
+    uint8_t aq[V_MAX_NQ];    // alignment: dense query residue ids ...
+    uint16_t at[V_MAX_NQ];   // ... and target residue indices
+};
+static_assert(sizeof(CompSpec) == 128, "CompSpec layout");
+
+template <class I>
+struct GatherPointsT { // CA, CB interleaved, gathered by residue index: point 2k = CA(res[k]), 2k+1 = CB(res[k])
+    const float *ca, *cb;
+    const I *res;
+    uint64_t base;
+    __device__ fdk::P3 operator()(uint32_t i) const {
+        const uint64_t r = base + res[i >> 1];
+        const float *s = (i & 1) ? cb : ca;
+        return {(double)s[3 * r], (double)s[3 * r + 1], (double)s[3 * r + 2]};
+    }
+};
+
+// amino-acid-pair table of a query in shared memory: aad[] sorted by (aa1, aa2), aa_range[aa1 * 20 + aa2] =
+// start << 8 | count of the pair's run (0 = pair not in the query).  NT cooperating threads, caller synchronises.
+template <int NT>
+__device__ __forceinline__ void load_aad_phase1(const VQDesc &Q, const VAad *vaad, VAad *aad, uint16_t *aa_range, int t) {
+    for (uint32_t k = t; k < Q.n_aad; k += NT) aad[k] = vaad[Q.aad_begin + k];
+    for (uint32_t k = t; k < 400; k += NT) aa_range[k] = 0;
+}
+template <int NT>
+__device__ __forceinline__ void load_aad_phase2(const VQDesc &Q, const VAad *aad, uint16_t *aa_range, int t) {
+    for (uint32_t k = t; k < Q.n_aad; k += NT) { // heads of runs of equal (aa1, aa2)
+        const uint32_t key = aad[k].aa1 * 20u + aad[k].aa2;
+        if (k == 0 || aad[k - 1].aa1 * 20u + aad[k - 1].aa2 != key) {
+            uint32_t e = k + 1;
+            while (e < Q.n_aad && aad[e].aa1 * 20u + aad[e].aa2 == key) e++;
+            aa_range[key] = (uint16_t)((k << 8) | (e - k));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k6a: candidate edges
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VA_THREADS)
+    k6a_edges(StoreView st, const VQDesc *vq, const VHash *vhash, const VAad *vaad, const uint32_t *cand_query,
+              const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp, float ca_cutoff, uint32_t *pool_key,
+              uint16_t *pool_ent, unsigned int *pool_count, uint32_t pool_cap, uint32_t *cand_ebegin,
+              uint32_t *cand_ne, uint8_t *cand_flags) {
     __shared__ uint16_t list1[V_LIST_CAP], list2[V_LIST_CAP];
-    __shared__ uint32_t n1, n2, q_n, n_e;
-    __shared__ uint32_t q_ij[V_CHUNK];
-    __shared__ float q_d[V_CHUNK];
-    __shared__ VAad aad[V_MAX_AAD];        // sorted by (aa1, aa2) on the host
-    __shared__ uint16_t aa_range[400];      // aa1 * 20 + aa2 -> start << 8 | count of its entries (0 = pair not in query)
-    __shared__ uint32_t e_key[V_MAX_E]; // i << 16 | j, sorted
+    __shared__ uint32_t n1, n2, q_n, n_e, s_base;
+    __shared__ uint32_t q_ij[VA_QUEUE];
+    __shared__ float q_d[VA_QUEUE];
+    __shared__ VAad aad[V_MAX_AAD];
+    __shared__ uint16_t aa_range[400];
+    __shared__ uint32_t e_key[V_MAX_E]; // i << 16 | j
     __shared__ uint16_t e_ent[V_MAX_E]; // index of the edge's hash inside the query's sorted hash set
-    __shared__ uint8_t e_a[V_MAX_E], e_b[V_MAX_E];
-    __shared__ uint16_t node_res[V_MAX_NODES];
-    __shared__ uint64_t comp_mask[V_MAX_C];
-    __shared__ uint64_t reach[V_MAX_NODES], und[V_MAX_NODES]; // directed / undirected reachability closures
-    __shared__ uint32_t n_nodes, n_comp, s_flag;
-    __shared__ uint8_t counts[V_MAX_NQ * V_MAX_NODES];
-    // per-component results
-    __shared__ float c_idf[V_MAX_C];
-    __shared__ uint32_t c_res[V_MAX_C][V_MAX_NQ]; // target residue index + 1 per query position
-    __shared__ uint32_t c_aq[V_MAX_C][V_MAX_NQ], c_at[V_MAX_C][V_MAX_NQ];
-    __shared__ uint32_t c_nal[V_MAX_C], c_nodes[V_MAX_C];
-    // rescue scratch
-    __shared__ uint32_t r_dq, r_max, r_nmax, r_arg, r_need, r_nridx;
-    __shared__ uint16_t r_ridx[V_MAX_NQ];
-    __shared__ unsigned int s_out_base;
-    __shared__ uint8_t m_qidx[V_MAX_NQ], m_ridx[V_MAX_NQ]; // mapping of the current component: dense query id, node id
-    __shared__ uint32_t m_n;
-    __shared__ uint32_t f_qscan[V_MAX_NQ], f_rscan[V_MAX_NQ], f_nscan, f_res[V_MAX_NQ], f_nres;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.x;
@@ -109,29 +145,17 @@ __global__ void __launch_bounds__(V_THREADS)
     const uint64_t base = st.row_offsets[t];
     const uint32_t n = (uint32_t)(st.row_offsets[t + 1] - base);
     const VHash *H = vhash + Q.hash_begin;
-    if (tid == 0) {
-        n1 = n2 = q_n = n_e = 0;
-        s_flag = 0;
-        n_comp = 0;
-    }
-    for (uint32_t k = tid; k < Q.n_aad; k += V_THREADS) aad[k] = vaad[Q.aad_begin + k];
-    for (uint32_t k = tid; k < 400; k += V_THREADS) aa_range[k] = 0;
+    if (tid == 0) n1 = n2 = q_n = n_e = 0;
+    load_aad_phase1<VA_THREADS>(Q, vaad, aad, aa_range, tid);
     __syncthreads();
     if (Q.n_hashes == 0 || Q.n_aad == 0) return;
-    for (uint32_t k = tid; k < Q.n_aad; k += V_THREADS) { // heads of runs of equal (aa1, aa2)
-        const uint32_t key = aad[k].aa1 * 20u + aad[k].aa2;
-        if (k == 0 || aad[k - 1].aa1 * 20u + aad[k - 1].aa2 != key) {
-            uint32_t e = k + 1;
-            while (e < Q.n_aad && aad[e].aa1 * 20u + aad[e].aa2 == key) e++;
-            aa_range[key] = (uint16_t)((k << 8) | (e - k));
-        }
-    }
+    load_aad_phase2<VA_THREADS>(Q, aad, aa_range, tid);
     __syncthreads();
 
     // ---- prefilter sets (prefilter_amino_acid, retrieve.rs:563-602) ----
     bool all_pairs = !Q.use_prefilter;
     if (!all_pairs) {
-        for (uint32_t r0 = 0; r0 < n; r0 += V_THREADS) {
+        for (uint32_t r0 = 0; r0 < n; r0 += VA_THREADS) {
             const uint32_t r = r0 + tid;
             bool in1 = false, in2 = false;
             if (r < n) {
@@ -154,7 +178,7 @@ __global__ void __launch_bounds__(V_THREADS)
         __syncthreads();
         if (n1 == 0 || n2 == 0) all_pairs = true; // CombinationVecIterator::is_empty (retrieve.rs:145-151)
         else if (n1 > V_LIST_CAP || n2 > V_LIST_CAP) {
-            if (tid == 0) cand_flags[c] = 1; // V_OVERFLOW: handled by the general path
+            if (tid == 0) cand_flags[c] = 1; // handled by the general path
             return;
         }
     }
@@ -162,9 +186,9 @@ __global__ void __launch_bounds__(V_THREADS)
     const uint64_t total = (uint64_t)rows * cols; // < 2^32: both factors are at most 65535
 
     // ---- retrieve_with_prefilter: screen, hash, keep pairs whose hash is in the query set ----
-    for (uint64_t p0 = 0; p0 < total; p0 += V_CHUNK) {
-        for (uint32_t u = 0; u < V_CHUNK / V_THREADS; u++) {
-            const uint64_t p = p0 + (uint64_t)u * V_THREADS + tid;
+    for (uint64_t p0 = 0; p0 < total; p0 += VA_CHUNK) {
+        for (uint32_t u = 0; u < VA_CHUNK / VA_THREADS; u++) {
+            const uint64_t p = p0 + (uint64_t)u * VA_THREADS + tid;
             bool pass = false;
             uint32_t i = 0, j = 0;
             float d = 0.f;
@@ -174,15 +198,17 @@ __global__ void __launch_bounds__(V_THREADS)
                 i = all_pairs ? a : list1[a];
                 j = all_pairs ? b : list2[b];
                 const uint8_t ai = st.aa[base + i], aj = st.aa[base + j];
-                if (i != j && ai != 255 && aj != 255 && aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)] != 0) {
-                    d = fdg::dist(ld3(st.ca_xyz, base + i), ld3(st.ca_xyz, base + j));
-                    if (d <= hp.dist_cutoff) {
-                        const uint32_t rg = aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)];
-                        for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
-                            if (fabsf(d - aad[k].dist) < ca_cutoff) {
-                                pass = true;
-                                break;
-                            }
+                if (i != j && ai != 255 && aj != 255) {
+                    const uint32_t rg = aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)];
+                    if (rg != 0) {
+                        d = fdg::dist(ld3(st.ca_xyz, base + i), ld3(st.ca_xyz, base + j));
+                        if (d <= hp.dist_cutoff) {
+                            for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
+                                if (fabsf(d - aad[k].dist) < ca_cutoff) {
+                                    pass = true;
+                                    break;
+                                }
+                        }
                     }
                 }
             }
@@ -198,32 +224,51 @@ __global__ void __launch_bounds__(V_THREADS)
             }
         }
         __syncthreads();
+        // hash the queued survivors once a full CTA of them is waiting (or at the end): the binary64 trig of the
+        // hash is the expensive part, it should not run on a handful of lanes per chunk
         const uint32_t qn = q_n;
-        for (uint32_t k = tid; k < qn; k += V_THREADS) {
-            const uint32_t i = q_ij[k] >> 16, j = q_ij[k] & 0xffffu;
-            const uint64_t ri = base + i, rj = base + j;
-            const bool cbok = st.cb_valid == nullptr || (st.cb_valid[ri] && st.cb_valid[rj]);
-            if (!cbok) continue;
-            const uint32_t h = fdg::pair_hash(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri), ld3(st.n_xyz, rj),
-                                              ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj), st.aa[ri] & 0x7Fu,
-                                              st.aa[rj] & 0x7Fu, q_d[k], hp);
-            uint32_t lo = 0, hi = Q.n_hashes;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (H[mid].hash < h) lo = mid + 1;
-                else hi = mid;
-            }
-            if (lo < Q.n_hashes && H[lo].hash == h) {
-                const uint32_t pos = atomicAdd(&n_e, 1u);
-                if (pos < V_MAX_E) {
-                    e_key[pos] = q_ij[k];
-                    e_ent[pos] = (uint16_t)lo;
+        const bool last = p0 + VA_CHUNK >= total;
+        if (qn >= VA_THREADS || last) {
+            const uint32_t take = last ? qn : (qn / VA_THREADS) * VA_THREADS;
+            for (uint32_t k = tid; k < take; k += VA_THREADS) {
+                const uint32_t i = q_ij[k] >> 16, j = q_ij[k] & 0xffffu;
+                const uint64_t ri = base + i, rj = base + j;
+                const bool cbok = st.cb_valid == nullptr || (st.cb_valid[ri] && st.cb_valid[rj]);
+                if (!cbok) continue;
+                const uint32_t h = fdg::pair_hash(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
+                                                  ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj),
+                                                  st.aa[ri] & 0x7Fu, st.aa[rj] & 0x7Fu, q_d[k], hp);
+                uint32_t lo = 0, hi = Q.n_hashes;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (H[mid].hash < h) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < Q.n_hashes && H[lo].hash == h) {
+                    const uint32_t pos = atomicAdd(&n_e, 1u);
+                    if (pos < V_MAX_E) {
+                        e_key[pos] = q_ij[k];
+                        e_ent[pos] = (uint16_t)lo;
+                    }
                 }
             }
+            __syncthreads();
+            // keep the (< VA_THREADS) unhashed tail at the front of the queue
+            const uint32_t rest = qn - take;
+            uint32_t kij = 0;
+            float kd = 0.f;
+            if ((uint32_t)tid < rest) {
+                kij = q_ij[take + tid];
+                kd = q_d[take + tid];
+            }
+            __syncthreads();
+            if ((uint32_t)tid < rest) {
+                q_ij[tid] = kij;
+                q_d[tid] = kd;
+            }
+            if (tid == 0) q_n = rest;
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0) q_n = 0;
-        __syncthreads();
     }
     const uint32_t ne = n_e;
     if (ne == 0) return;
@@ -234,11 +279,11 @@ __global__ void __launch_bounds__(V_THREADS)
     // ---- sort edges by (i, j): the reference's emission order (graph node numbering, f32 sum order) ----
     uint32_t sort_n = 2;
     while (sort_n < ne) sort_n <<= 1;
-    for (uint32_t k = ne + tid; k < sort_n; k += V_THREADS) e_key[k] = 0xffffffffu;
+    for (uint32_t k = ne + tid; k < sort_n; k += VA_THREADS) e_key[k] = 0xffffffffu;
     __syncthreads();
     for (uint32_t size = 2; size <= sort_n; size <<= 1)
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t k = tid; k < sort_n / 2; k += V_THREADS) {
+            for (uint32_t k = tid; k < sort_n / 2; k += VA_THREADS) {
                 const uint32_t lo_i = 2 * k - (k & (stride - 1));
                 const uint32_t hi_i = lo_i + stride;
                 const bool up = (lo_i & size) == 0;
@@ -253,47 +298,117 @@ __global__ void __launch_bounds__(V_THREADS)
             }
             __syncthreads();
         }
+    if (tid == 0) s_base = atomicAdd(pool_count, ne);
+    __syncthreads();
+    const uint32_t b0 = s_base;
+    if ((uint64_t)b0 + ne > pool_cap) return; // pool too small: the host sizes it exactly and runs again
+    for (uint32_t k = tid; k < ne; k += VA_THREADS) {
+        pool_key[b0 + k] = e_key[k];
+        pool_ent[b0 + k] = e_ent[k];
+    }
+    if (tid == 0) {
+        cand_ebegin[c] = b0;
+        cand_ne[c] = ne;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k6b: components, residue mapping, rescue -- one warp per candidate
+// ------------------------------------------------------------------------------------------------
+struct WarpState { // per-warp shared memory
+    uint32_t e_key[V_MAX_E];
+    uint16_t e_ent[V_MAX_E];
+    uint8_t e_a[V_MAX_E], e_b[V_MAX_E];
+    uint64_t comp_mask[V_MAX_C];
+    uint64_t reach[V_MAX_NODES], und[V_MAX_NODES]; // directed / undirected reachability closures
+    uint16_t node_res[V_MAX_NODES];
+    uint8_t counts[V_MAX_NQ * V_MAX_NODES];
+    VAad aad[V_MAX_AAD];
+    uint16_t aa_range[400];
+    uint32_t n_nodes, n_comp, s_flag;
+    uint32_t r_dq, r_need, r_nridx, s_out_base;
+    uint16_t r_ridx[V_MAX_NQ];
+    uint8_t m_qidx[V_MAX_NQ], m_ridx[V_MAX_NQ]; // mapping of the current component: dense query id, node id
+    uint32_t m_n;
+    uint32_t f_qscan[V_MAX_NQ], f_rscan[V_MAX_NQ], f_nscan, f_res[V_MAX_NQ], f_nres;
+    uint32_t c_res[V_MAX_NQ]; // res_vec_from_hash of the current component
+    float c_idf;
+};
+
+__global__ void __launch_bounds__(VB_WARPS * 32)
+    k6b_components(StoreView st, const VQDesc *vq, const VHash *vhash, const VAad *vaad, const uint8_t *idx_dense,
+                   const uint32_t *cand_query, const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp,
+                   float ca_cutoff, int skip_ca_match, const uint32_t *pool_key, const uint16_t *pool_ent,
+                   const uint32_t *cand_ebegin, const uint32_t *cand_ne, CompSpec *specs, unsigned int *spec_count,
+                   uint32_t spec_cap, uint32_t *cand_ncomp, uint8_t *cand_flags) {
+    extern __shared__ __align__(16) unsigned char k6b_smem[];
+    const int lane = threadIdx.x & 31;
+    WarpState &W = reinterpret_cast<WarpState *>(k6b_smem)[threadIdx.x >> 5];
+    const uint32_t c = blockIdx.x * VB_WARPS + (threadIdx.x >> 5);
+    if (c >= n_cand) return;
+    const uint32_t ne_word = cand_ne[c];
+    const uint32_t ne = ne_word & 0x7fffffffu;
+    if (ne == 0) return;
+    const bool all_pairs = (ne_word >> 31) != 0;
+    const VQDesc Q = vq[cand_query[c]];
+    const uint32_t t = cand_nid[c];
+    const uint64_t base = st.row_offsets[t];
+    const uint32_t n = (uint32_t)(st.row_offsets[t + 1] - base);
+    const VHash *H = vhash + Q.hash_begin;
+    const uint32_t eb = cand_ebegin[c];
+    for (uint32_t k = lane; k < ne; k += 32) {
+        W.e_key[k] = pool_key[eb + k];
+        W.e_ent[k] = pool_ent[eb + k];
+    }
+    load_aad_phase1<32>(Q, vaad, W.aad, W.aa_range, lane);
+    if (lane == 0) {
+        W.s_flag = 0;
+        W.n_comp = 0;
+    }
+    __syncwarp();
+    load_aad_phase2<32>(Q, W.aad, W.aa_range, lane);
+    __syncwarp();
 
     // ---- graph: nodes by first appearance, components = SCCs U weak components, size >= 2 ----
-    if (tid == 0) {
+    if (lane == 0) {
         uint32_t nn = 0;
         bool overflow = false;
         for (uint32_t k = 0; k < ne && !overflow; k++) {
-            const uint16_t ends[2] = {(uint16_t)(e_key[k] >> 16), (uint16_t)(e_key[k] & 0xffffu)};
+            const uint16_t ends[2] = {(uint16_t)(W.e_key[k] >> 16), (uint16_t)(W.e_key[k] & 0xffffu)};
             uint8_t ids[2];
             for (int s = 0; s < 2; s++) {
                 uint32_t f = 0;
-                while (f < nn && node_res[f] != ends[s]) f++;
+                while (f < nn && W.node_res[f] != ends[s]) f++;
                 if (f == nn) {
                     if (nn == V_MAX_NODES) {
                         overflow = true;
                         break;
                     }
-                    node_res[nn++] = ends[s];
+                    W.node_res[nn++] = ends[s];
                 }
                 ids[s] = (uint8_t)f;
             }
-            e_a[k] = ids[0];
-            e_b[k] = ids[1];
+            W.e_a[k] = ids[0];
+            W.e_b[k] = ids[1];
         }
         if (overflow) {
-            s_flag = 1;
+            W.s_flag = 1;
         } else {
-            n_nodes = nn;
-            for (uint32_t v = 0; v < nn; v++) reach[v] = und[v] = 1ull << v;
+            W.n_nodes = nn;
+            for (uint32_t v = 0; v < nn; v++) W.reach[v] = W.und[v] = 1ull << v;
             bool changed = true;
             while (changed) {
                 changed = false;
                 for (uint32_t k = 0; k < ne; k++) {
-                    const uint32_t a = e_a[k], b = e_b[k];
-                    const uint64_t ra = reach[a] | reach[b];
-                    if (ra != reach[a]) {
-                        reach[a] = ra;
+                    const uint32_t a = W.e_a[k], b = W.e_b[k];
+                    const uint64_t ra = W.reach[a] | W.reach[b];
+                    if (ra != W.reach[a]) {
+                        W.reach[a] = ra;
                         changed = true;
                     }
-                    const uint64_t u = und[a] | und[b];
-                    if (u != und[a] || u != und[b]) {
-                        und[a] = und[b] = u;
+                    const uint64_t u = W.und[a] | W.und[b];
+                    if (u != W.und[a] || u != W.und[b]) {
+                        W.und[a] = W.und[b] = u;
                         changed = true;
                     }
                 }
@@ -302,48 +417,55 @@ __global__ void __launch_bounds__(V_THREADS)
             auto add_mask = [&](uint64_t m) {
                 if (__popcll(m) < 2) return;
                 for (uint32_t k = 0; k < nc; k++)
-                    if (comp_mask[k] == m) return;
+                    if (W.comp_mask[k] == m) return;
                 if (nc == V_MAX_C) {
-                    s_flag = 1;
+                    W.s_flag = 1;
                     return;
                 }
-                comp_mask[nc++] = m;
+                W.comp_mask[nc++] = m;
             };
             for (uint32_t v = 0; v < nn; v++) {
                 uint64_t scc = 0;
-                for (uint64_t r = reach[v]; r; r &= r - 1) {
+                for (uint64_t r = W.reach[v]; r; r &= r - 1) {
                     const int w = ctz64(r);
-                    if ((reach[w] >> v) & 1ull) scc |= 1ull << w;
+                    if ((W.reach[w] >> v) & 1ull) scc |= 1ull << w;
                 }
                 add_mask(scc);
-                add_mask(und[v]);
+                add_mask(W.und[v]);
             }
             for (uint32_t a = 1; a < nc; a++) { // insertion sort, lexicographic by sorted node list
-                const uint64_t m = comp_mask[a];
+                const uint64_t m = W.comp_mask[a];
                 uint32_t b = a;
-                while (b > 0 && mask_less(m, comp_mask[b - 1])) {
-                    comp_mask[b] = comp_mask[b - 1];
+                while (b > 0 && mask_less(m, W.comp_mask[b - 1])) {
+                    W.comp_mask[b] = W.comp_mask[b - 1];
                     b--;
                 }
-                comp_mask[b] = m;
+                W.comp_mask[b] = m;
             }
-            n_comp = nc;
+            W.n_comp = nc;
         }
     }
-    __syncthreads();
-    if (s_flag) {
-        if (tid == 0) cand_flags[c] = 1;
+    __syncwarp();
+    if (W.s_flag) {
+        if (lane == 0) cand_flags[c] = 1;
         return;
     }
-    const uint32_t ncomp = n_comp;
+    const uint32_t ncomp = W.n_comp;
+    if (ncomp == 0) return;
     const uint8_t *IDX = idx_dense + Q.idx_begin;
+    if (lane == 0) {
+        W.s_out_base = atomicAdd(spec_count, ncomp);
+        cand_ncomp[c] = ncomp;
+    }
+    __syncwarp();
+    const uint32_t out_base = W.s_out_base;
 
     for (uint32_t ci = 0; ci < ncomp; ci++) {
-        // ---- mapping (thread 0): votes, best per query residue, greedy assignment ----
-        const uint64_t mask = comp_mask[ci];
-        for (uint32_t k = tid; k < Q.n_dq * V_MAX_NODES; k += V_THREADS) counts[k] = 0;
-        __syncthreads();
-        if (tid == 0) {
+        // ---- mapping (lane 0): votes, best per query residue, greedy assignment ----
+        const uint64_t mask = W.comp_mask[ci];
+        for (uint32_t k = lane; k < Q.n_dq * V_MAX_NODES; k += 32) W.counts[k] = 0;
+        __syncwarp();
+        if (lane == 0) {
             const uint32_t nq_d = Q.n_dq;
             uint8_t best_c[V_MAX_NQ], best_r[V_MAX_NQ];
             for (uint32_t q = 0; q < nq_d; q++) {
@@ -352,15 +474,15 @@ __global__ void __launch_bounds__(V_THREADS)
             }
             float idf = 0.f;
             for (uint32_t k = 0; k < ne; k++) {
-                const uint32_t a = e_a[k], b = e_b[k];
+                const uint32_t a = W.e_a[k], b = W.e_b[k];
                 if (!((mask >> a) & 1ull) || !((mask >> b) & 1ull)) continue;
-                const VHash h = H[e_ent[k]];
+                const VHash h = H[W.e_ent[k]];
                 idf += h.idf;
                 uint32_t pq[2], pr[2];
                 if (h.sym) {
                     pq[0] = min((uint32_t)h.dqi, (uint32_t)h.dqj);
                     pq[1] = max((uint32_t)h.dqi, (uint32_t)h.dqj);
-                    const bool ab = node_res[a] < node_res[b];
+                    const bool ab = W.node_res[a] < W.node_res[b];
                     pr[0] = ab ? a : b;
                     pr[1] = ab ? b : a;
                 } else {
@@ -370,18 +492,18 @@ __global__ void __launch_bounds__(V_THREADS)
                     pr[1] = b;
                 }
                 for (int s = 0; s < 2; s++) {
-                    uint8_t &cnt = counts[pq[s] * V_MAX_NODES + pr[s]];
+                    uint8_t &cnt = W.counts[pq[s] * V_MAX_NODES + pr[s]];
                     if (cnt != 255) cnt++;
                     const uint32_t q = pq[s];
                     // best = (count, target residue) starts at (0, 0): the tie rule `r < best.1` only ever compares
                     // against a residue that already has a vote (retrieve.rs:655-660)
-                    if (cnt > best_c[q] || (cnt == best_c[q] && node_res[pr[s]] < node_res[best_r[q]])) {
+                    if (cnt > best_c[q] || (cnt == best_c[q] && W.node_res[pr[s]] < W.node_res[best_r[q]])) {
                         best_c[q] = cnt;
                         best_r[q] = (uint8_t)pr[s];
                     }
                 }
             }
-            c_idf[ci] = idf;
+            W.c_idf = idf;
             // order: count descending, dense query id ascending (bucket sort of retrieve.rs:667-675)
             uint8_t order[V_MAX_NQ];
             uint32_t no = 0;
@@ -400,180 +522,202 @@ __global__ void __launch_bounds__(V_THREADS)
             for (uint32_t k = 0; k < no && nm < node_count; k++) {
                 const uint32_t q = order[k], r = best_r[q];
                 if (!((r_used >> r) & 1ull)) { // q_used is implied: each q appears once in `order`
-                    m_qidx[nm] = (uint8_t)q;
-                    m_ridx[nm] = (uint8_t)r;
+                    W.m_qidx[nm] = (uint8_t)q;
+                    W.m_ridx[nm] = (uint8_t)r;
                     r_used |= 1ull << r;
                     nm++;
                 }
             }
-            m_n = nm;
-            c_nodes[ci] = node_count;
-            f_nscan = 0;
-            f_nres = 0;
-            r_nridx = nm;
-            for (uint32_t k = 0; k < nm; k++) r_ridx[k] = node_res[m_ridx[k]];
+            W.m_n = nm;
+            W.f_nscan = 0;
+            W.f_nres = 0;
+            W.r_nridx = nm;
+            for (uint32_t k = 0; k < nm; k++) W.r_ridx[k] = W.node_res[W.m_ridx[k]];
         }
-        __syncthreads();
+        __syncwarp();
         // ---- rescue loop over the query residues (retrieve.rs:453-516) ----
         for (uint32_t pos = 0; pos < Q.n_idx; pos++) {
-            if (tid == 0) {
+            if (lane == 0) {
                 const uint32_t dq = IDX[pos];
                 int mapped = -1;
-                for (uint32_t k = 0; k < m_n; k++)
-                    if (m_qidx[k] == dq) mapped = (int)node_res[m_ridx[k]];
-                r_need = 0;
+                for (uint32_t k = 0; k < W.m_n; k++)
+                    if (W.m_qidx[k] == dq) mapped = (int)W.node_res[W.m_ridx[k]];
+                W.r_need = 0;
                 if (mapped >= 0) {
                     const uint32_t ri = (uint32_t)mapped;
-                    c_res[ci][pos] = ri + 1; // res_vec_from_hash
+                    W.c_res[pos] = ri + 1; // res_vec_from_hash
                     uint32_t pp = 0;
-                    while (pp < f_nscan && f_rscan[pp] != ri) pp++;
-                    if (pp == f_nscan) {
-                        f_res[f_nres++] = ri + 1;
-                        f_qscan[f_nscan] = dq;
-                        f_rscan[f_nscan++] = ri;
+                    while (pp < W.f_nscan && W.f_rscan[pp] != ri) pp++;
+                    if (pp == W.f_nscan) {
+                        W.f_res[W.f_nres++] = ri + 1;
+                        W.f_qscan[W.f_nscan] = dq;
+                        W.f_rscan[W.f_nscan++] = ri;
                     } else {
-                        f_res[pp] = 0; // sic (retrieve.rs:475)
-                        f_res[f_nres++] = ri + 1;
-                        for (uint32_t k = pp; k + 1 < f_nscan; k++) {
-                            f_qscan[k] = f_qscan[k + 1];
-                            f_rscan[k] = f_rscan[k + 1];
+                        W.f_res[pp] = 0; // sic (retrieve.rs:475)
+                        W.f_res[W.f_nres++] = ri + 1;
+                        for (uint32_t k = pp; k + 1 < W.f_nscan; k++) {
+                            W.f_qscan[k] = W.f_qscan[k + 1];
+                            W.f_rscan[k] = W.f_rscan[k + 1];
                         }
-                        f_qscan[f_nscan - 1] = dq;
-                        f_rscan[f_nscan - 1] = ri;
+                        W.f_qscan[W.f_nscan - 1] = dq;
+                        W.f_rscan[W.f_nscan - 1] = ri;
                     }
                 } else {
-                    c_res[ci][pos] = 0;
-                    r_need = 1;
-                    r_dq = dq;
-                    r_max = 0;
-                    r_nmax = 0;
-                    r_arg = 0;
+                    W.c_res[pos] = 0;
+                    W.r_need = 1;
+                    W.r_dq = dq;
                 }
             }
-            __syncthreads();
-            if (r_need) {
-                // count_map[i] = #(entries of this query residue, matched target residues rj) compatible with (i, rj)
-                const uint32_t dq = r_dq;
-                const uint32_t nrows = all_pairs ? n : n1;
-                auto row_count = [&](uint32_t a) -> uint32_t {
-                    const uint32_t i = all_pairs ? a : list1[a];
+            __syncwarp();
+            if (W.r_need) {
+                // count_map[i] = #(entries of this query residue, matched target residues rj) compatible with (i, rj),
+                // over the rows of the pair iteration (all residues, or those whose amino acid is a res1 of the query)
+                const uint32_t dq = W.r_dq;
+                auto row_count = [&](uint32_t i) -> uint32_t {
                     const uint8_t ai = st.aa[base + i];
+                    if (!all_pairs && !(((ai & 0x80u) == 0) && ((Q.aa1_mask >> (ai & 31u)) & 1u))) return 0u;
                     if (ai == 255 || (st.cb_valid != nullptr && !st.cb_valid[base + i])) return 0u;
                     const uint8_t cia = ai & 0x7Fu;
                     const fdg::V3 cai = ld3(st.ca_xyz, base + i);
                     uint32_t cnt = 0;
-                    for (uint32_t k = 0; k < r_nridx; k++) {
-                        const uint32_t rj = r_ridx[k];
+                    for (uint32_t k = 0; k < W.r_nridx; k++) {
+                        const uint32_t rj = W.r_ridx[k];
                         if (rj == i) continue;
                         const uint8_t aj = st.aa[base + rj];
                         if (aj == 255 || (st.cb_valid != nullptr && !st.cb_valid[base + rj])) continue;
                         if (!all_pairs && !(((aj & 0x80u) == 0) && ((Q.aa2_mask >> (aj & 31u)) & 1u))) continue;
+                        const uint32_t rg = W.aa_range[cia * 20u + (aj & 0x7Fu)];
+                        if (rg == 0) continue;
                         const float d = fdg::dist(cai, ld3(st.ca_xyz, base + rj));
                         if (!(d <= hp.dist_cutoff)) continue;
-                        const uint32_t rg = aa_range[cia * 20u + (aj & 0x7Fu)];
                         for (uint32_t e = rg >> 8, ee = (rg >> 8) + (rg & 0xffu); e < ee; e++)
-                            if (aad[e].dq == dq && fabsf(d - aad[e].dist) < ca_cutoff) cnt++;
+                            if (W.aad[e].dq == dq && fabsf(d - W.aad[e].dist) < ca_cutoff) cnt++;
                     }
                     return cnt;
                 };
-                for (uint32_t a = tid; a < nrows; a += V_THREADS) { // pass 1: the maximum count
-                    const uint32_t cnt = row_count(a);
-                    if (cnt) atomicMax(&r_max, cnt);
+                // one pass: per lane the maximum count, how many rows reach it, and one such row
+                uint32_t l_max = 0, l_n = 0, l_arg = 0;
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint32_t cnt = row_count(i);
+                    if (cnt > l_max) {
+                        l_max = cnt;
+                        l_n = 1;
+                        l_arg = i;
+                    } else if (cnt == l_max && cnt > 0) {
+                        l_n++;
+                    }
                 }
-                __syncthreads();
-                const uint32_t mx = r_max;
-                if (mx > 0)
-                    for (uint32_t a = tid; a < nrows; a += V_THREADS) // pass 2: who reaches it
-                        if (row_count(a) == mx) {
-                            atomicAdd(&r_nmax, 1u);
-                            r_arg = all_pairs ? a : list1[a];
-                        }
-                __syncthreads();
-                if (tid == 0) {
-                    bool ok = r_max >= 2 && r_nmax == 1;
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, l_max);
+                const uint32_t mine = (mx > 0 && l_max == mx) ? l_n : 0u;
+                const uint32_t nmax = __reduce_add_sync(0xffffffffu, mine);
+                const uint32_t who = __ballot_sync(0xffffffffu, mine != 0);
+                const uint32_t arg = who ? __shfl_sync(0xffffffffu, l_arg, __ffs(who) - 1) : 0u;
+                if (lane == 0) {
+                    bool ok = mx >= 2 && nmax == 1;
                     if (ok)
-                        for (uint32_t k = 0; k < f_nscan; k++)
-                            if (f_rscan[k] == r_arg) ok = false;
+                        for (uint32_t k = 0; k < W.f_nscan; k++)
+                            if (W.f_rscan[k] == arg) ok = false;
                     if (ok) {
-                        f_res[f_nres++] = r_arg + 1;
-                        f_qscan[f_nscan] = r_dq;
-                        f_rscan[f_nscan++] = r_arg;
+                        W.f_res[W.f_nres++] = arg + 1;
+                        W.f_qscan[W.f_nscan] = W.r_dq;
+                        W.f_rscan[W.f_nscan++] = arg;
                     } else {
-                        f_res[f_nres++] = 0;
+                        W.f_res[W.f_nres++] = 0;
                     }
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
-        // ---- choose the alignment and the reported residues ----
-        if (tid == 0) {
+        // ---- choose the alignment and the reported residues; write the component spec ----
+        if (lane == 0) {
             bool same = true;
-            for (uint32_t k = 0; k < Q.n_idx; k++) same = same && f_res[k] == c_res[ci][k];
-            uint32_t nal;
-            if (skip_ca_match || same) {
-                nal = m_n;
-                for (uint32_t k = 0; k < nal; k++) {
-                    c_aq[ci][k] = m_qidx[k];
-                    c_at[ci][k] = node_res[m_ridx[k]];
+            for (uint32_t k = 0; k < Q.n_idx; k++) same = same && W.f_res[k] == W.c_res[k];
+            const uint32_t slot = out_base + ci;
+            if (slot < spec_cap) {
+                CompSpec sp;
+                sp.cand = c;
+                sp.ci = (uint16_t)ci;
+                sp.idf = W.c_idf;
+                sp.pad = 0;
+                uint32_t nal;
+                if (skip_ca_match || same) {
+                    nal = W.m_n;
+                    for (uint32_t k = 0; k < nal; k++) {
+                        sp.aq[k] = W.m_qidx[k];
+                        sp.at[k] = W.node_res[W.m_ridx[k]];
+                    }
+                } else {
+                    nal = W.f_nscan;
+                    for (uint32_t k = 0; k < nal; k++) {
+                        sp.aq[k] = (uint8_t)W.f_qscan[k];
+                        sp.at[k] = (uint16_t)W.f_rscan[k];
+                    }
                 }
-            } else {
-                nal = f_nscan;
-                for (uint32_t k = 0; k < nal; k++) {
-                    c_aq[ci][k] = f_qscan[k];
-                    c_at[ci][k] = f_rscan[k];
+                for (uint32_t k = nal; k < V_MAX_NQ; k++) {
+                    sp.aq[k] = 0;
+                    sp.at[k] = 0;
                 }
+                sp.nal = (uint16_t)nal;
+                for (uint32_t k = 0; k < V_MAX_NQ; k++)
+                    sp.res[k] = k < Q.n_idx ? (skip_ca_match ? W.c_res[k] : W.f_res[k]) : 0u;
+                specs[slot] = sp;
             }
-            c_nal[ci] = nal;
-            if (!skip_ca_match)
-                for (uint32_t k = 0; k < Q.n_idx; k++) c_res[ci][k] = f_res[k];
         }
-        __syncthreads();
+        __syncwarp();
     }
+}
 
-    // ---- Kabsch per component (thread ci), append match records ----
-    if (tid == 0) {
-        const unsigned int b = atomicAdd(out_count, ncomp);
-        s_out_base = b;
+// ------------------------------------------------------------------------------------------------
+// k6c: Kabsch per component, records in (candidate, component) order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    k6c_kabsch(StoreView st, const VQDesc *vq, const float *q_ca, const float *q_cb, const uint32_t *cand_query,
+               const uint32_t *cand_nid, const CompSpec *specs, uint32_t n_specs, const uint32_t *cand_first,
+               fd_match_record *out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_specs) return;
+    const CompSpec sp = specs[k];
+    const VQDesc Q = vq[cand_query[sp.cand]];
+    const uint64_t base = st.row_offsets[cand_nid[sp.cand]];
+    fd_match_record rec;
+    rec.cand = sp.cand;
+    rec.idf = sp.idf;
+    uint32_t nodes = 0;
+    for (uint32_t j = 0; j < V_MAX_NQ; j++) {
+        rec.res[j] = sp.res[j];
+        nodes += sp.res[j] != 0;
     }
-    __syncthreads();
-    if ((uint32_t)tid < ncomp) {
-        const uint32_t ci = tid;
-        const unsigned int slot = s_out_base + ci;
-        if (slot < out_cap) {
-            fd_match_record rec;
-            rec.cand = c;
-            rec.idf = c_idf[ci];
-            uint32_t nodes = 0;
-            for (uint32_t k = 0; k < V_MAX_NQ; k++) {
-                rec.res[k] = k < Q.n_idx ? c_res[ci][k] : 0;
-                nodes += rec.res[k] != 0;
-            }
-            rec.node_count = nodes;
-            fdk::GatherPoints mov{st.ca_xyz, st.cb_xyz, c_at[ci], base};
-            fdk::GatherPoints ref{q_ca, q_cb, c_aq[ci], (uint64_t)Q.qres_base};
-            fdk::kabsch_one(mov, ref, 2 * c_nal[ci], rec.U, rec.t, &rec.rmsd);
-            out[slot] = rec;
-        }
-    }
+    rec.node_count = nodes;
+    GatherPointsT<uint16_t> mov{st.ca_xyz, st.cb_xyz, sp.at, base};
+    GatherPointsT<uint8_t> ref{q_ca, q_cb, sp.aq, (uint64_t)Q.qres_base};
+    fdk::kabsch_one(mov, ref, 2u * sp.nal, rec.U, rec.t, &rec.rmsd);
+    out[cand_first[sp.cand] + sp.ci] = rec;
 }
 
 } // namespace
 
-extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
-                                          const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
-                                          const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
-                                          fd_match_record **out_records, uint64_t *out_n, uint8_t **out_flags) {
+// Shared body of the two entry points.  Outputs are views of ctx's pinned staging buffers.
+static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq, const uint32_t *cand_query,
+                       const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params, float ca_dist_cutoff,
+                       int skip_ca_match, const fd_match_record **out_records, uint64_t *out_n,
+                       const uint32_t **out_first, const uint8_t **out_flags) {
     if (!ctx) return FD_ERR_ARG;
-    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates_batch: no structure store attached");
-    if ((nq && !queries) || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags)
-        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates_batch: NULL argument");
+    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: no structure store attached");
+    if ((nq && !queries) || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags ||
+        !out_first)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates: NULL argument");
     if (n_cand > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "too many candidates in one call");
     FD_ENTER(ctx);
     *out_records = nullptr;
     *out_flags = nullptr;
+    *out_first = nullptr;
     *out_n = 0;
-    uint8_t *h_flags = (uint8_t *)calloc(std::max<uint64_t>(n_cand, 1), 1);
-    if (!h_flags) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    uint8_t *h_flags = nullptr;
+    uint32_t *h_first = nullptr;
+    FD_TRY(fd_pinned(ctx, 1, std::max<uint64_t>(n_cand, 1), (void **)&h_flags));
+    FD_TRY(fd_pinned(ctx, 2, (n_cand + 1) * 4, (void **)&h_first));
+    memset(h_flags, 0, std::max<uint64_t>(n_cand, 1));
+    memset(h_first, 0, (n_cand + 1) * 4);
     // flatten queries; a query outside the kernel's limits marks all of its candidates for the general path
     std::vector<VQDesc> descs(nq);
     std::vector<VHash> f_hash;
@@ -607,7 +751,6 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
         auto dense = [&](uint32_t r) { return (uint8_t)(std::lower_bound(dq.begin(), dq.end(), r) - dq.begin()); };
         for (uint32_t k = 0; k < Q.n_hashes; k++) {
             if (k && Q.hashes_sorted[k] <= Q.hashes_sorted[k - 1]) {
-                free(h_flags);
                 return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: hashes_sorted must be strictly ascending");
             }
             f_hash.push_back(VHash{Q.hashes_sorted[k], Q.hash_idf[k], dense(Q.hash_qi[k]), dense(Q.hash_qj[k]),
@@ -623,8 +766,7 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
             });
             for (uint32_t k : ord) {
                 if (Q.aa1[k] >= 20 || Q.aa2[k] >= 20) {
-                    free(h_flags);
-                    return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
+                        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
                 }
                 f_aad.push_back(VAad{Q.aa1[k], Q.aa2[k], dense(Q.q_index[k]), 0, Q.ca_dist[k]});
             }
@@ -633,7 +775,6 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
         for (uint32_t k = 0; k < Q.n_indices; k++) f_idx.push_back(dense(Q.indices[k]));
         for (uint32_t r : dq) { // only the residues the query touches travel to the device
             if (r >= Q.n_residues) {
-                free(h_flags);
                 return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: residue index outside the query structure");
             }
             for (int x = 0; x < 3; x++) {
@@ -645,13 +786,17 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
     }
     for (uint64_t c = 0; c < n_cand; c++) {
         if (cand_query[c] >= nq || cand_nid[c] >= ctx->store.n_structs) {
-            free(h_flags);
             return fd_fail(ctx, FD_ERR_ARG, "candidate query / structure id out of range");
         }
     }
+    for (uint64_t c = 0; c < n_cand; c++)
+        if (q_unfit[cand_query[c]]) h_flags[c] = 1;
     if (n_cand == 0) {
-        *out_records = (fd_match_record *)malloc(sizeof(fd_match_record));
+        fd_match_record *none = nullptr;
+        FD_TRY(fd_pinned(ctx, 0, sizeof(fd_match_record), (void **)&none));
+        *out_records = none;
         *out_flags = h_flags;
+        *out_first = h_first;
         return FD_OK;
     }
     cudaStream_t s = ctx->stream;
@@ -659,10 +804,13 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
     DevBuf<VHash> d_hash;
     DevBuf<VAad> d_aad;
     DevBuf<uint8_t> d_idx, d_flags;
-    DevBuf<uint32_t> d_cq, d_cn;
+    DevBuf<uint32_t> d_cq, d_cn, d_ebegin, d_ne, d_ncomp, d_first, d_pool_key;
+    DevBuf<uint16_t> d_pool_ent;
     DevBuf<float> d_qca, d_qcb;
-    DevBuf<unsigned int> d_count;
+    DevBuf<unsigned int> d_counters; // [0] edge pool, [1] component specs
+    DevBuf<CompSpec> d_specs;
     DevBuf<fd_match_record> d_out;
+    DevBuf<uint8_t> d_tmp;
     FD_CUDA(ctx, d_desc.alloc(nq));
     FD_CUDA(ctx, d_hash.alloc(f_hash.size()));
     FD_CUDA(ctx, d_aad.alloc(f_aad.size()));
@@ -672,7 +820,11 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
     FD_CUDA(ctx, d_cq.alloc(n_cand));
     FD_CUDA(ctx, d_cn.alloc(n_cand));
     FD_CUDA(ctx, d_flags.alloc(n_cand));
-    FD_CUDA(ctx, d_count.alloc(1));
+    FD_CUDA(ctx, d_ebegin.alloc(n_cand));
+    FD_CUDA(ctx, d_ne.alloc(n_cand));
+    FD_CUDA(ctx, d_ncomp.alloc(n_cand + 1));
+    FD_CUDA(ctx, d_first.alloc(n_cand + 1));
+    FD_CUDA(ctx, d_counters.alloc(2));
     FD_CUDA(ctx, cudaMemcpyAsync(d_desc.p, descs.data(), nq * sizeof(VQDesc), cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d_hash.p, f_hash.data(), f_hash.size() * sizeof(VHash), cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d_aad.p, f_aad.data(), f_aad.size() * sizeof(VAad), cudaMemcpyHostToDevice, s));
@@ -685,50 +837,118 @@ extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *qu
     const FdDeviceStore &S = ctx->store;
     StoreView sv{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid};
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
-    uint64_t cap = std::max<uint64_t>(1024, 2 * n_cand);
-    fd_match_record *h_out = nullptr;
-    unsigned int produced = 0;
-    StageTimer st(ctx, "verify");
+    const uint32_t nc32 = (uint32_t)n_cand;
+    unsigned int h_counters[2] = {0, 0};
+    FD_CUDA(ctx, fd_ensure_events(ctx));
+    cudaEvent_t *ev = ctx->ev_extra;
+    FD_CUDA(ctx, cudaEventRecord(ev[0], s));
+    // ---- k6a: edges into a compact pool (sized for 48 edges per candidate; exact on the rare overflow) ----
+    uint64_t pool_cap = std::max<uint64_t>(1u << 20, 48 * n_cand);
     for (int attempt = 0; attempt < 2; attempt++) {
-        FD_CUDA(ctx, d_out.alloc(cap));
-        FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, 4, s));
-        FD_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, n_cand, s));
-        FD_LAUNCH(ctx, k6_verify, (uint32_t)n_cand, V_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_idx.p,
-                  d_qca.p, d_qcb.p, d_cq.p, d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, skip_ca_match, d_out.p,
-                  d_count.p, (uint32_t)std::min<uint64_t>(cap, 0xffffffffu), d_flags.p);
-        FD_CUDA(ctx, cudaMemcpyAsync(&produced, d_count.p, 4, cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, d_pool_key.alloc(pool_cap));
+        FD_CUDA(ctx, d_pool_ent.alloc(pool_cap));
+        FD_CUDA(ctx, cudaMemsetAsync(d_counters.p, 0, 8, s));
+        FD_CUDA(ctx, cudaMemsetAsync(d_ne.p, 0, n_cand * 4, s));
+        FD_LAUNCH(ctx, k6a_edges, nc32, VA_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p, d_cn.p, nc32, hp,
+                  ca_dist_cutoff, d_pool_key.p, d_pool_ent.p, d_counters.p, (uint32_t)std::min<uint64_t>(pool_cap, 0xffffffffu),
+                  d_ebegin.p, d_ne.p, d_flags.p);
+        FD_CUDA(ctx, cudaMemcpyAsync(h_counters, d_counters.p, 4, cudaMemcpyDeviceToHost, s));
         FD_CUDA(ctx, cudaStreamSynchronize(s));
-        if (produced <= cap) break;
-        cap = produced; // the pool was too small: size it exactly and run once more
+        if (h_counters[0] <= pool_cap) break;
+        pool_cap = h_counters[0];
     }
-    h_out = (fd_match_record *)malloc(std::max<uint64_t>(produced, 1) * sizeof(fd_match_record));
-    if (!h_out) {
-        free(h_flags);
-        return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    FD_CUDA(ctx, cudaEventRecord(ev[1], s));
+    // ---- k6b: components ----
+    uint64_t spec_cap = std::max<uint64_t>(1024, 2 * n_cand);
+    const size_t smem_b = sizeof(WarpState) * VB_WARPS;
+    FD_CUDA(ctx, cudaFuncSetAttribute(k6b_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        FD_CUDA(ctx, d_specs.alloc(spec_cap));
+        FD_CUDA(ctx, cudaMemsetAsync(d_counters.p + 1, 0, 4, s));
+        FD_CUDA(ctx, cudaMemsetAsync(d_ncomp.p, 0, (n_cand + 1) * 4, s));
+        FD_LAUNCH(ctx, k6b_components, fd_div_up(n_cand, VB_WARPS), VB_WARPS * 32, smem_b, sv, d_desc.p, d_hash.p,
+                  d_aad.p, d_idx.p, d_cq.p, d_cn.p, nc32, hp, ca_dist_cutoff, skip_ca_match, d_pool_key.p,
+                  d_pool_ent.p, d_ebegin.p, d_ne.p, d_specs.p, d_counters.p + 1,
+                  (uint32_t)std::min<uint64_t>(spec_cap, 0xffffffffu), d_ncomp.p, d_flags.p);
+        FD_CUDA(ctx, cudaMemcpyAsync(h_counters + 1, d_counters.p + 1, 4, cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, cudaStreamSynchronize(s));
+        if (h_counters[1] <= spec_cap) break;
+        spec_cap = h_counters[1];
     }
+    FD_CUDA(ctx, cudaEventRecord(ev[2], s));
+    const uint32_t produced = h_counters[1];
+    // ---- k6c: Kabsch, records in (candidate, component) order ----
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_ncomp.p, d_first.p, n_cand + 1, s);
+    FD_CUDA(ctx, d_tmp.alloc(tb));
+    FD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_ncomp.p, d_first.p, n_cand + 1, s));
+    ctx->launches += 2;
+    FD_CUDA(ctx, d_out.alloc(produced));
+    if (produced)
+        FD_LAUNCH(ctx, k6c_kabsch, fd_div_up(produced, 128), 128, 0, sv, d_desc.p, d_qca.p, d_qcb.p, d_cq.p, d_cn.p,
+                  d_specs.p, produced, d_first.p, d_out.p);
+    fd_match_record *h_out = nullptr;
+    uint8_t *h_kflags = nullptr;
+    FD_TRY(fd_pinned(ctx, 0, std::max<uint64_t>(produced, 1) * sizeof(fd_match_record), (void **)&h_out));
+    FD_TRY(fd_pinned(ctx, 3, n_cand, (void **)&h_kflags));
     FD_CUDA(ctx, cudaMemcpyAsync(h_out, d_out.p, (size_t)produced * sizeof(fd_match_record), cudaMemcpyDeviceToHost, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags.p, n_cand, cudaMemcpyDeviceToHost, s));
-    FD_CUDA(ctx, st.finish());
-    for (uint64_t c = 0; c < n_cand; c++)
-        if (q_unfit[cand_query[c]]) h_flags[c] = 1;
-    // records arrive in arbitrary CTA order (each candidate's block is contiguous and in component order):
-    // counting sort by candidate
-    if (produced) {
-        std::vector<uint32_t> start(n_cand + 1, 0);
-        for (unsigned int k = 0; k < produced; k++) start[h_out[k].cand + 1]++;
-        for (uint64_t c = 0; c < n_cand; c++) start[c + 1] += start[c];
-        fd_match_record *sorted = (fd_match_record *)malloc((size_t)produced * sizeof(fd_match_record));
-        if (!sorted) {
-            free(h_out);
-            free(h_flags);
-            return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    FD_CUDA(ctx, cudaMemcpyAsync(h_first, d_first.p, (n_cand + 1) * 4, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(h_kflags, d_flags.p, n_cand, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, cudaEventRecord(ev[3], s));
+    FD_CUDA(ctx, cudaEventSynchronize(ev[3]));
+    FD_CUDA(ctx, cudaGetLastError());
+    {
+        const char *names[4] = {"verify_edges", "verify_components", "verify_kabsch", "verify"};
+        for (int k = 0; k < 4; k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, k == 3 ? ev[0] : ev[k], k == 3 ? ev[3] : ev[k + 1]);
+            FdStage &stg = ctx->stages[names[k]];
+            stg.ms += ms;
+            stg.launches += 1;
         }
-        for (unsigned int k = 0; k < produced; k++) sorted[start[h_out[k].cand]++] = h_out[k];
-        free(h_out);
-        h_out = sorted;
     }
+    for (uint64_t c = 0; c < n_cand; c++) h_flags[c] |= h_kflags[c];
     *out_records = h_out;
     *out_n = produced;
+    *out_first = h_first;
     *out_flags = h_flags;
+    return FD_OK;
+}
+
+extern "C" int fd_verify_candidates_view(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
+                                         const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
+                                         const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
+                                         const fd_match_record **out_records, uint64_t *out_n,
+                                         const uint32_t **out_first, const uint8_t **out_flags) {
+    return verify_core(ctx, queries, nq, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match,
+                       out_records, out_n, out_first, out_flags);
+}
+
+extern "C" int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
+                                          const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
+                                          const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
+                                          fd_match_record **out_records, uint64_t *out_n, uint8_t **out_flags) {
+    if (!out_records || !out_n || !out_flags) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates_batch: NULL argument");
+    const fd_match_record *recs = nullptr;
+    const uint32_t *first = nullptr;
+    const uint8_t *flags = nullptr;
+    uint64_t n = 0;
+    *out_records = nullptr;
+    *out_flags = nullptr;
+    *out_n = 0;
+    FD_TRY(verify_core(ctx, queries, nq, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match, &recs, &n,
+                       &first, &flags));
+    fd_match_record *r = (fd_match_record *)malloc(std::max<uint64_t>(n, 1) * sizeof(fd_match_record));
+    uint8_t *f = (uint8_t *)malloc(std::max<uint64_t>(n_cand, 1));
+    if (!r || !f) {
+        free(r);
+        free(f);
+        return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    }
+    memcpy(r, recs, n * sizeof(fd_match_record));
+    memcpy(f, flags, n_cand);
+    *out_records = r;
+    *out_n = n;
+    *out_flags = f;
     return FD_OK;
 }

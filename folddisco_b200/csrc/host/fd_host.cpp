@@ -334,6 +334,11 @@ struct Query {
     std::vector<uint32_t> aad_qi;
     // hash-range shards (fdh_queries_set_shards): one vote bit per (query edge, rank that owns some of its hashes)
     std::vector<uint16_t> s_edge_of_hash, s_edge_node, s_edge_group;
+    // fd_verify_query arrays aligned with hashes_sorted (vs_idf is filled when the batch is finalised)
+    std::vector<uint32_t> vs_qi, vs_qj;
+    std::vector<uint8_t> vs_sym;
+    std::vector<float> vs_idf;
+    std::vector<uint32_t> vs_entry; // position in entries
 };
 
 // pdb_tr.rs:95-162 with default bins
@@ -558,6 +563,15 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     }
     Q.n_nodes = (uint32_t)nodes.size();
     std::sort(Q.hashes_sorted.begin(), Q.hashes_sorted.end());
+    for (uint32_t h : Q.hashes_sorted) {
+        const uint32_t pos = Q.pos.at(h);
+        const QEntry &e = Q.entries[pos];
+        Q.vs_entry.push_back(pos);
+        Q.vs_qi.push_back(e.qi);
+        Q.vs_qj.push_back(e.qj);
+        Q.vs_sym.push_back(Q.symmetric.at(h));
+    }
+    Q.vs_idf.assign(Q.hashes_sorted.size(), 0.f);
     for (auto &d : Q.aad) {
         Q.aad_aa1.push_back(d.aa1);
         Q.aad_aa2.push_back(d.aa2);
@@ -1475,7 +1489,12 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     R->wall_ms[0] = ms_since(t_stage);
     t_stage = now();
     R->d2h_bytes += n_cand * sizeof(fd_struct_hit) + (nq + 1) * 8ull + nq * 16ull;
-    std::vector<FinalMatch> fm; // all matches, grouped by candidate after the sort below
+    std::vector<FinalMatch> fm; // matches of the candidates that took the general path, grouped by candidate
+    const fd_match_record *recs = nullptr; // matches of everything else: views of ctx's pinned staging buffers
+    const uint32_t *rec_first = nullptr;
+    const uint8_t *flags = nullptr;
+    std::vector<uint8_t> all_general;
+    std::vector<uint32_t> cand_q;
     double host_ms = 0.0;
     auto fail = [&]() {
         fd_free(hits);
@@ -1484,61 +1503,37 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         return (fdh_results *)nullptr;
     };
     if (!p->skip_match && n_cand) {
-        std::vector<uint32_t> cand_q(n_cand), cand_n(n_cand);
+        cand_q.resize(n_cand);
+        std::vector<uint32_t> cand_n(n_cand);
         for (uint32_t q = 0; q < nq; q++)
             for (uint64_t k = hoff[q]; k < hoff[q + 1]; k++) {
                 cand_q[k] = q;
                 cand_n[k] = hits[k].nid;
             }
-        // --- K6: fused verification; candidates beyond its limits come back flagged ---
+        // --- K6: verification on the device; candidates beyond its limits come back flagged ---
         std::vector<fd_verify_query> vq(nq);
-        std::vector<std::vector<uint32_t>> v_qi(nq), v_qj(nq);
-        std::vector<std::vector<float>> v_idf(nq);
-        std::vector<std::vector<uint8_t>> v_sym(nq);
         for (uint32_t q = 0; q < nq; q++) {
             const Query &Q = qs->q[q_begin + q];
-            for (uint32_t h : Q.hashes_sorted) {
-                const QEntry &e = Q.entries[Q.pos.at(h)];
-                v_qi[q].push_back(e.qi);
-                v_qj[q].push_back(e.qj);
-                v_idf[q].push_back(e.idf);
-                v_sym[q].push_back(Q.symmetric.at(h));
-            }
-            vq[q] = fd_verify_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), v_qi[q].data(),
-                                    v_qj[q].data(), v_idf[q].data(), v_sym[q].data(), (uint32_t)Q.aad.size(),
+            vq[q] = fd_verify_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), Q.vs_qi.data(),
+                                    Q.vs_qj.data(), Q.vs_idf.data(), Q.vs_sym.data(), (uint32_t)Q.aad.size(),
                                     Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data(),
                                     (uint32_t)Q.indices.size(), Q.indices.data(), (uint32_t)Q.st->nres(), Q.st->ca.data(),
                                     Q.st->cb.data()};
             R->h2d_bytes += 14ull * Q.hashes_sorted.size() + 8ull * Q.aad.size() + Q.indices.size() + 24ull * 16 + 48;
         }
-        fd_match_record *recs = nullptr;
         uint64_t n_recs = 0;
-        uint8_t *flags = nullptr;
         if (p->verify_mode == 1) { // general path for everything
-            flags = (uint8_t *)malloc(n_cand);
-            recs = (fd_match_record *)malloc(sizeof(fd_match_record));
-            if (!flags || !recs) return fail();
-            memset(flags, 1, n_cand);
-        } else if (fd_verify_candidates_batch(ctx, vq.data(), nq, cand_q.data(), cand_n.data(), n_cand, &qs->p.hash,
-                                              p->ca_dist_cutoff, p->skip_ca_match, &recs, &n_recs, &flags) != FD_OK) {
+            all_general.assign(n_cand, 1);
+            flags = all_general.data();
+        } else if (fd_verify_candidates_view(ctx, vq.data(), nq, cand_q.data(), cand_n.data(), n_cand, &qs->p.hash,
+                                             p->ca_dist_cutoff, p->skip_ca_match, &recs, &n_recs, &rec_first,
+                                             &flags) != FD_OK) {
             set_err(fd_last_error(ctx));
             return fail();
         }
         R->h2d_bytes += 8ull * n_cand;
-        R->d2h_bytes += n_recs * sizeof(fd_match_record) + n_cand;
+        R->d2h_bytes += n_recs * sizeof(fd_match_record) + 5ull * n_cand;
         auto t0 = std::chrono::steady_clock::now();
-        fm.resize(n_recs);
-        for (uint64_t k = 0; k < n_recs; k++) {
-            FinalMatch &m = fm[k];
-            m.cand = recs[k].cand;
-            m.node_count = recs[k].node_count;
-            m.idf = recs[k].idf;
-            m.rmsd = recs[k].rmsd;
-            memcpy(m.U, recs[k].U, sizeof(m.U));
-            memcpy(m.t, recs[k].t, sizeof(m.t));
-            m.n_res = (uint32_t)std::min<size_t>(qs->q[q_begin + cand_q[m.cand]].indices.size(), 16);
-            memcpy(m.res16, recs[k].res, sizeof(m.res16));
-        }
         std::vector<uint32_t> fq_, fn_;
         std::vector<uint64_t> fglobal;
         for (uint64_t c = 0; c < n_cand; c++)
@@ -1548,8 +1543,6 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 fglobal.push_back(c);
             }
         host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        fd_free(recs);
-        fd_free(flags);
         if (!fglobal.empty()) {
             if (verify_general(ctx, qs, q_begin, nq, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
             std::stable_sort(fm.begin(), fm.end(), [](const FinalMatch &a, const FinalMatch &b) { return a.cand < b.cand; });
@@ -1566,23 +1559,47 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         std::vector<uint64_t> order;
     };
     std::vector<QOut> qout(nq);
-    std::vector<size_t> fm_begin(n_cand + 1, 0); // matches of candidate c: fm[fm_begin[c] .. fm_begin[c+1])
-    for (auto &m : fm) fm_begin[m.cand + 1]++;
-    for (uint64_t c = 0; c < n_cand; c++) fm_begin[c + 1] += fm_begin[c];
+    std::vector<size_t> fm_begin; // general-path matches of candidate c: fm[fm_begin[c] .. fm_begin[c+1])
+    if (!fm.empty()) {
+        fm_begin.assign(n_cand + 1, 0);
+        for (auto &m : fm) fm_begin[m.cand + 1]++;
+        for (uint64_t c = 0; c < n_cand; c++) fm_begin[c + 1] += fm_begin[c];
+    }
+    struct MatchView { // one verified component, from either source
+        uint32_t node_count;
+        float idf, rmsd;
+        const float *U, *t;
+        const uint32_t *res;
+    };
+    // number of matches of candidate c and the a-th of them
+    auto match_count = [&](uint64_t c) -> size_t {
+        if (flags && flags[c]) return fm_begin.empty() ? 0 : fm_begin[c + 1] - fm_begin[c];
+        return rec_first ? (size_t)(rec_first[c + 1] - rec_first[c]) : 0;
+    };
+    auto match_at = [&](uint64_t c, size_t a) -> MatchView {
+        if (flags && flags[c]) {
+            const FinalMatch &m = fm[fm_begin[c] + a];
+            return MatchView{m.node_count, m.idf, m.rmsd, m.U, m.t, m.res()};
+        }
+        const fd_match_record &r = recs[rec_first[c] + a];
+        return MatchView{r.node_count, r.idf, r.rmsd, r.U, r.t, r.res};
+    };
     auto build_query = [&](uint32_t q) {
         const Query &Q = qs->q[q_begin + q];
         QOut &O = qout[q];
         const float expected = (float)Q.indices.size();
+        const uint32_t n_res = (uint32_t)Q.indices.size();
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
-            const size_t a0 = fm_begin[c], a1 = fm_begin[c + 1];
+            const size_t na = match_count(c);
             uint32_t max_node = 0;
             float min_rmsd = 0.f;
-            for (size_t a = a0; a < a1; a++) {
-                if (fm[a].node_count > max_node) {
-                    max_node = fm[a].node_count;
-                    min_rmsd = fm[a].rmsd;
-                } else if (fm[a].node_count == max_node && fm[a].rmsd < min_rmsd) {
-                    min_rmsd = fm[a].rmsd;
+            for (size_t a = 0; a < na; a++) {
+                const MatchView m = match_at(c, a);
+                if (m.node_count > max_node) {
+                    max_node = m.node_count;
+                    min_rmsd = m.rmsd;
+                } else if (m.node_count == max_node && m.rmsd < min_rmsd) {
+                    min_rmsd = m.rmsd;
                 }
             }
             if (!p->skip_match) {
@@ -1595,8 +1612,8 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             fdh_struct_row sr{hits[c].nid, hits[c].match_count, hits[c].node_count, hits[c].edge_count, hits[c].idf,
                               max_node, min_rmsd, 0, 0};
             sr.match_begin = O.matches.size(); // relative to the query; rebased below
-            for (size_t a = a0; a < a1; a++) {
-                const FinalMatch &m = fm[a];
+            for (size_t a = 0; a < na; a++) {
+                const MatchView m = match_at(c, a);
                 bool pass = true;
                 if (p->connected_node_count > 0) pass = pass && m.node_count >= p->connected_node_count;
                 if (p->connected_node_ratio > 0.f) pass = pass && (float)m.node_count / expected >= p->connected_node_ratio;
@@ -1611,8 +1628,8 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 memcpy(mr.U, m.U, sizeof(mr.U));
                 memcpy(mr.t, m.t, sizeof(mr.t));
                 mr.res_begin = O.residues.size();
-                const uint32_t *res = m.res();
-                for (uint32_t k = 0; k < m.n_res; k++) {
+                const uint32_t *res = m.res;
+                for (uint32_t k = 0; k < n_res; k++) {
                     const uint32_t v = res[k];
                     fdh_residue_match rm{(uint8_t)(v != 0), 0, v ? (uint64_t)(v - 1) : 0};
                     if (v && labels && hits[c].nid < labels->names.size()) { // (chain, residue number) of the target
@@ -1796,6 +1813,7 @@ int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, ui
             const uint32_t c = counts[base + e.pair];
             e.idf = c > 0 ? log2f(total / (float)c) : 0.0f;
         }
+        for (size_t k = 0; k < Q.vs_entry.size(); k++) Q.vs_idf[k] = Q.entries[Q.vs_entry[k]].idf;
         base += Q.pair_hash.size();
     }
     qs->finalized = true;

@@ -41,7 +41,8 @@ const char *fd_version(void);
 /* number of this library's kernels launched through ctx since creation (bench.py's gpu_launches) */
 uint64_t fd_kernel_launches(const fd_ctx *ctx);
 /* cumulative device time (ms, CUDA events on the library's stream) of the named stage since creation:
- * "hash", "postings", "lookup", "scan", "select", "edges", "kabsch"; returns <0 if unknown */
+ * "hash", "postings", "attach", "lookup", "scan", "select", "verify" (= "verify_edges" + "verify_components" +
+ * "verify_kabsch"), "edges", "kabsch"; 0 if the stage never ran */
 double fd_stage_ms(const fd_ctx *ctx, const char *stage);
 uint64_t fd_stage_launches(const fd_ctx *ctx, const char *stage);
 
@@ -286,7 +287,7 @@ typedef struct {
 
 /* Fused replacement of retrieval_wrapper(...) (src/cli/workflows/query_pdb.rs:425-447, src/controller/
  * retrieve.rs:364-552) for n_cand (query, candidate) pairs against the attached store: candidate re-hash,
- * graph components, residue mapping + rescue and Kabsch RMSD in one kernel.  Library-allocated outputs:
+ * graph components, residue mapping + rescue and Kabsch RMSD on the device (three kernels, nothing but match records leaves HBM).  Library-allocated outputs:
  * records grouped by candidate in component order; flags[c] != 0 marks a candidate that exceeds the kernel's
  * shared-memory limits (more than 256 matching edges, 64 graph nodes, 16 components or 16 query residues) and
  * must be verified with fd_candidate_edges_batch + fd_kabsch_store_batch instead (no records are emitted
@@ -295,6 +296,16 @@ int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *queries, uint
                                const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
                                const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
                                fd_match_record **out_records, uint64_t *out_n, uint8_t **out_flags);
+
+/* The same computation without the output copies: *out_records (all records, grouped by candidate in component
+ * order), *out_first (n_cand + 1 offsets: candidate c owns records [first[c], first[c+1])) and *out_flags are views of
+ * pinned staging buffers owned by ctx, valid until the next verification call on ctx.  For hosts that consume the
+ * records immediately (the in-library host does). */
+int fd_verify_candidates_view(fd_ctx *ctx, const fd_verify_query *queries, uint32_t n_queries,
+                              const uint32_t *cand_query, const uint32_t *cand_nid, uint64_t n_cand,
+                              const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
+                              const fd_match_record **out_records, uint64_t *out_n, const uint32_t **out_first,
+                              const uint8_t **out_flags);
 
 /* number of structures of the attached index (lookup.len()); 0 if none */
 uint64_t fd_index_num_structs(const fd_ctx *ctx);

@@ -198,7 +198,7 @@ def run_ours(args, rank, world, local_rank):
     motif_structs = [(host.CompactStructure.from_atoms(a), q) for a, q in load_motif_atoms()]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     sp = host.SearchParams(top_n=args.top)
-    stages = ("lookup", "scan", "select", "verify", "edges", "kabsch")
+    stages = ("lookup", "scan", "select", "verify", "verify_edges", "verify_components", "verify_kabsch", "edges", "kabsch")
 
     def make_batch():
         qb = host.QueryBatch(index.params)

@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <functional>
 #include <array>
 #include <atomic>
 #include <charconv>
@@ -319,14 +320,12 @@ struct Query {
     std::string qstring;
     std::vector<uint32_t> indices;
     std::vector<QEntry> entries;
-    std::unordered_map<uint32_t, uint32_t> pos;
     std::vector<uint32_t> pair_hash; // observed hash per pair
     std::vector<AAD> aad;
     // derived
     std::vector<uint16_t> edge_of_hash, edge_node;
     uint32_t n_nodes = 0;
     std::vector<uint32_t> hashes_sorted;
-    std::unordered_map<uint32_t, uint8_t> symmetric;
     uint32_t max_q = 0;
     std::vector<uint32_t> hashes_flat;
     std::vector<uint8_t> aad_aa1, aad_aa2;
@@ -339,6 +338,10 @@ struct Query {
     std::vector<uint8_t> vs_sym;
     std::vector<float> vs_idf;
     std::vector<uint32_t> vs_entry; // position in entries
+    // position of hash h in hashes_sorted (and the vs_* arrays); h must be a hash of this query
+    size_t sorted_pos(uint32_t h) const {
+        return (size_t)(std::lower_bound(hashes_sorted.begin(), hashes_sorted.end(), h) - hashes_sorted.begin());
+    }
 };
 
 // pdb_tr.rs:95-162 with default bins
@@ -455,11 +458,49 @@ struct fdh_queries {
 
 namespace {
 
-void qinsert(Query &Q, const float *f, const fdg::HashParams &hp, uint32_t qi, uint32_t qj, bool primary,
-             uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
+// open-addressing set of the hashes already in Q.entries (local to build_query_map: nothing to free per query later)
+struct SeenHashes {
+    std::vector<uint32_t> slot; // entry index + 1, 0 = empty
+    uint32_t mask = 0, used = 0;
+    SeenHashes() { resize(256); }
+    void resize(uint32_t cap) {
+        slot.assign(cap, 0);
+        mask = cap - 1;
+    }
+    static uint32_t mix(uint32_t h) {
+        h ^= h >> 16;
+        h *= 0x7feb352du;
+        h ^= h >> 15;
+        return h;
+    }
+    // true if h was absent (and is now recorded as entry `idx`)
+    bool insert(uint32_t h, uint32_t idx, const std::vector<QEntry> &entries) {
+        if (2 * (used + 1) > slot.size()) {
+            std::vector<uint32_t> old;
+            old.swap(slot);
+            resize((uint32_t)old.size() * 2);
+            for (uint32_t v : old)
+                if (v) {
+                    uint32_t p = mix(entries[v - 1].hash) & mask;
+                    while (slot[p]) p = (p + 1) & mask;
+                    slot[p] = v;
+                }
+        }
+        uint32_t p = mix(h) & mask;
+        while (slot[p]) {
+            if (entries[slot[p] - 1].hash == h) return false;
+            p = (p + 1) & mask;
+        }
+        slot[p] = idx + 1;
+        used++;
+        return true;
+    }
+};
+
+void qinsert(Query &Q, SeenHashes &seen, const float *f, const fdg::HashParams &hp, uint32_t qi, uint32_t qj,
+             bool primary, uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
     const uint32_t h = fdg::perfect_hash(f, hp);
-    if (Q.pos.count(h)) return;
-    Q.pos[h] = (uint32_t)Q.entries.size();
+    if (!seen.insert(h, (uint32_t)Q.entries.size(), Q.entries)) return;
     Q.entries.push_back(QEntry{h, qi, qj, (uint8_t)primary, pair, 0.f});
 }
 
@@ -485,6 +526,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     }
     const float rad = 3.14159274101257324f / 180.0f; // f32::to_radians
     float f[7], fn[7], ff[7];
+    SeenHashes seen;
     const size_t K = Q.indices.size();
     for (size_t a = 0; a < K; a++)
         for (size_t b = 0; b < K; b++) {
@@ -497,7 +539,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
             if (f[2] <= 20.0f) Q.aad.push_back(AAD{(uint8_t)(c.aa[I] & 0x7F), (uint8_t)(c.aa[J] & 0x7F), f[2], I});
             const uint32_t pair = (uint32_t)Q.pair_hash.size();
             Q.pair_hash.push_back(fdg::perfect_hash(f, hp));
-            qinsert(Q, f, hp, I, J, true, pair);
+            qinsert(Q, seen, f, hp, I, J, true, pair);
             { // apply_substitutions (query.rs:86-156)
                 const float o1 = fn[0], o2 = fn[1];
                 auto si = submap.find(I), sj = submap.find(J);
@@ -506,14 +548,14 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
                         float t[7];
                         memcpy(t, fn, sizeof(t));
                         t[0] = (float)s;
-                        qinsert(Q, t, hp, I, J, false, pair);
+                        qinsert(Q, seen, t, hp, I, J, false, pair);
                     }
                     if (sj != submap.end())
                         for (uint8_t s : si->second)
                             for (uint8_t s2 : sj->second) {
                                 fn[0] = (float)s;
                                 fn[1] = (float)s2;
-                                qinsert(Q, fn, hp, I, J, false, pair);
+                                qinsert(Q, seen, fn, hp, I, J, false, pair);
                                 fn[0] = o1;
                                 fn[1] = o2;
                             }
@@ -522,7 +564,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
                         float t[7];
                         memcpy(t, fn, sizeof(t));
                         t[1] = (float)s;
-                        qinsert(Q, t, hp, I, J, false, pair);
+                        qinsert(Q, seen, t, hp, I, J, false, pair);
                     }
                 }
             }
@@ -532,8 +574,8 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
                     for (int k : idxs) {
                         fn[k] -= delta;
                         ff[k] += delta;
-                        qinsert(Q, fn, hp, I, J, false, pair);
-                        qinsert(Q, ff, hp, I, J, false, pair);
+                        qinsert(Q, seen, fn, hp, I, J, false, pair);
+                        qinsert(Q, seen, ff, hp, I, J, false, pair);
                         fn[k] += delta;
                         ff[k] -= delta;
                     }
@@ -557,21 +599,26 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
         }
         Q.edge_of_hash.push_back(it->second);
         Q.hashes_flat.push_back(e.hash);
-        Q.hashes_sorted.push_back(e.hash);
-        Q.symmetric[e.hash] = hash_is_symmetric(e.hash);
         Q.max_q = std::max(Q.max_q, std::max(e.qi, e.qj));
     }
     Q.n_nodes = (uint32_t)nodes.size();
-    std::sort(Q.hashes_sorted.begin(), Q.hashes_sorted.end());
-    for (uint32_t h : Q.hashes_sorted) {
-        const uint32_t pos = Q.pos.at(h);
-        const QEntry &e = Q.entries[pos];
-        Q.vs_entry.push_back(pos);
-        Q.vs_qi.push_back(e.qi);
-        Q.vs_qj.push_back(e.qj);
-        Q.vs_sym.push_back(Q.symmetric.at(h));
+    const size_t H = Q.entries.size();
+    Q.vs_entry.resize(H);
+    for (size_t k = 0; k < H; k++) Q.vs_entry[k] = (uint32_t)k;
+    std::sort(Q.vs_entry.begin(), Q.vs_entry.end(),
+              [&](uint32_t a, uint32_t b) { return Q.entries[a].hash < Q.entries[b].hash; });
+    Q.hashes_sorted.resize(H);
+    Q.vs_qi.resize(H);
+    Q.vs_qj.resize(H);
+    Q.vs_sym.resize(H);
+    for (size_t k = 0; k < H; k++) {
+        const QEntry &e = Q.entries[Q.vs_entry[k]];
+        Q.hashes_sorted[k] = e.hash;
+        Q.vs_qi[k] = e.qi;
+        Q.vs_qj[k] = e.qj;
+        Q.vs_sym[k] = hash_is_symmetric(e.hash);
     }
-    Q.vs_idf.assign(Q.hashes_sorted.size(), 0.f);
+    Q.vs_idf.assign(H, 0.f);
     for (auto &d : Q.aad) {
         Q.aad_aa1.push_back(d.aa1);
         Q.aad_aa2.push_back(d.aa2);
@@ -685,10 +732,11 @@ void match_component(const Query &Q, const std::vector<fd_cand_edge> &edges, con
     float idf = 0.f;
     for (uint32_t k : sub) {
         const fd_cand_edge &e = edges[k];
-        const QEntry &qe = Q.entries[Q.pos.at(e.hash)];
+        const size_t sp = Q.sorted_pos(e.hash);
+        const QEntry &qe = Q.entries[Q.vs_entry[sp]];
         idf += qe.idf; // calculate_subgraph_idf (retrieve.rs:705-719), edge order
         std::pair<uint32_t, uint32_t> pr[2];
-        if (Q.symmetric.at(e.hash)) {
+        if (Q.vs_sym[sp]) {
             const uint32_t q1 = std::min(qe.qi, qe.qj), q2 = std::max(qe.qi, qe.qj);
             const uint32_t r1 = std::min(e.i, e.j), r2 = std::max(e.i, e.j);
             pr[0] = {q1, r1};
@@ -795,11 +843,33 @@ void match_component(const Query &Q, const std::vector<fd_cand_edge> &edges, con
 
 } // namespace
 
+// result array without value-initialisation (the rows are written in place by the assembly threads)
+template <typename T>
+struct RawArray {
+    T *p = nullptr;
+    size_t n = 0;
+    RawArray() {}
+    RawArray(const RawArray &) = delete;
+    RawArray &operator=(const RawArray &) = delete;
+    ~RawArray() { free(p); }
+    bool alloc(size_t count) {
+        free(p);
+        n = count;
+        p = (T *)malloc(std::max<size_t>(count, 1) * sizeof(T));
+        return p != nullptr;
+    }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+};
+
 struct fdh_results {
-    std::vector<uint64_t> struct_off, match_off, match_order;
-    std::vector<fdh_struct_row> structs;
-    std::vector<fdh_match_row> matches;
-    std::vector<fdh_residue_match> residues;
+    std::vector<uint64_t> struct_off, match_off;
+    RawArray<uint64_t> match_order;
+    RawArray<fdh_struct_row> structs;
+    RawArray<fdh_match_row> matches;
+    RawArray<fdh_residue_match> residues;
     double host_ms = 0.0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0; // bytes this search moved between host and device
     double wall_ms[4] = {0, 0, 0, 0};      // count_query call, verification call(s), row assembly, total
@@ -1552,13 +1622,6 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     //     MatchFilter (:194-235), default sorts; query-parallel, then concatenated in query order ---
     R->wall_ms[1] = ms_since(t_stage);
     auto t1 = std::chrono::steady_clock::now();
-    struct QOut {
-        std::vector<fdh_struct_row> structs;
-        std::vector<fdh_match_row> matches;
-        std::vector<fdh_residue_match> residues;
-        std::vector<uint64_t> order;
-    };
-    std::vector<QOut> qout(nq);
     std::vector<size_t> fm_begin; // general-path matches of candidate c: fm[fm_begin[c] .. fm_begin[c+1])
     if (!fm.empty()) {
         fm_begin.assign(n_cand + 1, 0);
@@ -1584,50 +1647,89 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         const fd_match_record &r = recs[rec_first[c] + a];
         return MatchView{r.node_count, r.idf, r.rmsd, r.U, r.t, r.res};
     };
-    auto build_query = [&](uint32_t q) {
+    // per-candidate summary (retrieve.rs:539-551) + filter_after_matching (filter.rs:103-116)
+    auto summarize = [&](uint64_t c, size_t na, float expected, uint32_t *max_node_out, float *min_rmsd_out) -> bool {
+        uint32_t max_node = 0;
+        float min_rmsd = 0.f;
+        for (size_t a = 0; a < na; a++) {
+            const MatchView m = match_at(c, a);
+            if (m.node_count > max_node) {
+                max_node = m.node_count;
+                min_rmsd = m.rmsd;
+            } else if (m.node_count == max_node && m.rmsd < min_rmsd) {
+                min_rmsd = m.rmsd;
+            }
+        }
+        *max_node_out = max_node;
+        *min_rmsd_out = min_rmsd;
+        if (p->skip_match) return true;
+        bool pass = true;
+        if (p->max_matching_node_count > 0) pass = pass && max_node >= p->max_matching_node_count;
+        if (p->max_matching_node_ratio > 0.f) pass = pass && (float)max_node / expected >= p->max_matching_node_ratio;
+        if (p->rmsd_cutoff > 0.f) pass = pass && min_rmsd <= p->rmsd_cutoff;
+        return pass;
+    };
+    auto match_passes = [&](const MatchView &m, float expected) -> bool { // MatchFilter (filter.rs:194-235)
+        bool pass = true;
+        if (p->connected_node_count > 0) pass = pass && m.node_count >= p->connected_node_count;
+        if (p->connected_node_ratio > 0.f) pass = pass && (float)m.node_count / expected >= p->connected_node_ratio;
+        if (p->prefilter.idf_score_cutoff > 0.f) pass = pass && m.idf >= p->prefilter.idf_score_cutoff;
+        if (p->rmsd_cutoff > 0.f) pass = pass && m.rmsd <= p->rmsd_cutoff;
+        return pass;
+    };
+    const bool any_match_filter = p->connected_node_count > 0 || p->connected_node_ratio > 0.f ||
+                                  p->prefilter.idf_score_cutoff > 0.f || p->rmsd_cutoff > 0.f;
+    std::vector<uint64_t> res_off(nq + 1, 0);
+    // pass 1: rows per query
+    auto count_query_rows = [&](uint32_t q) {
         const Query &Q = qs->q[q_begin + q];
-        QOut &O = qout[q];
         const float expected = (float)Q.indices.size();
-        const uint32_t n_res = (uint32_t)Q.indices.size();
+        uint64_t ns = 0, nm = 0;
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
             const size_t na = match_count(c);
-            uint32_t max_node = 0;
-            float min_rmsd = 0.f;
-            for (size_t a = 0; a < na; a++) {
-                const MatchView m = match_at(c, a);
-                if (m.node_count > max_node) {
-                    max_node = m.node_count;
-                    min_rmsd = m.rmsd;
-                } else if (m.node_count == max_node && m.rmsd < min_rmsd) {
-                    min_rmsd = m.rmsd;
-                }
+            uint32_t max_node;
+            float min_rmsd;
+            if (!summarize(c, na, expected, &max_node, &min_rmsd)) continue;
+            ns++;
+            if (!any_match_filter) {
+                nm += na;
+            } else {
+                for (size_t a = 0; a < na; a++) nm += match_passes(match_at(c, a), expected) ? 1 : 0;
             }
-            if (!p->skip_match) {
-                bool pass = true;
-                if (p->max_matching_node_count > 0) pass = pass && max_node >= p->max_matching_node_count;
-                if (p->max_matching_node_ratio > 0.f) pass = pass && (float)max_node / expected >= p->max_matching_node_ratio;
-                if (p->rmsd_cutoff > 0.f) pass = pass && min_rmsd <= p->rmsd_cutoff;
-                if (!pass) continue;
-            }
+        }
+        R->struct_off[q + 1] = ns;
+        R->match_off[q + 1] = nm;
+        res_off[q + 1] = nm * Q.indices.size();
+    };
+    // pass 2: rows written in place, then the default sorts inside the query's ranges
+    auto build_query = [&](uint32_t q) {
+        const Query &Q = qs->q[q_begin + q];
+        const float expected = (float)Q.indices.size();
+        const uint32_t n_res = (uint32_t)Q.indices.size();
+        fdh_struct_row *S0 = R->structs.data() + R->struct_off[q], *S = S0;
+        const uint64_t mb = R->match_off[q];
+        fdh_match_row *M = R->matches.data();
+        fdh_residue_match *RM = R->residues.data();
+        uint64_t mpos = mb, rpos = res_off[q];
+        for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
+            const size_t na = match_count(c);
+            uint32_t max_node;
+            float min_rmsd;
+            if (!summarize(c, na, expected, &max_node, &min_rmsd)) continue;
             fdh_struct_row sr{hits[c].nid, hits[c].match_count, hits[c].node_count, hits[c].edge_count, hits[c].idf,
                               max_node, min_rmsd, 0, 0};
-            sr.match_begin = O.matches.size(); // relative to the query; rebased below
+            sr.match_begin = mpos;
             for (size_t a = 0; a < na; a++) {
                 const MatchView m = match_at(c, a);
-                bool pass = true;
-                if (p->connected_node_count > 0) pass = pass && m.node_count >= p->connected_node_count;
-                if (p->connected_node_ratio > 0.f) pass = pass && (float)m.node_count / expected >= p->connected_node_ratio;
-                if (p->prefilter.idf_score_cutoff > 0.f) pass = pass && m.idf >= p->prefilter.idf_score_cutoff;
-                if (p->rmsd_cutoff > 0.f) pass = pass && m.rmsd <= p->rmsd_cutoff;
-                if (!pass) continue;
-                fdh_match_row mr;
+                if (any_match_filter && !match_passes(m, expected)) continue;
+                fdh_match_row &mr = M[mpos++];
                 mr.nid = hits[c].nid;
                 mr.node_count = m.node_count;
                 mr.idf = m.idf;
                 mr.rmsd = m.rmsd;
                 memcpy(mr.U, m.U, sizeof(mr.U));
                 memcpy(mr.t, m.t, sizeof(mr.t));
-                mr.res_begin = O.residues.size();
+                mr.res_begin = rpos;
                 const uint32_t *res = m.res;
                 for (uint32_t k = 0; k < n_res; k++) {
                     const uint32_t v = res[k];
@@ -1637,23 +1739,22 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                         rm.chain = labels->chain[r];
                         rm.serial = labels->serial[r];
                     }
-                    O.residues.push_back(rm);
+                    RM[rpos++] = rm;
                 }
-                O.matches.push_back(mr);
             }
-            sr.match_end = O.matches.size();
-            O.structs.push_back(sr);
+            sr.match_end = mpos;
+            *S++ = sr;
         }
         // StructureSortStrategy::default: idf desc, min_rmsd asc (sort.rs:454-458), stable
-        std::stable_sort(O.structs.begin(), O.structs.end(), [](const fdh_struct_row &a, const fdh_struct_row &b) {
+        std::stable_sort(S0, S, [](const fdh_struct_row &a, const fdh_struct_row &b) {
             if (a.idf != b.idf) return a.idf > b.idf;
             return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
         });
         // MatchSortStrategy::default: idf desc, rmsd asc (sort.rs:218-222), stable over emission order
-        O.order.resize(O.matches.size());
-        for (size_t k = 0; k < O.order.size(); k++) O.order[k] = k;
-        std::stable_sort(O.order.begin(), O.order.end(), [&](uint64_t a, uint64_t b) {
-            const fdh_match_row &x = O.matches[a], &y = O.matches[b];
+        uint64_t *O = R->match_order.data() + mb, *Oe = R->match_order.data() + mpos;
+        for (uint64_t k = mb; k < mpos; k++) R->match_order[k] = k;
+        std::stable_sort(O, Oe, [&](uint64_t a, uint64_t b) {
+            const fdh_match_row &x = M[a], &y = M[b];
             if (x.idf != y.idf) return x.idf > y.idf;
             return x.rmsd < y.rmsd;
         });
@@ -1661,49 +1762,29 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     {
         int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
         nt = std::max(1, std::min(nt, 64));
-        std::atomic<uint32_t> next{0};
-        auto worker = [&] {
-            for (uint32_t q; (q = next.fetch_add(1)) < nq;) build_query(q);
+        auto run_parallel = [&](const std::function<void(uint32_t)> &fn) {
+            std::atomic<uint32_t> next{0};
+            auto worker = [&] {
+                for (uint32_t q0; (q0 = next.fetch_add(8)) < nq;)
+                    for (uint32_t q = q0; q < std::min(nq, q0 + 8); q++) fn(q);
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; t++) th.emplace_back(worker);
+            worker();
+            for (auto &t : th) t.join();
         };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(worker);
-        worker();
-        for (auto &t : th) t.join();
-        std::vector<uint64_t> res_off(nq + 1, 0);
+        run_parallel(count_query_rows);
         for (uint32_t q = 0; q < nq; q++) {
-            R->struct_off[q + 1] = R->struct_off[q] + qout[q].structs.size();
-            R->match_off[q + 1] = R->match_off[q] + qout[q].matches.size();
-            res_off[q + 1] = res_off[q] + qout[q].residues.size();
+            R->struct_off[q + 1] += R->struct_off[q];
+            R->match_off[q + 1] += R->match_off[q];
+            res_off[q + 1] += res_off[q];
         }
-        R->structs.resize(R->struct_off[nq]);
-        R->matches.resize(R->match_off[nq]);
-        R->match_order.resize(R->match_off[nq]);
-        R->residues.resize(res_off[nq]);
-        next = 0;
-        auto copier = [&] {
-            for (uint32_t q; (q = next.fetch_add(1)) < nq;) {
-                QOut &O = qout[q];
-                const uint64_t mb = R->match_off[q], rb = res_off[q];
-                for (size_t k = 0; k < O.structs.size(); k++) {
-                    fdh_struct_row sr = O.structs[k];
-                    sr.match_begin += mb;
-                    sr.match_end += mb;
-                    R->structs[R->struct_off[q] + k] = sr;
-                }
-                for (size_t k = 0; k < O.matches.size(); k++) {
-                    fdh_match_row mr = O.matches[k];
-                    mr.res_begin += rb;
-                    R->matches[mb + k] = mr;
-                    R->match_order[mb + k] = mb + O.order[k];
-                }
-                if (!O.residues.empty())
-                    memcpy(&R->residues[rb], O.residues.data(), O.residues.size() * sizeof(fdh_residue_match));
-            }
-        };
-        th.clear();
-        for (int t = 1; t < nt; t++) th.emplace_back(copier);
-        copier();
-        for (auto &t : th) t.join();
+        if (!R->structs.alloc(R->struct_off[nq]) || !R->matches.alloc(R->match_off[nq]) ||
+            !R->match_order.alloc(R->match_off[nq]) || !R->residues.alloc(res_off[nq])) {
+            set_err("fdh_search: host allocation failed");
+            return fail();
+        }
+        run_parallel(build_query);
     }
     host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     R->host_ms = host_ms;

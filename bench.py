@@ -10,8 +10,10 @@ aminopeptidase) replicated to a batch of 1024 queries against a human-proteome-s
 (23 400 structures per GPU, seeded generator of folddisco_b200/synth.py), reference default flags
 (-d 0.5 -a 5 --ca-distance 1.0) with --top 100.  One step = one batch through
 make_query_map -> count_query (posting scan + vote) -> filter/sort/top -> candidate re-hash -> Kabsch RMSD.
-With N > 1 GPUs the database grows with N (weak scaling): the index is hash-range sharded, every rank scans
-its shard for the whole batch and the per-structure vote vectors are merged with one NCCL allreduce.
+With N > 1 GPUs the problem grows with N (weak scaling): N x 23 400 structures, N x 1024 queries.  The index is
+hash-range sharded; every rank builds the query maps of its 1024 queries, scans its shard for the WHOLE batch,
+the non-empty vote cells are exchanged with one all-to-all over NVLink, and every rank finishes its own 1024 queries
+(folddisco_b200/sharded.py).
 """
 import argparse
 import json
@@ -40,9 +42,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--structs-per-gpu", type=int, default=23400)
-    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=1024, help="queries per GPU")
     ap.add_argument("--top", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=40, help="queries in the bounded CPU-baseline sample")
+    ap.add_argument("--sweep", default="4,8", help="index-size multipliers of the posting-scan sweep (N=1 only; '' = off)")
     return ap.parse_args()
 
 
@@ -90,6 +93,14 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def scan_traffic():
+    """DRAM bytes (read + write) of one k3_scan launch of this workload, from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "k3_scan_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
 
 
 def load_motif_atoms():
@@ -156,16 +167,18 @@ def run_reference(args, rank, world):
                                        "algorithm (oracle/), query-parallel over %d threads; index build %.1f s"
                                        % (sample, cores, build_s)},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world):
-    return {"workload": "configs[2]: batch of the 5 shipped motifs (replicated to %d queries) vs human-proteome-scale "
-                        "synthetic index, %d structures per GPU" % (args.batch, args.structs_per_gpu),
-            "structures": args.structs_per_gpu * world, "batch": args.batch, "top_n": args.top,
+    return {"workload": "configs[2]: batch of the 5 shipped motifs (replicated to %d queries per GPU) vs "
+                        "human-proteome-scale synthetic index, %d structures per GPU" % (args.batch, args.structs_per_gpu),
+            "structures": args.structs_per_gpu * world, "batch": args.batch * world, "top_n": args.top,
             "flags": "-d 0.5 -a 5 --ca-distance 1.0 --top %d, hash PDBTrRosetta 16/4 bins, cutoff 20 A" % args.top,
             "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-            "parallelism": "hash-range index shards x%d + NCCL vote allreduce" % world if world > 1 else "single GPU"}
+            "parallelism": ("hash-range index shards x%d, every rank scans its shard for the whole batch, sparse vote "
+                            "all-to-all (NCCL), every rank finishes %d queries" % (world, args.batch))
+            if world > 1 else "single GPU"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -201,13 +214,15 @@ def run_ours(args, rank, world, local_rank):
     stages = ("lookup", "scan", "select", "verify", "verify_edges", "verify_components", "verify_kabsch", "edges", "kabsch")
 
     def make_batch():
+        """this rank's args.batch queries of the global batch (query number q uses motif q mod 5)"""
         qb = host.QueryBatch(index.params)
-        qb.add_many([motif_structs[k % len(motif_structs)][0] for k in range(args.batch)],
-                    [motif_structs[k % len(motif_structs)][1] for k in range(args.batch)])
+        ks = range(rank * args.batch, (rank + 1) * args.batch)
+        qb.add_many([motif_structs[k % len(motif_structs)][0] for k in ks],
+                    [motif_structs[k % len(motif_structs)][1] for k in ks])
         if sharded is None:
             qb.finalize(ctx)
         else:
-            sharded.finalize(ctx, qb, dist)
+            sharded.prepare(ctx, qb, dist)
         return qb
 
     def search(qb):
@@ -224,18 +239,30 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: host structures -> results, every step (H2D of query descriptors, D2H of hits/edges/RMSD inside) ----
     for _ in range(args.warmup):
         search(make_batch())
-    e2e_t, res = [], None
-    for _ in range(args.steps):
+    def timed(fn):
+        """one step bracketed by barrier + synchronize and by CUDA events on the current stream (the library call is
+        synchronous, so the event interval covers host orchestration, copies and kernels of the step)"""
         flush.fill_(1)
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        res = search(make_batch())
+        e0.record()
+        out = fn()
+        e1.record()
         barrier()
-        e2e_t.append(time.perf_counter() - t0)
+        wall = time.perf_counter() - t0
+        return out, e0.elapsed_time(e1) * 1e-3, wall
+
+    e2e_t, res = [], None
+    for _ in range(args.steps):
+        res, dt, _ = timed(lambda: search(make_batch()))
+        e2e_t.append(dt)
     # ---- value: query batch prepared (inputs resident), timed region = the search itself ----
     qb = make_batch()
     for _ in range(args.warmup):
         search(qb)
+    if sharded is not None:
+        sharded.merge_ms, sharded.merge_bytes = 0.0, 0
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
@@ -243,13 +270,11 @@ def run_ours(args, rank, world, local_rank):
     st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages}
     bytes_scanned = 0
     val_t = []
+    wall_t = []
     for _ in range(args.steps):
-        flush.fill_(1)
-        barrier()
-        t0 = time.perf_counter()
-        res = search(qb)
-        barrier()
-        val_t.append(time.perf_counter() - t0)
+        res, dt, wall = timed(lambda: search(qb))
+        val_t.append(dt)
+        wall_t.append(wall)
         bytes_scanned += ctx.last_posting_bytes
     clocks = sampler.finish()
     launches = ctx.kernel_launches - launches0
@@ -272,30 +297,80 @@ def run_ours(args, rank, world, local_rank):
     survivors = int(res.struct_offsets[-1])
     algo_bytes = bytes_per_launch + 16 * survivors          # posting bytes + 16 B per survivor
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    if world > 1:  # every rank scanned its own shard: the launch's algorithmic bytes are this rank's
+        survivors = 0
     n_struct_rows, n_match_rows = int(res.struct_offsets[-1]), int(res.match_offsets[-1])
-    h2d, d2h = int(res.h2d_bytes), int(res.d2h_bytes)   # tallied by fdh_search from the buffers it copies
+    # tallied by fdh_search from the buffers it copies (rank 0's slice; every rank moves the same amount)
+    h2d, d2h = int(res.h2d_bytes) * world, int(res.d2h_bytes) * world
     line = {
-        "metric": METRIC, "value": args.batch / val_s,
+        "metric": METRIC, "value": args.batch * world / val_s,
         "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": val_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 hashes / u8 postings / f32 idf / f64 Kabsch", "data": "synthetic",
         "config": workload_config(args, world),
-        "e2e": {"value": args.batch / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": args.batch * world / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k3_scan (posting-list scan + vote)", "achieved": achieved, "peak": hbm,
-                     "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm, "traffic": scan_traffic() if world == 1 else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": scan_ms},
         "clocks": clocks,
         "stages_ms_per_step": {s: st1[s][0] / max(1, args.steps) for s in stages},
         "host_ms_per_step": res.host_ms, "search_wall_ms": res.wall_ms,
+        "timing": "CUDA events around each step (max over ranks); wall-clock cross-check %.3f ms/step" % (
+            1e3 * sum(wall_t) / max(1, args.steps)),
         "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows},
         "index": {"structures": len(store), "residues": int(store.num_residues), "build_s": build_s,
                   "k1_hash_ms": hash_ms, "k2_postings_ms": post_ms},
     }
+    if sharded is not None:
+        n_search = max(1, args.steps)
+        line["vote_merge"] = {"collective": "NCCL all_to_all of the non-empty vote cells (+ all_gather of the counts)",
+                              "ms_per_step": sharded.merge_ms / n_search,
+                              "bytes_sent_per_rank_per_step": sharded.merge_bytes // n_search,
+                              "results": "each rank finishes its own %d queries; rows stay on the rank that produced them" % args.batch}
     if world == 1:
+        if args.sweep:
+            line["scan_vs_index_size"] = scan_sweep(args, ctx, db, qb, sp, hbm, bytes_per_launch + 16 * survivors, scan_ms)
+            index.attach(ctx)
         line["cpu_baseline"] = cpu_baseline(args, db, index)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+def scan_sweep(args, ctx, db, qb, sp, hbm, base_bytes, base_ms):
+    """Posting-list GB/s of k3_scan vs index size: the database tiled k times (ids shifted), index rebuilt on the GPU,
+    count_query only (skip_match), same batch.  Larger indexes have longer lists: more bytes per launch."""
+    import torch
+    from folddisco_b200 import host
+    out = [{"structures": args.structs_per_gpu, "algorithmic_bytes_per_launch": base_bytes, "scan_ms": base_ms,
+            "GBps": base_bytes / (base_ms * 1e-3) / 1e9, "frac": base_bytes / (base_ms * 1e-3) / 1e9 / hbm}]
+    skip = host.SearchParams(top_n=args.top, skip_match=True)
+    for k in [int(x) for x in args.sweep.split(",") if x]:
+        S = len(db["row_offsets"]) - 1
+        R = int(db["row_offsets"][-1])
+        ro = np.concatenate([db["row_offsets"][:-1].astype(np.uint64) + np.uint64(j * R) for j in range(k)] +
+                            [np.array([k * R], np.uint64)])
+        tiled = dict(row_offsets=ro, n_xyz=np.tile(db["n_xyz"], (k, 1)), ca_xyz=np.tile(db["ca_xyz"], (k, 1)),
+                     cb_xyz=np.tile(db["cb_xyz"], (k, 1)), aa=np.tile(db["aa"], k))
+        store = host.Store()
+        store.add_soa(tiled)
+        del tiled
+        ix = host.FolddiscoIndex.build(ctx, store)
+        ix.attach(ctx)
+        for _ in range(2):
+            host.search(ctx, qb, skip)
+        ms0, n = ctx.stage_ms("scan"), 3
+        nbytes = 0
+        for _ in range(n):
+            r = host.search(ctx, qb, skip)
+            nbytes += ctx.last_posting_bytes + 16 * int(r.struct_offsets[-1])
+        ms = (ctx.stage_ms("scan") - ms0) / n
+        gbps = nbytes / n / (ms * 1e-3) / 1e9
+        out.append({"structures": S * k, "algorithmic_bytes_per_launch": nbytes / n, "scan_ms": ms, "GBps": gbps,
+                    "frac": gbps / hbm})
+        del ix, store
+    return out
 
 
 def cpu_baseline(args, db, index):
@@ -335,6 +410,10 @@ def cpu_baseline(args, db, index):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner) get stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -59,7 +59,7 @@ class PrefilterParams(C.Structure):
 class VotesLayout(C.Structure):
     """fd_votes_layout: u32 votes[planes][n_queries][n_structs] in device memory"""
     _fields_ = [("n_queries", C.c_uint32), ("n_structs", C.c_uint32), ("narrow", C.c_uint32), ("edge_words", C.c_uint32),
-                ("planes", C.c_uint32), ("words", C.c_uint64)]
+                ("planes", C.c_uint32), ("first_query", C.c_uint32), ("words", C.c_uint64)]
 
 
 class DeviceWords:
@@ -124,6 +124,10 @@ def lib():
                                           PP(PP(C.c_uint64))])
     sig("fd_last_posting_bytes", C.c_uint64, [VP])
     sig("fd_votes_scan", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), PP(VP)])
+    sig("fd_votes_scan_sparse", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), VP, C.c_uint32,
+                                          PP(VotesLayout), PP(VP), VP, VP])
+    sig("fd_votes_merge_begin", C.c_int, [VP, PP(VotesLayout), C.c_uint32, C.c_uint32, PP(VotesLayout), PP(VP)])
+    sig("fd_votes_apply", C.c_int, [VP, PP(VotesLayout), VP, VP, C.c_uint64])
     sig("fd_votes_select", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), VP, C.c_uint32,
                                      C.c_uint32, PP(PP(_StructHit)), PP(PP(C.c_uint64))])
     sig("fd_store_attach", C.c_int, [VP, PP(_StructBatch)])

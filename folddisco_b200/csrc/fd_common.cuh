@@ -67,6 +67,8 @@ struct fd_ctx {
     cudaEvent_t ev_extra[4] = {nullptr, nullptr, nullptr, nullptr}; // finer stage timing inside one call
     uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
     uint64_t votes_cap = 0;    // capacity in u32 words
+    uint32_t *merge = nullptr; // dense vote planes of this rank's slice of the batch (sparse merge), owned
+    uint64_t merge_cap = 0;
 };
 
 extern thread_local std::string fd_g_create_error;

@@ -108,6 +108,7 @@ void fd_destroy(fd_ctx *ctx) {
     fd_release_index(ctx->idx);
     fd_release_store(ctx->store);
     cudaFree(ctx->votes);
+    cudaFree(ctx->merge);
     for (auto &b : ctx->pinned)
         if (b.p) cudaFreeHost(b.p);
     for (auto &e : ctx->ev_extra)

@@ -306,6 +306,13 @@ struct HitRec { // 16 bytes; key/value for the segmented sort are derived from i
     float idf;
 };
 
+struct SparseOut { // MODE 2 of k3_scan
+    const uint32_t *slice_begin;        // [world + 1] first query of every rank's slice
+    const uint64_t *region_offset;      // [world] first record of every destination's region in the pool
+    unsigned long long *region_count;   // [world] records appended so far
+    uint32_t world;
+};
+
 struct FilterParams {
     float length_penalty;
     uint32_t total_match_count, covered_node_count;
@@ -341,6 +348,10 @@ __device__ __forceinline__ uint32_t varint_at(uint32_t x0, uint32_t x1) {
     return v;
 }
 
+template <bool NARROW, class F>
+__device__ __forceinline__ void compact_cells(const uint32_t *acc, const uint32_t *match, uint32_t T, uint32_t *wq,
+                                              F &process);
+
 // Count/filter/append epilogue over a range of vote cells [0, T) (ids lo .. lo+T).  acc / match / edge are the
 // planes (shared or global memory); edge plane i is edge + i * edge_stride.  Non-empty cells are compacted warp
 // by warp through a small shared-memory queue so that the per-cell work runs with full lanes.
@@ -353,8 +364,6 @@ __device__ __forceinline__ void emit_cells(const uint32_t *acc, const uint32_t *
                                            const FilterParams &fp, unsigned int *hit_count, HitRec *hits_out) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wq = wqueue + warp * K3_WQ;
-    uint32_t pending = 0;
-    const uint32_t n_chunks = (T + 127) >> 7;
     auto process = [&](uint32_t first, uint32_t n_take) { // queue entries [first, first + n_take), one per lane
         bool pass = false;
         HitRec rec{0, 0, 0, 0.f};
@@ -403,7 +412,18 @@ __device__ __forceinline__ void emit_cells(const uint32_t *acc, const uint32_t *
             if (pass) hits_out[pos] = rec;
         }
     };
-    // 128 cells per warp step (4 coalesced loads per lane); a warp prefix sum places the non-empty ones in the queue
+    compact_cells<NARROW>(acc, match, T, wq, process);
+}
+
+// Warp-level compaction of the non-empty vote cells of [0, T): every warp scans 128 cells per step (4 coalesced
+// loads per lane), a warp prefix sum places the non-empty ones in the warp's queue wq[K3_WQ], and process(first, n)
+// is called warp-wide for queue entries [first, first + n), n <= 32, one per lane.
+template <bool NARROW, class F>
+__device__ __forceinline__ void compact_cells(const uint32_t *acc, const uint32_t *match, uint32_t T, uint32_t *wq,
+                                              F &process) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t pending = 0;
+    const uint32_t n_chunks = (T + 127) >> 7;
     for (uint32_t c = warp; c < n_chunks; c += K3_WARPS) {
         const uint32_t x0 = (c << 7) + lane;
         uint32_t nz = 0;
@@ -450,14 +470,16 @@ __device__ __forceinline__ void build_edge_masks(const QueryDesc &qd, const uint
 }
 
 // Shared-memory vote tile.  NARROW: plane 0 = match_count (8 bits) | idf fixed point (24 bits);
-// wide: separate idf and match planes.  EW edge-bitmask planes.  DUMP: write the planes to the dense
+// wide: separate idf and match planes.  EW edge-bitmask planes.  MODE 0: count/filter/append epilogue;
+// 1: write the planes to the dense partial-vote buffer; 2: pack the non-empty cells as sparse records for the rank
+// that finishes the query (multi-GPU).
 // partial-vote buffer instead of running the epilogue (multi-GPU).
-template <bool NARROW, int EW, bool DUMP>
+template <bool NARROW, int EW, int MODE>
 __global__ void __launch_bounds__(K3_THREADS)
     k3_scan(IndexView ix, const QueryDesc *queries, const QHash *qh, const uint16_t *edge_of_hash,
             const uint16_t *edge_node, const uint16_t *edge_group, const float *idf_sum_per_query, const float *pen, uint32_t tile_ids,
             FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits,
-            uint32_t *dense /* DUMP: [planes][nq][N] */) {
+            uint32_t *dense /* MODE 1: [planes][nq][N]; MODE 2: sparse record pool */, SparseOut sp) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t q = blockIdx.y;
     const QueryDesc qd = queries[q];
@@ -635,7 +657,36 @@ __global__ void __launch_bounds__(K3_THREADS)
     }
     __syncthreads();
 
-    if (DUMP) {
+    if (MODE == 2) {
+        // records {key = (q - first query of the destination) * N + nid, planes...} appended to the region of the
+        // rank that finishes q
+        __shared__ uint32_t s_dest;
+        if (threadIdx.x == 0) {
+            uint32_t d = 0;
+            while (d + 1 < sp.world && q >= sp.slice_begin[d + 1]) d++;
+            s_dest = d;
+        }
+        __syncthreads();
+        const uint32_t dest = s_dest;
+        const uint32_t key0 = (q - sp.slice_begin[dest]) * ix.n_structs + lo;
+        uint32_t *region = dense + sp.region_offset[dest] * (1 + PLANES);
+        unsigned long long *counter = sp.region_count + dest;
+        const uint32_t lane = threadIdx.x & 31;
+        uint32_t *wq = wqueue + (threadIdx.x >> 5) * K3_WQ;
+        auto pack = [&](uint32_t first, uint32_t n_take) {
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(counter, (unsigned long long)n_take);
+            pos = __shfl_sync(0xffffffffu, pos, 0) + lane;
+            if (lane < n_take) {
+                const uint32_t x = wq[first + lane];
+                uint32_t *r = region + pos * (1 + PLANES);
+                r[0] = key0 + x;
+#pragma unroll
+                for (uint32_t p = 0; p < PLANES; p++) r[1 + p] = w_acc[(size_t)p * tile_ids + x];
+            }
+        };
+        compact_cells<NARROW>(w_acc, w_match, T, wq, pack);
+    } else if (MODE == 1) {
         // planes of this tile -> dense[plane][q][lo .. hi)
         const size_t plane_stride = (size_t)gridDim.y * ix.n_structs;
         uint32_t *dst = dense + (size_t)q * ix.n_structs + lo;
@@ -653,7 +704,7 @@ template <bool NARROW, int EW>
 __global__ void __launch_bounds__(K3_THREADS)
     k3_select_dense(IndexView ix, const QueryDesc *queries, const uint16_t *edge_node, const uint16_t *edge_group,
                     const float *idf_sum_per_query, const float *pen, const uint32_t *dense, uint32_t n_queries,
-                    uint32_t q_begin, uint32_t tile_ids, FilterParams fp,
+                    uint32_t first_query, uint32_t q_begin, uint32_t tile_ids, FilterParams fp,
                     const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits) {
     __shared__ uint32_t node_mask[K3_MAX_NODES * EW];
     __shared__ uint32_t cont_mask[EW];
@@ -669,11 +720,28 @@ __global__ void __launch_bounds__(K3_THREADS)
     __syncthreads();
     const float inv_scale = 1.0f / idf_scale<NARROW>(idf_sum_per_query[q]);
     const size_t plane_stride = (size_t)n_queries * ix.n_structs;
-    const uint32_t *acc = dense + (size_t)q * ix.n_structs + lo;
+    const uint32_t *acc = dense + (size_t)(q - first_query) * ix.n_structs + lo;
     const uint32_t *match = NARROW ? nullptr : acc + plane_stride;
     const uint32_t *edge = acc + (NARROW ? 1 : 2) * plane_stride;
     emit_cells<NARROW, EW>(acc, match, edge, plane_stride, hi - lo, lo, qd, node_mask, cont_mask, wqueue, inv_scale, ix,
                            pen, fp, &hit_counts[qs], hits + hit_offsets[qs]);
+}
+
+// Sparse records {key, planes...} -> dense planes [planes][n_queries][N] of the receiving rank's slice.
+__global__ void k3_apply_records(const uint32_t *records, uint64_t n_records, uint32_t planes, uint32_t acc_planes,
+                                 uint32_t n_queries, uint32_t n_structs, uint32_t *dense) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_records) return;
+    const uint32_t *r = records + k * (1 + planes);
+    const uint32_t key = r[0];
+    const size_t plane_stride = (size_t)n_queries * n_structs;
+    uint32_t *cell = dense + key; // key = local query * N + nid
+    for (uint32_t p = 0; p < planes; p++) {
+        const uint32_t v = r[1 + p];
+        if (v == 0) continue;
+        if (p < acc_planes) atomicAdd(cell + p * plane_stride, v);
+        else atomicOr(cell + p * plane_stride, v);
+    }
 }
 
 // sort key: idf descending, nid ascending  (query_pdb.rs:404 stable sort over ascending nid)
@@ -876,23 +944,24 @@ int plan_tiles(fd_ctx *ctx, const Batch &B, uint32_t N, TilePlan &tp) {
     return FD_OK;
 }
 
-template <bool NARROW, int EW, bool DUMP>
+template <bool NARROW, int EW, int MODE>
 int launch_scan_t(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
-                  const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense) {
-    auto kern = k3_scan<NARROW, EW, DUMP>;
+                  const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense, SparseOut sp) {
+    auto kern = k3_scan<NARROW, EW, MODE>;
     FD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
     kern<<<grid, K3_THREADS, tp.smem, ctx->stream>>>(ix, B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p,
                                                      B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, tp.tile_ids, fp, hit_offsets, hit_counts,
-                                                     hits, dense);
+                                                     hits, dense, sp);
     ctx->launches++;
     return FD_OK;
 }
 
-template <bool DUMP>
+template <int MODE>
 int launch_scan(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
-                const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense) {
+                const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense,
+                SparseOut sp = SparseOut{nullptr, nullptr, nullptr, 0}) {
 #define FD_SCAN_CASE(NARROW, EW) \
-    return launch_scan_t<NARROW, EW, DUMP>(ctx, grid, tp, ix, B, fp, hit_offsets, hit_counts, hits, dense)
+    return launch_scan_t<NARROW, EW, MODE>(ctx, grid, tp, ix, B, fp, hit_offsets, hit_counts, hits, dense, sp)
     if (B.narrow) {
         if (B.ew == 1) FD_SCAN_CASE(true, 1);
         else if (B.ew == 2) FD_SCAN_CASE(true, 2);
@@ -909,12 +978,12 @@ int launch_scan(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const 
 }
 
 template <bool NARROW, int EW>
-int launch_select_t(fd_ctx *ctx, dim3 grid, IndexView ix, const Batch &B, const uint32_t *dense, uint32_t q_begin,
-                    uint32_t tile_ids, FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts,
+int launch_select_t(fd_ctx *ctx, dim3 grid, IndexView ix, const Batch &B, const uint32_t *dense,
+                    uint32_t n_dense_queries, uint32_t first_query, uint32_t q_begin, uint32_t tile_ids, FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts,
                     HitRec *hits) {
     k3_select_dense<NARROW, EW><<<grid, K3_THREADS, 0, ctx->stream>>>(
-        ix, B.d_desc.p, B.d_edge_node.p, B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, dense, (uint32_t)B.descs.size(),
-        q_begin, tile_ids, fp, hit_offsets, hit_counts, hits);
+        ix, B.d_desc.p, B.d_edge_node.p, B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, dense, n_dense_queries,
+        first_query, q_begin, tile_ids, fp, hit_offsets, hit_counts, hits);
     ctx->launches++;
     return FD_OK;
 }
@@ -1126,7 +1195,7 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
         FD_TRY(plan_tiles(ctx, B, N, tp));
         {
             StageTimer st(ctx, "scan");
-            FD_TRY(launch_scan<false>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
+            FD_TRY(launch_scan<0>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
                                       d_hit_cnt.p, d_hits.p, nullptr));
             FD_CUDA(ctx, st.finish());
         }
@@ -1151,7 +1220,7 @@ int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
     Batch B;
     FD_TRY(prepare_batch(ctx, queries, nq, params, true, 1, B));
     const uint32_t planes = (B.narrow ? 1 : 2) + B.ew;
-    *layout = fd_votes_layout{nq, N, B.narrow ? 1u : 0u, (uint32_t)B.ew, planes, (uint64_t)planes * nq * N};
+    *layout = fd_votes_layout{nq, N, B.narrow ? 1u : 0u, (uint32_t)B.ew, planes, 0, (uint64_t)planes * nq * N};
     if (layout->words > ctx->votes_cap) {
         FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->votes);
@@ -1166,8 +1235,106 @@ int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
     FD_TRY(plan_tiles(ctx, B, N, tp));
     StageTimer st(ctx, "scan");
     // every (query, tile) CTA writes its planes, so the buffer needs no clearing
-    FD_TRY(launch_scan<true>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), nullptr, nullptr,
+    FD_TRY(launch_scan<1>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), nullptr, nullptr,
                              nullptr, ctx->votes));
+    FD_CUDA(ctx, st.finish());
+    return FD_OK;
+}
+
+int fd_votes_scan_sparse(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                         const uint32_t *slice_begin, uint32_t world, fd_votes_layout *layout, uint32_t **d_records,
+                         uint64_t *region_offset, uint64_t *region_count) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_votes_scan_sparse: no index attached");
+    if ((nq && !queries) || !params || !layout || !d_records || !slice_begin || !region_offset || !region_count ||
+        world == 0 || world > 64)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_votes_scan_sparse: bad argument");
+    if (slice_begin[0] != 0 || slice_begin[world] != nq)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_votes_scan_sparse: slice_begin must run from 0 to n_queries");
+    FD_ENTER(ctx);
+    const uint32_t N = (uint32_t)ctx->idx.n_structs;
+    for (uint32_t r = 0; r < world; r++) {
+        if (slice_begin[r] > slice_begin[r + 1]) return fd_fail(ctx, FD_ERR_ARG, "fd_votes_scan_sparse: slices must be ascending");
+        if ((uint64_t)(slice_begin[r + 1] - slice_begin[r]) * N > 0xffffffffull)
+            return fd_fail(ctx, FD_ERR_LIMIT, "a rank's slice of the batch times the number of structures must stay below 2^32");
+    }
+    Batch B;
+    FD_TRY(prepare_batch(ctx, queries, nq, params, true, 1, B));
+    const uint32_t planes = (B.narrow ? 1 : 2) + B.ew;
+    *layout = fd_votes_layout{nq, N, B.narrow ? 1u : 0u, (uint32_t)B.ew, planes, 0, 0};
+    // a (query, structure) cell is non-empty only if a posting of the query names the structure
+    region_offset[0] = 0;
+    for (uint32_t r = 0; r < world; r++) {
+        uint64_t cap = 0;
+        for (uint32_t q = slice_begin[r]; q < slice_begin[r + 1]; q++) cap += std::min<uint64_t>(N, B.h_postings.empty() ? 0 : B.h_postings[q]);
+        region_offset[r + 1] = region_offset[r] + cap;
+        region_count[r] = 0;
+    }
+    const uint64_t words = region_offset[world] * (1 + planes);
+    layout->words = words;
+    if (words > ctx->votes_cap) {
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->votes);
+        ctx->votes = nullptr;
+        ctx->votes_cap = 0;
+        FD_CUDA(ctx, cudaMalloc(&ctx->votes, std::max<uint64_t>(words, 1) * 4));
+        ctx->votes_cap = std::max<uint64_t>(words, 1);
+    }
+    *d_records = ctx->votes;
+    if (nq == 0 || N == 0) return FD_OK;
+    cudaStream_t s = ctx->stream;
+    DevBuf<uint32_t> d_slice;
+    DevBuf<uint64_t> d_off;
+    DevBuf<unsigned long long> d_cnt;
+    FD_CUDA(ctx, d_slice.alloc(world + 1));
+    FD_CUDA(ctx, d_off.alloc(world + 1));
+    FD_CUDA(ctx, d_cnt.alloc(world));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_slice.p, slice_begin, (world + 1) * 4, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_off.p, region_offset, (world + 1) * 8, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, world * 8, s));
+    TilePlan tp;
+    FD_TRY(plan_tiles(ctx, B, N, tp));
+    StageTimer st(ctx, "scan");
+    FD_TRY(launch_scan<2>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), nullptr, nullptr, nullptr,
+                          ctx->votes, SparseOut{d_slice.p, d_off.p, d_cnt.p, world}));
+    FD_CUDA(ctx, cudaMemcpyAsync(region_count, d_cnt.p, world * 8, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, st.finish());
+    return FD_OK;
+}
+
+int fd_votes_merge_begin(fd_ctx *ctx, const fd_votes_layout *layout, uint32_t first_query, uint32_t n_queries,
+                         fd_votes_layout *slice_layout, uint32_t **d_dense) {
+    if (!ctx || !layout || !slice_layout || !d_dense) return fd_fail(ctx, FD_ERR_ARG, "fd_votes_merge_begin: NULL argument");
+    FD_ENTER(ctx);
+    *slice_layout = *layout;
+    slice_layout->n_queries = n_queries;
+    slice_layout->first_query = first_query;
+    slice_layout->words = (uint64_t)layout->planes * n_queries * layout->n_structs;
+    const uint64_t words = std::max<uint64_t>(slice_layout->words, 1);
+    if (words > ctx->merge_cap) {
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->merge);
+        ctx->merge = nullptr;
+        ctx->merge_cap = 0;
+        FD_CUDA(ctx, cudaMalloc(&ctx->merge, words * 4));
+        ctx->merge_cap = words;
+    }
+    StageTimer st(ctx, "merge");
+    FD_CUDA(ctx, cudaMemsetAsync(ctx->merge, 0, words * 4, ctx->stream));
+    FD_CUDA(ctx, st.finish());
+    *d_dense = ctx->merge;
+    return FD_OK;
+}
+
+int fd_votes_apply(fd_ctx *ctx, const fd_votes_layout *slice_layout, uint32_t *d_dense, const uint32_t *d_records,
+                   uint64_t n_records) {
+    if (!ctx || !slice_layout || (n_records && (!d_dense || !d_records)))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_votes_apply: NULL argument");
+    FD_ENTER(ctx);
+    if (n_records == 0) return FD_OK;
+    StageTimer st(ctx, "merge");
+    FD_LAUNCH(ctx, k3_apply_records, fd_div_up(n_records, 256), 256, 0, d_records, n_records, slice_layout->planes,
+              slice_layout->narrow ? 1u : 2u, slice_layout->n_queries, slice_layout->n_structs, d_dense);
     FD_CUDA(ctx, st.finish());
     return FD_OK;
 }
@@ -1179,7 +1346,8 @@ int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_
     if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_votes_select: no index attached");
     if ((nq && !queries) || !params || !layout || !out_hits || !out_offsets || (layout->words && !d_votes))
         return fd_fail(ctx, FD_ERR_ARG, "fd_votes_select: NULL argument");
-    if (q_begin > q_end || q_end > nq || layout->n_queries != nq || layout->n_structs != ctx->idx.n_structs)
+    if (q_begin > q_end || q_end > nq || q_begin < layout->first_query ||
+        q_end > (uint64_t)layout->first_query + layout->n_queries || layout->n_structs != ctx->idx.n_structs)
         return fd_fail(ctx, FD_ERR_ARG, "fd_votes_select: layout / query range mismatch");
     FD_ENTER(ctx);
     *out_hits = nullptr;
@@ -1189,8 +1357,12 @@ int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_
     const uint32_t nsel = q_end - q_begin;
     Batch B;
     FD_TRY(prepare_batch(ctx, queries, nq, params, false, 1, B));
-    if ((B.narrow ? 1u : 0u) != layout->narrow || (uint32_t)B.ew != layout->edge_words)
+    // the layout was fixed by the scan over the WHOLE batch; the queries given here may be a slice of it
+    if ((layout->narrow && !B.narrow) || (uint32_t)B.ew > layout->edge_words ||
+        layout->planes != (layout->narrow ? 1u : 2u) + layout->edge_words)
         return fd_fail(ctx, FD_ERR_ARG, "fd_votes_select: layout does not match the batch");
+    B.narrow = layout->narrow != 0;
+    B.ew = (int)layout->edge_words;
     uint64_t *h_off = (uint64_t *)calloc((size_t)nsel + 1, 8);
     if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
     if (nsel == 0 || N == 0) {
@@ -1216,7 +1388,8 @@ int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_
         {
             StageTimer st(ctx, "select");
 #define FD_SEL_CASE(NARROW, EW) \
-    FD_TRY((launch_select_t<NARROW, EW>(ctx, grid, ix, B, d_votes, q_begin, tile_ids, fp, d_hit_off.p, d_hit_cnt.p, d_hits.p)))
+    FD_TRY((launch_select_t<NARROW, EW>(ctx, grid, ix, B, d_votes, layout->n_queries, layout->first_query, q_begin, \
+                                        tile_ids, fp, d_hit_off.p, d_hit_cnt.p, d_hits.p)))
             if (B.narrow) {
                 if (B.ew == 1) FD_SEL_CASE(true, 1);
                 else if (B.ew == 2) FD_SEL_CASE(true, 2);

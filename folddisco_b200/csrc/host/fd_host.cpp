@@ -1873,6 +1873,58 @@ void fdh_queries_get_vote_bits(const fdh_queries *qs, int64_t q, uint32_t *hashe
         if (bit_group) bit_group[e] = sh ? Q.s_edge_group[e] : (uint16_t)e;
     }
 }
+// Flat scan inputs of the batch for an all-gather between ranks (each rank builds the query maps of its own
+// slice only): per query the number of hashes, vote bits and pairs; then the concatenated arrays.
+void fdh_queries_scan_sizes(const fdh_queries *qs, uint64_t *n_hashes, uint64_t *n_pairs) {
+    uint64_t h = 0, pr = 0;
+    for (auto &Q : qs->q) {
+        h += Q.hashes_flat.size();
+        pr += Q.pair_hash.size();
+    }
+    *n_hashes = h;
+    *n_pairs = pr;
+}
+void fdh_queries_scan_arrays(const fdh_queries *qs, uint32_t *per_query /* 3 per query: hashes, bits, pairs */,
+                             uint32_t *hashes, uint32_t *bit_of_hash, uint32_t *pair_hashes) {
+    const bool sh = !qs->shard_bounds.empty();
+    size_t h = 0, pr = 0;
+    for (size_t q = 0; q < qs->q.size(); q++) {
+        const Query &Q = qs->q[q];
+        const std::vector<uint16_t> &eoh = sh ? Q.s_edge_of_hash : Q.edge_of_hash;
+        per_query[3 * q] = (uint32_t)Q.hashes_flat.size();
+        per_query[3 * q + 1] = (uint32_t)(sh ? Q.s_edge_node.size() : Q.edge_node.size());
+        per_query[3 * q + 2] = (uint32_t)Q.pair_hash.size();
+        for (size_t k = 0; k < Q.hashes_flat.size(); k++) {
+            hashes[h] = Q.hashes_flat[k];
+            bit_of_hash[h++] = eoh[k];
+        }
+        for (uint32_t v : Q.pair_hash) pair_hashes[pr++] = v;
+    }
+}
+// fd_votes_scan_sparse over flat arrays (the whole batch, gathered from all ranks)
+int fdh_votes_scan_sparse_flat(fd_ctx *ctx, uint32_t nq, const uint32_t *per_query, const uint32_t *hashes,
+                               const uint32_t *bit_of_hash, const fd_prefilter_params *prefilter,
+                               const uint32_t *slice_begin, uint32_t world, fd_votes_layout *layout,
+                               uint32_t **d_records, uint64_t *region_offset, uint64_t *region_count) {
+    std::vector<fd_query> fq(nq);
+    size_t total = 0, max_bits = 1;
+    for (uint32_t q = 0; q < nq; q++) {
+        total += per_query[3 * q];
+        max_bits = std::max<size_t>(max_bits, per_query[3 * q + 1]);
+    }
+    std::vector<uint16_t> eoh(total), zeros(max_bits, 0);
+    for (size_t k = 0; k < total; k++) eoh[k] = (uint16_t)bit_of_hash[k];
+    size_t h = 0;
+    for (uint32_t q = 0; q < nq; q++) {
+        // the pack epilogue does not look at nodes / groups: one node, no groups
+        fq[q] = fd_query{per_query[3 * q], hashes + h, eoh.data() + h, per_query[3 * q + 1], zeros.data(), 1, 1, nullptr};
+        h += per_query[3 * q];
+    }
+    const int rc = fd_votes_scan_sparse(ctx, fq.data(), nq, prefilter, slice_begin, world, layout, d_records,
+                                        region_offset, region_count);
+    if (rc != FD_OK) set_err(fd_last_error(ctx));
+    return rc;
+}
 int64_t fdh_queries_num_pairs(const fdh_queries *qs) {
     int64_t n = 0;
     for (auto &Q : qs->q) n += (int64_t)Q.pair_hash.size();

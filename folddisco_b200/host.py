@@ -101,6 +101,10 @@ def _lib():
     sig("fdh_queries_set_shards", C.c_int, [VP, VP, C.c_int])
     sig("fdh_queries_num_vote_bits", C.c_int64, [VP, C.c_int64])
     sig("fdh_queries_get_vote_bits", None, [VP, C.c_int64, VP, VP, VP, VP])
+    sig("fdh_queries_scan_sizes", None, [VP, PP(C.c_uint64), PP(C.c_uint64)])
+    sig("fdh_queries_scan_arrays", None, [VP, VP, VP, VP, VP])
+    sig("fdh_votes_scan_sparse_flat", C.c_int, [VP, C.c_uint32, VP, VP, VP, PP(PrefilterParams), VP, C.c_uint32,
+                                                PP(capi.VotesLayout), PP(VP), VP, VP])
     sig("fdh_queries_num_pairs", C.c_int64, [VP])
     sig("fdh_queries_pair_counts", C.c_int, [VP, VP, VP])
     sig("fdh_queries_finalize_with_counts", C.c_int, [VP, VP, C.c_uint64])
@@ -359,6 +363,18 @@ class QueryBatch:
         _lib().fdh_queries_get_vote_bits(self.h, q, *[_ptr(d[k]) for k in ("hashes", "bit_of_hash", "bit_node", "bit_group")])
         return d
 
+    def scan_arrays(self):
+        """flat scan inputs of this batch: per_query u32[nq, 3] = (hashes, vote bits, pairs), hashes, bit_of_hash,
+        pair_hashes (all uint32)"""
+        nh, npair = C.c_uint64(), C.c_uint64()
+        _lib().fdh_queries_scan_sizes(self.h, C.byref(nh), C.byref(npair))
+        nq = len(self)
+        per_query = np.zeros((nq, 3), np.uint32)
+        hashes, bits = np.zeros(nh.value, np.uint32), np.zeros(nh.value, np.uint32)
+        pairs = np.zeros(npair.value, np.uint32)
+        _lib().fdh_queries_scan_arrays(self.h, _ptr(per_query), _ptr(hashes), _ptr(bits), _ptr(pairs))
+        return per_query, hashes, bits, pairs
+
     def pair_counts(self, ctx):
         """posting counts of every query pair's observed hash in the index attached to ctx (0 if absent)"""
         out = np.zeros(_lib().fdh_queries_num_pairs(self.h), np.uint32)
@@ -445,6 +461,36 @@ def votes_scan(ctx, queries, prefilter):
     if _lib().fdh_votes_scan(ctx.h, queries.h, C.byref(prefilter), C.byref(lay), C.byref(ptr)) != 0:
         raise FdError(_err())
     return lay, ptr.value
+
+
+def votes_scan_sparse(ctx, per_query, hashes, bit_of_hash, prefilter, slice_begin):
+    """sparse partial votes of ctx's shard for the whole (gathered) batch -> (layout, device pointer of the record
+    pool, region_offset u64[world + 1], region_count u64[world]); records have 1 + layout.planes words"""
+    per_query = np.ascontiguousarray(per_query, np.uint32)
+    hashes = np.ascontiguousarray(hashes, np.uint32)
+    bits = np.ascontiguousarray(bit_of_hash, np.uint32)
+    sb = np.ascontiguousarray(slice_begin, np.uint32)
+    world = len(sb) - 1
+    lay, ptr = capi.VotesLayout(), VP()
+    off, cnt = np.zeros(world + 1, np.uint64), np.zeros(world, np.uint64)
+    if _lib().fdh_votes_scan_sparse_flat(ctx.h, len(per_query), _ptr(per_query), _ptr(hashes), _ptr(bits),
+                                         C.byref(prefilter), _ptr(sb), world, C.byref(lay), C.byref(ptr), _ptr(off),
+                                         _ptr(cnt)) != 0:
+        raise FdError(_err())
+    return lay, ptr.value, off, cnt
+
+
+def votes_merge_begin(ctx, layout, n_queries):
+    """cleared dense vote planes for this rank's n_queries queries -> (slice layout, device pointer)"""
+    sl, ptr = capi.VotesLayout(), VP()
+    ctx._check(capi.lib().fd_votes_merge_begin(ctx.h, C.byref(layout), 0, n_queries, C.byref(sl), C.byref(ptr)),
+               "fd_votes_merge_begin")
+    return sl, ptr.value
+
+
+def votes_apply(ctx, slice_layout, d_dense, d_records, n_records):
+    ctx._check(capi.lib().fd_votes_apply(ctx.h, C.byref(slice_layout), VP(d_dense), VP(d_records), int(n_records)),
+               "fd_votes_apply")
 
 
 def search_from_votes(ctx, queries, params, layout, d_votes, q_begin, q_end, labels=None):

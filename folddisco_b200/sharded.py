@@ -3,20 +3,26 @@
     rank r holds the posting lists of the hashes in [bounds[r], bounds[r+1])   (a slice of PREFIX / PREFIX.offset)
     every rank holds the compact-structure store (replicated; 38 B per residue) and the lookup
 
-Per batch of queries (the reference's `queries.into_par_iter()` body, src/cli/workflows/query_pdb.rs:348-452):
+Per batch of queries (the reference's `queries.into_par_iter()` body, src/cli/workflows/query_pdb.rs:348-452) every
+rank owns a SLICE of the batch: it builds the query maps of its slice, and finishes those queries.
 
-    0. QueryBatch.set_shards(bounds)           every (query edge, owning rank) pair gets its own vote bit
-    1. pair counts  -> all_reduce(SUM)          idf of every query edge needs the GLOBAL list length (query.rs:17-32);
-                                                a list lives on exactly one shard, so the sum is that length
-    2. fd_votes_scan on every rank              partial per-structure votes of the shard for the WHOLE batch (K3)
-       all_reduce(SUM) of the vote planes       the one exchange step: match counts and fixed-point idf add, the
-                                                edge bit masks are disjoint by construction so their sum is their OR
-    3. rank r finishes queries [q_r, q_{r+1})   node/edge counts, length penalty, filter, idf sort, --top
-                                                (fd_votes_select), then candidate verification (K6) against the store
+    prepare   0. QueryBatch.set_shards(bounds)    every (query edge, owning rank) pair gets its own vote bit
+              1. all_gather of the flat scan inputs (hashes + vote bit per hash, a few hundred bytes per query)
+              2. pair counts -> all_reduce(SUM)   idf of a query edge needs the GLOBAL list length (query.rs:17-32);
+                                                  a list lives on exactly one shard, so the sum is that length
+    search    3. fd_votes_scan_sparse             this rank's shard scanned for the WHOLE batch (K3); the non-empty
+                                                  (query, structure) cells are packed per destination rank
+              4. all_to_all of the records        the one exchange step: only non-empty cells travel over NVLink
+              5. fd_votes_merge_begin / apply     counts and fixed-point idf add, edge bits OR (disjoint by step 0)
+              6. fd_votes_select + verification   node/edge counts, length penalty, filter, idf sort, --top, then
+                                                  candidate verification (K6) against the replicated store
 
-Nothing here computes votes or decodes postings on the host: the tensors that torch.distributed reduces are views of
-library-owned device memory.  The same code runs under gloo on CPU tensors in tests/test_sharded_cpu.py (host logic
-only: shard planning, vote-bit assignment, merge semantics).
+`search_dense` is the north-star's literal form of steps 3-5 (dense vote planes + one NCCL all_reduce(SUM)); it moves
+planes * batch * structures words per rank whatever the votes are, which is why the sparse form is the default.
+
+Nothing here computes votes or decodes postings on the host: the tensors that torch.distributed moves are views of
+library-owned device memory.  The same collectives run under gloo on CPU tensors in tests/test_sharded_cpu.py (host
+logic only: shard planning, vote-bit assignment, gather / merge semantics).
 """
 import numpy as np
 
@@ -53,6 +59,40 @@ def shard_of(bounds, hashes):
 def query_slice(n_queries, rank, world):
     """the contiguous slice of the batch that rank finishes after the merge"""
     return (n_queries * rank) // world, (n_queries * (rank + 1)) // world
+
+
+def _active(dist):
+    return dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def all_gather_arrays(arrays, dist, device="cpu"):
+    """Every rank contributes a list of uint32 numpy arrays; returns, per rank, the list of that rank's arrays.
+    Two collectives: the lengths, then one padded all_gather_into_tensor."""
+    import torch
+    arrays = [np.ascontiguousarray(a, np.uint32).ravel() for a in arrays]
+    if not _active(dist):
+        return [arrays]
+    world = dist.get_world_size()
+    lens = torch.tensor([len(a) for a in arrays], dtype=torch.int64, device=device)
+    all_lens = torch.empty(world * len(arrays), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_lens, lens)
+    all_lens = all_lens.cpu().numpy().reshape(world, len(arrays))
+    width = int(all_lens.sum(axis=1).max())
+    flat = np.zeros(max(width, 1), np.uint32)
+    mine = np.concatenate(arrays) if arrays else np.zeros(0, np.uint32)
+    flat[:len(mine)] = mine
+    send = torch.from_numpy(flat.view(np.int32)).to(device)
+    recv = torch.empty(world * len(flat), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.cpu().numpy().view(np.uint32).reshape(world, len(flat))
+    out = []
+    for r in range(world):
+        pos, row = 0, []
+        for n in all_lens[r]:
+            row.append(recv[r, pos:pos + int(n)].copy())
+            pos += int(n)
+        out.append(row)
+    return out
 
 
 def all_reduce_sum(tensor, dist):
@@ -105,8 +145,67 @@ class ShardedIndex:
         hashes, _ = ctx.hash_structures(_BatchView(sub, ro), params)
         return hashes
 
+    # ---- sparse protocol: every rank owns a slice of the batch ----
+    def prepare(self, ctx, qb, dist):
+        """steps 0-2 for this rank's slice `qb` of the batch"""
+        import torch
+        nccl = _active(dist) and dist.get_backend() == "nccl"
+        dev = "cuda" if nccl else "cpu"
+        qb.set_shards(self.bounds)
+        per_query, hashes, bits, pairs = qb.scan_arrays()
+        g = all_gather_arrays([per_query, hashes, bits, pairs], dist, dev)
+        self.per_query = np.concatenate([x[0] for x in g]).reshape(-1, 3)
+        self.hashes = np.concatenate([x[1] for x in g])
+        self.bits = np.concatenate([x[2] for x in g])
+        all_pairs = np.concatenate([x[3] for x in g])
+        nq = [len(x[0]) // 3 for x in g]
+        self.slice_begin = np.concatenate([[0], np.cumsum(nq)]).astype(np.uint32)
+        pair_begin = np.concatenate([[0], np.cumsum([len(x[3]) for x in g])])
+        counts = torch.from_numpy(ctx.posting_counts(all_pairs).astype(np.int64)).to(dev)
+        all_reduce_sum(counts, dist)
+        counts = counts.cpu().numpy().astype(np.uint32)
+        r = self.rank if _active(dist) else 0
+        qb.finalize_with_counts(counts[pair_begin[r]:pair_begin[r + 1]], self.n_structs)
+
+    def search(self, ctx, qb, sp, dist, labels=None):
+        """steps 3-6 -> Results of this rank's slice `qb` (prepared by self.prepare)"""
+        import torch
+        lay, ptr, off, cnt = host.votes_scan_sparse(ctx, self.per_query, self.hashes, self.bits, sp.prefilter,
+                                                    self.slice_begin)
+        W = 1 + lay.planes
+        r = self.rank if _active(dist) else 0
+        sl, dense = host.votes_merge_begin(ctx, lay, len(qb))
+        host.votes_apply(ctx, sl, dense, ptr + int(off[r]) * W * 4, int(cnt[r]))
+        if _active(dist):
+            world = dist.get_world_size()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            mine = torch.from_numpy(cnt.astype(np.int64)).cuda()
+            table = torch.empty(world * world, dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(table, mine)
+            incoming = table.cpu().numpy().reshape(world, world)[:, r].copy()
+            incoming[r] = 0
+            recv = torch.empty(max(int(incoming.sum()) * W, 1), dtype=torch.int32, device="cuda")
+            empty = torch.empty(0, dtype=torch.int32, device="cuda")
+            inputs, outputs, pos = [], [], 0
+            for d in range(world):
+                n_out = int(cnt[d]) * W if d != r else 0
+                inputs.append(torch.as_tensor(capi.DeviceWords(ptr + int(off[d]) * W * 4, n_out), device="cuda")
+                              if n_out else empty)
+                n_in = int(incoming[d]) * W
+                outputs.append(recv[pos:pos + n_in] if n_in else empty)
+                pos += n_in
+            dist.all_to_all(outputs, inputs)
+            ev1.record()
+            ev1.synchronize()
+            self.merge_ms += ev0.elapsed_time(ev1)
+            self.merge_bytes += (int(cnt.sum()) - int(cnt[r])) * W * 4
+            host.votes_apply(ctx, sl, dense, recv.data_ptr(), int(incoming.sum()))
+        return host.search_from_votes(ctx, qb, sp, sl, dense, 0, len(qb), labels)
+
+    # ---- dense protocol (every rank holds the whole batch) ----
     def finalize(self, ctx, qb, dist):
-        """steps 0 and 1: vote bits + global per-edge idf"""
+        """steps 0 and 2 when every rank holds the whole batch: vote bits + global per-edge idf"""
         import torch
         qb.set_shards(self.bounds)
         counts = qb.pair_counts(ctx)
@@ -116,8 +215,8 @@ class ShardedIndex:
         all_reduce_sum(t, dist)
         qb.finalize_with_counts(t.cpu().numpy().astype(np.uint32), self.n_structs)
 
-    def search(self, ctx, qb, sp, dist, labels=None):
-        """steps 2 and 3 -> Results of this rank's slice of the batch (query_slice)"""
+    def search_dense(self, ctx, qb, sp, dist, labels=None):
+        """dense vote planes + one all_reduce(SUM) -> Results of this rank's slice of the batch (query_slice)"""
         import torch
         lay, ptr = host.votes_scan(ctx, qb, sp.prefilter)
         if lay.words:

@@ -188,13 +188,30 @@ typedef struct {
     uint32_t narrow;
     uint32_t edge_words;
     uint32_t planes;
-    uint64_t words; /* planes * n_queries * n_structs */
+    uint32_t first_query; /* the buffer holds queries first_query .. first_query + n_queries of the batch */
+    uint64_t words;       /* planes * n_queries * n_structs (dense); record words (sparse) */
 } fd_votes_layout;
 
 /* Scan this rank's shard for the whole batch.  *d_votes is a DEVICE pointer owned by ctx (valid until the next
  * fd_votes_scan / fd_destroy); the call returns after the scan has completed on the device. */
 int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,
                   fd_votes_layout *layout, uint32_t **d_votes);
+/* Sparse form of the same exchange (the default of folddisco_b200/sharded.py): only NON-EMPTY cells travel.
+ * slice_begin[world + 1] assigns the queries [slice_begin[r], slice_begin[r+1]) to rank r, which will finish them.
+ * The scan packs every non-empty (query, structure) cell of this rank's shard as a record of 1 + planes words
+ * {key = (query - slice_begin[dest]) * n_structs + nid, plane words...} into the region of its destination:
+ * records of rank r are (*d_records)[(region_offset[r] + k) * (1 + planes)], k < region_count[r]  (device memory
+ * owned by ctx; region_offset has world + 1 entries, region_count world).  The caller moves the regions with one
+ * all-to-all; the receiver clears a dense buffer for its slice (fd_votes_merge_begin), adds its own region and
+ * every received one (fd_votes_apply: plane 0[/1] add, edge planes OR) and finishes with fd_votes_select. */
+int fd_votes_scan_sparse(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,
+                         const uint32_t *slice_begin, uint32_t world, fd_votes_layout *layout, uint32_t **d_records,
+                         uint64_t *region_offset, uint64_t *region_count);
+int fd_votes_merge_begin(fd_ctx *ctx, const fd_votes_layout *layout, uint32_t first_query, uint32_t n_queries,
+                         fd_votes_layout *slice_layout, uint32_t **d_dense);
+int fd_votes_apply(fd_ctx *ctx, const fd_votes_layout *slice_layout, uint32_t *d_dense, const uint32_t *d_records,
+                   uint64_t n_records);
+
 /* Finish count_query from merged votes (any device pointer with the layout above) for queries
  * [q_begin, q_end) of the batch; outputs as fd_count_query_batch, offsets has q_end - q_begin + 1 entries. */
 int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,

@@ -157,6 +157,16 @@ int fdh_queries_set_shards(fdh_queries *qs, const uint64_t *bounds, int world);
 int64_t fdh_queries_num_vote_bits(const fdh_queries *qs, int64_t q);
 void fdh_queries_get_vote_bits(const fdh_queries *qs, int64_t q, uint32_t *hashes, uint16_t *bit_of_hash,
                                uint16_t *bit_node, uint16_t *bit_group);
+/* flat scan inputs of the batch, for the all-gather between ranks that each built the query maps of their own slice:
+ * per_query = {hashes, vote bits, pairs} per query; hashes / bit_of_hash in scan order; the observed hash per pair */
+void fdh_queries_scan_sizes(const fdh_queries *qs, uint64_t *n_hashes, uint64_t *n_pairs);
+void fdh_queries_scan_arrays(const fdh_queries *qs, uint32_t *per_query, uint32_t *hashes, uint32_t *bit_of_hash,
+                             uint32_t *pair_hashes);
+/* fd_votes_scan_sparse for a whole batch given as gathered flat arrays */
+int fdh_votes_scan_sparse_flat(fd_ctx *ctx, uint32_t nq, const uint32_t *per_query, const uint32_t *hashes,
+                               const uint32_t *bit_of_hash, const fd_prefilter_params *prefilter,
+                               const uint32_t *slice_begin, uint32_t world, fd_votes_layout *layout,
+                               uint32_t **d_records, uint64_t *region_offset, uint64_t *region_count);
 int64_t fdh_queries_num_pairs(const fdh_queries *qs);
 int fdh_queries_pair_counts(const fdh_queries *qs, fd_ctx *ctx, uint32_t *out_counts /* fdh_queries_num_pairs */);
 int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, uint64_t total_structures);

@@ -105,6 +105,84 @@ def test_two_shards_one_gpu():
         c.close()
 
 
+def _slice_batches(host, params, atoms, world, reps=1):
+    """the motif batch split into `world` contiguous slices, one QueryBatch per rank"""
+    structs = [host.CompactStructure.from_atoms(atoms[p]) for p, _, _ in F.MOTIFS]
+    structs.append(host.CompactStructure.from_atoms(atoms["query/4CHA.pdb"]))
+    strings = [q for _, q, _ in F.MOTIFS] + ["B57:X,B102,C195:ST"]
+    allq = [(structs[k % len(structs)], strings[k % len(strings)]) for k in range(len(structs) * reps)]
+    from folddisco_b200 import sharded
+    out = []
+    for r in range(world):
+        q0, q1 = sharded.query_slice(len(allq), r, world)
+        qb = host.QueryBatch(params)
+        qb.add_many([a for a, _ in allq[q0:q1]], [b for _, b in allq[q0:q1]])
+        out.append(qb)
+    return out
+
+
+def test_two_shards_one_gpu_sparse():
+    """the sparse protocol (packed non-empty cells per destination, apply, select) with the all_to_all done by hand
+    between two contexts of one GPU; every rank owns a slice of the batch"""
+    import folddisco_b200 as fd
+    from folddisco_b200 import host, sharded, synth
+    atoms = F.config1_atoms()
+    db = synth.generate(3000, 41, mean_len=150.0, max_len=500)
+    store = host.Store()
+    store.add_soa(db)
+    full = fd.Context(0)
+    ix = host.FolddiscoIndex.build(full, store)
+    ix.attach(full)
+    store.attach(full)
+    qb_full = _motif_batch(host, ix.params, atoms, reps=2)
+    qb_full.finalize(full)
+    sp = host.SearchParams(top_n=50)
+    want = host.search(full, qb_full, sp)
+    world = 2
+    ctxs = [fd.Context(0) for _ in range(world)]
+    shards = [sharded.ShardedIndex.build(ctxs[r], store, r, world) for r in range(world)]
+    for c in ctxs:
+        store.attach(c)
+    qbs = _slice_batches(host, ix.params, atoms, world, reps=2)
+    assert sum(len(q) for q in qbs) == len(qb_full)
+    for qb in qbs:
+        qb.set_shards(shards[0].bounds)
+    arrs = [qb.scan_arrays() for qb in qbs]
+    per_query = np.concatenate([a[0] for a in arrs])
+    hashes = np.concatenate([a[1] for a in arrs])
+    bits = np.concatenate([a[2] for a in arrs])
+    pairs = np.concatenate([a[3] for a in arrs])
+    counts = sum(c.posting_counts(pairs).astype(np.int64) for c in ctxs).astype(np.uint32)
+    pb = np.concatenate([[0], np.cumsum([len(a[3]) for a in arrs])])
+    slice_begin = np.concatenate([[0], np.cumsum([len(q) for q in qbs])]).astype(np.uint32)
+    for r, qb in enumerate(qbs):
+        qb.finalize_with_counts(counts[pb[r]:pb[r + 1]], len(store))
+    scans = [host.votes_scan_sparse(c, per_query, hashes, bits, sp.prefilter, slice_begin) for c in ctxs]
+    total = 0
+    for d in range(world):
+        lay = scans[d][0]
+        W = 1 + lay.planes
+        sl, dense = host.votes_merge_begin(ctxs[d], lay, len(qbs[d]))
+        n_cells = 0
+        for src in range(world):  # the all_to_all: region d of every source rank
+            _, ptr, off, cnt = scans[src]
+            host.votes_apply(ctxs[d], sl, dense, ptr + int(off[d]) * W * 4, int(cnt[d]))
+            n_cells += int(cnt[d])
+            assert int(cnt[d]) <= int(off[d + 1] - off[d])
+        assert n_cells > 0
+        got = host.search_from_votes(ctxs[d], qbs[d], sp, sl, dense, 0, len(qbs[d]))
+        for ql in range(len(qbs[d])):
+            q = int(slice_begin[d]) + ql
+            total += same_rows(got, want, ql, q)
+            n = len(qb_full.indices(q))
+            kg = sorted((int(m["nid"]), int(m["node_count"]), got.residue_string(m, n)) for m in got.sorted_matches(ql))
+            kw = sorted((int(m["nid"]), int(m["node_count"]), want.residue_string(m, n)) for m in want.sorted_matches(q))
+            assert kg == kw
+    assert total > 20
+    for c in ctxs + [full]:
+        c.close()
+
+
 def test_two_rank_nccl():
     import torch
     if torch.cuda.device_count() < 2:

@@ -150,6 +150,14 @@ def _worker(rank, world, port, out_q):
                 idf = float(merged[0, q, nid] & 0xffffff) / float(sc) * float(nres[nid]) ** -0.5
                 assert (int(mc[nid]), nc, ec) == w[nid][:3], (q, nid)
                 assert abs(idf - w[nid][3]) <= 1e-4 * max(1.0, abs(w[nid][3]))
+        # the variable-length gather of the sparse protocol's prepare step
+        mine = [np.arange(3 + rank, dtype=np.uint32) + 100 * rank, np.zeros(0, np.uint32),
+                np.full(5 * (rank + 1), 7 + rank, np.uint32)]
+        g = sharded.all_gather_arrays(mine, dist)
+        assert len(g) == world
+        for r in range(world):
+            assert g[r][0].tolist() == (np.arange(3 + r) + 100 * r).tolist()
+            assert len(g[r][1]) == 0 and g[r][2].tolist() == [7 + r] * (5 * (r + 1))
         dist.barrier()
         dist.destroy_process_group()
         out_q.put((rank, "ok", straddle))

@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1024, help="queries per GPU")
     ap.add_argument("--top", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=40, help="queries in the bounded CPU-baseline sample")
-    ap.add_argument("--sweep", default="4,8", help="index-size multipliers of the posting-scan sweep (N=1 only; '' = off)")
+    ap.add_argument("--sweep", default="2,4", help="index-size multipliers of the posting-scan sweep (N=1 only; '' = off)")
     return ap.parse_args()
 
 

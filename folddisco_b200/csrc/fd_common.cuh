@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -156,6 +157,19 @@ struct StageTimer {
         s.ms += ms;
         s.launches += ctx->launches - launches0;
         return cudaGetLastError();
+    }
+};
+
+// Accumulates host wall time of a scope into ctx->stages[name] (same table as the device stages).
+struct HostTimer {
+    fd_ctx *ctx;
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer(fd_ctx *c, const char *n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() {
+        FdStage &s = ctx->stages[name];
+        s.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        s.launches += 1;
     }
 };
 

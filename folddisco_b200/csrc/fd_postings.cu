@@ -105,16 +105,15 @@ int fd_postings_from_keys(fd_ctx *ctx, uint64_t *d_keys, uint64_t n_keys, uint64
     FD_CUDA(ctx, cudaStreamSynchronize(s));
 
     DevBuf<uint32_t> byte_len, is_head;
-    DevBuf<uint64_t> wide, byte_off, list_idx;
+    DevBuf<uint64_t> byte_off, list_idx;
     FD_CUDA(ctx, byte_len.alloc(n));
     FD_CUDA(ctx, is_head.alloc(n));
-    FD_CUDA(ctx, wide.alloc(n));
     FD_CUDA(ctx, byte_off.alloc(n + 1));
     FD_CUDA(ctx, list_idx.alloc(n + 1));
     const uint32_t grid = fd_div_up(n, 256);
     FD_LAUNCH(ctx, k2_measure, grid, 256, 0, d_keys, n, byte_len.p, is_head.p);
     size_t tb_scan = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, wide.p, byte_off.p, n + 1, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, byte_off.p, byte_off.p, n + 1, s);
     if (tb_scan > tmp.n) FD_CUDA(ctx, tmp.alloc(tb_scan));
     // exclusive sums over n+1 elements (the last input is a zero pad) give the totals in slot n
     DevBuf<uint64_t> widep;

@@ -761,6 +761,68 @@ __global__ void k3_make_sort_keys(const HitRec *hits, const uint64_t *hit_offset
         vals[base + k] = k;
     }
 }
+// ---- top-n pre-selection: only hits that can reach the top n of their query are sorted ----
+constexpr uint32_t K3_HIST_BINS = 4096; // bin = sign-less float bits >> 19: 8 exponent + 4 mantissa bits, monotone in idf
+__device__ __forceinline__ uint32_t idf_bin(float idf) {
+    const uint32_t u = __float_as_uint(idf);
+    return (u & 0x80000000u) ? 0u : (u >> 19);
+}
+__global__ void k3_idf_hist(const HitRec *hits, const uint64_t *hit_offsets, const unsigned int *hit_counts,
+                            uint32_t *hist) {
+    const uint32_t q = blockIdx.y;
+    const uint64_t base = hit_offsets[q];
+    const uint32_t n = hit_counts[q];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        atomicAdd(&hist[(size_t)q * K3_HIST_BINS + idf_bin(hits[base + k].idf)], 1u);
+}
+// one warp per query: the lowest bin such that the bins at or above it hold at least top_n hits
+__global__ void k3_idf_threshold(const uint32_t *hist, uint32_t n_queries, uint32_t top_n, uint32_t *thr_bin) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= n_queries) return;
+    const uint32_t *h = hist + (size_t)q * K3_HIST_BINS;
+    uint32_t above = 0, thr = 0;
+    for (int c = K3_HIST_BINS / 32 - 1; c >= 0; c--) { // chunks of 32 bins from the top; lane 31 = highest bin
+        const uint32_t v = h[c * 32 + lane];
+        uint32_t suf = v; // suffix sum over lanes >= lane
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+            if ((int)lane + o < 32) suf += t;
+        }
+        const uint32_t reach = __ballot_sync(0xffffffffu, above + suf >= top_n);
+        if (reach) {
+            thr = c * 32 + (31 - __clz(reach)); // highest lane whose suffix already reaches top_n
+            break;
+        }
+        above += __shfl_sync(0xffffffffu, suf, 0);
+    }
+    if (lane == 0) thr_bin[q] = thr;
+}
+__global__ void k3_make_sort_keys_top(const HitRec *hits, const uint64_t *hit_offsets, const unsigned int *hit_counts,
+                                      const uint32_t *thr_bin, unsigned int *kept, uint64_t *keys, uint32_t *vals) {
+    const uint32_t q = blockIdx.y, lane = threadIdx.x & 31;
+    const uint64_t base = hit_offsets[q];
+    const uint32_t n = hit_counts[q], thr = thr_bin[q];
+    const uint32_t n_round = (n + 31) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
+        HitRec r{0, 0, 0, 0.f};
+        bool keep = false;
+        if (k < n) {
+            r = hits[base + k];
+            keep = idf_bin(r.idf) >= thr;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(&kept[q], (unsigned int)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+            if (keep) {
+                keys[base + pos] = ((uint64_t)float_desc_key(r.idf) << 32) | r.nid;
+                vals[base + pos] = k;
+            }
+        }
+    }
+}
+
 __global__ void k3_segment_ends(const uint64_t *hit_offsets, const unsigned int *hit_counts, uint32_t n_queries,
                                 uint64_t *ends) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1006,8 +1068,26 @@ int select_and_copy(fd_ctx *ctx, uint32_t nsel, const std::vector<uint64_t> &hit
     FD_CUDA(ctx, d_vals2.alloc(pool));
     FD_CUDA(ctx, d_seg_end.alloc(nsel));
     dim3 g2(std::max<uint32_t>(1, std::min<uint32_t>(64, fd_div_up(N, 256))), nsel);
-    FD_LAUNCH(ctx, k3_make_sort_keys, g2, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, nsel, d_keys.p, d_vals.p);
-    FD_LAUNCH(ctx, k3_segment_ends, fd_div_up(nsel, 256), 256, 0, d_hit_off.p, d_hit_cnt.p, nsel, d_seg_end.p);
+    DevBuf<uint32_t> d_hist, d_thr;
+    DevBuf<unsigned int> d_kept;
+    uint64_t topsel_ratio = 128; // the pre-selection pays once the sort would be much larger than the histogram
+    if (const char *e = getenv("FD_K3_TOPSEL_RATIO")) topsel_ratio = strtoull(e, nullptr, 10);
+    if (top_n < 0x7fffffffull && pool > topsel_ratio * top_n * nsel) {
+        // only the hits that can reach the top n of their query take part in the sort
+        FD_CUDA(ctx, d_hist.alloc((size_t)nsel * K3_HIST_BINS));
+        FD_CUDA(ctx, d_thr.alloc(nsel));
+        FD_CUDA(ctx, d_kept.alloc(nsel));
+        FD_CUDA(ctx, cudaMemsetAsync(d_hist.p, 0, (size_t)nsel * K3_HIST_BINS * 4, s));
+        FD_CUDA(ctx, cudaMemsetAsync(d_kept.p, 0, nsel * 4, s));
+        FD_LAUNCH(ctx, k3_idf_hist, g2, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, d_hist.p);
+        FD_LAUNCH(ctx, k3_idf_threshold, fd_div_up((uint64_t)nsel * 32, 256), 256, 0, d_hist.p, nsel, (uint32_t)top_n, d_thr.p);
+        FD_LAUNCH(ctx, k3_make_sort_keys_top, g2, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, d_thr.p, d_kept.p, d_keys.p,
+                  d_vals.p);
+        FD_LAUNCH(ctx, k3_segment_ends, fd_div_up(nsel, 256), 256, 0, d_hit_off.p, d_kept.p, nsel, d_seg_end.p);
+    } else {
+        FD_LAUNCH(ctx, k3_make_sort_keys, g2, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, nsel, d_keys.p, d_vals.p);
+        FD_LAUNCH(ctx, k3_segment_ends, fd_div_up(nsel, 256), 256, 0, d_hit_off.p, d_hit_cnt.p, nsel, d_seg_end.p);
+    }
     size_t tb = 0;
     cub::DeviceSegmentedSort::SortPairs(nullptr, tb, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p, (int64_t)pool,
                                         (int64_t)nsel, d_hit_off.p, d_seg_end.p, s);

@@ -22,6 +22,9 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 
 #include "fd_common.cuh"
 #include "fd_geom.cuh"
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(VA_THREADS)
               uint32_t *cand_ne, uint8_t *cand_flags) {
     __shared__ uint16_t list1[V_LIST_CAP], list2[V_LIST_CAP];
     __shared__ uint32_t n1, n2, q_n, n_e, s_base;
+    __shared__ int s_dmax_bits, s_dmin_bits; // range of the query's CA distances (positive floats order like ints)
     __shared__ uint32_t q_ij[VA_QUEUE];
     __shared__ float q_d[VA_QUEUE];
     __shared__ VAad aad[V_MAX_AAD];
@@ -145,12 +149,22 @@ __global__ void __launch_bounds__(VA_THREADS)
     const uint64_t base = st.row_offsets[t];
     const uint32_t n = (uint32_t)(st.row_offsets[t + 1] - base);
     const VHash *H = vhash + Q.hash_begin;
-    if (tid == 0) n1 = n2 = q_n = n_e = 0;
+    if (tid == 0) {
+        n1 = n2 = q_n = n_e = 0;
+        s_dmax_bits = 0;
+        s_dmin_bits = 0x7f7fffff;
+    }
     load_aad_phase1<VA_THREADS>(Q, vaad, aad, aa_range, tid);
     __syncthreads();
     if (Q.n_hashes == 0 || Q.n_aad == 0) return;
     load_aad_phase2<VA_THREADS>(Q, aad, aa_range, tid);
+    for (uint32_t k = tid; k < Q.n_aad; k += VA_THREADS) {
+        const int bits = __float_as_int(fmaxf(aad[k].dist, 0.f));
+        atomicMax(&s_dmax_bits, bits);
+        atomicMin(&s_dmin_bits, bits);
+    }
     __syncthreads();
+    const float s_dmax = __int_as_float(s_dmax_bits), s_dmin = __int_as_float(s_dmin_bits);
 
     // ---- prefilter sets (prefilter_amino_acid, retrieve.rs:563-602) ----
     bool all_pairs = !Q.use_prefilter;
@@ -186,49 +200,60 @@ __global__ void __launch_bounds__(VA_THREADS)
     const uint64_t total = (uint64_t)rows * cols; // < 2^32: both factors are at most 65535
 
     // ---- retrieve_with_prefilter: screen, hash, keep pairs whose hash is in the query set ----
-    for (uint64_t p0 = 0; p0 < total; p0 += VA_CHUNK) {
-        for (uint32_t u = 0; u < VA_CHUNK / VA_THREADS; u++) {
-            const uint64_t p = p0 + (uint64_t)u * VA_THREADS + tid;
-            bool pass = false;
-            uint32_t i = 0, j = 0;
-            float d = 0.f;
-            if (p < total) {
-                const uint32_t p32 = (uint32_t)p;
-                const uint32_t a = p32 / cols, b = p32 - a * cols;
-                i = all_pairs ? a : list1[a];
-                j = all_pairs ? b : list2[b];
-                const uint8_t ai = st.aa[base + i], aj = st.aa[base + j];
-                if (i != j && ai != 255 && aj != 255) {
-                    const uint32_t rg = aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)];
-                    if (rg != 0) {
-                        d = fdg::dist(ld3(st.ca_xyz, base + i), ld3(st.ca_xyz, base + j));
-                        if (d <= hp.dist_cutoff) {
-                            for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
-                                if (fabsf(d - aad[k].dist) < ca_cutoff) {
-                                    pass = true;
-                                    break;
-                                }
-                        }
+    // Thread t owns row (t mod RP) of the current row block and every CS-th column: its row's residue stays in
+    // registers, the lanes of a warp walk the same column (one broadcast load), no index division.  A pair reaches
+    // sqrt + the exact |d - d_q| test only if its squared CA distance lies inside the query's distance range.
+    const uint32_t RP = min(rows, 32u);  // rows per block: one warp = 32 rows of one column phase
+    const uint32_t CS = VA_THREADS / RP; // >= 4 column phases
+    const bool t_active = (uint32_t)tid < RP * CS;
+    const uint32_t t_row = (uint32_t)tid % RP, t_cs = (uint32_t)tid / RP;
+    const uint32_t cols_per_round = CS * (VA_CHUNK / VA_THREADS);
+    const float pre_hi = fminf(hp.dist_cutoff, s_dmax + ca_cutoff), pre_lo = fmaxf(s_dmin - ca_cutoff, 0.f);
+    const float pre_hi2 = pre_hi * pre_hi * 1.0001f, pre_lo2 = pre_lo * pre_lo * 0.9999f;
+    for (uint32_t row0 = 0; row0 < rows; row0 += RP) {
+        const uint32_t a = row0 + t_row;
+        bool row_ok = t_active && a < rows;
+        uint32_t i = 0, aim = 0;
+        fdg::V3 cai{0.f, 0.f, 0.f};
+        if (row_ok) {
+            i = all_pairs ? a : list1[a];
+            const uint8_t ai = st.aa[base + i];
+            row_ok = ai != 255;
+            aim = (ai & 0x7Fu) * 20u;
+            cai = ld3(st.ca_xyz, base + i);
+        }
+        for (uint32_t col0 = 0; col0 < cols; col0 += cols_per_round) {
+            if (row_ok) {
+#pragma unroll 2
+                for (uint32_t u = 0; u < VA_CHUNK / VA_THREADS; u++) {
+                    const uint32_t b = col0 + u * CS + t_cs;
+                    if (b >= cols) break;
+                    const uint32_t j = all_pairs ? b : list2[b];
+                    const uint8_t aj = st.aa[base + j];
+                    if (j == i || aj == 255) continue;
+                    const uint32_t rg = aa_range[aim + (aj & 0x7Fu)];
+                    if (rg == 0) continue;
+                    const float d2 = fdg::dist2(cai, ld3(st.ca_xyz, base + j));
+                    if (d2 > pre_hi2 || d2 < pre_lo2) continue;
+                    const float d = FD_SQRT(d2); // == fdg::dist
+                    if (d <= hp.dist_cutoff) {
+                        for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
+                            if (fabsf(d - aad[k].dist) < ca_cutoff) {
+                                const uint32_t pos = atomicAdd(&q_n, 1u);
+                                q_ij[pos] = (i << 16) | j;
+                                q_d[pos] = d;
+                                break;
+                            }
                     }
                 }
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                uint32_t pos = 0;
-                if (lane == 0) pos = atomicAdd(&q_n, __popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
-                if (pass) {
-                    q_ij[pos] = (i << 16) | j;
-                    q_d[pos] = d;
-                }
-            }
-        }
-        __syncthreads();
-        // hash the queued survivors once a full CTA of them is waiting (or at the end): the binary64 trig of the
-        // hash is the expensive part, it should not run on a handful of lanes per chunk
-        const uint32_t qn = q_n;
-        const bool last = p0 + VA_CHUNK >= total;
-        if (qn >= VA_THREADS || last) {
+            __syncthreads();
+            // hash the queued survivors once a full CTA of them is waiting (or at the end): the binary64 trig of
+            // the hash is the expensive part, it should not run on a handful of lanes per round
+            const uint32_t qn = q_n;
+            const bool last = row0 + RP >= rows && col0 + cols_per_round >= cols;
+            __syncthreads(); // every thread has read q_n before the next round appends to the queue
+            if (!(qn >= VA_THREADS || last)) continue;
             const uint32_t take = last ? qn : (qn / VA_THREADS) * VA_THREADS;
             for (uint32_t k = tid; k < take; k += VA_THREADS) {
                 const uint32_t i = q_ij[k] >> 16, j = q_ij[k] & 0xffffu;
@@ -328,6 +353,8 @@ struct WarpState { // per-warp shared memory
     uint32_t n_nodes, n_comp, s_flag;
     uint32_t r_dq, r_need, r_nridx, s_out_base;
     uint16_t r_ridx[V_MAX_NQ];
+    float r_x[V_MAX_NQ], r_y[V_MAX_NQ], r_z[V_MAX_NQ]; // CA of the matched target residues (rescue)
+    uint8_t r_aa[V_MAX_NQ];                            // their amino acid, 0xff = cannot pair
     uint8_t m_qidx[V_MAX_NQ], m_ridx[V_MAX_NQ]; // mapping of the current component: dense query id, node id
     uint32_t m_n;
     uint32_t f_qscan[V_MAX_NQ], f_rscan[V_MAX_NQ], f_nscan, f_res[V_MAX_NQ], f_nres;
@@ -367,6 +394,18 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     }
     __syncwarp();
     load_aad_phase2<32>(Q, W.aad, W.aa_range, lane);
+    // range of the query's CA distances: a pair outside it cannot support a rescue
+    float dmax = 0.f, dmin = 3.0e38f;
+    for (uint32_t k = lane; k < Q.n_aad; k += 32) {
+        dmax = fmaxf(dmax, W.aad[k].dist);
+        dmin = fminf(dmin, W.aad[k].dist);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    }
+    const float pre_hi = fminf(hp.dist_cutoff, dmax + ca_cutoff), pre_lo = fmaxf(dmin - ca_cutoff, 0.f);
+    const float pre_hi2 = pre_hi * pre_hi * 1.0001f, pre_lo2 = pre_lo * pre_lo * 0.9999f;
     __syncwarp();
 
     // ---- graph: nodes by first appearance, components = SCCs U weak components, size >= 2 ----
@@ -535,6 +574,18 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
             for (uint32_t k = 0; k < nm; k++) W.r_ridx[k] = W.node_res[W.m_ridx[k]];
         }
         __syncwarp();
+        if ((uint32_t)lane < W.r_nridx) { // the matched residues' data, once per component
+            const uint32_t rj = W.r_ridx[lane];
+            const uint8_t aj = st.aa[base + rj];
+            bool ok = aj != 255 && (st.cb_valid == nullptr || st.cb_valid[base + rj]);
+            if (!all_pairs) ok = ok && ((aj & 0x80u) == 0) && ((Q.aa2_mask >> (aj & 31u)) & 1u);
+            const fdg::V3 c = ld3(st.ca_xyz, base + rj);
+            W.r_x[lane] = c.x;
+            W.r_y[lane] = c.y;
+            W.r_z[lane] = c.z;
+            W.r_aa[lane] = ok ? (uint8_t)(aj & 0x7Fu) : (uint8_t)0xff;
+        }
+        __syncwarp();
         // ---- rescue loop over the query residues (retrieve.rs:453-516) ----
         for (uint32_t pos = 0; pos < Q.n_idx; pos++) {
             if (lane == 0) {
@@ -577,18 +628,17 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                     const uint8_t ai = st.aa[base + i];
                     if (!all_pairs && !(((ai & 0x80u) == 0) && ((Q.aa1_mask >> (ai & 31u)) & 1u))) return 0u;
                     if (ai == 255 || (st.cb_valid != nullptr && !st.cb_valid[base + i])) return 0u;
-                    const uint8_t cia = ai & 0x7Fu;
+                    const uint32_t cia = (ai & 0x7Fu) * 20u;
                     const fdg::V3 cai = ld3(st.ca_xyz, base + i);
                     uint32_t cnt = 0;
                     for (uint32_t k = 0; k < W.r_nridx; k++) {
-                        const uint32_t rj = W.r_ridx[k];
-                        if (rj == i) continue;
-                        const uint8_t aj = st.aa[base + rj];
-                        if (aj == 255 || (st.cb_valid != nullptr && !st.cb_valid[base + rj])) continue;
-                        if (!all_pairs && !(((aj & 0x80u) == 0) && ((Q.aa2_mask >> (aj & 31u)) & 1u))) continue;
-                        const uint32_t rg = W.aa_range[cia * 20u + (aj & 0x7Fu)];
+                        const uint32_t aj = W.r_aa[k];
+                        if (aj == 0xffu || W.r_ridx[k] == i) continue;
+                        const uint32_t rg = W.aa_range[cia + aj];
                         if (rg == 0) continue;
-                        const float d = fdg::dist(cai, ld3(st.ca_xyz, base + rj));
+                        const float d2 = fdg::dist2(cai, fdg::V3{W.r_x[k], W.r_y[k], W.r_z[k]});
+                        if (d2 > pre_hi2 || d2 < pre_lo2) continue;
+                        const float d = FD_SQRT(d2); // == fdg::dist
                         if (!(d <= hp.dist_cutoff)) continue;
                         for (uint32_t e = rg >> 8, ee = (rg >> 8) + (rg & 0xffu); e < ee; e++)
                             if (W.aad[e].dq == dq && fabsf(d - W.aad[e].dist) < ca_cutoff) cnt++;
@@ -718,72 +768,133 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     FD_TRY(fd_pinned(ctx, 2, (n_cand + 1) * 4, (void **)&h_first));
     memset(h_flags, 0, std::max<uint64_t>(n_cand, 1));
     memset(h_first, 0, (n_cand + 1) * 4);
-    // flatten queries; a query outside the kernel's limits marks all of its candidates for the general path
+    // flatten queries (two passes, query-parallel, no per-query heap traffic); a query outside the kernel's limits
+    // marks all of its candidates for the general path
     std::vector<VQDesc> descs(nq);
-    std::vector<VHash> f_hash;
-    std::vector<VAad> f_aad;
-    std::vector<uint8_t> f_idx;
-    std::vector<float> q_ca, q_cb;
     std::vector<uint8_t> q_unfit(nq, 0);
-    for (uint32_t q = 0; q < nq; q++) {
+    struct DenseIds { // sorted distinct residue indices of one query (at most V_MAX_NQ when the query fits)
+        uint32_t v[V_MAX_NQ + 1];
+        uint32_t n;
+    };
+    std::vector<DenseIds> dqs(nq);
+    std::atomic<int> bad{0}; // 1 hashes not ascending, 2 amino-acid code, 3 residue index
+    auto parallel_queries = [&](const std::function<void(uint32_t)> &fn) {
+        int nt = (int)std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (nq < 64) nt = 1;
+        std::atomic<uint32_t> next{0};
+        auto worker = [&] {
+            for (uint32_t q0; (q0 = next.fetch_add(16)) < nq;)
+                for (uint32_t q = q0; q < std::min(nq, q0 + 16); q++) fn(q);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &t : th) t.join();
+    };
+    // pass 1: dense ids over every query residue index that occurs (ascending residue index), limits, masks
+    parallel_queries([&](uint32_t q) {
         const fd_verify_query &Q = queries[q];
+        DenseIds &D = dqs[q];
+        D.n = 0;
+        bool overflow = false;
+        auto add = [&](uint32_t r) {
+            if (overflow) return;
+            uint32_t p = 0;
+            while (p < D.n && D.v[p] < r) p++;
+            if (p < D.n && D.v[p] == r) return;
+            if (D.n == V_MAX_NQ + 1) {
+                overflow = true;
+                return;
+            }
+            for (uint32_t k = D.n; k > p; k--) D.v[k] = D.v[k - 1];
+            D.v[p] = r;
+            D.n++;
+        };
+        for (uint32_t k = 0; k < Q.n_hashes; k++) {
+            add(Q.hash_qi[k]);
+            add(Q.hash_qj[k]);
+        }
+        for (uint32_t k = 0; k < Q.n_indices; k++) add(Q.indices[k]);
+        for (uint32_t k = 0; k < Q.n_aa_dist; k++) add(Q.q_index[k]);
         VQDesc d{};
-        d.hash_begin = (uint32_t)f_hash.size();
         d.n_hashes = Q.n_hashes;
-        d.aad_begin = (uint32_t)f_aad.size();
         d.n_aad = Q.n_aa_dist;
         d.use_prefilter = Q.n_hashes <= V_PREFILTER_SKIP ? 1u : 0u;
-        d.idx_begin = (uint32_t)f_idx.size();
         d.n_idx = Q.n_indices;
-        d.qres_base = (uint32_t)(q_ca.size() / 3);
-        // dense ids over every query residue index that occurs (ascending residue index)
-        std::vector<uint32_t> dq;
-        for (uint32_t k = 0; k < Q.n_hashes; k++) {
-            dq.push_back(Q.hash_qi[k]);
-            dq.push_back(Q.hash_qj[k]);
+        d.n_dq = D.n;
+        if (overflow || D.n > V_MAX_NQ || Q.n_indices > V_MAX_NQ || Q.n_aa_dist > V_MAX_AAD || Q.n_hashes > 65535) {
+            q_unfit[q] = 1;
+            d.n_aad = 0; // the kernels return immediately for this query's candidates
+            D.n = std::min<uint32_t>(D.n, V_MAX_NQ);
+            d.n_dq = D.n;
         }
-        for (uint32_t k = 0; k < Q.n_indices; k++) dq.push_back(Q.indices[k]);
-        for (uint32_t k = 0; k < Q.n_aa_dist; k++) dq.push_back(Q.q_index[k]);
-        std::sort(dq.begin(), dq.end());
-        dq.erase(std::unique(dq.begin(), dq.end()), dq.end());
-        d.n_dq = (uint32_t)dq.size();
-        if (dq.size() > V_MAX_NQ || Q.n_indices > V_MAX_NQ || Q.n_aa_dist > V_MAX_AAD || Q.n_hashes > 65535) q_unfit[q] = 1;
-        auto dense = [&](uint32_t r) { return (uint8_t)(std::lower_bound(dq.begin(), dq.end(), r) - dq.begin()); };
         for (uint32_t k = 0; k < Q.n_hashes; k++) {
-            if (k && Q.hashes_sorted[k] <= Q.hashes_sorted[k - 1]) {
-                return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: hashes_sorted must be strictly ascending");
-            }
-            f_hash.push_back(VHash{Q.hashes_sorted[k], Q.hash_idf[k], dense(Q.hash_qi[k]), dense(Q.hash_qj[k]),
-                                   Q.hash_symmetric[k], 0});
+            if (k && Q.hashes_sorted[k] <= Q.hashes_sorted[k - 1]) bad = 1;
             d.aa1_mask |= 1u << ((Q.hashes_sorted[k] >> 25) & 31u);
             d.aa2_mask |= 1u << ((Q.hashes_sorted[k] >> 20) & 31u);
         }
-        if (!q_unfit[q]) { // entries grouped by amino-acid pair (the kernel indexes them through a 20x20 table)
-            std::vector<uint32_t> ord(Q.n_aa_dist);
-            for (uint32_t k = 0; k < Q.n_aa_dist; k++) ord[k] = k;
-            std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) {
-                return Q.aa1[a] * 20u + Q.aa2[a] < Q.aa1[b] * 20u + Q.aa2[b];
-            });
-            for (uint32_t k : ord) {
-                if (Q.aa1[k] >= 20 || Q.aa2[k] >= 20) {
-                        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
-                }
-                f_aad.push_back(VAad{Q.aa1[k], Q.aa2[k], dense(Q.q_index[k]), 0, Q.ca_dist[k]});
-            }
-        }
-        if (q_unfit[q]) d.n_aad = 0; // kernel returns immediately for this query's candidates
-        for (uint32_t k = 0; k < Q.n_indices; k++) f_idx.push_back(dense(Q.indices[k]));
-        for (uint32_t r : dq) { // only the residues the query touches travel to the device
-            if (r >= Q.n_residues) {
-                return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: residue index outside the query structure");
-            }
-            for (int x = 0; x < 3; x++) {
-                q_ca.push_back(Q.ca_xyz[3 * r + x]);
-                q_cb.push_back(Q.cb_xyz[3 * r + x]);
-            }
-        }
+        for (uint32_t k = 0; k < D.n; k++)
+            if (D.v[k] >= Q.n_residues) bad = 3;
         descs[q] = d;
+    });
+    if (bad == 1) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: hashes_sorted must be strictly ascending");
+    if (bad == 3) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: residue index outside the query structure");
+    uint64_t n_fh = 0, n_fa = 0, n_fi = 0, n_fr = 0;
+    for (uint32_t q = 0; q < nq; q++) {
+        VQDesc &d = descs[q];
+        d.hash_begin = (uint32_t)n_fh;
+        d.aad_begin = (uint32_t)n_fa;
+        d.idx_begin = (uint32_t)n_fi;
+        d.qres_base = (uint32_t)n_fr;
+        n_fh += d.n_hashes;
+        n_fa += d.n_aad;
+        n_fi += d.n_idx;
+        n_fr += d.n_dq;
     }
+    if (n_fh > 0xffffffffull || n_fr > 0xffffffffull) return fd_fail(ctx, FD_ERR_LIMIT, "query batch too large");
+    std::vector<VHash> f_hash(n_fh);
+    std::vector<VAad> f_aad(n_fa);
+    std::vector<uint8_t> f_idx(n_fi);
+    std::vector<float> q_ca(3 * n_fr), q_cb(3 * n_fr);
+    // pass 2: fill
+    parallel_queries([&](uint32_t q) {
+        const fd_verify_query &Q = queries[q];
+        const DenseIds &D = dqs[q];
+        const VQDesc &d = descs[q];
+        auto dense = [&](uint32_t r) {
+            uint32_t p = 0;
+            while (p < D.n && D.v[p] < r) p++;
+            return (uint8_t)p;
+        };
+        for (uint32_t k = 0; k < Q.n_hashes; k++)
+            f_hash[d.hash_begin + k] = VHash{Q.hashes_sorted[k], Q.hash_idf[k], dense(Q.hash_qi[k]), dense(Q.hash_qj[k]),
+                                             Q.hash_symmetric[k], 0};
+        if (!q_unfit[q]) { // entries grouped by amino-acid pair (the kernels index them through a 20x20 table):
+            // stable counting sort by aa1 * 20 + aa2
+            uint16_t start[401];
+            memset(start, 0, sizeof(start));
+            for (uint32_t k = 0; k < Q.n_aa_dist; k++) {
+                if (Q.aa1[k] >= 20 || Q.aa2[k] >= 20) {
+                    bad = 2;
+                    return;
+                }
+                start[Q.aa1[k] * 20u + Q.aa2[k] + 1]++;
+            }
+            for (int k = 0; k < 400; k++) start[k + 1] += start[k];
+            for (uint32_t k = 0; k < Q.n_aa_dist; k++)
+                f_aad[d.aad_begin + start[Q.aa1[k] * 20u + Q.aa2[k]]++] =
+                    VAad{Q.aa1[k], Q.aa2[k], dense(Q.q_index[k]), 0, Q.ca_dist[k]};
+        }
+        for (uint32_t k = 0; k < Q.n_indices; k++) f_idx[d.idx_begin + k] = dense(Q.indices[k]);
+        for (uint32_t k = 0; k < D.n; k++) { // only the residues the query touches travel to the device
+            const uint32_t r = D.v[k];
+            for (int x = 0; x < 3; x++) {
+                q_ca[3 * ((size_t)d.qres_base + k) + x] = Q.ca_xyz[3 * r + x];
+                q_cb[3 * ((size_t)d.qres_base + k) + x] = Q.cb_xyz[3 * r + x];
+            }
+        }
+    });
+    if (bad == 2) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
     for (uint64_t c = 0; c < n_cand; c++) {
         if (cand_query[c] >= nq || cand_nid[c] >= ctx->store.n_structs) {
             return fd_fail(ctx, FD_ERR_ARG, "candidate query / structure id out of range");

@@ -998,17 +998,73 @@ int fdh_store_batch(const fdh_store *s, fd_struct_batch *out) {
 void fdh_store_free(fdh_store *s) { delete s; }
 
 // ---- index ----
+// Folddisco::collect_and_count .. add_entries on the GPU.  The sort/encode stage needs ~50 bytes of device memory
+// per (hash, structure) posting, so large databases are built in hash-range chunks (every chunk re-hashes the
+// structures, which is cheap, and keeps only its range); the chunks concatenate to the index byte for byte.
 fdh_index *fdh_index_build(fd_ctx *ctx, const fdh_store *s, const fd_hash_params *params) {
     fd_struct_batch b;
     fdh_store_batch(s, &b);
-    fd_index_buffers out;
-    if (fd_build_index(ctx, &b, params, 0, 0, 1ull << 32, &out) != FD_OK) {
-        set_err(fd_last_error(ctx));
-        return nullptr;
+    const uint64_t S = b.n_structs, R = S ? b.row_offsets[S] : 0;
+    uint64_t chunk_keys = 600ull * 1000 * 1000;
+    if (const char *e = getenv("FD_BUILD_CHUNK_KEYS")) chunk_keys = std::max<uint64_t>(1000, strtoull(e, nullptr, 10));
+    std::vector<uint64_t> bounds{0, 1ull << 32};
+    if (R * 100 > chunk_keys) { // ~100 postings per residue: more than one chunk is likely, so plan from a sample
+        const uint64_t n_sample = std::min<uint64_t>(S, 256);
+        fd_struct_batch sb = b;
+        sb.n_structs = n_sample;
+        uint32_t *sh = nullptr;
+        uint64_t *sro = nullptr;
+        if (fd_hash_structures(ctx, &sb, params, &sh, &sro) != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return nullptr;
+        }
+        const uint64_t n_sh = sro[n_sample], r_sample = std::max<uint64_t>(1, b.row_offsets[n_sample]);
+        std::vector<uint64_t> hist(4096, 0); // by hash >> 20
+        for (uint64_t k = 0; k < n_sh; k++) hist[sh[k] >> 20]++;
+        fd_free(sh);
+        fd_free(sro);
+        const double scale = (double)R / (double)r_sample;
+        bounds.assign(1, 0);
+        double acc = 0;
+        for (uint32_t p = 0; p < 4096; p++) {
+            const double add = hist[p] * scale;
+            if (acc > 0 && acc + add > (double)chunk_keys) {
+                bounds.push_back((uint64_t)p << 20);
+                acc = 0;
+            }
+            acc += add;
+        }
+        bounds.push_back(1ull << 32);
     }
-    fdh_index *ix = fdh_index_from_buffers(&out, s, params);
-    fd_free_index_buffers(&out);
-    return ix;
+    fd_index_buffers all;
+    memset(&all, 0, sizeof(all));
+    std::vector<uint32_t> hashes;
+    std::vector<uint64_t> offsets(1, 0);
+    std::vector<uint8_t> values;
+    const bool single = bounds.size() == 2;
+    for (size_t c = 0; c + 1 < bounds.size(); c++) {
+        fd_index_buffers out;
+        if (fd_build_index(ctx, &b, params, 0, bounds[c], bounds[c + 1], &out) != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return nullptr;
+        }
+        if (single) {
+            fdh_index *ix = fdh_index_from_buffers(&out, s, params);
+            fd_free_index_buffers(&out);
+            return ix;
+        }
+        hashes.insert(hashes.end(), out.hashes, out.hashes + out.count);
+        const uint64_t base = values.size();
+        for (uint64_t k = 1; k <= out.count; k++) offsets.push_back(base + out.offsets[k]);
+        values.insert(values.end(), out.values, out.values + out.value_bytes);
+        fd_free_index_buffers(&out);
+    }
+    all.count = hashes.size();
+    all.hashes = hashes.data();
+    all.offsets = offsets.data();
+    all.value_bytes = values.size();
+    all.values = values.data();
+    return fdh_index_from_buffers(&all, s, params);
 }
 
 fdh_index *fdh_index_from_buffers(const fd_index_buffers *out, const fdh_store *s, const fd_hash_params *params) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line instruction counts of one kernel from an ncu report (SASS page) + nvdisasm line info.
 
-    python profiles/sass_lines.py REPORT.ncu-rep OBJECT.o MANGLED_SUBSTRING [top]
+    python profiles/sass_lines.py REPORT.ncu-rep OBJECT.o MANGLED_SUBSTRING [top [DEMANGLED_SUBSTRING]]
 """
 import collections
 import csv
@@ -40,7 +40,14 @@ def main():
     per = collections.Counter()
     stall = collections.Counter()
     total = 0
+    want = sys.argv[5] if len(sys.argv) > 5 else None  # substring of the demangled kernel name (multi-kernel reports)
+    active = True
     for r in rows:
+        if r and r[0] == "Kernel Name":
+            active = want is None or want in r[1]
+            continue
+        if not active:
+            continue
         if r and r[0] == "Address":
             hdr = r
             continue

@@ -3,6 +3,8 @@
 Bit-exact for hashes, index bytes, ids, counts; 1e-4 for idf and RMSD (tolerances written at each assert).
 Run on the B200 box:  python -m pytest tests -m gpu -x -q
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -296,6 +298,14 @@ def test_count_query_synthetic(ctx, n_structs, seed, kw):
     for qm, g in zip(qms, got):
         op = O.CountParams(-1.0, -1, -1.0, 0.3, 2, 2, 0.5, 0.01, 250, 40.0, len(qm.indices()), 25, 1)
         _compare_hits(g, O.count_query(qm, oix, nres, plddt, op), top_n=25)
+    # the histogram pre-selection of the top-N path (normally only used when the sort would be large)
+    os.environ["FD_K3_TOPSEL_RATIO"] = "0"
+    try:
+        got2 = ctx.count_query_batch(queries, p)
+    finally:
+        del os.environ["FD_K3_TOPSEL_RATIO"]
+    for g, g2 in zip(got, got2):
+        assert np.array_equal(g, g2)
     # freq filter and sampling (count_query.rs:124-128, 222-253)
     p = fd.PrefilterParams(freq_filter=0.02)
     got = ctx.count_query_batch(queries[:2], p)

@@ -424,6 +424,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if world > 1:  # the ranks share the box's cores: the library's host-side steps get cores / ranks threads each
+        os.environ.setdefault("FD_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     if world != args.gpus:
         if args.gpus != 1 or world != 1:
             sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; launch with torch.distributed.run\n" % (args.gpus, world))

@@ -109,6 +109,7 @@ def lib():
     sig("fd_last_error", C.c_char_p, [VP])
     sig("fd_free", None, [VP])
     sig("fd_version", C.c_char_p, [])
+    sig("fd_default_host_threads", C.c_int, [])
     sig("fd_kernel_launches", C.c_uint64, [VP])
     sig("fd_stage_ms", C.c_double, [VP, C.c_char_p])
     sig("fd_stage_launches", C.c_uint64, [VP, C.c_char_p])

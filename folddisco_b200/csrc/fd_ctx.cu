@@ -1,4 +1,7 @@
 // fd_ctx.cu -- lifecycle of the C ABI (include/folddisco_b200.h) and the math parity probes.
+#include <algorithm>
+#include <thread>
+
 #include "fd_common.cuh"
 #include "fd_geom.cuh"
 
@@ -70,6 +73,15 @@ __global__ void fd_math_probe_kernel(int op, const float *a, const float *b, uin
 }
 
 extern "C" {
+
+int fd_default_host_threads(void) {
+    if (const char *e = getenv("FD_HOST_THREADS")) {
+        const int n = atoi(e);
+        if (n > 0) return std::min(n, 256);
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
 
 const char *fd_version(void) { return "folddisco_b200 0.1 (sm_100a)"; }
 

@@ -779,7 +779,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     std::vector<DenseIds> dqs(nq);
     std::atomic<int> bad{0}; // 1 hashes not ascending, 2 amino-acid code, 3 residue index
     auto parallel_queries = [&](const std::function<void(uint32_t)> &fn) {
-        int nt = (int)std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        int nt = std::min(fd_default_host_threads(), 16);
         if (nq < 64) nt = 1;
         std::atomic<uint32_t> next{0};
         auto worker = [&] {

@@ -1315,7 +1315,7 @@ int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structur
     std::vector<Query> out((size_t)n);
     std::vector<std::string> errs((size_t)n);
     std::vector<uint8_t> ok((size_t)n, 0);
-    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    int nt = threads > 0 ? threads : fd_default_host_threads();
     nt = std::max(1, std::min<int>(nt, 64));
     std::atomic<int64_t> next{0};
     auto worker = [&] {
@@ -1435,7 +1435,7 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, uint32_t q_begin, uint32_
         e_begin[c + 1] += e_begin[c];
         p_begin[c + 1] += p_begin[c];
     }
-    int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+    int nt = p->host_threads > 0 ? p->host_threads : fd_default_host_threads();
     nt = std::max(1, std::min(nt, 64));
     std::vector<std::vector<MatchTmp>> per_thread(nt);
     std::atomic<uint64_t> next{0};
@@ -1816,7 +1816,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         });
     };
     {
-        int nt = p->host_threads > 0 ? p->host_threads : (int)std::thread::hardware_concurrency();
+        int nt = p->host_threads > 0 ? p->host_threads : fd_default_host_threads();
         nt = std::max(1, std::min(nt, 64));
         auto run_parallel = [&](const std::function<void(uint32_t)> &fn) {
             std::atomic<uint32_t> next{0};

@@ -40,6 +40,9 @@ void fd_free(void *p);                        /* for library-allocated host outp
 const char *fd_version(void);
 /* number of this library's kernels launched through ctx since creation (bench.py's gpu_launches) */
 uint64_t fd_kernel_launches(const fd_ctx *ctx);
+/* host threads the library uses for its query-parallel host steps when the caller passes 0: the environment variable
+ * FD_HOST_THREADS if set (several ranks share one box: cores / ranks), else the number of hardware threads */
+int fd_default_host_threads(void);
 /* cumulative device time (ms, CUDA events on the library's stream) of the named stage since creation:
  * "hash", "postings", "attach", "lookup", "scan", "select", "verify" (= "verify_edges" + "verify_components" +
  * "verify_kabsch"), "edges", "kabsch"; 0 if the stage never ran */

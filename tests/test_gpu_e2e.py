@@ -151,3 +151,92 @@ def test_skip_match_and_filters(env):
     r = host.search(ctx, qb, sp, labels=store)
     assert sorted(os.path.basename(env["names"][int(x)]) for x in r.structures(0)["nid"]) == ["1pq5.pdb", "4cha.pdb"]
     assert all(m["rmsd"] <= 0.3 for m in r.sorted_matches(0)) and len(r.sorted_matches(0)) == 3
+
+
+def test_full_size_properties(env):
+    """BASELINE configs[2] at its full size (23 400 synthetic structures, the five motifs): size-independent
+    properties instead of an oracle run (which would take minutes on the CPU).
+      * index invariants: hashes strictly ascending, offsets strictly increasing, lists decode to strictly
+        increasing ids < N, posting-count table == decoded lengths, sum of counts == number of varint terminators;
+      * checksum of checksums: with no filter and no top-N, the match counts of all hits of a query add up to the
+        posting counts of its hashes (every posting is exactly one vote);
+      * edge_count / node_count bounds, hits ordered by (idf desc, nid asc);
+      * idempotence: the same batch twice gives identical rows; top-N is a prefix of the full ranking;
+      * a sample of the verified matches re-superposed on the CPU (numpy Kabsch) reproduces the RMSD within 1e-4."""
+    from folddisco_b200 import synth
+    host, ctx, fd = env["host"], env["ctx"], env["fd"]
+    S = 23400
+    db = synth.generate(S, synth.SEED_BASE + 2)
+    store = host.Store()
+    store.add_soa(db)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    b = ix.buffers()
+    assert np.all(np.diff(b.hashes.astype(np.int64)) > 0)
+    assert b.offsets[0] == 0 and np.all(np.diff(b.offsets.astype(np.int64)) > 0) and b.offsets[-1] == len(b.values)
+    ix.attach(ctx)
+    store.attach(ctx)
+    n_term = int(np.count_nonzero(b.values < 128))
+    rng = np.random.default_rng(11)
+    lens = np.diff(b.offsets.astype(np.int64))
+    pick = np.concatenate([np.argsort(lens)[-20:], rng.integers(0, len(b.hashes), 300)])
+    counts = ctx.posting_counts(b.hashes[pick])
+    for k, li in enumerate(pick[:60]):
+        ids = ctx.get_entries(int(b.hashes[li]))
+        assert len(ids) == counts[k] and np.all(np.diff(ids.astype(np.int64)) > 0) and ids[-1] < S
+    # all counts in chunks (the count table must account for every varint of the value file)
+    total = 0
+    for c0 in range(0, len(b.hashes), 1 << 22):
+        total += int(ctx.posting_counts(b.hashes[c0:c0 + (1 << 22)]).astype(np.int64).sum())
+    assert total == n_term
+    qb = host.QueryBatch(ix.params)
+    for path, q, _ in F.MOTIFS:
+        qb.add(host.CompactStructure.from_atoms(env["atoms"][path]), q)
+    qb.finalize(ctx)
+    full = host.search(ctx, qb, host.SearchParams(skip_match=True))
+    for k in range(len(F.MOTIFS)):
+        rows = full.structures(k)
+        qm = qb.query_map(k)
+        assert int(rows["total_match_count"].astype(np.int64).sum()) == int(ctx.posting_counts(qm["hash"]).astype(np.int64).sum())
+        n_edges = len(set(zip(qm["qi"].tolist(), qm["qj"].tolist())))
+        n_nodes = len(set(qm["qi"].tolist()))
+        assert rows["edge_count"].max() <= n_edges and rows["node_count"].max() <= n_nodes
+        assert np.all(rows["edge_count"] <= rows["total_match_count"]) and np.all(rows["node_count"] <= rows["edge_count"])
+        assert np.all(rows["idf"][:-1] >= rows["idf"][1:])
+        assert len(np.unique(rows["nid"])) == len(rows) and rows["nid"].max() < S
+    sp = host.SearchParams(top_n=100)
+    r1 = host.search(ctx, qb, sp)
+    r2 = host.search(ctx, qb, sp)
+    def same(a, b):  # field by field: the padding bytes of the row structs are not defined
+        return all(np.array_equal(a[f], b[f]) for f in a.dtype.names if not f.startswith("_"))
+    assert same(r1.structs, r2.structs) and same(r1.matches, r2.matches) and same(r1.residues, r2.residues)
+    soa = {k: env["host"].CompactStructure.from_atoms(env["atoms"][p]).soa() for k, (p, _, _) in enumerate(F.MOTIFS)}
+    checked = 0
+    for k in range(len(F.MOTIFS)):
+        top = r1.structures(k)
+        assert len(top) == 100
+        # top-N is the head of the full ranking (up to ties at the cut)
+        cut = float(full.structures(k)["idf"][99])
+        assert np.all(top["idf"] >= cut - 1e-6)
+        assert set(top["nid"][top["idf"] > cut + 1e-6].tolist()) <= set(full.structures(k)["nid"][:100].tolist())
+        idx = qb.indices(k)
+        for m in r1.sorted_matches(k)[:25]:
+            res = r1.residues[int(m["res_begin"]):int(m["res_begin"]) + len(idx)]
+            sel = [j for j in range(len(idx)) if res[j]["some"]]
+            if len(sel) < 2:
+                continue
+            base = int(db["row_offsets"][int(m["nid"])])
+            tr = [base + int(res[j]["serial"]) for j in sel]
+            x = np.stack([np.stack([db["ca_xyz"][r], db["cb_xyz"][r]]) for r in tr]).reshape(-1, 3).astype(np.float64)
+            y = np.stack([np.stack([soa[k]["ca_xyz"][idx[j]], soa[k]["cb_xyz"][idx[j]]]) for j in sel]).reshape(-1, 3).astype(np.float64)
+            U, t = m["U"].reshape(3, 3).astype(np.float64), m["t"].astype(np.float64)
+            rmsd = np.sqrt((((x @ U.T + t) - y) ** 2).sum(axis=1).mean())
+            assert abs(rmsd - float(m["rmsd"])) <= 1e-4 * max(1.0, rmsd), (k, rmsd, float(m["rmsd"]))
+            # and no rigid transform does better than the reported one (Kabsch optimality, numpy SVD)
+            xc, yc = x - x.mean(0), y - y.mean(0)
+            Uo, _, Vt = np.linalg.svd(xc.T @ yc)
+            d = np.sign(np.linalg.det(Uo @ Vt))
+            R = (Uo @ np.diag([1, 1, d]) @ Vt).T
+            best = np.sqrt((((xc @ R.T) - yc) ** 2).sum(axis=1).mean())
+            assert rmsd <= best + 1e-3
+            checked += 1
+    assert checked > 50

@@ -110,6 +110,10 @@ def lib():
     sig("fd_free", None, [VP])
     sig("fd_version", C.c_char_p, [])
     sig("fd_default_host_threads", C.c_int, [])
+    sig("fd_fork", C.c_int, [VP, PP(VP)])
+    sig("fd_fork_refresh", C.c_int, [VP, VP])
+    sig("fd_lane", C.c_int, [VP, C.c_int, PP(VP)])
+    sig("fd_lanes_fold_stats", None, [VP])
     sig("fd_kernel_launches", C.c_uint64, [VP])
     sig("fd_stage_ms", C.c_double, [VP, C.c_char_p])
     sig("fd_stage_launches", C.c_uint64, [VP, C.c_char_p])

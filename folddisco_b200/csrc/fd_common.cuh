@@ -54,6 +54,8 @@ struct FdPinned {
 };
 
 struct fd_ctx {
+    bool borrowed = false;         // fd_fork child: idx / store point into the parent's device memory
+    std::vector<fd_ctx *> lanes;   // children kept by the in-library host for overlapped call sequences
     int device = 0;
     int num_sms = FD_NUM_SMS_FALLBACK;
     cudaStream_t stream = nullptr;
@@ -76,6 +78,8 @@ extern thread_local std::string fd_g_create_error;
 // pinned staging buffer `slot` of at least `bytes` bytes (contents not preserved when it grows)
 int fd_pinned(fd_ctx *ctx, int slot, size_t bytes, void **out);
 cudaError_t fd_ensure_events(fd_ctx *ctx);
+// adds a fork's stage times and launch count to its parent's and clears them (in-library host, after joining a lane)
+void fd_fold_stats(fd_ctx *parent, fd_ctx *child);
 
 inline int fd_fail(fd_ctx *ctx, int code, const std::string &msg) {
     if (ctx) ctx->err = msg;

@@ -43,6 +43,17 @@ int fd_pinned(fd_ctx *ctx, int slot, size_t bytes, void **out) {
     *out = b.p;
     return FD_OK;
 }
+void fd_fold_stats(fd_ctx *parent, fd_ctx *child) {
+    for (auto &kv : child->stages) {
+        FdStage &s = parent->stages[kv.first];
+        s.ms += kv.second.ms;
+        s.launches += kv.second.launches;
+    }
+    child->stages.clear();
+    parent->launches += child->launches;
+    child->launches = 0;
+}
+
 cudaError_t fd_ensure_events(fd_ctx *ctx) {
     for (auto &e : ctx->ev_extra)
         if (!e) {
@@ -114,11 +125,52 @@ int fd_create(fd_ctx **out, int device) {
     return FD_OK;
 }
 
+int fd_fork(fd_ctx *parent, fd_ctx **out) {
+    if (!parent || !out) return fd_fail(parent, FD_ERR_ARG, "fd_fork: NULL argument");
+    *out = nullptr;
+    fd_ctx *c = nullptr;
+    const int rc = fd_create(&c, parent->device);
+    if (rc != FD_OK) return fd_fail(parent, rc, fd_g_create_error);
+    c->borrowed = true;
+    c->idx = parent->idx;
+    c->store = parent->store;
+    *out = c;
+    return FD_OK;
+}
+
+int fd_fork_refresh(fd_ctx *parent, fd_ctx *child) {
+    if (!parent || !child || !child->borrowed) return fd_fail(parent, FD_ERR_ARG, "fd_fork_refresh: not a fork");
+    child->idx = parent->idx;
+    child->store = parent->store;
+    return FD_OK;
+}
+
+int fd_lane(fd_ctx *ctx, int i, fd_ctx **out) {
+    if (!ctx || !out || i < 0 || i >= 8) return fd_fail(ctx, FD_ERR_ARG, "fd_lane: bad argument");
+    while ((int)ctx->lanes.size() <= i) {
+        fd_ctx *child = nullptr;
+        FD_TRY(fd_fork(ctx, &child));
+        ctx->lanes.push_back(child);
+    }
+    FD_TRY(fd_fork_refresh(ctx, ctx->lanes[i]));
+    *out = ctx->lanes[i];
+    return FD_OK;
+}
+
+void fd_lanes_fold_stats(fd_ctx *ctx) {
+    if (!ctx) return;
+    for (fd_ctx *l : ctx->lanes) fd_fold_stats(ctx, l);
+}
+
 void fd_destroy(fd_ctx *ctx) {
     if (!ctx) return;
+    for (fd_ctx *l : ctx->lanes) fd_destroy(l);
+    ctx->lanes.clear();
     cudaSetDevice(ctx->device);
-    fd_release_index(ctx->idx);
-    fd_release_store(ctx->store);
+    if (!ctx->borrowed) {
+        fd_release_index(ctx->idx);
+        fd_release_store(ctx->store);
+    }
     cudaFree(ctx->votes);
     cudaFree(ctx->merge);
     for (auto &b : ctx->pinned)

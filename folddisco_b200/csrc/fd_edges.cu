@@ -249,6 +249,7 @@ extern "C" {
 
 int fd_store_attach(fd_ctx *ctx, const fd_struct_batch *batch) {
     if (!ctx) return FD_ERR_ARG;
+    if (ctx->borrowed) return fd_fail(ctx, FD_ERR_STATE, "fd_store_attach: a forked context shares its parent's store");
     FD_ENTER(ctx);
     FdDeviceBatch d;
     FD_TRY(fd_upload_batch(ctx, batch, &d));

@@ -1146,6 +1146,7 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     if (n_structs > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "structure ids must fit in 32 bits");
     if (offsets[0] != 0 || offsets[count] != value_bytes)
         return fd_fail(ctx, FD_ERR_ARG, "fd_index_attach: offsets[0] must be 0 and offsets[count] == value_bytes");
+    if (ctx->borrowed) return fd_fail(ctx, FD_ERR_STATE, "fd_index_attach: a forked context shares its parent's index");
     FD_ENTER(ctx);
     fd_ctx_release_index(ctx);
     FdDeviceIndex &d = ctx->idx;

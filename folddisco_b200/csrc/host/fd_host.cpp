@@ -497,9 +497,41 @@ struct SeenHashes {
     }
 };
 
-void qinsert(Query &Q, SeenHashes &seen, const float *f, const fdg::HashParams &hp, uint32_t qi, uint32_t qj,
-             bool primary, uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
-    const uint32_t h = fdg::perfect_hash(f, hp);
+// fdg::perfect_hash with the (sin, cos) bins of the angle features memoised on the exact f32 value: the ~11
+// variants of one residue pair (query.rs:179-206) perturb one feature at a time, so most of their binary64
+// sincos evaluations repeat.  Bit-identical to fdg::perfect_hash (same functions on the same inputs).
+struct AngleBinCache {
+    struct E {
+        uint32_t bits, bins; // f32 bits of the angle -> sin bin << 16 | cos bin
+    };
+    E e[3][12];
+    int n[3] = {0, 0, 0};
+    void reset() { n[0] = n[1] = n[2] = 0; }
+    uint32_t bins(int slot, float a, const fdg::HashParams &hp) {
+        uint32_t bits;
+        memcpy(&bits, &a, 4);
+        for (int k = 0; k < n[slot]; k++)
+            if (e[slot][k].bits == bits) return e[slot][k].bins;
+        float sn, cs;
+        fdm::sincosf_exact(a, &sn, &cs);
+        const uint32_t b = fdg::discretize(sn, -1.0f, 1.0f, hp.nbin_angle) << 16 | fdg::discretize(cs, -1.0f, 1.0f, hp.nbin_angle);
+        if (n[slot] < 12) e[slot][n[slot]++] = E{bits, b};
+        return b;
+    }
+    uint32_t hash(const float *f, const fdg::HashParams &hp) {
+        const uint32_t res1 = fdg::sat_u32(f[0]), res2 = fdg::sat_u32(f[1]);
+        const uint32_t ca = fdg::discretize(f[2], 2.0f, 20.0f, hp.nbin_dist);
+        const uint32_t cb = fdg::discretize(f[3], 2.0f, 20.0f, hp.nbin_dist);
+        const uint32_t b0 = bins(0, f[4], hp), b1 = bins(1, f[5], hp), b2 = bins(2, f[6], hp);
+        // the sin / cos bins are OR-ed in unmasked, exactly like perfect_hash (pdb_tr.rs:21-75: no field masking)
+        return res1 << 25 | res2 << 20 | ca << 16 | cb << 12 | (b0 >> 16) << 10 | (b0 & 0xffffu) << 8 |
+               (b1 >> 16) << 6 | (b1 & 0xffffu) << 4 | (b2 >> 16) << 2 | (b2 & 0xffffu);
+    }
+};
+
+void qinsert(Query &Q, SeenHashes &seen, AngleBinCache &bins, const float *f, const fdg::HashParams &hp, uint32_t qi,
+             uint32_t qj, bool primary, uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
+    const uint32_t h = bins.hash(f, hp);
     if (!seen.insert(h, (uint32_t)Q.entries.size(), Q.entries)) return;
     Q.entries.push_back(QEntry{h, qi, qj, (uint8_t)primary, pair, 0.f});
 }
@@ -527,6 +559,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     const float rad = 3.14159274101257324f / 180.0f; // f32::to_radians
     float f[7], fn[7], ff[7];
     SeenHashes seen;
+    AngleBinCache bins;
     const size_t K = Q.indices.size();
     for (size_t a = 0; a < K; a++)
         for (size_t b = 0; b < K; b++) {
@@ -538,8 +571,9 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
             memcpy(ff, f, sizeof(f));
             if (f[2] <= 20.0f) Q.aad.push_back(AAD{(uint8_t)(c.aa[I] & 0x7F), (uint8_t)(c.aa[J] & 0x7F), f[2], I});
             const uint32_t pair = (uint32_t)Q.pair_hash.size();
-            Q.pair_hash.push_back(fdg::perfect_hash(f, hp));
-            qinsert(Q, seen, f, hp, I, J, true, pair);
+            bins.reset();
+            Q.pair_hash.push_back(bins.hash(f, hp));
+            qinsert(Q, seen, bins, f, hp, I, J, true, pair);
             { // apply_substitutions (query.rs:86-156)
                 const float o1 = fn[0], o2 = fn[1];
                 auto si = submap.find(I), sj = submap.find(J);
@@ -548,14 +582,14 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
                         float t[7];
                         memcpy(t, fn, sizeof(t));
                         t[0] = (float)s;
-                        qinsert(Q, seen, t, hp, I, J, false, pair);
+                        qinsert(Q, seen, bins, t, hp, I, J, false, pair);
                     }
                     if (sj != submap.end())
                         for (uint8_t s : si->second)
                             for (uint8_t s2 : sj->second) {
                                 fn[0] = (float)s;
                                 fn[1] = (float)s2;
-                                qinsert(Q, seen, fn, hp, I, J, false, pair);
+                                qinsert(Q, seen, bins, fn, hp, I, J, false, pair);
                                 fn[0] = o1;
                                 fn[1] = o2;
                             }
@@ -564,7 +598,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
                         float t[7];
                         memcpy(t, fn, sizeof(t));
                         t[1] = (float)s;
-                        qinsert(Q, seen, t, hp, I, J, false, pair);
+                        qinsert(Q, seen, bins, t, hp, I, J, false, pair);
                     }
                 }
             }
@@ -574,8 +608,8 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
                     for (int k : idxs) {
                         fn[k] -= delta;
                         ff[k] += delta;
-                        qinsert(Q, seen, fn, hp, I, J, false, pair);
-                        qinsert(Q, seen, ff, hp, I, J, false, pair);
+                        qinsert(Q, seen, bins, fn, hp, I, J, false, pair);
+                        qinsert(Q, seen, bins, ff, hp, I, J, false, pair);
                         fn[k] += delta;
                         ff[k] -= delta;
                     }
@@ -1616,9 +1650,18 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     t_stage = now();
     R->d2h_bytes += n_cand * sizeof(fd_struct_hit) + (nq + 1) * 8ull + nq * 16ull;
     std::vector<FinalMatch> fm; // matches of the candidates that took the general path, grouped by candidate
-    const fd_match_record *recs = nullptr; // matches of everything else: views of ctx's pinned staging buffers
-    const uint32_t *rec_first = nullptr;
-    const uint8_t *flags = nullptr;
+    // matches of everything else: views of pinned staging buffers, one set per verification lane (a lane = a
+    // contiguous range of queries verified by one host thread on its own context / stream)
+    struct Lane {
+        uint64_t c0 = 0, c1 = 0; // candidate range
+        const fd_match_record *recs = nullptr;
+        const uint32_t *first = nullptr;
+        const uint8_t *flags = nullptr;
+        uint64_t n_recs = 0;
+        int rc = FD_OK;
+        std::string err;
+    };
+    std::vector<Lane> lanes;
     std::vector<uint8_t> all_general;
     std::vector<uint32_t> cand_q;
     double host_ms = 0.0;
@@ -1650,24 +1693,65 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         uint64_t n_recs = 0;
         if (p->verify_mode == 1) { // general path for everything
             all_general.assign(n_cand, 1);
-            flags = all_general.data();
-        } else if (fd_verify_candidates_view(ctx, vq.data(), nq, cand_q.data(), cand_n.data(), n_cand, &qs->p.hash,
-                                             p->ca_dist_cutoff, p->skip_ca_match, &recs, &n_recs, &rec_first,
-                                             &flags) != FD_OK) {
-            set_err(fd_last_error(ctx));
-            return fail();
+            lanes.resize(1);
+            lanes[0].c1 = n_cand;
+            lanes[0].flags = all_general.data();
+        } else {
+            // Optional lanes (FD_VERIFY_LANES=2..4): the queries are split into ranges verified by separate host
+            // threads on forked contexts (own stream, own staging), so one lane's host-side steps, synchronisations
+            // and record copy overlap another lane's kernels.  Measured on the bench workload: no gain (7.4 vs 7.2 ms,
+            // the verification kernels already fill the GPU), so the default is one lane.
+            int n_lanes = 1;
+            if (const char *e = getenv("FD_VERIFY_LANES")) n_lanes = std::max(1, std::min(atoi(e), (int)std::min<uint32_t>(nq, 4)));
+            std::vector<fd_ctx *> lane_ctx(n_lanes, ctx);
+            for (int l = 1; l < n_lanes; l++)
+                if (fd_lane(ctx, l - 1, &lane_ctx[l]) != FD_OK) {
+                    set_err(fd_last_error(ctx));
+                    return fail();
+                }
+            lanes.resize(n_lanes);
+            std::vector<uint32_t> cand_q_local(n_cand);
+            std::vector<uint32_t> q_split(n_lanes + 1);
+            for (int l = 0; l <= n_lanes; l++) q_split[l] = (uint32_t)((uint64_t)nq * l / n_lanes);
+            for (int l = 0; l < n_lanes; l++) {
+                lanes[l].c0 = hoff[q_split[l]];
+                lanes[l].c1 = hoff[q_split[l + 1]];
+                for (uint64_t c = lanes[l].c0; c < lanes[l].c1; c++) cand_q_local[c] = cand_q[c] - q_split[l];
+            }
+            auto run_lane = [&](int l) {
+                fd_ctx *lc = lane_ctx[l];
+                Lane &L = lanes[l];
+                L.rc = fd_verify_candidates_view(lc, vq.data() + q_split[l], q_split[l + 1] - q_split[l],
+                                                 cand_q_local.data() + L.c0, cand_n.data() + L.c0, L.c1 - L.c0,
+                                                 &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match, &L.recs, &L.n_recs,
+                                                 &L.first, &L.flags);
+                if (L.rc != FD_OK) L.err = fd_last_error(lc);
+            };
+            std::vector<std::thread> th;
+            for (int l = 1; l < n_lanes; l++) th.emplace_back(run_lane, l);
+            run_lane(0);
+            for (auto &t : th) t.join();
+            fd_lanes_fold_stats(ctx);
+            for (auto &L : lanes) {
+                if (L.rc != FD_OK) {
+                    set_err(L.err);
+                    return fail();
+                }
+                n_recs += L.n_recs;
+            }
         }
         R->h2d_bytes += 8ull * n_cand;
         R->d2h_bytes += n_recs * sizeof(fd_match_record) + 5ull * n_cand;
         auto t0 = std::chrono::steady_clock::now();
         std::vector<uint32_t> fq_, fn_;
         std::vector<uint64_t> fglobal;
-        for (uint64_t c = 0; c < n_cand; c++)
-            if (flags[c]) {
-                fq_.push_back(cand_q[c]);
-                fn_.push_back(cand_n[c]);
-                fglobal.push_back(c);
-            }
+        for (auto &L : lanes)
+            for (uint64_t c = L.c0; c < L.c1; c++)
+                if (L.flags[c - L.c0]) {
+                    fq_.push_back(cand_q[c]);
+                    fn_.push_back(cand_n[c]);
+                    fglobal.push_back(c);
+                }
         host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (!fglobal.empty()) {
             if (verify_general(ctx, qs, q_begin, nq, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
@@ -1691,16 +1775,24 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         const uint32_t *res;
     };
     // number of matches of candidate c and the a-th of them
+    auto lane_of = [&](uint64_t c) -> const Lane & {
+        size_t l = 0;
+        while (l + 1 < lanes.size() && c >= lanes[l].c1) l++;
+        return lanes[l];
+    };
     auto match_count = [&](uint64_t c) -> size_t {
-        if (flags && flags[c]) return fm_begin.empty() ? 0 : fm_begin[c + 1] - fm_begin[c];
-        return rec_first ? (size_t)(rec_first[c + 1] - rec_first[c]) : 0;
+        if (lanes.empty()) return 0;
+        const Lane &L = lane_of(c);
+        if (L.flags[c - L.c0]) return fm_begin.empty() ? 0 : fm_begin[c + 1] - fm_begin[c];
+        return L.first ? (size_t)(L.first[c - L.c0 + 1] - L.first[c - L.c0]) : 0;
     };
     auto match_at = [&](uint64_t c, size_t a) -> MatchView {
-        if (flags && flags[c]) {
+        const Lane &L = lane_of(c);
+        if (L.flags[c - L.c0]) {
             const FinalMatch &m = fm[fm_begin[c] + a];
             return MatchView{m.node_count, m.idf, m.rmsd, m.U, m.t, m.res()};
         }
-        const fd_match_record &r = recs[rec_first[c] + a];
+        const fd_match_record &r = L.recs[L.first[c - L.c0] + a];
         return MatchView{r.node_count, r.idf, r.rmsd, r.U, r.t, r.res};
     };
     // per-candidate summary (retrieve.rs:539-551) + filter_after_matching (filter.rs:103-116)

@@ -35,6 +35,16 @@ typedef struct fd_ctx fd_ctx;
 /* ---- lifecycle --------------------------------------------------------------------------------- */
 int fd_create(fd_ctx **out, int device);
 void fd_destroy(fd_ctx *ctx);
+/* A second context on the same device that SHARES the parent's attached index and structure store (read-only) but
+ * has its own stream, events and staging buffers: a host can run two synchronous call sequences (one per host
+ * thread) whose kernels, copies and host-side steps overlap.  The child must not attach anything itself and must be
+ * destroyed before the parent; after the parent attaches a new index / store call fd_fork_refresh. */
+int fd_fork(fd_ctx *parent, fd_ctx **out);
+int fd_fork_refresh(fd_ctx *parent, fd_ctx *child);
+/* the i-th (0..7) cached fork of ctx, created on first use, refreshed to ctx's current attachments, owned and
+ * destroyed by ctx; fd_lanes_fold_stats adds the lanes' stage times / launch counts to ctx's and clears them */
+int fd_lane(fd_ctx *ctx, int i, fd_ctx **out);
+void fd_lanes_fold_stats(fd_ctx *ctx);
 const char *fd_last_error(const fd_ctx *ctx); /* ctx may be NULL: last error of a failed fd_create */
 void fd_free(void *p);                        /* for library-allocated host outputs */
 const char *fd_version(void);

@@ -101,6 +101,15 @@ FD_HD uint32_t perfect_hash(const float *f, const HashParams &p) {
     return res1 << 25 | res2 << 20 | ca << 16 | cb << 12 | s0 << 10 | c0 << 8 | s1 << 6 | c1 << 4 | s2 << 2 | c2;
 }
 
+// Bits 12..31 of perfect_hash (amino acids, CA and CB distance bins; fields OR-ed in unmasked exactly as above).
+// The six sin / cos bins are at most nbin_angle - 1 <= 3, so they never reach bit 12: a pair can only hash into a
+// set that holds a hash with the same upper bits -- a trigonometry-free necessary condition for set membership.
+FD_HD uint32_t hash_upper(V3 cb1, V3 cb2, uint8_t aa1, uint8_t aa2, float ca_dist, const HashParams &p) {
+    uint32_t ca = discretize(ca_dist, 2.0f, 20.0f, p.nbin_dist);
+    uint32_t cb = discretize(dist(cb1, cb2), 2.0f, 20.0f, p.nbin_dist);
+    return ((uint32_t)aa1 << 25 | (uint32_t)aa2 << 20 | ca << 16 | cb << 12) >> 12;
+}
+
 // Geometry part of the feature for residues i -> j.  The caller has already checked aa != 255, cb_valid and
 // ca_dist <= cutoff (ca_dist is passed in so it is computed once, with dist()).
 FD_HD void pair_feature(V3 n1, V3 ca1, V3 cb1, V3 n2, V3 ca2, V3 cb2, float aa1, float aa2, float ca_dist,

@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <functional>
 #include <thread>
 
@@ -33,8 +34,7 @@
 namespace {
 
 constexpr int VA_THREADS = 128;            // k6a CTA
-constexpr int VA_CHUNK = VA_THREADS * 8;   // pairs screened per round
-constexpr int VA_QUEUE = VA_CHUNK + VA_THREADS; // survivor queue: hashed when >= VA_THREADS are waiting
+constexpr int VA_HASH_STAGE = 256;         // query hash sets up to this size are staged in shared memory
 constexpr int V_LIST_CAP = 2048;           // prefilter-list capacity (larger candidates take the general path)
 constexpr int VB_WARPS = 4;                // k6b: candidates per CTA
 constexpr int V_MAX_AAD = 255; // start and count of an amino-acid pair's run each fit 8 bits
@@ -132,10 +132,12 @@ __global__ void __launch_bounds__(VA_THREADS)
               uint16_t *pool_ent, unsigned int *pool_count, uint32_t pool_cap, uint32_t *cand_ebegin,
               uint32_t *cand_ne, uint8_t *cand_flags) {
     __shared__ uint16_t list1[V_LIST_CAP], list2[V_LIST_CAP];
-    __shared__ uint32_t n1, n2, q_n, n_e, s_base;
+    __shared__ uint32_t n1, n2, n_e, s_base;
     __shared__ int s_dmax_bits, s_dmin_bits; // range of the query's CA distances (positive floats order like ints)
-    __shared__ uint32_t q_ij[VA_QUEUE];
-    __shared__ float q_d[VA_QUEUE];
+    __shared__ uint32_t wq_ij[VA_THREADS / 32][64], wb_ij[VA_THREADS / 32][64]; // warp-private queues A and B
+    __shared__ float wq_d[VA_THREADS / 32][64], wb_d[VA_THREADS / 32][64];
+    __shared__ uint16_t wb_lo[VA_THREADS / 32][64];
+    __shared__ uint32_t s_hash[VA_HASH_STAGE];
     __shared__ VAad aad[V_MAX_AAD];
     __shared__ uint16_t aa_range[400];
     __shared__ uint32_t e_key[V_MAX_E]; // i << 16 | j
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(VA_THREADS)
     const uint32_t n = (uint32_t)(st.row_offsets[t + 1] - base);
     const VHash *H = vhash + Q.hash_begin;
     if (tid == 0) {
-        n1 = n2 = q_n = n_e = 0;
+        n1 = n2 = n_e = 0;
         s_dmax_bits = 0;
         s_dmin_bits = 0x7f7fffff;
     }
@@ -158,11 +160,22 @@ __global__ void __launch_bounds__(VA_THREADS)
     __syncthreads();
     if (Q.n_hashes == 0 || Q.n_aad == 0) return;
     load_aad_phase2<VA_THREADS>(Q, aad, aa_range, tid);
-    for (uint32_t k = tid; k < Q.n_aad; k += VA_THREADS) {
-        const int bits = __float_as_int(fmaxf(aad[k].dist, 0.f));
-        atomicMax(&s_dmax_bits, bits);
-        atomicMin(&s_dmin_bits, bits);
+    {
+        int bmax = 0, bmin = 0x7f7fffff;
+        for (uint32_t k = tid; k < Q.n_aad; k += VA_THREADS) {
+            const int bits = __float_as_int(fmaxf(aad[k].dist, 0.f));
+            bmax = max(bmax, bits);
+            bmin = min(bmin, bits);
+        }
+        bmax = __reduce_max_sync(0xffffffffu, bmax);
+        bmin = __reduce_min_sync(0xffffffffu, bmin);
+        if (lane == 0) {
+            atomicMax(&s_dmax_bits, bmax);
+            atomicMin(&s_dmin_bits, bmin);
+        }
     }
+    if (Q.n_hashes <= VA_HASH_STAGE)
+        for (uint32_t k = tid; k < Q.n_hashes; k += VA_THREADS) s_hash[k] = H[k].hash;
     __syncthreads();
     const float s_dmax = __int_as_float(s_dmax_bits), s_dmin = __int_as_float(s_dmin_bits);
 
@@ -197,19 +210,88 @@ __global__ void __launch_bounds__(VA_THREADS)
         }
     }
     const uint32_t rows = all_pairs ? n : n1, cols = all_pairs ? n : n2;
-    const uint64_t total = (uint64_t)rows * cols; // < 2^32: both factors are at most 65535
 
     // ---- retrieve_with_prefilter: screen, hash, keep pairs whose hash is in the query set ----
-    // Thread t owns row (t mod RP) of the current row block and every CS-th column: its row's residue stays in
-    // registers, the lanes of a warp walk the same column (one broadcast load), no index division.  A pair reaches
-    // sqrt + the exact |d - d_q| test only if its squared CA distance lies inside the query's distance range.
-    const uint32_t RP = min(rows, 32u);  // rows per block: one warp = 32 rows of one column phase
-    const uint32_t CS = VA_THREADS / RP; // >= 4 column phases
-    const bool t_active = (uint32_t)tid < RP * CS;
-    const uint32_t t_row = (uint32_t)tid % RP, t_cs = (uint32_t)tid / RP;
-    const uint32_t cols_per_round = CS * (VA_CHUNK / VA_THREADS);
+    // The four warps of the CTA work on the candidate independently (no CTA barrier inside the screen).  Inside a warp,
+    // lane -> (row of the current row block, column phase): the row's residue stays in registers and the lanes of a row
+    // block walk the same column (one broadcast load).  A pair reaches sqrt + the exact |d - d_q| test only if its
+    // squared CA distance lies inside the query's distance range.  Survivors go through two warp-private queues:
+    //   A -> stage 1 (no trigonometry): bits 12..31 of the hash (amino acids, CA / CB distance bins) must occur in the
+    //        query's hash set;
+    //   B -> stage 2: the full hash (binary64 trigonometry) on 32 full lanes, then membership.
+    const uint32_t warp = (uint32_t)tid >> 5;
+    const uint32_t RP = max(1u, min(rows, 32u));
+    const uint32_t CSW = 32u / RP;                     // column phases inside a warp
+    const uint32_t PH = CSW * (VA_THREADS / 32);       // column phases of the CTA
+    const bool t_active = (uint32_t)lane < RP * CSW;
+    const uint32_t t_row = (uint32_t)lane % RP, t_ph = warp * CSW + (uint32_t)lane / RP;
     const float pre_hi = fminf(hp.dist_cutoff, s_dmax + ca_cutoff), pre_lo = fmaxf(s_dmin - ca_cutoff, 0.f);
     const float pre_hi2 = pre_hi * pre_hi * 1.0001f, pre_lo2 = pre_lo * pre_lo * 0.9999f;
+    const bool staged = Q.n_hashes <= VA_HASH_STAGE; // the hash set is in shared memory (s_hash), else global
+    auto hash_at = [&](uint32_t k) -> uint32_t { return staged ? s_hash[k] : H[k].hash; };
+    uint32_t *qa_ij = wq_ij[warp], *qb_ij = wb_ij[warp];
+    float *qa_d = wq_d[warp], *qb_d = wb_d[warp];
+    uint16_t *qb_lo = wb_lo[warp];
+    uint32_t na = 0, nb = 0; // queue fill, warp-uniform
+    const uint32_t lt = (1u << lane) - 1u;
+    auto stage2 = [&](uint32_t first, uint32_t cnt) { // entries [first, first + cnt) of B, cnt <= 32
+        if ((uint32_t)lane < cnt) {
+            const uint32_t ij = qb_ij[first + lane];
+            const uint64_t ri = base + (ij >> 16), rj = base + (ij & 0xffffu);
+            const uint32_t h = fdg::pair_hash(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
+                                              ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj),
+                                              st.aa[ri] & 0x7Fu, st.aa[rj] & 0x7Fu, qb_d[first + lane], hp);
+            // the hashes that share the upper bits start at the stage-1 lower bound
+            for (uint32_t k = qb_lo[first + lane]; k < Q.n_hashes; k++) {
+                const uint32_t hk = hash_at(k);
+                if (hk >= h) {
+                    if (hk == h) {
+                        const uint32_t pos = atomicAdd(&n_e, 1u);
+                        if (pos < V_MAX_E) {
+                            e_key[pos] = ij;
+                            e_ent[pos] = (uint16_t)k;
+                        }
+                    }
+                    break;
+                }
+            }
+        }
+        __syncwarp();
+    };
+    auto stage1 = [&](uint32_t first, uint32_t cnt) { // entries [first, first + cnt) of A, cnt <= 32
+        bool keep = false;
+        uint32_t ij = 0, lo = 0;
+        float d = 0.f;
+        if ((uint32_t)lane < cnt) {
+            ij = qa_ij[first + lane];
+            d = qa_d[first + lane];
+            const uint64_t ri = base + (ij >> 16), rj = base + (ij & 0xffffu);
+            if (st.cb_valid == nullptr || (st.cb_valid[ri] && st.cb_valid[rj])) {
+                const uint32_t up = fdg::hash_upper(ld3(st.cb_xyz, ri), ld3(st.cb_xyz, rj), st.aa[ri] & 0x7Fu,
+                                                    st.aa[rj] & 0x7Fu, d, hp);
+                uint32_t hi = Q.n_hashes;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if ((hash_at(mid) >> 12) < up) lo = mid + 1;
+                    else hi = mid;
+                }
+                keep = lo < Q.n_hashes && (hash_at(lo) >> 12) == up;
+            }
+        }
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const uint32_t pos = nb + __popc(km & lt);
+            qb_ij[pos] = ij;
+            qb_d[pos] = d;
+            qb_lo[pos] = (uint16_t)lo;
+        }
+        nb += __popc(km);
+        __syncwarp();
+        if (nb >= 32) {
+            stage2(nb - 32, 32);
+            nb -= 32;
+        }
+    };
     for (uint32_t row0 = 0; row0 < rows; row0 += RP) {
         const uint32_t a = row0 + t_row;
         bool row_ok = t_active && a < rows;
@@ -222,79 +304,51 @@ __global__ void __launch_bounds__(VA_THREADS)
             aim = (ai & 0x7Fu) * 20u;
             cai = ld3(st.ca_xyz, base + i);
         }
-        for (uint32_t col0 = 0; col0 < cols; col0 += cols_per_round) {
-            if (row_ok) {
-#pragma unroll 2
-                for (uint32_t u = 0; u < VA_CHUNK / VA_THREADS; u++) {
-                    const uint32_t b = col0 + u * CS + t_cs;
-                    if (b >= cols) break;
-                    const uint32_t j = all_pairs ? b : list2[b];
-                    const uint8_t aj = st.aa[base + j];
-                    if (j == i || aj == 255) continue;
-                    const uint32_t rg = aa_range[aim + (aj & 0x7Fu)];
-                    if (rg == 0) continue;
+        for (uint32_t b0 = 0; b0 < cols; b0 += PH) {
+            const uint32_t b = b0 + t_ph;
+            bool surv = false;
+            uint32_t j = 0;
+            float d = 0.f;
+            if (row_ok && b < cols) {
+                j = all_pairs ? b : list2[b];
+                const uint8_t aj = st.aa[base + j];
+                const uint32_t rg = (j == i || aj == 255) ? 0u : aa_range[aim + (aj & 0x7Fu)];
+                if (rg != 0) {
                     const float d2 = fdg::dist2(cai, ld3(st.ca_xyz, base + j));
-                    if (d2 > pre_hi2 || d2 < pre_lo2) continue;
-                    const float d = FD_SQRT(d2); // == fdg::dist
-                    if (d <= hp.dist_cutoff) {
-                        for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
-                            if (fabsf(d - aad[k].dist) < ca_cutoff) {
-                                const uint32_t pos = atomicAdd(&q_n, 1u);
-                                q_ij[pos] = (i << 16) | j;
-                                q_d[pos] = d;
-                                break;
-                            }
+                    if (d2 <= pre_hi2 && d2 >= pre_lo2) {
+                        d = FD_SQRT(d2); // == fdg::dist
+                        if (d <= hp.dist_cutoff)
+                            for (uint32_t k = rg >> 8, ke = (rg >> 8) + (rg & 0xffu); k < ke; k++)
+                                if (fabsf(d - aad[k].dist) < ca_cutoff) {
+                                    surv = true;
+                                    break;
+                                }
                     }
                 }
             }
-            __syncthreads();
-            // hash the queued survivors once a full CTA of them is waiting (or at the end): the binary64 trig of
-            // the hash is the expensive part, it should not run on a handful of lanes per round
-            const uint32_t qn = q_n;
-            const bool last = row0 + RP >= rows && col0 + cols_per_round >= cols;
-            __syncthreads(); // every thread has read q_n before the next round appends to the queue
-            if (!(qn >= VA_THREADS || last)) continue;
-            const uint32_t take = last ? qn : (qn / VA_THREADS) * VA_THREADS;
-            for (uint32_t k = tid; k < take; k += VA_THREADS) {
-                const uint32_t i = q_ij[k] >> 16, j = q_ij[k] & 0xffffu;
-                const uint64_t ri = base + i, rj = base + j;
-                const bool cbok = st.cb_valid == nullptr || (st.cb_valid[ri] && st.cb_valid[rj]);
-                if (!cbok) continue;
-                const uint32_t h = fdg::pair_hash(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
-                                                  ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj),
-                                                  st.aa[ri] & 0x7Fu, st.aa[rj] & 0x7Fu, q_d[k], hp);
-                uint32_t lo = 0, hi = Q.n_hashes;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (H[mid].hash < h) lo = mid + 1;
-                    else hi = mid;
+            const uint32_t m = __ballot_sync(0xffffffffu, surv);
+            if (m) {
+                if (surv) {
+                    const uint32_t pos = na + __popc(m & lt);
+                    qa_ij[pos] = (i << 16) | j;
+                    qa_d[pos] = d;
                 }
-                if (lo < Q.n_hashes && H[lo].hash == h) {
-                    const uint32_t pos = atomicAdd(&n_e, 1u);
-                    if (pos < V_MAX_E) {
-                        e_key[pos] = q_ij[k];
-                        e_ent[pos] = (uint16_t)lo;
-                    }
+                na += __popc(m);
+                __syncwarp();
+                if (na >= 32) {
+                    stage1(na - 32, 32);
+                    na -= 32;
                 }
             }
-            __syncthreads();
-            // keep the (< VA_THREADS) unhashed tail at the front of the queue
-            const uint32_t rest = qn - take;
-            uint32_t kij = 0;
-            float kd = 0.f;
-            if ((uint32_t)tid < rest) {
-                kij = q_ij[take + tid];
-                kd = q_d[take + tid];
-            }
-            __syncthreads();
-            if ((uint32_t)tid < rest) {
-                q_ij[tid] = kij;
-                q_d[tid] = kd;
-            }
-            if (tid == 0) q_n = rest;
-            __syncthreads();
         }
     }
+    if (na) stage1(0, na);
+    if (nb > 32) {
+        stage2(32, nb - 32);
+        nb = 32;
+    }
+    if (nb) stage2(0, nb);
+    __syncthreads();
     const uint32_t ne = n_e;
     if (ne == 0) return;
     if (ne > V_MAX_E || Q.n_idx > V_MAX_NQ || Q.n_dq > V_MAX_NQ) {
@@ -345,11 +399,12 @@ struct WarpState { // per-warp shared memory
     uint16_t e_ent[V_MAX_E];
     uint8_t e_a[V_MAX_E], e_b[V_MAX_E];
     uint64_t comp_mask[V_MAX_C];
-    uint64_t reach[V_MAX_NODES], und[V_MAX_NODES]; // directed / undirected reachability closures
     uint16_t node_res[V_MAX_NODES];
     uint8_t counts[V_MAX_NQ * V_MAX_NODES];
     VAad aad[V_MAX_AAD];
     uint16_t aa_range[400];
+    uint16_t rows[64];         // rescue scan: compacted row residues
+    uint32_t dq_aa1[V_MAX_NQ]; // amino acids (bit set) that carry an entry of query residue dq: rows of the rescue scan
     uint32_t n_nodes, n_comp, s_flag;
     uint32_t r_dq, r_need, r_nridx, s_out_base;
     uint16_t r_ridx[V_MAX_NQ];
@@ -392,8 +447,11 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
         W.s_flag = 0;
         W.n_comp = 0;
     }
+    if (lane < V_MAX_NQ) W.dq_aa1[lane] = 0;
     __syncwarp();
     load_aad_phase2<32>(Q, W.aad, W.aa_range, lane);
+    for (uint32_t k = lane; k < Q.n_aad; k += 32)
+        if (W.aad[k].dq < V_MAX_NQ) atomicOr(&W.dq_aa1[W.aad[k].dq], 1u << (W.aad[k].aa1 & 31u));
     // range of the query's CA distances: a pair outside it cannot support a rescue
     float dmax = 0.f, dmin = 3.0e38f;
     for (uint32_t k = lane; k < Q.n_aad; k += 32) {
@@ -409,79 +467,123 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     __syncwarp();
 
     // ---- graph: nodes by first appearance, components = SCCs U weak components, size >= 2 ----
-    if (lane == 0) {
+    // All lanes cooperate: lane v keeps nodes v and v + 32 in registers (residue index, directed and undirected
+    // adjacency -> closure).  Node numbering = first appearance in the (i, j)-sorted edge list (graph.rs:16-31).
+    {
+        const uint32_t FULL = 0xffffffffu;
         uint32_t nn = 0;
         bool overflow = false;
+        uint32_t nr0 = 0xffffffffu, nr1 = 0xffffffffu; // residue of node lane / lane + 32 (edge ends are < 65536)
+        uint64_t r0 = 0, r1 = 0, u0 = 0, u1 = 0;
         for (uint32_t k = 0; k < ne && !overflow; k++) {
-            const uint16_t ends[2] = {(uint16_t)(W.e_key[k] >> 16), (uint16_t)(W.e_key[k] & 0xffffu)};
-            uint8_t ids[2];
+            const uint32_t key = W.e_key[k];
+            uint32_t ids[2] = {0, 0};
             for (int s = 0; s < 2; s++) {
-                uint32_t f = 0;
-                while (f < nn && W.node_res[f] != ends[s]) f++;
-                if (f == nn) {
+                const uint32_t end = s ? (key & 0xffffu) : (key >> 16);
+                const uint32_t m0 = __ballot_sync(FULL, nr0 == end), m1 = __ballot_sync(FULL, nr1 == end);
+                uint32_t f;
+                if (m0) f = (uint32_t)__ffs((int)m0) - 1u;
+                else if (m1) f = 31u + (uint32_t)__ffs((int)m1);
+                else {
                     if (nn == V_MAX_NODES) {
                         overflow = true;
                         break;
                     }
-                    W.node_res[nn++] = ends[s];
+                    f = nn;
+                    if ((uint32_t)lane == (nn & 31u)) {
+                        if (nn < 32) nr0 = end;
+                        else nr1 = end;
+                    }
+                    nn++;
                 }
-                ids[s] = (uint8_t)f;
+                ids[s] = f;
             }
-            W.e_a[k] = ids[0];
-            W.e_b[k] = ids[1];
+            if (overflow) break;
+            const uint32_t a = ids[0], b = ids[1];
+            if ((uint32_t)lane == (a & 31u)) {
+                if (a < 32) {
+                    r0 |= 1ull << b;
+                    u0 |= 1ull << b;
+                } else {
+                    r1 |= 1ull << b;
+                    u1 |= 1ull << b;
+                }
+            }
+            if ((uint32_t)lane == (b & 31u)) {
+                if (b < 32) u0 |= 1ull << a;
+                else u1 |= 1ull << a;
+            }
+            if (lane == 0) {
+                W.e_a[k] = (uint8_t)a;
+                W.e_b[k] = (uint8_t)b;
+            }
         }
         if (overflow) {
-            W.s_flag = 1;
+            if (lane == 0) W.s_flag = 1;
         } else {
-            W.n_nodes = nn;
-            for (uint32_t v = 0; v < nn; v++) W.reach[v] = W.und[v] = 1ull << v;
-            bool changed = true;
-            while (changed) {
-                changed = false;
-                for (uint32_t k = 0; k < ne; k++) {
-                    const uint32_t a = W.e_a[k], b = W.e_b[k];
-                    const uint64_t ra = W.reach[a] | W.reach[b];
-                    if (ra != W.reach[a]) {
-                        W.reach[a] = ra;
-                        changed = true;
+            if ((uint32_t)lane < nn) {
+                W.node_res[lane] = (uint16_t)nr0;
+                r0 |= 1ull << lane;
+                u0 |= 1ull << lane;
+            }
+            if ((uint32_t)lane + 32 < nn) {
+                W.node_res[lane + 32] = (uint16_t)nr1;
+                r1 |= 1ull << (lane + 32);
+                u1 |= 1ull << (lane + 32);
+            }
+            // Warshall closure, one pass over the pivot k (rows are 64-bit masks)
+            for (uint32_t k = 0; k < nn; k++) {
+                const unsigned long long rk = __shfl_sync(FULL, (unsigned long long)(k < 32 ? r0 : r1), (int)(k & 31u));
+                const unsigned long long uk = __shfl_sync(FULL, (unsigned long long)(k < 32 ? u0 : u1), (int)(k & 31u));
+                if ((r0 >> k) & 1ull) r0 |= rk;
+                if ((r1 >> k) & 1ull) r1 |= rk;
+                if ((u0 >> k) & 1ull) u0 |= uk;
+                if ((u1 >> k) & 1ull) u1 |= uk;
+            }
+            // strongly connected component of v: the w reachable from v that reach v
+            uint64_t s0 = 0, s1 = 0;
+            for (uint32_t k = 0; k < nn; k++) {
+                const unsigned long long rk = __shfl_sync(FULL, (unsigned long long)(k < 32 ? r0 : r1), (int)(k & 31u));
+                if (((r0 >> k) & 1ull) && ((rk >> lane) & 1ull)) s0 |= 1ull << k;
+                if (((r1 >> k) & 1ull) && ((rk >> (lane + 32)) & 1ull)) s1 |= 1ull << k;
+            }
+            // distinct masks of size >= 2: every component is added by its lowest node; a weak component that is
+            // strongly connected equals its SCC and is added once
+            const bool v0 = (uint32_t)lane < nn, v1 = (uint32_t)lane + 32 < nn;
+            const bool sr0 = v0 && __popcll(s0) >= 2 && ctz64(s0) == lane;
+            const bool sr1 = v1 && __popcll(s1) >= 2 && ctz64(s1) == lane + 32;
+            const bool ur0 = v0 && __popcll(u0) >= 2 && ctz64(u0) == lane && !(sr0 && s0 == u0);
+            const bool ur1 = v1 && __popcll(u1) >= 2 && ctz64(u1) == lane + 32 && !(sr1 && s1 == u1);
+            const uint32_t bs0 = __ballot_sync(FULL, sr0), bs1 = __ballot_sync(FULL, sr1);
+            const uint32_t bu0 = __ballot_sync(FULL, ur0), bu1 = __ballot_sync(FULL, ur1);
+            const uint32_t nc = __popc(bs0) + __popc(bs1) + __popc(bu0) + __popc(bu1);
+            if (nc > V_MAX_C) {
+                if (lane == 0) W.s_flag = 1;
+            } else {
+                const uint32_t lt = (1u << lane) - 1u;
+                uint32_t pos = __popc(bs0 & lt);
+                if (sr0) W.comp_mask[pos] = s0;
+                pos = __popc(bs0) + __popc(bs1 & lt);
+                if (sr1) W.comp_mask[pos] = s1;
+                pos = __popc(bs0) + __popc(bs1) + __popc(bu0 & lt);
+                if (ur0) W.comp_mask[pos] = u0;
+                pos = __popc(bs0) + __popc(bs1) + __popc(bu0) + __popc(bu1 & lt);
+                if (ur1) W.comp_mask[pos] = u1;
+                __syncwarp();
+                if (lane == 0) {
+                    for (uint32_t a = 1; a < nc; a++) { // insertion sort, lexicographic by sorted node list
+                        const uint64_t m = W.comp_mask[a];
+                        uint32_t b = a;
+                        while (b > 0 && mask_less(m, W.comp_mask[b - 1])) {
+                            W.comp_mask[b] = W.comp_mask[b - 1];
+                            b--;
+                        }
+                        W.comp_mask[b] = m;
                     }
-                    const uint64_t u = W.und[a] | W.und[b];
-                    if (u != W.und[a] || u != W.und[b]) {
-                        W.und[a] = W.und[b] = u;
-                        changed = true;
-                    }
+                    W.n_nodes = nn;
+                    W.n_comp = nc;
                 }
             }
-            uint32_t nc = 0;
-            auto add_mask = [&](uint64_t m) {
-                if (__popcll(m) < 2) return;
-                for (uint32_t k = 0; k < nc; k++)
-                    if (W.comp_mask[k] == m) return;
-                if (nc == V_MAX_C) {
-                    W.s_flag = 1;
-                    return;
-                }
-                W.comp_mask[nc++] = m;
-            };
-            for (uint32_t v = 0; v < nn; v++) {
-                uint64_t scc = 0;
-                for (uint64_t r = W.reach[v]; r; r &= r - 1) {
-                    const int w = ctz64(r);
-                    if ((W.reach[w] >> v) & 1ull) scc |= 1ull << w;
-                }
-                add_mask(scc);
-                add_mask(W.und[v]);
-            }
-            for (uint32_t a = 1; a < nc; a++) { // insertion sort, lexicographic by sorted node list
-                const uint64_t m = W.comp_mask[a];
-                uint32_t b = a;
-                while (b > 0 && mask_less(m, W.comp_mask[b - 1])) {
-                    W.comp_mask[b] = W.comp_mask[b - 1];
-                    b--;
-                }
-                W.comp_mask[b] = m;
-            }
-            W.n_comp = nc;
         }
     }
     __syncwarp();
@@ -624,11 +726,9 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                 // count_map[i] = #(entries of this query residue, matched target residues rj) compatible with (i, rj),
                 // over the rows of the pair iteration (all residues, or those whose amino acid is a res1 of the query)
                 const uint32_t dq = W.r_dq;
+                const uint32_t row_aa = W.dq_aa1[dq]; // an entry (aa1, aa2, dq) only matches rows whose amino acid is aa1
                 auto row_count = [&](uint32_t i) -> uint32_t {
-                    const uint8_t ai = st.aa[base + i];
-                    if (!all_pairs && !(((ai & 0x80u) == 0) && ((Q.aa1_mask >> (ai & 31u)) & 1u))) return 0u;
-                    if (ai == 255 || (st.cb_valid != nullptr && !st.cb_valid[base + i])) return 0u;
-                    const uint32_t cia = (ai & 0x7Fu) * 20u;
+                    const uint32_t cia = (st.aa[base + i] & 0x7Fu) * 20u;
                     const fdg::V3 cai = ld3(st.ca_xyz, base + i);
                     uint32_t cnt = 0;
                     for (uint32_t k = 0; k < W.r_nridx; k++) {
@@ -645,9 +745,9 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                     }
                     return cnt;
                 };
-                // one pass: per lane the maximum count, how many rows reach it, and one such row
+                // per lane the maximum count, how many rows reach it, and one such row
                 uint32_t l_max = 0, l_n = 0, l_arg = 0;
-                for (uint32_t i = lane; i < n; i += 32) {
+                auto take = [&](uint32_t i) {
                     const uint32_t cnt = row_count(i);
                     if (cnt > l_max) {
                         l_max = cnt;
@@ -656,7 +756,30 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                     } else if (cnt == l_max && cnt > 0) {
                         l_n++;
                     }
+                };
+                // The rows that can count at all (amino acid carries an entry of dq, in the pair iteration, has a CB) are
+                // few: they are compacted first so that the distance tests run on full lanes.
+                uint32_t nrow = 0; // rows waiting in W.rows (warp-uniform)
+                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    bool ok = false;
+                    if (i < n) {
+                        const uint8_t ai = st.aa[base + i];
+                        ok = ((row_aa >> (ai & 31u)) & 1u) && ai != 255 &&
+                             (all_pairs || (((ai & 0x80u) == 0) && ((Q.aa1_mask >> (ai & 31u)) & 1u))) &&
+                             (st.cb_valid == nullptr || st.cb_valid[base + i]);
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) W.rows[nrow + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    nrow += __popc(m);
+                    __syncwarp();
+                    if (nrow >= 32) {
+                        take(W.rows[nrow - 32 + lane]);
+                        nrow -= 32;
+                        __syncwarp();
+                    }
                 }
+                if ((uint32_t)lane < nrow) take(W.rows[lane]);
                 const uint32_t mx = __reduce_max_sync(0xffffffffu, l_max);
                 const uint32_t mine = (mx > 0 && l_max == mx) ? l_n : 0u;
                 const uint32_t nmax = __reduce_add_sync(0xffffffffu, mine);
@@ -762,6 +885,13 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     *out_flags = nullptr;
     *out_first = nullptr;
     *out_n = 0;
+    // host wall clock per phase (stage names "hv_*"; read with fd_stage_ms)
+    auto h_now = std::chrono::steady_clock::now();
+    auto h_mark = [&](const char *name) {
+        const auto t = std::chrono::steady_clock::now();
+        ctx->stages[name].ms += std::chrono::duration<double, std::milli>(t - h_now).count();
+        h_now = t;
+    };
     uint8_t *h_flags = nullptr;
     uint32_t *h_first = nullptr;
     FD_TRY(fd_pinned(ctx, 1, std::max<uint64_t>(n_cand, 1), (void **)&h_flags));
@@ -895,6 +1025,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
         }
     });
     if (bad == 2) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
+    h_mark("hv_flatten");
     for (uint64_t c = 0; c < n_cand; c++) {
         if (cand_query[c] >= nq || cand_nid[c] >= ctx->store.n_structs) {
             return fd_fail(ctx, FD_ERR_ARG, "candidate query / structure id out of range");
@@ -953,6 +1084,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     FD_CUDA(ctx, fd_ensure_events(ctx));
     cudaEvent_t *ev = ctx->ev_extra;
     FD_CUDA(ctx, cudaEventRecord(ev[0], s));
+    h_mark("hv_upload");
     // ---- k6a: edges into a compact pool (sized for 48 edges per candidate; exact on the rare overflow) ----
     uint64_t pool_cap = std::max<uint64_t>(1u << 20, 48 * n_cand);
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -969,6 +1101,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
         pool_cap = h_counters[0];
     }
     FD_CUDA(ctx, cudaEventRecord(ev[1], s));
+    h_mark("hv_k6a");
     // ---- k6b: components ----
     uint64_t spec_cap = std::max<uint64_t>(1024, 2 * n_cand);
     const size_t smem_b = sizeof(WarpState) * VB_WARPS;
@@ -987,6 +1120,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
         spec_cap = h_counters[1];
     }
     FD_CUDA(ctx, cudaEventRecord(ev[2], s));
+    h_mark("hv_k6b");
     const uint32_t produced = h_counters[1];
     // ---- k6c: Kabsch, records in (candidate, component) order ----
     size_t tb = 0;
@@ -1008,6 +1142,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     FD_CUDA(ctx, cudaEventRecord(ev[3], s));
     FD_CUDA(ctx, cudaEventSynchronize(ev[3]));
     FD_CUDA(ctx, cudaGetLastError());
+    h_mark("hv_k6c_d2h");
     {
         const char *names[4] = {"verify_edges", "verify_components", "verify_kabsch", "verify"};
         for (int k = 0; k < 4; k++) {

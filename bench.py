@@ -215,6 +215,7 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     sp = host.SearchParams(top_n=args.top)
     stages = ("lookup", "scan", "select", "verify", "verify_edges", "verify_components", "verify_kabsch", "edges", "kabsch")
+    hv = ("hv_flatten", "hv_upload", "hv_k6a", "hv_k6b", "hv_k6c_d2h")  # host wall clock inside the verification call
 
     def make_batch():
         """this rank's args.batch queries of the global batch (query number q uses motif q mod 5)"""
@@ -270,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     time.sleep(0.3)
     launches0 = ctx.kernel_launches
-    st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages}
+    st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages + hv}
     bytes_scanned = 0
     val_t = []
     wall_t = []
@@ -281,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
         bytes_scanned += ctx.last_posting_bytes
     clocks = sampler.finish()
     launches = ctx.kernel_launches - launches0
-    st1 = {s: (ctx.stage_ms(s) - st0[s][0], ctx.stage_launches(s) - st0[s][1]) for s in stages}
+    st1 = {s: (ctx.stage_ms(s) - st0[s][0], ctx.stage_launches(s) - st0[s][1]) for s in stages + hv}
 
     def reduce_max(x):
         if dist is None:
@@ -321,6 +322,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "stages_ms_per_step": {s: st1[s][0] / max(1, args.steps) for s in stages},
         "host_ms_per_step": res.host_ms, "search_wall_ms": res.wall_ms,
+        "verify_host_wall_ms": {s[3:]: st1[s][0] / max(1, args.steps) for s in hv},
         "timing": "CUDA events around each step (max over ranks); wall-clock cross-check %.3f ms/step" % (
             1e3 * sum(wall_t) / max(1, args.steps)),
         "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows},

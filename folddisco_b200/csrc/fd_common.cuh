@@ -1,5 +1,6 @@
 // fd_common.cuh -- context, error handling, device buffers, stage timers shared by the .cu files.
 #pragma once
+#include <functional>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -14,6 +15,9 @@
 #include "../../include/folddisco_b200.h"
 
 #define FD_NUM_SMS_FALLBACK 148
+
+// persistent host worker pool (fd_ctx.cu): fn(0) .. fn(nt - 1) concurrently, fn(0) on the caller
+void fd_parallel(int nt, const std::function<void(int)> &fn);
 
 struct FdStage {
     double ms = 0.0;

@@ -2,6 +2,10 @@
 #include <algorithm>
 #include <thread>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <vector>
 #include "fd_common.cuh"
 #include "fd_geom.cuh"
 
@@ -83,6 +87,86 @@ __global__ void fd_math_probe_kernel(int op, const float *a, const float *b, uin
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Host worker pool.  The host side above the kernels runs many short parallel regions per batch (query maps,
+// verification tables, row assembly); spawning std::threads for each costs more than the regions themselves
+// (~20 us per thread).  fd_parallel(nt, fn) runs fn(0) .. fn(nt - 1) concurrently -- fn(0) on the caller -- on
+// persistent workers that sleep on a condition variable between regions.  One region at a time; a nested or
+// concurrent region (verification lanes) falls back to plain threads.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct HostPool {
+    std::mutex region;              // held by the thread that runs a region
+    std::mutex m;
+    std::condition_variable cv_start, cv_done;
+    std::vector<std::thread> workers;
+    const std::function<void(int)> *job = nullptr;
+    int job_nt = 0, remaining = 0;
+    uint64_t gen = 0;
+
+    void worker(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *j = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_start.wait(lk, [&] { return gen != seen; });
+                seen = gen;
+                if (idx < job_nt) j = job;
+            }
+            if (!j) continue;
+            (*j)(idx);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--remaining == 0) cv_done.notify_one();
+            }
+        }
+    }
+    void grow(int nt) { // under `region`
+        while ((int)workers.size() + 1 < nt) {
+            const int idx = (int)workers.size() + 1;
+            workers.emplace_back([this, idx] { worker(idx); });
+            workers.back().detach();
+        }
+    }
+};
+HostPool *host_pool() {
+    static HostPool *p = new HostPool(); // leaked on purpose: detached workers may outlive static destructors
+    return p;
+}
+} // namespace
+
+void fd_parallel(int nt, const std::function<void(int)> &fn) {
+    if (nt <= 1) {
+        fn(0);
+        return;
+    }
+    HostPool *P = host_pool();
+    std::unique_lock<std::mutex> region(P->region, std::try_to_lock);
+    if (!region.owns_lock()) { // another region is running (nested call or a second host thread)
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back([&fn, t] { fn(t); });
+        fn(0);
+        for (auto &t : th) t.join();
+        return;
+    }
+    P->grow(nt);
+    {
+        std::lock_guard<std::mutex> lk(P->m);
+        P->job = &fn;
+        P->job_nt = nt;
+        P->remaining = nt - 1;
+        P->gen++;
+    }
+    P->cv_start.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> lk(P->m);
+    P->cv_done.wait(lk, [&] { return P->remaining == 0; });
+    P->job = nullptr;
+    P->job_nt = 0;
+}
+
 extern "C" {
 
 int fd_default_host_threads(void) {
@@ -93,6 +177,8 @@ int fd_default_host_threads(void) {
     const unsigned hc = std::thread::hardware_concurrency();
     return hc ? (int)hc : 1;
 }
+
+int fd_device(const fd_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 const char *fd_version(void) { return "folddisco_b200 0.1 (sm_100a)"; }
 

@@ -34,6 +34,7 @@
 namespace {
 
 constexpr int VA_THREADS = 128;            // k6a CTA
+constexpr int VA_COL_STAGE = 512;          // candidates with at most this many column residues stage them in shared memory
 constexpr int VA_HASH_STAGE = 256;         // query hash sets up to this size are staged in shared memory
 constexpr int V_LIST_CAP = 2048;           // prefilter-list capacity (larger candidates take the general path)
 constexpr int VB_WARPS = 4;                // k6b: candidates per CTA
@@ -126,7 +127,7 @@ __device__ __forceinline__ void load_aad_phase2(const VQDesc &Q, const VAad *aad
 // ------------------------------------------------------------------------------------------------
 // k6a: candidate edges
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VA_THREADS)
+__global__ void __launch_bounds__(VA_THREADS, 7)
     k6a_edges(StoreView st, const VQDesc *vq, const VHash *vhash, const VAad *vaad, const uint32_t *cand_query,
               const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp, float ca_cutoff, uint32_t *pool_key,
               uint16_t *pool_ent, unsigned int *pool_count, uint32_t pool_cap, uint32_t *cand_ebegin,
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(VA_THREADS)
     __shared__ float wq_d[VA_THREADS / 32][64], wb_d[VA_THREADS / 32][64];
     __shared__ uint16_t wb_lo[VA_THREADS / 32][64];
     __shared__ uint32_t s_hash[VA_HASH_STAGE];
+    __shared__ float4 s_col[VA_COL_STAGE]; // column residues: CA xyz, w = residue index << 8 | amino acid
     __shared__ VAad aad[V_MAX_AAD];
     __shared__ uint16_t aa_range[400];
     __shared__ uint32_t e_key[V_MAX_E]; // i << 16 | j
@@ -229,6 +231,15 @@ __global__ void __launch_bounds__(VA_THREADS)
     const float pre_hi2 = pre_hi * pre_hi * 1.0001f, pre_lo2 = pre_lo * pre_lo * 0.9999f;
     const bool staged = Q.n_hashes <= VA_HASH_STAGE; // the hash set is in shared memory (s_hash), else global
     auto hash_at = [&](uint32_t k) -> uint32_t { return staged ? s_hash[k] : H[k].hash; };
+    const bool cstaged = cols <= VA_COL_STAGE;
+    if (cstaged) {
+        for (uint32_t b = tid; b < cols; b += VA_THREADS) {
+            const uint32_t j = all_pairs ? b : list2[b];
+            const fdg::V3 cj = ld3(st.ca_xyz, base + j);
+            s_col[b] = make_float4(cj.x, cj.y, cj.z, __uint_as_float((j << 8) | st.aa[base + j]));
+        }
+        __syncthreads();
+    }
     uint32_t *qa_ij = wq_ij[warp], *qb_ij = wb_ij[warp];
     float *qa_d = wq_d[warp], *qb_d = wb_d[warp];
     uint16_t *qb_lo = wb_lo[warp];
@@ -310,11 +321,22 @@ __global__ void __launch_bounds__(VA_THREADS)
             uint32_t j = 0;
             float d = 0.f;
             if (row_ok && b < cols) {
-                j = all_pairs ? b : list2[b];
-                const uint8_t aj = st.aa[base + j];
+                fdg::V3 caj;
+                uint32_t aj;
+                if (cstaged) {
+                    const float4 cj = s_col[b];
+                    const uint32_t w = __float_as_uint(cj.w);
+                    j = w >> 8;
+                    aj = w & 0xffu;
+                    caj = fdg::V3{cj.x, cj.y, cj.z};
+                } else {
+                    j = all_pairs ? b : list2[b];
+                    aj = st.aa[base + j];
+                    caj = ld3(st.ca_xyz, base + j);
+                }
                 const uint32_t rg = (j == i || aj == 255) ? 0u : aa_range[aim + (aj & 0x7Fu)];
                 if (rg != 0) {
-                    const float d2 = fdg::dist2(cai, ld3(st.ca_xyz, base + j));
+                    const float d2 = fdg::dist2(cai, caj);
                     if (d2 <= pre_hi2 && d2 >= pre_lo2) {
                         d = FD_SQRT(d2); // == fdg::dist
                         if (d <= hp.dist_cutoff)
@@ -400,7 +422,9 @@ struct WarpState { // per-warp shared memory
     uint8_t e_a[V_MAX_E], e_b[V_MAX_E];
     uint64_t comp_mask[V_MAX_C];
     uint16_t node_res[V_MAX_NODES];
-    uint8_t counts[V_MAX_NQ * V_MAX_NODES];
+    uint32_t counts[V_MAX_NQ * V_MAX_NODES / 2]; // votes[q][node], two 16-bit counters per word
+    float e_idf[V_MAX_E];
+    uint8_t best_c[V_MAX_NQ], best_r[V_MAX_NQ];
     VAad aad[V_MAX_AAD];
     uint16_t aa_range[400];
     uint16_t rows[64];         // rescue scan: compacted row residues
@@ -439,8 +463,10 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     const VHash *H = vhash + Q.hash_begin;
     const uint32_t eb = cand_ebegin[c];
     for (uint32_t k = lane; k < ne; k += 32) {
+        const uint16_t ent = pool_ent[eb + k];
         W.e_key[k] = pool_key[eb + k];
-        W.e_ent[k] = pool_ent[eb + k];
+        W.e_ent[k] = ent;
+        W.e_idf[k] = H[ent].idf;
     }
     load_aad_phase1<32>(Q, vaad, W.aad, W.aa_range, lane);
     if (lane == 0) {
@@ -602,47 +628,62 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     const uint32_t out_base = W.s_out_base;
 
     for (uint32_t ci = 0; ci < ncomp; ci++) {
-        // ---- mapping (lane 0): votes, best per query residue, greedy assignment ----
+        // ---- mapping: votes (lanes over edges), best per query residue (lane per residue), greedy assignment ----
         const uint64_t mask = W.comp_mask[ci];
-        for (uint32_t k = lane; k < Q.n_dq * V_MAX_NODES; k += 32) W.counts[k] = 0;
+        for (uint32_t k = lane; k < Q.n_dq * (V_MAX_NODES / 2); k += 32) W.counts[k] = 0;
+        __syncwarp();
+        // votes[q][r]: 16-bit counters, two per word (a cell receives at most 2 * V_MAX_E votes); the reference's u8
+        // saturating counters (retrieve.rs:628-660) are min(count, 255) of these
+        for (uint32_t k = lane; k < ne; k += 32) {
+            const uint32_t a = W.e_a[k], b = W.e_b[k];
+            if (!((mask >> a) & 1ull) || !((mask >> b) & 1ull)) continue;
+            const VHash h = H[W.e_ent[k]];
+            uint32_t pq[2], pr[2];
+            if (h.sym) {
+                pq[0] = min((uint32_t)h.dqi, (uint32_t)h.dqj);
+                pq[1] = max((uint32_t)h.dqi, (uint32_t)h.dqj);
+                const bool ab = W.node_res[a] < W.node_res[b];
+                pr[0] = ab ? a : b;
+                pr[1] = ab ? b : a;
+            } else {
+                pq[0] = h.dqi;
+                pq[1] = h.dqj;
+                pr[0] = a;
+                pr[1] = b;
+            }
+            for (int s = 0; s < 2; s++) {
+                const uint32_t cell = pq[s] * V_MAX_NODES + pr[s];
+                atomicAdd(&W.counts[cell >> 1], 1u << (16u * (cell & 1u)));
+            }
+        }
+        __syncwarp();
+        // best[q] = (largest count, smallest target residue among the nodes that reach it): the state the reference's
+        // running update `cnt > best.0 || (cnt == best.0 && r < best.1)` ends in, whatever the edge order
+        if ((uint32_t)lane < Q.n_dq) {
+            uint32_t bc = 0, br = 0xff, bres = 0xffffffffu;
+            for (uint64_t m = mask; m; m &= m - 1) {
+                const uint32_t v = (uint32_t)ctz64(m);
+                const uint32_t cell = (uint32_t)lane * V_MAX_NODES + v;
+                const uint32_t cnt = min((W.counts[cell >> 1] >> (16u * (cell & 1u))) & 0xffffu, 255u);
+                if (cnt == 0) continue;
+                const uint32_t res = W.node_res[v];
+                if (cnt > bc || (cnt == bc && res < bres)) {
+                    bc = cnt;
+                    br = v;
+                    bres = res;
+                }
+            }
+            W.best_c[lane] = (uint8_t)bc;
+            W.best_r[lane] = (uint8_t)br;
+        }
         __syncwarp();
         if (lane == 0) {
             const uint32_t nq_d = Q.n_dq;
-            uint8_t best_c[V_MAX_NQ], best_r[V_MAX_NQ];
-            for (uint32_t q = 0; q < nq_d; q++) {
-                best_c[q] = 0;
-                best_r[q] = 0xff;
-            }
-            float idf = 0.f;
+            const uint8_t *best_c = W.best_c, *best_r = W.best_r;
+            float idf = 0.f; // calculate_subgraph_idf: f32 sum in edge order
             for (uint32_t k = 0; k < ne; k++) {
                 const uint32_t a = W.e_a[k], b = W.e_b[k];
-                if (!((mask >> a) & 1ull) || !((mask >> b) & 1ull)) continue;
-                const VHash h = H[W.e_ent[k]];
-                idf += h.idf;
-                uint32_t pq[2], pr[2];
-                if (h.sym) {
-                    pq[0] = min((uint32_t)h.dqi, (uint32_t)h.dqj);
-                    pq[1] = max((uint32_t)h.dqi, (uint32_t)h.dqj);
-                    const bool ab = W.node_res[a] < W.node_res[b];
-                    pr[0] = ab ? a : b;
-                    pr[1] = ab ? b : a;
-                } else {
-                    pq[0] = h.dqi;
-                    pq[1] = h.dqj;
-                    pr[0] = a;
-                    pr[1] = b;
-                }
-                for (int s = 0; s < 2; s++) {
-                    uint8_t &cnt = W.counts[pq[s] * V_MAX_NODES + pr[s]];
-                    if (cnt != 255) cnt++;
-                    const uint32_t q = pq[s];
-                    // best = (count, target residue) starts at (0, 0): the tie rule `r < best.1` only ever compares
-                    // against a residue that already has a vote (retrieve.rs:655-660)
-                    if (cnt > best_c[q] || (cnt == best_c[q] && W.node_res[pr[s]] < W.node_res[best_r[q]])) {
-                        best_c[q] = cnt;
-                        best_r[q] = (uint8_t)pr[s];
-                    }
-                }
+                if (((mask >> a) & 1ull) && ((mask >> b) & 1ull)) idf += W.e_idf[k];
             }
             W.c_idf = idf;
             // order: count descending, dense query id ascending (bucket sort of retrieve.rs:667-675)
@@ -869,35 +910,43 @@ __global__ void __launch_bounds__(128)
 
 } // namespace
 
-// Shared body of the two entry points.  Outputs are views of ctx's pinned staging buffers.
-static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq, const uint32_t *cand_query,
-                       const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params, float ca_dist_cutoff,
-                       int skip_ca_match, const fd_match_record **out_records, uint64_t *out_n,
-                       const uint32_t **out_first, const uint8_t **out_flags) {
-    if (!ctx) return FD_ERR_ARG;
-    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: no structure store attached");
-    if ((nq && !queries) || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags ||
-        !out_first)
-        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates: NULL argument");
-    if (n_cand > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "too many candidates in one call");
+// The query side of the verification (independent of the candidates): tables flattened on the host and resident on
+// the device.  Built once per query batch (fd_verify_prepare) and reused by every verification call on it.
+struct fd_verify_prepared {
+    uint32_t nq = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<uint8_t> q_unfit; // queries outside the kernels' limits: their candidates take the general path
+    VQDesc *d_desc = nullptr;
+    VHash *d_hash = nullptr;
+    VAad *d_aad = nullptr;
+    uint8_t *d_idx = nullptr;
+    float *d_qca = nullptr, *d_qcb = nullptr;
+    uint64_t h2d_bytes = 0;
+};
+
+static void verify_prepared_release(fd_verify_prepared *P) {
+    if (!P) return;
+    cudaSetDevice(P->device);
+    void *ptrs[6] = {P->d_desc, P->d_hash, P->d_aad, P->d_idx, P->d_qca, P->d_qcb};
+    // cudaFree, not cudaFreeAsync: the tables may outlive the context (and stream) that uploaded them
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    cudaGetLastError();
+    delete P;
+}
+
+static int verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq, fd_verify_prepared **out) {
+    if (!ctx || !out) return FD_ERR_ARG;
+    *out = nullptr;
+    if (nq && !queries) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_prepare: NULL argument");
     FD_ENTER(ctx);
-    *out_records = nullptr;
-    *out_flags = nullptr;
-    *out_first = nullptr;
-    *out_n = 0;
-    // host wall clock per phase (stage names "hv_*"; read with fd_stage_ms)
     auto h_now = std::chrono::steady_clock::now();
     auto h_mark = [&](const char *name) {
         const auto t = std::chrono::steady_clock::now();
         ctx->stages[name].ms += std::chrono::duration<double, std::milli>(t - h_now).count();
         h_now = t;
     };
-    uint8_t *h_flags = nullptr;
-    uint32_t *h_first = nullptr;
-    FD_TRY(fd_pinned(ctx, 1, std::max<uint64_t>(n_cand, 1), (void **)&h_flags));
-    FD_TRY(fd_pinned(ctx, 2, (n_cand + 1) * 4, (void **)&h_first));
-    memset(h_flags, 0, std::max<uint64_t>(n_cand, 1));
-    memset(h_first, 0, (n_cand + 1) * 4);
     // flatten queries (two passes, query-parallel, no per-query heap traffic); a query outside the kernel's limits
     // marks all of its candidates for the general path
     std::vector<VQDesc> descs(nq);
@@ -916,10 +965,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
             for (uint32_t q0; (q0 = next.fetch_add(16)) < nq;)
                 for (uint32_t q = q0; q < std::min(nq, q0 + 16); q++) fn(q);
         };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(worker);
-        worker();
-        for (auto &t : th) t.join();
+        fd_parallel(nt, [&](int) { worker(); });
     };
     // pass 1: dense ids over every query residue index that occurs (ascending residue index), limits, masks
     parallel_queries([&](uint32_t q) {
@@ -1026,6 +1072,64 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     });
     if (bad == 2) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_query: amino-acid code out of range");
     h_mark("hv_flatten");
+    fd_verify_prepared *P = new fd_verify_prepared();
+    P->nq = nq;
+    P->device = ctx->device;
+    P->stream = ctx->stream;
+    P->q_unfit = std::move(q_unfit);
+    cudaStream_t s = ctx->stream;
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMallocAsync(dst, std::max<size_t>(bytes, 16), s);
+        if (e != cudaSuccess) return e;
+        P->h2d_bytes += bytes;
+        return bytes ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    cudaError_t e = up((void **)&P->d_desc, descs.data(), nq * sizeof(VQDesc));
+    if (e == cudaSuccess) e = up((void **)&P->d_hash, f_hash.data(), f_hash.size() * sizeof(VHash));
+    if (e == cudaSuccess) e = up((void **)&P->d_aad, f_aad.data(), f_aad.size() * sizeof(VAad));
+    if (e == cudaSuccess) e = up((void **)&P->d_idx, f_idx.data(), f_idx.size());
+    if (e == cudaSuccess) e = up((void **)&P->d_qca, q_ca.data(), q_ca.size() * 4);
+    if (e == cudaSuccess) e = up((void **)&P->d_qcb, q_cb.data(), q_cb.size() * 4);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s); // the host vectors above go out of scope
+    if (e != cudaSuccess) {
+        verify_prepared_release(P);
+        return fd_fail(ctx, FD_ERR_CUDA, std::string("fd_verify_prepare: ") + cudaGetErrorString(e));
+    }
+    h_mark("hv_upload");
+    *out = P;
+    return FD_OK;
+}
+
+// Shared body of the entry points.  Outputs are views of ctx's pinned staging buffers.
+static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *cand_query, const uint32_t *cand_nid,
+                      uint64_t n_cand, const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
+                      const fd_match_record **out_records, uint64_t *out_n, const uint32_t **out_first,
+                      const uint8_t **out_flags) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: no structure store attached");
+    if (!P || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags || !out_first)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates: NULL argument");
+    if (P->device != ctx->device) return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates: tables prepared on another device");
+    if (n_cand > 0xfffffff0ull) return fd_fail(ctx, FD_ERR_LIMIT, "too many candidates in one call");
+    FD_ENTER(ctx);
+    *out_records = nullptr;
+    *out_flags = nullptr;
+    *out_first = nullptr;
+    *out_n = 0;
+    auto h_now = std::chrono::steady_clock::now();
+    auto h_mark = [&](const char *name) {
+        const auto t = std::chrono::steady_clock::now();
+        ctx->stages[name].ms += std::chrono::duration<double, std::milli>(t - h_now).count();
+        h_now = t;
+    };
+    const uint32_t nq = P->nq;
+    const std::vector<uint8_t> &q_unfit = P->q_unfit;
+    uint8_t *h_flags = nullptr;
+    uint32_t *h_first = nullptr;
+    FD_TRY(fd_pinned(ctx, 1, std::max<uint64_t>(n_cand, 1), (void **)&h_flags));
+    FD_TRY(fd_pinned(ctx, 2, (n_cand + 1) * 4, (void **)&h_first));
+    memset(h_flags, 0, std::max<uint64_t>(n_cand, 1));
+    memset(h_first, 0, (n_cand + 1) * 4);
     for (uint64_t c = 0; c < n_cand; c++) {
         if (cand_query[c] >= nq || cand_nid[c] >= ctx->store.n_structs) {
             return fd_fail(ctx, FD_ERR_ARG, "candidate query / structure id out of range");
@@ -1042,23 +1146,19 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
         return FD_OK;
     }
     cudaStream_t s = ctx->stream;
-    DevBuf<VQDesc> d_desc;
-    DevBuf<VHash> d_hash;
-    DevBuf<VAad> d_aad;
-    DevBuf<uint8_t> d_idx, d_flags;
+    // (fd_verify_prepare synchronises its stream before returning: the tables are complete on every stream)
+    struct { VQDesc *p; } d_desc{P->d_desc};
+    struct { VHash *p; } d_hash{P->d_hash};
+    struct { VAad *p; } d_aad{P->d_aad};
+    struct { uint8_t *p; } d_idx{P->d_idx};
+    struct { float *p; } d_qca{P->d_qca}, d_qcb{P->d_qcb};
+    DevBuf<uint8_t> d_flags;
     DevBuf<uint32_t> d_cq, d_cn, d_ebegin, d_ne, d_ncomp, d_first, d_pool_key;
     DevBuf<uint16_t> d_pool_ent;
-    DevBuf<float> d_qca, d_qcb;
     DevBuf<unsigned int> d_counters; // [0] edge pool, [1] component specs
     DevBuf<CompSpec> d_specs;
     DevBuf<fd_match_record> d_out;
     DevBuf<uint8_t> d_tmp;
-    FD_CUDA(ctx, d_desc.alloc(nq));
-    FD_CUDA(ctx, d_hash.alloc(f_hash.size()));
-    FD_CUDA(ctx, d_aad.alloc(f_aad.size()));
-    FD_CUDA(ctx, d_idx.alloc(f_idx.size()));
-    FD_CUDA(ctx, d_qca.alloc(q_ca.size()));
-    FD_CUDA(ctx, d_qcb.alloc(q_cb.size()));
     FD_CUDA(ctx, d_cq.alloc(n_cand));
     FD_CUDA(ctx, d_cn.alloc(n_cand));
     FD_CUDA(ctx, d_flags.alloc(n_cand));
@@ -1067,12 +1167,6 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     FD_CUDA(ctx, d_ncomp.alloc(n_cand + 1));
     FD_CUDA(ctx, d_first.alloc(n_cand + 1));
     FD_CUDA(ctx, d_counters.alloc(2));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_desc.p, descs.data(), nq * sizeof(VQDesc), cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_hash.p, f_hash.data(), f_hash.size() * sizeof(VHash), cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_aad.p, f_aad.data(), f_aad.size() * sizeof(VAad), cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_idx.p, f_idx.data(), f_idx.size(), cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_qca.p, q_ca.data(), q_ca.size() * 4, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_qcb.p, q_cb.data(), q_cb.size() * 4, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d_cq.p, cand_query, n_cand * 4, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d_cn.p, cand_nid, n_cand * 4, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, n_cand, s));
@@ -1084,7 +1178,7 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     FD_CUDA(ctx, fd_ensure_events(ctx));
     cudaEvent_t *ev = ctx->ev_extra;
     FD_CUDA(ctx, cudaEventRecord(ev[0], s));
-    h_mark("hv_upload");
+    h_mark("hv_candidates");
     // ---- k6a: edges into a compact pool (sized for 48 edges per candidate; exact on the rare overflow) ----
     uint64_t pool_cap = std::max<uint64_t>(1u << 20, 48 * n_cand);
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -1159,6 +1253,38 @@ static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,
     *out_first = h_first;
     *out_flags = h_flags;
     return FD_OK;
+}
+
+// one-shot form: prepare the query tables, verify, release
+static int verify_core(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq, const uint32_t *cand_query,
+                       const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params, float ca_dist_cutoff,
+                       int skip_ca_match, const fd_match_record **out_records, uint64_t *out_n,
+                       const uint32_t **out_first, const uint8_t **out_flags) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: no structure store attached");
+    fd_verify_prepared *P = nullptr;
+    FD_TRY(verify_prepare(ctx, queries, nq, &P));
+    const int rc = verify_run(ctx, P, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match, out_records,
+                              out_n, out_first, out_flags);
+    verify_prepared_release(P);
+    return rc;
+}
+
+extern "C" int fd_verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq, fd_verify_prepared **out) {
+    return verify_prepare(ctx, queries, nq, out);
+}
+
+extern "C" void fd_verify_prepared_free(fd_verify_prepared *p) { verify_prepared_release(p); }
+
+extern "C" uint64_t fd_verify_prepared_bytes(const fd_verify_prepared *p) { return p ? p->h2d_bytes : 0; }
+
+extern "C" int fd_verify_candidates_prepared(fd_ctx *ctx, const fd_verify_prepared *prepared, const uint32_t *cand_query,
+                                             const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params,
+                                             float ca_dist_cutoff, int skip_ca_match,
+                                             const fd_match_record **out_records, uint64_t *out_n,
+                                             const uint32_t **out_first, const uint8_t **out_flags) {
+    return verify_run(ctx, prepared, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match, out_records,
+                      out_n, out_first, out_flags);
 }
 
 extern "C" int fd_verify_candidates_view(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,

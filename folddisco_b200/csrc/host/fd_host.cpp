@@ -29,6 +29,9 @@
 #include "../../../include/folddisco_b200_host.h"
 #include "../fd_geom.cuh"
 
+// persistent host worker pool (fd_ctx.cu): fn(0) .. fn(nt - 1) concurrently, fn(0) on the caller
+void fd_parallel(int nt, const std::function<void(int)> &fn);
+
 namespace {
 thread_local std::string g_err;
 void set_err(const std::string &s) { g_err = s; }
@@ -454,6 +457,11 @@ struct fdh_queries {
     std::vector<Query> q;
     bool finalized = false;
     std::vector<uint64_t> shard_bounds; // world + 1 ascending hash boundaries; empty = unsharded
+    // query side of the verification, resident on the device of the context that searched first (fd_verify_prepare);
+    // built by fdh_queries_finalize (or lazily by the first search), dropped whenever the idf values change
+    mutable fd_verify_prepared *vprep = nullptr;
+    mutable int vprep_device = -1;
+    ~fdh_queries() { fd_verify_prepared_free(vprep); }
 };
 
 namespace {
@@ -1355,10 +1363,7 @@ int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structur
     auto worker = [&] {
         for (int64_t k; (k = next.fetch_add(1)) < n;) ok[k] = prepare_query(qs, sp[k], query_strings[k], out[k], errs[k]);
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(worker);
-    worker();
-    for (auto &t : th) t.join();
+    fd_parallel(nt, [&](int) { worker(); });
     for (int64_t k = 0; k < n; k++)
         if (!ok[k]) {
             set_err(errs[k]);
@@ -1371,6 +1376,7 @@ int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structur
 }
 int64_t fdh_queries_size(const fdh_queries *qs) { return (int64_t)qs->q.size(); }
 
+static int ensure_verify_prepared(fd_ctx *ctx, const fdh_queries *qs);
 int fdh_queries_finalize(fdh_queries *qs, fd_ctx *ctx) {
     // calculate_idf_for_hash (query.rs:17-32) for the observed hash of every query pair, one device call
     std::vector<uint32_t> all;
@@ -1384,7 +1390,9 @@ int fdh_queries_finalize(fdh_queries *qs, fd_ctx *ctx) {
         }
     }
     // total_structures = lookup.len() as f32
-    return fdh_queries_finalize_with_counts(qs, counts.data(), fd_index_num_structs(ctx));
+    const int rc = fdh_queries_finalize_with_counts(qs, counts.data(), fd_index_num_structs(ctx));
+    if (rc != FD_OK) return rc;
+    return ensure_verify_prepared(ctx, qs);
 }
 int64_t fdh_queries_num_hashes(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].entries.size(); }
 void fdh_queries_get_map(const fdh_queries *qs, int64_t q, uint32_t *hash, int64_t *qi, int64_t *qj,
@@ -1525,12 +1533,7 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, uint32_t q_begin, uint32_
             chunks[tid].push_back(Chunk{c0, tid, begin, outv.size()});
         }
     };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
-        worker(0);
-        for (auto &t : th) t.join();
-    }
+    fd_parallel(nt, [&](int t) { worker(t); });
     std::vector<MatchTmp> mt;
     std::vector<Chunk> allc;
     for (auto &v : chunks) allc.insert(allc.end(), v.begin(), v.end());
@@ -1603,6 +1606,31 @@ static void make_fd_queries(const fdh_queries *qs, uint32_t q_begin, uint32_t q_
                                        (uint32_t)Q.indices.size(), nullptr};
         if (h2d_bytes) *h2d_bytes += 6ull * Q.hashes_flat.size() + 2ull * Q.edge_node.size() + 24;
     }
+}
+
+// verification tables of the whole batch (cand_query = index into qs->q), cached on qs
+static int ensure_verify_prepared(fd_ctx *ctx, const fdh_queries *qs) {
+    const int dev = fd_device(ctx);
+    if (qs->vprep && qs->vprep_device == dev) return FD_OK;
+    fd_verify_prepared_free(qs->vprep);
+    qs->vprep = nullptr;
+    const uint32_t nq = (uint32_t)qs->q.size();
+    std::vector<fd_verify_query> vq(nq);
+    for (uint32_t q = 0; q < nq; q++) {
+        const Query &Q = qs->q[q];
+        vq[q] = fd_verify_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), Q.vs_qi.data(),
+                                Q.vs_qj.data(), Q.vs_idf.data(), Q.vs_sym.data(), (uint32_t)Q.aad.size(),
+                                Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data(),
+                                (uint32_t)Q.indices.size(), Q.indices.data(), (uint32_t)Q.st->nres(), Q.st->ca.data(),
+                                Q.st->cb.data()};
+    }
+    const int rc = fd_verify_prepare(ctx, vq.data(), nq, &qs->vprep);
+    if (rc != FD_OK) {
+        set_err(fd_last_error(ctx));
+        return rc;
+    }
+    qs->vprep_device = dev;
+    return FD_OK;
 }
 
 // query_pdb.rs:348-452 for queries [q_begin, q_end) of the batch.  votes == nullptr: count_query on this
@@ -1680,15 +1708,9 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 cand_n[k] = hits[k].nid;
             }
         // --- K6: verification on the device; candidates beyond its limits come back flagged ---
-        std::vector<fd_verify_query> vq(nq);
-        for (uint32_t q = 0; q < nq; q++) {
-            const Query &Q = qs->q[q_begin + q];
-            vq[q] = fd_verify_query{(uint32_t)Q.hashes_sorted.size(), Q.hashes_sorted.data(), Q.vs_qi.data(),
-                                    Q.vs_qj.data(), Q.vs_idf.data(), Q.vs_sym.data(), (uint32_t)Q.aad.size(),
-                                    Q.aad_aa1.data(), Q.aad_aa2.data(), Q.aad_dist.data(), Q.aad_qi.data(),
-                                    (uint32_t)Q.indices.size(), Q.indices.data(), (uint32_t)Q.st->nres(), Q.st->ca.data(),
-                                    Q.st->cb.data()};
-            R->h2d_bytes += 14ull * Q.hashes_sorted.size() + 8ull * Q.aad.size() + Q.indices.size() + 24ull * 16 + 48;
+        if (p->verify_mode != 1) {
+            if (ensure_verify_prepared(ctx, qs) != FD_OK) return fail();
+            R->h2d_bytes += fd_verify_prepared_bytes(qs->vprep) * nq / std::max<size_t>(1, qs->q.size());
         }
         uint64_t n_recs = 0;
         if (p->verify_mode == 1) { // general path for everything
@@ -1710,21 +1732,20 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                     return fail();
                 }
             lanes.resize(n_lanes);
-            std::vector<uint32_t> cand_q_local(n_cand);
+            std::vector<uint32_t> cand_q_global(n_cand); // index into the prepared tables of the whole batch
+            for (uint64_t c = 0; c < n_cand; c++) cand_q_global[c] = cand_q[c] + q_begin;
             std::vector<uint32_t> q_split(n_lanes + 1);
             for (int l = 0; l <= n_lanes; l++) q_split[l] = (uint32_t)((uint64_t)nq * l / n_lanes);
             for (int l = 0; l < n_lanes; l++) {
                 lanes[l].c0 = hoff[q_split[l]];
                 lanes[l].c1 = hoff[q_split[l + 1]];
-                for (uint64_t c = lanes[l].c0; c < lanes[l].c1; c++) cand_q_local[c] = cand_q[c] - q_split[l];
             }
             auto run_lane = [&](int l) {
                 fd_ctx *lc = lane_ctx[l];
                 Lane &L = lanes[l];
-                L.rc = fd_verify_candidates_view(lc, vq.data() + q_split[l], q_split[l + 1] - q_split[l],
-                                                 cand_q_local.data() + L.c0, cand_n.data() + L.c0, L.c1 - L.c0,
-                                                 &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match, &L.recs, &L.n_recs,
-                                                 &L.first, &L.flags);
+                L.rc = fd_verify_candidates_prepared(lc, qs->vprep, cand_q_global.data() + L.c0, cand_n.data() + L.c0,
+                                                     L.c1 - L.c0, &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match,
+                                                     &L.recs, &L.n_recs, &L.first, &L.flags);
                 if (L.rc != FD_OK) L.err = fd_last_error(lc);
             };
             std::vector<std::thread> th;
@@ -1916,10 +1937,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 for (uint32_t q0; (q0 = next.fetch_add(8)) < nq;)
                     for (uint32_t q = q0; q < std::min(nq, q0 + 8); q++) fn(q);
             };
-            std::vector<std::thread> th;
-            for (int t = 1; t < nt; t++) th.emplace_back(worker);
-            worker();
-            for (auto &t : th) t.join();
+            fd_parallel(nt, [&](int) { worker(); });
         };
         run_parallel(count_query_rows);
         for (uint32_t q = 0; q < nq; q++) {
@@ -2087,6 +2105,8 @@ int fdh_queries_pair_counts(const fdh_queries *qs, fd_ctx *ctx, uint32_t *out_co
     return rc;
 }
 int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, uint64_t total_structures) {
+    fd_verify_prepared_free(qs->vprep); // the tables carry the per-hash idf
+    qs->vprep = nullptr;
     size_t base = 0;
     const float total = (float)total_structures;
     for (auto &Q : qs->q) {

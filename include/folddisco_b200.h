@@ -45,6 +45,7 @@ int fd_fork_refresh(fd_ctx *parent, fd_ctx *child);
  * destroyed by ctx; fd_lanes_fold_stats adds the lanes' stage times / launch counts to ctx's and clears them */
 int fd_lane(fd_ctx *ctx, int i, fd_ctx **out);
 void fd_lanes_fold_stats(fd_ctx *ctx);
+int fd_device(const fd_ctx *ctx);             /* CUDA device index of the context */
 const char *fd_last_error(const fd_ctx *ctx); /* ctx may be NULL: last error of a failed fd_create */
 void fd_free(void *p);                        /* for library-allocated host outputs */
 const char *fd_version(void);
@@ -336,6 +337,20 @@ int fd_verify_candidates_view(fd_ctx *ctx, const fd_verify_query *queries, uint3
                               const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
                               const fd_match_record **out_records, uint64_t *out_n, const uint32_t **out_first,
                               const uint8_t **out_flags);
+
+/* The query side of the verification is independent of the candidates (the reference rebuilds it per query inside
+ * retrieval_wrapper, retrieve.rs:364-452: hash set, observed_distance_map, query residues).  fd_verify_prepare
+ * flattens it once per query batch and keeps it resident on ctx's device; fd_verify_candidates_prepared is
+ * fd_verify_candidates_view on those tables (cand_query indexes the prepared batch).  Release with
+ * fd_verify_prepared_free before fd_destroy(ctx).  fd_verify_prepared_bytes: bytes uploaded by the prepare call. */
+typedef struct fd_verify_prepared fd_verify_prepared;
+int fd_verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t n_queries, fd_verify_prepared **out);
+void fd_verify_prepared_free(fd_verify_prepared *p);
+uint64_t fd_verify_prepared_bytes(const fd_verify_prepared *p);
+int fd_verify_candidates_prepared(fd_ctx *ctx, const fd_verify_prepared *prepared, const uint32_t *cand_query,
+                                  const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params,
+                                  float ca_dist_cutoff, int skip_ca_match, const fd_match_record **out_records,
+                                  uint64_t *out_n, const uint32_t **out_first, const uint8_t **out_flags);
 
 /* number of structures of the attached index (lookup.len()); 0 if none */
 uint64_t fd_index_num_structs(const fd_ctx *ctx);

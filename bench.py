@@ -215,7 +215,7 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     sp = host.SearchParams(top_n=args.top)
     stages = ("lookup", "scan", "select", "verify", "verify_edges", "verify_components", "verify_kabsch", "edges", "kabsch")
-    hv = ("hv_flatten", "hv_upload", "hv_k6a", "hv_k6b", "hv_k6c_d2h")  # host wall clock inside the verification call
+    hv = ("hv_flatten", "hv_upload", "hv_candidates", "hv_issue", "hv_wait_chunks", "hv_copy_tail")  # host wall clock inside the verification call
 
     def make_batch():
         """this rank's args.batch queries of the global batch (query number q uses motif q mod 5)"""

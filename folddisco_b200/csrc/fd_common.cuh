@@ -72,6 +72,8 @@ struct fd_ctx {
     uint64_t last_posting_bytes = 0;
     FdPinned pinned[8];
     cudaEvent_t ev_extra[4] = {nullptr, nullptr, nullptr, nullptr}; // finer stage timing inside one call
+    cudaStream_t aux_stream[2] = {nullptr, nullptr}; // second compute stream + copy stream of the chunked verification
+    std::vector<cudaEvent_t> ev_pool;                // events of the chunked verification, created on demand
     uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
     uint64_t votes_cap = 0;    // capacity in u32 words
     uint32_t *merge = nullptr; // dense vote planes of this rank's slice of the batch (sparse merge), owned
@@ -180,6 +182,12 @@ struct HostTimer {
         s.launches += 1;
     }
 };
+
+#define FD_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                 \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);               \
+        (ctx)->launches++;                                                      \
+    } while (0)
 
 #define FD_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
     do {                                                                        \

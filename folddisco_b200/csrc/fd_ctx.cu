@@ -263,6 +263,10 @@ void fd_destroy(fd_ctx *ctx) {
         if (b.p) cudaFreeHost(b.p);
     for (auto &e : ctx->ev_extra)
         if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_pool)
+        if (e) cudaEventDestroy(e);
+    for (auto &st : ctx->aux_stream)
+        if (st) cudaStreamDestroy(st);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

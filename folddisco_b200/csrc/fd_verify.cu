@@ -886,15 +886,15 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
     k6c_kabsch(StoreView st, const VQDesc *vq, const float *q_ca, const float *q_cb, const uint32_t *cand_query,
-               const uint32_t *cand_nid, const CompSpec *specs, uint32_t n_specs, const uint32_t *cand_first,
-               fd_match_record *out) {
+               const uint32_t *cand_nid, const CompSpec *specs, const unsigned int *spec_count, uint32_t spec_cap,
+               uint32_t cand_base, const uint32_t *cand_first, fd_match_record *out) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_specs) return;
+    if (k >= min(*spec_count, spec_cap)) return; // the grid is sized for the capacity: no host round trip for the count
     const CompSpec sp = specs[k];
     const VQDesc Q = vq[cand_query[sp.cand]];
     const uint64_t base = st.row_offsets[cand_nid[sp.cand]];
     fd_match_record rec;
-    rec.cand = sp.cand;
+    rec.cand = sp.cand + cand_base;
     rec.idf = sp.idf;
     uint32_t nodes = 0;
     for (uint32_t j = 0; j < V_MAX_NQ; j++) {
@@ -905,7 +905,8 @@ __global__ void __launch_bounds__(128)
     GatherPointsT<uint16_t> mov{st.ca_xyz, st.cb_xyz, sp.at, base};
     GatherPointsT<uint8_t> ref{q_ca, q_cb, sp.aq, (uint64_t)Q.qres_base};
     fdk::kabsch_one(mov, ref, 2u * sp.nal, rec.U, rec.t, &rec.rmsd);
-    out[cand_first[sp.cand] + sp.ci] = rec;
+    const uint32_t pos = cand_first[sp.cand] + sp.ci;
+    if (pos < spec_cap) out[pos] = rec; // (an overflowing chunk is re-issued with exact sizes)
 }
 
 } // namespace
@@ -1145,107 +1146,193 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         *out_first = h_first;
         return FD_OK;
     }
-    cudaStream_t s = ctx->stream;
-    // (fd_verify_prepare synchronises its stream before returning: the tables are complete on every stream)
-    struct { VQDesc *p; } d_desc{P->d_desc};
-    struct { VHash *p; } d_hash{P->d_hash};
-    struct { VAad *p; } d_aad{P->d_aad};
-    struct { uint8_t *p; } d_idx{P->d_idx};
-    struct { float *p; } d_qca{P->d_qca}, d_qcb{P->d_qcb};
+    // ---- chunked pipeline ----
+    // The candidates are cut into a few contiguous chunks issued back to back on two compute streams without any
+    // host synchronisation in between (k6c sizes itself from the device-side component count).  The host then walks
+    // the chunks in order: waits for a chunk's event, reads its counts and starts the copy of its records on a third
+    // stream -- so the record copy of chunk i (PCIe, the longest serial piece of the old sequence) runs under the
+    // kernels of chunks i+1...  Pools are sized for 48 edges / 2 components per candidate; a chunk that overflows is
+    // re-issued with exact sizes.
+    cudaStream_t s0 = ctx->stream;
+    for (auto &st : ctx->aux_stream)
+        if (!st) FD_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t s1 = ctx->aux_stream[0], sc = ctx->aux_stream[1];
+    uint32_t n_chunks = 4;
+    if (const char *e = getenv("FD_VERIFY_CHUNKS")) n_chunks = (uint32_t)std::max(1, std::min(atoi(e), 16));
+    n_chunks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, n_cand / 4096));
+    auto event_at = [&](size_t k) -> cudaEvent_t {
+        while (ctx->ev_pool.size() <= k) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            ctx->ev_pool.push_back(e);
+        }
+        return ctx->ev_pool[k];
+    };
+    if (!event_at(5 * n_chunks + 3)) return fd_fail(ctx, FD_ERR_CUDA, "cudaEventCreate failed");
+    struct Chunk {
+        uint64_t c0 = 0, n = 0;
+        cudaStream_t st = nullptr;
+        uint64_t pool_cap = 0, spec_cap = 0;
+        DevBuf<uint32_t> pool_key, ncomp, first;
+        DevBuf<uint16_t> pool_ent;
+        DevBuf<unsigned int> counters; // [0] edge pool, [1] component specs
+        DevBuf<CompSpec> specs;
+        DevBuf<fd_match_record> out;
+        DevBuf<uint8_t> tmp;
+        unsigned int *h_counters = nullptr; // pinned
+        uint32_t *h_first_rel = nullptr;    // pinned, n + 1
+        uint64_t rec_base = 0;
+    };
+    std::vector<Chunk> chunks(n_chunks);
     DevBuf<uint8_t> d_flags;
-    DevBuf<uint32_t> d_cq, d_cn, d_ebegin, d_ne, d_ncomp, d_first, d_pool_key;
-    DevBuf<uint16_t> d_pool_ent;
-    DevBuf<unsigned int> d_counters; // [0] edge pool, [1] component specs
-    DevBuf<CompSpec> d_specs;
-    DevBuf<fd_match_record> d_out;
-    DevBuf<uint8_t> d_tmp;
+    DevBuf<uint32_t> d_cq, d_cn, d_ebegin, d_ne;
     FD_CUDA(ctx, d_cq.alloc(n_cand));
     FD_CUDA(ctx, d_cn.alloc(n_cand));
     FD_CUDA(ctx, d_flags.alloc(n_cand));
     FD_CUDA(ctx, d_ebegin.alloc(n_cand));
     FD_CUDA(ctx, d_ne.alloc(n_cand));
-    FD_CUDA(ctx, d_ncomp.alloc(n_cand + 1));
-    FD_CUDA(ctx, d_first.alloc(n_cand + 1));
-    FD_CUDA(ctx, d_counters.alloc(2));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_cq.p, cand_query, n_cand * 4, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d_cn.p, cand_nid, n_cand * 4, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, n_cand, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_cq.p, cand_query, n_cand * 4, cudaMemcpyHostToDevice, s0));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_cn.p, cand_nid, n_cand * 4, cudaMemcpyHostToDevice, s0));
+    FD_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, n_cand, s0));
+    FD_CUDA(ctx, cudaMemsetAsync(d_ne.p, 0, n_cand * 4, s0));
+    // pinned staging: records (upper bound 2 per candidate, grown on overflow), per-chunk counters, relative firsts
+    uint8_t *h_kflags = nullptr;
+    unsigned int *h_counters_all = nullptr;
+    uint32_t *h_first_rel_all = nullptr;
+    FD_TRY(fd_pinned(ctx, 3, n_cand, (void **)&h_kflags));
+    FD_TRY(fd_pinned(ctx, 4, 2 * sizeof(unsigned int) * n_chunks, (void **)&h_counters_all));
+    FD_TRY(fd_pinned(ctx, 5, (n_cand + n_chunks) * 4, (void **)&h_first_rel_all));
     const FdDeviceStore &S = ctx->store;
     StoreView sv{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid};
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
-    const uint32_t nc32 = (uint32_t)n_cand;
-    unsigned int h_counters[2] = {0, 0};
-    FD_CUDA(ctx, fd_ensure_events(ctx));
-    cudaEvent_t *ev = ctx->ev_extra;
-    FD_CUDA(ctx, cudaEventRecord(ev[0], s));
-    h_mark("hv_candidates");
-    // ---- k6a: edges into a compact pool (sized for 48 edges per candidate; exact on the rare overflow) ----
-    uint64_t pool_cap = std::max<uint64_t>(1u << 20, 48 * n_cand);
-    for (int attempt = 0; attempt < 2; attempt++) {
-        FD_CUDA(ctx, d_pool_key.alloc(pool_cap));
-        FD_CUDA(ctx, d_pool_ent.alloc(pool_cap));
-        FD_CUDA(ctx, cudaMemsetAsync(d_counters.p, 0, 8, s));
-        FD_CUDA(ctx, cudaMemsetAsync(d_ne.p, 0, n_cand * 4, s));
-        FD_LAUNCH(ctx, k6a_edges, nc32, VA_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p, d_cn.p, nc32, hp,
-                  ca_dist_cutoff, d_pool_key.p, d_pool_ent.p, d_counters.p, (uint32_t)std::min<uint64_t>(pool_cap, 0xffffffffu),
-                  d_ebegin.p, d_ne.p, d_flags.p);
-        FD_CUDA(ctx, cudaMemcpyAsync(h_counters, d_counters.p, 4, cudaMemcpyDeviceToHost, s));
-        FD_CUDA(ctx, cudaStreamSynchronize(s));
-        if (h_counters[0] <= pool_cap) break;
-        pool_cap = h_counters[0];
-    }
-    FD_CUDA(ctx, cudaEventRecord(ev[1], s));
-    h_mark("hv_k6a");
-    // ---- k6b: components ----
-    uint64_t spec_cap = std::max<uint64_t>(1024, 2 * n_cand);
     const size_t smem_b = sizeof(WarpState) * VB_WARPS;
     FD_CUDA(ctx, cudaFuncSetAttribute(k6b_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    for (int attempt = 0; attempt < 2; attempt++) {
-        FD_CUDA(ctx, d_specs.alloc(spec_cap));
-        FD_CUDA(ctx, cudaMemsetAsync(d_counters.p + 1, 0, 4, s));
-        FD_CUDA(ctx, cudaMemsetAsync(d_ncomp.p, 0, (n_cand + 1) * 4, s));
-        FD_LAUNCH(ctx, k6b_components, fd_div_up(n_cand, VB_WARPS), VB_WARPS * 32, smem_b, sv, d_desc.p, d_hash.p,
-                  d_aad.p, d_idx.p, d_cq.p, d_cn.p, nc32, hp, ca_dist_cutoff, skip_ca_match, d_pool_key.p,
-                  d_pool_ent.p, d_ebegin.p, d_ne.p, d_specs.p, d_counters.p + 1,
-                  (uint32_t)std::min<uint64_t>(spec_cap, 0xffffffffu), d_ncomp.p, d_flags.p);
-        FD_CUDA(ctx, cudaMemcpyAsync(h_counters + 1, d_counters.p + 1, 4, cudaMemcpyDeviceToHost, s));
-        FD_CUDA(ctx, cudaStreamSynchronize(s));
-        if (h_counters[1] <= spec_cap) break;
-        spec_cap = h_counters[1];
+    for (uint32_t k = 0; k < n_chunks; k++) {
+        Chunk &C = chunks[k];
+        C.c0 = n_cand * k / n_chunks;
+        C.n = n_cand * (k + 1) / n_chunks - C.c0;
+        C.st = (k & 1) ? s1 : s0;
+        C.pool_cap = std::max<uint64_t>(1u << 16, 48 * C.n);
+        C.spec_cap = std::max<uint64_t>(1024, 2 * C.n);
+        C.h_counters = h_counters_all + 2 * k;
+        C.h_first_rel = h_first_rel_all + C.c0 + k;
+        FD_CUDA(ctx, C.ncomp.alloc(C.n + 1));
+        FD_CUDA(ctx, C.first.alloc(C.n + 1));
+        FD_CUDA(ctx, C.counters.alloc(2));
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, C.ncomp.p, C.first.p, C.n + 1, s0);
+        FD_CUDA(ctx, C.tmp.alloc(tb));
     }
-    FD_CUDA(ctx, cudaEventRecord(ev[2], s));
-    h_mark("hv_k6b");
-    const uint32_t produced = h_counters[1];
-    // ---- k6c: Kabsch, records in (candidate, component) order ----
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_ncomp.p, d_first.p, n_cand + 1, s);
-    FD_CUDA(ctx, d_tmp.alloc(tb));
-    FD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_ncomp.p, d_first.p, n_cand + 1, s));
-    ctx->launches += 2;
-    FD_CUDA(ctx, d_out.alloc(produced));
-    if (produced)
-        FD_LAUNCH(ctx, k6c_kabsch, fd_div_up(produced, 128), 128, 0, sv, d_desc.p, d_qca.p, d_qcb.p, d_cq.p, d_cn.p,
-                  d_specs.p, produced, d_first.p, d_out.p);
-    fd_match_record *h_out = nullptr;
-    uint8_t *h_kflags = nullptr;
-    FD_TRY(fd_pinned(ctx, 0, std::max<uint64_t>(produced, 1) * sizeof(fd_match_record), (void **)&h_out));
-    FD_TRY(fd_pinned(ctx, 3, n_cand, (void **)&h_kflags));
-    FD_CUDA(ctx, cudaMemcpyAsync(h_out, d_out.p, (size_t)produced * sizeof(fd_match_record), cudaMemcpyDeviceToHost, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(h_first, d_first.p, (n_cand + 1) * 4, cudaMemcpyDeviceToHost, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(h_kflags, d_flags.p, n_cand, cudaMemcpyDeviceToHost, s));
-    FD_CUDA(ctx, cudaEventRecord(ev[3], s));
-    FD_CUDA(ctx, cudaEventSynchronize(ev[3]));
-    FD_CUDA(ctx, cudaGetLastError());
-    h_mark("hv_k6c_d2h");
-    {
-        const char *names[4] = {"verify_edges", "verify_components", "verify_kabsch", "verify"};
-        for (int k = 0; k < 4; k++) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, k == 3 ? ev[0] : ev[k], k == 3 ? ev[3] : ev[k + 1]);
-            FdStage &stg = ctx->stages[names[k]];
-            stg.ms += ms;
-            stg.launches += 1;
+    // allocations and uploads were ordered on s0: the other streams start after them
+    cudaEvent_t ev_begin = event_at(5 * n_chunks), ev_end = event_at(5 * n_chunks + 1), ev_tmp = event_at(5 * n_chunks + 2);
+    FD_CUDA(ctx, cudaEventRecord(ev_begin, s0));
+    FD_CUDA(ctx, cudaStreamWaitEvent(s1, ev_begin, 0));
+    FD_CUDA(ctx, cudaStreamWaitEvent(sc, ev_begin, 0));
+    h_mark("hv_candidates");
+    auto issue = [&](uint32_t k) -> int {
+        Chunk &C = chunks[k];
+        cudaStream_t st = C.st;
+        const uint32_t n32 = (uint32_t)C.n;
+        // pools are (re)allocated stream-ordered on s0; on the first pass that happened before ev_begin
+        FD_CUDA(ctx, C.pool_key.alloc(C.pool_cap));
+        FD_CUDA(ctx, C.pool_ent.alloc(C.pool_cap));
+        FD_CUDA(ctx, C.specs.alloc(C.spec_cap));
+        FD_CUDA(ctx, C.out.alloc(C.spec_cap));
+        if (st != s0) {
+            FD_CUDA(ctx, cudaEventRecord(ev_tmp, s0));
+            FD_CUDA(ctx, cudaStreamWaitEvent(st, ev_tmp, 0));
         }
+        FD_CUDA(ctx, cudaEventRecord(event_at(5 * k), st));
+        FD_CUDA(ctx, cudaMemsetAsync(C.counters.p, 0, 8, st));
+        FD_CUDA(ctx, cudaMemsetAsync(C.ncomp.p, 0, (C.n + 1) * 4, st));
+        FD_LAUNCH_ON(ctx, st, k6a_edges, n32, VA_THREADS, 0, sv, P->d_desc, P->d_hash, P->d_aad, d_cq.p + C.c0,
+                     d_cn.p + C.c0, n32, hp, ca_dist_cutoff, C.pool_key.p, C.pool_ent.p, C.counters.p,
+                     (uint32_t)std::min<uint64_t>(C.pool_cap, 0xffffffffu), d_ebegin.p + C.c0, d_ne.p + C.c0,
+                     d_flags.p + C.c0);
+        FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 1), st));
+        FD_LAUNCH_ON(ctx, st, k6b_components, fd_div_up(C.n, VB_WARPS), VB_WARPS * 32, smem_b, sv, P->d_desc, P->d_hash,
+                     P->d_aad, P->d_idx, d_cq.p + C.c0, d_cn.p + C.c0, n32, hp, ca_dist_cutoff, skip_ca_match,
+                     C.pool_key.p, C.pool_ent.p, d_ebegin.p + C.c0, d_ne.p + C.c0, C.specs.p, C.counters.p + 1,
+                     (uint32_t)std::min<uint64_t>(C.spec_cap, 0xffffffffu), C.ncomp.p, d_flags.p + C.c0);
+        FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 2), st));
+        size_t tb = C.tmp.n;
+        FD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(C.tmp.p, tb, C.ncomp.p, C.first.p, C.n + 1, st));
+        ctx->launches += 2;
+        FD_LAUNCH_ON(ctx, st, k6c_kabsch, fd_div_up(C.spec_cap, 128), 128, 0, sv, P->d_desc, P->d_qca, P->d_qcb,
+                     d_cq.p + C.c0, d_cn.p + C.c0, C.specs.p, C.counters.p + 1,
+                     (uint32_t)std::min<uint64_t>(C.spec_cap, 0xffffffffu), (uint32_t)C.c0, C.first.p, C.out.p);
+        FD_CUDA(ctx, cudaMemcpyAsync(C.h_counters, C.counters.p, 8, cudaMemcpyDeviceToHost, st));
+        FD_CUDA(ctx, cudaMemcpyAsync(C.h_first_rel, C.first.p, (C.n + 1) * 4, cudaMemcpyDeviceToHost, st));
+        FD_CUDA(ctx, cudaMemcpyAsync(h_kflags + C.c0, d_flags.p + C.c0, C.n, cudaMemcpyDeviceToHost, st));
+        FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 3), st));
+        return FD_OK;
+    };
+    for (uint32_t k = 0; k < n_chunks; k++) FD_TRY(issue(k));
+    h_mark("hv_issue");
+    fd_match_record *h_out = nullptr;
+    uint64_t h_out_cap = 0, produced = 0;
+    {
+        uint64_t cap = 0;
+        for (auto &C : chunks) cap += C.spec_cap;
+        FD_TRY(fd_pinned(ctx, 0, cap * sizeof(fd_match_record), (void **)&h_out));
+        h_out_cap = cap;
+    }
+    for (uint32_t k = 0; k < n_chunks; k++) {
+        Chunk &C = chunks[k];
+        for (int attempt = 0;; attempt++) {
+            FD_CUDA(ctx, cudaEventSynchronize(event_at(5 * k + 3)));
+            const bool pool_over = C.h_counters[0] > C.pool_cap, spec_over = C.h_counters[1] > C.spec_cap;
+            if (!pool_over && !spec_over) break;
+            if (attempt == 2) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: pool sizing did not converge");
+            if (pool_over) C.pool_cap = C.h_counters[0];
+            if (spec_over) C.spec_cap = C.h_counters[1]; // upper bound: the first pass may have stopped counting early
+            if (pool_over) C.spec_cap = std::max<uint64_t>(C.spec_cap, 2 * C.n);
+            FD_CUDA(ctx, cudaMemsetAsync(d_ne.p + C.c0, 0, C.n * 4, C.st));
+            FD_CUDA(ctx, cudaMemsetAsync(d_flags.p + C.c0, 0, C.n, C.st));
+            FD_TRY(issue(k));
+        }
+        C.rec_base = produced;
+        const uint64_t np = C.h_counters[1];
+        if (produced + np > h_out_cap) { // only after a re-issue with more components than the first estimate
+            FD_CUDA(ctx, cudaStreamSynchronize(sc));
+            fd_match_record *bigger = nullptr;
+            std::vector<fd_match_record> keep(h_out, h_out + produced);
+            FD_TRY(fd_pinned(ctx, 0, (produced + np + (n_cand - C.c0) * 2) * sizeof(fd_match_record), (void **)&bigger));
+            memcpy(bigger, keep.data(), produced * sizeof(fd_match_record));
+            h_out = bigger;
+            h_out_cap = produced + np + (n_cand - C.c0) * 2;
+        }
+        if (np) {
+            // the records are complete (event above); copy them on the copy stream, under the other chunks' kernels
+            FD_CUDA(ctx, cudaMemcpyAsync(h_out + produced, C.out.p, np * sizeof(fd_match_record), cudaMemcpyDeviceToHost, sc));
+        }
+        for (uint64_t c = 0; c <= C.n; c++) h_first[C.c0 + c] = (uint32_t)(produced + C.h_first_rel[c]);
+        produced += np;
+    }
+    h_mark("hv_wait_chunks");
+    FD_CUDA(ctx, cudaEventRecord(ev_tmp, sc));
+    FD_CUDA(ctx, cudaStreamWaitEvent(s0, ev_tmp, 0));
+    FD_CUDA(ctx, cudaEventRecord(ev_tmp, s1));
+    FD_CUDA(ctx, cudaStreamWaitEvent(s0, ev_tmp, 0));
+    FD_CUDA(ctx, cudaEventRecord(ev_end, s0));
+    FD_CUDA(ctx, cudaEventSynchronize(ev_end)); // every stream is idle: the DevBufs can be released on s0
+    FD_CUDA(ctx, cudaGetLastError());
+    h_mark("hv_copy_tail");
+    {
+        const char *names[3] = {"verify_edges", "verify_components", "verify_kabsch"};
+        for (uint32_t k = 0; k < n_chunks; k++)
+            for (int j = 0; j < 3; j++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, event_at(5 * k + j), event_at(5 * k + j + 1));
+                FdStage &stg = ctx->stages[names[j]];
+                stg.ms += ms; // chunks overlap on two streams: these intervals add up to more than the wall time
+                stg.launches += k == 0 ? 1 : 0;
+            }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        FdStage &stg = ctx->stages["verify"];
+        stg.ms += ms;
+        stg.launches += 1;
     }
     for (uint64_t c = 0; c < n_cand; c++) h_flags[c] |= h_kflags[c];
     *out_records = h_out;

@@ -480,7 +480,8 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
     k3_scan(IndexView ix, const QueryDesc *queries, const QHash *qh, const uint16_t *edge_of_hash,
             const uint16_t *edge_node, const uint16_t *edge_group, const float *idf_sum_per_query, const float *pen, uint32_t tile_ids,
             FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits,
-            uint32_t *dense /* MODE 1: [planes][nq][N]; MODE 2: sparse record pool */, SparseOut sp) {
+            uint32_t *dense /* MODE 1: [planes][nq][N]; MODE 2: sparse record pool */, SparseOut sp,
+            int stage_lists /* per-list byte range / vote word / edge bit staged in shared memory */) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t q = blockIdx.y;
     const QueryDesc qd = queries[q];
@@ -495,18 +496,17 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
     uint32_t *w_acc = smem;                                  // [tile_ids] narrow: packed; wide: idf fixed
     uint32_t *w_match = NARROW ? nullptr : w_acc + tile_ids; // [tile_ids] wide only
     uint32_t *w_edge = w_acc + (NARROW ? 1 : 2) * tile_ids;  // EW planes of [tile_ids]
-    uint32_t *item_prefix = w_acc + (size_t)PLANES * tile_ids; // [Q + 1]
+    uint64_t *l_range = reinterpret_cast<uint64_t *>(w_acc + (size_t)PLANES * tile_ids); // [2 Q] start, end (staged)
+    uint32_t *l_vote = reinterpret_cast<uint32_t *>(l_range + (stage_lists ? 2 * Q : 0)); // [2 Q] vote word, edge
+    uint32_t *item_prefix = l_vote + (stage_lists ? 2 * Q : 0); // [Q + 1]
     uint32_t *seg_lo = item_prefix + (Q + 1);                // [Q] first relevant granule of each list
     uint32_t *node_mask = seg_lo + Q;                        // [n_nodes * EW]
     uint32_t *cont_mask = node_mask + qd.n_nodes * EW;       // [EW]
     uint32_t *wqueue = cont_mask + EW;                       // [K3_WARPS * K3_WQ]
     __shared__ uint32_t s_total_items;
 
-    {
-        uint4 *z = reinterpret_cast<uint4 *>(smem);
-        const uint32_t n4 = (PLANES * tile_ids) >> 2;
-        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-    }
+    const float scale = idf_scale<NARROW>(idf_sum_per_query[q]);
+    const float inv_scale = 1.0f / scale;
     for (uint32_t i = threadIdx.x; i < qd.n_nodes * EW + EW; i += blockDim.x) node_mask[i] = 0; // + cont_mask
 
     // ---- which 64-byte granules of each list intersect this tile ----
@@ -544,6 +544,13 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
         }
         seg_lo[k] = first;
         item_prefix[k + 1] = n_items;
+        if (stage_lists) {
+            l_range[2 * k] = h.start;
+            l_range[2 * k + 1] = h.end;
+            const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
+            l_vote[2 * k] = NARROW ? ((1u << 24) | wgt) : wgt;
+            l_vote[2 * k + 1] = edge_of_hash[qd.hash_begin + k];
+        }
     }
     if (threadIdx.x == 0) item_prefix[0] = 0;
     __syncthreads();
@@ -566,13 +573,20 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
     }
     __syncthreads();
     const uint32_t total_items = s_total_items;
-
-    const float scale = idf_scale<NARROW>(idf_sum_per_query[q]);
-    const float inv_scale = 1.0f / scale;
+    // nothing of this query's lists falls into this tile (common for hash-range shards: a rank holds the lists of
+    // a few amino-acid pairs only): no votes, no hits, no records -- the tile is neither cleared nor scanned
+    if (MODE != 1 && total_items == 0) return;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem);
+        const uint32_t n4 = (PLANES * tile_ids) >> 2;
+        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
 
     // ---- decode + vote: 8 lanes per granule, 32 granules per CTA step ----
     const uint32_t sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
     for (uint32_t it0 = 0; it0 < total_items; it0 += (blockDim.x >> 3)) {
+        if (it0 + ((threadIdx.x >> 5) << 2) >= total_items) break; // none of this warp's four granules exists
         const uint32_t it = it0 + grp;
         const bool act = it < total_items;
         uint32_t w0 = 0, w1 = 0, w2 = 0, base = 0, add = 0, ebit = 0, eword = 0;
@@ -585,27 +599,38 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
                 else b = m;
             }
             const uint32_t k = a;
-            const QHash h = qh[qd.hash_begin + k];
+            uint64_t h_start, h_end;
+            uint32_t e;
+            if (stage_lists) {
+                h_start = l_range[2 * k];
+                h_end = l_range[2 * k + 1];
+                add = l_vote[2 * k];
+                e = l_vote[2 * k + 1];
+            } else {
+                const QHash h = qh[qd.hash_begin + k];
+                h_start = h.start;
+                h_end = h.end;
+                e = edge_of_hash[qd.hash_begin + k];
+                const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
+                add = NARROW ? ((1u << 24) | wgt) : wgt;
+            }
             const uint32_t seg = seg_lo[k] + (it - item_prefix[k]);
-            const uint64_t gi = (h.start >> SKIP_SHIFT) + seg;
+            const uint64_t gi = (h_start >> SKIP_SHIFT) + seg;
             const uint64_t G0 = gi << SKIP_SHIFT;
             if (seg == 0) {
-                start_pos = h.start;
+                start_pos = h_start;
             } else {
                 start_pos = G0 + ix.skip_off[gi];
                 base = ix.skip_id[gi];
             }
-            lim = min(h.end, G0 + SKIP_BYTES);
+            lim = min(h_end, G0 + SKIP_BYTES);
             A = G0 + 8u * sub;
             const uint2 w = *reinterpret_cast<const uint2 *>(ix.values + A);
             w0 = w.x;
             w1 = w.y;
             if (sub == 7) w2 = *reinterpret_cast<const uint32_t *>(ix.values + G0 + SKIP_BYTES);
-            const uint32_t e = edge_of_hash[qd.hash_begin + k];
             ebit = 1u << (e & 31);
             eword = e >> 5;
-            const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
-            add = NARROW ? ((1u << 24) | wgt) : wgt;
         }
         const uint32_t nxt = __shfl_down_sync(0xffffffffu, w0, 1, 8);
         if (sub != 7) w2 = nxt;
@@ -985,6 +1010,9 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
     return FD_OK;
 }
 
+// motif-sized queries keep their per-list descriptors in shared memory (24 B per hash)
+static inline bool k3_stage_lists(uint32_t max_hashes) { return max_hashes <= 512; }
+
 struct TilePlan {
     uint32_t tile_ids, n_tiles, threads;
     size_t smem;
@@ -996,7 +1024,8 @@ int plan_tiles(fd_ctx *ctx, const Batch &B, uint32_t N, TilePlan &tp) {
     // fits the shared memory of one or two SMs a query gets 1024-thread CTAs with 220 KB tiles; otherwise 256-thread
     // CTAs with 72 KB tiles, three per SM.
     auto fixed_for = [&](uint32_t threads) {
-        return (size_t)(2 * B.max_hashes + 2 + B.max_nodes * B.ew + B.ew + (threads / 32) * K3_WQ) * 4 + 64;
+        return (size_t)((k3_stage_lists(B.max_hashes) ? 8 : 2) * B.max_hashes + 2 + B.max_nodes * B.ew + B.ew +
+                        (threads / 32) * K3_WQ) * 4 + 64;
     };
     uint32_t threads = K3_THREADS;
     size_t budget = 72 * 1024;
@@ -1027,7 +1056,7 @@ int launch_scan_t(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, cons
     FD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
     kern<<<grid, tp.threads, tp.smem, ctx->stream>>>(ix, B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p,
                                                      B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, tp.tile_ids, fp, hit_offsets, hit_counts,
-                                                     hits, dense, sp);
+                                                     hits, dense, sp, k3_stage_lists(B.max_hashes) ? 1 : 0);
     ctx->launches++;
     return FD_OK;
 }

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libfolddisco_b200.so")
+CLI = os.path.join(HERE, "folddisco-b200")  # `index` / `query` front end (csrc/host/fd_cli.cpp), links the .so
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = ["fd_ctx.cu", "fd_hash.cu", "fd_postings.cu", "fd_query.cu", "fd_edges.cu", "fd_kabsch.cu", "fd_verify.cu"]
@@ -31,7 +32,7 @@ def _deps():
 
 
 def needs_build():
-    if not os.path.exists(SO):
+    if not os.path.exists(SO) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(SO)
     return any(os.path.getmtime(p) > t for p in _deps())
@@ -63,6 +64,9 @@ def build(force=False, verbose=False):
         print("\n".join(log))
     link = [NVCC, "-shared", "-o", SO] + [o for _, o, _, _ in results] + ["-Xcompiler", "-pthread"]
     subprocess.check_call(link)
+    cli = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", os.path.join(CSRC, "host", "fd_cli.cpp"), "-o", CLI,
+           "-L" + HERE, "-lfolddisco_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + os.path.dirname(NVCC) + "/../lib64"]
+    subprocess.check_call(cli)
     return SO
 
 

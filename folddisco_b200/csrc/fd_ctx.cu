@@ -178,6 +178,22 @@ int fd_default_host_threads(void) {
     return hc ? (int)hc : 1;
 }
 
+// parity / debug probe: runs a region of nt workers that each spin for `spin_us`; returns how many distinct host
+// threads took part (the pool is healthy when the answer is nt)
+int fd_parallel_probe(int nt, int spin_us) {
+    std::mutex m;
+    std::vector<std::thread::id> ids;
+    fd_parallel(nt, [&](int) {
+        const auto t0 = std::chrono::steady_clock::now();
+        while (std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() < spin_us) {
+        }
+        std::lock_guard<std::mutex> lk(m);
+        ids.push_back(std::this_thread::get_id());
+    });
+    std::sort(ids.begin(), ids.end());
+    return (int)(std::unique(ids.begin(), ids.end()) - ids.begin());
+}
+
 int fd_device(const fd_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 const char *fd_version(void) { return "folddisco_b200 0.1 (sm_100a)"; }

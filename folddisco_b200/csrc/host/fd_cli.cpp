@@ -1,0 +1,520 @@
+// fd_cli.cpp -- `folddisco-b200 index | query`: the reference's two hot-path sub-commands on top of the host C ABI
+// (include/folddisco_b200_host.h), with the reference's flag surface and TSV outputs so that results diff against a
+// `folddisco` run elsewhere.
+//
+//   flags and defaults      src/cli/main.rs:26-141
+//   index workflow          src/cli/workflows/build_index.rs (files in sorted path order; the reference uses read_dir
+//                           order, loader.rs:12, which is unspecified -- sorted is what its README outputs show)
+//   query workflow          src/cli/workflows/query_pdb.rs:186-512 (query file = lines of path \t residues \t output)
+//   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
+//   ids                     src/controller/mode.rs:70-125
+//
+// Not here (fails loudly): `benchmark` / `analyze`, --sort-by other than the default, --format-output, --superpose,
+// --web, --partial-fit, the TM / GDT / Chamfer / Hausdorff filters, hash types other than the default, mmCIF / .gz /
+// Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
+#include <dirent.h>
+#include <limits.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/folddisco_b200_host.h"
+
+namespace {
+
+[[noreturn]] void die(const std::string &msg) {
+    fprintf(stderr, "[FAIL] %s\n", msg.c_str());
+    exit(1);
+}
+
+struct Args { // pico_args-like: options may appear anywhere after the sub-command
+    std::vector<std::string> v;
+    std::vector<bool> used;
+    Args(int argc, char **argv) {
+        for (int i = 2; i < argc; i++) v.push_back(argv[i]);
+        used.assign(v.size(), false);
+    }
+    bool flag(std::initializer_list<const char *> names) {
+        bool found = false;
+        for (size_t i = 0; i < v.size(); i++)
+            for (const char *n : names)
+                if (!used[i] && v[i] == n) used[i] = found = true;
+        return found;
+    }
+    bool value(std::initializer_list<const char *> names, std::string &out) {
+        for (size_t i = 0; i < v.size(); i++)
+            for (const char *n : names) {
+                if (used[i]) continue;
+                const std::string key = n;
+                if (v[i] == key) {
+                    if (i + 1 >= v.size()) die("option " + key + " needs a value");
+                    used[i] = used[i + 1] = true;
+                    out = v[i + 1];
+                    return true;
+                }
+                if (v[i].compare(0, key.size() + 1, key + "=") == 0) {
+                    used[i] = true;
+                    out = v[i].substr(key.size() + 1);
+                    return true;
+                }
+            }
+        return false;
+    }
+    std::string str(std::initializer_list<const char *> names, const std::string &dflt) {
+        std::string s;
+        return value(names, s) ? s : dflt;
+    }
+    double num(std::initializer_list<const char *> names, double dflt) {
+        std::string s;
+        if (!value(names, s)) return dflt;
+        char *end = nullptr;
+        const double x = strtod(s.c_str(), &end);
+        if (end == s.c_str() || *end) die("invalid number '" + s + "'");
+        return x;
+    }
+    void reject(std::initializer_list<const char *> names, const char *why) {
+        for (const char *n : names)
+            for (size_t i = 0; i < v.size(); i++)
+                if (v[i] == n || v[i].compare(0, strlen(n) + 1, std::string(n) + "=") == 0)
+                    die(std::string(n) + " is not supported by folddisco-b200: " + why);
+    }
+    void finish() {
+        for (size_t i = 0; i < v.size(); i++)
+            if (!used[i]) die("unknown or repeated argument: " + v[i]);
+    }
+};
+
+bool ends_with(const std::string &s, const char *suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+bool is_dir(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+bool is_file(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+
+void list_files(const std::string &dir, bool recursive, std::vector<std::string> &out) { // loader.rs:9-37
+    DIR *d = opendir(dir.c_str());
+    if (!d) die("cannot read directory " + dir);
+    std::vector<std::string> names;
+    while (dirent *e = readdir(d)) {
+        const std::string n = e->d_name;
+        if (n == "." || n == "..") continue;
+        names.push_back(n);
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    const std::string base = !dir.empty() && dir.back() == '/' ? dir : dir + "/";
+    for (auto &n : names) {
+        const std::string p = base + n;
+        if (is_dir(p)) {
+            if (recursive) list_files(p, true, out);
+        } else {
+            out.push_back(p);
+        }
+    }
+}
+
+std::string file_stem(const std::string &p) {
+    const size_t sl = p.find_last_of('/');
+    std::string f = sl == std::string::npos ? p : p.substr(sl + 1);
+    const size_t dot = f.find_last_of('.');
+    if (dot != std::string::npos && dot > 0) f = f.substr(0, dot);
+    return f;
+}
+
+std::string make_id(const std::string &path, const std::string &id_type) { // mode.rs:19-31, 70-125
+    auto is = [&](std::initializer_list<const char *> a) {
+        for (const char *x : a)
+            if (id_type == x) return true;
+        return false;
+    };
+    if (is({"Pdb", "PDB", "pdb"})) {
+        const std::string s = file_stem(path);
+        return s.compare(0, 3, "pdb") == 0 ? s.substr(3) : s;
+    }
+    if (is({"BasenameWithoutExt", "basename_without_ext", "basename_no_ext", "filename"})) return file_stem(path);
+    if (is({"BasenameWithExt", "basename_with_ext", "basename", "file"})) {
+        const size_t sl = path.find_last_of('/');
+        return sl == std::string::npos ? path : path.substr(sl + 1);
+    }
+    if (is({"AbsPath", "Abspath", "abspath", "absolute_path", "path"})) {
+        char buf[PATH_MAX];
+        return realpath(path.c_str(), buf) ? std::string(buf) : path;
+    }
+    if (is({"Afdb", "AFDB", "afdb", "Uniprot", "UniProt", "uniprot"}))
+        die("--id " + id_type + " is not supported by folddisco-b200 (use relpath, abspath, basename, filename or pdb)");
+    return path; // relpath / default / other
+}
+
+std::vector<float> parse_thresholds(const std::string &s) { // comma-separated list (query_pdb.rs parse_threshold_string)
+    std::vector<float> out;
+    size_t a = 0;
+    while (a <= s.size()) {
+        const size_t b = s.find(',', a);
+        const std::string tok = s.substr(a, b == std::string::npos ? std::string::npos : b - a);
+        if (!tok.empty()) {
+            char *end = nullptr;
+            const float x = strtof(tok.c_str(), &end);
+            if (end == tok.c_str()) die("invalid threshold '" + tok + "'");
+            out.push_back(x);
+        }
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    return out;
+}
+
+const char *HELP =
+    "usage: folddisco-b200 <command> [<args>]\n\n"
+    "subcommands:\n"
+    "  index     Create a new index table from a directory of PDB files (GPU)\n"
+    "  query     Query a motif from an index table (GPU)\n"
+    "  version   Print version information\n\n"
+    "index:  -p/--pdbs DIR  -i/--index PREFIX  [-t N] [-d NBIN_DIST] [-a NBIN_ANGLE] [-g GRID] [-n MAX_RESIDUE]\n"
+    "        [-r] [--id relpath|abspath|basename|filename|pdb] [--no-store] [-v]\n"
+    "query:  -p/--pdb FILE -q/--query RESIDUES | -q FILE.txt|.tsv   -i/--index PREFIX  [-t N]\n"
+    "        [-d DIST_THR[,..]] [-a ANGLE_THR[,..]] [--ca-distance X] [--total-match N] [--covered-node N]\n"
+    "        [--covered-node-ratio X] [--max-node N] [--max-node-ratio X] [--score X] [--connected-node N]\n"
+    "        [--connected-node-ratio X] [--num-residue N] [--plddt X] [--rmsd X] [--top N] [--sampling-count N]\n"
+    "        [--sampling-ratio X] [--freq-filter X] [--length-penalty X] [--per-structure|--per-match] [--skip-match]\n"
+    "        [--skip-ca-match] [--serial-index] [--header] [-o FILE] [-v]\n";
+
+int cmd_index(Args &a) {
+    a.reject({"--multiple-bins"}, "multiple-bin encoding is outside the ported path");
+    a.reject({"--mmap-on-disk"}, "the index is built in GPU memory");
+    const std::string dir = a.str({"-p", "--pdbs"}, "");
+    const std::string type = a.str({"-y", "--type"}, "default");
+    const std::string prefix = a.str({"-i", "--index"}, "");
+    const int threads = (int)a.num({"-t", "--threads"}, 1);
+    fd_hash_params hp;
+    hp.nbin_dist = (uint32_t)a.num({"-d", "--distance"}, 0);
+    hp.nbin_angle = (uint32_t)a.num({"-a", "--angle"}, 0);
+    hp.dist_cutoff = (float)a.num({"-g", "--grid"}, 20.0);
+    const uint64_t max_residue = (uint64_t)a.num({"-n", "--residue"}, 50000);
+    const bool recursive = a.flag({"-r", "--recursive"});
+    const std::string id_type = a.str({"--id"}, "relpath");
+    const bool verbose = a.flag({"-v", "--verbose"});
+    const bool no_store = a.flag({"--no-store"});
+    if (a.flag({"-h", "--help"})) {
+        fputs(HELP, stdout);
+        return 0;
+    }
+    a.finish();
+    if (type != "default" && type != "pdbtr" && type != "PDBTrRosetta" && type != "pdbtrrosetta")
+        die("hash type '" + type + "' is not supported by folddisco-b200 (only the default PDBTrRosetta encoding)");
+    if (dir.empty() || prefix.empty()) die("index needs -p DIR and -i PREFIX");
+    if (threads > 0) setenv("FD_HOST_THREADS", std::to_string(threads).c_str(), 0);
+    std::vector<std::string> files;
+    if (is_dir(dir)) list_files(dir, recursive, files);
+    else die(dir + " is not a directory (Foldcomp databases are not supported)");
+    if (files.empty()) die("no input files in " + dir);
+    for (auto &f : files)
+        if (!(ends_with(f, ".pdb") || ends_with(f, ".ent") || ends_with(f, ".PDB")))
+            die("unsupported input format (only .pdb / .ent): " + f);
+    if (verbose) fprintf(stderr, "[INFO] Indexing %zu files with PDBTrRosetta\n", files.size());
+    // parse on the host (file-parallel like the reference, mod.rs:298), keep file order
+    std::vector<fdh_compact *> comps(files.size(), nullptr);
+    {
+        std::vector<std::string> errs(files.size());
+        const int nt = std::max(1, std::min(fd_default_host_threads(), 64));
+        auto work = [&](int t) { // static interleaved partition
+            for (size_t k = (size_t)t; k < files.size(); k += (size_t)nt) {
+                comps[k] = fdh_compact_read_pdb(files[k].c_str());
+                if (!comps[k]) errs[k] = fdh_last_error();
+            }
+        };
+        { // the library's worker pool is internal; plain threads are fine for a once-per-run parse
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+        }
+        for (size_t k = 0; k < files.size(); k++)
+            if (!comps[k]) die("Failed to read structure " + files[k] + ": " + errs[k]);
+    }
+    fdh_store *store = fdh_store_new();
+    fdh_compact *empty = fdh_compact_from_soa(0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    for (size_t k = 0; k < files.size(); k++) {
+        const std::string id = make_id(files[k], id_type);
+        if ((uint64_t)fdh_compact_num_residues_raw(comps[k]) > max_residue) { // mod.rs:313-319: skipped, id slot kept
+            fprintf(stderr, "[WARN] %s has too many residues. Skipping\n", files[k].c_str());
+            if (!empty) die("internal: cannot create an empty structure");
+            fdh_store_add(store, empty, id.c_str());
+        } else {
+            fdh_store_add(store, comps[k], id.c_str());
+        }
+        fdh_compact_free(comps[k]);
+    }
+    if (empty) fdh_compact_free(empty);
+    fd_ctx *ctx = nullptr;
+    if (fd_create(&ctx, 0) != FD_OK) die(fd_last_error(nullptr));
+    fdh_index *ix = fdh_index_build(ctx, store, &hp);
+    if (!ix) die(fdh_last_error());
+    if (fdh_index_save(ix, store, prefix.c_str(), max_residue, nullptr) != FD_OK) die(fdh_last_error());
+    if (!no_store && fdh_store_save(store, (prefix + ".store").c_str()) != FD_OK) die(fdh_last_error());
+    if (verbose) {
+        fd_index_buffers b;
+        fdh_index_get(ix, &b);
+        fprintf(stderr, "[INFO] %llu structures, %llu residues, %llu hashes, %llu posting bytes -> %s\n",
+                (unsigned long long)fdh_store_size(store), (unsigned long long)fdh_store_num_residues(store),
+                (unsigned long long)b.count, (unsigned long long)b.value_bytes, prefix.c_str());
+    }
+    fdh_index_free(ix);
+    fdh_store_free(store);
+    fd_destroy(ctx);
+    return 0;
+}
+
+struct QueryJob {
+    std::string pdb, residues, output;
+};
+
+std::string residues_of(const fdh_results *R, const fdh_match_row &m, int64_t n_res) {
+    const fdh_residue_match *res = fdh_results_residues(R) + m.res_begin;
+    std::string s;
+    for (int64_t k = 0; k < n_res; k++) {
+        if (k) s += ',';
+        if (res[k].some) {
+            s += (char)res[k].chain;
+            s += std::to_string((unsigned long long)res[k].serial);
+        } else {
+            s += '_';
+        }
+    }
+    return s;
+}
+
+std::string escape_tsv(std::string s) { // formatter.rs:186-188
+    for (char &c : s)
+        if (c == '\t' || c == '\n') c = ' ';
+    return s;
+}
+
+int cmd_query(Args &a) {
+    a.reject({"--sort-by"}, "only the default sort orders are implemented");
+    a.reject({"--format-output"}, "only the default columns are implemented");
+    a.reject({"--superpose", "--web"}, "superposition output columns are not implemented");
+    a.reject({"--partial-fit"}, "LMS-QCP partial fit is outside the ported path");
+    a.reject({"--tm-score", "--gdt-ts", "--gdt-ha", "--chamfer", "--hausdorff"}, "similarity-metric filters are outside the ported path");
+    const std::string pdb_path = a.str({"-p", "--pdb"}, "");
+    const std::string query_string = a.str({"-q", "--query"}, "");
+    const int threads = (int)a.num({"-t", "--threads"}, 1);
+    const std::string prefix = a.str({"-i", "--index"}, "");
+    fdh_search_params sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.skip_match = a.flag({"--skip-match"}) ? 1 : 0;
+    const std::vector<float> dist_thr = parse_thresholds(a.str({"-d", "--distance"}, "0.5"));
+    const std::vector<float> angle_thr = parse_thresholds(a.str({"-a", "--angle"}, "5"));
+    sp.ca_dist_cutoff = (float)a.num({"--ca-distance"}, 1.0);
+    sp.prefilter.total_match_count = (uint64_t)a.num({"--total-match"}, 0);
+    sp.prefilter.covered_node_count = (uint64_t)a.num({"--covered-node"}, 0);
+    sp.prefilter.covered_node_ratio = (float)a.num({"--covered-node-ratio"}, 0.0);
+    sp.max_matching_node_count = (uint64_t)a.num({"--max-node"}, 0);
+    sp.max_matching_node_ratio = (float)a.num({"--max-node-ratio"}, 0.0);
+    sp.prefilter.idf_score_cutoff = (float)a.num({"--score"}, 0.0);
+    sp.connected_node_count = (uint64_t)a.num({"--connected-node"}, 0);
+    sp.connected_node_ratio = (float)a.num({"--connected-node-ratio"}, 0.0);
+    sp.prefilter.num_res_cutoff = (uint64_t)a.num({"--num-residue"}, 50000);
+    sp.prefilter.plddt_cutoff = (float)a.num({"--plddt"}, 0.0);
+    sp.rmsd_cutoff = (float)a.num({"--rmsd"}, 0.0);
+    const double top = a.num({"--top"}, -1);
+    sp.prefilter.top_n = top < 0 ? UINT64_MAX : (uint64_t)top;
+    sp.prefilter.sampling_count = (int64_t)a.num({"--sampling-count"}, -1);
+    sp.prefilter.sampling_ratio = (float)a.num({"--sampling-ratio"}, -1.0);
+    sp.prefilter.freq_filter = (float)a.num({"--freq-filter"}, -1.0);
+    sp.prefilter.length_penalty = (float)a.num({"--length-penalty"}, 0.5);
+    bool per_structure = a.flag({"--per-structure"});
+    const bool per_match = a.flag({"--per-match"});
+    sp.skip_ca_match = a.flag({"--skip-ca-match"}) ? 1 : 0;
+    const bool header = a.flag({"--header"});
+    const bool serial_query = a.flag({"--serial-index"});
+    const std::string output = a.str({"-o", "--output"}, "");
+    const bool verbose = a.flag({"-v", "--verbose"});
+    if (a.flag({"-h", "--help"})) {
+        fputs(HELP, stdout);
+        return 0;
+    }
+    a.finish();
+    if (per_structure && per_match)
+        die("Cannot print output per structure and per match at the same time. Use either --per-structure or --per-match");
+    if (sp.skip_match) per_structure = true; // QueryMode::SkipMatch prints structure rows (query_pdb.rs:186-203)
+    if (prefix.empty()) die("query needs -i PREFIX");
+    if (threads > 0) setenv("FD_HOST_THREADS", std::to_string(threads).c_str(), 0);
+
+    std::vector<QueryJob> jobs; // query_pdb.rs:297-315
+    if (ends_with(query_string, ".txt") || ends_with(query_string, ".tsv")) {
+        std::ifstream in(query_string);
+        if (!in) die("Failed to open query file: " + query_string);
+        std::string line;
+        while (std::getline(in, line)) {
+            if (line.empty()) continue;
+            QueryJob j;
+            const size_t t1 = line.find('\t');
+            j.pdb = line.substr(0, t1);
+            if (t1 != std::string::npos) {
+                const size_t t2 = line.find('\t', t1 + 1);
+                j.residues = line.substr(t1 + 1, t2 == std::string::npos ? std::string::npos : t2 - t1 - 1);
+                if (t2 != std::string::npos) {
+                    const size_t t3 = line.find('\t', t2 + 1);
+                    j.output = line.substr(t2 + 1, t3 == std::string::npos ? std::string::npos : t3 - t2 - 1);
+                }
+            }
+            jobs.push_back(j);
+        }
+    } else {
+        jobs.push_back(QueryJob{pdb_path, query_string, output});
+    }
+    if (jobs.empty()) die("no queries");
+    for (auto &j : jobs) {
+        if (j.pdb.empty()) die("query needs -p PDB (or a query file)");
+        if (j.residues.empty()) die("whole-structure queries (empty -q) are not supported by folddisco-b200");
+    }
+
+    fd_ctx *ctx = nullptr;
+    if (fd_create(&ctx, 0) != FD_OK) die(fd_last_error(nullptr));
+    fdh_index *ix = fdh_index_load(prefix.c_str());
+    if (!ix) die(fdh_last_error());
+    if (fdh_index_attach(ctx, ix) != FD_OK) die(fd_last_error(ctx));
+    const uint64_t S = fdh_index_num_structs(ix);
+    std::vector<uint32_t> nres(S);
+    std::vector<float> plddt(S);
+    fdh_index_get_lookup(ix, nres.data(), plddt.data());
+    // structures for the verification: PREFIX.store, else the files named by the lookup (index built by `folddisco`)
+    fdh_store *store = nullptr;
+    if (!sp.skip_match) {
+        const std::string sp_path = prefix + ".store";
+        if (is_file(sp_path)) {
+            store = fdh_store_load(sp_path.c_str());
+            if (!store) die(fdh_last_error());
+            if (fdh_store_size(store) != S) die(sp_path + " does not belong to this index (structure count differs)");
+        } else {
+            if (verbose) fprintf(stderr, "[INFO] %s not found: parsing the %llu structures named in the lookup\n", sp_path.c_str(), (unsigned long long)S);
+            store = fdh_store_new();
+            const size_t sl = prefix.find_last_of('/');
+            const std::string index_dir = sl == std::string::npos ? "" : prefix.substr(0, sl + 1);
+            for (uint64_t k = 0; k < S; k++) {
+                std::string p = fdh_index_name(ix, k);
+                if (!is_file(p)) p = index_dir + p; // resolve_tid_path_from_index_prefix (controller/io.rs:488-528)
+                fdh_compact *c = fdh_compact_read_pdb(p.c_str());
+                if (!c) die(std::string("Failed to read structure ") + fdh_index_name(ix, k) + ": " + fdh_last_error());
+                fdh_store_add(store, c, fdh_index_name(ix, k));
+                fdh_compact_free(c);
+            }
+        }
+        fd_struct_batch b;
+        if (fdh_store_batch(store, &b) != FD_OK) die(fdh_last_error());
+        if (fd_store_attach(ctx, &b) != FD_OK) die(fd_last_error(ctx));
+    }
+
+    fdh_query_params qp;
+    fdh_index_get_params(ix, &qp.hash);
+    qp.dist_thr = dist_thr.data();
+    qp.n_dist_thr = (int)dist_thr.size();
+    qp.angle_thr = angle_thr.data();
+    qp.n_angle_thr = (int)angle_thr.size();
+    qp.serial_query = serial_query ? 1 : 0;
+    fdh_queries *qs = fdh_queries_new(&qp);
+    {
+        std::vector<std::pair<std::string, fdh_compact *>> cache; // a query file usually repeats structures
+        for (auto &j : jobs) {
+            fdh_compact *c = nullptr;
+            for (auto &e : cache)
+                if (e.first == j.pdb) c = e.second;
+            if (!c) {
+                c = fdh_compact_read_pdb(j.pdb.c_str());
+                if (!c) die("Failed to read structure: " + j.pdb + ": " + fdh_last_error());
+                cache.emplace_back(j.pdb, c);
+            }
+            if (fdh_queries_add(qs, c, j.residues.c_str()) < 0) die(fdh_last_error());
+        }
+        for (auto &e : cache) fdh_compact_free(e.second);
+    }
+    if (fdh_queries_finalize(qs, ctx) != FD_OK) die(fdh_last_error());
+    if (verbose) fprintf(stderr, "[INFO] Querying %zu motif(s) to %s\n", jobs.size(), prefix.c_str());
+    fdh_results *R = fdh_search(ctx, qs, &sp, store);
+    if (!R) die(fdh_last_error());
+
+    const uint64_t *soff = fdh_results_struct_offsets(R), *moff = fdh_results_match_offsets(R);
+    const fdh_struct_row *srows = fdh_results_struct_rows(R);
+    const fdh_match_row *mrows = fdh_results_match_rows(R);
+    const uint64_t *morder = fdh_results_match_order(R);
+    for (size_t q = 0; q < jobs.size(); q++) {
+        FILE *out = stdout;
+        if (!jobs[q].output.empty()) {
+            out = fopen(jobs[q].output.c_str(), "wb");
+            if (!out) die("Failed to create file: " + jobs[q].output);
+        }
+        const int64_t n_res = fdh_queries_num_indices(qs, (int64_t)q);
+        const std::string qres = escape_tsv(jobs[q].residues);
+        if (per_structure) { // STRUCTURE_RESULT_DEFAULT_COLUMNS (result.rs:300-313)
+            if (header)
+                fputs("tid\tidf\ttotal_match_count\tnode_count\tedge_count\tmax_node_cov\tmin_rmsd\tnres\tplddt\t"
+                      "matching_residues\tdb_key\tquery_residues\n", out);
+            for (uint64_t k = soff[q]; k < soff[q + 1]; k++) {
+                const fdh_struct_row &r = srows[k];
+                std::string mr;
+                for (uint64_t m = r.match_begin; m < r.match_end; m++) {
+                    char buf[32];
+                    snprintf(buf, sizeof(buf), ":%.4f", (double)mrows[m].rmsd);
+                    if (!mr.empty()) mr += ';';
+                    mr += residues_of(R, mrows[m], n_res);
+                    mr += buf;
+                }
+                if (mr.empty()) mr = "NA";
+                fprintf(out, "%s\t%.4f\t%u\t%u\t%u\t%u\t%.4f\t%u\t%.2f\t%s\t%llu\t%s\n",
+                        escape_tsv(fdh_index_name(ix, r.nid)).c_str(), (double)r.idf, r.total_match_count, r.node_count,
+                        r.edge_count, r.max_matching_node_count, (double)r.min_rmsd_with_max_match, nres[r.nid],
+                        (double)plddt[r.nid], mr.c_str(), (unsigned long long)fdh_index_db_key(ix, r.nid), qres.c_str());
+            }
+        } else { // MATCH_RESULT_DEFAULT_COLUMNS (result.rs:330-338); --top truncates the sorted rows too (:466-471)
+            if (header) fputs("tid\tnode_count\tidf\trmsd\tmatching_residues\tquery_residues\n", out);
+            uint64_t printed = 0;
+            for (uint64_t k = moff[q]; k < moff[q + 1] && printed < sp.prefilter.top_n; k++, printed++) {
+                const fdh_match_row &m = mrows[morder[k]];
+                fprintf(out, "%s\t%u\t%.4f\t%.4f\t%s\t%s\n", escape_tsv(fdh_index_name(ix, m.nid)).c_str(), m.node_count,
+                        (double)m.idf, (double)m.rmsd, residues_of(R, m, n_res).c_str(), qres.c_str());
+            }
+        }
+        if (out != stdout) fclose(out);
+    }
+    fdh_results_free(R);
+    fdh_queries_free(qs);
+    if (store) fdh_store_free(store);
+    fdh_index_free(ix);
+    fd_destroy(ctx);
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
+        fputs(HELP, stdout);
+        return argc < 2 ? 1 : 0;
+    }
+    const std::string cmd = argv[1];
+    Args a(argc, argv);
+    if (cmd == "index") return cmd_index(a);
+    if (cmd == "query") return cmd_query(a);
+    if (cmd == "version") {
+        printf("%s\n", fd_version());
+        return 0;
+    }
+    if (cmd == "benchmark" || cmd == "analyze")
+        die("sub-command '" + cmd + "' is outside the ported path (use the reference binary on the produced TSV)");
+    die("Invalid subcommand");
+}

@@ -297,6 +297,7 @@ struct fdh_index {
     std::vector<std::string> names;
     std::vector<uint32_t> nres;
     std::vector<float> plddt;
+    std::vector<uint64_t> db_key; // 5th lookup column (lookup.rs:17-58); empty = the structure id
     fd_hash_params params{0, 0, 20.0f};
     ~fdh_index() {
         if (map_off) munmap(map_off, map_off_len);
@@ -1018,6 +1019,92 @@ int64_t fdh_store_add_soa(fdh_store *s, uint64_t S, const uint64_t *ro, const fl
     }
     return first;
 }
+// ---- PREFIX.store: on-disk companion of the index holding the compact structures (SoA), so that a query run needs
+// no per-candidate file parse (the reference re-reads and re-parses every candidate, retrieve.rs:375).  Layout:
+//   "FDB2STR1" | u64 n_structs | u64 n_residues | row_offsets u64[S+1] | n, ca, cb f32[3R] each | aa u8[R] |
+//   cb_valid u8[R] | chain u8[R] | serial u64[R] | plddt f32[S] | names: S x (u32 length, bytes)
+int fdh_store_save(const fdh_store *s, const char *path) {
+    FILE *f = fopen(path, "wb");
+    if (!f) {
+        set_err(std::string("cannot write ") + path);
+        return FD_ERR_ARG;
+    }
+    const uint64_t S = s->names.size(), R = s->row_offsets.back();
+    bool ok = fwrite("FDB2STR1", 1, 8, f) == 8 && fwrite(&S, 8, 1, f) == 1 && fwrite(&R, 8, 1, f) == 1;
+    auto wr = [&](const void *p, size_t bytes) { ok = ok && (bytes == 0 || fwrite(p, 1, bytes, f) == bytes); };
+    wr(s->row_offsets.data(), 8 * (S + 1));
+    wr(s->n.data(), 12 * R);
+    wr(s->ca.data(), 12 * R);
+    wr(s->cb.data(), 12 * R);
+    wr(s->aa.data(), R);
+    wr(s->cb_valid.data(), R);
+    wr(s->chain.data(), R);
+    wr(s->serial.data(), 8 * R);
+    wr(s->plddt.data(), 4 * S);
+    for (uint64_t k = 0; k < S; k++) {
+        const uint32_t len = (uint32_t)s->names[k].size();
+        wr(&len, 4);
+        wr(s->names[k].data(), len);
+    }
+    if (fclose(f) != 0) ok = false;
+    if (!ok) {
+        set_err(std::string("write error on ") + path);
+        return FD_ERR_ARG;
+    }
+    return FD_OK;
+}
+
+fdh_store *fdh_store_load(const char *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_err(std::string("cannot open ") + path);
+        return nullptr;
+    }
+    char magic[8];
+    uint64_t S = 0, R = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "FDB2STR1", 8) == 0 && fread(&S, 8, 1, f) == 1 &&
+              fread(&R, 8, 1, f) == 1;
+    fdh_store *s = new fdh_store();
+    auto rd = [&](void *p, size_t bytes) { ok = ok && (bytes == 0 || fread(p, 1, bytes, f) == bytes); };
+    if (ok) {
+        s->row_offsets.resize(S + 1);
+        s->n.resize(3 * R);
+        s->ca.resize(3 * R);
+        s->cb.resize(3 * R);
+        s->aa.resize(R);
+        s->cb_valid.resize(R);
+        s->chain.resize(R);
+        s->serial.resize(R);
+        s->plddt.resize(S);
+        s->names.resize(S);
+        rd(s->row_offsets.data(), 8 * (S + 1));
+        rd(s->n.data(), 12 * R);
+        rd(s->ca.data(), 12 * R);
+        rd(s->cb.data(), 12 * R);
+        rd(s->aa.data(), R);
+        rd(s->cb_valid.data(), R);
+        rd(s->chain.data(), R);
+        rd(s->serial.data(), 8 * R);
+        rd(s->plddt.data(), 4 * S);
+        for (uint64_t k = 0; k < S && ok; k++) {
+            uint32_t len = 0;
+            rd(&len, 4);
+            if (ok && len > (1u << 20)) ok = false;
+            if (ok) {
+                s->names[k].resize(len);
+                rd(&s->names[k][0], len);
+            }
+        }
+        ok = ok && s->row_offsets[0] == 0 && s->row_offsets[S] == R;
+    }
+    fclose(f);
+    if (!ok) {
+        set_err(std::string("not a structure store (or truncated): ") + path);
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
 uint64_t fdh_store_size(const fdh_store *s) { return s->names.size(); }
 uint64_t fdh_store_num_residues(const fdh_store *s) { return s->row_offsets.back(); }
 void fdh_store_get_lookup(const fdh_store *s, uint32_t *nres, float *plddt) {
@@ -1237,6 +1324,8 @@ fdh_index *fdh_index_load(const char *prefix) {
             ix->names.push_back(line.substr(a + 1, b - a - 1));
             ix->nres.push_back((uint32_t)strtoul(line.substr(b + 1, c - b - 1).c_str(), nullptr, 10));
             ix->plddt.push_back(strtof(line.substr(c + 1, d == std::string::npos ? std::string::npos : d - c - 1).c_str(), nullptr));
+            ix->db_key.push_back(d == std::string::npos ? (uint64_t)(ix->names.size() - 1)
+                                                        : (uint64_t)strtoull(line.c_str() + d + 1, nullptr, 10));
         }
     }
     { // type (TOML subset written by the reference)
@@ -1267,6 +1356,7 @@ void fdh_index_get_lookup(const fdh_index *ix, uint32_t *nres, float *plddt) {
     if (nres) memcpy(nres, ix->nres.data(), 4 * ix->nres.size());
     if (plddt) memcpy(plddt, ix->plddt.data(), 4 * ix->plddt.size());
 }
+uint64_t fdh_index_db_key(const fdh_index *ix, uint64_t id) { return id < ix->db_key.size() ? ix->db_key[id] : id; }
 const char *fdh_index_name(const fdh_index *ix, uint64_t id) { return id < ix->names.size() ? ix->names[id].c_str() : ""; }
 void fdh_index_get_params(const fdh_index *ix, fd_hash_params *p) { *p = ix->params; }
 int fdh_index_attach(fd_ctx *ctx, const fdh_index *ix) {

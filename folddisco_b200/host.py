@@ -75,6 +75,8 @@ def _lib():
     sig("fdh_store_name", C.c_char_p, [VP, C.c_uint64])
     sig("fdh_store_batch", C.c_int, [VP, PP(_StructBatch)])
     sig("fdh_store_free", None, [VP])
+    sig("fdh_store_save", C.c_int, [VP, C.c_char_p])
+    sig("fdh_store_load", VP, [C.c_char_p])
     sig("fdh_index_build", VP, [VP, VP, PP(HashParams)])
     sig("fdh_index_from_buffers", VP, [PP(_IndexBuffers), VP, PP(HashParams)])
     sig("fdh_index_save", C.c_int, [VP, VP, C.c_char_p, C.c_uint64, C.c_char_p])
@@ -204,8 +206,20 @@ def parse_query_string(q, default_chain=ord("A")):
 class Store:
     """The database: an ordered set of CompactStructures (ids = positions = `.lookup` ids)."""
 
-    def __init__(self):
-        self.h = _lib().fdh_store_new()
+    def __init__(self, handle=None):
+        self.h = handle if handle is not None else _lib().fdh_store_new()
+
+    def save(self, path):
+        """PREFIX.store: the on-disk companion of the index (fdh_store_save)"""
+        if _lib().fdh_store_save(self.h, path.encode()) != 0:
+            raise FdError(_err())
+
+    @classmethod
+    def load(cls, path):
+        h = _lib().fdh_store_load(path.encode())
+        if not h:
+            raise FdError(_err())
+        return cls(h)
 
     def add(self, compact, name):
         return _lib().fdh_store_add(self.h, compact.h, name.encode())

@@ -60,6 +60,10 @@ int64_t fdh_store_add(fdh_store *s, const fdh_compact *c, const char *name);
 /* bulk add of n structures from one SoA (synthetic data); names are "prefix%llu" */
 int64_t fdh_store_add_soa(fdh_store *s, uint64_t n_structs, const uint64_t *row_offsets, const float *n_xyz,
                           const float *ca_xyz, const float *cb_xyz, const uint8_t *aa, const char *name_prefix);
+/* PREFIX.store: binary companion of the index with the compact structures, so `query` needs no per-candidate file
+ * parse (the reference re-reads every candidate structure, retrieve.rs:375).  Layout in fd_host.cpp. */
+int fdh_store_save(const fdh_store *s, const char *path);
+fdh_store *fdh_store_load(const char *path); /* NULL + fdh_last_error() on failure */
 uint64_t fdh_store_size(const fdh_store *s);
 uint64_t fdh_store_num_residues(const fdh_store *s);
 void fdh_store_get_lookup(const fdh_store *s, uint32_t *nres, float *plddt);
@@ -82,6 +86,7 @@ int fdh_index_get(const fdh_index *ix, fd_index_buffers *view); /* pointers owne
 uint64_t fdh_index_num_structs(const fdh_index *ix);
 void fdh_index_get_lookup(const fdh_index *ix, uint32_t *nres, float *plddt);
 const char *fdh_index_name(const fdh_index *ix, uint64_t id);
+uint64_t fdh_index_db_key(const fdh_index *ix, uint64_t id); /* 5th column of PREFIX.lookup */
 void fdh_index_get_params(const fdh_index *ix, fd_hash_params *params);
 /* fd_index_attach with this index and its lookup */
 int fdh_index_attach(fd_ctx *ctx, const fdh_index *ix);

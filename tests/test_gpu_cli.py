@@ -1,0 +1,132 @@
+"""`folddisco-b200 index | query` (csrc/host/fd_cli.cpp) end to end on the GPU: the reference's config 1
+(README.md:200-241) through the command line -- files on disk in the reference's layout, TSV rows equal to the
+README's.  PDB files are re-written from the committed atom fixtures (/root/reference does not exist on the GPU box).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fixtures as F
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "folddisco_b200", "folddisco-b200")
+
+
+def write_pdb(path, a):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        for k in range(len(a["x"])):
+            f.write("ATOM  %5d %4s %3s %c%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (
+                (k + 1) % 100000, bytes(a["atom_name"][k]).decode(), bytes(a["res_name"][k]).decode(),
+                chr(int(a["chain"][k])), int(a["res_serial"][k]), a["x"][k], a["y"][k], a["z"][k], 1.0,
+                a["b_factor"][k]))
+        f.write("END\n")
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("cli"))
+    for name, atoms in F.config1_atoms().items():
+        write_pdb(os.path.join(d, name), atoms)
+    os.makedirs(os.path.join(d, "idx"))
+    r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/serine", "-t", "4", "-v"], cwd=d,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return d
+
+
+def run(d, *args):
+    r = subprocess.run([CLI] + list(args), cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return [ln.split("\t") for ln in r.stdout.splitlines()]
+
+
+def test_index_files_have_the_reference_layout(workdir):
+    p = os.path.join(workdir, "idx", "serine")
+    assert os.path.getsize(p) == F.CONFIG1_VALUE_BYTES
+    assert os.path.getsize(p + ".offset") == F.CONFIG1_OFFSET_FILE_BYTES
+    with open(p + ".offset", "rb") as f:
+        assert int(np.frombuffer(f.read(8), np.uint64)[0]) == F.CONFIG1_NUM_HASHES
+    lookup = [ln.rstrip("\n").split("\t") for ln in open(p + ".lookup")]
+    assert [r[1] for r in lookup] == ["data/serine_peptidases/%s" % n for n in
+                                      ("1azw.pdb", "1ju3.pdb", "1l7a.pdb", "1pq5.pdb", "4cha.pdb")]
+    for r in lookup:  # id, path, nres, plddt, db_key (lookup.rs:17-58)
+        want = F.README_STRUCT_ROWS[os.path.basename(r[1])]
+        assert int(r[2]) == want[4] and abs(float(r[3]) - want[5]) < 1e-3 and int(r[4]) == want[6] == int(r[0])
+    t = open(p + ".type").read()
+    assert 'hash_type = "PDBTrRosetta"' in t and "num_bin_dist = 0" in t and "grid_width = 20.0" in t
+    assert os.path.exists(p + ".store")
+
+
+def test_query_match_rows_equal_readme(workdir):
+    rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine", "--header")
+    assert rows[0] == ["tid", "node_count", "idf", "rmsd", "matching_residues", "query_residues"]
+    want = [["data/serine_peptidases/" + t, str(n), "%.4f" % i, "%.4f" % r, s, "B57,B102,C195"]
+            for t, n, i, r, s in F.README_MATCH_ROWS_DEFAULT]
+    assert rows[1:] == want  # README.md:218-223, in the README's order
+    rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine", "--ca-distance", "1.5")
+    t, n, i, r, s = F.README_MATCH_ROW_1AZW_CA15
+    assert ["data/serine_peptidases/" + t, str(n), "%.4f" % i, "%.4f" % r, s, "B57,B102,C195"] in rows
+    rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine", "--top", "2")
+    assert rows == want[:2]  # --top limits the candidates (query_pdb.rs:404-411) and the printed rows (result.rs:466-471)
+
+
+def test_query_structure_rows_equal_readme(workdir):
+    rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine", "--per-structure",
+               "--header")
+    assert rows[0] == ["tid", "idf", "total_match_count", "node_count", "edge_count", "max_node_cov", "min_rmsd", "nres",
+                       "plddt", "matching_residues", "db_key", "query_residues"]
+    got = {os.path.basename(r[0]): r for r in rows[1:]}
+    # the 1azw match needs --ca-distance 1.5 under the current code (golden 3): its row stays, without
+    # matches, only if filter_after_matching keeps it -- it does not at the defaults
+    for tid, (idf, tot, nc, ec, nres, plddt, key) in F.README_STRUCT_ROWS.items():
+        if tid == "1azw.pdb":
+            continue
+        r = got[tid]
+        assert r[1] == "%.4f" % idf and [int(x) for x in r[2:5]] == [tot, nc, ec]
+        assert int(r[7]) == nres and r[8] == "%.2f" % plddt and int(r[10]) == key and r[11] == "B57,B102,C195"
+    assert got["4cha.pdb"][9] == "B57,B102,C195:0.0000;F57,F102,G195:0.0874" and got["4cha.pdb"][5:7] == ["3", "0.0000"]
+    assert got["1l7a.pdb"][9] == "_,A146,A127:0.7883;_,B146,B127:0.8078"
+    # idf descending (query_pdb.rs:404, sort.rs:454-458)
+    idfs = [float(r[1]) for r in rows[1:]]
+    assert idfs == sorted(idfs, reverse=True)
+
+
+def test_query_skip_match_and_query_file(workdir):
+    rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine", "--skip-match")
+    assert len(rows) == 5 and all(r[9] == "NA" for r in rows)
+    assert {os.path.basename(r[0]): r[1] for r in rows} == {t: "%.4f" % v[0] for t, v in F.README_STRUCT_ROWS.items()}
+    with open(os.path.join(workdir, "queries.tsv"), "w") as f:
+        f.write("query/4CHA.pdb\tB57,B102,C195\tout_serine.tsv\n")
+        f.write("query/1G2F.pdb\tF207,F212,F225,F229\tout_zinc.tsv\n")
+    assert run(workdir, "query", "-q", "queries.tsv", "-i", "idx/serine") == []
+    got = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(workdir, "out_serine.tsv"))]
+    assert [r[:5] for r in got] == [["data/serine_peptidases/" + t, str(n), "%.4f" % i, "%.4f" % r, s]
+                                    for t, n, i, r, s in F.README_MATCH_ROWS_DEFAULT]
+    assert os.path.exists(os.path.join(workdir, "out_zinc.tsv"))
+
+
+def test_query_without_store_parses_the_lookup_files(workdir):
+    """an index written by the reference has no PREFIX.store: the structures are parsed from the lookup's paths"""
+    p = os.path.join(workdir, "idx", "serine.store")
+    os.rename(p, p + ".away")
+    try:
+        rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine")
+    finally:
+        os.rename(p + ".away", p)
+    assert [r[:5] for r in rows] == [["data/serine_peptidases/" + t, str(n), "%.4f" % i, "%.4f" % r, s]
+                                     for t, n, i, r, s in F.README_MATCH_ROWS_DEFAULT]
+
+
+def test_unsupported_options_fail_loudly(workdir):
+    for extra in (["--partial-fit"], ["--sort-by", "rmsd"], ["--tm-score", "0.5"]):
+        r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"] + extra,
+                           cwd=workdir, capture_output=True, text=True)
+        assert r.returncode != 0 and "not supported" in r.stderr
+    r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", "pdb"], cwd=workdir,
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported" in r.stderr

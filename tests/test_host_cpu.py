@@ -154,3 +154,40 @@ def test_pdb_reader_on_reference_files(host):
     assert host.read_structure_from_path(REF + "/data/homeobox/1akha-.pdb").num_residues == 49  # pdb.rs:142
     with pytest.raises(Exception):
         host.read_structure_from_path("/nonexistent/x.pdb")
+
+
+def test_store_file_round_trip(host, tmp_path):
+    """PREFIX.store (fdh_store_save / fdh_store_load): the arrays a query run attaches come back bit for bit"""
+    import ctypes as C
+    atoms = F.config1_atoms()
+    st = host.Store()
+    names = F.serine_names()
+    for n in names:
+        st.add(host.CompactStructure.from_atoms(atoms[n]), n)
+    p = str(tmp_path / "x.store")
+    st.save(p)
+    back = host.Store.load(p)
+    assert len(back) == len(st) == 5 and back.num_residues == st.num_residues
+    assert [back.name(i) for i in range(5)] == names
+    for a, b in zip(st.lookup(), back.lookup()):
+        assert np.array_equal(a, b)
+    va, vb = st.batch_view(), back.batch_view()
+    R = st.num_residues
+    for f, n in (("n_xyz", 12 * R), ("ca_xyz", 12 * R), ("cb_xyz", 12 * R), ("aa", R), ("cb_valid", R)):
+        assert C.string_at(getattr(va, f), n) == C.string_at(getattr(vb, f), n)
+    with open(p, "r+b") as fh:  # a truncated or foreign file is refused
+        fh.truncate(1000)
+    with pytest.raises(Exception):
+        host.Store.load(p)
+
+
+def test_cli_fails_loudly_without_a_gpu():
+    """the command-line front end has no CPU path either"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "folddisco_b200", "folddisco-b200")
+    r = subprocess.run([cli, "query", "-p", "x.pdb", "-q", "A1,A2", "-i", "nowhere"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    assert subprocess.run([cli, "version"], capture_output=True, text=True).stdout.startswith("folddisco_b200")

@@ -217,16 +217,24 @@ def run_ours(args, rank, world, local_rank):
     stages = ("lookup", "scan", "select", "verify", "verify_edges", "verify_components", "verify_kabsch", "edges", "kabsch")
     hv = ("hv_flatten", "hv_upload", "hv_candidates", "hv_issue", "hv_wait_chunks", "hv_copy_tail")  # host wall clock inside the verification call
 
+    prep_ms = {"query_maps": 0.0, "finalize": 0.0, "calls": 0}  # host wall clock of the e2e-only part of a step
+
     def make_batch():
         """this rank's args.batch queries of the global batch (query number q uses motif q mod 5)"""
+        t0 = time.perf_counter()
         qb = host.QueryBatch(index.params)
         ks = range(rank * args.batch, (rank + 1) * args.batch)
         qb.add_many([motif_structs[k % len(motif_structs)][0] for k in ks],
                     [motif_structs[k % len(motif_structs)][1] for k in ks])
+        t1 = time.perf_counter()
         if sharded is None:
             qb.finalize(ctx)
         else:
             sharded.prepare(ctx, qb, dist)
+        t2 = time.perf_counter()
+        prep_ms["query_maps"] += (t1 - t0) * 1e3
+        prep_ms["finalize"] += (t2 - t1) * 1e3
+        prep_ms["calls"] += 1
         return qb
 
     def search(qb):
@@ -323,6 +331,9 @@ def run_ours(args, rank, world, local_rank):
         "stages_ms_per_step": {s: st1[s][0] / max(1, args.steps) for s in stages},
         "host_ms_per_step": res.host_ms, "search_wall_ms": res.wall_ms,
         "verify_host_wall_ms": {s[3:]: st1[s][0] / max(1, args.steps) for s in hv},
+        "e2e_prepare_host_ms": {"query_maps (make_query_map x batch)": prep_ms["query_maps"] / max(1, prep_ms["calls"]),
+                                "finalize (posting counts -> idf, verification tables -> device)":
+                                    prep_ms["finalize"] / max(1, prep_ms["calls"])},
         "timing": "CUDA events around each step (max over ranks); wall-clock cross-check %.3f ms/step" % (
             1e3 * sum(wall_t) / max(1, args.steps)),
         "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows},

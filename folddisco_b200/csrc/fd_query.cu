@@ -481,9 +481,10 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
             const uint16_t *edge_node, const uint16_t *edge_group, const float *idf_sum_per_query, const float *pen, uint32_t tile_ids,
             FilterParams fp, const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits,
             uint32_t *dense /* MODE 1: [planes][nq][N]; MODE 2: sparse record pool */, SparseOut sp,
-            int stage_lists /* per-list byte range / vote word / edge bit staged in shared memory */) {
+            int stage_lists /* per-list byte range / vote word / edge bit staged in shared memory */,
+            const uint32_t *qlist /* MODE 0: the queries of this launch (one launch per edge-word class), or NULL */) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const uint32_t q = blockIdx.y;
+    const uint32_t q = qlist ? qlist[blockIdx.y] : blockIdx.y;
     const QueryDesc qd = queries[q];
     const uint32_t lo = blockIdx.x * tile_ids;
     const uint32_t hi = min(ix.n_structs, lo + tile_ids);
@@ -1018,7 +1019,12 @@ struct TilePlan {
     size_t smem;
 };
 
-int plan_tiles(fd_ctx *ctx, const Batch &B, uint32_t N, TilePlan &tp) {
+int plan_tiles(fd_ctx *ctx, const Batch &B0, uint32_t N, TilePlan &tp, int ew = 0) {
+    struct {
+        bool narrow;
+        int ew;
+        uint32_t max_hashes, max_nodes;
+    } B{B0.narrow, ew > 0 ? ew : B0.ew, B0.max_hashes, B0.max_nodes};
     const uint32_t bytes_per_id = (B.narrow ? 4 : 8) + 4 * B.ew;
     // Every tile's CTA walks all of the query's short lists, so fewer, larger tiles decode less: when the id range
     // fits the shared memory of one or two SMs a query gets 1024-thread CTAs with 220 KB tiles; otherwise 256-thread
@@ -1051,12 +1057,13 @@ int plan_tiles(fd_ctx *ctx, const Batch &B, uint32_t N, TilePlan &tp) {
 
 template <bool NARROW, int EW, int MODE>
 int launch_scan_t(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
-                  const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense, SparseOut sp) {
+                  const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense, SparseOut sp,
+                  const uint32_t *qlist) {
     auto kern = k3_scan<NARROW, EW, MODE>;
     FD_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem));
     kern<<<grid, tp.threads, tp.smem, ctx->stream>>>(ix, B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p,
                                                      B.d_edge_group.p, B.d_idfsum.p, B.d_pen.p, tp.tile_ids, fp, hit_offsets, hit_counts,
-                                                     hits, dense, sp, k3_stage_lists(B.max_hashes) ? 1 : 0);
+                                                     hits, dense, sp, k3_stage_lists(B.max_hashes) ? 1 : 0, qlist);
     ctx->launches++;
     return FD_OK;
 }
@@ -1064,18 +1071,19 @@ int launch_scan_t(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, cons
 template <int MODE>
 int launch_scan(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
                 const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense,
-                SparseOut sp = SparseOut{nullptr, nullptr, nullptr, 0}) {
+                SparseOut sp = SparseOut{nullptr, nullptr, nullptr, 0}, const uint32_t *qlist = nullptr, int ew = 0) {
+    if (ew <= 0) ew = B.ew;
 #define FD_SCAN_CASE(NARROW, EW) \
-    return launch_scan_t<NARROW, EW, MODE>(ctx, grid, tp, ix, B, fp, hit_offsets, hit_counts, hits, dense, sp)
+    return launch_scan_t<NARROW, EW, MODE>(ctx, grid, tp, ix, B, fp, hit_offsets, hit_counts, hits, dense, sp, qlist)
     if (B.narrow) {
-        if (B.ew == 1) FD_SCAN_CASE(true, 1);
-        else if (B.ew == 2) FD_SCAN_CASE(true, 2);
-        else if (B.ew == 4) FD_SCAN_CASE(true, 4);
+        if (ew == 1) FD_SCAN_CASE(true, 1);
+        else if (ew == 2) FD_SCAN_CASE(true, 2);
+        else if (ew == 4) FD_SCAN_CASE(true, 4);
         else FD_SCAN_CASE(true, 8);
     } else {
-        if (B.ew == 1) FD_SCAN_CASE(false, 1);
-        else if (B.ew == 2) FD_SCAN_CASE(false, 2);
-        else if (B.ew == 4) FD_SCAN_CASE(false, 4);
+        if (ew == 1) FD_SCAN_CASE(false, 1);
+        else if (ew == 2) FD_SCAN_CASE(false, 2);
+        else if (ew == 4) FD_SCAN_CASE(false, 4);
         else FD_SCAN_CASE(false, 8);
     }
 #undef FD_SCAN_CASE
@@ -1315,12 +1323,35 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
         FD_CUDA(ctx, d_hits.alloc(hit_off[nq]));
         FD_CUDA(ctx, cudaMemcpyAsync(d_hit_off.p, hit_off.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s));
         FD_CUDA(ctx, cudaMemsetAsync(d_hit_cnt.p, 0, nq * 4, s));
-        TilePlan tp;
-        FD_TRY(plan_tiles(ctx, B, N, tp));
+        // One launch per edge-word class: a query with <= 32 vote bits needs 8 B of shared memory per structure, one
+        // with 33..64 needs 12 B, ...; sizing every tile for the widest query of the batch would split the narrow ones
+        // into more tiles than they need (every tile of a query walks all of its short lists again).
+        std::vector<uint32_t> qorder;
+        uint32_t class_begin[5] = {0, 0, 0, 0, 0};
+        const int class_ew[4] = {1, 2, 4, 8};
+        for (int c = 0; c < 4; c++) {
+            for (uint32_t q = 0; q < nq; q++) {
+                const uint32_t need = std::max(1u, (B.descs[q].n_edges + 31) / 32);
+                const int cls = need <= 1 ? 0 : need <= 2 ? 1 : need <= 4 ? 2 : 3;
+                if (cls == c) qorder.push_back(q);
+            }
+            class_begin[c + 1] = (uint32_t)qorder.size();
+        }
+        DevBuf<uint32_t> d_qorder;
+        FD_CUDA(ctx, d_qorder.alloc(nq));
+        FD_CUDA(ctx, cudaMemcpyAsync(d_qorder.p, qorder.data(), nq * 4, cudaMemcpyHostToDevice, s));
         {
             StageTimer st(ctx, "scan");
-            FD_TRY(launch_scan<0>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
-                                      d_hit_cnt.p, d_hits.p, nullptr));
+            for (int c = 0; c < 4; c++) {
+                const uint32_t nc = class_begin[c + 1] - class_begin[c];
+                if (!nc) continue;
+                const int ew = std::min(class_ew[c], B.ew);
+                TilePlan tp;
+                FD_TRY(plan_tiles(ctx, B, N, tp, ew));
+                FD_TRY(launch_scan<0>(ctx, dim3(tp.n_tiles, nc), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
+                                      d_hit_cnt.p, d_hits.p, nullptr, SparseOut{nullptr, nullptr, nullptr, 0},
+                                      d_qorder.p + class_begin[c], ew));
+            }
             FD_CUDA(ctx, st.finish());
         }
         return select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, params->top_n, N, out_hits, h_off);

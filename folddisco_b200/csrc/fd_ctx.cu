@@ -178,6 +178,26 @@ int fd_default_host_threads(void) {
     return hc ? (int)hc : 1;
 }
 
+// parity probe (host build of fd_geom.cuh, no device needed): for residue pairs (i, j) of one SoA structure the exact
+// hash, the fast-route hash (0 when the fast route declined) and whether it declined
+void fd_pair_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_xyz, const uint8_t *aa,
+                       const uint32_t *pi, const uint32_t *pj, uint64_t n_pairs, const fd_hash_params *params,
+                       uint32_t *out_exact, uint32_t *out_fast, uint8_t *out_declined) {
+    const fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
+    auto ld = [](const float *p, uint64_t r) { return fdg::V3{p[3 * r], p[3 * r + 1], p[3 * r + 2]}; };
+    for (uint64_t k = 0; k < n_pairs; k++) {
+        const uint64_t i = pi[k], j = pj[k];
+        const float d = fdg::dist(ld(ca_xyz, i), ld(ca_xyz, j));
+        out_exact[k] = fdg::pair_hash(ld(n_xyz, i), ld(ca_xyz, i), ld(cb_xyz, i), ld(n_xyz, j), ld(ca_xyz, j),
+                                      ld(cb_xyz, j), aa[i], aa[j], d, hp);
+        uint32_t h = 0;
+        const bool ok = fdg::pair_hash_fast(ld(n_xyz, i), ld(ca_xyz, i), ld(cb_xyz, i), ld(n_xyz, j), ld(ca_xyz, j),
+                                            ld(cb_xyz, j), aa[i], aa[j], d, hp, &h);
+        out_fast[k] = ok ? h : 0u;
+        out_declined[k] = ok ? 0 : 1;
+    }
+}
+
 // parity / debug probe: runs a region of nt workers that each spin for `spin_us`; returns how many distinct host
 // threads took part (the pool is healthy when the answer is nt)
 int fd_parallel_probe(int nt, int spin_us) {

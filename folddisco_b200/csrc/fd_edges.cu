@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(K4_THREADS)
                             np++;
                         }
                     if (MODE == 0 && np) atomicAdd(n_pairs, (unsigned long long)np);
-                    const uint32_t h = fdg::pair_hash(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
+                    const uint32_t h = fdg::pair_hash_auto(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
                                                       ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj), ci,
                                                       cj, d, hp);
                     // membership in the query hash set

@@ -136,4 +136,67 @@ FD_HD uint32_t pair_hash(V3 n1, V3 ca1, V3 cb1, V3 n2, V3 ca2, V3 cb2, uint8_t a
     return perfect_hash(f, p);
 }
 
+// ---- fast path of the angle bins ---------------------------------------------------------------------------------
+// perfect_hash needs only the BINS of sin / cos of the three angles, and the angles are themselves acos / atan2 of
+// quantities the feature already has:
+//     ca_cb_angle = acos(c)       =>  cos = c,  sin = sqrt(1 - c^2)
+//     torsion     = -atan2(y, x)  =>  sin = -y / sqrt(x^2 + y^2),  cos = x / sqrt(x^2 + y^2)
+// The reference's f32 chain (acosf / atan2f rounded to f32, then sinf / cosf rounded to f32) stays within 4e-7 of
+// these closed forms (half an ulp of an angle <= pi is 1.2e-7, sin and cos are 1-Lipschitz, one more rounding of
+// 6e-8), the f32 evaluation below adds < 4e-6, and discretize() scales by at most 1.5: the value that is truncated
+// to the bin differs by < 1e-5 between the two routes.  So when that value is at least 1e-4 away from an integer
+// the bin is decided without any trigonometry; otherwise (about one pair in a thousand, and for degenerate
+// geometry) the caller falls back to the exact route.  pair_hash_auto therefore returns exactly pair_hash's value.
+FD_HD bool fast_bin(float val, float nbin, uint32_t *out) {
+    float cont_f = FD_DIV(FD_SUB(1.0f, -1.0f), FD_SUB(nbin, 1.0f));
+    float disc_f = FD_DIV(1.0f, cont_f);
+    float t = FD_ADD(FD_MUL(FD_SUB(val, -1.0f), disc_f), 0.5f);
+    float fr = FD_SUB(t, floorf(t));
+    if (!(fr > 1.0e-4f && fr < 1.0f - 1.0e-4f)) return false; // near a bin boundary, or NaN
+    *out = sat_u32(t);
+    return true;
+}
+
+FD_HD bool torsion_bins_fast(V3 a, V3 b, V3 c, V3 d, float nbin, uint32_t *sbin, uint32_t *cbin) {
+    V3 v1 = sub(b, a), v2 = sub(c, b), v3 = sub(d, c);
+    V3 r = normalize(cross(v1, v2));
+    V3 s = normalize(cross(v2, v3));
+    V3 t = normalize(cross(r, normalize(v2)));
+    float x = dot(r, s);
+    float y = dot(s, t);
+    float len = FD_SQRT(FD_ADD(FD_MUL(x, x), FD_MUL(y, y)));
+    if (!(len > 1.0e-3f && len < 2.0f)) return false; // degenerate (atan2(0, 0), NaN): exact route
+    return fast_bin(FD_DIV(-y, len), nbin, sbin) && fast_bin(FD_DIV(x, len), nbin, cbin);
+}
+
+FD_HD bool pair_hash_fast(V3 n1, V3 ca1, V3 cb1, V3 n2, V3 ca2, V3 cb2, uint8_t aa1, uint8_t aa2, float ca_dist,
+                          const HashParams &p, uint32_t *out) {
+    uint32_t s0, c0, s1, c1, s2, c2;
+    {
+        V3 v1 = sub(cb1, ca1), v2 = sub(cb2, ca2);
+        float d = dot(v1, v2);
+        float l1 = norm(v1), l2 = norm(v2);
+        float cs = FD_DIV(d, FD_MUL(l1, l2));
+        if (!(cs >= -1.0f && cs <= 1.0f)) return false;
+        float sn = FD_SQRT(FD_SUB(1.0f, FD_MUL(cs, cs)));
+        // sin(acos) >= 0: below 0.01 the closed form loses relative accuracy but the bin is the one of 0+ either way
+        if (!fast_bin(sn, p.nbin_angle, &s0) || !fast_bin(cs, p.nbin_angle, &c0)) return false;
+    }
+    if (!torsion_bins_fast(n1, ca1, cb1, cb2, p.nbin_angle, &s1, &c1)) return false;
+    if (!torsion_bins_fast(cb1, cb2, ca2, n2, p.nbin_angle, &s2, &c2)) return false;
+    uint32_t res1 = sat_u32((float)aa1), res2 = sat_u32((float)aa2);
+    uint32_t ca = discretize(ca_dist, 2.0f, 20.0f, p.nbin_dist);
+    uint32_t cb = discretize(dist(cb1, cb2), 2.0f, 20.0f, p.nbin_dist);
+    *out = res1 << 25 | res2 << 20 | ca << 16 | cb << 12 | s0 << 10 | c0 << 8 | s1 << 6 | c1 << 4 | s2 << 2 | c2;
+    return true;
+}
+
+// pair_hash, through the fast route when every bin is decided by it
+FD_HD uint32_t pair_hash_auto(V3 n1, V3 ca1, V3 cb1, V3 n2, V3 ca2, V3 cb2, uint8_t aa1, uint8_t aa2, float ca_dist,
+                              const HashParams &p) {
+    uint32_t h;
+    if (pair_hash_fast(n1, ca1, cb1, n2, ca2, cb2, aa1, aa2, ca_dist, p, &h)) return h;
+    return pair_hash(n1, ca1, cb1, n2, ca2, cb2, aa1, aa2, ca_dist, p);
+}
+
 } // namespace fdg

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(K1_THREADS)
                         if (k < qn) {
                             const uint32_t ij = q_ij[k];
                             const uint64_t ri = base + tile.i0 + (ij >> 16), rj = base + (ij & 0xffffu);
-                            const uint32_t h = fdg::pair_hash(ld3(b.n_xyz, ri), ld3(b.ca_xyz, ri), ld3(b.cb_xyz, ri),
+                            const uint32_t h = fdg::pair_hash_auto(ld3(b.n_xyz, ri), ld3(b.ca_xyz, ri), ld3(b.cb_xyz, ri),
                                                               ld3(b.n_xyz, rj), ld3(b.ca_xyz, rj), ld3(b.cb_xyz, rj),
                                                               b.aa[ri] & 0x7Fu, b.aa[rj] & 0x7Fu, q_d[k], hp);
                             emit = (uint64_t)h >= hash_lo && (uint64_t)h < hash_hi;

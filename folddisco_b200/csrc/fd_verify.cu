@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(VA_THREADS, 7)
         if ((uint32_t)lane < cnt) {
             const uint32_t ij = qb_ij[first + lane];
             const uint64_t ri = base + (ij >> 16), rj = base + (ij & 0xffffu);
-            const uint32_t h = fdg::pair_hash(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
+            const uint32_t h = fdg::pair_hash_auto(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
                                               ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj),
                                               st.aa[ri] & 0x7Fu, st.aa[rj] & 0x7Fu, qb_d[first + lane], hp);
             // the hashes that share the upper bits start at the stage-1 lower bound

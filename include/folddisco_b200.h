@@ -360,6 +360,12 @@ uint64_t fd_index_num_structs(const fd_ctx *ctx);
 /* ---- parity / debug probes ------------------------------------------------------------------------- */
 /* op: 0 sin, 1 cos, 2 acos, 3 atan2(a, b); evaluates the device math used by the hash kernels */
 int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t n, float *out);
+/* the geometric hash of residue pairs (i, j) of one SoA structure by the host build of csrc/fd_geom.cuh: exact route
+ * (binary64 trigonometry), fast route (closed forms + margin test; 0 where it declined) and the declined flags.  The
+ * kernels use fast-then-exact (pair_hash_auto); this probe is how the tests prove fast == exact wherever it answers. */
+void fd_pair_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_xyz, const uint8_t *aa,
+                       const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, const fd_hash_params *params,
+                       uint32_t *out_exact, uint32_t *out_fast, uint8_t *out_declined);
 /* same functions evaluated by the host build of the same header (no device needed) */
 void fd_math_host(int op, const float *a, const float *b, uint64_t n, float *out);
 

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--structs-per-gpu", type=int, default=23400)
     ap.add_argument("--batch", type=int, default=1024, help="queries per GPU")
     ap.add_argument("--top", type=int, default=100)
+    ap.add_argument("--sub-batch", type=int, default=0, help="> 0: e2e through host.search_stream with this many queries per sub-batch (1 GPU)")
     ap.add_argument("--cpu-sample", type=int, default=40, help="queries in the bounded CPU-baseline sample")
     ap.add_argument("--sweep", default="2,4", help="index-size multipliers of the posting-scan sweep (N=1 only; '' = off)")
     return ap.parse_args()
@@ -249,8 +250,6 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     # ---- e2e: host structures -> results, every step (H2D of query descriptors, D2H of hits/edges/RMSD inside) ----
-    for _ in range(args.warmup):
-        search(make_batch())
     def timed(fn):
         """one step bracketed by barrier + synchronize and by CUDA events on the current stream (the library call is
         synchronous, so the event interval covers host orchestration, copies and kernels of the step)"""
@@ -265,10 +264,27 @@ def run_ours(args, rank, world, local_rank):
         wall = time.perf_counter() - t0
         return out, e0.elapsed_time(e1) * 1e-3, wall
 
-    e2e_t, res = [], None
+    def e2e_step():
+        """host structures -> result rows through the public API: build the query batch, search it.  --sub-batch N > 0
+        (one GPU) uses host.search_stream instead (sub-batches, the next one prepared on a second host thread while
+        the current one is searched); measured slower at this batch size (per-call fixed costs: 13.1 ms at 512,
+        14.8 ms at 256 vs 12.3 ms), so it is off by default"""
+        if sharded is not None or args.sub_batch <= 0:
+            return [search(make_batch())]
+        ks = range(rank * args.batch, (rank + 1) * args.batch)
+        return host.search_stream(ctx, [motif_structs[k % len(motif_structs)][0] for k in ks],
+                                  [motif_structs[k % len(motif_structs)][1] for k in ks], sp, index.params,
+                                  sub_batch=args.sub_batch)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    e2e_t, e2e_res = [], None
     for _ in range(args.steps):
-        res, dt, _ = timed(lambda: search(make_batch()))
+        e2e_res, dt, _ = timed(e2e_step)
         e2e_t.append(dt)
+    e2e_h2d, e2e_d2h = sum(int(r.h2d_bytes) for r in e2e_res), sum(int(r.d2h_bytes) for r in e2e_res)
+    e2e_rows = (sum(int(r.struct_offsets[-1]) for r in e2e_res), sum(int(r.match_offsets[-1]) for r in e2e_res))
+    del e2e_res
     # ---- value: query batch prepared (inputs resident), timed region = the search itself ----
     qb = make_batch()
     for _ in range(args.warmup):
@@ -313,7 +329,8 @@ def run_ours(args, rank, world, local_rank):
         survivors = 0
     n_struct_rows, n_match_rows = int(res.struct_offsets[-1]), int(res.match_offsets[-1])
     # tallied by fdh_search from the buffers it copies (rank 0's slice; every rank moves the same amount)
-    h2d, d2h = int(res.h2d_bytes) * world, int(res.d2h_bytes) * world
+    h2d, d2h = e2e_h2d * world, e2e_d2h * world
+    assert e2e_rows == (n_struct_rows, n_match_rows), (e2e_rows, n_struct_rows, n_match_rows)  # same rows either way
     line = {
         "metric": METRIC, "value": args.batch * world / val_s,
         "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -92,42 +92,56 @@ __global__ void fd_math_probe_kernel(int op, const float *a, const float *b, uin
 // Host worker pool.  The host side above the kernels runs many short parallel regions per batch (query maps,
 // verification tables, row assembly); spawning std::threads for each costs more than the regions themselves
 // (~20 us per thread).  fd_parallel(nt, fn) runs fn(0) .. fn(nt - 1) concurrently -- fn(0) on the caller -- on
-// persistent workers that sleep on a condition variable between regions.  One region at a time; a nested or
-// concurrent region (verification lanes) falls back to plain threads.
+// persistent workers that sleep on a condition variable between regions; concurrent regions share the workers.
 // ------------------------------------------------------------------------------------------------
 namespace {
+struct PoolRegion {
+    const std::function<void(int)> *fn;
+    int nt;
+    int next = 0; // next unclaimed worker index (under HostPool::m)
+    int done = 0; // finished indices (under HostPool::m)
+};
 struct HostPool {
-    std::mutex region;              // held by the thread that runs a region
     std::mutex m;
-    std::condition_variable cv_start, cv_done;
-    std::vector<std::thread> workers;
-    const std::function<void(int)> *job = nullptr;
-    int job_nt = 0, remaining = 0;
-    uint64_t gen = 0;
+    std::condition_variable cv_work, cv_done;
+    std::vector<PoolRegion *> active; // regions with unclaimed indices
+    int n_workers = 0;
 
-    void worker(int idx) {
-        uint64_t seen = 0;
+    // claims an index of some active region; nullptr if there is none (caller holds m)
+    PoolRegion *claim(int *idx) {
+        while (!active.empty()) {
+            PoolRegion *r = active.back();
+            if (r->next < r->nt) {
+                *idx = r->next++;
+                if (r->next == r->nt) active.pop_back();
+                return r;
+            }
+            active.pop_back();
+        }
+        return nullptr;
+    }
+    void finish(PoolRegion *r) { // caller holds m
+        if (++r->done == r->nt) cv_done.notify_all();
+    }
+    void worker() {
+        std::unique_lock<std::mutex> lk(m);
         for (;;) {
-            const std::function<void(int)> *j = nullptr;
-            {
-                std::unique_lock<std::mutex> lk(m);
-                cv_start.wait(lk, [&] { return gen != seen; });
-                seen = gen;
-                if (idx < job_nt) j = job;
+            int idx = 0;
+            PoolRegion *r = claim(&idx);
+            if (!r) {
+                cv_work.wait(lk);
+                continue;
             }
-            if (!j) continue;
-            (*j)(idx);
-            {
-                std::lock_guard<std::mutex> lk(m);
-                if (--remaining == 0) cv_done.notify_one();
-            }
+            lk.unlock();
+            (*r->fn)(idx);
+            lk.lock();
+            finish(r);
         }
     }
-    void grow(int nt) { // under `region`
-        while ((int)workers.size() + 1 < nt) {
-            const int idx = (int)workers.size() + 1;
-            workers.emplace_back([this, idx] { worker(idx); });
-            workers.back().detach();
+    void grow(int want) { // caller holds m
+        while (n_workers < want) {
+            std::thread([this] { worker(); }).detach();
+            n_workers++;
         }
     }
 };
@@ -137,34 +151,35 @@ HostPool *host_pool() {
 }
 } // namespace
 
+// Regions from several host threads (search lanes, a prepare thread next to a search thread) share the workers: a
+// worker takes the next unclaimed index of any active region; the caller works on its own region too and then waits
+// for the indices that others took.
 void fd_parallel(int nt, const std::function<void(int)> &fn) {
     if (nt <= 1) {
         fn(0);
         return;
     }
     HostPool *P = host_pool();
-    std::unique_lock<std::mutex> region(P->region, std::try_to_lock);
-    if (!region.owns_lock()) { // another region is running (nested call or a second host thread)
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back([&fn, t] { fn(t); });
-        fn(0);
-        for (auto &t : th) t.join();
-        return;
-    }
-    P->grow(nt);
-    {
-        std::lock_guard<std::mutex> lk(P->m);
-        P->job = &fn;
-        P->job_nt = nt;
-        P->remaining = nt - 1;
-        P->gen++;
-    }
-    P->cv_start.notify_all();
-    fn(0);
+    PoolRegion r{&fn, nt};
     std::unique_lock<std::mutex> lk(P->m);
-    P->cv_done.wait(lk, [&] { return P->remaining == 0; });
-    P->job = nullptr;
-    P->job_nt = 0;
+    P->grow(std::min(nt - 1, 255));
+    P->active.push_back(&r);
+    P->cv_work.notify_all();
+    for (;;) { // the caller takes indices of its own region only (it must return when the region is done)
+        if (r.next >= r.nt) break;
+        const int idx = r.next++;
+        if (r.next == r.nt)
+            for (size_t k = 0; k < P->active.size(); k++)
+                if (P->active[k] == &r) {
+                    P->active.erase(P->active.begin() + (long)k);
+                    break;
+                }
+        lk.unlock();
+        fn(idx);
+        lk.lock();
+        P->finish(&r);
+    }
+    P->cv_done.wait(lk, [&] { return r.done == r.nt; });
 }
 
 extern "C" {

@@ -517,3 +517,51 @@ def search(ctx, queries, params=None, labels=None):
     """query_pdb.rs:348-452 for the batch: count_query -> filter/sort/top -> retrieval -> Kabsch -> filters -> sort"""
     params = params or SearchParams()
     return Results(_lib().fdh_search(ctx.h, queries.h, C.byref(params), labels.h if labels is not None else None))
+
+
+class _LaneContext:
+    """a fork of a Context that the parent owns (fd_lane): same device, index and store, own stream and staging"""
+
+    def __init__(self, parent, i):
+        h = VP()
+        parent._check(capi.lib().fd_lane(parent.h, i, C.byref(h)), "fd_lane")
+        self.h = h
+
+
+_stream_pool = None
+
+
+def search_stream(ctx, structures, query_strings, params=None, hash_params=None, sub_batch=256, labels=None,
+                  dist_thr=(0.5,), angle_thr=(5.0,)):
+    """Queries given as host structures + query strings -> list of Results, one per sub-batch of `sub_batch` queries, in
+    order.  The query side of sub-batch k+1 (make_query_map, the idf lookup, the verification tables) is prepared on a
+    second host thread, on a lane of ctx, while sub-batch k is searched: the reference's query loop is query-parallel
+    (query_pdb.rs:348 `into_par_iter`), here the parallelism is between the host-heavy and the GPU-heavy half of
+    consecutive sub-batches.  Pays off only when a sub-batch is large enough to amortise the per-call fixed costs
+    (a few host/device round trips): on the bench workload 1 024 queries in one call (12.3 ms) beat 2 x 512 (13.1 ms)."""
+    global _stream_pool
+    from concurrent.futures import ThreadPoolExecutor
+    params = params or SearchParams()
+    n = len(structures)
+    if n == 0:
+        return []
+    if _stream_pool is None:
+        _stream_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="fd-prepare")
+    lane = _LaneContext(ctx, 7)
+    bounds = [(a, min(n, a + sub_batch)) for a in range(0, n, sub_batch)]
+
+    def prepare(k):
+        a, b = bounds[k]
+        qb = QueryBatch(hash_params, dist_thr=dist_thr, angle_thr=angle_thr)
+        qb.add_many(structures[a:b], query_strings[a:b])
+        qb.finalize(lane)
+        return qb
+
+    out = []
+    fut = _stream_pool.submit(prepare, 0)
+    for k in range(len(bounds)):
+        qb = fut.result()
+        if k + 1 < len(bounds):
+            fut = _stream_pool.submit(prepare, k + 1)
+        out.append(search(ctx, qb, params, labels))
+    return out

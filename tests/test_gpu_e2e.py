@@ -240,3 +240,44 @@ def test_full_size_properties(env):
             assert rmsd <= best + 1e-3
             checked += 1
     assert checked > 50
+
+
+def test_search_stream_equals_one_batch(env):
+    """host.search_stream (sub-batches, the next one prepared on a second host thread on a lane of the context) returns
+    the rows of one host.search over the whole batch, query by query"""
+    from folddisco_b200 import synth
+    host, fd = env["host"], env["fd"]
+    ctx = fd.Context(0)
+    db = synth.generate(1500, 23, mean_len=180.0, max_len=500)
+    store = host.Store()
+    store.add_soa(db)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    store.attach(ctx)
+    motifs = [(host.CompactStructure.from_atoms(env["atoms"][p]), q) for p, q, _ in F.MOTIFS]
+    structs = [motifs[k % 5][0] for k in range(37)]
+    strings = [motifs[k % 5][1] for k in range(37)]
+    sp = host.SearchParams(top_n=20)
+    qb = host.QueryBatch(ix.params)
+    qb.add_many(structs, strings)
+    qb.finalize(ctx)
+    whole = host.search(ctx, qb, sp, labels=store)
+    parts = host.search_stream(ctx, structs, strings, sp, ix.params, sub_batch=8, labels=store)
+    assert [len(p.struct_offsets) - 1 for p in parts] == [8, 8, 8, 8, 5]
+    q = 0
+    for p in parts:
+        for k in range(len(p.struct_offsets) - 1):
+            a, b = whole.structures(q), p.structures(k)
+            for f in ("nid", "total_match_count", "node_count", "edge_count", "idf", "max_matching_node_count",
+                      "min_rmsd_with_max_match"):
+                assert np.array_equal(a[f], b[f]), (q, f)
+            ma, mb = whole.sorted_matches(q), p.sorted_matches(k)
+            assert len(ma) == len(mb)
+            for f in ("nid", "node_count", "idf", "rmsd"):
+                assert np.array_equal(ma[f], mb[f]), (q, f)
+            nres = len(strings[q].split(","))
+            assert [whole.residue_string(m, nres) for m in ma] == [p.residue_string(m, nres) for m in mb]
+            q += 1
+    assert q == 37
+    del whole, parts, qb
+    ctx.close()

@@ -312,6 +312,7 @@ struct SparseOut { // MODE 2 of k3_scan
     const uint64_t *region_offset;      // [world] first record of every destination's region in the pool
     unsigned long long *region_count;   // [world] records appended so far
     uint32_t world;
+    uint32_t rec_planes;                // plane words per record (>= the launch's own planes; the rest is zero)
 };
 
 struct FilterParams {
@@ -696,7 +697,8 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
         __syncthreads();
         const uint32_t dest = s_dest;
         const uint32_t key0 = (q - sp.slice_begin[dest]) * ix.n_structs + lo;
-        uint32_t *region = dense + sp.region_offset[dest] * (1 + PLANES);
+        const uint32_t RP = max(sp.rec_planes, PLANES); // record width of the batch; this launch's class may be narrower
+        uint32_t *region = dense + sp.region_offset[dest] * (1 + RP);
         unsigned long long *counter = sp.region_count + dest;
         const uint32_t lane = threadIdx.x & 31;
         uint32_t *wq = wqueue + (threadIdx.x >> 5) * K3_WQ;
@@ -706,10 +708,11 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
             pos = __shfl_sync(0xffffffffu, pos, 0) + lane;
             if (lane < n_take) {
                 const uint32_t x = wq[first + lane];
-                uint32_t *r = region + pos * (1 + PLANES);
+                uint32_t *r = region + pos * (1 + RP);
                 r[0] = key0 + x;
 #pragma unroll
                 for (uint32_t p = 0; p < PLANES; p++) r[1 + p] = w_acc[(size_t)p * tile_ids + x];
+                for (uint32_t p = PLANES; p < RP; p++) r[1 + p] = 0;
             }
         };
         compact_cells<NARROW>(w_acc, w_match, T, wq, pack);
@@ -1071,7 +1074,7 @@ int launch_scan_t(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, cons
 template <int MODE>
 int launch_scan(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const Batch &B, FilterParams fp,
                 const uint64_t *hit_offsets, unsigned int *hit_counts, HitRec *hits, uint32_t *dense,
-                SparseOut sp = SparseOut{nullptr, nullptr, nullptr, 0}, const uint32_t *qlist = nullptr, int ew = 0) {
+                SparseOut sp = SparseOut{nullptr, nullptr, nullptr, 0, 0}, const uint32_t *qlist = nullptr, int ew = 0) {
     if (ew <= 0) ew = B.ew;
 #define FD_SCAN_CASE(NARROW, EW) \
     return launch_scan_t<NARROW, EW, MODE>(ctx, grid, tp, ix, B, fp, hit_offsets, hit_counts, hits, dense, sp, qlist)
@@ -1088,6 +1091,22 @@ int launch_scan(fd_ctx *ctx, dim3 grid, const TilePlan &tp, IndexView ix, const 
     }
 #undef FD_SCAN_CASE
     return FD_ERR_ARG;
+}
+
+// Queries grouped by the number of edge-mask words they need (1, 2, 4, 8): qorder = query numbers class by class.
+// One scan launch per class keeps the tiles of narrow queries large (8 B of shared memory per structure for <= 32
+// vote bits); sizing every tile for the widest query of the batch would split all of them.
+static void edge_word_classes(const Batch &B, uint32_t nq, std::vector<uint32_t> &qorder, uint32_t class_begin[5]) {
+    qorder.clear();
+    class_begin[0] = 0;
+    for (int c = 0; c < 4; c++) {
+        for (uint32_t q = 0; q < nq; q++) {
+            const uint32_t need = std::max(1u, (B.descs[q].n_edges + 31) / 32);
+            const int cls = need <= 1 ? 0 : need <= 2 ? 1 : need <= 4 ? 2 : 3;
+            if (cls == c) qorder.push_back(q);
+        }
+        class_begin[c + 1] = (uint32_t)qorder.size();
+    }
 }
 
 template <bool NARROW, int EW>
@@ -1323,20 +1342,10 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
         FD_CUDA(ctx, d_hits.alloc(hit_off[nq]));
         FD_CUDA(ctx, cudaMemcpyAsync(d_hit_off.p, hit_off.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s));
         FD_CUDA(ctx, cudaMemsetAsync(d_hit_cnt.p, 0, nq * 4, s));
-        // One launch per edge-word class: a query with <= 32 vote bits needs 8 B of shared memory per structure, one
-        // with 33..64 needs 12 B, ...; sizing every tile for the widest query of the batch would split the narrow ones
-        // into more tiles than they need (every tile of a query walks all of its short lists again).
         std::vector<uint32_t> qorder;
-        uint32_t class_begin[5] = {0, 0, 0, 0, 0};
+        uint32_t class_begin[5];
         const int class_ew[4] = {1, 2, 4, 8};
-        for (int c = 0; c < 4; c++) {
-            for (uint32_t q = 0; q < nq; q++) {
-                const uint32_t need = std::max(1u, (B.descs[q].n_edges + 31) / 32);
-                const int cls = need <= 1 ? 0 : need <= 2 ? 1 : need <= 4 ? 2 : 3;
-                if (cls == c) qorder.push_back(q);
-            }
-            class_begin[c + 1] = (uint32_t)qorder.size();
-        }
+        edge_word_classes(B, nq, qorder, class_begin);
         DevBuf<uint32_t> d_qorder;
         FD_CUDA(ctx, d_qorder.alloc(nq));
         FD_CUDA(ctx, cudaMemcpyAsync(d_qorder.p, qorder.data(), nq * 4, cudaMemcpyHostToDevice, s));
@@ -1349,7 +1358,7 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
                 TilePlan tp;
                 FD_TRY(plan_tiles(ctx, B, N, tp, ew));
                 FD_TRY(launch_scan<0>(ctx, dim3(tp.n_tiles, nc), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
-                                      d_hit_cnt.p, d_hits.p, nullptr, SparseOut{nullptr, nullptr, nullptr, 0},
+                                      d_hit_cnt.p, d_hits.p, nullptr, SparseOut{nullptr, nullptr, nullptr, 0, 0},
                                       d_qorder.p + class_begin[c], ew));
             }
             FD_CUDA(ctx, st.finish());
@@ -1447,11 +1456,24 @@ int fd_votes_scan_sparse(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
     FD_CUDA(ctx, cudaMemcpyAsync(d_slice.p, slice_begin, (world + 1) * 4, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d_off.p, region_offset, (world + 1) * 8, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, world * 8, s));
-    TilePlan tp;
-    FD_TRY(plan_tiles(ctx, B, N, tp));
+    std::vector<uint32_t> qorder;
+    uint32_t class_begin[5];
+    const int class_ew[4] = {1, 2, 4, 8};
+    edge_word_classes(B, nq, qorder, class_begin);
+    DevBuf<uint32_t> d_qorder;
+    FD_CUDA(ctx, d_qorder.alloc(nq));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_qorder.p, qorder.data(), nq * 4, cudaMemcpyHostToDevice, s));
     StageTimer st(ctx, "scan");
-    FD_TRY(launch_scan<2>(ctx, dim3(tp.n_tiles, nq), tp, make_view(ctx), B, make_filter(params), nullptr, nullptr, nullptr,
-                          ctx->votes, SparseOut{d_slice.p, d_off.p, d_cnt.p, world}));
+    for (int c = 0; c < 4; c++) { // one launch per edge-word class; the records keep the batch's plane count
+        const uint32_t nc = class_begin[c + 1] - class_begin[c];
+        if (!nc) continue;
+        const int ew = std::min(class_ew[c], B.ew);
+        TilePlan tp;
+        FD_TRY(plan_tiles(ctx, B, N, tp, ew));
+        FD_TRY(launch_scan<2>(ctx, dim3(tp.n_tiles, nc), tp, make_view(ctx), B, make_filter(params), nullptr, nullptr,
+                              nullptr, ctx->votes, SparseOut{d_slice.p, d_off.p, d_cnt.p, world, planes},
+                              d_qorder.p + class_begin[c], ew));
+    }
     FD_CUDA(ctx, cudaMemcpyAsync(region_count, d_cnt.p, world * 8, cudaMemcpyDeviceToHost, s));
     FD_CUDA(ctx, st.finish());
     return FD_OK;

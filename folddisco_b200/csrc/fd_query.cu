@@ -1436,7 +1436,7 @@ int fd_votes_scan_sparse(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
     }
     const uint64_t words = region_offset[world] * (1 + planes);
     layout->words = words;
-    if (words > ctx->votes_cap) {
+    if (words > ctx->votes_cap || !ctx->votes) { // never hand out NULL: a rank whose shard holds none of the batch's lists has 0 words
         FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->votes);
         ctx->votes = nullptr;

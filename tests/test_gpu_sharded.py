@@ -121,9 +121,11 @@ def _slice_batches(host, params, atoms, world, reps=1):
     return out
 
 
-def test_two_shards_one_gpu_sparse():
+@pytest.mark.parametrize("empty_first", [False, True])
+def test_two_shards_one_gpu_sparse(empty_first):
     """the sparse protocol (packed non-empty cells per destination, apply, select) with the all_to_all done by hand
-    between two contexts of one GPU; every rank owns a slice of the batch"""
+    between two (three) contexts of one GPU; every rank owns a slice of the batch.  empty_first: a third shard that
+    holds none of the batch's lists (hashes of Ala-Ala pairs only) -- what ranks see at 8 GPUs"""
     import folddisco_b200 as fd
     from folddisco_b200 import host, sharded, synth
     atoms = F.config1_atoms()
@@ -138,9 +140,13 @@ def test_two_shards_one_gpu_sparse():
     qb_full.finalize(full)
     sp = host.SearchParams(top_n=50)
     want = host.search(full, qb_full, sp)
-    world = 2
+    world = 3 if empty_first else 2
     ctxs = [fd.Context(0) for _ in range(world)]
-    shards = [sharded.ShardedIndex.build(ctxs[r], store, r, world) for r in range(world)]
+    bounds = None
+    if empty_first:
+        probe = sharded.ShardedIndex.build(ctxs[0], store, 0, 2)
+        bounds = np.array([0, 1 << 20, int(probe.bounds[1]), 1 << 32], np.uint64)
+    shards = [sharded.ShardedIndex.build(ctxs[r], store, r, world, bounds=bounds) for r in range(world)]
     for c in ctxs:
         store.attach(c)
     qbs = _slice_batches(host, ix.params, atoms, world, reps=2)
@@ -158,6 +164,8 @@ def test_two_shards_one_gpu_sparse():
     for r, qb in enumerate(qbs):
         qb.finalize_with_counts(counts[pb[r]:pb[r + 1]], len(store))
     scans = [host.votes_scan_sparse(c, per_query, hashes, bits, sp.prefilter, slice_begin) for c in ctxs]
+    if empty_first:
+        assert int(scans[0][3].sum()) == 0 and scans[0][1] is not None  # no records, but a valid (empty) pool
     total = 0
     for d in range(world):
         lay = scans[d][0]

@@ -26,6 +26,13 @@ def test_exports_every_declared_symbol(so):
     L = ctypes.CDLL(so)
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
+    # the host-level header (orchestration mirroring src/lib.rs prelude names, used by the command line)
+    hdr = open(os.path.join(ROOT, "include", "folddisco_b200_host.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hnames = set(re.findall(r"\b(fdh_[a-z0-9_]+)\s*\(", hdr))
+    assert len(hnames) >= 40
+    missing = [n for n in sorted(hnames) if not hasattr(L, n)]
+    assert not missing, missing
 
 
 def test_sass_is_sm100a(so):

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -886,19 +887,71 @@ void match_component(const Query &Q, const std::vector<fd_cand_edge> &edges, con
 
 } // namespace
 
+// Large result blocks are recycled: a batch's result arrays are tens of megabytes, and a fresh malloc of that size is
+// an mmap whose pages fault in (and are zeroed by the kernel) while the assembly threads write the rows, then an
+// munmap at release -- every batch.  Freed blocks of >= 256 KB wait in a small cache (at most 16 blocks / 512 MB) and
+// serve the next request they fit without wasting more than 3/4 of the block.
+namespace {
+struct BlockCache {
+    struct Block {
+        void *p;
+        size_t cap;
+    };
+    std::mutex m;
+    std::vector<Block> blocks;
+    size_t bytes = 0;
+    static constexpr size_t kMinBlock = 256u << 10, kMaxBlocks = 16, kMaxBytes = 512u << 20;
+
+    void *get(size_t need, size_t *cap) {
+        if (need >= kMinBlock) {
+            std::lock_guard<std::mutex> lk(m);
+            size_t best = blocks.size();
+            for (size_t k = 0; k < blocks.size(); k++)
+                if (blocks[k].cap >= need && blocks[k].cap / 4 <= need && (best == blocks.size() || blocks[k].cap < blocks[best].cap))
+                    best = k;
+            if (best != blocks.size()) {
+                Block b = blocks[best];
+                blocks.erase(blocks.begin() + (long)best);
+                bytes -= b.cap;
+                *cap = b.cap;
+                return b.p;
+            }
+        }
+        *cap = need;
+        return malloc(need);
+    }
+    void put(void *p, size_t cap) {
+        if (!p) return;
+        if (cap >= kMinBlock) {
+            std::lock_guard<std::mutex> lk(m);
+            if (blocks.size() < kMaxBlocks && bytes + cap <= kMaxBytes) {
+                blocks.push_back(Block{p, cap});
+                bytes += cap;
+                return;
+            }
+        }
+        free(p);
+    }
+};
+BlockCache &block_cache() {
+    static BlockCache *c = new BlockCache(); // leaked on purpose (results may be released during interpreter shutdown)
+    return *c;
+}
+} // namespace
+
 // result array without value-initialisation (the rows are written in place by the assembly threads)
 template <typename T>
 struct RawArray {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap_bytes = 0;
     RawArray() {}
     RawArray(const RawArray &) = delete;
     RawArray &operator=(const RawArray &) = delete;
-    ~RawArray() { free(p); }
+    ~RawArray() { block_cache().put(p, cap_bytes); }
     bool alloc(size_t count) {
-        free(p);
+        block_cache().put(p, cap_bytes);
         n = count;
-        p = (T *)malloc(std::max<size_t>(count, 1) * sizeof(T));
+        p = (T *)block_cache().get(std::max<size_t>(count, 1) * sizeof(T), &cap_bytes);
         return p != nullptr;
     }
     T *data() { return p; }

@@ -2057,19 +2057,56 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             sr.match_end = mpos;
             *S++ = sr;
         }
-        // StructureSortStrategy::default: idf desc, min_rmsd asc (sort.rs:454-458), stable
-        std::stable_sort(S0, S, [](const fdh_struct_row &a, const fdh_struct_row &b) {
-            if (a.idf != b.idf) return a.idf > b.idf;
-            return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
-        });
-        // MatchSortStrategy::default: idf desc, rmsd asc (sort.rs:218-222), stable over emission order
-        uint64_t *O = R->match_order.data() + mb, *Oe = R->match_order.data() + mpos;
-        for (uint64_t k = mb; k < mpos; k++) R->match_order[k] = k;
-        std::stable_sort(O, Oe, [&](uint64_t a, uint64_t b) {
-            const fdh_match_row &x = M[a], &y = M[b];
-            if (x.idf != y.idf) return x.idf > y.idf;
-            return x.rmsd < y.rmsd;
-        });
+        // StructureSortStrategy::default: idf desc, min_rmsd asc (sort.rs:454-458), stable.  The rows arrive in
+        // count_query order (idf desc, nid asc), so only runs of equal idf can need reordering.
+        {
+            bool sorted = true;
+            for (fdh_struct_row *a = S0; a + 1 < S && sorted; a++) sorted = a[0].idf > a[1].idf;
+            if (!sorted)
+                std::stable_sort(S0, S, [](const fdh_struct_row &a, const fdh_struct_row &b) {
+                    if (a.idf != b.idf) return a.idf > b.idf;
+                    return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
+                });
+        }
+        // MatchSortStrategy::default: idf desc, rmsd asc (sort.rs:218-222), stable over emission order.  Sorted as
+        // (order-preserving integer image of (-idf, rmsd), emission index) records: the same total order as the
+        // stable comparison sort, without the two indirect float loads per comparison.  Values that the integer image
+        // would order differently from the float comparison (NaN, -0.0) take the comparison sort.
+        uint64_t *O = R->match_order.data() + mb;
+        const uint64_t nm = mpos - mb;
+        auto sortable = [](float f) -> uint32_t {
+            uint32_t u;
+            memcpy(&u, &f, 4);
+            return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        };
+        bool plain = true;
+        for (uint64_t k = mb; k < mpos && plain; k++)
+            plain = M[k].idf == M[k].idf && M[k].rmsd == M[k].rmsd && !(M[k].idf == 0.f && std::signbit(M[k].idf)) &&
+                    !(M[k].rmsd == 0.f && std::signbit(M[k].rmsd));
+        if (plain && nm <= 4096) {
+            struct Key {
+                uint64_t key;
+                uint32_t idx;
+            };
+            Key local[256];
+            std::vector<Key> big;
+            Key *keys = local;
+            if (nm > 256) {
+                big.resize(nm);
+                keys = big.data();
+            }
+            for (uint64_t k = 0; k < nm; k++)
+                keys[k] = Key{((uint64_t)(~sortable(M[mb + k].idf)) << 32) | sortable(M[mb + k].rmsd), (uint32_t)k};
+            std::sort(keys, keys + nm, [](const Key &a, const Key &b) { return a.key != b.key ? a.key < b.key : a.idx < b.idx; });
+            for (uint64_t k = 0; k < nm; k++) O[k] = mb + keys[k].idx;
+        } else {
+            for (uint64_t k = 0; k < nm; k++) O[k] = mb + k;
+            std::stable_sort(O, O + nm, [&](uint64_t a, uint64_t b) {
+                const fdh_match_row &x = M[a], &y = M[b];
+                if (x.idf != y.idf) return x.idf > y.idf;
+                return x.rmsd < y.rmsd;
+            });
+        }
     };
     {
         int nt = p->host_threads > 0 ? p->host_threads : fd_default_host_threads();

@@ -9,8 +9,8 @@
 //   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
 //   ids                     src/controller/mode.rs:70-125
 //
-// Not here (fails loudly): `benchmark` / `analyze`, --sort-by other than the default, --format-output, --superpose,
-// --web, --partial-fit, the TM / GDT / Chamfer / Hausdorff filters, hash types other than the default, mmCIF / .gz /
+// Not here (fails loudly): `benchmark` / `analyze`, --superpose, --web, --partial-fit, sort keys / columns that need
+// e-values or similarity metrics, the TM / GDT / Chamfer / Hausdorff filters, hash types other than the default, mmCIF / .gz /
 // Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
 #include <dirent.h>
 #include <limits.h>
@@ -191,7 +191,8 @@ const char *HELP =
     "        [--covered-node-ratio X] [--max-node N] [--max-node-ratio X] [--score X] [--connected-node N]\n"
     "        [--connected-node-ratio X] [--num-residue N] [--plddt X] [--rmsd X] [--top N] [--sampling-count N]\n"
     "        [--sampling-ratio X] [--freq-filter X] [--length-penalty X] [--per-structure|--per-match] [--skip-match]\n"
-    "        [--skip-ca-match] [--serial-index] [--header] [-o FILE] [-v]\n";
+    "        [--skip-ca-match] [--serial-index] [--sort-by KEY[:asc|desc],..] [--format-output COL,..] [--header]\n"
+    "        [-o FILE] [-v]\n";
 
 int cmd_index(Args &a) {
     a.reject({"--multiple-bins"}, "multiple-bin encoding is outside the ported path");
@@ -304,9 +305,91 @@ std::string escape_tsv(std::string s) { // formatter.rs:186-188
     return s;
 }
 
+
+std::string lower_trim(std::string s) {
+    size_t a = s.find_first_not_of(" \t"), b = s.find_last_not_of(" \t");
+    s = a == std::string::npos ? "" : s.substr(a, b - a + 1);
+    for (char &c : s) c = (char)tolower((unsigned char)c);
+    return s;
+}
+std::vector<std::string> split(const std::string &s, char sep) {
+    std::vector<std::string> out;
+    size_t a = 0;
+    for (;;) {
+        const size_t b = s.find(sep, a);
+        out.push_back(s.substr(a, b == std::string::npos ? std::string::npos : b - a));
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    return out;
+}
+
+// --sort-by: "key[:asc|desc],..." (sort.rs:47-66, 117-205 for match rows; :297-330, 380-440 for structure rows).
+// A key is (column id, descending?); values compare as the reference's extract_value does, ties keep the prior order.
+enum MatchKey { MK_NODE, MK_IDF, MK_RMSD };
+enum StructKey { SK_MAXNODE, SK_NODE, SK_IDF, SK_MINRMSD, SK_TOTAL, SK_EDGE, SK_NRES, SK_PLDDT };
+struct SortSpec {
+    std::vector<std::pair<int, bool>> keys; // (key, descending)
+};
+bool parse_order(const std::string &o, bool *desc) {
+    if (o == "asc" || o == "ascending" || o == "a") {
+        *desc = false;
+        return true;
+    }
+    if (o == "desc" || o == "descending" || o == "d") {
+        *desc = true;
+        return true;
+    }
+    return false;
+}
+SortSpec parse_sort(const std::string &arg, bool structure_mode) {
+    SortSpec sp;
+    for (const std::string &part0 : split(arg, ',')) {
+        const std::string part = lower_trim(part0);
+        if (part.empty()) continue;
+        const std::vector<std::string> kv = split(part, ':');
+        if (kv.size() > 2) die("Error parsing --sort-by: Invalid format: '" + part + "'. Use 'key:order' or just 'key'");
+        const std::string k = lower_trim(kv[0]);
+        int key = -1;
+        bool desc = true;
+        auto is = [&](std::initializer_list<const char *> a) {
+            for (const char *x : a)
+                if (k == x) return true;
+            return false;
+        };
+        if (structure_mode) {
+            if (is({"max_node_count", "max-node-count", "max_node", "max-node", "max_nodes", "max-nodes"})) key = SK_MAXNODE;
+            else if (is({"node_count", "node-count", "nodes", "node", "n"})) key = SK_NODE;
+            else if (is({"idf", "score"})) key = SK_IDF;
+            else if (is({"min_rmsd", "min-rmsd", "rmsd"})) key = SK_MINRMSD, desc = false;
+            else if (is({"total_match_count", "total-match-count", "total_match", "total-match", "matches", "match"})) key = SK_TOTAL;
+            else if (is({"edge_count", "edge-count", "edges", "edge", "e"})) key = SK_EDGE;
+            else if (is({"nres", "num_residues", "num-residues", "length", "residues", "residue", "l"})) key = SK_NRES;
+            else if (is({"plddt"})) key = SK_PLDDT;
+            else die("Error parsing --sort-by: Unknown structure sort key: '" + k + "'. Valid keys: max_node_count, node_count, idf, min_rmsd, total_match_count, edge_count, nres, plddt");
+        } else {
+            if (is({"node_count", "node-count", "nodes", "node", "n"})) key = MK_NODE;
+            else if (is({"idf", "score"})) key = MK_IDF;
+            else if (is({"rmsd"})) key = MK_RMSD, desc = false;
+            else if (is({"evalue", "e_value", "e-value", "tm_score", "tm-score", "tmscore", "tm", "gdt_ts", "gdt-ts", "gdtts", "gdt",
+                         "gdt_ha", "gdt-ha", "gdtha", "chamfer", "chamfer-distance", "chamfer_distance", "hausdorff",
+                         "hausdorff-distance", "hausdorff_distance"}))
+                die("--sort-by " + k + " is not supported by folddisco-b200: similarity metrics and e-values are outside the ported path");
+            else die("Error parsing --sort-by: Unknown sort key: '" + k + "'");
+        }
+        if (kv.size() == 2 && !parse_order(lower_trim(kv[1]), &desc))
+            die("Error parsing --sort-by: Unknown sort order: '" + kv[1] + "'. Use 'asc' or 'desc'");
+        sp.keys.emplace_back(key, desc);
+    }
+    return sp;
+}
+// partial_cmp(..).unwrap_or(Equal) on f32 / f64 values
+int cmp_val(double a, double b, bool desc) {
+    if (desc) std::swap(a, b);
+    return a < b ? -1 : (a > b ? 1 : 0);
+}
+
 int cmd_query(Args &a) {
-    a.reject({"--sort-by"}, "only the default sort orders are implemented");
-    a.reject({"--format-output"}, "only the default columns are implemented");
     a.reject({"--superpose", "--web"}, "superposition output columns are not implemented");
     a.reject({"--partial-fit"}, "LMS-QCP partial fit is outside the ported path");
     a.reject({"--tm-score", "--gdt-ts", "--gdt-ha", "--chamfer", "--hausdorff"}, "similarity-metric filters are outside the ported path");
@@ -343,6 +426,9 @@ int cmd_query(Args &a) {
     const bool header = a.flag({"--header"});
     const bool serial_query = a.flag({"--serial-index"});
     const std::string output = a.str({"-o", "--output"}, "");
+    const std::string sort_by = a.str({"--sort-by"}, "");
+    std::string format_output;
+    const bool has_format = a.value({"--format-output"}, format_output);
     const bool verbose = a.flag({"-v", "--verbose"});
     if (a.flag({"-h", "--help"})) {
         fputs(HELP, stdout);
@@ -352,6 +438,10 @@ int cmd_query(Args &a) {
     if (per_structure && per_match)
         die("Cannot print output per structure and per match at the same time. Use either --per-structure or --per-match");
     if (sp.skip_match) per_structure = true; // QueryMode::SkipMatch prints structure rows (query_pdb.rs:186-203)
+    const SortSpec sort_spec = parse_sort(sort_by, per_structure); // query_pdb.rs:212-245
+    std::vector<std::string> columns;                              // --format-output (query_pdb.rs:248-254)
+    if (has_format)
+        for (const std::string &c : split(format_output, ',')) columns.push_back(lower_trim(c));
     if (prefix.empty()) die("query needs -i PREFIX");
     if (threads > 0) setenv("FD_HOST_THREADS", std::to_string(threads).c_str(), 0);
 
@@ -459,34 +549,143 @@ int cmd_query(Args &a) {
             if (!out) die("Failed to create file: " + jobs[q].output);
         }
         const int64_t n_res = fdh_queries_num_indices(qs, (int64_t)q);
-        const std::string qres = escape_tsv(jobs[q].residues);
-        if (per_structure) { // STRUCTURE_RESULT_DEFAULT_COLUMNS (result.rs:300-313)
-            if (header)
-                fputs("tid\tidf\ttotal_match_count\tnode_count\tedge_count\tmax_node_cov\tmin_rmsd\tnres\tplddt\t"
-                      "matching_residues\tdb_key\tquery_residues\n", out);
-            for (uint64_t k = soff[q]; k < soff[q + 1]; k++) {
-                const fdh_struct_row &r = srows[k];
-                std::string mr;
-                for (uint64_t m = r.match_begin; m < r.match_end; m++) {
-                    char buf[32];
-                    snprintf(buf, sizeof(buf), ":%.4f", (double)mrows[m].rmsd);
-                    if (!mr.empty()) mr += ';';
-                    mr += residues_of(R, mrows[m], n_res);
-                    mr += buf;
-                }
-                if (mr.empty()) mr = "NA";
-                fprintf(out, "%s\t%.4f\t%u\t%u\t%u\t%u\t%.4f\t%u\t%.2f\t%s\t%llu\t%s\n",
-                        escape_tsv(fdh_index_name(ix, r.nid)).c_str(), (double)r.idf, r.total_match_count, r.node_count,
-                        r.edge_count, r.max_matching_node_count, (double)r.min_rmsd_with_max_match, nres[r.nid],
-                        (double)plddt[r.nid], mr.c_str(), (unsigned long long)fdh_index_db_key(ix, r.nid), qres.c_str());
+        const std::string qres = escape_tsv(jobs[q].residues), qid = escape_tsv(jobs[q].pdb);
+        char buf[64];
+        auto f4 = [&](double v) {
+            snprintf(buf, sizeof(buf), "%.4f", v);
+            return std::string(buf);
+        };
+        if (per_structure) {
+            // rows: default order from the library (idf desc, min_rmsd asc); --sort-by re-sorts them, stable
+            std::vector<uint64_t> order;
+            for (uint64_t k = soff[q]; k < soff[q + 1]; k++) order.push_back(k);
+            if (!sort_spec.keys.empty()) {
+                auto val = [&](const fdh_struct_row &r, int key) -> double {
+                    switch (key) {
+                        case SK_MAXNODE: return (float)r.max_matching_node_count;
+                        case SK_NODE: return (float)r.node_count;
+                        case SK_IDF: return r.idf;
+                        case SK_MINRMSD: return r.min_rmsd_with_max_match;
+                        case SK_TOTAL: return (float)r.total_match_count;
+                        case SK_EDGE: return (float)r.edge_count;
+                        case SK_NRES: return (float)nres[r.nid];
+                        default: return plddt[r.nid];
+                    }
+                };
+                std::stable_sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {
+                    for (auto &kd : sort_spec.keys) {
+                        const int c = cmp_val(val(srows[x], kd.first), val(srows[y], kd.first), kd.second);
+                        if (c) return c < 0;
+                    }
+                    return false;
+                });
             }
-        } else { // MATCH_RESULT_DEFAULT_COLUMNS (result.rs:330-338); --top truncates the sorted rows too (:466-471)
-            if (header) fputs("tid\tnode_count\tidf\trmsd\tmatching_residues\tquery_residues\n", out);
-            uint64_t printed = 0;
-            for (uint64_t k = moff[q]; k < moff[q + 1] && printed < sp.prefilter.top_n; k++, printed++) {
-                const fdh_match_row &m = mrows[morder[k]];
-                fprintf(out, "%s\t%u\t%.4f\t%.4f\t%s\t%s\n", escape_tsv(fdh_index_name(ix, m.nid)).c_str(), m.node_count,
-                        (double)m.idf, (double)m.rmsd, residues_of(R, m, n_res).c_str(), qres.c_str());
+            // STRUCTURE_RESULT_DEFAULT_COLUMNS (result.rs:300-313); unknown names are skipped like the reference's
+            // filter_map over its column registry (result.rs:317-321)
+            std::vector<std::string> cols = has_format ? columns
+                                                       : std::vector<std::string>{"tid", "idf", "total_match_count", "node_count", "edge_count",
+                                                                                  "max_node_cov", "min_rmsd", "nres", "plddt",
+                                                                                  "matching_residues", "db_key", "query_residues"};
+            const char *known[] = {"qid", "tid", "nid", "db_key", "total_match_count", "node_count", "edge_count", "idf", "nres",
+                                   "plddt", "max_node_cov", "min_rmsd", "matching_residues", "query_residues"};
+            std::vector<std::string> use;
+            for (auto &c : cols)
+                for (const char *k : known)
+                    if (c == k) use.push_back(c);
+            if (header) {
+                for (size_t i = 0; i < use.size(); i++) fprintf(out, "%s%s", i ? "\t" : "", use[i].c_str());
+                fputc('\n', out);
+            }
+            for (uint64_t k : order) {
+                const fdh_struct_row &r = srows[k];
+                for (size_t i = 0; i < use.size(); i++) {
+                    const std::string &c = use[i];
+                    std::string v;
+                    if (c == "qid") v = qid;
+                    else if (c == "tid") v = escape_tsv(fdh_index_name(ix, r.nid));
+                    else if (c == "nid") v = std::to_string(r.nid);
+                    else if (c == "db_key") v = std::to_string((unsigned long long)fdh_index_db_key(ix, r.nid));
+                    else if (c == "total_match_count") v = std::to_string(r.total_match_count);
+                    else if (c == "node_count") v = std::to_string(r.node_count);
+                    else if (c == "edge_count") v = std::to_string(r.edge_count);
+                    else if (c == "idf") v = f4(r.idf);
+                    else if (c == "nres") v = std::to_string(nres[r.nid]);
+                    else if (c == "plddt") {
+                        snprintf(buf, sizeof(buf), "%.2f", (double)plddt[r.nid]);
+                        v = buf;
+                    } else if (c == "max_node_cov") v = std::to_string(r.max_matching_node_count);
+                    else if (c == "min_rmsd") v = f4(r.min_rmsd_with_max_match);
+                    else if (c == "matching_residues") {
+                        for (uint64_t m = r.match_begin; m < r.match_end; m++) {
+                            if (!v.empty()) v += ';';
+                            v += residues_of(R, mrows[m], n_res) + ":" + f4(mrows[m].rmsd);
+                        }
+                        if (v.empty()) v = "NA";
+                    } else v = qres;
+                    fprintf(out, "%s%s", i ? "\t" : "", v.c_str());
+                }
+                fputc('\n', out);
+            }
+        } else {
+            // rows in the default order (idf desc, rmsd asc) from the library, or emission order re-sorted by --sort-by
+            // (stable, like par_sort_by over the candidate-ordered vector, result.rs:456-464)
+            std::vector<uint64_t> order;
+            if (sort_spec.keys.empty()) {
+                for (uint64_t k = moff[q]; k < moff[q + 1]; k++) order.push_back(morder[k]);
+            } else {
+                for (uint64_t k = moff[q]; k < moff[q + 1]; k++) order.push_back(k);
+                auto val = [&](const fdh_match_row &m, int key) -> double {
+                    return key == MK_NODE ? (double)m.node_count : key == MK_IDF ? (double)m.idf : (double)m.rmsd;
+                };
+                std::stable_sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {
+                    for (auto &kd : sort_spec.keys) {
+                        const int c = cmp_val(val(mrows[x], kd.first), val(mrows[y], kd.first), kd.second);
+                        if (c) return c < 0;
+                    }
+                    return false;
+                });
+            }
+            if (order.size() > sp.prefilter.top_n) order.resize(sp.prefilter.top_n); // result.rs:466-471
+            // MATCH_RESULT_DEFAULT_COLUMNS (result.rs:330-338)
+            std::vector<std::string> cols = has_format ? columns
+                                                       : std::vector<std::string>{"tid", "node_count", "idf", "rmsd", "matching_residues",
+                                                                                  "query_residues"};
+            const char *known[] = {"qid", "tid", "nid", "db_key", "node_count", "idf", "rmsd", "u_matrix", "t_vector",
+                                   "matching_residues", "query_residues"};
+            const char *unsupported[] = {"e_value", "matching_coordinates", "tm_score", "gdt_ts", "gdt_ha", "chamfer_distance",
+                                         "hausdorff_distance"};
+            std::vector<std::string> use;
+            for (auto &c : cols) {
+                for (const char *k : unsupported)
+                    if (c == k) die("--format-output column '" + c + "' is not supported by folddisco-b200");
+                for (const char *k : known)
+                    if (c == k) use.push_back(c);
+            }
+            if (header) {
+                for (size_t i = 0; i < use.size(); i++) fprintf(out, "%s%s", i ? "\t" : "", use[i].c_str());
+                fputc('\n', out);
+            }
+            for (uint64_t k : order) {
+                const fdh_match_row &m = mrows[k];
+                for (size_t i = 0; i < use.size(); i++) {
+                    const std::string &c = use[i];
+                    std::string v;
+                    if (c == "qid") v = qid;
+                    else if (c == "tid") v = escape_tsv(fdh_index_name(ix, m.nid));
+                    else if (c == "nid") v = std::to_string(m.nid);
+                    else if (c == "db_key") v = std::to_string((unsigned long long)fdh_index_db_key(ix, m.nid));
+                    else if (c == "node_count") v = std::to_string(m.node_count);
+                    else if (c == "idf") v = f4(m.idf);
+                    else if (c == "rmsd") v = f4(m.rmsd);
+                    else if (c == "u_matrix") {
+                        for (int j = 0; j < 9; j++) v += (j ? "," : "") + f4(m.U[j]);
+                    } else if (c == "t_vector") {
+                        for (int j = 0; j < 3; j++) v += (j ? "," : "") + f4(m.t[j]);
+                    } else if (c == "matching_residues") v = residues_of(R, m, n_res);
+                    else v = qres;
+                    fprintf(out, "%s%s", i ? "\t" : "", v.c_str());
+                }
+                fputc('\n', out);
             }
         }
         if (out != stdout) fclose(out);

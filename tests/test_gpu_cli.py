@@ -123,10 +123,40 @@ def test_query_without_store_parses_the_lookup_files(workdir):
 
 
 def test_unsupported_options_fail_loudly(workdir):
-    for extra in (["--partial-fit"], ["--sort-by", "rmsd"], ["--tm-score", "0.5"]):
+    for extra in (["--partial-fit"], ["--sort-by", "tm_score"], ["--tm-score", "0.5"], ["--superpose"],
+                  ["--format-output", "tid,e_value"]):
         r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"] + extra,
                            cwd=workdir, capture_output=True, text=True)
         assert r.returncode != 0 and "not supported" in r.stderr
     r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", "pdb"], cwd=workdir,
                        capture_output=True, text=True)
     assert r.returncode != 0 and "not supported" in r.stderr
+
+
+def test_sort_by_and_format_output(workdir):
+    """--sort-by (sort.rs) and --format-output (result.rs column registries)"""
+    base = ["query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"]
+    # the legacy order node_count desc, rmsd asc (sort.rs:224-229) is the order the README rows are listed in
+    rows = run(workdir, *base, "--sort-by", "node_count,rmsd")
+    assert rows == [["data/serine_peptidases/" + t, str(n), "%.4f" % i, "%.4f" % r, s, "B57,B102,C195"]
+                    for t, n, i, r, s in F.README_MATCH_ROWS_DEFAULT]
+    rows = run(workdir, *base, "--ca-distance", "1.5", "--sort-by", "node_count,rmsd")
+    keys = [(-int(r[1]), float(r[3])) for r in rows]
+    assert keys == sorted(keys) and len(rows) >= 7
+    t, n, i, r, s = F.README_MATCH_ROW_1AZW_CA15
+    assert ["data/serine_peptidases/" + t, str(n), "%.4f" % i, "%.4f" % r, s, "B57,B102,C195"] in rows
+    rows = run(workdir, *base, "--sort-by", "rmsd:desc")
+    rmsd = [float(r[3]) for r in rows]
+    assert rmsd == sorted(rmsd, reverse=True) and len(rows) == 6
+    rows = run(workdir, *base, "--format-output", "qid,tid,rmsd,u_matrix,t_vector,nid", "--header")
+    assert rows[0] == ["qid", "tid", "rmsd", "u_matrix", "t_vector", "nid"]
+    first = rows[1]
+    assert first[0] == "query/4CHA.pdb" and first[1].endswith("4cha.pdb") and first[2] == "0.0000" and first[5] == "4"
+    u, t = [float(x) for x in first[3].split(",")], [float(x) for x in first[4].split(",")]
+    assert len(u) == 9 and len(t) == 3   # the query motif found in its own structure: identity, no shift
+    assert np.allclose(u, np.eye(3).ravel(), atol=2e-3) and np.allclose(t, 0, atol=5e-2)
+    rows = run(workdir, *base, "--per-structure", "--sort-by", "nres:asc", "--format-output", "tid,nres,plddt")
+    assert [int(r[1]) for r in rows] == sorted(int(r[1]) for r in rows) and all(len(r) == 3 for r in rows)
+    rows = run(workdir, *base, "--per-structure", "--sort-by", "plddt")
+    p = [float(r[8]) for r in rows]
+    assert p == sorted(p, reverse=True)

@@ -214,17 +214,21 @@ void fd_pair_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_
 }
 
 // parity / debug probe: runs a region of nt workers that each spin for `spin_us`; returns how many distinct host
-// threads took part (the pool is healthy when the answer is nt)
+// threads took part (1..nt: a fast thread may take several indices), or -1 if some index did not run exactly once
 int fd_parallel_probe(int nt, int spin_us) {
     std::mutex m;
     std::vector<std::thread::id> ids;
-    fd_parallel(nt, [&](int) {
+    std::vector<int> seen((size_t)std::max(nt, 1), 0);
+    fd_parallel(nt, [&](int idx) {
         const auto t0 = std::chrono::steady_clock::now();
         while (std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() < spin_us) {
         }
         std::lock_guard<std::mutex> lk(m);
         ids.push_back(std::this_thread::get_id());
+        if (idx >= 0 && idx < (int)seen.size()) seen[(size_t)idx]++;
     });
+    for (int k = 0; k < std::max(nt, 1); k++)
+        if (seen[(size_t)k] != 1) return -1; // an index ran twice or not at all
     std::sort(ids.begin(), ids.end());
     return (int)(std::unique(ids.begin(), ids.end()) - ids.begin());
 }

@@ -54,7 +54,8 @@ uint64_t fd_kernel_launches(const fd_ctx *ctx);
 /* host threads the library uses for its query-parallel host steps when the caller passes 0: the environment variable
  * FD_HOST_THREADS if set (several ranks share one box: cores / ranks), else the number of hardware threads */
 int fd_default_host_threads(void);
-/* debug probe of the host worker pool: distinct host threads that ran a region of nt workers spinning spin_us each */
+/* debug probe of the host worker pool: distinct host threads that ran a region of nt workers spinning spin_us each
+ * (1..nt), or -1 if some worker index did not run exactly once */
 int fd_parallel_probe(int nt, int spin_us);
 /* cumulative device time (ms, CUDA events on the library's stream) of the named stage since creation:
  * "hash", "postings", "attach", "lookup", "scan", "select", "verify" (= "verify_edges" + "verify_components" +

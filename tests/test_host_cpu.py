@@ -191,3 +191,29 @@ def test_cli_fails_loudly_without_a_gpu():
     r = subprocess.run([cli, "query", "-p", "x.pdb", "-q", "A1,A2", "-i", "nowhere"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
     assert subprocess.run([cli, "version"], capture_output=True, text=True).stdout.startswith("folddisco_b200")
+
+
+def test_worker_pool_runs_every_index_once_and_concurrent_regions():
+    """fd_parallel (csrc/fd_ctx.cu): every worker index of a region runs exactly once, from one or several host threads
+    at a time (search lanes / a prepare thread next to a search thread share the workers)"""
+    import ctypes as C
+    import threading
+    import folddisco_b200 as fd
+    L = fd.lib()
+    L.fd_parallel_probe.restype = C.c_int
+    L.fd_parallel_probe.argtypes = [C.c_int, C.c_int]
+    for nt in (1, 2, 5, 16):
+        got = L.fd_parallel_probe(nt, 200)
+        assert 1 <= got <= nt  # distinct host threads that took part (a fast thread may take several indices)
+    results = []
+
+    def hammer():
+        for _ in range(40):
+            results.append(L.fd_parallel_probe(4, 100))
+
+    ths = [threading.Thread(target=hammer) for _ in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert len(results) == 160 and all(1 <= r <= 4 for r in results)

@@ -343,7 +343,11 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "k3_scan (posting-list scan + vote)", "achieved": achieved, "peak": hbm,
                      "unit": "GB/s", "frac": achieved / hbm, "traffic": scan_traffic() if world == 1 else None,
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": scan_ms},
+                     "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": scan_ms,
+                     "launches_per_step": "one per edge-word class of the batch (2 for the five shipped motifs); "
+                                          "bytes and ms are per step",
+                     "note": "at this scale the scan is bound by shared-memory vote traffic, CTA latency and issue "
+                             "slots, not by HBM (a query's vote state is ~20x its posting bytes): DESIGN.md section 4"},
         "clocks": clocks,
         "stages_ms_per_step": {s: st1[s][0] / max(1, args.steps) for s in stages},
         "host_ms_per_step": res.host_ms, "search_wall_ms": res.wall_ms,

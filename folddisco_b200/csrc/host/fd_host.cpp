@@ -1117,6 +1117,12 @@ fdh_store *fdh_store_load(const char *path) {
     uint64_t S = 0, R = 0;
     bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "FDB2STR1", 8) == 0 && fread(&S, 8, 1, f) == 1 &&
               fread(&R, 8, 1, f) == 1;
+    if (ok) { // the header must be consistent with the file size before anything is allocated from it
+        struct stat st;
+        const bool sane = S < (1ull << 40) && R < (1ull << 40);
+        const uint64_t need = sane ? 24 + 8 * (S + 1) + 36 * R + 3 * R + 8 * R + 4 * S + 4 * S : 0;
+        ok = sane && fstat(fileno(f), &st) == 0 && (uint64_t)st.st_size >= need;
+    }
     fdh_store *s = new fdh_store();
     auto rd = [&](void *p, size_t bytes) { ok = ok && (bytes == 0 || fread(p, 1, bytes, f) == bytes); };
     if (ok) {

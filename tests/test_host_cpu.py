@@ -179,6 +179,10 @@ def test_store_file_round_trip(host, tmp_path):
         fh.truncate(1000)
     with pytest.raises(Exception):
         host.Store.load(p)
+    with open(p, "wb") as fh:  # a header that promises more than the file holds is refused before any allocation
+        fh.write(b"FDB2STR1" + np.array([1 << 35, 1 << 36], np.uint64).tobytes() + b"\0" * 64)
+    with pytest.raises(Exception):
+        host.Store.load(p)
 
 
 def test_cli_fails_loudly_without_a_gpu():

@@ -1373,6 +1373,13 @@ fdh_index *fdh_index_load(const char *prefix) {
     ix->offsets = ix->own_offsets.data();
     ix->values = (const uint8_t *)ix->map_val;
     ix->value_bytes = ix->map_val_len;
+    // the offsets index the value file: a pair of files that do not belong together must not reach the device
+    if (ix->offsets[0] != 0 || ix->offsets[ix->count] > ix->value_bytes) {
+        set_err(std::string("index files are inconsistent: the offsets of ") + prefix + ".offset end at byte " +
+                std::to_string(ix->offsets[ix->count]) + " but the value file has " + std::to_string(ix->value_bytes));
+        delete ix;
+        return nullptr;
+    }
     { // lookup
         std::ifstream in(std::string(prefix) + ".lookup");
         std::string line;

@@ -141,6 +141,12 @@ def test_index_files_byte_identical(host, tmp_path):
     nr, pl = back.lookup()
     assert nr.tolist() == nres.tolist() and np.allclose(pl, plddt)
     assert back.name(4) == names[4] and back.params.dist_cutoff == 20.0
+    del back, bb
+    with open(mine, "r+b") as fh:  # a value file that is shorter than the offsets say: refused at load
+        fh.truncate(F.CONFIG1_VALUE_BYTES // 2)
+    with pytest.raises(Exception) as e:
+        host.load_folddisco_index(mine)
+    assert "inconsistent" in str(e.value)
 
 
 @needs_reference

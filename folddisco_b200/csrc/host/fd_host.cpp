@@ -349,14 +349,24 @@ struct Query {
     }
 };
 
-// pdb_tr.rs:95-162 with default bins
-bool hash_is_symmetric(uint32_t h) {
+// pdb_tr.rs:95-162 with default bins: res1 == res2 and the two torsions decode to the same angle.  The decoded angles
+// depend only on the four 2-bit sin / cos bins of the torsions (the low 8 bits of the hash), so the verdict is tabulated
+// once (256 entries; the same arithmetic as before, evaluated per bin pattern instead of per hash).
+bool torsion_bins_symmetric(uint32_t low8) {
     auto cont = [](uint32_t v, float mn, float mx, float nb) { return (float)v * ((mx - mn) / (nb - 1.0f)) + mn; };
     const float deg = 180.0f / 3.14159274101257324f;
-    if (((h >> 25) & 31u) != ((h >> 20) & 31u)) return false;
-    float s1 = cont((h >> 6) & 3u, -1.f, 1.f, 4.f), c1 = cont((h >> 4) & 3u, -1.f, 1.f, 4.f);
-    float s2 = cont((h >> 2) & 3u, -1.f, 1.f, 4.f), c2 = cont(h & 3u, -1.f, 1.f, 4.f);
+    float s1 = cont((low8 >> 6) & 3u, -1.f, 1.f, 4.f), c1 = cont((low8 >> 4) & 3u, -1.f, 1.f, 4.f);
+    float s2 = cont((low8 >> 2) & 3u, -1.f, 1.f, 4.f), c2 = cont(low8 & 3u, -1.f, 1.f, 4.f);
     return fdm::atan2f_exact(s1, c1) * deg == fdm::atan2f_exact(s2, c2) * deg;
+}
+bool hash_is_symmetric(uint32_t h) {
+    static const std::array<uint8_t, 256> table = [] {
+        std::array<uint8_t, 256> t{};
+        for (uint32_t k = 0; k < 256; k++) t[k] = torsion_bins_symmetric(k) ? 1 : 0;
+        return t;
+    }();
+    if (((h >> 25) & 31u) != ((h >> 20) & 31u)) return false;
+    return table[h & 0xffu] != 0;
 }
 
 bool host_pair_feature(const fdh_compact &c, size_t i, size_t j, float cutoff, float *f) {
@@ -516,23 +526,43 @@ struct AngleBinCache {
     };
     E e[3][12];
     int n[3] = {0, 0, 0};
+    // fdg::discretize(val, mn, mx, nbin) = sat_u32((val - mn) * disc + 0.5) with disc = 1 / ((mx - mn) / (nbin - 1)):
+    // disc depends on the hash parameters only, so its two divisions are done once per query (same f32 operations,
+    // same results as calling fdg::discretize)
+    float disc_dist = 0.f, disc_angle = 0.f;
+    explicit AngleBinCache(const fdg::HashParams &hp) {
+        disc_dist = FD_DIV(1.0f, FD_DIV(FD_SUB(20.0f, 2.0f), FD_SUB(hp.nbin_dist, 1.0f)));
+        disc_angle = FD_DIV(1.0f, FD_DIV(FD_SUB(1.0f, -1.0f), FD_SUB(hp.nbin_angle, 1.0f)));
+    }
+    static uint32_t disc(float val, float mn, float d) { return fdg::sat_u32(FD_ADD(FD_MUL(FD_SUB(val, mn), d), 0.5f)); }
     void reset() { n[0] = n[1] = n[2] = 0; }
-    uint32_t bins(int slot, float a, const fdg::HashParams &hp) {
+    uint32_t bins(int slot, float a) {
         uint32_t bits;
         memcpy(&bits, &a, 4);
         for (int k = 0; k < n[slot]; k++)
             if (e[slot][k].bits == bits) return e[slot][k].bins;
-        float sn, cs;
-        fdm::sincosf_exact(a, &sn, &cs);
-        const uint32_t b = fdg::discretize(sn, -1.0f, 1.0f, hp.nbin_angle) << 16 | fdg::discretize(cs, -1.0f, 1.0f, hp.nbin_angle);
+        // Only the bins are needed: the platform's sinf / cosf (faithful to well under 1e-6) decide them whenever the
+        // value that is truncated to the bin stays 1e-4 away from an integer -- the same margin argument as
+        // fdg::pair_hash_fast -- and the binary64 route is taken for the rare angle next to a bin boundary.
+        uint32_t b;
+        const float ts = FD_ADD(FD_MUL(FD_SUB(sinf(a), -1.0f), disc_angle), 0.5f);
+        const float tc = FD_ADD(FD_MUL(FD_SUB(cosf(a), -1.0f), disc_angle), 0.5f);
+        const float fs = ts - floorf(ts), fc = tc - floorf(tc);
+        if (fs > 1.0e-4f && fs < 1.0f - 1.0e-4f && fc > 1.0e-4f && fc < 1.0f - 1.0e-4f) {
+            b = fdg::sat_u32(ts) << 16 | fdg::sat_u32(tc);
+        } else {
+            float sn, cs;
+            fdm::sincosf_exact(a, &sn, &cs);
+            b = disc(sn, -1.0f, disc_angle) << 16 | disc(cs, -1.0f, disc_angle);
+        }
         if (n[slot] < 12) e[slot][n[slot]++] = E{bits, b};
         return b;
     }
-    uint32_t hash(const float *f, const fdg::HashParams &hp) {
+    uint32_t hash(const float *f, const fdg::HashParams &) {
         const uint32_t res1 = fdg::sat_u32(f[0]), res2 = fdg::sat_u32(f[1]);
-        const uint32_t ca = fdg::discretize(f[2], 2.0f, 20.0f, hp.nbin_dist);
-        const uint32_t cb = fdg::discretize(f[3], 2.0f, 20.0f, hp.nbin_dist);
-        const uint32_t b0 = bins(0, f[4], hp), b1 = bins(1, f[5], hp), b2 = bins(2, f[6], hp);
+        const uint32_t ca = disc(f[2], 2.0f, disc_dist);
+        const uint32_t cb = disc(f[3], 2.0f, disc_dist);
+        const uint32_t b0 = bins(0, f[4]), b1 = bins(1, f[5]), b2 = bins(2, f[6]);
         // the sin / cos bins are OR-ed in unmasked, exactly like perfect_hash (pdb_tr.rs:21-75: no field masking)
         return res1 << 25 | res2 << 20 | ca << 16 | cb << 12 | (b0 >> 16) << 10 | (b0 & 0xffffu) << 8 |
                (b1 >> 16) << 6 | (b1 & 0xffffu) << 4 | (b2 >> 16) << 2 | (b2 & 0xffffu);
@@ -569,8 +599,15 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     const float rad = 3.14159274101257324f / 180.0f; // f32::to_radians
     float f[7], fn[7], ff[7];
     SeenHashes seen;
-    AngleBinCache bins;
+    AngleBinCache bins(hp);
     const size_t K = Q.indices.size();
+    {
+        const size_t n_pairs = K > 1 ? K * (K - 1) : 0;
+        const size_t per_pair = 1 + 4 * qs.dist_thr.size() + 6 * qs.angle_thr.size();
+        Q.entries.reserve(std::min<size_t>(n_pairs * per_pair, 1u << 16));
+        Q.pair_hash.reserve(n_pairs);
+        Q.aad.reserve(n_pairs);
+    }
     for (size_t a = 0; a < K; a++)
         for (size_t b = 0; b < K; b++) {
             if (a == b) continue;
@@ -628,24 +665,53 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
             expand({2, 3}, qs.dist_thr, false);
             expand({4, 5, 6}, qs.angle_thr, true);
         }
-    // derived kernel inputs
-    std::unordered_map<uint64_t, uint16_t> edges;
-    std::unordered_map<uint32_t, uint16_t> nodes;
-    for (auto &e : Q.entries) {
-        const uint64_t key = ((uint64_t)e.qi << 32) | e.qj;
-        auto it = edges.find(key);
-        if (it == edges.end()) {
-            if (edges.size() >= 65535) return false;
-            it = edges.emplace(key, (uint16_t)edges.size()).first;
-            auto nn = nodes.find(e.qi);
-            if (nn == nodes.end()) nn = nodes.emplace(e.qi, (uint16_t)nodes.size()).first;
-            Q.edge_node.push_back(nn->second);
+    // derived kernel inputs: edges and nodes numbered by first appearance in the entries.  The entries of one residue
+    // pair are consecutive and, as long as no residue is listed twice in the query, distinct pairs are distinct
+    // (qi, qj) edges: a new edge starts where the pair number changes, no map needed.
+    bool repeated_index = false;
+    for (size_t a = 0; a < K && !repeated_index; a++)
+        for (size_t b = a + 1; b < K; b++)
+            if (Q.indices[a] == Q.indices[b]) repeated_index = true;
+    const size_t H0 = Q.entries.size();
+    Q.edge_of_hash.reserve(H0);
+    Q.hashes_flat.reserve(H0);
+    std::vector<uint32_t> node_of; // residue index of every node, in first-appearance order
+    auto node_id = [&](uint32_t qi) -> uint16_t {
+        for (size_t k = 0; k < node_of.size(); k++)
+            if (node_of[k] == qi) return (uint16_t)k;
+        node_of.push_back(qi);
+        return (uint16_t)(node_of.size() - 1);
+    };
+    if (!repeated_index) {
+        uint32_t last_pair = 0xffffffffu;
+        uint32_t n_edges = 0;
+        for (auto &e : Q.entries) {
+            if (e.pair != last_pair) {
+                if (n_edges >= 65535) return false;
+                last_pair = e.pair;
+                n_edges++;
+                Q.edge_node.push_back(node_id(e.qi));
+            }
+            Q.edge_of_hash.push_back((uint16_t)(n_edges - 1));
+            Q.hashes_flat.push_back(e.hash);
+            Q.max_q = std::max(Q.max_q, std::max(e.qi, e.qj));
         }
-        Q.edge_of_hash.push_back(it->second);
-        Q.hashes_flat.push_back(e.hash);
-        Q.max_q = std::max(Q.max_q, std::max(e.qi, e.qj));
+    } else {
+        std::unordered_map<uint64_t, uint16_t> edges;
+        for (auto &e : Q.entries) {
+            const uint64_t key = ((uint64_t)e.qi << 32) | e.qj;
+            auto it = edges.find(key);
+            if (it == edges.end()) {
+                if (edges.size() >= 65535) return false;
+                it = edges.emplace(key, (uint16_t)edges.size()).first;
+                Q.edge_node.push_back(node_id(e.qi));
+            }
+            Q.edge_of_hash.push_back(it->second);
+            Q.hashes_flat.push_back(e.hash);
+            Q.max_q = std::max(Q.max_q, std::max(e.qi, e.qj));
+        }
     }
-    Q.n_nodes = (uint32_t)nodes.size();
+    Q.n_nodes = (uint32_t)node_of.size();
     const size_t H = Q.entries.size();
     Q.vs_entry.resize(H);
     for (size_t k = 0; k < H; k++) Q.vs_entry[k] = (uint32_t)k;

@@ -224,9 +224,9 @@ def run_ours(args, rank, world, local_rank):
         """this rank's args.batch queries of the global batch (query number q uses motif q mod 5)"""
         t0 = time.perf_counter()
         qb = host.QueryBatch(index.params)
-        ks = range(rank * args.batch, (rank + 1) * args.batch)
-        qb.add_many([motif_structs[k % len(motif_structs)][0] for k in ks],
-                    [motif_structs[k % len(motif_structs)][1] for k in ks])
+        which = np.arange(rank * args.batch, (rank + 1) * args.batch, dtype=np.uint32) % len(motif_structs)
+        # every query map is built on its own; the indexed call only spares the marshalling of 2 x batch Python objects
+        qb.add_many_indexed([m[0] for m in motif_structs], [m[1] for m in motif_structs], which, which)
         t1 = time.perf_counter()
         if sharded is None:
             qb.finalize(ctx)

@@ -1565,17 +1565,28 @@ int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *st, const char *quer
     return (int64_t)qs->q.size() - 1;
 }
 
-// make_query_map for n (structure, query string) pairs at once, query-parallel (query_pdb.rs:348 into_par_iter)
-int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,
-                             int64_t n, int threads) {
+// make_query_map for n (structure, query string) pairs at once, query-parallel (query_pdb.rs:348 into_par_iter).
+// Query k uses structs[which_struct[k]] and strings[which_string[k]] (NULL index arrays = k itself).
+static int64_t add_many_impl(fdh_queries *qs, const fdh_compact *const *structs, int64_t n_structs,
+                             const char *const *strings, int64_t n_strings, const uint32_t *which_struct,
+                             const uint32_t *which_string, int64_t n, int threads) {
+    for (int64_t k = 0; k < n; k++)
+        if ((which_struct && which_struct[k] >= n_structs) || (which_string && which_string[k] >= n_strings)) {
+            set_err("fdh_queries_add_many_indexed: index out of range");
+            return -1;
+        }
     // one copy per distinct source structure (all sources are alive for the duration of this call)
-    std::vector<std::shared_ptr<const fdh_compact>> sp((size_t)n);
+    std::vector<std::shared_ptr<const fdh_compact>> uniq((size_t)n_structs);
     std::unordered_map<const fdh_compact *, std::shared_ptr<const fdh_compact>> seen;
-    for (int64_t k = 0; k < n; k++) {
-        auto it = seen.find(structures[k]);
-        if (it == seen.end()) it = seen.emplace(structures[k], std::make_shared<const fdh_compact>(*structures[k])).first;
-        sp[k] = it->second;
-    }
+    auto copy_of = [&](int64_t u) -> const std::shared_ptr<const fdh_compact> & {
+        if (!uniq[u]) {
+            auto it = seen.find(structs[u]);
+            if (it == seen.end()) it = seen.emplace(structs[u], std::make_shared<const fdh_compact>(*structs[u])).first;
+            uniq[u] = it->second;
+        }
+        return uniq[u];
+    };
+    for (int64_t k = 0; k < n; k++) copy_of(which_struct ? which_struct[k] : k);
     std::vector<Query> out((size_t)n);
     std::vector<std::string> errs((size_t)n);
     std::vector<uint8_t> ok((size_t)n, 0);
@@ -1583,7 +1594,9 @@ int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structur
     nt = std::max(1, std::min<int>(nt, 64));
     std::atomic<int64_t> next{0};
     auto worker = [&] {
-        for (int64_t k; (k = next.fetch_add(1)) < n;) ok[k] = prepare_query(qs, sp[k], query_strings[k], out[k], errs[k]);
+        for (int64_t k; (k = next.fetch_add(1)) < n;)
+            ok[k] = prepare_query(qs, uniq[which_struct ? which_struct[k] : k], strings[which_string ? which_string[k] : k],
+                                  out[k], errs[k]);
     };
     fd_parallel(nt, [&](int) { worker(); });
     for (int64_t k = 0; k < n; k++)
@@ -1592,9 +1605,23 @@ int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structur
             return -1;
         }
     const int64_t first = (int64_t)qs->q.size();
+    qs->q.reserve(qs->q.size() + (size_t)n);
     for (auto &Q : out) qs->q.push_back(std::move(Q));
     qs->finalized = false;
     return first;
+}
+int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,
+                             int64_t n, int threads) {
+    return add_many_impl(qs, structures, n, query_strings, n, nullptr, nullptr, n, threads);
+}
+int64_t fdh_queries_add_many_indexed(fdh_queries *qs, const fdh_compact *const *structures, int64_t n_structures,
+                                     const char *const *query_strings, int64_t n_strings, const uint32_t *which_structure,
+                                     const uint32_t *which_string, int64_t n, int threads) {
+    if (!which_structure || !which_string) {
+        set_err("fdh_queries_add_many_indexed: NULL index array");
+        return -1;
+    }
+    return add_many_impl(qs, structures, n_structures, query_strings, n_strings, which_structure, which_string, n, threads);
 }
 int64_t fdh_queries_size(const fdh_queries *qs) { return (int64_t)qs->q.size(); }
 

@@ -92,6 +92,7 @@ def _lib():
     sig("fdh_queries_new", VP, [PP(_QueryParams)])
     sig("fdh_queries_add", C.c_int64, [VP, VP, C.c_char_p])
     sig("fdh_queries_add_many", C.c_int64, [VP, PP(VP), PP(C.c_char_p), C.c_int64, C.c_int])
+    sig("fdh_queries_add_many_indexed", C.c_int64, [VP, PP(VP), C.c_int64, PP(C.c_char_p), C.c_int64, VP, VP, C.c_int64, C.c_int])
     sig("fdh_queries_size", C.c_int64, [VP])
     sig("fdh_queries_finalize", C.c_int, [VP, VP])
     sig("fdh_queries_num_hashes", C.c_int64, [VP, C.c_int64])
@@ -353,6 +354,22 @@ class QueryBatch:
         if first < 0:
             raise FdError(_err())
         self.query_strings.extend(query_strings)
+        return first
+
+    def add_many_indexed(self, compacts, query_strings, which_compact, which_string, threads=0):
+        """add_many for batches that reuse a few structures / query strings: query k is
+        (compacts[which_compact[k]], query_strings[which_string[k]]).  Every query map is still built on its own; only
+        the marshalling of 2 x n Python objects per call goes away (~1 ms per 1 024 queries)."""
+        wc = np.ascontiguousarray(which_compact, np.uint32)
+        ws = np.ascontiguousarray(which_string, np.uint32)
+        assert len(wc) == len(ws)
+        hs = (VP * len(compacts))(*[c.h for c in compacts])
+        qs = (C.c_char_p * len(query_strings))(*[q.encode() for q in query_strings])
+        first = _lib().fdh_queries_add_many_indexed(self.h, hs, len(compacts), qs, len(query_strings), _ptr(wc), _ptr(ws),
+                                                    len(wc), threads)
+        if first < 0:
+            raise FdError(_err())
+        self.query_strings.extend(query_strings[int(k)] for k in ws)
         return first
 
     def __len__(self):

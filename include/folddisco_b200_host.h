@@ -115,6 +115,11 @@ int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *structure, const cha
 /* n queries at once, query maps built on `threads` host threads (0 = all cores); returns the first query number */
 int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,
                              int64_t n, int threads);
+/* the same for batches that reuse a few structures / query strings (a query file usually does): query k is
+ * (structures[which_structure[k]], query_strings[which_string[k]]); every query map is still built on its own */
+int64_t fdh_queries_add_many_indexed(fdh_queries *qs, const fdh_compact *const *structures, int64_t n_structures,
+                                     const char *const *query_strings, int64_t n_strings, const uint32_t *which_structure,
+                                     const uint32_t *which_string, int64_t n, int threads);
 int64_t fdh_queries_size(const fdh_queries *qs);
 /* finishes make_query_map for the whole batch: one fd_posting_counts call supplies the per-edge idf
  * (calculate_idf_for_hash, query.rs:17-32).  Needs an attached index. */

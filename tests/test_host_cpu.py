@@ -227,3 +227,24 @@ def test_worker_pool_runs_every_index_once_and_concurrent_regions():
     for t in ths:
         t.join()
     assert len(results) == 160 and all(1 <= r <= 4 for r in results)
+
+
+def test_add_many_indexed_equals_add_many(host):
+    """fdh_queries_add_many_indexed (few structures / strings referenced by index) builds the same query maps"""
+    atoms = F.config1_atoms()
+    motifs = [(host.CompactStructure.from_atoms(atoms[p]), q) for p, q, _ in F.MOTIFS]
+    n = 23
+    which = np.arange(n) % 5
+    a = host.QueryBatch()
+    a.add_many([motifs[k][0] for k in which], [motifs[k][1] for k in which], threads=2)
+    b = host.QueryBatch()
+    b.add_many_indexed([m[0] for m in motifs], [m[1] for m in motifs], which, which, threads=2)
+    assert len(a) == len(b) == n and a.query_strings == b.query_strings
+    for q in range(n):
+        ma, mb = a.query_map(q), b.query_map(q)
+        assert len(ma["hash"]) == F.MOTIFS[q % 5][2]
+        for f in ("hash", "qi", "qj", "primary"):
+            assert np.array_equal(ma[f], mb[f]), (q, f)
+        assert np.array_equal(a.indices(q), b.indices(q))
+    with pytest.raises(Exception):
+        b.add_many_indexed([m[0] for m in motifs], [m[1] for m in motifs], [7], [0])

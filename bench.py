@@ -110,6 +110,69 @@ def load_motif_atoms():
     return [(atoms[p], q) for p, q in MOTIFS]
 
 
+def tile_db(db, k):
+    """the database repeated k times (structure ids shifted): k-fold longer posting lists, same per-hash frequencies"""
+    R = int(db["row_offsets"][-1])
+    ro = np.concatenate([db["row_offsets"][:-1].astype(np.uint64) + np.uint64(j * R) for j in range(k)] +
+                        [np.array([k * R], np.uint64)])
+    return dict(row_offsets=ro, n_xyz=np.tile(db["n_xyz"], (k, 1)), ca_xyz=np.tile(db["ca_xyz"], (k, 1)),
+                cb_xyz=np.tile(db["cb_xyz"], (k, 1)), aa=np.tile(db["aa"], k))
+
+
+def distinct_motifs(db, n, first, seed=0x5EED):
+    """n DISTINCT motif queries sampled from the database itself: query number first + k takes structure
+    (first + k) * 7919 mod S, a seeded centre residue and 3-8 residues whose C-alpha lies within 12 A of it
+    (chain A, residue numbers = position + 1: the labels CompactStructure.from_soa gives).
+    -> list of (structure number, residue positions, query string)"""
+    ro = db["row_offsets"].astype(np.int64)
+    S = len(ro) - 1
+    out = []
+    for k in range(first, first + n):
+        rng = np.random.Generator(np.random.PCG64([seed, k]))
+        s = (k * 7919) % S
+        ca = db["ca_xyz"][ro[s]:ro[s + 1]]
+        while True:
+            c = int(rng.integers(0, len(ca)))
+            near = np.flatnonzero(np.linalg.norm(ca - ca[c], axis=1) <= 12.0)
+            near = near[db["aa"][ro[s]:ro[s + 1]][near] < 20]
+            if len(near) >= 3:
+                break
+        m = int(min(len(near), rng.integers(3, 9)))
+        pick = np.sort(rng.choice(near, m, replace=False))
+        out.append((s, pick, ",".join("A%d" % (i + 1) for i in pick)))
+    return out
+
+
+def make_query_batch(ctx, index, db, n, first, sharded=None, dist=None, timing=None):
+    """host.QueryBatch of n queries starting at global query number `first`: distinct motifs sampled from db, or (db is
+    None) the five shipped motifs cycled"""
+    from folddisco_b200 import host
+    t0 = time.perf_counter()
+    qb = host.QueryBatch(index.params)
+    if db is None:
+        motif_structs = [(host.CompactStructure.from_atoms(a), q) for a, q in load_motif_atoms()]
+        which = np.arange(first, first + n, dtype=np.uint32) % len(motif_structs)
+        qb.add_many_indexed([m[0] for m in motif_structs], [m[1] for m in motif_structs], which, which)
+    else:
+        ro = db["row_offsets"].astype(np.int64)
+        motifs = distinct_motifs(db, n, first)
+        comps = [host.CompactStructure.from_soa(db["n_xyz"][ro[s]:ro[s + 1]], db["ca_xyz"][ro[s]:ro[s + 1]],
+                                                db["cb_xyz"][ro[s]:ro[s + 1]], db["aa"][ro[s]:ro[s + 1]])
+                 for s, _, _ in motifs]
+        idx = np.arange(n, dtype=np.uint32)
+        qb.add_many_indexed(comps, [m[2] for m in motifs], idx, idx)
+    t1 = time.perf_counter()
+    if sharded is None:
+        qb.finalize(ctx)
+    else:
+        sharded.prepare(ctx, qb, dist)
+    if timing is not None:
+        timing["query_maps"] += (t1 - t0) * 1e3
+        timing["finalize"] += (time.perf_counter() - t1) * 1e3
+        timing["calls"] += 1
+    return qb
+
+
 def database(rank, world, structs_per_gpu):
     """The same global database on every rank (weak scaling: world * structs_per_gpu structures)."""
     from folddisco_b200 import synth

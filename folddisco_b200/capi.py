@@ -127,6 +127,8 @@ def lib():
     sig("fd_get_entries", C.c_int, [VP, C.c_uint32, PP(PP(C.c_uint64)), PP(C.c_uint64)])
     sig("fd_count_query_batch", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(PP(_StructHit)),
                                           PP(PP(C.c_uint64))])
+    sig("fd_count_query_batch_ex", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), VP, C.c_uint64,
+                                             PP(PP(_StructHit)), PP(PP(C.c_uint64))])
     sig("fd_last_posting_bytes", C.c_uint64, [VP])
     sig("fd_votes_scan", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), PP(VP)])
     sig("fd_votes_scan_sparse", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), VP, C.c_uint32,
@@ -330,15 +332,23 @@ class Context:
                             int(q.get("expected_node_count", q["n_nodes"])), _ptr(eg))
         return arr, keep
 
-    def count_query_batch(self, queries, params=None):
+    def count_query_batch(self, queries, params=None, global_counts=None, global_n_structs=0):
         """queries: list of dicts {hashes u32[], edge_of_hash u16[], edge_node u16[], n_nodes, expected_node_count
-        [, edge_group u16[]]} -> list of structured arrays (HIT_DTYPE), one per query, idf descending / nid ascending"""
+        [, edge_group u16[]]} -> list of structured arrays (HIT_DTYPE), one per query, idf descending / nid ascending.
+        global_counts (u32, one per query hash in batch order) + global_n_structs: the attached index is one id-range
+        shard of a larger database (fd_count_query_batch_ex)"""
         params = params or PrefilterParams()
         nq = len(queries)
         arr, keep = self._query_array(queries)
         ph, po = C.POINTER(_StructHit)(), C.POINTER(C.c_uint64)()
-        self._check(lib().fd_count_query_batch(self.h, arr, nq, C.byref(params), C.byref(ph), C.byref(po)),
-                    "fd_count_query_batch")
+        if global_counts is not None:
+            gc = np.ascontiguousarray(global_counts, np.uint32)
+            assert len(gc) == sum(len(q["hashes"]) for q in queries)
+            self._check(lib().fd_count_query_batch_ex(self.h, arr, nq, C.byref(params), _ptr(gc), int(global_n_structs),
+                                                      C.byref(ph), C.byref(po)), "fd_count_query_batch_ex")
+        else:
+            self._check(lib().fd_count_query_batch(self.h, arr, nq, C.byref(params), C.byref(ph), C.byref(po)),
+                        "fd_count_query_batch")
         off = _take(po, nq + 1, np.uint64)
         hits = _take(ph, int(off[-1]), HIT_DTYPE)
         return [hits[int(off[k]):int(off[k + 1])] for k in range(nq)]

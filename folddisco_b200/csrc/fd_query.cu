@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "fd_async.cuh"
 #include "fd_common.cuh"
 
 void fd_ctx_release_index(fd_ctx *ctx);
@@ -57,13 +58,18 @@ constexpr int K3_MAX_NODES = 256;
 // attach-time kernels
 // ------------------------------------------------------------------------------------------------
 
+// dir[b] = first position whose bucket (hash >> DIR_SHIFT) is >= b, for b in [0, DIR_SIZE]: one thread per bucket,
+// lower bound by binary search (a thread per hash walking the empty buckets after it serialises on sparse indexes)
 __global__ void k3_build_dir(const uint32_t *hashes, uint64_t count, uint32_t *dir) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > count) return;
-    // dir[b] = first position whose bucket >= b
-    const uint32_t lo = k == 0 ? 0u : (hashes[k - 1] >> DIR_SHIFT) + 1u;
-    const uint32_t hi = k == count ? DIR_SIZE : (hashes[k] >> DIR_SHIFT);
-    for (uint32_t b = lo; b <= hi && b <= DIR_SIZE; b++) dir[b] = (uint32_t)k;
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > DIR_SIZE) return;
+    uint64_t lo = 0, hi = count;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)(hashes[mid] >> DIR_SHIFT) < b) lo = mid + 1;
+        else hi = mid;
+    }
+    dir[b] = (uint32_t)lo;
 }
 
 // number of varint terminators (bytes with the top bit clear) per granule
@@ -221,22 +227,28 @@ struct QueryDesc {       // one per query (device copy)
     uint32_t group_iters; // (largest number of vote bits that stand for one query edge) - 1; 0 = no groups
 };
 
-__global__ void k3_lookup(IndexView ix, const uint32_t *qhashes, uint32_t n_qhashes, float freq_filter, QHash *out) {
+// gcounts / g_structs (id-range shards, fd_count_query_batch_ex): the list length and the structure count of the
+// WHOLE database, so that every shard weighs a hash exactly as the unsharded index does (count_query.rs:130); the
+// byte range and QHash::count (pool sizing) stay those of the local list, which may be absent.
+__global__ void k3_lookup(IndexView ix, const uint32_t *qhashes, uint32_t n_qhashes, float freq_filter,
+                          const uint32_t *gcounts, uint32_t g_structs, QHash *out) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_qhashes) return;
     QHash r{0, 0, 0, 0.f};
     const int64_t l = find_list(ix, qhashes[k]);
-    if (l >= 0) {
-        const uint32_t c = ix.counts[l];
-        bool keep = c > 0;
-        // count_query.rs:124-128: skip hashes more frequent than freq_filter
-        if (keep && freq_filter >= 0.f && (float)c / (float)ix.n_structs > freq_filter) keep = false;
-        if (keep) {
+    const uint32_t c_local = l >= 0 ? ix.counts[l] : 0u;
+    const uint32_t c = gcounts ? gcounts[k] : c_local;
+    const uint32_t n_total = gcounts ? g_structs : ix.n_structs;
+    bool keep = c > 0;
+    // count_query.rs:124-128: skip hashes more frequent than freq_filter
+    if (keep && freq_filter >= 0.f && (float)c / (float)n_total > freq_filter) keep = false;
+    if (keep) {
+        if (c_local > 0) {
             r.start = ix.offsets[l];
             r.end = ix.offsets[l + 1];
-            r.count = c;
-            r.idf = log2f((float)ix.n_structs / (float)c);
+            r.count = c_local;
         }
+        r.idf = log2f((float)n_total / (float)c);
     }
     out[k] = r;
 }
@@ -298,6 +310,20 @@ __global__ void k3_decode_list(IndexView ix, uint32_t hash, uint64_t *out, unsig
 __global__ void k3_length_penalty(const uint32_t *nres, uint32_t n, float lp, float *pen) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) pen[k] = powf((float)nres[k], -lp);
+}
+
+// the same table with the static structure filters folded into the sign: negative where the structure fails
+// --num-residue or --plddt (filter.rs:92-98), so that k3_scan_v2 needs one gather per non-empty cell
+__global__ void k3_length_penalty_signed(const uint32_t *nres, const float *plddt, uint32_t n, float lp,
+                                         uint32_t num_res_cutoff, float plddt_cutoff, float *pen) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t nr = nres[k];
+    bool pass = true;
+    if (num_res_cutoff > 0) pass = pass && nr <= num_res_cutoff;
+    if (plddt_cutoff > 0.f) pass = pass && plddt[k] >= plddt_cutoff;
+    const float p = powf((float)nr, -lp);
+    pen[k] = pass ? p : -p;
 }
 
 struct HitRec { // 16 bytes; key/value for the segmented sort are derived from it
@@ -729,6 +755,521 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k3_scan_v2: the single-rank / id-range-shard scan (fd_count_query_batch[_ex]).
+//
+// What changed against k3_scan (kept above for the dense / sparse vote exchange of hash-range shards) and why
+// (profiles/r03*): the first kernel ran one 1024-thread CTA per SM whose phases -- list setup, tile clear, decode,
+// compaction, per-hit gathers -- were each a chain of dependent latencies (28 k cycles per (tile, query) pair for
+// ~5 k postings; the shared-memory atomics themselves sustain 5.5 votes / clock / SM, tools/ubench/smem_atomics.cu),
+// and it appended every non-empty cell to an N-sized hit pool.  Here:
+//   * persistent CTAs (2-3 per SM) take (query, id tile) work items, costliest first, from an atomic counter, so the
+//     phases of different items overlap on an SM and the tail of a launch is short;
+//   * the vote planes are cleared once per CTA; afterwards the epilogue zeroes exactly the cells it visits (lazy
+//     clear), so a work item no longer pays 8-12 B of shared-memory stores per structure up front;
+//   * posting bytes are STAGED: every warp owns a two-stage ring in shared memory; the leader of each 8-lane group
+//     issues one cp.async.bulk (TMA engine, 1-D) of its 64-byte granule + 16 bytes of look-ahead, completion is
+//     counted on the stage's mbarrier, and the copies of step s + 1 are in flight while step s is decoded (the skip
+//     entries of step s + 1 ride in registers the same way);
+//   * the epilogue keeps only the hits that can reach the query's top n: pass 1 builds a shared-memory histogram of
+//     the idf of the passing cells (2048 monotone bins), one warp finds the tile's threshold bin, pass 2 emits the
+//     cells at or above it -- a superset of the tile's top n, hence of the query's -- and the global selection sorts
+//     hundreds of hits per query instead of thousands (no N-sized pool: capacity tiles x (n + slack), overflow is
+//     detected and the batch re-run unlimited);
+//   * the static structure filters (--num-residue, --plddt) ride in the sign of the length-penalty table, so a
+//     non-empty cell costs one 4-byte gather.
+// ------------------------------------------------------------------------------------------------
+constexpr int K3V_MAX_THREADS = 512;              // two co-resident CTAs per SM at <= 64 registers per thread
+constexpr uint32_t K3V_HIST_BINS = 2048;           // idf bin = float bits >> 20 (sign-less): 8 exponent + 3 mantissa bits
+constexpr uint32_t K3V_GRANULE_STAGE = 80;         // 64-byte granule + 16 bytes of look-ahead (a varint may spill 4 bytes)
+constexpr uint32_t K3V_WARP_STAGE = 32 * K3V_GRANULE_STAGE; // one granule per lane per warp step
+constexpr int K3V_DECODE_WARPS = 8;                // warps of a CTA that decode (each owns a stage); all warps run the epilogue
+
+struct ScanItem {
+    uint32_t q, tile;
+};
+
+struct ScanV2Args {
+    const QueryDesc *queries;
+    const QHash *qh;
+    const uint16_t *edge_of_hash, *edge_node, *edge_group;
+    const float *idf_sum;
+    const float *pen; // nres^-lp, negative where the structure fails --num-residue / --plddt
+    const ScanItem *items;
+    uint32_t n_items;
+    unsigned int *item_counter;
+    uint32_t tile_words;                  // u32 words of vote planes per CTA (multiple of 4)
+    uint32_t max_hashes, max_nodes, max_ew; // sizes of the fixed shared-memory arrays
+    uint32_t stage_lists;
+    uint32_t limit_n;                     // > 0: keep only hits that can reach the tile's top limit_n
+    FilterParams fp;
+    const uint64_t *hit_offsets;          // [nq + 1] hit regions
+    unsigned int *hit_counts;
+    HitRec *hits;
+    unsigned int *overflow;               // set when a region was too small (host re-runs unlimited)
+    uint32_t *scratch;                    // [grid][3][scratch_cap] per-CTA entry lists of the epilogue
+    uint32_t scratch_cap;                 // >= the largest tile (cells)
+    uint32_t use_bulk;                    // posting bytes staged by bulk copies (else: plain vector loads; A/B switch)
+};
+
+__host__ __device__ __forceinline__ uint32_t k3v_edge_words(uint32_t n_edges) {
+    return n_edges <= 32 ? 1u : (n_edges + 31u) >> 5;
+}
+__host__ __device__ __forceinline__ uint32_t k3v_tile_ids(uint32_t tile_words, uint32_t planes, uint32_t n_structs) {
+    uint32_t t = (tile_words / planes) & ~31u;
+    const uint32_t n32 = (n_structs + 31u) & ~31u;
+    return t > n32 ? n32 : t;
+}
+__device__ __forceinline__ uint32_t k3v_idf_bin(float idf) {
+    const uint32_t u = __float_as_uint(idf);
+    return (u & 0x80000000u) ? 0u : (u >> 20);
+}
+
+template <bool NARROW>
+__global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, ScanV2Args a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t MQ = a.max_hashes;
+    // ---- shared-memory carve-up ----
+    uint32_t *planes = smem;                                                            // [tile_words]
+    uint64_t *l_range = reinterpret_cast<uint64_t *>(planes + a.tile_words);            // [2 MQ] start, end (staged)
+    uint32_t *l_vote = reinterpret_cast<uint32_t *>(l_range + (a.stage_lists ? 2 * MQ : 0)); // [2 MQ] vote word, edge
+    uint32_t *item_prefix = l_vote + (a.stage_lists ? 2 * MQ : 0);                      // [MQ + 1]
+    uint32_t *seg_lo = item_prefix + (MQ + 1);                                          // [MQ]
+    uint32_t *node_mask = seg_lo + MQ;                                                  // [max_nodes * max_ew + max_ew]
+    uint32_t *hist = node_mask + a.max_nodes * a.max_ew + a.max_ew;                     // [K3V_HIST_BINS]
+    uint32_t *wqueue = hist + K3V_HIST_BINS;                                            // [nwarps * K3_WQ]
+    uintptr_t sp = reinterpret_cast<uintptr_t>(wqueue + nwarps * K3_WQ);
+    sp = (sp + 15) & ~(uintptr_t)15;
+    const uint32_t n_dwarps = min(nwarps, (uint32_t)K3V_DECODE_WARPS);
+    uint8_t *stage = reinterpret_cast<uint8_t *>(sp);                                   // [n_dwarps][K3V_WARP_STAGE]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage + (size_t)n_dwarps * K3V_WARP_STAGE); // [n_dwarps]
+    __shared__ uint32_t s_item, s_total_items, s_thr, s_n, s_nk;
+
+    uint8_t *wstage = stage + (size_t)min(warp, n_dwarps - 1) * K3V_WARP_STAGE;
+    uint64_t *wbar = bars + min(warp, n_dwarps - 1);
+    if (lane == 0 && warp < n_dwarps) fda::mbar_init(wbar, 1);
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(planes);
+        for (uint32_t i = tid; i < (a.tile_words >> 2); i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < K3V_HIST_BINS; i += blockDim.x) hist[i] = 0;
+    }
+    fda::mbar_fence_init();
+    __syncthreads();
+    uint32_t phase = 0; // parity of the warp's stage barrier
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(a.item_counter, 1u);
+        __syncthreads();
+        const uint32_t item_no = s_item;
+        if (item_no >= a.n_items) break;
+        const ScanItem item = a.items[item_no];
+        const uint32_t q = item.q;
+        const QueryDesc qd = a.queries[q];
+        const uint32_t Q = qd.n_hashes;
+        const uint32_t EW = k3v_edge_words(qd.n_edges);
+        const uint32_t PL = (NARROW ? 1u : 2u) + EW;
+        const uint32_t tile_ids = k3v_tile_ids(a.tile_words, PL, ix.n_structs);
+        const uint32_t lo = item.tile * tile_ids;
+        const uint32_t hi = min(ix.n_structs, lo + tile_ids);
+        const uint32_t T = hi - lo;
+        const bool single_tile = tile_ids >= ix.n_structs;
+        uint32_t *w_acc = planes;
+        uint32_t *w_match = NARROW ? nullptr : planes + tile_ids;
+        uint32_t *w_edge = planes + (NARROW ? 1 : 2) * tile_ids;
+        uint32_t *cont_mask = node_mask + qd.n_nodes * EW;
+        const float scale = idf_scale<NARROW>(a.idf_sum[q]);
+        const float inv_scale = 1.0f / scale;
+        for (uint32_t i = tid; i < qd.n_nodes * EW + EW; i += blockDim.x) node_mask[i] = 0; // + cont_mask
+
+        // ---- which 64-byte granules of each list intersect this tile ----
+        for (uint32_t k = tid; k < Q; k += blockDim.x) {
+            const QHash h = a.qh[qd.hash_begin + k];
+            uint32_t n_items = 0, first = 0;
+            if (h.end > h.start) {
+                const uint64_t b0 = h.start >> SKIP_SHIFT, b1 = (h.end - 1) >> SKIP_SHIFT;
+                const uint32_t nseg = (uint32_t)(b1 - b0) + 1;
+                if (single_tile || nseg == 1) {
+                    n_items = nseg;
+                } else {
+                    // r(k') = skip_id[b0 + k'], k' in [1, nseg - 1], non-decreasing: the id of the last posting that
+                    // starts before granule k'
+                    const uint32_t *r = ix.skip_id + b0;
+                    uint32_t x = 1, y = nseg; // first k' with r(k') >= lo
+                    while (x < y) {
+                        const uint32_t m = (x + y) >> 1;
+                        if (r[m] < lo) x = m + 1;
+                        else y = m;
+                    }
+                    const uint32_t below_lo = x - 1;
+                    y = nseg; // continue from x: first k' with r(k') >= hi
+                    while (x < y) {
+                        const uint32_t m = (x + y) >> 1;
+                        if (r[m] < hi) x = m + 1;
+                        else y = m;
+                    }
+                    const uint32_t below_hi = x - 1;
+                    first = below_lo;                  // granule below_lo may still hold ids >= lo
+                    n_items = below_hi + 1 - below_lo; // granules [below_lo, below_hi]
+                }
+            }
+            seg_lo[k] = first;
+            item_prefix[k + 1] = n_items;
+            if (a.stage_lists) {
+                l_range[2 * k] = h.start;
+                l_range[2 * k + 1] = h.end;
+                const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
+                l_vote[2 * k] = NARROW ? ((1u << 24) | wgt) : wgt;
+                l_vote[2 * k + 1] = a.edge_of_hash[qd.hash_begin + k];
+            }
+        }
+        if (tid == 0) item_prefix[0] = 0;
+        __syncthreads();
+        for (uint32_t e = tid; e < qd.n_edges; e += blockDim.x) {
+            atomicOr(&node_mask[a.edge_node[qd.edge_begin + e] * EW + (e >> 5)], 1u << (e & 31));
+            if (qd.group_iters && (e & 31) && a.edge_group[qd.edge_begin + e] == a.edge_group[qd.edge_begin + e - 1])
+                atomicOr(&cont_mask[e >> 5], 1u << (e & 31));
+        }
+        if (tid < 32) { // inclusive scan of item_prefix[1..Q]
+            uint32_t carry = 0;
+            for (uint32_t base = 1; base <= Q; base += 32) {
+                const uint32_t idx = base + tid;
+                uint32_t v = idx <= Q ? item_prefix[idx] : 0;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+                    if ((int)tid >= o) v += t;
+                }
+                v += carry;
+                if (idx <= Q) item_prefix[idx] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+            if (tid == 0) s_total_items = carry;
+        }
+        __syncthreads();
+        const uint32_t total_items = s_total_items;
+        if (total_items == 0) continue; // nothing of this query's lists falls into the tile; the planes stay clean
+
+        // ---- decode + vote: ONE LANE PER GRANULE ----
+        // A decode warp takes 32 granules per step.  Lane leaders issue one bulk copy (granule + 16 bytes of look-ahead)
+        // each into the warp's stage; after the mbarrier wait every lane pulls its 80 bytes into registers (five
+        // conflict-free LDS.128), the copies of the next step are issued into the same stage, and the lane walks its
+        // bytes with a fully unrolled LEB128 state machine (~9 instructions per byte, ~18 per posting; the 8-lanes-per-
+        // granule decoder of k3_scan spent ~200 on short lists).  Votes are fire-and-forget shared-memory atomics.
+        if (warp < n_dwarps) {
+            const uint32_t gpc = n_dwarps << 5; // granules per CTA step
+            const uint32_t nsteps = (total_items + gpc - 1) / gpc;
+            uint8_t *myslot = wstage + lane * K3V_GRANULE_STAGE;
+            uint32_t pk = 0, pseg = 0, psid = 0, psoff = 0, pn = 0;
+            uint64_t pgi = 0;
+            bool pact = false;
+            auto prefetch = [&](uint32_t s) {
+                const uint32_t it = s * gpc + (warp << 5) + lane;
+                pact = it < total_items;
+                pk = pseg = psid = psoff = 0;
+                uint64_t gi = 0;
+                if (pact) {
+                    uint32_t x = 0, y = Q; // list index: last k with item_prefix[k] <= it
+                    while (y - x > 1) {
+                        const uint32_t m = (x + y) >> 1;
+                        if (item_prefix[m] <= it) x = m;
+                        else y = m;
+                    }
+                    pk = x;
+                    pseg = seg_lo[x] + (it - item_prefix[x]);
+                    const uint64_t h_start = a.stage_lists ? l_range[2 * x] : a.qh[qd.hash_begin + x].start;
+                    gi = (h_start >> SKIP_SHIFT) + pseg;
+                    if (pseg) {
+                        psoff = ix.skip_off[gi];
+                        psid = ix.skip_id[gi];
+                    }
+                }
+                pn = __popc(__ballot_sync(0xffffffffu, pact));
+                pgi = gi;
+                if (pn && a.use_bulk) {
+                    if (lane == 0) fda::mbar_arrive_expect_tx(wbar, pn * K3V_GRANULE_STAGE);
+                    __syncwarp();
+                    if (pact) fda::bulk_g2s(myslot, ix.values + (gi << SKIP_SHIFT), K3V_GRANULE_STAGE, wbar);
+                }
+            };
+            prefetch(0);
+            for (uint32_t s = 0; s < nsteps; s++) {
+                const uint32_t ck = pk, cseg = pseg, csid = psid, csoff = psoff, cn = pn;
+                const bool act = pact;
+                if (cn == 0) break; // the items are handed out in ascending order: no later step has one for this warp
+                if (a.use_bulk) {
+                    fda::mbar_wait(wbar, phase);
+                    phase ^= 1u;
+                }
+                uint32_t W[20];
+                {
+                    const uint4 *src = a.use_bulk ? reinterpret_cast<const uint4 *>(myslot)
+                                                  : reinterpret_cast<const uint4 *>(ix.values + (pgi << SKIP_SHIFT));
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        const uint4 v = src[j];
+                        W[4 * j] = v.x;
+                        W[4 * j + 1] = v.y;
+                        W[4 * j + 2] = v.z;
+                        W[4 * j + 3] = v.w;
+                    }
+                }
+                __syncwarp(); // every lane holds its bytes in registers: the stage is free for the next step's copies
+                if (s + 1 < nsteps) prefetch(s + 1);
+                else pn = 0;
+                uint32_t lp0 = 0xff, lp1 = 0, lid = 0, ladd = 0, lebit = 0; // this lane's byte range [lp0, lp1), running id, vote
+                uint32_t *ledge = w_edge;
+                if (act) {
+                    uint64_t h_start, h_end;
+                    uint32_t add, e;
+                    if (a.stage_lists) {
+                        h_start = l_range[2 * ck];
+                        h_end = l_range[2 * ck + 1];
+                        add = l_vote[2 * ck];
+                        e = l_vote[2 * ck + 1];
+                    } else {
+                        const QHash h = a.qh[qd.hash_begin + ck];
+                        h_start = h.start;
+                        h_end = h.end;
+                        e = a.edge_of_hash[qd.hash_begin + ck];
+                        const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
+                        add = NARROW ? ((1u << 24) | wgt) : wgt;
+                    }
+                    const uint64_t G0 = ((h_start >> SKIP_SHIFT) + cseg) << SKIP_SHIFT;
+                    // varints that START in [p0, p1) of this granule are this lane's; the last one may end in the look-ahead
+                    const uint32_t p0 = cseg == 0 ? (uint32_t)(h_start - G0) : csoff;
+                    const uint32_t p1 = (uint32_t)min(h_end - G0, (uint64_t)SKIP_BYTES);
+                    uint32_t id = (cseg == 0 ? 0u : csid) - lo; // tile-relative running id (wraps below the tile)
+                    const uint32_t ebit = 1u << (e & 31);
+                    uint32_t *edge_plane = w_edge + (e >> 5) * tile_ids;
+                    lp0 = p0;
+                    lp1 = p1;
+                    lid = id;
+                    ladd = add;
+                    lebit = ebit;
+                    ledge = edge_plane;
+                }
+                // the warp walks only the words that hold bytes of some lane's range (short lists fill a fraction of
+                // their granule); a varint that starts before byte 64 may end in the look-ahead word
+                const uint32_t wlo = __reduce_min_sync(0xffffffffu, act ? lp0 : 0xffu) >> 2;
+                const uint32_t whi = __reduce_max_sync(0xffffffffu, act ? lp1 : 0u);
+                uint32_t cur = 0, shift = 0;
+#pragma unroll
+                for (int w = 0; w < (int)(SKIP_BYTES / 4) + 1; w++) {
+                    if (w < (int)(SKIP_BYTES / 4) ? ((uint32_t)w < wlo || (uint32_t)(4 * w) >= whi) : whi < SKIP_BYTES) continue;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int p = 4 * w + b;
+                        const uint32_t byte = (W[w] >> (8 * b)) & 0xffu;
+                        const bool on = p < (int)SKIP_BYTES ? ((uint32_t)p >= lp0 && ((uint32_t)p < lp1 || shift != 0)) : shift != 0;
+                        if (on) {
+                            cur |= (byte & 0x7fu) << shift;
+                            if (byte & 0x80u) {
+                                shift += 7;
+                            } else {
+                                lid += cur;
+                                cur = 0;
+                                shift = 0;
+                                if (lid < T) {
+                                    atomicAdd(&w_acc[lid], ladd);
+                                    if (!NARROW) atomicAdd(&w_match[lid], 1u);
+                                    atomicOr(&ledge[lid], lebit);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- epilogue ----
+        // one non-empty cell: match count, idf, filter_before_matching (filter.rs:76-100) without the node filters
+        auto eval = [&](uint32_t x, uint32_t v, uint32_t &mc, float &idf) -> bool {
+            mc = NARROW ? (v >> 24) : w_match[x];
+            const uint32_t fixed = NARROW ? (v & 0xffffffu) : v;
+            const float p = a.pen[lo + x];
+            idf = ((float)fixed * inv_scale) * fabsf(p);
+            bool pass = (__float_as_uint(p) >> 31) == 0u; // --num-residue, --plddt
+            if (a.fp.total_match_count > 0) pass = pass && mc >= a.fp.total_match_count;
+            if (a.fp.idf_score_cutoff > 0.f) pass = pass && idf >= a.fp.idf_score_cutoff;
+            return pass;
+        };
+        auto node_count = [&](uint32_t x) -> uint32_t {
+            uint32_t nc = 0;
+            if (EW == 1) {
+                const uint32_t ebits = w_edge[x];
+                for (uint32_t nd = 0; nd < qd.n_nodes; nd++) nc += (ebits & node_mask[nd]) != 0;
+            } else {
+                for (uint32_t nd = 0; nd < qd.n_nodes; nd++) {
+                    uint32_t any = 0;
+                    for (uint32_t i = 0; i < EW; i++) any |= w_edge[i * tile_ids + x] & node_mask[nd * EW + i];
+                    nc += any != 0;
+                }
+            }
+            return nc;
+        };
+        const bool node_filters = a.fp.covered_node_count > 0 || a.fp.covered_node_ratio > 0.f;
+        auto node_pass = [&](uint32_t nc) -> bool {
+            bool pass = true;
+            if (a.fp.covered_node_count > 0) pass = pass && nc >= a.fp.covered_node_count;
+            if (a.fp.covered_node_ratio > 0.f)
+                pass = pass && (float)nc / (float)qd.expected_node_count >= a.fp.covered_node_ratio;
+            return pass;
+        };
+        // Phase A: the voted cells are compacted (warp by warp: four cells per lane, ballot-free prefix sums) and each
+        // is evaluated ONCE on full lanes; entry = (cell | FAIL flag, idf) in the CTA's scratch lists (global memory,
+        // L2-resident), cells that fail the filters are cleared at once.  With a top-n limit the idf of the passing
+        // cells also feeds the tile's histogram.
+        // Phase B (limit only): entries at or above the tile's threshold bin are appended to the keep list, the rest
+        // cleared.  Phase C: node / edge counts and the hit records of the kept entries, on full lanes; clears them.
+        const uint32_t *occ = NARROW ? w_acc : w_match; // the plane whose word is non-zero exactly in the voted cells
+        const uint32_t T4 = (T + 3) >> 2;               // cells are scanned four at a time (the planes are padded to 32)
+        uint32_t *ent_x = a.scratch + (size_t)blockIdx.x * 3 * a.scratch_cap;
+        float *ent_idf = reinterpret_cast<float *>(ent_x + a.scratch_cap);
+        uint32_t *keep_e = ent_x + 2 * a.scratch_cap;
+        constexpr uint32_t FAIL = 0x80000000u;
+        auto clear_cell = [&](uint32_t x) {
+            w_acc[x] = 0;
+            if (!NARROW) w_match[x] = 0;
+            for (uint32_t i = 0; i < EW; i++) w_edge[i * tile_ids + x] = 0;
+        };
+        if (tid == 0) {
+            s_n = 0;
+            s_nk = 0;
+        }
+        __syncthreads();
+        {
+            uint32_t *wq = wqueue + warp * K3_WQ;
+            const uint32_t n_iter = (T4 + blockDim.x - 1) / blockDim.x;
+            for (uint32_t itn = 0; itn < n_iter; itn++) {
+                const uint32_t x4 = (itn * nwarps + warp) * 32 + lane; // a warp reads 512 contiguous bytes
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (x4 < T4) o = reinterpret_cast<const uint4 *>(occ)[x4];
+                const uint32_t nz = (o.x ? 1u : 0u) | (o.y ? 2u : 0u) | (o.z ? 4u : 0u) | (o.w ? 8u : 0u);
+                const uint32_t cnt = __popc(nz);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, ofs);
+                    if ((int)lane >= ofs) incl += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total == 0) continue;
+                uint32_t pos = incl - cnt;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if ((nz >> j) & 1u) wq[pos++] = 4 * x4 + j;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                __syncwarp();
+                for (uint32_t r = lane; r < total; r += 32) {
+                    const uint32_t x = wq[r];
+                    uint32_t mc;
+                    float idf;
+                    bool pass = eval(x, w_acc[x], mc, idf);
+                    if (pass && node_filters) pass = node_pass(node_count(x));
+                    if (pass) {
+                        if (a.limit_n) atomicAdd(&hist[k3v_idf_bin(idf)], 1u);
+                    } else {
+                        clear_cell(x);
+                    }
+                    ent_x[base + r] = pass ? x : (x | FAIL);
+                    ent_idf[base + r] = idf;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const uint32_t n_ent = s_n;
+        uint32_t n_keep = n_ent;
+        if (a.limit_n) {
+            if (warp == 0) { // highest bin such that the bins at or above it hold at least limit_n cells
+                uint32_t above = 0, t = 0;
+                for (int c = (int)(K3V_HIST_BINS / 32) - 1; c >= 0; c--) {
+                    const uint32_t v = hist[c * 32 + lane];
+                    uint32_t suf = v; // suffix sum over lanes >= lane
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t u = __shfl_down_sync(0xffffffffu, suf, o);
+                        if ((int)lane + o < 32) suf += u;
+                    }
+                    const uint32_t reach = __ballot_sync(0xffffffffu, above + suf >= a.limit_n);
+                    if (reach) {
+                        t = c * 32 + (31 - __clz(reach));
+                        break;
+                    }
+                    above += __shfl_sync(0xffffffffu, suf, 0);
+                }
+                if (lane == 0) s_thr = t;
+            }
+            __syncthreads();
+            const uint32_t thr = s_thr;
+            for (uint32_t i = tid; i < K3V_HIST_BINS; i += blockDim.x) hist[i] = 0;
+            const uint32_t n_round = (n_ent + 31) & ~31u;
+            for (uint32_t e0 = tid; e0 < n_round; e0 += blockDim.x) {
+                bool keep = false;
+                if (e0 < n_ent) {
+                    const uint32_t xf = ent_x[e0];
+                    if (!(xf & FAIL)) {
+                        keep = k3v_idf_bin(ent_idf[e0]) >= thr;
+                        if (!keep) clear_cell(xf);
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    uint32_t pos = 0;
+                    if (lane == 0) pos = atomicAdd(&s_nk, (uint32_t)__popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                    if (keep) keep_e[pos] = e0;
+                }
+            }
+            __syncthreads();
+            n_keep = s_nk;
+        }
+        {
+            const uint64_t hbase = a.hit_offsets[q];
+            const uint32_t hcap = (uint32_t)(a.hit_offsets[q + 1] - hbase);
+            const uint32_t n_round = (n_keep + 31) & ~31u;
+            for (uint32_t k0 = tid; k0 < n_round; k0 += blockDim.x) {
+                bool emit = false;
+                HitRec rec{0, 0, 0, 0.f};
+                if (k0 < n_keep) {
+                    const uint32_t e0 = a.limit_n ? keep_e[k0] : k0;
+                    const uint32_t xf = ent_x[e0];
+                    if (!(xf & FAIL)) {
+                        const uint32_t x = xf;
+                        const uint32_t mc = NARROW ? (w_acc[x] >> 24) : w_match[x];
+                        uint32_t ec = 0;
+                        for (uint32_t i = 0; i < EW; i++) {
+                            // bits of one group (fd_query.edge_group) count once: smear every set bit down to the
+                            // first bit of its group, then count first bits
+                            uint32_t g = w_edge[i * tile_ids + x];
+                            const uint32_t cm = cont_mask[i];
+                            for (uint32_t itg = 0; itg < qd.group_iters; itg++) g |= (g & cm) >> 1;
+                            ec += __popc(g & ~cm);
+                        }
+                        rec = HitRec{lo + x, mc, (node_count(x) << 16) | (ec & 0xffffu), ent_idf[e0]};
+                        emit = true;
+                        clear_cell(x);
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                if (m) {
+                    uint32_t pos = 0;
+                    if (lane == 0) pos = atomicAdd(&a.hit_counts[q], (unsigned int)__popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                    if (emit) {
+                        if (pos < hcap) a.hits[hbase + pos] = rec;
+                        else atomicOr(a.overflow, 1u);
+                    }
+                }
+            }
+        }
+        // the next item's setup writes only the list arrays and masks, which nobody reads any more after the
+        // barrier at the top of the loop
+    }
+}
+
 // The epilogue of k3_scan over merged dense votes: grid (id tiles, queries of the slice).
 template <bool NARROW, int EW>
 __global__ void __launch_bounds__(K3_THREADS)
@@ -891,13 +1432,13 @@ FilterParams make_filter(const fd_prefilter_params *params) {
 
 // The batch flattened on the host and uploaded: per-hash arrays, per-edge node ids, query descriptors.
 struct Batch {
-    std::vector<uint32_t> f_hash;
+    std::vector<uint32_t> f_hash, f_gcount;
     std::vector<uint16_t> f_edge, f_edge_node, f_edge_group;
     std::vector<QueryDesc> descs;
     uint32_t max_hashes = 0, max_edges = 0, max_nodes = 0;
     bool narrow = true;
     int ew = 1;
-    DevBuf<uint32_t> d_hash;
+    DevBuf<uint32_t> d_hash, d_gcount;
     DevBuf<uint16_t> d_edge, d_edge_node, d_edge_group;
     DevBuf<QueryDesc> d_desc;
     DevBuf<QHash> d_qh;
@@ -909,7 +1450,7 @@ struct Batch {
 // flatten + sample_query (count_query.rs:222-253) + upload + lookup + per-query sums + length-penalty table.
 // need_hashes = false: only descriptors and edge nodes are needed (fd_votes_select).
 int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
-                  bool need_hashes, int bound_mode, Batch &B) {
+                  bool need_hashes, int bound_mode, Batch &B, const uint32_t *gcounts = nullptr, uint64_t g_structs = 0) {
     cudaStream_t s = ctx->stream;
     const uint32_t N = (uint32_t)ctx->idx.n_structs;
     const bool has_r = params->sampling_ratio >= 0.f, has_c = params->sampling_count >= 0;
@@ -920,8 +1461,10 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
         std::vector<uint32_t> all;
         for (uint32_t q = 0; q < nq; q++) all.insert(all.end(), queries[q].hashes, queries[q].hashes + queries[q].n_hashes);
         sample_counts.resize(all.size());
-        FD_TRY(fd_posting_counts(ctx, all.data(), all.size(), sample_counts.data()));
+        if (gcounts) std::copy(gcounts, gcounts + all.size(), sample_counts.begin()); // id-range shards: global list lengths
+        else FD_TRY(fd_posting_counts(ctx, all.data(), all.size(), sample_counts.data()));
     }
+    size_t gbase = 0; // position of the query's first hash in gcounts
     size_t sample_base = 0;
     std::vector<uint32_t> order;
     for (uint32_t q = 0; q < nq; q++) {
@@ -957,7 +1500,9 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
             if (Q.edge_of_hash[k] >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
             B.f_hash.push_back(Q.hashes[k]);
             B.f_edge.push_back(Q.edge_of_hash[k]);
+            if (gcounts) B.f_gcount.push_back(gcounts[gbase + k]);
         }
+        gbase += Q.n_hashes;
         for (uint32_t e = 0; e < Q.n_edges; e++) {
             if (Q.edge_node[e] >= Q.n_nodes) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_node out of range");
             B.f_edge_node.push_back(Q.edge_node[e]);
@@ -995,12 +1540,17 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
     if (need_hashes && nqh) {
         FD_CUDA(ctx, cudaMemcpyAsync(B.d_hash.p, B.f_hash.data(), nqh * 4, cudaMemcpyHostToDevice, s));
         FD_CUDA(ctx, cudaMemcpyAsync(B.d_edge.p, B.f_edge.data(), nqh * 2, cudaMemcpyHostToDevice, s));
-        FD_LAUNCH(ctx, k3_lookup, fd_div_up(nqh, 256), 256, 0, ix, B.d_hash.p, nqh, params->freq_filter, B.d_qh.p);
+        if (gcounts) {
+            FD_CUDA(ctx, B.d_gcount.alloc(nqh));
+            FD_CUDA(ctx, cudaMemcpyAsync(B.d_gcount.p, B.f_gcount.data(), nqh * 4, cudaMemcpyHostToDevice, s));
+        }
+        FD_LAUNCH(ctx, k3_lookup, fd_div_up(nqh, 256), 256, 0, ix, B.d_hash.p, nqh, params->freq_filter,
+                  gcounts ? B.d_gcount.p : (const uint32_t *)nullptr, (uint32_t)g_structs, B.d_qh.p);
     } else if (nqh) {
         FD_CUDA(ctx, cudaMemsetAsync(B.d_qh.p, 0, nqh * sizeof(QHash), s));
     }
-    FD_LAUNCH(ctx, k3_query_sums, fd_div_up(nq, 128), 128, 0, B.d_desc.p, B.d_qh.p, nq, N, bound_mode, B.d_postings.p,
-              B.d_bytes.p, B.d_idfsum.p);
+    FD_LAUNCH(ctx, k3_query_sums, fd_div_up(nq, 128), 128, 0, B.d_desc.p, B.d_qh.p, nq,
+              gcounts ? (uint32_t)g_structs : N, bound_mode, B.d_postings.p, B.d_bytes.p, B.d_idfsum.p);
     if (need_hashes) {
         std::vector<unsigned long long> h_bytes(nq);
         FD_CUDA(ctx, cudaMemcpyAsync(B.h_postings.data(), B.d_postings.p, nq * 8, cudaMemcpyDeviceToHost, s));
@@ -1232,7 +1782,7 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     else FD_CUDA(ctx, cudaMemsetAsync(d.plddt, 0, std::max<uint64_t>(n_structs, 1) * 4, s));
 
     StageTimer st(ctx, "attach");
-    FD_LAUNCH(ctx, k3_build_dir, fd_div_up(count + 1, 256), 256, 0, d.hashes, count, d.dir);
+    FD_LAUNCH(ctx, k3_build_dir, fd_div_up((uint64_t)DIR_SIZE + 1, 256), 256, 0, d.hashes, count, d.dir);
     // posting counts per list
     DevBuf<uint32_t> terms;
     DevBuf<uint64_t> terms64, block_prefix, partial, scanned;
@@ -1308,20 +1858,89 @@ int fd_get_entries(fd_ctx *ctx, uint32_t hash, uint64_t **out_ids, uint64_t *out
     return FD_OK;
 }
 
-int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
-                         fd_struct_hit **out_hits, uint64_t **out_offsets) {
-    if (!ctx) return FD_ERR_ARG;
-    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_count_query_batch: no index attached");
-    if ((nq && !queries) || !params || !out_hits || !out_offsets)
-        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_batch: NULL argument");
-    FD_ENTER(ctx);
+// the first scan kernel (one CTA per (tile, query), one launch per edge-word class); FD_K3_V1=1 selects it
+static int scan_v1(fd_ctx *ctx, const Batch &B, uint32_t nq, uint32_t N, const fd_prefilter_params *params,
+                   const DevBuf<uint64_t> &d_hit_off, DevBuf<unsigned int> &d_hit_cnt, DevBuf<HitRec> &d_hits) {
+    cudaStream_t s = ctx->stream;
+    std::vector<uint32_t> qorder;
+    uint32_t class_begin[5];
+    const int class_ew[4] = {1, 2, 4, 8};
+    edge_word_classes(B, nq, qorder, class_begin);
+    DevBuf<uint32_t> d_qorder;
+    FD_CUDA(ctx, d_qorder.alloc(nq));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_qorder.p, qorder.data(), nq * 4, cudaMemcpyHostToDevice, s));
+    StageTimer st(ctx, "scan");
+    for (int c = 0; c < 4; c++) {
+        const uint32_t nc = class_begin[c + 1] - class_begin[c];
+        if (!nc) continue;
+        const int ew = std::min(class_ew[c], B.ew);
+        TilePlan tp;
+        FD_TRY(plan_tiles(ctx, B, N, tp, ew));
+        FD_TRY(launch_scan<0>(ctx, dim3(tp.n_tiles, nc), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
+                              d_hit_cnt.p, d_hits.p, nullptr, SparseOut{nullptr, nullptr, nullptr, 0, 0},
+                              d_qorder.p + class_begin[c], ew));
+    }
+    FD_CUDA(ctx, st.finish());
+    return FD_OK;
+}
+
+// Shared-memory plan of k3_scan_v2: CTAs per SM, threads, bytes per CTA, words of vote planes.
+struct ScanV2Plan {
+    uint32_t ctas_per_sm, threads, tile_words;
+    size_t smem;
+    bool stage_lists;
+};
+static int plan_scan_v2(fd_ctx *ctx, const Batch &B, ScanV2Plan &pl) {
+    uint32_t ctas = 2, threads = 512;
+    if (const char *e = getenv("FD_K3_CTAS")) ctas = (uint32_t)std::min(4, std::max(1, atoi(e)));
+    if (const char *e = getenv("FD_K3_THREADS")) threads = (uint32_t)std::min(K3V_MAX_THREADS, std::max(64, atoi(e) & ~31));
+    if (ctas * threads > 1024) threads = (1024 / ctas) & ~31u; // the kernel is compiled for 64 registers per thread
+    const uint32_t max_ew = k3v_edge_words(B.max_edges);
+    pl.stage_lists = k3_stage_lists(B.max_hashes);
+    // 228 KB per SM, 1 KB reserved per resident CTA, at most 227 KB per CTA
+    const size_t per_cta = std::min<size_t>(227 * 1024, (228 * 1024) / ctas - 1024 - 128); // 1 KB reserved per CTA + the kernel's static shared memory
+    const size_t fixed = ((size_t)(pl.stage_lists ? 8 : 2) * B.max_hashes + 2 + (size_t)B.max_nodes * max_ew + max_ew +
+                          K3V_HIST_BINS + (size_t)(threads / 32) * K3_WQ) * 4 + 16 +
+                         (size_t)std::min<uint32_t>(threads / 32, K3V_DECODE_WARPS) * (K3V_WARP_STAGE + 8) + 64;
+    const uint32_t planes_max = (B.narrow ? 1u : 2u) + max_ew;
+    if (per_cta < fixed + (size_t)256 * planes_max * 4) {
+        if (ctas > 1) { // very wide queries: one CTA per SM
+            ctas = 1;
+            threads = std::min<uint32_t>(threads, K3V_MAX_THREADS);
+            const size_t one = 227 * 1024;
+            if (one < fixed + (size_t)256 * planes_max * 4)
+                return fd_fail(ctx, FD_ERR_LIMIT, "query needs more shared memory than one SM has");
+            pl.ctas_per_sm = 1;
+            pl.threads = threads;
+            pl.tile_words = (uint32_t)((one - fixed) / 4) & ~3u;
+            pl.smem = (size_t)pl.tile_words * 4 + fixed;
+            return FD_OK;
+        }
+        return fd_fail(ctx, FD_ERR_LIMIT, "query needs more shared memory than one SM has");
+    }
+    pl.ctas_per_sm = ctas;
+    pl.threads = threads;
+    pl.tile_words = (uint32_t)((per_cta - fixed) / 4) & ~3u;
+    pl.smem = (size_t)pl.tile_words * 4 + fixed;
+    return FD_OK;
+}
+
+struct CountOpts {
+    const uint32_t *gcounts = nullptr; // id-range shards: global posting count of every query hash (flattened, batch order)
+    uint64_t g_structs = 0;            // and the structure count of the whole database
+};
+
+static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                            const CountOpts &opts, fd_struct_hit **out_hits, uint64_t **out_offsets) {
     *out_hits = nullptr;
     *out_offsets = nullptr;
     cudaStream_t s = ctx->stream;
     const uint32_t N = (uint32_t)ctx->idx.n_structs;
     ctx->last_posting_bytes = 0;
     Batch B;
-    FD_TRY(prepare_batch(ctx, queries, nq, params, true, 0, B));
+    // id-range shards: the fixed-point scale of the idf sum must be the same on every rank -> bound from the global
+    // list lengths (k3_query_sums sums the idf of all query hashes, present locally or not)
+    FD_TRY(prepare_batch(ctx, queries, nq, params, true, 0, B, opts.gcounts, opts.g_structs));
     uint64_t *h_off = (uint64_t *)calloc((size_t)nq + 1, 8);
     if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
     if (nq == 0 || N == 0 || B.f_hash.empty()) {
@@ -1329,49 +1948,124 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, cons
         *out_hits = (fd_struct_hit *)malloc(sizeof(fd_struct_hit));
         return FD_OK;
     }
-    // hit regions: a query can hit at most min(N, its postings) structures
-    std::vector<uint64_t> hit_off(nq + 1, 0);
-    for (uint32_t q = 0; q < nq; q++) hit_off[q + 1] = hit_off[q] + std::min<uint64_t>(N, B.h_postings[q]);
-    DevBuf<uint64_t> d_hit_off;
-    DevBuf<unsigned int> d_hit_cnt;
-    DevBuf<HitRec> d_hits;
-    int rc = FD_OK;
-    auto body = [&]() -> int {
+    const bool use_v1 = getenv("FD_K3_V1") && atoi(getenv("FD_K3_V1")) != 0;
+    ScanV2Plan pl{};
+    if (!use_v1) {
+        const int rc = plan_scan_v2(ctx, B, pl);
+        if (rc != FD_OK) {
+            free(h_off);
+            return rc;
+        }
+    }
+    // work items (query, id tile), costliest queries first
+    std::vector<ScanItem> items;
+    std::vector<uint32_t> n_tiles(nq, 1);
+    if (!use_v1) {
+        std::vector<uint32_t> qorder(nq);
+        for (uint32_t q = 0; q < nq; q++) qorder[q] = q;
+        std::stable_sort(qorder.begin(), qorder.end(),
+                         [&](uint32_t x, uint32_t y) { return B.h_postings[x] > B.h_postings[y]; });
+        for (uint32_t q : qorder) {
+            if (B.h_postings[q] == 0) continue;
+            const uint32_t planes = (B.narrow ? 1u : 2u) + k3v_edge_words(B.descs[q].n_edges);
+            const uint32_t tile_ids = k3v_tile_ids(pl.tile_words, planes, N);
+            n_tiles[q] = fd_div_up(N, tile_ids);
+            for (uint32_t t = 0; t < n_tiles[q]; t++) items.push_back(ScanItem{q, t});
+        }
+    }
+    const uint64_t top_n = params->top_n;
+    auto attempt = [&](bool limit) -> int {
+        // hit regions: a query can hit at most min(N, its postings) structures; with the tile-level pre-selection a
+        // tile emits its top n plus the rest of the threshold bin
+        std::vector<uint64_t> hit_off(nq + 1, 0);
+        for (uint32_t q = 0; q < nq; q++) {
+            uint64_t cap = std::min<uint64_t>(N, B.h_postings[q]);
+            if (limit) cap = std::min<uint64_t>(cap, (uint64_t)n_tiles[q] * (top_n + std::max<uint64_t>(1024, top_n)));
+            hit_off[q + 1] = hit_off[q] + cap;
+        }
+        DevBuf<uint64_t> d_hit_off;
+        DevBuf<unsigned int> d_hit_cnt, d_flags;
+        DevBuf<HitRec> d_hits;
+        DevBuf<ScanItem> d_items;
+        DevBuf<float> d_pen2;
         FD_CUDA(ctx, d_hit_off.alloc(nq + 1));
         FD_CUDA(ctx, d_hit_cnt.alloc(nq));
         FD_CUDA(ctx, d_hits.alloc(hit_off[nq]));
+        FD_CUDA(ctx, d_flags.alloc(2)); // [0] work counter, [1] overflow
         FD_CUDA(ctx, cudaMemcpyAsync(d_hit_off.p, hit_off.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, s));
         FD_CUDA(ctx, cudaMemsetAsync(d_hit_cnt.p, 0, nq * 4, s));
-        std::vector<uint32_t> qorder;
-        uint32_t class_begin[5];
-        const int class_ew[4] = {1, 2, 4, 8};
-        edge_word_classes(B, nq, qorder, class_begin);
-        DevBuf<uint32_t> d_qorder;
-        FD_CUDA(ctx, d_qorder.alloc(nq));
-        FD_CUDA(ctx, cudaMemcpyAsync(d_qorder.p, qorder.data(), nq * 4, cudaMemcpyHostToDevice, s));
-        {
+        FD_CUDA(ctx, cudaMemsetAsync(d_flags.p, 0, 8, s));
+        unsigned int h_flags[2] = {0, 0};
+        if (use_v1) {
+            FD_TRY(scan_v1(ctx, B, nq, N, params, d_hit_off, d_hit_cnt, d_hits));
+        } else if (!items.empty()) {
+            FD_CUDA(ctx, d_items.alloc(items.size()));
+            FD_CUDA(ctx, d_pen2.alloc(N));
+            FD_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(ScanItem), cudaMemcpyHostToDevice, s));
+            const FilterParams fp = make_filter(params);
+            IndexView ix = make_view(ctx);
             StageTimer st(ctx, "scan");
-            for (int c = 0; c < 4; c++) {
-                const uint32_t nc = class_begin[c + 1] - class_begin[c];
-                if (!nc) continue;
-                const int ew = std::min(class_ew[c], B.ew);
-                TilePlan tp;
-                FD_TRY(plan_tiles(ctx, B, N, tp, ew));
-                FD_TRY(launch_scan<0>(ctx, dim3(tp.n_tiles, nc), tp, make_view(ctx), B, make_filter(params), d_hit_off.p,
-                                      d_hit_cnt.p, d_hits.p, nullptr, SparseOut{nullptr, nullptr, nullptr, 0, 0},
-                                      d_qorder.p + class_begin[c], ew));
+            FD_LAUNCH(ctx, k3_length_penalty_signed, fd_div_up(N, 256), 256, 0, ix.nres, ix.plddt, N, fp.length_penalty,
+                      fp.num_res_cutoff, fp.plddt_cutoff, d_pen2.p);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(items.size(), (uint64_t)ctx->num_sms * pl.ctas_per_sm);
+            const uint32_t scratch_cap = k3v_tile_ids(pl.tile_words, B.narrow ? 2u : 3u, N) + 32;
+            DevBuf<uint32_t> d_scratch;
+            FD_CUDA(ctx, d_scratch.alloc((size_t)grid * 3 * scratch_cap));
+            ScanV2Args a{B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p, B.d_edge_group.p, B.d_idfsum.p, d_pen2.p,
+                         d_items.p, (uint32_t)items.size(), d_flags.p, pl.tile_words, B.max_hashes, B.max_nodes,
+                         k3v_edge_words(B.max_edges), pl.stage_lists ? 1u : 0u, limit ? (uint32_t)top_n : 0u, fp,
+                         d_hit_off.p, d_hit_cnt.p, d_hits.p, d_flags.p + 1, d_scratch.p, scratch_cap,
+                         (getenv("FD_K3_BULK") && atoi(getenv("FD_K3_BULK")) == 0) ? 0u : 1u};
+            if (B.narrow) {
+                FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                FD_LAUNCH(ctx, k3_scan_v2<true>, grid, pl.threads, pl.smem, ix, a);
+            } else {
+                FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                FD_LAUNCH(ctx, k3_scan_v2<false>, grid, pl.threads, pl.smem, ix, a);
             }
+            FD_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags.p, 8, cudaMemcpyDeviceToHost, s));
             FD_CUDA(ctx, st.finish());
         }
-        return select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, params->top_n, N, out_hits, h_off);
+        if (h_flags[1]) return 1; // a hit region overflowed
+        return select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, top_n, N, out_hits, h_off);
     };
-    rc = body();
+    // the pre-selection pays when the top n is a small part of a tile
+    bool limit = !use_v1 && top_n > 0 && top_n <= 0xffffu && top_n * 8 <= N;
+    if (const char *e = getenv("FD_K3_LIMIT")) limit = limit && atoi(e) != 0;
+    int rc = attempt(limit);
+    if (rc == 1) rc = attempt(false);
     if (rc != FD_OK) {
         free(h_off);
         return rc;
     }
     *out_offsets = h_off;
     return FD_OK;
+}
+
+int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                         fd_struct_hit **out_hits, uint64_t **out_offsets) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_count_query_batch: no index attached");
+    if ((nq && !queries) || !params || !out_hits || !out_offsets)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_batch: NULL argument");
+    FD_ENTER(ctx);
+    return count_query_impl(ctx, queries, nq, params, CountOpts(), out_hits, out_offsets);
+}
+
+int fd_count_query_batch_ex(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                            const uint32_t *global_counts, uint64_t global_n_structs, fd_struct_hit **out_hits,
+                            uint64_t **out_offsets) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_count_query_batch_ex: no index attached");
+    if ((nq && !queries) || !params || !out_hits || !out_offsets)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_batch_ex: NULL argument");
+    if (global_counts && (global_n_structs == 0 || global_n_structs > 0xfffffff0ull))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_batch_ex: global_n_structs out of range");
+    FD_ENTER(ctx);
+    CountOpts o;
+    o.gcounts = global_counts;
+    o.g_structs = global_n_structs;
+    return count_query_impl(ctx, queries, nq, params, o, out_hits, out_offsets);
 }
 
 int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,

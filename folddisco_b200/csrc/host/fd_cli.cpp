@@ -266,7 +266,12 @@ int cmd_index(Args &a) {
     fdh_index *ix = fdh_index_build(ctx, store, &hp);
     if (!ix) die(fdh_last_error());
     if (fdh_index_save(ix, store, prefix.c_str(), max_residue, nullptr) != FD_OK) die(fdh_last_error());
-    if (!no_store && fdh_store_save(store, (prefix + ".store").c_str()) != FD_OK) die(fdh_last_error());
+    if (!no_store) {
+        if (fdh_store_save(store, (prefix + ".store").c_str()) != FD_OK) die(fdh_last_error());
+    } else {
+        // a store left by an earlier build at this prefix would describe other coordinates: remove it
+        remove((prefix + ".store").c_str());
+    }
     if (verbose) {
         fd_index_buffers b;
         fdh_index_get(ix, &b);
@@ -491,6 +496,18 @@ int cmd_query(Args &a) {
             store = fdh_store_load(sp_path.c_str());
             if (!store) die(fdh_last_error());
             if (fdh_store_size(store) != S) die(sp_path + " does not belong to this index (structure count differs)");
+            // same count is not enough (an index rebuilt at this prefix, e.g. by the reference binary, leaves the old
+            // store behind): every structure must agree with the lookup in residue count and name
+            {
+                std::vector<uint32_t> s_nres(S);
+                std::vector<float> s_plddt(S);
+                fdh_store_get_lookup(store, s_nres.data(), s_plddt.data());
+                for (uint64_t k = 0; k < S; k++)
+                    if (s_nres[k] != nres[k] || strcmp(fdh_store_name(store, k), fdh_index_name(ix, k)) != 0)
+                        die(sp_path + " does not belong to this index (structure " + std::to_string(k) + ": " +
+                            fdh_store_name(store, k) + " / " + std::to_string(s_nres[k]) + " residues, lookup says " +
+                            fdh_index_name(ix, k) + " / " + std::to_string(nres[k]) + "); re-run `index` or delete it");
+            }
         } else {
             if (verbose) fprintf(stderr, "[INFO] %s not found: parsing the %llu structures named in the lookup\n", sp_path.c_str(), (unsigned long long)S);
             store = fdh_store_new();

@@ -324,6 +324,9 @@ struct Query {
     std::shared_ptr<const fdh_compact> st; // shared between the queries of a batch that use the same structure
     std::string qstring;
     std::vector<uint32_t> indices;
+    // residue_count of query_pdb.rs:355-359: the PARSED query residues (the structure's residues for an empty query),
+    // including those make_query_map cannot resolve in the structure; the denominator of the node-ratio filters
+    uint32_t residue_count = 0;
     std::vector<QEntry> entries;
     std::vector<uint32_t> pair_hash; // observed hash per pair
     std::vector<AAD> aad;
@@ -1545,6 +1548,7 @@ static bool prepare_query(const fdh_queries *qs, std::shared_ptr<const fdh_compa
     }
     Q.st = std::move(st);
     Q.qstring = query_string;
+    Q.residue_count = (uint32_t)pq.chains.size();
     if (!build_query_map(Q, pq, *qs)) {
         err = "query has too many edges";
         return false;
@@ -1848,11 +1852,11 @@ static void make_fd_queries(const fdh_queries *qs, uint32_t q_begin, uint32_t q_
         if (!qs->shard_bounds.empty())
             fq[q - q_begin] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.s_edge_of_hash.data(),
                                        (uint32_t)Q.s_edge_node.size(), Q.s_edge_node.data(), Q.n_nodes,
-                                       (uint32_t)Q.indices.size(), Q.s_edge_group.data()};
+                                       Q.residue_count, Q.s_edge_group.data()};
         else
             fq[q - q_begin] = fd_query{(uint32_t)Q.hashes_flat.size(), Q.hashes_flat.data(), Q.edge_of_hash.data(),
                                        (uint32_t)Q.edge_node.size(), Q.edge_node.data(), Q.n_nodes,
-                                       (uint32_t)Q.indices.size(), nullptr};
+                                       Q.residue_count, nullptr};
         if (h2d_bytes) *h2d_bytes += 6ull * Q.hashes_flat.size() + 2ull * Q.edge_node.size() + 24;
     }
 }
@@ -2101,7 +2105,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     // pass 1: rows per query
     auto count_query_rows = [&](uint32_t q) {
         const Query &Q = qs->q[q_begin + q];
-        const float expected = (float)Q.indices.size();
+        const float expected = (float)Q.residue_count;
         uint64_t ns = 0, nm = 0;
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
             const size_t na = match_count(c);
@@ -2122,7 +2126,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     // pass 2: rows written in place, then the default sorts inside the query's ranges
     auto build_query = [&](uint32_t q) {
         const Query &Q = qs->q[q_begin + q];
-        const float expected = (float)Q.indices.size();
+        const float expected = (float)Q.residue_count;
         const uint32_t n_res = (uint32_t)Q.indices.size();
         fdh_struct_row *S0 = R->structs.data() + R->struct_off[q], *S = S0;
         const uint64_t mb = R->match_off[q];

@@ -180,6 +180,17 @@ typedef struct {
  * idf descending, ties by ascending nid. */
 int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries,
                          const fd_prefilter_params *params, fd_struct_hit **out_hits, uint64_t **out_offsets);
+/* The same for one ID-RANGE SHARD of a larger database (multi-GPU, SURVEY 8e ablation / fd_search_sharded): the
+ * attached index holds the postings of a contiguous range of structure ids (local ids 0 .. n_structs) and
+ * global_counts[k] is the length of the k-th query hash's list in the WHOLE database (hashes of all queries
+ * concatenated in batch order; the sum over shards of fd_posting_counts), global_n_structs its structure count.  Every
+ * shard then weighs a hash by log2(N / len) exactly as the unsharded index does (count_query.rs:130) and uses the same
+ * fixed-point scale, so a structure's row is bit-identical to the unsharded one; the caller merges the shards'
+ * per-query top-n lists (idf descending, id ascending) after adding each shard's first id.  global_counts == NULL
+ * is fd_count_query_batch. */
+int fd_count_query_batch_ex(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries,
+                            const fd_prefilter_params *params, const uint32_t *global_counts,
+                            uint64_t global_n_structs, fd_struct_hit **out_hits, uint64_t **out_offsets);
 /* posting bytes the last fd_count_query_batch had to read (sum over found query hashes of their list
  * length in bytes) -- the algorithmic bytes of SURVEY 8d */
 uint64_t fd_last_posting_bytes(const fd_ctx *ctx);

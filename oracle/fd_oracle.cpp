@@ -559,6 +559,9 @@ struct fdo_qmap {
     std::vector<QEntry> entries;                 // insertion order
     std::unordered_map<uint32_t, size_t> lookup; // hash -> position in entries
     std::vector<size_t> indices;                 // query.rs:236-246
+    // residue_count of query_pdb.rs:355-359: the parsed query residues (all residues of the structure for an empty
+    // query), whether or not make_query_map resolves them; denominator of the node-ratio filters
+    size_t residue_count = 0;
     // observed_distance_map: (aa_i, aa_j) -> [(ca_dist, index_i)]  query.rs:271-280
     std::map<std::pair<uint8_t, uint8_t>, std::vector<std::pair<float, size_t>>> aa_dist;
     const QEntry *find(uint32_t h) const {
@@ -1704,6 +1707,7 @@ fdo_qmap *fdo_qmap_make(const fdo_compact *c, const uint8_t *chains, const uint6
             qsub.emplace_back();
         }
     }
+    m->residue_count = qres.size();
     std::unordered_map<size_t, std::vector<uint8_t>> submap;
     for (size_t i = 0; i < qres.size(); i++) {
         int64_t idx = serial_query ? (int64_t)qres[i].second : fdo_compact_get_index(c, qres[i].first, qres[i].second);
@@ -1788,6 +1792,7 @@ void fdo_qmap_get(const fdo_qmap *m, uint32_t *hash, int64_t *qi, int64_t *qj, u
     }
 }
 int64_t fdo_qmap_num_indices(const fdo_qmap *m) { return (int64_t)m->indices.size(); }
+int64_t fdo_qmap_residue_count(const fdo_qmap *m) { return (int64_t)m->residue_count; }
 void fdo_qmap_get_indices(const fdo_qmap *m, int64_t *indices) {
     for (size_t i = 0; i < m->indices.size(); i++) indices[i] = (int64_t)m->indices[i];
 }
@@ -1870,7 +1875,7 @@ int64_t fdo_query_batch(const fdo_qmap *const *maps, const fdo_compact *const *q
             std::vector<Hit> hits;
             uint64_t bytes = 0;
             fdo_count_params pp = *p;
-            pp.expected_node_count = maps[q]->indices.size();
+            pp.expected_node_count = maps[q]->residue_count;
             count_query(*maps[q], *ix, S, nres, pp, 1, hits, &bytes);
             filter_sort_top(hits, nres, plddt, pp);
             uint64_t nm = 0;

@@ -114,6 +114,8 @@ int64_t fdo_qmap_size(const fdo_qmap *m);
 /* insertion order */
 void fdo_qmap_get(const fdo_qmap *m, uint32_t *hash, int64_t *qi, int64_t *qj, uint8_t *primary, float *idf);
 int64_t fdo_qmap_num_indices(const fdo_qmap *m);
+/* residue_count of src/cli/workflows/query_pdb.rs:355-359 (parsed query residues, resolved or not) */
+int64_t fdo_qmap_residue_count(const fdo_qmap *m);
 void fdo_qmap_get_indices(const fdo_qmap *m, int64_t *indices);
 void fdo_qmap_free(fdo_qmap *m);
 

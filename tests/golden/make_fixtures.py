@@ -57,3 +57,24 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def long_structure():
+    """long_6FF7.npz: the UNCROPPED CompactStructure of data/long/6FF7.pdb (16 769 residues, the largest shipped
+    input; SURVEY section 7 minimum slice) with the oracle's answer for it: number of ordered residue pairs that get a
+    hash, number of distinct hashes and the sha256 of the sorted unique u32 hash list (src/controller/feature.rs:198-231
+    + sort_unstable + dedup of src/controller/mod.rs:343-344)."""
+    import hashlib
+    c = O.Structure.read_pdb(REF + "/data/long/6FF7.pdb").compact()
+    d = c.soa()
+    raw = c.hashes()
+    uniq = np.unique(raw)
+    np.savez_compressed(os.path.join(HERE, "long_6FF7.npz"), n_xyz=d["n_xyz"], ca_xyz=d["ca_xyz"], cb_xyz=d["cb_xyz"],
+                        aa=d["aa"], cb_valid=d["cb_valid"], res_name=d["res_name"], chain=d["chain"], serial=d["serial"],
+                        n_pairs=np.int64(len(raw)), n_unique=np.int64(len(uniq)),
+                        sha256=np.array(hashlib.sha256(uniq.astype("<u4").tobytes()).hexdigest()))
+    print("long_6FF7:", len(d["aa"]), "residues,", len(raw), "hashed pairs,", len(uniq), "distinct hashes")
+
+
+if __name__ == "__main__" and "--long" in sys.argv:
+    long_structure()

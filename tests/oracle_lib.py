@@ -110,6 +110,7 @@ def lib():
     sig("fdo_qmap_size", C.c_int64, [VP])
     sig("fdo_qmap_get", None, [VP, u32p, i64p, i64p, u8p, f32p])
     sig("fdo_qmap_num_indices", C.c_int64, [VP])
+    sig("fdo_qmap_residue_count", C.c_int64, [VP])
     sig("fdo_qmap_get_indices", None, [VP, i64p])
     sig("fdo_qmap_free", None, [VP])
     sig("fdo_count_query", VP, [VP, VP, C.c_uint64, u64p, f32p, C.POINTER(CountParams)])
@@ -361,6 +362,11 @@ class QueryMap:
             lib().fdo_qmap_get(self.h, d["hash"], d["qi"], d["qj"], d["primary"], d["idf"])
         return d
 
+    @property
+    def residue_count(self):
+        """residue_count of query_pdb.rs:355-359 (the denominator of the node-ratio filters)"""
+        return lib().fdo_qmap_residue_count(self.h)
+
     def indices(self):
         n = lib().fdo_qmap_num_indices(self.h)
         out = np.zeros(max(n, 1), np.int64)
@@ -377,7 +383,7 @@ def count_query(qmap, index, nres, plddt=None, params=None):
     S = len(nres)
     nres = np.ascontiguousarray(nres, np.uint64)
     plddt = np.zeros(S, np.float32) if plddt is None else np.ascontiguousarray(plddt, np.float32)
-    p = params or CountParams.defaults(expected_node_count=len(qmap.indices()))
+    p = params or CountParams.defaults(expected_node_count=qmap.residue_count)
     h = lib().fdo_count_query(qmap.h, index.h, S, nres, plddt, C.byref(p))
     n = lib().fdo_hits_size(h)
     d = dict(nid=np.zeros(n, np.uint64), match_count=np.zeros(n, np.uint32), node_count=np.zeros(n, np.uint32),

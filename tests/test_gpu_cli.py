@@ -160,3 +160,32 @@ def test_sort_by_and_format_output(workdir):
     rows = run(workdir, *base, "--per-structure", "--sort-by", "plddt")
     p = [float(r[8]) for r in rows]
     assert p == sorted(p, reverse=True)
+
+
+def test_stale_store_is_refused_and_no_store_removes_it(workdir):
+    """PREFIX.store must belong to the index beside it: a store with the same structure count but other structures is
+    refused (not silently used for verification), and `index --no-store` removes a store left by an earlier build."""
+    import shutil
+    d = workdir
+    # a second index over the same number of structures in another order/naming: its store has the same count
+    os.makedirs(os.path.join(d, "data", "renamed"), exist_ok=True)
+    names = sorted(os.listdir(os.path.join(d, "data", "serine_peptidases")))
+    for k, n in enumerate(names):
+        shutil.copy(os.path.join(d, "data", "serine_peptidases", n),
+                    os.path.join(d, "data", "renamed", names[(k + 1) % len(names)]))
+    r = subprocess.run([CLI, "index", "-p", "data/renamed", "-i", "idx/renamed", "-t", "2"], cwd=d, capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    shutil.copy(os.path.join(d, "idx", "serine.store"), os.path.join(d, "idx", "serine.store.bak"))
+    try:
+        shutil.copy(os.path.join(d, "idx", "renamed.store"), os.path.join(d, "idx", "serine.store"))
+        r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"], cwd=d,
+                           capture_output=True, text=True)
+        assert r.returncode != 0 and "does not belong to this index" in r.stderr
+    finally:
+        shutil.move(os.path.join(d, "idx", "serine.store.bak"), os.path.join(d, "idx", "serine.store"))
+    assert os.path.exists(os.path.join(d, "idx", "renamed.store"))
+    r = subprocess.run([CLI, "index", "-p", "data/renamed", "-i", "idx/renamed", "-t", "2", "--no-store"], cwd=d,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not os.path.exists(os.path.join(d, "idx", "renamed.store"))

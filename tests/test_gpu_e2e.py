@@ -281,3 +281,146 @@ def test_search_stream_equals_one_batch(env):
     assert q == 37
     del whole, parts, qb
     ctx.close()
+
+
+def _soa_comps(db):
+    from folddisco_b200 import synth
+    return [O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"],
+                               serial=np.arange(1, len(p["aa"]) + 1, dtype=np.uint64)) for p in synth.split(db)]
+
+
+def test_full_size_rows_vs_oracle(env):
+    """BASELINE configs[2] at its FULL size -- the bench's own database (23 400 synthetic structures, --top 100) --
+    compared row for row with the oracle: the five shipped motifs and the first distinct motifs of the bench batch.
+    Structure rows (ids, match / node / edge counts exact, idf 1e-4) and match rows (residues exact, idf / RMSD 1e-4)."""
+    import bench
+    import parity
+    from folddisco_b200 import synth
+    host, ctx = env["host"], env["ctx"]
+    S = 23400
+    db = synth.generate(S, synth.SEED_BASE + 2)
+    store = host.Store()
+    store.add_soa(db)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    store.attach(ctx)
+    b = ix.buffers()
+    oix = O.Index.from_buffers(b.hashes, b.offsets, b.values)
+    comps = _soa_comps(db)
+    nres, plddt = ix.lookup()
+    qb = host.QueryBatch(ix.params)
+    oqms = []
+    for path, q, _ in F.MOTIFS:
+        a = env["atoms"][path]
+        qb.add(host.CompactStructure.from_atoms(a), q)
+        s = O.Structure.from_atoms(a)
+        ch, se, subs = O.parse_query_string(q, s.first_chain)
+        oqms.append(O.QueryMap(s.compact(), ch, se, subs, index=oix, total_structures=S))
+    ro = db["row_offsets"].astype(np.int64)
+    for s, pick, qstr in bench.distinct_motifs(db, 11, 0):
+        qb.add(host.CompactStructure.from_soa(db["n_xyz"][ro[s]:ro[s + 1]], db["ca_xyz"][ro[s]:ro[s + 1]],
+                                              db["cb_xyz"][ro[s]:ro[s + 1]], db["aa"][ro[s]:ro[s + 1]]), qstr)
+        ch, se, subs = O.parse_query_string(qstr, ord("A"))
+        oqms.append(O.QueryMap(comps[s], ch, se, subs, index=oix, total_structures=S))
+    qb.finalize(ctx)
+    res = host.search(ctx, qb, host.SearchParams(top_n=100), labels=store)
+    bad, n_match = [], 0
+    for k, om in enumerate(oqms):
+        hits, rows = parity.oracle_query(om, oix, comps, nres, plddt, top_n=100)
+        bad += parity.diff_query(res, k, len(om.indices()), hits, rows, top_n=100)
+        n_match += len(rows)
+    assert not bad, bad[:10]
+    assert n_match > 1000
+
+
+def test_missing_query_residue_counts_in_the_ratio(env):
+    """A -q residue that the query structure does not have still counts in residue_count (query_pdb.rs:355-359), the
+    denominator of --covered-node-ratio: with B57,B102,C195,C999 a two-node hit has ratio 2/4, not 2/3."""
+    host, ctx, store, names = env["host"], env["ctx"], env["store"], env["names"]
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    store.attach(ctx)
+    b = ix.buffers()
+    oix = O.Index.from_buffers(b.hashes, b.offsets, b.values)
+    nres, plddt = ix.lookup()
+    q = "B57,B102,C195,C999"
+    a = env["atoms"]["query/4CHA.pdb"]
+    qb = host.QueryBatch(ix.params)
+    qb.add(host.CompactStructure.from_atoms(a), q)
+    qb.finalize(ctx)
+    s = O.Structure.from_atoms(a)
+    ch, se, subs = O.parse_query_string(q, s.first_chain)
+    om = O.QueryMap(s.compact(), ch, se, subs, index=oix, total_structures=len(names))
+    assert om.residue_count == 4 and len(om.indices()) == 3
+    sp = host.SearchParams(covered_node_ratio=0.6)
+    res = host.search(ctx, qb, sp, labels=store)
+    op = O.CountParams.defaults(om.residue_count)
+    op.covered_node_ratio = 0.6
+    hits = O.count_query(om, oix, nres.astype(np.uint64), plddt, op)
+    assert sorted(int(x) for x in res.structures(0)["nid"]) == sorted(int(x) for x in hits["nid"])
+    got = {os.path.basename(names[int(x)]) for x in res.structures(0)["nid"]}
+    assert got == {"4cha.pdb", "1pq5.pdb"}  # the three two-node structures pass 2/3 >= 0.6 but not 2/4
+
+
+def test_long_structure_16769_residues(env):
+    """data/long/6FF7.pdb uncropped (16 769 residues: the largest shipped input, 2.8e8 ordered pairs): K1 hashes ==
+    the oracle's and the committed digest; the index of a database that contains it is byte-identical to the oracle's;
+    a motif taken from it is found and verified in it with the oracle's rows (K3 + K6 on a 16 k-residue candidate)."""
+    import hashlib
+    import parity
+    from folddisco_b200 import synth
+    host, ctx, fd = env["host"], env["ctx"], env["fd"]
+    z = np.load(os.path.join(F.GOLDEN, "long_6FF7.npz"))
+    n = len(z["aa"])
+    assert n == 16769
+    big = dict(n_xyz=z["n_xyz"], ca_xyz=z["ca_xyz"], cb_xyz=z["cb_xyz"], aa=z["aa"], cb_valid=z["cb_valid"])
+    batch = fd.StructBatch.from_list([big])
+    hashes, ro = ctx.hash_structures(batch)
+    assert len(hashes) == int(z["n_unique"])
+    assert hashlib.sha256(hashes.astype("<u4").tobytes()).hexdigest() == str(z["sha256"])
+    ocomp = O.Compact.from_soa(z["n_xyz"], z["ca_xyz"], z["cb_xyz"], z["aa"], cb_valid=z["cb_valid"], chain=z["chain"],
+                               serial=z["serial"])
+    assert np.array_equal(hashes, ocomp.hashes(sorted_unique=True))
+    # a small database around it
+    db = synth.generate(60, 99, mean_len=150.0, max_len=400)
+    parts = synth.split(db)
+    store = host.Store()
+    comps = []
+
+    def add_synth(p, name):
+        store.add(host.CompactStructure.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"]), name)
+        comps.append(O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"],
+                                        serial=np.arange(1, len(p["aa"]) + 1, dtype=np.uint64)))
+
+    for k, p in enumerate(parts[:30]):
+        add_synth(p, "s%d" % k)
+    store.add(host.CompactStructure.from_soa(z["n_xyz"], z["ca_xyz"], z["cb_xyz"], z["aa"], cb_valid=z["cb_valid"],
+                                             chain=z["chain"], serial=z["serial"]), "6FF7")
+    comps.append(ocomp)
+    for k, p in enumerate(parts[30:]):
+        add_synth(p, "t%d" % k)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    want = O.Index.build(comps, threads=8)
+    b = ix.buffers()
+    assert np.array_equal(b.hashes, want.hashes) and np.array_equal(b.offsets, want.offsets)
+    assert np.array_equal(b.values, want.values)
+    ix.attach(ctx)
+    store.attach(ctx)
+    nres, plddt = ix.lookup()
+    assert int(nres[30]) == n
+    # a motif from the middle of the long structure: residues near residue 9000 with a usable amino acid
+    ca = z["ca_xyz"]
+    near = np.flatnonzero((np.linalg.norm(ca - ca[9000], axis=1) <= 11.0) & (z["aa"] < 20) & (z["cb_valid"] == 1))[:5]
+    qstr = ",".join("%s%d" % (chr(int(z["chain"][i])), int(z["serial"][i])) for i in near)
+    qb = host.QueryBatch(ix.params)
+    qb.add(host.CompactStructure.from_soa(z["n_xyz"], z["ca_xyz"], z["cb_xyz"], z["aa"], cb_valid=z["cb_valid"],
+                                          chain=z["chain"], serial=z["serial"]), qstr)
+    qb.finalize(ctx)
+    ch, se, subs = O.parse_query_string(qstr, int(z["chain"][0]))
+    om = O.QueryMap(ocomp, ch, se, subs, index=want, total_structures=len(comps))
+    res = host.search(ctx, qb, host.SearchParams(), labels=store)
+    hits, rows = parity.oracle_query(om, want, comps, nres, plddt)
+    bad = parity.diff_query(res, 0, len(om.indices()), hits, rows)
+    assert not bad, bad[:10]
+    assert 30 in set(int(x) for x in res.structures(0)["nid"])
+    assert any(r[0] == 30 and r[1] == len(near) for r in rows)  # the motif itself, all residues matched

@@ -320,6 +320,84 @@ def test_count_query_synthetic(ctx, n_structs, seed, kw):
     assert len(ctx.count_query_batch([none])[0]) == 0
 
 
+@pytest.mark.parametrize("env", [dict(FD_K3_CTAS="4", FD_K3_THREADS="128"), dict(FD_K3_CTAS="1", FD_K3_THREADS="512"),
+                                 dict(FD_K3_CTAS="3", FD_K3_THREADS="256", FD_K3_LIMIT="0"), dict(FD_K3_V1="1")])
+def test_scan_v2_variants(ctx, env):
+    """k3_scan_v2 under other shared-memory plans (4 small tiles per SM: every query of the 12 000-structure case is
+    split into several id tiles; one large tile; the tile-level top-n pre-selection off) returns exactly the rows of
+    the default plan (so does the first-generation kernel, FD_K3_V1=1), and those equal the oracle."""
+    import folddisco_b200 as fd
+    e = _attach_synth(ctx, 12000, 23, jitter=0.05, mutate=0.02, template_ids=[4, 5, 9, 10])
+    oix, nres, plddt = e["oix"], e["nres"], e["plddt"]
+    qms = _motif_qmaps(oix, 12000, extra=[("query/4CHA.pdb", "B57:X,B102,C195:ST", None)])
+    queries = [_query_inputs(qm) for qm in qms] * 7  # more work items than one wave of CTAs takes
+    p_all = fd.PrefilterParams()
+    p_top = fd.PrefilterParams(top_n=40)
+    base_all = ctx.count_query_batch(queries, p_all)
+    base_top = ctx.count_query_batch(queries, p_top)
+    for qm, g in zip(qms, base_all):
+        _compare_hits(g, O.count_query(qm, oix, nres, plddt))
+    for k, v in env.items():
+        os.environ[k] = v
+    try:
+        got_all = ctx.count_query_batch(queries, p_all)
+        got_top = ctx.count_query_batch(queries, p_top)
+    finally:
+        for k in env:
+            del os.environ[k]
+    for a, b in zip(base_all, got_all):
+        assert np.array_equal(a, b)
+    for a, b in zip(base_top, got_top):
+        assert np.array_equal(a, b)
+        assert len(a) <= 40
+    assert max(len(a) for a in base_top) == 40
+
+
+def test_count_query_id_range_shards(ctx):
+    """SURVEY 8e ablation / fd_count_query_batch_ex: the database cut into three id ranges, one index per range, every
+    shard given the GLOBAL list lengths -> the merged rows are bit-identical to the unsharded search (same idf
+    weights, same fixed-point scale, a structure's postings all live on its shard)."""
+    import folddisco_b200 as fd
+    n = 6000
+    b, parts, comps = synth_compacts(n, 31)
+    batch = fd.StructBatch(b["row_offsets"], b["n_xyz"], b["ca_xyz"], b["cb_xyz"], b["aa"])
+    nres = batch.nres
+    plddt = np.random.default_rng(5).uniform(30, 95, n).astype(np.float32)
+    full = ctx.build_index(batch)
+    ctx.index_attach(full, nres, plddt)
+    oix = O.Index.from_buffers(full.hashes, full.offsets, full.values)
+    qms = _motif_qmaps(oix, n)
+    queries = [_query_inputs(qm) for qm in qms]
+    flat = np.concatenate([q["hashes"] for q in queries])
+    for p in (fd.PrefilterParams(), fd.PrefilterParams(top_n=30),
+              fd.PrefilterParams(top_n=30, freq_filter=0.05, num_res_cutoff=200)):
+        ctx.index_attach(full, nres, plddt)
+        want = ctx.count_query_batch(queries, p)
+        gcounts = ctx.posting_counts(flat)
+        cuts = [0, 1500, 3100, n]
+        ro = b["row_offsets"].astype(np.int64)
+        merged = [[] for _ in queries]
+        total = np.zeros(len(flat), np.uint64)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sl = slice(ro[lo], ro[hi])
+            sb = fd.StructBatch(b["row_offsets"][lo:hi + 1] - b["row_offsets"][lo], b["n_xyz"][sl], b["ca_xyz"][sl],
+                                b["cb_xyz"][sl], b["aa"][sl])
+            six = ctx.build_index(sb)
+            ctx.index_attach(six, nres[lo:hi], plddt[lo:hi])
+            total += ctx.posting_counts(flat)
+            got = ctx.count_query_batch(queries, p, global_counts=gcounts, global_n_structs=n)
+            for k, g in enumerate(got):
+                g = g.copy()
+                g["nid"] += lo
+                merged[k].append(g)
+        assert np.array_equal(total, gcounts.astype(np.uint64))  # a list is the concatenation of its shards' pieces
+        for k, w in enumerate(want):
+            m = np.concatenate(merged[k])
+            order = np.lexsort((m["nid"], -m["idf"].astype(np.float64)))
+            m = m[order][:len(w)] if p.top_n < 1 << 62 else m[order]
+            assert np.array_equal(m, w), k
+
+
 def test_kabsch_batch(ctx):
     """K5 vs the oracle's f64 Kabsch: rmsd / U / t within 1e-4 (north_star tolerance)."""
     rng = np.random.default_rng(9)

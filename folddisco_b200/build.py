@@ -17,7 +17,8 @@ SO = os.path.join(HERE, "libfolddisco_b200.so")
 CLI = os.path.join(HERE, "folddisco-b200")  # `index` / `query` front end (csrc/host/fd_cli.cpp), links the .so
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU = ["fd_ctx.cu", "fd_hash.cu", "fd_postings.cu", "fd_query.cu", "fd_edges.cu", "fd_kabsch.cu", "fd_verify.cu"]
+CU = ["fd_ctx.cu", "fd_hash.cu", "fd_postings.cu", "fd_query.cu", "fd_edges.cu", "fd_kabsch.cu", "fd_verify.cu",
+      "fd_comm.cu"]
 CPP = ["host/fd_host.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function,-pthread", "-Xptxas", "-v"]
@@ -62,7 +63,9 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    link = [NVCC, "-shared", "-o", SO] + [o for _, o, _, _ in results] + ["-Xcompiler", "-pthread"]
+    # NCCL: the multi-GPU exchange lives inside the library (fd_comm.cu); libnccl.so.2 is bound with dlopen on the first
+    # fd_comm_* call, so that a host process that already carries an NCCL (PyTorch bundles its own) keeps exactly one
+    link = [NVCC, "-shared", "-o", SO] + [o for _, o, _, _ in results] + ["-Xcompiler", "-pthread", "-ldl"]
     subprocess.check_call(link)
     cli = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", os.path.join(CSRC, "host", "fd_cli.cpp"), "-o", CLI,
            "-L" + HERE, "-lfolddisco_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + os.path.dirname(NVCC) + "/../lib64"]

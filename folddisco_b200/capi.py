@@ -6,6 +6,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfolddisco_b200.so")
+COMM_ID_BYTES = 128
 UINT64_MAX = (1 << 64) - 1
 VP = C.c_void_p
 
@@ -130,6 +131,17 @@ def lib():
     sig("fd_count_query_batch_ex", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), VP, C.c_uint64,
                                              PP(PP(_StructHit)), PP(PP(C.c_uint64))])
     sig("fd_last_posting_bytes", C.c_uint64, [VP])
+    sig("fd_comm_unique_id", C.c_int, [VP])
+    sig("fd_comm_init", C.c_int, [VP, VP, C.c_int, C.c_int])
+    sig("fd_comm_destroy", None, [VP])
+    sig("fd_comm_rank", C.c_int, [VP])
+    sig("fd_comm_world", C.c_int, [VP])
+    sig("fd_comm_allgather", C.c_int, [VP, VP, C.c_uint64, VP])
+    sig("fd_comm_allreduce_u32", C.c_int, [VP, VP, C.c_uint64])
+    sig("fd_comm_barrier", C.c_int, [VP])
+    sig("fd_count_query_sharded", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), VP, C.c_uint64, C.c_uint64,
+                                            VP, PP(PP(_StructHit)), PP(PP(C.c_uint64))])
+    sig("fd_last_exchange_bytes", C.c_uint64, [VP])
     sig("fd_votes_scan", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), PP(VP)])
     sig("fd_votes_scan_sparse", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), VP, C.c_uint32,
                                           PP(VotesLayout), PP(VP), VP, VP])
@@ -352,6 +364,56 @@ class Context:
         off = _take(po, nq + 1, np.uint64)
         hits = _take(ph, int(off[-1]), HIT_DTYPE)
         return [hits[int(off[k]):int(off[k + 1])] for k in range(nq)]
+
+    # ---- multi-GPU: NCCL inside the library, id-range shards ----
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from ncclGetUniqueId: rank 0 creates them, every rank passes them to comm_init"""
+        buf = np.zeros(COMM_ID_BYTES, np.uint8)
+        if lib().fd_comm_unique_id(_ptr(buf)) != 0:
+            raise FdError("fd_comm_unique_id failed")
+        return buf
+
+    def comm_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert len(uid) == COMM_ID_BYTES
+        self._check(lib().fd_comm_init(self.h, _ptr(uid), int(rank), int(world)), "fd_comm_init")
+
+    @property
+    def comm_rank(self):
+        return lib().fd_comm_rank(self.h)
+
+    @property
+    def comm_world(self):
+        return lib().fd_comm_world(self.h)
+
+    def comm_allreduce_u32(self, a):
+        a = np.ascontiguousarray(a, np.uint32).copy()
+        self._check(lib().fd_comm_allreduce_u32(self.h, _ptr(a), len(a)), "fd_comm_allreduce_u32")
+        return a
+
+    def comm_barrier(self):
+        self._check(lib().fd_comm_barrier(self.h), "fd_comm_barrier")
+
+    def count_query_sharded(self, queries, params, global_counts, global_n_structs, first_id, slice_begin):
+        """fd_count_query_sharded: queries = the WHOLE batch; -> hits of this rank's own queries (global ids)"""
+        nq = len(queries)
+        arr, keep = self._query_array(queries)
+        gc = np.ascontiguousarray(global_counts, np.uint32)
+        sb = np.ascontiguousarray(slice_begin, np.uint32)
+        ph, po = C.POINTER(_StructHit)(), C.POINTER(C.c_uint64)()
+        self._check(lib().fd_count_query_sharded(self.h, arr, nq, C.byref(params), _ptr(gc), int(global_n_structs),
+                                                 int(first_id), _ptr(sb), C.byref(ph), C.byref(po)),
+                    "fd_count_query_sharded")
+        r = self.comm_rank
+        n = int(sb[r + 1] - sb[r])
+        off = _take(po, n + 1, np.uint64)
+        hits = _take(ph, int(off[-1]), HIT_DTYPE)
+        return [hits[int(off[k]):int(off[k + 1])] for k in range(n)]
+
+    @property
+    def last_exchange_bytes(self):
+        return lib().fd_last_exchange_bytes(self.h)
 
     # ---- multi-GPU: partial votes of a hash-range shard ----
     def votes_scan(self, queries, params=None):

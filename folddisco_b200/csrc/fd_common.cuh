@@ -57,7 +57,10 @@ struct FdPinned {
     size_t cap = 0;
 };
 
+struct FdComm; // fd_comm.cu: the rank's NCCL communicator
+
 struct fd_ctx {
+    FdComm *comm = nullptr;        // multi-GPU: set by fd_comm_init, released by fd_comm_destroy / fd_destroy
     bool borrowed = false;         // fd_fork child: idx / store point into the parent's device memory
     std::vector<fd_ctx *> lanes;   // children kept by the in-library host for overlapped call sequences
     int device = 0;
@@ -70,6 +73,7 @@ struct fd_ctx {
     FdDeviceIndex idx;
     FdDeviceStore store;
     uint64_t last_posting_bytes = 0;
+    uint64_t last_exchange_bytes = 0; // bytes this rank sent to other ranks in the last sharded count_query
     FdPinned pinned[8];
     cudaEvent_t ev_extra[4] = {nullptr, nullptr, nullptr, nullptr}; // finer stage timing inside one call
     cudaStream_t aux_stream[2] = {nullptr, nullptr}; // second compute stream + copy stream of the chunked verification
@@ -196,6 +200,13 @@ struct HostTimer {
     } while (0)
 
 inline uint32_t fd_div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// fd_comm.cu
+void fd_comm_release(fd_ctx *ctx);
+int fd_comm_world_of(const fd_ctx *ctx);
+int fd_comm_rank_of(const fd_ctx *ctx);
+int fd_comm_alltoallv_dev(fd_ctx *ctx, const uint8_t *d_send, const uint64_t *send_off, const uint64_t *send_bytes,
+                          uint8_t *d_recv, const uint64_t *recv_off, const uint64_t *recv_bytes);
 
 // Shared between fd_hash.cu (index build) and fd_postings.cu
 int fd_postings_from_keys(fd_ctx *ctx, uint64_t *d_keys /* hash<<32|id, consumed */, uint64_t n_keys,

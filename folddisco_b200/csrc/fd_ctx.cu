@@ -308,6 +308,7 @@ void fd_destroy(fd_ctx *ctx) {
     for (fd_ctx *l : ctx->lanes) fd_destroy(l);
     ctx->lanes.clear();
     cudaSetDevice(ctx->device);
+    fd_comm_release(ctx);
     if (!ctx->borrowed) {
         fd_release_index(ctx->idx);
         fd_release_store(ctx->store);

@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
     const uint32_t n_dwarps = min(nwarps, (uint32_t)K3V_DECODE_WARPS);
     uint8_t *stage = reinterpret_cast<uint8_t *>(sp);                                   // [n_dwarps][K3V_WARP_STAGE]
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage + (size_t)n_dwarps * K3V_WARP_STAGE); // [n_dwarps]
-    __shared__ uint32_t s_item, s_total_items, s_thr, s_n, s_nk;
+    __shared__ uint32_t s_item, s_total_items, s_thr, s_n, s_nk, s_maxbin;
 
     uint8_t *wstage = stage + (size_t)min(warp, n_dwarps - 1) * K3V_WARP_STAGE;
     uint64_t *wbar = bars + min(warp, n_dwarps - 1);
@@ -1136,6 +1136,7 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
         if (tid == 0) {
             s_n = 0;
             s_nk = 0;
+            s_maxbin = 0;
         }
         __syncthreads();
         {
@@ -1163,20 +1164,30 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
                 if (lane == 0) base = atomicAdd(&s_n, total);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 __syncwarp();
-                for (uint32_t r = lane; r < total; r += 32) {
-                    const uint32_t x = wq[r];
-                    uint32_t mc;
-                    float idf;
-                    bool pass = eval(x, w_acc[x], mc, idf);
-                    if (pass && node_filters) pass = node_pass(node_count(x));
-                    if (pass) {
-                        if (a.limit_n) atomicAdd(&hist[k3v_idf_bin(idf)], 1u);
-                    } else {
-                        clear_cell(x);
+                uint32_t wmax = 0;
+                for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+                    const uint32_t r = r0 + lane;
+                    uint32_t bin = 0;
+                    if (r < total) {
+                        const uint32_t x = wq[r];
+                        uint32_t mc;
+                        float idf;
+                        bool pass = eval(x, w_acc[x], mc, idf);
+                        if (pass && node_filters) pass = node_pass(node_count(x));
+                        if (pass) {
+                            if (a.limit_n) {
+                                bin = k3v_idf_bin(idf);
+                                atomicAdd(&hist[bin], 1u);
+                            }
+                        } else {
+                            clear_cell(x);
+                        }
+                        ent_x[base + r] = pass ? x : (x | FAIL);
+                        ent_idf[base + r] = idf;
                     }
-                    ent_x[base + r] = pass ? x : (x | FAIL);
-                    ent_idf[base + r] = idf;
+                    wmax = max(wmax, __reduce_max_sync(0xffffffffu, bin));
                 }
+                if (lane == 0 && wmax) atomicMax(&s_maxbin, wmax);
                 __syncwarp();
             }
         }
@@ -1186,7 +1197,7 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
         if (a.limit_n) {
             if (warp == 0) { // highest bin such that the bins at or above it hold at least limit_n cells
                 uint32_t above = 0, t = 0;
-                for (int c = (int)(K3V_HIST_BINS / 32) - 1; c >= 0; c--) {
+                for (int c = (int)(s_maxbin >> 5); c >= 0; c--) { // from the highest occupied bin down
                     const uint32_t v = hist[c * 32 + lane];
                     uint32_t suf = v; // suffix sum over lanes >= lane
                     for (int o = 1; o < 32; o <<= 1) {
@@ -1408,6 +1419,128 @@ __global__ void k3_gather(const HitRec *hits, const uint32_t *sorted_vals, const
         const HitRec r = hits[base + sorted_vals[base + k]];
         out[obase + k] = fd_struct_hit{r.nid, r.match_count, r.node_edge >> 16, r.node_edge & 0xffffu, r.idf};
     }
+}
+
+// ---- per-query top-n in one kernel (pools of at most K3_TOPN_SORT_MAX hits per query) ----
+// One CTA per query: the hits of the query's region go to shared memory as 64-bit keys (idf descending, nid ascending:
+// query_pdb.rs:404 is a stable sort over ascending nid) with their position, a bitonic sort orders them, and the first
+// top_n become fd_struct_hit rows of the PADDED output out[q][top_n] (nid + id_offset: id-range shards report global
+// ids), out_count[q] = rows written.  Replaces hist / keys / segmented sort / gather (about ten launches and a host
+// round trip) when the tile-level pre-selection has already cut the pools to a few hundred hits.  A larger pool sets
+// *too_big and the host falls back to the segmented sort.
+constexpr uint32_t K3_TOPN_SORT_MAX = 4096;
+__global__ void __launch_bounds__(256) k3_topn_sort(const HitRec *hits, const uint64_t *hit_offsets,
+                                                     const unsigned int *hit_counts, uint32_t top_n, uint32_t id_offset,
+                                                     fd_struct_hit *out, uint32_t *out_count, unsigned int *too_big) {
+    __shared__ uint64_t key[K3_TOPN_SORT_MAX];
+    __shared__ uint16_t pos[K3_TOPN_SORT_MAX];
+    const uint32_t q = blockIdx.x;
+    const uint64_t base = hit_offsets[q];
+    const uint32_t cap = (uint32_t)(hit_offsets[q + 1] - base);
+    const uint32_t n = min(hit_counts[q], cap);
+    if (n > K3_TOPN_SORT_MAX) {
+        if (threadIdx.x == 0) {
+            atomicOr(too_big, 1u);
+            out_count[q] = 0;
+        }
+        return;
+    }
+    uint32_t m = 32;
+    while (m < n) m <<= 1;
+    for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {
+        if (k < n) {
+            const HitRec r = hits[base + k];
+            key[k] = ((uint64_t)float_desc_key(r.idf) << 32) | r.nid;
+        } else {
+            key[k] = ~0ull;
+        }
+        pos[k] = (uint16_t)k;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= m; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t k = threadIdx.x; k < (m >> 1); k += blockDim.x) {
+                const uint32_t lo_i = 2 * k - (k & (stride - 1));
+                const uint32_t hi_i = lo_i + stride;
+                const bool up = (lo_i & size) == 0;
+                const uint64_t x = key[lo_i], y = key[hi_i];
+                if ((x > y) == up) {
+                    key[lo_i] = y;
+                    key[hi_i] = x;
+                    const uint16_t t = pos[lo_i];
+                    pos[lo_i] = pos[hi_i];
+                    pos[hi_i] = t;
+                }
+            }
+            __syncthreads();
+        }
+    const uint32_t n_out = min(n, top_n);
+    for (uint32_t k = threadIdx.x; k < n_out; k += blockDim.x) {
+        const HitRec r = hits[base + pos[k]];
+        out[(size_t)q * top_n + k] = fd_struct_hit{r.nid + id_offset, r.match_count, r.node_edge >> 16, r.node_edge & 0xffffu, r.idf};
+    }
+    if (threadIdx.x == 0) out_count[q] = n_out;
+}
+
+// Owner-side merge of the id-range shards' per-query top-n lists (count_query.rs:172-217 is a per-structure merge, so
+// disjoint id ranges merge by concatenation; query_pdb.rs:404-411 sort + truncate then keeps the global top n).
+// One CTA per own query: rows lists[r][q][0 .. counts[r][q]) of the world ranks -> out[q][0 .. min(total, top_n)).
+__global__ void __launch_bounds__(256) k3_merge_topn(const fd_struct_hit *lists, const uint32_t *counts, uint32_t world,
+                                                      uint32_t n_own, uint32_t top_n, fd_struct_hit *out,
+                                                      uint32_t *out_count) {
+    __shared__ uint64_t key[K3_TOPN_SORT_MAX];
+    __shared__ uint16_t pos[K3_TOPN_SORT_MAX]; // r * top_n + k
+    __shared__ uint32_t s_off[65];
+    const uint32_t q = blockIdx.x;
+    if (threadIdx.x == 0) {
+        uint32_t o = 0;
+        for (uint32_t r = 0; r < world; r++) {
+            s_off[r] = o;
+            o += min(counts[(size_t)r * n_own + q], top_n);
+        }
+        s_off[world] = o;
+    }
+    __syncthreads();
+    const uint32_t n = s_off[world];
+    uint32_t m = 32;
+    while (m < n) m <<= 1;
+    for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {
+        key[k] = ~0ull;
+        pos[k] = 0;
+    }
+    __syncthreads();
+    for (uint32_t r = 0; r < world; r++) {
+        const uint32_t c = s_off[r + 1] - s_off[r];
+        for (uint32_t k = threadIdx.x; k < c; k += blockDim.x) {
+            const fd_struct_hit h = lists[((size_t)r * n_own + q) * top_n + k];
+            key[s_off[r] + k] = ((uint64_t)float_desc_key(h.idf) << 32) | h.nid;
+            pos[s_off[r] + k] = (uint16_t)(r * top_n + k);
+        }
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= m; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t k = threadIdx.x; k < (m >> 1); k += blockDim.x) {
+                const uint32_t lo_i = 2 * k - (k & (stride - 1));
+                const uint32_t hi_i = lo_i + stride;
+                const bool up = (lo_i & size) == 0;
+                const uint64_t x = key[lo_i], y = key[hi_i];
+                if ((x > y) == up) {
+                    key[lo_i] = y;
+                    key[hi_i] = x;
+                    const uint16_t t = pos[lo_i];
+                    pos[lo_i] = pos[hi_i];
+                    pos[hi_i] = t;
+                }
+            }
+            __syncthreads();
+        }
+    const uint32_t n_out = min(n, top_n);
+    for (uint32_t k = threadIdx.x; k < n_out; k += blockDim.x) {
+        const uint32_t r = pos[k] / top_n, j = pos[k] % top_n;
+        out[(size_t)q * top_n + k] = lists[((size_t)r * n_own + q) * top_n + j];
+    }
+    if (threadIdx.x == 0) out_count[q] = n_out;
 }
 
 IndexView make_view(const fd_ctx *ctx) {
@@ -1928,6 +2061,8 @@ static int plan_scan_v2(fd_ctx *ctx, const Batch &B, ScanV2Plan &pl) {
 struct CountOpts {
     const uint32_t *gcounts = nullptr; // id-range shards: global posting count of every query hash (flattened, batch order)
     uint64_t g_structs = 0;            // and the structure count of the whole database
+    uint32_t id_offset = 0;            // first structure id of the shard: added to the reported nid
+    const uint32_t *slice_begin = nullptr; // [world + 1] owner rank of every query: exchange + merge (fd_count_query_sharded)
 };
 
 static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
@@ -1943,6 +2078,10 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
     FD_TRY(prepare_batch(ctx, queries, nq, params, true, 0, B, opts.gcounts, opts.g_structs));
     uint64_t *h_off = (uint64_t *)calloc((size_t)nq + 1, 8);
     if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+    if (opts.slice_begin && (nq == 0 || N == 0 || B.f_hash.empty())) {
+        free(h_off);
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_sharded: empty batch or empty shard (every rank takes part in the exchange)");
+    }
     if (nq == 0 || N == 0 || B.f_hash.empty()) {
         *out_offsets = h_off;
         *out_hits = (fd_struct_hit *)malloc(sizeof(fd_struct_hit));
@@ -2027,7 +2166,119 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
             FD_CUDA(ctx, st.finish());
         }
         if (h_flags[1]) return 1; // a hit region overflowed
-        return select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, top_n, N, out_hits, h_off);
+        const bool sharded = opts.slice_begin != nullptr;
+        if ((limit && top_n <= 4096 && !(getenv("FD_K3_TOPN_SORT") && atoi(getenv("FD_K3_TOPN_SORT")) == 0)) || sharded) {
+            // pools of a few hundred hits per query: one sort kernel, padded rows, one copy
+            DevBuf<fd_struct_hit> d_pad;
+            DevBuf<uint32_t> d_cnt;
+            DevBuf<unsigned int> d_big;
+            FD_CUDA(ctx, d_pad.alloc((size_t)nq * top_n));
+            FD_CUDA(ctx, d_cnt.alloc(nq + 1));
+            FD_CUDA(ctx, d_big.alloc(1));
+            FD_CUDA(ctx, cudaMemsetAsync(d_big.p, 0, 4, s));
+            unsigned int h_big = 0;
+            {
+                StageTimer st(ctx, "select");
+                FD_LAUNCH(ctx, k3_topn_sort, nq, 256, 0, d_hits.p, d_hit_off.p, d_hit_cnt.p, (uint32_t)top_n,
+                          opts.id_offset, d_pad.p, d_cnt.p, d_big.p);
+                FD_CUDA(ctx, cudaMemcpyAsync(&h_big, d_big.p, 4, cudaMemcpyDeviceToHost, s));
+                FD_CUDA(ctx, st.finish());
+            }
+            if (h_big && sharded) {
+                // a pool too large for the sort kernel: the segmented-sort path on the host side, then back to the
+                // padded device layout for the exchange
+                fd_struct_hit *hh = nullptr;
+                std::vector<uint64_t> ho(nq + 1, 0);
+                FD_TRY(select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, top_n, N, &hh, ho.data()));
+                std::vector<fd_struct_hit> pad((size_t)nq * top_n);
+                std::vector<uint32_t> cnt(nq);
+                for (uint32_t q = 0; q < nq; q++) {
+                    cnt[q] = (uint32_t)(ho[q + 1] - ho[q]);
+                    for (uint32_t k = 0; k < cnt[q]; k++) {
+                        pad[(size_t)q * top_n + k] = hh[ho[q] + k];
+                        pad[(size_t)q * top_n + k].nid += opts.id_offset;
+                    }
+                }
+                free(hh);
+                FD_CUDA(ctx, cudaMemcpyAsync(d_pad.p, pad.data(), pad.size() * sizeof(fd_struct_hit), cudaMemcpyHostToDevice, s));
+                FD_CUDA(ctx, cudaMemcpyAsync(d_cnt.p, cnt.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+                FD_CUDA(ctx, cudaStreamSynchronize(s));
+                h_big = 0;
+            }
+            if (!h_big) {
+                const fd_struct_hit *d_rows = d_pad.p;
+                const uint32_t *d_rows_cnt = d_cnt.p;
+                uint32_t n_out_q = nq;
+                DevBuf<fd_struct_hit> d_recv, d_merged;
+                DevBuf<uint32_t> d_rcnt, d_mcnt;
+                if (sharded) {
+                    // all-to-all of the fixed-size per-query blocks to the rank that owns the query, then the merge
+                    const int world = fd_comm_world_of(ctx), rank = fd_comm_rank_of(ctx);
+                    const uint32_t own0 = opts.slice_begin[rank], n_own = opts.slice_begin[rank + 1] - own0;
+                    FD_CUDA(ctx, d_recv.alloc((size_t)world * n_own * top_n));
+                    FD_CUDA(ctx, d_rcnt.alloc((size_t)world * n_own));
+                    FD_CUDA(ctx, d_merged.alloc((size_t)n_own * top_n));
+                    FD_CUDA(ctx, d_mcnt.alloc(n_own + 1));
+                    std::vector<uint64_t> so(world), sb(world), ro(world), rb(world), so2(world), sb2(world), ro2(world), rb2(world);
+                    for (int r = 0; r < world; r++) {
+                        const uint64_t nr = opts.slice_begin[r + 1] - opts.slice_begin[r];
+                        so[r] = (uint64_t)opts.slice_begin[r] * top_n * sizeof(fd_struct_hit);
+                        sb[r] = nr * top_n * sizeof(fd_struct_hit);
+                        ro[r] = (uint64_t)r * n_own * top_n * sizeof(fd_struct_hit);
+                        rb[r] = (uint64_t)n_own * top_n * sizeof(fd_struct_hit);
+                        so2[r] = (uint64_t)opts.slice_begin[r] * 4;
+                        sb2[r] = nr * 4;
+                        ro2[r] = (uint64_t)r * n_own * 4;
+                        rb2[r] = (uint64_t)n_own * 4;
+                    }
+                    {
+                        StageTimer st(ctx, "exchange");
+                        FD_TRY(fd_comm_alltoallv_dev(ctx, (const uint8_t *)d_pad.p, so.data(), sb.data(), (uint8_t *)d_recv.p,
+                                                     ro.data(), rb.data()));
+                        FD_TRY(fd_comm_alltoallv_dev(ctx, (const uint8_t *)d_cnt.p, so2.data(), sb2.data(), (uint8_t *)d_rcnt.p,
+                                                     ro2.data(), rb2.data()));
+                        FD_CUDA(ctx, st.finish());
+                    }
+                    ctx->last_exchange_bytes = 0;
+                    for (int r = 0; r < world; r++)
+                        if (r != rank) ctx->last_exchange_bytes += sb[r] + sb2[r];
+                    if (n_own) {
+                        StageTimer st(ctx, "merge");
+                        FD_LAUNCH(ctx, k3_merge_topn, n_own, 256, 0, d_recv.p, d_rcnt.p, (uint32_t)world, n_own, (uint32_t)top_n,
+                                  d_merged.p, d_mcnt.p);
+                        FD_CUDA(ctx, st.finish());
+                    }
+                    d_rows = d_merged.p;
+                    d_rows_cnt = d_mcnt.p;
+                    n_out_q = n_own;
+                }
+                void *h_pad_v = nullptr, *h_cnt_v = nullptr;
+                FD_TRY(fd_pinned(ctx, 6, (size_t)n_out_q * top_n * sizeof(fd_struct_hit) + 16, &h_pad_v));
+                FD_TRY(fd_pinned(ctx, 7, (size_t)n_out_q * 4 + 4, &h_cnt_v));
+                fd_struct_hit *h_pad = (fd_struct_hit *)h_pad_v;
+                uint32_t *h_cnt = (uint32_t *)h_cnt_v;
+                {
+                    StageTimer st(ctx, "select");
+                    FD_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_rows_cnt, (size_t)n_out_q * 4, cudaMemcpyDeviceToHost, s));
+                    FD_CUDA(ctx, cudaMemcpyAsync(h_pad, d_rows, (size_t)n_out_q * top_n * sizeof(fd_struct_hit), cudaMemcpyDeviceToHost, s));
+                    FD_CUDA(ctx, st.finish());
+                }
+                h_off[0] = 0;
+                for (uint32_t q = 0; q < n_out_q; q++) h_off[q + 1] = h_off[q] + h_cnt[q];
+                fd_struct_hit *h_hits = (fd_struct_hit *)malloc(std::max<uint64_t>(h_off[n_out_q], 1) * sizeof(fd_struct_hit));
+                if (!h_hits) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+                for (uint32_t q = 0; q < n_out_q; q++)
+                    memcpy(h_hits + h_off[q], h_pad + (size_t)q * top_n, (size_t)h_cnt[q] * sizeof(fd_struct_hit));
+                *out_hits = h_hits;
+                return FD_OK;
+            }
+        }
+        {
+            const int rc2 = select_and_copy(ctx, nq, hit_off, d_hit_off, d_hit_cnt, d_hits, top_n, N, out_hits, h_off);
+            if (rc2 == FD_OK && opts.id_offset)
+                for (uint64_t k = 0; k < h_off[nq]; k++) (*out_hits)[k].nid += opts.id_offset;
+            return rc2;
+        }
     };
     // the pre-selection pays when the top n is a small part of a tile
     bool limit = !use_v1 && top_n > 0 && top_n <= 0xffffu && top_n * 8 <= N;
@@ -2067,6 +2318,35 @@ int fd_count_query_batch_ex(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
     o.g_structs = global_n_structs;
     return count_query_impl(ctx, queries, nq, params, o, out_hits, out_offsets);
 }
+
+int fd_count_query_sharded(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
+                           const uint32_t *global_counts, uint64_t global_n_structs, uint64_t first_id,
+                           const uint32_t *slice_begin, fd_struct_hit **out_hits, uint64_t **out_offsets) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->idx.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_count_query_sharded: no index attached");
+    if (!ctx->comm) return fd_fail(ctx, FD_ERR_STATE, "fd_count_query_sharded: call fd_comm_init first");
+    if ((nq && !queries) || !params || !out_hits || !out_offsets || !global_counts || !slice_begin)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_sharded: NULL argument");
+    const int world = fd_comm_world_of(ctx);
+    if (slice_begin[0] != 0 || slice_begin[world] != nq)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_sharded: slice_begin must run from 0 to n_queries");
+    for (int r = 0; r < world; r++)
+        if (slice_begin[r] > slice_begin[r + 1]) return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_sharded: slices must be ascending");
+    if (global_n_structs == 0 || global_n_structs > 0xfffffff0ull || first_id + ctx->idx.n_structs > global_n_structs)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_count_query_sharded: id range outside the database");
+    if (params->top_n == 0 || params->top_n > 4096 / (uint64_t)world)
+        return fd_fail(ctx, FD_ERR_LIMIT,
+                       "the sharded search exchanges fixed-size per-query blocks: --top must be between 1 and 4096 / ranks");
+    FD_ENTER(ctx);
+    CountOpts o;
+    o.gcounts = global_counts;
+    o.g_structs = global_n_structs;
+    o.id_offset = (uint32_t)first_id;
+    o.slice_begin = slice_begin;
+    return count_query_impl(ctx, queries, nq, params, o, out_hits, out_offsets);
+}
+
+uint64_t fd_last_exchange_bytes(const fd_ctx *ctx) { return ctx ? ctx->last_exchange_bytes : 0; }
 
 int fd_votes_scan(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_prefilter_params *params,
                   fd_votes_layout *layout, uint32_t **d_votes) {

@@ -476,6 +476,16 @@ struct fdh_queries {
     // built by fdh_queries_finalize (or lazily by the first search), dropped whenever the idf values change
     mutable fd_verify_prepared *vprep = nullptr;
     mutable int vprep_device = -1;
+    // id-range shards (fdh_queries_finalize_sharded): the WHOLE batch -- the queries of every rank, rank by rank -- as
+    // the flat scan inputs of fd_count_query_sharded, with the global list length of every hash
+    struct ShardedBatch {
+        int world = 0, rank = 0;
+        uint64_t first_id = 0, total_structs = 0;
+        std::vector<uint32_t> slice_begin;                    // [world + 1]
+        std::vector<uint32_t> q_nh, q_ne, q_nn, q_expected;   // per query of the whole batch
+        std::vector<uint32_t> hashes, gcounts;                // per hash
+        std::vector<uint16_t> edge_of_hash, edge_node;        // per hash / per edge
+    } sh;
     ~fdh_queries() { fd_verify_prepared_free(vprep); }
 };
 
@@ -1889,7 +1899,8 @@ static int ensure_verify_prepared(fd_ctx *ctx, const fdh_queries *qs) {
 // query_pdb.rs:348-452 for queries [q_begin, q_end) of the batch.  votes == nullptr: count_query on this
 // context's index (fd_count_query_batch); otherwise finish count_query from merged dense votes (fd_votes_select).
 static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels,
-                                uint32_t q_begin, uint32_t q_end, const fd_votes_layout *layout, const uint32_t *votes) {
+                                uint32_t q_begin, uint32_t q_end, const fd_votes_layout *layout, const uint32_t *votes,
+                                bool sharded = false) {
     if (!qs->finalized) {
         set_err("fdh_search: call fdh_queries_finalize first");
         return nullptr;
@@ -1914,7 +1925,22 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     const auto t_all = now();
     auto t_stage = now();
     int rc;
-    if (votes) {
+    if (sharded) {
+        // id-range shards: this rank scans its local index for the whole batch; the owners get the global top n
+        const fdh_queries::ShardedBatch &S = qs->sh;
+        const uint32_t nb = (uint32_t)S.q_nh.size();
+        fq.resize(nb);
+        size_t hb = 0, eb = 0;
+        for (uint32_t q = 0; q < nb; q++) {
+            fq[q] = fd_query{S.q_nh[q], S.hashes.data() + hb, S.edge_of_hash.data() + hb, S.q_ne[q], S.edge_node.data() + eb,
+                             S.q_nn[q], S.q_expected[q], nullptr};
+            hb += S.q_nh[q];
+            eb += S.q_ne[q];
+        }
+        R->h2d_bytes += 6ull * hb + 2ull * eb + 24ull * nb + 4ull * hb;
+        rc = fd_count_query_sharded(ctx, fq.data(), nb, &p->prefilter, S.gcounts.data(), S.total_structs, S.first_id,
+                                    S.slice_begin.data(), &hits, &hoff);
+    } else if (votes) {
         make_fd_queries(qs, 0, (uint32_t)qs->q.size(), fq, nullptr);
         rc = fd_votes_select(ctx, fq.data(), (uint32_t)fq.size(), &p->prefilter, layout, votes, q_begin, q_end, &hits, &hoff);
     } else {
@@ -2426,6 +2452,105 @@ fdh_results *fdh_search_from_votes(fd_ctx *ctx, const fdh_queries *qs, const fdh
         return nullptr;
     }
     return search_impl(ctx, qs, p, labels, q_begin, q_end, layout, d_votes);
+}
+
+// ---- id-range shards over NCCL (fd_comm_*): gather the ranks' query descriptors, all-reduce the list lengths ----
+int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id, uint64_t total_structs) {
+    const int world = fd_comm_world(ctx), rank = fd_comm_rank(ctx);
+    // this rank's blob: n_queries | per query {n_hashes, n_edges, n_nodes, residue_count, n_pairs} | hashes | pair
+    // hashes | edge_of_hash | edge_node (u16 arrays last, padded to 4 bytes)
+    std::vector<uint32_t> blob;
+    const uint32_t nq = (uint32_t)qs->q.size();
+    blob.push_back(nq);
+    for (auto &Q : qs->q) {
+        blob.push_back((uint32_t)Q.hashes_flat.size());
+        blob.push_back((uint32_t)Q.edge_node.size());
+        blob.push_back(Q.n_nodes);
+        blob.push_back(Q.residue_count);
+        blob.push_back((uint32_t)Q.pair_hash.size());
+    }
+    for (auto &Q : qs->q) blob.insert(blob.end(), Q.hashes_flat.begin(), Q.hashes_flat.end());
+    for (auto &Q : qs->q) blob.insert(blob.end(), Q.pair_hash.begin(), Q.pair_hash.end());
+    std::vector<uint16_t> u16;
+    for (auto &Q : qs->q) u16.insert(u16.end(), Q.edge_of_hash.begin(), Q.edge_of_hash.end());
+    for (auto &Q : qs->q) u16.insert(u16.end(), Q.edge_node.begin(), Q.edge_node.end());
+    if (u16.size() & 1) u16.push_back(0);
+    const size_t words32 = blob.size();
+    blob.resize(words32 + u16.size() / 2);
+    memcpy(blob.data() + words32, u16.data(), u16.size() * 2);
+    uint64_t my_bytes = blob.size() * 4;
+    std::vector<uint64_t> sizes(world);
+    if (fd_comm_allgather(ctx, &my_bytes, 8, sizes.data()) != FD_OK) {
+        set_err(fd_last_error(ctx));
+        return FD_ERR_CUDA;
+    }
+    uint64_t mx = 0;
+    for (uint64_t b : sizes) mx = std::max(mx, b);
+    blob.resize(mx / 4, 0);
+    std::vector<uint32_t> all((size_t)world * (mx / 4));
+    if (fd_comm_allgather(ctx, blob.data(), mx, all.data()) != FD_OK) {
+        set_err(fd_last_error(ctx));
+        return FD_ERR_CUDA;
+    }
+    fdh_queries::ShardedBatch &S = qs->sh;
+    S = fdh_queries::ShardedBatch();
+    S.world = world;
+    S.rank = rank;
+    S.first_id = first_id;
+    S.total_structs = total_structs;
+    S.slice_begin.assign(world + 1, 0);
+    std::vector<uint32_t> pair_all;       // pair hashes of every rank, rank by rank
+    std::vector<size_t> pair_begin(world + 1, 0);
+    for (int r = 0; r < world; r++) {
+        const uint32_t *b = all.data() + (size_t)r * (mx / 4);
+        const uint32_t n = b[0];
+        S.slice_begin[r + 1] = S.slice_begin[r] + n;
+        size_t nh = 0, ne = 0, np = 0;
+        for (uint32_t q = 0; q < n; q++) {
+            S.q_nh.push_back(b[1 + 5 * q]);
+            S.q_ne.push_back(b[2 + 5 * q]);
+            S.q_nn.push_back(b[3 + 5 * q]);
+            S.q_expected.push_back(b[4 + 5 * q]);
+            nh += b[1 + 5 * q];
+            ne += b[2 + 5 * q];
+            np += b[5 + 5 * q];
+        }
+        const uint32_t *hp = b + 1 + 5 * (size_t)n;
+        S.hashes.insert(S.hashes.end(), hp, hp + nh);
+        pair_all.insert(pair_all.end(), hp + nh, hp + nh + np);
+        pair_begin[r + 1] = pair_all.size();
+        const uint16_t *up = reinterpret_cast<const uint16_t *>(hp + nh + np);
+        S.edge_of_hash.insert(S.edge_of_hash.end(), up, up + nh);
+        S.edge_node.insert(S.edge_node.end(), up + nh, up + nh + ne);
+    }
+    // global list lengths: local counts of [batch hashes | pair hashes], summed over the ranks
+    std::vector<uint32_t> probe(S.hashes);
+    probe.insert(probe.end(), pair_all.begin(), pair_all.end());
+    std::vector<uint32_t> counts(probe.size());
+    if (!probe.empty()) {
+        if (fd_posting_counts(ctx, probe.data(), probe.size(), counts.data()) != FD_OK ||
+            fd_comm_allreduce_u32(ctx, counts.data(), counts.size()) != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return FD_ERR_CUDA;
+        }
+    }
+    S.gcounts.assign(counts.begin(), counts.begin() + S.hashes.size());
+    // calculate_idf_for_hash (query.rs:17-32) of this rank's own query pairs, from the global lengths
+    const int rc = fdh_queries_finalize_with_counts(qs, counts.data() + S.hashes.size() + pair_begin[rank], total_structs);
+    if (rc != FD_OK) return rc;
+    return ensure_verify_prepared(ctx, qs);
+}
+
+fdh_results *fdh_search_sharded(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels) {
+    if (qs->sh.world == 0 || qs->sh.slice_begin.empty()) {
+        set_err("fdh_search_sharded: call fdh_queries_finalize_sharded first");
+        return nullptr;
+    }
+    if (qs->sh.slice_begin[qs->sh.rank + 1] - qs->sh.slice_begin[qs->sh.rank] != qs->q.size()) {
+        set_err("fdh_search_sharded: the batch changed since fdh_queries_finalize_sharded");
+        return nullptr;
+    }
+    return search_impl(ctx, qs, p, labels, 0, (uint32_t)qs->q.size(), nullptr, nullptr, true);
 }
 
 uint64_t fdh_results_num_queries(const fdh_results *r) { return r->struct_off.size() - 1; }

@@ -101,6 +101,8 @@ def _lib():
     sig("fdh_queries_get_indices", None, [VP, C.c_int64, VP])
     sig("fdh_queries_free", None, [VP])
     sig("fdh_search", VP, [VP, VP, PP(SearchParams), VP])
+    sig("fdh_queries_finalize_sharded", C.c_int, [VP, VP, C.c_uint64, C.c_uint64])
+    sig("fdh_search_sharded", VP, [VP, VP, PP(SearchParams), VP])
     sig("fdh_queries_set_shards", C.c_int, [VP, VP, C.c_int])
     sig("fdh_queries_num_vote_bits", C.c_int64, [VP, C.c_int64])
     sig("fdh_queries_get_vote_bits", None, [VP, C.c_int64, VP, VP, VP, VP])
@@ -380,6 +382,12 @@ class QueryBatch:
         if rc != 0:
             raise FdError(_err())
 
+    # ---- id-range shards over the library's own NCCL communicator (ctx.comm_init) ----
+    def finalize_sharded(self, ctx, first_id, total_structs):
+        """collective: all-gather of the ranks' query descriptors + all-reduce of the posting counts"""
+        if _lib().fdh_queries_finalize_sharded(self.h, ctx.h, int(first_id), int(total_structs)) != 0:
+            raise FdError(_err())
+
     # ---- hash-range shards (see folddisco_b200/sharded.py) ----
     def set_shards(self, bounds):
         b = np.ascontiguousarray(bounds, np.uint64)
@@ -534,6 +542,12 @@ def search(ctx, queries, params=None, labels=None):
     """query_pdb.rs:348-452 for the batch: count_query -> filter/sort/top -> retrieval -> Kabsch -> filters -> sort"""
     params = params or SearchParams()
     return Results(_lib().fdh_search(ctx.h, queries.h, C.byref(params), labels.h if labels is not None else None))
+
+
+def search_sharded(ctx, queries, params=None, labels=None):
+    """collective: this rank's own queries against the id-range sharded database (QueryBatch.finalize_sharded first)"""
+    params = params or SearchParams()
+    return Results(_lib().fdh_search_sharded(ctx.h, queries.h, C.byref(params), labels.h if labels is not None else None))
 
 
 class _LaneContext:

@@ -230,3 +230,62 @@ class ShardedIndex:
             self.merge_bytes += int(lay.words) * 4
         q0, q1 = query_slice(len(qb), self.rank, self.world)
         return host.search_from_votes(ctx, qb, sp, lay, ptr, q0, q1, labels)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# id-range shards (SURVEY 8e ablation -> the default multi-GPU partition): rank r indexes the structures
+# [cuts[r], cuts[r + 1]) only; every rank scans its local index for the WHOLE batch with the global list lengths, one
+# all-to-all of fixed-size per-query top-n blocks goes to the query's owner, the owner merges and verifies.  All
+# collectives run inside the library (csrc/fd_comm.cu, NCCL): Python only hands the 128-byte unique id around.
+# ----------------------------------------------------------------------------------------------------------------
+def id_range_cuts(n_structs, world):
+    """cuts[world + 1]: contiguous, near-equal id ranges"""
+    return np.array([(n_structs * r) // world for r in range(world + 1)], np.int64)
+
+
+def comm_init(ctx, rank, world, dist=None):
+    """NCCL communicator of the library on ctx; the unique id travels over torch.distributed when world > 1"""
+    uid = capi.Context.comm_unique_id()
+    if world > 1:
+        import torch
+        t = torch.from_numpy(uid.copy())
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        uid = t.cpu().numpy()
+    ctx.comm_init(uid, rank, world)
+
+
+class IdRangeShards:
+    """This rank's id-range shard: local index attached to ctx (local ids), the whole structure store attached for
+    the verification of the rank's own queries."""
+
+    def __init__(self, index, first_id, n_local, total_structs, rank, world):
+        self.index, self.first_id, self.n_local, self.total = index, int(first_id), int(n_local), int(total_structs)
+        self.rank, self.world = rank, world
+
+    @classmethod
+    def build(cls, ctx, db, rank, world, hash_params=None):
+        """db: SoA dict of the whole database (row_offsets, n_xyz, ca_xyz, cb_xyz, aa); the rank builds the index of its
+        id range on its GPU.  Returns (shards, full_store)"""
+        S = len(db["row_offsets"]) - 1
+        cuts = id_range_cuts(S, world)
+        lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+        ro = db["row_offsets"].astype(np.int64)
+        sl = slice(ro[lo], ro[hi])
+        local = dict(row_offsets=(db["row_offsets"][lo:hi + 1] - db["row_offsets"][lo]).astype(np.uint64),
+                     n_xyz=db["n_xyz"][sl], ca_xyz=db["ca_xyz"][sl], cb_xyz=db["cb_xyz"][sl], aa=db["aa"][sl])
+        local_store = host.Store()
+        local_store.add_soa(local)
+        index = host.FolddiscoIndex.build(ctx, local_store, hash_params)
+        index.attach(ctx)
+        full = host.Store()
+        full.add_soa(db)
+        full.attach(ctx)
+        return cls(index, lo, hi - lo, S, rank, world), full
+
+    def prepare(self, ctx, qb):
+        qb.finalize_sharded(ctx, self.first_id, self.total)
+
+    def search(self, ctx, qb, params=None, labels=None):
+        return host.search_sharded(ctx, qb, params, labels)

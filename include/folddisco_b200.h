@@ -191,6 +191,37 @@ int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t n_querie
 int fd_count_query_batch_ex(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries,
                             const fd_prefilter_params *params, const uint32_t *global_counts,
                             uint64_t global_n_structs, fd_struct_hit **out_hits, uint64_t **out_offsets);
+/* ---- multi-GPU: NCCL inside the library + id-range shards ---------------------------------------------
+ * One context per rank / GPU.  Rank 0 obtains a unique id (fd_comm_unique_id) and hands its FD_COMM_ID_BYTES bytes to
+ * the other ranks by any means (a file, MPI, torch.distributed ...); every rank then calls fd_comm_init.  The
+ * collectives below run on the context's stream; the *_host helpers stage host buffers through device memory. */
+#define FD_COMM_ID_BYTES 128
+int fd_comm_unique_id(uint8_t *out_id /* FD_COMM_ID_BYTES */);
+int fd_comm_init(fd_ctx *ctx, const uint8_t *id /* FD_COMM_ID_BYTES */, int rank, int world);
+void fd_comm_destroy(fd_ctx *ctx); /* also done by fd_destroy */
+int fd_comm_rank(const fd_ctx *ctx);
+int fd_comm_world(const fd_ctx *ctx);
+int fd_comm_allgather(fd_ctx *ctx, const void *send, uint64_t bytes, void *recv /* world * bytes */);
+int fd_comm_allreduce_u32(fd_ctx *ctx, uint32_t *inout, uint64_t n); /* sum */
+int fd_comm_barrier(fd_ctx *ctx);
+
+/* count_query over a database whose structures are split into contiguous ID RANGES, one per rank (the
+ * reference's merge is per structure id, src/controller/count_query.rs:172-217, and its top-n a sort + truncate,
+ * src/cli/workflows/query_pdb.rs:404-411, so id-range shards need only a top-n exchange).  Every rank passes the SAME
+ * batch (all ranks' queries in the same order) and the global list lengths (all-reduced fd_posting_counts); rank r owns
+ * the queries [slice_begin[r], slice_begin[r + 1]).  The rank scans its local index (ids 0 .. n_structs, reported as
+ * first_id + id) for the whole batch, keeps its top_n per query, ONE all-to-all of fixed-size blocks (ncclSend /
+ * ncclRecv group) sends every query's block to its owner, the owner merges (idf descending, id ascending) and returns
+ * the global top_n of ITS OWN queries: *out_offsets has slice_begin[r + 1] - slice_begin[r] + 1 entries.  Rows are
+ * bit-identical to fd_count_query_batch on the unsharded index.  top_n must be in [1, 4096 / world]; every rank must
+ * hold at least one structure. */
+int fd_count_query_sharded(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,
+                           const uint32_t *global_counts, uint64_t global_n_structs, uint64_t first_id,
+                           const uint32_t *slice_begin /* world + 1 */, fd_struct_hit **out_hits,
+                           uint64_t **out_offsets);
+/* bytes this rank sent to other ranks in the last fd_count_query_sharded */
+uint64_t fd_last_exchange_bytes(const fd_ctx *ctx);
+
 /* posting bytes the last fd_count_query_batch had to read (sum over found query hashes of their list
  * length in bytes) -- the algorithmic bytes of SURVEY 8d */
 uint64_t fd_last_posting_bytes(const fd_ctx *ctx);

@@ -152,6 +152,16 @@ typedef struct {
 /* labels (may be NULL): store whose per-residue (chain, residue number) label the matched target residues;
  * without it fdh_residue_match.serial is the residue index inside the target and chain is 0. */
 fdh_results *fdh_search(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels);
+/* The same over a database whose structures are split into contiguous id ranges, one per rank / GPU (fd_comm_init on
+ * every rank's ctx first).  qs holds THIS RANK'S OWN queries; ctx has the rank's LOCAL index attached (ids 0 ..,
+ * database ids first_id ..) and a structure store with ALL structures of the database (the owner of a query verifies
+ * its candidates wherever they live; 38 B per residue).  fdh_queries_finalize_sharded all-gathers the ranks' query
+ * descriptors and all-reduces the local posting counts into global list lengths (the reference's idf weights);
+ * fdh_search_sharded = fd_count_query_sharded (local scan of the whole batch, one all-to-all of per-query top-n
+ * blocks, owner-side merge) + verification + rows of the rank's own queries.  Collective calls: every rank calls
+ * both, with the same search parameters.  Rows are identical to fdh_search on the unsharded database. */
+int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id, uint64_t total_structs);
+fdh_results *fdh_search_sharded(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels);
 
 /* ---- hash-range sharded index (one rank per GPU): the same search in three steps around the caller's collective.
  *   0. every rank: fdh_queries_set_shards (gives every (query edge, owning rank) pair its own vote bit)

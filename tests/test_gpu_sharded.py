@@ -199,3 +199,21 @@ def test_two_rank_nccl():
            "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "sharded_worker.py")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "sharded ok rank 0" in r.stdout and "sharded ok rank 1" in r.stdout, r.stdout[-4000:]
+
+
+def test_id_range_world1():
+    """the id-range path end to end on one GPU (world = 1: the all-to-all is a self send / receive): NCCL communicator
+    inside the library, gather / all-reduce of the query descriptors and list lengths, fd_count_query_sharded, merge,
+    verification -- rows identical to the unsharded search"""
+    import idrange_worker
+    idrange_worker.run(0, 1, 0, None)
+
+
+def test_id_range_two_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", os.path.join(HERE, "idrange_worker.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "id-range ok rank 0" in r.stdout and "id-range ok rank 1" in r.stdout, r.stdout[-4000:]

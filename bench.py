@@ -5,15 +5,22 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      (CPU restatement of the reference)
 
-Workload (BASELINE.json configs[2]): the five shipped motifs (serine peptidase, zinc finger, knottin, enolase,
-aminopeptidase) replicated to a batch of 1024 queries against a human-proteome-scale synthetic database
-(23 400 structures per GPU, seeded generator of folddisco_b200/synth.py), reference default flags
+Workload (BASELINE.json configs[2] scale): a batch of 1024 DISTINCT motif queries per GPU (3-8 residues within 12 A,
+sampled with a fixed seed from the database's own structures; `distinct_motifs`) against a human-proteome-scale
+synthetic database (23 400 structures per GPU, seeded generator of folddisco_b200/synth.py), reference default flags
 (-d 0.5 -a 5 --ca-distance 1.0) with --top 100.  One step = one batch through
-make_query_map -> count_query (posting scan + vote) -> filter/sort/top -> candidate re-hash -> Kabsch RMSD.
-With N > 1 GPUs the problem grows with N (weak scaling): N x 23 400 structures, N x 1024 queries.  The index is
-hash-range sharded; every rank builds the query maps of its 1024 queries, scans its shard for the WHOLE batch,
-the non-empty vote cells are exchanged with one all-to-all over NVLink, and every rank finishes its own 1024 queries
-(folddisco_b200/sharded.py).
+make_query_map -> count_query (posting scan + vote) -> filter/sort/top -> candidate re-hash -> Kabsch RMSD -> rows.
+The batch of the five shipped motifs replicated 205 x (round 1's headline) is kept as the secondary `shipped_motifs`.
+
+With N > 1 GPUs the problem grows with N (weak scaling): N x 23 400 structures, N x 1024 queries.  The structures are
+split into contiguous ID RANGES, one per rank; every rank builds the query maps of its own 1024 queries, scans its
+local index for the WHOLE batch (global list lengths all-reduced, so the idf weights are the unsharded ones), one
+NCCL all-to-all of fixed-size per-query top-n blocks goes to the query's owner, which merges and verifies its own
+queries.  All collectives run inside libfolddisco_b200.so (csrc/fd_comm.cu); torch.distributed only carries the
+barrier / max-over-ranks of the timing and the 128-byte NCCL id.
+
+Every line carries `parity_check`: the first queries of rank 0's slice, answered by the CPU oracle on the same
+database, are compared row for row with the GPU's rows of the timed configuration.
 """
 import argparse
 import json
@@ -29,10 +36,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "motif queries/sec (batch of shipped motifs vs synthetic index; posting-list GB/s vs HBM peak in roofline)"
+METRIC = "motif queries/sec (batch of distinct motifs vs synthetic index; posting-list GB/s vs HBM peak in roofline)"
 MOTIFS = [("query/4CHA.pdb", "B57,B102,C195"), ("query/1G2F.pdb", "F207,F212,F225,F229"),
           ("query/2N6N.pdb", "3,10,15,16,21,23,28,30"), ("query/2MNR.pdb", "164:H,195,221,247:ND,297:H"),
           ("query/1LAP.pdb", "250,255,273,332,334")]
+DTYPE = "u32 hashes / u8 postings / f32 idf / f64 Kabsch"
 
 
 def parse_args():
@@ -44,9 +52,13 @@ def parse_args():
     ap.add_argument("--structs-per-gpu", type=int, default=23400)
     ap.add_argument("--batch", type=int, default=1024, help="queries per GPU")
     ap.add_argument("--top", type=int, default=100)
-    ap.add_argument("--sub-batch", type=int, default=0, help="> 0: e2e through host.search_stream with this many queries per sub-batch (1 GPU)")
-    ap.add_argument("--cpu-sample", type=int, default=40, help="queries in the bounded CPU-baseline sample")
-    ap.add_argument("--sweep", default="2,4", help="index-size multipliers of the posting-scan sweep (N=1 only; '' = off)")
+    ap.add_argument("--parity-queries", type=int, default=40, help="queries of rank 0's slice diffed against the oracle")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries per step of the CPU arm (0 = 16 x cores)")
+    ap.add_argument("--sweep", default="4", help="index-size multipliers of the posting-scan sweep (N=1 only; '' = off; "
+                                                 "23 = Swiss-Prot scale, 538 200 structures, about two more minutes)")
+    ap.add_argument("--pair-table", type=int, default=1, help="build the structure store's pair table (verification by "
+                                                             "hash lookup instead of re-hashing candidates)")
+    ap.add_argument("--shipped", type=int, default=1, help="also time the five shipped motifs x 205 (secondary line)")
     return ap.parse_args()
 
 
@@ -97,7 +109,7 @@ class ClockSampler(threading.Thread):
 
 
 def scan_traffic():
-    """DRAM bytes (read + write) of one k3_scan launch of this workload, from the committed ncu --set full capture"""
+    """DRAM bytes (read + write) of one scan launch of this workload, from the committed ncu --set full capture"""
     p = os.path.join(ROOT, "profiles", "k3_scan_traffic.json")
     if os.path.exists(p):
         return json.load(open(p)).get("dram_bytes_per_launch")
@@ -143,29 +155,38 @@ def distinct_motifs(db, n, first, seed=0x5EED):
     return out
 
 
-def make_query_batch(ctx, index, db, n, first, sharded=None, dist=None, timing=None):
-    """host.QueryBatch of n queries starting at global query number `first`: distinct motifs sampled from db, or (db is
-    None) the five shipped motifs cycled"""
+def query_inputs(db, n, first):
+    """the host-side INPUTS of a batch, as a user holds them: (CompactStructure objects, query strings) of n queries
+    starting at global query number `first` -- distinct motifs sampled from db, or (db is None) the five shipped
+    motifs cycled"""
     from folddisco_b200 import host
-    t0 = time.perf_counter()
-    qb = host.QueryBatch(index.params)
     if db is None:
         motif_structs = [(host.CompactStructure.from_atoms(a), q) for a, q in load_motif_atoms()]
         which = np.arange(first, first + n, dtype=np.uint32) % len(motif_structs)
-        qb.add_many_indexed([m[0] for m in motif_structs], [m[1] for m in motif_structs], which, which)
-    else:
-        ro = db["row_offsets"].astype(np.int64)
-        motifs = distinct_motifs(db, n, first)
-        comps = [host.CompactStructure.from_soa(db["n_xyz"][ro[s]:ro[s + 1]], db["ca_xyz"][ro[s]:ro[s + 1]],
-                                                db["cb_xyz"][ro[s]:ro[s + 1]], db["aa"][ro[s]:ro[s + 1]])
-                 for s, _, _ in motifs]
-        idx = np.arange(n, dtype=np.uint32)
-        qb.add_many_indexed(comps, [m[2] for m in motifs], idx, idx)
+        return [m[0] for m in motif_structs], [m[1] for m in motif_structs], which, which
+    ro = db["row_offsets"].astype(np.int64)
+    motifs = distinct_motifs(db, n, first)
+    comps = [host.CompactStructure.from_soa(db["n_xyz"][ro[s]:ro[s + 1]], db["ca_xyz"][ro[s]:ro[s + 1]],
+                                            db["cb_xyz"][ro[s]:ro[s + 1]], db["aa"][ro[s]:ro[s + 1]])
+             for s, _, _ in motifs]
+    idx = np.arange(n, dtype=np.uint32)
+    return comps, [m[2] for m in motifs], idx, idx
+
+
+def make_query_batch(ctx, index, db, n, first, shards=None, timing=None, inputs=None):
+    """host.QueryBatch from the batch's inputs: make_query_map of every query (add_many_indexed), then the idf lookup
+    and the upload of the verification tables (finalize; with id-range shards the collective form)"""
+    from folddisco_b200 import host
+    if inputs is None:
+        inputs = query_inputs(db, n, first)
+    t0 = time.perf_counter()
+    qb = host.QueryBatch(index.params)
+    qb.add_many_indexed(*inputs)
     t1 = time.perf_counter()
-    if sharded is None:
+    if shards is None:
         qb.finalize(ctx)
     else:
-        sharded.prepare(ctx, qb, dist)
+        shards.prepare(ctx, qb)
     if timing is not None:
         timing["query_maps"] += (t1 - t0) * 1e3
         timing["finalize"] += (time.perf_counter() - t1) * 1e3
@@ -173,86 +194,134 @@ def make_query_batch(ctx, index, db, n, first, sharded=None, dist=None, timing=N
     return qb
 
 
-def database(rank, world, structs_per_gpu):
+def database(world, structs_per_gpu):
     """The same global database on every rank (weak scaling: world * structs_per_gpu structures)."""
     from folddisco_b200 import synth
     return synth.generate(structs_per_gpu * world, synth.SEED_BASE + 2)
 
 
-# --------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    """CPU arm: the oracle (C++ restatement of the reference algorithm; the Rust crate cannot be built here),
-    all host threads, on a bounded sample of the same workload."""
-    if rank != 0:
-        return
-    import oracle_lib as O
-    cores = os.cpu_count() or 1
-    # CPU index build is ~30 s per 23 400 structures: beyond 4 GPUs' worth the reference arm searches a 4x database
-    # (a smaller index only makes the CPU arm faster)
-    ref_gpus = min(args.gpus, 4)
-    db = database(0, ref_gpus, args.structs_per_gpu)
-    from folddisco_b200 import synth
-    parts = synth.split(db)
-    t0 = time.time()
-    comps = [O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"]) for p in parts]
-    index = O.Index.build(comps, threads=cores)
-    build_s = time.time() - t0
-    nres = np.array([len(p["aa"]) for p in parts], np.uint64)
-    plddt = np.zeros(len(parts), np.float32)
-    qms, qcs = [], []
-    for atoms, q in load_motif_atoms():
-        s = O.Structure.from_atoms(atoms)
-        ch, se, subs = O.parse_query_string(q, s.first_chain)
-        qc = s.compact()
-        qms.append(O.QueryMap(qc, ch, se, subs, index=index, total_structures=len(parts)))
-        qcs.append(qc)
-    sample = max(len(qms), args.cpu_sample)
-    import ctypes as C
-    maps = (O.VP * sample)(*[qms[k % len(qms)].h for k in range(sample)])
-    qarr = (O.VP * sample)(*[qcs[k % len(qms)].h for k in range(sample)])
-    store = (O.VP * len(comps))(*[c.h for c in comps])
-    p = O.CountParams.defaults(top_n=args.top)
-
-    def step():
-        return O.lib().fdo_query_batch(maps, qarr, sample, index.h, store, len(comps), nres, plddt, C.byref(p), 0, 0,
-                                       20.0, 1.0, 0, cores, None, None, None)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / max(1, args.steps)
-    qps = sample / dt
-    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32 hashes / u8 postings / f32 idf / f64 Kabsch",
-            "data": "synthetic",
-            "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                             "sample": "%d queries (the five motifs cycled) per step, C++ restatement of the reference "
-                                       "algorithm (oracle/), query-parallel over %d threads; index of %d structures, build %.1f s"
-                                       % (sample, cores, len(parts), build_s)},
-            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
-
-
 def workload_config(args, world):
-    return {"workload": "configs[2]: batch of the 5 shipped motifs (replicated to %d queries per GPU) vs "
-                        "human-proteome-scale synthetic index, %d structures per GPU" % (args.batch, args.structs_per_gpu),
+    return {"workload": "configs[2] scale: batch of %d DISTINCT motifs per GPU (3-8 residues within 12 A, sampled from "
+                        "the database) vs human-proteome-scale synthetic index, %d structures per GPU"
+                        % (args.batch, args.structs_per_gpu),
             "structures": args.structs_per_gpu * world, "batch": args.batch * world, "top_n": args.top,
             "flags": "-d 0.5 -a 5 --ca-distance 1.0 --top %d, hash PDBTrRosetta 16/4 bins, cutoff 20 A" % args.top,
             "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-            "parallelism": ("hash-range index shards x%d, every rank scans its shard for the whole batch, sparse vote "
-                            "all-to-all (NCCL), every rank finishes %d queries" % (world, args.batch))
-            if world > 1 else "single GPU"}
+            "parallelism": ("id-range index shards x%d: every rank scans its local index for the whole batch, one NCCL "
+                            "all-to-all of per-query top-%d blocks, every rank merges and verifies its own %d queries"
+                            % (world, args.top, args.batch)) if world > 1 else "single GPU"}
+
+
+# --------------------------------------------------------------------------------------------------
+class Oracle:
+    """The CPU oracle over the bench database (checker / CPU arm; never on the measured GPU path)."""
+
+    def __init__(self, db, index_buffers=None, threads=1):
+        import oracle_lib as O
+        from folddisco_b200 import synth
+        self.O, self.db = O, db
+        self.parts = synth.split(db)
+        self.S = len(self.parts)
+        self.nres = np.array([len(p["aa"]) for p in self.parts], np.uint64)
+        self.plddt = np.zeros(self.S, np.float32)
+        self._comps = {}
+        t0 = time.perf_counter()
+        if index_buffers is not None:  # byte-identical to the oracle's own build (tests/test_gpu_parity.py)
+            self.index = O.Index.from_buffers(index_buffers.hashes, index_buffers.offsets, index_buffers.values)
+        else:
+            self.index = O.Index.build([self.comp(s) for s in range(self.S)], threads=threads)
+        self.build_s = time.perf_counter() - t0
+
+    def comp(self, s):
+        c = self._comps.get(s)
+        if c is None:
+            p = self.parts[s]
+            c = self.O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"],
+                                        serial=np.arange(1, len(p["aa"]) + 1, dtype=np.uint64))
+            self._comps[s] = c
+        return c
+
+    def query_maps(self, first, n):
+        """oracle query maps of the distinct motifs first .. first + n"""
+        O = self.O
+        out = []
+        for s, pick, qstr in distinct_motifs(self.db, n, first):
+            ch, se, subs = O.parse_query_string(qstr, ord("A"))
+            out.append(O.QueryMap(self.comp(s), ch, se, subs, index=self.index, total_structures=self.S))
+        return out
+
+    def parity(self, res, first, n, top_n):
+        """diff of the GPU rows (host.Results, query k = global query first + k) against the oracle's"""
+        import parity
+        outer = self
+
+        class Lazy(dict):
+            def __missing__(self, k):
+                return outer.comp(k)
+
+        comps = Lazy()
+        bad = []
+        rows_checked = 0
+        for k, om in enumerate(self.query_maps(first, n)):
+            hits, rows = parity.oracle_query(om, self.index, comps, self.nres, self.plddt, top_n=top_n)
+            bad += parity.diff_query(res, k, len(om.indices()), hits, rows, top_n=top_n)
+            rows_checked += len(hits["nid"]) + len(rows)
+        return {"queries": n, "rows_checked": rows_checked, "mismatches": len(bad), "first_mismatches": bad[:5],
+                "checker": "CPU oracle (oracle/) on the same database; integer fields and residues exact, idf / RMSD 1e-4"}
+
+    def batch_qps(self, first, n, top_n, threads, repeats=3):
+        """count_query + retrieval of n distinct queries on `threads` host threads: best-of-repeats queries/s"""
+        import ctypes as C
+        O = self.O
+        qms = self.query_maps(first, n)
+        maps = (O.VP * n)(*[q.h for q in qms])
+        qarr = (O.VP * n)(*[q.query.h for q in qms])
+        store = (O.VP * self.S)(*[self.comp(s).h for s in range(self.S)])
+        p = O.CountParams.defaults(top_n=top_n)
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.lib().fdo_query_batch(maps, qarr, n, self.index.h, store, self.S, self.nres, self.plddt, C.byref(p), 0, 0,
+                                    20.0, 1.0, 0, threads, None, None, None)
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+        return n / best, best
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (C++ restatement of the reference algorithm; the Rust crate cannot be built here), all host
+    threads, same database size and the same distinct-motif workload as the GPU arm; each step a bounded sample."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    db = database(args.gpus, args.structs_per_gpu)
+    orc = Oracle(db, threads=cores)
+    sample = args.cpu_sample or 16 * cores
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
+        orc.batch_qps(0, sample, args.top, cores, repeats=1)
+    times = []
+    for _ in range(max(1, min(args.steps, 5))):
+        times.append(orc.batch_qps(0, sample, args.top, cores, repeats=1)[1])
+    dt = float(np.mean(times))
+    qps = sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": "%d distinct queries per step (the first of the GPU arm's batch; %d steps timed), C++ "
+                                       "restatement of the reference algorithm (oracle/, -O3), query-parallel over %d "
+                                       "threads; index of %d structures built on the CPU in %.1f s"
+                                       % (sample, len(times), cores, orc.S, orc.build_s)},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
     import folddisco_b200 as fd
-    from folddisco_b200 import host
+    from folddisco_b200 import host, sharded
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -260,51 +329,41 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = fd.Context(local_rank)
-    db = database(rank, world, args.structs_per_gpu)
-    store = host.Store()
-    store.add_soa(db)
+    db = database(world, args.structs_per_gpu)
     t0 = time.perf_counter()
     if world == 1:
+        store = host.Store()
+        store.add_soa(db)
         index = host.FolddiscoIndex.build(ctx, store)
         index.attach(ctx)
-        sharded = None
+        build_s = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        table_bytes = store.attach(ctx, pair_table=args.pair_table != 0, hash_params=index.params)
+        table_s = time.perf_counter() - t1
+        shards = None
     else:
-        from folddisco_b200 import sharded as sh
-        sharded = sh.ShardedIndex.build(ctx, store, rank, world)
-        index = sharded.index
-    build_s = time.perf_counter() - t0
-    store.attach(ctx)
+        sharded.comm_init(ctx, rank, world, dist)
+        shards, store = sharded.IdRangeShards.build(ctx, db, rank, world, pair_table=args.pair_table != 0)
+        index = shards.index
+        build_s = time.perf_counter() - t0
+        table_bytes, table_s = shards.table_bytes, shards.table_s
     hash_ms, post_ms = ctx.stage_ms("hash"), ctx.stage_ms("postings")
-    motif_structs = [(host.CompactStructure.from_atoms(a), q) for a, q in load_motif_atoms()]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     sp = host.SearchParams(top_n=args.top)
-    stages = ("lookup", "scan", "select", "verify", "verify_edges", "verify_components", "verify_kabsch", "edges", "kabsch")
-    hv = ("hv_flatten", "hv_upload", "hv_candidates", "hv_issue", "hv_wait_chunks", "hv_copy_tail")  # host wall clock inside the verification call
-
+    stages = ("lookup", "scan", "select", "exchange", "merge", "verify", "verify_edges", "verify_components",
+              "verify_kabsch", "edges", "kabsch")
+    hv = ("hv_flatten", "hv_upload", "hv_candidates", "hv_issue", "hv_wait_chunks", "hv_copy_tail")
     prep_ms = {"query_maps": 0.0, "finalize": 0.0, "calls": 0}  # host wall clock of the e2e-only part of a step
 
-    def make_batch():
-        """this rank's args.batch queries of the global batch (query number q uses motif q mod 5)"""
-        t0 = time.perf_counter()
-        qb = host.QueryBatch(index.params)
-        which = np.arange(rank * args.batch, (rank + 1) * args.batch, dtype=np.uint32) % len(motif_structs)
-        # every query map is built on its own; the indexed call only spares the marshalling of 2 x batch Python objects
-        qb.add_many_indexed([m[0] for m in motif_structs], [m[1] for m in motif_structs], which, which)
-        t1 = time.perf_counter()
-        if sharded is None:
-            qb.finalize(ctx)
-        else:
-            sharded.prepare(ctx, qb, dist)
-        t2 = time.perf_counter()
-        prep_ms["query_maps"] += (t1 - t0) * 1e3
-        prep_ms["finalize"] += (t2 - t1) * 1e3
-        prep_ms["calls"] += 1
-        return qb
+    inputs = query_inputs(db, args.batch, rank * args.batch)  # host structures + query strings: the step's inputs
+
+    def make_batch(timing=prep_ms):
+        return make_query_batch(ctx, index, db, args.batch, rank * args.batch, shards, timing, inputs)
 
     def search(qb):
-        if sharded is None:
-            return host.search(ctx, qb, sp, labels=None)
-        return sharded.search(ctx, qb, sp, dist)
+        if shards is None:
+            return host.search(ctx, qb, sp, labels=store)
+        return shards.search(ctx, qb, sp, labels=store)
 
     def barrier():
         torch.cuda.synchronize()
@@ -312,7 +371,6 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- e2e: host structures -> results, every step (H2D of query descriptors, D2H of hits/edges/RMSD inside) ----
     def timed(fn):
         """one step bracketed by barrier + synchronize and by CUDA events on the current stream (the library call is
         synchronous, so the event interval covers host orchestration, copies and kernels of the step)"""
@@ -327,50 +385,6 @@ def run_ours(args, rank, world, local_rank):
         wall = time.perf_counter() - t0
         return out, e0.elapsed_time(e1) * 1e-3, wall
 
-    def e2e_step():
-        """host structures -> result rows through the public API: build the query batch, search it.  --sub-batch N > 0
-        (one GPU) uses host.search_stream instead (sub-batches, the next one prepared on a second host thread while
-        the current one is searched); measured slower at this batch size (per-call fixed costs: 13.1 ms at 512,
-        14.8 ms at 256 vs 12.3 ms), so it is off by default"""
-        if sharded is not None or args.sub_batch <= 0:
-            return [search(make_batch())]
-        ks = range(rank * args.batch, (rank + 1) * args.batch)
-        return host.search_stream(ctx, [motif_structs[k % len(motif_structs)][0] for k in ks],
-                                  [motif_structs[k % len(motif_structs)][1] for k in ks], sp, index.params,
-                                  sub_batch=args.sub_batch)
-
-    for _ in range(args.warmup):
-        e2e_step()
-    e2e_t, e2e_res = [], None
-    for _ in range(args.steps):
-        e2e_res, dt, _ = timed(e2e_step)
-        e2e_t.append(dt)
-    e2e_h2d, e2e_d2h = sum(int(r.h2d_bytes) for r in e2e_res), sum(int(r.d2h_bytes) for r in e2e_res)
-    e2e_rows = (sum(int(r.struct_offsets[-1]) for r in e2e_res), sum(int(r.match_offsets[-1]) for r in e2e_res))
-    del e2e_res
-    # ---- value: query batch prepared (inputs resident), timed region = the search itself ----
-    qb = make_batch()
-    for _ in range(args.warmup):
-        search(qb)
-    if sharded is not None:
-        sharded.merge_ms, sharded.merge_bytes = 0.0, 0
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    launches0 = ctx.kernel_launches
-    st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages + hv}
-    bytes_scanned = 0
-    val_t = []
-    wall_t = []
-    for _ in range(args.steps):
-        res, dt, wall = timed(lambda: search(qb))
-        val_t.append(dt)
-        wall_t.append(wall)
-        bytes_scanned += ctx.last_posting_bytes
-    clocks = sampler.finish()
-    launches = ctx.kernel_launches - launches0
-    st1 = {s: (ctx.stage_ms(s) - st0[s][0], ctx.stage_launches(s) - st0[s][1]) for s in stages + hv}
-
     def reduce_max(x):
         if dist is None:
             return x
@@ -378,86 +392,197 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    val_s = reduce_max(sum(val_t)) / args.steps
-    e2e_s = reduce_max(sum(e2e_t)) / args.steps
+    # ---- e2e: host structures -> result rows through the public API, every step (H2D / D2H inside) ----
+    for _ in range(args.warmup):
+        search(make_batch())
+    e2e_t, e2e_res = [], None
+    for _ in range(args.steps):
+        e2e_res, dt, _ = timed(lambda: search(make_batch()))
+        e2e_t.append(dt)
+    e2e_h2d, e2e_d2h = int(e2e_res.h2d_bytes), int(e2e_res.d2h_bytes)
+    e2e_rows = (int(e2e_res.struct_offsets[-1]), int(e2e_res.match_offsets[-1]))
+    del e2e_res
+    # ---- value: query batch prepared (inputs resident), timed region = the search itself ----
+    qb = make_batch(timing=None)
+    for _ in range(args.warmup):
+        search(qb)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = ctx.kernel_launches
+    general0 = ctx.stage_launches("general_candidates")
+    st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages + hv}
+    bytes_scanned, exch_bytes = 0, 0
+    val_t, wall_t = [], []
+    res = None
+    for _ in range(args.steps):
+        res, dt, wall = timed(lambda: search(qb))
+        val_t.append(dt)
+        wall_t.append(wall)
+        bytes_scanned += ctx.last_posting_bytes
+        exch_bytes += ctx.last_exchange_bytes if shards is not None else 0
+    clocks = sampler.finish()
+    launches = ctx.kernel_launches - launches0
+    st1 = {s: (ctx.stage_ms(s) - st0[s][0], ctx.stage_launches(s) - st0[s][1]) for s in stages + hv}
+    steps = max(1, args.steps)
+    val_s = reduce_max(sum(val_t)) / steps
+    e2e_s = reduce_max(sum(e2e_t)) / steps
+    scan_ms = st1["scan"][0] / steps
+    scan_ms_max = reduce_max(scan_ms)
+    bytes_per_launch = bytes_scanned / steps
+    bytes_max = reduce_max(bytes_per_launch)
+    exch_ms_max = reduce_max(st1["exchange"][0] / steps)
+    n_struct_rows, n_match_rows = int(res.struct_offsets[-1]), int(res.match_offsets[-1])
+    assert e2e_rows == (n_struct_rows, n_match_rows), (e2e_rows, n_struct_rows, n_match_rows)  # same rows either way
     if rank != 0:
         return
     hbm, peak_src = peaks()
-    scan_ms = st1["scan"][0] / max(1, args.steps)          # one k3_scan launch per step
-    bytes_per_launch = bytes_scanned / max(1, args.steps)
-    survivors = int(res.struct_offsets[-1])
-    algo_bytes = bytes_per_launch + 16 * survivors          # posting bytes + 16 B per survivor
+    # posting bytes + 16 B per survivor.  With id-range shards every rank scans for the WHOLE batch and
+    # keeps its top n per query: the launch's algorithmic bytes are this rank's (max over ranks reported beside)
+    survivors = n_struct_rows if world == 1 else args.batch * world * args.top
+    algo_bytes = bytes_per_launch + 16 * survivors
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    if world > 1:  # every rank scanned its own shard: the launch's algorithmic bytes are this rank's
-        survivors = 0
-    n_struct_rows, n_match_rows = int(res.struct_offsets[-1]), int(res.match_offsets[-1])
-    # tallied by fdh_search from the buffers it copies (rank 0's slice; every rank moves the same amount)
-    h2d, d2h = e2e_h2d * world, e2e_d2h * world
-    assert e2e_rows == (n_struct_rows, n_match_rows), (e2e_rows, n_struct_rows, n_match_rows)  # same rows either way
     line = {
         "metric": METRIC, "value": args.batch * world / val_s,
         "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": val_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 hashes / u8 postings / f32 idf / f64 Kabsch", "data": "synthetic",
+        "dtype": DTYPE, "data": "synthetic",
         "config": workload_config(args, world),
-        "e2e": {"value": args.batch * world / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3},
+        "e2e": {"value": args.batch * world / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": e2e_h2d * world,
+                "d2h_bytes_per_step": e2e_d2h * world, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k3_scan (posting-list scan + vote)", "achieved": achieved, "peak": hbm,
-                     "unit": "GB/s", "frac": achieved / hbm, "traffic": scan_traffic() if world == 1 else None,
-                     "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "k3_scan_v2 (posting-list scan + vote + tile-level top-n)",
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": scan_traffic() if world == 1 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": scan_ms,
-                     "launches_per_step": "one per edge-word class of the batch (2 for the five shipped motifs); "
-                                          "bytes and ms are per step",
-                     "note": "at this scale the scan is bound by shared-memory vote traffic, CTA latency and issue "
-                             "slots, not by HBM (a query's vote state is ~20x its posting bytes): DESIGN.md section 4"},
+                     "launch_ms_max_over_ranks": scan_ms_max,
+                     "algorithmic_bytes_max_over_ranks": bytes_max + 16 * survivors,
+                     "note": "one launch per step; the kernel is bound by per-(query, id tile) latency chains and by "
+                             "shared-memory vote throughput (measured ceiling 5.5 votes/clock/SM = 0.3 of the HBM "
+                             "roofline for 1.3-byte postings), not by HBM: DESIGN.md section 4"},
         "clocks": clocks,
-        "stages_ms_per_step": {s: st1[s][0] / max(1, args.steps) for s in stages},
+        "stages_ms_per_step": {s: st1[s][0] / steps for s in stages},
         "host_ms_per_step": res.host_ms, "search_wall_ms": res.wall_ms,
-        "verify_host_wall_ms": {s[3:]: st1[s][0] / max(1, args.steps) for s in hv},
+        "verify_host_wall_ms": {s[3:]: st1[s][0] / steps for s in hv},
         "e2e_prepare_host_ms": {"query_maps (make_query_map x batch)": prep_ms["query_maps"] / max(1, prep_ms["calls"]),
                                 "finalize (posting counts -> idf, verification tables -> device)":
                                     prep_ms["finalize"] / max(1, prep_ms["calls"])},
         "timing": "CUDA events around each step (max over ranks); wall-clock cross-check %.3f ms/step" % (
-            1e3 * sum(wall_t) / max(1, args.steps)),
-        "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows},
-        "index": {"structures": len(store), "residues": int(store.num_residues), "build_s": build_s,
-                  "k1_hash_ms": hash_ms, "k2_postings_ms": post_ms},
+            1e3 * sum(wall_t) / steps),
+        "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows,
+                             "candidates_on_the_general_verification_path":
+                                 (ctx.stage_launches("general_candidates") - general0) // steps},
     }
-    if sharded is not None:
-        n_search = max(1, args.steps)
-        line["vote_merge"] = {"collective": "NCCL all_to_all of the non-empty vote cells (+ all_gather of the counts)",
-                              "ms_per_step": sharded.merge_ms / n_search,
-                              "bytes_sent_per_rank_per_step": sharded.merge_bytes // n_search,
-                              "results": "each rank finishes its own %d queries; rows stay on the rank that produced them" % args.batch}
+    if shards is not None:
+        line["exchange"] = {"collective": "ncclSend/ncclRecv group (all-to-all) of per-query top-%d blocks + counts, "
+                                          "inside fd_count_query_sharded" % args.top,
+                            "ms_per_step_max_over_ranks": exch_ms_max,
+                            "bytes_sent_per_rank_per_step": exch_bytes // steps}
+    # ---- parity: the timed configuration's rows against the CPU oracle (rank 0's first queries) ----
+    t0 = time.perf_counter()
     if world == 1:
+        full_buffers = index.buffers()
+    else:  # the oracle needs the whole index: built once more on this GPU from the full store (not timed)
+        full_buffers = host.FolddiscoIndex.build(ctx, store).buffers()
+    orc = Oracle(db, index_buffers=full_buffers)
+    line["parity_check"] = orc.parity(res, rank * args.batch, min(args.parity_queries, args.batch), args.top)
+    line["parity_check"]["seconds"] = time.perf_counter() - t0
+    # ---- index build (path (i)) ----
+    line["index_build"] = index_build_block(ctx, host, store if world == 1 else None, db, orc, build_s, hash_ms, post_ms,
+                                            hbm)
+    line["pair_table"] = {"bytes": table_bytes, "build_s": table_s, "device_ms": ctx.stage_ms("pair_table"),
+                          "what": "per structure the (hash, i, j) of every hashed residue pair, sorted by hash (8 B each): "
+                                  "verification looks query hashes up instead of re-hashing candidates; built once at "
+                                  "store attach, outside the timed region (like the index)"}
+    if world == 1:
+        if args.shipped:
+            line["shipped_motifs"] = shipped_line(args, ctx, host, index, sp, timed)
         if args.sweep:
-            line["scan_vs_index_size"] = scan_sweep(args, ctx, db, qb, sp, hbm, bytes_per_launch + 16 * survivors, scan_ms)
+            line["scan_vs_index_size"] = scan_sweep(args, ctx, db, qb, hbm, algo_bytes, scan_ms)
             index.attach(ctx)
-        line["cpu_baseline"] = cpu_baseline(args, db, index)
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or 16 * cores
+        qps, secs = orc.batch_qps(0, sample, args.top, cores)
+        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "sample": "%d distinct queries (the first of the batch), best of 3 (%.2f s each), C++ "
+                                          "restatement of the reference algorithm (oracle/, -O3), query-parallel over %d "
+                                          "threads" % (sample, secs, cores)}
     print(json.dumps(line), flush=True)
 
 
-def scan_sweep(args, ctx, db, qb, sp, hbm, base_bytes, base_ms):
-    """Posting-list GB/s of k3_scan vs index size: the database tiled k times (ids shifted), index rebuilt on the GPU,
-    count_query only (skip_match), same batch.  Larger indexes have longer lists: more bytes per launch."""
-    import torch
+def shipped_line(args, ctx, host, index, sp, timed):
+    """round 1's headline batch (the five shipped motifs x 205), device-timed, for continuity"""
+    qb = make_query_batch(ctx, index, None, args.batch, 0)
+    for _ in range(2):
+        host.search(ctx, qb, sp)
+    s0 = ctx.stage_ms("scan")
+    ts = []
+    n = max(2, args.steps // 2)
+    for _ in range(n):
+        _, dt, _ = timed(lambda: host.search(ctx, qb, sp))
+        ts.append(dt)
+    del qb
+    return {"queries_per_s": args.batch / (sum(ts) / n), "ms_per_step": 1e3 * sum(ts) / n,
+            "scan_ms": (ctx.stage_ms("scan") - s0) / n, "posting_bytes_per_step": int(ctx.last_posting_bytes),
+            "workload": "the five shipped motifs cycled to %d queries (BENCH_r01's batch)" % args.batch}
+
+
+def index_build_block(ctx, host, store, db, orc, build_s, hash_ms, post_ms, hbm):
+    """path (i): the rank's index build as it ran at start-up (cold: first launches of the process) and, on one GPU, a
+    second, warm build timed stage by stage, beside the CPU oracle's build of a bounded sample"""
+    ro = db["row_offsets"].astype(np.int64)
+    out = {"first_build_s": build_s, "first_build_k1_hash_ms": hash_ms, "first_build_k2_postings_ms": post_ms,
+           "note": "the first build includes CUDA module load and cold allocator pools; k2_postings_ms includes the copy "
+                   "of the finished index to host memory (the drop-in files are written from it)"}
+    if store is None:
+        return out
+    S = len(ro) - 1
+    n = np.diff(ro)
+    pair_tests = int((n * (n - 1)).sum())
+    h0, p0 = ctx.stage_ms("hash"), ctx.stage_ms("postings")
+    t0 = time.perf_counter()
+    ix = host.FolddiscoIndex.build(ctx, store)
+    warm_s = time.perf_counter() - t0
+    b = ix.buffers()
+    k1 = ctx.stage_ms("hash") - h0
+    k2 = ctx.stage_ms("postings") - p0
+    postings = int(np.count_nonzero(b.values < 128))
+    # CPU: the oracle's build of the first 2000 structures on all cores (two passes over the pairs, like the reference)
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    m = min(2000, S)
+    t0 = time.perf_counter()
+    O.Index.build([orc.comp(s) for s in range(m)], threads=cores)
+    cpu_s = time.perf_counter() - t0
+    cpu_pairs = int((n[:m] * (n[:m] - 1)).sum())
+    out.update({"structures": S, "residues": int(ro[-1]), "pair_tests": pair_tests, "postings": postings,
+                "posting_bytes": int(len(b.values)), "warm_build_s": warm_s, "k1_hash_ms": k1, "k2_postings_ms": k2,
+                "pair_tests_per_s": pair_tests / (k1 * 1e-3) if k1 > 0 else None,
+                "postings_per_s": postings / (k1 * 1e-3) if k1 > 0 else None,
+                "k2_GBps": (8.0 * postings + len(b.values)) / (k2 * 1e-3) / 1e9 if k2 > 0 else None,
+                "k2_frac_of_hbm": (8.0 * postings + len(b.values)) / (k2 * 1e-3) / 1e9 / hbm if k2 > 0 else None,
+                "cpu_build": {"structures": m, "seconds": cpu_s, "cores": cores, "pair_tests_per_s": cpu_pairs / cpu_s,
+                              "kind": "port"},
+                "ratio_pair_tests_per_s_whole_build": (pair_tests / warm_s) / (cpu_pairs / cpu_s)})
+    return out
+
+
+def scan_sweep(args, ctx, db, qb, hbm, base_bytes, base_ms):
+    """Posting-list GB/s of the scan vs index size: the database tiled k times (ids shifted), index rebuilt on the GPU,
+    count_query only (skip_match), same batch of distinct motifs.  Larger indexes have longer lists."""
     from folddisco_b200 import host
     out = [{"structures": args.structs_per_gpu, "algorithmic_bytes_per_launch": base_bytes, "scan_ms": base_ms,
             "GBps": base_bytes / (base_ms * 1e-3) / 1e9, "frac": base_bytes / (base_ms * 1e-3) / 1e9 / hbm}]
     skip = host.SearchParams(top_n=args.top, skip_match=True)
     for k in [int(x) for x in args.sweep.split(",") if x]:
         S = len(db["row_offsets"]) - 1
-        R = int(db["row_offsets"][-1])
-        ro = np.concatenate([db["row_offsets"][:-1].astype(np.uint64) + np.uint64(j * R) for j in range(k)] +
-                            [np.array([k * R], np.uint64)])
-        tiled = dict(row_offsets=ro, n_xyz=np.tile(db["n_xyz"], (k, 1)), ca_xyz=np.tile(db["ca_xyz"], (k, 1)),
-                     cb_xyz=np.tile(db["cb_xyz"], (k, 1)), aa=np.tile(db["aa"], k))
         store = host.Store()
-        store.add_soa(tiled)
-        del tiled
+        store.add_soa(tile_db(db, k))
+        t0 = time.perf_counter()
         ix = host.FolddiscoIndex.build(ctx, store)
         ix.attach(ctx)
+        build_s = time.perf_counter() - t0
+        qb.finalize(ctx)  # idf weights of the larger database
         for _ in range(2):
             host.search(ctx, qb, skip)
         ms0, n = ctx.stage_ms("scan"), 3
@@ -468,45 +593,9 @@ def scan_sweep(args, ctx, db, qb, sp, hbm, base_bytes, base_ms):
         ms = (ctx.stage_ms("scan") - ms0) / n
         gbps = nbytes / n / (ms * 1e-3) / 1e9
         out.append({"structures": S * k, "algorithmic_bytes_per_launch": nbytes / n, "scan_ms": ms, "GBps": gbps,
-                    "frac": gbps / hbm})
+                    "frac": gbps / hbm, "index_build_s": build_s})
         del ix, store
     return out
-
-
-def cpu_baseline(args, db, index):
-    """The oracle (kind "port") on this box's host cores, bounded sample of the same workload."""
-    import ctypes as C
-    import oracle_lib as O
-    from folddisco_b200 import synth
-    cores = os.cpu_count() or 1
-    parts = synth.split(db)
-    comps = [O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"]) for p in parts]
-    b = index.buffers()
-    oix = O.Index.from_buffers(b.hashes, b.offsets, b.values)  # byte-identical to the oracle's own (tests)
-    nres = np.array([len(p["aa"]) for p in parts], np.uint64)
-    plddt = np.zeros(len(parts), np.float32)
-    qms, qcs = [], []
-    for atoms, q in load_motif_atoms():
-        s = O.Structure.from_atoms(atoms)
-        ch, se, subs = O.parse_query_string(q, s.first_chain)
-        qc = s.compact()
-        qms.append(O.QueryMap(qc, ch, se, subs, index=oix, total_structures=len(parts)))
-        qcs.append(qc)
-    sample = max(len(qms), args.cpu_sample)
-    maps = (O.VP * sample)(*[qms[k % len(qms)].h for k in range(sample)])
-    qarr = (O.VP * sample)(*[qcs[k % len(qms)].h for k in range(sample)])
-    store = (O.VP * len(comps))(*[c.h for c in comps])
-    p = O.CountParams.defaults(top_n=args.top)
-    best = None
-    for it in range(3):
-        t0 = time.perf_counter()
-        O.lib().fdo_query_batch(maps, qarr, sample, oix.h, store, len(comps), nres, plddt, C.byref(p), 0, 0, 20.0, 1.0, 0,
-                                cores, None, None, None)
-        dt = time.perf_counter() - t0
-        best = dt if best is None or dt < best else best
-    return {"value": sample / best, "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": "%d queries (the five motifs cycled), best of 3, C++ restatement of the reference algorithm "
-                      "(oracle/), query-parallel over %d threads" % (sample, cores)}
 
 
 def main():

@@ -150,6 +150,7 @@ def lib():
     sig("fd_votes_select", C.c_int, [VP, PP(_Query), C.c_uint32, PP(PrefilterParams), PP(VotesLayout), VP, C.c_uint32,
                                      C.c_uint32, PP(PP(_StructHit)), PP(PP(C.c_uint64))])
     sig("fd_store_attach", C.c_int, [VP, PP(_StructBatch)])
+    sig("fd_store_build_pair_table", C.c_int, [VP, PP(HashParams), C.c_uint64, PP(C.c_uint64)])
     sig("fd_candidate_edges_batch", C.c_int, [VP, PP(_RetrievalQuery), C.c_uint32, VP, VP, C.c_uint64, PP(HashParams),
                                               C.c_float, PP(VP), PP(C.c_uint64), PP(VP), PP(C.c_uint64)])
     sig("fd_kabsch_batch", C.c_int, [VP, VP, VP, VP, C.c_uint32, VP, VP, VP])
@@ -438,6 +439,16 @@ class Context:
 
     def store_attach(self, batch):
         self._check(lib().fd_store_attach(self.h, C.byref(batch.c)), "fd_store_attach")
+
+    def store_build_pair_table(self, params=None, max_bytes=0):
+        """fd_store_build_pair_table -> bytes of the table, or None when it exceeds max_bytes (re-hash path stays)"""
+        params = params or HashParams()
+        nbytes = C.c_uint64()
+        rc = lib().fd_store_build_pair_table(self.h, C.byref(params), int(max_bytes), C.byref(nbytes))
+        if rc == -5 and max_bytes:
+            return None
+        self._check(rc, "fd_store_build_pair_table")
+        return int(nbytes.value)
 
     def candidate_edges_batch(self, rqueries, cand_query, cand_nid, params=None, ca_dist_cutoff=1.0):
         """rqueries: list of dicts {hashes_sorted, aa1, aa2, ca_dist, q_index}; -> (edges EDGE_DTYPE[], pairs PAIR_DTYPE[])"""

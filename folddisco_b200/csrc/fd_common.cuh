@@ -42,6 +42,25 @@ struct FdDeviceIndex {
     float *plddt = nullptr;   // [n_structs]
 };
 
+// Pair table of the structure store (fd_store_build_pair_table): for every stored structure the residue pairs that
+// get a geometric hash -- exactly the pairs the index build emitted for it (K1) -- sorted by hash:
+//   hash[offsets[s] .. offsets[s + 1])  ascending,   ij[...] = i << 16 | j of the same entry,
+//   dir[s * FD_PT_DIR + p] = first entry of structure s whose hash >> 20 (the amino-acid pair) is >= p.
+// This is the (structure, res_i, res_j) array of the task's north star: with it the verification looks a query hash
+// up (one directory read + a short binary search) instead of re-screening and re-hashing n1 x n2 residue pairs of
+// every candidate (retrieve.rs:52-156 recomputes them per candidate).  8 B per hashed pair, ~115 pairs per residue.
+constexpr uint32_t FD_PT_DIR = 1025; // prefixes 0 .. 1023 and the end sentinel
+struct FdPairTable {
+    bool built = false;
+    uint64_t n = 0;
+    uint32_t nbin_dist = 0, nbin_angle = 0;
+    float dist_cutoff = 0.f;
+    uint64_t *offsets = nullptr; // [n_structs + 1]
+    uint32_t *hash = nullptr;    // [n]
+    uint32_t *ij = nullptr;      // [n]
+    uint32_t *dir = nullptr;     // [n_structs * FD_PT_DIR] relative to offsets[s]
+};
+
 // Device copy of the compact-structure store used by candidate verification.
 struct FdDeviceStore {
     bool attached = false;
@@ -49,6 +68,8 @@ struct FdDeviceStore {
     uint64_t *row_offsets = nullptr;
     float *n_xyz = nullptr, *ca_xyz = nullptr, *cb_xyz = nullptr;
     uint8_t *aa = nullptr, *cb_valid = nullptr;
+    std::vector<uint64_t> h_row_offsets; // host copy (tile planning of the pair-table build)
+    FdPairTable pt;
 };
 
 // Pinned host staging buffer (grow-only) for results that the host side consumes right after the call.

@@ -31,6 +31,10 @@ static void fd_release_store(FdDeviceStore &st) {
     cudaFree(st.cb_xyz);
     cudaFree(st.aa);
     cudaFree(st.cb_valid);
+    cudaFree(st.pt.offsets);
+    cudaFree(st.pt.hash);
+    cudaFree(st.pt.ij);
+    cudaFree(st.pt.dir);
     st = FdDeviceStore();
 }
 int fd_pinned(fd_ctx *ctx, int slot, size_t bytes, void **out) {
@@ -327,6 +331,10 @@ void fd_destroy(fd_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+void fd_note_general_path(fd_ctx *ctx, uint64_t n) {
+    if (ctx) ctx->stages["general_candidates"].launches += n;
 }
 
 const char *fd_last_error(const fd_ctx *ctx) { return ctx ? ctx->err.c_str() : fd_g_create_error.c_str(); }

@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(K4_THREADS)
     // ---- 1. prefilter sets (ascending order does not matter here: outputs are sorted afterwards) ----
     bool all_pairs = !Q.use_prefilter;
     if (!all_pairs) {
+        // the lists are filled in ASCENDING residue order (block-wide prefix per step, no atomics): the CTAs that share
+        // a candidate (gridDim.y) split the pair space by position in list1 x list2, so they must all see the same lists
+        __shared__ uint32_t w1[K4_THREADS / 32], w2[K4_THREADS / 32];
         for (uint32_t r0 = 0; r0 < n; r0 += K4_THREADS) {
             const uint32_t r = r0 + threadIdx.x;
             bool in1 = false, in2 = false;
@@ -98,17 +101,29 @@ __global__ void __launch_bounds__(K4_THREADS)
                 in2 = canonical && code < 32 && ((Q.aa2_mask >> code) & 1u);
             }
             const uint32_t m1 = __ballot_sync(0xffffffffu, in1), m2 = __ballot_sync(0xffffffffu, in2);
-            uint32_t p1 = 0, p2 = 0;
             if (lane == 0) {
-                if (m1) p1 = atomicAdd(&n1, __popc(m1));
-                if (m2) p2 = atomicAdd(&n2, __popc(m2));
+                w1[threadIdx.x >> 5] = __popc(m1);
+                w2[threadIdx.x >> 5] = __popc(m2);
             }
-            p1 = __shfl_sync(0xffffffffu, p1, 0) + __popc(m1 & ((1u << lane) - 1));
-            p2 = __shfl_sync(0xffffffffu, p2, 0) + __popc(m2 & ((1u << lane) - 1));
+            __syncthreads();
+            uint32_t p1 = n1, p2 = n2;
+            for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) {
+                p1 += w1[w];
+                p2 += w2[w];
+            }
+            p1 += __popc(m1 & ((1u << lane) - 1));
+            p2 += __popc(m2 & ((1u << lane) - 1));
             if (in1 && p1 < K4_LIST_CAP) list1[p1] = (uint16_t)r;
             if (in2 && p2 < K4_LIST_CAP) list2[p2] = (uint16_t)r;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (uint32_t w = 0; w < K4_THREADS / 32; w++) {
+                    n1 += w1[w];
+                    n2 += w2[w];
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // CombinationVecIterator::is_empty -> fall back to every pair (retrieve.rs:145-151)
         if (n1 == 0 || n2 == 0) all_pairs = true;
     }
@@ -118,7 +133,10 @@ __global__ void __launch_bounds__(K4_THREADS)
     const uint64_t cols = (all_pairs || masked_sweep) ? n : n2;
     const uint64_t total = rows * cols;
 
-    for (uint64_t p0 = 0; p0 < total; p0 += K4_CHUNK) {
+    // the chunks of the pair space are dealt round-robin to the CTAs of the candidate (gridDim.y: a handful of large
+    // all-pairs candidates would otherwise occupy a handful of SMs; outputs are appended with global atomics and
+    // sorted afterwards, so any split is fine)
+    for (uint64_t p0 = (uint64_t)blockIdx.y * K4_CHUNK; p0 < total; p0 += (uint64_t)gridDim.y * K4_CHUNK) {
         // ---- 2. cheap screen ----
         for (uint32_t u = 0; u < K4_CHUNK / K4_THREADS; u++) {
             const uint64_t p = p0 + (uint64_t)u * K4_THREADS + threadIdx.x;
@@ -267,6 +285,7 @@ int fd_store_attach(fd_ctx *ctx, const fd_struct_batch *batch) {
     st.cb_xyz = d.cb_xyz.take();
     st.aa = d.aa.take();
     if (batch->cb_valid) st.cb_valid = d.cb_valid.take();
+    st.h_row_offsets.assign(batch->row_offsets, batch->row_offsets + batch->n_structs + 1);
     st.attached = true;
     return FD_OK;
 }
@@ -342,7 +361,11 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     StoreView sv{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid};
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
     StageTimer st(ctx, "edges");
-    FD_LAUNCH(ctx, k4_candidate_edges<0>, (uint32_t)n_cand, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
+    // few candidates (the rare ones beyond the fused kernels' limits): several CTAs per candidate fill the GPU
+    uint32_t split = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, ((uint64_t)ctx->num_sms * 8) / std::max<uint64_t>(n_cand, 1)));
+    if (const char *e = getenv("FD_K4_SPLIT")) split = (uint32_t)std::max(1, std::min(64, atoi(e)));
+    const dim3 k4_grid((uint32_t)n_cand, split);
+    FD_LAUNCH(ctx, k4_candidate_edges<0>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
               d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, (uint64_t *)nullptr,
               (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr);
     unsigned long long cnt[2] = {0, 0};
@@ -355,7 +378,7 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     FD_CUDA(ctx, d_pair_q.alloc(np));
     FD_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 16, s));
     if (ne || np)
-        FD_LAUNCH(ctx, k4_candidate_edges<1>, (uint32_t)n_cand, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p,
+        FD_LAUNCH(ctx, k4_candidate_edges<1>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p,
                   d_cq.p, d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, d_edge_keys.p,
                   d_edge_hash.p, d_pair_keys.p, d_pair_q.p);
     FD_TRY(sort_pairs_u64_u32(ctx, d_edge_keys, d_edge_hash, ne, 56));

@@ -50,10 +50,12 @@ __device__ __forceinline__ bool residue_ok(const BatchView &b, uint64_t r) {
 // MODE 0: count survivors per tile (sizes the key buffer exactly).
 // MODE 1: emit key = hash << 32 | (first_id + s)   (posting build)
 // MODE 2: emit key = s << 32 | hash                (per-structure sorted unique output)
+// MODE 3: emit key = (s - first_id) << 30 | hash, val = i << 16 | j   (pair table of the structure store)
 template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS)
     k1_pair_hash(BatchView b, const Tile *tiles, uint32_t n_tiles, fdg::HashParams hp, uint64_t first_id,
-                 uint64_t hash_lo, uint64_t hash_hi, uint64_t *out_keys, unsigned long long *out_count) {
+                 uint64_t hash_lo, uint64_t hash_hi, uint64_t *out_keys, unsigned long long *out_count,
+                 uint32_t *out_vals = nullptr) {
     __shared__ uint32_t q_ij[MODE == 0 ? 1 : K1_QUEUE_CAP]; // i_local << 16 | j
     __shared__ float q_d[MODE == 0 ? 1 : K1_QUEUE_CAP];     // ca_dist of the survivor
     __shared__ uint32_t q_n;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(K1_THREADS)
                         const uint32_t k = k0 + threadIdx.x;
                         bool emit = false;
                         uint64_t key = 0;
+                        uint32_t val = 0;
                         if (k < qn) {
                             const uint32_t ij = q_ij[k];
                             const uint64_t ri = base + tile.i0 + (ij >> 16), rj = base + (ij & 0xffffu);
@@ -121,15 +124,20 @@ __global__ void __launch_bounds__(K1_THREADS)
                                                               ld3(b.n_xyz, rj), ld3(b.ca_xyz, rj), ld3(b.cb_xyz, rj),
                                                               b.aa[ri] & 0x7Fu, b.aa[rj] & 0x7Fu, q_d[k], hp);
                             emit = (uint64_t)h >= hash_lo && (uint64_t)h < hash_hi;
-                            key = MODE == 1 ? ((uint64_t)h << 32) | (first_id + tile.s)
-                                            : ((uint64_t)tile.s << 32) | h;
+                            key = MODE == 1   ? ((uint64_t)h << 32) | (first_id + tile.s)
+                                  : MODE == 3 ? (((uint64_t)tile.s - first_id) << 30) | h
+                                              : ((uint64_t)tile.s << 32) | h;
+                            val = ((tile.i0 + (ij >> 16)) << 16) | (ij & 0xffffu);
                         }
                         const uint32_t m = __ballot_sync(0xffffffffu, emit);
                         if (m) {
                             unsigned long long pos = 0;
                             if (lane == 0) pos = atomicAdd(out_count, (unsigned long long)__popc(m));
                             pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
-                            if (emit) out_keys[pos] = key;
+                            if (emit) {
+                                out_keys[pos] = key;
+                                if (MODE == 3) out_vals[pos] = val;
+                            }
                         }
                     }
                     __syncthreads();
@@ -189,19 +197,29 @@ int run_pair_hash(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_param
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
     const uint32_t n_tiles = (uint32_t)tiles.size();
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms * 8);
-    StageTimer st(ctx, "hash");
-    FD_LAUNCH(ctx, k1_pair_hash<0>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo, hash_hi,
-              (uint64_t *)nullptr, d_count.p);
     unsigned long long total = 0;
-    FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    FD_CUDA(ctx, keys.alloc(total));
-    FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), ctx->stream));
-    if (total)
-        FD_LAUNCH(ctx, k1_pair_hash<MODE>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo,
-                  hash_hi, keys.p, d_count.p);
-    FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
-    FD_CUDA(ctx, st.finish());
+    {
+        StageTimer st(ctx, "hash");
+        FD_LAUNCH(ctx, k1_pair_hash<0>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo, hash_hi,
+                  (uint64_t *)nullptr, d_count.p);
+        FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, st.finish());
+    }
+    {
+        // the key buffer comes from the stream-ordered pool; growing the pool by gigabytes is host time, not kernel time
+        HostTimer ht(ctx, "hash_alloc");
+        FD_CUDA(ctx, keys.alloc(total));
+        FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), ctx->stream));
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        StageTimer st(ctx, "hash");
+        if (total)
+            FD_LAUNCH(ctx, k1_pair_hash<MODE>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo,
+                      hash_hi, keys.p, d_count.p);
+        FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, st.finish());
+    }
     *n_keys = total;
     return FD_OK;
 }
@@ -233,6 +251,166 @@ int fd_upload_batch(fd_ctx *ctx, const fd_struct_batch *b, FdDeviceBatch *d) {
         FD_CUDA(ctx, cudaMemcpyAsync(d->aa.p, b->aa, R, cudaMemcpyHostToDevice, st));
         if (b->cb_valid) FD_CUDA(ctx, cudaMemcpyAsync(d->cb_valid.p, b->cb_valid, R, cudaMemcpyHostToDevice, st));
     }
+    return FD_OK;
+}
+
+// ---- pair table of the attached structure store ----
+namespace {
+__global__ void k1_table_offsets(const uint64_t *sorted_keys, uint64_t n, uint32_t n_structs_chunk, uint64_t base,
+                                 uint64_t *offsets /* [s0 ..] of the chunk, + 1 */) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_structs_chunk) return;
+    const uint64_t want = (uint64_t)s << 30; // first key of structure s
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    offsets[s] = base + lo;
+}
+__global__ void k1_table_split(const uint64_t *sorted_keys, const uint32_t *sorted_vals, uint64_t n, uint32_t *hash,
+                               uint32_t *ij) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    hash[k] = (uint32_t)(sorted_keys[k] & 0x3fffffffull);
+    ij[k] = sorted_vals[k];
+}
+// dir[s][p] = first entry (relative to offsets[s]) of structure s with hash >> 20 >= p
+__global__ void k1_table_dir(const uint32_t *hash, const uint64_t *offsets, uint64_t n_structs, uint32_t *dir) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_structs * FD_PT_DIR) return;
+    const uint64_t s = t / FD_PT_DIR;
+    const uint32_t p = (uint32_t)(t % FD_PT_DIR);
+    const uint32_t *h = hash + offsets[s];
+    uint32_t lo = 0, hi = (uint32_t)(offsets[s + 1] - offsets[s]);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((h[mid] >> 20) < p) lo = mid + 1;
+        else hi = mid;
+    }
+    dir[t] = lo;
+}
+} // namespace
+
+extern "C" int fd_store_build_pair_table(fd_ctx *ctx, const fd_hash_params *params, uint64_t max_bytes,
+                                         uint64_t *out_bytes) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!params) return fd_fail(ctx, FD_ERR_ARG, "fd_store_build_pair_table: NULL argument");
+    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_store_build_pair_table: no structure store attached");
+    if (ctx->borrowed) return fd_fail(ctx, FD_ERR_STATE, "fd_store_build_pair_table: a forked context shares its parent's store");
+    FD_ENTER(ctx);
+    FdDeviceStore &S = ctx->store;
+    cudaStream_t st = ctx->stream;
+    if (out_bytes) *out_bytes = 0;
+    FD_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(S.pt.offsets);
+    cudaFree(S.pt.hash);
+    cudaFree(S.pt.ij);
+    cudaFree(S.pt.dir);
+    S.pt = FdPairTable();
+    const uint64_t NS = S.n_structs;
+    if (NS == 0) return FD_OK;
+    const std::vector<uint64_t> &ro = S.h_row_offsets;
+    BatchView v{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid};
+    fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
+    // chunks of structures: at most ~2^28 residue-pairs-worth of tiles and 2^20 structures (key = s_local << 30 | hash)
+    struct Chunk {
+        uint64_t s0, s1, n_keys;
+        std::vector<Tile> tiles;
+    };
+    std::vector<Chunk> chunks;
+    const uint64_t chunk_res = 24ull * 1000 * 1000; // ~2.8 G table entries per chunk at 115 pairs per residue / 8 = sort scratch 3 x 12 B each
+    {
+        uint64_t s = 0;
+        while (s < NS) {
+            Chunk c;
+            c.s0 = s;
+            uint64_t r = 0;
+            while (s < NS && (s == c.s0 || (r + (ro[s + 1] - ro[s]) <= chunk_res / 8 && s - c.s0 < (1u << 20)))) {
+                const uint64_t n = ro[s + 1] - ro[s];
+                for (uint64_t i0 = 0; i0 < n; i0 += K1_TILE_ROWS) c.tiles.push_back({(uint32_t)s, (uint32_t)i0});
+                r += n;
+                s++;
+            }
+            c.s1 = s;
+            c.n_keys = 0;
+            chunks.push_back(std::move(c));
+        }
+    }
+    StageTimer stt(ctx, "pair_table");
+    // pass 1: exact sizes
+    DevBuf<unsigned long long> d_count;
+    FD_CUDA(ctx, d_count.alloc(1));
+    uint64_t total = 0;
+    for (auto &c : chunks) {
+        DevBuf<Tile> d_tiles;
+        FD_CUDA(ctx, d_tiles.alloc(c.tiles.size()));
+        FD_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, c.tiles.data(), c.tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+        FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, 8, st));
+        const uint32_t n_tiles = (uint32_t)c.tiles.size();
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms * 8);
+        FD_LAUNCH(ctx, k1_pair_hash<0>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, 0, 0, 1ull << 32,
+                  (uint64_t *)nullptr, d_count.p, (uint32_t *)nullptr);
+        unsigned long long n = 0;
+        FD_CUDA(ctx, cudaMemcpyAsync(&n, d_count.p, 8, cudaMemcpyDeviceToHost, st));
+        FD_CUDA(ctx, cudaStreamSynchronize(st));
+        c.n_keys = n;
+        total += n;
+    }
+    const uint64_t bytes = total * 8 + (NS + 1) * 8 + NS * FD_PT_DIR * 4ull;
+    if (out_bytes) *out_bytes = bytes;
+    if (max_bytes && bytes > max_bytes) {
+        FD_CUDA(ctx, stt.finish());
+        return fd_fail(ctx, FD_ERR_LIMIT, "pair table larger than the caller's budget (verification keeps re-hashing candidates)");
+    }
+    FD_CUDA(ctx, cudaMalloc(&S.pt.offsets, (NS + 1) * 8));
+    FD_CUDA(ctx, cudaMalloc(&S.pt.hash, std::max<uint64_t>(total, 1) * 4));
+    FD_CUDA(ctx, cudaMalloc(&S.pt.ij, std::max<uint64_t>(total, 1) * 4));
+    FD_CUDA(ctx, cudaMalloc(&S.pt.dir, NS * FD_PT_DIR * 4ull));
+    uint64_t base = 0;
+    for (auto &c : chunks) {
+        const uint64_t n = c.n_keys;
+        const uint32_t ns_chunk = (uint32_t)(c.s1 - c.s0);
+        DevBuf<Tile> d_tiles;
+        DevBuf<uint64_t> k_in, k_out;
+        DevBuf<uint32_t> v_in, v_out;
+        DevBuf<uint8_t> tmp;
+        FD_CUDA(ctx, d_tiles.alloc(c.tiles.size()));
+        FD_CUDA(ctx, k_in.alloc(n));
+        FD_CUDA(ctx, k_out.alloc(n));
+        FD_CUDA(ctx, v_in.alloc(n));
+        FD_CUDA(ctx, v_out.alloc(n));
+        FD_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, c.tiles.data(), c.tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+        FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, 8, st));
+        const uint32_t n_tiles = (uint32_t)c.tiles.size();
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms * 8);
+        if (n)
+            FD_LAUNCH(ctx, k1_pair_hash<3>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, c.s0, 0, 1ull << 32, k_in.p,
+                      d_count.p, v_in.p);
+        int end_bit = 31;
+        for (uint32_t x = ns_chunk; x > 1; x >>= 1) end_bit++;
+        end_bit = std::min(64, end_bit + 1);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in.p, k_out.p, v_in.p, v_out.p, n, 0, end_bit, st);
+        FD_CUDA(ctx, tmp.alloc(tb));
+        if (n) {
+            FD_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tb, k_in.p, k_out.p, v_in.p, v_out.p, n, 0, end_bit, st));
+            ctx->launches += 4;
+            FD_LAUNCH(ctx, k1_table_split, fd_div_up(n, 256), 256, 0, k_out.p, v_out.p, n, S.pt.hash + base, S.pt.ij + base);
+        }
+        FD_LAUNCH(ctx, k1_table_offsets, fd_div_up((uint64_t)ns_chunk + 1, 256), 256, 0, k_out.p, n, ns_chunk, base,
+                  S.pt.offsets + c.s0);
+        FD_CUDA(ctx, cudaStreamSynchronize(st));
+        base += n;
+    }
+    FD_LAUNCH(ctx, k1_table_dir, fd_div_up(NS * FD_PT_DIR, 256), 256, 0, S.pt.hash, S.pt.offsets, NS, S.pt.dir);
+    FD_CUDA(ctx, stt.finish());
+    S.pt.n = total;
+    S.pt.nbin_dist = params->nbin_dist;
+    S.pt.nbin_angle = params->nbin_angle;
+    S.pt.dist_cutoff = params->dist_cutoff;
+    S.pt.built = true;
     return FD_OK;
 }
 

@@ -409,7 +409,151 @@ __global__ void __launch_bounds__(VA_THREADS, 7)
     }
     if (tid == 0) {
         cand_ebegin[c] = b0;
-        cand_ne[c] = ne;
+        cand_ne[c] = ne | (all_pairs ? 0x80000000u : 0u); // k6b's rescue scan needs to know which pair domain was used
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k6a_table: candidate edges from the store's PAIR TABLE (fd_store_build_pair_table) -- one warp per candidate
+// ------------------------------------------------------------------------------------------------
+// retrieve_with_prefilter keeps the residue pairs (i, j) of the candidate whose geometric hash is in the query's hash
+// set (plus the amino-acid / CA-distance conditions of retrieve.rs:85-143).  k6a_edges finds them by screening n1 x n2
+// pairs and re-hashing the survivors -- work the index build already did once per structure.  With the table the
+// question is turned round: for every query hash, which pairs of this structure carry it?  One read of the
+// structure's amino-acid-pair directory + a binary search inside that pair's run (~75 entries) per query hash; the
+// conditions that do not follow from hash equality (exact residue names under the amino-acid prefilter, the pair's
+// presence in the observed-distance map, |d - d_q| < --ca-distance) are checked on the few matches.  Same outputs as
+// k6a_edges: the candidate's edges sorted by (i, j) in the pool, cand_ne with the pair-domain flag.
+constexpr int VT_WARPS = 4;
+struct TableWarp { // per-warp shared memory
+    uint32_t e_key[V_MAX_E];
+    uint16_t e_ent[V_MAX_E];
+    VAad aad[V_MAX_AAD];
+    uint16_t aa_range[400];
+    uint32_t n_e, has1, has2;
+};
+struct PairTableView {
+    const uint64_t *offsets;
+    const uint32_t *hash, *ij, *dir;
+};
+
+__global__ void __launch_bounds__(VT_WARPS * 32)
+    k6a_table(StoreView st, PairTableView pt, const VQDesc *vq, const VHash *vhash, const VAad *vaad,
+              const uint32_t *cand_query, const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp, float ca_cutoff,
+              uint32_t *pool_key, uint16_t *pool_ent, unsigned int *pool_count, uint32_t pool_cap, uint32_t *cand_ebegin,
+              uint32_t *cand_ne, uint8_t *cand_flags) {
+    __shared__ TableWarp tw[VT_WARPS];
+    const int lane = threadIdx.x & 31;
+    TableWarp &W = tw[threadIdx.x >> 5];
+    const uint32_t c = blockIdx.x * VT_WARPS + (threadIdx.x >> 5);
+    if (c >= n_cand) return;
+    const VQDesc Q = vq[cand_query[c]];
+    if (Q.n_hashes == 0 || Q.n_aad == 0) return;
+    const uint32_t t = cand_nid[c];
+    const uint64_t base = st.row_offsets[t];
+    const uint32_t n = (uint32_t)(st.row_offsets[t + 1] - base);
+    const VHash *H = vhash + Q.hash_begin;
+    if (lane == 0) {
+        W.n_e = 0;
+        W.has1 = 0;
+        W.has2 = 0;
+    }
+    load_aad_phase1<32>(Q, vaad, W.aad, W.aa_range, lane);
+    __syncwarp();
+    load_aad_phase2<32>(Q, W.aad, W.aa_range, lane);
+    // prefilter_amino_acid (retrieve.rs:563-602): with it the pair domain is list1 x list2 (residues whose exact name
+    // is an amino acid of the query); an empty list means every pair (CombinationVecIterator::is_empty, :145-151)
+    bool all_pairs = !Q.use_prefilter;
+    if (!all_pairs) {
+        bool any1 = false, any2 = false;
+        for (uint32_t r = lane; r < n; r += 32) {
+            const uint8_t a = st.aa[base + r];
+            const bool canonical = (a & 0x80u) == 0;
+            any1 = any1 || (canonical && ((Q.aa1_mask >> (a & 31u)) & 1u));
+            any2 = any2 || (canonical && ((Q.aa2_mask >> (a & 31u)) & 1u));
+        }
+        if (!__any_sync(0xffffffffu, any1) || !__any_sync(0xffffffffu, any2)) all_pairs = true;
+    }
+    __syncwarp();
+    const uint64_t seg = pt.offsets[t];
+    const uint32_t *th = pt.hash + seg;
+    const uint32_t *tij = pt.ij + seg;
+    const uint32_t *dir = pt.dir + (uint64_t)t * FD_PT_DIR;
+    for (uint32_t k0 = 0; k0 < Q.n_hashes; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        if (k < Q.n_hashes) {
+            const uint32_t h = H[k].hash;
+            const uint32_t p = h >> 20;
+            uint32_t lo = dir[p], hi = dir[p + 1];
+            const uint32_t end = hi;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (th[mid] < h) lo = mid + 1;
+                else hi = mid;
+            }
+            for (uint32_t e = lo; e < end && th[e] == h; e++) {
+                const uint32_t ij = tij[e];
+                const uint32_t i = ij >> 16, j = ij & 0xffffu;
+                const uint8_t ai = st.aa[base + i], aj = st.aa[base + j];
+                if (!all_pairs && ((ai | aj) & 0x80u)) continue; // modified residues are not in the prefilter lists
+                const uint32_t rg = W.aa_range[(ai & 0x7Fu) * 20u + (aj & 0x7Fu)];
+                if (rg == 0) continue; // the pair's amino acids carry no observed distance (substituted hashes)
+                const float d = fdg::dist(ld3(st.ca_xyz, base + i), ld3(st.ca_xyz, base + j));
+                bool ok = false;
+                for (uint32_t a = rg >> 8, ae = (rg >> 8) + (rg & 0xffu); a < ae; a++)
+                    if (fabsf(d - W.aad[a].dist) < ca_cutoff) {
+                        ok = true;
+                        break;
+                    }
+                if (!ok) continue;
+                const uint32_t pos = atomicAdd(&W.n_e, 1u);
+                if (pos < V_MAX_E) {
+                    W.e_key[pos] = ij;
+                    W.e_ent[pos] = (uint16_t)k;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const uint32_t ne = W.n_e;
+    if (ne == 0) return;
+    if (ne > V_MAX_E || Q.n_idx > V_MAX_NQ || Q.n_dq > V_MAX_NQ) {
+        if (lane == 0) cand_flags[c] = 1;
+        return;
+    }
+    // ---- sort edges by (i, j): the reference's emission order (graph node numbering, f32 sum order) ----
+    uint32_t sort_n = 2;
+    while (sort_n < ne) sort_n <<= 1;
+    for (uint32_t k = ne + lane; k < sort_n; k += 32) W.e_key[k] = 0xffffffffu;
+    __syncwarp();
+    for (uint32_t size = 2; size <= sort_n; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t k = lane; k < sort_n / 2; k += 32) {
+                const uint32_t lo_i = 2 * k - (k & (stride - 1));
+                const uint32_t hi_i = lo_i + stride;
+                const bool up = (lo_i & size) == 0;
+                const uint32_t a = W.e_key[lo_i], b = W.e_key[hi_i];
+                if ((a > b) == up) {
+                    W.e_key[lo_i] = b;
+                    W.e_key[hi_i] = a;
+                    const uint16_t ta = W.e_ent[lo_i];
+                    W.e_ent[lo_i] = W.e_ent[hi_i];
+                    W.e_ent[hi_i] = ta;
+                }
+            }
+            __syncwarp();
+        }
+    uint32_t b0 = 0;
+    if (lane == 0) b0 = atomicAdd(pool_count, ne);
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    if ((uint64_t)b0 + ne > pool_cap) return; // pool too small: the host sizes it exactly and runs again
+    for (uint32_t k = lane; k < ne; k += 32) {
+        pool_key[b0 + k] = W.e_key[k];
+        pool_ent[b0 + k] = W.e_ent[k];
+    }
+    if (lane == 0) {
+        cand_ebegin[c] = b0;
+        cand_ne[c] = ne | (all_pairs ? 0x80000000u : 0u);
     }
 }
 
@@ -1205,6 +1349,12 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
     const FdDeviceStore &S = ctx->store;
     StoreView sv{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid};
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
+    // the store's pair table answers "which pairs carry this hash" directly -- if it was built with these hash parameters
+    const FdPairTable &PT = S.pt;
+    const bool use_table = PT.built && PT.nbin_dist == params->nbin_dist && PT.nbin_angle == params->nbin_angle &&
+                           PT.dist_cutoff == params->dist_cutoff &&
+                           !(getenv("FD_VERIFY_TABLE") && atoi(getenv("FD_VERIFY_TABLE")) == 0);
+    const PairTableView ptv{PT.offsets, PT.hash, PT.ij, PT.dir};
     const size_t smem_b = sizeof(WarpState) * VB_WARPS;
     FD_CUDA(ctx, cudaFuncSetAttribute(k6b_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     for (uint32_t k = 0; k < n_chunks; k++) {
@@ -1245,10 +1395,16 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         FD_CUDA(ctx, cudaEventRecord(event_at(5 * k), st));
         FD_CUDA(ctx, cudaMemsetAsync(C.counters.p, 0, 8, st));
         FD_CUDA(ctx, cudaMemsetAsync(C.ncomp.p, 0, (C.n + 1) * 4, st));
-        FD_LAUNCH_ON(ctx, st, k6a_edges, n32, VA_THREADS, 0, sv, P->d_desc, P->d_hash, P->d_aad, d_cq.p + C.c0,
-                     d_cn.p + C.c0, n32, hp, ca_dist_cutoff, C.pool_key.p, C.pool_ent.p, C.counters.p,
-                     (uint32_t)std::min<uint64_t>(C.pool_cap, 0xffffffffu), d_ebegin.p + C.c0, d_ne.p + C.c0,
-                     d_flags.p + C.c0);
+        if (use_table)
+            FD_LAUNCH_ON(ctx, st, k6a_table, fd_div_up(C.n, VT_WARPS), VT_WARPS * 32, 0, sv, ptv, P->d_desc, P->d_hash,
+                         P->d_aad, d_cq.p + C.c0, d_cn.p + C.c0, n32, hp, ca_dist_cutoff, C.pool_key.p, C.pool_ent.p,
+                         C.counters.p, (uint32_t)std::min<uint64_t>(C.pool_cap, 0xffffffffu), d_ebegin.p + C.c0,
+                         d_ne.p + C.c0, d_flags.p + C.c0);
+        else
+            FD_LAUNCH_ON(ctx, st, k6a_edges, n32, VA_THREADS, 0, sv, P->d_desc, P->d_hash, P->d_aad, d_cq.p + C.c0,
+                         d_cn.p + C.c0, n32, hp, ca_dist_cutoff, C.pool_key.p, C.pool_ent.p, C.counters.p,
+                         (uint32_t)std::min<uint64_t>(C.pool_cap, 0xffffffffu), d_ebegin.p + C.c0, d_ne.p + C.c0,
+                         d_flags.p + C.c0);
         FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 1), st));
         FD_LAUNCH_ON(ctx, st, k6b_components, fd_div_up(C.n, VB_WARPS), VB_WARPS * 32, smem_b, sv, P->d_desc, P->d_hash,
                      P->d_aad, P->d_idx, d_cq.p + C.c0, d_cn.p + C.c0, n32, hp, ca_dist_cutoff, skip_ca_match,

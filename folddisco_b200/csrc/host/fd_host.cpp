@@ -1099,6 +1099,7 @@ int64_t fdh_compact_nres(const fdh_compact *c) { return (int64_t)c->nres(); }
 int64_t fdh_compact_num_residues_raw(const fdh_compact *c) { return (int64_t)c->raw_residues; }
 int fdh_compact_first_chain(const fdh_compact *c) { return c->chains.empty() ? -1 : c->chains[0]; }
 float fdh_compact_avg_plddt(const fdh_compact *c) { // core.rs:446-456
+    if (c->nres() == 0) return 0.f; // a skipped structure's slot (mod.rs:313-319): nres 0, plddt 0, not 0 / 0
     float s = 0.f;
     for (float b : c->bfac) s += b;
     return s / (float)c->nres();
@@ -1234,6 +1235,7 @@ fdh_store *fdh_store_load(const char *path) {
             }
         }
         ok = ok && s->row_offsets[0] == 0 && s->row_offsets[S] == R;
+        for (uint64_t k = 0; ok && k < S; k++) ok = s->row_offsets[k] <= s->row_offsets[k + 1]; // labels are indexed through them
     }
     fclose(f);
     if (!ok) {
@@ -1440,6 +1442,12 @@ fdh_index *fdh_index_load(const char *prefix) {
         return nullptr;
     }
     memcpy(&ix->count, o, 8);
+    // a corrupt count must not wrap the size computation (12 bytes per hash + the 16 bytes around them)
+    if (ix->count > (ix->map_off_len - 8) / 12) {
+        set_err("Offset file appears to be in old format or corrupted");
+        delete ix;
+        return nullptr;
+    }
     const size_t need = 8 + ix->count * 4 + (ix->count + 1) * 8;
     if (ix->map_off_len < need) { // indextable.rs:347-355
         set_err("Offset file appears to be in old format or corrupted");
@@ -1452,8 +1460,16 @@ fdh_index *fdh_index_load(const char *prefix) {
     ix->offsets = ix->own_offsets.data();
     ix->values = (const uint8_t *)ix->map_val;
     ix->value_bytes = ix->map_val_len;
-    // the offsets index the value file: a pair of files that do not belong together must not reach the device
-    if (ix->offsets[0] != 0 || ix->offsets[ix->count] > ix->value_bytes) {
+    // the offsets index the value file: a pair of files that do not belong together must not reach the device, and
+    // an offset that runs backwards would send the scan out of bounds
+    bool monotone = true;
+    for (uint64_t k = 0; k < ix->count && monotone; k++) monotone = ix->offsets[k] <= ix->offsets[k + 1];
+    if (!monotone) {
+        set_err(std::string("index files are corrupt: the offsets of ") + prefix + ".offset are not ascending");
+        delete ix;
+        return nullptr;
+    }
+    if (ix->offsets[0] != 0 || ix->offsets[ix->count] != ix->value_bytes) {
         set_err(std::string("index files are inconsistent: the offsets of ") + prefix + ".offset end at byte " +
                 std::to_string(ix->offsets[ix->count]) + " but the value file has " + std::to_string(ix->value_bytes));
         delete ix;
@@ -1744,7 +1760,8 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, uint32_t q_begin, uint32_
     nt = std::max(1, std::min(nt, 64));
     std::vector<std::vector<MatchTmp>> per_thread(nt);
     std::atomic<uint64_t> next{0};
-    const uint64_t GRAIN = 256;
+    // few, heavy candidates (the ones beyond the fused kernels' limits) must still spread over the threads
+    const uint64_t GRAIN = std::max<uint64_t>(1, std::min<uint64_t>(256, n_cand / (4 * (uint64_t)nt)));
     struct Chunk {
         uint64_t c0;
         int thread;
@@ -2053,6 +2070,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                     fglobal.push_back(c);
                 }
         host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fd_note_general_path(ctx, fglobal.size());
         if (!fglobal.empty()) {
             if (verify_general(ctx, qs, q_begin, nq, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
             std::stable_sort(fm.begin(), fm.end(), [](const FinalMatch &a, const FinalMatch &b) { return a.cand < b.cand; });

@@ -256,10 +256,15 @@ class Store:
         _lib().fdh_store_batch(self.h, C.byref(b))
         return b
 
-    def attach(self, ctx):
-        """fd_store_attach: copy the compact structures to HBM for candidate verification"""
+    def attach(self, ctx, pair_table=False, hash_params=None, max_table_bytes=0):
+        """fd_store_attach: copy the compact structures to HBM for candidate verification.  pair_table=True also
+        builds the store's pair table (fd_store_build_pair_table: 8 B per hashed residue pair) so that verification
+        looks query hashes up instead of re-hashing candidates; returns its size in bytes (None: over the budget)"""
         b = self.batch_view()
         ctx._check(capi.lib().fd_store_attach(ctx.h, C.byref(b)), "fd_store_attach")
+        if pair_table:
+            return ctx.store_build_pair_table(hash_params, max_table_bytes)
+        return 0
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -482,7 +487,8 @@ class Results:
             self.h = None
 
     def structures(self, q):
-        return self.structs[int(self.struct_offsets[q]):int(self.struct_offsets[q + 1])]
+        """per-structure rows of query q (a copy: the library-owned block is recycled when this object is freed)"""
+        return self.structs[int(self.struct_offsets[q]):int(self.struct_offsets[q + 1])].copy()
 
     def sorted_matches(self, q):
         """per-match rows of query q in the default output order (idf desc, rmsd asc)"""

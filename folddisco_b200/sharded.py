@@ -263,9 +263,10 @@ class IdRangeShards:
     def __init__(self, index, first_id, n_local, total_structs, rank, world):
         self.index, self.first_id, self.n_local, self.total = index, int(first_id), int(n_local), int(total_structs)
         self.rank, self.world = rank, world
+        self.table_bytes, self.table_s = 0, 0.0
 
     @classmethod
-    def build(cls, ctx, db, rank, world, hash_params=None):
+    def build(cls, ctx, db, rank, world, hash_params=None, pair_table=False):
         """db: SoA dict of the whole database (row_offsets, n_xyz, ca_xyz, cb_xyz, aa); the rank builds the index of its
         id range on its GPU.  Returns (shards, full_store)"""
         S = len(db["row_offsets"]) - 1
@@ -281,8 +282,12 @@ class IdRangeShards:
         index.attach(ctx)
         full = host.Store()
         full.add_soa(db)
-        full.attach(ctx)
-        return cls(index, lo, hi - lo, S, rank, world), full
+        import time
+        t0 = time.perf_counter()
+        tb = full.attach(ctx, pair_table=pair_table, hash_params=index.params)
+        sh = cls(index, lo, hi - lo, S, rank, world)
+        sh.table_bytes, sh.table_s = tb, time.perf_counter() - t0
+        return sh, full
 
     def prepare(self, ctx, qb):
         qb.finalize_sharded(ctx, self.first_id, self.total)

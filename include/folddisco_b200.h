@@ -61,6 +61,9 @@ int fd_parallel_probe(int nt, int spin_us);
  * "hash", "postings", "attach", "lookup", "scan", "select", "verify" (= "verify_edges" + "verify_components" +
  * "verify_kabsch"), "edges", "kabsch"; 0 if the stage never ran */
 double fd_stage_ms(const fd_ctx *ctx, const char *stage);
+/* bookkeeping of the in-library host: n candidates of the last search took the general verification path
+ * (reported as the launch count of the pseudo-stage "general_candidates") */
+void fd_note_general_path(fd_ctx *ctx, uint64_t n);
 uint64_t fd_stage_launches(const fd_ctx *ctx, const char *stage);
 
 /* ---- structures ---------------------------------------------------------------------------------- */
@@ -280,6 +283,16 @@ int fd_votes_select(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, co
 /* HBM-resident compact-structure store replacing the per-candidate file re-read of retrieval_wrapper
  * (src/controller/retrieve.rs:375-376); ids = positions in the batch = posting ids. */
 int fd_store_attach(fd_ctx *ctx, const fd_struct_batch *batch);
+
+/* Optional: the PAIR TABLE of the attached store -- for every structure the residue pairs (i, j) that get a geometric
+ * hash, sorted by hash (8 bytes per pair, about 115 pairs per residue), i.e. exactly what
+ * get_geometric_hash_as_u32_from_structure (src/controller/feature.rs:198-231) enumerates, kept instead of thrown
+ * away.  With it fd_verify_candidates_* looks every query hash up in the candidate (directory + short binary search)
+ * instead of re-screening and re-hashing the candidate's residue pairs (retrieve.rs:85-143 does that per candidate);
+ * results are identical.  params must be the hash parameters of the searches that follow (otherwise the table is
+ * ignored).  max_bytes > 0: fail with FD_ERR_LIMIT (and keep the re-hash path) when the table would be larger;
+ * *out_bytes = its size (may be NULL). */
+int fd_store_build_pair_table(fd_ctx *ctx, const fd_hash_params *params, uint64_t max_bytes, uint64_t *out_bytes);
 
 /* Per-query inputs of retrieve_with_prefilter (src/controller/retrieve.rs:52-156). */
 typedef struct {

@@ -424,3 +424,56 @@ def test_long_structure_16769_residues(env):
     assert not bad, bad[:10]
     assert 30 in set(int(x) for x in res.structures(0)["nid"])
     assert any(r[0] == 30 and r[1] == len(near) for r in rows)  # the motif itself, all residues matched
+
+
+def test_pair_table_verification_equals_rehash(env):
+    """fd_store_build_pair_table: verification by hash lookup in the store's pair table returns exactly the rows of
+    the re-hash path (k6a_table vs k6a_edges), for motif-sized queries (amino-acid prefilter) and for queries of more
+    than 200 hashes (every pair; retrieve.rs:24, 569), with and without a table that matches the hash parameters."""
+    import bench
+    from folddisco_b200 import synth
+    host, ctx = env["host"], env["ctx"]
+    db = synth.generate(2500, 77, mean_len=180.0, max_len=600)
+    store = host.Store()
+    store.add_soa(db)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    qb = host.QueryBatch(ix.params)
+    for path, q, _ in F.MOTIFS:
+        qb.add(host.CompactStructure.from_atoms(env["atoms"][path]), q)
+    inputs = bench.query_inputs(db, 40, 3)
+    qb.add_many_indexed(*inputs)
+    qb.finalize(ctx)
+    assert max(len(qb.query_map(k)["hash"]) for k in range(len(qb))) > 200
+    sp = host.SearchParams(top_n=60)
+
+    def rows(res):
+        out = []
+        for k in range(len(qb)):
+            s = res.structures(k)
+            m = res.sorted_matches(k)
+            n = len(qb.indices(k))
+            srow = [tuple(x[f].item() for f in ("nid", "total_match_count", "node_count", "edge_count", "idf",
+                                                "max_matching_node_count", "min_rmsd_with_max_match")) for x in s]
+            out.append((srow, [(int(x["nid"]), int(x["node_count"]), float(x["idf"]), float(x["rmsd"]),
+                                res.residue_string(x, n)) for x in m]))
+        return out
+
+    store.attach(ctx)
+    base = rows(host.search(ctx, qb, sp, labels=store))
+    nbytes = store.attach(ctx, pair_table=True, hash_params=ix.params)
+    assert nbytes > 8 * 50 * int(db["row_offsets"][-1])
+    t0 = ctx.stage_launches("pair_table")
+    got = rows(host.search(ctx, qb, sp, labels=store))
+    assert got == base
+    assert sum(len(m) for _, m in got) > 500
+    os.environ["FD_VERIFY_TABLE"] = "0"
+    try:
+        assert rows(host.search(ctx, qb, sp, labels=store)) == base
+    finally:
+        del os.environ["FD_VERIFY_TABLE"]
+    # a table built with other hash parameters is ignored, a budget that is too small keeps the re-hash path
+    assert store.attach(ctx, pair_table=True, hash_params=env["fd"].HashParams(8, 3, 20.0)) > 0
+    assert rows(host.search(ctx, qb, sp, labels=store)) == base
+    assert store.attach(ctx, pair_table=True, hash_params=ix.params, max_table_bytes=1000) is None
+    assert rows(host.search(ctx, qb, sp, labels=store)) == base

@@ -147,6 +147,22 @@ def test_index_files_byte_identical(host, tmp_path):
     with pytest.raises(Exception) as e:
         host.load_folddisco_index(mine)
     assert "inconsistent" in str(e.value)
+    # hostile / corrupt offset files: a count that would wrap the size computation, offsets that run backwards
+    raw = bytearray(open(mine + ".offset", "rb").read())
+    bad = bytearray(raw)
+    bad[0:8] = np.uint64(1 << 62).tobytes()
+    open(mine + ".offset", "wb").write(bad)
+    with pytest.raises(Exception) as e:
+        host.load_folddisco_index(mine)
+    assert "corrupted" in str(e.value)
+    bad = bytearray(raw)
+    count = int(np.frombuffer(raw[:8], np.uint64)[0])
+    pos = 8 + 4 * count + 8 * 100  # offsets[100] := a value beyond its successor
+    bad[pos:pos + 8] = np.uint64(F.CONFIG1_VALUE_BYTES).tobytes()
+    open(mine + ".offset", "wb").write(bad)
+    with pytest.raises(Exception) as e:
+        host.load_folddisco_index(mine)
+    assert "not ascending" in str(e.value)
 
 
 @needs_reference

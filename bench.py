@@ -411,6 +411,10 @@ def run_ours(args, rank, world, local_rank):
     time.sleep(0.3)
     launches0 = ctx.kernel_launches
     general0 = ctx.stage_launches("general_candidates")
+    gnames = ("general_reason_query", "general_reason_edges", "general_reason_nodes", "general_reason_components",
+              "general_reason_lists")
+    greason0 = {k: ctx.stage_launches(k) for k in gnames}
+    gwall0 = ctx.stage_ms("general_path_wall")
     st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages + hv}
     bytes_scanned, exch_bytes = 0, 0
     val_t, wall_t = [], []
@@ -471,9 +475,14 @@ def run_ours(args, rank, world, local_rank):
             1e3 * sum(wall_t) / steps),
         "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows,
                              "candidates_on_the_general_verification_path":
-                                 (ctx.stage_launches("general_candidates") - general0) // steps},
+                                 (ctx.stage_launches("general_candidates") - general0) // steps,
+                             "general_path_reasons": {k[15:]: (ctx.stage_launches(k) - greason0[k]) // steps for k in gnames},
+                             "general_path_wall_ms": (ctx.stage_ms("general_path_wall") - gwall0) / steps},
     }
     if shards is not None:
+        fs = ("fs_flatten", "fs_allgather", "fs_parse", "fs_counts", "fs_allreduce", "fs_tables")
+        line["e2e_prepare_host_ms"]["finalize_sharded breakdown (mean per call)"] = {
+            k[3:]: ctx.stage_ms(k) / max(1, ctx.stage_launches(k)) for k in fs}
         line["exchange"] = {"collective": "ncclSend/ncclRecv group (all-to-all) of per-query top-%d blocks + counts, "
                                           "inside fd_count_query_sharded" % args.top,
                             "ms_per_step_max_over_ranks": exch_ms_max,

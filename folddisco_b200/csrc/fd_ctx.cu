@@ -333,6 +333,13 @@ void fd_destroy(fd_ctx *ctx) {
     delete ctx;
 }
 
+void fd_note_host_ms(fd_ctx *ctx, const char *stage, double ms) {
+    if (!ctx || !stage) return;
+    FdStage &s = ctx->stages[stage];
+    s.ms += ms;
+    s.launches += 1;
+}
+
 void fd_note_general_path(fd_ctx *ctx, uint64_t n) {
     if (ctx) ctx->stages["general_candidates"].launches += n;
 }

@@ -810,6 +810,7 @@ struct ScanV2Args {
     uint32_t *scratch;                    // [grid][3][scratch_cap] per-CTA entry lists of the epilogue
     uint32_t scratch_cap;                 // >= the largest tile (cells)
     uint32_t use_bulk;                    // posting bytes staged by bulk copies (else: plain vector loads; A/B switch)
+    uint32_t n_dwarps;                    // warps of a CTA that decode (each owns a stage); all warps run the epilogue
 };
 
 __host__ __device__ __forceinline__ uint32_t k3v_edge_words(uint32_t n_edges) {
@@ -841,7 +842,7 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
     uint32_t *wqueue = hist + K3V_HIST_BINS;                                            // [nwarps * K3_WQ]
     uintptr_t sp = reinterpret_cast<uintptr_t>(wqueue + nwarps * K3_WQ);
     sp = (sp + 15) & ~(uintptr_t)15;
-    const uint32_t n_dwarps = min(nwarps, (uint32_t)K3V_DECODE_WARPS);
+    const uint32_t n_dwarps = min(nwarps, a.n_dwarps);
     uint8_t *stage = reinterpret_cast<uint8_t *>(sp);                                   // [n_dwarps][K3V_WARP_STAGE]
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage + (size_t)n_dwarps * K3V_WARP_STAGE); // [n_dwarps]
     __shared__ uint32_t s_item, s_total_items, s_thr, s_n, s_nk, s_maxbin;
@@ -1604,9 +1605,9 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
         const fd_query &Q = queries[q];
         if (Q.n_hashes && (!Q.hashes || !Q.edge_of_hash)) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL array");
         if (Q.n_edges && !Q.edge_node) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL edge_node");
-        order.resize(Q.n_hashes);
-        for (uint32_t k = 0; k < Q.n_hashes; k++) order[k] = k;
         if (sampling) {
+            order.resize(Q.n_hashes);
+            for (uint32_t k = 0; k < Q.n_hashes; k++) order[k] = k;
             const uint32_t *cnt = sample_counts.data() + sample_base;
             std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cnt[a] < cnt[b]; });
             size_t keep = has_r ? (size_t)std::ceil(params->sampling_ratio * (float)Q.n_hashes)
@@ -1627,21 +1628,33 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
                 group_iters = std::max(group_iters, run - 1);
             }
         }
-        B.descs[q] = QueryDesc{(uint32_t)B.f_hash.size(), (uint32_t)order.size(), (uint32_t)B.f_edge_node.size(),
+        const uint32_t n_kept = sampling ? (uint32_t)order.size() : Q.n_hashes;
+        B.descs[q] = QueryDesc{(uint32_t)B.f_hash.size(), n_kept, (uint32_t)B.f_edge_node.size(),
                                Q.n_edges, Q.n_nodes, Q.expected_node_count, group_iters};
-        for (uint32_t k : order) {
-            if (Q.edge_of_hash[k] >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
-            B.f_hash.push_back(Q.hashes[k]);
-            B.f_edge.push_back(Q.edge_of_hash[k]);
-            if (gcounts) B.f_gcount.push_back(gcounts[gbase + k]);
+        if (!sampling) { // the common case: the arrays are taken as they are (bulk copies; a sharded rank flattens
+            // the whole batch of every rank, millions of hashes per call)
+            uint32_t worst = 0;
+            for (uint32_t k = 0; k < Q.n_hashes; k++) worst = std::max<uint32_t>(worst, Q.edge_of_hash[k]);
+            if (Q.n_hashes && worst >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
+            B.f_hash.insert(B.f_hash.end(), Q.hashes, Q.hashes + Q.n_hashes);
+            B.f_edge.insert(B.f_edge.end(), Q.edge_of_hash, Q.edge_of_hash + Q.n_hashes);
+            if (gcounts) B.f_gcount.insert(B.f_gcount.end(), gcounts + gbase, gcounts + gbase + Q.n_hashes);
+        } else {
+            for (uint32_t k : order) {
+                if (Q.edge_of_hash[k] >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
+                B.f_hash.push_back(Q.hashes[k]);
+                B.f_edge.push_back(Q.edge_of_hash[k]);
+                if (gcounts) B.f_gcount.push_back(gcounts[gbase + k]);
+            }
         }
         gbase += Q.n_hashes;
-        for (uint32_t e = 0; e < Q.n_edges; e++) {
+        for (uint32_t e = 0; e < Q.n_edges; e++)
             if (Q.edge_node[e] >= Q.n_nodes) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_node out of range");
-            B.f_edge_node.push_back(Q.edge_node[e]);
-            B.f_edge_group.push_back(Q.edge_group ? Q.edge_group[e] : (uint16_t)e);
-        }
-        B.max_hashes = std::max<uint32_t>(B.max_hashes, (uint32_t)order.size());
+        B.f_edge_node.insert(B.f_edge_node.end(), Q.edge_node, Q.edge_node + Q.n_edges);
+        if (Q.edge_group) B.f_edge_group.insert(B.f_edge_group.end(), Q.edge_group, Q.edge_group + Q.n_edges);
+        else
+            for (uint32_t e = 0; e < Q.n_edges; e++) B.f_edge_group.push_back((uint16_t)e);
+        B.max_hashes = std::max<uint32_t>(B.max_hashes, n_kept);
         B.max_edges = std::max(B.max_edges, Q.n_edges);
         B.max_nodes = std::max(B.max_nodes, Q.n_nodes);
     }
@@ -2019,7 +2032,7 @@ static int scan_v1(fd_ctx *ctx, const Batch &B, uint32_t nq, uint32_t N, const f
 
 // Shared-memory plan of k3_scan_v2: CTAs per SM, threads, bytes per CTA, words of vote planes.
 struct ScanV2Plan {
-    uint32_t ctas_per_sm, threads, tile_words;
+    uint32_t ctas_per_sm, threads, tile_words, n_dwarps;
     size_t smem;
     bool stage_lists;
 };
@@ -2029,12 +2042,15 @@ static int plan_scan_v2(fd_ctx *ctx, const Batch &B, ScanV2Plan &pl) {
     if (const char *e = getenv("FD_K3_THREADS")) threads = (uint32_t)std::min(K3V_MAX_THREADS, std::max(64, atoi(e) & ~31));
     if (ctas * threads > 1024) threads = (1024 / ctas) & ~31u; // the kernel is compiled for 64 registers per thread
     const uint32_t max_ew = k3v_edge_words(B.max_edges);
+    pl.n_dwarps = K3V_DECODE_WARPS;
+    if (const char *e = getenv("FD_K3_DWARPS")) pl.n_dwarps = (uint32_t)std::min(32, std::max(1, atoi(e)));
+    pl.n_dwarps = std::min(pl.n_dwarps, threads / 32);
     pl.stage_lists = k3_stage_lists(B.max_hashes);
     // 228 KB per SM, 1 KB reserved per resident CTA, at most 227 KB per CTA
     const size_t per_cta = std::min<size_t>(227 * 1024, (228 * 1024) / ctas - 1024 - 128); // 1 KB reserved per CTA + the kernel's static shared memory
     const size_t fixed = ((size_t)(pl.stage_lists ? 8 : 2) * B.max_hashes + 2 + (size_t)B.max_nodes * max_ew + max_ew +
                           K3V_HIST_BINS + (size_t)(threads / 32) * K3_WQ) * 4 + 16 +
-                         (size_t)std::min<uint32_t>(threads / 32, K3V_DECODE_WARPS) * (K3V_WARP_STAGE + 8) + 64;
+                         (size_t)pl.n_dwarps * (K3V_WARP_STAGE + 8) + 64;
     const uint32_t planes_max = (B.narrow ? 1u : 2u) + max_ew;
     if (per_cta < fixed + (size_t)256 * planes_max * 4) {
         if (ctas > 1) { // very wide queries: one CTA per SM
@@ -2154,7 +2170,7 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
                          d_items.p, (uint32_t)items.size(), d_flags.p, pl.tile_words, B.max_hashes, B.max_nodes,
                          k3v_edge_words(B.max_edges), pl.stage_lists ? 1u : 0u, limit ? (uint32_t)top_n : 0u, fp,
                          d_hit_off.p, d_hit_cnt.p, d_hits.p, d_flags.p + 1, d_scratch.p, scratch_cap,
-                         (getenv("FD_K3_BULK") && atoi(getenv("FD_K3_BULK")) == 0) ? 0u : 1u};
+                         (getenv("FD_K3_BULK") && atoi(getenv("FD_K3_BULK")) == 0) ? 0u : 1u, pl.n_dwarps};
             if (B.narrow) {
                 FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
                 FD_LAUNCH(ctx, k3_scan_v2<true>, grid, pl.threads, pl.smem, ix, a);

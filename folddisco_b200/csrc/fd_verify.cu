@@ -41,7 +41,7 @@ constexpr int VB_WARPS = 4;                // k6b: candidates per CTA
 constexpr int V_MAX_AAD = 255; // start and count of an amino-acid pair's run each fit 8 bits
 constexpr int V_MAX_E = 256;
 constexpr int V_MAX_NODES = 64;
-constexpr int V_MAX_C = 16;
+constexpr int V_MAX_C = 64; // <= 64 nodes give at most 32 SCCs + 32 weak components of size >= 2: the limit never binds
 constexpr int V_MAX_NQ = 16;
 constexpr uint32_t V_PREFILTER_SKIP = 200; // retrieve.rs:24
 
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(VA_THREADS, 7)
         __syncthreads();
         if (n1 == 0 || n2 == 0) all_pairs = true; // CombinationVecIterator::is_empty (retrieve.rs:145-151)
         else if (n1 > V_LIST_CAP || n2 > V_LIST_CAP) {
-            if (tid == 0) cand_flags[c] = 1; // handled by the general path
+            if (tid == 0) cand_flags[c] = 16; // prefilter list beyond the shared-memory capacity: // handled by the general path
             return;
         }
     }
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(VA_THREADS, 7)
     const uint32_t ne = n_e;
     if (ne == 0) return;
     if (ne > V_MAX_E || Q.n_idx > V_MAX_NQ || Q.n_dq > V_MAX_NQ) {
-        if (tid == 0) cand_flags[c] = 1;
+        if (tid == 0) cand_flags[c] = 2; // more matching edges (or query residues) than the fused kernels hold
         return;
     }
     // ---- sort edges by (i, j): the reference's emission order (graph node numbering, f32 sum order) ----
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32)
     const uint32_t ne = W.n_e;
     if (ne == 0) return;
     if (ne > V_MAX_E || Q.n_idx > V_MAX_NQ || Q.n_dq > V_MAX_NQ) {
-        if (lane == 0) cand_flags[c] = 1;
+        if (lane == 0) cand_flags[c] = 2;
         return;
     }
     // ---- sort edges by (i, j): the reference's emission order (graph node numbering, f32 sum order) ----
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
             }
         }
         if (overflow) {
-            if (lane == 0) W.s_flag = 1;
+            if (lane == 0) W.s_flag = 4; // more than 64 graph nodes
         } else {
             if ((uint32_t)lane < nn) {
                 W.node_res[lane] = (uint16_t)nr0;
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
             const uint32_t bu0 = __ballot_sync(FULL, ur0), bu1 = __ballot_sync(FULL, ur1);
             const uint32_t nc = __popc(bs0) + __popc(bs1) + __popc(bu0) + __popc(bu1);
             if (nc > V_MAX_C) {
-                if (lane == 0) W.s_flag = 1;
+                if (lane == 0) W.s_flag = 8; // more components than V_MAX_C (cannot happen with <= 64 nodes)
             } else {
                 const uint32_t lt = (1u << lane) - 1u;
                 uint32_t pos = __popc(bs0 & lt);
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     }
     __syncwarp();
     if (W.s_flag) {
-        if (lane == 0) cand_flags[c] = 1;
+        if (lane == 0) cand_flags[c] = (uint8_t)W.s_flag;
         return;
     }
     const uint32_t ncomp = W.n_comp;

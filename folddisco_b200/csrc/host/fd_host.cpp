@@ -2062,18 +2062,31 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         auto t0 = std::chrono::steady_clock::now();
         std::vector<uint32_t> fq_, fn_;
         std::vector<uint64_t> fglobal;
+        uint64_t general_reason[5] = {0, 0, 0, 0, 0};
         for (auto &L : lanes)
             for (uint64_t c = L.c0; c < L.c1; c++)
                 if (L.flags[c - L.c0]) {
                     fq_.push_back(cand_q[c]);
                     fn_.push_back(cand_n[c]);
                     fglobal.push_back(c);
+                    // why the candidate left the fused kernels (fd_verify.cu): 1 query beyond their limits, 2 more than
+                    // 256 matching edges, 4 more than 64 graph nodes, 8 more than 16 components, 16 prefilter list cap
+                    for (int b = 0; b < 5; b++)
+                        if (L.flags[c - L.c0] & (1u << b)) general_reason[b]++;
                 }
         host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         fd_note_general_path(ctx, fglobal.size());
+        {
+            static const char *names[5] = {"general_reason_query", "general_reason_edges", "general_reason_nodes",
+                                           "general_reason_components", "general_reason_lists"};
+            for (int b = 0; b < 5; b++)
+                for (uint64_t k = 0; k < general_reason[b]; k++) fd_note_host_ms(ctx, names[b], 0.0);
+        }
+        const auto t_general = std::chrono::steady_clock::now();
         if (!fglobal.empty()) {
             if (verify_general(ctx, qs, q_begin, nq, p, fq_, fn_, fglobal, fm, R, &host_ms) != FD_OK) return fail();
             std::stable_sort(fm.begin(), fm.end(), [](const FinalMatch &a, const FinalMatch &b) { return a.cand < b.cand; });
+            fd_note_host_ms(ctx, "general_path_wall", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_general).count());
         }
     }
     // --- assemble rows: per-candidate summary (retrieve.rs:539-551), filter_after_matching (filter.rs:103-116),
@@ -2475,6 +2488,12 @@ fdh_results *fdh_search_from_votes(fd_ctx *ctx, const fdh_queries *qs, const fdh
 // ---- id-range shards over NCCL (fd_comm_*): gather the ranks' query descriptors, all-reduce the list lengths ----
 int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id, uint64_t total_structs) {
     const int world = fd_comm_world(ctx), rank = fd_comm_rank(ctx);
+    auto t_mark = std::chrono::steady_clock::now();
+    auto mark = [&](const char *name) { // host wall time of the step that just ended -> fd_stage_ms(ctx, name)
+        const auto t = std::chrono::steady_clock::now();
+        fd_note_host_ms(ctx, name, std::chrono::duration<double, std::milli>(t - t_mark).count());
+        t_mark = t;
+    };
     // this rank's blob: n_queries | per query {n_hashes, n_edges, n_nodes, residue_count, n_pairs} | hashes | pair
     // hashes | edge_of_hash | edge_node (u16 arrays last, padded to 4 bytes)
     std::vector<uint32_t> blob;
@@ -2496,6 +2515,7 @@ int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id
     const size_t words32 = blob.size();
     blob.resize(words32 + u16.size() / 2);
     memcpy(blob.data() + words32, u16.data(), u16.size() * 2);
+    mark("fs_flatten");
     uint64_t my_bytes = blob.size() * 4;
     std::vector<uint64_t> sizes(world);
     if (fd_comm_allgather(ctx, &my_bytes, 8, sizes.data()) != FD_OK) {
@@ -2510,6 +2530,7 @@ int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id
         set_err(fd_last_error(ctx));
         return FD_ERR_CUDA;
     }
+    mark("fs_allgather");
     fdh_queries::ShardedBatch &S = qs->sh;
     S = fdh_queries::ShardedBatch();
     S.world = world;
@@ -2545,18 +2566,26 @@ int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id
     std::vector<uint32_t> probe(S.hashes);
     probe.insert(probe.end(), pair_all.begin(), pair_all.end());
     std::vector<uint32_t> counts(probe.size());
+    mark("fs_parse");
     if (!probe.empty()) {
-        if (fd_posting_counts(ctx, probe.data(), probe.size(), counts.data()) != FD_OK ||
-            fd_comm_allreduce_u32(ctx, counts.data(), counts.size()) != FD_OK) {
+        if (fd_posting_counts(ctx, probe.data(), probe.size(), counts.data()) != FD_OK) {
             set_err(fd_last_error(ctx));
             return FD_ERR_CUDA;
         }
+        mark("fs_counts");
+        if (fd_comm_allreduce_u32(ctx, counts.data(), counts.size()) != FD_OK) {
+            set_err(fd_last_error(ctx));
+            return FD_ERR_CUDA;
+        }
+        mark("fs_allreduce");
     }
     S.gcounts.assign(counts.begin(), counts.begin() + S.hashes.size());
     // calculate_idf_for_hash (query.rs:17-32) of this rank's own query pairs, from the global lengths
     const int rc = fdh_queries_finalize_with_counts(qs, counts.data() + S.hashes.size() + pair_begin[rank], total_structs);
     if (rc != FD_OK) return rc;
-    return ensure_verify_prepared(ctx, qs);
+    const int rc2 = ensure_verify_prepared(ctx, qs);
+    mark("fs_tables");
+    return rc2;
 }
 
 fdh_results *fdh_search_sharded(fd_ctx *ctx, const fdh_queries *qs, const fdh_search_params *p, const fdh_store *labels) {

@@ -64,6 +64,8 @@ double fd_stage_ms(const fd_ctx *ctx, const char *stage);
 /* bookkeeping of the in-library host: n candidates of the last search took the general verification path
  * (reported as the launch count of the pseudo-stage "general_candidates") */
 void fd_note_general_path(fd_ctx *ctx, uint64_t n);
+/* adds host wall time to the named pseudo-stage (read back with fd_stage_ms) */
+void fd_note_host_ms(fd_ctx *ctx, const char *stage, double ms);
 uint64_t fd_stage_launches(const fd_ctx *ctx, const char *stage);
 
 /* ---- structures ---------------------------------------------------------------------------------- */
@@ -378,7 +380,7 @@ typedef struct {
  * retrieve.rs:364-552) for n_cand (query, candidate) pairs against the attached store: candidate re-hash,
  * graph components, residue mapping + rescue and Kabsch RMSD on the device (three kernels, nothing but match records leaves HBM).  Library-allocated outputs:
  * records grouped by candidate in component order; flags[c] != 0 marks a candidate that exceeds the kernel's
- * shared-memory limits (more than 256 matching edges, 64 graph nodes, 16 components or 16 query residues) and
+ * shared-memory limits (more than 256 matching edges, 64 graph nodes or 16 query residues) and
  * must be verified with fd_candidate_edges_batch + fd_kabsch_store_batch instead (no records are emitted
  * for it). */
 int fd_verify_candidates_batch(fd_ctx *ctx, const fd_verify_query *queries, uint32_t n_queries,

@@ -95,8 +95,10 @@ int main(int argc, char **argv) {
     uint64_t *serial = (uint64_t *)slurp(f, R * 8);
     uint64_t qs_id = 0, qlen = 0;
     if (fread(&qs_id, 8, 1, f) != 1 || fread(&qlen, 8, 1, f) != 1) return 2;
-    char *qstr = (char *)slurp(f, qlen + 1);
-    qstr[qlen] = 0;
+    char *qraw = (char *)slurp(f, qlen);
+    char *qstr = (char *)calloc(qlen + 1, 1);
+    memcpy(qstr, qraw, qlen);
+    free(qraw);
     fclose(f);
 
     /* the database: a store of CompactStructures; the index from it (K1 + K2), attached with its lookup */

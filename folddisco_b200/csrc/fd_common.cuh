@@ -50,6 +50,7 @@ struct FdDeviceIndex {
 // up (one directory read + a short binary search) instead of re-screening and re-hashing n1 x n2 residue pairs of
 // every candidate (retrieve.rs:52-156 recomputes them per candidate).  8 B per hashed pair, ~115 pairs per residue.
 constexpr uint32_t FD_PT_DIR = 1025; // prefixes 0 .. 1023 and the end sentinel
+constexpr uint32_t FD_AA_DIR = 42;   // 41 amino-acid buckets of a structure's residues and the end sentinel
 struct FdPairTable {
     bool built = false;
     uint64_t n = 0;
@@ -69,6 +70,14 @@ struct FdDeviceStore {
     float *n_xyz = nullptr, *ca_xyz = nullptr, *cb_xyz = nullptr;
     uint8_t *aa = nullptr, *cb_valid = nullptr;
     std::vector<uint64_t> h_row_offsets; // host copy (tile planning of the pair-table build)
+    // residues of every structure grouped by amino acid (built at attach, fd_edges.cu: k_store_aa_rows):
+    //   aa_rows[row_offsets[s] + k]  residue indices of structure s, ordered by bucket, ascending inside a bucket;
+    //   aa_dir[s * FD_AA_DIR + b]    first k of bucket b (b = 0..19 canonical amino acid, 20..39 modified residue of
+    //                                that code, 40 = cannot pair: unknown amino acid or no CB), [.. + 41] = n.
+    // The rescue vote of the verification (retrieve.rs:453-516) visits the residues of ONE amino acid per unmapped
+    // query residue; with the directory it reads those ~n/20 rows instead of scanning all n.
+    uint16_t *aa_rows = nullptr;
+    uint16_t *aa_dir = nullptr;
     FdPairTable pt;
 };
 

@@ -31,6 +31,8 @@ static void fd_release_store(FdDeviceStore &st) {
     cudaFree(st.cb_xyz);
     cudaFree(st.aa);
     cudaFree(st.cb_valid);
+    cudaFree(st.aa_rows);
+    cudaFree(st.aa_dir);
     cudaFree(st.pt.offsets);
     cudaFree(st.pt.hash);
     cudaFree(st.pt.ij);

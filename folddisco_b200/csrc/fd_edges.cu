@@ -55,6 +55,58 @@ struct AADist {
 
 __device__ __forceinline__ fdg::V3 ld3(const float *p, uint64_t r) { return {p[3 * r], p[3 * r + 1], p[3 * r + 2]}; }
 
+
+// Residues of every stored structure grouped by amino acid (FdDeviceStore::aa_rows / aa_dir): one warp per
+// structure, counting sort over the 41 buckets, ascending residue index inside a bucket.
+constexpr int AAD_WARPS = 8;
+__device__ __forceinline__ uint32_t aa_bucket(uint8_t a, bool cb_ok) {
+    if (a == 255 || !cb_ok) return 40u;
+    const uint32_t code = a & 0x7fu;
+    if (code >= 20u) return 40u;
+    return (a & 0x80u) ? 20u + code : code;
+}
+__global__ void __launch_bounds__(AAD_WARPS * 32)
+    k_store_aa_rows(const uint64_t *row_offsets, const uint8_t *aa, const uint8_t *cb_valid, uint64_t n_structs,
+                    uint16_t *rows, uint16_t *dir) {
+    __shared__ uint32_t s_cnt[AAD_WARPS][FD_AA_DIR];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t s = (uint64_t)blockIdx.x * AAD_WARPS + w;
+    if (s >= n_structs) return;
+    uint32_t *cnt = s_cnt[w];
+    const uint64_t base = row_offsets[s];
+    const uint32_t n = (uint32_t)(row_offsets[s + 1] - base);
+    for (uint32_t b = lane; b < FD_AA_DIR; b += 32) cnt[b] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32)
+        atomicAdd(&cnt[aa_bucket(aa[base + i], cb_valid == nullptr || cb_valid[base + i] != 0)], 1u);
+    __syncwarp();
+    if (lane == 0) { // exclusive scan: cnt[b] becomes the cursor of bucket b
+        uint32_t run = 0;
+        for (uint32_t b = 0; b < FD_AA_DIR - 1; b++) {
+            const uint32_t c = cnt[b];
+            cnt[b] = run;
+            dir[s * FD_AA_DIR + b] = (uint16_t)run;
+            run += c;
+        }
+        dir[s * FD_AA_DIR + FD_AA_DIR - 1] = (uint16_t)run;
+    }
+    __syncwarp();
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t b = i < n ? aa_bucket(aa[base + i], cb_valid == nullptr || cb_valid[base + i] != 0) : 64u + lane;
+        const uint32_t m = __match_any_sync(0xffffffffu, b);
+        const uint32_t leader = (uint32_t)__ffs((int)m) - 1u;
+        uint32_t at = 0;
+        if (lane == leader && i < n) {
+            at = cnt[b];
+            cnt[b] = at + (uint32_t)__popc(m);
+        }
+        at = __shfl_sync(0xffffffffu, at, (int)leader);
+        if (i < n) rows[base + at + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+        __syncwarp();
+    }
+}
+
 template <int MODE> // 0 = count, 1 = emit
 __global__ void __launch_bounds__(K4_THREADS)
     k4_candidate_edges(StoreView st, const RQDesc *rq, const uint32_t *q_hashes, const AADist *q_aad,
@@ -285,6 +337,17 @@ int fd_store_attach(fd_ctx *ctx, const fd_struct_batch *batch) {
     st.cb_xyz = d.cb_xyz.take();
     st.aa = d.aa.take();
     if (batch->cb_valid) st.cb_valid = d.cb_valid.take();
+    {
+        DevBuf<uint16_t> rows, dir;
+        FD_CUDA(ctx, rows.alloc(std::max<uint64_t>(st.n_res, 1)));
+        FD_CUDA(ctx, dir.alloc(std::max<uint64_t>(st.n_structs, 1) * FD_AA_DIR));
+        if (st.n_structs)
+            FD_LAUNCH(ctx, k_store_aa_rows, fd_div_up(st.n_structs, (uint64_t)AAD_WARPS), AAD_WARPS * 32, 0, st.row_offsets,
+                      st.aa, st.cb_valid, st.n_structs, rows.p, dir.p);
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        st.aa_rows = rows.take();
+        st.aa_dir = dir.take();
+    }
     st.h_row_offsets.assign(batch->row_offsets, batch->row_offsets + batch->n_structs + 1);
     st.attached = true;
     return FD_OK;

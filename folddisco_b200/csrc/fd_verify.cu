@@ -49,6 +49,7 @@ struct StoreView {
     const uint64_t *row_offsets;
     const float *n_xyz, *ca_xyz, *cb_xyz;
     const uint8_t *aa, *cb_valid;
+    const uint16_t *aa_rows, *aa_dir; // residues grouped by amino acid (FdDeviceStore)
 };
 
 struct VQDesc {                 // per query
@@ -571,7 +572,7 @@ struct WarpState { // per-warp shared memory
     uint8_t best_c[V_MAX_NQ], best_r[V_MAX_NQ];
     VAad aad[V_MAX_AAD];
     uint16_t aa_range[400];
-    uint16_t rows[64];         // rescue scan: compacted row residues
+    uint16_t aa_dir[FD_AA_DIR + 2]; // the candidate's amino-acid directory (FdDeviceStore::aa_dir)
     uint32_t dq_aa1[V_MAX_NQ]; // amino acids (bit set) that carry an entry of query residue dq: rows of the rescue scan
     uint32_t n_nodes, n_comp, s_flag;
     uint32_t r_dq, r_need, r_nridx, s_out_base;
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
         W.n_comp = 0;
     }
     if (lane < V_MAX_NQ) W.dq_aa1[lane] = 0;
+    for (uint32_t b = lane; b < FD_AA_DIR; b += 32) W.aa_dir[b] = st.aa_dir[(uint64_t)t * FD_AA_DIR + b];
     __syncwarp();
     load_aad_phase2<32>(Q, W.aad, W.aa_range, lane);
     for (uint32_t k = lane; k < Q.n_aad; k += 32)
@@ -942,29 +944,17 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                         l_n++;
                     }
                 };
-                // The rows that can count at all (amino acid carries an entry of dq, in the pair iteration, has a CB) are
-                // few: they are compacted first so that the distance tests run on full lanes.
-                uint32_t nrow = 0; // rows waiting in W.rows (warp-uniform)
-                for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    bool ok = false;
-                    if (i < n) {
-                        const uint8_t ai = st.aa[base + i];
-                        ok = ((row_aa >> (ai & 31u)) & 1u) && ai != 255 &&
-                             (all_pairs || (((ai & 0x80u) == 0) && ((Q.aa1_mask >> (ai & 31u)) & 1u))) &&
-                             (st.cb_valid == nullptr || st.cb_valid[base + i]);
-                    }
-                    const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                    if (ok) W.rows[nrow + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
-                    nrow += __popc(m);
-                    __syncwarp();
-                    if (nrow >= 32) {
-                        take(W.rows[nrow - 32 + lane]);
-                        nrow -= 32;
-                        __syncwarp();
+                // The rows that can count at all -- amino acid carries an entry of dq (in practice ONE amino acid: that
+                // of the query residue, plus its substitutions), in the pair iteration, has a CB -- come from the
+                // store's amino-acid directory: ~n / 20 rows instead of a scan over all n.
+                for (uint32_t am = row_aa & 0xfffffu; am; am &= am - 1u) {
+                    const uint32_t a = (uint32_t)__ffs((int)am) - 1u;
+                    for (uint32_t mod = 0; mod < (all_pairs ? 2u : 1u); mod++) {
+                        if (!all_pairs && !((Q.aa1_mask >> a) & 1u)) continue;
+                        const uint32_t b = a + 20u * mod;
+                        for (uint32_t r = W.aa_dir[b] + lane, re = W.aa_dir[b + 1]; r < re; r += 32) take(st.aa_rows[base + r]);
                     }
                 }
-                if ((uint32_t)lane < nrow) take(W.rows[lane]);
                 const uint32_t mx = __reduce_max_sync(0xffffffffu, l_max);
                 const uint32_t mine = (mx > 0 && l_max == mx) ? l_n : 0u;
                 const uint32_t nmax = __reduce_add_sync(0xffffffffu, mine);
@@ -1347,7 +1337,7 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
     FD_TRY(fd_pinned(ctx, 4, 2 * sizeof(unsigned int) * n_chunks, (void **)&h_counters_all));
     FD_TRY(fd_pinned(ctx, 5, (n_cand + n_chunks) * 4, (void **)&h_first_rel_all));
     const FdDeviceStore &S = ctx->store;
-    StoreView sv{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid};
+    StoreView sv{S.row_offsets, S.n_xyz, S.ca_xyz, S.cb_xyz, S.aa, S.cb_valid, S.aa_rows, S.aa_dir};
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
     // the store's pair table answers "which pairs carry this hash" directly -- if it was built with these hash parameters
     const FdPairTable &PT = S.pt;

@@ -61,8 +61,7 @@ def main():
         n = int(float(d["Instructions Executed"] or 0))
         s = int(float(d.get("Warp Stall Sampling (All Samples)") or 0))
         # ncu addresses are absolute; nvdisasm offsets are relative to the function start
-        per[addr] = (n, s)
-        total += n
+        per[addr] = (n, s)  # several launches of the kernel in the report: the last one
     base = min(per) if per else 0
     agg, agg_s = collections.Counter(), collections.Counter()
     for addr, (n, s) in per.items():
@@ -70,6 +69,15 @@ def main():
         agg[key] += n
         agg_s[key] += s
     ts = sum(agg_s.values()) or 1
+    total = sum(n for n, _ in per.values())
+    regions = os.environ.get("SASS_REGIONS")  # "name:first-last,name:first-last" of the main .cu file: region sums
+    if regions:
+        for spec in regions.split(","):
+            name, rng = spec.split(":")
+            lo, hi = [int(x) for x in rng.split("-")]
+            rn = sum(n for (f, l), n in agg.items() if f.endswith(".cu") and lo <= l <= hi)
+            rs = sum(n for (f, l), n in agg_s.items() if f.endswith(".cu") and lo <= l <= hi)
+            print("# region %-28s lines %5d-%-5d %12d insts %5.1f%%  stalls %5.1f%%" % (name, lo, hi, rn, 100.0 * rn / max(total, 1), 100.0 * rs / ts))
     print("# %s: %d warp instructions in the captured launch" % (sub, total))
     print("%-22s %14s %7s %8s" % ("file:line", "warp insts", "share", "stalls"))
     for key, n in agg.most_common(top):

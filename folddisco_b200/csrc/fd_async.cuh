@@ -48,4 +48,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// fire-and-forget reductions on a 32-bit shared-memory address (votes of the posting scan)
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 } // namespace fda

@@ -231,6 +231,10 @@ struct HostTimer {
 
 inline uint32_t fd_div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// fd_postings.cu: large copies between pageable host memory and the device through two pinned staging buffers
+int fd_copy_to_host_staged(fd_ctx *ctx, void *dst, const void *d_src, size_t bytes);
+int fd_copy_to_device_staged(fd_ctx *ctx, void *d_dst, const void *src, size_t bytes);
+
 // fd_comm.cu
 void fd_comm_release(fd_ctx *ctx);
 int fd_comm_world_of(const fd_ctx *ctx);

@@ -313,7 +313,7 @@ __global__ void k3_length_penalty(const uint32_t *nres, uint32_t n, float lp, fl
 }
 
 // the same table with the static structure filters folded into the sign: negative where the structure fails
-// --num-residue or --plddt (filter.rs:92-98), so that k3_scan_v2 needs one gather per non-empty cell
+// --num-residue or --plddt (filter.rs:92-98), so that k3_scan_v3 needs one load per non-empty cell
 __global__ void k3_length_penalty_signed(const uint32_t *nres, const float *plddt, uint32_t n, float lp,
                                          uint32_t num_res_cutoff, float plddt_cutoff, float *pen) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -756,28 +756,26 @@ __global__ void __launch_bounds__(K3_MAX_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k3_scan_v2: the single-rank / id-range-shard scan (fd_count_query_batch[_ex]).
+// k3_scan_v3: the single-rank / id-range-shard scan (fd_count_query_batch[_ex], fd_count_query_sharded).
 //
-// What changed against k3_scan (kept above for the dense / sparse vote exchange of hash-range shards) and why
-// (profiles/r03*): the first kernel ran one 1024-thread CTA per SM whose phases -- list setup, tile clear, decode,
-// compaction, per-hit gathers -- were each a chain of dependent latencies (28 k cycles per (tile, query) pair for
-// ~5 k postings; the shared-memory atomics themselves sustain 5.5 votes / clock / SM, tools/ubench/smem_atomics.cu),
-// and it appended every non-empty cell to an N-sized hit pool.  Here:
-//   * persistent CTAs (2-3 per SM) take (query, id tile) work items, costliest first, from an atomic counter, so the
-//     phases of different items overlap on an SM and the tail of a launch is short;
-//   * the vote planes are cleared once per CTA; afterwards the epilogue zeroes exactly the cells it visits (lazy
-//     clear), so a work item no longer pays 8-12 B of shared-memory stores per structure up front;
-//   * posting bytes are STAGED: every warp owns a two-stage ring in shared memory; the leader of each 8-lane group
-//     issues one cp.async.bulk (TMA engine, 1-D) of its 64-byte granule + 16 bytes of look-ahead, completion is
-//     counted on the stage's mbarrier, and the copies of step s + 1 are in flight while step s is decoded (the skip
-//     entries of step s + 1 ride in registers the same way);
-//   * the epilogue keeps only the hits that can reach the query's top n: pass 1 builds a shared-memory histogram of
-//     the idf of the passing cells (2048 monotone bins), one warp finds the tile's threshold bin, pass 2 emits the
-//     cells at or above it -- a superset of the tile's top n, hence of the query's -- and the global selection sorts
-//     hundreds of hits per query instead of thousands (no N-sized pool: capacity tiles x (n + slack), overflow is
-//     detected and the batch re-run unlimited);
-//   * the static structure filters (--num-residue, --plddt) ride in the sign of the length-penalty table, so a
-//     non-empty cell costs one 4-byte gather.
+// A work item is (query, run of consecutive id tiles); persistent CTAs (two per SM) take items, costliest query
+// first, from an atomic counter.  What changed against k3_scan_v2 and why (profiles/r03a_ncu_full.txt: 70 k warp
+// instructions per 6 k postings, 55 % of the stall samples at CTA barriers, issue slots 37 % busy):
+//   * the query's list descriptors are staged ONCE per item and the tiles of the run are walked in ascending id
+//     order, so the granule range of a list in the next tile is found by a short galloping search from the current
+//     position (one dependent skip-table load or two) instead of two full binary searches per (list, tile);
+//   * the epilogue no longer compacts the voted cells through queues and global scratch lists: two dense passes over
+//     the tile, four cells per thread (one LDS.128 of the occupancy plane + one coalesced LDG.128 of the signed
+//     length-penalty table): pass A bins the idf of the passing cells into the item's histogram, pass B emits the
+//     cells at or above the threshold bin and zeroes the planes with vector stores;
+//   * the histogram is CUMULATIVE over the tiles of the run: the threshold bin only rises, so later tiles emit
+//     fewer and fewer hits (still a superset of the query's top n: a cell of the global top n has fewer than n better
+//     cells in ANY subset of the structures);
+//   * pipelining across the barriers: the search for tile t + 1 runs in front of pass A of tile t, the scan of its
+//     granule counts beside the threshold search, and the bulk copies (cp.async.bulk -> per-warp stage, completion on
+//     the warp's mbarrier) of its first decode step are issued before pass B, so they land while the tile is emitted.
+// Posting bytes are decoded one 64-byte granule per lane (fully unrolled LEB128 walk); votes are fire-and-forget
+// shared-memory atomics into the tile's planes.
 // ------------------------------------------------------------------------------------------------
 constexpr int K3V_MAX_THREADS = 512;              // two co-resident CTAs per SM at <= 64 registers per thread
 constexpr uint32_t K3V_HIST_BINS = 2048;           // idf bin = float bits >> 20 (sign-less): 8 exponent + 3 mantissa bits
@@ -786,29 +784,27 @@ constexpr uint32_t K3V_WARP_STAGE = 32 * K3V_GRANULE_STAGE; // one granule per l
 constexpr int K3V_DECODE_WARPS = 8;                // warps of a CTA that decode (each owns a stage); all warps run the epilogue
 
 struct ScanItem {
-    uint32_t q, tile;
+    uint32_t q, tile_begin, tile_end;
 };
 
-struct ScanV2Args {
+struct ScanV3Args {
     const QueryDesc *queries;
     const QHash *qh;
     const uint16_t *edge_of_hash, *edge_node, *edge_group;
     const float *idf_sum;
-    const float *pen; // nres^-lp, negative where the structure fails --num-residue / --plddt
+    const float *pen; // nres^-lp, negative where the structure fails --num-residue / --plddt; padded to a multiple of 4
     const ScanItem *items;
     uint32_t n_items;
     unsigned int *item_counter;
     uint32_t tile_words;                  // u32 words of vote planes per CTA (multiple of 4)
     uint32_t max_hashes, max_nodes, max_ew; // sizes of the fixed shared-memory arrays
-    uint32_t stage_lists;
-    uint32_t limit_n;                     // > 0: keep only hits that can reach the tile's top limit_n
+    uint32_t stage_lists;                 // list descriptors staged in shared memory (else read from a.qh)
+    uint32_t limit_n;                     // > 0: keep only hits that can reach the run's top limit_n
     FilterParams fp;
     const uint64_t *hit_offsets;          // [nq + 1] hit regions
     unsigned int *hit_counts;
     HitRec *hits;
     unsigned int *overflow;               // set when a region was too small (host re-runs unlimited)
-    uint32_t *scratch;                    // [grid][3][scratch_cap] per-CTA entry lists of the epilogue
-    uint32_t scratch_cap;                 // >= the largest tile (cells)
     uint32_t use_bulk;                    // posting bytes staged by bulk copies (else: plain vector loads; A/B switch)
     uint32_t n_dwarps;                    // warps of a CTA that decode (each owns a stage); all warps run the epilogue
 };
@@ -825,9 +821,11 @@ __device__ __forceinline__ uint32_t k3v_idf_bin(float idf) {
     const uint32_t u = __float_as_uint(idf);
     return (u & 0x80000000u) ? 0u : (u >> 20);
 }
+__device__ __forceinline__ uint32_t u4_get(const uint4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float f4_get(const float4 &v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
 
 template <bool NARROW>
-__global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, ScanV2Args a) {
+__global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v3(IndexView ix, ScanV3Args a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t MQ = a.max_hashes;
@@ -835,25 +833,26 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
     uint32_t *planes = smem;                                                            // [tile_words]
     uint64_t *l_range = reinterpret_cast<uint64_t *>(planes + a.tile_words);            // [2 MQ] start, end (staged)
     uint32_t *l_vote = reinterpret_cast<uint32_t *>(l_range + (a.stage_lists ? 2 * MQ : 0)); // [2 MQ] vote word, edge
-    uint32_t *item_prefix = l_vote + (a.stage_lists ? 2 * MQ : 0);                      // [MQ + 1]
-    uint32_t *seg_lo = item_prefix + (MQ + 1);                                          // [MQ]
-    uint32_t *node_mask = seg_lo + MQ;                                                  // [max_nodes * max_ew + max_ew]
+    uint32_t *item_prefix = l_vote + (a.stage_lists ? 2 * MQ : 0);                      // [MQ + 1] granules of the tile, scanned
+    uint32_t *seg_lo = item_prefix + (MQ + 1);                                          // [MQ] first granule of the tile
+    uint32_t *b_next = seg_lo + MQ;                                                     // [MQ] first granule of the next tile
+    uint32_t *node_mask = b_next + MQ;                                                  // [max_nodes * max_ew + max_ew]
     uint32_t *hist = node_mask + a.max_nodes * a.max_ew + a.max_ew;                     // [K3V_HIST_BINS]
-    uint32_t *wqueue = hist + K3V_HIST_BINS;                                            // [nwarps * K3_WQ]
+    uint32_t *wqueue = hist + K3V_HIST_BINS;                                            // [nwarps * K3_WQ] candidate cells
     uintptr_t sp = reinterpret_cast<uintptr_t>(wqueue + nwarps * K3_WQ);
     sp = (sp + 15) & ~(uintptr_t)15;
     const uint32_t n_dwarps = min(nwarps, a.n_dwarps);
     uint8_t *stage = reinterpret_cast<uint8_t *>(sp);                                   // [n_dwarps][K3V_WARP_STAGE]
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage + (size_t)n_dwarps * K3V_WARP_STAGE); // [n_dwarps]
-    __shared__ uint32_t s_item, s_total_items, s_thr, s_n, s_nk, s_maxbin;
+    __shared__ uint32_t s_item, s_total[2], s_thr, s_maxbin;
 
     uint8_t *wstage = stage + (size_t)min(warp, n_dwarps - 1) * K3V_WARP_STAGE;
     uint64_t *wbar = bars + min(warp, n_dwarps - 1);
+    uint8_t *myslot = wstage + lane * K3V_GRANULE_STAGE;
     if (lane == 0 && warp < n_dwarps) fda::mbar_init(wbar, 1);
     {
         uint4 *z = reinterpret_cast<uint4 *>(planes);
         for (uint32_t i = tid; i < (a.tile_words >> 2); i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-        for (uint32_t i = tid; i < K3V_HIST_BINS; i += blockDim.x) hist[i] = 0;
     }
     fda::mbar_fence_init();
     __syncthreads();
@@ -871,51 +870,115 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
         const uint32_t EW = k3v_edge_words(qd.n_edges);
         const uint32_t PL = (NARROW ? 1u : 2u) + EW;
         const uint32_t tile_ids = k3v_tile_ids(a.tile_words, PL, ix.n_structs);
-        const uint32_t lo = item.tile * tile_ids;
-        const uint32_t hi = min(ix.n_structs, lo + tile_ids);
-        const uint32_t T = hi - lo;
-        const bool single_tile = tile_ids >= ix.n_structs;
         uint32_t *w_acc = planes;
         uint32_t *w_match = NARROW ? nullptr : planes + tile_ids;
         uint32_t *w_edge = planes + (NARROW ? 1 : 2) * tile_ids;
         uint32_t *cont_mask = node_mask + qd.n_nodes * EW;
+        // 32-bit shared-memory addresses of the planes for the votes (red.shared)
+        const uint32_t acc_sa = fda::smem_u32(w_acc), edge_sa0 = fda::smem_u32(w_edge);
+        const uint32_t match_sa = NARROW ? 0u : fda::smem_u32(planes + tile_ids);
         const float scale = idf_scale<NARROW>(a.idf_sum[q]);
         const float inv_scale = 1.0f / scale;
+        const uint64_t hbase = a.hit_offsets[q];
+        const uint32_t hcap = (uint32_t)(a.hit_offsets[q + 1] - hbase);
         for (uint32_t i = tid; i < qd.n_nodes * EW + EW; i += blockDim.x) node_mask[i] = 0; // + cont_mask
+        for (uint32_t i = tid; i < K3V_HIST_BINS; i += blockDim.x) hist[i] = 0;
+        if (tid == 0) s_maxbin = 0;
+        uint32_t run_thr = 0; // threshold bin of the run so far (CTA-uniform)
 
-        // ---- which 64-byte granules of each list intersect this tile ----
+        // granules of list k that may hold ids of [from, to): [B(from), B(to)], B(v) = (first granule g >= 1 whose
+        // running id skip_id[b0 + g] -- the id of the last posting that starts before g -- is >= v) - 1.
+        // `c` = B(from) is known; the search for B(to) gallops from it (tiles are walked in ascending order).
+        auto list_range = [&](uint32_t k, uint64_t &h_start, uint64_t &h_end) {
+            if (a.stage_lists) {
+                h_start = l_range[2 * k];
+                h_end = l_range[2 * k + 1];
+            } else {
+                const QHash h = a.qh[qd.hash_begin + k];
+                h_start = h.start;
+                h_end = h.end;
+            }
+        };
+        auto advance = [&](uint32_t k, uint32_t c, uint32_t to) -> uint32_t {
+            uint64_t h_start, h_end;
+            list_range(k, h_start, h_end);
+            if (h_end <= h_start) return 0;
+            const uint64_t b0 = h_start >> SKIP_SHIFT;
+            const uint32_t nseg = (uint32_t)(((h_end - 1) >> SKIP_SHIFT) - b0) + 1;
+            if (to >= ix.n_structs) return nseg - 1;
+            const uint32_t *r = ix.skip_id + b0;
+            uint32_t x = c + 1, y = nseg, probe = c + 1, step = 1;
+            while (probe < nseg) {
+                if (r[probe] >= to) {
+                    y = probe;
+                    break;
+                }
+                x = probe + 1;
+                probe += step;
+                step <<= 1;
+            }
+            while (x < y) {
+                const uint32_t m = (x + y) >> 1;
+                if (r[m] < to) x = m + 1;
+                else y = m;
+            }
+            return x - 1;
+        };
+        // tile `t`: granule counts of the lists (item_prefix[k + 1], not yet scanned), first granules (seg_lo), and
+        // the positions the next tile starts from (b_next); `from_pos` = position array of the tile's lower bound
+        auto setup_tile = [&](uint32_t t) {
+            const uint32_t hi_t = min(ix.n_structs, (t + 1) * tile_ids);
+            for (uint32_t k = tid; k < Q; k += blockDim.x) {
+                uint64_t h_start, h_end;
+                list_range(k, h_start, h_end);
+                const uint32_t c = b_next[k];
+                uint32_t n_gr = 0, nx = c;
+                if (h_end > h_start) {
+                    nx = advance(k, c, hi_t);
+                    n_gr = nx - c + 1;
+                }
+                seg_lo[k] = c;
+                b_next[k] = nx;
+                item_prefix[k + 1] = n_gr;
+            }
+        };
+        auto scan_prefix = [&](uint32_t slot) { // one warp: inclusive scan of item_prefix[1..Q], total -> s_total[slot]
+            uint32_t carry = 0;
+            for (uint32_t base = 1; base <= Q; base += 32) {
+                const uint32_t idx = base + lane;
+                uint32_t v = idx <= Q ? item_prefix[idx] : 0;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t tt = __shfl_up_sync(0xffffffffu, v, o);
+                    if ((int)lane >= o) v += tt;
+                }
+                v += carry;
+                if (idx <= Q) item_prefix[idx] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+            if (lane == 0) {
+                item_prefix[0] = 0;
+                s_total[slot] = carry;
+            }
+        };
+
+        // ---- item setup: descriptors, position of every list at the run's first id ----
+        const uint32_t lo_first = item.tile_begin * tile_ids;
         for (uint32_t k = tid; k < Q; k += blockDim.x) {
             const QHash h = a.qh[qd.hash_begin + k];
-            uint32_t n_items = 0, first = 0;
-            if (h.end > h.start) {
-                const uint64_t b0 = h.start >> SKIP_SHIFT, b1 = (h.end - 1) >> SKIP_SHIFT;
-                const uint32_t nseg = (uint32_t)(b1 - b0) + 1;
-                if (single_tile || nseg == 1) {
-                    n_items = nseg;
-                } else {
-                    // r(k') = skip_id[b0 + k'], k' in [1, nseg - 1], non-decreasing: the id of the last posting that
-                    // starts before granule k'
-                    const uint32_t *r = ix.skip_id + b0;
-                    uint32_t x = 1, y = nseg; // first k' with r(k') >= lo
-                    while (x < y) {
-                        const uint32_t m = (x + y) >> 1;
-                        if (r[m] < lo) x = m + 1;
-                        else y = m;
-                    }
-                    const uint32_t below_lo = x - 1;
-                    y = nseg; // continue from x: first k' with r(k') >= hi
-                    while (x < y) {
-                        const uint32_t m = (x + y) >> 1;
-                        if (r[m] < hi) x = m + 1;
-                        else y = m;
-                    }
-                    const uint32_t below_hi = x - 1;
-                    first = below_lo;                  // granule below_lo may still hold ids >= lo
-                    n_items = below_hi + 1 - below_lo; // granules [below_lo, below_hi]
+            uint32_t c = 0;
+            if (h.end > h.start && lo_first > 0) {
+                const uint64_t b0 = h.start >> SKIP_SHIFT;
+                const uint32_t nseg = (uint32_t)(((h.end - 1) >> SKIP_SHIFT) - b0) + 1;
+                const uint32_t *r = ix.skip_id + b0;
+                uint32_t x = 1, y = nseg; // first g with r(g) >= lo_first
+                while (x < y) {
+                    const uint32_t m = (x + y) >> 1;
+                    if (r[m] < lo_first) x = m + 1;
+                    else y = m;
                 }
+                c = x - 1;
             }
-            seg_lo[k] = first;
-            item_prefix[k + 1] = n_items;
+            b_next[k] = c;
             if (a.stage_lists) {
                 l_range[2 * k] = h.start;
                 l_range[2 * k + 1] = h.end;
@@ -924,361 +987,384 @@ __global__ void __launch_bounds__(K3V_MAX_THREADS, 2) k3_scan_v2(IndexView ix, S
                 l_vote[2 * k + 1] = a.edge_of_hash[qd.hash_begin + k];
             }
         }
-        if (tid == 0) item_prefix[0] = 0;
         __syncthreads();
         for (uint32_t e = tid; e < qd.n_edges; e += blockDim.x) {
             atomicOr(&node_mask[a.edge_node[qd.edge_begin + e] * EW + (e >> 5)], 1u << (e & 31));
             if (qd.group_iters && (e & 31) && a.edge_group[qd.edge_begin + e] == a.edge_group[qd.edge_begin + e - 1])
                 atomicOr(&cont_mask[e >> 5], 1u << (e & 31));
         }
-        if (tid < 32) { // inclusive scan of item_prefix[1..Q]
-            uint32_t carry = 0;
-            for (uint32_t base = 1; base <= Q; base += 32) {
-                const uint32_t idx = base + tid;
-                uint32_t v = idx <= Q ? item_prefix[idx] : 0;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-                    if ((int)tid >= o) v += t;
-                }
-                v += carry;
-                if (idx <= Q) item_prefix[idx] = v;
-                carry = __shfl_sync(0xffffffffu, v, 31);
-            }
-            if (tid == 0) s_total_items = carry;
-        }
+        setup_tile(item.tile_begin);
         __syncthreads();
-        const uint32_t total_items = s_total_items;
-        if (total_items == 0) continue; // nothing of this query's lists falls into the tile; the planes stay clean
+        if (warp == 0) scan_prefix(item.tile_begin & 1u);
+        __syncthreads();
 
-        // ---- decode + vote: ONE LANE PER GRANULE ----
-        // A decode warp takes 32 granules per step.  Lane leaders issue one bulk copy (granule + 16 bytes of look-ahead)
-        // each into the warp's stage; after the mbarrier wait every lane pulls its 80 bytes into registers (five
-        // conflict-free LDS.128), the copies of the next step are issued into the same stage, and the lane walks its
-        // bytes with a fully unrolled LEB128 state machine (~9 instructions per byte, ~18 per posting; the 8-lanes-per-
-        // granule decoder of k3_scan spent ~200 on short lists).  Votes are fire-and-forget shared-memory atomics.
-        if (warp < n_dwarps) {
-            const uint32_t gpc = n_dwarps << 5; // granules per CTA step
-            const uint32_t nsteps = (total_items + gpc - 1) / gpc;
-            uint8_t *myslot = wstage + lane * K3V_GRANULE_STAGE;
-            uint32_t pk = 0, pseg = 0, psid = 0, psoff = 0, pn = 0;
-            uint64_t pgi = 0;
-            bool pact = false;
-            auto prefetch = [&](uint32_t s) {
-                const uint32_t it = s * gpc + (warp << 5) + lane;
-                pact = it < total_items;
-                pk = pseg = psid = psoff = 0;
-                uint64_t gi = 0;
-                if (pact) {
-                    uint32_t x = 0, y = Q; // list index: last k with item_prefix[k] <= it
-                    while (y - x > 1) {
-                        const uint32_t m = (x + y) >> 1;
-                        if (item_prefix[m] <= it) x = m;
-                        else y = m;
+        // ---- decode state of this lane: the granule it decodes next (prefetched) ----
+        uint32_t pk = 0, pseg = 0, psid = 0, psoff = 0, pn = 0;
+        uint64_t pgi = 0;
+        bool pact = false;
+        const uint32_t gpc = n_dwarps << 5; // granules per CTA step
+        auto prefetch = [&](uint32_t s, uint32_t total_items) {
+            const uint32_t it = s * gpc + (warp << 5) + lane;
+            pact = it < total_items;
+            pk = pseg = psid = psoff = 0;
+            uint64_t gi = 0;
+            if (pact) {
+                uint32_t x = 0, y = Q; // list index: last k with item_prefix[k] <= it
+                while (y - x > 1) {
+                    const uint32_t m = (x + y) >> 1;
+                    if (item_prefix[m] <= it) x = m;
+                    else y = m;
+                }
+                pk = x;
+                pseg = seg_lo[x] + (it - item_prefix[x]);
+                uint64_t h_start, h_end;
+                list_range(x, h_start, h_end);
+                gi = (h_start >> SKIP_SHIFT) + pseg;
+                if (pseg) {
+                    psoff = ix.skip_off[gi];
+                    psid = ix.skip_id[gi];
+                }
+            }
+            pn = __popc(__ballot_sync(0xffffffffu, pact));
+            pgi = gi;
+            if (pn && a.use_bulk) {
+                if (lane == 0) fda::mbar_arrive_expect_tx(wbar, pn * K3V_GRANULE_STAGE);
+                __syncwarp();
+                if (pact) fda::bulk_g2s(myslot, ix.values + (gi << SKIP_SHIFT), K3V_GRANULE_STAGE, wbar);
+            }
+        };
+        if (warp < n_dwarps) prefetch(0, s_total[item.tile_begin & 1u]);
+
+        for (uint32_t t = item.tile_begin; t < item.tile_end; t++) {
+            const uint32_t lo = t * tile_ids;
+            const uint32_t hi = min(ix.n_structs, lo + tile_ids);
+            const uint32_t T = hi - lo;
+            const uint32_t total_items = s_total[t & 1u];
+            const bool has_next = t + 1 < item.tile_end;
+
+            // ---- decode + vote: ONE LANE PER GRANULE ----
+            if (warp < n_dwarps && total_items) {
+                const uint32_t nsteps = (total_items + gpc - 1) / gpc;
+                for (uint32_t s = 0; s < nsteps; s++) {
+                    const uint32_t ck = pk, cseg = pseg, csid = psid, csoff = psoff, cn = pn;
+                    const bool act = pact;
+                    if (cn == 0) break; // the granules are handed out in ascending order: no later step has one for this warp
+                    if (a.use_bulk) {
+                        fda::mbar_wait(wbar, phase);
+                        phase ^= 1u;
                     }
-                    pk = x;
-                    pseg = seg_lo[x] + (it - item_prefix[x]);
-                    const uint64_t h_start = a.stage_lists ? l_range[2 * x] : a.qh[qd.hash_begin + x].start;
-                    gi = (h_start >> SKIP_SHIFT) + pseg;
-                    if (pseg) {
-                        psoff = ix.skip_off[gi];
-                        psid = ix.skip_id[gi];
-                    }
-                }
-                pn = __popc(__ballot_sync(0xffffffffu, pact));
-                pgi = gi;
-                if (pn && a.use_bulk) {
-                    if (lane == 0) fda::mbar_arrive_expect_tx(wbar, pn * K3V_GRANULE_STAGE);
-                    __syncwarp();
-                    if (pact) fda::bulk_g2s(myslot, ix.values + (gi << SKIP_SHIFT), K3V_GRANULE_STAGE, wbar);
-                }
-            };
-            prefetch(0);
-            for (uint32_t s = 0; s < nsteps; s++) {
-                const uint32_t ck = pk, cseg = pseg, csid = psid, csoff = psoff, cn = pn;
-                const bool act = pact;
-                if (cn == 0) break; // the items are handed out in ascending order: no later step has one for this warp
-                if (a.use_bulk) {
-                    fda::mbar_wait(wbar, phase);
-                    phase ^= 1u;
-                }
-                uint32_t W[20];
-                {
-                    const uint4 *src = a.use_bulk ? reinterpret_cast<const uint4 *>(myslot)
-                                                  : reinterpret_cast<const uint4 *>(ix.values + (pgi << SKIP_SHIFT));
+                    uint32_t W[20];
+                    {
+                        const uint4 *src = a.use_bulk ? reinterpret_cast<const uint4 *>(myslot)
+                                                      : reinterpret_cast<const uint4 *>(ix.values + (pgi << SKIP_SHIFT));
 #pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        const uint4 v = src[j];
-                        W[4 * j] = v.x;
-                        W[4 * j + 1] = v.y;
-                        W[4 * j + 2] = v.z;
-                        W[4 * j + 3] = v.w;
-                    }
-                }
-                __syncwarp(); // every lane holds its bytes in registers: the stage is free for the next step's copies
-                if (s + 1 < nsteps) prefetch(s + 1);
-                else pn = 0;
-                uint32_t lp0 = 0xff, lp1 = 0, lid = 0, ladd = 0, lebit = 0; // this lane's byte range [lp0, lp1), running id, vote
-                uint32_t *ledge = w_edge;
-                if (act) {
-                    uint64_t h_start, h_end;
-                    uint32_t add, e;
-                    if (a.stage_lists) {
-                        h_start = l_range[2 * ck];
-                        h_end = l_range[2 * ck + 1];
-                        add = l_vote[2 * ck];
-                        e = l_vote[2 * ck + 1];
-                    } else {
-                        const QHash h = a.qh[qd.hash_begin + ck];
-                        h_start = h.start;
-                        h_end = h.end;
-                        e = a.edge_of_hash[qd.hash_begin + ck];
-                        const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
-                        add = NARROW ? ((1u << 24) | wgt) : wgt;
-                    }
-                    const uint64_t G0 = ((h_start >> SKIP_SHIFT) + cseg) << SKIP_SHIFT;
-                    // varints that START in [p0, p1) of this granule are this lane's; the last one may end in the look-ahead
-                    const uint32_t p0 = cseg == 0 ? (uint32_t)(h_start - G0) : csoff;
-                    const uint32_t p1 = (uint32_t)min(h_end - G0, (uint64_t)SKIP_BYTES);
-                    uint32_t id = (cseg == 0 ? 0u : csid) - lo; // tile-relative running id (wraps below the tile)
-                    const uint32_t ebit = 1u << (e & 31);
-                    uint32_t *edge_plane = w_edge + (e >> 5) * tile_ids;
-                    lp0 = p0;
-                    lp1 = p1;
-                    lid = id;
-                    ladd = add;
-                    lebit = ebit;
-                    ledge = edge_plane;
-                }
-                // the warp walks only the words that hold bytes of some lane's range (short lists fill a fraction of
-                // their granule); a varint that starts before byte 64 may end in the look-ahead word
-                const uint32_t wlo = __reduce_min_sync(0xffffffffu, act ? lp0 : 0xffu) >> 2;
-                const uint32_t whi = __reduce_max_sync(0xffffffffu, act ? lp1 : 0u);
-                uint32_t cur = 0, shift = 0;
-#pragma unroll
-                for (int w = 0; w < (int)(SKIP_BYTES / 4) + 1; w++) {
-                    if (w < (int)(SKIP_BYTES / 4) ? ((uint32_t)w < wlo || (uint32_t)(4 * w) >= whi) : whi < SKIP_BYTES) continue;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int p = 4 * w + b;
-                        const uint32_t byte = (W[w] >> (8 * b)) & 0xffu;
-                        const bool on = p < (int)SKIP_BYTES ? ((uint32_t)p >= lp0 && ((uint32_t)p < lp1 || shift != 0)) : shift != 0;
-                        if (on) {
-                            cur |= (byte & 0x7fu) << shift;
-                            if (byte & 0x80u) {
-                                shift += 7;
-                            } else {
-                                lid += cur;
-                                cur = 0;
-                                shift = 0;
-                                if (lid < T) {
-                                    atomicAdd(&w_acc[lid], ladd);
-                                    if (!NARROW) atomicAdd(&w_match[lid], 1u);
-                                    atomicOr(&ledge[lid], lebit);
-                                }
-                            }
+                        for (int j = 0; j < 5; j++) {
+                            const uint4 v = src[j];
+                            W[4 * j] = v.x;
+                            W[4 * j + 1] = v.y;
+                            W[4 * j + 2] = v.z;
+                            W[4 * j + 3] = v.w;
                         }
                     }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- epilogue ----
-        // one non-empty cell: match count, idf, filter_before_matching (filter.rs:76-100) without the node filters
-        auto eval = [&](uint32_t x, uint32_t v, uint32_t &mc, float &idf) -> bool {
-            mc = NARROW ? (v >> 24) : w_match[x];
-            const uint32_t fixed = NARROW ? (v & 0xffffffu) : v;
-            const float p = a.pen[lo + x];
-            idf = ((float)fixed * inv_scale) * fabsf(p);
-            bool pass = (__float_as_uint(p) >> 31) == 0u; // --num-residue, --plddt
-            if (a.fp.total_match_count > 0) pass = pass && mc >= a.fp.total_match_count;
-            if (a.fp.idf_score_cutoff > 0.f) pass = pass && idf >= a.fp.idf_score_cutoff;
-            return pass;
-        };
-        auto node_count = [&](uint32_t x) -> uint32_t {
-            uint32_t nc = 0;
-            if (EW == 1) {
-                const uint32_t ebits = w_edge[x];
-                for (uint32_t nd = 0; nd < qd.n_nodes; nd++) nc += (ebits & node_mask[nd]) != 0;
-            } else {
-                for (uint32_t nd = 0; nd < qd.n_nodes; nd++) {
-                    uint32_t any = 0;
-                    for (uint32_t i = 0; i < EW; i++) any |= w_edge[i * tile_ids + x] & node_mask[nd * EW + i];
-                    nc += any != 0;
-                }
-            }
-            return nc;
-        };
-        const bool node_filters = a.fp.covered_node_count > 0 || a.fp.covered_node_ratio > 0.f;
-        auto node_pass = [&](uint32_t nc) -> bool {
-            bool pass = true;
-            if (a.fp.covered_node_count > 0) pass = pass && nc >= a.fp.covered_node_count;
-            if (a.fp.covered_node_ratio > 0.f)
-                pass = pass && (float)nc / (float)qd.expected_node_count >= a.fp.covered_node_ratio;
-            return pass;
-        };
-        // Phase A: the voted cells are compacted (warp by warp: four cells per lane, ballot-free prefix sums) and each
-        // is evaluated ONCE on full lanes; entry = (cell | FAIL flag, idf) in the CTA's scratch lists (global memory,
-        // L2-resident), cells that fail the filters are cleared at once.  With a top-n limit the idf of the passing
-        // cells also feeds the tile's histogram.
-        // Phase B (limit only): entries at or above the tile's threshold bin are appended to the keep list, the rest
-        // cleared.  Phase C: node / edge counts and the hit records of the kept entries, on full lanes; clears them.
-        const uint32_t *occ = NARROW ? w_acc : w_match; // the plane whose word is non-zero exactly in the voted cells
-        const uint32_t T4 = (T + 3) >> 2;               // cells are scanned four at a time (the planes are padded to 32)
-        uint32_t *ent_x = a.scratch + (size_t)blockIdx.x * 3 * a.scratch_cap;
-        float *ent_idf = reinterpret_cast<float *>(ent_x + a.scratch_cap);
-        uint32_t *keep_e = ent_x + 2 * a.scratch_cap;
-        constexpr uint32_t FAIL = 0x80000000u;
-        auto clear_cell = [&](uint32_t x) {
-            w_acc[x] = 0;
-            if (!NARROW) w_match[x] = 0;
-            for (uint32_t i = 0; i < EW; i++) w_edge[i * tile_ids + x] = 0;
-        };
-        if (tid == 0) {
-            s_n = 0;
-            s_nk = 0;
-            s_maxbin = 0;
-        }
-        __syncthreads();
-        {
-            uint32_t *wq = wqueue + warp * K3_WQ;
-            const uint32_t n_iter = (T4 + blockDim.x - 1) / blockDim.x;
-            for (uint32_t itn = 0; itn < n_iter; itn++) {
-                const uint32_t x4 = (itn * nwarps + warp) * 32 + lane; // a warp reads 512 contiguous bytes
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (x4 < T4) o = reinterpret_cast<const uint4 *>(occ)[x4];
-                const uint32_t nz = (o.x ? 1u : 0u) | (o.y ? 2u : 0u) | (o.z ? 4u : 0u) | (o.w ? 8u : 0u);
-                const uint32_t cnt = __popc(nz);
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int ofs = 1; ofs < 32; ofs <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, ofs);
-                    if ((int)lane >= ofs) incl += t;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total == 0) continue;
-                uint32_t pos = incl - cnt;
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if ((nz >> j) & 1u) wq[pos++] = 4 * x4 + j;
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&s_n, total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                __syncwarp();
-                uint32_t wmax = 0;
-                for (uint32_t r0 = 0; r0 < total; r0 += 32) {
-                    const uint32_t r = r0 + lane;
-                    uint32_t bin = 0;
-                    if (r < total) {
-                        const uint32_t x = wq[r];
-                        uint32_t mc;
-                        float idf;
-                        bool pass = eval(x, w_acc[x], mc, idf);
-                        if (pass && node_filters) pass = node_pass(node_count(x));
-                        if (pass) {
-                            if (a.limit_n) {
-                                bin = k3v_idf_bin(idf);
-                                atomicAdd(&hist[bin], 1u);
-                            }
+                    __syncwarp(); // every lane holds its bytes in registers: the stage is free for the next step's copies
+                    if (s + 1 < nsteps) prefetch(s + 1, total_items);
+                    else pn = 0;
+                    uint32_t lp0 = 0xff, lp1 = 0, lid = 0, ladd = 0, lebit = 0; // byte range [lp0, lp1), running id, vote
+                    uint32_t edge_sa = edge_sa0;
+                    if (act) {
+                        uint64_t h_start, h_end;
+                        uint32_t add, e;
+                        list_range(ck, h_start, h_end);
+                        if (a.stage_lists) {
+                            add = l_vote[2 * ck];
+                            e = l_vote[2 * ck + 1];
                         } else {
-                            clear_cell(x);
+                            const QHash h = a.qh[qd.hash_begin + ck];
+                            e = a.edge_of_hash[qd.hash_begin + ck];
+                            const uint32_t wgt = (uint32_t)(fmaxf(h.idf, 0.f) * scale + 0.5f);
+                            add = NARROW ? ((1u << 24) | wgt) : wgt;
                         }
-                        ent_x[base + r] = pass ? x : (x | FAIL);
-                        ent_idf[base + r] = idf;
+                        const uint64_t G0 = ((h_start >> SKIP_SHIFT) + cseg) << SKIP_SHIFT;
+                        // varints that START in [p0, p1) of this granule are this lane's; the last may end in the look-ahead
+                        lp0 = cseg == 0 ? (uint32_t)(h_start - G0) : csoff;
+                        lp1 = (uint32_t)min(h_end - G0, (uint64_t)SKIP_BYTES);
+                        lid = (cseg == 0 ? 0u : csid) - lo; // tile-relative running id (wraps below the tile)
+                        ladd = add;
+                        lebit = 1u << (e & 31);
+                        edge_sa = edge_sa0 + (e >> 5) * tile_ids * 4u;
                     }
-                    wmax = max(wmax, __reduce_max_sync(0xffffffffu, bin));
+                    // The warp walks only the words that hold bytes of some lane's range (short lists fill a fraction of
+                    // their granule); a varint that starts before byte 64 may end in the look-ahead word.  The byte step is
+                    // written without branches (selects + two predicated reductions on 32-bit shared addresses): every
+                    // lane runs the same ~14 instructions per byte whatever its list looks like.
+                    const uint32_t wlo = __reduce_min_sync(0xffffffffu, act ? lp0 : 0xffu) >> 2;
+                    const uint32_t whi = __reduce_max_sync(0xffffffffu, act ? lp1 : 0u);
+                    const uint64_t rmask = act && lp1 > lp0 ? ((lp1 >= 64u ? ~0ull : ((1ull << lp1) - 1ull)) & ~((1ull << lp0) - 1ull)) : 0ull;
+                    const uint32_t rm_lo = (uint32_t)rmask, rm_hi = (uint32_t)(rmask >> 32);
+                    uint32_t cur = 0, shift = 0;
+#pragma unroll
+                    for (int w = 0; w < (int)(SKIP_BYTES / 4) + 1; w++) {
+                        if (w < (int)(SKIP_BYTES / 4) ? ((uint32_t)w < wlo || (uint32_t)(4 * w) >= whi) : whi < SKIP_BYTES) continue;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int p = 4 * w + b;
+                            const uint32_t byte = (W[w] >> (8 * b)) & 0xffu;
+                            const bool inr = p < 32 ? ((rm_lo >> p) & 1u) != 0u : (p < 64 ? ((rm_hi >> (p - 32)) & 1u) != 0u : false);
+                            const bool on = inr || shift != 0u;
+                            const bool cont = (byte & 0x80u) != 0u;
+                            cur |= on ? ((byte & 0x7fu) << shift) : 0u;
+                            const uint32_t nid = lid + cur;
+                            const bool fin = on && !cont;
+                            if (fin && nid < T) {
+                                fda::red_add_shared(acc_sa + nid * 4u, ladd);
+                                if (!NARROW) fda::red_add_shared(match_sa + nid * 4u, 1u);
+                                fda::red_or_shared(edge_sa + nid * 4u, lebit);
+                            }
+                            lid = fin ? nid : lid;
+                            const bool more = on && cont;
+                            shift = more ? shift + 7u : 0u;
+                            cur = more ? cur : 0u;
+                        }
+                    }
                 }
-                if (lane == 0 && wmax) atomicMax(&s_maxbin, wmax);
-                __syncwarp();
             }
-        }
-        __syncthreads();
-        const uint32_t n_ent = s_n;
-        uint32_t n_keep = n_ent;
-        if (a.limit_n) {
-            if (warp == 0) { // highest bin such that the bins at or above it hold at least limit_n cells
-                uint32_t above = 0, t = 0;
+            __syncthreads();
+
+            // ---- the next tile's granule ranges (latency of the skip-table loads hides under the epilogue of the others) ----
+            if (has_next) setup_tile(t + 1);
+            if (!total_items) { // nothing of the query falls into this tile: the planes are clean
+                __syncthreads();
+                if (has_next && warp == 0) scan_prefix((t + 1) & 1u);
+                __syncthreads();
+                if (has_next && warp < n_dwarps) prefetch(0, s_total[(t + 1) & 1u]);
+                continue;
+            }
+
+            // ---- epilogue ----
+            // The tile holds far more cells than votes (half a posting per cell on the bench), so the pass over the
+            // cells must cost a few instructions per cell: four cells per thread from one LDS.128 of the occupancy
+            // plane, and a voted cell is first held against an INTEGER bound -- the smallest fixed-point idf that
+            // could reach the run's threshold bin under the largest length penalty of the database -- before its
+            // penalty is loaded and its idf evaluated.  Cells that reach the threshold go to a CTA queue and are
+            // turned into hit records on full lanes (node / edge counts are ~100 instructions per record).
+            // First tile of a run: pass A (idf histogram of every passing cell) -> threshold -> pass B1 (queue) -> B2.
+            // Later tiles: ONE pass B1 against the threshold of the tiles before (it only rises), feeding the histogram.
+            const uint32_t *occ = NARROW ? w_acc : w_match; // the plane whose word is non-zero exactly in the voted cells
+            const uint32_t T4 = (T + 3) >> 2;               // four cells per thread (planes and pen are padded)
+            const uint4 *occ4 = reinterpret_cast<const uint4 *>(occ);
+            const uint4 *acc4 = reinterpret_cast<const uint4 *>(w_acc);
+            const float4 *pen4 = reinterpret_cast<const float4 *>(a.pen + lo);
+            auto node_count = [&](uint32_t x) -> uint32_t {
+                uint32_t nc = 0;
+                if (EW == 1) {
+                    const uint32_t ebits = w_edge[x];
+                    for (uint32_t nd = 0; nd < qd.n_nodes; nd++) nc += (ebits & node_mask[nd]) != 0;
+                } else {
+                    for (uint32_t nd = 0; nd < qd.n_nodes; nd++) {
+                        uint32_t any = 0;
+                        for (uint32_t i = 0; i < EW; i++) any |= w_edge[i * tile_ids + x] & node_mask[nd * EW + i];
+                        nc += any != 0;
+                    }
+                }
+                return nc;
+            };
+            auto edge_count = [&](uint32_t x) -> uint32_t {
+                uint32_t ec = 0;
+                for (uint32_t i = 0; i < EW; i++) {
+                    // bits of one group (fd_query.edge_group) count once: smear every set bit down to the first bit
+                    // of its group, then count first bits
+                    uint32_t g = w_edge[i * tile_ids + x];
+                    const uint32_t cm = cont_mask[i];
+                    for (uint32_t itg = 0; itg < qd.group_iters; itg++) g |= (g & cm) >> 1;
+                    ec += __popc(g & ~cm);
+                }
+                return ec;
+            };
+            const bool node_filters = a.fp.covered_node_count > 0 || a.fp.covered_node_ratio > 0.f;
+            // one voted cell: match count, idf, filter_before_matching (filter.rs:76-100)
+            auto eval = [&](uint32_t x, uint32_t o, uint32_t v, float p, uint32_t &mc, float &idf) -> bool {
+                mc = NARROW ? (v >> 24) : o;
+                const uint32_t fixed = NARROW ? (v & 0xffffffu) : v;
+                idf = ((float)fixed * inv_scale) * fabsf(p);
+                bool pass = (__float_as_uint(p) >> 31) == 0u; // --num-residue, --plddt
+                if (a.fp.total_match_count > 0) pass = pass && mc >= a.fp.total_match_count;
+                if (a.fp.idf_score_cutoff > 0.f) pass = pass && idf >= a.fp.idf_score_cutoff;
+                if (pass && node_filters) {
+                    const uint32_t nc = node_count(x);
+                    if (a.fp.covered_node_count > 0) pass = pass && nc >= a.fp.covered_node_count;
+                    if (a.fp.covered_node_ratio > 0.f)
+                        pass = pass && (float)nc / (float)qd.expected_node_count >= a.fp.covered_node_ratio;
+                }
+                return pass;
+            };
+            auto clear_cell = [&](uint32_t x) {
+                w_acc[x] = 0;
+                if (!NARROW) w_match[x] = 0;
+                for (uint32_t i = 0; i < EW; i++) w_edge[i * tile_ids + x] = 0;
+            };
+            auto find_thr = [&]() { // one warp: highest bin such that the bins at or above it hold at least limit_n cells
+                uint32_t above = 0, tb = 0;
                 for (int c = (int)(s_maxbin >> 5); c >= 0; c--) { // from the highest occupied bin down
-                    const uint32_t v = hist[c * 32 + lane];
-                    uint32_t suf = v; // suffix sum over lanes >= lane
+                    const uint32_t hv = hist[c * 32 + lane];
+                    uint32_t suf = hv; // suffix sum over lanes >= lane
                     for (int o = 1; o < 32; o <<= 1) {
                         const uint32_t u = __shfl_down_sync(0xffffffffu, suf, o);
                         if ((int)lane + o < 32) suf += u;
                     }
                     const uint32_t reach = __ballot_sync(0xffffffffu, above + suf >= a.limit_n);
                     if (reach) {
-                        t = c * 32 + (31 - __clz(reach));
+                        tb = c * 32 + (31 - __clz(reach));
                         break;
                     }
                     above += __shfl_sync(0xffffffffu, suf, 0);
                 }
-                if (lane == 0) s_thr = t;
-            }
-            __syncthreads();
-            const uint32_t thr = s_thr;
-            for (uint32_t i = tid; i < K3V_HIST_BINS; i += blockDim.x) hist[i] = 0;
-            const uint32_t n_round = (n_ent + 31) & ~31u;
-            for (uint32_t e0 = tid; e0 < n_round; e0 += blockDim.x) {
-                bool keep = false;
-                if (e0 < n_ent) {
-                    const uint32_t xf = ent_x[e0];
-                    if (!(xf & FAIL)) {
-                        keep = k3v_idf_bin(ent_idf[e0]) >= thr;
-                        if (!keep) clear_cell(xf);
+                if (lane == 0) s_thr = tb;
+            };
+            const bool two_pass = a.limit_n && t == item.tile_begin;
+            if (two_pass) {
+                // pass A: idf histogram of the passing cells
+                uint32_t mybin = 0;
+                for (uint32_t x4 = tid; x4 < T4; x4 += blockDim.x) {
+                    const uint4 o = occ4[x4];
+                    if (!(o.x | o.y | o.z | o.w)) continue;
+                    const float4 p = pen4[x4];
+                    const uint4 v = NARROW ? o : acc4[x4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t oj = u4_get(o, j);
+                        if (!oj) continue;
+                        uint32_t mc;
+                        float idf;
+                        if (eval(4 * x4 + j, oj, u4_get(v, j), f4_get(p, j), mc, idf)) {
+                            const uint32_t bin = k3v_idf_bin(idf);
+                            atomicAdd(&hist[bin], 1u);
+                            mybin = max(mybin, bin);
+                        }
                     }
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, keep);
-                if (m) {
-                    uint32_t pos = 0;
-                    if (lane == 0) pos = atomicAdd(&s_nk, (uint32_t)__popc(m));
-                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
-                    if (keep) keep_e[pos] = e0;
-                }
+                mybin = __reduce_max_sync(0xffffffffu, mybin);
+                if (lane == 0 && mybin) atomicMax(&s_maxbin, mybin);
+                __syncthreads();
+                if (warp == 0) find_thr();
+                else if (warp == 1 && has_next) scan_prefix((t + 1) & 1u);
+                __syncthreads();
+                run_thr = s_thr;
             }
-            __syncthreads();
-            n_keep = s_nk;
-        }
-        {
-            const uint64_t hbase = a.hit_offsets[q];
-            const uint32_t hcap = (uint32_t)(a.hit_offsets[q + 1] - hbase);
-            const uint32_t n_round = (n_keep + 31) & ~31u;
-            for (uint32_t k0 = tid; k0 < n_round; k0 += blockDim.x) {
-                bool emit = false;
-                HitRec rec{0, 0, 0, 0.f};
-                if (k0 < n_keep) {
-                    const uint32_t e0 = a.limit_n ? keep_e[k0] : k0;
-                    const uint32_t xf = ent_x[e0];
-                    if (!(xf & FAIL)) {
-                        const uint32_t x = xf;
-                        const uint32_t mc = NARROW ? (w_acc[x] >> 24) : w_match[x];
-                        uint32_t ec = 0;
-                        for (uint32_t i = 0; i < EW; i++) {
-                            // bits of one group (fd_query.edge_group) count once: smear every set bit down to the
-                            // first bit of its group, then count first bits
-                            uint32_t g = w_edge[i * tile_ids + x];
-                            const uint32_t cm = cont_mask[i];
-                            for (uint32_t itg = 0; itg < qd.group_iters; itg++) g |= (g & cm) >> 1;
-                            ec += __popc(g & ~cm);
+            // pass B: every voted cell is held against the run's threshold with three instructions (fixed-point idf x
+            // penalty >= lower edge of the threshold bin, all scaled by the query's power-of-two factor: the same
+            // comparison as idf_bin(idf) >= thr); the few cells that reach it are compacted through the warp's queue
+            // and turned into hit records on full lanes; the planes are zeroed on the way.
+            {
+                const bool feed_hist = a.limit_n && !two_pass;
+                const float thr_s = run_thr ? __uint_as_float(run_thr << 20) * scale : 0.f;
+                uint32_t *wq = wqueue + warp * K3_WQ;
+                uint32_t wq_n = 0; // warp-uniform
+                uint32_t mybin = 0;
+                auto drain = [&](uint32_t first, uint32_t n_take) { // queue entries [first, first + n_take), one per lane
+                    bool emit = false;
+                    HitRec rec{0, 0, 0, 0.f};
+                    if (lane < n_take) {
+                        const uint32_t x = wq[first + lane];
+                        uint32_t mc;
+                        float idf;
+                        if (eval(x, occ[x], w_acc[x], a.pen[lo + x], mc, idf)) {
+                            const uint32_t bin = k3v_idf_bin(idf);
+                            if (feed_hist) {
+                                atomicAdd(&hist[bin], 1u);
+                                mybin = max(mybin, bin);
+                            }
+                            if (bin >= run_thr) {
+                                rec = HitRec{lo + x, mc, (node_count(x) << 16) | (edge_count(x) & 0xffffu), idf};
+                                emit = true;
+                            }
                         }
-                        rec = HitRec{lo + x, mc, (node_count(x) << 16) | (ec & 0xffffu), ent_idf[e0]};
-                        emit = true;
                         clear_cell(x);
                     }
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, emit);
-                if (m) {
-                    uint32_t pos = 0;
-                    if (lane == 0) pos = atomicAdd(&a.hit_counts[q], (unsigned int)__popc(m));
-                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
-                    if (emit) {
-                        if (pos < hcap) a.hits[hbase + pos] = rec;
-                        else atomicOr(a.overflow, 1u);
+                    const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                    if (m) {
+                        uint32_t pos = 0;
+                        if (lane == 0) pos = atomicAdd(&a.hit_counts[q], (unsigned int)__popc(m));
+                        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                        if (emit) {
+                            if (pos < hcap) a.hits[hbase + pos] = rec;
+                            else atomicOr(a.overflow, 1u);
+                        }
                     }
+                };
+                const uint32_t n_iter = (T4 + blockDim.x - 1) / blockDim.x;
+                for (uint32_t itn = 0; itn < n_iter; itn++) {
+                    const uint32_t x4 = (itn * nwarps + warp) * 32 + lane; // a warp reads 512 contiguous bytes
+                    uint4 o = make_uint4(0, 0, 0, 0);
+                    if (x4 < T4) o = occ4[x4];
+                    const bool any = (o.x | o.y | o.z | o.w) != 0;
+                    if (!__any_sync(0xffffffffu, any)) continue;
+                    uint32_t cmask = 0;
+                    if (any) {
+                        const float4 p = pen4[x4];
+                        const uint4 v = NARROW ? o : acc4[x4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t vj = u4_get(v, j);
+                            const float sj = (float)(NARROW ? (vj & 0xffffffu) : vj) * fabsf(f4_get(p, j));
+                            cmask |= (u4_get(o, j) != 0u && sj >= thr_s) ? (1u << j) : 0u;
+                        }
+                        if (!cmask) {
+                            const uint4 z = make_uint4(0, 0, 0, 0);
+                            reinterpret_cast<uint4 *>(w_acc)[x4] = z;
+                            if (!NARROW) reinterpret_cast<uint4 *>(w_match)[x4] = z;
+                            for (uint32_t i = 0; i < EW; i++) reinterpret_cast<uint4 *>(w_edge + i * tile_ids)[x4] = z;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (!((cmask >> j) & 1u) && u4_get(o, j)) clear_cell(4 * x4 + j);
+                        }
+                    }
+                    const uint32_t cnt = __popc(cmask);
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, ofs);
+                        if ((int)lane >= ofs) incl += u;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total == 0) continue;
+                    uint32_t pos = wq_n + incl - cnt;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if ((cmask >> j) & 1u) wq[pos++] = 4 * x4 + j;
+                    wq_n += total;
+                    __syncwarp();
+                    uint32_t done = 0;
+                    while (wq_n - done >= 32) {
+                        drain(done, 32);
+                        done += 32;
+                    }
+                    if (done) { // move the remainder to the front
+                        const uint32_t rem = wq_n - done;
+                        uint32_t keepv = 0;
+                        if (lane < rem) keepv = wq[done + lane];
+                        __syncwarp();
+                        if (lane < rem) wq[lane] = keepv;
+                        wq_n = rem;
+                    }
+                    __syncwarp();
+                }
+                if (wq_n) drain(0, wq_n);
+                if (feed_hist) {
+                    mybin = __reduce_max_sync(0xffffffffu, mybin);
+                    if (lane == 0 && mybin) atomicMax(&s_maxbin, mybin);
                 }
             }
+            __syncthreads(); // the planes are clean and the next tile's votes may start
+            if (!two_pass) { // the threshold for the next tile and the scan of its granule counts
+                if (warp == 0 && a.limit_n) find_thr();
+                else if (warp == 1 && has_next) scan_prefix((t + 1) & 1u);
+                __syncthreads();
+                if (a.limit_n) run_thr = s_thr;
+            }
+            // the first decode step of the next tile
+            if (has_next && warp < n_dwarps) prefetch(0, s_total[(t + 1) & 1u]);
         }
-        // the next item's setup writes only the list arrays and masks, which nobody reads any more after the
-        // barrier at the top of the loop
     }
 }
 
@@ -1919,7 +2005,7 @@ int fd_index_attach(fd_ctx *ctx, const uint32_t *hashes, const uint64_t *offsets
     d.n_skip = nblocks;
     FD_CUDA(ctx, cudaMemcpyAsync(d.hashes, hashes, count * 4, cudaMemcpyHostToDevice, s));
     FD_CUDA(ctx, cudaMemcpyAsync(d.offsets, offsets, (count + 1) * 8, cudaMemcpyHostToDevice, s));
-    FD_CUDA(ctx, cudaMemcpyAsync(d.values, values, value_bytes, cudaMemcpyHostToDevice, s));
+    FD_TRY(fd_copy_to_device_staged(ctx, d.values, values, value_bytes));
     FD_CUDA(ctx, cudaMemsetAsync(d.values + value_bytes, 0, VALUES_PAD, s));
     FD_CUDA(ctx, cudaMemsetAsync(d.skip_off, 0, nblocks, s));
     FD_CUDA(ctx, cudaMemsetAsync(d.skip_id, 0, nblocks * 4, s));
@@ -2030,13 +2116,13 @@ static int scan_v1(fd_ctx *ctx, const Batch &B, uint32_t nq, uint32_t N, const f
     return FD_OK;
 }
 
-// Shared-memory plan of k3_scan_v2: CTAs per SM, threads, bytes per CTA, words of vote planes.
-struct ScanV2Plan {
+// Shared-memory plan of k3_scan_v3: CTAs per SM, threads, bytes per CTA, words of vote planes.
+struct ScanV3Plan {
     uint32_t ctas_per_sm, threads, tile_words, n_dwarps;
     size_t smem;
     bool stage_lists;
 };
-static int plan_scan_v2(fd_ctx *ctx, const Batch &B, ScanV2Plan &pl) {
+static int plan_scan_v3(fd_ctx *ctx, const Batch &B, ScanV3Plan &pl) {
     uint32_t ctas = 2, threads = 512;
     if (const char *e = getenv("FD_K3_CTAS")) ctas = (uint32_t)std::min(4, std::max(1, atoi(e)));
     if (const char *e = getenv("FD_K3_THREADS")) threads = (uint32_t)std::min(K3V_MAX_THREADS, std::max(64, atoi(e) & ~31));
@@ -2048,9 +2134,8 @@ static int plan_scan_v2(fd_ctx *ctx, const Batch &B, ScanV2Plan &pl) {
     pl.stage_lists = k3_stage_lists(B.max_hashes);
     // 228 KB per SM, 1 KB reserved per resident CTA, at most 227 KB per CTA
     const size_t per_cta = std::min<size_t>(227 * 1024, (228 * 1024) / ctas - 1024 - 128); // 1 KB reserved per CTA + the kernel's static shared memory
-    const size_t fixed = ((size_t)(pl.stage_lists ? 8 : 2) * B.max_hashes + 2 + (size_t)B.max_nodes * max_ew + max_ew +
-                          K3V_HIST_BINS + (size_t)(threads / 32) * K3_WQ) * 4 + 16 +
-                         (size_t)pl.n_dwarps * (K3V_WARP_STAGE + 8) + 64;
+    const size_t fixed = ((size_t)(pl.stage_lists ? 9 : 3) * B.max_hashes + 2 + (size_t)B.max_nodes * max_ew + max_ew +
+                          K3V_HIST_BINS + (size_t)(threads / 32) * K3_WQ) * 4 + 16 + (size_t)pl.n_dwarps * (K3V_WARP_STAGE + 8) + 64;
     const uint32_t planes_max = (B.narrow ? 1u : 2u) + max_ew;
     if (per_cta < fixed + (size_t)256 * planes_max * 4) {
         if (ctas > 1) { // very wide queries: one CTA per SM
@@ -2104,28 +2189,40 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
         return FD_OK;
     }
     const bool use_v1 = getenv("FD_K3_V1") && atoi(getenv("FD_K3_V1")) != 0;
-    ScanV2Plan pl{};
+    ScanV3Plan pl{};
     if (!use_v1) {
-        const int rc = plan_scan_v2(ctx, B, pl);
+        const int rc = plan_scan_v3(ctx, B, pl);
         if (rc != FD_OK) {
             free(h_off);
             return rc;
         }
     }
-    // work items (query, id tile), costliest queries first
+    // work items (query, run of consecutive id tiles), costliest queries first; a query is cut into as many runs as
+    // it takes to give every resident CTA a few items (a single query still spreads over the whole GPU)
     std::vector<ScanItem> items;
     std::vector<uint32_t> n_tiles(nq, 1);
     if (!use_v1) {
         std::vector<uint32_t> qorder(nq);
-        for (uint32_t q = 0; q < nq; q++) qorder[q] = q;
+        uint32_t n_live = 0;
+        for (uint32_t q = 0; q < nq; q++) {
+            qorder[q] = q;
+            n_live += B.h_postings[q] != 0;
+        }
         std::stable_sort(qorder.begin(), qorder.end(),
                          [&](uint32_t x, uint32_t y) { return B.h_postings[x] > B.h_postings[y]; });
+        const uint32_t want_items = 2u * (uint32_t)ctx->num_sms * pl.ctas_per_sm;
+        uint32_t runs_per_query = n_live ? fd_div_up(want_items, n_live) : 1;
+        if (const char *e = getenv("FD_K3_RUNS")) runs_per_query = (uint32_t)std::max(1, atoi(e));
         for (uint32_t q : qorder) {
             if (B.h_postings[q] == 0) continue;
             const uint32_t planes = (B.narrow ? 1u : 2u) + k3v_edge_words(B.descs[q].n_edges);
             const uint32_t tile_ids = k3v_tile_ids(pl.tile_words, planes, N);
             n_tiles[q] = fd_div_up(N, tile_ids);
-            for (uint32_t t = 0; t < n_tiles[q]; t++) items.push_back(ScanItem{q, t});
+            const uint32_t runs = std::min(runs_per_query, n_tiles[q]);
+            for (uint32_t r = 0; r < runs; r++) {
+                const uint32_t t0 = (uint32_t)((uint64_t)n_tiles[q] * r / runs), t1 = (uint32_t)((uint64_t)n_tiles[q] * (r + 1) / runs);
+                if (t1 > t0) items.push_back(ScanItem{q, t0, t1});
+            }
         }
     }
     const uint64_t top_n = params->top_n;
@@ -2155,7 +2252,8 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
             FD_TRY(scan_v1(ctx, B, nq, N, params, d_hit_off, d_hit_cnt, d_hits));
         } else if (!items.empty()) {
             FD_CUDA(ctx, d_items.alloc(items.size()));
-            FD_CUDA(ctx, d_pen2.alloc(N));
+            FD_CUDA(ctx, d_pen2.alloc((size_t)N + 4)); // the epilogue reads it four cells at a time
+            FD_CUDA(ctx, cudaMemsetAsync(d_pen2.p + N, 0, 16, s));
             FD_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(ScanItem), cudaMemcpyHostToDevice, s));
             const FilterParams fp = make_filter(params);
             IndexView ix = make_view(ctx);
@@ -2163,20 +2261,17 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
             FD_LAUNCH(ctx, k3_length_penalty_signed, fd_div_up(N, 256), 256, 0, ix.nres, ix.plddt, N, fp.length_penalty,
                       fp.num_res_cutoff, fp.plddt_cutoff, d_pen2.p);
             const uint32_t grid = (uint32_t)std::min<uint64_t>(items.size(), (uint64_t)ctx->num_sms * pl.ctas_per_sm);
-            const uint32_t scratch_cap = k3v_tile_ids(pl.tile_words, B.narrow ? 2u : 3u, N) + 32;
-            DevBuf<uint32_t> d_scratch;
-            FD_CUDA(ctx, d_scratch.alloc((size_t)grid * 3 * scratch_cap));
-            ScanV2Args a{B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p, B.d_edge_group.p, B.d_idfsum.p, d_pen2.p,
+            ScanV3Args a{B.d_desc.p, B.d_qh.p, B.d_edge.p, B.d_edge_node.p, B.d_edge_group.p, B.d_idfsum.p, d_pen2.p,
                          d_items.p, (uint32_t)items.size(), d_flags.p, pl.tile_words, B.max_hashes, B.max_nodes,
                          k3v_edge_words(B.max_edges), pl.stage_lists ? 1u : 0u, limit ? (uint32_t)top_n : 0u, fp,
-                         d_hit_off.p, d_hit_cnt.p, d_hits.p, d_flags.p + 1, d_scratch.p, scratch_cap,
+                         d_hit_off.p, d_hit_cnt.p, d_hits.p, d_flags.p + 1,
                          (getenv("FD_K3_BULK") && atoi(getenv("FD_K3_BULK")) == 0) ? 0u : 1u, pl.n_dwarps};
             if (B.narrow) {
-                FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-                FD_LAUNCH(ctx, k3_scan_v2<true>, grid, pl.threads, pl.smem, ix, a);
+                FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                FD_LAUNCH(ctx, k3_scan_v3<true>, grid, pl.threads, pl.smem, ix, a);
             } else {
-                FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-                FD_LAUNCH(ctx, k3_scan_v2<false>, grid, pl.threads, pl.smem, ix, a);
+                FD_CUDA(ctx, cudaFuncSetAttribute(k3_scan_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                FD_LAUNCH(ctx, k3_scan_v3<false>, grid, pl.threads, pl.smem, ix, a);
             }
             FD_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags.p, 8, cudaMemcpyDeviceToHost, s));
             FD_CUDA(ctx, st.finish());

@@ -1605,23 +1605,40 @@ static int64_t add_many_impl(fdh_queries *qs, const fdh_compact *const *structs,
             set_err("fdh_queries_add_many_indexed: index out of range");
             return -1;
         }
-    // one copy per distinct source structure (all sources are alive for the duration of this call)
+    // one copy per distinct source structure (all sources are alive for the duration of this call); the copies are
+    // made on the worker pool (a 1024-query batch of distinct structures copies ~15 MB)
     std::vector<std::shared_ptr<const fdh_compact>> uniq((size_t)n_structs);
-    std::unordered_map<const fdh_compact *, std::shared_ptr<const fdh_compact>> seen;
-    auto copy_of = [&](int64_t u) -> const std::shared_ptr<const fdh_compact> & {
-        if (!uniq[u]) {
+    std::vector<int64_t> owner((size_t)n_structs, -1); // slot that holds the copy of this slot's structure
+    std::vector<int64_t> to_copy;
+    {
+        std::unordered_map<const fdh_compact *, int64_t> seen;
+        for (int64_t k = 0; k < n; k++) {
+            const int64_t u = which_struct ? which_struct[k] : k;
+            if (owner[u] >= 0) continue;
             auto it = seen.find(structs[u]);
-            if (it == seen.end()) it = seen.emplace(structs[u], std::make_shared<const fdh_compact>(*structs[u])).first;
-            uniq[u] = it->second;
+            if (it == seen.end()) {
+                seen.emplace(structs[u], u);
+                owner[u] = u;
+                to_copy.push_back(u);
+            } else {
+                owner[u] = it->second;
+            }
         }
-        return uniq[u];
-    };
-    for (int64_t k = 0; k < n; k++) copy_of(which_struct ? which_struct[k] : k);
+    }
+    int nt = threads > 0 ? threads : fd_default_host_threads();
+    nt = std::max(1, std::min<int>(nt, 64));
+    {
+        std::atomic<size_t> next_copy{0};
+        fd_parallel(nt, [&](int) {
+            for (size_t k; (k = next_copy.fetch_add(1)) < to_copy.size();)
+                uniq[to_copy[k]] = std::make_shared<const fdh_compact>(*structs[to_copy[k]]);
+        });
+        for (int64_t u = 0; u < n_structs; u++)
+            if (owner[u] >= 0 && owner[u] != u) uniq[u] = uniq[owner[u]];
+    }
     std::vector<Query> out((size_t)n);
     std::vector<std::string> errs((size_t)n);
     std::vector<uint8_t> ok((size_t)n, 0);
-    int nt = threads > 0 ? threads : fd_default_host_threads();
-    nt = std::max(1, std::min<int>(nt, 64));
     std::atomic<int64_t> next{0};
     auto worker = [&] {
         for (int64_t k; (k = next.fetch_add(1)) < n;)

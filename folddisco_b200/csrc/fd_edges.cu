@@ -375,7 +375,7 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     for (uint32_t q = 0; q < nq; q++) {
         const fd_retrieval_query &Q = queries[q];
         if (Q.n_aa_dist > K4_MAX_AADIST)
-            return fd_fail(ctx, FD_ERR_LIMIT, "more than 512 observed query pairs; whole-structure queries are not supported in this version");
+            return fd_fail(ctx, FD_ERR_LIMIT, "more than 512 observed query pairs: verification of whole-structure queries is not available (search them with skip_match / --skip-match; count_query handles them)");
         RQDesc d{(uint32_t)f_hash.size(), Q.n_hashes, (uint32_t)f_aad.size(), Q.n_aa_dist, 0, 0,
                  Q.n_hashes <= PREFILTER_AA_SKIPPING_SIZE ? 1u : 0u};
         for (uint32_t k = 0; k < Q.n_hashes; k++) {

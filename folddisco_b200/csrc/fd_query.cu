@@ -1747,7 +1747,7 @@ int prepare_batch(fd_ctx *ctx, const fd_query *queries, uint32_t nq, const fd_pr
     if (B.max_hashes > K3_MAX_HASHES || B.max_edges > 32 * K3_MAX_EDGE_WORDS || B.max_nodes > K3_MAX_NODES)
         return fd_fail(ctx, FD_ERR_LIMIT,
                        "query too large for the shared-memory vote kernel (limits: 4095 hashes, 256 edges, 256 "
-                       "nodes per query); whole-structure queries are not supported in this version");
+                       "nodes per query); the dense / sparse vote exchange of hash-range shards has no wide path");
     B.narrow = B.max_hashes <= K3_MAX_HASHES_NARROW;
     B.ew = B.max_edges <= 32 ? 1 : (B.max_edges <= 64 ? 2 : (B.max_edges <= 128 ? 4 : 8));
     if (nq == 0 || N == 0) return FD_OK;
@@ -2159,6 +2159,389 @@ static int plan_scan_v3(fd_ctx *ctx, const Batch &B, ScanV3Plan &pl) {
     return FD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide queries (whole-structure queries: an empty -q makes every residue a query residue, query.rs:226-233; a
+// 300-residue chain has ~3 10^4 query edges and ~10^5 hashes).  Their vote state does not fit shared memory, so
+// count_query (count_query.rs:82-220) runs in global memory, organised like the reference itself -- by NODE GROUP
+// (the hashes whose edge starts at one query residue): all four fields are sums over the node groups, so the groups
+// are processed in chunks whose decoded postings fit a budget:
+//   k3w_count / k3w_decode   one thread per 64-byte granule of the chunk's posting lists (skip table -> any granule
+//                            decodes on its own): postings -> keys  nid << kbits | k   (k = position of the hash in
+//                            the query's (node, edge)-sorted hash order)
+//   radix sort of the keys over the bits in use, then ONE segmented reduction by nid whose values are computed on
+//   the fly from adjacent keys: {1, idf weight of k, first key of its (nid, edge), first key of its (nid, node)}
+//   k3w_accumulate           the chunk's per-structure sums into the dense accumulators (a structure appears once
+//                            per chunk: plain adds)
+//   k3w_emit                 length penalty, filter_before_matching, hit records; the usual top-n selection follows.
+// The idf sum is accumulated in 2^-32 fixed point (64 bits): independent of the summation order.
+// ------------------------------------------------------------------------------------------------
+struct WideAgg {
+    uint32_t match, edge, node, pad;
+    unsigned long long idf;
+};
+struct WideAggSum {
+    __host__ __device__ WideAgg operator()(const WideAgg &a, const WideAgg &b) const {
+        return WideAgg{a.match + b.match, a.edge + b.edge, a.node + b.node, 0u, a.idf + b.idf};
+    }
+};
+struct WideKeyNid { // sorted key -> structure id
+    const uint64_t *keys;
+    uint32_t kbits;
+    __host__ __device__ uint32_t operator()(uint64_t i) const { return (uint32_t)(keys[i] >> kbits); }
+};
+struct WideKeyValue { // sorted key -> the posting's contribution
+    const uint64_t *keys;
+    const uint32_t *edge_of_k, *node_of_k;
+    const unsigned long long *w_of_k;
+    uint32_t kbits;
+    __host__ __device__ WideAgg operator()(uint64_t i) const {
+        const uint64_t key = keys[i], kmask = (1ull << kbits) - 1ull;
+        const uint32_t k = (uint32_t)(key & kmask);
+        bool new_edge = true, new_node = true;
+        if (i > 0) {
+            const uint64_t prev = keys[i - 1];
+            if ((prev >> kbits) == (key >> kbits)) {
+                const uint32_t pk = (uint32_t)(prev & kmask);
+                new_edge = edge_of_k[pk] != edge_of_k[k];
+                new_node = node_of_k[pk] != node_of_k[k];
+            }
+        }
+        return WideAgg{1u, new_edge ? 1u : 0u, new_node ? 1u : 0u, 0u, w_of_k[k]};
+    }
+};
+
+__global__ void k3w_list_granules(const QHash *qh, uint32_t k0, uint32_t n, uint64_t *nseg) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const QHash h = qh[k0 + k];
+    nseg[k] = h.end > h.start ? ((h.end - 1) >> SKIP_SHIFT) - (h.start >> SKIP_SHIFT) + 1 : 0;
+}
+
+// the granule `item` of the chunk: its list and byte range; false if no varint starts in it
+__device__ __forceinline__ bool k3w_item(const IndexView &ix, const QHash *qh, uint32_t k0, const uint64_t *gprefix,
+                                         uint32_t n_lists, uint64_t item, uint32_t &k, uint64_t &gi, uint32_t &p0,
+                                         uint32_t &p1, uint32_t &id0) {
+    uint32_t x = 0, y = n_lists; // last list with gprefix[list] <= item
+    while (y - x > 1) {
+        const uint32_t m = (x + y) >> 1;
+        if (gprefix[m] <= item) x = m;
+        else y = m;
+    }
+    k = k0 + x;
+    const QHash h = qh[k];
+    const uint64_t g = item - gprefix[x];
+    gi = (h.start >> SKIP_SHIFT) + g;
+    const uint64_t G0 = gi << SKIP_SHIFT;
+    p0 = g == 0 ? (uint32_t)(h.start - G0) : ix.skip_off[gi];
+    id0 = g == 0 ? 0u : ix.skip_id[gi];
+    p1 = (uint32_t)min(h.end - G0, (uint64_t)SKIP_BYTES);
+    return p0 < p1;
+}
+
+// varints that start in [p0, p1) = 1 + terminators in [p0, p1 - 1)
+__global__ void k3w_count(IndexView ix, const QHash *qh, uint32_t k0, const uint64_t *gprefix, uint32_t n_lists,
+                          uint64_t n_items, uint64_t *counts) {
+    const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    uint32_t k, p0, p1, id0;
+    uint64_t gi;
+    uint64_t c = 0;
+    if (k3w_item(ix, qh, k0, gprefix, n_lists, item, k, gi, p0, p1, id0)) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ix.values + (gi << SKIP_SHIFT));
+        uint64_t term = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint4 v = src[j];
+            term |= (uint64_t)(term_mask4(v.x) | (term_mask4(v.y) << 4) | (term_mask4(v.z) << 8) | (term_mask4(v.w) << 12)) << (16 * j);
+        }
+        const uint64_t lo_mask = ~((1ull << p0) - 1ull);
+        const uint64_t hi_mask = p1 - 1 >= 64 ? ~0ull : ((1ull << (p1 - 1)) - 1ull);
+        c = 1 + __popcll(term & lo_mask & hi_mask);
+    }
+    counts[item] = c;
+}
+
+__global__ void k3w_decode(IndexView ix, const QHash *qh, uint32_t k0, const uint64_t *gprefix, uint32_t n_lists,
+                           uint64_t n_items, const uint64_t *out_pos, uint32_t kbits, uint32_t id_cap, uint64_t *keys) {
+    const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    uint32_t k, p0, p1, id;
+    uint64_t gi;
+    if (!k3w_item(ix, qh, k0, gprefix, n_lists, item, k, gi, p0, p1, id)) return;
+    const uint8_t *src = ix.values + (gi << SKIP_SHIFT);
+    uint64_t pos = out_pos[item];
+    uint32_t p = p0;
+    while (p < p1) { // a varint that starts before p1 may end in the bytes after it (the value array is padded)
+        uint32_t v = 0, shift = 0, byte;
+        do {
+            byte = src[p++];
+            v |= (byte & 0x7fu) << shift;
+            shift += 7;
+        } while (byte & 0x80u);
+        id += v;
+        keys[pos++] = ((uint64_t)min(id, id_cap) << kbits) | k; // ids beyond the lookup share one key prefix, skipped later
+    }
+}
+
+__global__ void k3w_accumulate(const uint32_t *nids, const WideAgg *agg, const uint32_t *n_runs, uint32_t n_structs,
+                               uint32_t *match, uint32_t *edges, uint32_t *nodes, unsigned long long *idf) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *n_runs) return;
+    const uint32_t nid = nids[r];
+    if (nid >= n_structs) return; // count_query.rs:133: ids beyond the lookup are skipped
+    const WideAgg a = agg[r];
+    match[nid] += a.match;
+    edges[nid] += a.edge;
+    nodes[nid] += a.node;
+    idf[nid] += a.idf;
+}
+
+__global__ void k3w_emit(const uint32_t *match, const uint32_t *edges, const uint32_t *nodes, const unsigned long long *idf,
+                         const float *pen_signed, uint32_t n_structs, FilterParams fp, uint32_t expected_node_count,
+                         HitRec *hits, unsigned int *n_hits) {
+    const uint32_t nid = blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    HitRec rec{0, 0, 0, 0.f};
+    if (nid < n_structs && match[nid] > 0) {
+        const float p = pen_signed[nid];
+        const float sum = (float)((double)idf[nid] * (1.0 / 4294967296.0));
+        const float v = sum * fabsf(p);
+        pass = (__float_as_uint(p) >> 31) == 0u;
+        if (fp.total_match_count > 0) pass = pass && match[nid] >= fp.total_match_count;
+        if (fp.idf_score_cutoff > 0.f) pass = pass && v >= fp.idf_score_cutoff;
+        if (fp.covered_node_count > 0) pass = pass && nodes[nid] >= fp.covered_node_count;
+        if (fp.covered_node_ratio > 0.f) pass = pass && (float)nodes[nid] / (float)expected_node_count >= fp.covered_node_ratio;
+        // HitRec packs node and edge counts in 16 bits each; wide queries report them through the side arrays
+        rec = HitRec{nid, match[nid], 0u, v};
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+        uint32_t pos = 0;
+        if ((threadIdx.x & 31) == 0) pos = atomicAdd(n_hits, (unsigned int)__popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
+        if (pass) hits[pos] = rec;
+    }
+}
+
+// count_query + filter + sort + top for ONE wide query; hits appended to `out` (idf descending, nid ascending)
+static int count_query_wide(fd_ctx *ctx, const fd_query &Q, const fd_prefilter_params *params, const uint32_t *gcounts,
+                            uint64_t g_structs, uint32_t id_offset, std::vector<fd_struct_hit> &out) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t N = (uint32_t)ctx->idx.n_structs;
+    if (Q.n_hashes == 0 || N == 0) return FD_OK;
+    if (!Q.hashes || !Q.edge_of_hash || (Q.n_edges && !Q.edge_node)) return fd_fail(ctx, FD_ERR_ARG, "fd_query: NULL array");
+    if (Q.edge_group) return fd_fail(ctx, FD_ERR_LIMIT, "edge groups (hash-range shards) are not supported for whole-structure queries");
+    for (uint32_t k = 0; k < Q.n_hashes; k++)
+        if (Q.edge_of_hash[k] >= Q.n_edges) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_of_hash out of range");
+    for (uint32_t e = 0; e < Q.n_edges; e++)
+        if (Q.edge_node[e] >= Q.n_nodes) return fd_fail(ctx, FD_ERR_ARG, "fd_query: edge_node out of range");
+    IndexView ix = make_view(ctx);
+    // hash order: by (node, edge), so that a structure's sorted keys list its edges and nodes in runs
+    std::vector<uint32_t> order(Q.n_hashes);
+    for (uint32_t k = 0; k < Q.n_hashes; k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const uint32_t ea = Q.edge_of_hash[a], eb = Q.edge_of_hash[b];
+        const uint32_t na = Q.edge_node[ea], nb = Q.edge_node[eb];
+        return na != nb ? na < nb : ea < eb;
+    });
+    std::vector<uint32_t> f_hash(Q.n_hashes), f_edge(Q.n_hashes), f_node(Q.n_hashes), f_gcount;
+    for (uint32_t k = 0; k < Q.n_hashes; k++) {
+        f_hash[k] = Q.hashes[order[k]];
+        f_edge[k] = Q.edge_of_hash[order[k]];
+        f_node[k] = Q.edge_node[f_edge[k]];
+    }
+    if (gcounts) {
+        f_gcount.resize(Q.n_hashes);
+        for (uint32_t k = 0; k < Q.n_hashes; k++) f_gcount[k] = gcounts[order[k]];
+    }
+    const uint32_t nh = Q.n_hashes;
+    DevBuf<uint32_t> d_hash, d_edge, d_node, d_gcount;
+    DevBuf<QHash> d_qh;
+    FD_CUDA(ctx, d_hash.alloc(nh));
+    FD_CUDA(ctx, d_edge.alloc(nh));
+    FD_CUDA(ctx, d_node.alloc(nh));
+    FD_CUDA(ctx, d_qh.alloc(nh));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_hash.p, f_hash.data(), nh * 4ull, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_edge.p, f_edge.data(), nh * 4ull, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_node.p, f_node.data(), nh * 4ull, cudaMemcpyHostToDevice, s));
+    if (gcounts) {
+        FD_CUDA(ctx, d_gcount.alloc(nh));
+        FD_CUDA(ctx, cudaMemcpyAsync(d_gcount.p, f_gcount.data(), nh * 4ull, cudaMemcpyHostToDevice, s));
+    }
+    std::vector<QHash> h_qh(nh);
+    {
+        StageTimer st(ctx, "lookup");
+        FD_LAUNCH(ctx, k3_lookup, fd_div_up(nh, 256), 256, 0, ix, d_hash.p, nh, params->freq_filter,
+                  gcounts ? d_gcount.p : (const uint32_t *)nullptr, (uint32_t)g_structs, d_qh.p);
+        FD_CUDA(ctx, cudaMemcpyAsync(h_qh.data(), d_qh.p, nh * sizeof(QHash), cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, st.finish());
+    }
+    // sample_query (count_query.rs:222-253): keep the rarest hashes (ties in the caller's hash order)
+    const bool has_r = params->sampling_ratio >= 0.f, has_c = params->sampling_count >= 0;
+    if (has_r != has_c) {
+        std::vector<uint32_t> cnt(nh);
+        if (gcounts) cnt = f_gcount;
+        else {
+            // list lengths irrespective of the frequency filter
+            DevBuf<uint32_t> d_cnt;
+            FD_CUDA(ctx, d_cnt.alloc(nh));
+            FD_LAUNCH(ctx, k3_counts_only, fd_div_up(nh, 256), 256, 0, ix, d_hash.p, (uint64_t)nh, d_cnt.p);
+            FD_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_cnt.p, nh * 4ull, cudaMemcpyDeviceToHost, s));
+            FD_CUDA(ctx, cudaStreamSynchronize(s));
+        }
+        std::vector<uint32_t> by_caller(nh); // position in the caller's order -> position in the (node, edge) order
+        for (uint32_t k = 0; k < nh; k++) by_caller[order[k]] = k;
+        std::vector<uint32_t> rank(nh);
+        for (uint32_t k = 0; k < nh; k++) rank[k] = by_caller[k];
+        std::stable_sort(rank.begin(), rank.end(), [&](uint32_t a, uint32_t b) { return cnt[a] < cnt[b]; });
+        const size_t keep = has_r ? (size_t)std::ceil(params->sampling_ratio * (float)nh) : (size_t)params->sampling_count;
+        std::vector<uint8_t> kept(nh, 0);
+        for (size_t k = 0; k < std::min<size_t>(keep, nh); k++) kept[rank[k]] = 1;
+        for (uint32_t k = 0; k < nh; k++)
+            if (!kept[k]) h_qh[k] = QHash{0, 0, 0, 0.f};
+        FD_CUDA(ctx, cudaMemcpyAsync(d_qh.p, h_qh.data(), nh * sizeof(QHash), cudaMemcpyHostToDevice, s));
+    }
+    // per-hash idf weights in 2^-32 fixed point; chunks of whole node groups within the key budget
+    std::vector<unsigned long long> f_w(nh);
+    uint64_t total_postings = 0, total_bytes = 0;
+    for (uint32_t k = 0; k < nh; k++) {
+        f_w[k] = h_qh[k].end > h_qh[k].start ? (unsigned long long)((double)std::max(h_qh[k].idf, 0.f) * 4294967296.0 + 0.5) : 0ull;
+        total_postings += h_qh[k].count;
+        total_bytes += h_qh[k].end - h_qh[k].start;
+    }
+    ctx->last_posting_bytes += total_bytes;
+    DevBuf<unsigned long long> d_w;
+    FD_CUDA(ctx, d_w.alloc(nh));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_w.p, f_w.data(), nh * 8ull, cudaMemcpyHostToDevice, s));
+    DevBuf<uint32_t> a_match, a_edge, a_node;
+    DevBuf<unsigned long long> a_idf;
+    FD_CUDA(ctx, a_match.alloc(N));
+    FD_CUDA(ctx, a_edge.alloc(N));
+    FD_CUDA(ctx, a_node.alloc(N));
+    FD_CUDA(ctx, a_idf.alloc(N));
+    FD_CUDA(ctx, cudaMemsetAsync(a_match.p, 0, N * 4ull, s));
+    FD_CUDA(ctx, cudaMemsetAsync(a_edge.p, 0, N * 4ull, s));
+    FD_CUDA(ctx, cudaMemsetAsync(a_node.p, 0, N * 4ull, s));
+    FD_CUDA(ctx, cudaMemsetAsync(a_idf.p, 0, N * 8ull, s));
+    uint64_t budget = 256ull << 20; // keys per chunk (2 x 8 B each)
+    if (const char *e = getenv("FD_K3W_CHUNK_KEYS")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+    uint32_t kbits = 1, nbits = 1;
+    while ((1ull << kbits) < nh) kbits++;
+    while ((1ull << nbits) < (uint64_t)N + 1) nbits++;
+    StageTimer st(ctx, "scan");
+    for (uint32_t k0 = 0; k0 < nh;) {
+        uint32_t k1 = k0;
+        uint64_t chunk_postings = 0;
+        while (k1 < nh) { // whole node groups
+            uint32_t k2 = k1;
+            uint64_t g = 0;
+            while (k2 < nh && f_node[k2] == f_node[k1]) g += h_qh[k2++].count;
+            if (k1 > k0 && chunk_postings + g > budget) break;
+            chunk_postings += g;
+            k1 = k2;
+        }
+        const uint32_t nl = k1 - k0;
+        if (chunk_postings) {
+            DevBuf<uint64_t> d_nseg, d_gprefix, d_counts, d_pos, d_keys, d_keys2;
+            DevBuf<uint8_t> d_tmp;
+            FD_CUDA(ctx, d_nseg.alloc(nl + 1));
+            FD_CUDA(ctx, d_gprefix.alloc(nl + 1));
+            FD_CUDA(ctx, cudaMemsetAsync(d_nseg.p + nl, 0, 8, s));
+            FD_LAUNCH(ctx, k3w_list_granules, fd_div_up(nl, 256), 256, 0, d_qh.p, k0, nl, d_nseg.p);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nseg.p, d_gprefix.p, nl + 1, s);
+            FD_CUDA(ctx, d_tmp.alloc(tb));
+            FD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_nseg.p, d_gprefix.p, nl + 1, s));
+            uint64_t n_items = 0;
+            FD_CUDA(ctx, cudaMemcpyAsync(&n_items, d_gprefix.p + nl, 8, cudaMemcpyDeviceToHost, s));
+            FD_CUDA(ctx, cudaStreamSynchronize(s));
+            FD_CUDA(ctx, d_counts.alloc(n_items + 1));
+            FD_CUDA(ctx, d_pos.alloc(n_items + 1));
+            FD_CUDA(ctx, cudaMemsetAsync(d_counts.p + n_items, 0, 8, s));
+            FD_LAUNCH(ctx, k3w_count, fd_div_up(n_items, 256), 256, 0, ix, d_qh.p, k0, d_gprefix.p, nl, n_items, d_counts.p);
+            size_t tb2 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_counts.p, d_pos.p, n_items + 1, s);
+            if (tb2 > d_tmp.n) FD_CUDA(ctx, d_tmp.alloc(tb2));
+            FD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(d_tmp.p, tb2, d_counts.p, d_pos.p, n_items + 1, s));
+            uint64_t n_keys = 0;
+            FD_CUDA(ctx, cudaMemcpyAsync(&n_keys, d_pos.p + n_items, 8, cudaMemcpyDeviceToHost, s));
+            FD_CUDA(ctx, cudaStreamSynchronize(s));
+            if (n_keys != chunk_postings) return fd_fail(ctx, FD_ERR_STATE, "wide count_query: posting count table disagrees with decode");
+            FD_CUDA(ctx, d_keys.alloc(n_keys));
+            FD_CUDA(ctx, d_keys2.alloc(n_keys));
+            FD_LAUNCH(ctx, k3w_decode, fd_div_up(n_items, 256), 256, 0, ix, d_qh.p, k0, d_gprefix.p, nl, n_items, d_pos.p,
+                      kbits, N, d_keys.p);
+            size_t tb3 = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, tb3, d_keys.p, d_keys2.p, n_keys, 0, (int)(kbits + nbits), s);
+            if (tb3 > d_tmp.n) FD_CUDA(ctx, d_tmp.alloc(tb3));
+            FD_CUDA(ctx, cub::DeviceRadixSort::SortKeys(d_tmp.p, tb3, d_keys.p, d_keys2.p, n_keys, 0, (int)(kbits + nbits), s));
+            ctx->launches += 10;
+            // segmented reduction by structure id
+            const uint64_t max_runs = std::min<uint64_t>(n_keys, (uint64_t)N + 1);
+            DevBuf<uint32_t> d_nids, d_nruns;
+            DevBuf<WideAgg> d_agg;
+            FD_CUDA(ctx, d_nids.alloc(max_runs));
+            FD_CUDA(ctx, d_agg.alloc(max_runs));
+            FD_CUDA(ctx, d_nruns.alloc(1));
+            cub::CountingInputIterator<uint64_t> idx(0);
+            cub::TransformInputIterator<uint32_t, WideKeyNid, cub::CountingInputIterator<uint64_t>> key_it(idx, WideKeyNid{d_keys2.p, kbits});
+            cub::TransformInputIterator<WideAgg, WideKeyValue, cub::CountingInputIterator<uint64_t>> val_it(
+                idx, WideKeyValue{d_keys2.p, d_edge.p, d_node.p, d_w.p, kbits});
+            size_t tb4 = 0;
+            cub::DeviceReduce::ReduceByKey(nullptr, tb4, key_it, d_nids.p, val_it, d_agg.p, d_nruns.p, WideAggSum(), n_keys, s);
+            if (tb4 > d_tmp.n) FD_CUDA(ctx, d_tmp.alloc(tb4));
+            FD_CUDA(ctx, cub::DeviceReduce::ReduceByKey(d_tmp.p, tb4, key_it, d_nids.p, val_it, d_agg.p, d_nruns.p, WideAggSum(), n_keys, s));
+            ctx->launches += 2;
+            FD_LAUNCH(ctx, k3w_accumulate, fd_div_up(max_runs, 256), 256, 0, d_nids.p, d_agg.p, d_nruns.p, N, a_match.p,
+                      a_edge.p, a_node.p, a_idf.p);
+            FD_CUDA(ctx, cudaStreamSynchronize(s)); // the chunk's buffers are released here
+        }
+        k0 = k1;
+    }
+    // length penalty + filters + hit records, then sort + top
+    const FilterParams fp = make_filter(params);
+    DevBuf<float> d_pen;
+    DevBuf<HitRec> d_hits;
+    DevBuf<unsigned int> d_nh;
+    FD_CUDA(ctx, d_pen.alloc(N));
+    FD_CUDA(ctx, d_hits.alloc(N));
+    FD_CUDA(ctx, d_nh.alloc(1));
+    FD_CUDA(ctx, cudaMemsetAsync(d_nh.p, 0, 4, s));
+    FD_LAUNCH(ctx, k3_length_penalty_signed, fd_div_up(N, 256), 256, 0, ix.nres, ix.plddt, N, fp.length_penalty,
+              fp.num_res_cutoff, fp.plddt_cutoff, d_pen.p);
+    FD_LAUNCH(ctx, k3w_emit, fd_div_up(N, 256), 256, 0, a_match.p, a_edge.p, a_node.p, a_idf.p, d_pen.p, N, fp,
+              Q.expected_node_count, d_hits.p, d_nh.p);
+    unsigned int n_hits = 0;
+    FD_CUDA(ctx, cudaMemcpyAsync(&n_hits, d_nh.p, 4, cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, st.finish());
+    if (n_hits == 0) return FD_OK;
+    // sort (idf descending, nid ascending) and keep top n; node / edge counts come from the dense accumulators
+    std::vector<HitRec> h_hits(n_hits);
+    std::vector<uint32_t> h_edge(N), h_node(N);
+    {
+        StageTimer st2(ctx, "select");
+        FD_CUDA(ctx, cudaMemcpyAsync(h_hits.data(), d_hits.p, (size_t)n_hits * sizeof(HitRec), cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, cudaMemcpyAsync(h_edge.data(), a_edge.p, N * 4ull, cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, cudaMemcpyAsync(h_node.data(), a_node.p, N * 4ull, cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, st2.finish());
+    }
+    const size_t keep_n = (size_t)std::min<uint64_t>(params->top_n, n_hits);
+    auto better = [](const HitRec &a, const HitRec &b) { return a.idf != b.idf ? a.idf > b.idf : a.nid < b.nid; };
+    if (keep_n < h_hits.size()) {
+        std::partial_sort(h_hits.begin(), h_hits.begin() + keep_n, h_hits.end(), better);
+        h_hits.resize(keep_n);
+    } else {
+        std::sort(h_hits.begin(), h_hits.end(), better);
+    }
+    for (const HitRec &r : h_hits)
+        out.push_back(fd_struct_hit{r.nid + id_offset, r.match_count, h_node[r.nid], h_edge[r.nid], r.idf});
+    return FD_OK;
+}
+
+static inline bool query_is_wide(const fd_query &Q) {
+    return Q.n_hashes > (uint32_t)K3_MAX_HASHES || Q.n_edges > 32u * K3_MAX_EDGE_WORDS || Q.n_nodes > (uint32_t)K3_MAX_NODES;
+}
+
 struct CountOpts {
     const uint32_t *gcounts = nullptr; // id-range shards: global posting count of every query hash (flattened, batch order)
     uint64_t g_structs = 0;            // and the structure count of the whole database
@@ -2173,6 +2556,54 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
     cudaStream_t s = ctx->stream;
     const uint32_t N = (uint32_t)ctx->idx.n_structs;
     ctx->last_posting_bytes = 0;
+    {
+        // whole-structure queries do not fit the shared-memory vote kernel: they take the global-memory path one by
+        // one, the rest of the batch the usual one; the rows are put back in the caller's order
+        std::vector<uint32_t> wide, small;
+        for (uint32_t q = 0; q < nq; q++) (query_is_wide(queries[q]) ? wide : small).push_back(q);
+        if (!wide.empty()) {
+            if (opts.slice_begin)
+                return fd_fail(ctx, FD_ERR_LIMIT, "whole-structure queries are not supported by the sharded search (use fd_count_query_batch_ex per shard)");
+            std::vector<size_t> gbase(nq + 1, 0);
+            for (uint32_t q = 0; q < nq; q++) gbase[q + 1] = gbase[q] + queries[q].n_hashes;
+            std::vector<std::vector<fd_struct_hit>> rows(nq);
+            uint64_t bytes = 0;
+            if (!small.empty()) {
+                std::vector<fd_query> sq;
+                std::vector<uint32_t> sg;
+                for (uint32_t q : small) {
+                    sq.push_back(queries[q]);
+                    if (opts.gcounts) sg.insert(sg.end(), opts.gcounts + gbase[q], opts.gcounts + gbase[q + 1]);
+                }
+                CountOpts so = opts;
+                so.gcounts = opts.gcounts ? sg.data() : nullptr;
+                fd_struct_hit *sh = nullptr;
+                uint64_t *soff = nullptr;
+                FD_TRY(count_query_impl(ctx, sq.data(), (uint32_t)sq.size(), params, so, &sh, &soff));
+                for (size_t k = 0; k < small.size(); k++) rows[small[k]].assign(sh + soff[k], sh + soff[k + 1]);
+                free(sh);
+                free(soff);
+                bytes = ctx->last_posting_bytes;
+            }
+            ctx->last_posting_bytes = bytes;
+            for (uint32_t q : wide)
+                FD_TRY(count_query_wide(ctx, queries[q], params, opts.gcounts ? opts.gcounts + gbase[q] : nullptr,
+                                        opts.g_structs, opts.id_offset, rows[q]));
+            uint64_t *h_off = (uint64_t *)calloc((size_t)nq + 1, 8);
+            if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+            for (uint32_t q = 0; q < nq; q++) h_off[q + 1] = h_off[q] + rows[q].size();
+            fd_struct_hit *h_hits = (fd_struct_hit *)malloc(std::max<uint64_t>(h_off[nq], 1) * sizeof(fd_struct_hit));
+            if (!h_hits) {
+                free(h_off);
+                return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
+            }
+            for (uint32_t q = 0; q < nq; q++)
+                if (!rows[q].empty()) memcpy(h_hits + h_off[q], rows[q].data(), rows[q].size() * sizeof(fd_struct_hit));
+            *out_hits = h_hits;
+            *out_offsets = h_off;
+            return FD_OK;
+        }
+    }
     Batch B;
     // id-range shards: the fixed-point scale of the idf sum must be the same on every rank -> bound from the global
     // list lengths (k3_query_sums sums the idf of all query hashes, present locally or not)

@@ -570,8 +570,6 @@ struct WarpState { // per-warp shared memory
     uint32_t counts[V_MAX_NQ * V_MAX_NODES / 2]; // votes[q][node], two 16-bit counters per word
     float e_idf[V_MAX_E];
     uint8_t best_c[V_MAX_NQ], best_r[V_MAX_NQ];
-    VAad aad[V_MAX_AAD];
-    uint16_t aa_range[400];
     uint16_t aa_dir[FD_AA_DIR + 2]; // the candidate's amino-acid directory (FdDeviceStore::aa_dir)
     uint32_t dq_aa1[V_MAX_NQ]; // amino acids (bit set) that carry an entry of query residue dq: rows of the rescue scan
     uint32_t n_nodes, n_comp, s_flag;
@@ -587,7 +585,8 @@ struct WarpState { // per-warp shared memory
 };
 
 __global__ void __launch_bounds__(VB_WARPS * 32)
-    k6b_components(StoreView st, const VQDesc *vq, const VHash *vhash, const VAad *vaad, const uint8_t *idx_dense,
+    k6b_components(StoreView st, const VQDesc *vq, const VHash *vhash, const VAad *vaad, const uint16_t *aa_ranges,
+                   const uint8_t *idx_dense,
                    const uint32_t *cand_query, const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp,
                    float ca_cutoff, int skip_ca_match, const uint32_t *pool_key, const uint16_t *pool_ent,
                    const uint32_t *cand_ebegin, const uint32_t *cand_ne, CompSpec *specs, unsigned int *spec_count,
@@ -613,7 +612,11 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
         W.e_ent[k] = ent;
         W.e_idf[k] = H[ent].idf;
     }
-    load_aad_phase1<32>(Q, vaad, W.aad, W.aa_range, lane);
+    // the query's (amino-acid pair -> CA distances) table stays in global memory (read-only, L1-resident: the four
+    // candidates of a CTA usually belong to the same query); a per-warp copy cost 2.8 KB of the 9.4 KB that limited
+    // the kernel to 24 warps per SM
+    const VAad *AAD = vaad + Q.aad_begin;
+    const uint16_t *AAR = aa_ranges + (size_t)cand_query[c] * 400u;
     if (lane == 0) {
         W.s_flag = 0;
         W.n_comp = 0;
@@ -621,14 +624,13 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     if (lane < V_MAX_NQ) W.dq_aa1[lane] = 0;
     for (uint32_t b = lane; b < FD_AA_DIR; b += 32) W.aa_dir[b] = st.aa_dir[(uint64_t)t * FD_AA_DIR + b];
     __syncwarp();
-    load_aad_phase2<32>(Q, W.aad, W.aa_range, lane);
     for (uint32_t k = lane; k < Q.n_aad; k += 32)
-        if (W.aad[k].dq < V_MAX_NQ) atomicOr(&W.dq_aa1[W.aad[k].dq], 1u << (W.aad[k].aa1 & 31u));
+        if (AAD[k].dq < V_MAX_NQ) atomicOr(&W.dq_aa1[AAD[k].dq], 1u << (AAD[k].aa1 & 31u));
     // range of the query's CA distances: a pair outside it cannot support a rescue
     float dmax = 0.f, dmin = 3.0e38f;
     for (uint32_t k = lane; k < Q.n_aad; k += 32) {
-        dmax = fmaxf(dmax, W.aad[k].dist);
-        dmin = fminf(dmin, W.aad[k].dist);
+        dmax = fmaxf(dmax, AAD[k].dist);
+        dmin = fminf(dmin, AAD[k].dist);
     }
     for (int o = 16; o > 0; o >>= 1) {
         dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
@@ -921,14 +923,14 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                     for (uint32_t k = 0; k < W.r_nridx; k++) {
                         const uint32_t aj = W.r_aa[k];
                         if (aj == 0xffu || W.r_ridx[k] == i) continue;
-                        const uint32_t rg = W.aa_range[cia + aj];
+                        const uint32_t rg = AAR[cia + aj];
                         if (rg == 0) continue;
                         const float d2 = fdg::dist2(cai, fdg::V3{W.r_x[k], W.r_y[k], W.r_z[k]});
                         if (d2 > pre_hi2 || d2 < pre_lo2) continue;
                         const float d = FD_SQRT(d2); // == fdg::dist
                         if (!(d <= hp.dist_cutoff)) continue;
                         for (uint32_t e = rg >> 8, ee = (rg >> 8) + (rg & 0xffu); e < ee; e++)
-                            if (W.aad[e].dq == dq && fabsf(d - W.aad[e].dist) < ca_cutoff) cnt++;
+                            if (AAD[e].dq == dq && fabsf(d - AAD[e].dist) < ca_cutoff) cnt++;
                     }
                     return cnt;
                 };
@@ -1055,6 +1057,7 @@ struct fd_verify_prepared {
     VQDesc *d_desc = nullptr;
     VHash *d_hash = nullptr;
     VAad *d_aad = nullptr;
+    uint16_t *d_aar = nullptr; // [nq][400] run of every amino-acid pair in d_aad: start << 8 | count (0 = pair not in the query)
     uint8_t *d_idx = nullptr;
     float *d_qca = nullptr, *d_qcb = nullptr;
     uint64_t h2d_bytes = 0;
@@ -1063,7 +1066,7 @@ struct fd_verify_prepared {
 static void verify_prepared_release(fd_verify_prepared *P) {
     if (!P) return;
     cudaSetDevice(P->device);
-    void *ptrs[6] = {P->d_desc, P->d_hash, P->d_aad, P->d_idx, P->d_qca, P->d_qcb};
+    void *ptrs[7] = {P->d_desc, P->d_hash, P->d_aad, P->d_idx, P->d_qca, P->d_qcb, P->d_aar};
     // cudaFree, not cudaFreeAsync: the tables may outlive the context (and stream) that uploaded them
     for (void *q : ptrs)
         if (q) cudaFree(q);
@@ -1165,6 +1168,7 @@ static int verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t 
     if (n_fh > 0xffffffffull || n_fr > 0xffffffffull) return fd_fail(ctx, FD_ERR_LIMIT, "query batch too large");
     std::vector<VHash> f_hash(n_fh);
     std::vector<VAad> f_aad(n_fa);
+    std::vector<uint16_t> f_aar((size_t)nq * 400, 0);
     std::vector<uint8_t> f_idx(n_fi);
     std::vector<float> q_ca(3 * n_fr), q_cb(3 * n_fr);
     // pass 2: fill
@@ -1192,6 +1196,8 @@ static int verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t 
                 start[Q.aa1[k] * 20u + Q.aa2[k] + 1]++;
             }
             for (int k = 0; k < 400; k++) start[k + 1] += start[k];
+            for (int k = 0; k < 400; k++) // at most V_MAX_AAD = 255 entries per query: start and count fit 8 bits each
+                if (start[k + 1] > start[k]) f_aar[(size_t)q * 400 + k] = (uint16_t)((start[k] << 8) | (start[k + 1] - start[k]));
             for (uint32_t k = 0; k < Q.n_aa_dist; k++)
                 f_aad[d.aad_begin + start[Q.aa1[k] * 20u + Q.aa2[k]]++] =
                     VAad{Q.aa1[k], Q.aa2[k], dense(Q.q_index[k]), 0, Q.ca_dist[k]};
@@ -1222,6 +1228,7 @@ static int verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t 
     cudaError_t e = up((void **)&P->d_desc, descs.data(), nq * sizeof(VQDesc));
     if (e == cudaSuccess) e = up((void **)&P->d_hash, f_hash.data(), f_hash.size() * sizeof(VHash));
     if (e == cudaSuccess) e = up((void **)&P->d_aad, f_aad.data(), f_aad.size() * sizeof(VAad));
+    if (e == cudaSuccess) e = up((void **)&P->d_aar, f_aar.data(), f_aar.size() * sizeof(uint16_t));
     if (e == cudaSuccess) e = up((void **)&P->d_idx, f_idx.data(), f_idx.size());
     if (e == cudaSuccess) e = up((void **)&P->d_qca, q_ca.data(), q_ca.size() * 4);
     if (e == cudaSuccess) e = up((void **)&P->d_qcb, q_cb.data(), q_cb.size() * 4);
@@ -1397,7 +1404,7 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
                          d_flags.p + C.c0);
         FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 1), st));
         FD_LAUNCH_ON(ctx, st, k6b_components, fd_div_up(C.n, VB_WARPS), VB_WARPS * 32, smem_b, sv, P->d_desc, P->d_hash,
-                     P->d_aad, P->d_idx, d_cq.p + C.c0, d_cn.p + C.c0, n32, hp, ca_dist_cutoff, skip_ca_match,
+                     P->d_aad, P->d_aar, P->d_idx, d_cq.p + C.c0, d_cn.p + C.c0, n32, hp, ca_dist_cutoff, skip_ca_match,
                      C.pool_key.p, C.pool_ent.p, d_ebegin.p + C.c0, d_ne.p + C.c0, C.specs.p, C.counters.p + 1,
                      (uint32_t)std::min<uint64_t>(C.spec_cap, 0xffffffffu), C.ncomp.p, d_flags.p + C.c0);
         FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 2), st));

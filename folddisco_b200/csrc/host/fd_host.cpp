@@ -1569,14 +1569,19 @@ static bool prepare_query(const fdh_queries *qs, std::shared_ptr<const fdh_compa
         return false;
     }
     if (pq.chains.empty()) {
-        err = "whole-structure queries (empty query string) are not supported in this version";
-        return false;
+        // an empty query string makes every residue of the structure a query residue (query.rs:226-233)
+        for (size_t i = 0; i < st->nres(); i++) {
+            pq.chains.push_back(st->chain[i]);
+            pq.serials.push_back(st->serial[i]);
+            pq.has_sub.push_back(0);
+            pq.subs.emplace_back();
+        }
     }
     Q.st = std::move(st);
     Q.qstring = query_string;
     Q.residue_count = (uint32_t)pq.chains.size();
     if (!build_query_map(Q, pq, *qs)) {
-        err = "query has too many edges";
+        err = "query has more than 65535 edges (residue pairs with a feature); whole-structure queries are limited to chains of a few hundred residues";
         return false;
     }
     return true;

@@ -477,3 +477,47 @@ def test_pair_table_verification_equals_rehash(env):
     assert rows(host.search(ctx, qb, sp, labels=store)) == base
     assert store.attach(ctx, pair_table=True, hash_params=ix.params, max_table_bytes=1000) is None
     assert rows(host.search(ctx, qb, sp, labels=store)) == base
+
+
+def test_whole_structure_query_skip_match(env):
+    """an empty query string (query.rs:226-233: every residue) through the host API with skip_match: the query map,
+    the per-structure rows and their order equal the oracle's; mixed in one batch with a motif query.  Verification of
+    whole-structure queries is refused with a message (not silently skipped)."""
+    from folddisco_b200 import synth
+    host, ctx, fd = env["host"], env["ctx"], env["fd"]
+    n_structs = 900
+    b = synth.generate(n_structs, 9, mean_len=150.0, max_len=500)
+    store = host.Store()
+    store.add_soa(b)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    store.attach(ctx)
+    bufs = ix.buffers()
+    oix = O.Index.from_buffers(bufs.hashes, bufs.offsets, bufs.values)
+    nres, plddt = ix.lookup()
+    a = env["atoms"]["query/1G2F.pdb"]
+    qb = host.QueryBatch(ix.params)
+    qb.add(host.CompactStructure.from_atoms(a), "")
+    qb.add(host.CompactStructure.from_atoms(env["atoms"]["query/4CHA.pdb"]), "B57,B102,C195")
+    qb.finalize(ctx)
+    s = O.Structure.from_atoms(a)
+    om = O.QueryMap(s.compact(), *O.parse_query_string("", s.first_chain), index=oix, total_structures=n_structs)
+    gm, wm = qb.query_map(0), om.entries()
+    assert len(gm["hash"]) == len(wm["hash"]) > 4095
+    assert np.array_equal(gm["hash"], wm["hash"]) and np.array_equal(gm["qi"], wm["qi"]) and np.array_equal(gm["qj"], wm["qj"])
+    res = host.search(ctx, qb, host.SearchParams(top_n=50, skip_match=True), labels=store)
+    op = O.CountParams.defaults(len(om.indices()), top_n=50)
+    want = O.count_query(om, oix, nres.astype(np.uint64), plddt, op)
+    rows = res.structures(0)
+    assert len(rows) == len(want["nid"]) == 50
+    w = {int(n): (int(m), int(nc), int(ec), float(i)) for n, m, nc, ec, i in
+         zip(want["nid"], want["match_count"], want["node_count"], want["edge_count"], want["idf"])}
+    common = [r for r in rows if int(r["nid"]) in w]
+    assert len(common) >= 45  # the cut may fall inside a group of near-equal idf
+    for r in common:
+        g = (int(r["total_match_count"]), int(r["node_count"]), int(r["edge_count"]))
+        assert g == w[int(r["nid"])][:3]
+        assert abs(float(r["idf"]) - w[int(r["nid"])][3]) <= 1e-4 * max(1.0, w[int(r["nid"])][3])
+    assert len(res.structures(1)) > 0
+    with pytest.raises(fd.FdError, match="whole-structure"):
+        host.search(ctx, qb, host.SearchParams(top_n=5), labels=store)

@@ -320,6 +320,55 @@ def test_count_query_synthetic(ctx, n_structs, seed, kw):
     assert len(ctx.count_query_batch([none])[0]) == 0
 
 
+def test_count_query_whole_structure(ctx):
+    """whole-structure queries (empty query string: every residue is a query residue, query.rs:226-233) take the
+    global-memory count_query path: thousands of edges, ~10^4-10^5 hashes.  Rows == oracle for the whole chain of
+    1G2F and a ~200-residue synthetic chain, alone, chunked by node group (tiny key budget), mixed with motif-sized
+    queries in one batch, and with filters / top-n / sampling."""
+    import folddisco_b200 as fd
+    n_structs = 1500
+    env = _attach_synth(ctx, n_structs, 31)
+    oix, nres, plddt = env["oix"], env["nres"], env["plddt"]
+    atoms = F.config1_atoms()
+    s = O.Structure.from_atoms(atoms["query/1G2F.pdb"])
+    big = max(range(n_structs), key=lambda i: env["comps"][i].nres if env["comps"][i].nres <= 220 else 0)
+    whole = [O.QueryMap(s.compact(), *O.parse_query_string("", s.first_chain), index=oix, total_structures=n_structs),
+             O.QueryMap(env["comps"][big], *O.parse_query_string("", ord("A")), index=oix, total_structures=n_structs)]
+    for qm in whole:
+        assert len(qm.entries()["hash"]) > 4095 and len(qm.indices()) > 100
+    small = _motif_qmaps(oix, n_structs)[:2]
+    queries = [_query_inputs(qm) for qm in whole]
+    got = ctx.count_query_batch(queries)
+    want = [O.count_query(qm, oix, nres, plddt) for qm in whole]
+    for g, w in zip(got, want):
+        assert len(g) > 100
+        _compare_hits(g, w)
+    os.environ["FD_K3W_CHUNK_KEYS"] = "20000"  # many chunks of a few node groups each
+    try:
+        got_chunked = ctx.count_query_batch(queries)
+    finally:
+        del os.environ["FD_K3W_CHUNK_KEYS"]
+    for g, g2 in zip(got, got_chunked):
+        assert np.array_equal(g, g2)
+    # mixed batch: rows come back in the caller's order
+    mixed = [_query_inputs(small[0]), queries[0], _query_inputs(small[1]), queries[1]]
+    got_m = ctx.count_query_batch(mixed)
+    assert np.array_equal(got_m[1], got[0]) and np.array_equal(got_m[3], got[1])
+    for qm, g in zip(small, (got_m[0], got_m[2])):
+        _compare_hits(g, O.count_query(qm, oix, nres, plddt))
+    # filters + top-n, then sampling of the rarest hashes
+    p = fd.PrefilterParams(top_n=30, length_penalty=0.3, total_match_count=3, covered_node_count=2,
+                           covered_node_ratio=0.02, idf_score_cutoff=0.01, num_res_cutoff=300, plddt_cutoff=0.0)
+    for qm, g in zip(whole, ctx.count_query_batch(queries, p)):
+        op = O.CountParams(-1.0, -1, -1.0, 0.3, 3, 2, 0.02, 0.01, 300, 0.0, len(qm.indices()), 30, 1)
+        _compare_hits(g, O.count_query(qm, oix, nres, plddt, op), top_n=30)
+    p = fd.PrefilterParams(sampling_ratio=0.25)
+    for qm, g in zip(whole[:1], ctx.count_query_batch(queries[:1], p)):
+        op = O.CountParams.defaults(len(qm.indices()))
+        op.sampling_ratio = 0.25
+        _compare_hits(g, O.count_query(qm, oix, nres, plddt, op))
+
+
 @pytest.mark.parametrize("env", [dict(FD_K3_CTAS="4", FD_K3_THREADS="128"), dict(FD_K3_CTAS="1", FD_K3_THREADS="512"),
                                  dict(FD_K3_CTAS="3", FD_K3_THREADS="256", FD_K3_LIMIT="0"), dict(FD_K3_V1="1")])
 def test_scan_v2_variants(ctx, env):

@@ -87,7 +87,8 @@ def test_query_map_matches_oracle(host, dist_thr, angle_thr):
     """make_query_map: same hashes, same edge per hash, same insertion order as the oracle (idf needs the GPU)."""
     atoms = F.config1_atoms()
     qb = host.QueryBatch(dist_thr=dist_thr, angle_thr=angle_thr)
-    cases = list(F.MOTIFS) + [("query/4CHA.pdb", "B57:X,B102,C195:ST", None), ("query/4CHA.pdb", "B57,B57,Z9,C195", None)]
+    cases = list(F.MOTIFS) + [("query/4CHA.pdb", "B57:X,B102,C195:ST", None), ("query/4CHA.pdb", "B57,B57,Z9,C195", None),
+                              ("query/1G2F.pdb", "", None)]  # empty query string = every residue (query.rs:226-233)
     for path, q, _ in cases:
         qb.add(host.CompactStructure.from_atoms(atoms[path]), q)
     for k, (path, q, want_n) in enumerate(cases):

@@ -558,6 +558,11 @@ __global__ void __launch_bounds__(VT_WARPS * 32)
     }
 }
 
+__global__ void k6_iota(uint32_t *out, uint32_t n) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = k;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k6b: components, residue mapping, rescue -- one warp per candidate
 // ------------------------------------------------------------------------------------------------
@@ -590,12 +595,15 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                    const uint32_t *cand_query, const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp,
                    float ca_cutoff, int skip_ca_match, const uint32_t *pool_key, const uint16_t *pool_ent,
                    const uint32_t *cand_ebegin, const uint32_t *cand_ne, CompSpec *specs, unsigned int *spec_count,
-                   uint32_t spec_cap, uint32_t *cand_ncomp, uint8_t *cand_flags) {
+                   uint32_t spec_cap, uint32_t *cand_ncomp, uint8_t *cand_flags, const uint32_t *order) {
     extern __shared__ __align__(16) unsigned char k6b_smem[];
     const int lane = threadIdx.x & 31;
     WarpState &W = reinterpret_cast<WarpState *>(k6b_smem)[threadIdx.x >> 5];
-    const uint32_t c = blockIdx.x * VB_WARPS + (threadIdx.x >> 5);
-    if (c >= n_cand) return;
+    const uint32_t slot = blockIdx.x * VB_WARPS + (threadIdx.x >> 5);
+    if (slot >= n_cand) return;
+    // candidates are taken in descending order of their edge count (longest first: a candidate with dozens of
+    // components that started last kept one SM busy for half of the launch, profiles/r03h_ncu_k6.txt)
+    const uint32_t c = order ? order[slot] : slot;
     const uint32_t ne_word = cand_ne[c];
     const uint32_t ne = ne_word & 0x7fffffffu;
     if (ne == 0) return;
@@ -1319,7 +1327,8 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         DevBuf<unsigned int> counters; // [0] edge pool, [1] component specs
         DevBuf<CompSpec> specs;
         DevBuf<fd_match_record> out;
-        DevBuf<uint8_t> tmp;
+        DevBuf<uint8_t> tmp, sort_tmp;
+        DevBuf<uint32_t> order, ne_sorted; // candidates in descending order of their edge count
         unsigned int *h_counters = nullptr; // pinned
         uint32_t *h_first_rel = nullptr;    // pinned, n + 1
         uint64_t rec_base = 0;
@@ -1353,6 +1362,8 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
                            !(getenv("FD_VERIFY_TABLE") && atoi(getenv("FD_VERIFY_TABLE")) == 0);
     const PairTableView ptv{PT.offsets, PT.hash, PT.ij, PT.dir};
     const size_t smem_b = sizeof(WarpState) * VB_WARPS;
+    const bool lpt = !(getenv("FD_VERIFY_LPT") && atoi(getenv("FD_VERIFY_LPT")) == 0);
+    uint64_t max_chunk = 0;
     FD_CUDA(ctx, cudaFuncSetAttribute(k6b_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     for (uint32_t k = 0; k < n_chunks; k++) {
         Chunk &C = chunks[k];
@@ -1369,6 +1380,19 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, C.ncomp.p, C.first.p, C.n + 1, s0);
         FD_CUDA(ctx, C.tmp.alloc(tb));
+        if (lpt) {
+            FD_CUDA(ctx, C.order.alloc(C.n + 1));
+            FD_CUDA(ctx, C.ne_sorted.alloc(C.n + 1));
+            size_t tbs = 0;
+            cub::DeviceRadixSort::SortPairsDescending(nullptr, tbs, d_ne.p, C.ne_sorted.p, C.order.p, C.order.p, (int)C.n, 0, 9, s0);
+            FD_CUDA(ctx, C.sort_tmp.alloc(tbs));
+            max_chunk = std::max<uint64_t>(max_chunk, C.n);
+        }
+    }
+    DevBuf<uint32_t> d_iota;
+    if (lpt) {
+        FD_CUDA(ctx, d_iota.alloc(max_chunk + 1));
+        FD_LAUNCH_ON(ctx, s0, k6_iota, fd_div_up(max_chunk, 256), 256, 0, d_iota.p, (uint32_t)max_chunk);
     }
     // allocations and uploads were ordered on s0: the other streams start after them
     cudaEvent_t ev_begin = event_at(5 * n_chunks), ev_end = event_at(5 * n_chunks + 1), ev_tmp = event_at(5 * n_chunks + 2);
@@ -1403,10 +1427,17 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
                          (uint32_t)std::min<uint64_t>(C.pool_cap, 0xffffffffu), d_ebegin.p + C.c0, d_ne.p + C.c0,
                          d_flags.p + C.c0);
         FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 1), st));
+        if (lpt) { // edge counts are at most V_MAX_E = 256 (bit 31 = pair-domain flag): nine key bits
+            size_t tbs = C.sort_tmp.n;
+            FD_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(C.sort_tmp.p, tbs, d_ne.p + C.c0, C.ne_sorted.p, d_iota.p,
+                                                                   C.order.p, (int)n32, 0, 9, st));
+            ctx->launches += 2;
+        }
         FD_LAUNCH_ON(ctx, st, k6b_components, fd_div_up(C.n, VB_WARPS), VB_WARPS * 32, smem_b, sv, P->d_desc, P->d_hash,
                      P->d_aad, P->d_aar, P->d_idx, d_cq.p + C.c0, d_cn.p + C.c0, n32, hp, ca_dist_cutoff, skip_ca_match,
                      C.pool_key.p, C.pool_ent.p, d_ebegin.p + C.c0, d_ne.p + C.c0, C.specs.p, C.counters.p + 1,
-                     (uint32_t)std::min<uint64_t>(C.spec_cap, 0xffffffffu), C.ncomp.p, d_flags.p + C.c0);
+                     (uint32_t)std::min<uint64_t>(C.spec_cap, 0xffffffffu), C.ncomp.p, d_flags.p + C.c0,
+                     lpt ? C.order.p : (const uint32_t *)nullptr);
         FD_CUDA(ctx, cudaEventRecord(event_at(5 * k + 2), st));
         size_t tb = C.tmp.n;
         FD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(C.tmp.p, tb, C.ncomp.p, C.first.p, C.n + 1, st));

@@ -352,7 +352,8 @@ def run_ours(args, rank, world, local_rank):
     sp = host.SearchParams(top_n=args.top)
     stages = ("lookup", "scan", "select", "exchange", "merge", "verify", "verify_edges", "verify_components",
               "verify_kabsch", "edges", "kabsch")
-    hv = ("hv_flatten", "hv_upload", "hv_candidates", "hv_issue", "hv_wait_chunks", "hv_copy_tail")
+    hv = ("hv_flatten", "hv_upload", "hv_candidates", "hv_issue", "hv_wait_chunks", "hv_copy_tail", "cq_host_prepare",
+          "cq_host_rest")
     prep_ms = {"query_maps": 0.0, "finalize": 0.0, "calls": 0}  # host wall clock of the e2e-only part of a step
 
     inputs = query_inputs(db, args.batch, rank * args.batch)  # host structures + query strings: the step's inputs
@@ -467,7 +468,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "stages_ms_per_step": {s: st1[s][0] / steps for s in stages},
         "host_ms_per_step": res.host_ms, "search_wall_ms": res.wall_ms,
-        "verify_host_wall_ms": {s[3:]: st1[s][0] / steps for s in hv},
+        "verify_host_wall_ms": {s[3:]: st1[s][0] / steps for s in hv if s.startswith("hv_")},
+        "count_query_host_wall_ms": {s[8:]: st1[s][0] / steps for s in hv if s.startswith("cq_host_")},
         "e2e_prepare_host_ms": {"query_maps (make_query_map x batch)": prep_ms["query_maps"] / max(1, prep_ms["calls"]),
                                 "finalize (posting counts -> idf, verification tables -> device)":
                                     prep_ms["finalize"] / max(1, prep_ms["calls"])},

@@ -108,6 +108,7 @@ struct fd_ctx {
     cudaEvent_t ev_extra[4] = {nullptr, nullptr, nullptr, nullptr}; // finer stage timing inside one call
     cudaStream_t aux_stream[2] = {nullptr, nullptr}; // second compute stream + copy stream of the chunked verification
     std::vector<cudaEvent_t> ev_pool;                // events of the chunked verification, created on demand
+    double verify_edges_per_cand = 0.0, verify_comps_per_cand = 0.0; // pool sizing of the chunked verification
     uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
     uint64_t votes_cap = 0;    // capacity in u32 words
     uint32_t *merge = nullptr; // dense vote planes of this rank's slice of the batch (sparse merge), owned

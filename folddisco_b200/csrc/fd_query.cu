@@ -2607,7 +2607,11 @@ static int count_query_impl(fd_ctx *ctx, const fd_query *queries, uint32_t nq, c
     Batch B;
     // id-range shards: the fixed-point scale of the idf sum must be the same on every rank -> bound from the global
     // list lengths (k3_query_sums sums the idf of all query hashes, present locally or not)
-    FD_TRY(prepare_batch(ctx, queries, nq, params, true, 0, B, opts.gcounts, opts.g_structs));
+    {
+        HostTimer ht(ctx, "cq_host_prepare"); // flatten + upload + lookup (includes the lookup kernels' wait)
+        FD_TRY(prepare_batch(ctx, queries, nq, params, true, 0, B, opts.gcounts, opts.g_structs));
+    }
+    HostTimer ht_rest(ctx, "cq_host_rest"); // work items, pools, scan, select, exchange, copies
     uint64_t *h_off = (uint64_t *)calloc((size_t)nq + 1, 8);
     if (!h_off) return fd_fail(ctx, FD_ERR_NOMEM, "host allocation failed");
     if (opts.slice_begin && (nq == 0 || N == 0 || B.f_hash.empty())) {

@@ -578,6 +578,8 @@ struct WarpState { // per-warp shared memory
     uint16_t aa_dir[FD_AA_DIR + 2]; // the candidate's amino-acid directory (FdDeviceStore::aa_dir)
     uint32_t dq_aa1[V_MAX_NQ]; // amino acids (bit set) that carry an entry of query residue dq: rows of the rescue scan
     uint32_t n_nodes, n_comp, s_flag;
+    uint32_t cand, ne_word; // the warp's own candidate and its edge-count word (owner state, like the arrays above)
+    float pre_hi2, pre_lo2; // squared CA-distance window outside which a pair cannot support a rescue (owner state)
     uint32_t r_dq, r_need, r_nridx, s_out_base;
     uint16_t r_ridx[V_MAX_NQ];
     float r_x[V_MAX_NQ], r_y[V_MAX_NQ], r_z[V_MAX_NQ]; // CA of the matched target residues (rescue)
@@ -597,21 +599,29 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                    const uint32_t *cand_ebegin, const uint32_t *cand_ne, CompSpec *specs, unsigned int *spec_count,
                    uint32_t spec_cap, uint32_t *cand_ncomp, uint8_t *cand_flags, const uint32_t *order) {
     extern __shared__ __align__(16) unsigned char k6b_smem[];
-    const int lane = threadIdx.x & 31;
-    WarpState &W = reinterpret_cast<WarpState *>(k6b_smem)[threadIdx.x >> 5];
-    const uint32_t slot = blockIdx.x * VB_WARPS + (threadIdx.x >> 5);
-    if (slot >= n_cand) return;
+    __shared__ uint32_t s_next; // next (candidate, component) work item of the CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpState *states = reinterpret_cast<WarpState *>(k6b_smem);
+    WarpState &W = states[warp];
+    if (threadIdx.x == 0) s_next = 0;
+    // ---- phase 1: every warp builds the graph of its own candidate (edges, node numbering, component masks) ----
+    const uint32_t slot = blockIdx.x * VB_WARPS + warp;
     // candidates are taken in descending order of their edge count (longest first: a candidate with dozens of
     // components that started last kept one SM busy for half of the launch, profiles/r03h_ncu_k6.txt)
-    const uint32_t c = order ? order[slot] : slot;
-    const uint32_t ne_word = cand_ne[c];
-    const uint32_t ne = ne_word & 0x7fffffffu;
-    if (ne == 0) return;
-    const bool all_pairs = (ne_word >> 31) != 0;
+    const uint32_t c_own = slot < n_cand ? (order ? order[slot] : slot) : 0u;
+    const uint32_t ne_word_own = slot < n_cand ? cand_ne[c_own] : 0u;
+    if (lane == 0) {
+        W.s_flag = 0;
+        W.n_comp = 0;
+        W.cand = c_own;
+        W.ne_word = ne_word_own;
+    }
+    __syncwarp();
+    if ((ne_word_own & 0x7fffffffu) != 0) {
+    const uint32_t c = c_own;
+    const uint32_t ne = ne_word_own & 0x7fffffffu;
     const VQDesc Q = vq[cand_query[c]];
     const uint32_t t = cand_nid[c];
-    const uint64_t base = st.row_offsets[t];
-    const uint32_t n = (uint32_t)(st.row_offsets[t + 1] - base);
     const VHash *H = vhash + Q.hash_begin;
     const uint32_t eb = cand_ebegin[c];
     for (uint32_t k = lane; k < ne; k += 32) {
@@ -620,32 +630,28 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
         W.e_ent[k] = ent;
         W.e_idf[k] = H[ent].idf;
     }
-    // the query's (amino-acid pair -> CA distances) table stays in global memory (read-only, L1-resident: the four
-    // candidates of a CTA usually belong to the same query); a per-warp copy cost 2.8 KB of the 9.4 KB that limited
-    // the kernel to 24 warps per SM
     const VAad *AAD = vaad + Q.aad_begin;
-    const uint16_t *AAR = aa_ranges + (size_t)cand_query[c] * 400u;
-    if (lane == 0) {
-        W.s_flag = 0;
-        W.n_comp = 0;
-    }
     if (lane < V_MAX_NQ) W.dq_aa1[lane] = 0;
     for (uint32_t b = lane; b < FD_AA_DIR; b += 32) W.aa_dir[b] = st.aa_dir[(uint64_t)t * FD_AA_DIR + b];
     __syncwarp();
     for (uint32_t k = lane; k < Q.n_aad; k += 32)
         if (AAD[k].dq < V_MAX_NQ) atomicOr(&W.dq_aa1[AAD[k].dq], 1u << (AAD[k].aa1 & 31u));
-    // range of the query's CA distances: a pair outside it cannot support a rescue
-    float dmax = 0.f, dmin = 3.0e38f;
-    for (uint32_t k = lane; k < Q.n_aad; k += 32) {
-        dmax = fmaxf(dmax, AAD[k].dist);
-        dmin = fminf(dmin, AAD[k].dist);
+    { // range of the query's CA distances: a pair outside it cannot support a rescue
+        float dmax = 0.f, dmin = 3.0e38f;
+        for (uint32_t k = lane; k < Q.n_aad; k += 32) {
+            dmax = fmaxf(dmax, AAD[k].dist);
+            dmin = fminf(dmin, AAD[k].dist);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+            dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        }
+        const float pre_hi = fminf(hp.dist_cutoff, dmax + ca_cutoff), pre_lo = fmaxf(dmin - ca_cutoff, 0.f);
+        if (lane == 0) {
+            W.pre_hi2 = pre_hi * pre_hi * 1.0001f;
+            W.pre_lo2 = pre_lo * pre_lo * 0.9999f;
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    }
-    const float pre_hi = fminf(hp.dist_cutoff, dmax + ca_cutoff), pre_lo = fmaxf(dmin - ca_cutoff, 0.f);
-    const float pre_hi2 = pre_hi * pre_hi * 1.0001f, pre_lo2 = pre_lo * pre_lo * 0.9999f;
     __syncwarp();
 
     // ---- graph: nodes by first appearance, components = SCCs U weak components, size >= 2 ----
@@ -770,35 +776,62 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
     }
     __syncwarp();
     if (W.s_flag) {
-        if (lane == 0) cand_flags[c] = (uint8_t)W.s_flag;
-        return;
+        if (lane == 0) {
+            cand_flags[c] = (uint8_t)W.s_flag;
+            W.n_comp = 0;
+        }
+    } else if (lane == 0 && W.n_comp) {
+        W.s_out_base = atomicAdd(spec_count, W.n_comp);
+        cand_ncomp[c] = W.n_comp;
     }
-    const uint32_t ncomp = W.n_comp;
-    if (ncomp == 0) return;
-    const uint8_t *IDX = idx_dense + Q.idx_begin;
-    if (lane == 0) {
-        W.s_out_base = atomicAdd(spec_count, ncomp);
-        cand_ncomp[c] = ncomp;
-    }
-    __syncwarp();
-    const uint32_t out_base = W.s_out_base;
+    } // phase 1
+    __syncthreads();
 
-    for (uint32_t ci = 0; ci < ncomp; ci++) {
+    // ---- phase 2: the components of the CTA's candidates are work items shared by its warps (a candidate with
+    // dozens of components no longer runs them one after another on a single warp); the component's owner state
+    // O (edges, nodes, masks) is read-only here, the mapping / rescue scratch is this warp's own W ----
+    uint32_t comp_begin[VB_WARPS + 1];
+    comp_begin[0] = 0;
+#pragma unroll
+    for (int w = 0; w < VB_WARPS; w++) comp_begin[w + 1] = comp_begin[w] + states[w].n_comp;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&s_next, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= comp_begin[VB_WARPS]) break;
+        int ow = 0;
+#pragma unroll
+        for (int w = 1; w < VB_WARPS; w++)
+            if (item >= comp_begin[w]) ow = w;
+        const WarpState &O = states[ow];
+        const uint32_t ci = item - comp_begin[ow];
+        const uint32_t c = O.cand;
+        const uint32_t ne = O.ne_word & 0x7fffffffu;
+        const bool all_pairs = (O.ne_word >> 31) != 0;
+        const VQDesc Q = vq[cand_query[c]];
+        const uint32_t t = cand_nid[c];
+        const uint64_t base = st.row_offsets[t];
+        const VHash *H = vhash + Q.hash_begin;
+        const VAad *AAD = vaad + Q.aad_begin; // (amino-acid pair -> CA distances) of the query: global, L1-resident
+        const uint16_t *AAR = aa_ranges + (size_t)cand_query[c] * 400u;
+        const uint8_t *IDX = idx_dense + Q.idx_begin;
+        const uint32_t out_base = O.s_out_base;
+        const float pre_hi2 = O.pre_hi2, pre_lo2 = O.pre_lo2;
         // ---- mapping: votes (lanes over edges), best per query residue (lane per residue), greedy assignment ----
-        const uint64_t mask = W.comp_mask[ci];
+        const uint64_t mask = O.comp_mask[ci];
         for (uint32_t k = lane; k < Q.n_dq * (V_MAX_NODES / 2); k += 32) W.counts[k] = 0;
         __syncwarp();
         // votes[q][r]: 16-bit counters, two per word (a cell receives at most 2 * V_MAX_E votes); the reference's u8
         // saturating counters (retrieve.rs:628-660) are min(count, 255) of these
         for (uint32_t k = lane; k < ne; k += 32) {
-            const uint32_t a = W.e_a[k], b = W.e_b[k];
+            const uint32_t a = O.e_a[k], b = O.e_b[k];
             if (!((mask >> a) & 1ull) || !((mask >> b) & 1ull)) continue;
-            const VHash h = H[W.e_ent[k]];
+            const VHash h = H[O.e_ent[k]];
             uint32_t pq[2], pr[2];
             if (h.sym) {
                 pq[0] = min((uint32_t)h.dqi, (uint32_t)h.dqj);
                 pq[1] = max((uint32_t)h.dqi, (uint32_t)h.dqj);
-                const bool ab = W.node_res[a] < W.node_res[b];
+                const bool ab = O.node_res[a] < O.node_res[b];
                 pr[0] = ab ? a : b;
                 pr[1] = ab ? b : a;
             } else {
@@ -822,7 +855,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                 const uint32_t cell = (uint32_t)lane * V_MAX_NODES + v;
                 const uint32_t cnt = min((W.counts[cell >> 1] >> (16u * (cell & 1u))) & 0xffffu, 255u);
                 if (cnt == 0) continue;
-                const uint32_t res = W.node_res[v];
+                const uint32_t res = O.node_res[v];
                 if (cnt > bc || (cnt == bc && res < bres)) {
                     bc = cnt;
                     br = v;
@@ -838,8 +871,8 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
             const uint8_t *best_c = W.best_c, *best_r = W.best_r;
             float idf = 0.f; // calculate_subgraph_idf: f32 sum in edge order
             for (uint32_t k = 0; k < ne; k++) {
-                const uint32_t a = W.e_a[k], b = W.e_b[k];
-                if (((mask >> a) & 1ull) && ((mask >> b) & 1ull)) idf += W.e_idf[k];
+                const uint32_t a = O.e_a[k], b = O.e_b[k];
+                if (((mask >> a) & 1ull) && ((mask >> b) & 1ull)) idf += O.e_idf[k];
             }
             W.c_idf = idf;
             // order: count descending, dense query id ascending (bucket sort of retrieve.rs:667-675)
@@ -870,7 +903,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
             W.f_nscan = 0;
             W.f_nres = 0;
             W.r_nridx = nm;
-            for (uint32_t k = 0; k < nm; k++) W.r_ridx[k] = W.node_res[W.m_ridx[k]];
+            for (uint32_t k = 0; k < nm; k++) W.r_ridx[k] = O.node_res[W.m_ridx[k]];
         }
         __syncwarp();
         if ((uint32_t)lane < W.r_nridx) { // the matched residues' data, once per component
@@ -891,7 +924,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                 const uint32_t dq = IDX[pos];
                 int mapped = -1;
                 for (uint32_t k = 0; k < W.m_n; k++)
-                    if (W.m_qidx[k] == dq) mapped = (int)W.node_res[W.m_ridx[k]];
+                    if (W.m_qidx[k] == dq) mapped = (int)O.node_res[W.m_ridx[k]];
                 W.r_need = 0;
                 if (mapped >= 0) {
                     const uint32_t ri = (uint32_t)mapped;
@@ -923,7 +956,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                 // count_map[i] = #(entries of this query residue, matched target residues rj) compatible with (i, rj),
                 // over the rows of the pair iteration (all residues, or those whose amino acid is a res1 of the query)
                 const uint32_t dq = W.r_dq;
-                const uint32_t row_aa = W.dq_aa1[dq]; // an entry (aa1, aa2, dq) only matches rows whose amino acid is aa1
+                const uint32_t row_aa = O.dq_aa1[dq]; // an entry (aa1, aa2, dq) only matches rows whose amino acid is aa1
                 auto row_count = [&](uint32_t i) -> uint32_t {
                     const uint32_t cia = (st.aa[base + i] & 0x7Fu) * 20u;
                     const fdg::V3 cai = ld3(st.ca_xyz, base + i);
@@ -962,7 +995,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                     for (uint32_t mod = 0; mod < (all_pairs ? 2u : 1u); mod++) {
                         if (!all_pairs && !((Q.aa1_mask >> a) & 1u)) continue;
                         const uint32_t b = a + 20u * mod;
-                        for (uint32_t r = W.aa_dir[b] + lane, re = W.aa_dir[b + 1]; r < re; r += 32) take(st.aa_rows[base + r]);
+                        for (uint32_t r = O.aa_dir[b] + lane, re = O.aa_dir[b + 1]; r < re; r += 32) take(st.aa_rows[base + r]);
                     }
                 }
                 const uint32_t mx = __reduce_max_sync(0xffffffffu, l_max);
@@ -1002,7 +1035,7 @@ __global__ void __launch_bounds__(VB_WARPS * 32)
                     nal = W.m_n;
                     for (uint32_t k = 0; k < nal; k++) {
                         sp.aq[k] = W.m_qidx[k];
-                        sp.at[k] = W.node_res[W.m_ridx[k]];
+                        sp.at[k] = O.node_res[W.m_ridx[k]];
                     }
                 } else {
                     nal = W.f_nscan;
@@ -1370,8 +1403,11 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         C.c0 = n_cand * k / n_chunks;
         C.n = n_cand * (k + 1) / n_chunks - C.c0;
         C.st = (k & 1) ? s1 : s0;
-        C.pool_cap = std::max<uint64_t>(1u << 16, 48 * C.n);
-        C.spec_cap = std::max<uint64_t>(1024, 2 * C.n);
+        // pools sized from what the previous calls on this context needed (+50 %), at least 64 edges and 3 components
+        // per candidate: a chunk that overflows is re-issued with exact sizes, which doubles its cost and stalls the
+        // pipeline behind it (at 4x the database the bench's 2.01 components per candidate overflowed the old 2 x n)
+        C.pool_cap = std::max<uint64_t>(1u << 16, (uint64_t)(std::max(64.0, 1.5 * ctx->verify_edges_per_cand) * (double)C.n));
+        C.spec_cap = std::max<uint64_t>(1024, (uint64_t)(std::max(3.0, 1.5 * ctx->verify_comps_per_cand) * (double)C.n));
         C.h_counters = h_counters_all + 2 * k;
         C.h_first_rel = h_first_rel_all + C.c0 + k;
         FD_CUDA(ctx, C.ncomp.alloc(C.n + 1));
@@ -1519,6 +1555,12 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         stg.launches += 1;
     }
     for (uint64_t c = 0; c < n_cand; c++) h_flags[c] |= h_kflags[c];
+    {
+        uint64_t edges = 0;
+        for (auto &C : chunks) edges += C.h_counters[0];
+        ctx->verify_edges_per_cand = std::max(ctx->verify_edges_per_cand * 0.9, (double)edges / (double)n_cand);
+        ctx->verify_comps_per_cand = std::max(ctx->verify_comps_per_cand * 0.9, (double)produced / (double)n_cand);
+    }
     *out_records = h_out;
     *out_n = produced;
     *out_first = h_first;

@@ -397,9 +397,13 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         search(make_batch())
     e2e_t, e2e_res = [], None
+    e2e_names = ("hv_flatten", "hv_upload", "lookup", "cq_host_prepare", "cq_host_rest", "fs_flatten", "fs_allgather",
+                 "fs_parse", "fs_counts", "fs_allreduce", "fs_tables")
+    e2e_s0 = {k: ctx.stage_ms(k) for k in e2e_names}
     for _ in range(args.steps):
         e2e_res, dt, _ = timed(lambda: search(make_batch()))
         e2e_t.append(dt)
+    e2e_stage = {k: (ctx.stage_ms(k) - e2e_s0[k]) / max(1, args.steps) for k in e2e_names}
     e2e_h2d, e2e_d2h = int(e2e_res.h2d_bytes), int(e2e_res.d2h_bytes)
     e2e_rows = (int(e2e_res.struct_offsets[-1]), int(e2e_res.match_offsets[-1]))
     del e2e_res
@@ -473,6 +477,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e_prepare_host_ms": {"query_maps (make_query_map x batch)": prep_ms["query_maps"] / max(1, prep_ms["calls"]),
                                 "finalize (posting counts -> idf, verification tables -> device)":
                                     prep_ms["finalize"] / max(1, prep_ms["calls"])},
+        "e2e_stage_ms_per_step": {k: v for k, v in e2e_stage.items() if v > 0},
         "timing": "CUDA events around each step (max over ranks); wall-clock cross-check %.3f ms/step" % (
             1e3 * sum(wall_t) / steps),
         "results_per_step": {"structure_rows": n_struct_rows, "match_rows": n_match_rows,

@@ -104,7 +104,7 @@ struct fd_ctx {
     FdDeviceStore store;
     uint64_t last_posting_bytes = 0;
     uint64_t last_exchange_bytes = 0; // bytes this rank sent to other ranks in the last sharded count_query
-    FdPinned pinned[8];
+    FdPinned pinned[10];
     cudaEvent_t ev_extra[4] = {nullptr, nullptr, nullptr, nullptr}; // finer stage timing inside one call
     cudaStream_t aux_stream[2] = {nullptr, nullptr}; // second compute stream + copy stream of the chunked verification
     std::vector<cudaEvent_t> ev_pool;                // events of the chunked verification, created on demand

@@ -37,7 +37,7 @@ constexpr int VA_THREADS = 128;            // k6a CTA
 constexpr int VA_COL_STAGE = 512;          // candidates with at most this many column residues stage them in shared memory
 constexpr int VA_HASH_STAGE = 256;         // query hash sets up to this size are staged in shared memory
 constexpr int V_LIST_CAP = 2048;           // prefilter-list capacity (larger candidates take the general path)
-constexpr int VB_WARPS = 4;                // k6b: candidates per CTA
+constexpr int VB_WARPS = 8;                // k6b: candidates per CTA (their components are shared by the CTA's warps)
 constexpr int V_MAX_AAD = 255; // start and count of an amino-acid pair's run each fit 8 bits
 constexpr int V_MAX_E = 256;
 constexpr int V_MAX_NODES = 64;
@@ -1108,9 +1108,11 @@ static void verify_prepared_release(fd_verify_prepared *P) {
     if (!P) return;
     cudaSetDevice(P->device);
     void *ptrs[7] = {P->d_desc, P->d_hash, P->d_aad, P->d_idx, P->d_qca, P->d_qcb, P->d_aar};
-    // cudaFree, not cudaFreeAsync: the tables may outlive the context (and stream) that uploaded them
+    // The tables may outlive the context (and stream) that uploaded them, and every search that used them has
+    // returned: they go back to the device's pool through the default stream (cudaFree would synchronise the whole
+    // device at every released batch).
     for (void *q : ptrs)
-        if (q) cudaFree(q);
+        if (q && cudaFreeAsync(q, (cudaStream_t)0) != cudaSuccess) cudaFree(q);
     cudaGetLastError();
     delete P;
 }
@@ -1260,11 +1262,24 @@ static int verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t 
     P->stream = ctx->stream;
     P->q_unfit = std::move(q_unfit);
     cudaStream_t s = ctx->stream;
+    // the flattened tables travel through one pinned staging buffer (pageable uploads of a few MB ran at ~5 GB/s)
+    const size_t stage_bytes = nq * sizeof(VQDesc) + f_hash.size() * sizeof(VHash) + f_aad.size() * sizeof(VAad) +
+                               f_aar.size() * sizeof(uint16_t) + f_idx.size() + (q_ca.size() + q_cb.size()) * 4 + 7 * 16;
+    uint8_t *stage = nullptr;
+    if (fd_pinned(ctx, 8, stage_bytes, (void **)&stage) != FD_OK) {
+        delete P;
+        return FD_ERR_NOMEM;
+    }
+    size_t stage_pos = 0;
     auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMallocAsync(dst, std::max<size_t>(bytes, 16), s);
         if (e != cudaSuccess) return e;
         P->h2d_bytes += bytes;
-        return bytes ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+        if (!bytes) return cudaSuccess;
+        memcpy(stage + stage_pos, src, bytes);
+        e = cudaMemcpyAsync(*dst, stage + stage_pos, bytes, cudaMemcpyHostToDevice, s);
+        stage_pos += (bytes + 15) & ~(size_t)15;
+        return e;
     };
     cudaError_t e = up((void **)&P->d_desc, descs.data(), nq * sizeof(VQDesc));
     if (e == cudaSuccess) e = up((void **)&P->d_hash, f_hash.data(), f_hash.size() * sizeof(VHash));

@@ -2180,12 +2180,22 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     };
     const bool any_match_filter = p->connected_node_count > 0 || p->connected_node_ratio > 0.f ||
                                   p->prefilter.idf_score_cutoff > 0.f || p->rmsd_cutoff > 0.f;
+    const bool any_struct_filter = !p->skip_match && (p->max_matching_node_count > 0 || p->max_matching_node_ratio > 0.f ||
+                                                      p->rmsd_cutoff > 0.f);
     std::vector<uint64_t> res_off(nq + 1, 0);
     // pass 1: rows per query
     auto count_query_rows = [&](uint32_t q) {
         const Query &Q = qs->q[q_begin + q];
         const float expected = (float)Q.residue_count;
         uint64_t ns = 0, nm = 0;
+        if (!any_struct_filter && !any_match_filter) { // default flags: every candidate and every match is a row
+            ns = hoff[q + 1] - hoff[q];
+            for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) nm += match_count(c);
+            R->struct_off[q + 1] = ns;
+            R->match_off[q + 1] = nm;
+            res_off[q + 1] = nm * Q.indices.size();
+            return;
+        }
         for (uint64_t c = hoff[q]; c < hoff[q + 1]; c++) {
             const size_t na = match_count(c);
             uint32_t max_node;
@@ -2476,16 +2486,22 @@ int fdh_queries_pair_counts(const fdh_queries *qs, fd_ctx *ctx, uint32_t *out_co
 int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, uint64_t total_structures) {
     fd_verify_prepared_free(qs->vprep); // the tables carry the per-hash idf
     qs->vprep = nullptr;
-    size_t base = 0;
     const float total = (float)total_structures;
-    for (auto &Q : qs->q) {
-        for (auto &e : Q.entries) {
-            const uint32_t c = counts[base + e.pair];
-            e.idf = c > 0 ? log2f(total / (float)c) : 0.0f;
-        }
-        for (size_t k = 0; k < Q.vs_entry.size(); k++) Q.vs_idf[k] = Q.entries[Q.vs_entry[k]].idf;
-        base += Q.pair_hash.size();
-    }
+    const size_t nq = qs->q.size();
+    std::vector<size_t> base(nq + 1, 0);
+    for (size_t q = 0; q < nq; q++) base[q + 1] = base[q] + qs->q[q].pair_hash.size();
+    std::atomic<size_t> next{0};
+    fd_parallel(nq >= 64 ? std::min(fd_default_host_threads(), 16) : 1, [&](int) {
+        for (size_t q0; (q0 = next.fetch_add(16)) < nq;)
+            for (size_t q = q0; q < std::min(nq, q0 + 16); q++) {
+                Query &Q = qs->q[q];
+                for (auto &e : Q.entries) {
+                    const uint32_t c = counts[base[q] + e.pair];
+                    e.idf = c > 0 ? log2f(total / (float)c) : 0.0f;
+                }
+                for (size_t k = 0; k < Q.vs_entry.size(); k++) Q.vs_idf[k] = Q.entries[Q.vs_entry[k]].idf;
+            }
+    });
     qs->finalized = true;
     return FD_OK;
 }

@@ -78,6 +78,9 @@ struct FdDeviceStore {
     // query residue; with the directory it reads those ~n/20 rows instead of scanning all n.
     uint16_t *aa_rows = nullptr;
     uint16_t *aa_dir = nullptr;
+    // (chain, residue number) of every residue (fd_store_attach_labels; optional): the device writes result rows
+    uint8_t *label_chain = nullptr;
+    uint64_t *label_serial = nullptr;
     FdPairTable pt;
 };
 
@@ -85,6 +88,14 @@ struct FdDeviceStore {
 struct FdPinned {
     void *p = nullptr;
     size_t cap = 0;
+};
+
+// Match records of the last fd_verify_candidates_device call, kept on the device for fd_verify_rows (fd_verify.cu)
+struct FdVerifyKeep {
+    void *recs = nullptr; // fd_match_record[n], grouped by candidate in emission order
+    uint64_t n = 0, cap = 0, n_cand = 0;
+    uint32_t *d_cand_query = nullptr; // [n_cand] index into the prepared batch
+    const void *prepared = nullptr;   // fd_verify_prepared of the call
 };
 
 struct FdComm; // fd_comm.cu: the rank's NCCL communicator
@@ -109,6 +120,7 @@ struct fd_ctx {
     cudaStream_t aux_stream[2] = {nullptr, nullptr}; // second compute stream + copy stream of the chunked verification
     std::vector<cudaEvent_t> ev_pool;                // events of the chunked verification, created on demand
     double verify_edges_per_cand = 0.0, verify_comps_per_cand = 0.0; // pool sizing of the chunked verification
+    FdVerifyKeep vkeep;
     uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
     uint64_t votes_cap = 0;    // capacity in u32 words
     uint32_t *merge = nullptr; // dense vote planes of this rank's slice of the batch (sparse merge), owned

@@ -33,6 +33,8 @@ static void fd_release_store(FdDeviceStore &st) {
     cudaFree(st.cb_valid);
     cudaFree(st.aa_rows);
     cudaFree(st.aa_dir);
+    cudaFree(st.label_chain);
+    cudaFree(st.label_serial);
     cudaFree(st.pt.offsets);
     cudaFree(st.pt.hash);
     cudaFree(st.pt.ij);
@@ -321,6 +323,8 @@ void fd_destroy(fd_ctx *ctx) {
     }
     cudaFree(ctx->votes);
     cudaFree(ctx->merge);
+    cudaFree(ctx->vkeep.recs);
+    cudaFree(ctx->vkeep.d_cand_query);
     for (auto &b : ctx->pinned)
         if (b.p) cudaFreeHost(b.p);
     for (auto &e : ctx->ev_extra)

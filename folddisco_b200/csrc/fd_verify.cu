@@ -1298,11 +1298,179 @@ static int verify_prepare(fd_ctx *ctx, const fd_verify_query *queries, uint32_t 
     return FD_OK;
 }
 
+
+static void verify_keep_release(fd_ctx *ctx) {
+    FdVerifyKeep &K = ctx->vkeep;
+    if (K.recs) cudaFreeAsync(K.recs, ctx->stream);
+    if (K.d_cand_query) cudaFreeAsync(K.d_cand_query, ctx->stream);
+    K = FdVerifyKeep();
+}
+
+// ------------------------------------------------------------------------------------------------
+// k6d: result rows on the device -- one CTA per query.  Replaces the host's row assembly (per-candidate summary of
+// retrieve.rs:539-551, the default sorts of sort.rs:218-222 / 454-458, residue labels): the host only receives the
+// finished arrays.  Queries the kernel cannot order (pool larger than its shared memory, NaN / -0.0 sort keys) are
+// flagged and left in emission order for the host.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t VD_MAX_MATCHES = 2048; // bitonic sort of a query's matches in shared memory
+constexpr uint32_t VD_MAX_CANDS = 2048;   // summaries of a query's candidates in shared memory
+constexpr int VD_THREADS = 256;
+
+__device__ __forceinline__ uint32_t vd_sortable(float f) { // order-preserving integer image of a float
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ bool vd_plain(float f) { return f == f && !(f == 0.f && (__float_as_uint(f) >> 31)); }
+
+__global__ void __launch_bounds__(VD_THREADS)
+    k6d_rows(const VQDesc *vq, const uint32_t *cand_query, const uint64_t *cand_off, const fd_struct_hit *hits,
+             const uint32_t *first, const fd_match_record *recs, const uint64_t *store_row_offsets,
+             const uint8_t *label_chain, const uint64_t *label_serial, const uint64_t *res_off,
+             fd_struct_row *structs_tmp, fd_struct_row *structs, fd_match_row *matches, unsigned long long *match_order, fd_residue_row *residues, uint8_t *needs_host) {
+    __shared__ unsigned long long s_key[VD_MAX_MATCHES];
+    __shared__ uint16_t s_idx[VD_MAX_MATCHES];
+    __shared__ float s_idf[VD_MAX_CANDS], s_rmsd[VD_MAX_CANDS];
+    __shared__ uint32_t s_flag;
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint64_t c0 = cand_off[q], c1 = cand_off[q + 1];
+    const uint32_t nc = (uint32_t)(c1 - c0);
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    if (nc == 0) {
+        if (tid == 0) needs_host[q] = 0;
+        return;
+    }
+    const uint32_t m0 = first[c0], m1 = first[c1], nm = m1 - m0;
+    const uint32_t n_res = vq[cand_query[c0]].n_idx;
+    const bool cands_fit = nc <= VD_MAX_CANDS, matches_fit = nm <= VD_MAX_MATCHES;
+    // ---- per-candidate summary: max node count, smallest RMSD among the matches that reach it ----
+    for (uint32_t k = tid; k < nc; k += blockDim.x) {
+        const uint64_t c = c0 + k;
+        uint32_t max_node = 0;
+        float min_rmsd = 0.f;
+        for (uint32_t m = first[c]; m < first[c + 1]; m++) {
+            const uint32_t node = recs[m].node_count;
+            const float r = recs[m].rmsd;
+            if (node > max_node) {
+                max_node = node;
+                min_rmsd = r;
+            } else if (node == max_node && r < min_rmsd) {
+                min_rmsd = r;
+            }
+        }
+        const fd_struct_hit h = hits[c];
+        if (cands_fit) {
+            s_idf[k] = h.idf;
+            s_rmsd[k] = min_rmsd;
+        }
+        if (!vd_plain(h.idf) || !vd_plain(min_rmsd)) atomicOr(&s_flag, 1u);
+        // provisional position = count_query order; moved below when the run of equal idf needs reordering
+        fd_struct_row sr;
+        sr.nid = h.nid;
+        sr.total_match_count = h.match_count;
+        sr.node_count = h.node_count;
+        sr.edge_count = h.edge_count;
+        sr.idf = h.idf;
+        sr.max_matching_node_count = max_node;
+        sr.min_rmsd_with_max_match = min_rmsd;
+        sr.match_begin = first[c];
+        sr.match_end = first[c + 1];
+        structs_tmp[c] = sr;
+    }
+    // ---- match rows + matched residues, emission order ----
+    for (uint32_t k = tid; k < nm; k += blockDim.x) {
+        const uint32_t m = m0 + k;
+        const fd_match_record r = recs[m];
+        const uint32_t nid = hits[r.cand].nid;
+        fd_match_row mr;
+        mr.nid = nid;
+        mr.node_count = r.node_count;
+        mr.idf = r.idf;
+        mr.rmsd = r.rmsd;
+#pragma unroll
+        for (int x = 0; x < 9; x++) mr.U[x] = r.U[x];
+#pragma unroll
+        for (int x = 0; x < 3; x++) mr.t[x] = r.t[x];
+        const uint64_t rb = res_off[q] + (uint64_t)k * n_res;
+        mr.res_begin = rb;
+        matches[m] = mr;
+        const uint64_t base = store_row_offsets[nid];
+        for (uint32_t x = 0; x < n_res; x++) {
+            const uint32_t v = r.res[x];
+            fd_residue_row rr;
+            memset(&rr, 0, sizeof(rr));
+            rr.some = v != 0;
+            rr.serial = v ? (uint64_t)(v - 1) : 0;
+            if (v && label_chain) {
+                rr.chain = label_chain[base + v - 1];
+                rr.serial = label_serial[base + v - 1];
+            }
+            residues[rb + x] = rr;
+        }
+        if (!vd_plain(r.idf) || !vd_plain(r.rmsd)) atomicOr(&s_flag, 1u);
+        if (matches_fit) {
+            s_key[k] = ((unsigned long long)(~vd_sortable(r.idf)) << 32) | vd_sortable(r.rmsd);
+            s_idx[k] = (uint16_t)k;
+        }
+    }
+    __syncthreads();
+    const bool host_sorts = s_flag != 0 || !cands_fit || !matches_fit;
+    if (tid == 0) needs_host[q] = host_sorts ? 1 : 0;
+    if (host_sorts) {
+        __syncthreads();
+        for (uint32_t k = tid; k < nc; k += blockDim.x) structs[c0 + k] = structs_tmp[c0 + k];
+        for (uint32_t k = tid; k < nm; k += blockDim.x) match_order[m0 + k] = m0 + k;
+        return;
+    }
+    // ---- structure rows: idf desc, min_rmsd asc, stable.  They arrive idf desc (ties by nid): only runs of equal idf
+    // can need reordering (StructureSortStrategy::default, sort.rs:454-458): rank inside the run, copy to the final array
+    for (uint32_t k = tid; k < nc; k += blockDim.x) {
+        const float idf = s_idf[k], rm = s_rmsd[k];
+        uint32_t lo = k, hi = k + 1;
+        while (lo > 0 && s_idf[lo - 1] == idf) lo--;
+        while (hi < nc && s_idf[hi] == idf) hi++;
+        uint32_t rank = k;
+        if (hi - lo > 1) {
+            rank = lo;
+            for (uint32_t j = lo; j < hi; j++)
+                if (s_rmsd[j] < rm || (s_rmsd[j] == rm && j < k)) rank++;
+        }
+        structs[c0 + rank] = structs_tmp[c0 + k];
+    }
+    // ---- match order: idf desc, rmsd asc, emission index (MatchSortStrategy::default, sort.rs:218-222) ----
+    uint32_t mpow = 32;
+    while (mpow < nm) mpow <<= 1;
+    for (uint32_t k = nm + tid; k < mpow; k += blockDim.x) {
+        s_key[k] = ~0ull;
+        s_idx[k] = (uint16_t)k;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= mpow; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t k = tid; k < (mpow >> 1); k += blockDim.x) {
+                const uint32_t lo_i = 2 * k - (k & (stride - 1));
+                const uint32_t hi_i = lo_i + stride;
+                const bool up = (lo_i & size) == 0;
+                const unsigned long long x = s_key[lo_i], y = s_key[hi_i];
+                const uint16_t ix = s_idx[lo_i], iy = s_idx[hi_i];
+                const bool gt = x > y || (x == y && ix > iy); // emission index breaks ties: a total order
+                if (gt == up) {
+                    s_key[lo_i] = y;
+                    s_key[hi_i] = x;
+                    s_idx[lo_i] = iy;
+                    s_idx[hi_i] = ix;
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t k = tid; k < nm; k += blockDim.x) match_order[m0 + k] = (unsigned long long)m0 + s_idx[k];
+}
+
 // Shared body of the entry points.  Outputs are views of ctx's pinned staging buffers.
 static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *cand_query, const uint32_t *cand_nid,
                       uint64_t n_cand, const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
                       const fd_match_record **out_records, uint64_t *out_n, const uint32_t **out_first,
-                      const uint8_t **out_flags) {
+                      const uint8_t **out_flags, bool keep_device = false) {
     if (!ctx) return FD_ERR_ARG;
     if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: no structure store attached");
     if (!P || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags || !out_first)
@@ -1314,6 +1482,7 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
     *out_flags = nullptr;
     *out_first = nullptr;
     *out_n = 0;
+    verify_keep_release(ctx);
     auto h_now = std::chrono::steady_clock::now();
     auto h_mark = [&](const char *name) {
         const auto t = std::chrono::steady_clock::now();
@@ -1504,12 +1673,13 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
     };
     for (uint32_t k = 0; k < n_chunks; k++) FD_TRY(issue(k));
     h_mark("hv_issue");
-    fd_match_record *h_out = nullptr;
+    fd_match_record *h_out = nullptr; // all records in emission order: pinned host staging, or (keep_device) device memory
     uint64_t h_out_cap = 0, produced = 0;
     {
         uint64_t cap = 0;
         for (auto &C : chunks) cap += C.spec_cap;
-        FD_TRY(fd_pinned(ctx, 0, cap * sizeof(fd_match_record), (void **)&h_out));
+        if (keep_device) FD_CUDA(ctx, cudaMallocAsync((void **)&h_out, std::max<uint64_t>(cap, 1) * sizeof(fd_match_record), sc));
+        else FD_TRY(fd_pinned(ctx, 0, cap * sizeof(fd_match_record), (void **)&h_out));
         h_out_cap = cap;
     }
     for (uint32_t k = 0; k < n_chunks; k++) {
@@ -1529,17 +1699,27 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         C.rec_base = produced;
         const uint64_t np = C.h_counters[1];
         if (produced + np > h_out_cap) { // only after a re-issue with more components than the first estimate
-            FD_CUDA(ctx, cudaStreamSynchronize(sc));
-            fd_match_record *bigger = nullptr;
-            std::vector<fd_match_record> keep(h_out, h_out + produced);
-            FD_TRY(fd_pinned(ctx, 0, (produced + np + (n_cand - C.c0) * 2) * sizeof(fd_match_record), (void **)&bigger));
-            memcpy(bigger, keep.data(), produced * sizeof(fd_match_record));
-            h_out = bigger;
-            h_out_cap = produced + np + (n_cand - C.c0) * 2;
+            const uint64_t new_cap = produced + np + (n_cand - C.c0) * 2;
+            if (keep_device) {
+                fd_match_record *bigger = nullptr;
+                FD_CUDA(ctx, cudaMallocAsync((void **)&bigger, new_cap * sizeof(fd_match_record), sc));
+                FD_CUDA(ctx, cudaMemcpyAsync(bigger, h_out, produced * sizeof(fd_match_record), cudaMemcpyDeviceToDevice, sc));
+                FD_CUDA(ctx, cudaFreeAsync(h_out, sc));
+                h_out = bigger;
+            } else {
+                FD_CUDA(ctx, cudaStreamSynchronize(sc));
+                fd_match_record *bigger = nullptr;
+                std::vector<fd_match_record> keep(h_out, h_out + produced);
+                FD_TRY(fd_pinned(ctx, 0, new_cap * sizeof(fd_match_record), (void **)&bigger));
+                memcpy(bigger, keep.data(), produced * sizeof(fd_match_record));
+                h_out = bigger;
+            }
+            h_out_cap = new_cap;
         }
         if (np) {
             // the records are complete (event above); copy them on the copy stream, under the other chunks' kernels
-            FD_CUDA(ctx, cudaMemcpyAsync(h_out + produced, C.out.p, np * sizeof(fd_match_record), cudaMemcpyDeviceToHost, sc));
+            FD_CUDA(ctx, cudaMemcpyAsync(h_out + produced, C.out.p, np * sizeof(fd_match_record),
+                                         keep_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sc));
         }
         for (uint64_t c = 0; c <= C.n; c++) h_first[C.c0 + c] = (uint32_t)(produced + C.h_first_rel[c]);
         produced += np;
@@ -1576,7 +1756,17 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         ctx->verify_edges_per_cand = std::max(ctx->verify_edges_per_cand * 0.9, (double)edges / (double)n_cand);
         ctx->verify_comps_per_cand = std::max(ctx->verify_comps_per_cand * 0.9, (double)produced / (double)n_cand);
     }
-    *out_records = h_out;
+    if (keep_device) {
+        ctx->vkeep.recs = h_out;
+        ctx->vkeep.n = produced;
+        ctx->vkeep.cap = h_out_cap;
+        ctx->vkeep.n_cand = n_cand;
+        ctx->vkeep.d_cand_query = d_cq.take();
+        ctx->vkeep.prepared = P;
+        *out_records = nullptr;
+    } else {
+        *out_records = h_out;
+    }
     *out_n = produced;
     *out_first = h_first;
     *out_flags = h_flags;
@@ -1613,6 +1803,106 @@ extern "C" int fd_verify_candidates_prepared(fd_ctx *ctx, const fd_verify_prepar
                                              const uint32_t **out_first, const uint8_t **out_flags) {
     return verify_run(ctx, prepared, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match, out_records,
                       out_n, out_first, out_flags);
+}
+
+extern "C" int fd_verify_candidates_device(fd_ctx *ctx, const fd_verify_prepared *prepared, const uint32_t *cand_query,
+                                           const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params,
+                                           float ca_dist_cutoff, int skip_ca_match, uint64_t *out_n,
+                                           const uint32_t **out_first, const uint8_t **out_flags) {
+    const fd_match_record *none = nullptr;
+    return verify_run(ctx, prepared, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match, &none, out_n,
+                      out_first, out_flags, true);
+}
+
+extern "C" int fd_verify_records_fetch(fd_ctx *ctx, const fd_match_record **out_records) {
+    if (!ctx || !out_records) return FD_ERR_ARG;
+    FD_ENTER(ctx);
+    const FdVerifyKeep &K = ctx->vkeep;
+    fd_match_record *h = nullptr;
+    FD_TRY(fd_pinned(ctx, 0, std::max<uint64_t>(K.n, 1) * sizeof(fd_match_record), (void **)&h));
+    if (K.n) {
+        if (!K.recs) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_records_fetch: no records kept on the device");
+        FD_CUDA(ctx, cudaMemcpyAsync(h, K.recs, K.n * sizeof(fd_match_record), cudaMemcpyDeviceToHost, ctx->stream));
+        FD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out_records = h;
+    return FD_OK;
+}
+
+extern "C" int fd_verify_rows(fd_ctx *ctx, const fd_rows_request *rq) {
+    if (!ctx || !rq) return FD_ERR_ARG;
+    FD_ENTER(ctx);
+    const FdVerifyKeep &K = ctx->vkeep;
+    if (!K.prepared || (K.n && !K.recs)) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_rows: no records kept on the device (call fd_verify_candidates_device first)");
+    if (!rq->cand_offsets || !rq->res_offsets || !rq->needs_host_sort || (K.n_cand && (!rq->hits || !rq->structs)) ||
+        (K.n && (!rq->matches || !rq->match_order)))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_rows: NULL argument");
+    const uint32_t nq = rq->n_queries;
+    if (rq->cand_offsets[0] != 0 || rq->cand_offsets[nq] != K.n_cand)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_rows: cand_offsets must cover the verified candidates");
+    const fd_verify_prepared *P = (const fd_verify_prepared *)K.prepared;
+    cudaStream_t s = ctx->stream;
+    const FdDeviceStore &S = ctx->store;
+    const uint64_t n_cand = K.n_cand, n_rec = K.n, n_res = rq->res_offsets[nq];
+    const uint32_t *h_first = (const uint32_t *)ctx->pinned[2].p; // the first[] of the verification call (pinned)
+    DevBuf<uint64_t> d_coff, d_roff;
+    DevBuf<fd_struct_hit> d_hits;
+    DevBuf<uint32_t> d_first;
+    DevBuf<fd_struct_row> d_structs, d_structs_tmp;
+    DevBuf<fd_match_row> d_matches;
+    DevBuf<unsigned long long> d_order;
+    DevBuf<fd_residue_row> d_res;
+    DevBuf<uint8_t> d_need;
+    FD_CUDA(ctx, d_coff.alloc(nq + 1));
+    FD_CUDA(ctx, d_roff.alloc(nq + 1));
+    FD_CUDA(ctx, d_hits.alloc(std::max<uint64_t>(n_cand, 1)));
+    FD_CUDA(ctx, d_first.alloc(n_cand + 1));
+    FD_CUDA(ctx, d_structs.alloc(std::max<uint64_t>(n_cand, 1)));
+    FD_CUDA(ctx, d_structs_tmp.alloc(std::max<uint64_t>(n_cand, 1)));
+    FD_CUDA(ctx, d_matches.alloc(std::max<uint64_t>(n_rec, 1)));
+    FD_CUDA(ctx, d_order.alloc(std::max<uint64_t>(n_rec, 1)));
+    FD_CUDA(ctx, d_res.alloc(std::max<uint64_t>(n_res, 1)));
+    FD_CUDA(ctx, d_need.alloc(std::max<uint32_t>(nq, 1)));
+    StageTimer st(ctx, "rows");
+    FD_CUDA(ctx, cudaMemcpyAsync(d_coff.p, rq->cand_offsets, (nq + 1) * 8ull, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_roff.p, rq->res_offsets, (nq + 1) * 8ull, cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_hits.p, rq->hits, n_cand * sizeof(fd_struct_hit), cudaMemcpyHostToDevice, s));
+    FD_CUDA(ctx, cudaMemcpyAsync(d_first.p, h_first, (n_cand + 1) * 4ull, cudaMemcpyHostToDevice, s));
+    if (nq)
+        FD_LAUNCH(ctx, k6d_rows, nq, VD_THREADS, 0, P->d_desc, K.d_cand_query, d_coff.p, d_hits.p, d_first.p,
+                  (const fd_match_record *)K.recs, S.row_offsets, S.label_chain, S.label_serial, d_roff.p, d_structs_tmp.p,
+                  d_structs.p, d_matches.p, d_order.p, d_res.p, d_need.p);
+    FD_CUDA(ctx, cudaMemcpyAsync(rq->needs_host_sort, d_need.p, nq, cudaMemcpyDeviceToHost, s));
+    if (n_cand) FD_CUDA(ctx, cudaMemcpyAsync(rq->structs, d_structs.p, n_cand * sizeof(fd_struct_row), cudaMemcpyDeviceToHost, s));
+    if (n_rec) {
+        FD_CUDA(ctx, cudaMemcpyAsync(rq->matches, d_matches.p, n_rec * sizeof(fd_match_row), cudaMemcpyDeviceToHost, s));
+        FD_CUDA(ctx, cudaMemcpyAsync(rq->match_order, d_order.p, n_rec * 8ull, cudaMemcpyDeviceToHost, s));
+    }
+    if (n_res) FD_CUDA(ctx, cudaMemcpyAsync(rq->residues, d_res.p, n_res * sizeof(fd_residue_row), cudaMemcpyDeviceToHost, s));
+    FD_CUDA(ctx, st.finish());
+    verify_keep_release(ctx);
+    return FD_OK;
+}
+
+extern "C" int fd_store_has_labels(const fd_ctx *ctx) { return ctx && ctx->store.label_chain ? 1 : 0; }
+
+extern "C" int fd_store_attach_labels(fd_ctx *ctx, const uint8_t *chain, const uint64_t *serial, uint64_t n_residues) {
+    if (!ctx) return FD_ERR_ARG;
+    if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_store_attach_labels: no structure store attached");
+    if (ctx->borrowed) return fd_fail(ctx, FD_ERR_STATE, "fd_store_attach_labels: a forked context shares its parent's store");
+    if (!chain || !serial || n_residues != ctx->store.n_res)
+        return fd_fail(ctx, FD_ERR_ARG, "fd_store_attach_labels: one label per residue of the attached store");
+    FD_ENTER(ctx);
+    FdDeviceStore &S = ctx->store;
+    cudaFree(S.label_chain);
+    cudaFree(S.label_serial);
+    S.label_chain = nullptr;
+    S.label_serial = nullptr;
+    FD_CUDA(ctx, cudaMalloc((void **)&S.label_chain, std::max<uint64_t>(n_residues, 1)));
+    FD_CUDA(ctx, cudaMalloc((void **)&S.label_serial, std::max<uint64_t>(n_residues, 1) * 8));
+    FD_TRY(fd_copy_to_device_staged(ctx, S.label_chain, chain, n_residues));
+    FD_TRY(fd_copy_to_device_staged(ctx, S.label_serial, serial, n_residues * 8));
+    return FD_OK;
 }
 
 extern "C" int fd_verify_candidates_view(fd_ctx *ctx, const fd_verify_query *queries, uint32_t nq,

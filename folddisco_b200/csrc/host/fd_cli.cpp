@@ -522,9 +522,7 @@ int cmd_query(Args &a) {
                 fdh_compact_free(c);
             }
         }
-        fd_struct_batch b;
-        if (fdh_store_batch(store, &b) != FD_OK) die(fdh_last_error());
-        if (fd_store_attach(ctx, &b) != FD_OK) die(fd_last_error(ctx));
+        if (fdh_store_attach(store, ctx) != FD_OK) die(fdh_last_error());
     }
 
     fdh_query_params qp;

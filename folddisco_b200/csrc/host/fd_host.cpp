@@ -27,6 +27,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "../../../include/folddisco_b200_host.h"
 #include "../fd_geom.cuh"
 
@@ -997,17 +999,28 @@ struct BlockCache {
             }
         }
         *cap = need;
+        if (need >= kMinBlock) { // large blocks are page-locked: the device writes result rows straight into them
+            void *p = nullptr;
+            if (cudaHostAlloc(&p, need, cudaHostAllocDefault) == cudaSuccess) return p;
+            cudaGetLastError();
+            return nullptr;
+        }
         return malloc(need);
     }
     void put(void *p, size_t cap) {
         if (!p) return;
         if (cap >= kMinBlock) {
-            std::lock_guard<std::mutex> lk(m);
-            if (blocks.size() < kMaxBlocks && bytes + cap <= kMaxBytes) {
-                blocks.push_back(Block{p, cap});
-                bytes += cap;
-                return;
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (blocks.size() < kMaxBlocks && bytes + cap <= kMaxBytes) {
+                    blocks.push_back(Block{p, cap});
+                    bytes += cap;
+                    return;
+                }
             }
+            cudaFreeHost(p);
+            cudaGetLastError(); // (a result released after the CUDA context is gone)
+            return;
         }
         free(p);
     }
@@ -1263,6 +1276,15 @@ int fdh_store_batch(const fdh_store *s, fd_struct_batch *out) {
     out->aa = s->aa.data();
     out->cb_valid = s->cb_valid.data();
     return FD_OK;
+}
+int fdh_store_attach(const fdh_store *s, fd_ctx *ctx) {
+    fd_struct_batch b;
+    fdh_store_batch(s, &b);
+    int rc = fd_store_attach(ctx, &b);
+    if (rc == FD_OK && s->chain.size() == s->aa.size() && s->serial.size() == s->aa.size() && !s->aa.empty())
+        rc = fd_store_attach_labels(ctx, s->chain.data(), s->serial.data(), s->aa.size());
+    if (rc != FD_OK) set_err(fd_last_error(ctx));
+    return rc;
 }
 void fdh_store_free(fdh_store *s) { delete s; }
 
@@ -1995,6 +2017,10 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
     R->wall_ms[0] = ms_since(t_stage);
     t_stage = now();
     R->d2h_bytes += n_cand * sizeof(fd_struct_hit) + (nq + 1) * 8ull + nq * 16ull;
+    const bool any_match_filter = p->connected_node_count > 0 || p->connected_node_ratio > 0.f ||
+                                  p->prefilter.idf_score_cutoff > 0.f || p->rmsd_cutoff > 0.f;
+    const bool any_struct_filter = !p->skip_match && (p->max_matching_node_count > 0 || p->max_matching_node_ratio > 0.f ||
+                                                      p->rmsd_cutoff > 0.f);
     std::vector<FinalMatch> fm; // matches of the candidates that took the general path, grouped by candidate
     // matches of everything else: views of pinned staging buffers, one set per verification lane (a lane = a
     // contiguous range of queries verified by one host thread on its own context / stream)
@@ -2058,13 +2084,71 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 lanes[l].c0 = hoff[q_split[l]];
                 lanes[l].c1 = hoff[q_split[l + 1]];
             }
+            // Row assembly on the device (fd_verify_rows): the records stay in HBM and the finished row arrays are
+            // copied straight into this result's page-locked blocks.  Taken with the default flags (no after-match
+            // filter), one lane, labels on the device iff the caller passed them; a batch with candidates on the
+            // general path falls back to the host assembly below.
+            const bool device_rows = n_lanes == 1 && !any_match_filter && !any_struct_filter &&
+                                     (labels != nullptr) == (fd_store_has_labels(ctx) != 0) &&
+                                     !(getenv("FD_DEVICE_ROWS") && atoi(getenv("FD_DEVICE_ROWS")) == 0);
+            bool rows_done = false;
             auto run_lane = [&](int l) {
                 fd_ctx *lc = lane_ctx[l];
                 Lane &L = lanes[l];
-                L.rc = fd_verify_candidates_prepared(lc, qs->vprep, cand_q_global.data() + L.c0, cand_n.data() + L.c0,
-                                                     L.c1 - L.c0, &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match,
-                                                     &L.recs, &L.n_recs, &L.first, &L.flags);
-                if (L.rc != FD_OK) L.err = fd_last_error(lc);
+                if (device_rows) {
+                    L.rc = fd_verify_candidates_device(lc, qs->vprep, cand_q_global.data() + L.c0, cand_n.data() + L.c0,
+                                                       L.c1 - L.c0, &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match,
+                                                       &L.n_recs, &L.first, &L.flags);
+                    if (L.rc == FD_OK) {
+                        bool general = false;
+                        for (uint64_t c = 0; c < n_cand && !general; c++) general = L.flags[c] != 0;
+                        if (!general) {
+                            // offsets from the per-candidate record counts, then one call fills the arrays
+                            std::vector<uint64_t> res_off(nq + 1, 0);
+                            for (uint32_t q = 0; q < nq; q++) {
+                                R->struct_off[q + 1] = hoff[q + 1];
+                                R->match_off[q + 1] = L.first[hoff[q + 1]];
+                                res_off[q + 1] = res_off[q] + (uint64_t)(L.first[hoff[q + 1]] - L.first[hoff[q]]) *
+                                                                  qs->q[q_begin + q].indices.size();
+                            }
+                            std::vector<uint8_t> needs(nq, 0);
+                            if (!R->structs.alloc(n_cand) || !R->matches.alloc(L.n_recs) || !R->match_order.alloc(L.n_recs) ||
+                                !R->residues.alloc(res_off[nq])) {
+                                L.rc = FD_ERR_NOMEM;
+                                L.err = "fdh_search: host allocation failed";
+                                return;
+                            }
+                            fd_rows_request rq{nq, hoff, hits, res_off.data(), R->structs.data(), R->matches.data(),
+                                               R->match_order.data(), R->residues.data(), needs.data()};
+                            L.rc = fd_verify_rows(lc, &rq);
+                            if (L.rc == FD_OK) {
+                                rows_done = true;
+                                for (uint32_t q = 0; q < nq; q++) { // queries the kernel left in emission order
+                                    if (!needs[q]) continue;
+                                    fdh_struct_row *S0 = R->structs.data() + R->struct_off[q], *S1 = R->structs.data() + R->struct_off[q + 1];
+                                    std::stable_sort(S0, S1, [](const fdh_struct_row &a, const fdh_struct_row &b) {
+                                        if (a.idf != b.idf) return a.idf > b.idf;
+                                        return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
+                                    });
+                                    const fdh_match_row *M = R->matches.data();
+                                    uint64_t *O0 = R->match_order.data() + R->match_off[q], *O1 = R->match_order.data() + R->match_off[q + 1];
+                                    std::stable_sort(O0, O1, [&](uint64_t a, uint64_t b) {
+                                        const fdh_match_row &x = M[a], &y = M[b];
+                                        if (x.idf != y.idf) return x.idf > y.idf;
+                                        return x.rmsd < y.rmsd;
+                                    });
+                                }
+                            }
+                        } else {
+                            L.rc = fd_verify_records_fetch(lc, &L.recs);
+                        }
+                    }
+                } else {
+                    L.rc = fd_verify_candidates_prepared(lc, qs->vprep, cand_q_global.data() + L.c0, cand_n.data() + L.c0,
+                                                         L.c1 - L.c0, &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match,
+                                                         &L.recs, &L.n_recs, &L.first, &L.flags);
+                }
+                if (L.rc != FD_OK && L.err.empty()) L.err = fd_last_error(lc);
             };
             std::vector<std::thread> th;
             for (int l = 1; l < n_lanes; l++) th.emplace_back(run_lane, l);
@@ -2077,6 +2161,18 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                     return fail();
                 }
                 n_recs += L.n_recs;
+            }
+            if (rows_done) {
+                R->h2d_bytes += 8ull * n_cand + n_cand * sizeof(fd_struct_hit) + 4ull * n_cand + 16ull * nq;
+                R->d2h_bytes += n_cand * sizeof(fdh_struct_row) + n_recs * (sizeof(fdh_match_row) + 8) +
+                                R->residues.size() * sizeof(fdh_residue_match) + 5ull * n_cand + nq;
+                R->wall_ms[1] = ms_since(t_stage);
+                R->wall_ms[2] = 0.0;
+                R->wall_ms[3] = ms_since(t_all);
+                R->host_ms = 0.0;
+                fd_free(hits);
+                fd_free(hoff);
+                return R;
             }
         }
         R->h2d_bytes += 8ull * n_cand;
@@ -2178,10 +2274,6 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         if (p->rmsd_cutoff > 0.f) pass = pass && m.rmsd <= p->rmsd_cutoff;
         return pass;
     };
-    const bool any_match_filter = p->connected_node_count > 0 || p->connected_node_ratio > 0.f ||
-                                  p->prefilter.idf_score_cutoff > 0.f || p->rmsd_cutoff > 0.f;
-    const bool any_struct_filter = !p->skip_match && (p->max_matching_node_count > 0 || p->max_matching_node_ratio > 0.f ||
-                                                      p->rmsd_cutoff > 0.f);
     std::vector<uint64_t> res_off(nq + 1, 0);
     // pass 1: rows per query
     auto count_query_rows = [&](uint32_t q) {
@@ -2213,7 +2305,11 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         res_off[q + 1] = nm * Q.indices.size();
     };
     // pass 2: rows written in place, then the default sorts inside the query's ranges
+    const bool prof = getenv("FD_ASSEMBLE_PROFILE") != nullptr;
+    std::atomic<uint64_t> prof_rows{0}, prof_ssort{0}, prof_msort{0};
+    auto tick = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     auto build_query = [&](uint32_t q) {
+        const uint64_t pt0 = prof ? tick() : 0;
         const Query &Q = qs->q[q_begin + q];
         const float expected = (float)Q.residue_count;
         const uint32_t n_res = (uint32_t)Q.indices.size();
@@ -2256,6 +2352,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             sr.match_end = mpos;
             *S++ = sr;
         }
+        const uint64_t pt1 = prof ? tick() : 0;
         // StructureSortStrategy::default: idf desc, min_rmsd asc (sort.rs:454-458), stable.  The rows arrive in
         // count_query order (idf desc, nid asc), so only runs of equal idf can need reordering.
         {
@@ -2271,6 +2368,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
         // (order-preserving integer image of (-idf, rmsd), emission index) records: the same total order as the
         // stable comparison sort, without the two indirect float loads per comparison.  Values that the integer image
         // would order differently from the float comparison (NaN, -0.0) take the comparison sort.
+        const uint64_t pt2 = prof ? tick() : 0;
         uint64_t *O = R->match_order.data() + mb;
         const uint64_t nm = mpos - mb;
         auto sortable = [](float f) -> uint32_t {
@@ -2306,6 +2404,12 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 return x.rmsd < y.rmsd;
             });
         }
+        if (prof) {
+            const uint64_t pt3 = tick();
+            prof_rows += pt1 - pt0;
+            prof_ssort += pt2 - pt1;
+            prof_msort += pt3 - pt2;
+        }
     };
     {
         int nt = p->host_threads > 0 ? p->host_threads : fd_default_host_threads();
@@ -2329,7 +2433,13 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             set_err("fdh_search: host allocation failed");
             return fail();
         }
+        const auto tb0 = std::chrono::steady_clock::now();
         run_parallel(build_query);
+        if (prof)
+            fprintf(stderr, "assemble: pass1+alloc %.3f ms, pass2 wall %.3f ms (%d threads); cpu: rows %.3f ms, struct sort %.3f ms, match sort %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(tb0 - t1).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count(), nt,
+                    prof_rows.load() * 1e-6, prof_ssort.load() * 1e-6, prof_msort.load() * 1e-6);
     }
     host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     R->host_ms = host_ms;

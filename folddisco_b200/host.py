@@ -74,6 +74,7 @@ def _lib():
     sig("fdh_store_get_lookup", None, [VP, VP, VP])
     sig("fdh_store_name", C.c_char_p, [VP, C.c_uint64])
     sig("fdh_store_batch", C.c_int, [VP, PP(_StructBatch)])
+    sig("fdh_store_attach", C.c_int, [VP, VP])
     sig("fdh_store_free", None, [VP])
     sig("fdh_store_save", C.c_int, [VP, C.c_char_p])
     sig("fdh_store_load", VP, [C.c_char_p])
@@ -260,8 +261,8 @@ class Store:
         """fd_store_attach: copy the compact structures to HBM for candidate verification.  pair_table=True also
         builds the store's pair table (fd_store_build_pair_table: 8 B per hashed residue pair) so that verification
         looks query hashes up instead of re-hashing candidates; returns its size in bytes (None: over the budget)"""
-        b = self.batch_view()
-        ctx._check(capi.lib().fd_store_attach(ctx.h, C.byref(b)), "fd_store_attach")
+        if _lib().fdh_store_attach(self.h, ctx.h) != 0:  # structures + (chain, residue number) labels
+            raise FdError(_err())
         if pair_table:
             return ctx.store_build_pair_table(hash_params, max_table_bytes)
         return 0

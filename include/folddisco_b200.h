@@ -412,6 +412,64 @@ int fd_verify_candidates_prepared(fd_ctx *ctx, const fd_verify_prepared *prepare
                                   float ca_dist_cutoff, int skip_ca_match, const fd_match_record **out_records,
                                   uint64_t *out_n, const uint32_t **out_first, const uint8_t **out_flags);
 
+/* ---- result rows on the device ------------------------------------------------------------------------
+ * The rows a search hands out (folddisco_b200_host.h names them fdh_struct_row / fdh_match_row /
+ * fdh_residue_match): per-candidate summary (src/controller/retrieve.rs:539-551), per-match rows, matched residues with
+ * their (chain, residue number) labels, and the default sort orders (src/controller/sort.rs:218-222, 454-458). */
+typedef struct {
+    uint32_t nid, total_match_count, node_count, edge_count;
+    float idf;
+    uint32_t max_matching_node_count;
+    float min_rmsd_with_max_match;
+    uint64_t match_begin, match_end; /* this structure's matches in match-emission order (unsorted view) */
+} fd_struct_row;
+typedef struct {
+    uint32_t nid;
+    uint32_t node_count;
+    float idf;
+    float rmsd;
+    float U[9];
+    float t[3];
+    uint64_t res_begin; /* n_query_residues entries in the residue arrays */
+} fd_match_row;
+typedef struct {
+    uint8_t some;
+    uint8_t chain;
+    uint64_t serial;
+} fd_residue_row;
+/* (chain, residue number) of every residue of the attached structure store, for fd_verify_rows (optional: without
+ * them a matched residue is reported as chain 0, number = residue index). */
+int fd_store_attach_labels(fd_ctx *ctx, const uint8_t *chain, const uint64_t *serial, uint64_t n_residues);
+int fd_store_has_labels(const fd_ctx *ctx); /* 1 after fd_store_attach_labels on the current store */
+/* fd_verify_candidates_prepared that leaves the match records ON THE DEVICE (no record copy): *out_n records,
+ * *out_first / *out_flags as above.  The records stay until the next verification call on ctx, fd_verify_rows or
+ * fd_verify_records_fetch. */
+int fd_verify_candidates_device(fd_ctx *ctx, const fd_verify_prepared *prepared, const uint32_t *cand_query,
+                                const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params,
+                                float ca_dist_cutoff, int skip_ca_match, uint64_t *out_n, const uint32_t **out_first,
+                                const uint8_t **out_flags);
+/* the kept records copied to pinned staging owned by ctx (the path of hosts that assemble rows themselves) */
+int fd_verify_records_fetch(fd_ctx *ctx, const fd_match_record **out_records);
+/* Row assembly on the device for the kept records: query q owns candidates [cand_offsets[q], cand_offsets[q+1]) in
+ * count_query order, hits[c] is the count_query row of candidate c, res_offsets[q] the first residue row of query q
+ * (res_offsets[q+1] - res_offsets[q] = matches of q x query residues of q).  Outputs are caller-allocated host
+ * memory (pinned memory makes the copies asynchronous): structs[n_cand] sorted per query (idf desc, min_rmsd asc,
+ * stable), matches[n_records] in emission order, match_order[n_records] (sorted position -> emission index: idf desc,
+ * rmsd asc, stable), residues[res_offsets[n_queries]].  needs_host_sort[q] = 1: the query's orders were left as
+ * emitted (more than 2048 matches or candidates, NaN / -0.0 keys) and the caller sorts them. */
+typedef struct {
+    uint32_t n_queries;
+    const uint64_t *cand_offsets;
+    const fd_struct_hit *hits;
+    const uint64_t *res_offsets;
+    fd_struct_row *structs;
+    fd_match_row *matches;
+    uint64_t *match_order;
+    fd_residue_row *residues;
+    uint8_t *needs_host_sort;
+} fd_rows_request;
+int fd_verify_rows(fd_ctx *ctx, const fd_rows_request *request);
+
 /* number of structures of the attached index (lookup.len()); 0 if none */
 uint64_t fd_index_num_structs(const fd_ctx *ctx);
 

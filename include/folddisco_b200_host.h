@@ -70,6 +70,9 @@ void fdh_store_get_lookup(const fdh_store *s, uint32_t *nres, float *plddt);
 const char *fdh_store_name(const fdh_store *s, uint64_t id);
 /* view usable with fd_build_index / fd_store_attach; valid until the store changes */
 int fdh_store_batch(const fdh_store *s, fd_struct_batch *out);
+/* fd_store_attach of the store's structures + fd_store_attach_labels of its (chain, residue number) labels: with the
+ * labels on the device a search assembles its result rows there (fd_verify_rows) */
+int fdh_store_attach(const fdh_store *s, fd_ctx *ctx);
 void fdh_store_free(fdh_store *s);
 
 /* ---- index files ---- */
@@ -196,29 +199,13 @@ fdh_results *fdh_search_from_votes(fd_ctx *ctx, const fdh_queries *qs, const fdh
                                    const fdh_store *labels, const fd_votes_layout *layout, const uint32_t *d_votes,
                                    uint32_t q_begin, uint32_t q_end);
 
-/* per-structure rows: query q owns [struct_offsets[q], struct_offsets[q+1]) ordered idf desc, min_rmsd asc */
-typedef struct {
-    uint32_t nid, total_match_count, node_count, edge_count;
-    float idf;
-    uint32_t max_matching_node_count;
-    float min_rmsd_with_max_match;
-    uint64_t match_begin, match_end; /* this structure's matches in match-emission order (unsorted view) */
-} fdh_struct_row;
-/* per-match rows: query q owns [match_offsets[q], match_offsets[q+1]) ordered idf desc, rmsd asc */
-typedef struct {
-    uint32_t nid;
-    uint32_t node_count;
-    float idf;
-    float rmsd;
-    float U[9];
-    float t[3];
-    uint64_t res_begin; /* n_query_residues entries in the residue arrays */
-} fdh_match_row;
-typedef struct {
-    uint8_t some;
-    uint8_t chain;
-    uint64_t serial;
-} fdh_residue_match;
+/* per-structure rows: query q owns [struct_offsets[q], struct_offsets[q+1]) ordered idf desc, min_rmsd asc;
+ * per-match rows: query q owns [match_offsets[q], match_offsets[q+1]) in emission order, fdh_results_match_order gives
+ * the order idf desc, rmsd asc; matched residues: n_query_residues entries per match from res_begin.
+ * (layouts declared in folddisco_b200.h: the device writes them, fd_verify_rows) */
+typedef fd_struct_row fdh_struct_row;
+typedef fd_match_row fdh_match_row;
+typedef fd_residue_row fdh_residue_match;
 
 uint64_t fdh_results_num_queries(const fdh_results *r);
 const uint64_t *fdh_results_struct_offsets(const fdh_results *r);

@@ -91,6 +91,8 @@ def parse(text):
         structs.append((m.group(2), fields))
     body = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", " ", text, flags=re.S)
     body = re.sub(r"typedef\s+struct\s+\w+\s+\w+\s*;", " ", body)
+    aliases = re.findall(r"typedef\s+(fdh?_\w+)\s+(fdh?_\w+)\s*;", body)  # typedef fd_struct_row fdh_struct_row;
+    body = re.sub(r"typedef\s+fdh?_\w+\s+fdh?_\w+\s*;", " ", body)
     funcs = []
     for m in re.finditer(r"([\w\s\*]+?)\b(fdh?_\w+)\s*\(([^()]*)\)\s*;", " ".join(body.split())):
         ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
@@ -102,17 +104,18 @@ def parse(text):
                     ctype, pname = p.strip(), "arg%d" % k
                 ps.append((ctype, pname))
         funcs.append((ret, name, ps))
-    return opaque, structs, funcs
+    return opaque, structs, funcs, aliases
 
 
 def generate():
-    opaque, structs, funcs = [], [], []
+    opaque, structs, funcs, aliases = [], [], [], []
     for h in HEADERS:
-        o, s, f = parse(open(os.path.join(ROOT, h)).read())
+        o, s, f, a = parse(open(os.path.join(ROOT, h)).read())
         opaque += o
         structs += s
         funcs += f
-    known = set(opaque) | {n for n, _ in structs}
+        aliases += a
+    known = set(opaque) | {n for n, _ in structs} | {b for _, b in aliases}
     out = ["// GENERATED by tools/gen_rust_ffi.py from include/folddisco_b200.h and include/folddisco_b200_host.h.",
            "// Do not edit: re-run the script.  Analogue of lib/foldcomp/bindings.rs in the reference tree; see",
            "// INTEGRATION.md for the build.rs lines and the call sites this replaces.",
@@ -131,6 +134,10 @@ def generate():
                 rt = "[%s; %d]" % (rt, arr)
             out.append("    pub %s: %s," % ("r#type" if fname == "type" else fname, rt))
         out.append("}")
+        out.append("")
+    for a, b in aliases:
+        out.append("pub type %s = %s;" % (b, a))
+    if aliases:
         out.append("")
     consts = []
     for h in HEADERS:

@@ -394,9 +394,10 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- e2e: host structures -> result rows through the public API, every step (H2D / D2H inside) ----
-    for _ in range(args.warmup):
-        search(make_batch())
-    e2e_t, e2e_res = [], None
+    e2e_res = None
+    for _ in range(args.warmup):  # the previous result stays alive during a step, exactly as in the timed loop: the
+        e2e_res = search(make_batch())  # second set of page-locked result blocks is allocated here, not under the clock
+    e2e_t = []
     e2e_names = ("hv_flatten", "hv_upload", "lookup", "cq_host_prepare", "cq_host_rest", "fs_flatten", "fs_allgather",
                  "fs_parse", "fs_counts", "fs_allreduce", "fs_tables")
     e2e_s0 = {k: ctx.stage_ms(k) for k in e2e_names}
@@ -409,8 +410,9 @@ def run_ours(args, rank, world, local_rank):
     del e2e_res
     # ---- value: query batch prepared (inputs resident), timed region = the search itself ----
     qb = make_batch(timing=None)
+    res = None
     for _ in range(args.warmup):
-        search(qb)
+        res = search(qb)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
@@ -423,7 +425,6 @@ def run_ours(args, rank, world, local_rank):
     st0 = {s: (ctx.stage_ms(s), ctx.stage_launches(s)) for s in stages + hv}
     bytes_scanned, exch_bytes = 0, 0
     val_t, wall_t = [], []
-    res = None
     for _ in range(args.steps):
         res, dt, wall = timed(lambda: search(qb))
         val_t.append(dt)

@@ -121,6 +121,9 @@ struct fd_ctx {
     std::vector<cudaEvent_t> ev_pool;                // events of the chunked verification, created on demand
     double verify_edges_per_cand = 0.0, verify_comps_per_cand = 0.0; // pool sizing of the chunked verification
     FdVerifyKeep vkeep;
+    uint64_t idx_generation = 0;            // bumped by every fd_index_attach
+    void *cq_cache = nullptr;               // fd_query.cu: the last batch that carried an id, with its lookup results
+    void (*cq_cache_free)(void *) = nullptr;
     uint32_t *votes = nullptr; // dense partial-vote planes of the last fd_votes_scan (device, owned)
     uint64_t votes_cap = 0;    // capacity in u32 words
     uint32_t *merge = nullptr; // dense vote planes of this rank's slice of the batch (sparse merge), owned

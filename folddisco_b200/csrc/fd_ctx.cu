@@ -323,6 +323,8 @@ void fd_destroy(fd_ctx *ctx) {
     }
     cudaFree(ctx->votes);
     cudaFree(ctx->merge);
+    fd_tls_stream = ctx->stream; // the cached batch releases its device buffers stream-ordered
+    if (ctx->cq_cache && ctx->cq_cache_free) ctx->cq_cache_free(ctx->cq_cache);
     cudaFree(ctx->vkeep.recs);
     cudaFree(ctx->vkeep.d_cand_query);
     for (auto &b : ctx->pinned)

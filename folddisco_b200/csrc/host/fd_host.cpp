@@ -474,6 +474,15 @@ struct fdh_queries {
     std::vector<float> dist_thr, angle_thr;
     std::vector<Query> q;
     bool finalized = false;
+    // identity of the batch for fd_count_query_*_id: a process-wide serial number and a generation that every
+    // modification (add, finalize, set_shards) bumps -- a search of an unchanged batch reuses its uploaded form
+    uint64_t uid = next_uid();
+    mutable uint64_t generation = 1;
+    static uint64_t next_uid() {
+        static std::atomic<uint64_t> n{1};
+        return n.fetch_add(1);
+    }
+    uint64_t batch_id() const { return (uid << 24) | (generation & 0xffffffull); }
     std::vector<uint64_t> shard_bounds; // world + 1 ascending hash boundaries; empty = unsharded
     // query side of the verification, resident on the device of the context that searched first (fd_verify_prepare);
     // built by fdh_queries_finalize (or lazily by the first search), dropped whenever the idf values change
@@ -1620,6 +1629,7 @@ int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *st, const char *quer
     }
     qs->q.push_back(std::move(Q));
     qs->finalized = false;
+    qs->generation++;
     return (int64_t)qs->q.size() - 1;
 }
 
@@ -1683,6 +1693,7 @@ static int64_t add_many_impl(fdh_queries *qs, const fdh_compact *const *structs,
     qs->q.reserve(qs->q.size() + (size_t)n);
     for (auto &Q : out) qs->q.push_back(std::move(Q));
     qs->finalized = false;
+    qs->generation++;
     return first;
 }
 int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,
@@ -2038,14 +2049,16 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             eb += S.q_ne[q];
         }
         R->h2d_bytes += 6ull * hb + 2ull * eb + 24ull * nb + 4ull * hb;
-        rc = fd_count_query_sharded(ctx, fq.data(), nb, &p->prefilter, S.gcounts.data(), S.total_structs, S.first_id,
-                                    S.slice_begin.data(), &hits, &hoff);
+        rc = fd_count_query_sharded_id(ctx, fq.data(), nb, &p->prefilter, S.gcounts.data(), S.total_structs, S.first_id,
+                                       S.slice_begin.data(), qs->batch_id(), &hits, &hoff);
     } else if (votes) {
         make_fd_queries(qs, 0, (uint32_t)qs->q.size(), fq, nullptr);
         rc = fd_votes_select(ctx, fq.data(), (uint32_t)fq.size(), &p->prefilter, layout, votes, q_begin, q_end, &hits, &hoff);
     } else {
         make_fd_queries(qs, q_begin, q_end, fq, &R->h2d_bytes);
-        rc = fd_count_query_batch(ctx, fq.data(), nq, &p->prefilter, &hits, &hoff);
+        // (a sub-range of the batch is a different batch: the id covers the whole one)
+        rc = fd_count_query_batch_id(ctx, fq.data(), nq, &p->prefilter, q_begin == 0 && q_end == qs->q.size() ? qs->batch_id() : 0,
+                                     &hits, &hoff);
     }
     if (rc != FD_OK) {
         set_err(fd_last_error(ctx));
@@ -2508,6 +2521,7 @@ int fdh_queries_set_shards(fdh_queries *qs, const uint64_t *bounds, int world) {
             return FD_ERR_ARG;
         }
     std::vector<uint64_t> b(bounds, bounds + world + 1);
+    qs->generation++;
     for (auto &Q : qs->q) {
         const size_t E = Q.edge_node.size();
         std::vector<uint64_t> owners(E, 0);
@@ -2652,6 +2666,7 @@ int fdh_queries_finalize_with_counts(fdh_queries *qs, const uint32_t *counts, ui
             }
     });
     qs->finalized = true;
+    qs->generation++;
     return FD_OK;
 }
 int fdh_votes_scan(fd_ctx *ctx, const fdh_queries *qs, const fd_prefilter_params *prefilter, fd_votes_layout *layout,
@@ -2674,6 +2689,7 @@ fdh_results *fdh_search_from_votes(fd_ctx *ctx, const fdh_queries *qs, const fdh
 
 // ---- id-range shards over NCCL (fd_comm_*): gather the ranks' query descriptors, all-reduce the list lengths ----
 int fdh_queries_finalize_sharded(fdh_queries *qs, fd_ctx *ctx, uint64_t first_id, uint64_t total_structs) {
+    qs->generation++;
     const int world = fd_comm_world(ctx), rank = fd_comm_rank(ctx);
     auto t_mark = std::chrono::steady_clock::now();
     auto mark = [&](const char *name) { // host wall time of the step that just ended -> fd_stage_ms(ctx, name)

@@ -185,6 +185,13 @@ typedef struct {
  * idf descending, ties by ascending nid. */
 int fd_count_query_batch(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries,
                          const fd_prefilter_params *params, fd_struct_hit **out_hits, uint64_t **out_offsets);
+/* fd_count_query_batch for a batch the caller may search again: batch_id != 0 is the caller's promise that queries and
+ * params are identical to the previous call on ctx that carried the same id (and the attached index is the same; a new
+ * fd_index_attach invalidates the cache).  The library then reuses the uploaded batch and its lookup results instead
+ * of flattening, uploading and looking the hashes up again.  batch_id == 0: no caching (= fd_count_query_batch). */
+int fd_count_query_batch_id(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries,
+                            const fd_prefilter_params *params, uint64_t batch_id, fd_struct_hit **out_hits,
+                            uint64_t **out_offsets);
 /* The same for one ID-RANGE SHARD of a larger database (multi-GPU, SURVEY 8e ablation / fd_search_sharded): the
  * attached index holds the postings of a contiguous range of structure ids (local ids 0 .. n_structs) and
  * global_counts[k] is the length of the k-th query hash's list in the WHOLE database (hashes of all queries
@@ -224,6 +231,12 @@ int fd_count_query_sharded(fd_ctx *ctx, const fd_query *queries, uint32_t n_quer
                            const uint32_t *global_counts, uint64_t global_n_structs, uint64_t first_id,
                            const uint32_t *slice_begin /* world + 1 */, fd_struct_hit **out_hits,
                            uint64_t **out_offsets);
+/* the same with a batch id (see fd_count_query_batch_id): every rank scans the whole batch of all ranks, so the
+ * flatten + upload + lookup saved per repeated batch grows with the number of ranks */
+int fd_count_query_sharded_id(fd_ctx *ctx, const fd_query *queries, uint32_t n_queries, const fd_prefilter_params *params,
+                              const uint32_t *global_counts, uint64_t global_n_structs, uint64_t first_id,
+                              const uint32_t *slice_begin /* world + 1 */, uint64_t batch_id, fd_struct_hit **out_hits,
+                              uint64_t **out_offsets);
 /* bytes this rank sent to other ranks in the last fd_count_query_sharded */
 uint64_t fd_last_exchange_bytes(const fd_ctx *ctx);
 

@@ -521,3 +521,69 @@ def test_whole_structure_query_skip_match(env):
     assert len(res.structures(1)) > 0
     with pytest.raises(fd.FdError, match="whole-structure"):
         host.search(ctx, qb, host.SearchParams(top_n=5), labels=store)
+
+
+def _rows(res, nq):
+    out = []
+    for q in range(nq):
+        out.append(([tuple(r) for r in res.structures(q).tolist()],
+                    [(int(m["nid"]), int(m["node_count"]), float(m["idf"]), float(m["rmsd"])) for m in res.sorted_matches(q)]))
+    return out
+
+
+def test_repeated_batch_and_device_rows(env):
+    """(1) A query batch searched again carries its batch id: count_query reuses the uploaded batch and its lookup
+    results -- the rows must not change, and they must follow a changed filter, a changed batch and a newly attached
+    index.  (2) Rows assembled on the device (fd_verify_rows, the default) equal the host assembly
+    (FD_DEVICE_ROWS=0) row for row: summaries, both sort orders, residue labels."""
+    from folddisco_b200 import synth
+    host, ctx = env["host"], env["ctx"]
+    b = synth.generate(800, 11, mean_len=150.0, max_len=500)
+    store = host.Store()
+    store.add_soa(b)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    store.attach(ctx)
+    qb = host.QueryBatch(ix.params)
+    for path, q, _ in F.MOTIFS:
+        qb.add(host.CompactStructure.from_atoms(env["atoms"][path]), q)
+    qb.finalize(ctx)
+    sp = host.SearchParams(top_n=60)
+    first = host.search(ctx, qb, sp, labels=store)
+    again = host.search(ctx, qb, sp, labels=store)  # cache hit
+    nq = len(F.MOTIFS)
+    assert _rows(first, nq) == _rows(again, nq)
+    for q in range(nq):  # residue labels of every match row
+        for m in first.sorted_matches(q)[:20]:
+            assert first.residue_string(m, len(qb.indices(q))) == again.residue_string(m, len(qb.indices(q)))
+    os.environ["FD_DEVICE_ROWS"] = "0"
+    try:
+        on_host = host.search(ctx, qb, sp, labels=store)
+    finally:
+        del os.environ["FD_DEVICE_ROWS"]
+    assert _rows(first, nq) == _rows(on_host, nq)
+    for q in range(nq):
+        ms, mh = first.sorted_matches(q), on_host.sorted_matches(q)
+        assert len(ms) == len(mh)
+        for x, y in zip(ms, mh):
+            assert first.residue_string(x, len(qb.indices(q))) == on_host.residue_string(y, len(qb.indices(q)))
+            assert np.array_equal(x["U"], y["U"]) and np.array_equal(x["t"], y["t"])
+    assert sum(len(first.sorted_matches(q)) for q in range(nq)) > 50
+    # a changed filter is a different cache key; a changed batch has a new id
+    sp2 = host.SearchParams(top_n=10)
+    few = host.search(ctx, qb, sp2, labels=store)
+    assert all(len(few.structures(q)) <= 10 for q in range(nq)) and any(len(first.structures(q)) > 10 for q in range(nq))
+    qb.add(host.CompactStructure.from_atoms(env["atoms"]["query/4CHA.pdb"]), "B57,B102,C195")
+    qb.finalize(ctx)
+    more = host.search(ctx, qb, sp, labels=store)
+    assert _rows(more, nq) == _rows(first, nq) and _rows(more, nq + 1)[nq] == _rows(first, 1)[0]
+    # a newly attached index invalidates the cached lookup results
+    b2 = synth.generate(300, 12, mean_len=150.0, max_len=500)
+    store2 = host.Store()
+    store2.add_soa(b2)
+    ix2 = host.FolddiscoIndex.build(ctx, store2)
+    ix2.attach(ctx)
+    store2.attach(ctx)
+    qb.finalize(ctx)
+    other = host.search(ctx, qb, sp, labels=store2)
+    assert all(int(r["nid"]) < 300 for q in range(nq) for r in other.structures(q))

@@ -1326,12 +1326,12 @@ __global__ void __launch_bounds__(VD_THREADS)
     k6d_rows(const VQDesc *vq, const uint32_t *cand_query, const uint64_t *cand_off, const fd_struct_hit *hits,
              const uint32_t *first, const fd_match_record *recs, const uint64_t *store_row_offsets,
              const uint8_t *label_chain, const uint64_t *label_serial, const uint64_t *res_off,
-             fd_struct_row *structs_tmp, fd_struct_row *structs, fd_match_row *matches, unsigned long long *match_order, fd_residue_row *residues, uint8_t *needs_host) {
+             fd_struct_row *structs_tmp, fd_struct_row *structs, fd_match_row *matches, unsigned long long *match_order, fd_residue_row *residues, uint8_t *needs_host, uint32_t q_base) {
     __shared__ unsigned long long s_key[VD_MAX_MATCHES];
     __shared__ uint16_t s_idx[VD_MAX_MATCHES];
     __shared__ float s_idf[VD_MAX_CANDS], s_rmsd[VD_MAX_CANDS];
     __shared__ uint32_t s_flag;
-    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t q = q_base + blockIdx.x, tid = threadIdx.x;
     const uint64_t c0 = cand_off[q], c1 = cand_off[q + 1];
     const uint32_t nc = (uint32_t)(c1 - c0);
     if (tid == 0) s_flag = 0;
@@ -1366,6 +1366,7 @@ __global__ void __launch_bounds__(VD_THREADS)
         if (!vd_plain(h.idf) || !vd_plain(min_rmsd)) atomicOr(&s_flag, 1u);
         // provisional position = count_query order; moved below when the run of equal idf needs reordering
         fd_struct_row sr;
+        memset(&sr, 0, sizeof(sr)); // (padding bytes travel to the host)
         sr.nid = h.nid;
         sr.total_match_count = h.match_count;
         sr.node_count = h.node_count;
@@ -1470,7 +1471,7 @@ __global__ void __launch_bounds__(VD_THREADS)
 static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *cand_query, const uint32_t *cand_nid,
                       uint64_t n_cand, const fd_hash_params *params, float ca_dist_cutoff, int skip_ca_match,
                       const fd_match_record **out_records, uint64_t *out_n, const uint32_t **out_first,
-                      const uint8_t **out_flags, bool keep_device = false) {
+                      const uint8_t **out_flags, bool keep_device = false, fd_rows_plan *plan = nullptr) {
     if (!ctx) return FD_ERR_ARG;
     if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_verify_candidates: no structure store attached");
     if (!P || (n_cand && (!cand_query || !cand_nid)) || !params || !out_records || !out_n || !out_flags || !out_first)
@@ -1550,6 +1551,32 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         uint32_t *h_first_rel = nullptr;    // pinned, n + 1
         uint64_t rec_base = 0;
     };
+    // with a rows plan the chunks are cut at query boundaries, so that a finished chunk holds whole queries
+    std::vector<uint64_t> cut(n_chunks + 1);
+    std::vector<uint32_t> cut_q(n_chunks + 1, 0);
+    for (uint32_t k = 0; k <= n_chunks; k++) cut[k] = n_cand * k / n_chunks;
+    bool rows_on = plan != nullptr;
+    if (plan) {
+        plan->done = 0;
+        if (plan->cand_offsets[0] != 0 || plan->cand_offsets[plan->n_queries] != n_cand)
+            return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates_rows: cand_offsets must cover the candidates");
+        std::vector<uint64_t> c2{0};
+        std::vector<uint32_t> q2{0};
+        for (uint32_t k = 1; k < n_chunks; k++) {
+            const uint64_t *lo = std::lower_bound(plan->cand_offsets, plan->cand_offsets + plan->n_queries + 1, cut[k]);
+            const uint32_t q = (uint32_t)(lo - plan->cand_offsets);
+            if (*lo > c2.back() && *lo < n_cand) {
+                c2.push_back(*lo);
+                q2.push_back(q);
+            }
+        }
+        c2.push_back(n_cand);
+        q2.push_back(plan->n_queries);
+        n_chunks = (uint32_t)c2.size() - 1;
+        cut = c2;
+        cut_q = q2;
+        for (uint64_t c = 0; c < n_cand && rows_on; c++) rows_on = h_flags[c] == 0; // a query outside the kernels' limits
+    }
     std::vector<Chunk> chunks(n_chunks);
     DevBuf<uint8_t> d_flags;
     DevBuf<uint32_t> d_cq, d_cn, d_ebegin, d_ne;
@@ -1584,8 +1611,8 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
     FD_CUDA(ctx, cudaFuncSetAttribute(k6b_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     for (uint32_t k = 0; k < n_chunks; k++) {
         Chunk &C = chunks[k];
-        C.c0 = n_cand * k / n_chunks;
-        C.n = n_cand * (k + 1) / n_chunks - C.c0;
+        C.c0 = cut[k];
+        C.n = cut[k + 1] - C.c0;
         C.st = (k & 1) ? s1 : s0;
         // pools sized from what the previous calls on this context needed (+50 %), at least 64 edges and 3 components
         // per candidate: a chunk that overflows is re-issued with exact sizes, which doubles its cost and stalls the
@@ -1613,6 +1640,34 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
     if (lpt) {
         FD_CUDA(ctx, d_iota.alloc(max_chunk + 1));
         FD_LAUNCH_ON(ctx, s0, k6_iota, fd_div_up(max_chunk, 256), 256, 0, d_iota.p, (uint32_t)max_chunk);
+    }
+    // rows plan: the row kernel's inputs and outputs on the device (filled chunk by chunk on the copy stream)
+    DevBuf<uint64_t> r_coff, r_roff;
+    DevBuf<fd_struct_hit> r_hits;
+    DevBuf<uint32_t> r_first;
+    DevBuf<fd_struct_row> r_structs, r_structs_tmp;
+    DevBuf<fd_match_row> r_matches;
+    DevBuf<unsigned long long> r_order;
+    DevBuf<fd_residue_row> r_res;
+    DevBuf<uint8_t> r_need;
+    uint64_t *h_roff = nullptr; // pinned: res_offsets of the plan
+    uint64_t res_produced = 0;
+    if (rows_on) {
+        const uint32_t pq = plan->n_queries;
+        FD_TRY(fd_pinned(ctx, 9, (pq + 1) * 8ull, (void **)&h_roff));
+        h_roff[0] = 0;
+        FD_CUDA(ctx, r_coff.alloc(pq + 1));
+        FD_CUDA(ctx, r_roff.alloc(pq + 1));
+        FD_CUDA(ctx, r_hits.alloc(n_cand));
+        FD_CUDA(ctx, r_first.alloc(n_cand + 1));
+        FD_CUDA(ctx, r_structs.alloc(n_cand));
+        FD_CUDA(ctx, r_structs_tmp.alloc(n_cand));
+        FD_CUDA(ctx, r_matches.alloc(std::max<uint64_t>(plan->match_capacity, 1)));
+        FD_CUDA(ctx, r_order.alloc(std::max<uint64_t>(plan->match_capacity, 1)));
+        FD_CUDA(ctx, r_res.alloc(std::max<uint64_t>(plan->residue_capacity, 1)));
+        FD_CUDA(ctx, r_need.alloc(std::max<uint32_t>(pq, 1)));
+        FD_CUDA(ctx, cudaMemcpyAsync(r_coff.p, plan->cand_offsets, (pq + 1) * 8ull, cudaMemcpyHostToDevice, s0));
+        FD_CUDA(ctx, cudaMemcpyAsync(r_hits.p, plan->hits, n_cand * sizeof(fd_struct_hit), cudaMemcpyHostToDevice, s0));
     }
     // allocations and uploads were ordered on s0: the other streams start after them
     cudaEvent_t ev_begin = event_at(5 * n_chunks), ev_end = event_at(5 * n_chunks + 1), ev_tmp = event_at(5 * n_chunks + 2);
@@ -1722,6 +1777,36 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
                                          keep_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sc));
         }
         for (uint64_t c = 0; c <= C.n; c++) h_first[C.c0 + c] = (uint32_t)(produced + C.h_first_rel[c]);
+        if (rows_on) {
+            // rows of the chunk's queries: assembled and copied on the copy stream, under the next chunks' kernels
+            const uint32_t qa = cut_q[k], qb = cut_q[k + 1];
+            for (uint64_t c = 0; c < C.n && rows_on; c++) rows_on = h_kflags[C.c0 + c] == 0; // general-path candidate
+            uint64_t res_end = res_produced;
+            for (uint32_t q = qa; q < qb && rows_on; q++) {
+                const uint64_t nm_q = h_first[plan->cand_offsets[q + 1]] - h_first[plan->cand_offsets[q]];
+                res_end += nm_q * plan->n_res[q];
+                h_roff[q + 1] = res_end;
+            }
+            if (produced + np > plan->match_capacity || res_end > plan->residue_capacity) rows_on = false;
+            if (rows_on) {
+                FD_CUDA(ctx, cudaMemcpyAsync(r_first.p + C.c0, h_first + C.c0, (C.n + 1) * 4ull, cudaMemcpyHostToDevice, sc));
+                FD_CUDA(ctx, cudaMemcpyAsync(r_roff.p + qa, h_roff + qa, (qb - qa + 1) * 8ull, cudaMemcpyHostToDevice, sc));
+                if (qb > qa)
+                    FD_LAUNCH_ON(ctx, sc, k6d_rows, qb - qa, VD_THREADS, 0, P->d_desc, d_cq.p, r_coff.p, r_hits.p, r_first.p,
+                                 h_out, S.row_offsets, S.label_chain, S.label_serial, r_roff.p, r_structs_tmp.p, r_structs.p,
+                                 r_matches.p, r_order.p, r_res.p, r_need.p, qa);
+                FD_CUDA(ctx, cudaMemcpyAsync(plan->needs_host_sort + qa, r_need.p + qa, qb - qa, cudaMemcpyDeviceToHost, sc));
+                FD_CUDA(ctx, cudaMemcpyAsync(plan->structs + C.c0, r_structs.p + C.c0, C.n * sizeof(fd_struct_row), cudaMemcpyDeviceToHost, sc));
+                if (np) {
+                    FD_CUDA(ctx, cudaMemcpyAsync(plan->matches + produced, r_matches.p + produced, np * sizeof(fd_match_row), cudaMemcpyDeviceToHost, sc));
+                    FD_CUDA(ctx, cudaMemcpyAsync(plan->match_order + produced, r_order.p + produced, np * 8ull, cudaMemcpyDeviceToHost, sc));
+                }
+                if (res_end > res_produced)
+                    FD_CUDA(ctx, cudaMemcpyAsync(plan->residues + res_produced, r_res.p + res_produced,
+                                                 (res_end - res_produced) * sizeof(fd_residue_row), cudaMemcpyDeviceToHost, sc));
+                res_produced = res_end;
+            }
+        }
         produced += np;
     }
     h_mark("hv_wait_chunks");
@@ -1755,6 +1840,10 @@ static int verify_run(fd_ctx *ctx, const fd_verify_prepared *P, const uint32_t *
         for (auto &C : chunks) edges += C.h_counters[0];
         ctx->verify_edges_per_cand = std::max(ctx->verify_edges_per_cand * 0.9, (double)edges / (double)n_cand);
         ctx->verify_comps_per_cand = std::max(ctx->verify_comps_per_cand * 0.9, (double)produced / (double)n_cand);
+    }
+    if (plan) {
+        plan->done = rows_on ? 1 : 0;
+        if (rows_on) memcpy(plan->res_offsets, h_roff, (plan->n_queries + 1) * 8ull);
     }
     if (keep_device) {
         ctx->vkeep.recs = h_out;
@@ -1814,6 +1903,25 @@ extern "C" int fd_verify_candidates_device(fd_ctx *ctx, const fd_verify_prepared
                       out_first, out_flags, true);
 }
 
+extern "C" uint64_t fd_verify_match_capacity(const fd_ctx *ctx, uint64_t n_cand) {
+    const double per = std::max(3.0, 1.5 * (ctx ? ctx->verify_comps_per_cand : 0.0));
+    return (uint64_t)(per * (double)n_cand) + n_cand + 16 * 1024;
+}
+
+extern "C" int fd_verify_candidates_rows(fd_ctx *ctx, const fd_verify_prepared *prepared, const uint32_t *cand_query,
+                                         const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params,
+                                         float ca_dist_cutoff, int skip_ca_match, fd_rows_plan *plan, uint64_t *out_n,
+                                         const uint32_t **out_first, const uint8_t **out_flags) {
+    if (!plan || !plan->cand_offsets || !plan->n_res || !plan->needs_host_sort || !plan->res_offsets ||
+        (n_cand && (!plan->hits || !plan->structs)) || (plan->match_capacity && (!plan->matches || !plan->match_order)) ||
+        (plan->residue_capacity && !plan->residues))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_verify_candidates_rows: NULL argument");
+    plan->done = 0;
+    const fd_match_record *none = nullptr;
+    return verify_run(ctx, prepared, cand_query, cand_nid, n_cand, params, ca_dist_cutoff, skip_ca_match, &none, out_n,
+                      out_first, out_flags, true, n_cand ? plan : nullptr);
+}
+
 extern "C" int fd_verify_records_fetch(fd_ctx *ctx, const fd_match_record **out_records) {
     if (!ctx || !out_records) return FD_ERR_ARG;
     FD_ENTER(ctx);
@@ -1871,7 +1979,7 @@ extern "C" int fd_verify_rows(fd_ctx *ctx, const fd_rows_request *rq) {
     if (nq)
         FD_LAUNCH(ctx, k6d_rows, nq, VD_THREADS, 0, P->d_desc, K.d_cand_query, d_coff.p, d_hits.p, d_first.p,
                   (const fd_match_record *)K.recs, S.row_offsets, S.label_chain, S.label_serial, d_roff.p, d_structs_tmp.p,
-                  d_structs.p, d_matches.p, d_order.p, d_res.p, d_need.p);
+                  d_structs.p, d_matches.p, d_order.p, d_res.p, d_need.p, 0u);
     FD_CUDA(ctx, cudaMemcpyAsync(rq->needs_host_sort, d_need.p, nq, cudaMemcpyDeviceToHost, s));
     if (n_cand) FD_CUDA(ctx, cudaMemcpyAsync(rq->structs, d_structs.p, n_cand * sizeof(fd_struct_row), cudaMemcpyDeviceToHost, s));
     if (n_rec) {

@@ -1056,6 +1056,7 @@ struct RawArray {
         p = (T *)block_cache().get(std::max<size_t>(count, 1) * sizeof(T), &cap_bytes);
         return p != nullptr;
     }
+    void shrink(size_t count) { n = std::min(n, count); } // rows in use (the block keeps its capacity)
     T *data() { return p; }
     const T *data() const { return p; }
     size_t size() const { return n; }
@@ -2148,24 +2149,37 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 fd_ctx *lc = lane_ctx[l];
                 Lane &L = lanes[l];
                 if (device_rows) {
-                    L.rc = fd_verify_candidates_device(lc, qs->vprep, cand_q_global.data() + L.c0, cand_n.data() + L.c0,
-                                                       L.c1 - L.c0, &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match,
-                                                       &L.n_recs, &L.first, &L.flags);
+                    // one pipelined call: chunks cut at query boundaries, the rows of a finished chunk are assembled
+                    // and copied while the next chunks are verified
+                    std::vector<uint32_t> n_res_q(nq);
+                    uint32_t max_res = 1;
+                    for (uint32_t q = 0; q < nq; q++) {
+                        n_res_q[q] = (uint32_t)qs->q[q_begin + q].indices.size();
+                        max_res = std::max(max_res, n_res_q[q]);
+                    }
+                    const uint64_t mcap = fd_verify_match_capacity(lc, n_cand);
+                    std::vector<uint64_t> res_off(nq + 1, 0);
+                    std::vector<uint8_t> needs(nq, 0);
+                    if (!R->structs.alloc(n_cand) || !R->matches.alloc(mcap) || !R->match_order.alloc(mcap) ||
+                        !R->residues.alloc(mcap * max_res)) {
+                        L.rc = FD_ERR_NOMEM;
+                        L.err = "fdh_search: host allocation failed";
+                        return;
+                    }
+                    fd_rows_plan plan{nq, hoff, hits, n_res_q.data(), mcap, mcap * max_res, R->structs.data(), R->matches.data(),
+                                      R->match_order.data(), R->residues.data(), needs.data(), res_off.data(), 0};
+                    L.rc = fd_verify_candidates_rows(lc, qs->vprep, cand_q_global.data() + L.c0, cand_n.data() + L.c0,
+                                                     L.c1 - L.c0, &qs->p.hash, p->ca_dist_cutoff, p->skip_ca_match, &plan,
+                                                     &L.n_recs, &L.first, &L.flags);
                     if (L.rc == FD_OK) {
                         bool general = false;
                         for (uint64_t c = 0; c < n_cand && !general; c++) general = L.flags[c] != 0;
-                        if (!general) {
-                            // offsets from the per-candidate record counts, then one call fills the arrays
-                            std::vector<uint64_t> res_off(nq + 1, 0);
-                            for (uint32_t q = 0; q < nq; q++) {
-                                R->struct_off[q + 1] = hoff[q + 1];
-                                R->match_off[q + 1] = L.first[hoff[q + 1]];
-                                res_off[q + 1] = res_off[q] + (uint64_t)(L.first[hoff[q + 1]] - L.first[hoff[q]]) *
-                                                                  qs->q[q_begin + q].indices.size();
-                            }
-                            std::vector<uint8_t> needs(nq, 0);
-                            if (!R->structs.alloc(n_cand) || !R->matches.alloc(L.n_recs) || !R->match_order.alloc(L.n_recs) ||
-                                !R->residues.alloc(res_off[nq])) {
+                        bool have_rows = plan.done != 0;
+                        if (!have_rows && !general) {
+                            // a capacity was too small: the records are still on the device, assemble in one piece
+                            for (uint32_t q = 0; q < nq; q++)
+                                res_off[q + 1] = res_off[q] + (uint64_t)(L.first[hoff[q + 1]] - L.first[hoff[q]]) * n_res_q[q];
+                            if (!R->matches.alloc(L.n_recs) || !R->match_order.alloc(L.n_recs) || !R->residues.alloc(res_off[nq])) {
                                 L.rc = FD_ERR_NOMEM;
                                 L.err = "fdh_search: host allocation failed";
                                 return;
@@ -2173,25 +2187,33 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                             fd_rows_request rq{nq, hoff, hits, res_off.data(), R->structs.data(), R->matches.data(),
                                                R->match_order.data(), R->residues.data(), needs.data()};
                             L.rc = fd_verify_rows(lc, &rq);
-                            if (L.rc == FD_OK) {
-                                rows_done = true;
-                                for (uint32_t q = 0; q < nq; q++) { // queries the kernel left in emission order
-                                    if (!needs[q]) continue;
-                                    fdh_struct_row *S0 = R->structs.data() + R->struct_off[q], *S1 = R->structs.data() + R->struct_off[q + 1];
-                                    std::stable_sort(S0, S1, [](const fdh_struct_row &a, const fdh_struct_row &b) {
-                                        if (a.idf != b.idf) return a.idf > b.idf;
-                                        return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
-                                    });
-                                    const fdh_match_row *M = R->matches.data();
-                                    uint64_t *O0 = R->match_order.data() + R->match_off[q], *O1 = R->match_order.data() + R->match_off[q + 1];
-                                    std::stable_sort(O0, O1, [&](uint64_t a, uint64_t b) {
-                                        const fdh_match_row &x = M[a], &y = M[b];
-                                        if (x.idf != y.idf) return x.idf > y.idf;
-                                        return x.rmsd < y.rmsd;
-                                    });
-                                }
+                            have_rows = L.rc == FD_OK;
+                        }
+                        if (have_rows) {
+                            rows_done = true;
+                            R->matches.shrink(L.n_recs);
+                            R->match_order.shrink(L.n_recs);
+                            R->residues.shrink(res_off[nq]);
+                            for (uint32_t q = 0; q < nq; q++) {
+                                R->struct_off[q + 1] = hoff[q + 1];
+                                R->match_off[q + 1] = L.first[hoff[q + 1]];
                             }
-                        } else {
+                            for (uint32_t q = 0; q < nq; q++) { // queries the kernel left in emission order
+                                if (!needs[q]) continue;
+                                fdh_struct_row *S0 = R->structs.data() + R->struct_off[q], *S1 = R->structs.data() + R->struct_off[q + 1];
+                                std::stable_sort(S0, S1, [](const fdh_struct_row &a, const fdh_struct_row &b) {
+                                    if (a.idf != b.idf) return a.idf > b.idf;
+                                    return a.min_rmsd_with_max_match < b.min_rmsd_with_max_match;
+                                });
+                                const fdh_match_row *M = R->matches.data();
+                                uint64_t *O0 = R->match_order.data() + R->match_off[q], *O1 = R->match_order.data() + R->match_off[q + 1];
+                                std::stable_sort(O0, O1, [&](uint64_t a, uint64_t b) {
+                                    const fdh_match_row &x = M[a], &y = M[b];
+                                    if (x.idf != y.idf) return x.idf > y.idf;
+                                    return x.rmsd < y.rmsd;
+                                });
+                            }
+                        } else if (L.rc == FD_OK) {
                             L.rc = fd_verify_records_fetch(lc, &L.recs);
                         }
                     }

@@ -482,6 +482,33 @@ typedef struct {
     uint8_t *needs_host_sort;
 } fd_rows_request;
 int fd_verify_rows(fd_ctx *ctx, const fd_rows_request *request);
+/* The two steps as ONE pipelined call: the candidates are verified in a few chunks cut at query boundaries, and the rows
+ * of a finished chunk are assembled and copied to the host while the next chunks are still being verified (the copy of
+ * the finished rows is the longest piece of a search once everything else runs on the device).  The caller provides the
+ * output arrays with capacities (fd_verify_match_capacity rows for matches / match_order, that many times the largest
+ * n_res for residues) and n_res[q], the number of query residues of query q.  On return `done` tells whether the rows
+ * were delivered; 0 (a candidate needs the general verification path, or a capacity was too small): the records are
+ * kept on the device as after fd_verify_candidates_device, and the caller uses fd_verify_rows / fd_verify_records_fetch.
+ * res_offsets[n_queries + 1] is filled like fd_rows_request.res_offsets. */
+typedef struct {
+    uint32_t n_queries;
+    const uint64_t *cand_offsets;
+    const fd_struct_hit *hits;
+    const uint32_t *n_res;
+    uint64_t match_capacity, residue_capacity;
+    fd_struct_row *structs;
+    fd_match_row *matches;
+    uint64_t *match_order;
+    fd_residue_row *residues;
+    uint8_t *needs_host_sort;
+    uint64_t *res_offsets;
+    int done;
+} fd_rows_plan;
+uint64_t fd_verify_match_capacity(const fd_ctx *ctx, uint64_t n_cand);
+int fd_verify_candidates_rows(fd_ctx *ctx, const fd_verify_prepared *prepared, const uint32_t *cand_query,
+                              const uint32_t *cand_nid, uint64_t n_cand, const fd_hash_params *params,
+                              float ca_dist_cutoff, int skip_ca_match, fd_rows_plan *plan, uint64_t *out_n,
+                              const uint32_t **out_first, const uint8_t **out_flags);
 
 /* number of structures of the attached index (lookup.len()); 0 if none */
 uint64_t fd_index_num_structs(const fd_ctx *ctx);

@@ -47,6 +47,7 @@ _Static_assert(sizeof(fdh_match_row) == 72, "fdh_match_row");
 _Static_assert(sizeof(fdh_residue_match) == 16, "fdh_residue_match");
 _Static_assert(sizeof(fd_struct_row) == 48 && sizeof(fd_match_row) == 72 && sizeof(fd_residue_row) == 16, "device row layouts");
 _Static_assert(sizeof(fd_rows_request) == 72, "fd_rows_request");
+_Static_assert(sizeof(fd_rows_plan) == 104, "fd_rows_plan");
 _Static_assert(FD_COMM_ID_BYTES == 128, "NCCL unique id");
 
 /* entry points that the run below does not call: taking their address makes the link step check them */

@@ -524,11 +524,25 @@ def test_whole_structure_query_skip_match(env):
 
 
 def _rows(res, nq):
+    """rows of every query as plain tuples (without the padding bytes of the row structs and the positions of a
+    structure's matches in the batch-wide match array)"""
     out = []
     for q in range(nq):
-        out.append(([tuple(r) for r in res.structures(q).tolist()],
+        st = res.structures(q)
+        out.append(([tuple(r[k].item() for k in st.dtype.names if k not in ("_pad", "match_begin", "match_end")) +
+                     (int(r["match_end"] - r["match_begin"]),) for r in st],
                     [(int(m["nid"]), int(m["node_count"]), float(m["idf"]), float(m["rmsd"])) for m in res.sorted_matches(q)]))
     return out
+
+
+def _same_rows(a, b):
+    assert len(a) == len(b)
+    for q, ((sa, ma), (sb, mb)) in enumerate(zip(a, b)):
+        assert len(sa) == len(sb) and len(ma) == len(mb), (q, len(sa), len(sb), len(ma), len(mb))
+        for k, (x, y) in enumerate(zip(sa, sb)):
+            assert x == y, ("structure row", q, k, x, y)
+        for k, (x, y) in enumerate(zip(ma, mb)):
+            assert x == y, ("match row", q, k, x, y)
 
 
 def test_repeated_batch_and_device_rows(env):
@@ -552,7 +566,7 @@ def test_repeated_batch_and_device_rows(env):
     first = host.search(ctx, qb, sp, labels=store)
     again = host.search(ctx, qb, sp, labels=store)  # cache hit
     nq = len(F.MOTIFS)
-    assert _rows(first, nq) == _rows(again, nq)
+    _same_rows(_rows(first, nq), _rows(again, nq))
     for q in range(nq):  # residue labels of every match row
         for m in first.sorted_matches(q)[:20]:
             assert first.residue_string(m, len(qb.indices(q))) == again.residue_string(m, len(qb.indices(q)))
@@ -561,7 +575,7 @@ def test_repeated_batch_and_device_rows(env):
         on_host = host.search(ctx, qb, sp, labels=store)
     finally:
         del os.environ["FD_DEVICE_ROWS"]
-    assert _rows(first, nq) == _rows(on_host, nq)
+    _same_rows(_rows(first, nq), _rows(on_host, nq))
     for q in range(nq):
         ms, mh = first.sorted_matches(q), on_host.sorted_matches(q)
         assert len(ms) == len(mh)
@@ -576,7 +590,8 @@ def test_repeated_batch_and_device_rows(env):
     qb.add(host.CompactStructure.from_atoms(env["atoms"]["query/4CHA.pdb"]), "B57,B102,C195")
     qb.finalize(ctx)
     more = host.search(ctx, qb, sp, labels=store)
-    assert _rows(more, nq) == _rows(first, nq) and _rows(more, nq + 1)[nq] == _rows(first, 1)[0]
+    _same_rows(_rows(more, nq), _rows(first, nq))
+    _same_rows(_rows(more, nq + 1)[nq:], _rows(first, 1))
     # a newly attached index invalidates the cached lookup results
     b2 = synth.generate(300, 12, mean_len=150.0, max_len=500)
     store2 = host.Store()

@@ -484,7 +484,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": args.batch * world / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": e2e_h2d * world,
                 "d2h_bytes_per_step": e2e_d2h * world, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k3_scan_v2 (posting-list scan + vote + tile-level top-n)",
+        "roofline": {"bound": "hbm", "kernel": "k3_scan_v3 (posting-list scan + vote + tile-level top-n)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": scan_traffic() if world == 1 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": scan_ms,

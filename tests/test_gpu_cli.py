@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import fixtures as F
+import oracle_lib as O
 
 pytestmark = pytest.mark.gpu
 
@@ -189,3 +190,29 @@ def test_stale_store_is_refused_and_no_store_removes_it(workdir):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert not os.path.exists(os.path.join(d, "idx", "renamed.store"))
+
+
+def test_whole_structure_query_with_skip_match(workdir):
+    """no -q: every residue of the query structure is a query residue (query.rs:226-233).  count_query answers it
+    through its global-memory path; verification of such a query is refused with a message, so the search needs
+    --skip-match.  The five structures come back with the oracle's idf values in the oracle's order."""
+    rows = run(workdir, "query", "-p", "query/1G2F.pdb", "-i", "idx/serine", "--skip-match")
+    assert 1 <= len(rows) <= 5 and all(r[9] == "NA" for r in rows)
+    atoms = F.config1_atoms()
+    names = F.serine_names()
+    comps = [O.Structure.from_atoms(atoms[n]).compact() for n in names]
+    oix = O.Index.build(comps)
+    s = O.Structure.from_atoms(atoms["query/1G2F.pdb"])
+    om = O.QueryMap(s.compact(), *O.parse_query_string("", s.first_chain), index=oix, total_structures=len(comps))
+    nres = np.array([c.nres for c in comps], np.uint64)
+    plddt = np.array([c.avg_plddt for c in comps], np.float32)
+    want = O.count_query(om, oix, nres, plddt, O.CountParams.defaults(len(om.indices())))
+    got = {os.path.basename(r[0]): float(r[1]) for r in rows}
+    exp = {os.path.basename(names[int(n)]): float(i) for n, i in zip(want["nid"], want["idf"])}
+    assert set(got) == set(exp)
+    for k in got:
+        assert abs(got[k] - exp[k]) <= 1e-4 * max(1.0, exp[k]) + 5e-5  # printed with four decimals
+    idfs = [float(r[1]) for r in rows]
+    assert idfs == sorted(idfs, reverse=True)
+    bad = subprocess.run([CLI, "query", "-p", "query/1G2F.pdb", "-i", "idx/serine"], cwd=workdir, capture_output=True, text=True)
+    assert bad.returncode != 0 and "whole-structure" in bad.stderr

@@ -371,8 +371,8 @@ def test_count_query_whole_structure(ctx):
 
 @pytest.mark.parametrize("env", [dict(FD_K3_CTAS="4", FD_K3_THREADS="128"), dict(FD_K3_CTAS="1", FD_K3_THREADS="512"),
                                  dict(FD_K3_CTAS="3", FD_K3_THREADS="256", FD_K3_LIMIT="0"), dict(FD_K3_V1="1")])
-def test_scan_v2_variants(ctx, env):
-    """k3_scan_v2 under other shared-memory plans (4 small tiles per SM: every query of the 12 000-structure case is
+def test_scan_plan_variants(ctx, env):
+    """k3_scan_v3 under other shared-memory plans (4 small tiles per SM: every query of the 12 000-structure case is
     split into several id tiles; one large tile; the tile-level top-n pre-selection off) returns exactly the rows of
     the default plan (so does the first-generation kernel, FD_K3_V1=1), and those equal the oracle."""
     import folddisco_b200 as fd

@@ -4,7 +4,7 @@
     python tools/k3_probe.py [--structs 23400] [--batch 1024] [--top 100] [--steps 5] [--tile K] [--distinct]
 
 --tile K: the database tiled K times (ids shifted) -- longer posting lists, the same per-hash frequencies.
-Used under ncu for the k3_scan_v2 captures in profiles/.
+Used under ncu for the k3_scan captures in profiles/.
 """
 import argparse
 import json

@@ -27,11 +27,26 @@ class _StructBatch(C.Structure):
                 ("aa", VP), ("cb_valid", VP)]
 
 
-class HashParams(C.Structure):
-    _fields_ = [("nbin_dist", C.c_uint32), ("nbin_angle", C.c_uint32), ("dist_cutoff", C.c_float)]
+# FD_HASH_* of include/folddisco_b200.h: the reference's HashType index + 1, 0 = default (PDBTrRosetta)
+HASH_TYPES = {"default": 0, "PDBMotif": 1, "PDBMotifSinCos": 2, "TrRosetta": 3, "PDBTrRosetta": 4, "PointPairFeature": 5,
+              "FolddiscoAngle": 8, "FolddiscoDist": 9}
+MAX_MULTIPLE_BINS = 8
 
-    def __init__(self, nbin_dist=0, nbin_angle=0, dist_cutoff=20.0):
-        super().__init__(nbin_dist, nbin_angle, dist_cutoff)
+
+class HashParams(C.Structure):
+    """fd_hash_params: bins, cutoff, encoding (`--type`) and the `--multiple-bins` list of (dist, angle) pairs"""
+    _fields_ = [("nbin_dist", C.c_uint32), ("nbin_angle", C.c_uint32), ("dist_cutoff", C.c_float),
+                ("hash_type", C.c_uint32), ("n_multiple_bins", C.c_uint32),
+                ("multiple_bins", C.c_uint32 * (2 * MAX_MULTIPLE_BINS))]
+
+    def __init__(self, nbin_dist=0, nbin_angle=0, dist_cutoff=20.0, hash_type=0, multiple_bins=()):
+        if isinstance(hash_type, str):
+            hash_type = HASH_TYPES[hash_type]
+        mb = [int(v) for pair in multiple_bins for v in pair]
+        if len(mb) > 2 * MAX_MULTIPLE_BINS:
+            raise ValueError("at most %d (dist, angle) pairs" % MAX_MULTIPLE_BINS)
+        arr = (C.c_uint32 * (2 * MAX_MULTIPLE_BINS))(*mb)
+        super().__init__(nbin_dist, nbin_angle, dist_cutoff, hash_type, len(mb) // 2, arr)
 
 
 class _IndexBuffers(C.Structure):
@@ -118,6 +133,8 @@ def lib():
     sig("fd_kernel_launches", C.c_uint64, [VP])
     sig("fd_stage_ms", C.c_double, [VP, C.c_char_p])
     sig("fd_stage_launches", C.c_uint64, [VP, C.c_char_p])
+    sig("fd_typed_hash_host", C.c_int64, [VP, VP, VP, VP, VP, C.c_uint64, PP(HashParams), VP, C.c_int64])
+    sig("fd_typed_is_symmetric_host", C.c_int, [C.c_uint32, C.c_uint32])
     sig("fd_hash_structures", C.c_int, [VP, PP(_StructBatch), PP(HashParams), PP(PP(C.c_uint32)), PP(PP(C.c_uint64))])
     sig("fd_build_postings", C.c_int, [VP, VP, VP, C.c_uint64, C.c_uint64, PP(_IndexBuffers)])
     sig("fd_build_index", C.c_int, [VP, PP(_StructBatch), PP(HashParams), C.c_uint64, C.c_uint64, C.c_uint64,
@@ -498,3 +515,24 @@ def math_host(op, a, b=None):
     out = np.zeros(len(a), np.float32)
     lib().fd_math_host(op, _ptr(a), _ptr(b), len(a), _ptr(out))
     return out
+
+
+def typed_hash_host(n_xyz, ca_xyz, cb_xyz, aa, cb_valid=None, params=None):
+    """every ordered residue pair of one structure hashed on the host by csrc/fd_hashtypes.cuh (parity probe of the
+    other encodings / `--multiple-bins`): pairs in row-major order, the bin pairs of one residue pair in list order"""
+    n_xyz, ca_xyz, cb_xyz = (np.ascontiguousarray(a, np.float32) for a in (n_xyz, ca_xyz, cb_xyz))
+    aa = np.ascontiguousarray(aa, np.uint8)
+    cbv = None if cb_valid is None else np.ascontiguousarray(cb_valid, np.uint8)
+    params = params or HashParams()
+    n = lib().fd_typed_hash_host(_ptr(n_xyz), _ptr(ca_xyz), _ptr(cb_xyz), _ptr(aa), _ptr(cbv), len(aa), C.byref(params),
+                                 None, 0)
+    if n < 0:
+        raise FdError("fd_typed_hash_host: parameters refused")
+    out = np.zeros(max(n, 1), np.uint32)
+    lib().fd_typed_hash_host(_ptr(n_xyz), _ptr(ca_xyz), _ptr(cb_xyz), _ptr(aa), _ptr(cbv), len(aa), C.byref(params),
+                             _ptr(out), n)
+    return out[:n]
+
+
+def typed_is_symmetric_host(hash_type, h):
+    return lib().fd_typed_is_symmetric_host(hash_type, int(h))

@@ -8,6 +8,7 @@
 #include <vector>
 #include "fd_common.cuh"
 #include "fd_geom.cuh"
+#include "fd_hashtypes.cuh"
 
 thread_local std::string fd_g_create_error;
 thread_local cudaStream_t fd_tls_stream = nullptr;
@@ -219,6 +220,35 @@ void fd_pair_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_
         out_fast[k] = ok ? h : 0u;
         out_declined[k] = ok ? 0 : 1;
     }
+}
+
+// parity probe of the other encodings: every ordered residue pair of one structure through fd_hashtypes.cuh on the host
+int64_t fd_typed_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_xyz, const uint8_t *aa,
+                           const uint8_t *cb_valid, uint64_t n_res, const fd_hash_params *params, uint32_t *out,
+                           int64_t cap) {
+    fdg::TypedParams tp;
+    if (fdg::typed_params_from(params, &tp)) return -1;
+    auto ld = [](const float *p, uint64_t r) { return fdg::V3{p[3 * r], p[3 * r + 1], p[3 * r + 2]}; };
+    int64_t n = 0;
+    float f[9];
+    for (uint64_t i = 0; i < n_res; i++)
+        for (uint64_t j = 0; j < n_res; j++) {
+            if (i == j || aa[i] == 255 || aa[j] == 255 || (cb_valid && (!cb_valid[i] || !cb_valid[j]))) continue;
+            const float d = fdg::typed_screen_dist(tp.type, ld(ca_xyz, i), ld(cb_xyz, i), ld(ca_xyz, j), ld(cb_xyz, j));
+            if (d > tp.dist_cutoff) continue;
+            fdg::typed_feature(tp.type, ld(n_xyz, i), ld(ca_xyz, i), ld(cb_xyz, i), ld(n_xyz, j), ld(ca_xyz, j),
+                               ld(cb_xyz, j), (float)(aa[i] & 0x7Fu), (float)(aa[j] & 0x7Fu), d, f);
+            for (uint32_t b = 0; b < tp.n_bins; b++) {
+                const uint32_t h = fdg::typed_hash(tp.type, f, tp.nbd[b], tp.nba[b]);
+                if (n < cap) out[n] = h;
+                n++;
+            }
+        }
+    return n;
+}
+int fd_typed_is_symmetric_host(uint32_t hash_type, uint32_t hash) {
+    if (!fdg::ht_supported(hash_type)) return -1;
+    return fdg::typed_is_symmetric(fdg::ht_canon(hash_type), hash) ? 1 : 0;
 }
 
 // parity / debug probe: runs a region of nt workers that each spin for `spin_us`; returns how many distinct host

@@ -22,6 +22,7 @@
 
 #include "fd_common.cuh"
 #include "fd_geom.cuh"
+#include "fd_hashtypes.cuh"
 
 void fd_ctx_release_store(fd_ctx *ctx);
 
@@ -107,12 +108,16 @@ __global__ void __launch_bounds__(AAD_WARPS * 32)
     }
 }
 
-template <int MODE> // 0 = count, 1 = emit
+// MODE 0 = count, 1 = emit.  TYPED: any encoding of fd_hashtypes.cuh and `--multiple-bins` (tp); the default
+// encoding with one bin pair keeps pair_hash_auto.  Edge key = cand << 36 | i << 20 | j << 4 | bin-pair index, so the
+// sort restores the reference's emission order (pair order, then the order of the bin list: retrieve.rs:124-131).
+template <int MODE, bool TYPED = false>
 __global__ void __launch_bounds__(K4_THREADS)
     k4_candidate_edges(StoreView st, const RQDesc *rq, const uint32_t *q_hashes, const AADist *q_aad,
                        const uint32_t *cand_query, const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp,
                        float ca_cutoff, unsigned long long *n_edges, unsigned long long *n_pairs,
-                       uint64_t *edge_keys, uint32_t *edge_hash, uint64_t *pair_keys, uint32_t *pair_q) {
+                       uint64_t *edge_keys, uint32_t *edge_hash, uint64_t *pair_keys, uint32_t *pair_q,
+                       fdg::TypedParams tp = fdg::TypedParams()) {
     __shared__ uint16_t list1[K4_LIST_CAP], list2[K4_LIST_CAP];
     __shared__ uint32_t n1, n2;
     __shared__ uint32_t q_ij[K4_CHUNK];
@@ -239,8 +244,16 @@ __global__ void __launch_bounds__(K4_THREADS)
                 const uint64_t ri = base + i, rj = base + j;
                 const uint8_t ai = st.aa[ri], aj = st.aa[rj];
                 const bool cbok = st.cb_valid == nullptr || (st.cb_valid[ri] && st.cb_valid[rj]);
-                // get_single_feature (feature.rs:11-24): i != j, both amino acids known, CB present
-                if (i != j && ai != 255 && aj != 255 && cbok) {
+                // get_single_feature (feature.rs:11-24): i != j, both amino acids known, CB present -- and, for the
+                // encodings whose cutoff is not on the CA distance, their own distance within the cutoff
+                bool is_feature = i != j && ai != 255 && aj != 255 && cbok;
+                float ds = d;
+                if (TYPED && is_feature && (tp.type == fdg::HT_TRROSETTA || tp.type == fdg::HT_PPF)) {
+                    ds = fdg::typed_screen_dist(tp.type, ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri), ld3(st.ca_xyz, rj),
+                                                ld3(st.cb_xyz, rj));
+                    is_feature = !(ds > hp.dist_cutoff);
+                }
+                if (is_feature) {
                     const uint8_t ci = ai & 0x7Fu, cj = aj & 0x7Fu;
                     uint32_t np = 0;
                     for (uint32_t e = 0; e < Q.n_aad; e++)
@@ -254,22 +267,31 @@ __global__ void __launch_bounds__(K4_THREADS)
                             np++;
                         }
                     if (MODE == 0 && np) atomicAdd(n_pairs, (unsigned long long)np);
-                    const uint32_t h = fdg::pair_hash_auto(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
-                                                      ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj), ci,
-                                                      cj, d, hp);
-                    // membership in the query hash set
-                    uint32_t lo = 0, hi = Q.n_hashes;
-                    const uint32_t *hs = q_hashes + Q.hash_begin;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (hs[mid] < h) lo = mid + 1;
-                        else hi = mid;
-                    }
-                    if (lo < Q.n_hashes && hs[lo] == h) {
-                        const unsigned long long pos = atomicAdd(n_edges, 1ull);
-                        if (MODE == 1) {
-                            edge_keys[pos] = ((uint64_t)c << 32) | ((uint64_t)i << 16) | j;
-                            edge_hash[pos] = h;
+                    float f[9];
+                    if (TYPED)
+                        fdg::typed_feature(tp.type, ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
+                                           ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj), (float)ci, (float)cj,
+                                           ds, f);
+                    const uint32_t nb = TYPED ? tp.n_bins : 1u;
+                    for (uint32_t bi = 0; bi < nb; bi++) {
+                        const uint32_t h = TYPED ? fdg::typed_hash(tp.type, f, tp.nbd[bi], tp.nba[bi])
+                                                 : fdg::pair_hash_auto(ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri),
+                                                                       ld3(st.cb_xyz, ri), ld3(st.n_xyz, rj),
+                                                                       ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj), ci, cj, d, hp);
+                        // membership in the query hash set
+                        uint32_t lo = 0, hi = Q.n_hashes;
+                        const uint32_t *hs = q_hashes + Q.hash_begin;
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (hs[mid] < h) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo < Q.n_hashes && hs[lo] == h) {
+                            const unsigned long long pos = atomicAdd(n_edges, 1ull);
+                            if (MODE == 1) {
+                                edge_keys[pos] = ((uint64_t)c << 36) | ((uint64_t)i << 20) | ((uint64_t)j << 4) | bi;
+                                edge_hash[pos] = h;
+                            }
                         }
                     }
                 }
@@ -285,7 +307,7 @@ __global__ void k4_unpack_edges(const uint64_t *keys, const uint32_t *hash, uint
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint64_t key = keys[k];
-    out[k] = fd_cand_edge{(uint32_t)(key >> 32), (uint32_t)((key >> 16) & 0xffffu), (uint32_t)(key & 0xffffu), hash[k]};
+    out[k] = fd_cand_edge{(uint32_t)(key >> 36), (uint32_t)((key >> 20) & 0xffffu), (uint32_t)((key >> 4) & 0xffffu), hash[k]};
 }
 __global__ void k4_unpack_pairs(const uint64_t *keys, const uint32_t *qidx, uint64_t n, fd_cand_pair *out) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,6 +386,9 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
         return fd_fail(ctx, FD_ERR_ARG, "fd_candidate_edges_batch: NULL argument");
     if (n_cand >= (1ull << 24))
         return fd_fail(ctx, FD_ERR_LIMIT, "at most 2^24 - 1 candidates per call; split the batch");
+    fdg::TypedParams tp;
+    if (const char *why = fdg::typed_params_from(params, &tp)) return fd_fail(ctx, FD_ERR_ARG, why);
+    const bool typed = !fdg::ht_default_route(params);
     FD_ENTER(ctx);
     *out_edges = nullptr;
     *out_pairs = nullptr;
@@ -382,8 +407,10 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
             if (k && Q.hashes_sorted[k] <= Q.hashes_sorted[k - 1])
                 return fd_fail(ctx, FD_ERR_ARG, "fd_retrieval_query: hashes_sorted must be strictly ascending");
             f_hash.push_back(Q.hashes_sorted[k]);
-            d.aa1_mask |= 1u << ((Q.hashes_sorted[k] >> 25) & 31u);
-            d.aa2_mask |= 1u << ((Q.hashes_sorted[k] >> 20) & 31u);
+            uint32_t a1, a2; // prefilter_amino_acid reads them from reverse_hash_default (retrieve.rs:575-577)
+            fdg::typed_hash_aa(tp.type, Q.hashes_sorted[k], &a1, &a2);
+            d.aa1_mask |= 1u << (a1 & 31u);
+            d.aa2_mask |= 1u << (a2 & 31u);
         }
         for (uint32_t k = 0; k < Q.n_aa_dist; k++) {
             uint16_t pos = 0;
@@ -428,9 +455,14 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     uint32_t split = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(64, ((uint64_t)ctx->num_sms * 8) / std::max<uint64_t>(n_cand, 1)));
     if (const char *e = getenv("FD_K4_SPLIT")) split = (uint32_t)std::max(1, std::min(64, atoi(e)));
     const dim3 k4_grid((uint32_t)n_cand, split);
-    FD_LAUNCH(ctx, k4_candidate_edges<0>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
-              d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, (uint64_t *)nullptr,
-              (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr);
+    if (typed)
+        FD_LAUNCH(ctx, (k4_candidate_edges<0, true>), k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
+                  d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, (uint64_t *)nullptr,
+                  (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, tp);
+    else
+        FD_LAUNCH(ctx, k4_candidate_edges<0>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
+                  d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, (uint64_t *)nullptr,
+                  (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr);
     unsigned long long cnt[2] = {0, 0};
     FD_CUDA(ctx, cudaMemcpyAsync(cnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, s));
     FD_CUDA(ctx, cudaStreamSynchronize(s));
@@ -440,11 +472,15 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     FD_CUDA(ctx, d_pair_keys.alloc(np));
     FD_CUDA(ctx, d_pair_q.alloc(np));
     FD_CUDA(ctx, cudaMemsetAsync(d_cnt.p, 0, 16, s));
-    if (ne || np)
+    if ((ne || np) && typed)
+        FD_LAUNCH(ctx, (k4_candidate_edges<1, true>), k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p,
+                  d_cq.p, d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, d_edge_keys.p,
+                  d_edge_hash.p, d_pair_keys.p, d_pair_q.p, tp);
+    else if (ne || np)
         FD_LAUNCH(ctx, k4_candidate_edges<1>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p,
                   d_cq.p, d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, d_edge_keys.p,
                   d_edge_hash.p, d_pair_keys.p, d_pair_q.p);
-    FD_TRY(sort_pairs_u64_u32(ctx, d_edge_keys, d_edge_hash, ne, 56));
+    FD_TRY(sort_pairs_u64_u32(ctx, d_edge_keys, d_edge_hash, ne, 60));
     FD_TRY(sort_pairs_u64_u32(ctx, d_pair_keys, d_pair_q, np, 64));
     DevBuf<fd_cand_edge> d_oe;
     DevBuf<fd_cand_pair> d_op;

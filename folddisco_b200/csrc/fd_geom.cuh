@@ -74,6 +74,9 @@ struct HashParams {
 
 FD_HD HashParams make_params(uint32_t nbd, uint32_t nba, float cutoff) {
     HashParams p;
+    // every call site of the reference takes perfect_hash_default when EITHER count is 0 (feature.rs:215-221,
+    // query.rs:72-76, retrieve.rs:133-137)
+    if (nbd == 0 || nba == 0) nbd = nba = 0;
     p.nbin_dist = nbd > 16 ? 16.0f : (nbd == 0 ? 16.0f : (float)nbd);
     p.nbin_angle = nba > 4 ? 4.0f : (nba == 0 ? 4.0f : (float)nba);
     p.dist_cutoff = cutoff;

@@ -19,6 +19,7 @@
 
 #include "fd_common.cuh"
 #include "fd_geom.cuh"
+#include "fd_hashtypes.cuh"
 
 namespace {
 
@@ -51,11 +52,14 @@ __device__ __forceinline__ bool residue_ok(const BatchView &b, uint64_t r) {
 // MODE 1: emit key = hash << 32 | (first_id + s)   (posting build)
 // MODE 2: emit key = s << 32 | hash                (per-structure sorted unique output)
 // MODE 3: emit key = (s - first_id) << 30 | hash, val = i << 16 | j   (pair table of the structure store)
-template <int MODE>
+// TYPED: any encoding of fd_hashtypes.cuh and `--multiple-bins` (tp): the screen uses the encoding's own cutoff
+// distance, a survivor's feature is computed once and hashed once per (nbin_dist, nbin_angle) pair.  The default
+// encoding with a single bin pair keeps the tuned route (TYPED = false: hp, pair_hash_auto).
+template <int MODE, bool TYPED = false>
 __global__ void __launch_bounds__(K1_THREADS)
     k1_pair_hash(BatchView b, const Tile *tiles, uint32_t n_tiles, fdg::HashParams hp, uint64_t first_id,
                  uint64_t hash_lo, uint64_t hash_hi, uint64_t *out_keys, unsigned long long *out_count,
-                 uint32_t *out_vals = nullptr) {
+                 uint32_t *out_vals = nullptr, fdg::TypedParams tp = fdg::TypedParams()) {
     __shared__ uint32_t q_ij[MODE == 0 ? 1 : K1_QUEUE_CAP]; // i_local << 16 | j
     __shared__ float q_d[MODE == 0 ? 1 : K1_QUEUE_CAP];     // ca_dist of the survivor
     __shared__ uint32_t q_n;
@@ -77,11 +81,12 @@ __global__ void __launch_bounds__(K1_THREADS)
             const uint32_t il = r0 + warp; // this warp's row within the tile
             const bool row_live = il < rows;
             const uint32_t i = tile.i0 + il;
-            fdg::V3 cai = {0.f, 0.f, 0.f};
+            fdg::V3 cai = {0.f, 0.f, 0.f}, cbi = {0.f, 0.f, 0.f};
             bool iok = false;
             if (row_live) {
                 iok = residue_ok(b, base + i);
                 cai = ld3(b.ca_xyz, base + i);
+                if (TYPED) cbi = ld3(b.cb_xyz, base + i);
             }
             for (uint32_t c0 = 0; c0 < n; c0 += K1_COL_CHUNK) {
                 // ---- phase A: distance screen ----
@@ -90,11 +95,14 @@ __global__ void __launch_bounds__(K1_THREADS)
                     bool pass = false;
                     float d = 0.f;
                     if (iok && j < cend && j != i && residue_ok(b, base + j)) {
-                        d = fdg::dist(cai, ld3(b.ca_xyz, base + j));
+                        if (TYPED)
+                            d = fdg::typed_screen_dist(tp.type, cai, cbi, ld3(b.ca_xyz, base + j), ld3(b.cb_xyz, base + j));
+                        else
+                            d = fdg::dist(cai, ld3(b.ca_xyz, base + j));
                         pass = !(d > hp.dist_cutoff); // reference: `if ca_dist > dist_cutoff { return None }`
                     }
                     if (MODE == 0) {
-                        my_count += pass;
+                        my_count += pass ? (TYPED ? tp.n_bins : 1u) : 0u;
                     } else {
                         const uint32_t m = __ballot_sync(0xffffffffu, pass);
                         if (m) {
@@ -112,7 +120,34 @@ __global__ void __launch_bounds__(K1_THREADS)
                     __syncthreads();
                     // ---- phase B: dense drain ----
                     const uint32_t qn = q_n;
-                    for (uint32_t k0 = 0; k0 < qn; k0 += K1_THREADS) {
+                    for (uint32_t k0 = 0; TYPED && k0 < qn; k0 += K1_THREADS) {
+                        const uint32_t k = k0 + threadIdx.x;
+                        float f[9];
+                        if (k < qn) {
+                            const uint32_t ij = q_ij[k];
+                            const uint64_t ri = base + tile.i0 + (ij >> 16), rj = base + (ij & 0xffffu);
+                            fdg::typed_feature(tp.type, ld3(b.n_xyz, ri), ld3(b.ca_xyz, ri), ld3(b.cb_xyz, ri),
+                                               ld3(b.n_xyz, rj), ld3(b.ca_xyz, rj), ld3(b.cb_xyz, rj),
+                                               (float)(b.aa[ri] & 0x7Fu), (float)(b.aa[rj] & 0x7Fu), q_d[k], f);
+                        }
+                        for (uint32_t bi = 0; bi < tp.n_bins; bi++) { // uniform trip count
+                            bool emit = false;
+                            uint64_t key = 0;
+                            if (k < qn) {
+                                const uint32_t h = fdg::typed_hash(tp.type, f, tp.nbd[bi], tp.nba[bi]);
+                                emit = (uint64_t)h >= hash_lo && (uint64_t)h < hash_hi;
+                                key = MODE == 1 ? ((uint64_t)h << 32) | (first_id + tile.s) : ((uint64_t)tile.s << 32) | h;
+                            }
+                            const uint32_t m = __ballot_sync(0xffffffffu, emit);
+                            if (m) {
+                                unsigned long long pos = 0;
+                                if (lane == 0) pos = atomicAdd(out_count, (unsigned long long)__popc(m));
+                                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1));
+                                if (emit) out_keys[pos] = key;
+                            }
+                        }
+                    }
+                    for (uint32_t k0 = 0; !TYPED && k0 < qn; k0 += K1_THREADS) {
                         const uint32_t k = k0 + threadIdx.x;
                         bool emit = false;
                         uint64_t key = 0;
@@ -195,13 +230,20 @@ int run_pair_hash(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_param
     FD_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), ctx->stream));
     BatchView v{d.row_offsets.p, d.n_xyz.p, d.ca_xyz.p, d.cb_xyz.p, d.aa.p, batch->cb_valid ? d.cb_valid.p : nullptr};
     fdg::HashParams hp = fdg::make_params(params->nbin_dist, params->nbin_angle, params->dist_cutoff);
+    fdg::TypedParams tp;
+    if (const char *why = fdg::typed_params_from(params, &tp)) return fd_fail(ctx, FD_ERR_ARG, why);
+    const bool typed = !fdg::ht_default_route(params);
     const uint32_t n_tiles = (uint32_t)tiles.size();
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms * 8);
     unsigned long long total = 0;
     {
         StageTimer st(ctx, "hash");
-        FD_LAUNCH(ctx, k1_pair_hash<0>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo, hash_hi,
-                  (uint64_t *)nullptr, d_count.p);
+        if (typed)
+            FD_LAUNCH(ctx, (k1_pair_hash<0, true>), grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo,
+                      hash_hi, (uint64_t *)nullptr, d_count.p, (uint32_t *)nullptr, tp);
+        else
+            FD_LAUNCH(ctx, k1_pair_hash<0>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo, hash_hi,
+                      (uint64_t *)nullptr, d_count.p);
         FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
         FD_CUDA(ctx, st.finish());
     }
@@ -214,7 +256,10 @@ int run_pair_hash(fd_ctx *ctx, const fd_struct_batch *batch, const fd_hash_param
     }
     {
         StageTimer st(ctx, "hash");
-        if (total)
+        if (total && typed)
+            FD_LAUNCH(ctx, (k1_pair_hash<MODE, true>), grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo,
+                      hash_hi, keys.p, d_count.p, (uint32_t *)nullptr, tp);
+        else if (total)
             FD_LAUNCH(ctx, k1_pair_hash<MODE>, grid, K1_THREADS, 0, v, d_tiles.p, n_tiles, hp, first_id, hash_lo,
                       hash_hi, keys.p, d_count.p);
         FD_CUDA(ctx, cudaMemcpyAsync(&total, d_count.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
@@ -299,6 +344,8 @@ extern "C" int fd_store_build_pair_table(fd_ctx *ctx, const fd_hash_params *para
     if (!params) return fd_fail(ctx, FD_ERR_ARG, "fd_store_build_pair_table: NULL argument");
     if (!ctx->store.attached) return fd_fail(ctx, FD_ERR_STATE, "fd_store_build_pair_table: no structure store attached");
     if (ctx->borrowed) return fd_fail(ctx, FD_ERR_STATE, "fd_store_build_pair_table: a forked context shares its parent's store");
+    if (!fdg::ht_default_route(params))
+        return fd_fail(ctx, FD_ERR_ARG, "fd_store_build_pair_table: the pair table holds 30-bit PDBTrRosetta hashes of one bin pair; other encodings / multiple bins are verified through fd_candidate_edges_batch");
     FD_ENTER(ctx);
     FdDeviceStore &S = ctx->store;
     cudaStream_t st = ctx->stream;

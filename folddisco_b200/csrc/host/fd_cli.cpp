@@ -195,13 +195,14 @@ const char *HELP =
     "        [-o FILE] [-v]\n";
 
 int cmd_index(Args &a) {
-    a.reject({"--multiple-bins"}, "multiple-bin encoding is outside the ported path");
     a.reject({"--mmap-on-disk"}, "the index is built in GPU memory");
+    const std::string multiple_bins = a.str({"--multiple-bins"}, "");
     const std::string dir = a.str({"-p", "--pdbs"}, "");
     const std::string type = a.str({"-y", "--type"}, "default");
     const std::string prefix = a.str({"-i", "--index"}, "");
     const int threads = (int)a.num({"-t", "--threads"}, 1);
     fd_hash_params hp;
+    memset(&hp, 0, sizeof(hp));
     hp.nbin_dist = (uint32_t)a.num({"-d", "--distance"}, 0);
     hp.nbin_angle = (uint32_t)a.num({"-a", "--angle"}, 0);
     hp.dist_cutoff = (float)a.num({"-g", "--grid"}, 20.0);
@@ -215,8 +216,34 @@ int cmd_index(Args &a) {
         return 0;
     }
     a.finish();
-    if (type != "default" && type != "pdbtr" && type != "PDBTrRosetta" && type != "pdbtrrosetta")
-        die("hash type '" + type + "' is not supported by folddisco-b200 (only the default PDBTrRosetta encoding)");
+    { // HashType::get_with_str (geometry/core.rs:42-57)
+        const int t = fdh_hash_type_from_string(type.c_str());
+        if (t < 0) die("unknown hash type '" + type + "'");
+        if (t == 6 || t == 7)
+            die("hash type '" + type + "' is not supported by folddisco-b200 (TertiaryInteraction and Hybrid hash over the "
+                "neighbouring residues and are not built)");
+        hp.hash_type = (uint32_t)t;
+    }
+    if (!multiple_bins.empty()) { // parse_distance_angle_pairs (utils/cli.rs:1-16): "16-4,8-3"; malformed pairs are skipped
+        size_t pos = 0;
+        while (pos <= multiple_bins.size()) {
+            const size_t comma = multiple_bins.find(',', pos);
+            std::string pr = multiple_bins.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+            pos = comma == std::string::npos ? multiple_bins.size() + 1 : comma + 1;
+            while (!pr.empty() && pr.front() == ' ') pr.erase(pr.begin());
+            while (!pr.empty() && pr.back() == ' ') pr.pop_back();
+            const size_t dash = pr.find('-');
+            if (dash == std::string::npos || pr.find('-', dash + 1) != std::string::npos) continue;
+            char *e1 = nullptr, *e2 = nullptr;
+            const std::string a1 = pr.substr(0, dash), a2 = pr.substr(dash + 1);
+            const unsigned long d = strtoul(a1.c_str(), &e1, 10), g = strtoul(a2.c_str(), &e2, 10);
+            if (a1.empty() || a2.empty() || *e1 || *e2) continue;
+            if (hp.n_multiple_bins >= FD_MAX_MULTIPLE_BINS) die("--multiple-bins: at most 8 pairs");
+            hp.multiple_bins[2 * hp.n_multiple_bins] = (uint32_t)d;
+            hp.multiple_bins[2 * hp.n_multiple_bins + 1] = (uint32_t)g;
+            hp.n_multiple_bins++;
+        }
+    }
     if (dir.empty() || prefix.empty()) die("index needs -p DIR and -i PREFIX");
     if (threads > 0) setenv("FD_HOST_THREADS", std::to_string(threads).c_str(), 0);
     std::vector<std::string> files;
@@ -226,7 +253,7 @@ int cmd_index(Args &a) {
     for (auto &f : files)
         if (!(ends_with(f, ".pdb") || ends_with(f, ".ent") || ends_with(f, ".PDB")))
             die("unsupported input format (only .pdb / .ent): " + f);
-    if (verbose) fprintf(stderr, "[INFO] Indexing %zu files with PDBTrRosetta\n", files.size());
+    if (verbose) fprintf(stderr, "[INFO] Indexing %zu files with %s\n", files.size(), fdh_hash_type_name(hp.hash_type));
     // parse on the host (file-parallel like the reference, mod.rs:298), keep file order
     std::vector<fdh_compact *> comps(files.size(), nullptr);
     {
@@ -536,6 +563,7 @@ int cmd_query(Args &a) {
     qp.n_angle_thr = (int)angle_thr.size();
     qp.serial_query = serial_query ? 1 : 0;
     fdh_queries *qs = fdh_queries_new(&qp);
+    if (!qs) die(fdh_last_error()); // an index of an encoding that is not built (TertiaryInteraction, Hybrid)
     {
         std::vector<std::pair<std::string, fdh_compact *>> cache; // a query file usually repeats structures
         for (auto &j : jobs) {

@@ -32,6 +32,7 @@
 
 #include "../../../include/folddisco_b200_host.h"
 #include "../fd_geom.cuh"
+#include "../fd_hashtypes.cuh"
 
 // persistent host worker pool (fd_ctx.cu): fn(0) .. fn(nt - 1) concurrently, fn(0) on the caller
 void fd_parallel(int nt, const std::function<void(int)> &fn);
@@ -302,7 +303,7 @@ struct fdh_index {
     std::vector<uint32_t> nres;
     std::vector<float> plddt;
     std::vector<uint64_t> db_key; // 5th lookup column (lookup.rs:17-58); empty = the structure id
-    fd_hash_params params{0, 0, 20.0f};
+    fd_hash_params params{0, 0, 20.0f, 0, 0, {0}};
     ~fdh_index() {
         if (map_off) munmap(map_off, map_off_len);
         if (map_val) munmap(map_val, map_val_len);
@@ -594,11 +595,45 @@ struct AngleBinCache {
     }
 };
 
-void qinsert(Query &Q, SeenHashes &seen, AngleBinCache &bins, const float *f, const fdg::HashParams &hp, uint32_t qi,
-             uint32_t qj, bool primary, uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
-    const uint32_t h = bins.hash(f, hp);
-    if (!seen.insert(h, (uint32_t)Q.entries.size(), Q.entries)) return;
-    Q.entries.push_back(QEntry{h, qi, qj, (uint8_t)primary, pair, 0.f});
+// Hashing of one query: the tuned PDBTrRosetta single-bin route (memoised angle bins), or any encoding /
+// `--multiple-bins` list through fd_hashtypes.cuh
+struct QueryHasher {
+    bool typed;
+    fdg::HashParams hp;
+    fdg::TypedParams tp;
+    uint32_t obs_nbd = 0, obs_nba = 0; // bins of the observed hash that carries a pair's idf (query.rs:283-287)
+    AngleBinCache bins;
+    explicit QueryHasher(const fd_hash_params &p)
+        : typed(!fdg::ht_default_route(&p)), hp(fdg::make_params(p.nbin_dist, p.nbin_angle, p.dist_cutoff)), bins(hp) {
+        fdg::typed_params_from(&p, &tp); // validated by fdh_queries_new
+        fdg::ht_resolve_single(tp.type, p.nbin_dist, p.nbin_angle, &obs_nbd, &obs_nba);
+        if (p.n_multiple_bins) // insert_binned_hash: a pair with a zero takes the defaults (query.rs:60-64)
+            for (uint32_t k = 0; k < tp.n_bins; k++) fdg::ht_resolve_single(tp.type, tp.nbd[k], tp.nba[k], &tp.nbd[k], &tp.nba[k]);
+    }
+    uint32_t observed(const float *f) { return typed ? fdg::typed_hash(tp.type, f, obs_nbd, obs_nba) : bins.hash(f, hp); }
+};
+
+void qinsert(Query &Q, SeenHashes &seen, QueryHasher &H, const float *f, uint32_t qi, uint32_t qj, bool primary,
+             uint32_t pair) { // insert_binned_hash (query.rs:53-84): first writer wins
+    const uint32_t nb = H.typed ? H.tp.n_bins : 1u;
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t h = H.typed ? fdg::typed_hash(H.tp.type, f, H.tp.nbd[b], H.tp.nba[b]) : H.bins.hash(f, H.hp);
+        if (!seen.insert(h, (uint32_t)Q.entries.size(), Q.entries)) continue;
+        Q.entries.push_back(QEntry{h, qi, qj, (uint8_t)primary, pair, 0.f});
+    }
+}
+
+// get_single_feature (feature.rs:11-190) of the selected encoding on the host; *ca_dist = the CA-CA distance
+bool host_typed_feature(const fdh_compact &c, size_t i, size_t j, const fdg::TypedParams &tp, float *f, float *ca_dist) {
+    if (i == j) return false;
+    const uint8_t a1 = c.aa[i], a2 = c.aa[j];
+    if (a1 == 255 || a2 == 255 || !c.cb_valid[i] || !c.cb_valid[j]) return false;
+    const float d = fdg::typed_screen_dist(tp.type, c.CA(i), c.CB(i), c.CA(j), c.CB(j));
+    if (d > tp.dist_cutoff) return false;
+    fdg::typed_feature(tp.type, c.N(i), c.CA(i), c.CB(i), c.N(j), c.CA(j), c.CB(j), (float)(a1 & 0x7F), (float)(a2 & 0x7F),
+                       d, f);
+    *ca_dist = fdg::dist(c.CA(i), c.CA(j));
+    return true;
 }
 
 // make_query_map (src/controller/query.rs:208-329) minus the idf values, which need the index
@@ -622,13 +657,16 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
         if (pq.has_sub[i]) submap[(uint32_t)idx] = pq.subs[i];
     }
     const float rad = 3.14159274101257324f / 180.0f; // f32::to_radians
-    float f[7], fn[7], ff[7];
+    float f[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, fn[9], ff[9];
     SeenHashes seen;
-    AngleBinCache bins(hp);
+    QueryHasher QH(qs.p.hash);
+    AngleBinCache &bins = QH.bins;
+    int dist_idx[2], angle_idx[5];
+    const int n_dist_idx = fdg::typed_dist_index(QH.tp.type, dist_idx), n_angle_idx = fdg::typed_angle_index(QH.tp.type, angle_idx);
     const size_t K = Q.indices.size();
     {
         const size_t n_pairs = K > 1 ? K * (K - 1) : 0;
-        const size_t per_pair = 1 + 4 * qs.dist_thr.size() + 6 * qs.angle_thr.size();
+        const size_t per_pair = (1 + 4 * qs.dist_thr.size() + 10 * qs.angle_thr.size()) * (QH.typed ? QH.tp.n_bins : 1);
         Q.entries.reserve(std::min<size_t>(n_pairs * per_pair, 1u << 16));
         Q.pair_hash.reserve(n_pairs);
         Q.aad.reserve(n_pairs);
@@ -638,57 +676,65 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
             if (a == b) continue;
             const uint32_t I = Q.indices[a], J = Q.indices[b];
             if (I >= c.nres() || J >= c.nres()) continue;
-            if (!host_pair_feature(c, I, J, hp.dist_cutoff, f)) continue;
+            float ca_dist;
+            if (QH.typed) {
+                if (!host_typed_feature(c, I, J, QH.tp, f, &ca_dist)) continue;
+            } else {
+                if (!host_pair_feature(c, I, J, hp.dist_cutoff, f)) continue;
+                ca_dist = f[2];
+            }
             memcpy(fn, f, sizeof(f));
             memcpy(ff, f, sizeof(f));
-            if (f[2] <= 20.0f) Q.aad.push_back(AAD{(uint8_t)(c.aa[I] & 0x7F), (uint8_t)(c.aa[J] & 0x7F), f[2], I});
+            // get_list_amino_acids_and_distances (core.rs:462-477): always the CA distance
+            if (ca_dist <= 20.0f) Q.aad.push_back(AAD{(uint8_t)(c.aa[I] & 0x7F), (uint8_t)(c.aa[J] & 0x7F), ca_dist, I});
             const uint32_t pair = (uint32_t)Q.pair_hash.size();
             bins.reset();
-            Q.pair_hash.push_back(bins.hash(f, hp));
-            qinsert(Q, seen, bins, f, hp, I, J, true, pair);
+            Q.pair_hash.push_back(QH.observed(f));
+            qinsert(Q, seen, QH, f, I, J, true, pair);
             { // apply_substitutions (query.rs:86-156)
                 const float o1 = fn[0], o2 = fn[1];
                 auto si = submap.find(I), sj = submap.find(J);
                 if (si != submap.end()) {
                     for (uint8_t s : si->second) {
-                        float t[7];
+                        float t[9];
                         memcpy(t, fn, sizeof(t));
                         t[0] = (float)s;
-                        qinsert(Q, seen, bins, t, hp, I, J, false, pair);
+                        qinsert(Q, seen, QH, t, I, J, false, pair);
                     }
                     if (sj != submap.end())
                         for (uint8_t s : si->second)
                             for (uint8_t s2 : sj->second) {
                                 fn[0] = (float)s;
                                 fn[1] = (float)s2;
-                                qinsert(Q, seen, bins, fn, hp, I, J, false, pair);
+                                qinsert(Q, seen, QH, fn, I, J, false, pair);
                                 fn[0] = o1;
                                 fn[1] = o2;
                             }
                 } else if (sj != submap.end()) {
                     for (uint8_t s : sj->second) {
-                        float t[7];
+                        float t[9];
                         memcpy(t, fn, sizeof(t));
                         t[1] = (float)s;
-                        qinsert(Q, seen, bins, t, hp, I, J, false, pair);
+                        qinsert(Q, seen, QH, t, I, J, false, pair);
                     }
                 }
             }
-            auto expand = [&](std::initializer_list<int> idxs, const std::vector<float> &thr, bool to_rad) {
+            auto expand = [&](const int *idxs, int n_idx, const std::vector<float> &thr, bool to_rad) {
                 for (float t : thr) { // expand_and_insert (query.rs:179-206): mutate, hash, restore
                     const float delta = to_rad ? t * rad : t;
-                    for (int k : idxs) {
+                    for (int u = 0; u < n_idx; u++) {
+                        const int k = idxs[u];
                         fn[k] -= delta;
                         ff[k] += delta;
-                        qinsert(Q, seen, bins, fn, hp, I, J, false, pair);
-                        qinsert(Q, seen, bins, ff, hp, I, J, false, pair);
+                        qinsert(Q, seen, QH, fn, I, J, false, pair);
+                        qinsert(Q, seen, QH, ff, I, J, false, pair);
                         fn[k] += delta;
                         ff[k] -= delta;
                     }
                 }
             };
-            expand({2, 3}, qs.dist_thr, false);
-            expand({4, 5, 6}, qs.angle_thr, true);
+            expand(dist_idx, n_dist_idx, qs.dist_thr, false);    // HashType::dist_index (feature.rs:269-277)
+            expand(angle_idx, n_angle_idx, qs.angle_thr, true);  // HashType::angle_index (feature.rs:279-289)
         }
     // derived kernel inputs: edges and nodes numbered by first appearance in the entries.  The entries of one residue
     // pair are consecutive and, as long as no residue is listed twice in the query, distinct pairs are distinct
@@ -751,7 +797,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
         Q.hashes_sorted[k] = e.hash;
         Q.vs_qi[k] = e.qi;
         Q.vs_qj[k] = e.qj;
-        Q.vs_sym[k] = hash_is_symmetric(e.hash);
+        Q.vs_sym[k] = QH.typed ? fdg::typed_is_symmetric(QH.tp.type, e.hash) : hash_is_symmetric(e.hash);
     }
     Q.vs_idf.assign(H, 0.f);
     for (auto &d : Q.aad) {
@@ -1387,6 +1433,40 @@ fdh_index *fdh_index_from_buffers(const fd_index_buffers *out, const fdh_store *
     return ix;
 }
 
+// HashType::get_with_str / to_string (src/geometry/core.rs:42-75) -> FD_HASH_*; -1 = unknown
+int fdh_hash_type_from_string(const char *name) {
+    const std::string t = name ? name : "";
+    auto is = [&](std::initializer_list<const char *> l) {
+        for (const char *x : l)
+            if (t == x) return true;
+        return false;
+    };
+    if (is({"0", "PDBMotif", "pyscomotif", "orig_pdb"})) return FD_HASH_PDBMOTIF;
+    if (is({"1", "PDBMotifSinCos", "pdb"})) return FD_HASH_PDBMOTIFSINCOS;
+    if (is({"2", "TrRosetta", "trrosetta", "tr"})) return FD_HASH_TRROSETTA;
+    if (is({"3", "PDBTrRosetta", "pdbtr", "default", "folddisco"})) return FD_HASH_PDBTRROSETTA;
+    if (is({"4", "PointPairFeature", "ppf"})) return FD_HASH_POINTPAIRFEATURE;
+    if (is({"5", "TertiaryInteraction", "tertiary", "3di"})) return 6;
+    if (is({"6", "Hybrid", "hybrid"})) return 7;
+    if (is({"7", "FolddiscoAngle", "angle", "folddisco_angle"})) return FD_HASH_FOLDDISCOANGLE;
+    if (is({"8", "FolddiscoDist", "distance", "dist", "folddisco_dist"})) return FD_HASH_FOLDDISCODIST;
+    return -1;
+}
+const char *hash_type_name(uint32_t t) {
+    switch (t) {
+        case FD_HASH_PDBMOTIF: return "PDBMotif";
+        case FD_HASH_PDBMOTIFSINCOS: return "PDBMotifSinCos";
+        case FD_HASH_TRROSETTA: return "TrRosetta";
+        case FD_HASH_POINTPAIRFEATURE: return "PointPairFeature";
+        case 6: return "TertiaryInteraction";
+        case 7: return "Hybrid";
+        case FD_HASH_FOLDDISCOANGLE: return "FolddiscoAngle";
+        case FD_HASH_FOLDDISCODIST: return "FolddiscoDist";
+        default: return "PDBTrRosetta";
+    }
+}
+const char *fdh_hash_type_name(uint32_t hash_type) { return hash_type_name(hash_type); }
+
 int fdh_index_save(const fdh_index *ix, const fdh_store *s, const char *prefix, uint64_t max_residue,
                    const char *foldcomp_db) {
     auto wr = [&](const std::string &path, const void *p, size_t n, FILE *f) {
@@ -1437,9 +1517,15 @@ int fdh_index_save(const fdh_index *ix, const fdh_store *s, const char *prefix, 
         if (g.find('.') == std::string::npos) g += ".0";
         fprintf(f, "chunk_size = %zu\n", ix->names.size());
         if (foldcomp_db) fprintf(f, "foldcomp_db = \"%s\"\n", foldcomp_db);
-        fprintf(f, "grid_width = %s\nhash_type = \"PDBTrRosetta\"\ninput_format = \"PDB\"\nmax_residue = %llu\n"
-                   "num_bin_angle = %u\nnum_bin_dist = %u\n",
-                g.c_str(), (unsigned long long)max_residue, ix->params.nbin_angle, ix->params.nbin_dist);
+        fprintf(f, "grid_width = %s\nhash_type = \"%s\"\ninput_format = \"PDB\"\nmax_residue = %llu\n", g.c_str(),
+                hash_type_name(ix->params.hash_type), (unsigned long long)max_residue);
+        if (ix->params.n_multiple_bins) { // multiple_bin = [[16, 4], [8, 3]] (config.rs:78-85)
+            fprintf(f, "multiple_bin = [");
+            for (uint32_t k = 0; k < ix->params.n_multiple_bins; k++)
+                fprintf(f, "%s[%u, %u]", k ? ", " : "", ix->params.multiple_bins[2 * k], ix->params.multiple_bins[2 * k + 1]);
+            fprintf(f, "]\n");
+        }
+        fprintf(f, "num_bin_angle = %u\nnum_bin_dist = %u\n", ix->params.nbin_angle, ix->params.nbin_dist);
         fclose(f);
     }
     return FD_OK;
@@ -1533,6 +1619,34 @@ fdh_index *fdh_index_load(const char *prefix) {
             if (k == "num_bin_dist") ix->params.nbin_dist = (uint32_t)atoi(v.c_str());
             else if (k == "num_bin_angle") ix->params.nbin_angle = (uint32_t)atoi(v.c_str());
             else if (k == "grid_width") ix->params.dist_cutoff = strtof(v.c_str(), nullptr);
+            else if (k == "hash_type") {
+                const size_t a = v.find('"'), b = v.rfind('"');
+                const int t = a != std::string::npos && b > a ? fdh_hash_type_from_string(v.substr(a + 1, b - a - 1).c_str()) : -1;
+                if (t < 0) {
+                    set_err("unknown hash_type in " + std::string(prefix) + ".type:" + v);
+                    delete ix;
+                    return nullptr;
+                }
+                ix->params.hash_type = (uint32_t)t;
+            } else if (k == "multiple_bin") {
+                std::vector<uint32_t> nums;
+                for (size_t pos = 0; pos < v.size();) {
+                    if (isdigit((unsigned char)v[pos])) {
+                        char *end = nullptr;
+                        nums.push_back((uint32_t)strtoul(v.c_str() + pos, &end, 10));
+                        pos = (size_t)(end - v.c_str());
+                    } else {
+                        pos++;
+                    }
+                }
+                if (nums.size() % 2 != 0 || nums.size() / 2 > FD_MAX_MULTIPLE_BINS) {
+                    set_err("multiple_bin in " + std::string(prefix) + ".type: expected at most 8 [dist, angle] pairs");
+                    delete ix;
+                    return nullptr;
+                }
+                ix->params.n_multiple_bins = (uint32_t)(nums.size() / 2);
+                for (size_t q = 0; q < nums.size(); q++) ix->params.multiple_bins[q] = nums[q];
+            }
         }
     }
     return ix;
@@ -1585,6 +1699,13 @@ int64_t fdh_parse_query_string(const char *q, uint8_t default_chain, uint8_t *ch
 }
 
 fdh_queries *fdh_queries_new(const fdh_query_params *p) {
+    {
+        fdg::TypedParams tp;
+        if (const char *why = fdg::typed_params_from(&p->hash, &tp)) {
+            set_err(why);
+            return nullptr;
+        }
+    }
     fdh_queries *qs = new fdh_queries();
     qs->p = *p;
     qs->dist_thr.assign(p->dist_thr, p->dist_thr + p->n_dist_thr);
@@ -1728,6 +1849,7 @@ int fdh_queries_finalize(fdh_queries *qs, fd_ctx *ctx) {
     // total_structures = lookup.len() as f32
     const int rc = fdh_queries_finalize_with_counts(qs, counts.data(), fd_index_num_structs(ctx));
     if (rc != FD_OK) return rc;
+    if (!fdg::ht_default_route(&qs->p.hash)) return FD_OK; // verified through the general path: no fused-kernel tables
     return ensure_verify_prepared(ctx, qs);
 }
 int64_t fdh_queries_num_hashes(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].entries.size(); }
@@ -2105,12 +2227,13 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 cand_n[k] = hits[k].nid;
             }
         // --- K6: verification on the device; candidates beyond its limits come back flagged ---
-        if (p->verify_mode != 1) {
+        if (p->verify_mode != 1 && fdg::ht_default_route(&qs->p.hash)) {
             if (ensure_verify_prepared(ctx, qs) != FD_OK) return fail();
             R->h2d_bytes += fd_verify_prepared_bytes(qs->vprep) * nq / std::max<size_t>(1, qs->q.size());
         }
         uint64_t n_recs = 0;
-        if (p->verify_mode == 1) { // general path for everything
+        // other encodings / `--multiple-bins`: the fused kernels and the pair table are PDBTrRosetta single-bin only
+        if (p->verify_mode == 1 || !fdg::ht_default_route(&qs->p.hash)) { // general path for everything
             all_general.assign(n_cand, 1);
             lanes.resize(1);
             lanes[0].c1 = n_cand;

@@ -344,6 +344,8 @@ class QueryBatch:
         p = _QueryParams(hash_params or HashParams(), _ptr(self._dt), len(self._dt), _ptr(self._at), len(self._at),
                          int(serial_query))
         self.h = _lib().fdh_queries_new(C.byref(p))
+        if not self.h:
+            raise FdError(_err())
         self.query_strings = []
 
     def add(self, compact, query_string):

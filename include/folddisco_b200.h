@@ -86,11 +86,31 @@ typedef struct {
     const uint8_t *cb_valid;
 } fd_struct_batch;
 
-/* hash_type PDBTrRosetta; nbin 0 = default (16 / 4), larger values clamp (src/geometry/pdb_tr.rs:21-35) */
+/* Encodings of the reference's `--type` (HashType, src/geometry/core.rs:10-60): the values of fd_hash_params.hash_type
+ * are the reference's HashType index + 1, 0 selects the default.  TertiaryInteraction (6) and Hybrid (7) are not
+ * built: every entry point refuses them with FD_ERR_ARG. */
+#define FD_HASH_DEFAULT 0          /* = PDBTrRosetta */
+#define FD_HASH_PDBMOTIF 1         /* src/geometry/pdb_motif.rs */
+#define FD_HASH_PDBMOTIFSINCOS 2   /* src/geometry/pdb_motif_sincos.rs */
+#define FD_HASH_TRROSETTA 3        /* src/geometry/trrosetta.rs */
+#define FD_HASH_PDBTRROSETTA 4     /* src/geometry/pdb_tr.rs */
+#define FD_HASH_POINTPAIRFEATURE 5 /* src/geometry/ppf.rs */
+#define FD_HASH_FOLDDISCOANGLE 8   /* src/geometry/folddisco_angle.rs */
+#define FD_HASH_FOLDDISCODIST 9    /* src/geometry/folddisco_dist.rs */
+#define FD_MAX_MULTIPLE_BINS 8
+
+/* The hashing parameters of one index (IndexConfig, src/cli/config.rs:9-19).  nbin_dist / nbin_angle: if either is
+ * 0 the encoding's defaults are used for both (feature.rs:215-221; PDBTrRosetta 16 / 4); larger values clamp the way
+ * each encoding's perfect_hash does.  n_multiple_bins > 0 = `--multiple-bins`: every residue pair is hashed once per
+ * (multiple_bins[2k], multiple_bins[2k+1]) = (dist, angle) pair instead (feature.rs:210-214).  A zero-initialised tail
+ * (hash_type, n_multiple_bins) is the default PDBTrRosetta single-bin index. */
 typedef struct {
     uint32_t nbin_dist;
     uint32_t nbin_angle;
     float dist_cutoff; /* IndexConfig.grid_width, default 20.0 (src/cli/main.rs:41) */
+    uint32_t hash_type; /* FD_HASH_* */
+    uint32_t n_multiple_bins;
+    uint32_t multiple_bins[16]; /* 2 * FD_MAX_MULTIPLE_BINS: dist, angle, dist, angle ... */
 } fd_hash_params;
 
 /* ---- (i) index build ----------------------------------------------------------------------------- */
@@ -522,6 +542,15 @@ int fd_math_probe(fd_ctx *ctx, int op, const float *a, const float *b, uint64_t 
 void fd_pair_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_xyz, const uint8_t *aa,
                        const uint32_t *pair_i, const uint32_t *pair_j, uint64_t n_pairs, const fd_hash_params *params,
                        uint32_t *out_exact, uint32_t *out_fast, uint8_t *out_declined);
+/* Other encodings (fd_hash_params.hash_type / multiple_bins): every ordered residue pair (i, j), i != j, of one SoA
+ * structure hashed on the HOST by the header the kernels compile (csrc/fd_hashtypes.cuh), pairs in row-major order and
+ * the bin pairs of one residue pair in list order -- get_geometric_hash_as_u32_from_structure before its sort + dedup
+ * (src/controller/feature.rs:198-231).  Returns the number of hashes (writes at most cap), -1 for refused parameters.
+ * fd_typed_is_symmetric_host: HashValue::is_symmetric of the encoding (1 / 0; -1 = encoding not built). */
+int64_t fd_typed_hash_host(const float *n_xyz, const float *ca_xyz, const float *cb_xyz, const uint8_t *aa,
+                           const uint8_t *cb_valid, uint64_t n_res, const fd_hash_params *params, uint32_t *out,
+                           int64_t cap);
+int fd_typed_is_symmetric_host(uint32_t hash_type, uint32_t hash);
 /* same functions evaluated by the host build of the same header (no device needed) */
 void fd_math_host(int op, const float *a, const float *b, uint64_t n, float *out);
 

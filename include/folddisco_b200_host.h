@@ -91,6 +91,11 @@ void fdh_index_get_lookup(const fdh_index *ix, uint32_t *nres, float *plddt);
 const char *fdh_index_name(const fdh_index *ix, uint64_t id);
 uint64_t fdh_index_db_key(const fdh_index *ix, uint64_t id); /* 5th column of PREFIX.lookup */
 void fdh_index_get_params(const fdh_index *ix, fd_hash_params *params);
+/* HashType::get_with_str / to_string (src/geometry/core.rs:42-75): a `--type` spelling ("default", "pdb", "ppf", "3",
+ * "PDBMotifSinCos" ...) -> FD_HASH_* (6 / 7 for the two encodings that are not built), -1 if unknown; and back to the
+ * name PREFIX.type stores */
+int fdh_hash_type_from_string(const char *name);
+const char *fdh_hash_type_name(uint32_t hash_type);
 /* fd_index_attach with this index and its lookup */
 int fdh_index_attach(fd_ctx *ctx, const fdh_index *ix);
 void fdh_index_free(fdh_index *ix);

@@ -317,26 +317,79 @@ fdo_compact *build_compact(const fdo_structure &o) {
     return c;
 }
 
-// core.rs:378-403 + feature.rs:11-24,84-99
+// Encoding selected for the whole oracle (fdo_set_hash_type): the reference's HashType index (geometry/core.rs:25-38)
+// 0 PDBMotif, 1 PDBMotifSinCos, 2 TrRosetta, 3 PDBTrRosetta (default), 4 PointPairFeature, 7 FolddiscoAngle,
+// 8 FolddiscoDist; and the --multiple-bins list (empty = none).
+int g_hash_type = 3;
+std::vector<std::pair<uint32_t, uint32_t>> g_multi_bins;
+
+// coordinate.rs:151-162
+inline float calc_angle_radian(V3 a, V3 b, V3 c) {
+    float v1x = a.x - b.x, v1y = a.y - b.y, v1z = a.z - b.z;
+    float v2x = c.x - b.x, v2y = c.y - b.y, v2z = c.z - b.z;
+    float dot = v1x * v2x + v1y * v2y + v1z * v2z;
+    float l1 = sqrtf(v1x * v1x + v1y * v1y + v1z * v1z);
+    float l2 = sqrtf(v2x * v2x + v2y * v2y + v2z * v2z);
+    return fdo_acosf(dot / (l1 * l2));
+}
+// f32::to_degrees multiplies by the literal 57.29577951...f32 (not by 180 / PI evaluated in f32)
+inline float to_degrees(float r) { return r * 57.2957795130823208767981548141051703f; }
+
+// get_single_feature (feature.rs:11-190) for the encodings over the N / CA / CB atoms of the two residues
 bool pair_feature(const fdo_compact &c, size_t i, size_t j, float cutoff, float *f) {
     if (i == j) return false;
     uint8_t r1 = c.aa[i], r2 = c.aa[j];
     if (r1 == 255 || r2 == 255) return false;
     if (!c.cb_valid[i] || !c.cb_valid[j]) return false;
-    float ca_dist = calc_distance(c.ca[i], c.ca[j]);
-    if (ca_dist > cutoff) return false;
-    float cb_dist = calc_distance(c.cb[i], c.cb[j]);
-    float angle = calc_angle(c.ca[i], c.cb[i], c.ca[j], c.cb[j]);
-    float t1 = calc_torsion_radian(c.n[i], c.ca[i], c.cb[i], c.cb[j]);
-    float t2 = calc_torsion_radian(c.cb[i], c.cb[j], c.ca[j], c.n[j]);
+    for (int k = 0; k < 9; k++) f[k] = 0.0f;
     f[0] = (float)r1;
     f[1] = (float)r2;
-    f[2] = ca_dist;
-    f[3] = cb_dist;
-    f[4] = angle;
-    f[5] = t1;
-    f[6] = t2;
-    return true;
+    switch (g_hash_type) {
+        case 0:   // PDBMotif: ca_dist, cb_dist, CA-CB angle in degrees (feature.rs:26-45)
+        case 1: { // PDBMotifSinCos: the same with the angle in radians (feature.rs:47-66)
+            float ca_dist = calc_distance(c.ca[i], c.ca[j]);
+            if (ca_dist > cutoff) return false;
+            f[2] = ca_dist;
+            f[3] = calc_distance(c.cb[i], c.cb[j]);
+            float a = calc_angle(c.ca[i], c.cb[i], c.ca[j], c.cb[j]);
+            f[4] = g_hash_type == 0 ? to_degrees(a) : a;
+            return true;
+        }
+        case 2: { // TrRosetta (core.rs:319-343): cutoff on the CB distance
+            float cb_dist = calc_distance(c.cb[i], c.cb[j]);
+            if (cb_dist > cutoff) return false;
+            f[2] = cb_dist;
+            f[3] = calc_torsion_radian(c.ca[i], c.cb[i], c.cb[j], c.ca[j]);
+            f[4] = calc_torsion_radian(c.n[i], c.ca[i], c.cb[i], c.cb[j]);
+            f[5] = calc_torsion_radian(c.cb[i], c.cb[j], c.ca[j], c.n[j]);
+            f[6] = calc_angle_radian(c.ca[i], c.cb[i], c.cb[j]);
+            f[7] = calc_angle_radian(c.cb[i], c.cb[j], c.ca[j]);
+            return true;
+        }
+        case 4: { // PointPairFeature (core.rs:302-317, coordinate.rs:93-102)
+            V3 rel1 = vsub(c.cb[i], c.ca[i]), rel2 = vsub(c.cb[j], c.ca[i]);
+            V3 n1 = vnormalize(rel1), n2 = vnormalize(rel2);
+            V3 d = vsub(rel2, rel1);
+            V3 nd = vnormalize(d);
+            float dn = vnorm(d);
+            if (dn > cutoff) return false;
+            f[2] = dn;
+            f[3] = fdo_acosf(vdot(n1, nd));
+            f[4] = fdo_acosf(vdot(n2, nd));
+            f[5] = fdo_acosf(vdot(n1, n2));
+            return true;
+        }
+        default: { // PDBTrRosetta / FolddiscoAngle / FolddiscoDist: core.rs:378-403 + feature.rs:84-99
+            float ca_dist = calc_distance(c.ca[i], c.ca[j]);
+            if (ca_dist > cutoff) return false;
+            f[2] = ca_dist;
+            f[3] = calc_distance(c.cb[i], c.cb[j]);
+            f[4] = calc_angle(c.ca[i], c.cb[i], c.ca[j], c.cb[j]);
+            f[5] = calc_torsion_radian(c.n[i], c.ca[i], c.cb[i], c.cb[j]);
+            f[6] = calc_torsion_radian(c.cb[i], c.cb[j], c.ca[j], c.n[j]);
+            return true;
+        }
+    }
 }
 
 // convert.rs:32-36
@@ -351,7 +404,7 @@ inline float continuize(uint32_t v, float mn, float mx, float nbin) {
 }
 
 // geometry/pdb_tr.rs:21-75 (nbin 0 -> default 16/4; >16 / >4 clamp)
-uint32_t perfect_hash(const float *f, uint32_t nbd, uint32_t nba) {
+uint32_t perfect_hash_pdbtr(const float *f, uint32_t nbd, uint32_t nba) {
     float nbin_dist = nbd > 16 ? 16.0f : (nbd == 0 ? 16.0f : (float)nbd);
     float nbin_angle = nba > 4 ? 4.0f : (nba == 0 ? 4.0f : (float)nba);
     uint32_t res1 = sat_u32(f[0]), res2 = sat_u32(f[1]);
@@ -365,6 +418,89 @@ uint32_t perfect_hash(const float *f, uint32_t nbd, uint32_t nba) {
     uint32_t c2 = discretize(fdo_cosf(f[6]), -1.0f, 1.0f, nbin_angle);
     // Rust `<<` on u32 with an in-range shift never panics; bits shifted past 31 are dropped.
     return res1 << 25 | res2 << 20 | ca << 16 | cb << 12 | s0 << 10 | c0 << 8 | s1 << 6 | c1 << 4 | s2 << 2 | c2;
+}
+
+const float PI_F32 = 3.14159274101257324f;
+
+// HashValue::perfect_hash(feature, nbin_dist, nbin_angle) of the selected encoding, each with its file's clamping
+uint32_t perfect_hash_raw(const float *f, uint32_t nbd, uint32_t nba) {
+    uint32_t res1 = sat_u32(f[0]), res2 = sat_u32(f[1]);
+    switch (g_hash_type) {
+        case 0: { // pdb_motif.rs:26-50 (defaults 18 / 9, clamp 32 / 32, angle in degrees over [0, 180])
+            float nd = nbd > 32 ? 32.0f : (nbd == 0 ? 18.0f : (float)nbd);
+            float na = nba > 32 ? 32.0f : (nba == 0 ? 9.0f : (float)nba);
+            uint32_t ca = discretize(f[2], 2.0f, 20.0f, nd), cb = discretize(f[3], 2.0f, 20.0f, nd);
+            uint32_t an = discretize(f[4], 0.0f, 180.0f, na);
+            return res1 << 20 | res2 << 15 | ca << 10 | cb << 5 | an;
+        }
+        case 1: { // pdb_motif_sincos.rs:17-53 (defaults 8 / 3, clamp 16 / 16)
+            float nd = nbd > 16 ? 16.0f : (nbd == 0 ? 8.0f : (float)nbd);
+            float na = nba > 16 ? 16.0f : (nba == 0 ? 3.0f : (float)nba);
+            uint32_t ca = discretize(f[2], 2.0f, 20.0f, nd), cb = discretize(f[3], 2.0f, 20.0f, nd);
+            uint32_t sn = discretize(fdo_sinf(f[4]), -1.0f, 1.0f, na), cs = discretize(fdo_cosf(f[4]), -1.0f, 1.0f, na);
+            return res1 << 21 | res2 << 16 | ca << 12 | cb << 8 | sn << 4 | cs;
+        }
+        case 2: { // trrosetta.rs:51-91 (clamp 8 / 4, zeros are NOT replaced here)
+            float nd = (float)nbd > 8.0f ? 8.0f : (float)nbd;
+            float na = (float)nba > 4.0f ? 4.0f : (float)nba;
+            uint32_t pair = res1 * 20 + res2; // map_aa_u32_pair_to_u32 (convert.rs:203-207)
+            uint32_t h = pair << 23 | discretize(f[2], 2.0f, 20.0f, nd) << 20;
+            int shift = 18;
+            for (int k = 3; k <= 7; k++) { // omega, theta1, theta2, phi1, phi2: sin then cos, two bits each
+                h |= discretize(fdo_sinf(f[k]), -1.0f, 1.0f, na) << shift;
+                h |= discretize(fdo_cosf(f[k]), -1.0f, 1.0f, na) << (shift - 2);
+                shift -= 4;
+            }
+            return h;
+        }
+        case 4: { // ppf.rs:15-51 (defaults 8 / 3, clamp 16 / 8)
+            float nd = nbd > 16 ? 16.0f : (nbd == 0 ? 8.0f : (float)nbd);
+            float na = nba > 8 ? 8.0f : (nba == 0 ? 3.0f : (float)nba);
+            uint32_t hd = discretize(f[2], 2.0f, 20.0f, nd);
+            uint32_t s[3], c[3];
+            for (int k = 0; k < 3; k++) {
+                s[k] = discretize(fdo_sinf(f[3 + k]), -1.0f, 1.0f, na);
+                c[k] = discretize(fdo_cosf(f[3 + k]), -1.0f, 1.0f, na);
+            }
+            return (res1 << 27) | (res2 << 22) | (hd << 18) | (s[0] << 15) | (c[0] << 12) | (s[1] << 9) | (c[1] << 6) |
+                   (s[2] << 3) | c[2];
+        }
+        case 7: { // folddisco_angle.rs:24-71 (defaults 8 / 32, radians binned directly)
+            float nd = nbd > 8 ? 8.0f : (nbd == 0 ? 8.0f : (float)nbd);
+            float na = nba > 32 ? 32.0f : (nba == 0 ? 32.0f : (float)nba);
+            uint32_t pair = res1 * 20 + res2;
+            uint32_t ca = discretize(f[2], 2.0f, 20.0f, nd), cb = discretize(f[3], 2.0f, 20.0f, nd);
+            uint32_t an = discretize(f[4], 0.0f, PI_F32, std::min(na, 32.0f));
+            uint32_t p1 = discretize(f[5], -PI_F32, PI_F32, na), p2 = discretize(f[6], -PI_F32, PI_F32, na);
+            return pair << 21 | ca << 18 | cb << 15 | an << 10 | p1 << 5 | p2;
+        }
+        case 8: { // folddisco_dist.rs:22-68 (defaults 32 / 16; the CA-CB angle gets at most 8 bins)
+            float nd = nbd > 32 ? 32.0f : (nbd == 0 ? 32.0f : (float)nbd);
+            float na = nba > 16 ? 16.0f : (nba == 0 ? 16.0f : (float)nba);
+            uint32_t pair = res1 * 20 + res2;
+            uint32_t ca = discretize(f[2], 2.0f, 20.0f, nd), cb = discretize(f[3], 2.0f, 20.0f, nd);
+            uint32_t an = discretize(f[4], 0.0f, PI_F32, std::min(na, 8.0f));
+            uint32_t p1 = discretize(f[5], -PI_F32, PI_F32, na), p2 = discretize(f[6], -PI_F32, PI_F32, na);
+            return pair << 21 | ca << 16 | cb << 11 | an << 8 | p1 << 4 | p2;
+        }
+        default: return perfect_hash_pdbtr(f, nbd, nba);
+    }
+}
+// HashType::default_dist_bin / default_angle_bin (geometry/core.rs:118-147)
+void default_bins(uint32_t *nbd, uint32_t *nba) {
+    switch (g_hash_type) {
+        case 0: *nbd = 18, *nba = 9; break;
+        case 3: *nbd = 16, *nba = 4; break;
+        case 7: *nbd = 8, *nba = 32; break;
+        case 8: *nbd = 32, *nba = 16; break;
+        default: *nbd = 8, *nba = 3; break;
+    }
+}
+// `if nbin_dist == 0 || nbin_angle == 0 { perfect_hash_default } else { perfect_hash }` -- the form every single-bin
+// call site uses (feature.rs:215-221, query.rs:72-76 and :283-287, retrieve.rs:133-137)
+uint32_t perfect_hash(const float *f, uint32_t nbd, uint32_t nba) {
+    if (nbd == 0 || nba == 0) default_bins(&nbd, &nba);
+    return perfect_hash_raw(f, nbd, nba);
 }
 
 // pdb_tr.rs:95-136 (default bins) -> [res1,res2,ca,cb,angle_deg,phi1_deg,phi2_deg]
@@ -381,11 +517,45 @@ void reverse_hash_default(uint32_t h, float *o) {
     o[5] = fdo_atan2f(s1, c1) * deg;
     o[6] = fdo_atan2f(s2, c2) * deg;
 }
-// pdb_tr.rs:158-162
+// (res1, res2) of HashValue::reverse_hash_default for the selected encoding
+void hash_amino_acids(uint32_t h, uint32_t *a1, uint32_t *a2) {
+    switch (g_hash_type) {
+        case 0: *a1 = (h >> 20) & 31u, *a2 = (h >> 15) & 31u; break;               // pdb_motif.rs:57-58
+        case 1: *a1 = (h >> 21) & 31u, *a2 = (h >> 16) & 31u; break;               // pdb_motif_sincos.rs:60-61
+        case 2: *a1 = ((h >> 23) & 511u) / 20, *a2 = ((h >> 23) & 511u) % 20; break; // trrosetta.rs:94-95
+        case 4: *a1 = (h >> 27) & 31u, *a2 = (h >> 22) & 31u; break;               // ppf.rs:59-60
+        case 7:
+        case 8: *a1 = ((h >> 21) & 511u) / 20, *a2 = ((h >> 21) & 511u) % 20; break; // folddisco_*.rs reverse_hash
+        default: *a1 = (h >> 25) & 31u, *a2 = (h >> 20) & 31u; break;
+    }
+}
+// HashValue::is_symmetric: pdb_tr.rs:158-162 and its counterparts (always over reverse_hash_default)
 bool hash_is_symmetric(uint32_t h) {
-    float v[7];
-    reverse_hash_default(h, v);
-    return v[0] == v[1] && v[5] == v[6];
+    uint32_t a1, a2;
+    hash_amino_acids(h, &a1, &a2);
+    auto angle = [](uint32_t sbin, uint32_t cbin, float nb) {
+        return to_degrees(fdo_atan2f(continuize(sbin, -1.0f, 1.0f, nb), continuize(cbin, -1.0f, 1.0f, nb)));
+    };
+    switch (g_hash_type) {
+        case 0:
+        case 1: return a1 == a2; // pdb_motif.rs:98-102, pdb_motif_sincos.rs:105-109
+        case 2: // trrosetta.rs:158-162: theta1 == theta2 and phi1 == phi2 (3 default sin / cos bins)
+            return a1 == a2 && angle((h >> 14) & 3u, (h >> 12) & 3u, 3.0f) == angle((h >> 10) & 3u, (h >> 8) & 3u, 3.0f) &&
+                   angle((h >> 6) & 3u, (h >> 4) & 3u, 3.0f) == angle((h >> 2) & 3u, h & 3u, 3.0f);
+        case 4: // ppf.rs:124-127
+            return a1 == a2 && angle((h >> 15) & 7u, (h >> 12) & 7u, 3.0f) == angle((h >> 9) & 7u, (h >> 6) & 7u, 3.0f);
+        case 7: // folddisco_angle.rs:133-137
+            return a1 == a2 && to_degrees(continuize((h >> 5) & 31u, -PI_F32, PI_F32, 32.0f)) ==
+                                   to_degrees(continuize(h & 31u, -PI_F32, PI_F32, 32.0f));
+        case 8: // folddisco_dist.rs:126-130
+            return a1 == a2 && to_degrees(continuize((h >> 4) & 15u, -PI_F32, PI_F32, 16.0f)) ==
+                                   to_degrees(continuize(h & 15u, -PI_F32, PI_F32, 16.0f));
+        default: {
+            float v[7];
+            reverse_hash_default(h, v);
+            return v[0] == v[1] && v[5] == v[6];
+        }
+    }
 }
 
 // feature.rs:198-231 + combination.rs:24-44 (row-major ordered pairs, i != j)
@@ -395,7 +565,12 @@ void hash_compact(const fdo_compact &c, uint32_t nbd, uint32_t nba, float cutoff
     for (size_t i = 0; i < n; i++)
         for (size_t j = 0; j < n; j++) {
             if (i == j) continue;
-            if (pair_feature(c, i, j, cutoff, f)) out.push_back(perfect_hash(f, nbd, nba));
+            if (!pair_feature(c, i, j, cutoff, f)) continue;
+            if (!g_multi_bins.empty()) { // feature.rs:210-214: no default substitution on this branch
+                for (auto &b : g_multi_bins) out.push_back(perfect_hash_raw(f, b.first, b.second));
+            } else {
+                out.push_back(perfect_hash(f, nbd, nba));
+            }
         }
 }
 
@@ -572,13 +747,19 @@ struct fdo_qmap {
 
 namespace {
 
-// query.rs:53-84 (no multiple_bin)
+// query.rs:53-84
 void insert_binned_hash(fdo_qmap &m, const float *f, size_t qi, size_t qj, uint32_t nbd, uint32_t nba,
                         bool primary, float idf) {
-    uint32_t h = perfect_hash(f, nbd, nba);
-    if (m.lookup.count(h)) return;
-    m.lookup[h] = m.entries.size();
-    m.entries.push_back({h, qi, qj, primary, idf});
+    auto put = [&](uint32_t h) {
+        if (m.lookup.count(h)) return;
+        m.lookup[h] = m.entries.size();
+        m.entries.push_back({h, qi, qj, primary, idf});
+    };
+    if (!g_multi_bins.empty()) {
+        for (auto &b : g_multi_bins) put(perfect_hash(f, b.first, b.second));
+    } else {
+        put(perfect_hash(f, nbd, nba));
+    }
 }
 
 // query.rs:17-32
@@ -1184,8 +1365,10 @@ fdo_matches *retrieve(const fdo_qmap &m, const fdo_compact &query, const fdo_com
     if (m.entries.size() <= 200) {
         std::set<uint8_t> aa1s, aa2s;
         for (auto &e : m.entries) {
-            aa1s.insert((uint8_t)((e.hash >> 25) & 31u));
-            aa2s.insert((uint8_t)((e.hash >> 20) & 31u));
+            uint32_t a1, a2;
+            hash_amino_acids(e.hash, &a1, &a2);
+            aa1s.insert((uint8_t)a1);
+            aa2s.insert((uint8_t)a2);
         }
         for (size_t i = 0; i < t.nres(); i++) {
             for (uint8_t a : aa1s)
@@ -1216,8 +1399,15 @@ fdo_matches *retrieve(const fdo_qmap &m, const fdo_compact &query, const fdo_com
         if (tmp.empty()) return;
         if (pair_feature(t, i, j, dist_cutoff, f)) {
             cand.insert(cand.end(), tmp.begin(), tmp.end());
-            uint32_t h = perfect_hash(f, nbd, nba);
-            if (m.lookup.count(h)) found.push_back({i, j, h});
+            if (!g_multi_bins.empty()) { // retrieve.rs:124-131
+                for (auto &b : g_multi_bins) {
+                    uint32_t h = perfect_hash_raw(f, b.first, b.second);
+                    if (m.lookup.count(h)) found.push_back({i, j, h});
+                }
+            } else {
+                uint32_t h = perfect_hash(f, nbd, nba);
+                if (m.lookup.count(h)) found.push_back({i, j, h});
+            }
         }
     };
     if (set1.empty() || set2.empty()) { // CombinationVecIterator::is_empty -> all pairs (combination.rs:24-44)
@@ -1449,7 +1639,21 @@ int fdo_pair_feature(const fdo_compact *c, int64_t i, int64_t j, float cutoff, f
     memcpy(out7, f, 7 * sizeof(float));
     return 1;
 }
+int fdo_pair_feature9(const fdo_compact *c, int64_t i, int64_t j, float cutoff, float *out9) {
+    return pair_feature(*c, (size_t)i, (size_t)j, cutoff, out9) ? 1 : 0;
+}
 uint32_t fdo_perfect_hash(const float *f, uint32_t nbd, uint32_t nba) { return perfect_hash(f, nbd, nba); }
+uint32_t fdo_perfect_hash_raw(const float *f9, uint32_t nbd, uint32_t nba) { return perfect_hash_raw(f9, nbd, nba); }
+int fdo_set_hash_type(int t) {
+    if (!(t == 0 || t == 1 || t == 2 || t == 3 || t == 4 || t == 7 || t == 8)) return -1;
+    g_hash_type = t;
+    return 0;
+}
+int fdo_get_hash_type(void) { return g_hash_type; }
+void fdo_set_multiple_bins(int n, const uint32_t *dist_angle_pairs) {
+    g_multi_bins.clear();
+    for (int k = 0; k < n; k++) g_multi_bins.push_back({dist_angle_pairs[2 * k], dist_angle_pairs[2 * k + 1]});
+}
 int fdo_hash_is_symmetric(uint32_t h) { return hash_is_symmetric(h) ? 1 : 0; }
 int64_t fdo_hash_compact(const fdo_compact *c, uint32_t nbd, uint32_t nba, float cutoff, int su, uint32_t *out,
                          int64_t cap) {
@@ -1775,9 +1979,17 @@ fdo_qmap *fdo_qmap_make(const fdo_compact *c, const uint8_t *chains, const uint6
                     }
                 }
             };
-            static const int di[2] = {2, 3}, ai[3] = {4, 5, 6};
-            expand(di, 2, dist_thr, n_dt, 1.0f, false);
-            expand(ai, 3, angle_thr, n_at, rad, true);
+            // HashType::dist_index / angle_index (feature.rs:269-289)
+            int di[2] = {2, 3}, ai[5] = {4, 5, 6, 0, 0}, ndi = 2, nai = 3;
+            if (g_hash_type == 2 || g_hash_type == 4) ndi = 1;
+            if (g_hash_type == 0 || g_hash_type == 1) nai = 1;
+            if (g_hash_type == 2) {
+                for (int k = 0; k < 5; k++) ai[k] = 3 + k;
+                nai = 5;
+            }
+            if (g_hash_type == 4) ai[0] = 3, ai[1] = 4, ai[2] = 5;
+            expand(di, ndi, dist_thr, n_dt, 1.0f, false);
+            expand(ai, nai, angle_thr, n_at, rad, true);
         }
     return m;
 }

@@ -70,6 +70,19 @@ uint8_t fdo_map_aa_to_u8(const uint8_t *res_name3);
 int fdo_pair_feature(const fdo_compact *c, int64_t i, int64_t j, float dist_cutoff, float *out7);
 uint32_t fdo_perfect_hash(const float *feature7, uint32_t nbin_dist, uint32_t nbin_angle);
 int fdo_hash_is_symmetric(uint32_t hash);
+/* Other encodings.  Process-wide selection, like fdo_set_math_mode: t = the reference's HashType index
+ * (src/geometry/core.rs:25-38): 0 PDBMotif, 1 PDBMotifSinCos, 2 TrRosetta, 3 PDBTrRosetta (default), 4 PointPairFeature,
+ * 7 FolddiscoAngle, 8 FolddiscoDist (5 TertiaryInteraction and 6 Hybrid are not restated: returns -1).  Every function
+ * below that takes nbin_dist / nbin_angle then hashes with that encoding (features get 9 slots, unused ones 0), and
+ * fdo_pair_feature / fdo_perfect_hash / fdo_hash_is_symmetric follow it too.
+ * fdo_set_multiple_bins: the --multiple-bins list as n (dist, angle) pairs; n = 0 turns it off
+ * (feature.rs:210-214, query.rs:59-71, retrieve.rs:124-131). */
+int fdo_set_hash_type(int t);
+/* the 9-slot feature of the selected encoding, and HashValue::perfect_hash without the zero -> default substitution */
+int fdo_pair_feature9(const fdo_compact *c, int64_t i, int64_t j, float dist_cutoff, float *out9);
+uint32_t fdo_perfect_hash_raw(const float *feature9, uint32_t nbin_dist, uint32_t nbin_angle);
+int fdo_get_hash_type(void);
+void fdo_set_multiple_bins(int n, const uint32_t *dist_angle_pairs);
 /* all ordered pairs, row-major (feature.rs:198-231).  sorted_unique != 0 applies sort+dedup
  * (controller/mod.rs:343-344).  Returns the number of hashes; writes at most cap. */
 int64_t fdo_hash_compact(const fdo_compact *c, uint32_t nbin_dist, uint32_t nbin_angle, float dist_cutoff,

@@ -24,7 +24,8 @@
 #include "folddisco_b200_host.h"
 
 _Static_assert(sizeof(fd_struct_batch) == 56, "fd_struct_batch");
-_Static_assert(sizeof(fd_hash_params) == 12, "fd_hash_params");
+_Static_assert(sizeof(fd_hash_params) == 84, "fd_hash_params");
+_Static_assert(offsetof(fd_hash_params, hash_type) == 12 && offsetof(fd_hash_params, multiple_bins) == 20, "fd_hash_params tail");
 _Static_assert(sizeof(fd_index_buffers) == 40, "fd_index_buffers");
 _Static_assert(sizeof(fd_query) == 56, "fd_query");
 _Static_assert(offsetof(fd_query, expected_node_count) == 44, "fd_query.expected_node_count");
@@ -40,7 +41,7 @@ _Static_assert(sizeof(fd_match_record) == 128, "fd_match_record");
 _Static_assert(offsetof(fd_match_record, res) == 64, "fd_match_record.res");
 _Static_assert(sizeof(fd_verify_query) == 128, "fd_verify_query");
 _Static_assert(offsetof(fd_verify_query, cb_xyz) == 120, "fd_verify_query.cb_xyz");
-_Static_assert(sizeof(fdh_query_params) == 48, "fdh_query_params");
+_Static_assert(sizeof(fdh_query_params) == 120, "fdh_query_params");
 _Static_assert(sizeof(fdh_search_params) == 120, "fdh_search_params");
 _Static_assert(sizeof(fdh_struct_row) == 48, "fdh_struct_row");
 _Static_assert(sizeof(fdh_match_row) == 72, "fdh_match_row");
@@ -117,7 +118,7 @@ int main(int argc, char **argv) {
         if (s == qs_id) query_struct = c;
         else fdh_compact_free(c);
     }
-    fd_hash_params hp = {0, 0, 20.0f};
+    fd_hash_params hp = {0, 0, 20.0f, FD_HASH_DEFAULT, 0, {0}};
     fd_struct_batch batch;
     if (fdh_store_batch(store, &batch) != FD_OK) return 4;
     fd_index_buffers ib;

@@ -89,6 +89,11 @@ def lib():
     sig("fdo_pair_feature", C.c_int, [VP, C.c_int64, C.c_int64, C.c_float, f32p])
     sig("fdo_perfect_hash", C.c_uint32, [f32p, C.c_uint32, C.c_uint32])
     sig("fdo_hash_is_symmetric", C.c_int, [C.c_uint32])
+    sig("fdo_set_hash_type", C.c_int, [C.c_int])
+    sig("fdo_get_hash_type", C.c_int, [])
+    sig("fdo_set_multiple_bins", None, [C.c_int, VP])
+    sig("fdo_pair_feature9", C.c_int, [VP, C.c_int64, C.c_int64, C.c_float, f32p])
+    sig("fdo_perfect_hash_raw", C.c_uint32, [f32p, C.c_uint32, C.c_uint32])
     sig("fdo_hash_compact", C.c_int64, [VP, C.c_uint32, C.c_uint32, C.c_float, C.c_int, VP, C.c_int64])
     sig("fdo_index_from_csr", VP, [u32p, u64p, C.c_uint64])
     sig("fdo_index_build", VP, [C.POINTER(VP), C.c_uint64, C.c_uint32, C.c_uint32, C.c_float, C.c_int])
@@ -237,6 +242,36 @@ class Compact:
         if getattr(self, "h", None):
             lib().fdo_compact_free(self.h)
             self.h = None
+
+
+class hash_mode:
+    """with oracle_lib.hash_mode(hash_type, multiple_bins): ... -- selects the oracle's encoding (the reference's
+    HashType index: 0 PDBMotif, 1 PDBMotifSinCos, 2 TrRosetta, 3 PDBTrRosetta, 4 PointPairFeature, 7 FolddiscoAngle,
+    8 FolddiscoDist) and the --multiple-bins list for the duration of the block; the default is restored on exit."""
+
+    def __init__(self, hash_type=3, multiple_bins=()):
+        self.t, self.mb = hash_type, list(multiple_bins)
+
+    def __enter__(self):
+        if lib().fdo_set_hash_type(self.t) != 0:
+            raise ValueError("hash type %r is not restated by the oracle" % (self.t,))
+        a = np.ascontiguousarray(np.array(self.mb, np.uint32).reshape(-1))
+        lib().fdo_set_multiple_bins(len(self.mb), a.ctypes.data if len(self.mb) else None)
+        return self
+
+    def __exit__(self, *exc):
+        lib().fdo_set_hash_type(3)
+        lib().fdo_set_multiple_bins(0, None)
+        return False
+
+
+def pair_feature9(compact, i, j, cutoff=20.0):
+    f = np.zeros(9, np.float32)
+    return f if lib().fdo_pair_feature9(compact.h, i, j, cutoff, f) else None
+
+
+def perfect_hash_raw(feature9, nbin_dist, nbin_angle):
+    return int(lib().fdo_perfect_hash_raw(np.ascontiguousarray(feature9, np.float32), nbin_dist, nbin_angle))
 
 
 def perfect_hash(feature7, nbin_dist=0, nbin_angle=0):

@@ -11,7 +11,7 @@ import numpy as np
 import fixtures as F
 
 
-class _HP(C.Structure):
+class _HP_unused(C.Structure):
     _fields_ = [("nbin_dist", C.c_uint32), ("nbin_angle", C.c_uint32), ("dist_cutoff", C.c_float)]
 
 
@@ -37,7 +37,7 @@ def _compare(db, nbin_dist, nbin_angle, max_structs=None):
         i, j = i.astype(np.uint32), j.astype(np.uint32)
         exact, fast = np.zeros(len(i), np.uint32), np.zeros(len(i), np.uint32)
         dec = np.zeros(len(i), np.uint8)
-        hp = _HP(nbin_dist, nbin_angle, 20.0)
+        hp = fd.HashParams(nbin_dist, nbin_angle, 20.0)
         L.fd_pair_hash_host(_p(n), _p(ca), _p(cb), _p(aa), _p(i), _p(j), C.c_uint64(len(i)), C.byref(hp), _p(exact),
                             _p(fast), _p(dec))
         ok = dec == 0

@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "libfolddisco_b200.so")
 CLI = os.path.join(HERE, "folddisco-b200")  # `index` / `query` front end (csrc/host/fd_cli.cpp), links the .so
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU = ["fd_ctx.cu", "fd_hash.cu", "fd_postings.cu", "fd_query.cu", "fd_edges.cu", "fd_kabsch.cu", "fd_verify.cu",
+CU = ["fd_ctx.cu", "fd_hash.cu", "fd_postings.cu", "fd_query.cu", "fd_edges.cu", "fd_kabsch.cu", "fd_metrics.cu", "fd_verify.cu",
       "fd_comm.cu"]
 CPP = ["host/fd_host.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

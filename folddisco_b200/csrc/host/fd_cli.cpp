@@ -9,14 +9,14 @@
 //   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
 //   ids                     src/controller/mode.rs:70-125
 //
-// Not here (fails loudly): `benchmark` / `analyze`, --superpose, --web, --partial-fit, sort keys / columns that need
-// e-values or similarity metrics, the TM / GDT / Chamfer / Hausdorff filters, hash types other than the default, mmCIF / .gz /
-// Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
+// Not here (fails loudly): `benchmark` / `analyze`, --web, --partial-fit, the TertiaryInteraction / Hybrid encodings,
+// mmCIF / .gz / Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
 #include <dirent.h>
 #include <limits.h>
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -185,6 +185,7 @@ const char *HELP =
     "  query     Query a motif from an index table (GPU)\n"
     "  version   Print version information\n\n"
     "index:  -p/--pdbs DIR  -i/--index PREFIX  [-t N] [-d NBIN_DIST] [-a NBIN_ANGLE] [-g GRID] [-n MAX_RESIDUE]\n"
+    "        [-y/--type default|pdbtr|pdb|orig_pdb|tr|ppf|angle|dist] [--multiple-bins D1-A1,D2-A2,..]\n"
     "        [-r] [--id relpath|abspath|basename|filename|pdb] [--no-store] [-v]\n"
     "query:  -p/--pdb FILE -q/--query RESIDUES | -q FILE.txt|.tsv   -i/--index PREFIX  [-t N]\n"
     "        [-d DIST_THR[,..]] [-a ANGLE_THR[,..]] [--ca-distance X] [--total-match N] [--covered-node N]\n"
@@ -192,7 +193,9 @@ const char *HELP =
     "        [--connected-node-ratio X] [--num-residue N] [--plddt X] [--rmsd X] [--top N] [--sampling-count N]\n"
     "        [--sampling-ratio X] [--freq-filter X] [--length-penalty X] [--per-structure|--per-match] [--skip-match]\n"
     "        [--skip-ca-match] [--serial-index] [--sort-by KEY[:asc|desc],..] [--format-output COL,..] [--header]\n"
-    "        [-o FILE] [-v]\n";
+    "        [--tm-score X] [--gdt-ts X] [--gdt-ha X] [--chamfer X] [--hausdorff X] [--superpose] [-o FILE] [-v]\n"
+    "        match columns: qid tid nid db_key node_count idf rmsd e_value u_matrix t_vector matching_residues\n"
+    "                       matching_coordinates query_residues tm_score gdt_ts gdt_ha chamfer_distance hausdorff_distance\n";
 
 int cmd_index(Args &a) {
     a.reject({"--mmap-on-disk"}, "the index is built in GPU memory");
@@ -358,7 +361,7 @@ std::vector<std::string> split(const std::string &s, char sep) {
 
 // --sort-by: "key[:asc|desc],..." (sort.rs:47-66, 117-205 for match rows; :297-330, 380-440 for structure rows).
 // A key is (column id, descending?); values compare as the reference's extract_value does, ties keep the prior order.
-enum MatchKey { MK_NODE, MK_IDF, MK_RMSD };
+enum MatchKey { MK_NODE, MK_IDF, MK_RMSD, MK_EVALUE, MK_TM, MK_GDT_TS, MK_GDT_HA, MK_CHAMFER, MK_HAUSDORFF };
 enum StructKey { SK_MAXNODE, SK_NODE, SK_IDF, SK_MINRMSD, SK_TOTAL, SK_EDGE, SK_NRES, SK_PLDDT };
 struct SortSpec {
     std::vector<std::pair<int, bool>> keys; // (key, descending)
@@ -403,10 +406,12 @@ SortSpec parse_sort(const std::string &arg, bool structure_mode) {
             if (is({"node_count", "node-count", "nodes", "node", "n"})) key = MK_NODE;
             else if (is({"idf", "score"})) key = MK_IDF;
             else if (is({"rmsd"})) key = MK_RMSD, desc = false;
-            else if (is({"evalue", "e_value", "e-value", "tm_score", "tm-score", "tmscore", "tm", "gdt_ts", "gdt-ts", "gdtts", "gdt",
-                         "gdt_ha", "gdt-ha", "gdtha", "chamfer", "chamfer-distance", "chamfer_distance", "hausdorff",
-                         "hausdorff-distance", "hausdorff_distance"}))
-                die("--sort-by " + k + " is not supported by folddisco-b200: similarity metrics and e-values are outside the ported path");
+            else if (is({"evalue", "e_value", "e-value"})) key = MK_EVALUE, desc = false; // sort.rs:52-60, 78-85
+            else if (is({"tm_score", "tm-score", "tmscore", "tm"})) key = MK_TM;
+            else if (is({"gdt_ts", "gdt-ts", "gdtts", "gdt"})) key = MK_GDT_TS;
+            else if (is({"gdt_ha", "gdt-ha", "gdtha"})) key = MK_GDT_HA;
+            else if (is({"chamfer", "chamfer-distance", "chamfer_distance"})) key = MK_CHAMFER, desc = false;
+            else if (is({"hausdorff", "hausdorff-distance", "hausdorff_distance"})) key = MK_HAUSDORFF, desc = false;
             else die("Error parsing --sort-by: Unknown sort key: '" + k + "'");
         }
         if (kv.size() == 2 && !parse_order(lower_trim(kv[1]), &desc))
@@ -421,10 +426,36 @@ int cmp_val(double a, double b, bool desc) {
     return a < b ? -1 : (a > b ? 1 : 0);
 }
 
+// evalue_fitting (src/controller/result.rs:357-378): x = match idf, m = structures in the index, l = query residues
+double evalue_fitting(float x, float m, float l) {
+    const double x_d = x, m_d = m, l_d = l;
+    const double mu = 4.2161 * std::exp(l_d * 0.0489) + 3.6661;
+    const double lam = 0.2894 * std::exp(l_d * -0.0762) + 0.0316;
+    const double k_val = std::exp(lam * mu) / 10546.0;
+    const double e_val_raw = k_val * m_d * l_d * std::exp(-lam * x_d);
+    return (e_val_raw * m_d) / (e_val_raw + m_d);
+}
+// Rust `{:.4e}`: mantissa with four decimals, exponent without sign padding ("1.2345e-3", "9.8765e2")
+std::string rust_sci4(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.4e", v);
+    std::string t = buf;
+    const size_t e = t.find('e');
+    if (e == std::string::npos) return t;
+    const int ex = atoi(t.c_str() + e + 1);
+    return t.substr(0, e) + "e" + std::to_string(ex);
+}
+
 int cmd_query(Args &a) {
-    a.reject({"--superpose", "--web"}, "superposition output columns are not implemented");
+    a.reject({"--web"}, "the web output mode is not implemented");
     a.reject({"--partial-fit"}, "LMS-QCP partial fit is outside the ported path");
-    a.reject({"--tm-score", "--gdt-ts", "--gdt-ha", "--chamfer", "--hausdorff"}, "similarity-metric filters are outside the ported path");
+    const bool superpose = a.flag({"--superpose"});
+    // MatchFilter cutoffs over the similarity metrics (src/cli/workflows/query_pdb.rs:80-83, filter.rs:217-236); 0 = off
+    const float tm_cut = (float)a.num({"--tm-score"}, 0.0), gdt_ts_cut = (float)a.num({"--gdt-ts"}, 0.0),
+                gdt_ha_cut = (float)a.num({"--gdt-ha"}, 0.0), chamfer_cut = (float)a.num({"--chamfer"}, 0.0),
+                hausdorff_cut = (float)a.num({"--hausdorff"}, 0.0);
     const std::string pdb_path = a.str({"-p", "--pdb"}, "");
     const std::string query_string = a.str({"-q", "--query"}, "");
     const int threads = (int)a.num({"-t", "--threads"}, 1);
@@ -476,6 +507,15 @@ int cmd_query(Args &a) {
         for (const std::string &c : split(format_output, ',')) columns.push_back(lower_trim(c));
     if (prefix.empty()) die("query needs -i PREFIX");
     if (threads > 0) setenv("FD_HOST_THREADS", std::to_string(threads).c_str(), 0);
+    // the similarity metrics (one small kernel per search, fd_metrics_store_batch) and the residue indices behind
+    // matching_coordinates are computed only when a filter, sort key or column asks for them
+    bool need_metrics = tm_cut > 0.f || gdt_ts_cut > 0.f || gdt_ha_cut > 0.f || chamfer_cut > 0.f || hausdorff_cut > 0.f;
+    for (auto &kd : sort_spec.keys) need_metrics = need_metrics || (!per_structure && kd.first >= MK_TM);
+    for (auto &c : columns)
+        need_metrics = need_metrics || c == "tm_score" || c == "gdt_ts" || c == "gdt_ha" || c == "chamfer_distance" ||
+                       c == "hausdorff_distance" || c == "matching_coordinates";
+    if (superpose && !per_structure) need_metrics = true; // MATCH_RESULT_SUPERPOSE_COLUMNS has matching_coordinates
+    sp.want_metrics = need_metrics && !sp.skip_match ? 1 : 0;
 
     std::vector<QueryJob> jobs; // query_pdb.rs:297-315
     if (ends_with(query_string, ".txt") || ends_with(query_string, ".tsv")) {
@@ -676,16 +716,41 @@ int cmd_query(Args &a) {
             // rows in the default order (idf desc, rmsd asc) from the library, or emission order re-sorted by --sort-by
             // (stable, like par_sort_by over the candidate-ordered vector, result.rs:456-464)
             std::vector<uint64_t> order;
+            const float *metrics = fdh_results_metrics(R);          // 5 per match row, or NULL
+            const uint32_t *res_index = fdh_results_residue_index(R); // per residue entry, or NULL
+            const float n_query_res = (float)fdh_queries_residue_count(qs, (int64_t)q);
+            auto evalue_of = [&](const fdh_match_row &m) { return evalue_fitting(m.idf, (float)S, n_query_res); };
+            // match_results.retain(|v| match_filter.filter(v)) for the metric cutoffs (query_pdb.rs:474, filter.rs:217-236)
+            auto passes = [&](uint64_t k) {
+                if (!metrics) return true;
+                const float *mt = metrics + 5 * k;
+                bool pass = true;
+                if (tm_cut > 0.f) pass = pass && mt[0] >= tm_cut;
+                if (gdt_ts_cut > 0.f) pass = pass && mt[1] >= gdt_ts_cut;
+                if (gdt_ha_cut > 0.f) pass = pass && mt[2] >= gdt_ha_cut;
+                if (chamfer_cut > 0.f) pass = pass && mt[3] <= chamfer_cut;
+                if (hausdorff_cut > 0.f) pass = pass && mt[4] <= hausdorff_cut;
+                return pass;
+            };
             if (sort_spec.keys.empty()) {
-                for (uint64_t k = moff[q]; k < moff[q + 1]; k++) order.push_back(morder[k]);
+                for (uint64_t k = moff[q]; k < moff[q + 1]; k++)
+                    if (passes(morder[k])) order.push_back(morder[k]);
             } else {
-                for (uint64_t k = moff[q]; k < moff[q + 1]; k++) order.push_back(k);
-                auto val = [&](const fdh_match_row &m, int key) -> double {
-                    return key == MK_NODE ? (double)m.node_count : key == MK_IDF ? (double)m.idf : (double)m.rmsd;
+                for (uint64_t k = moff[q]; k < moff[q + 1]; k++)
+                    if (passes(k)) order.push_back(k);
+                auto val = [&](uint64_t k, int key) -> double {
+                    const fdh_match_row &m = mrows[k];
+                    switch (key) {
+                        case MK_NODE: return (double)m.node_count;
+                        case MK_IDF: return (double)m.idf;
+                        case MK_RMSD: return (double)m.rmsd;
+                        case MK_EVALUE: return evalue_of(m);
+                        default: return metrics ? (double)metrics[5 * k + (key - MK_TM)] : 0.0;
+                    }
                 };
                 std::stable_sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {
                     for (auto &kd : sort_spec.keys) {
-                        const int c = cmp_val(val(mrows[x], kd.first), val(mrows[y], kd.first), kd.second);
+                        const int c = cmp_val(val(x, kd.first), val(y, kd.first), kd.second);
                         if (c) return c < 0;
                     }
                     return false;
@@ -693,20 +758,20 @@ int cmd_query(Args &a) {
             }
             if (order.size() > sp.prefilter.top_n) order.resize(sp.prefilter.top_n); // result.rs:466-471
             // MATCH_RESULT_DEFAULT_COLUMNS (result.rs:330-338)
-            std::vector<std::string> cols = has_format ? columns
-                                                       : std::vector<std::string>{"tid", "node_count", "idf", "rmsd", "matching_residues",
-                                                                                  "query_residues"};
-            const char *known[] = {"qid", "tid", "nid", "db_key", "node_count", "idf", "rmsd", "u_matrix", "t_vector",
-                                   "matching_residues", "query_residues"};
-            const char *unsupported[] = {"e_value", "matching_coordinates", "tm_score", "gdt_ts", "gdt_ha", "chamfer_distance",
-                                         "hausdorff_distance"};
+            // MATCH_RESULT_SUPERPOSE_COLUMNS with --superpose (result.rs:341-352, :476-484)
+            std::vector<std::string> cols =
+                has_format ? columns
+                : superpose ? std::vector<std::string>{"tid", "node_count", "idf", "rmsd", "matching_residues", "u_matrix",
+                                                       "t_vector", "matching_coordinates", "db_key", "query_residues"}
+                            : std::vector<std::string>{"tid", "node_count", "idf", "rmsd", "matching_residues", "query_residues"};
+            const char *known[] = {"qid", "tid", "nid", "db_key", "node_count", "idf", "rmsd", "e_value", "u_matrix", "t_vector",
+                                   "matching_residues", "matching_coordinates", "query_residues", "tm_score", "gdt_ts",
+                                   "gdt_ha", "chamfer_distance", "hausdorff_distance"};
+            static const char *metric_cols[5] = {"tm_score", "gdt_ts", "gdt_ha", "chamfer_distance", "hausdorff_distance"};
             std::vector<std::string> use;
-            for (auto &c : cols) {
-                for (const char *k : unsupported)
-                    if (c == k) die("--format-output column '" + c + "' is not supported by folddisco-b200");
+            for (auto &c : cols)
                 for (const char *k : known)
                     if (c == k) use.push_back(c);
-            }
             if (header) {
                 for (size_t i = 0; i < use.size(); i++) fprintf(out, "%s%s", i ? "\t" : "", use[i].c_str());
                 fputc('\n', out);
@@ -728,7 +793,23 @@ int cmd_query(Args &a) {
                     } else if (c == "t_vector") {
                         for (int j = 0; j < 3; j++) v += (j ? "," : "") + f4(m.t[j]);
                     } else if (c == "matching_residues") v = residues_of(R, m, n_res);
-                    else v = qres;
+                    else if (c == "e_value") v = rust_sci4(evalue_of(m));
+                    else if (c == "matching_coordinates") { // C-alpha of the matched target residues (retrieve.rs:769-771)
+                        bool first = true;
+                        for (int64_t r = 0; r < n_res && res_index && store; r++) {
+                            const uint32_t idx = res_index[m.res_begin + r];
+                            float xyz[3];
+                            if (!idx || fdh_store_get_ca(store, m.nid, idx - 1, xyz) != FD_OK) continue;
+                            for (int j = 0; j < 3; j++) {
+                                v += (first ? "" : ",") + f4(xyz[j]);
+                                first = false;
+                            }
+                        }
+                    } else if (c == "query_residues") v = qres;
+                    else {
+                        for (int j = 0; j < 5; j++)
+                            if (c == metric_cols[j]) v = f4(metrics ? metrics[5 * k + j] : 0.0);
+                    }
                     fprintf(out, "%s%s", i ? "\t" : "", v.c_str());
                 }
                 fputc('\n', out);

@@ -1115,6 +1115,10 @@ struct fdh_results {
     RawArray<fdh_struct_row> structs;
     RawArray<fdh_match_row> matches;
     RawArray<fdh_residue_match> residues;
+    // fdh_search_params.want_metrics: per residue entry the target residue index + 1 (0 = none), per match row the
+    // five similarity metrics (fd_metrics_store_batch)
+    std::vector<uint32_t> res_index;
+    std::vector<float> metrics;
     double host_ms = 0.0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0; // bytes this search moved between host and device
     double wall_ms[4] = {0, 0, 0, 0};      // count_query call, verification call(s), row assembly, total
@@ -1865,6 +1869,7 @@ void fdh_queries_get_map(const fdh_queries *qs, int64_t q, uint32_t *hash, int64
     }
 }
 int64_t fdh_queries_num_indices(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].indices.size(); }
+int64_t fdh_queries_residue_count(const fdh_queries *qs, int64_t q) { return (int64_t)qs->q[q].residue_count; }
 void fdh_queries_get_indices(const fdh_queries *qs, int64_t q, int64_t *indices) {
     for (size_t k = 0; k < qs->q[q].indices.size(); k++) indices[k] = qs->q[q].indices[k];
 }
@@ -2264,7 +2269,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             // copied straight into this result's page-locked blocks.  Taken with the default flags (no after-match
             // filter), one lane, labels on the device iff the caller passed them; a batch with candidates on the
             // general path falls back to the host assembly below.
-            const bool device_rows = n_lanes == 1 && !any_match_filter && !any_struct_filter &&
+            const bool device_rows = n_lanes == 1 && !any_match_filter && !any_struct_filter && !p->want_metrics &&
                                      (labels != nullptr) == (fd_store_has_labels(ctx) != 0) &&
                                      !(getenv("FD_DEVICE_ROWS") && atoi(getenv("FD_DEVICE_ROWS")) == 0);
             bool rows_done = false;
@@ -2543,6 +2548,7 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                         rm.chain = labels->chain[r];
                         rm.serial = labels->serial[r];
                     }
+                    if (!R->res_index.empty()) R->res_index[rpos] = v;
                     RM[rpos++] = rm;
                 }
             }
@@ -2630,8 +2636,48 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
             set_err("fdh_search: host allocation failed");
             return fail();
         }
+        if (p->want_metrics) R->res_index.assign(res_off[nq], 0);
         const auto tb0 = std::chrono::steady_clock::now();
         run_parallel(build_query);
+        // StructureSimilarityMetrics of every match row (retrieve.rs:776-831) on the device, from the rows' own
+        // superpositions and matched residues
+        if (p->want_metrics && R->match_off[nq] > 0) {
+            const uint64_t NM = R->match_off[nq];
+            std::vector<uint64_t> q_res_off(nq + 1, 0);
+            for (uint32_t q = 0; q < nq; q++) q_res_off[q + 1] = q_res_off[q] + qs->q[q_begin + q].st->nres();
+            std::vector<float> q_ca(3 * q_res_off[nq]), q_cb(3 * q_res_off[nq]);
+            for (uint32_t q = 0; q < nq; q++) {
+                const Query &Q = qs->q[q_begin + q];
+                memcpy(q_ca.data() + 3 * q_res_off[q], Q.st->ca.data(), 12 * Q.st->nres());
+                memcpy(q_cb.data() + 3 * q_res_off[q], Q.st->cb.data(), 12 * Q.st->nres());
+            }
+            std::vector<uint32_t> a_nid(NM), a_off(NM + 1, 0), pq_, pt_;
+            std::vector<float> U(9 * NM), T(3 * NM);
+            for (uint32_t q = 0; q < nq; q++) {
+                const Query &Q = qs->q[q_begin + q];
+                for (uint64_t m = R->match_off[q]; m < R->match_off[q + 1]; m++) {
+                    const fdh_match_row &mr = R->matches[m];
+                    a_nid[m] = mr.nid;
+                    memcpy(&U[9 * m], mr.U, sizeof(mr.U));
+                    memcpy(&T[3 * m], mr.t, sizeof(mr.t));
+                    for (size_t k = 0; k < Q.indices.size(); k++) {
+                        const uint32_t v = R->res_index[mr.res_begin + k];
+                        if (!v) continue;
+                        pq_.push_back((uint32_t)(q_res_off[q] + Q.indices[k]));
+                        pt_.push_back(v - 1);
+                    }
+                    a_off[m + 1] = (uint32_t)pq_.size();
+                }
+            }
+            R->metrics.assign(5 * NM, 0.f);
+            R->h2d_bytes += 4ull * (q_ca.size() + q_cb.size() + a_nid.size() + a_off.size() + pq_.size() + pt_.size() + U.size() + T.size());
+            R->d2h_bytes += 20ull * NM;
+            if (fd_metrics_store_batch(ctx, q_ca.data(), q_cb.data(), q_res_off[nq], a_nid.data(), a_off.data(), (uint32_t)NM,
+                                       pq_.data(), pt_.data(), U.data(), T.data(), R->metrics.data()) != FD_OK) {
+                set_err(fd_last_error(ctx));
+                return fail();
+            }
+        }
         if (prof)
             fprintf(stderr, "assemble: pass1+alloc %.3f ms, pass2 wall %.3f ms (%d threads); cpu: rows %.3f ms, struct sort %.3f ms, match sort %.3f ms\n",
                     std::chrono::duration<double, std::milli>(tb0 - t1).count(),
@@ -2956,6 +3002,13 @@ const fdh_match_row *fdh_results_match_rows(const fdh_results *r) { return r->ma
 const uint64_t *fdh_results_match_order(const fdh_results *r) { return r->match_order.data(); }
 const fdh_residue_match *fdh_results_residues(const fdh_results *r) { return r->residues.data(); }
 uint64_t fdh_results_num_residues(const fdh_results *r) { return r->residues.size(); }
+const float *fdh_results_metrics(const fdh_results *r) { return r->metrics.empty() ? nullptr : r->metrics.data(); }
+const uint32_t *fdh_results_residue_index(const fdh_results *r) { return r->res_index.empty() ? nullptr : r->res_index.data(); }
+int fdh_store_get_ca(const fdh_store *s, uint64_t id, uint64_t residue, float *xyz) {
+    if (id >= s->names.size() || residue >= s->row_offsets[id + 1] - s->row_offsets[id]) return FD_ERR_ARG;
+    memcpy(xyz, &s->ca[3 * (s->row_offsets[id] + residue)], 12);
+    return FD_OK;
+}
 double fdh_results_host_ms(const fdh_results *r) { return r->host_ms; }
 uint64_t fdh_results_h2d_bytes(const fdh_results *r) { return r->h2d_bytes; }
 double fdh_results_wall_ms(const fdh_results *r, int which) { return which >= 0 && which < 4 ? r->wall_ms[which] : -1.0; }

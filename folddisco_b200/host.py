@@ -25,12 +25,13 @@ class SearchParams(C.Structure):
     _fields_ = [("prefilter", PrefilterParams), ("ca_dist_cutoff", C.c_float), ("skip_match", C.c_int),
                 ("max_matching_node_count", C.c_uint64), ("max_matching_node_ratio", C.c_float),
                 ("rmsd_cutoff", C.c_float), ("connected_node_count", C.c_uint64), ("connected_node_ratio", C.c_float),
-                ("skip_ca_match", C.c_int), ("host_threads", C.c_int), ("verify_mode", C.c_int)]
+                ("skip_ca_match", C.c_int), ("host_threads", C.c_int), ("verify_mode", C.c_int),
+                ("want_metrics", C.c_int)]
 
     def __init__(self, top_n=UINT64_MAX, ca_dist_cutoff=1.0, skip_match=False, host_threads=0, verify_mode=0,
-                 **prefilter):
+                 want_metrics=False, **prefilter):
         super().__init__(PrefilterParams(top_n=top_n, **prefilter), ca_dist_cutoff, int(skip_match), 0, 0.0, 0.0, 0,
-                         0.0, 0, host_threads, verify_mode)
+                         0.0, 0, host_threads, verify_mode, int(want_metrics))
 
 
 STRUCT_ROW = np.dtype([("nid", np.uint32), ("total_match_count", np.uint32), ("node_count", np.uint32),
@@ -120,6 +121,9 @@ def _lib():
     for n in ("struct_offsets", "struct_rows", "match_offsets", "match_rows", "match_order", "residues"):
         sig("fdh_results_" + n, VP, [VP])
     sig("fdh_results_num_residues", C.c_uint64, [VP])
+    sig("fdh_results_metrics", VP, [VP])
+    sig("fdh_results_residue_index", VP, [VP])
+    sig("fdh_store_get_ca", C.c_int, [VP, C.c_uint64, C.c_uint64, VP])
     sig("fdh_results_host_ms", C.c_double, [VP])
     sig("fdh_results_h2d_bytes", C.c_uint64, [VP])
     sig("fdh_results_wall_ms", C.c_double, [VP, C.c_int])
@@ -477,6 +481,11 @@ class Results:
         self.matches = arr(L.fdh_results_match_rows(handle), nm, MATCH_ROW)
         self.match_order = arr(L.fdh_results_match_order(handle), nm, np.uint64)
         self.residues = arr(L.fdh_results_residues(handle), L.fdh_results_num_residues(handle), RES_MATCH)
+        # SearchParams(want_metrics=True): [nm, 5] = tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance per
+        # match row, and the target residue index + 1 behind every residue entry (copies; None otherwise)
+        mp, rp = L.fdh_results_metrics(handle), L.fdh_results_residue_index(handle)
+        self.metrics = arr(mp, 5 * nm, np.float32).reshape(-1, 5).copy() if mp else None
+        self.residue_index = arr(rp, L.fdh_results_num_residues(handle), np.uint32).copy() if rp else None
         self.host_ms = L.fdh_results_host_ms(handle)
         self.h2d_bytes = L.fdh_results_h2d_bytes(handle)
         self.d2h_bytes = L.fdh_results_d2h_bytes(handle)

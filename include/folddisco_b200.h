@@ -373,6 +373,22 @@ int fd_kabsch_batch(fd_ctx *ctx, const float *mov_xyz, const float *ref_xyz, con
 int fd_kabsch_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_xyz, uint64_t n_q_res,
                           const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
                           const uint32_t *pair_qres, const uint32_t *pair_tres, float *rmsd, float *U9, float *t3);
+
+/* Similarity metrics of verified matches: StructureSimilarityMetrics::calculate_all as
+ * rmsd_with_calpha_and_rottran evaluates it for every match (src/controller/retrieve.rs:776-831,
+ * src/structure/metrics.rs:44-345; the columns tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance of
+ * src/controller/result.rs:280-284 and the MatchFilter cutoffs of src/controller/filter.rs:217-236).  Same alignment
+ * description as fd_kabsch_store_batch plus the superposition (U9 row-major, t3) it returned; out_metrics[5 * a] =
+ * {tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance} of alignment a.  One thread per match on the device;
+ * the reference's distance-vs-squared-distance quirk of TM / GDT is reproduced. */
+int fd_metrics_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_xyz, uint64_t n_q_res,
+                           const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
+                           const uint32_t *pair_qres, const uint32_t *pair_tres, const float *U9, const float *t3,
+                           float *out_metrics);
+/* the same arithmetic by the host build of csrc/fd_metrics.cuh over explicit point lists (parity probe, no device):
+ * ref = query points, mov = target points, n_points each */
+void fd_metrics_host(const float *ref_xyz, const float *mov_xyz, uint32_t n_points, const float *U9, const float *t3,
+                     float *out5);
 /* One verified match = one connected component of one candidate (a row of retrieval_wrapper's result vector,
  * src/controller/retrieve.rs:364-552).  res[k] = 1 + index of the target residue matched to the k-th query
  * residue, 0 = none ("_"). */

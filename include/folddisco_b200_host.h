@@ -137,6 +137,9 @@ int64_t fdh_queries_num_hashes(const fdh_queries *qs, int64_t q);
 void fdh_queries_get_map(const fdh_queries *qs, int64_t q, uint32_t *hash, int64_t *qi, int64_t *qj,
                          uint8_t *primary, float *idf);
 int64_t fdh_queries_num_indices(const fdh_queries *qs, int64_t q);
+/* residue_count of src/cli/workflows/query_pdb.rs:355-359: the PARSED query residues, resolved in the structure or not
+ * (the denominator of the node-ratio filters and the query length of the e-value fit, result.rs:145) */
+int64_t fdh_queries_residue_count(const fdh_queries *qs, int64_t q);
 void fdh_queries_get_indices(const fdh_queries *qs, int64_t q, int64_t *indices);
 void fdh_queries_free(fdh_queries *qs);
 
@@ -152,6 +155,10 @@ typedef struct {
     int skip_ca_match;                /* --skip-ca-match */
     int host_threads;                 /* threads for the graph / residue-mapping step, 0 = all cores */
     int verify_mode;                  /* 0: fused kernel, general path only for flagged candidates; 1: general path only */
+    /* != 0: every match row also gets its StructureSimilarityMetrics (tm_score, gdt_ts, gdt_ha, chamfer_distance,
+     * hausdorff_distance; src/controller/retrieve.rs:776-831, src/structure/metrics.rs) from fd_metrics_store_batch,
+     * and the residue indices behind the matched residues are kept (fdh_results_metrics / _residue_index) */
+    int want_metrics;
 } fdh_search_params;
 
 /* query_pdb.rs:348-452 for the whole batch: count_query -> filter/sort/top -> retrieval -> Kabsch ->
@@ -220,6 +227,13 @@ const fdh_match_row *fdh_results_match_rows(const fdh_results *r);
 const uint64_t *fdh_results_match_order(const fdh_results *r); /* sorted position -> emission index */
 const fdh_residue_match *fdh_results_residues(const fdh_results *r);
 uint64_t fdh_results_num_residues(const fdh_results *r);
+/* want_metrics searches only (NULL otherwise): five floats per match row, aligned with fdh_results_match_rows --
+ * {tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance} (the MatchResult.metrics columns of
+ * src/controller/result.rs:280-284) -- and per residue entry the target residue index + 1 (0 = unmatched) */
+const float *fdh_results_metrics(const fdh_results *r);
+const uint32_t *fdh_results_residue_index(const fdh_results *r);
+/* C-alpha of residue `residue` of structure `id` (the matching_coordinates column, retrieve.rs:769-771) */
+int fdh_store_get_ca(const fdh_store *s, uint64_t id, uint64_t residue, float *xyz3);
 /* wall-clock milliseconds of the host-only part of the last search (graph + mapping + assembly) */
 double fdh_results_host_ms(const fdh_results *r);
 /* bytes the search copied host->device (query descriptors, candidate lists, alignment indices) and

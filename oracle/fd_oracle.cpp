@@ -1178,6 +1178,8 @@ struct MatchRow {
     float rmsd;
     float U[9], T[3];
     float idf;
+    float metrics[5] = {0, 0, 0, 0, 0}; // tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance
+    std::vector<std::array<float, 3>> target_ca; // matching_coordinates (retrieve.rs:769-771)
 };
 struct fdo_matches {
     size_t n_query = 0;
@@ -1340,6 +1342,56 @@ void map_query_and_retrieved(const std::vector<Edge> &sub_edges, const fdo_qmap 
     }
 }
 
+// src/structure/metrics.rs:44-273 over PrecomputedDistances::new(reference, transformed): the n x n matrix of f32
+// distances (f64 inside), then the five metrics with the reference's use of a distance where a squared distance is meant
+void similarity_metrics(const std::vector<std::array<float, 3>> &ref, const std::vector<std::array<float, 3>> &mov,
+                        const float *U, const float *T, float *out) {
+    const size_t n = ref.size();
+    if (n == 0 || n != mov.size()) {
+        out[0] = out[1] = out[2] = 0.0f;
+        out[3] = out[4] = INFINITY;
+        return;
+    }
+    // kabsch.rs:84-93, 141-151: transformed = rot * coord + tran in f32
+    std::vector<std::array<float, 3>> tr(n);
+    for (size_t i = 0; i < n; i++)
+        for (int r = 0; r < 3; r++)
+            tr[i][r] = (U[3 * r] * mov[i][0] + U[3 * r + 1] * mov[i][1] + U[3 * r + 2] * mov[i][2]) + T[r];
+    std::vector<float> pd(n * n); // pairwise_dist[i * n + j] = dist(reference[j], coords[i])  (metrics.rs:74-78)
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j < n; j++) {
+            double dx = (double)ref[j][0] - (double)tr[i][0], dy = (double)ref[j][1] - (double)tr[i][1],
+                   dz = (double)ref[j][2] - (double)tr[i][2];
+            pd[i * n + j] = (float)std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+    float d0 = n > 21 ? 1.24f * powf((float)n - 15.0f, 1.0f / 3.0f) - 1.8f : 0.5f; // metrics.rs:116-122
+    double d0_sq = (double)(d0 * d0), sum = 0.0;
+    for (size_t i = 0; i < n; i++) sum += 1.0 / (1.0 + (double)pd[i * n + i] / d0_sq); // metrics.rs:141-147
+    out[0] = (float)(sum / (double)n);
+    auto gdt = [&](const double *cut) { // metrics.rs:152-173
+        double s2 = 0.0;
+        for (int k = 0; k < 4; k++) {
+            size_t cnt = 0;
+            for (size_t i = 0; i < n; i++) cnt += (double)pd[i * n + i] <= cut[k] * cut[k] ? 1 : 0;
+            s2 += (double)cnt / (double)n;
+        }
+        return (float)(s2 / 4.0);
+    };
+    const double ts[4] = {1.0, 2.0, 4.0, 8.0}, ha[4] = {0.5, 1.0, 2.0, 4.0};
+    out[1] = gdt(ts);
+    out[2] = gdt(ha);
+    double cs = 0.0; // metrics.rs:205-221, 235-252
+    float hd = 0.0f;
+    for (size_t i = 0; i < n; i++) {
+        float mn = pd[i * n];
+        for (size_t j = 1; j < n; j++) mn = std::min(mn, pd[i * n + j]);
+        cs += (double)mn;
+        hd = i == 0 ? mn : std::max(hd, mn);
+    }
+    out[3] = (float)(cs / (double)n);
+    out[4] = hd;
+}
+
 // retrieve.rs:756-834 (no partial fit): CA,CB interleaved; target is rotated onto query.
 void rmsd_with_calpha(const fdo_compact &query, const fdo_compact &target, const std::vector<size_t> &qi,
                       const std::vector<size_t> &ti, MatchRow &row) {
@@ -1353,6 +1405,9 @@ void rmsd_with_calpha(const fdo_compact &query, const fdo_compact &target, const
         mov.push_back({target.cb[i].x, target.cb[i].y, target.cb[i].z});
     }
     kabsch(mov, ref, row.U, row.T, &row.rmsd);
+    similarity_metrics(ref, mov, row.U, row.T, row.metrics); // retrieve.rs:819-830
+    row.target_ca.clear();
+    for (size_t i : ti) row.target_ca.push_back({target.ca[i].x, target.ca[i].y, target.ca[i].z});
 }
 
 fdo_matches *retrieve(const fdo_qmap &m, const fdo_compact &query, const fdo_compact &t, uint32_t nbd,
@@ -2050,6 +2105,19 @@ void fdo_matches_get(const fdo_matches *r, int which, uint8_t *some, uint8_t *ch
         if (U) memcpy(U + 9 * k, rows[k].U, 9 * sizeof(float));
         if (t) memcpy(t + 3 * k, rows[k].T, 3 * sizeof(float));
     }
+}
+void fdo_matches_get_metrics(const fdo_matches *r, int which, float *out5) {
+    const auto &rows = which ? r->from_hash : r->result;
+    for (size_t k = 0; k < rows.size(); k++) memcpy(out5 + 5 * k, rows[k].metrics, 5 * sizeof(float));
+}
+void fdo_similarity_metrics(int64_t n, const float *ref3, const float *mov3, const float *U9, const float *t3, float *out5) {
+    std::vector<std::array<float, 3>> ref((size_t)n), mov((size_t)n);
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            ref[i][k] = ref3[3 * i + k];
+            mov[i][k] = mov3[3 * i + k];
+        }
+    similarity_metrics(ref, mov, U9, t3, out5);
 }
 int64_t fdo_matches_max_node_count(const fdo_matches *r) { return (int64_t)r->max_node; }
 float fdo_matches_min_rmsd(const fdo_matches *r) { return r->min_rmsd; }

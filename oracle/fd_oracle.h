@@ -166,6 +166,11 @@ int64_t fdo_matches_num_query(const fdo_matches *r);
  * res_some/res_chain/res_serial are [n_matches * n_query]; U is 9 per match, t is 3. */
 void fdo_matches_get(const fdo_matches *r, int which, uint8_t *res_some, uint8_t *res_chain,
                      uint64_t *res_serial, float *rmsd, float *idf, float *U, float *t);
+/* StructureSimilarityMetrics of every match (src/structure/metrics.rs:44-345, computed in
+ * rmsd_with_calpha_and_rottran, retrieve.rs:776-831): out5[5 * k] = tm_score, gdt_ts, gdt_ha, chamfer, hausdorff */
+void fdo_matches_get_metrics(const fdo_matches *r, int which, float *out5);
+/* the same over explicit point lists: n reference (query) points, n moving (target) points, the superposition U9 / t3 */
+void fdo_similarity_metrics(int64_t n, const float *ref3, const float *mov3, const float *U9, const float *t3, float *out5);
 int64_t fdo_matches_max_node_count(const fdo_matches *r);
 float fdo_matches_min_rmsd(const fdo_matches *r);
 /* retrieve_with_prefilter output: (i, j, hash) triples in emission order */

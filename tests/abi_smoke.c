@@ -42,7 +42,7 @@ _Static_assert(offsetof(fd_match_record, res) == 64, "fd_match_record.res");
 _Static_assert(sizeof(fd_verify_query) == 128, "fd_verify_query");
 _Static_assert(offsetof(fd_verify_query, cb_xyz) == 120, "fd_verify_query.cb_xyz");
 _Static_assert(sizeof(fdh_query_params) == 120, "fdh_query_params");
-_Static_assert(sizeof(fdh_search_params) == 120, "fdh_search_params");
+_Static_assert(sizeof(fdh_search_params) == 128, "fdh_search_params");
 _Static_assert(sizeof(fdh_struct_row) == 48, "fdh_struct_row");
 _Static_assert(sizeof(fdh_match_row) == 72, "fdh_match_row");
 _Static_assert(sizeof(fdh_residue_match) == 16, "fdh_residue_match");

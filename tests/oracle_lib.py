@@ -126,6 +126,8 @@ def lib():
     sig("fdo_matches_size", C.c_int64, [VP])
     sig("fdo_matches_num_query", C.c_int64, [VP])
     sig("fdo_matches_get", None, [VP, C.c_int, u8p, u8p, u64p, f32p, f32p, f32p, f32p])
+    sig("fdo_matches_get_metrics", None, [VP, C.c_int, f32p])
+    sig("fdo_similarity_metrics", None, [C.c_int64, f32p, f32p, f32p, f32p, f32p])
     sig("fdo_matches_max_node_count", C.c_int64, [VP])
     sig("fdo_matches_min_rmsd", C.c_float, [VP])
     sig("fdo_matches_num_edges", C.c_int64, [VP])
@@ -439,6 +441,9 @@ def retrieve(qmap, target, nbin_dist=0, nbin_angle=0, cutoff=20.0, ca_cutoff=1.0
     if n:
         lib().fdo_matches_get(r, which, d["some"].reshape(-1), d["chain"].reshape(-1), d["serial"].reshape(-1),
                               d["rmsd"], d["idf"], d["U"].reshape(-1), d["t"].reshape(-1))
+    d["metrics"] = np.zeros((n, 5), np.float32)  # tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance
+    if n:
+        lib().fdo_matches_get_metrics(r, which, d["metrics"].reshape(-1))
     d["max_node_count"] = lib().fdo_matches_max_node_count(r)
     d["min_rmsd"] = lib().fdo_matches_min_rmsd(r)
     ne = lib().fdo_matches_num_edges(r)
@@ -448,6 +453,16 @@ def retrieve(qmap, target, nbin_dist=0, nbin_angle=0, cutoff=20.0, ca_cutoff=1.0
     d["edges"] = (ei[:ne], ej[:ne], eh[:ne])
     lib().fdo_matches_free(r)
     return d
+
+
+def similarity_metrics(ref, mov, U, t):
+    """src/structure/metrics.rs over explicit points: -> [tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance]"""
+    ref = np.ascontiguousarray(ref, np.float32).reshape(-1)
+    mov = np.ascontiguousarray(mov, np.float32).reshape(-1)
+    out = np.zeros(5, np.float32)
+    lib().fdo_similarity_metrics(len(ref) // 3, ref, mov, np.ascontiguousarray(U, np.float32).reshape(-1),
+                                 np.ascontiguousarray(t, np.float32).reshape(-1), out)
+    return out
 
 
 def residues_to_string(some, chain, serial):

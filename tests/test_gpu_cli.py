@@ -124,14 +124,54 @@ def test_query_without_store_parses_the_lookup_files(workdir):
 
 
 def test_unsupported_options_fail_loudly(workdir):
-    for extra in (["--partial-fit"], ["--sort-by", "tm_score"], ["--tm-score", "0.5"], ["--superpose"],
-                  ["--format-output", "tid,e_value"]):
+    for extra in (["--partial-fit"], ["--web"]):
         r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"] + extra,
                            cwd=workdir, capture_output=True, text=True)
         assert r.returncode != 0 and "not supported" in r.stderr
-    r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", "pdb"], cwd=workdir,
+    for t in ("3di", "hybrid"):  # TertiaryInteraction / Hybrid hash over neighbouring residues: not built
+        r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", t], cwd=workdir,
+                           capture_output=True, text=True)
+        assert r.returncode != 0 and "not supported" in r.stderr
+    r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", "nonsense"], cwd=workdir,
                        capture_output=True, text=True)
-    assert r.returncode != 0 and "not supported" in r.stderr
+    assert r.returncode != 0 and "unknown hash type" in r.stderr
+
+
+def test_other_encoding_and_multiple_bins_through_the_cli(workdir):
+    """`index --type pdb --multiple-bins 8-3,16-4` (PDBMotifSinCos, two bin pairs per residue pair): PREFIX.type records
+    both (config.rs:64-97), `query` reads them back and its rows equal the oracle run in the same encoding."""
+    mb = [(8, 3), (16, 4)]
+    r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/pdbmb", "-y", "pdb", "--multiple-bins",
+                        "8-3,16-4", "-t", "2"], cwd=workdir, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    t = open(os.path.join(workdir, "idx", "pdbmb.type")).read()
+    assert 'hash_type = "PDBMotifSinCos"' in t and "multiple_bin = [[8, 3], [16, 4]]" in t
+    atoms = F.config1_atoms()
+    names = F.serine_names()
+    comps = [O.Structure.from_atoms(atoms[n]).compact() for n in names]
+    with O.hash_mode(1, mb):
+        oix = O.Index.build(comps)
+        assert os.path.getsize(os.path.join(workdir, "idx", "pdbmb")) == oix.value_bytes
+        s = O.Structure.from_atoms(atoms["query/4CHA.pdb"])
+        om = O.QueryMap(s.compact(), *O.parse_query_string("B57,B102,C195", s.first_chain), index=oix,
+                        total_structures=len(comps))
+        nres = np.array([c.nres for c in comps], np.uint64)
+        plddt = np.array([c.avg_plddt for c in comps], np.float32)
+        hits = O.count_query(om, oix, nres, plddt, O.CountParams.defaults(om.residue_count))
+        want = []
+        for nid in hits["nid"]:
+            m = O.retrieve(om, comps[int(nid)])
+            for k in range(len(m["rmsd"])):
+                want.append((names[int(nid)], int(m["some"][k].sum()), float(m["idf"][k]), float(m["rmsd"][k]),
+                             O.residues_to_string(m["some"][k], m["chain"][k], m["serial"][k])))
+    rows = run(workdir, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/pdbmb")
+    assert len(rows) == len(want) > 0
+    got = sorted((r[0], int(r[1]), r[4]) for r in rows)
+    assert got == sorted((w[0], w[1], w[4]) for w in want)
+    by_key = {(w[0], w[4], round(w[3], 2)): w for w in want}
+    for r in rows:
+        w = by_key[(r[0], r[4], round(float(r[3]), 2))]
+        assert abs(float(r[2]) - w[2]) <= 1e-4 * max(1.0, w[2]) + 5e-5 and abs(float(r[3]) - w[3]) <= 1e-4 + 5e-5
 
 
 def test_sort_by_and_format_output(workdir):

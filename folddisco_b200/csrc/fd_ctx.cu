@@ -233,11 +233,17 @@ int64_t fd_typed_hash_host(const float *n_xyz, const float *ca_xyz, const float 
     float f[9];
     for (uint64_t i = 0; i < n_res; i++)
         for (uint64_t j = 0; j < n_res; j++) {
-            if (i == j || aa[i] == 255 || aa[j] == 255 || (cb_valid && (!cb_valid[i] || !cb_valid[j]))) continue;
+            if (i == j || aa[i] == 255 || aa[j] == 255) continue;
+            if (fdg::ht_needs_cb(tp.type) && cb_valid && (!cb_valid[i] || !cb_valid[j])) continue;
+            fdg::Nbr nb;
+            if (fdg::ht_needs_neighbours(tp.type)) {
+                if (i == 0 || j == 0 || i + 1 >= n_res || j + 1 >= n_res) continue;
+                nb = fdg::Nbr{ld(ca_xyz, i - 1), ld(ca_xyz, i + 1), ld(ca_xyz, j - 1), ld(ca_xyz, j + 1), (float)j - (float)i};
+            }
             const float d = fdg::typed_screen_dist(tp.type, ld(ca_xyz, i), ld(cb_xyz, i), ld(ca_xyz, j), ld(cb_xyz, j));
             if (d > tp.dist_cutoff) continue;
             fdg::typed_feature(tp.type, ld(n_xyz, i), ld(ca_xyz, i), ld(cb_xyz, i), ld(n_xyz, j), ld(ca_xyz, j),
-                               ld(cb_xyz, j), (float)(aa[i] & 0x7Fu), (float)(aa[j] & 0x7Fu), d, f);
+                               ld(cb_xyz, j), (float)(aa[i] & 0x7Fu), (float)(aa[j] & 0x7Fu), d, f, &nb);
             for (uint32_t b = 0; b < tp.n_bins; b++) {
                 const uint32_t h = fdg::typed_hash(tp.type, f, tp.nbd[b], tp.nba[b]);
                 if (n < cap) out[n] = h;

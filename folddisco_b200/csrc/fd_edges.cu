@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(K4_THREADS)
                 const bool cbok = st.cb_valid == nullptr || (st.cb_valid[ri] && st.cb_valid[rj]);
                 // get_single_feature (feature.rs:11-24): i != j, both amino acids known, CB present -- and, for the
                 // encodings whose cutoff is not on the CA distance, their own distance within the cutoff
-                bool is_feature = i != j && ai != 255 && aj != 255 && cbok;
+                bool is_feature = i != j && ai != 255 && aj != 255 && (cbok || (TYPED && !fdg::ht_needs_cb(tp.type)));
+                const bool need_nb = TYPED && fdg::ht_needs_neighbours(tp.type);
+                if (need_nb) is_feature = is_feature && i > 0 && j > 0 && i + 1 < n && j + 1 < n; // feature.rs:113, 163
                 float ds = d;
                 if (TYPED && is_feature && (tp.type == fdg::HT_TRROSETTA || tp.type == fdg::HT_PPF)) {
                     ds = fdg::typed_screen_dist(tp.type, ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri), ld3(st.ca_xyz, rj),
@@ -268,10 +270,19 @@ __global__ void __launch_bounds__(K4_THREADS)
                         }
                     if (MODE == 0 && np) atomicAdd(n_pairs, (unsigned long long)np);
                     float f[9];
-                    if (TYPED)
+                    if (TYPED) {
+                        fdg::Nbr nb;
+                        if (need_nb) {
+                            nb.ca_pre1 = ld3(st.ca_xyz, ri - 1);
+                            nb.ca_next1 = ld3(st.ca_xyz, ri + 1);
+                            nb.ca_pre2 = ld3(st.ca_xyz, rj - 1);
+                            nb.ca_next2 = ld3(st.ca_xyz, rj + 1);
+                            nb.seq_dist = (float)j - (float)i;
+                        }
                         fdg::typed_feature(tp.type, ld3(st.n_xyz, ri), ld3(st.ca_xyz, ri), ld3(st.cb_xyz, ri),
                                            ld3(st.n_xyz, rj), ld3(st.ca_xyz, rj), ld3(st.cb_xyz, rj), (float)ci, (float)cj,
-                                           ds, f);
+                                           ds, f, &nb);
+                    }
                     const uint32_t nb = TYPED ? tp.n_bins : 1u;
                     for (uint32_t bi = 0; bi < nb; bi++) {
                         const uint32_t h = TYPED ? fdg::typed_hash(tp.type, f, tp.nbd[bi], tp.nba[bi])
@@ -401,8 +412,9 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
         const fd_retrieval_query &Q = queries[q];
         if (Q.n_aa_dist > K4_MAX_AADIST)
             return fd_fail(ctx, FD_ERR_LIMIT, "more than 512 observed query pairs: verification of whole-structure queries is not available (search them with skip_match / --skip-match; count_query handles them)");
+        // no amino-acid prefilter for the encodings without amino-acid fields (retrieve.rs:385-390)
         RQDesc d{(uint32_t)f_hash.size(), Q.n_hashes, (uint32_t)f_aad.size(), Q.n_aa_dist, 0, 0,
-                 Q.n_hashes <= PREFILTER_AA_SKIPPING_SIZE ? 1u : 0u};
+                 Q.n_hashes <= PREFILTER_AA_SKIPPING_SIZE && fdg::ht_has_aa_index(tp.type) ? 1u : 0u};
         for (uint32_t k = 0; k < Q.n_hashes; k++) {
             if (k && Q.hashes_sorted[k] <= Q.hashes_sorted[k - 1])
                 return fd_fail(ctx, FD_ERR_ARG, "fd_retrieval_query: hashes_sorted must be strictly ascending");

@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(K1_THREADS)
         }
         __syncthreads();
         unsigned long long my_count = 0;
+        // TertiaryInteraction needs no CB; it and Hybrid exist only for residues with both sequence neighbours
+        const bool need_cb = !TYPED || fdg::ht_needs_cb(tp.type);
+        const bool need_nb = TYPED && fdg::ht_needs_neighbours(tp.type);
         for (uint32_t r0 = 0; r0 < rows; r0 += K1_WARPS) {
             const uint32_t il = r0 + warp; // this warp's row within the tile
             const bool row_live = il < rows;
@@ -84,7 +87,8 @@ __global__ void __launch_bounds__(K1_THREADS)
             fdg::V3 cai = {0.f, 0.f, 0.f}, cbi = {0.f, 0.f, 0.f};
             bool iok = false;
             if (row_live) {
-                iok = residue_ok(b, base + i);
+                iok = need_cb ? residue_ok(b, base + i) : b.aa[base + i] != 255;
+                if (need_nb) iok = iok && i > 0 && i + 1 < n;
                 cai = ld3(b.ca_xyz, base + i);
                 if (TYPED) cbi = ld3(b.cb_xyz, base + i);
             }
@@ -94,7 +98,8 @@ __global__ void __launch_bounds__(K1_THREADS)
                 for (uint32_t j = c0 + lane; j < c0 + K1_COL_CHUNK; j += 32) { // uniform trip count per warp
                     bool pass = false;
                     float d = 0.f;
-                    if (iok && j < cend && j != i && residue_ok(b, base + j)) {
+                    if (iok && j < cend && j != i && (need_cb ? residue_ok(b, base + j) : b.aa[base + j] != 255) &&
+                        (!need_nb || (j > 0 && j + 1 < n))) {
                         if (TYPED)
                             d = fdg::typed_screen_dist(tp.type, cai, cbi, ld3(b.ca_xyz, base + j), ld3(b.cb_xyz, base + j));
                         else
@@ -126,9 +131,17 @@ __global__ void __launch_bounds__(K1_THREADS)
                         if (k < qn) {
                             const uint32_t ij = q_ij[k];
                             const uint64_t ri = base + tile.i0 + (ij >> 16), rj = base + (ij & 0xffffu);
+                            fdg::Nbr nb;
+                            if (need_nb) { // both residues are interior (screened in phase A)
+                                nb.ca_pre1 = ld3(b.ca_xyz, ri - 1);
+                                nb.ca_next1 = ld3(b.ca_xyz, ri + 1);
+                                nb.ca_pre2 = ld3(b.ca_xyz, rj - 1);
+                                nb.ca_next2 = ld3(b.ca_xyz, rj + 1);
+                                nb.seq_dist = (float)(ij & 0xffffu) - (float)(tile.i0 + (ij >> 16)); // j as f32 - i as f32
+                            }
                             fdg::typed_feature(tp.type, ld3(b.n_xyz, ri), ld3(b.ca_xyz, ri), ld3(b.cb_xyz, ri),
                                                ld3(b.n_xyz, rj), ld3(b.ca_xyz, rj), ld3(b.cb_xyz, rj),
-                                               (float)(b.aa[ri] & 0x7Fu), (float)(b.aa[rj] & 0x7Fu), q_d[k], f);
+                                               (float)(b.aa[ri] & 0x7Fu), (float)(b.aa[rj] & 0x7Fu), q_d[k], f, &nb);
                         }
                         for (uint32_t bi = 0; bi < tp.n_bins; bi++) { // uniform trip count
                             bool emit = false;

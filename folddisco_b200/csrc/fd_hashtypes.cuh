@@ -10,9 +10,10 @@
 //   perfect_hash / reverse_hash /          src/geometry/pdb_motif.rs:26-103, pdb_motif_sincos.rs:17-150,
 //     is_symmetric per encoding              trrosetta.rs:22-162, ppf.rs:15-127, folddisco_angle.rs:24-137,
 //                                            folddisco_dist.rs:22-130
+//                                            tertiary_interaction.rs:19-151, hybrid.rs:19-189
 // The default encoding (PDBTrRosetta, pdb_tr.rs) keeps its own tuned route in fd_geom.cuh; typed_* below covers it
-// too so that one code path can serve any `--type`.  TertiaryInteraction and Hybrid (features over the neighbouring
-// residues i-1 / i+1) are not built.
+// too so that one code path can serve any `--type`.  TertiaryInteraction and Hybrid also read the C-alpha atoms of the
+// neighbouring residues i-1 / i+1 (Nbr) and exist only for residues that are neither first nor last in their structure.
 #pragma once
 #include "../../include/folddisco_b200.h"
 #include "fd_geom.cuh"
@@ -27,17 +28,21 @@ enum : uint32_t {
     HT_TRROSETTA = 3,
     HT_PDBTR = 4,
     HT_PPF = 5,
-    HT_TERTIARY = 6, // not built
-    HT_HYBRID = 7,   // not built
+    HT_TERTIARY = 6,
+    HT_HYBRID = 7,
     HT_FDANGLE = 8,
     HT_FDDIST = 9,
 };
 constexpr int HT_MAX_BINS = 8;
 
-FD_HD bool ht_supported(uint32_t t) {
-    return t == HT_DEFAULT || t == HT_PDBMOTIF || t == HT_PDBMOTIFSINCOS || t == HT_TRROSETTA || t == HT_PDBTR ||
-           t == HT_PPF || t == HT_FDANGLE || t == HT_FDDIST;
-}
+FD_HD bool ht_supported(uint32_t t) { return t <= HT_FDDIST; }
+// encodings whose feature reads CA(i-1), CA(i+1), CA(j-1), CA(j+1) and is undefined for the first / last residue
+FD_HD bool ht_needs_neighbours(uint32_t t) { return t == HT_TERTIARY || t == HT_HYBRID; }
+// TertiaryInteraction is built from C-alpha atoms only: a residue without CB still gets features (feature.rs:112-131)
+FD_HD bool ht_needs_cb(uint32_t t) { return t != HT_TERTIARY; }
+// HashType::amino_acid_index (feature.rs:260-267): None for the two neighbour encodings -- no amino-acid prefilter
+// (retrieve.rs:385-390) and no substitutions (query.rs:301-306) with them
+FD_HD bool ht_has_aa_index(uint32_t t) { return !ht_needs_neighbours(t); }
 FD_HD uint32_t ht_canon(uint32_t t) { return t == HT_DEFAULT ? (uint32_t)HT_PDBTR : t; }
 
 // HashType::default_dist_bin / default_angle_bin (src/geometry/core.rs:118-147)
@@ -45,15 +50,17 @@ FD_HD uint32_t ht_default_dist_bin(uint32_t t) {
     switch (ht_canon(t)) {
         case HT_PDBMOTIF: return 18;
         case HT_PDBTR: return 16;
+        case HT_HYBRID: return 16;
         case HT_FDANGLE: return 8;
         case HT_FDDIST: return 32;
-        default: return 8; // PDBMotifSinCos, TrRosetta, PointPairFeature: utils/convert.rs NBIN_DIST
+        default: return 8; // PDBMotifSinCos, TrRosetta, PointPairFeature, TertiaryInteraction: utils/convert.rs NBIN_DIST
     }
 }
 FD_HD uint32_t ht_default_angle_bin(uint32_t t) {
     switch (ht_canon(t)) {
         case HT_PDBMOTIF: return 9;
         case HT_PDBTR: return 4;
+        case HT_HYBRID: return 4;
         case HT_FDANGLE: return 32;
         case HT_FDDIST: return 16;
         default: return 3; // NBIN_SIN_COS
@@ -83,9 +90,7 @@ FD_HD void ht_resolve_single(uint32_t type, uint32_t nbd, uint32_t nba, uint32_t
 
 // fd_hash_params -> TypedParams.  Returns nullptr, or the reason the parameters are refused.
 inline const char *typed_params_from(const fd_hash_params *p, TypedParams *tp) {
-    if (!ht_supported(p->hash_type))
-        return "hash_type: only PDBMotif, PDBMotifSinCos, TrRosetta, PDBTrRosetta, PointPairFeature, FolddiscoAngle and "
-               "FolddiscoDist are built (TertiaryInteraction and Hybrid are not)";
+    if (!ht_supported(p->hash_type)) return "hash_type: unknown encoding (FD_HASH_* of folddisco_b200.h)";
     if (p->n_multiple_bins > (uint32_t)HT_MAX_BINS) return "at most 8 (dist, angle) pairs in multiple_bins";
     tp->type = ht_canon(p->hash_type);
     tp->dist_cutoff = p->dist_cutoff;
@@ -134,14 +139,48 @@ FD_HD float typed_screen_dist(uint32_t type, V3 ca1, V3 cb1, V3 ca2, V3 cb2) {
     }
 }
 
-// get_single_feature for residues i -> j whose amino acids are known and whose CB exist; d = typed_screen_dist of
-// the pair, already tested (`> dist_cutoff` rejects).  Fills f[0..9).
+// C-alpha atoms around the two residues and j - i, for the encodings of ht_needs_neighbours (zero otherwise)
+struct Nbr {
+    V3 ca_pre1, ca_next1, ca_pre2, ca_next2;
+    float seq_dist;
+};
+// map_aa_to_u8_group (utils/convert.rs:85-131) as a function of the amino-acid code: 0 small / aliphatic (A C G P S),
+// 1 hydrophobic (I L M F W V), 2 polar (N Q T Y), 3 charged (R D E H K)
+FD_HD float ht_aa_group(float aa) {
+    const uint32_t a = sat_u32(aa);
+    //                         A  R  N  D  C  Q  E  G  H  I  L  K  M  F  P  S  T  W  Y  V
+    const uint8_t group[20] = {0, 3, 2, 3, 0, 2, 3, 0, 3, 1, 1, 3, 1, 1, 0, 0, 2, 1, 2, 1};
+    return a < 20 ? (float)group[a] : 255.0f;
+}
+
+// get_single_feature for residues i -> j whose amino acids are known and whose CB exist (where the encoding needs
+// them); d = typed_screen_dist of the pair, already tested (`> dist_cutoff` rejects).  Fills f[0..9).
 FD_HD void typed_feature(uint32_t type, V3 n1, V3 ca1, V3 cb1, V3 n2, V3 ca2, V3 cb2, float aa1, float aa2, float d,
-                         float *f) {
+                         float *f, const Nbr *nb = nullptr) {
     for (int k = 0; k < 9; k++) f[k] = 0.0f;
     f[0] = aa1;
     f[1] = aa2;
     switch (type) {
+        case HT_TERTIARY: { // feature.rs:112-161: seven angles between the CA-trace directions around i and j
+            const V3 u1 = normalize(sub(ca1, nb->ca_pre1)), u2 = normalize(sub(nb->ca_next1, ca1));
+            const V3 u3 = normalize(sub(ca2, nb->ca_pre2)), u4 = normalize(sub(nb->ca_next2, ca2));
+            const V3 u5 = normalize(sub(ca2, ca1));
+            f[0] = fdm::acosf_exact(dot(u1, u2));
+            f[1] = fdm::acosf_exact(dot(u3, u4));
+            f[2] = fdm::acosf_exact(dot(u1, u5));
+            f[3] = fdm::acosf_exact(dot(u3, u5));
+            f[4] = fdm::acosf_exact(dot(u1, u4));
+            f[5] = fdm::acosf_exact(dot(u2, u3));
+            f[6] = fdm::acosf_exact(dot(u1, u3));
+            f[7] = d;
+            f[8] = nb->seq_dist;
+            break;
+        }
+        case HT_HYBRID: // feature.rs:162-186 + core.rs:405-436: amino-acid groups, the PDBTrRosetta geometry, two CA-trace torsions
+            pair_feature(n1, ca1, cb1, n2, ca2, cb2, ht_aa_group(aa1), ht_aa_group(aa2), d, f);
+            f[7] = torsion(nb->ca_pre1, n1, ca1, nb->ca_next1);
+            f[8] = torsion(nb->ca_pre2, n2, ca2, nb->ca_next2);
+            break;
         case HT_PDBMOTIF:
         case HT_PDBMOTIFSINCOS: {
             f[2] = d;
@@ -217,6 +256,20 @@ FD_HD uint32_t typed_hash(uint32_t type, const float *f, uint32_t nbd_u, uint32_
                 h |= ht_sin_bin(f[3 + k], nba) << (15 - 6 * k) | ht_cos_bin(f[3 + k], nba) << (12 - 6 * k);
             return h;
         }
+        case HT_TERTIARY: { // tertiary_interaction.rs:21-83: seven cos bins, the CA distance, the clamped sequence distance
+            const float nbd = ht_clamp(nbd_u, 16, 8.0f), nba = ht_clamp(nba_u, 8, 3.0f);
+            uint32_t h = 0;
+            for (int k = 0; k < 7; k++) h |= ht_cos_bin(f[k], nba) << (26 - 3 * k);
+            const uint32_t sd = f[8] < -4.0f ? 0u : (f[8] > 4.0f ? 8u : sat_u32(f[8]) + 4u);
+            return h | discretize(f[7], 2.0f, 20.0f, nbd) << 4 | sd;
+        }
+        case HT_HYBRID: { // hybrid.rs:21-96
+            const float nbd = ht_clamp(nbd_u, 16, 16.0f), nba = ht_clamp(nba_u, 4, 4.0f);
+            uint32_t h = r1 << 30 | r2 << 28 | discretize(f[2], 2.0f, 20.0f, nbd) << 24 | discretize(f[3], 2.0f, 20.0f, nbd) << 20;
+            for (int k = 0; k < 5; k++)
+                h |= ht_sin_bin(f[4 + k], nba) << (18 - 4 * k) | ht_cos_bin(f[4 + k], nba) << (16 - 4 * k);
+            return h;
+        }
         case HT_FDANGLE: {
             const float nbd = ht_clamp(nbd_u, 8, 8.0f), nba = ht_clamp(nba_u, 32, 32.0f);
             const uint32_t ca = discretize(f[2], 2.0f, 20.0f, nbd), cb = discretize(f[3], 2.0f, 20.0f, nbd);
@@ -261,12 +314,16 @@ FD_HD void typed_hash_aa(uint32_t type, uint32_t h, uint32_t *aa1, uint32_t *aa2
 // HashValue::is_symmetric of the encoding: always through reverse_hash_default, i.e. with the DEFAULT bin counts
 // whatever the index was built with.  Host only (the verification receives the verdicts as a per-hash table).
 inline bool typed_is_symmetric(uint32_t type, uint32_t h) {
-    uint32_t a1, a2;
-    typed_hash_aa(type, h, &a1, &a2);
-    if (a1 != a2) return false;
     auto ang = [](uint32_t sb, uint32_t cb, float nb) {
         return ht_deg(fdm::atan2f_exact(ht_cont(sb, -1.0f, 1.0f, nb), ht_cont(cb, -1.0f, 1.0f, nb)));
     };
+    if (type == HT_TERTIARY) return false; // tertiary_interaction.rs:145-150
+    if (type == HT_HYBRID)                 // hybrid.rs:185-189: equal groups and phi1 == phi2 (default 4 bins)
+        return ((h >> 30) & 3u) == ((h >> 28) & 3u) &&
+               ang((h >> 14) & 3u, (h >> 12) & 3u, 4.0f) == ang((h >> 10) & 3u, (h >> 8) & 3u, 4.0f);
+    uint32_t a1, a2;
+    typed_hash_aa(type, h, &a1, &a2);
+    if (a1 != a2) return false;
     const float PI_F = 3.14159274101257324f;
     switch (type) {
         case HT_PDBMOTIF:
@@ -290,6 +347,7 @@ inline int typed_dist_index(uint32_t type, int *idx) {
     switch (type) {
         case HT_TRROSETTA:
         case HT_PPF: idx[0] = 2; return 1;
+        case HT_TERTIARY: idx[0] = 7; return 1;
         default: idx[0] = 2, idx[1] = 3; return 2;
     }
 }
@@ -301,6 +359,12 @@ inline int typed_angle_index(uint32_t type, int *idx) {
             for (int k = 0; k < 5; k++) idx[k] = 3 + k;
             return 5;
         case HT_PPF: idx[0] = 3, idx[1] = 4, idx[2] = 5; return 3;
+        case HT_TERTIARY:
+            for (int k = 0; k < 7; k++) idx[k] = k;
+            return 7;
+        case HT_HYBRID:
+            for (int k = 0; k < 5; k++) idx[k] = 4 + k;
+            return 5;
         default: idx[0] = 4, idx[1] = 5, idx[2] = 6; return 3;
     }
 }

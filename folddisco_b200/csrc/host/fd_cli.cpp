@@ -9,8 +9,7 @@
 //   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
 //   ids                     src/controller/mode.rs:70-125
 //
-// Not here (fails loudly): `benchmark` / `analyze`, --web, --partial-fit, the TertiaryInteraction / Hybrid encodings,
-// mmCIF / .gz / Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
+// Not here (fails loudly): `benchmark` / `analyze`, --web, --partial-fit, mmCIF / .gz / Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
 #include <dirent.h>
 #include <limits.h>
 #include <sys/stat.h>
@@ -185,7 +184,7 @@ const char *HELP =
     "  query     Query a motif from an index table (GPU)\n"
     "  version   Print version information\n\n"
     "index:  -p/--pdbs DIR  -i/--index PREFIX  [-t N] [-d NBIN_DIST] [-a NBIN_ANGLE] [-g GRID] [-n MAX_RESIDUE]\n"
-    "        [-y/--type default|pdbtr|pdb|orig_pdb|tr|ppf|angle|dist] [--multiple-bins D1-A1,D2-A2,..]\n"
+    "        [-y/--type default|pdbtr|pdb|orig_pdb|tr|ppf|3di|hybrid|angle|dist] [--multiple-bins D1-A1,D2-A2,..]\n"
     "        [-r] [--id relpath|abspath|basename|filename|pdb] [--no-store] [-v]\n"
     "query:  -p/--pdb FILE -q/--query RESIDUES | -q FILE.txt|.tsv   -i/--index PREFIX  [-t N]\n"
     "        [-d DIST_THR[,..]] [-a ANGLE_THR[,..]] [--ca-distance X] [--total-match N] [--covered-node N]\n"
@@ -222,9 +221,6 @@ int cmd_index(Args &a) {
     { // HashType::get_with_str (geometry/core.rs:42-57)
         const int t = fdh_hash_type_from_string(type.c_str());
         if (t < 0) die("unknown hash type '" + type + "'");
-        if (t == 6 || t == 7)
-            die("hash type '" + type + "' is not supported by folddisco-b200 (TertiaryInteraction and Hybrid hash over the "
-                "neighbouring residues and are not built)");
         hp.hash_type = (uint32_t)t;
     }
     if (!multiple_bins.empty()) { // parse_distance_angle_pairs (utils/cli.rs:1-16): "16-4,8-3"; malformed pairs are skipped

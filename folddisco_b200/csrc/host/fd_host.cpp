@@ -627,11 +627,17 @@ void qinsert(Query &Q, SeenHashes &seen, QueryHasher &H, const float *f, uint32_
 bool host_typed_feature(const fdh_compact &c, size_t i, size_t j, const fdg::TypedParams &tp, float *f, float *ca_dist) {
     if (i == j) return false;
     const uint8_t a1 = c.aa[i], a2 = c.aa[j];
-    if (a1 == 255 || a2 == 255 || !c.cb_valid[i] || !c.cb_valid[j]) return false;
+    if (a1 == 255 || a2 == 255) return false;
+    if (fdg::ht_needs_cb(tp.type) && (!c.cb_valid[i] || !c.cb_valid[j])) return false;
+    fdg::Nbr nb;
+    if (fdg::ht_needs_neighbours(tp.type)) { // feature.rs:113, 163: not for the first / last residue
+        if (i == 0 || j == 0 || i + 1 >= c.nres() || j + 1 >= c.nres()) return false;
+        nb = fdg::Nbr{c.CA(i - 1), c.CA(i + 1), c.CA(j - 1), c.CA(j + 1), (float)j - (float)i};
+    }
     const float d = fdg::typed_screen_dist(tp.type, c.CA(i), c.CB(i), c.CA(j), c.CB(j));
     if (d > tp.dist_cutoff) return false;
     fdg::typed_feature(tp.type, c.N(i), c.CA(i), c.CB(i), c.N(j), c.CA(j), c.CB(j), (float)(a1 & 0x7F), (float)(a2 & 0x7F),
-                       d, f);
+                       d, f, &nb);
     *ca_dist = fdg::dist(c.CA(i), c.CA(j));
     return true;
 }
@@ -661,7 +667,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     SeenHashes seen;
     QueryHasher QH(qs.p.hash);
     AngleBinCache &bins = QH.bins;
-    int dist_idx[2], angle_idx[5];
+    int dist_idx[2], angle_idx[7];
     const int n_dist_idx = fdg::typed_dist_index(QH.tp.type, dist_idx), n_angle_idx = fdg::typed_angle_index(QH.tp.type, angle_idx);
     const size_t K = Q.indices.size();
     {
@@ -691,7 +697,7 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
             bins.reset();
             Q.pair_hash.push_back(QH.observed(f));
             qinsert(Q, seen, QH, f, I, J, true, pair);
-            { // apply_substitutions (query.rs:86-156)
+            if (fdg::ht_has_aa_index(QH.tp.type)) { // apply_substitutions (query.rs:86-156, :301-306)
                 const float o1 = fn[0], o2 = fn[1];
                 auto si = submap.find(I), sj = submap.find(J);
                 if (si != submap.end()) {
@@ -1450,8 +1456,8 @@ int fdh_hash_type_from_string(const char *name) {
     if (is({"2", "TrRosetta", "trrosetta", "tr"})) return FD_HASH_TRROSETTA;
     if (is({"3", "PDBTrRosetta", "pdbtr", "default", "folddisco"})) return FD_HASH_PDBTRROSETTA;
     if (is({"4", "PointPairFeature", "ppf"})) return FD_HASH_POINTPAIRFEATURE;
-    if (is({"5", "TertiaryInteraction", "tertiary", "3di"})) return 6;
-    if (is({"6", "Hybrid", "hybrid"})) return 7;
+    if (is({"5", "TertiaryInteraction", "tertiary", "3di"})) return FD_HASH_TERTIARYINTERACTION;
+    if (is({"6", "Hybrid", "hybrid"})) return FD_HASH_HYBRID;
     if (is({"7", "FolddiscoAngle", "angle", "folddisco_angle"})) return FD_HASH_FOLDDISCOANGLE;
     if (is({"8", "FolddiscoDist", "distance", "dist", "folddisco_dist"})) return FD_HASH_FOLDDISCODIST;
     return -1;
@@ -1462,8 +1468,8 @@ const char *hash_type_name(uint32_t t) {
         case FD_HASH_PDBMOTIFSINCOS: return "PDBMotifSinCos";
         case FD_HASH_TRROSETTA: return "TrRosetta";
         case FD_HASH_POINTPAIRFEATURE: return "PointPairFeature";
-        case 6: return "TertiaryInteraction";
-        case 7: return "Hybrid";
+        case FD_HASH_TERTIARYINTERACTION: return "TertiaryInteraction";
+        case FD_HASH_HYBRID: return "Hybrid";
         case FD_HASH_FOLDDISCOANGLE: return "FolddiscoAngle";
         case FD_HASH_FOLDDISCODIST: return "FolddiscoDist";
         default: return "PDBTrRosetta";

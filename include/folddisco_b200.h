@@ -87,14 +87,15 @@ typedef struct {
 } fd_struct_batch;
 
 /* Encodings of the reference's `--type` (HashType, src/geometry/core.rs:10-60): the values of fd_hash_params.hash_type
- * are the reference's HashType index + 1, 0 selects the default.  TertiaryInteraction (6) and Hybrid (7) are not
- * built: every entry point refuses them with FD_ERR_ARG. */
+ * are the reference's HashType index + 1, 0 selects the default. */
 #define FD_HASH_DEFAULT 0          /* = PDBTrRosetta */
 #define FD_HASH_PDBMOTIF 1         /* src/geometry/pdb_motif.rs */
 #define FD_HASH_PDBMOTIFSINCOS 2   /* src/geometry/pdb_motif_sincos.rs */
 #define FD_HASH_TRROSETTA 3        /* src/geometry/trrosetta.rs */
 #define FD_HASH_PDBTRROSETTA 4     /* src/geometry/pdb_tr.rs */
 #define FD_HASH_POINTPAIRFEATURE 5 /* src/geometry/ppf.rs */
+#define FD_HASH_TERTIARYINTERACTION 6 /* src/geometry/tertiary_interaction.rs (CA trace around i and j) */
+#define FD_HASH_HYBRID 7           /* src/geometry/hybrid.rs (amino-acid groups + PDBTrRosetta geometry + CA-trace torsions) */
 #define FD_HASH_FOLDDISCOANGLE 8   /* src/geometry/folddisco_angle.rs */
 #define FD_HASH_FOLDDISCODIST 9    /* src/geometry/folddisco_dist.rs */
 #define FD_MAX_MULTIPLE_BINS 8

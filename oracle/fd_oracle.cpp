@@ -336,15 +336,61 @@ inline float calc_angle_radian(V3 a, V3 b, V3 c) {
 inline float to_degrees(float r) { return r * 57.2957795130823208767981548141051703f; }
 
 // get_single_feature (feature.rs:11-190) for the encodings over the N / CA / CB atoms of the two residues
+// map_aa_to_u8_group (convert.rs:85-131), by amino-acid code
+uint8_t aa_group(uint8_t aa) {
+    switch (aa) {
+        case 0: case 4: case 7: case 14: case 15: return 0; // ALA CYS GLY PRO SER (small / aliphatic)
+        case 9: case 10: case 12: case 13: case 17: case 19: return 1; // ILE LEU MET PHE TRP VAL (hydrophobic)
+        case 2: case 5: case 16: case 18: return 2; // ASN GLN THR TYR (polar)
+        case 1: case 3: case 6: case 8: case 11: return 3; // ARG ASP GLU HIS LYS (charged)
+        default: return 255;
+    }
+}
+
 bool pair_feature(const fdo_compact &c, size_t i, size_t j, float cutoff, float *f) {
     if (i == j) return false;
     uint8_t r1 = c.aa[i], r2 = c.aa[j];
     if (r1 == 255 || r2 == 255) return false;
-    if (!c.cb_valid[i] || !c.cb_valid[j]) return false;
+    if (g_hash_type != 5 && (!c.cb_valid[i] || !c.cb_valid[j])) return false; // TertiaryInteraction reads CA only
     for (int k = 0; k < 9; k++) f[k] = 0.0f;
     f[0] = (float)r1;
     f[1] = (float)r2;
     switch (g_hash_type) {
+        case 5: { // TertiaryInteraction (feature.rs:112-161)
+            const size_t n = c.nres();
+            if (i == 0 || j == 0 || i == n - 1 || j == n - 1) return false;
+            float ca_dist = calc_distance(c.ca[i], c.ca[j]);
+            if (ca_dist > cutoff) return false;
+            V3 u1 = vnormalize(vsub(c.ca[i], c.ca[i - 1])), u2 = vnormalize(vsub(c.ca[i + 1], c.ca[i]));
+            V3 u3 = vnormalize(vsub(c.ca[j], c.ca[j - 1])), u4 = vnormalize(vsub(c.ca[j + 1], c.ca[j]));
+            V3 u5 = vnormalize(vsub(c.ca[j], c.ca[i]));
+            f[0] = fdo_acosf(vdot(u1, u2)); // phi_12
+            f[1] = fdo_acosf(vdot(u3, u4)); // phi_34
+            f[2] = fdo_acosf(vdot(u1, u5)); // phi_15
+            f[3] = fdo_acosf(vdot(u3, u5)); // phi_35
+            f[4] = fdo_acosf(vdot(u1, u4)); // phi_14
+            f[5] = fdo_acosf(vdot(u2, u3)); // phi_23
+            f[6] = fdo_acosf(vdot(u1, u3)); // phi_13
+            f[7] = ca_dist;
+            f[8] = (float)j - (float)i;
+            return true;
+        }
+        case 6: { // Hybrid (feature.rs:162-186, core.rs:405-436)
+            const size_t n = c.nres();
+            if (i == 0 || j == 0 || i == n - 1 || j == n - 1) return false;
+            float ca_dist = calc_distance(c.ca[i], c.ca[j]);
+            if (ca_dist > cutoff) return false;
+            f[0] = (float)aa_group(r1);
+            f[1] = (float)aa_group(r2);
+            f[2] = ca_dist;
+            f[3] = calc_distance(c.cb[i], c.cb[j]);
+            f[4] = calc_angle(c.ca[i], c.cb[i], c.ca[j], c.cb[j]);
+            f[5] = calc_torsion_radian(c.n[i], c.ca[i], c.cb[i], c.cb[j]);
+            f[6] = calc_torsion_radian(c.cb[i], c.cb[j], c.ca[j], c.n[j]);
+            f[7] = calc_torsion_radian(c.ca[i - 1], c.n[i], c.ca[i], c.ca[i + 1]);
+            f[8] = calc_torsion_radian(c.ca[j - 1], c.n[j], c.ca[j], c.ca[j + 1]);
+            return true;
+        }
         case 0:   // PDBMotif: ca_dist, cb_dist, CA-CB angle in degrees (feature.rs:26-45)
         case 1: { // PDBMotifSinCos: the same with the angle in radians (feature.rs:47-66)
             float ca_dist = calc_distance(c.ca[i], c.ca[j]);
@@ -465,6 +511,28 @@ uint32_t perfect_hash_raw(const float *f, uint32_t nbd, uint32_t nba) {
             return (res1 << 27) | (res2 << 22) | (hd << 18) | (s[0] << 15) | (c[0] << 12) | (s[1] << 9) | (c[1] << 6) |
                    (s[2] << 3) | c[2];
         }
+        case 5: { // tertiary_interaction.rs:21-83 (defaults 8 / 3, clamp 16 / 8)
+            float nd = nbd > 16 ? 16.0f : (nbd == 0 ? 8.0f : (float)nbd);
+            float na = nba > 8 ? 8.0f : (nba == 0 ? 3.0f : (float)nba);
+            uint32_t c[7];
+            for (int k = 0; k < 7; k++) c[k] = discretize(fdo_cosf(f[k]), -1.0f, 1.0f, na);
+            uint32_t ca = discretize(f[7], 2.0f, 20.0f, nd);
+            uint32_t sd = f[8] < -4.0f ? 0u : (f[8] > 4.0f ? 8u : sat_u32(f[8]) + 4u);
+            return (c[0] << 26) | (c[1] << 23) | (c[2] << 20) | (c[3] << 17) | (c[4] << 14) | (c[5] << 11) | (c[6] << 8) |
+                   (ca << 4) | sd;
+        }
+        case 6: { // hybrid.rs:21-96 (defaults 16 / 4)
+            float nd = nbd > 16 ? 16.0f : (nbd == 0 ? 16.0f : (float)nbd);
+            float na = nba > 4 ? 4.0f : (nba == 0 ? 4.0f : (float)nba);
+            uint32_t h = res1 << 30 | res2 << 28 | discretize(f[2], 2.0f, 20.0f, nd) << 24 | discretize(f[3], 2.0f, 20.0f, nd) << 20;
+            int shift = 18;
+            for (int k = 4; k <= 8; k++) { // ca-cb angle, phi1, phi2, bb_phi1, bb_phi2
+                h |= discretize(fdo_sinf(f[k]), -1.0f, 1.0f, na) << shift;
+                h |= discretize(fdo_cosf(f[k]), -1.0f, 1.0f, na) << (shift - 2);
+                shift -= 4;
+            }
+            return h;
+        }
         case 7: { // folddisco_angle.rs:24-71 (defaults 8 / 32, radians binned directly)
             float nd = nbd > 8 ? 8.0f : (nbd == 0 ? 8.0f : (float)nbd);
             float na = nba > 32 ? 32.0f : (nba == 0 ? 32.0f : (float)nba);
@@ -491,6 +559,7 @@ void default_bins(uint32_t *nbd, uint32_t *nba) {
     switch (g_hash_type) {
         case 0: *nbd = 18, *nba = 9; break;
         case 3: *nbd = 16, *nba = 4; break;
+        case 6: *nbd = 16, *nba = 4; break;
         case 7: *nbd = 8, *nba = 32; break;
         case 8: *nbd = 32, *nba = 16; break;
         default: *nbd = 8, *nba = 3; break;
@@ -537,6 +606,10 @@ bool hash_is_symmetric(uint32_t h) {
         return to_degrees(fdo_atan2f(continuize(sbin, -1.0f, 1.0f, nb), continuize(cbin, -1.0f, 1.0f, nb)));
     };
     switch (g_hash_type) {
+        case 5: return false; // tertiary_interaction.rs:145-150
+        case 6: // hybrid.rs:185-189: groups equal, phi1 == phi2
+            return ((h >> 30) & 3u) == ((h >> 28) & 3u) &&
+                   angle((h >> 14) & 3u, (h >> 12) & 3u, 4.0f) == angle((h >> 10) & 3u, (h >> 8) & 3u, 4.0f);
         case 0:
         case 1: return a1 == a2; // pdb_motif.rs:98-102, pdb_motif_sincos.rs:105-109
         case 2: // trrosetta.rs:158-162: theta1 == theta2 and phi1 == phi2 (3 default sin / cos bins)
@@ -1417,7 +1490,7 @@ fdo_matches *retrieve(const fdo_qmap &m, const fdo_compact &query, const fdo_com
     if (m.entries.empty()) return res;
     // prefilter_amino_acid (retrieve.rs:563-602): exact canonical residue-name match
     std::vector<size_t> set1, set2;
-    if (m.entries.size() <= 200) {
+    if (m.entries.size() <= 200 && g_hash_type != 5 && g_hash_type != 6) { // amino_acid_index() is None for those two
         std::set<uint8_t> aa1s, aa2s;
         for (auto &e : m.entries) {
             uint32_t a1, a2;
@@ -1569,6 +1642,8 @@ fdo_matches *retrieve(const fdo_qmap &m, const fdo_compact &query, const fdo_com
             rr.rmsd = rh.rmsd;
             memcpy(rr.U, rh.U, sizeof(rh.U));
             memcpy(rr.T, rh.T, sizeof(rh.T));
+            memcpy(rr.metrics, rh.metrics, sizeof(rh.metrics)); // retrieve.rs:522-523: ca_coords and metrics too
+            rr.target_ca = rh.target_ca;
         } else {
             rmsd_with_calpha(query, t, q_scan, r_scan, rr);
         }
@@ -1700,7 +1775,7 @@ int fdo_pair_feature9(const fdo_compact *c, int64_t i, int64_t j, float cutoff, 
 uint32_t fdo_perfect_hash(const float *f, uint32_t nbd, uint32_t nba) { return perfect_hash(f, nbd, nba); }
 uint32_t fdo_perfect_hash_raw(const float *f9, uint32_t nbd, uint32_t nba) { return perfect_hash_raw(f9, nbd, nba); }
 int fdo_set_hash_type(int t) {
-    if (!(t == 0 || t == 1 || t == 2 || t == 3 || t == 4 || t == 7 || t == 8)) return -1;
+    if (t < 0 || t > 8) return -1;
     g_hash_type = t;
     return 0;
 }
@@ -1992,7 +2067,7 @@ fdo_qmap *fdo_qmap_make(const fdo_compact *c, const uint8_t *chains, const uint6
             uint32_t observed = perfect_hash(f, nbd, nba);
             float idf = idf_for_hash(observed, ix, total);
             insert_binned_hash(*m, f, I, J, nbd, nba, true, idf);
-            { // apply_substitutions, query.rs:86-156 (operates on feature_near == feature here)
+            if (g_hash_type != 5 && g_hash_type != 6) { // apply_substitutions, query.rs:86-156 (only with amino_acid_index)
                 float o1 = fn[0], o2 = fn[1];
                 auto si = submap.find(I), sj = submap.find(J);
                 if (si != submap.end()) {
@@ -2035,7 +2110,16 @@ fdo_qmap *fdo_qmap_make(const fdo_compact *c, const uint8_t *chains, const uint6
                 }
             };
             // HashType::dist_index / angle_index (feature.rs:269-289)
-            int di[2] = {2, 3}, ai[5] = {4, 5, 6, 0, 0}, ndi = 2, nai = 3;
+            int di[2] = {2, 3}, ai[7] = {4, 5, 6, 0, 0, 0, 0}, ndi = 2, nai = 3;
+            if (g_hash_type == 5) {
+                di[0] = 7, ndi = 1;
+                for (int k = 0; k < 7; k++) ai[k] = k;
+                nai = 7;
+            }
+            if (g_hash_type == 6) {
+                for (int k = 0; k < 5; k++) ai[k] = 4 + k;
+                nai = 5;
+            }
             if (g_hash_type == 2 || g_hash_type == 4) ndi = 1;
             if (g_hash_type == 0 || g_hash_type == 1) nai = 1;
             if (g_hash_type == 2) {

@@ -128,10 +128,6 @@ def test_unsupported_options_fail_loudly(workdir):
         r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"] + extra,
                            cwd=workdir, capture_output=True, text=True)
         assert r.returncode != 0 and "not supported" in r.stderr
-    for t in ("3di", "hybrid"):  # TertiaryInteraction / Hybrid hash over neighbouring residues: not built
-        r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", t], cwd=workdir,
-                           capture_output=True, text=True)
-        assert r.returncode != 0 and "not supported" in r.stderr
     r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", "nonsense"], cwd=workdir,
                        capture_output=True, text=True)
     assert r.returncode != 0 and "unknown hash type" in r.stderr

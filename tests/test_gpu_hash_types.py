@@ -18,6 +18,8 @@ CASES = [
     ("PDBMotifSinCos", 2, 1, 0, 0, []),
     ("TrRosetta", 3, 2, 0, 0, []),
     ("PointPairFeature", 5, 4, 12, 5, []),
+    ("TertiaryInteraction", 6, 5, 0, 0, []),
+    ("Hybrid", 7, 6, 0, 0, []),
     ("FolddiscoAngle", 8, 7, 0, 0, []),
     ("FolddiscoDist", 9, 8, 0, 0, []),
     ("PDBTrRosetta-multiple-bins", 0, 3, 0, 0, [(16, 4), (8, 3)]),
@@ -93,12 +95,12 @@ def test_typed_index_and_search_vs_oracle(env, name, fd_type, ref_type, nbd, nba
         assert n_rows > 0
 
 
-def test_unbuilt_encodings_are_refused(env):
+def test_unknown_encodings_are_refused(env):
     fd, ctx = env["fd"], env["ctx"]
     p = env["parts"][0]
     batch = fd.StructBatch.from_list([dict(n_xyz=p["n_xyz"], ca_xyz=p["ca_xyz"], cb_xyz=p["cb_xyz"], aa=p["aa"],
                                            cb_valid=None)])
-    for t in (6, 7):  # TertiaryInteraction, Hybrid
+    for t in (10, 1000):  # not a HashType
         with pytest.raises(fd.FdError):
             ctx.hash_structures(batch, fd.HashParams(0, 0, 20.0, t))
     with pytest.raises(fd.FdError):  # the pair table is PDBTrRosetta single-bin only

@@ -20,6 +20,8 @@ TYPES = [
     ("TrRosetta", 3, 2, [(0, 0), (6, 3), (20, 9)]),
     ("PDBTrRosetta", 4, 3, [(0, 0), (8, 3), (0, 3)]),
     ("PointPairFeature", 5, 4, [(0, 0), (12, 5)]),
+    ("TertiaryInteraction", 6, 5, [(0, 0), (12, 6), (20, 9)]),
+    ("Hybrid", 7, 6, [(0, 0), (8, 3)]),
     ("FolddiscoAngle", 8, 7, [(0, 0), (6, 12)]),
     ("FolddiscoDist", 9, 8, [(0, 0), (20, 10)]),
 ]
@@ -51,7 +53,7 @@ def test_typed_hashes_equal_oracle(structs, name, fd_type, ref_type, bins):
     assert total > 50_000
 
 
-@pytest.mark.parametrize("fd_type,ref_type", [(0, 3), (2, 1), (3, 2), (9, 8)])
+@pytest.mark.parametrize("fd_type,ref_type", [(0, 3), (2, 1), (3, 2), (6, 5), (7, 6), (9, 8)])
 def test_multiple_bins_equal_oracle(structs, fd_type, ref_type):
     from folddisco_b200 import capi
     mb = [(16, 4), (8, 3), (4, 2)]
@@ -75,7 +77,7 @@ def test_is_symmetric_equals_oracle(structs, name, fd_type, ref_type, bins):
         want = np.array([O.lib().fdo_hash_is_symmetric(int(h)) for h in hashes])
     got = np.array([capi.typed_is_symmetric_host(fd_type, h) for h in hashes])
     assert np.array_equal(got, want)
-    if name not in ("PDBMotif", "PDBMotifSinCos"):
+    if name not in ("PDBMotif", "PDBMotifSinCos", "TertiaryInteraction"):
         assert 0 < want.sum() < len(want)
 
 
@@ -96,7 +98,7 @@ def test_reference_pins():
 
 def test_refused_types():
     from folddisco_b200 import capi
-    for t in (6, 7, 10):
+    for t in (10, 99):
         with pytest.raises(capi.FdError):
             capi.typed_hash_host(np.zeros((2, 3)), np.zeros((2, 3)), np.zeros((2, 3)), np.zeros(2, np.uint8), None,
                                  capi.HashParams(0, 0, 20.0, t))

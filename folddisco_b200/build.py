@@ -65,7 +65,7 @@ def build(force=False, verbose=False):
         print("\n".join(log))
     # NCCL: the multi-GPU exchange lives inside the library (fd_comm.cu); libnccl.so.2 is bound with dlopen on the first
     # fd_comm_* call, so that a host process that already carries an NCCL (PyTorch bundles its own) keeps exactly one
-    link = [NVCC, "-shared", "-o", SO] + [o for _, o, _, _ in results] + ["-Xcompiler", "-pthread", "-ldl"]
+    link = [NVCC, "-shared", "-o", SO] + [o for _, o, _, _ in results] + ["-Xcompiler", "-pthread", "-ldl", "-lz"]
     subprocess.check_call(link)
     cli = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", os.path.join(CSRC, "host", "fd_cli.cpp"), "-o", CLI,
            "-L" + HERE, "-lfolddisco_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + os.path.dirname(NVCC) + "/../lib64"]

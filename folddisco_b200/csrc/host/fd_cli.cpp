@@ -9,7 +9,7 @@
 //   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
 //   ids                     src/controller/mode.rs:70-125
 //
-// Not here (fails loudly): `benchmark` / `analyze`, --web, --partial-fit, mmCIF / .gz / Foldcomp inputs.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
+// Not here (fails loudly): `benchmark` / `analyze`, --web, --partial-fit, Foldcomp databases.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
 #include <dirent.h>
 #include <limits.h>
 #include <sys/stat.h>
@@ -249,9 +249,11 @@ int cmd_index(Args &a) {
     if (is_dir(dir)) list_files(dir, recursive, files);
     else die(dir + " is not a directory (Foldcomp databases are not supported)");
     if (files.empty()) die("no input files in " + dir);
-    for (auto &f : files)
-        if (!(ends_with(f, ".pdb") || ends_with(f, ".ent") || ends_with(f, ".PDB")))
-            die("unsupported input format (only .pdb / .ent): " + f);
+    for (auto &f : files) { // read_structure_from_path (controller/io.rs:337-379)
+        const std::string b = ends_with(f, ".gz") ? f.substr(0, f.size() - 3) : f;
+        if (!(ends_with(b, ".pdb") || ends_with(b, ".ent") || ends_with(b, ".PDB") || ends_with(b, ".cif")))
+            die("unsupported input format (.pdb / .ent / .cif, optionally .gz): " + f);
+    }
     if (verbose) fprintf(stderr, "[INFO] Indexing %zu files with %s\n", files.size(), fdh_hash_type_name(hp.hash_type));
     // parse on the host (file-parallel like the reference, mod.rs:298), keep file order
     std::vector<fdh_compact *> comps(files.size(), nullptr);
@@ -260,7 +262,7 @@ int cmd_index(Args &a) {
         const int nt = std::max(1, std::min(fd_default_host_threads(), 64));
         auto work = [&](int t) { // static interleaved partition
             for (size_t k = (size_t)t; k < files.size(); k += (size_t)nt) {
-                comps[k] = fdh_compact_read_pdb(files[k].c_str());
+                comps[k] = fdh_compact_read_structure(files[k].c_str());
                 if (!comps[k]) errs[k] = fdh_last_error();
             }
         };
@@ -582,7 +584,7 @@ int cmd_query(Args &a) {
             for (uint64_t k = 0; k < S; k++) {
                 std::string p = fdh_index_name(ix, k);
                 if (!is_file(p)) p = index_dir + p; // resolve_tid_path_from_index_prefix (controller/io.rs:488-528)
-                fdh_compact *c = fdh_compact_read_pdb(p.c_str());
+                fdh_compact *c = fdh_compact_read_structure(p.c_str());
                 if (!c) die(std::string("Failed to read structure ") + fdh_index_name(ix, k) + ": " + fdh_last_error());
                 fdh_store_add(store, c, fdh_index_name(ix, k));
                 fdh_compact_free(c);
@@ -607,7 +609,7 @@ int cmd_query(Args &a) {
             for (auto &e : cache)
                 if (e.first == j.pdb) c = e.second;
             if (!c) {
-                c = fdh_compact_read_pdb(j.pdb.c_str());
+                c = fdh_compact_read_structure(j.pdb.c_str());
                 if (!c) die("Failed to read structure: " + j.pdb + ": " + fdh_last_error());
                 cache.emplace_back(j.pdb, c);
             }

@@ -8,6 +8,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <functional>
@@ -223,16 +224,29 @@ bool field_u64(const char *s, size_t len, uint64_t *out) {
     return true;
 }
 
-// PDB reader: src/structure/io/pdb.rs:37-76 + parser.rs:3-55 (first model, ATOM records only; records whose
-// fixed columns do not parse are skipped, negative residue numbers included)
-bool read_pdb_atoms(const char *path, Atoms &a) {
+// Whole file as text; .gz (and plain) through zlib like the reference's flate2 GzDecoder (pdb.rs:96-118, cif.rs:62-94)
+bool read_file_text(const char *path, bool gz, std::string &data) {
+    char buf[1 << 16];
+    if (gz) {
+        gzFile g = gzopen(path, "rb");
+        if (!g) return false;
+        int r;
+        while ((r = gzread(g, buf, sizeof(buf))) > 0) data.append(buf, (size_t)r);
+        const bool ok = r == 0;
+        gzclose(g);
+        return ok;
+    }
     FILE *f = fopen(path, "rb");
     if (!f) return false;
-    std::string data;
-    char buf[1 << 16];
     size_t r;
     while ((r = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, r);
     fclose(f);
+    return true;
+}
+
+// PDB reader: src/structure/io/pdb.rs:37-76 + parser.rs:3-55 (first model, ATOM records only; records whose
+// fixed columns do not parse are skipped, negative residue numbers included)
+bool parse_pdb_atoms(const std::string &data, Atoms &a) {
     int model = 0;
     size_t pos = 0;
     while (pos < data.size()) {
@@ -264,6 +278,192 @@ bool read_pdb_atoms(const char *path, Atoms &a) {
         a.serial.push_back(rs);
     }
     return true;
+}
+
+// mmCIF reader: src/structure/io/cif.rs:97-287 over the `_atom_site` loop (lexing of pdbtbx_cif 0.x: whitespace-separated
+// values, '...' / "..." quoting, # comments, ; text fields).  Every row of the loop becomes an atom -- the reference
+// does not separate HETATM here (cif.rs:262-270) -- until the model number changes (:239-245).  Residue number =
+// auth_seq_id, else label_seq_id; chain = a one-character auth_asym_id, else label_asym_id (:253-259); B = 1.0 when absent.
+bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
+    struct Tok {
+        std::string text;
+        bool quoted;
+    };
+    size_t pos = 0;
+    const size_t N = data.size();
+    bool at_line_start = true;
+    auto next = [&](Tok &t) -> bool {
+        for (;;) {
+            while (pos < N && (data[pos] == ' ' || data[pos] == '\t' || data[pos] == '\r' || data[pos] == '\n')) {
+                at_line_start = data[pos] == '\n';
+                pos++;
+            }
+            if (pos >= N) return false;
+            if (data[pos] == '#') { // comment to the end of the line
+                while (pos < N && data[pos] != '\n') pos++;
+                continue;
+            }
+            break;
+        }
+        t.quoted = false;
+        t.text.clear();
+        if (data[pos] == ';' && (at_line_start || pos == 0)) { // text field: up to a line that starts with ';'
+            size_t b = pos + 1, e = data.find("\n;", b);
+            if (e == std::string::npos) e = N;
+            t.text = data.substr(b, e - b);
+            t.quoted = true;
+            pos = std::min(N, e + 2);
+            at_line_start = false;
+            return true;
+        }
+        at_line_start = false;
+        if (data[pos] == '\'' || data[pos] == '"') { // closes at the same quote followed by white space
+            const char q = data[pos++];
+            const size_t b = pos;
+            while (pos < N && !(data[pos] == q && (pos + 1 >= N || isspace((unsigned char)data[pos + 1]))) && data[pos] != '\n') pos++;
+            t.text = data.substr(b, pos - b);
+            t.quoted = true;
+            if (pos < N && data[pos] == q) pos++;
+            return true;
+        }
+        const size_t b = pos;
+        while (pos < N && !isspace((unsigned char)data[pos])) pos++;
+        t.text = data.substr(b, pos - b);
+        return true;
+    };
+    auto lower = [](std::string s) {
+        for (char &c : s) c = (char)tolower((unsigned char)c);
+        return s;
+    };
+    auto is_keyword = [&](const Tok &t) {
+        if (t.quoted) return false;
+        const std::string l = lower(t.text);
+        return l == "loop_" || l.rfind("data_", 0) == 0 || l.rfind("save_", 0) == 0 || l == "stop_" || l == "global_";
+    };
+    Tok t;
+    bool have = next(t);
+    while (have) {
+        if (t.quoted || lower(t.text) != "loop_") {
+            have = next(t);
+            continue;
+        }
+        std::vector<std::string> header;
+        while ((have = next(t)) && !t.quoted && !t.text.empty() && t.text[0] == '_') header.push_back(t.text.substr(1));
+        if (std::find(header.begin(), header.end(), "atom_site.group_PDB") == header.end()) continue; // another loop
+        auto col = [&](const char *name) -> int {
+            auto it = std::find(header.begin(), header.end(), name);
+            return it == header.end() ? -1 : (int)(it - header.begin());
+        };
+        const int c_asym = col("atom_site.label_asym_id"), c_auth_asym = col("atom_site.auth_asym_id"),
+                  c_b = col("atom_site.B_iso_or_equiv"), c_comp = col("atom_site.label_comp_id"), c_id = col("atom_site.id"),
+                  c_model = col("atom_site.pdbx_PDB_model_num"), c_name = col("atom_site.label_atom_id"),
+                  c_seq = col("atom_site.label_seq_id"), c_auth_seq = col("atom_site.auth_seq_id"),
+                  c_type = col("atom_site.type_symbol"), c_x = col("atom_site.Cartn_x"), c_y = col("atom_site.Cartn_y"),
+                  c_z = col("atom_site.Cartn_z");
+        if (c_asym < 0 || c_comp < 0 || c_id < 0 || c_name < 0 || c_seq < 0 || c_type < 0 || c_x < 0 || c_y < 0 || c_z < 0) {
+            err = "Missing column in coordinate atoms data loop"; // cif.rs:190-201: the loop is not parsed
+            return true;
+        }
+        const size_t W = header.size();
+        std::vector<Tok> row(W);
+        // a value that is `.` / `?` (unquoted) is inapplicable / unknown: None
+        auto missing = [](const Tok &v) { return !v.quoted && (v.text == "." || v.text == "?"); };
+        auto num = [&](const Tok &v, float *out) { // Value::Numeric is an f32 (integers travel through it too)
+            if (v.quoted || missing(v)) return false;
+            return field_f32(v.text.data(), v.text.size(), out);
+        };
+        bool first = true;
+        long long first_model = 0;
+        while (have && !is_keyword(t) && !(!t.quoted && !t.text.empty() && t.text[0] == '_')) {
+            row[0] = t;
+            size_t k = 1;
+            for (; k < W && (have = next(t)); k++) row[k] = t;
+            if (k < W) break; // truncated last row
+            have = next(t);
+            float fv;
+            long long model = 1;
+            if (c_model >= 0 && num(row[c_model], &fv)) model = (long long)fv;
+            if (first) first_model = model;
+            else if (model != first_model) break;
+            first = false;
+            const std::string &an = row[c_name].text;
+            if (missing(row[c_name]) || an.empty() || an.size() > 4) {
+                err = "Invalid atom name in the atom_site loop";
+                return false;
+            }
+            uint8_t name4[4] = {' ', ' ', ' ', ' '};
+            if (an.size() == 4) memcpy(name4, an.data(), 4);
+            else memcpy(name4 + 1, an.data(), an.size());
+            uint8_t res3[3] = {' ', ' ', ' '};
+            const std::string &rn = row[c_comp].text;
+            if (missing(row[c_comp])) {
+                err = "Residue name should be provided";
+                return false;
+            }
+            if (rn.size() <= 3) memcpy(res3, rn.data(), rn.size()); // longer names become blank (cif.rs:319-321)
+            float seq;
+            if (!(c_auth_seq >= 0 && num(row[c_auth_seq], &seq) && truncf(seq) == seq) &&
+                !(num(row[c_seq], &seq) && truncf(seq) == seq)) {
+                err = "Residue number should be provided";
+                return false;
+            }
+            uint8_t chain = 0;
+            if (c_auth_asym >= 0 && !missing(row[c_auth_asym]) && row[c_auth_asym].text.size() == 1) chain = (uint8_t)row[c_auth_asym].text[0];
+            else if (!missing(row[c_asym]) && row[c_asym].text.size() == 1) chain = (uint8_t)row[c_asym].text[0];
+            else {
+                err = "Chain name should be provided (one character)";
+                return false;
+            }
+            float x, y, z, b = 1.0f;
+            if (!num(row[c_x], &x) || !num(row[c_y], &y) || !num(row[c_z], &z)) {
+                err = "Atom position should be provided";
+                return false;
+            }
+            if (c_b >= 0) {
+                float bv;
+                if (num(row[c_b], &bv)) b = bv;
+            }
+            a.x.push_back(x);
+            a.y.push_back(y);
+            a.z.push_back(z);
+            a.b.push_back(b);
+            a.name.insert(a.name.end(), name4, name4 + 4);
+            a.rname.insert(a.rname.end(), res3, res3 + 3);
+            a.chain.push_back(chain);
+            a.serial.push_back((uint64_t)(int64_t)seq); // `isize as u64`
+        }
+        // (a second atom_site loop would be parsed as well, like the reference's walk over every loop)
+    }
+    return true;
+}
+
+bool has_suffix(const std::string &s, const char *suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+// read_structure_from_path (src/controller/io.rs:337-379): .pdb / .ent / .cif, each optionally .gz
+bool read_structure_atoms(const char *path, Atoms &a, std::string &err) {
+    const std::string p = path;
+    const bool gz = has_suffix(p, ".gz");
+    const std::string base = gz ? p.substr(0, p.size() - 3) : p;
+    const bool cif = has_suffix(base, ".cif");
+    if (!cif && !has_suffix(base, ".pdb") && !has_suffix(base, ".ent") && !has_suffix(base, ".PDB")) {
+        err = std::string("unsupported structure file extension (expected .pdb, .ent or .cif, optionally .gz): ") + path;
+        return false;
+    }
+    std::string data;
+    if (!read_file_text(path, gz, data)) {
+        err = std::string(cif ? "Failed to read CIF file: " : "Failed to read PDB file: ") + path;
+        return false;
+    }
+    if (cif) {
+        if (!parse_cif_atoms(data, a, err)) {
+            err = std::string("Failed to read structure from CIF file: ") + path + ": " + err;
+            return false;
+        }
+        return true;
+    }
+    return parse_pdb_atoms(data, a);
 }
 
 std::string rust_f32(float v) { // Rust `{}`: shortest round-trip, never scientific
@@ -1135,14 +1335,16 @@ extern "C" {
 
 const char *fdh_last_error(void) { return g_err.c_str(); }
 
-fdh_compact *fdh_compact_read_pdb(const char *path) {
+fdh_compact *fdh_compact_read_structure(const char *path) {
     Atoms a;
-    if (!read_pdb_atoms(path, a)) {
-        set_err(std::string("Failed to read PDB file: ") + path);
+    std::string err;
+    if (!read_structure_atoms(path, a, err)) {
+        set_err(err);
         return nullptr;
     }
     return compact_from_atoms(a);
 }
+fdh_compact *fdh_compact_read_pdb(const char *path) { return fdh_compact_read_structure(path); }
 fdh_compact *fdh_compact_from_atoms(int64_t n, const float *x, const float *y, const float *z, const uint8_t *an,
                                     const uint8_t *ch, const uint8_t *rn, const uint64_t *rs, const float *bf) {
     Atoms a;

@@ -59,6 +59,7 @@ def _lib():
     PP = C.POINTER
     sig("fdh_last_error", C.c_char_p, [])
     sig("fdh_compact_read_pdb", VP, [C.c_char_p])
+    sig("fdh_compact_read_structure", VP, [C.c_char_p])
     sig("fdh_compact_from_atoms", VP, [C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP])
     sig("fdh_compact_from_soa", VP, [C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP])
     sig("fdh_compact_nres", C.c_int64, [VP])
@@ -191,10 +192,8 @@ class CompactStructure:
 
 
 def read_structure_from_path(path):
-    """read_structure_from_path(path).to_compact()  (src/controller/io.rs:337-379); PDB only."""
-    if not (path.endswith(".pdb") or path.endswith(".ent")):
-        raise FdError("only .pdb/.ent inputs are supported in this version: %s" % path)
-    return CompactStructure(_lib().fdh_compact_read_pdb(os.fsencode(path)))
+    """read_structure_from_path(path).to_compact()  (src/controller/io.rs:337-379): .pdb / .ent / .cif, optionally .gz"""
+    return CompactStructure(_lib().fdh_compact_read_structure(os.fsencode(path)))
 
 
 def parse_query_string(q, default_chain=ord("A")):

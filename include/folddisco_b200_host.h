@@ -37,7 +37,11 @@ typedef struct fdh_results fdh_results; /* per-structure and per-match rows of a
 const char *fdh_last_error(void);
 
 /* ---- structures ---- */
-fdh_compact *fdh_compact_read_pdb(const char *path); /* NULL + fdh_last_error() on failure */
+/* read_structure_from_path (src/controller/io.rs:337-379) + Structure::to_compact: .pdb / .ent (src/structure/io/pdb.rs)
+ * and .cif (src/structure/io/cif.rs: the atom_site loop, first model), each optionally gzip-compressed (.gz).
+ * NULL + fdh_last_error() on failure.  fdh_compact_read_pdb is the older name of the same function. */
+fdh_compact *fdh_compact_read_structure(const char *path);
+fdh_compact *fdh_compact_read_pdb(const char *path);
 fdh_compact *fdh_compact_from_atoms(int64_t n_atoms, const float *x, const float *y, const float *z,
                                     const uint8_t *atom_name4, const uint8_t *chain, const uint8_t *res_name3,
                                     const uint64_t *res_serial, const float *b_factor);

@@ -265,3 +265,68 @@ def test_add_many_indexed_equals_add_many(host):
         assert np.array_equal(a.indices(q), b.indices(q))
     with pytest.raises(Exception):
         b.add_many_indexed([m[0] for m in motifs], [m[1] for m in motifs], [7], [0])
+
+
+@needs_reference
+def test_cif_and_gz_readers_on_reference_files(host):
+    """read_structure_from_path (src/controller/io.rs:337-379): the mmCIF reader (src/structure/io/cif.rs: atom_site loop,
+    auth ids, first model) and gzip inputs give the same CompactStructure as the PDB file of the same entry, on the
+    reference's own io_test files.  The reference's CIF reader does not drop HETATM rows (cif.rs:262-270), so an entry
+    with hetero residues that carry N and CA atoms has MORE residues than its PDB file."""
+    io = REF + "/data/io_test/"
+
+    def same(a, b):
+        da, db = a.soa(), b.soa()
+        return all(da[k].shape == db[k].shape and np.array_equal(da[k], db[k]) for k in da)
+
+    af = host.read_structure_from_path(io + "cif/AF-A0A4S3KKF6-F1-model_v4.cif")
+    assert af.num_residues == 738
+    assert same(af, host.read_structure_from_path(io + "cif/AF-A0A4S3KKF6-F1-model_v4.pdb"))
+    assert same(af, host.read_structure_from_path(io + "cif/AF-A0A4S3KKF6-F1-model_v4.cif.gz"))
+    _same_compact(af, O.Structure.read_pdb(io + "cif/AF-A0A4S3KKF6-F1-model_v4.pdb").compact())
+    g2f = host.read_structure_from_path(io + "cif/1G2F.cif")
+    pdb = host.read_structure_from_path(REF + "/query/1G2F.pdb")
+    assert g2f.num_residues == pdb.num_residues == 176
+    da, db = g2f.soa(), pdb.soa()
+    for k in ("ca_xyz", "n_xyz", "cb_xyz", "aa", "serial"):
+        assert np.array_equal(da[k], db[k]), k
+    # the chain of a residue is the chain of the atom that triggered its flush (SURVEY 8a quirk Q2): after the last protein
+    # residue the CIF loop goes on with hetero atoms of another chain, the PDB file does not
+    assert np.array_equal(da["chain"][:-1], db["chain"][:-1])
+    wnb, wnb_pdb = host.read_structure_from_path(io + "cif/2wnb.cif"), host.read_structure_from_path(io + "cif/2wnb.pdb")
+    assert wnb.num_residues >= wnb_pdb.num_residues == 270
+    assert same(wnb, host.read_structure_from_path(io + "cif/2wnb.cif.gz"))
+    assert same(host.read_structure_from_path(io + "inner/1akha-.pdb.gz"), host.read_structure_from_path(io + "1akha-.pdb"))
+    assert same(host.read_structure_from_path(io + "1b72a-.ent.gz"), host.read_structure_from_path(io + "1b72a-.pdb"))
+    assert same(host.read_structure_from_path(io + "inner/1b72a-.ent"), host.read_structure_from_path(io + "1b72a-.pdb"))
+    with pytest.raises(Exception):
+        host.read_structure_from_path(io + "cif/2wnb.xyz")
+
+
+def test_cif_reader_small_cases(host, tmp_path):
+    """quoting, missing values, the model cut and the chain / residue-number fallbacks of cif.rs:239-259"""
+    head = "data_t\n#\nloop_\n" + "".join("_atom_site.%s\n" % c for c in (
+        "group_PDB", "id", "type_symbol", "label_atom_id", "label_alt_id", "label_comp_id", "label_asym_id", "label_seq_id",
+        "Cartn_x", "Cartn_y", "Cartn_z", "B_iso_or_equiv", "auth_seq_id", "auth_asym_id", "pdbx_PDB_model_num"))
+    rows = []
+    k = 0
+    for model in (1, 2):
+        for res, (name, auth_seq, auth_asym) in enumerate((("ALA", "10", "A"), ("GLY", ".", "AA"), ("SER", "12", "B"))):
+            for atom, (x, y, z) in ((("N"), (0.0, 0.0, 0.0)), ("CA", (1.458, 0.0, 0.0)), ("C", (2.0, 1.4, 0.0)),
+                                    ('"O5\'"' if res == 2 else "O", (1.5, 2.4, 0.1)), ("CB", (2.0, -0.8, -1.2))):
+                if name == "GLY" and atom == "CB":
+                    continue
+                k += 1
+                rows.append("ATOM %d C %s . %s Z %d %.3f %.3f %.3f %s %s %s %d" % (
+                    k, atom, name, res + 1, x + 3.8 * res + 50 * (model - 1), y, z, "?" if res == 1 else "42.50", auth_seq,
+                    auth_asym, model))
+    p = tmp_path / "t.cif"
+    p.write_text(head + "\n".join(rows) + "\n#\n_other.item 1\n")
+    d = host.read_structure_from_path(str(p)).soa()
+    assert d["aa"].tolist() == [0, 7, 15]                       # second model ignored
+    assert d["serial"].tolist() == [10, 2, 12]                  # auth_seq_id, `.` falls back to label_seq_id
+    # the atoms' chains are A, Z (a two-character auth chain falls back to label_asym_id), B; a residue takes the chain of
+    # the atom that triggered its flush (quirk Q2), the last one its own
+    assert d["chain"].tolist() == [ord("Z"), ord("B"), ord("B")]
+    assert d["b_factor"].tolist() == [1.0, 42.5, 42.5]          # `?` -> default 1.0; same flush quirk as the chain
+    assert d["cb_valid"].tolist() == [1, 1, 1] and abs(d["ca_xyz"][2][0] - (1.458 + 7.6)) < 1e-4

@@ -9,7 +9,7 @@
 //   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
 //   ids                     src/controller/mode.rs:70-125
 //
-// Not here (fails loudly): `benchmark` / `analyze`, --web, --partial-fit, Foldcomp databases.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
+// Not here (fails loudly): `benchmark` / `analyze`, --web, Foldcomp databases.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
 #include <dirent.h>
 #include <limits.h>
 #include <sys/stat.h>
@@ -192,7 +192,7 @@ const char *HELP =
     "        [--connected-node-ratio X] [--num-residue N] [--plddt X] [--rmsd X] [--top N] [--sampling-count N]\n"
     "        [--sampling-ratio X] [--freq-filter X] [--length-penalty X] [--per-structure|--per-match] [--skip-match]\n"
     "        [--skip-ca-match] [--serial-index] [--sort-by KEY[:asc|desc],..] [--format-output COL,..] [--header]\n"
-    "        [--tm-score X] [--gdt-ts X] [--gdt-ha X] [--chamfer X] [--hausdorff X] [--superpose] [-o FILE] [-v]\n"
+    "        [--tm-score X] [--gdt-ts X] [--gdt-ha X] [--chamfer X] [--hausdorff X] [--superpose] [--partial-fit] [-o FILE] [-v]\n"
     "        match columns: qid tid nid db_key node_count idf rmsd e_value u_matrix t_vector matching_residues\n"
     "                       matching_coordinates query_residues tm_score gdt_ts gdt_ha chamfer_distance hausdorff_distance\n";
 
@@ -448,7 +448,6 @@ std::string rust_sci4(double v) {
 
 int cmd_query(Args &a) {
     a.reject({"--web"}, "the web output mode is not implemented");
-    a.reject({"--partial-fit"}, "LMS-QCP partial fit is outside the ported path");
     const bool superpose = a.flag({"--superpose"});
     // MatchFilter cutoffs over the similarity metrics (src/cli/workflows/query_pdb.rs:80-83, filter.rs:217-236); 0 = off
     const float tm_cut = (float)a.num({"--tm-score"}, 0.0), gdt_ts_cut = (float)a.num({"--gdt-ts"}, 0.0),
@@ -484,6 +483,7 @@ int cmd_query(Args &a) {
     bool per_structure = a.flag({"--per-structure"});
     const bool per_match = a.flag({"--per-match"});
     sp.skip_ca_match = a.flag({"--skip-ca-match"}) ? 1 : 0;
+    sp.partial_fit = a.flag({"--partial-fit"}) ? 1 : 0; // LMS-QCP superposition of matches above three residues
     const bool header = a.flag({"--header"});
     const bool serial_query = a.flag({"--serial-index"});
     const std::string output = a.str({"-o", "--output"}, "");

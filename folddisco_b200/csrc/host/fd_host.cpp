@@ -2275,8 +2275,10 @@ int verify_general(fd_ctx *ctx, const fdh_queries *qs, uint32_t q_begin, uint32_
     }
     R->h2d_bytes += 4ull * (q_ca.size() + q_cb.size()) + 4ull * (a_nid.size() + a_off.size() + pq_.size() + pt_.size());
     R->d2h_bytes += 52ull * n_align;
-    if (fd_kabsch_store_batch(ctx, q_ca.data(), q_cb.data(), q_res_off[nq], a_nid.data(), a_off.data(), n_align,
-                              pq_.data(), pt_.data(), rmsd.data(), U.data(), T.data()) != FD_OK) {
+    // `--partial-fit`: LMS-QCP above three matched residues (retrieve.rs:773-814), else Kabsch
+    if ((p->partial_fit ? fd_lmsqcp_store_batch : fd_kabsch_store_batch)(ctx, q_ca.data(), q_cb.data(), q_res_off[nq], a_nid.data(),
+                                                                         a_off.data(), n_align, pq_.data(), pt_.data(),
+                                                                         rmsd.data(), U.data(), T.data()) != FD_OK) {
         set_err(fd_last_error(ctx));
         return FD_ERR_CUDA;
     }
@@ -2440,13 +2442,16 @@ static fdh_results *search_impl(fd_ctx *ctx, const fdh_queries *qs, const fdh_se
                 cand_n[k] = hits[k].nid;
             }
         // --- K6: verification on the device; candidates beyond its limits come back flagged ---
-        if (p->verify_mode != 1 && fdg::ht_default_route(&qs->p.hash)) {
+        // the fused kernels superpose with Kabsch only: a partial-fit search takes the general path (K4 -> host graph
+        // step -> fd_lmsqcp_store_batch)
+        const bool general_only = p->verify_mode == 1 || !fdg::ht_default_route(&qs->p.hash) || p->partial_fit != 0;
+        if (!general_only) {
             if (ensure_verify_prepared(ctx, qs) != FD_OK) return fail();
             R->h2d_bytes += fd_verify_prepared_bytes(qs->vprep) * nq / std::max<size_t>(1, qs->q.size());
         }
         uint64_t n_recs = 0;
         // other encodings / `--multiple-bins`: the fused kernels and the pair table are PDBTrRosetta single-bin only
-        if (p->verify_mode == 1 || !fdg::ht_default_route(&qs->p.hash)) { // general path for everything
+        if (general_only) { // general path for everything
             all_general.assign(n_cand, 1);
             lanes.resize(1);
             lanes[0].c1 = n_cand;

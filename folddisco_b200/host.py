@@ -26,12 +26,12 @@ class SearchParams(C.Structure):
                 ("max_matching_node_count", C.c_uint64), ("max_matching_node_ratio", C.c_float),
                 ("rmsd_cutoff", C.c_float), ("connected_node_count", C.c_uint64), ("connected_node_ratio", C.c_float),
                 ("skip_ca_match", C.c_int), ("host_threads", C.c_int), ("verify_mode", C.c_int),
-                ("want_metrics", C.c_int)]
+                ("want_metrics", C.c_int), ("partial_fit", C.c_int)]
 
     def __init__(self, top_n=UINT64_MAX, ca_dist_cutoff=1.0, skip_match=False, host_threads=0, verify_mode=0,
-                 want_metrics=False, **prefilter):
+                 want_metrics=False, partial_fit=False, **prefilter):
         super().__init__(PrefilterParams(top_n=top_n, **prefilter), ca_dist_cutoff, int(skip_match), 0, 0.0, 0.0, 0,
-                         0.0, 0, host_threads, verify_mode, int(want_metrics))
+                         0.0, 0, host_threads, verify_mode, int(want_metrics), int(partial_fit))
 
 
 STRUCT_ROW = np.dtype([("nid", np.uint32), ("total_match_count", np.uint32), ("node_count", np.uint32),

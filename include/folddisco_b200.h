@@ -375,6 +375,19 @@ int fd_kabsch_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_
                           const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
                           const uint32_t *pair_qres, const uint32_t *pair_tres, float *rmsd, float *U9, float *t3);
 
+/* `--partial-fit`: rmsd_with_calpha_and_rottran with lms = true (src/controller/retrieve.rs:773-814) for a
+ * batch.  Same arguments as fd_kabsch_store_batch.  An alignment of more than three residues is superposed by LMS-QCP
+ * (LmsQcpSuperimposer::run with its default parameters, src/structure/lms_qcp.rs:28-40, 91-236: 500 deterministic seed
+ * triples scored by their median residual, forward growth of the inlier core up to 2 A) and rmsd[a] is the RMSD over the
+ * core; three residues or fewer use Kabsch.  At most 64 residues per alignment (FD_ERR_LIMIT). */
+int fd_lmsqcp_store_batch(fd_ctx *ctx, const float *q_ca_xyz, const float *q_cb_xyz, uint64_t n_q_res,
+                          const uint32_t *align_nid, const uint32_t *pair_offsets, uint32_t n_align,
+                          const uint32_t *pair_qres, const uint32_t *pair_tres, float *rmsd, float *U9, float *t3);
+/* LMS-QCP by the host build of csrc/fd_lmsqcp.cuh over explicit point lists (parity probe, no device): ref = query
+ * points, mov = target points; 0, or -1 when n_points is outside 3 .. 128 */
+int fd_lmsqcp_host(const float *ref_xyz, const float *mov_xyz, uint32_t n_points, float *U9, float *t3,
+                   float *rms_inliers);
+
 /* Similarity metrics of verified matches: StructureSimilarityMetrics::calculate_all as
  * rmsd_with_calpha_and_rottran evaluates it for every match (src/controller/retrieve.rs:776-831,
  * src/structure/metrics.rs:44-345; the columns tm_score, gdt_ts, gdt_ha, chamfer_distance, hausdorff_distance of

@@ -163,6 +163,9 @@ typedef struct {
      * hausdorff_distance; src/controller/retrieve.rs:776-831, src/structure/metrics.rs) from fd_metrics_store_batch,
      * and the residue indices behind the matched residues are kept (fdh_results_metrics / _residue_index) */
     int want_metrics;
+    /* --partial-fit: matches of more than three residues are superposed by LMS-QCP (fd_lmsqcp_store_batch) and report
+     * the RMSD of the inlier core (src/controller/retrieve.rs:773-814); the search then verifies through the general path */
+    int partial_fit;
 } fdh_search_params;
 
 /* query_pdb.rs:348-452 for the whole batch: count_query -> filter/sort/top -> retrieval -> Kabsch ->

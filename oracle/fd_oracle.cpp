@@ -1465,6 +1465,233 @@ void similarity_metrics(const std::vector<std::array<float, 3>> &ref, const std:
     out[4] = hd;
 }
 
+// ---------------------------------------------------------------------------------------------
+// LMS-QCP partial superposition (src/structure/lms_qcp.rs), default parameters (:28-40)
+// ---------------------------------------------------------------------------------------------
+int g_partial_fit = 0; // fdo_set_partial_fit: retrieve() superposes like `--partial-fit`
+
+struct LmsStats { // RunningStats :245-287
+    size_t n = 0;
+    double sum_x[3] = {0, 0, 0}, sum_y[3] = {0, 0, 0}, sxx = 0, syy = 0, syx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    void add(const std::array<float, 3> &m, const std::array<float, 3> &r) {
+        double x[3] = {m[0], m[1], m[2]}, y[3] = {r[0], r[1], r[2]};
+        n += 1;
+        sum_x[0] += x[0]; sum_x[1] += x[1]; sum_x[2] += x[2];
+        sum_y[0] += y[0]; sum_y[1] += y[1]; sum_y[2] += y[2];
+        sxx += x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+        syy += y[0] * y[0] + y[1] * y[1] + y[2] * y[2];
+        syx[0][0] += y[0] * x[0]; syx[0][1] += y[0] * x[1]; syx[0][2] += y[0] * x[2];
+        syx[1][0] += y[1] * x[0]; syx[1][1] += y[1] * x[1]; syx[1][2] += y[1] * x[2];
+        syx[2][0] += y[2] * x[0]; syx[2][1] += y[2] * x[1]; syx[2][2] += y[2] * x[2];
+    }
+};
+struct RotTran {
+    float r[3][3], t[3];
+};
+// qcp_from_a_e0 :330-447
+void lms_qcp_rotation(const double a[3][3], double e0, double rot[3][3]) {
+    double sxx = a[0][0], sxy = a[0][1], sxz = a[0][2], syx = a[1][0], syy = a[1][1], syz = a[1][2], szx = a[2][0], szy = a[2][1], szz = a[2][2];
+    double sxx2 = sxx * sxx, syy2 = syy * syy, szz2 = szz * szz, sxy2 = sxy * sxy, syz2 = syz * syz, sxz2 = sxz * sxz;
+    double syx2 = syx * syx, szy2 = szy * szy, szx2 = szx * szx;
+    double syz_szy_m_syy_szz2 = 2.0 * (syz * szy - syy * szz);
+    double sxx2_syy2_szz2_syz2_szy2 = syy2 + szz2 - sxx2 + syz2 + szy2;
+    double c2 = -2.0 * (sxx2 + syy2 + szz2 + sxy2 + syx2 + sxz2 + szx2 + syz2 + szy2);
+    double c1 = 8.0 * (sxx * syz * szy + syy * szx * sxz + szz * sxy * syx - sxx * syy * szz - syz * szx * sxy - szy * syx * sxz);
+    double sxz_p_szx = sxz + szx, syz_p_szy = syz + szy, sxy_p_syx = sxy + syx;
+    double syz_m_szy = syz - szy, sxz_m_szx = sxz - szx, sxy_m_syx = sxy - syx;
+    double sxx_p_syy = sxx + syy, sxx_m_syy = sxx - syy;
+    double sxy2_sxz2_syx2_szx2 = sxy2 + sxz2 - syx2 - szx2;
+    double neg_sxz_p_szx = -sxz_p_szx, neg_sxz_m_szx = -sxz_m_szx, neg_sxy_m_syx = -sxy_m_syx;
+    double sxx_p_syy_p_szz = sxx_p_syy + szz;
+    double c0 = sxy2_sxz2_syx2_szx2 * sxy2_sxz2_syx2_szx2
+        + (sxx2_syy2_szz2_syz2_szy2 + syz_szy_m_syy_szz2) * (sxx2_syy2_szz2_syz2_szy2 - syz_szy_m_syy_szz2)
+        + (neg_sxz_p_szx * (syz_m_szy) + (sxy_m_syx) * (sxx_m_syy - szz)) * (neg_sxz_m_szx * (syz_p_szy) + (sxy_m_syx) * (sxx_m_syy + szz))
+        + (neg_sxz_p_szx * (syz_p_szy) - (sxy_p_syx) * (sxx_p_syy - szz)) * (neg_sxz_m_szx * (syz_m_szy) - (sxy_p_syx) * sxx_p_syy_p_szz)
+        + ((sxy_p_syx) * (syz_p_szy) + (sxz_p_szx) * (sxx_m_syy + szz)) * (neg_sxy_m_syx * (syz_m_szy) + (sxz_p_szx) * sxx_p_syy_p_szz)
+        + ((sxy_p_syx) * (syz_m_szy) + (sxz_m_szx) * (sxx_m_syy - szz)) * (neg_sxy_m_syx * (syz_p_szy) + (sxz_m_szx) * (sxx_p_syy - szz));
+    double lam = std::max(e0, 0.0);
+    const double eps = 1e-15;
+    for (int it = 0; it < 10; it++) {
+        double x2 = lam * lam;
+        double b = (x2 + c2) * lam;
+        double aa = b + c1;
+        double f = aa * lam + c0;
+        double fp = 2.0 * x2 * lam + b + aa;
+        double delta = f / (fp + eps);
+        double nlam = std::fabs(lam - delta);
+        if (std::fabs(nlam - lam) < eps * nlam) {
+            lam = nlam;
+            break;
+        }
+        lam = nlam;
+    }
+    double a11 = sxx_p_syy + szz - lam, a12 = syz_m_szy, a13 = neg_sxz_m_szx, a14 = sxy_m_syx;
+    double a21 = a12, a22 = sxx_m_syy - szz - lam, a23 = sxy_p_syx, a24 = sxz_p_szx;
+    double a31 = a13, a32 = a23, a33 = syy - sxx - szz - lam, a34 = syz_p_szy;
+    double a41 = a14, a42 = a24, a43 = a34, a44 = szz - sxx_p_syy - lam;
+    double a3344_4334 = a33 * a44 - a43 * a34, a3244_4234 = a32 * a44 - a42 * a34, a3243_4233 = a32 * a43 - a42 * a33;
+    double a3143_4133 = a31 * a43 - a41 * a33, a3144_4134 = a31 * a44 - a41 * a34, a3142_4132 = a31 * a42 - a41 * a32;
+    double q1 = a22 * a3344_4334 - a23 * a3244_4234 + a24 * a3243_4233;
+    double q2 = -a21 * a3344_4334 + a23 * a3144_4134 - a24 * a3143_4133;
+    double q3 = a21 * a3244_4234 - a22 * a3144_4134 + a24 * a3142_4132;
+    double q4 = -a21 * a3243_4233 + a22 * a3143_4133 - a23 * a3142_4132;
+    double qsqr = q1 * q1 + q2 * q2 + q3 * q3 + q4 * q4;
+    if (qsqr < 1e-12) {
+        q1 = a12 * a3344_4334 - a13 * a3244_4234 + a14 * a3243_4233;
+        q2 = -a11 * a3344_4334 + a13 * a3144_4134 - a14 * a3143_4133;
+        q3 = a11 * a3244_4234 - a12 * a3144_4134 + a14 * a3142_4132;
+        q4 = -a11 * a3243_4233 + a12 * a3143_4133 - a13 * a3142_4132;
+        qsqr = q1 * q1 + q2 * q2 + q3 * q3 + q4 * q4;
+        if (qsqr < 1e-12) {
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) rot[r][c] = r == c ? 1.0 : 0.0;
+            return;
+        }
+    }
+    double inv = 1.0 / std::sqrt(qsqr);
+    q1 *= inv; q2 *= inv; q3 *= inv; q4 *= inv;
+    double a2 = q1 * q1, x2 = q2 * q2, y2 = q3 * q3, z2 = q4 * q4;
+    double xy = q2 * q3, az = q1 * q4, zx = q4 * q2, ay = q1 * q3, yz = q3 * q4, ax = q1 * q2;
+    rot[0][0] = a2 + x2 - y2 - z2; rot[0][1] = 2.0 * (xy + az);     rot[0][2] = 2.0 * (zx - ay);
+    rot[1][0] = 2.0 * (xy - az);     rot[1][1] = a2 - x2 + y2 - z2; rot[1][2] = 2.0 * (yz + ax);
+    rot[2][0] = 2.0 * (zx + ay);     rot[2][1] = 2.0 * (yz - ax);     rot[2][2] = a2 - x2 - y2 + z2;
+}
+// qcp_from_stats :294-326
+RotTran lms_qcp_from_stats(const LmsStats &st) {
+    double inv = 1.0 / (double)st.n;
+    double mux[3] = {st.sum_x[0] * inv, st.sum_x[1] * inv, st.sum_x[2] * inv};
+    double muy[3] = {st.sum_y[0] * inv, st.sum_y[1] * inv, st.sum_y[2] * inv};
+    double a[3][3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) a[r][c] = st.syx[r][c] - (double)st.n * (muy[r] * mux[c]);
+    double mu2x = mux[0] * mux[0] + mux[1] * mux[1] + mux[2] * mux[2];
+    double mu2y = muy[0] * muy[0] + muy[1] * muy[1] + muy[2] * muy[2];
+    double e0 = 0.5 * std::max((st.syy - (double)st.n * mu2y) + (st.sxx - (double)st.n * mu2x), 0.0);
+    double rot[3][3];
+    lms_qcp_rotation(a, e0, rot);
+    RotTran o;
+    for (int r = 0; r < 3; r++) {
+        double rx = rot[r][0] * mux[0] + rot[r][1] * mux[1] + rot[r][2] * mux[2];
+        o.t[r] = (float)(muy[r] - rx);
+        for (int c = 0; c < 3; c++) o.r[r][c] = (float)rot[r][c];
+    }
+    return o;
+}
+inline std::array<float, 3> lms_apply(const RotTran &q, const std::array<float, 3> &v) { // :479-499
+    std::array<float, 3> w;
+    for (int r = 0; r < 3; r++) w[r] = (q.r[r][0] * v[0] + q.r[r][1] * v[1] + q.r[r][2] * v[2]) + q.t[r];
+    return w;
+}
+inline float lms_dist2(const std::array<float, 3> &a, const std::array<float, 3> &b) {
+    float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    return dx * dx + dy * dy + dz * dz;
+}
+float lms_quantile(std::vector<float> &v, float q) { // select_quantile_squared :451-463
+    if (v.empty()) return 0.0f;
+    if (v.size() == 1) return v[0];
+    size_t pos = (size_t)std::round(q * (float)(v.size() - 1));
+    std::nth_element(v.begin(), v.begin() + pos, v.end());
+    return v[pos];
+}
+struct LmsRng { // SmallRng :543-564
+    uint64_t state;
+    explicit LmsRng(uint64_t seed) {
+        uint64_t x = seed + 0x9E3779B97F4A7C15ull;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        state = x ^ (x >> 31);
+    }
+    uint64_t next() {
+        uint64_t x = state;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        state = x;
+        return x;
+    }
+    size_t below(size_t end) { return (size_t)(next() % end); }
+};
+// LmsQcpSuperimposer::run + finish (:91-236).  mov is rotated onto ref.  Returns the inlier indices.
+std::vector<size_t> lms_qcp(const std::vector<std::array<float, 3>> &mov, const std::vector<std::array<float, 3>> &ref,
+                            float *U, float *T, float *rms_inliers) {
+    const size_t n = mov.size();
+    LmsRng rng(0xC0FFEE005EEDull);
+    size_t best_seed[3] = {0, 1, 2};
+    float best_q = INFINITY;
+    std::vector<float> res;
+    for (int trial = 0; trial < 500; trial++) {
+        size_t seed[3];
+        bool found = false;
+        for (int tries = 0; tries < 64 && !found; tries++) { // sample_three_non_collinear :509-526
+            size_t i = rng.below(n);
+            size_t j = rng.below(n);
+            if (j == i) j = (j + 1) % n;
+            size_t k = rng.below(n);
+            while (k == i || k == j) k = (k + 1) % n;
+            float v1[3] = {mov[j][0] - mov[i][0], mov[j][1] - mov[i][1], mov[j][2] - mov[i][2]};
+            float v2[3] = {mov[k][0] - mov[i][0], mov[k][1] - mov[i][1], mov[k][2] - mov[i][2]};
+            float cx = v1[1] * v2[2] - v1[2] * v2[1], cy = v1[2] * v2[0] - v1[0] * v2[2], cz = v1[0] * v2[1] - v1[1] * v2[0];
+            float area2 = cx * cx + cy * cy + cz * cz;
+            if (area2 > 1e-6f) {
+                seed[0] = i; seed[1] = j; seed[2] = k;
+                found = true;
+            }
+        }
+        if (!found) continue;
+        LmsStats st;
+        for (size_t s : seed) st.add(mov[s], ref[s]);
+        RotTran q = lms_qcp_from_stats(st);
+        res.clear();
+        for (size_t i = 0; i < n; i++) {
+            if (i == seed[0] || i == seed[1] || i == seed[2]) continue;
+            res.push_back(lms_dist2(lms_apply(q, mov[i]), ref[i]));
+        }
+        float qv = lms_quantile(res, 0.5f);
+        if (qv < best_q) {
+            best_q = qv;
+            best_seed[0] = seed[0]; best_seed[1] = seed[1]; best_seed[2] = seed[2];
+        }
+    }
+    const size_t min_core = std::max<size_t>(n / 2, 3);
+    const float r2_max = 2.0f * 2.0f;
+    LmsStats st;
+    std::vector<uint8_t> in_core(n, 0);
+    std::vector<size_t> core;
+    for (size_t s : best_seed) {
+        st.add(mov[s], ref[s]);
+        in_core[s] = 1;
+        core.push_back(s);
+    }
+    RotTran q;
+    for (;;) {
+        q = lms_qcp_from_stats(st);
+        bool any = false;
+        size_t best_i = 0;
+        float best_r2 = INFINITY;
+        for (size_t i = 0; i < n; i++) {
+            if (in_core[i]) continue;
+            float d2 = lms_dist2(lms_apply(q, mov[i]), ref[i]);
+            if (d2 < best_r2) {
+                best_r2 = d2;
+                best_i = i;
+                any = true;
+            }
+        }
+        if (!any) break;
+        if (core.size() >= min_core && best_r2 > r2_max) break;
+        st.add(mov[best_i], ref[best_i]);
+        in_core[best_i] = 1;
+        core.push_back(best_i);
+        if (core.size() == n) break;
+    }
+    float sum = 0.0f;
+    for (size_t i : core) sum += lms_dist2(lms_apply(q, mov[i]), ref[i]);
+    *rms_inliers = std::sqrt(sum / (float)core.size());
+    for (int r = 0; r < 3; r++) {
+        T[r] = q.t[r];
+        for (int c = 0; c < 3; c++) U[3 * r + c] = q.r[r][c];
+    }
+    return core;
+}
+
 // retrieve.rs:756-834 (no partial fit): CA,CB interleaved; target is rotated onto query.
 void rmsd_with_calpha(const fdo_compact &query, const fdo_compact &target, const std::vector<size_t> &qi,
                       const std::vector<size_t> &ti, MatchRow &row) {
@@ -1477,7 +1704,10 @@ void rmsd_with_calpha(const fdo_compact &query, const fdo_compact &target, const
         mov.push_back({target.ca[i].x, target.ca[i].y, target.ca[i].z});
         mov.push_back({target.cb[i].x, target.cb[i].y, target.cb[i].z});
     }
-    kabsch(mov, ref, row.U, row.T, &row.rmsd);
+    if (g_partial_fit && qi.size() > 3) // retrieve.rs:773-814: LMS-QCP above three residues, RMSD of the inlier core
+        lms_qcp(mov, ref, row.U, row.T, &row.rmsd);
+    else
+        kabsch(mov, ref, row.U, row.T, &row.rmsd);
     similarity_metrics(ref, mov, row.U, row.T, row.metrics); // retrieve.rs:819-830
     row.target_ca.clear();
     for (size_t i : ti) row.target_ca.push_back({target.ca[i].x, target.ca[i].y, target.ca[i].z});
@@ -2189,6 +2419,19 @@ void fdo_matches_get(const fdo_matches *r, int which, uint8_t *some, uint8_t *ch
         if (U) memcpy(U + 9 * k, rows[k].U, 9 * sizeof(float));
         if (t) memcpy(t + 3 * k, rows[k].T, 3 * sizeof(float));
     }
+}
+void fdo_set_partial_fit(int on) { g_partial_fit = on ? 1 : 0; }
+int64_t fdo_lms_qcp(int64_t n, const float *ref3, const float *mov3, float *U9, float *t3, float *rms_inliers,
+                    int64_t *inliers, int64_t cap) {
+    std::vector<std::array<float, 3>> ref((size_t)n), mov((size_t)n);
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            ref[i][k] = ref3[3 * i + k];
+            mov[i][k] = mov3[3 * i + k];
+        }
+    std::vector<size_t> core = lms_qcp(mov, ref, U9, t3, rms_inliers);
+    for (size_t k = 0; k < core.size() && (int64_t)k < cap; k++) inliers[k] = (int64_t)core[k];
+    return (int64_t)core.size();
 }
 void fdo_matches_get_metrics(const fdo_matches *r, int which, float *out5) {
     const auto &rows = which ? r->from_hash : r->result;

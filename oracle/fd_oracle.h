@@ -166,6 +166,13 @@ int64_t fdo_matches_num_query(const fdo_matches *r);
  * res_some/res_chain/res_serial are [n_matches * n_query]; U is 9 per match, t is 3. */
 void fdo_matches_get(const fdo_matches *r, int which, uint8_t *res_some, uint8_t *res_chain,
                      uint64_t *res_serial, float *rmsd, float *idf, float *U, float *t);
+/* `--partial-fit`: retrieve() superposes more than three matched residues with LMS-QCP (src/structure/lms_qcp.rs,
+ * default parameters; retrieve.rs:773-814) and reports the RMSD of the inlier core.  Process-wide, like the hash type. */
+void fdo_set_partial_fit(int on);
+/* LmsQcpSuperimposer::run over explicit point lists (n >= 3): mov is rotated onto ref; returns the size of the inlier
+ * core and writes at most cap of its indices in the order they joined */
+int64_t fdo_lms_qcp(int64_t n, const float *ref3, const float *mov3, float *U9, float *t3, float *rms_inliers,
+                    int64_t *inliers, int64_t cap);
 /* StructureSimilarityMetrics of every match (src/structure/metrics.rs:44-345, computed in
  * rmsd_with_calpha_and_rottran, retrieve.rs:776-831): out5[5 * k] = tm_score, gdt_ts, gdt_ha, chamfer, hausdorff */
 void fdo_matches_get_metrics(const fdo_matches *r, int which, float *out5);

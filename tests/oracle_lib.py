@@ -127,6 +127,8 @@ def lib():
     sig("fdo_matches_num_query", C.c_int64, [VP])
     sig("fdo_matches_get", None, [VP, C.c_int, u8p, u8p, u64p, f32p, f32p, f32p, f32p])
     sig("fdo_matches_get_metrics", None, [VP, C.c_int, f32p])
+    sig("fdo_set_partial_fit", None, [C.c_int])
+    sig("fdo_lms_qcp", C.c_int64, [C.c_int64, f32p, f32p, f32p, f32p, f32p, i64p, C.c_int64])
     sig("fdo_similarity_metrics", None, [C.c_int64, f32p, f32p, f32p, f32p, f32p])
     sig("fdo_matches_max_node_count", C.c_int64, [VP])
     sig("fdo_matches_min_rmsd", C.c_float, [VP])
@@ -453,6 +455,29 @@ def retrieve(qmap, target, nbin_dist=0, nbin_angle=0, cutoff=20.0, ca_cutoff=1.0
     d["edges"] = (ei[:ne], ej[:ne], eh[:ne])
     lib().fdo_matches_free(r)
     return d
+
+
+class partial_fit:
+    """with oracle_lib.partial_fit(): retrieve() superposes like `--partial-fit` (LMS-QCP above three residues)"""
+
+    def __enter__(self):
+        lib().fdo_set_partial_fit(1)
+        return self
+
+    def __exit__(self, *exc):
+        lib().fdo_set_partial_fit(0)
+        return False
+
+
+def lms_qcp(ref, mov):
+    """LmsQcpSuperimposer::run: -> (U[3,3], t[3], rms over the inlier core, inlier indices)"""
+    ref = np.ascontiguousarray(ref, np.float32).reshape(-1)
+    mov = np.ascontiguousarray(mov, np.float32).reshape(-1)
+    n = len(ref) // 3
+    U, t, rms = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(1, np.float32)
+    idx = np.zeros(n, np.int64)
+    k = lib().fdo_lms_qcp(n, ref, mov, U, t, rms, idx, n)
+    return U.reshape(3, 3), t, float(rms[0]), idx[:k]
 
 
 def similarity_metrics(ref, mov, U, t):

@@ -124,7 +124,7 @@ def test_query_without_store_parses_the_lookup_files(workdir):
 
 
 def test_unsupported_options_fail_loudly(workdir):
-    for extra in (["--partial-fit"], ["--web"]):
+    for extra in (["--web"],):
         r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"] + extra,
                            cwd=workdir, capture_output=True, text=True)
         assert r.returncode != 0 and "not supported" in r.stderr

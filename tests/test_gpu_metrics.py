@@ -78,6 +78,53 @@ def test_metrics_of_every_match_vs_oracle(env, verify_mode):
     assert abs(best[0] - 1) < 1e-4 and best[1] == 1 and best[2] == 1 and best[3] < 1e-3 and best[4] < 1e-3
 
 
+def test_partial_fit_vs_oracle():
+    """`--partial-fit` (retrieve.rs:773-814): matches above three residues are superposed by LMS-QCP on the device
+    (fd_lmsqcp_store_batch) and report the RMSD of the inlier core; three residues or fewer keep Kabsch.  Rows (residues,
+    idf, RMSD) against the oracle's LMS-QCP restatement on a synthetic database; metrics ride on the LMS superposition."""
+    import folddisco_b200 as fd
+    import parity
+    from folddisco_b200 import host, synth
+    ctx = fd.Context(0)
+    b = synth.generate(400, 21, mean_len=140.0, max_len=400)
+    comps = [O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"],
+                                serial=np.arange(1, len(p["aa"]) + 1, dtype=np.uint64)) for p in synth.split(b)]
+    store = host.Store()
+    store.add_soa(b)
+    ix = host.FolddiscoIndex.build(ctx, store)
+    ix.attach(ctx)
+    store.attach(ctx)
+    bufs = ix.buffers()
+    oix = O.Index.from_buffers(bufs.hashes, bufs.offsets, bufs.values)
+    nres, plddt = ix.lookup()
+    atoms = F.config1_atoms()
+    qb = host.QueryBatch(ix.params)
+    oqms = []
+    for path, q, _ in F.MOTIFS:
+        qb.add(host.CompactStructure.from_atoms(atoms[path]), q)
+        s = O.Structure.from_atoms(atoms[path])
+        ch, se, subs = O.parse_query_string(q, s.first_chain)
+        oqms.append(O.QueryMap(s.compact(), ch, se, subs, index=oix, total_structures=len(comps)))
+    qb.finalize(ctx)
+    res = host.search(ctx, qb, host.SearchParams(partial_fit=True, want_metrics=True), labels=store)
+    plain = host.search(ctx, qb, host.SearchParams(), labels=store)
+    n_rows = n_lms = 0
+    with O.partial_fit():
+        for k, om in enumerate(oqms):
+            hits, rows = parity.oracle_query(om, oix, comps, nres, plddt)
+            bad = parity.diff_query(res, k, len(om.indices()), hits, rows)
+            assert not bad, bad[:5]
+            n_rows += len(rows)
+            n_lms += sum(1 for r in rows if r[1] > 3)
+    assert n_rows > 20 and n_lms > 0
+    # the inlier RMSD never exceeds the full Kabsch RMSD of the same match by more than rounding
+    assert len(res.matches) == len(plain.matches)
+    big = res.matches["node_count"] > 3
+    assert big.any() and (res.matches["rmsd"][big] <= plain.matches["rmsd"][big] + 1e-3).all()
+    assert np.allclose(res.matches["rmsd"][~big], plain.matches["rmsd"][~big], atol=1e-5)
+    ctx.close()
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLI = os.path.join(ROOT, "folddisco_b200", "folddisco-b200")
 
@@ -152,3 +199,5 @@ def test_cli_metric_columns_sort_filter_and_superpose(env, workdir):
     assert np.allclose(ca, d["ca_xyz"][idx], atol=1e-3)
     partial = [r for r in sup[1:] if "_" in r[4]][0]  # an unmatched query residue contributes no coordinates
     assert len(partial[7].split(",")) == 3 * int(partial[1])
+    # --partial-fit on a three-residue motif: Kabsch (retrieve.rs:774-778), so the rows do not change
+    assert _run(workdir, "--partial-fit") == _run(workdir)

@@ -58,6 +58,7 @@ def parse_args():
                                                  "23 = Swiss-Prot scale, 538 200 structures, about two more minutes)")
     ap.add_argument("--pair-table", type=int, default=1, help="build the structure store's pair table (verification by "
                                                              "hash lookup instead of re-hashing candidates)")
+    ap.add_argument("--extras", type=int, default=1, help="secondary block: K1 per encoding, metrics / partial-fit step cost")
     ap.add_argument("--shipped", type=int, default=1, help="also time the five shipped motifs x 205 (secondary line)")
     return ap.parse_args()
 
@@ -544,6 +545,11 @@ def run_ours(args, rank, world, local_rank):
         if args.sweep:
             line["scan_vs_index_size"] = scan_sweep(args, ctx, db, qb, hbm, algo_bytes, scan_ms)
             index.attach(ctx)
+        if args.extras:
+            try:
+                line["widened_rows"] = widened_block(args, ctx, fd, host, db, store, index, timed)
+            except Exception as e:  # secondary measurements never cost the headline line
+                line["widened_rows"] = {"error": "%s: %s" % (type(e).__name__, e)}
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or 16 * cores
         qps, secs = orc.batch_qps(0, sample, args.top, cores)
@@ -569,6 +575,55 @@ def shipped_line(args, ctx, host, index, sp, timed):
     return {"queries_per_s": args.batch / (sum(ts) / n), "ms_per_step": 1e3 * sum(ts) / n,
             "scan_ms": (ctx.stage_ms("scan") - s0) / n, "posting_bytes_per_step": int(ctx.last_posting_bytes),
             "workload": "the five shipped motifs cycled to %d queries (BENCH_r01's batch)" % args.batch}
+
+
+def widened_block(args, ctx, fd, host, db, store, index, timed):
+    """the rows of SURVEY 8f built this round, measured on the bench's own data (secondary; N = 1 only):
+    K1 with every encoding of `--type` on the first structures of the database, and the per-step cost of the similarity
+    metrics (K7) and of the LMS-QCP partial fit on the timed query batch"""
+    out = {}
+    ro = db["row_offsets"].astype(np.int64)
+    m = min(3000, len(ro) - 1)
+    R = int(ro[m])
+    batch = fd.StructBatch(db["row_offsets"][:m + 1].astype(np.uint64), db["n_xyz"][:R], db["ca_xyz"][:R], db["cb_xyz"][:R],
+                           db["aa"][:R])
+    n = np.diff(ro[:m + 1])
+    pair_tests = int((n * (n - 1)).sum())
+    enc = {}
+    for name, t, mb in (("PDBTrRosetta (default, tuned route)", 0, ()), ("PDBMotif", 1, ()), ("PDBMotifSinCos", 2, ()),
+                        ("TrRosetta", 3, ()), ("PointPairFeature", 5, ()), ("TertiaryInteraction", 6, ()), ("Hybrid", 7, ()),
+                        ("FolddiscoAngle", 8, ()), ("FolddiscoDist", 9, ()),
+                        ("PDBTrRosetta --multiple-bins 16-4,8-3", 0, ((16, 4), (8, 3)))):
+        hp = fd.HashParams(0, 0, 20.0, t, multiple_bins=mb)
+        ctx.build_index(batch, hp)  # warm
+        h0 = ctx.stage_ms("hash")
+        ix = ctx.build_index(batch, hp)
+        k1 = ctx.stage_ms("hash") - h0
+        enc[name] = {"k1_hash_ms": k1, "pair_tests_per_s": pair_tests / (k1 * 1e-3) if k1 > 0 else None,
+                     "hashes": int(ix.count), "posting_bytes": int(ix.value_bytes)}
+    out["k1_encodings"] = {"structures": m, "pair_tests": pair_tests, "per_encoding": enc}
+    # similarity metrics and partial fit on a 128-query slice of the timed batch (one warm-up, one timed step each; the
+    # general path keeps every candidate's edge list on the host, so the slice bounds its memory)
+    nq = min(128, args.batch)
+    qb = make_query_batch(ctx, index, db, nq, 0)
+    out["queries"] = nq
+    base = host.SearchParams(top_n=args.top)
+    for key, sp in (("default", base), ("want_metrics", host.SearchParams(top_n=args.top, want_metrics=True)),
+                    ("partial_fit", host.SearchParams(top_n=args.top, partial_fit=True))):
+        if key == "default":
+            os.environ["FD_DEVICE_ROWS"] = "0"  # the same host row assembly as the two variants, for a like-for-like delta
+        host.search(ctx, qb, sp, labels=store)
+        m0, k0 = ctx.stage_ms("metrics"), ctx.stage_ms("kabsch")
+        res, dt, _ = timed(lambda: host.search(ctx, qb, sp, labels=store))
+        out[key] = {"ms_per_step": 1e3 * dt, "match_rows": int(len(res.matches)),
+                    "k7_metrics_device_ms": ctx.stage_ms("metrics") - m0, "k5_superpose_device_ms": ctx.stage_ms("kabsch") - k0}
+        os.environ.pop("FD_DEVICE_ROWS", None)
+        del res
+    del qb
+    out["note"] = ("default = a 128-query slice of the timed batch with host row assembly (FD_DEVICE_ROWS=0); want_metrics adds one "
+                   "fd_metrics_store_batch call (K7, thread per match); partial_fit verifies through the general path "
+                   "(K4 + host graph step) and superposes with LMS-QCP (k5_lmsqcp_store)")
+    return out
 
 
 def index_build_block(ctx, host, store, db, orc, build_s, hash_ms, post_ms, hbm):

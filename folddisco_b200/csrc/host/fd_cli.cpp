@@ -9,7 +9,7 @@
 //   TSV columns, precision  src/controller/result.rs:213-353, src/utils/formatter.rs:7, 117-183
 //   ids                     src/controller/mode.rs:70-125
 //
-// Not here (fails loudly): `benchmark` / `analyze`, --web, Foldcomp databases.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
+// Not here (fails loudly): `benchmark` / `analyze`, Foldcomp databases.  There is no CPU path: without a CUDA device fd_create fails and the command exits non-zero.
 #include <dirent.h>
 #include <limits.h>
 #include <sys/stat.h>
@@ -192,7 +192,7 @@ const char *HELP =
     "        [--connected-node-ratio X] [--num-residue N] [--plddt X] [--rmsd X] [--top N] [--sampling-count N]\n"
     "        [--sampling-ratio X] [--freq-filter X] [--length-penalty X] [--per-structure|--per-match] [--skip-match]\n"
     "        [--skip-ca-match] [--serial-index] [--sort-by KEY[:asc|desc],..] [--format-output COL,..] [--header]\n"
-    "        [--tm-score X] [--gdt-ts X] [--gdt-ha X] [--chamfer X] [--hausdorff X] [--superpose] [--partial-fit] [-o FILE] [-v]\n"
+    "        [--tm-score X] [--gdt-ts X] [--gdt-ha X] [--chamfer X] [--hausdorff X] [--superpose] [--web] [--partial-fit] [-o FILE] [-v]\n"
     "        match columns: qid tid nid db_key node_count idf rmsd e_value u_matrix t_vector matching_residues\n"
     "                       matching_coordinates query_residues tm_score gdt_ts gdt_ha chamfer_distance hausdorff_distance\n";
 
@@ -447,8 +447,10 @@ std::string rust_sci4(double v) {
 }
 
 int cmd_query(Args &a) {
-    a.reject({"--web"}, "the web output mode is not implemented");
-    const bool superpose = a.flag({"--superpose"});
+    // QueryMode::Web (controller/mode.rs:230-246, query_pdb.rs:481-493): per-match rows with the superposition columns,
+    // at most MAX_NUM_LINES_FOR_WEB = 1000 of them; takes precedence over --skip-match / --per-structure
+    const bool web = a.flag({"--web"});
+    const bool superpose = a.flag({"--superpose"}) || web;
     // MatchFilter cutoffs over the similarity metrics (src/cli/workflows/query_pdb.rs:80-83, filter.rs:217-236); 0 = off
     const float tm_cut = (float)a.num({"--tm-score"}, 0.0), gdt_ts_cut = (float)a.num({"--gdt-ts"}, 0.0),
                 gdt_ha_cut = (float)a.num({"--gdt-ha"}, 0.0), chamfer_cut = (float)a.num({"--chamfer"}, 0.0),
@@ -499,6 +501,7 @@ int cmd_query(Args &a) {
     if (per_structure && per_match)
         die("Cannot print output per structure and per match at the same time. Use either --per-structure or --per-match");
     if (sp.skip_match) per_structure = true; // QueryMode::SkipMatch prints structure rows (query_pdb.rs:186-203)
+    if (web) per_structure = false;
     const SortSpec sort_spec = parse_sort(sort_by, per_structure); // query_pdb.rs:212-245
     std::vector<std::string> columns;                              // --format-output (query_pdb.rs:248-254)
     if (has_format)
@@ -754,7 +757,8 @@ int cmd_query(Args &a) {
                     return false;
                 });
             }
-            if (order.size() > sp.prefilter.top_n) order.resize(sp.prefilter.top_n); // result.rs:466-471
+            const uint64_t print_limit = web ? 1000 : sp.prefilter.top_n; // result.rs:466-471, query_pdb.rs:489
+            if (order.size() > print_limit) order.resize(print_limit);
             // MATCH_RESULT_DEFAULT_COLUMNS (result.rs:330-338)
             // MATCH_RESULT_SUPERPOSE_COLUMNS with --superpose (result.rs:341-352, :476-484)
             std::vector<std::string> cols =

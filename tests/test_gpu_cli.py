@@ -124,10 +124,11 @@ def test_query_without_store_parses_the_lookup_files(workdir):
 
 
 def test_unsupported_options_fail_loudly(workdir):
-    for extra in (["--web"],):
-        r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine"] + extra,
-                           cwd=workdir, capture_output=True, text=True)
-        assert r.returncode != 0 and "not supported" in r.stderr
+    r = subprocess.run([CLI, "query", "-p", "query/4CHA.pdb", "-q", "B57,B102,C195", "-i", "idx/serine", "--mmap-on-disk"],
+                       cwd=workdir, capture_output=True, text=True)
+    assert r.returncode != 0
+    r = subprocess.run([CLI, "benchmark", "-r", "x", "-a", "y"], cwd=workdir, capture_output=True, text=True)
+    assert r.returncode != 0 and "outside the ported path" in r.stderr
     r = subprocess.run([CLI, "index", "-p", "data/serine_peptidases", "-i", "idx/x", "-y", "nonsense"], cwd=workdir,
                        capture_output=True, text=True)
     assert r.returncode != 0 and "unknown hash type" in r.stderr

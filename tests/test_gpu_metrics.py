@@ -201,5 +201,7 @@ def test_cli_metric_columns_sort_filter_and_superpose(env, workdir):
     assert np.allclose(ca, d["ca_xyz"][idx], atol=1e-3)
     partial = [r for r in sup[1:] if "_" in r[4]][0]  # an unmatched query residue contributes no coordinates
     assert len(partial[7].split(",")) == 3 * int(partial[1])
+    # --web = per-match rows with the superposition columns (QueryMode::Web, query_pdb.rs:481-493)
+    assert _run(workdir, "--web", "--header") == sup
     # --partial-fit on a three-residue motif: Kabsch (retrieve.rs:774-778), so the rows do not change
     assert _run(workdir, "--partial-fit") == _run(workdir)

@@ -45,6 +45,9 @@ struct RQDesc { // per query
     uint32_t aad_begin, n_aad;
     uint32_t aa1_mask, aa2_mask;
     uint32_t use_prefilter;
+    // queries with more than K4_MAX_AADIST observed pairs (whole-structure queries, query.rs:226-233): their entries stay
+    // in global memory grouped by amino-acid pair, run_begin indexes the 401-entry run table; 0xFFFFFFFF otherwise
+    uint32_t run_begin;
 };
 
 struct AADist {
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(K4_THREADS)
                        const uint32_t *cand_query, const uint32_t *cand_nid, uint32_t n_cand, fdg::HashParams hp,
                        float ca_cutoff, unsigned long long *n_edges, unsigned long long *n_pairs,
                        uint64_t *edge_keys, uint32_t *edge_hash, uint64_t *pair_keys, uint32_t *pair_q,
-                       fdg::TypedParams tp = fdg::TypedParams()) {
+                       fdg::TypedParams tp = fdg::TypedParams(), const uint32_t *aad_runs = nullptr) {
     __shared__ uint16_t list1[K4_LIST_CAP], list2[K4_LIST_CAP];
     __shared__ uint32_t n1, n2;
     __shared__ uint32_t q_ij[K4_CHUNK];
@@ -136,7 +139,11 @@ __global__ void __launch_bounds__(K4_THREADS)
         n2 = 0;
         q_n = 0;
     }
-    for (uint32_t k = threadIdx.x; k < Q.n_aad; k += K4_THREADS) aad[k] = q_aad[Q.aad_begin + k];
+    const bool big = Q.run_begin != 0xFFFFFFFFu; // entries read from global memory through the amino-acid-pair runs
+    const AADist *gaad = q_aad + Q.aad_begin;
+    const uint32_t *runs = big ? aad_runs + Q.run_begin : nullptr;
+    if (!big)
+        for (uint32_t k = threadIdx.x; k < Q.n_aad; k += K4_THREADS) aad[k] = q_aad[Q.aad_begin + k];
     __syncthreads();
     if (Q.n_hashes == 0 || Q.n_aad == 0) return;
 
@@ -214,11 +221,20 @@ __global__ void __launch_bounds__(K4_THREADS)
                     d = fdg::dist(ld3(st.ca_xyz, base + i), ld3(st.ca_xyz, base + j));
                     if (d <= hp.dist_cutoff) {
                         const uint8_t ci = ai == 255 ? 255 : (ai & 0x7Fu), cj = aj == 255 ? 255 : (aj & 0x7Fu);
-                        for (uint32_t k = 0; k < Q.n_aad; k++)
-                            if (aad[k].aa1 == ci && aad[k].aa2 == cj && fabsf(d - aad[k].dist) < ca_cutoff) {
-                                pass = true;
-                                break;
-                            }
+                        if (big) {
+                            if (ci < 20 && cj < 20)
+                                for (uint32_t k = runs[ci * 20u + cj]; k < runs[ci * 20u + cj + 1]; k++)
+                                    if (fabsf(d - gaad[k].dist) < ca_cutoff) {
+                                        pass = true;
+                                        break;
+                                    }
+                        } else {
+                            for (uint32_t k = 0; k < Q.n_aad; k++)
+                                if (aad[k].aa1 == ci && aad[k].aa2 == cj && fabsf(d - aad[k].dist) < ca_cutoff) {
+                                    pass = true;
+                                    break;
+                                }
+                        }
                     }
                 }
             }
@@ -258,16 +274,21 @@ __global__ void __launch_bounds__(K4_THREADS)
                 if (is_feature) {
                     const uint8_t ci = ai & 0x7Fu, cj = aj & 0x7Fu;
                     uint32_t np = 0;
-                    for (uint32_t e = 0; e < Q.n_aad; e++)
-                        if (aad[e].aa1 == ci && aad[e].aa2 == cj && fabsf(d - aad[e].dist) < ca_cutoff) {
+                    const uint32_t e0 = big ? ((ci < 20 && cj < 20) ? runs[ci * 20u + cj] : 0u) : 0u;
+                    const uint32_t e1 = big ? ((ci < 20 && cj < 20) ? runs[ci * 20u + cj + 1] : 0u) : Q.n_aad;
+                    for (uint32_t e = e0; e < e1; e++) {
+                        const AADist a = big ? gaad[e] : aad[e];
+                        if (a.aa1 == ci && a.aa2 == cj && fabsf(d - a.dist) < ca_cutoff) {
                             if (MODE == 1) {
                                 const unsigned long long pos = atomicAdd(n_pairs, 1ull);
+                                // (the low byte only orders the records of one residue pair; consumers count them)
                                 pair_keys[pos] = ((uint64_t)c << 40) | ((uint64_t)i << 24) | ((uint64_t)j << 8) |
-                                                 (uint64_t)(aad[e].k & 0xffu);
-                                pair_q[pos] = aad[e].q_index;
+                                                 (uint64_t)(a.k & 0xffu);
+                                pair_q[pos] = a.q_index;
                             }
                             np++;
                         }
+                    }
                     if (MODE == 0 && np) atomicAdd(n_pairs, (unsigned long long)np);
                     float f[9];
                     if (TYPED) {
@@ -406,15 +427,13 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     *out_n_edges = 0;
     *out_n_pairs = 0;
     std::vector<RQDesc> descs(nq);
-    std::vector<uint32_t> f_hash;
+    std::vector<uint32_t> f_hash, f_runs;
     std::vector<AADist> f_aad;
     for (uint32_t q = 0; q < nq; q++) {
         const fd_retrieval_query &Q = queries[q];
-        if (Q.n_aa_dist > K4_MAX_AADIST)
-            return fd_fail(ctx, FD_ERR_LIMIT, "more than 512 observed query pairs: verification of whole-structure queries is not available (search them with skip_match / --skip-match; count_query handles them)");
         // no amino-acid prefilter for the encodings without amino-acid fields (retrieve.rs:385-390)
         RQDesc d{(uint32_t)f_hash.size(), Q.n_hashes, (uint32_t)f_aad.size(), Q.n_aa_dist, 0, 0,
-                 Q.n_hashes <= PREFILTER_AA_SKIPPING_SIZE && fdg::ht_has_aa_index(tp.type) ? 1u : 0u};
+                 Q.n_hashes <= PREFILTER_AA_SKIPPING_SIZE && fdg::ht_has_aa_index(tp.type) ? 1u : 0u, 0xFFFFFFFFu};
         for (uint32_t k = 0; k < Q.n_hashes; k++) {
             if (k && Q.hashes_sorted[k] <= Q.hashes_sorted[k - 1])
                 return fd_fail(ctx, FD_ERR_ARG, "fd_retrieval_query: hashes_sorted must be strictly ascending");
@@ -424,11 +443,31 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
             d.aa1_mask |= 1u << (a1 & 31u);
             d.aa2_mask |= 1u << (a2 & 31u);
         }
-        for (uint32_t k = 0; k < Q.n_aa_dist; k++) {
-            uint16_t pos = 0;
-            for (uint32_t m = 0; m < k; m++)
-                if (Q.aa1[m] == Q.aa1[k] && Q.aa2[m] == Q.aa2[k]) pos++;
-            f_aad.push_back(AADist{Q.aa1[k], Q.aa2[k], pos, Q.ca_dist[k], Q.q_index[k]});
+        if (Q.n_aa_dist <= (uint32_t)K4_MAX_AADIST) {
+            for (uint32_t k = 0; k < Q.n_aa_dist; k++) {
+                uint16_t pos = 0;
+                for (uint32_t m = 0; m < k; m++)
+                    if (Q.aa1[m] == Q.aa1[k] && Q.aa2[m] == Q.aa2[k]) pos++;
+                f_aad.push_back(AADist{Q.aa1[k], Q.aa2[k], pos, Q.ca_dist[k], Q.q_index[k]});
+            }
+        } else { // stable counting sort by amino-acid pair; k = position inside the pair's list, as above
+            std::vector<uint32_t> start(401, 0);
+            for (uint32_t k = 0; k < Q.n_aa_dist; k++) {
+                if (Q.aa1[k] >= 20 || Q.aa2[k] >= 20)
+                    return fd_fail(ctx, FD_ERR_ARG, "fd_retrieval_query: amino-acid code out of range");
+                start[Q.aa1[k] * 20u + Q.aa2[k] + 1]++;
+            }
+            for (int b = 0; b < 400; b++) start[b + 1] += start[b];
+            d.run_begin = (uint32_t)f_runs.size();
+            f_runs.insert(f_runs.end(), start.begin(), start.end());
+            const size_t base = f_aad.size();
+            f_aad.resize(base + Q.n_aa_dist);
+            std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+            for (uint32_t k = 0; k < Q.n_aa_dist; k++) {
+                const uint32_t b = Q.aa1[k] * 20u + Q.aa2[k];
+                f_aad[base + cur[b]] = AADist{Q.aa1[k], Q.aa2[k], (uint16_t)((cur[b] - start[b]) & 0xffffu), Q.ca_dist[k], Q.q_index[k]};
+                cur[b]++;
+            }
         }
         descs[q] = d;
     }
@@ -443,13 +482,16 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     }
     cudaStream_t s = ctx->stream;
     DevBuf<RQDesc> d_desc;
-    DevBuf<uint32_t> d_hash, d_cq, d_cn, d_edge_hash, d_pair_q;
+    DevBuf<uint32_t> d_hash, d_cq, d_cn, d_edge_hash, d_pair_q, d_runs;
     DevBuf<AADist> d_aad;
     DevBuf<unsigned long long> d_cnt;
     DevBuf<uint64_t> d_edge_keys, d_pair_keys;
     FD_CUDA(ctx, d_desc.alloc(nq));
     FD_CUDA(ctx, d_hash.alloc(f_hash.size()));
     FD_CUDA(ctx, d_aad.alloc(f_aad.size()));
+    FD_CUDA(ctx, d_runs.alloc(f_runs.size()));
+    if (!f_runs.empty())
+        FD_CUDA(ctx, cudaMemcpyAsync(d_runs.p, f_runs.data(), f_runs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     FD_CUDA(ctx, d_cq.alloc(n_cand));
     FD_CUDA(ctx, d_cn.alloc(n_cand));
     FD_CUDA(ctx, d_cnt.alloc(2));
@@ -470,11 +512,11 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     if (typed)
         FD_LAUNCH(ctx, (k4_candidate_edges<0, true>), k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
                   d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, (uint64_t *)nullptr,
-                  (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, tp);
+                  (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, tp, d_runs.p);
     else
         FD_LAUNCH(ctx, k4_candidate_edges<0>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p, d_cq.p,
                   d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, (uint64_t *)nullptr,
-                  (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr);
+                  (uint32_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, tp, d_runs.p);
     unsigned long long cnt[2] = {0, 0};
     FD_CUDA(ctx, cudaMemcpyAsync(cnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, s));
     FD_CUDA(ctx, cudaStreamSynchronize(s));
@@ -487,11 +529,11 @@ int fd_candidate_edges_batch(fd_ctx *ctx, const fd_retrieval_query *queries, uin
     if ((ne || np) && typed)
         FD_LAUNCH(ctx, (k4_candidate_edges<1, true>), k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p,
                   d_cq.p, d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, d_edge_keys.p,
-                  d_edge_hash.p, d_pair_keys.p, d_pair_q.p, tp);
+                  d_edge_hash.p, d_pair_keys.p, d_pair_q.p, tp, d_runs.p);
     else if (ne || np)
         FD_LAUNCH(ctx, k4_candidate_edges<1>, k4_grid, K4_THREADS, 0, sv, d_desc.p, d_hash.p, d_aad.p,
                   d_cq.p, d_cn.p, (uint32_t)n_cand, hp, ca_dist_cutoff, d_cnt.p, d_cnt.p + 1, d_edge_keys.p,
-                  d_edge_hash.p, d_pair_keys.p, d_pair_q.p);
+                  d_edge_hash.p, d_pair_keys.p, d_pair_q.p, tp, d_runs.p);
     FD_TRY(sort_pairs_u64_u32(ctx, d_edge_keys, d_edge_hash, ne, 60));
     FD_TRY(sort_pairs_u64_u32(ctx, d_pair_keys, d_pair_q, np, 64));
     DevBuf<fd_cand_edge> d_oe;

@@ -544,10 +544,8 @@ int cmd_query(Args &a) {
     if (jobs.empty()) die("no queries");
     for (auto &j : jobs) {
         if (j.pdb.empty()) die("query needs -p PDB (or a query file)");
-        // an empty -q makes every residue a query residue (query.rs:226-233): count_query handles it; its verification
-        // is not available, so the search must be a --skip-match one
-        if (j.residues.empty() && !sp.skip_match)
-            die("whole-structure queries (empty -q) need --skip-match: their verification is not available in folddisco-b200");
+        // (an empty -q makes every residue a query residue, query.rs:226-233: count_query answers it through its
+        // global-memory path, the verification through the general path)
     }
 
     fd_ctx *ctx = nullptr;

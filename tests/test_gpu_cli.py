@@ -231,8 +231,8 @@ def test_stale_store_is_refused_and_no_store_removes_it(workdir):
 
 def test_whole_structure_query_with_skip_match(workdir):
     """no -q: every residue of the query structure is a query residue (query.rs:226-233).  count_query answers it
-    through its global-memory path; verification of such a query is refused with a message, so the search needs
-    --skip-match.  The five structures come back with the oracle's idf values in the oracle's order."""
+    through its global-memory path: with --skip-match the five structures come back with the oracle's idf values in
+    the oracle's order; without it the candidates are verified through the general path."""
     rows = run(workdir, "query", "-p", "query/1G2F.pdb", "-i", "idx/serine", "--skip-match")
     assert 1 <= len(rows) <= 5 and all(r[9] == "NA" for r in rows)
     atoms = F.config1_atoms()
@@ -251,5 +251,36 @@ def test_whole_structure_query_with_skip_match(workdir):
         assert abs(got[k] - exp[k]) <= 1e-4 * max(1.0, exp[k]) + 5e-5  # printed with four decimals
     idfs = [float(r[1]) for r in rows]
     assert idfs == sorted(idfs, reverse=True)
-    bad = subprocess.run([CLI, "query", "-p", "query/1G2F.pdb", "-i", "idx/serine"], cwd=workdir, capture_output=True, text=True)
-    assert bad.returncode != 0 and "whole-structure" in bad.stderr
+
+
+def test_whole_structure_query_verification(workdir):
+    """no -q and no --skip-match: the candidates of a whole-chain query are verified through the general path (K4 with the
+    query's ~5 000 observed pairs in global memory, grouped by amino-acid pair -> host graph step -> K5); rows equal the
+    oracle's retrieval of the same query, with matches of up to ~57 residues (retrieve.rs:364-552)."""
+    atoms = F.config1_atoms()
+    names = F.serine_names()
+    comps = [O.Structure.from_atoms(atoms[n]).compact() for n in names]
+    oix = O.Index.build(comps)
+    s = O.Structure.from_atoms(atoms["query/1G2F.pdb"])
+    om = O.QueryMap(s.compact(), *O.parse_query_string("", s.first_chain), index=oix, total_structures=len(comps))
+    nres = np.array([c.nres for c in comps], np.uint64)
+    plddt = np.array([c.avg_plddt for c in comps], np.float32)
+    want = O.count_query(om, oix, nres, plddt, O.CountParams.defaults(len(om.indices())))
+    rows = run(workdir, "query", "-p", "query/1G2F.pdb", "-i", "idx/serine", "--format-output",
+               "tid,node_count,idf,rmsd,matching_residues")
+    hit_ids = [int(n) for n in want["nid"]]
+    want = []
+    for nid in hit_ids:
+        m = O.retrieve(om, comps[nid])
+        for k in range(len(m["rmsd"])):
+            want.append((names[nid], int(m["some"][k].sum()), float(m["idf"][k]), float(m["rmsd"][k]),
+                         O.residues_to_string(m["some"][k], m["chain"][k], m["serial"][k])))
+    assert len(rows) == len(want) > 100
+    assert sorted((r[0], int(r[1]), r[4]) for r in rows) == sorted((w[0], w[1], w[4]) for w in want)
+    assert max(int(r[1]) for r in rows) > 16  # more matched residues than the fused kernels hold
+    by_key = {}
+    for w in want:
+        by_key.setdefault((w[0], w[4]), []).append(w)
+    for r in rows:
+        w = min(by_key[(r[0], r[4])], key=lambda e: abs(e[3] - float(r[3])))
+        assert abs(float(r[2]) - w[2]) <= 1e-4 * max(1.0, w[2]) + 5e-5 and abs(float(r[3]) - w[3]) <= 1e-4 * max(1.0, w[3]) + 5e-5

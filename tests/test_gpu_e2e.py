@@ -481,8 +481,8 @@ def test_pair_table_verification_equals_rehash(env):
 
 def test_whole_structure_query_skip_match(env):
     """an empty query string (query.rs:226-233: every residue) through the host API with skip_match: the query map,
-    the per-structure rows and their order equal the oracle's; mixed in one batch with a motif query.  Verification of
-    whole-structure queries is refused with a message (not silently skipped)."""
+    the per-structure rows and their order equal the oracle's; mixed in one batch with a motif query; and, with
+    matching, the verification of the whole-chain query through the general path."""
     from folddisco_b200 import synth
     host, ctx, fd = env["host"], env["ctx"], env["fd"]
     n_structs = 900
@@ -519,8 +519,31 @@ def test_whole_structure_query_skip_match(env):
         assert g == w[int(r["nid"])][:3]
         assert abs(float(r["idf"]) - w[int(r["nid"])][3]) <= 1e-4 * max(1.0, w[int(r["nid"])][3])
     assert len(res.structures(1)) > 0
-    with pytest.raises(fd.FdError, match="whole-structure"):
-        host.search(ctx, qb, host.SearchParams(top_n=5), labels=store)
+    # with matching: the whole-chain query's candidates go through the general verification path (more than 16 query
+    # residues, thousands of observed pairs); their matches equal the oracle's retrieval, structure by structure
+    res5 = host.search(ctx, qb, host.SearchParams(top_n=5), labels=store)
+    parts = synth.split(b)
+    nq = len(om.indices())
+    n_matches = 0
+    for r in res5.structures(0):
+        nid = int(r["nid"])
+        p = parts[nid]
+        comp = O.Compact.from_soa(p["n_xyz"], p["ca_xyz"], p["cb_xyz"], p["aa"],
+                                  serial=np.arange(1, len(p["aa"]) + 1, dtype=np.uint64))
+        m = O.retrieve(om, comp)
+        want_rows = sorted((int(m["some"][k].sum()), O.residues_to_string(m["some"][k], m["chain"][k], m["serial"][k]))
+                           for k in range(len(m["rmsd"])))
+        got = [x for x in res5.sorted_matches(0) if int(x["nid"]) == nid]
+        got_rows = sorted((int(x["node_count"]), res5.residue_string(x, nq)) for x in got)
+        assert got_rows == want_rows, nid
+        for x in got:
+            key = res5.residue_string(x, nq)
+            cands = [k for k in range(len(m["rmsd"])) if O.residues_to_string(m["some"][k], m["chain"][k], m["serial"][k]) == key]
+            k = min(cands, key=lambda k: abs(float(m["rmsd"][k]) - float(x["rmsd"])))
+            assert abs(float(m["rmsd"][k]) - float(x["rmsd"])) <= 1e-4 * max(1.0, float(m["rmsd"][k]))
+            assert abs(float(m["idf"][k]) - float(x["idf"])) <= 1e-4 * max(1.0, float(m["idf"][k]))
+        n_matches += len(got)
+    assert n_matches > 0
 
 
 def _rows(res, nq):

@@ -230,6 +230,10 @@ bool read_file_text(const char *path, bool gz, std::string &data) {
     if (gz) {
         gzFile g = gzopen(path, "rb");
         if (!g) return false;
+        if (gzdirect(g)) { // not a gzip stream: zlib would hand the bytes through; the reference's GzDecoder fails
+            gzclose(g);
+            return false;
+        }
         int r;
         while ((r = gzread(g, buf, sizeof(buf))) > 0) data.append(buf, (size_t)r);
         const bool ok = r == 0;

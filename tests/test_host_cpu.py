@@ -330,3 +330,14 @@ def test_cif_reader_small_cases(host, tmp_path):
     assert d["chain"].tolist() == [ord("Z"), ord("B"), ord("B")]
     assert d["b_factor"].tolist() == [1.0, 42.5, 42.5]          # `?` -> default 1.0; same flush quirk as the chain
     assert d["cb_valid"].tolist() == [1, 1, 1] and abs(d["ca_xyz"][2][0] - (1.458 + 7.6)) < 1e-4
+    # gzip inputs: the same rows through zlib; a .gz file that is not a gzip stream is refused, an empty loop is empty
+    import gzip
+    with gzip.open(str(tmp_path / "t.cif.gz"), "wt") as f:
+        f.write(head + "\n".join(rows) + "\n#\n")
+    dz = host.read_structure_from_path(str(tmp_path / "t.cif.gz")).soa()
+    assert all(np.array_equal(d[k], dz[k]) for k in d)
+    (tmp_path / "bad.cif.gz").write_text(head + "\n".join(rows))
+    with pytest.raises(Exception):
+        host.read_structure_from_path(str(tmp_path / "bad.cif.gz"))
+    (tmp_path / "none.cif").write_text("data_x\n_entry.id X\n")
+    assert host.read_structure_from_path(str(tmp_path / "none.cif")).num_residues == 0

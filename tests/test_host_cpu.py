@@ -341,3 +341,22 @@ def test_cif_reader_small_cases(host, tmp_path):
         host.read_structure_from_path(str(tmp_path / "bad.cif.gz"))
     (tmp_path / "none.cif").write_text("data_x\n_entry.id X\n")
     assert host.read_structure_from_path(str(tmp_path / "none.cif")).num_residues == 0
+
+
+def test_prepared_query_inputs_equal_add_many(host):
+    """QueryInputs + QueryBatch.add_prepared (inputs marshalled once) build the same query maps as add_many_indexed"""
+    atoms = F.config1_atoms()
+    comps = [host.CompactStructure.from_atoms(atoms[p]) for p, _, _ in F.MOTIFS]
+    strings = [q for _, q, _ in F.MOTIFS]
+    wc = np.array([0, 1, 2, 3, 4, 0, 2], np.uint32)
+    ws = np.array([0, 1, 2, 3, 4, 0, 2], np.uint32)
+    a, b = host.QueryBatch(), host.QueryBatch()
+    a.add_many_indexed(comps, strings, wc, ws)
+    inp = host.QueryInputs(comps, strings, wc, ws)
+    b.add_prepared(inp)
+    b2 = host.QueryBatch()
+    b2.add_prepared(inp)  # reusable
+    assert len(a) == len(b) == len(b2) == 7 and b.query_strings == a.query_strings
+    for k in range(7):
+        for f in ("hash", "qi", "qj", "primary"):
+            assert np.array_equal(a.query_map(k)[f], b.query_map(k)[f]) and np.array_equal(a.query_map(k)[f], b2.query_map(k)[f])

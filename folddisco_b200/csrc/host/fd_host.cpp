@@ -102,6 +102,16 @@ struct fdh_compact {
     std::vector<float> bfac;
     std::vector<uint8_t> chains;
     uint64_t raw_residues = 0;
+    // A handle returned by the library owns itself through `self` (adopt_compact); fdh_compact_free drops that
+    // reference, and query batches that were given the handle hold their own: a batch shares the structure instead of
+    // copying it (a structure is immutable once built) and stays valid after the caller frees the handle.  Copies of
+    // the object do not inherit the reference.
+    struct SelfRef {
+        std::shared_ptr<const fdh_compact> p;
+        SelfRef() = default;
+        SelfRef(const SelfRef &) {}
+        SelfRef &operator=(const SelfRef &) { return *this; }
+    } self;
     size_t nres() const { return aa.size(); }
     fdg::V3 N(size_t i) const { return {n[3 * i], n[3 * i + 1], n[3 * i + 2]}; }
     fdg::V3 CA(size_t i) const { return {ca[3 * i], ca[3 * i + 1], ca[3 * i + 2]}; }
@@ -109,6 +119,15 @@ struct fdh_compact {
 };
 
 namespace {
+
+fdh_compact *adopt_compact(fdh_compact *c) {
+    c->self.p.reset(c);
+    return c;
+}
+// the structure behind a handle: shared (handles made by the library) or copied (any other object)
+std::shared_ptr<const fdh_compact> share_compact(const fdh_compact *c) {
+    return c->self.p ? c->self.p : std::make_shared<const fdh_compact>(*c);
+}
 
 // virtual C-beta (src/structure/coordinate.rs:167-186), f32, same operation order
 fdg::V3 approx_cb(fdg::V3 ca, fdg::V3 n, fdg::V3 c) {
@@ -1346,7 +1365,7 @@ fdh_compact *fdh_compact_read_structure(const char *path) {
         set_err(err);
         return nullptr;
     }
-    return compact_from_atoms(a);
+    return adopt_compact(compact_from_atoms(a));
 }
 fdh_compact *fdh_compact_read_pdb(const char *path) { return fdh_compact_read_structure(path); }
 fdh_compact *fdh_compact_from_atoms(int64_t n, const float *x, const float *y, const float *z, const uint8_t *an,
@@ -1360,7 +1379,7 @@ fdh_compact *fdh_compact_from_atoms(int64_t n, const float *x, const float *y, c
     a.rname.assign(rn, rn + 3 * n);
     a.chain.assign(ch, ch + n);
     a.serial.assign(rs, rs + n);
-    return compact_from_atoms(a);
+    return adopt_compact(compact_from_atoms(a));
 }
 fdh_compact *fdh_compact_from_soa(int64_t n, const float *nx, const float *cax, const float *cbx, const uint8_t *cbv,
                                   const uint8_t *aa, const uint8_t *chain, const uint64_t *serial, const float *bf) {
@@ -1379,7 +1398,7 @@ fdh_compact *fdh_compact_from_soa(int64_t n, const float *nx, const float *cax, 
     else c->bfac.assign((size_t)n, 0.f);
     if (n) c->chains.push_back(c->chain[0]);
     c->raw_residues = (uint64_t)n;
-    return c;
+    return adopt_compact(c);
 }
 int64_t fdh_compact_nres(const fdh_compact *c) { return (int64_t)c->nres(); }
 int64_t fdh_compact_num_residues_raw(const fdh_compact *c) { return (int64_t)c->raw_residues; }
@@ -1402,7 +1421,11 @@ void fdh_compact_get(const fdh_compact *c, float *nx, float *cax, float *cbx, ui
     if (serial) memcpy(serial, c->serial.data(), 8 * n);
     if (bf) memcpy(bf, c->bfac.data(), 4 * n);
 }
-void fdh_compact_free(fdh_compact *c) { delete c; }
+void fdh_compact_free(fdh_compact *c) {
+    if (!c) return;
+    std::shared_ptr<const fdh_compact> last = std::move(c->self.p); // destroyed here unless a query batch still shares it
+    if (!last) delete c;
+}
 
 // ---- store ----
 fdh_store *fdh_store_new(void) { return new fdh_store(); }
@@ -1961,7 +1984,7 @@ static bool prepare_query(const fdh_queries *qs, std::shared_ptr<const fdh_compa
 int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *st, const char *query_string) {
     Query Q;
     std::string err;
-    if (!prepare_query(qs, std::make_shared<const fdh_compact>(*st), query_string, Q, err)) {
+    if (!prepare_query(qs, share_compact(st), query_string, Q, err)) {
         set_err(err);
         return -1;
     }
@@ -1981,37 +2004,14 @@ static int64_t add_many_impl(fdh_queries *qs, const fdh_compact *const *structs,
             set_err("fdh_queries_add_many_indexed: index out of range");
             return -1;
         }
-    // one copy per distinct source structure (all sources are alive for the duration of this call); the copies are
-    // made on the worker pool (a 1024-query batch of distinct structures copies ~15 MB)
+    // the structures are shared with the handles, not copied (share_compact)
     std::vector<std::shared_ptr<const fdh_compact>> uniq((size_t)n_structs);
-    std::vector<int64_t> owner((size_t)n_structs, -1); // slot that holds the copy of this slot's structure
-    std::vector<int64_t> to_copy;
-    {
-        std::unordered_map<const fdh_compact *, int64_t> seen;
-        for (int64_t k = 0; k < n; k++) {
-            const int64_t u = which_struct ? which_struct[k] : k;
-            if (owner[u] >= 0) continue;
-            auto it = seen.find(structs[u]);
-            if (it == seen.end()) {
-                seen.emplace(structs[u], u);
-                owner[u] = u;
-                to_copy.push_back(u);
-            } else {
-                owner[u] = it->second;
-            }
-        }
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t u = which_struct ? which_struct[k] : k;
+        if (!uniq[u]) uniq[u] = share_compact(structs[u]);
     }
     int nt = threads > 0 ? threads : fd_default_host_threads();
     nt = std::max(1, std::min<int>(nt, 64));
-    {
-        std::atomic<size_t> next_copy{0};
-        fd_parallel(nt, [&](int) {
-            for (size_t k; (k = next_copy.fetch_add(1)) < to_copy.size();)
-                uniq[to_copy[k]] = std::make_shared<const fdh_compact>(*structs[to_copy[k]]);
-        });
-        for (int64_t u = 0; u < n_structs; u++)
-            if (owner[u] >= 0 && owner[u] != u) uniq[u] = uniq[owner[u]];
-    }
     std::vector<Query> out((size_t)n);
     std::vector<std::string> errs((size_t)n);
     std::vector<uint8_t> ok((size_t)n, 0);

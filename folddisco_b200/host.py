@@ -602,6 +602,80 @@ def search_sharded(ctx, queries, params=None, labels=None):
     return Results(_lib().fdh_search_sharded(ctx.h, queries.h, C.byref(params), labels.h if labels is not None else None))
 
 
+class QueryMapWorker:
+    """make_query_map of a whole batch (QueryBatch.add_prepared) on a second host thread, for a serving loop that
+    answers batch after batch: the query maps of batch k+1 are built while batch k is finalized and searched.  A batch
+    that has not been finalized touches no context and no device, so the thread does host work only (on the library's
+    worker pool, which concurrent regions share); finalize and search stay on the caller's thread -- with id-range
+    shards they are collectives and must be issued in the same order on every rank.  The reference's loop is
+    query-parallel (query_pdb.rs:348 `into_par_iter`); here the parallelism is between the host half of one batch
+    and the device half of the previous one.
+
+        w = QueryMapWorker(index.params); w.start(inputs[0])
+        for k in range(n): qb = w.take(); w.start(inputs[k + 1]); qb.finalize(ctx); rows = search(ctx, qb, ...)"""
+
+    def __init__(self, hash_params=None, dist_thr=(0.5,), angle_thr=(5.0,), serial_query=False, threads=0):
+        from concurrent.futures import ThreadPoolExecutor
+        self._args = (hash_params, tuple(dist_thr), tuple(angle_thr), serial_query)
+        self._threads = threads
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="fd-query-maps")
+        self._fut = None
+
+    def _build(self, inputs):
+        hp, dt, at, serial = self._args
+        qb = QueryBatch(hp, dist_thr=dt, angle_thr=at, serial_query=serial)
+        qb.add_prepared(inputs, self._threads)  # ctypes releases the GIL for the duration of the call
+        return qb
+
+    def start(self, inputs):
+        """begin the query maps of one batch (a QueryInputs); one batch in flight at a time"""
+        if self._fut is not None:
+            raise FdError("QueryMapWorker.start: the previous batch has not been taken")
+        self._fut = self._pool.submit(self._build, inputs)
+
+    def wait(self):
+        """block until the batch in flight is built (it stays with the worker until take)"""
+        if self._fut is not None:
+            self._fut.exception()
+
+    def take(self):
+        """the finished QueryBatch (not finalized); raises what add_prepared raised"""
+        if self._fut is None:
+            raise FdError("QueryMapWorker.take: nothing was started")
+        fut, self._fut = self._fut, None
+        return fut.result()
+
+    def close(self):
+        self._fut = None
+        self._pool.shutdown(wait=True)
+
+
+def search_batches(ctx, batches, params=None, hash_params=None, labels=None, dist_thr=(0.5,), angle_thr=(5.0,),
+                   finalize=None, search_fn=None):
+    """Generator: one Results per QueryInputs of `batches`, in order, with the query maps of the next batch built on a
+    second host thread (QueryMapWorker) while the current one is finalized and searched.  finalize(qb) / search_fn(qb)
+    replace QueryBatch.finalize(ctx) / search(ctx, qb, params, labels) for sharded databases."""
+    params = params or SearchParams()
+    w = QueryMapWorker(hash_params, dist_thr, angle_thr)
+    try:
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is not None:
+            w.start(nxt)
+        while nxt is not None:
+            qb = w.take()
+            nxt = next(it, None)
+            if nxt is not None:
+                w.start(nxt)
+            if finalize is not None:
+                finalize(qb)
+            else:
+                qb.finalize(ctx)
+            yield search_fn(qb) if search_fn is not None else search(ctx, qb, params, labels)
+    finally:
+        w.close()
+
+
 class _LaneContext:
     """a fork of a Context that the parent owns (fd_lane): same device, index and store, own stream and staging"""
 

@@ -360,3 +360,103 @@ def test_prepared_query_inputs_equal_add_many(host):
     for k in range(7):
         for f in ("hash", "qi", "qj", "primary"):
             assert np.array_equal(a.query_map(k)[f], b.query_map(k)[f]) and np.array_equal(a.query_map(k)[f], b2.query_map(k)[f])
+
+
+def _synthetic_inputs(host, n_queries, first=0, structures=60):
+    from folddisco_b200 import synth
+    import bench
+    db = synth.generate(structures, synth.SEED_BASE + 5)
+    return host.QueryInputs(*bench.query_inputs(db, n_queries, first))
+
+
+def test_query_batch_shares_structures_and_outlives_the_handles(host):
+    """a batch shares the caller's CompactStructure instead of copying it (fdh_compact is immutable and reference
+    counted inside the library): the query maps are the same as before, and they stay readable after every handle
+    was freed"""
+    atoms = F.config1_atoms()
+    comps = [host.CompactStructure.from_atoms(atoms[p]) for p, _, _ in F.MOTIFS]
+    strings = [q for _, q, _ in F.MOTIFS]
+    a = host.QueryBatch()
+    a.add_many(comps, strings)
+    single = host.QueryBatch()
+    for c, q in zip(comps, strings):
+        single.add(c, q)
+    want = [{f: a.query_map(k)[f].copy() for f in ("hash", "qi", "qj", "primary")} for k in range(len(strings))]
+    idx = [a.indices(k).copy() for k in range(len(strings))]
+    del comps, c  # fdh_compact_free of every handle: the batches hold the last references
+    import gc
+    gc.collect()
+    junk = [host.CompactStructure.from_atoms(atoms[p]) for p, _, _ in F.MOTIFS]  # reuse the freed heap blocks, if any
+    for k in range(len(strings)):
+        assert np.array_equal(a.indices(k), idx[k]) and np.array_equal(single.indices(k), idx[k])
+        for f in want[k]:
+            assert np.array_equal(a.query_map(k)[f], want[k][f]) and np.array_equal(single.query_map(k)[f], want[k][f])
+    # a batch added after the free of OTHER handles to the same data sees the same maps (nothing dangling is read)
+    b = host.QueryBatch()
+    b.add_many(junk, strings)
+    for k in range(len(strings)):
+        assert np.array_equal(b.query_map(k)["hash"], want[k]["hash"])
+    del junk
+
+
+def test_query_map_worker_builds_the_same_batches_concurrently(host):
+    """QueryMapWorker: the maps of the next batch on a second host thread, while the caller builds maps of its own on
+    the shared worker pool; same maps as a direct add_prepared, errors surface in take()"""
+    batches = [_synthetic_inputs(host, 48, first) for first in (0, 48, 96)]
+    direct = []
+    for inp in batches:
+        qb = host.QueryBatch()
+        qb.add_prepared(inp)
+        direct.append(qb)
+    w = host.QueryMapWorker()
+    with pytest.raises(host.FdError):
+        w.take()
+    w.start(batches[0])
+    with pytest.raises(host.FdError):
+        w.start(batches[1])
+    for k in range(3):
+        got = w.take()
+        if k + 1 < 3:
+            w.start(batches[k + 1])
+        busy = host.QueryBatch()  # the caller's own parallel region, concurrent with the worker's
+        busy.add_prepared(batches[k])
+        w.wait()
+        assert len(got) == len(direct[k]) == 48 and got.query_strings == direct[k].query_strings
+        for q in range(48):
+            for f in ("hash", "qi", "qj", "primary"):
+                assert np.array_equal(got.query_map(q)[f], direct[k].query_map(q)[f])
+                assert np.array_equal(busy.query_map(q)[f], direct[k].query_map(q)[f])
+    bad = host.QueryInputs([host.CompactStructure.from_soa(np.zeros((2, 3), np.float32), np.zeros((2, 3), np.float32),
+                                                           np.zeros((2, 3), np.float32), np.zeros(2, np.uint8))], ["A1-x"])
+    w.start(bad)
+    w.wait()
+    with pytest.raises(host.FdError):
+        w.take()
+    w.close()
+
+
+def test_bench_serving_loop_builds_one_batch_per_step(host):
+    """bench.serving_loop (the e2e serving loop of the bench line) with stand-ins for the device half: every step takes a
+    batch whose maps were built on the worker thread, starts exactly one more, and the batches are complete"""
+    import bench
+    inp = _synthetic_inputs(host, 32)
+    seen = []
+
+    class R:
+        struct_offsets = [0, 7]
+        match_offsets = [0, 9]
+
+    def search(qb):
+        seen.append(len(qb))
+        assert qb.query_map(5)["hash"].size > 0
+        return R()
+
+    finalized = []
+    ts, res = bench.serving_loop(host, None, inp, finalized.append, search, lambda fn: (fn(), 0.002, 0.002), 2, 3, (7, 9))
+    assert ts == [0.002] * 3 and isinstance(res, R) and seen == [32] * 5 and len(finalized) == 5
+    with pytest.raises(RuntimeError):
+        bench.serving_loop(host, None, inp, finalized.append, search, lambda fn: (fn(), 0.002, 0.002), 1, 1, (1, 1))
+    blk = bench.e2e_block(type("A", (), {"batch": 32})(), 2, 0.010, 0.005, None, 100, 200)
+    assert blk["value"] == 64 / 0.005 and blk["one_batch_at_a_time"]["value"] == 64 / 0.010 and blk["h2d_bytes_per_step"] == 200
+    blk = bench.e2e_block(type("A", (), {"batch": 32})(), 1, 0.010, None, "X: y", 100, 200)
+    assert blk["value"] == 32 / 0.010 and blk["serving_loop_error"] == "X: y" and "one_batch_at_a_time" not in blk

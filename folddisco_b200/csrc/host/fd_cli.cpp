@@ -183,7 +183,7 @@ const char *HELP =
     "  index     Create a new index table from a directory of PDB files (GPU)\n"
     "  query     Query a motif from an index table (GPU)\n"
     "  version   Print version information\n\n"
-    "index:  -p/--pdbs DIR  -i/--index PREFIX  [-t N] [-d NBIN_DIST] [-a NBIN_ANGLE] [-g GRID] [-n MAX_RESIDUE]\n"
+    "index:  -p/--pdbs DIR|FOLDCOMP_DB  -i/--index PREFIX  [-t N] [-d NBIN_DIST] [-a NBIN_ANGLE] [-g GRID] [-n MAX_RESIDUE]\n"
     "        [-y/--type default|pdbtr|pdb|orig_pdb|tr|ppf|3di|hybrid|angle|dist] [--multiple-bins D1-A1,D2-A2,..]\n"
     "        [-r] [--id relpath|abspath|basename|filename|pdb] [--no-store] [-v]\n"
     "query:  -p/--pdb FILE -q/--query RESIDUES | -q FILE.txt|.tsv   -i/--index PREFIX  [-t N]\n"
@@ -245,15 +245,27 @@ int cmd_index(Args &a) {
     }
     if (dir.empty() || prefix.empty()) die("index needs -p DIR and -i PREFIX");
     if (threads > 0) setenv("FD_HOST_THREADS", std::to_string(threads).c_str(), 0);
+    // -p is a directory of structure files or a Foldcomp database (build_index.rs:104-123)
     std::vector<std::string> files;
-    if (is_dir(dir)) list_files(dir, recursive, files);
-    else die(dir + " is not a directory (Foldcomp databases are not supported)");
-    if (files.empty()) die("no input files in " + dir);
-    for (auto &f : files) { // read_structure_from_path (controller/io.rs:337-379)
-        const std::string b = ends_with(f, ".gz") ? f.substr(0, f.size() - 3) : f;
-        if (!(ends_with(b, ".pdb") || ends_with(b, ".ent") || ends_with(b, ".PDB") || ends_with(b, ".cif")))
-            die("unsupported input format (.pdb / .ent / .cif, optionally .gz): " + f);
+    std::vector<uint64_t> db_keys;
+    fdh_fcz_db *fcz = nullptr;
+    if (is_dir(dir)) {
+        list_files(dir, recursive, files);
+    } else {
+        fcz = fdh_fcz_db_open(dir.c_str());
+        if (!fcz) die(dir + " is neither a directory nor a Foldcomp database: " + fdh_last_error());
+        for (int64_t k = 0; k < fdh_fcz_db_size(fcz); k++) {
+            files.push_back(fdh_fcz_db_name(fcz, k));
+            db_keys.push_back(fdh_fcz_db_key(fcz, k));
+        }
     }
+    if (files.empty()) die("no input files in " + dir);
+    if (!fcz)
+        for (auto &f : files) { // read_structure_from_path (controller/io.rs:337-379)
+            const std::string b = ends_with(f, ".gz") ? f.substr(0, f.size() - 3) : f;
+            if (!(ends_with(b, ".pdb") || ends_with(b, ".ent") || ends_with(b, ".PDB") || ends_with(b, ".cif")))
+                die("unsupported input format (.pdb / .ent / .cif, optionally .gz): " + f);
+        }
     if (verbose) fprintf(stderr, "[INFO] Indexing %zu files with %s\n", files.size(), fdh_hash_type_name(hp.hash_type));
     // parse on the host (file-parallel like the reference, mod.rs:298), keep file order
     std::vector<fdh_compact *> comps(files.size(), nullptr);
@@ -262,7 +274,7 @@ int cmd_index(Args &a) {
         const int nt = std::max(1, std::min(fd_default_host_threads(), 64));
         auto work = [&](int t) { // static interleaved partition
             for (size_t k = (size_t)t; k < files.size(); k += (size_t)nt) {
-                comps[k] = fdh_compact_read_structure(files[k].c_str());
+                comps[k] = fcz ? fdh_fcz_db_read(fcz, (int64_t)k) : fdh_compact_read_structure(files[k].c_str());
                 if (!comps[k]) errs[k] = fdh_last_error();
             }
         };
@@ -275,6 +287,7 @@ int cmd_index(Args &a) {
         for (size_t k = 0; k < files.size(); k++)
             if (!comps[k]) die("Failed to read structure " + files[k] + ": " + errs[k]);
     }
+    if (fcz) fdh_fcz_db_close(fcz);
     fdh_store *store = fdh_store_new();
     fdh_compact *empty = fdh_compact_from_soa(0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     for (size_t k = 0; k < files.size(); k++) {
@@ -293,7 +306,10 @@ int cmd_index(Args &a) {
     if (fd_create(&ctx, 0) != FD_OK) die(fd_last_error(nullptr));
     fdh_index *ix = fdh_index_build(ctx, store, &hp);
     if (!ix) die(fdh_last_error());
-    if (fdh_index_save(ix, store, prefix.c_str(), max_residue, nullptr) != FD_OK) die(fdh_last_error());
+    if (!db_keys.empty() && fdh_index_set_db_keys(ix, db_keys.data(), db_keys.size()) != FD_OK) die(fdh_last_error());
+    // the reference's default build (feature "foldcomp") records the -p argument as foldcomp_db for every input
+    // (build_index.rs:228-232); input_format says whether it is a Foldcomp database
+    if (fdh_index_save(ix, store, prefix.c_str(), max_residue, dir.c_str()) != FD_OK) die(fdh_last_error());
     if (!no_store) {
         if (fdh_store_save(store, (prefix + ".store").c_str()) != FD_OK) die(fdh_last_error());
     } else {
@@ -582,14 +598,40 @@ int cmd_query(Args &a) {
             store = fdh_store_new();
             const size_t sl = prefix.find_last_of('/');
             const std::string index_dir = sl == std::string::npos ? "" : prefix.substr(0, sl + 1);
+            // an index built from a Foldcomp database reads its structures from that database (query_pdb.rs:320-341):
+            // the recorded path, else PREFIX-without-_folddisco + "_foldcomp", else PREFIX-without-_folddisco
+            // (get_foldcomp_db_path_with_prefix, controller/io.rs:423-448)
+            fdh_fcz_db *fcz = nullptr;
+            if (*fdh_index_foldcomp_db(ix)) {
+                std::string dbp = fdh_index_foldcomp_db(ix);
+                if (!is_file(dbp)) {
+                    std::string base = prefix;
+                    if (ends_with(base, "_folddisco")) base = base.substr(0, base.size() - 10);
+                    for (const std::string &cand : {base + "_foldcomp", base})
+                        if (is_file(cand) && is_file(cand + ".index") && is_file(cand + ".lookup")) {
+                            dbp = cand;
+                            break;
+                        }
+                }
+                fcz = fdh_fcz_db_open(dbp.c_str());
+                if (!fcz) die(std::string("cannot open the Foldcomp database of this index: ") + fdh_last_error());
+            }
             for (uint64_t k = 0; k < S; k++) {
                 std::string p = fdh_index_name(ix, k);
-                if (!is_file(p)) p = index_dir + p; // resolve_tid_path_from_index_prefix (controller/io.rs:488-528)
-                fdh_compact *c = fdh_compact_read_structure(p.c_str());
+                fdh_compact *c = nullptr;
+                if (fcz) {
+                    const int64_t e = fdh_fcz_db_find(fcz, p.c_str());
+                    if (e < 0) die("Entry with name " + p + " not found.");
+                    c = fdh_fcz_db_read(fcz, e);
+                } else {
+                    if (!is_file(p)) p = index_dir + p; // resolve_tid_path_from_index_prefix (controller/io.rs:488-528)
+                    c = fdh_compact_read_structure(p.c_str());
+                }
                 if (!c) die(std::string("Failed to read structure ") + fdh_index_name(ix, k) + ": " + fdh_last_error());
                 fdh_store_add(store, c, fdh_index_name(ix, k));
                 fdh_compact_free(c);
             }
+            if (fcz) fdh_fcz_db_close(fcz);
         }
         if (fdh_store_attach(store, ctx) != FD_OK) die(fdh_last_error());
     }

@@ -68,6 +68,17 @@ def _lib():
     sig("fdh_compact_avg_plddt", C.c_float, [VP])
     sig("fdh_compact_get", None, [VP] + [VP] * 8)
     sig("fdh_compact_free", None, [VP])
+    sig("fdh_fcz_db_open", VP, [C.c_char_p])
+    sig("fdh_fcz_db_close", None, [VP])
+    sig("fdh_fcz_db_size", C.c_int64, [VP])
+    sig("fdh_fcz_db_name", C.c_char_p, [VP, C.c_int64])
+    sig("fdh_fcz_db_key", C.c_uint64, [VP, C.c_int64])
+    sig("fdh_fcz_db_find", C.c_int64, [VP, C.c_char_p])
+    sig("fdh_fcz_db_read", VP, [VP, C.c_int64])
+    sig("fdh_compact_from_fcz", VP, [C.c_char_p, C.c_uint64])
+    sig("fdh_index_db_key", C.c_uint64, [VP, C.c_uint64])
+    sig("fdh_index_set_db_keys", C.c_int, [VP, VP, C.c_uint64])
+    sig("fdh_index_foldcomp_db", C.c_char_p, [VP])
     sig("fdh_store_new", VP, [])
     sig("fdh_store_add", C.c_int64, [VP, VP, C.c_char_p])
     sig("fdh_store_add_soa", C.c_int64, [VP, C.c_uint64, VP, VP, VP, VP, VP, C.c_char_p])
@@ -196,6 +207,49 @@ def read_structure_from_path(path):
     return CompactStructure(_lib().fdh_compact_read_structure(os.fsencode(path)))
 
 
+class FoldcompDb:
+    """FoldcompDbReader (src/structure/io/fcz.rs:21-136): PATH + PATH.index + PATH.lookup.  Entries are decoded by the
+    Foldcomp codec library, bound at run time through the C ABI the reference binds ($FD_FOLDCOMP_LIB or
+    libfoldcomp_ffi.so on the loader path); the named entries are listed in ascending key order (get_paths)."""
+
+    def __init__(self, path):
+        self.h = _lib().fdh_fcz_db_open(os.fsencode(path))
+        if not self.h:
+            raise FdError(_err())
+
+    def __len__(self):
+        return _lib().fdh_fcz_db_size(self.h)
+
+    def names(self):
+        return [_lib().fdh_fcz_db_name(self.h, k).decode() for k in range(len(self))]
+
+    def keys(self):
+        return [int(_lib().fdh_fcz_db_key(self.h, k)) for k in range(len(self))]
+
+    def find(self, name):
+        return _lib().fdh_fcz_db_find(self.h, name.encode())
+
+    def read(self, k):
+        """read_single_structure_by_id(...).to_compact() of the k-th named entry"""
+        return CompactStructure(_lib().fdh_fcz_db_read(self.h, k))
+
+    def read_by_name(self, name):
+        k = self.find(name)
+        if k < 0:
+            raise FdError("Entry with name %s not found." % name)
+        return self.read(k)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().fdh_fcz_db_close(self.h)
+            self.h = None
+
+
+def compact_from_fcz(data):
+    """one Foldcomp-compressed entry (bytes) -> CompactStructure"""
+    return CompactStructure(_lib().fdh_compact_from_fcz(data, len(data)))
+
+
 def parse_query_string(q, default_chain=ord("A")):
     """src/controller/query.rs:331-384 -> ([(chain, residue)], [None | [aa,...]])"""
     cap = 1 << 16
@@ -295,6 +349,17 @@ class FolddiscoIndex:
                                    None if foldcomp_db is None else foldcomp_db.encode())
         if rc != 0:
             raise FdError(_err())
+
+    def set_db_keys(self, keys):
+        """the database keys of an index built from a Foldcomp database (Folddisco::numeric_db_key_vec): 5th lookup
+        column; save() then records input_format FCZDB"""
+        k = np.ascontiguousarray(keys, np.uint64)
+        if _lib().fdh_index_set_db_keys(self.h, _ptr(k), len(k)) != 0:
+            raise FdError(_err())
+
+    @property
+    def foldcomp_db(self):
+        return _lib().fdh_index_foldcomp_db(self.h).decode()
 
     def buffers(self):
         v = _IndexBuffers()

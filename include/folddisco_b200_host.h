@@ -49,6 +49,23 @@ fdh_compact *fdh_compact_from_atoms(int64_t n_atoms, const float *x, const float
 fdh_compact *fdh_compact_from_soa(int64_t n, const float *n_xyz, const float *ca_xyz, const float *cb_xyz,
                                   const uint8_t *cb_valid, const uint8_t *aa, const uint8_t *chain,
                                   const uint64_t *serial, const float *b_factor);
+/* ---- Foldcomp input (src/structure/io/fcz.rs) ----
+ * The codec itself is the third-party Foldcomp library, bound at run time through the C ABI the reference binds
+ * (lib/foldcomp/foldcompffi.h:18-21; fcz.rs:80-94): dlopen of $FD_FOLDCOMP_LIB, else "libfoldcomp_ffi.so".  Without it
+ * every function below that decodes an entry fails with a message (NULL + fdh_last_error()).
+ * fdh_compact_read_structure also accepts "DB:name" (an entry of a database, controller/io.rs:303-334) and "*.fcz"
+ * (one entry in a file of its own). */
+typedef struct fdh_fcz_db fdh_fcz_db; /* FoldcompDbReader (fcz.rs:21-136): PATH + PATH.index + PATH.lookup */
+fdh_fcz_db *fdh_fcz_db_open(const char *path);
+void fdh_fcz_db_close(fdh_fcz_db *db);
+/* the named entries in ascending key order = get_paths / get_db_key_vector (fcz.rs:123-136, 208-219) */
+int64_t fdh_fcz_db_size(const fdh_fcz_db *db);
+const char *fdh_fcz_db_name(const fdh_fcz_db *db, int64_t k);
+uint64_t fdh_fcz_db_key(const fdh_fcz_db *db, int64_t k);
+int64_t fdh_fcz_db_find(const fdh_fcz_db *db, const char *name); /* position of the entry with this name, -1 if none */
+fdh_compact *fdh_fcz_db_read(const fdh_fcz_db *db, int64_t k);   /* read_single_structure_by_id + to_compact */
+fdh_compact *fdh_compact_from_fcz(const uint8_t *bytes, uint64_t n_bytes); /* one compressed entry */
+
 int64_t fdh_compact_nres(const fdh_compact *c);
 int64_t fdh_compact_num_residues_raw(const fdh_compact *c); /* Structure.num_residues (serial changes) */
 int fdh_compact_first_chain(const fdh_compact *c);
@@ -94,6 +111,10 @@ uint64_t fdh_index_num_structs(const fdh_index *ix);
 void fdh_index_get_lookup(const fdh_index *ix, uint32_t *nres, float *plddt);
 const char *fdh_index_name(const fdh_index *ix, uint64_t id);
 uint64_t fdh_index_db_key(const fdh_index *ix, uint64_t id); /* 5th column of PREFIX.lookup */
+/* keys of an index built from a Foldcomp database (mod.rs:151, lookup.rs:36-40); save then writes input_format "FCZDB" */
+int fdh_index_set_db_keys(fdh_index *ix, const uint64_t *keys, uint64_t n);
+/* the Foldcomp database a loaded index was built from (PREFIX.type: input_format = "FCZDB" + foldcomp_db), "" if none */
+const char *fdh_index_foldcomp_db(const fdh_index *ix);
 void fdh_index_get_params(const fdh_index *ix, fd_hash_params *params);
 /* HashType::get_with_str / to_string (src/geometry/core.rs:42-75): a `--type` spelling ("default", "pdb", "ppf", "3",
  * "PDBMotifSinCos" ...) -> FD_HASH_* (6 / 7 for the two encodings that are not built), -1 if unknown; and back to the

@@ -53,6 +53,51 @@ def build(force=False):
     return _SO
 
 
+_REF_SO = os.path.join(_ROOT, "oracle", "_ref", "libfoldcomp_ffi.so")
+
+
+def build_ref():
+    """oracle/_ref/libfoldcomp_ffi.so: the Foldcomp codec the reference vendors, compiled from the reference tree where it
+    lies (oracle/Makefile `ref`).  -> path, or None when neither the file nor /root/reference exists"""
+    if not os.path.exists(_REF_SO):
+        if not os.path.isdir("/root/reference/lib/foldcomp"):
+            return None
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    return _REF_SO
+
+
+class _FczAtom(C.Structure):  # atom_t (lib/foldcomp/foldcompffi.h:8-16)
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("atom", C.c_uint8 * 4), ("atom_idx", C.c_uint64),
+                ("chain", C.c_uint8), ("aa", C.c_uint8 * 3), ("res_idx", C.c_uint64), ("bfactor", C.c_float)]
+
+
+def foldcomp_atoms(data):
+    """one Foldcomp entry through the codec itself (create / process / destroy / free, the calls of fcz.rs:80-94) -> the
+    atoms dict Structure.from_atoms takes (Atom::from_c: the same fields under the reference's names)"""
+    L = C.CDLL(build_ref())
+    L.foldcomp_create.restype = C.c_void_p
+    L.foldcomp_process.restype = C.POINTER(_FczAtom)
+    L.foldcomp_process.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.foldcomp_free.argtypes = [C.POINTER(_FczAtom)]
+    L.foldcomp_destroy.argtypes = [C.c_void_p]
+    inst = L.foldcomp_create()
+    n = C.c_size_t()
+    p = L.foldcomp_process(inst, data, len(data), C.byref(n))
+    n = n.value
+    a = dict(x=np.zeros(n, np.float32), y=np.zeros(n, np.float32), z=np.zeros(n, np.float32),
+             atom_name=np.zeros((n, 4), np.uint8), chain=np.zeros(n, np.uint8), res_name=np.zeros((n, 3), np.uint8),
+             res_serial=np.zeros(n, np.uint64), b_factor=np.zeros(n, np.float32))
+    for i in range(n):
+        t = p[i]
+        a["x"][i], a["y"][i], a["z"][i], a["b_factor"][i] = t.x, t.y, t.z, t.bfactor
+        a["atom_name"][i] = list(t.atom)
+        a["res_name"][i] = list(t.aa)
+        a["chain"][i], a["res_serial"][i] = t.chain, t.res_idx
+    L.foldcomp_destroy(inst)
+    L.foldcomp_free(p)
+    return a
+
+
 _lib = None
 
 

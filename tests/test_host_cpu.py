@@ -460,3 +460,146 @@ def test_bench_serving_loop_builds_one_batch_per_step(host):
     assert blk["value"] == 64 / 0.005 and blk["one_batch_at_a_time"]["value"] == 64 / 0.010 and blk["h2d_bytes_per_step"] == 200
     blk = bench.e2e_block(type("A", (), {"batch": 32})(), 1, 0.010, None, "X: y", 100, 200)
     assert blk["value"] == 32 / 0.010 and blk["serving_loop_error"] == "X: y" and "one_batch_at_a_time" not in blk
+
+
+# ---- Foldcomp input (src/structure/io/fcz.rs) ----
+@pytest.fixture()
+def foldcomp_codec(monkeypatch):
+    so = O.build_ref()
+    if so is None:
+        pytest.skip("no Foldcomp codec (oracle/_ref/libfoldcomp_ffi.so) and no reference tree to build it from")
+    monkeypatch.setenv("FD_FOLDCOMP_LIB", so)
+    return so
+
+
+@needs_reference
+def test_foldcomp_database_reader(host, foldcomp_codec):
+    """FoldcompDb on the reference's data/foldcomp/example_db (the database of fcz.rs:366-392): entries in key order with
+    their names and keys, every entry = the oracle's CompactStructure of the atoms the codec itself returns, lookup by
+    name, "DB:name" paths (controller/io.rs:303-334), the single-entry file 7m0y.fcz"""
+    dbp = os.path.join(REF, "data", "foldcomp", "example_db")
+    index = [ln.split("\t") for ln in open(dbp + ".index").read().splitlines()]
+    lookup = dict((int(r[0]), r[1]) for r in (ln.split("\t") for ln in open(dbp + ".lookup").read().splitlines()))
+    raw = open(dbp, "rb").read()
+    db = host.FoldcompDb(dbp)
+    assert len(db) == len(index) == 24
+    assert db.keys() == sorted(int(r[0]) for r in index) and db.names() == [lookup[k] for k in db.keys()]
+    assert db.find("d1asha_") == 0 and db.find("nope") == -1
+    for k, (key, start, length) in enumerate(index):
+        want = O.Structure.from_atoms(O.foldcomp_atoms(raw[int(start):int(start) + int(length)])).compact()
+        got = db.read(k)
+        assert got.num_residues == want.nres > 50
+        _same_compact(got, want)
+    _same_compact(db.read_by_name("d1cg5b_"), O.Structure.from_atoms(O.foldcomp_atoms(
+        raw[int(index[3][1]):int(index[3][1]) + int(index[3][2])])).compact())
+    with pytest.raises(host.FdError):
+        db.read_by_name("nope")
+    with pytest.raises(host.FdError):
+        db.read(24)
+    # read_compact_structure: "DB:name"
+    _same_compact(host.read_structure_from_path(dbp + ":d1asha_"), O.Structure.from_atoms(O.foldcomp_atoms(
+        raw[:int(index[0][2])])).compact())
+    with pytest.raises(host.FdError):
+        host.read_structure_from_path(dbp + ":nope")
+    # one entry in a file of its own (the file of fcz.rs:300-316): 2 187 atoms, residues 449 .. 721 of chain A
+    one = open(os.path.join(REF, "data", "foldcomp", "7m0y.fcz"), "rb").read()
+    atoms = O.foldcomp_atoms(one)
+    assert len(atoms["x"]) == 2187 and int(atoms["res_serial"][0]) == 449 and int(atoms["res_serial"][-1]) == 721
+    want = O.Structure.from_atoms(atoms).compact()
+    _same_compact(host.compact_from_fcz(one), want)
+    _same_compact(host.read_structure_from_path(os.path.join(REF, "data", "foldcomp", "7m0y.fcz")), want)
+    with pytest.raises(host.FdError):
+        host.compact_from_fcz(b"not a foldcomp entry")
+    with pytest.raises(host.FdError):
+        host.FoldcompDb(os.path.join(REF, "data", "foldcomp", "missing_db"))
+
+
+def test_foldcomp_database_files_are_validated(host, tmp_path):
+    """entries outside the database file, malformed rows and entries without a name (no codec needed)"""
+    p = str(tmp_path / "db")
+    open(p, "wb").write(b"FCMP" + b"\0" * 60)
+    open(p + ".lookup", "w").write("0\tfirst\t0\n2\tthird\t0\n")
+    open(p + ".index", "w").write("2\t32\t32\n0\t0\t32\n1\t16\t8\n")
+    db = host.FoldcompDb(p)
+    assert db.names() == ["first", "third"] and db.keys() == [0, 2]  # key 1 has no name: not a path (fcz.rs:211-217)
+    open(p + ".index", "w").write("0\t0\t65\n")
+    with pytest.raises(host.FdError):
+        host.FoldcompDb(p)
+    open(p + ".index", "w").write("0\tx\t6\n")
+    with pytest.raises(host.FdError):
+        host.FoldcompDb(p)
+
+
+def test_index_of_a_foldcomp_database_records_keys_and_format(host, tmp_path):
+    """an index whose structures came from a Foldcomp database: the database keys are the 5th lookup column
+    (lookup.rs:36-40), PREFIX.type says input_format = "FCZDB" and names the database (config.rs:64-97); read back"""
+    import ctypes as C
+    from folddisco_b200 import capi
+    atoms = F.config1_atoms()
+    names = F.serine_names()
+    store = host.Store()
+    comps = []
+    for n in names:
+        store.add(host.CompactStructure.from_atoms(atoms[n]), n)
+        comps.append(O.Structure.from_atoms(atoms[n]).compact())
+    oix = O.Index.build(comps)
+    hashes, offsets, values = oix.hashes, oix.offsets, oix.values
+    b = capi._IndexBuffers(len(hashes), hashes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                           offsets.ctypes.data_as(C.POINTER(C.c_uint64)), len(values),
+                           values.ctypes.data_as(C.POINTER(C.c_uint8)))
+    p = capi.HashParams(0, 0, 20.0)
+    ix = host.FolddiscoIndex(host._lib().fdh_index_from_buffers(C.byref(b), store.h, C.byref(p)))
+    assert ix.foldcomp_db == ""
+    with pytest.raises(host.FdError):
+        ix.set_db_keys([1, 2])
+    keys = [100, 110, 200, 201, 7]
+    ix.set_db_keys(keys)
+    prefix = str(tmp_path / "fcz_index")
+    ix.save(store, prefix, foldcomp_db="data/foldcomp/example_db")
+    rows = [ln.split("\t") for ln in open(prefix + ".lookup").read().splitlines()]
+    assert [int(r[0]) for r in rows] == [0, 1, 2, 3, 4] and [int(r[4]) for r in rows] == keys
+    t = open(prefix + ".type").read()
+    assert 'input_format = "FCZDB"' in t and 'foldcomp_db = "data/foldcomp/example_db"' in t
+    back = host.load_folddisco_index(prefix)
+    assert back.foldcomp_db == "data/foldcomp/example_db"
+    assert [int(host._lib().fdh_index_db_key(back.h, k)) for k in range(5)] == keys
+    # a directory index names its -p argument too (the reference's default build does), but is not a Foldcomp index
+    plain = host.FolddiscoIndex(host._lib().fdh_index_from_buffers(C.byref(b), store.h, C.byref(p)))
+    plain.save(store, prefix + "2", foldcomp_db="data/serine_peptidases")
+    assert 'input_format = "PDB"' in open(prefix + "2.type").read()
+    assert host.load_folddisco_index(prefix + "2").foldcomp_db == ""
+
+
+def test_foldcomp_input_fails_loudly_without_the_codec(tmp_path):
+    """no codec library: decoding a Foldcomp entry is an error that says what is missing (never a silent skip)"""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "from folddisco_b200 import host\n"
+            "try:\n"
+            "    host.compact_from_fcz(b'FCMP' + bytes(64))\n"
+            "except host.FdError as e:\n"
+            "    print('ERR', e)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, FD_FOLDCOMP_LIB=str(tmp_path / "no_such_codec.so"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "ERR" in r.stdout and "FD_FOLDCOMP_LIB" in r.stdout, (r.stdout, r.stderr)
+
+
+@needs_reference
+def test_cli_index_reads_a_foldcomp_database(foldcomp_codec, tmp_path):
+    """`index -p FOLDCOMP_DB` (build_index.rs:104-123): the 24 entries are decoded on the host, then the build needs the
+    GPU; without the codec library, or for a file that is not a database, the command says so"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU (the GPU run of this path is not part of the CPU suite)")
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "folddisco_b200", "folddisco-b200")
+    dbp = os.path.join(REF, "data", "foldcomp", "example_db")
+    r = subprocess.run([cli, "index", "-p", dbp, "-i", str(tmp_path / "ix"), "-v"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Indexing 24 files" in r.stderr and "no CPU fallback" in r.stderr
+    env = dict(os.environ, FD_FOLDCOMP_LIB=str(tmp_path / "none.so"))
+    r = subprocess.run([cli, "index", "-p", dbp, "-i", str(tmp_path / "ix")], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "Foldcomp codec library" in r.stderr
+    r = subprocess.run([cli, "index", "-p", os.path.join(REF, "data", "foldcomp", "7m0y.fcz"), "-i", str(tmp_path / "ix")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "neither a directory nor a Foldcomp database" in r.stderr

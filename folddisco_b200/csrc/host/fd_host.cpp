@@ -1104,9 +1104,12 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     Q.n_nodes = (uint32_t)node_of.size();
     const size_t H = Q.entries.size();
     Q.vs_entry.resize(H);
-    for (size_t k = 0; k < H; k++) Q.vs_entry[k] = (uint32_t)k;
-    std::sort(Q.vs_entry.begin(), Q.vs_entry.end(),
-              [&](uint32_t a, uint32_t b) { return Q.entries[a].hash < Q.entries[b].hash; });
+    { // entries ordered by hash (the hashes of a query are distinct): sort (hash, position) keys, not positions
+        std::vector<uint64_t> keys(H);
+        for (size_t k = 0; k < H; k++) keys[k] = (uint64_t)Q.entries[k].hash << 32 | (uint64_t)k;
+        std::sort(keys.begin(), keys.end());
+        for (size_t k = 0; k < H; k++) Q.vs_entry[k] = (uint32_t)keys[k];
+    }
     Q.hashes_sorted.resize(H);
     Q.vs_qi.resize(H);
     Q.vs_qj.resize(H);

@@ -603,3 +603,19 @@ def test_cli_index_reads_a_foldcomp_database(foldcomp_codec, tmp_path):
     r = subprocess.run([cli, "index", "-p", os.path.join(REF, "data", "foldcomp", "7m0y.fcz"), "-i", str(tmp_path / "ix")],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "neither a directory nor a Foldcomp database" in r.stderr
+
+
+def test_search_batches_generator_with_stand_ins(host):
+    """host.search_batches: one result per batch, in order, the next batch's maps started before the current one is
+    finalized; stand-ins replace the device half (finalize / search)"""
+    batches = [_synthetic_inputs(host, n, first) for n, first in ((8, 0), (12, 8), (5, 20))]
+    order = []
+    out = list(host.search_batches(None, batches, finalize=lambda qb: order.append(("f", len(qb))),
+                                   search_fn=lambda qb: (order.append(("s", len(qb))), qb.query_strings)[1]))
+    assert order == [("f", 8), ("s", 8), ("f", 12), ("s", 12), ("f", 5), ("s", 5)]
+    assert [len(o) for o in out] == [8, 12, 5] and out[1] == batches[1].per_query
+    assert list(host.search_batches(None, [], finalize=order.append, search_fn=order.append)) == []
+    # a consumer that stops early leaves no thread behind
+    gen = host.search_batches(None, batches, finalize=lambda qb: None, search_fn=len)
+    assert next(gen) == 8
+    gen.close()

@@ -821,7 +821,8 @@ namespace {
 struct SeenHashes {
     std::vector<uint32_t> slot; // entry index + 1, 0 = empty
     uint32_t mask = 0, used = 0;
-    SeenHashes() { resize(256); }
+    // cap = a power of two, at least twice the number of hashes expected (no rehash while the query map is built)
+    explicit SeenHashes(uint32_t cap = 256) { resize(cap); }
     void resize(uint32_t cap) {
         slot.assign(cap, 0);
         mask = cap - 1;
@@ -977,19 +978,21 @@ bool build_query_map(Query &Q, const ParsedQuery &pq, const fdh_queries &qs) {
     }
     const float rad = 3.14159274101257324f / 180.0f; // f32::to_radians
     float f[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, fn[9], ff[9];
-    SeenHashes seen;
     QueryHasher QH(qs.p.hash);
     AngleBinCache &bins = QH.bins;
     int dist_idx[2], angle_idx[7];
     const int n_dist_idx = fdg::typed_dist_index(QH.tp.type, dist_idx), n_angle_idx = fdg::typed_angle_index(QH.tp.type, angle_idx);
     const size_t K = Q.indices.size();
+    uint32_t seen_cap = 256;
     {
         const size_t n_pairs = K > 1 ? K * (K - 1) : 0;
         const size_t per_pair = (1 + 4 * qs.dist_thr.size() + 10 * qs.angle_thr.size()) * (QH.typed ? QH.tp.n_bins : 1);
         Q.entries.reserve(std::min<size_t>(n_pairs * per_pair, 1u << 16));
         Q.pair_hash.reserve(n_pairs);
         Q.aad.reserve(n_pairs);
+        while (seen_cap < 2 * n_pairs * per_pair && seen_cap < (1u << 16)) seen_cap *= 2;
     }
+    SeenHashes seen(seen_cap);
     for (size_t a = 0; a < K; a++)
         for (size_t b = 0; b < K; b++) {
             if (a == b) continue;

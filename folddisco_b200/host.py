@@ -682,6 +682,8 @@ class QueryMapWorker:
     def __init__(self, hash_params=None, dist_thr=(0.5,), angle_thr=(5.0,), serial_query=False, threads=0):
         from concurrent.futures import ThreadPoolExecutor
         self._args = (hash_params, tuple(dist_thr), tuple(angle_thr), serial_query)
+        if threads <= 0:  # leave a quarter of the host threads to the caller's finalize / search, which run meanwhile
+            threads = max(1, capi.lib().fd_default_host_threads() * 3 // 4)
         self._threads = threads
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="fd-query-maps")
         self._fut = None

@@ -26,6 +26,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -217,6 +218,35 @@ bool field_f32(const char *s, size_t len, float *out) {
     while (len && isspace((unsigned char)*s)) s++, len--;
     while (len && isspace((unsigned char)s[len - 1])) len--;
     if (!len || len > 63) return false;
+    { // plain decimals of at most 7 digits (every coordinate / B-factor column of a PDB file): m / 10^e in binary64 and
+      // one rounding to f32 is the correctly rounded value -- m < 2^24 and 10^e <= 10^7 are exact, and the quotient is
+      // either exactly a tie of two floats or more than 2^-49 (relative) away from one, out of reach of the 2^-53 of the
+      // division -- i.e. what strtof / Rust's f32::from_str return.  Anything else takes strtof below.
+        static const double P10[8] = {1.0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7};
+        size_t i = 0;
+        const bool neg = s[0] == '-';
+        if (s[0] == '-' || s[0] == '+') i = 1;
+        uint32_t m = 0;
+        int digits = 0, frac = -1;
+        for (; i < len; i++) {
+            const unsigned d = (unsigned)(s[i] - '0');
+            if (d <= 9) {
+                m = m * 10 + d;
+                digits++;
+                if (frac >= 0) frac++;
+            } else if (s[i] == '.' && frac < 0) {
+                frac = 0;
+            } else {
+                digits = 99;
+                break;
+            }
+        }
+        if (digits >= 1 && digits <= 7) {
+            const float v = (float)((double)m / P10[frac < 0 ? 0 : frac]);
+            *out = neg ? -v : v;
+            return true;
+        }
+    }
     char buf[64];
     memcpy(buf, s, len);
     buf[len] = 0;
@@ -262,8 +292,14 @@ bool read_file_text(const char *path, bool gz, std::string &data) {
     }
     FILE *f = fopen(path, "rb");
     if (!f) return false;
+    struct stat st;
+    if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) { // one read into the final buffer
+        data.resize((size_t)st.st_size);
+        const size_t got = fread(&data[0], 1, data.size(), f);
+        data.resize(got);
+    }
     size_t r;
-    while ((r = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, r);
+    while ((r = fread(buf, 1, sizeof(buf), f)) > 0) data.append(buf, r); // (a file that grew, or not a regular file)
     fclose(f);
     return true;
 }
@@ -273,9 +309,20 @@ bool read_file_text(const char *path, bool gz, std::string &data) {
 bool parse_pdb_atoms(const std::string &data, Atoms &a) {
     int model = 0;
     size_t pos = 0;
+    { // an ATOM record is 81 bytes
+        const size_t guess = data.size() / 81 + 1;
+        a.x.reserve(guess);
+        a.y.reserve(guess);
+        a.z.reserve(guess);
+        a.b.reserve(guess);
+        a.name.reserve(4 * guess);
+        a.rname.reserve(3 * guess);
+        a.chain.reserve(guess);
+        a.serial.reserve(guess);
+    }
     while (pos < data.size()) {
-        size_t nl = data.find('\n', pos);
-        if (nl == std::string::npos) nl = data.size();
+        const char *nlp = (const char *)memchr(data.data() + pos, '\n', data.size() - pos);
+        size_t nl = nlp ? (size_t)(nlp - data.data()) : data.size();
         size_t len = nl - pos;
         const char *l = data.data() + pos;
         pos = nl + 1;
@@ -309,10 +356,12 @@ bool parse_pdb_atoms(const std::string &data, Atoms &a) {
 // does not separate HETATM here (cif.rs:262-270) -- until the model number changes (:239-245).  Residue number =
 // auth_seq_id, else label_seq_id; chain = a one-character auth_asym_id, else label_asym_id (:253-259); B = 1.0 when absent.
 bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
-    struct Tok {
-        std::string text;
+    struct Tok { // a view into `data` (no copy per value: an atom_site loop has ~20 values per atom)
+        std::string_view text;
         bool quoted;
     };
+    const std::string_view dv(data);
+    auto is_ws = [](char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }; // isspace of the C locale, inlined
     size_t pos = 0;
     const size_t N = data.size();
     bool at_line_start = true;
@@ -330,11 +379,11 @@ bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
             break;
         }
         t.quoted = false;
-        t.text.clear();
+        t.text = std::string_view();
         if (data[pos] == ';' && (at_line_start || pos == 0)) { // text field: up to a line that starts with ';'
             size_t b = pos + 1, e = data.find("\n;", b);
             if (e == std::string::npos) e = N;
-            t.text = data.substr(b, e - b);
+            t.text = dv.substr(b, e - b);
             t.quoted = true;
             pos = std::min(N, e + 2);
             at_line_start = false;
@@ -344,35 +393,38 @@ bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
         if (data[pos] == '\'' || data[pos] == '"') { // closes at the same quote followed by white space
             const char q = data[pos++];
             const size_t b = pos;
-            while (pos < N && !(data[pos] == q && (pos + 1 >= N || isspace((unsigned char)data[pos + 1]))) && data[pos] != '\n') pos++;
-            t.text = data.substr(b, pos - b);
+            while (pos < N && !(data[pos] == q && (pos + 1 >= N || is_ws(data[pos + 1]))) && data[pos] != '\n') pos++;
+            t.text = dv.substr(b, pos - b);
             t.quoted = true;
             if (pos < N && data[pos] == q) pos++;
             return true;
         }
         const size_t b = pos;
-        while (pos < N && !isspace((unsigned char)data[pos])) pos++;
-        t.text = data.substr(b, pos - b);
+        while (pos < N && !is_ws(data[pos])) pos++;
+        t.text = dv.substr(b, pos - b);
         return true;
     };
-    auto lower = [](std::string s) {
+    auto lower = [](std::string_view v) {
+        std::string s(v);
         for (char &c : s) c = (char)tolower((unsigned char)c);
         return s;
     };
     auto is_keyword = [&](const Tok &t) {
-        if (t.quoted) return false;
+        if (t.quoted || t.text.empty()) return false;
+        const char c0 = (char)tolower((unsigned char)t.text[0]); // loop_ / data_ / save_ / stop_ / global_
+        if (c0 != 'l' && c0 != 'd' && c0 != 's' && c0 != 'g') return false;
         const std::string l = lower(t.text);
         return l == "loop_" || l.rfind("data_", 0) == 0 || l.rfind("save_", 0) == 0 || l == "stop_" || l == "global_";
     };
     Tok t;
     bool have = next(t);
     while (have) {
-        if (t.quoted || lower(t.text) != "loop_") {
+        if (t.quoted || t.text.size() != 5 || lower(t.text) != "loop_") {
             have = next(t);
             continue;
         }
         std::vector<std::string> header;
-        while ((have = next(t)) && !t.quoted && !t.text.empty() && t.text[0] == '_') header.push_back(t.text.substr(1));
+        while ((have = next(t)) && !t.quoted && !t.text.empty() && t.text[0] == '_') header.push_back(std::string(t.text.substr(1)));
         if (std::find(header.begin(), header.end(), "atom_site.group_PDB") == header.end()) continue; // another loop
         auto col = [&](const char *name) -> int {
             auto it = std::find(header.begin(), header.end(), name);
@@ -410,7 +462,7 @@ bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
             if (first) first_model = model;
             else if (model != first_model) break;
             first = false;
-            const std::string &an = row[c_name].text;
+            const std::string_view an = row[c_name].text;
             if (missing(row[c_name]) || an.empty() || an.size() > 4) {
                 err = "Invalid atom name in the atom_site loop";
                 return false;
@@ -419,7 +471,7 @@ bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
             if (an.size() == 4) memcpy(name4, an.data(), 4);
             else memcpy(name4 + 1, an.data(), an.size());
             uint8_t res3[3] = {' ', ' ', ' '};
-            const std::string &rn = row[c_comp].text;
+            const std::string_view rn = row[c_comp].text;
             if (missing(row[c_comp])) {
                 err = "Residue name should be provided";
                 return false;

@@ -622,3 +622,47 @@ def test_search_batches_generator_with_stand_ins(host):
     gen = host.search_batches(None, batches, finalize=lambda qb: None, search_fn=len)
     assert next(gen) == 8
     gen.close()
+
+
+def test_pdb_decimal_fields_are_correctly_rounded(host, tmp_path):
+    """the PDB reader's short-decimal route (m / 10^e in binary64, one rounding) returns the correctly rounded f32 of
+    every coordinate / B-factor column: 60 000 random %8.3f / %6.2f fields, edge values included, against Python's
+    decimal -> binary64 -> f32 (exact for <= 7 digits, same argument) and against the oracle's reader (strtof)"""
+    rng = np.random.default_rng(7)
+    n_res = 6000
+    vals = rng.uniform(-999.999, 9999.999, size=(n_res, 3, 3))
+    vals[:50] = rng.uniform(-0.01, 0.01, size=(50, 3, 3))
+    vals[50:60] = [[[-0.0004, 0.0005, 9999.999], [-999.999, 0.001, 1.0], [16777.216 % 9999, 8388.608, 0.125]]] * 10
+    bf = rng.uniform(0, 999.99, size=n_res)
+    lines, want = [], np.zeros((n_res, 3, 3), np.float32)
+    wb = np.zeros(n_res, np.float32)
+    serial = 1
+    for r in range(n_res):
+        for a, name in enumerate((" N  ", " CA ", " CB ")):
+            xs = ["%8.3f" % v for v in vals[r, a]]
+            b = "%6.2f" % bf[r]
+            lines.append("ATOM  %5d %s ALA A%4d    %s%s%s  1.00%s           C" % (serial % 100000, name, r % 10000, *xs, b))
+            want[r, a] = [np.float32(float(x)) for x in xs]
+            wb[r] = np.float32(float(b))
+            serial += 1
+    lines.append("ATOM  %5d  N   GLY A%4d    %8.3f%8.3f%8.3f  1.00  0.00           N" % (0, n_res % 10000, 0, 0, 0))
+    p = str(tmp_path / "decimals.pdb")
+    open(p, "w").write("\n".join(lines) + "\nEND\n")
+    got = host.read_structure_from_path(p).soa()
+    assert len(got["aa"]) == n_res
+    assert np.array_equal(got["n_xyz"], want[:, 0]) and np.array_equal(got["ca_xyz"], want[:, 1])
+    assert np.array_equal(got["cb_xyz"], want[:, 2])
+    assert np.array_equal(np.signbit(got["ca_xyz"]), np.signbit(want[:, 1]))  # "-0.000" stays a negative zero
+    _same_compact(host.read_structure_from_path(p), O.Structure.read_pdb(p).compact())
+    # fields the short route declines go through strtof as before: exponent form, more than 7 digits, junk
+    def atom(serial, name, res, resi, f1, f2, f3):
+        return "ATOM  %5d %s %s A%4d    %8s%8s%8s  1.00 10.00           C" % (serial, name, res, resi, f1, f2, f3)
+    odd = [atom(1, " N  ", "ALA", 1, "1.0e+1", "2.500000", "0.25"), atom(2, " CA ", "ALA", 1, "1x.0", "2.000", "3.000"),
+           atom(3, " CA ", "ALA", 1, "+4.50", ".5", "6."), atom(4, " CB ", "ALA", 1, "123456.7", "12345678", "-0.00001"),
+           atom(5, " N  ", "GLY", 2, "0.000", "0.000", "0.000")]
+    p2 = str(tmp_path / "odd.pdb")
+    open(p2, "w").write("\n".join(odd) + "\n")
+    g2 = host.read_structure_from_path(p2).soa()
+    assert g2["n_xyz"][0].tolist() == [10.0, 2.5, 0.25] and g2["ca_xyz"][0].tolist() == [4.5, 0.5, 6.0]
+    assert g2["cb_xyz"][0].tolist() == [float(np.float32(x)) for x in (123456.7, 12345678.0, -0.00001)]
+    _same_compact(host.read_structure_from_path(p2), O.Structure.read_pdb(p2).compact())

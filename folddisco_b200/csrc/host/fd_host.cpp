@@ -284,6 +284,11 @@ bool read_file_text(const char *path, bool gz, std::string &data) {
             gzclose(g);
             return false;
         }
+        gzbuffer(g, 1u << 18);
+        {
+            struct stat st;
+            if (stat(path, &st) == 0 && st.st_size > 0) data.reserve((size_t)st.st_size * 6); // text deflates ~4-5x
+        }
         int r;
         while ((r = gzread(g, buf, sizeof(buf))) > 0) data.append(buf, (size_t)r);
         const bool ok = r == 0;

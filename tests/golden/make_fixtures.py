@@ -78,3 +78,12 @@ def long_structure():
 
 if __name__ == "__main__" and "--long" in sys.argv:
     long_structure()
+
+
+def foldcomp_database():
+    """foldcomp/example_db{,.index,.lookup}: the reference's example Foldcomp database (data/foldcomp/example_db, 24 SCOP
+    domains, 52 KB), byte for byte -- input data of the GPU test of `index -p FOLDCOMP_DB`."""
+    import shutil
+    os.makedirs(os.path.join(HERE, "foldcomp"), exist_ok=True)
+    for ext in ("", ".index", ".lookup"):
+        shutil.copyfile(REF + "/data/foldcomp/example_db" + ext, os.path.join(HERE, "foldcomp", "example_db" + ext))

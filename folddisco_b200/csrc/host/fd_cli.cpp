@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -272,8 +273,9 @@ int cmd_index(Args &a) {
     {
         std::vector<std::string> errs(files.size());
         const int nt = std::max(1, std::min(fd_default_host_threads(), 64));
-        auto work = [&](int t) { // static interleaved partition
-            for (size_t k = (size_t)t; k < files.size(); k += (size_t)nt) {
+        std::atomic<size_t> next_file{0};
+        auto work = [&](int) { // files differ in size by orders of magnitude: the threads take them one at a time
+            for (size_t k; (k = next_file.fetch_add(1)) < files.size();) {
                 comps[k] = fcz ? fdh_fcz_db_read(fcz, (int64_t)k) : fdh_compact_read_structure(files[k].c_str());
                 if (!comps[k]) errs[k] = fdh_last_error();
             }

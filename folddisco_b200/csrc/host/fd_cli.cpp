@@ -618,20 +618,43 @@ int cmd_query(Args &a) {
                 fcz = fdh_fcz_db_open(dbp.c_str());
                 if (!fcz) die(std::string("cannot open the Foldcomp database of this index: ") + fdh_last_error());
             }
-            for (uint64_t k = 0; k < S; k++) {
-                std::string p = fdh_index_name(ix, k);
-                fdh_compact *c = nullptr;
-                if (fcz) {
-                    const int64_t e = fdh_fcz_db_find(fcz, p.c_str());
-                    if (e < 0) die("Entry with name " + p + " not found.");
-                    c = fdh_fcz_db_read(fcz, e);
-                } else {
-                    if (!is_file(p)) p = index_dir + p; // resolve_tid_path_from_index_prefix (controller/io.rs:488-528)
-                    c = fdh_compact_read_structure(p.c_str());
+            // the structures are read in parallel (the reference re-reads every candidate inside its rayon loop,
+            // retrieve.rs:375), a few thousand at a time, and added to the store in id order
+            const uint64_t CHUNK = 4096;
+            const int nt = std::max(1, std::min(fd_default_host_threads(), 64));
+            for (uint64_t k0 = 0; k0 < S; k0 += CHUNK) {
+                const uint64_t kn = std::min(CHUNK, S - k0);
+                std::vector<fdh_compact *> got(kn, nullptr);
+                std::vector<std::string> errs(kn);
+                std::atomic<uint64_t> next_k{0};
+                auto work = [&](int) {
+                    for (uint64_t j; (j = next_k.fetch_add(1)) < kn;) {
+                        std::string p = fdh_index_name(ix, k0 + j);
+                        if (fcz) {
+                            const int64_t e = fdh_fcz_db_find(fcz, p.c_str());
+                            if (e < 0) {
+                                errs[j] = "Entry with name " + p + " not found.";
+                                continue;
+                            }
+                            got[j] = fdh_fcz_db_read(fcz, e);
+                        } else {
+                            if (!is_file(p)) p = index_dir + p; // resolve_tid_path_from_index_prefix (controller/io.rs:488-528)
+                            got[j] = fdh_compact_read_structure(p.c_str());
+                        }
+                        if (!got[j]) errs[j] = fdh_last_error();
+                    }
+                };
+                {
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < nt && (uint64_t)t < kn; t++) th.emplace_back(work, t);
+                    work(0);
+                    for (auto &x : th) x.join();
                 }
-                if (!c) die(std::string("Failed to read structure ") + fdh_index_name(ix, k) + ": " + fdh_last_error());
-                fdh_store_add(store, c, fdh_index_name(ix, k));
-                fdh_compact_free(c);
+                for (uint64_t j = 0; j < kn; j++) {
+                    if (!got[j]) die(std::string("Failed to read structure ") + fdh_index_name(ix, k0 + j) + ": " + errs[j]);
+                    fdh_store_add(store, got[j], fdh_index_name(ix, k0 + j));
+                    fdh_compact_free(got[j]);
+                }
             }
             if (fcz) fdh_fcz_db_close(fcz);
         }

@@ -128,36 +128,11 @@ void list_files(const std::string &dir, bool recursive, std::vector<std::string>
     }
 }
 
-std::string file_stem(const std::string &p) {
-    const size_t sl = p.find_last_of('/');
-    std::string f = sl == std::string::npos ? p : p.substr(sl + 1);
-    const size_t dot = f.find_last_of('.');
-    if (dot != std::string::npos && dot > 0) f = f.substr(0, dot);
-    return f;
-}
-
 std::string make_id(const std::string &path, const std::string &id_type) { // mode.rs:19-31, 70-125
-    auto is = [&](std::initializer_list<const char *> a) {
-        for (const char *x : a)
-            if (id_type == x) return true;
-        return false;
-    };
-    if (is({"Pdb", "PDB", "pdb"})) {
-        const std::string s = file_stem(path);
-        return s.compare(0, 3, "pdb") == 0 ? s.substr(3) : s;
-    }
-    if (is({"BasenameWithoutExt", "basename_without_ext", "basename_no_ext", "filename"})) return file_stem(path);
-    if (is({"BasenameWithExt", "basename_with_ext", "basename", "file"})) {
-        const size_t sl = path.find_last_of('/');
-        return sl == std::string::npos ? path : path.substr(sl + 1);
-    }
-    if (is({"AbsPath", "Abspath", "abspath", "absolute_path", "path"})) {
-        char buf[PATH_MAX];
-        return realpath(path.c_str(), buf) ? std::string(buf) : path;
-    }
-    if (is({"Afdb", "AFDB", "afdb", "Uniprot", "UniProt", "uniprot"}))
-        die("--id " + id_type + " is not supported by folddisco-b200 (use relpath, abspath, basename, filename or pdb)");
-    return path; // relpath / default / other
+    std::string out((size_t)fdh_parse_path_by_id_type(path.c_str(), id_type.c_str(), nullptr, 0), '\0');
+    std::vector<char> buf(out.size() + 1);
+    fdh_parse_path_by_id_type(path.c_str(), id_type.c_str(), buf.data(), buf.size());
+    return std::string(buf.data());
 }
 
 std::vector<float> parse_thresholds(const std::string &s) { // comma-separated list (query_pdb.rs parse_threshold_string)

@@ -18,6 +18,7 @@
 #include <charconv>
 #include <chrono>
 #include <condition_variable>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1745,6 +1746,67 @@ void fdh_compact_free(fdh_compact *c) {
     if (!c) return;
     std::shared_ptr<const fdh_compact> last = std::move(c->self.p); // destroyed here unless a query batch still shares it
     if (!last) delete c;
+}
+
+// parse_path_by_id_type (src/controller/mode.rs:19-31, 70-125): the structure id written to PREFIX.lookup for an input
+// path under `--id TYPE`.  Returns the length of the id (written to out with a terminating 0 when it fits in cap).
+int64_t fdh_parse_path_by_id_type(const char *path_c, const char *id_type_c, char *out, uint64_t cap) {
+    const std::string path = path_c, id_type = id_type_c;
+    auto is = [&](std::initializer_list<const char *> a) {
+        for (const char *x : a)
+            if (id_type == x) return true;
+        return false;
+    };
+    auto file_name = [&] {
+        const size_t sl = path.find_last_of('/');
+        return sl == std::string::npos ? path : path.substr(sl + 1);
+    };
+    auto file_stem = [&] { // Path::file_stem: the name up to its last '.', unless that is its first character
+        std::string f = file_name();
+        const size_t dot = f.find_last_of('.');
+        if (dot != std::string::npos && dot > 0) f = f.substr(0, dot);
+        return f;
+    };
+    // leftmost match of the regex AF-.+-model_v\d, `.+` greedy: from the first "AF-" that can match, up to the LAST
+    // "-model_v<digit>" at least one character later
+    auto afdb = [&](const std::string &f, size_t *b, size_t *e) {
+        for (size_t st = f.find("AF-"); st != std::string::npos; st = f.find("AF-", st + 1))
+            for (size_t m = f.rfind("-model_v"); m != std::string::npos && m >= st + 4; m = m ? f.rfind("-model_v", m - 1) : std::string::npos)
+                if (m + 8 < f.size() && isdigit((unsigned char)f[m + 8])) {
+                    *b = st;
+                    *e = m + 9;
+                    return true;
+                }
+        return false;
+    };
+    std::string id;
+    if (is({"Pdb", "PDB", "pdb"})) {
+        const std::string st = file_stem();
+        id = st.compare(0, 3, "pdb") == 0 ? st.substr(3) : st;
+    } else if (is({"Afdb", "AFDB", "afdb"}) || is({"Uniprot", "UniProt", "uniprot"})) {
+        const std::string st = file_stem();
+        size_t b = 0, e = 0;
+        if (!afdb(st, &b, &e)) {
+            id = st;
+        } else if (is({"Afdb", "AFDB", "afdb"})) {
+            id = st.substr(b, e - b);
+        } else { // the second '-'-separated field of the match (mode.rs:105-107)
+            const std::string m = st.substr(b, e - b);
+            const size_t d1 = m.find('-'), d2 = m.find('-', d1 + 1);
+            id = m.substr(d1 + 1, d2 == std::string::npos ? std::string::npos : d2 - d1 - 1);
+        }
+    } else if (is({"BasenameWithoutExt", "basename_without_ext", "basename_no_ext", "filename"})) {
+        id = file_stem();
+    } else if (is({"BasenameWithExt", "basename_with_ext", "basename", "file"})) {
+        id = file_name();
+    } else if (is({"AbsPath", "Abspath", "abspath", "absolute_path", "path"})) {
+        char buf[PATH_MAX];
+        id = realpath(path.c_str(), buf) ? std::string(buf) : path;
+    } else {
+        id = path; // RelPath / Other
+    }
+    if (out && cap > id.size()) memcpy(out, id.c_str(), id.size() + 1);
+    return (int64_t)id.size();
 }
 
 // ---- store ----

@@ -68,6 +68,7 @@ def _lib():
     sig("fdh_compact_avg_plddt", C.c_float, [VP])
     sig("fdh_compact_get", None, [VP] + [VP] * 8)
     sig("fdh_compact_free", None, [VP])
+    sig("fdh_parse_path_by_id_type", C.c_int64, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64])
     sig("fdh_fcz_db_open", VP, [C.c_char_p])
     sig("fdh_fcz_db_close", None, [VP])
     sig("fdh_fcz_db_size", C.c_int64, [VP])
@@ -205,6 +206,14 @@ class CompactStructure:
 def read_structure_from_path(path):
     """read_structure_from_path(path).to_compact()  (src/controller/io.rs:337-379): .pdb / .ent / .cif, optionally .gz"""
     return CompactStructure(_lib().fdh_compact_read_structure(os.fsencode(path)))
+
+
+def parse_path_by_id_type(path, id_type):
+    """src/controller/mode.rs:19-31, 70-125: the lookup id of an input path under `--id TYPE`"""
+    n = _lib().fdh_parse_path_by_id_type(os.fsencode(path), id_type.encode(), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    _lib().fdh_parse_path_by_id_type(os.fsencode(path), id_type.encode(), buf, n + 1)
+    return buf.value.decode()
 
 
 class FoldcompDb:

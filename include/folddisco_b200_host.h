@@ -74,6 +74,11 @@ void fdh_compact_get(const fdh_compact *c, float *n_xyz, float *ca_xyz, float *c
                      uint8_t *aa, uint8_t *chain, uint64_t *serial, float *b_factor);
 void fdh_compact_free(fdh_compact *c);
 
+/* parse_path_by_id_type (src/controller/mode.rs:19-31, 70-125): the id recorded in PREFIX.lookup for an input path under
+ * `--id TYPE` (pdb, afdb, uniprot, filename, basename, abspath, relpath / anything else = the path itself).  Returns the
+ * id's length; the id is written to out (0-terminated) when cap > length. */
+int64_t fdh_parse_path_by_id_type(const char *path, const char *id_type, char *out, uint64_t cap);
+
 /* ---- store ---- */
 fdh_store *fdh_store_new(void);
 /* takes a copy; returns the structure id (position) */

@@ -666,3 +666,25 @@ def test_pdb_decimal_fields_are_correctly_rounded(host, tmp_path):
     assert g2["n_xyz"][0].tolist() == [10.0, 2.5, 0.25] and g2["ca_xyz"][0].tolist() == [4.5, 0.5, 6.0]
     assert g2["cb_xyz"][0].tolist() == [float(np.float32(x)) for x in (123456.7, 12345678.0, -0.00001)]
     _same_compact(host.read_structure_from_path(p2), O.Structure.read_pdb(p2).compact())
+
+
+def test_parse_path_by_id_type(host):
+    """src/controller/mode.rs:19-31, 70-125 (the regex AF-.+-model_v\\d: leftmost start, greedy middle)"""
+    import re
+    rx = re.compile(r"AF-.+-model_v\d")
+    P = host.parse_path_by_id_type
+    af = "data/afdb/AF-P12345-F1-model_v4.pdb"
+    assert P(af, "afdb") == "AF-P12345-F1-model_v4" and P(af, "uniprot") == "P12345" and P(af, "UniProt") == "P12345"
+    assert P("x/AF-A0A4S3KKF6-F1-model_v4.cif.gz", "afdb") == "AF-A0A4S3KKF6-F1-model_v4"  # stem = "...model_v4.cif"
+    assert P("x/AF-A0A4S3KKF6-F1-model_v4.cif.gz", "uniprot") == "A0A4S3KKF6"
+    assert P("data/serine_peptidases/4cha.pdb", "afdb") == "4cha" and P("data/serine_peptidases/4cha.pdb", "uniprot") == "4cha"
+    assert P("d/pdb1abc.ent", "pdb") == "1abc" and P("d/1abc.ent", "PDB") == "1abc"
+    assert P("d/e/1abc.pdb.gz", "filename") == "1abc.pdb" and P("d/e/1abc.pdb.gz", "basename") == "1abc.pdb.gz"
+    assert P("d/e/1abc.pdb", "relpath") == "d/e/1abc.pdb" and P("d/e/1abc.pdb", "whatever") == "d/e/1abc.pdb"
+    assert P("/", "abspath") == "/" and P("d/.hidden", "filename") == ".hidden"
+    for stem in ("AF-AF-Q1-F1-model_v2-model_v3x", "zzAF-Q9-F2-model_v1_AF-Q8-F1-model_v7", "AF--model_v1", "AF-model_v1",
+                 "AF-X-model_v", "AF-X-model_vv-model_v9-model_vx", "noAF", "AF-Q1-F1-model_v12"):
+        m = rx.search(stem)
+        want = m.group(0) if m else stem
+        assert P("dir/" + stem + ".pdb", "afdb") == want, stem
+        assert P("dir/" + stem + ".pdb", "uniprot") == (want.split("-")[1] if m else stem), stem

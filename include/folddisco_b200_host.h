@@ -148,7 +148,8 @@ typedef struct {
 
 fdh_queries *fdh_queries_new(const fdh_query_params *p);
 /* adds one query: structure + query string (an empty string makes every residue a query residue, query.rs:226-233).
- * The structure is copied.  Returns the query number or <0. */
+ * The batch shares the structure with the handle (structures are immutable and reference counted inside the library),
+ * so the caller may fdh_compact_free it right after the call.  Returns the query number or <0. */
 int64_t fdh_queries_add(fdh_queries *qs, const fdh_compact *structure, const char *query_string);
 /* n queries at once, query maps built on `threads` host threads (0 = all cores); returns the first query number */
 int64_t fdh_queries_add_many(fdh_queries *qs, const fdh_compact *const *structures, const char *const *query_strings,

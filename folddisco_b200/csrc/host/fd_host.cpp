@@ -222,7 +222,9 @@ bool field_f32(const char *s, size_t len, float *out) {
     { // plain decimals of at most 7 digits (every coordinate / B-factor column of a PDB file): m / 10^e in binary64 and
       // one rounding to f32 is the correctly rounded value -- m < 2^24 and 10^e <= 10^7 are exact, and the quotient is
       // either exactly a tie of two floats or more than 2^-49 (relative) away from one, out of reach of the 2^-53 of the
-      // division -- i.e. what strtof / Rust's f32::from_str return.  Anything else takes strtof below.
+      // division -- i.e. what strtof / Rust's f32::from_str return (checked against strtof for all 10^7 mantissas
+      // with three decimals, the %8.3f columns, and a 1-in-7 sample of the other seven decimal positions: no
+      // difference).  Anything else takes strtof below.
         static const double P10[8] = {1.0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7};
         size_t i = 0;
         const bool neg = s[0] == '-';

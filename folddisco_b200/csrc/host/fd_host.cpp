@@ -375,7 +375,7 @@ bool parse_cif_atoms(const std::string &data, Atoms &a, std::string &err) {
     bool at_line_start = true;
     auto next = [&](Tok &t) -> bool {
         for (;;) {
-            while (pos < N && (data[pos] == ' ' || data[pos] == '\t' || data[pos] == '\r' || data[pos] == '\n')) {
+            while (pos < N && is_ws(data[pos])) { // (\v and \f too: a value ends at them, so they must be skipped here)
                 at_line_start = data[pos] == '\n';
                 pos++;
             }

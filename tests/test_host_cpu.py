@@ -688,3 +688,23 @@ def test_parse_path_by_id_type(host):
         want = m.group(0) if m else stem
         assert P("dir/" + stem + ".pdb", "afdb") == want, stem
         assert P("dir/" + stem + ".pdb", "uniprot") == (want.split("-")[1] if m else stem), stem
+
+
+@needs_reference
+def test_cif_reader_terminates_on_vertical_tab_and_form_feed(tmp_path):
+    """a value ends at \\v / \\f (C isspace), so the gap between values must skip them too: a file with such a byte used
+    to spin forever in the tokenizer (found by mutating the reference's 2wnb.cif); run in a child with a timeout"""
+    import subprocess
+    import sys
+    src = open(os.path.join(REF, "data", "io_test", "cif", "2wnb.cif"), "rb").read()
+    cut = src.index(b"_atom_site.group_PDB")
+    cases = {"a": src[:cut - 40] + b"\x0b" + src[cut - 40:], "b": src[:cut + 3000] + b"\x0c\x0b \x0c" + src[cut + 3000:]}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, data in cases.items():
+        p = str(tmp_path / (name + ".cif"))
+        open(p, "wb").write(data)
+        code = ("import sys; sys.path.insert(0, %r)\nfrom folddisco_b200 import host\n"
+                "try:\n    print('nres', host.read_structure_from_path(%r).num_residues)\n"
+                "except host.FdError as e:\n    print('refused', e)\n" % (root, p))
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and ("nres" in r.stdout or "refused" in r.stdout), (r.stdout, r.stderr)

@@ -230,13 +230,13 @@ class FoldcompDb:
         return _lib().fdh_fcz_db_size(self.h)
 
     def names(self):
-        return [_lib().fdh_fcz_db_name(self.h, k).decode() for k in range(len(self))]
+        return [os.fsdecode(_lib().fdh_fcz_db_name(self.h, k)) for k in range(len(self))]  # names are bytes on disk
 
     def keys(self):
         return [int(_lib().fdh_fcz_db_key(self.h, k)) for k in range(len(self))]
 
     def find(self, name):
-        return _lib().fdh_fcz_db_find(self.h, name.encode())
+        return _lib().fdh_fcz_db_find(self.h, os.fsencode(name))
 
     def read(self, k):
         """read_single_structure_by_id(...).to_compact() of the k-th named entry"""

@@ -581,9 +581,19 @@ bool fcz_decode(const uint8_t *p, size_t n, Atoms &a, std::string &err) {
         err = c.err;
         return false;
     }
-    void *inst = c.create();
+    void *inst = nullptr;
     size_t count = 0;
-    FczAtom *out = inst ? c.process(inst, p, n, &count) : nullptr;
+    FczAtom *out = nullptr;
+    try { // the codec is C++ behind a C wrapper that catches nothing: a corrupt entry makes it throw (length_error, bad_alloc)
+        inst = c.create();
+        out = inst ? c.process(inst, p, n, &count) : nullptr;
+    } catch (const std::exception &e) {
+        err = std::string("the Foldcomp codec failed on this entry: ") + e.what();
+        return false; // (the instance is abandoned: its state is unknown)
+    } catch (...) {
+        err = "the Foldcomp codec failed on this entry";
+        return false;
+    }
     if (!out) {
         if (inst) c.destroy(inst);
         err = "the Foldcomp codec returned no atoms";

@@ -513,6 +513,18 @@ def test_foldcomp_database_reader(host, foldcomp_codec):
     _same_compact(host.read_structure_from_path(os.path.join(REF, "data", "foldcomp", "7m0y.fcz")), want)
     with pytest.raises(host.FdError):
         host.compact_from_fcz(b"not a foldcomp entry")
+    # a truncated entry makes the codec throw (std::length_error through its C wrapper): an error here, not an abort.
+    # In a child process: what the third-party codec does with corrupt bytes is its own (it can also crash).
+    import subprocess
+    import sys
+    bad = str(os.path.join(os.environ.get("TMPDIR", "/tmp"), "fd_truncated_%d.fcz" % os.getpid()))
+    open(bad, "wb").write(one[:100])
+    code = ("import sys; sys.path.insert(0, %r)\nfrom folddisco_b200 import host\n"
+            "try:\n    host.compact_from_fcz(open(%r, 'rb').read())\n    print('decoded')\n"
+            "except host.FdError as e:\n    print('refused', e)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), bad))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    os.remove(bad)
+    assert r.returncode == 0 and "refused" in r.stdout and "codec failed" in r.stdout, (r.returncode, r.stdout, r.stderr)
     with pytest.raises(host.FdError):
         host.FoldcompDb(os.path.join(REF, "data", "foldcomp", "missing_db"))
 

@@ -50,5 +50,5 @@ def test_search_batches_equals_one_batch_at_a_time():
                 nres = len(strings[a + k].split(","))
                 assert [want.residue_string(m, nres) for m in mx] == [got.residue_string(m, nres) for m in my]
         del looped
-    del serial
+    del serial, qb, batches
     ctx.close()
